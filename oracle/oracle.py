@@ -1,0 +1,219 @@
+"""ctypes binding for oracle/_build/libpsoracle.so (our plain-C restatement, ps_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's
+CPU-baseline legs; never from pocketsphinx_b200/.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_build", "libpsoracle.so")
+
+KIND_ID = {"ptm": 0, "s2_semi": 1, "ms": 2}
+MAX_FEAT = 8
+
+# same layout as the reference's 88-byte hmm_t (src/hmm.h:169-182)
+HMM_DTYPE = np.dtype({
+    "names": ["ctx", "score", "history", "out_score", "out_history", "ssid", "senid",
+              "bestscore", "tmatid", "frame", "mpx", "n_emit_state"],
+    "formats": ["<u8", ("<i4", 5), ("<i4", 5), "<i4", "<i4", "<u2", ("<u2", 5),
+                "<i4", "<i2", "<i4", "u1", "u1"],
+    "offsets": [0, 8, 28, 48, 52, 56, 58, 68, 72, 76, 80, 81],
+    "itemsize": 88,
+})
+
+
+class _Model(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_sen", C.c_int32), ("n_mgau", C.c_int32),
+                ("n_feat", C.c_int32), ("n_density", C.c_int32), ("topn", C.c_int32),
+                ("featlen", C.c_int32 * MAX_FEAT), ("ds_ratio", C.c_int32), ("aw", C.c_int32),
+                ("mixw_4bit", C.c_int32), ("pdf_transposed", C.c_int32),
+                ("logadd_ms_size", C.c_int32), ("logadd_ms_zero", C.c_int32),
+                ("mean", C.c_void_p), ("var", C.c_void_p), ("det", C.c_void_p),
+                ("mixw", C.c_void_p), ("mixw_cb", C.c_void_p), ("sen2cb", C.c_void_p),
+                ("logadd8", C.c_void_p), ("logadd_ms", C.c_void_p), ("topn_beam", C.c_void_p)]
+
+
+class _HmmCtx(C.Structure):
+    _fields_ = [("n_emit_state", C.c_int32), ("tp", C.c_void_p), ("sseq", C.c_void_p),
+                ("senscore", C.c_void_p)]
+
+
+def build(force=False):
+    if force or not os.path.exists(LIB_PATH) or \
+            os.path.getmtime(LIB_PATH) < os.path.getmtime(os.path.join(HERE, "ps_oracle.c")):
+        subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        L.pso_gmm_new.restype = C.c_void_p
+        L.pso_gmm_new.argtypes = [C.c_void_p, C.c_int32]
+        L.pso_gmm_free.argtypes = [C.c_void_p]
+        L.pso_gmm_reset.argtypes = [C.c_void_p]
+        L.pso_frame_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                     C.c_int32, C.c_int32]
+        L.pso_score_utt.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        L.pso_flags2list.restype = C.c_int32
+        L.pso_flags2list.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.pso_time_score_utt.restype = C.c_double
+        L.pso_time_score_utt.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+        L.pso_hmm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.pso_hmm_vit_eval_batch.restype = C.c_int32
+        L.pso_hmm_vit_eval_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        L.pso_phoneloop_new.restype = C.c_void_p
+        L.pso_phoneloop_new.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                        C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_double]
+        L.pso_phoneloop_free.argtypes = [C.c_void_p]
+        L.pso_phoneloop_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None or (hasattr(a, "size") and a.size == 0) else a.ctypes.data
+
+
+class OracleModel:
+    """Wraps a pocketsphinx_b200.model.PackedModel (or equivalent dict) for the C oracle."""
+
+    def __init__(self, pm):
+        self.pm = pm
+        m = _Model()
+        m.kind = KIND_ID[pm.kind]
+        m.n_sen, m.n_mgau, m.n_feat, m.n_density, m.topn = pm.n_sen, pm.n_mgau, pm.n_feat, pm.n_density, pm.topn
+        for i, v in enumerate(pm.featlen):
+            m.featlen[i] = int(v)
+        m.ds_ratio = max(1, int(pm.ds_ratio))
+        m.aw = int(pm.aw) if pm.aw else 1
+        m.mixw_4bit = int(pm.mixw_4bit)
+        m.pdf_transposed = int(pm.n_mgau == 1)
+        m.logadd_ms_size = int(pm.logadd_ms.size)
+        m.logadd_ms_zero = int(pm.logadd_ms_zero)
+        m.mean, m.var, m.det = _p(pm.mean), _p(pm.var), _p(pm.det)
+        m.mixw, m.mixw_cb, m.sen2cb = _p(pm.mixw), _p(pm.mixw_cb), _p(pm.sen2cb)
+        m.logadd8, m.logadd_ms = _p(pm.logadd8), _p(pm.logadd_ms)
+        m.topn_beam = _p(pm.topn_beam) if pm.topn_beam.size and pm.topn_beam.any() else None
+        self.c = m
+
+    def score_utt(self, feats, want_topn=False):
+        pm = self.pm
+        feats = np.ascontiguousarray(feats, np.float32)
+        T = feats.shape[0]
+        scr = np.zeros((T, pm.n_sen), np.int16)
+        topn = None
+        if want_topn and pm.kind == "ptm":
+            topn = np.zeros((T, pm.n_mgau, pm.n_feat, pm.topn, 2), np.int32)
+        elif want_topn and pm.kind == "s2_semi":
+            topn = np.zeros((T, pm.n_feat, pm.topn, 2), np.int32)
+        lib().pso_score_utt(C.byref(self.c), _p(feats), T, _p(scr), _p(topn))
+        return (scr, topn) if want_topn else scr
+
+    def time_score_utt(self, feats, reps=1):
+        feats = np.ascontiguousarray(feats, np.float32)
+        return lib().pso_time_score_utt(C.byref(self.c), _p(feats), feats.shape[0], reps)
+
+    def decoder(self, n_hist=2):
+        return OracleGmm(self, n_hist)
+
+
+class OracleGmm:
+    """One ps_mgau_t-like scorer with its top-N history ring and frame_idx."""
+
+    def __init__(self, om, n_hist):
+        self.om = om
+        self.h = lib().pso_gmm_new(C.byref(om.c), n_hist)
+        self.frame_idx_off = None
+
+    def close(self):
+        if self.h:
+            lib().pso_gmm_free(self.h)
+            self.h = None
+
+    def reset(self):
+        lib().pso_gmm_reset(self.h)
+
+    def set_frame_idx(self, v):
+        # pso_gmm_t: {m*, n_hist, frame_idx, ...}: frame_idx sits after an 8-byte ptr + int32
+        C.c_int32.from_address(self.h + 12).value = int(v)
+
+    def frame_eval(self, feat, frame, active_list=None, compallsen=True):
+        pm = self.om.pm
+        feat = np.ascontiguousarray(feat, np.float32)
+        scr = np.zeros(pm.n_sen, np.int16)
+        if active_list is not None:
+            active_list = np.ascontiguousarray(active_list, np.uint8)
+        n = 0 if active_list is None else len(active_list)
+        lib().pso_frame_eval(self.h, _p(scr), _p(active_list), n, _p(feat), frame, int(compallsen))
+        return scr
+
+    def frame_eval_into(self, scr, feat, frame, active_list=None, compallsen=True):
+        """Like frame_eval but writes into a caller buffer (stale entries kept, as the ms
+        back-end leaves inactive senones untouched)."""
+        feat = np.ascontiguousarray(feat, np.float32)
+        if active_list is not None:
+            active_list = np.ascontiguousarray(active_list, np.uint8)
+        n = 0 if active_list is None else len(active_list)
+        lib().pso_frame_eval(self.h, _p(scr), _p(active_list), n, _p(feat), frame, int(compallsen))
+        return scr
+
+
+def flags2list(flags):
+    flags = np.ascontiguousarray(flags, np.uint8)
+    out = np.zeros(len(flags), np.uint8)
+    n = lib().pso_flags2list(_p(flags), len(flags), _p(out))
+    return out[:n].copy()
+
+
+class OracleHmmCtx:
+    def __init__(self, tp, sseq):
+        self.tp = np.ascontiguousarray(tp, np.uint8)
+        self.sseq = np.ascontiguousarray(sseq, np.uint16)
+        self.n_emit = self.tp.shape[1]
+        c = _HmmCtx()
+        c.n_emit_state = self.n_emit
+        c.tp = _p(self.tp)
+        c.sseq = _p(self.sseq)
+        self.c = c
+
+    def init(self, n, mpx, ssid, tmatid):
+        hm = np.zeros(n, HMM_DTYPE)
+        for i in range(n):
+            lib().pso_hmm_init(C.byref(self.c), hm[i:i + 1].ctypes.data, int(mpx[i]), int(ssid[i]), int(tmatid[i]))
+        return hm
+
+    def vit_eval(self, hmms, senscr):
+        senscr = np.ascontiguousarray(senscr, np.int16)
+        assert hmms.dtype == HMM_DTYPE and hmms.flags.c_contiguous
+        self.c.senscore = _p(senscr)
+        return int(lib().pso_hmm_vit_eval_batch(C.byref(self.c), _p(hmms), len(hmms)))
+
+
+def phoneloop_run(tp, sseq, ssid, tmatid, senscr, window, beam, pbeam, pip, penalty_weight):
+    """phone_loop_search.c semantics over a [T][n_sen] senone score matrix."""
+    tp = np.ascontiguousarray(tp, np.uint8)
+    sseq = np.ascontiguousarray(sseq, np.uint16)
+    ssid = np.ascontiguousarray(ssid, np.int32)
+    tmatid = np.ascontiguousarray(tmatid, np.int32)
+    senscr = np.ascontiguousarray(senscr, np.int16)
+    T, n_sen = senscr.shape
+    n = len(ssid)
+    p = lib().pso_phoneloop_new(tp.shape[1], _p(tp), _p(sseq), n, _p(ssid), _p(tmatid),
+                                window, beam, pbeam, pip, float(penalty_weight))
+    hm = np.zeros((T, n), HMM_DTYPE)
+    best = np.zeros(T, np.int32)
+    pen = np.zeros((T, n), np.int32)
+    lib().pso_phoneloop_run(p, _p(senscr), n_sen, T, _p(hm), _p(best), _p(pen))
+    lib().pso_phoneloop_free(p)
+    return dict(hmm=hm, best=best, pen=pen)

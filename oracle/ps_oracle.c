@@ -1,0 +1,1152 @@
+/* oracle/ps_oracle.c -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * CPU restatement of the PocketSphinx acoustic-scoring + Viterbi hot path; see ps_oracle.h.
+ * Citations are to /root/reference (cmusphinx/pocketsphinx 5.1.1 @ 511126b), default float
+ * build.  Compile with -ffp-contract=off: the reference accumulates the Gaussian exponent
+ * with separate subtract / multiply / multiply / subtract roundings (ptm_mgau.c:64-69).
+ */
+#include "ps_oracle.h"
+
+#include <limits.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+/* ------------------------------------------------------------------------------------ */
+/* helpers                                                                               */
+
+/* (int32)d with the clamp both tied back-ends apply first (ptm_mgau.c:129-132,219-222;
+ * s2_semi_mgau.c:97-100,143-146). */
+static int32_t
+f2i_clamped(float d)
+{
+    if (d < (float)INT32_MIN)
+        return INT32_MIN;
+    return (int32_t)d;
+}
+
+/* fast_logmath_add on negated logs (tied_mgau_common.h:111-127). */
+static int
+logadd8(const uint8_t *tab, int mlx, int mly)
+{
+    int d, r;
+    if (mlx > mly) { d = mlx - mly; r = mly; }
+    else { d = mly - mlx; r = mlx; }
+    return r - tab[d];
+}
+
+static size_t
+gau_offset(const pso_model_t *m, int cb, int f)
+{
+    /* start of (cb, f) inside mean/var: [n_mgau][n_feat][n_density][featlen[f]] */
+    size_t sum = 0, off = 0;
+    int i;
+    for (i = 0; i < m->n_feat; ++i) sum += m->featlen[i];
+    for (i = 0; i < f; ++i) off += m->featlen[i];
+    return ((size_t)cb * sum + off) * m->n_density;
+}
+
+/* Full (no early exit) log-density of one codeword: det - sum_j ((x_j - mu_j)^2 * v_j), each
+ * product and difference rounded separately, dimensions in ascending order.  The chunked
+ * order of ptm_mgau.c:107-128 (ceplen%4 leading dims, then groups of four MAP then REDUCE)
+ * performs the same operations on d in the same order. */
+static float
+gau_full(const float *mean, const float *var, float det, const float *x, int len)
+{
+    float d = det;
+    int j;
+    for (j = 0; j < len; ++j) {
+        float diff = x[j] - mean[j];
+        float sq = diff * diff;
+        float c = sq * var[j];
+        d = d - c;
+    }
+    return d;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* state                                                                                 */
+
+pso_gmm_t *
+pso_gmm_new(const pso_model_t *m, int32_t n_hist)
+{
+    pso_gmm_t *g = calloc(1, sizeof(*g));
+    int i;
+    g->m = m;
+    g->n_hist = n_hist < 1 ? 1 : n_hist;
+    for (i = 0; i < m->n_feat; ++i) g->sumlen += m->featlen[i];
+    if (m->kind == PSO_KIND_PTM) {
+        g->hist = calloc((size_t)g->n_hist * m->n_mgau * m->n_feat * m->topn, sizeof(pso_topn_t));
+        g->cb_active = calloc((size_t)g->n_hist * m->n_mgau, 1);
+    }
+    else if (m->kind == PSO_KIND_SEMI) {
+        g->hist = calloc((size_t)g->n_hist * m->n_feat * m->topn, sizeof(pso_topn_t));
+        g->hist_n = calloc((size_t)g->n_hist * m->n_feat, 1);
+    }
+    else {
+        g->ms_dist = calloc((size_t)m->n_mgau * m->n_feat * m->topn, sizeof(pso_topn_t));
+    }
+    pso_gmm_reset(g);
+    return g;
+}
+
+void
+pso_gmm_free(pso_gmm_t *g)
+{
+    if (!g) return;
+    free(g->hist); free(g->cb_active); free(g->hist_n); free(g->ms_dist);
+    free(g);
+}
+
+/* ptm_mgau_reset_fast_hist (ptm_mgau.c:777-803); s2_semi_mgau_init (s2_semi_mgau.c:1319-1327):
+ * codewords 0..N-1 with WORST_DIST, every codebook active. */
+void
+pso_gmm_reset(pso_gmm_t *g)
+{
+    const pso_model_t *m = g->m;
+    size_t n, i;
+    g->frame_idx = 0;
+    if (m->kind == PSO_KIND_PTM) {
+        n = (size_t)g->n_hist * m->n_mgau * m->n_feat;
+        for (i = 0; i < n * m->topn; ++i) {
+            g->hist[i].cw = (int32_t)(i % m->topn);
+            g->hist[i].score = PSO_WORST_DIST;
+        }
+        memset(g->cb_active, 1, (size_t)g->n_hist * m->n_mgau);
+    }
+    else if (m->kind == PSO_KIND_SEMI) {
+        n = (size_t)g->n_hist * m->n_feat;
+        for (i = 0; i < n * m->topn; ++i) {
+            g->hist[i].cw = (int32_t)(i % m->topn);
+            g->hist[i].score = PSO_WORST_DIST;
+        }
+        memset(g->hist_n, 0, n);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* tied back-ends: re-score last frame's list, then scan the codebook                    */
+
+/* eval_topn (ptm_mgau.c:88-136, s2_semi_mgau.c:70-109): re-score the N listed codewords
+ * for this frame; stable insertion sort, descending, strict '>' (ptm_mgau.c:72-85). */
+static void
+rescore_topn(const pso_model_t *m, pso_topn_t *topn, int cb, int f, const float *x)
+{
+    int len = m->featlen[f], i, j;
+    size_t base = gau_offset(m, cb, f);
+    const float *det = m->det + ((size_t)cb * m->n_feat + f) * m->n_density;
+
+    for (i = 0; i < m->topn; ++i) {
+        int32_t cw = topn[i].cw;
+        pso_topn_t v;
+        float d = gau_full(m->mean + base + (size_t)cw * len, m->var + base + (size_t)cw * len,
+                           det[cw], x, len);
+        v.cw = cw;
+        v.score = f2i_clamped(d);
+        for (j = i - 1; j >= 0 && v.score > topn[j].score; --j)
+            topn[j + 1] = topn[j];
+        topn[j + 1] = v;
+    }
+}
+
+/* insertion_sort_cb (ptm_mgau.c:140-149) / the tail of eval_cb (s2_semi_mgau.c:156-161):
+ * drop the worst entry, shift down every entry whose score is <= intd. */
+static void
+insert_cw(pso_topn_t *topn, int n, int32_t cw, int32_t intd)
+{
+    int k = n - 1;
+    while (k > 0 && intd >= topn[k - 1].score) {
+        topn[k] = topn[k - 1];
+        --k;
+    }
+    topn[k].cw = cw;
+    topn[k].score = intd;
+}
+
+static int
+listed(const pso_topn_t *topn, int n, int32_t cw)
+{
+    int i;
+    for (i = 0; i < n; ++i)
+        if (topn[i].cw == cw) return 1;
+    return 0;
+}
+
+/* eval_cb, PTM flavour (ptm_mgau.c:152-226): early exit tested in float against
+ * (float)worst->score before the leading ceplen%4 dims one at a time, then before each group
+ * of four, and once more after the last dimension. */
+static void
+scan_cb_ptm(const pso_model_t *m, pso_topn_t *topn, int cb, int f, const float *x)
+{
+    int len = m->featlen[f], n = m->topn, cw;
+    size_t base = gau_offset(m, cb, f);
+    const float *det = m->det + ((size_t)cb * m->n_feat + f) * m->n_density;
+
+    for (cw = 0; cw < m->n_density; ++cw) {
+        const float *mean = m->mean + base + (size_t)cw * len;
+        const float *var = m->var + base + (size_t)cw * len;
+        float d = det[cw];
+        float thresh = (float)topn[n - 1].score;
+        int j = 0, k;
+
+        while (j < len % 4 && d >= thresh) {
+            float diff = x[j] - mean[j];
+            float sq = diff * diff;
+            d = d - sq * var[j];
+            ++j;
+        }
+        while (j < len && d >= thresh) {
+            float c[4];
+            for (k = 0; k < 4; ++k) {
+                float diff = x[j + k] - mean[j + k];
+                float sq = diff * diff;
+                c[k] = sq * var[j + k];
+            }
+            for (k = 0; k < 4; ++k)
+                d = d - c[k];
+            j += 4;
+        }
+        if (j < len) continue;          /* knocked out early */
+        if (d < thresh) continue;
+        if (listed(topn, n, cw)) continue;
+        insert_cw(topn, n, cw, f2i_clamped(d));
+    }
+}
+
+/* eval_cb, semi-continuous flavour (s2_semi_mgau.c:112-170): the per-dimension test compares
+ * float d with the int worst score (promoted to float); after a complete pass the test is on
+ * the truncated int. */
+static void
+scan_cb_semi(const pso_model_t *m, pso_topn_t *topn, int f, const float *x)
+{
+    int len = m->featlen[f], n = m->topn, cw;
+    size_t base = gau_offset(m, 0, f);
+    const float *det = m->det + (size_t)f * m->n_density;
+
+    for (cw = 0; cw < m->n_density; ++cw) {
+        const float *mean = m->mean + base + (size_t)cw * len;
+        const float *var = m->var + base + (size_t)cw * len;
+        float d = det[cw];
+        int32_t di;
+        int j;
+
+        for (j = 0; j < len && d >= (float)topn[n - 1].score; ++j) {
+            float diff = x[j] - mean[j];
+            float sq = diff * diff;
+            d = d - sq * var[j];
+        }
+        if (j < len) continue;
+        di = f2i_clamped(d);
+        if (di < topn[n - 1].score) continue;
+        if (listed(topn, n, cw)) continue;
+        insert_cw(topn, n, cw, di);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* PTM                                                                                   */
+
+/* ptm_mgau_codebook_norm (ptm_mgau.c:266-295): per stream, max over active codebooks of
+ * (best score >> 10); every listed score becomes min(96, -((score >> 10) - norm)). */
+static void
+ptm_norm(const pso_model_t *m, pso_topn_t *slot, const uint8_t *active)
+{
+    int f, cb, k;
+    for (f = 0; f < m->n_feat; ++f) {
+        int32_t norm = PSO_WORST_SCORE;
+        for (cb = 0; cb < m->n_mgau; ++cb) {
+            int32_t top;
+            if (!active[cb]) continue;
+            top = slot[((size_t)cb * m->n_feat + f) * m->topn].score >> PSO_SENSCR_SHIFT;
+            if (norm < top) norm = top;
+        }
+        for (cb = 0; cb < m->n_mgau; ++cb) {
+            pso_topn_t *t = slot + ((size_t)cb * m->n_feat + f) * m->topn;
+            if (!active[cb]) continue;
+            for (k = 0; k < m->topn; ++k) {
+                int32_t s = t[k].score >> PSO_SENSCR_SHIFT;
+                s = -(s - norm);
+                if (s > PSO_MAX_NEG_ASCR) s = PSO_MAX_NEG_ASCR;
+                t[k].score = s;
+            }
+        }
+    }
+}
+
+/* ptm_mgau_senone_eval (ptm_mgau.c:327-403). */
+static void
+ptm_senones(const pso_model_t *m, pso_topn_t *slot, const uint8_t *active, int16_t *senscr,
+            const uint8_t *list, int32_t n_list, int compall)
+{
+    int32_t i, last = 0, best = 0x7fffffff;
+    size_t row = m->mixw_4bit ? (size_t)(m->n_sen + 1) / 2 : (size_t)m->n_sen;
+
+    memset(senscr, 0, (size_t)m->n_sen * sizeof(*senscr));
+    if (compall) n_list = m->n_sen;
+    for (i = 0; i < n_list; ++i) {
+        int32_t sen = compall ? i : list[i] + last;
+        int cb, f, j, ascore = 0;
+        last = sen;
+        cb = m->sen2cb[sen];
+        if (!active[cb]) {
+            /* senones of a pruned codebook see every density at the floor (:353-364) */
+            for (f = 0; f < m->n_feat; ++f)
+                for (j = 0; j < m->topn; ++j)
+                    slot[((size_t)cb * m->n_feat + f) * m->topn + j].score = PSO_MAX_NEG_ASCR;
+        }
+        for (f = 0; f < m->n_feat; ++f) {
+            const pso_topn_t *t = slot + ((size_t)cb * m->n_feat + f) * m->topn;
+            int fden = 0;
+            for (j = 0; j < m->topn; ++j) {
+                const uint8_t *r = m->mixw + ((size_t)f * m->n_density + t[j].cw) * row;
+                int w;
+                if (m->mixw_4bit) {
+                    int b = r[sen / 2];
+                    /* NB the reference tests the low bit of the *byte*, not of sen (:376-377) */
+                    b = (b & 1) ? b >> 4 : b & 0x0f;
+                    w = m->mixw_cb[b];
+                }
+                else
+                    w = r[sen];
+                fden = j == 0 ? w + t[j].score : logadd8(m->logadd8, fden, w + t[j].score);
+            }
+            ascore += fden;
+        }
+        if (ascore < best) best = ascore;
+        senscr[sen] = (int16_t)ascore;
+    }
+    for (i = 0; i < m->n_sen; ++i)
+        senscr[i] = (int16_t)(senscr[i] - best);
+}
+
+/* ptm_mgau_frame_eval (ptm_mgau.c:409-454). */
+static int
+ptm_frame_eval(pso_gmm_t *g, int16_t *senscr, const uint8_t *list, int32_t n_list,
+               const float *feat, int32_t frame, int32_t compall)
+{
+    const pso_model_t *m = g->m;
+    size_t per = (size_t)m->n_mgau * m->n_feat * m->topn;
+    int idx = frame % g->n_hist;
+    pso_topn_t *slot = g->hist + per * idx;
+    uint8_t *active = g->cb_active + (size_t)idx * m->n_mgau;
+    int cb, f, off;
+
+    if (frame >= g->frame_idx) {
+        int prev = idx == 0 ? g->n_hist - 1 : idx - 1;
+        int32_t i, last = 0;
+        if (prev != idx)
+            memcpy(slot, g->hist + per * prev, per * sizeof(*slot));
+        /* ptm_mgau_calc_cb_active (:298-321) */
+        if (compall)
+            memset(active, 1, m->n_mgau);
+        else {
+            memset(active, 0, m->n_mgau);
+            for (i = 0; i < n_list; ++i) {
+                int32_t sen = list[i] + last;
+                active[m->sen2cb[sen]] = 1;
+                last = sen;
+            }
+        }
+        /* ptm_mgau_codebook_eval (:232-254) */
+        for (cb = 0; cb < m->n_mgau; ++cb)
+            for (f = 0, off = 0; f < m->n_feat; off += m->featlen[f], ++f)
+                rescore_topn(m, slot + ((size_t)cb * m->n_feat + f) * m->topn, cb, f, feat + off);
+        if (frame % m->ds_ratio == 0)
+            for (cb = 0; cb < m->n_mgau; ++cb) {
+                if (!active[cb]) continue;
+                for (f = 0, off = 0; f < m->n_feat; off += m->featlen[f], ++f)
+                    scan_cb_ptm(m, slot + ((size_t)cb * m->n_feat + f) * m->topn, cb, f, feat + off);
+            }
+        ptm_norm(m, slot, active);
+    }
+    ptm_senones(m, slot, active, senscr, list, n_list, compall);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* semi-continuous                                                                       */
+
+/* mgau_norm (s2_semi_mgau.c:186-203): returns how many entries survive topn_beam. */
+static int
+semi_norm(const pso_model_t *m, pso_topn_t *t, int f)
+{
+    int32_t norm = t[0].score >> PSO_SENSCR_SHIFT;
+    int beam = m->topn_beam ? m->topn_beam[f] : 0;
+    int j;
+    for (j = 0; j < m->topn; ++j) {
+        t[j].score = -((t[j].score >> PSO_SENSCR_SHIFT) - norm);
+        if (t[j].score > PSO_MAX_NEG_ASCR) t[j].score = PSO_MAX_NEG_ASCR;
+        if (beam && t[j].score > beam) break;
+    }
+    return j;
+}
+
+static int
+nib(const uint8_t *row, int sen)
+{
+    return (sen & 1) ? row[sen / 2] >> 4 : row[sen / 2] & 0x0f;
+}
+
+/* get_scores_{8b,4b}_feat{_N,_any,_all} (s2_semi_mgau.c:206-831), one stream.  All 8-bit
+ * variants compute the same int expression.  4-bit: the unrolled N=1..6 active-list variants
+ * pre-add mixw_cb + score into uint8 (wraps mod 256, :453-463); _any and _all use int;
+ * _all stops at n_sen & ~1 (:809). */
+static void
+semi_senones(const pso_model_t *m, const pso_topn_t *t, int f, int topn, int16_t *senscr,
+             const uint8_t *list, int32_t n_list, int compall)
+{
+    size_t row = m->mixw_4bit ? (size_t)(m->n_sen + 1) / 2 : (size_t)m->n_sen;
+    const uint8_t *base = m->mixw + (size_t)f * m->n_density * row;
+    int wrap8 = m->mixw_4bit && !compall && topn >= 1 && topn <= 6;
+    int32_t n = compall ? (m->mixw_4bit ? (m->n_sen & ~1) : m->n_sen) : n_list;
+    int32_t i, last = 0;
+    int k;
+
+    for (i = 0; i < n; ++i) {
+        int32_t sen = compall ? i : list[i] + last;
+        int tmp = 0;
+        last = sen;
+        for (k = 0; k == 0 || k < topn; ++k) {
+            const uint8_t *r = base + (size_t)t[k].cw * row;
+            int w = m->mixw_4bit ? m->mixw_cb[nib(r, sen)] : r[sen];
+            int v = w + t[k].score;
+            if (wrap8) v &= 0xff;
+            tmp = k == 0 ? v : logadd8(m->logadd8, tmp, v);
+        }
+        senscr[sen] = (int16_t)(senscr[sen] + tmp);
+    }
+}
+
+/* s2_semi_mgau_frame_eval (s2_semi_mgau.c:837-883). */
+static int
+semi_frame_eval(pso_gmm_t *g, int16_t *senscr, const uint8_t *list, int32_t n_list,
+                const float *feat, int32_t frame, int32_t compall)
+{
+    const pso_model_t *m = g->m;
+    size_t per = (size_t)m->n_feat * m->topn;
+    int idx = frame % g->n_hist, f, off = 0;
+    pso_topn_t *slot = g->hist + per * idx;
+
+    memset(senscr, 0, (size_t)m->n_sen * sizeof(*senscr));
+    for (f = 0; f < m->n_feat; off += m->featlen[f], ++f) {
+        pso_topn_t *t = slot + (size_t)f * m->topn;
+        if (frame >= g->frame_idx) {
+            int prev = idx == 0 ? g->n_hist - 1 : idx - 1;
+            if (prev != idx)
+                memcpy(t, g->hist + per * prev + (size_t)f * m->topn, m->topn * sizeof(*t));
+            /* mgau_dist (:172-183) */
+            rescore_topn(m, t, 0, f, feat + off);
+            if (frame % m->ds_ratio == 0)
+                scan_cb_semi(m, t, f, feat + off);
+            g->hist_n[(size_t)idx * m->n_feat + f] = (uint8_t)semi_norm(m, t, f);
+        }
+        semi_senones(m, t, f, g->hist_n[(size_t)idx * m->n_feat + f], senscr, list, n_list, compall);
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* ms (continuous / generic multi-stream)                                                */
+
+typedef struct { int32_t id; float dist; } ms_dist_t;
+
+/* compute_dist / compute_dist_all (ms_gauden.c:378-489). */
+static void
+ms_compute_dist(const pso_model_t *m, ms_dist_t *out, int cb, int f, const float *x)
+{
+    int len = m->featlen[f], n = m->topn, d, i, j;
+    size_t base = gau_offset(m, cb, f);
+    const float *det = m->det + ((size_t)cb * m->n_feat + f) * m->n_density;
+
+    if (n >= m->n_density) {
+        for (d = 0; d < m->n_density; ++d) {
+            out[d].dist = gau_full(m->mean + base + (size_t)d * len, m->var + base + (size_t)d * len,
+                                   det[d], x, len);
+            out[d].id = d;
+        }
+        return;
+    }
+    for (i = 0; i < n; ++i) {
+        out[i].dist = (float)PSO_WORST_DIST;
+        out[i].id = 0;   /* ckd_calloc'ed, and never read before being overwritten... */
+    }
+    for (d = 0; d < m->n_density; ++d) {
+        const float *mean = m->mean + base + (size_t)d * len;
+        const float *var = m->var + base + (size_t)d * len;
+        float dv = det[d];
+        for (i = 0; i < len && dv >= out[n - 1].dist; ++i) {
+            float diff = x[i] - mean[i];
+            dv -= diff * diff * var[i];
+        }
+        if (i < len || dv < out[n - 1].dist) continue;
+        for (i = 0; i < n && dv < out[i].dist; ++i) ;
+        for (j = n - 1; j > i; --j) out[j] = out[j - 1];
+        out[i].dist = dv;
+        out[i].id = d;
+    }
+}
+
+/* logmath_add with a shifted table (logmath.c:402-446). */
+static int
+logadd_wide(const pso_model_t *m, int x, int y)
+{
+    int d, r;
+    if (x <= m->logadd_ms_zero) return y;
+    if (y <= m->logadd_ms_zero) return x;
+    if (x > y) { d = x - y; r = x; }
+    else { d = y - x; r = y; }
+    if (d < 0) return r;
+    if (d >= m->logadd_ms_size) return r;
+    return r + (int)m->logadd_ms[d];
+}
+
+/* senone_eval (ms_senone.c:358-407). */
+static int32_t
+ms_senone(const pso_model_t *m, int id, const ms_dist_t *dist /* [n_feat][topn] */)
+{
+    int32_t scr = 0;
+    int f, t, n = m->topn < m->n_density ? m->topn : m->n_density;
+    for (f = 0; f < m->n_feat; ++f) {
+        const ms_dist_t *fd = dist + (size_t)f * m->topn;
+        int32_t fscr = 0;
+        for (t = 0; t < n; ++t) {
+            int32_t fden, w, fw;
+            if (fd[t].dist < (float)INT32_MIN)
+                fden = INT32_MIN >> PSO_SENSCR_SHIFT;
+            else
+                fden = ((int32_t)fd[t].dist + ((1 << PSO_SENSCR_SHIFT) - 1)) >> PSO_SENSCR_SHIFT;
+            w = m->pdf_transposed
+                ? m->mixw[((size_t)f * m->n_density + fd[t].id) * m->n_sen + id]
+                : m->mixw[((size_t)id * m->n_feat + f) * m->n_density + fd[t].id];
+            fw = fden - w;
+            fscr = t == 0 ? fw : logadd_wide(m, fscr, fw);
+        }
+        scr -= fscr;
+    }
+    scr /= m->aw;
+    if (scr > 32767) scr = 32767;
+    if (scr < -32768) scr = -32768;
+    return scr;
+}
+
+/* ms_cont_mgau_frame_eval (ms_mgau.c:192-282). */
+static int
+ms_frame_eval(pso_gmm_t *g, int16_t *senscr, const uint8_t *list, int32_t n_list,
+              const float *feat, int32_t compall)
+{
+    const pso_model_t *m = g->m;
+    ms_dist_t *dist = (ms_dist_t *)g->ms_dist;
+    size_t per = (size_t)m->n_feat * m->topn;
+    uint8_t *active = calloc(m->n_mgau, 1);
+    int32_t i, last, best = INT32_MAX;
+    int cb, f, off;
+
+    if (compall)
+        memset(active, 1, m->n_mgau);
+    else
+        for (i = 0, last = 0; i < n_list; ++i) {
+            last += list[i];
+            active[m->sen2cb[last]] = 1;
+        }
+    for (cb = 0; cb < m->n_mgau; ++cb) {
+        if (!active[cb]) continue;
+        for (f = 0, off = 0; f < m->n_feat; off += m->featlen[f], ++f)
+            ms_compute_dist(m, dist + per * cb + (size_t)f * m->topn, cb, f, feat + off);
+    }
+    free(active);
+    if (compall) n_list = m->n_sen;
+    for (i = 0, last = 0; i < n_list; ++i) {
+        int32_t s = compall ? i : last + list[i];
+        last = s;
+        senscr[s] = (int16_t)ms_senone(m, s, dist + per * m->sen2cb[s]);
+        if (best > senscr[s]) best = senscr[s];
+    }
+    for (i = 0, last = 0; i < n_list; ++i) {
+        int32_t s = compall ? i : last + list[i];
+        int32_t bs;
+        last = s;
+        bs = senscr[s] - best;
+        if (bs > 32767) bs = 32767;
+        if (bs < -32768) bs = -32768;
+        senscr[s] = (int16_t)bs;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+
+int
+pso_frame_eval(pso_gmm_t *g, int16_t *senscr, const uint8_t *senone_active,
+               int32_t n_senone_active, const float *feat, int32_t frame, int32_t compallsen)
+{
+    switch (g->m->kind) {
+    case PSO_KIND_PTM:
+        return ptm_frame_eval(g, senscr, senone_active, n_senone_active, feat, frame, compallsen);
+    case PSO_KIND_SEMI:
+        return semi_frame_eval(g, senscr, senone_active, n_senone_active, feat, frame, compallsen);
+    default:
+        return ms_frame_eval(g, senscr, senone_active, n_senone_active, feat, compallsen);
+    }
+}
+
+int
+pso_score_utt(const pso_model_t *m, const float *feats, int32_t T, int16_t *senscr,
+              int32_t *topn_out)
+{
+    pso_gmm_t *g = pso_gmm_new(m, 2);
+    int32_t t;
+    for (t = 0; t < T; ++t) {
+        pso_frame_eval(g, senscr + (size_t)t * m->n_sen, NULL, 0, feats + (size_t)t * g->sumlen, t, 1);
+        g->frame_idx = t + 1;       /* acmod_advance (acmod.c:868-877) */
+        if (topn_out && m->kind != PSO_KIND_MS) {
+            size_t per = (size_t)(m->kind == PSO_KIND_PTM ? m->n_mgau : 1) * m->n_feat * m->topn;
+            memcpy(topn_out + (size_t)t * per * 2, g->hist + per * (t % g->n_hist), per * sizeof(pso_topn_t));
+        }
+    }
+    pso_gmm_free(g);
+    return 0;
+}
+
+/* acmod_flags2list (acmod.c:1224-1275): ascending senone ids as uint8 deltas from the
+ * previous listed id (first from 0); a gap above 255 is bridged by 255-steps, which makes the
+ * intermediate senones part of the list. */
+int32_t
+pso_flags2list(const uint8_t *flags, int32_t n_sen, uint8_t *list)
+{
+    int32_t s, last = 0, n = 0;
+    for (s = 0; s < n_sen; ++s) {
+        int32_t delta;
+        if (!flags[s]) continue;
+        delta = s - last;
+        while (delta > 255) {
+            list[n++] = 255;
+            delta -= 255;
+        }
+        list[n++] = (uint8_t)delta;
+        last = s;
+    }
+    return n;
+}
+
+double
+pso_time_score_utt(const pso_model_t *m, const float *feats, int32_t T, int32_t reps)
+{
+    int16_t *scr = malloc((size_t)T * m->n_sen * sizeof(*scr));
+    struct timespec a, b;
+    int r;
+    pso_score_utt(m, feats, T < 16 ? T : 16, scr, NULL);
+    clock_gettime(CLOCK_MONOTONIC, &a);
+    for (r = 0; r < reps; ++r)
+        pso_score_utt(m, feats, T, scr, NULL);
+    clock_gettime(CLOCK_MONOTONIC, &b);
+    free(scr);
+    return (b.tv_sec - a.tv_sec) + 1e-9 * (b.tv_nsec - a.tv_nsec);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* HMM                                                                                   */
+
+void
+pso_hmm_clear_scores(pso_hmm_t *h)        /* hmm.c:167-178 */
+{
+    int i;
+    for (i = 0; i < h->n_emit_state; ++i) h->score[i] = PSO_WORST_SCORE;
+    h->out_score = PSO_WORST_SCORE;
+    h->bestscore = PSO_WORST_SCORE;
+}
+
+void
+pso_hmm_clear(pso_hmm_t *h)               /* hmm.c:180-196 */
+{
+    int i;
+    for (i = 0; i < h->n_emit_state; ++i) {
+        h->score[i] = PSO_WORST_SCORE;
+        h->history[i] = -1;
+    }
+    h->out_score = PSO_WORST_SCORE;
+    h->out_history = -1;
+    h->bestscore = PSO_WORST_SCORE;
+    h->frame = -1;
+}
+
+void
+pso_hmm_init(const pso_hmmctx_t *c, pso_hmm_t *h, int mpx, int ssid, int tmatid)  /* hmm.c:85-105 */
+{
+    int i;
+    h->ctx = NULL;
+    h->mpx = (uint8_t)mpx;
+    h->n_emit_state = (uint8_t)c->n_emit_state;
+    if (mpx) {
+        h->ssid = PSO_BAD_SSID;
+        h->senid[0] = (uint16_t)ssid;
+        for (i = 1; i < c->n_emit_state; ++i) h->senid[i] = PSO_BAD_SSID;
+    }
+    else {
+        h->ssid = (uint16_t)ssid;
+        for (i = 0; i < c->n_emit_state; ++i)
+            h->senid[i] = c->sseq[(size_t)ssid * c->n_emit_state + i];
+    }
+    h->tmatid = (int16_t)tmatid;
+    pso_hmm_clear(h);
+}
+
+void
+pso_hmm_enter(pso_hmm_t *h, int32_t score, int32_t histid, int frame)   /* hmm.c:198-204 */
+{
+    h->score[0] = score;
+    h->history[0] = histid;
+    h->frame = frame;
+}
+
+void
+pso_hmm_normalize(pso_hmm_t *h, int32_t bestscr)                        /* hmm.c:206-216 */
+{
+    int i;
+    for (i = 0; i < h->n_emit_state; ++i)
+        if (h->score[i] > PSO_WORST_SCORE) h->score[i] -= bestscr;
+    if (h->out_score > PSO_WORST_SCORE) h->out_score -= bestscr;
+}
+
+/* Three-way max with the reference's tie order (e.g. hmm.c:257-271): returns which
+ * candidate wins: 0 = self loop t0, 1 = from the state below t1, 2 = skip t2. */
+static int
+pick3(int32_t t0, int32_t t1, int32_t t2, int32_t *out)
+{
+    if (t0 > t1) {
+        if (t2 > t0) { *out = t2; return 2; }
+        *out = t0; return 0;
+    }
+    if (t2 > t1) { *out = t2; return 2; }
+    *out = t1; return 1;
+}
+
+#define FLOOR(s) do { if ((s) < PSO_WORST_SCORE) (s) = PSO_WORST_SCORE; } while (0)
+#define RAISE(b, s) do { if ((s) > (b)) (b) = (s); } while (0)
+
+/* hmm_vit_eval_5st_lr / _3st_lr share this shape (hmm.c:223-353, 530-607); they differ in
+ * which blocks are guarded and in the 3-state skip-arc handling, so they stay separate. */
+static int32_t
+vit_5st(const pso_hmmctx_t *c, pso_hmm_t *h)
+{
+    const uint8_t *tp = c->tp + (size_t)h->tmatid * 30;
+    const int16_t *sen = c->senscore;
+#define TP(i, j) (-(int32_t)tp[(i) * 6 + (j)])
+#define OBS(i) (-(int32_t)sen[h->senid[i]])
+    int32_t s0, s1, s2, s3, s4, s5, t0, t1, t2, best = PSO_WORST_SCORE;
+
+    s4 = h->score[4] + OBS(4);
+    s3 = h->score[3] + OBS(3);
+    if (s3 > PSO_WORST_SCORE) {                       /* exit state (:237-250) */
+        t1 = s4 + TP(4, 5);
+        t2 = s3 + TP(3, 5);
+        if (t1 > t2) { s5 = t1; h->out_history = h->history[4]; }
+        else { s5 = t2; h->out_history = h->history[3]; }
+        FLOOR(s5);
+        h->out_score = s5;
+        best = s5;
+    }
+    s2 = h->score[2] + OBS(2);
+    if (s2 > PSO_WORST_SCORE) {                       /* state 4 (:254-276) */
+        int w = pick3(s4 + TP(4, 4), s3 + TP(3, 4), s2 + TP(2, 4), &s4);
+        if (w == 2) h->history[4] = h->history[2];
+        else if (w == 1) h->history[4] = h->history[3];
+        FLOOR(s4); RAISE(best, s4);
+        h->score[4] = s4;
+    }
+    s1 = h->score[1] + OBS(1);
+    if (s1 > PSO_WORST_SCORE) {                       /* state 3 (:280-302) */
+        int w = pick3(s3 + TP(3, 3), s2 + TP(2, 3), s1 + TP(1, 3), &s3);
+        if (w == 2) h->history[3] = h->history[1];
+        else if (w == 1) h->history[3] = h->history[2];
+        FLOOR(s3); RAISE(best, s3);
+        h->score[3] = s3;
+    }
+    s0 = h->score[0] + OBS(0);
+    {                                                 /* state 2 (:306-326) */
+        int w = pick3(s2 + TP(2, 2), s1 + TP(1, 2), s0 + TP(0, 2), &s2);
+        if (w == 2) h->history[2] = h->history[0];
+        else if (w == 1) h->history[2] = h->history[1];
+        FLOOR(s2); RAISE(best, s2);
+        h->score[2] = s2;
+    }
+    t0 = s1 + TP(1, 1);                               /* state 1 (:329-340) */
+    t1 = s0 + TP(0, 1);
+    if (t0 > t1) s1 = t0;
+    else { s1 = t1; h->history[1] = h->history[0]; }
+    FLOOR(s1); RAISE(best, s1);
+    h->score[1] = s1;
+    s0 = s0 + TP(0, 0);                               /* state 0 (:342-346) */
+    FLOOR(s0); RAISE(best, s0);
+    h->score[0] = s0;
+    h->bestscore = best;
+    return best;
+#undef TP
+#undef OBS
+}
+
+static int32_t
+vit_3st(const pso_hmmctx_t *c, pso_hmm_t *h)
+{
+    const uint8_t *tp = c->tp + (size_t)h->tmatid * 12;
+    const int16_t *sen = c->senscore;
+#define TP(i, j) (-(int32_t)tp[(i) * 4 + (j)])
+#define OBS(i) (-(int32_t)sen[h->senid[i]])
+    int32_t s0, s1, s2, s3, t0, t1, t2, best = PSO_WORST_SCORE;
+
+    s2 = h->score[2] + OBS(2);
+    s1 = h->score[1] + OBS(1);
+    s0 = h->score[0] + OBS(0);
+    t2 = INT32_MIN;          /* only overwritten when a skip arc exists (:543) */
+    if (s1 > PSO_WORST_SCORE) {                       /* exit state (:546-559) */
+        t1 = s2 + TP(2, 3);
+        if (TP(1, 3) > PSO_TMAT_WORST_SCORE) t2 = s1 + TP(1, 3);
+        if (t1 > t2) { s3 = t1; h->out_history = h->history[2]; }
+        else { s3 = t2; h->out_history = h->history[1]; }
+        FLOOR(s3);
+        h->out_score = s3;
+        best = s3;
+    }
+    t0 = s2 + TP(2, 2);                               /* state 2 (:562-583); stale t2 reused */
+    t1 = s1 + TP(1, 2);
+    if (TP(0, 2) > PSO_TMAT_WORST_SCORE) t2 = s0 + TP(0, 2);
+    {
+        int w = pick3(t0, t1, t2, &s2);
+        if (w == 2) h->history[2] = h->history[0];
+        else if (w == 1) h->history[2] = h->history[1];
+    }
+    FLOOR(s2); RAISE(best, s2);
+    h->score[2] = s2;
+    t0 = s1 + TP(1, 1);                               /* state 1 (:586-596) */
+    t1 = s0 + TP(0, 1);
+    if (t0 > t1) s1 = t0;
+    else { s1 = t1; h->history[1] = h->history[0]; }
+    FLOOR(s1); RAISE(best, s1);
+    h->score[1] = s1;
+    s0 = s0 + TP(0, 0);                               /* state 0 (:599-602) */
+    FLOOR(s0); RAISE(best, s0);
+    h->score[0] = s0;
+    h->bestscore = best;
+    return best;
+#undef TP
+#undef OBS
+}
+
+/* Multiplexed variants: senid[] holds per-state senone-sequence ids which travel with the
+ * winning predecessor (hmm.c:356-525, 610-706). */
+#define MPX_OBS(st) (-(int32_t)sen[c->sseq[(size_t)h->senid[st] * c->n_emit_state + (st)]])
+
+static int32_t
+vit_5st_mpx(const pso_hmmctx_t *c, pso_hmm_t *h)
+{
+    const uint8_t *tp = c->tp + (size_t)h->tmatid * 30;
+    const int16_t *sen = c->senscore;
+    uint16_t *ssid = h->senid;
+#define TP(i, j) (-(int32_t)tp[(i) * 6 + (j)])
+    int32_t s0, s1, s2, s3, s4, s5, t0, t1, t2, best;
+    int w;
+
+    if (ssid[4] == PSO_BAD_SSID) s4 = t1 = PSO_WORST_SCORE;
+    else { s4 = h->score[4] + MPX_OBS(4); t1 = s4 + TP(4, 5); }
+    if (ssid[3] == PSO_BAD_SSID) s3 = t2 = PSO_WORST_SCORE;
+    else { s3 = h->score[3] + MPX_OBS(3); t2 = s3 + TP(3, 5); }
+    if (t1 > t2) { s5 = t1; h->out_history = h->history[4]; }
+    else { s5 = t2; h->out_history = h->history[3]; }
+    FLOOR(s5);
+    h->out_score = s5;
+    best = s5;
+
+    if (ssid[2] == PSO_BAD_SSID) s2 = t2 = PSO_WORST_SCORE;
+    else { s2 = h->score[2] + MPX_OBS(2); t2 = s2 + TP(2, 4); }
+    t0 = t1 = PSO_WORST_SCORE;
+    if (s4 != PSO_WORST_SCORE) t0 = s4 + TP(4, 4);
+    if (s3 != PSO_WORST_SCORE) t1 = s3 + TP(3, 4);
+    w = pick3(t0, t1, t2, &s4);
+    if (w == 2) { h->history[4] = h->history[2]; ssid[4] = ssid[2]; }
+    else if (w == 1) { h->history[4] = h->history[3]; ssid[4] = ssid[3]; }
+    FLOOR(s4); RAISE(best, s4);
+    h->score[4] = s4;
+
+    if (ssid[1] == PSO_BAD_SSID) s1 = t2 = PSO_WORST_SCORE;
+    else { s1 = h->score[1] + MPX_OBS(1); t2 = s1 + TP(1, 3); }
+    t0 = t1 = PSO_WORST_SCORE;
+    if (s3 != PSO_WORST_SCORE) t0 = s3 + TP(3, 3);
+    if (s2 != PSO_WORST_SCORE) t1 = s2 + TP(2, 3);
+    w = pick3(t0, t1, t2, &s3);
+    if (w == 2) { h->history[3] = h->history[1]; ssid[3] = ssid[1]; }
+    else if (w == 1) { h->history[3] = h->history[2]; ssid[3] = ssid[2]; }
+    FLOOR(s3); RAISE(best, s3);
+    h->score[3] = s3;
+
+    s0 = h->score[0] + MPX_OBS(0);
+    t0 = t1 = PSO_WORST_SCORE;
+    if (s2 != PSO_WORST_SCORE) t0 = s2 + TP(2, 2);
+    if (s1 != PSO_WORST_SCORE) t1 = s1 + TP(1, 2);
+    t2 = s0 + TP(0, 2);
+    w = pick3(t0, t1, t2, &s2);
+    if (w == 2) { h->history[2] = h->history[0]; ssid[2] = ssid[0]; }
+    else if (w == 1) { h->history[2] = h->history[1]; ssid[2] = ssid[1]; }
+    FLOOR(s2); RAISE(best, s2);
+    h->score[2] = s2;
+
+    t0 = PSO_WORST_SCORE;
+    if (s1 != PSO_WORST_SCORE) t0 = s1 + TP(1, 1);
+    t1 = s0 + TP(0, 1);
+    if (t0 > t1) s1 = t0;
+    else { s1 = t1; h->history[1] = h->history[0]; ssid[1] = ssid[0]; }
+    FLOOR(s1); RAISE(best, s1);
+    h->score[1] = s1;
+
+    s0 += TP(0, 0);
+    FLOOR(s0); RAISE(best, s0);
+    h->score[0] = s0;
+    h->bestscore = best;
+    return best;
+#undef TP
+}
+
+static int32_t
+vit_3st_mpx(const pso_hmmctx_t *c, pso_hmm_t *h)
+{
+    const uint8_t *tp = c->tp + (size_t)h->tmatid * 12;
+    const int16_t *sen = c->senscore;
+    uint16_t *ssid = h->senid;
+#define TP(i, j) (-(int32_t)tp[(i) * 4 + (j)])
+    int32_t s0, s1, s2, s3, t0, t1, t2, best;
+    int w;
+
+    t2 = INT32_MIN;
+    if (ssid[2] == PSO_BAD_SSID) s2 = t1 = PSO_WORST_SCORE;
+    else { s2 = h->score[2] + MPX_OBS(2); t1 = s2 + TP(2, 3); }
+    if (ssid[1] == PSO_BAD_SSID) s1 = t2 = PSO_WORST_SCORE;
+    else {
+        s1 = h->score[1] + MPX_OBS(1);
+        if (TP(1, 3) > PSO_TMAT_WORST_SCORE) t2 = s1 + TP(1, 3);
+    }
+    if (t1 > t2) { s3 = t1; h->out_history = h->history[2]; }
+    else { s3 = t2; h->out_history = h->history[1]; }
+    FLOOR(s3);
+    h->out_score = s3;
+    best = s3;
+
+    s0 = h->score[0] + MPX_OBS(0);
+    t0 = t1 = PSO_WORST_SCORE;
+    if (s2 != PSO_WORST_SCORE) t0 = s2 + TP(2, 2);
+    if (s1 != PSO_WORST_SCORE) t1 = s1 + TP(1, 2);
+    if (TP(0, 2) > PSO_TMAT_WORST_SCORE) t2 = s0 + TP(0, 2);
+    w = pick3(t0, t1, t2, &s2);
+    if (w == 2) { h->history[2] = h->history[0]; ssid[2] = ssid[0]; }
+    else if (w == 1) { h->history[2] = h->history[1]; ssid[2] = ssid[1]; }
+    FLOOR(s2); RAISE(best, s2);
+    h->score[2] = s2;
+
+    t0 = PSO_WORST_SCORE;
+    if (s1 != PSO_WORST_SCORE) t0 = s1 + TP(1, 1);
+    t1 = s0 + TP(0, 1);
+    if (t0 > t1) s1 = t0;
+    else { s1 = t1; h->history[1] = h->history[0]; ssid[1] = ssid[0]; }
+    FLOOR(s1); RAISE(best, s1);
+    h->score[1] = s1;
+
+    s0 += TP(0, 0);
+    FLOOR(s0); RAISE(best, s0);
+    h->score[0] = s0;
+    h->bestscore = best;
+    return best;
+#undef TP
+}
+
+/* hmm_vit_eval_anytopo (hmm.c:709-784), any n_emit_state <= 5, mpx or not. */
+static int32_t
+vit_any(const pso_hmmctx_t *c, pso_hmm_t *h)
+{
+    int n = h->n_emit_state, to, from, bestfrom;
+    const uint8_t *tp = c->tp + (size_t)h->tmatid * n * (n + 1);
+    int32_t st[PSO_MAX_NSTATE], scr, nscr, best;
+#define TP(i, j) (-(int32_t)tp[(i) * (n + 1) + (j)])
+
+    for (from = 0; from < n; ++from) {
+        /* hmm_senscr (hmm.h:207-209) with hmm_senid (hmm.h:199-205) */
+        uint16_t sid;
+        int32_t o;
+        if (h->mpx)
+            sid = h->senid[from] == PSO_BAD_SSID ? PSO_BAD_SSID
+                : c->sseq[(size_t)h->senid[from] * c->n_emit_state + from];
+        else
+            sid = h->senid[from];
+        o = sid == PSO_BAD_SSID ? PSO_WORST_SCORE : -(int32_t)c->senscore[sid];
+        st[from] = h->score[from] + o;
+        if (from > 0 && st[from] < PSO_WORST_SCORE) st[from] = PSO_WORST_SCORE;
+    }
+    to = n;
+    scr = PSO_WORST_SCORE;
+    bestfrom = -1;
+    for (from = to - 1; from >= 0; --from)
+        if (TP(from, to) > PSO_TMAT_WORST_SCORE && (nscr = st[from] + TP(from, to)) > scr) {
+            scr = nscr;
+            bestfrom = from;
+        }
+    h->out_score = scr;
+    if (bestfrom >= 0) h->out_history = h->history[bestfrom];
+    best = scr;
+    for (to = n - 1; to >= 0; --to) {
+        scr = TP(to, to) > PSO_TMAT_WORST_SCORE ? st[to] + TP(to, to) : PSO_WORST_SCORE;
+        bestfrom = -1;
+        for (from = to - 1; from >= 0; --from)
+            if (TP(from, to) > PSO_TMAT_WORST_SCORE && (nscr = st[from] + TP(from, to)) > scr) {
+                scr = nscr;
+                bestfrom = from;
+            }
+        h->score[to] = scr;
+        if (bestfrom >= 0) {
+            h->history[to] = h->history[bestfrom];
+            if (h->mpx) h->senid[to] = h->senid[bestfrom];
+        }
+        if (best < scr) best = scr;
+    }
+    h->bestscore = best;
+    return best;
+#undef TP
+}
+
+int32_t
+pso_hmm_vit_eval(const pso_hmmctx_t *c, pso_hmm_t *h)      /* dispatcher: hmm.c:786-805 */
+{
+    if (h->mpx) {
+        if (h->n_emit_state == 5) return vit_5st_mpx(c, h);
+        if (h->n_emit_state == 3) return vit_3st_mpx(c, h);
+        return vit_any(c, h);
+    }
+    if (h->n_emit_state == 5) return vit_5st(c, h);
+    if (h->n_emit_state == 3) return vit_3st(c, h);
+    return vit_any(c, h);
+}
+
+int32_t
+pso_hmm_vit_eval_batch(const pso_hmmctx_t *c, pso_hmm_t *h, int32_t n)
+{
+    int32_t best = PSO_WORST_SCORE, i;
+    for (i = 0; i < n; ++i) {
+        int32_t s = pso_hmm_vit_eval(c, &h[i]);
+        if (s > best) best = s;
+    }
+    return best;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* phone loop (phone_loop_search.c)                                                      */
+
+pso_phoneloop_t *
+pso_phoneloop_new(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq,
+                  int32_t n_phones, const int32_t *ssid, const int32_t *tmatid,
+                  int32_t window, int32_t beam, int32_t pbeam, int32_t pip, double penalty_weight)
+{
+    pso_phoneloop_t *p = calloc(1, sizeof(*p));
+    int i;
+    p->ctx.n_emit_state = n_emit_state;
+    p->ctx.tp = tp;
+    p->ctx.sseq = sseq;
+    p->n_phones = n_phones;
+    p->window = window;
+    p->beam = beam; p->pbeam = pbeam; p->pip = pip;
+    p->penalty_weight = penalty_weight;
+    p->hmms = calloc(n_phones, sizeof(*p->hmms));
+    p->pen_buf = calloc((size_t)window * n_phones, sizeof(int32_t));
+    p->penalties = calloc(n_phones, sizeof(int32_t));
+    for (i = 0; i < n_phones; ++i)                    /* :98-103 */
+        pso_hmm_init(&p->ctx, &p->hmms[i], 0, ssid[i], tmatid[i]);
+    return p;
+}
+
+void
+pso_phoneloop_free(pso_phoneloop_t *p)
+{
+    if (!p) return;
+    free(p->hmms); free(p->pen_buf); free(p->penalties); free(p);
+}
+
+void
+pso_phoneloop_start(pso_phoneloop_t *p)               /* :155-175 */
+{
+    int i;
+    for (i = 0; i < p->n_phones; ++i) {
+        pso_hmm_clear(&p->hmms[i]);
+        pso_hmm_enter(&p->hmms[i], 0, -1, 0);
+    }
+    memset(p->penalties, 0, p->n_phones * sizeof(int32_t));
+    memset(p->pen_buf, 0, (size_t)p->window * p->n_phones * sizeof(int32_t));
+    p->best_score = 0;
+    p->pen_buf_ptr = 0;
+    p->n_renorm = 0;
+}
+
+void
+pso_phoneloop_step(pso_phoneloop_t *p, const int16_t *senscr, int32_t frame_idx)   /* :301-337 */
+{
+    int32_t bs = PSO_WORST_SCORE, thresh, nf = frame_idx + 1;
+    int i, j, itr;
+
+    /* renormalize_hmms (:177-191) */
+    if (p->best_score + 2 * p->beam < PSO_WORST_SCORE) {
+        for (i = 0; i < p->n_phones; ++i)
+            pso_hmm_normalize(&p->hmms[i], p->best_score);
+        p->n_renorm++;
+    }
+    /* evaluate_hmms (:193-214) */
+    p->ctx.senscore = senscr;
+    for (i = 0; i < p->n_phones; ++i) {
+        int32_t s;
+        if (p->hmms[i].frame < frame_idx) continue;
+        s = pso_hmm_vit_eval(&p->ctx, &p->hmms[i]);
+        if (s > bs) bs = s;
+    }
+    p->best_score = bs;
+    /* store_scores (:216-239) */
+    for (i = 0; i < p->n_phones; ++i)
+        p->pen_buf[(size_t)p->pen_buf_ptr * p->n_phones + i] =
+            (int32_t)((p->hmms[i].bestscore - p->best_score) * p->penalty_weight);
+    p->pen_buf_ptr = (p->pen_buf_ptr + 1) % p->window;
+    for (i = 0; i < p->n_phones; ++i) {
+        p->penalties[i] = PSO_WORST_SCORE;
+        for (j = 0, itr = p->pen_buf_ptr + 1; j < p->window; ++j, ++itr) {
+            itr = itr % p->window;
+            if (p->pen_buf[(size_t)itr * p->n_phones + i] > p->penalties[i])
+                p->penalties[i] = p->pen_buf[(size_t)itr * p->n_phones + i];
+        }
+    }
+    /* prune_hmms (:241-261) */
+    thresh = p->best_score + p->beam;
+    for (i = 0; i < p->n_phones; ++i) {
+        pso_hmm_t *h = &p->hmms[i];
+        if (h->frame < frame_idx) continue;
+        if (h->bestscore > thresh) h->frame = nf;
+        else pso_hmm_clear_scores(h);
+    }
+    /* phone_transition (:263-299) */
+    thresh = p->best_score + p->pbeam;
+    for (i = 0; i < p->n_phones; ++i) {
+        pso_hmm_t *h = &p->hmms[i];
+        int32_t ns;
+        if (h->frame != nf) continue;
+        ns = h->out_score + p->pip;
+        if (ns > thresh)
+            for (j = 0; j < p->n_phones; ++j) {
+                pso_hmm_t *nh = &p->hmms[j];
+                if (nh->frame < frame_idx || ns > nh->score[0])
+                    pso_hmm_enter(nh, ns, h->out_history, nf);
+            }
+    }
+}
+
+void
+pso_phoneloop_run(pso_phoneloop_t *p, const int16_t *senscr, int32_t n_sen, int32_t T,
+                  pso_hmm_t *hmm_out, int32_t *best_out, int32_t *pen_out)
+{
+    int32_t t;
+    pso_phoneloop_start(p);
+    for (t = 0; t < T; ++t) {
+        pso_phoneloop_step(p, senscr + (size_t)t * n_sen, t);
+        if (hmm_out) memcpy(hmm_out + (size_t)t * p->n_phones, p->hmms, p->n_phones * sizeof(pso_hmm_t));
+        if (best_out) best_out[t] = p->best_score;
+        if (pen_out) memcpy(pen_out + (size_t)t * p->n_phones, p->penalties, p->n_phones * sizeof(int32_t));
+    }
+}

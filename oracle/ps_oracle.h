@@ -1,0 +1,149 @@
+/* oracle/ps_oracle.h -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * Plain-C CPU restatement of the PocketSphinx hot path (GMM senone evaluation for the
+ * ptm / s2_semi / ms back-ends, hmm_vit_eval, and the phone-loop caller), written from the
+ * algorithm, each function citing the reference file:line it follows (paths relative to
+ * /root/reference).  Default float build (mfcc_t = float32) semantics.
+ *
+ * Pinned: tests/test_oracle_vs_ref.py compares every function here with the compiled
+ * reference (oracle/_ref/libpsref.so) when it is present, and tests/test_oracle_golden.py
+ * compares it with committed fixtures (tests/golden/) generated from that reference by
+ * oracle/make_golden.py.
+ */
+#ifndef PS_ORACLE_H
+#define PS_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSO_MAX_FEAT 8
+#define PSO_MAX_TOPN 16
+#define PSO_MAX_NSTATE 5                       /* hmm.h:159 HMM_MAX_NSTATE */
+#define PSO_SENSCR_SHIFT 10                    /* hmm.h:72 */
+#define PSO_WORST_SCORE ((int32_t)0xE0000000)  /* hmm.h:83 */
+#define PSO_TMAT_WORST_SCORE (-255)            /* hmm.h:89 */
+#define PSO_BAD_SSID 0xffff                    /* bin_mdef.h BAD_SSID / BAD_SENID */
+#define PSO_MAX_NEG_ASCR 96                    /* tied_mgau_common.h:91 */
+#define PSO_WORST_DIST INT32_MIN               /* tied_mgau_common.h:60 */
+
+enum { PSO_KIND_PTM = 0, PSO_KIND_SEMI = 1, PSO_KIND_MS = 2 };
+
+/* Acoustic model, as flat arrays in the reference's in-memory order. */
+typedef struct pso_model_s {
+    int32_t kind, n_sen, n_mgau, n_feat, n_density, topn;
+    int32_t featlen[PSO_MAX_FEAT];
+    int32_t ds_ratio;              /* -ds; 1 = every frame */
+    int32_t aw;                    /* ms: inverse acoustic weight (-aw) */
+    int32_t mixw_4bit;             /* sendump with cluster_bits 4 */
+    int32_t pdf_transposed;        /* ms: 1 = pdf[feat][cw][sen] (n_gauden==1), 0 = pdf[sen][feat][cw] */
+    int32_t logadd_ms_size, logadd_ms_zero;
+    const float *mean;             /* [n_mgau][n_feat][n_density][featlen[f]] */
+    const float *var;              /* same; precomputed 1/(2 sigma^2) in log-base units */
+    const float *det;              /* [n_mgau][n_feat][n_density] */
+    const uint8_t *mixw;           /* ptm/semi: [n_feat][n_density][row]; ms: pdf */
+    const uint8_t *mixw_cb;        /* 16 entries when mixw_4bit */
+    const int32_t *sen2cb;         /* [n_sen] */
+    const uint8_t *logadd8;        /* 256-entry table of logmath_init(base, 10, 1) */
+    const uint32_t *logadd_ms;     /* ms: wide table widened to uint32 */
+    const uint8_t *topn_beam;      /* semi: [n_feat] or NULL */
+} pso_model_t;
+
+typedef struct pso_topn_s { int32_t cw, score; } pso_topn_t;
+
+/* Per-decoder GMM state: the top-N history ring (ptm_mgau.h:64-94, s2_semi_mgau.h:79-82). */
+typedef struct pso_gmm_s {
+    const pso_model_t *m;
+    int32_t n_hist;        /* pl_window + 2 */
+    int32_t frame_idx;     /* ps_mgau_t.frame_idx (acmod.h:113-116) */
+    pso_topn_t *hist;      /* ptm: [n_hist][n_mgau][n_feat][topn]; semi: [n_hist][n_feat][topn] */
+    uint8_t *cb_active;    /* ptm: [n_hist][n_mgau] */
+    uint8_t *hist_n;       /* semi: [n_hist][n_feat] */
+    pso_topn_t *ms_dist;   /* ms scratch: [n_mgau][n_feat][topn], score field holds float bits */
+    int32_t sumlen;
+} pso_gmm_t;
+
+pso_gmm_t *pso_gmm_new(const pso_model_t *m, int32_t n_hist);
+void pso_gmm_free(pso_gmm_t *g);
+void pso_gmm_reset(pso_gmm_t *g);
+
+/* One ps_mgau frame_eval call (acmod.h:101-107).  feat = one row of sumlen floats. */
+int pso_frame_eval(pso_gmm_t *g, int16_t *senscr, const uint8_t *senone_active,
+                   int32_t n_senone_active, const float *feat, int32_t frame, int32_t compallsen);
+
+/* Fresh state, compallsen, frames 0..T-1, frame_idx advanced like acmod_advance.
+ * topn_out optional: ptm [T][n_mgau][n_feat][topn]{cw,score}, semi [T][n_feat][topn]. */
+int pso_score_utt(const pso_model_t *m, const float *feats, int32_t T, int16_t *senscr,
+                  int32_t *topn_out);
+
+/* acmod_flags2list (acmod.c:1224-1275): flags[n_sen] bytes -> delta list; returns count. */
+int32_t pso_flags2list(const uint8_t *flags, int32_t n_sen, uint8_t *list);
+
+/* ---- HMM ---- */
+
+/* Same 88-byte LP64 layout as the reference's hmm_t (hmm.h:169-182). */
+typedef struct pso_hmm_s {
+    void *ctx;
+    int32_t score[PSO_MAX_NSTATE];
+    int32_t history[PSO_MAX_NSTATE];
+    int32_t out_score;
+    int32_t out_history;
+    uint16_t ssid;
+    uint16_t senid[PSO_MAX_NSTATE];
+    int32_t bestscore;
+    int16_t tmatid;
+    int32_t frame;
+    uint8_t mpx;
+    uint8_t n_emit_state;
+} pso_hmm_t;
+
+typedef struct pso_hmmctx_s {
+    int32_t n_emit_state;
+    const uint8_t *tp;        /* [n_tmat][n_emit][n_emit+1] */
+    const uint16_t *sseq;     /* [n_sseq][n_emit] */
+    const int16_t *senscore;
+} pso_hmmctx_t;
+
+void pso_hmm_init(const pso_hmmctx_t *c, pso_hmm_t *h, int mpx, int ssid, int tmatid);
+void pso_hmm_clear(pso_hmm_t *h);
+void pso_hmm_clear_scores(pso_hmm_t *h);
+void pso_hmm_enter(pso_hmm_t *h, int32_t score, int32_t histid, int frame);
+void pso_hmm_normalize(pso_hmm_t *h, int32_t bestscr);
+int32_t pso_hmm_vit_eval(const pso_hmmctx_t *c, pso_hmm_t *h);
+/* loop + max, like evaluate_hmms (phone_loop_search.c:202-221) without the frame test */
+int32_t pso_hmm_vit_eval_batch(const pso_hmmctx_t *c, pso_hmm_t *h, int32_t n);
+
+/* ---- phone loop (phone_loop_search.c) ---- */
+typedef struct pso_phoneloop_s {
+    pso_hmmctx_t ctx;
+    int32_t n_phones, window;
+    int32_t beam, pbeam, pip;
+    double penalty_weight;
+    pso_hmm_t *hmms;
+    int32_t *pen_buf;      /* [window][n_phones] */
+    int32_t *penalties;    /* [n_phones] */
+    int32_t pen_buf_ptr;
+    int32_t best_score;
+    int32_t n_renorm;
+} pso_phoneloop_t;
+
+pso_phoneloop_t *pso_phoneloop_new(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq,
+                                   int32_t n_phones, const int32_t *ssid, const int32_t *tmatid,
+                                   int32_t window, int32_t beam, int32_t pbeam, int32_t pip,
+                                   double penalty_weight);
+void pso_phoneloop_free(pso_phoneloop_t *p);
+void pso_phoneloop_start(pso_phoneloop_t *p);
+void pso_phoneloop_step(pso_phoneloop_t *p, const int16_t *senscr, int32_t frame_idx);
+/* start + T steps; optional per-frame dumps: hmm_out [T][n_phones] pso_hmm_t, best_out [T],
+ * pen_out [T][n_phones]. */
+void pso_phoneloop_run(pso_phoneloop_t *p, const int16_t *senscr, int32_t n_sen, int32_t T,
+                       pso_hmm_t *hmm_out, int32_t *best_out, int32_t *pen_out);
+
+double pso_time_score_utt(const pso_model_t *m, const float *feats, int32_t T, int32_t reps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,607 @@
+/* oracle/ref_driver.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * A thin, ctypes-friendly driver over the UNMODIFIED reference (cmusphinx/pocketsphinx
+ * 5.1.1), compiled from the sources where they lie under /root/reference by oracle/Makefile
+ * into oracle/_ref/libpsref.so.  Nothing here is shipped or linked into the product: it is
+ * the checker (golden-vector generator, parity oracle, and the "reference" CPU baseline).
+ *
+ * It reaches the reference through the same internal headers its own unit tests use
+ * (test/unit/CMakeLists.txt:60-64): acmod.h, ptm_mgau.h, s2_semi_mgau.h, ms_mgau.h, hmm.h,
+ * phone_loop_search.h.  All arithmetic is the reference's; this file only moves arrays.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include <pocketsphinx.h>
+
+#include "pocketsphinx_internal.h"
+#include "acmod.h"
+#include "ptm_mgau.h"
+#include "s2_semi_mgau.h"
+#include "ms_mgau.h"
+#include "hmm.h"
+#include "tmat.h"
+#include "bin_mdef.h"
+#include "phone_loop_search.h"
+#include "util/ckd_alloc.h"
+#include "tied_mgau_common.h"
+
+/* s2_semi_mgau.c:64-67 keeps this struct private; layout restated for history reset/dump. */
+struct vqFeature_s {
+    int32 score;
+    int32 codeword;
+};
+
+enum { KIND_PTM = 0, KIND_SEMI = 1, KIND_MS = 2 };
+
+typedef struct refdrv_s {
+    ps_config_t *config;
+    logmath_t *lmath;
+    acmod_t *acmod;
+    int kind;
+    int sumlen;
+    ps_search_t *pls;
+    /* CMN state right after init: restored before every utterance so that each one is
+     * featurised like the first utterance of a fresh decoder (live CMN carries over otherwise). */
+    mfcc_t cmn_mean0[64], cmn_sum0[64];
+    int32 cmn_nframe0;
+} refdrv_t;
+
+static double
+now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+static gauden_t *
+drv_gauden(refdrv_t *d)
+{
+    switch (d->kind) {
+    case KIND_PTM: return ((ptm_mgau_t *)d->acmod->mgau)->g;
+    case KIND_SEMI: return ((s2_semi_mgau_t *)d->acmod->mgau)->g;
+    default: return ((ms_mgau_model_t *)d->acmod->mgau)->g;
+    }
+}
+
+static void
+cmn_snapshot(refdrv_t *d, int restore)
+{
+    cmn_t *c = d->acmod->fcb->cmn_struct;
+    int i;
+    if (c == NULL) return;
+    for (i = 0; i < c->veclen && i < 64; ++i) {
+        if (restore) { c->cmn_mean[i] = d->cmn_mean0[i]; c->sum[i] = d->cmn_sum0[i]; }
+        else { d->cmn_mean0[i] = c->cmn_mean[i]; d->cmn_sum0[i] = c->sum[i]; }
+    }
+    if (restore) c->nframe = d->cmn_nframe0; else d->cmn_nframe0 = c->nframe;
+}
+
+/* kv: newline-separated "key=value" overrides applied after feat.params. */
+refdrv_t *
+refdrv_open(const char *hmmdir, const char *kv)
+{
+    refdrv_t *d = calloc(1, sizeof(*d));
+    const char *name;
+    gauden_t *g;
+    int i;
+
+    err_set_loglevel(ERR_ERROR);
+    d->config = ps_config_init(NULL);
+    ps_config_set_str(d->config, "hmm", hmmdir);
+    ps_config_set_str(d->config, "lm", NULL);
+    ps_config_set_bool(d->config, "compallsen", TRUE);
+    ps_config_set_int(d->config, "pl_window", 0);
+    ps_config_set_str(d->config, "dither", "no");
+    ps_expand_model_config(d->config);
+    if (kv) {
+        char *buf = strdup(kv), *save = NULL, *tok;
+        for (tok = strtok_r(buf, "\n", &save); tok; tok = strtok_r(NULL, "\n", &save)) {
+            char *eq = strchr(tok, '=');
+            if (!eq) continue;
+            *eq = 0;
+            if (ps_config_set_str(d->config, tok, eq[1] ? eq + 1 : NULL) == NULL && eq[1])
+                fprintf(stderr, "refdrv: could not set %s\n", tok);
+        }
+        free(buf);
+    }
+    d->lmath = logmath_init(ps_config_float(d->config, "logbase"), 0, TRUE);
+    d->acmod = acmod_init(d->config, d->lmath, NULL, NULL);
+    if (d->acmod == NULL) {
+        fprintf(stderr, "refdrv: acmod_init failed for %s\n", hmmdir);
+        free(d);
+        return NULL;
+    }
+    acmod_set_grow(d->acmod, TRUE);
+    cmn_snapshot(d, 0);
+    name = d->acmod->mgau->vt->name;
+    d->kind = !strcmp(name, "ptm") ? KIND_PTM : !strcmp(name, "s2_semi") ? KIND_SEMI : KIND_MS;
+    g = drv_gauden(d);
+    for (i = 0; i < g->n_feat; ++i)
+        d->sumlen += g->featlen[i];
+    return d;
+}
+
+void
+refdrv_close(refdrv_t *d)
+{
+    if (!d) return;
+    if (d->pls) ps_search_free(d->pls);
+    acmod_free(d->acmod);
+    logmath_free(d->lmath);
+    ps_config_free(d->config);
+    free(d);
+}
+
+/* dims[]: 0 kind, 1 n_sen, 2 n_mgau, 3 n_feat, 4 n_density, 5 topn, 6 sumlen, 7 n_emit_state,
+ * 8 n_tmat, 9 n_sseq, 10 n_ciphone, 11 n_ci_sen, 12 mixw_4bit, 13 logadd8 size, 14 ds_ratio,
+ * 15 aw, 16 ms logadd size, 17 ms logadd width, 18 ms logadd zero, 19 n_hist, 20.. featlen[] */
+int
+refdrv_dims(refdrv_t *d, int32 *out)
+{
+    gauden_t *g = drv_gauden(d);
+    bin_mdef_t *m = d->acmod->mdef;
+    int i;
+
+    memset(out, 0, 32 * sizeof(*out));
+    out[0] = d->kind;
+    out[1] = bin_mdef_n_sen(m);
+    out[2] = g->n_mgau;
+    out[3] = g->n_feat;
+    out[4] = g->n_density;
+    out[6] = d->sumlen;
+    out[7] = m->n_emit_state;
+    out[8] = d->acmod->tmat->n_tmat;
+    out[9] = m->n_sseq;
+    out[10] = m->n_ciphone;
+    out[11] = m->n_ci_sen;
+    if (d->kind == KIND_PTM) {
+        ptm_mgau_t *s = (ptm_mgau_t *)d->acmod->mgau;
+        out[5] = s->max_topn;
+        out[12] = s->mixw_cb != NULL;
+        out[13] = LOGMATH_TABLE(s->lmath_8b)->table_size;
+        out[14] = s->ds_ratio;
+        out[19] = s->n_fast_hist;
+    }
+    else if (d->kind == KIND_SEMI) {
+        s2_semi_mgau_t *s = (s2_semi_mgau_t *)d->acmod->mgau;
+        out[5] = s->max_topn;
+        out[12] = s->mixw_cb != NULL;
+        out[13] = LOGMATH_TABLE(s->lmath_8b)->table_size;
+        out[14] = s->ds_ratio;
+        out[19] = s->n_topn_hist;
+    }
+    else {
+        ms_mgau_model_t *s = (ms_mgau_model_t *)d->acmod->mgau;
+        logadd_t *t = LOGMATH_TABLE(s->s->lmath);
+        out[5] = s->topn;
+        out[15] = s->s->aw;
+        out[16] = t->table_size;
+        out[17] = t->width;
+        out[18] = logmath_get_zero(s->s->lmath);
+    }
+    for (i = 0; i < g->n_feat && i < 12; ++i)
+        out[20 + i] = g->featlen[i];
+    return 0;
+}
+
+/* Copy a named model array into out (cap bytes); returns bytes needed, or -1. */
+long
+refdrv_export(refdrv_t *d, const char *what, void *out, long cap)
+{
+    gauden_t *g = drv_gauden(d);
+    bin_mdef_t *m = d->acmod->mdef;
+    tmat_t *tm = d->acmod->tmat;
+    long need = -1;
+    int i, f, c, k;
+
+#define EMIT(ptr, nbytes) do { need = (long)(nbytes); \
+        if (out && cap >= need) memcpy(out, (ptr), need); } while (0)
+
+    if (!strcmp(what, "mean") || !strcmp(what, "var")) {
+        /* [n_mgau][n_feat][n_density][featlen[f]] floats, as precomputed by
+         * gauden_dist_precompute (ms_gauden.c:264-308). */
+        mfcc_t ****src = !strcmp(what, "mean") ? g->mean : g->var;
+        char *o = out;
+        need = (long)g->n_mgau * g->n_density * d->sumlen * sizeof(mfcc_t);
+        if (out && cap >= need)
+            for (i = 0; i < g->n_mgau; ++i)
+                for (f = 0; f < g->n_feat; ++f) {
+                    size_t nb = (size_t)g->n_density * g->featlen[f] * sizeof(mfcc_t);
+                    memcpy(o, src[i][f][0], nb);
+                    o += nb;
+                }
+    }
+    else if (!strcmp(what, "det")) {
+        EMIT(g->det[0][0], (long)g->n_mgau * g->n_feat * g->n_density * sizeof(mfcc_t));
+    }
+    else if (!strcmp(what, "mixw")) {
+        uint8 ***mixw = NULL; uint8 *cb = NULL; int n_sen = bin_mdef_n_sen(m);
+        if (d->kind == KIND_PTM) { mixw = ((ptm_mgau_t *)d->acmod->mgau)->mixw; cb = ((ptm_mgau_t *)d->acmod->mgau)->mixw_cb; }
+        else if (d->kind == KIND_SEMI) { mixw = ((s2_semi_mgau_t *)d->acmod->mgau)->mixw; cb = ((s2_semi_mgau_t *)d->acmod->mgau)->mixw_cb; }
+        if (mixw) {
+            /* [n_feat][n_density][row] with row = n_sen bytes (8-bit) or (n_sen+1)/2 (4-bit). */
+            long row = cb ? (n_sen + 1) / 2 : n_sen;
+            char *o = out;
+            need = (long)g->n_feat * g->n_density * row;
+            if (out && cap >= need)
+                for (f = 0; f < g->n_feat; ++f)
+                    for (c = 0; c < g->n_density; ++c) {
+                        memcpy(o, mixw[f][c], row);
+                        o += row;
+                    }
+        }
+        else {
+            /* ms: senone_t.pdf, either [sen][feat][cw] (n_gauden>1) or [feat][cw][sen]. */
+            senone_t *s = ((ms_mgau_model_t *)d->acmod->mgau)->s;
+            EMIT(s->pdf[0][0], (long)s->n_sen * s->n_feat * s->n_cw);
+        }
+    }
+    else if (!strcmp(what, "mixw_cb")) {
+        uint8 *cb = NULL;
+        if (d->kind == KIND_PTM) cb = ((ptm_mgau_t *)d->acmod->mgau)->mixw_cb;
+        else if (d->kind == KIND_SEMI) cb = ((s2_semi_mgau_t *)d->acmod->mgau)->mixw_cb;
+        if (cb) EMIT(cb, 16); else need = 0;
+    }
+    else if (!strcmp(what, "sen2cb")) {
+        int n_sen = bin_mdef_n_sen(m);
+        int32 *tmp = calloc(n_sen, sizeof(*tmp));
+        for (i = 0; i < n_sen; ++i) {
+            if (d->kind == KIND_PTM) tmp[i] = ((ptm_mgau_t *)d->acmod->mgau)->sen2cb[i];
+            else if (d->kind == KIND_SEMI) tmp[i] = 0;
+            else tmp[i] = ((ms_mgau_model_t *)d->acmod->mgau)->s->mgau[i];
+        }
+        EMIT(tmp, (long)n_sen * sizeof(*tmp));
+        free(tmp);
+    }
+    else if (!strcmp(what, "logadd8")) {
+        logmath_t *l8 = d->kind == KIND_PTM ? ((ptm_mgau_t *)d->acmod->mgau)->lmath_8b
+            : d->kind == KIND_SEMI ? ((s2_semi_mgau_t *)d->acmod->mgau)->lmath_8b : NULL;
+        if (l8) EMIT(LOGMATH_TABLE(l8)->table, LOGMATH_TABLE(l8)->table_size); else need = 0;
+    }
+    else if (!strcmp(what, "logadd_ms")) {
+        if (d->kind == KIND_MS) {
+            logadd_t *t = LOGMATH_TABLE(((ms_mgau_model_t *)d->acmod->mgau)->s->lmath);
+            EMIT(t->table, (long)t->table_size * t->width);
+        } else need = 0;
+    }
+    else if (!strcmp(what, "topn_beam")) {
+        if (d->kind == KIND_SEMI) EMIT(((s2_semi_mgau_t *)d->acmod->mgau)->topn_beam, g->n_feat);
+        else need = 0;
+    }
+    else if (!strcmp(what, "tp")) {
+        /* uint8 [n_tmat][n_state][n_state+1] (tmat.h:57-63); rows are contiguous. */
+        EMIT(tm->tp[0][0], (long)tm->n_tmat * tm->n_state * (tm->n_state + 1));
+    }
+    else if (!strcmp(what, "sseq")) {
+        uint16 *tmp = calloc((size_t)m->n_sseq * m->n_emit_state, sizeof(*tmp));
+        for (i = 0; i < m->n_sseq; ++i)
+            for (k = 0; k < m->n_emit_state; ++k)
+                tmp[i * m->n_emit_state + k] = m->sseq[i][k];
+        EMIT(tmp, (long)m->n_sseq * m->n_emit_state * sizeof(*tmp));
+        free(tmp);
+    }
+    else if (!strcmp(what, "phone_ssid") || !strcmp(what, "phone_tmat")) {
+        /* per phone (CI first, then CD): ssid / tmat (bin_mdef.h:159-160). */
+        int32 *tmp = calloc(m->n_phone, sizeof(*tmp));
+        for (i = 0; i < m->n_phone; ++i)
+            tmp[i] = !strcmp(what, "phone_ssid") ? bin_mdef_pid2ssid(m, i) : bin_mdef_pid2tmatid(m, i);
+        EMIT(tmp, (long)m->n_phone * sizeof(*tmp));
+        free(tmp);
+    }
+#undef EMIT
+    return need;
+}
+
+/* PCM -> dynamic features through the reference fe/ + feat/ (full-utterance mode, as
+ * ps_decode_raw does).  out is [T][sumlen] floats.  Returns the number of frames. */
+int
+refdrv_featurize(refdrv_t *d, const int16 *pcm, long n_samples, float *out, int max_frames)
+{
+    acmod_t *a = d->acmod;
+    const int16 *p = pcm;
+    size_t n = n_samples;
+    int T, t;
+
+    cmn_snapshot(d, 1);
+    acmod_start_utt(a);
+    acmod_process_raw(a, &p, &n, TRUE);
+    acmod_end_utt(a);
+    T = a->n_feat_frame;
+    if (T > max_frames) T = max_frames;
+    for (t = 0; t < T; ++t)
+        memcpy(out + (size_t)t * d->sumlen, a->feat_buf[t][0], d->sumlen * sizeof(float));
+    return a->n_feat_frame;
+}
+
+/* Restore the top-N history to its post-init state (ptm_mgau.c:777-803, s2_semi_mgau.c:1319-1327)
+ * in place, so every utterance starts like a fresh decoder. */
+void
+refdrv_reset(refdrv_t *d)
+{
+    ps_mgau_t *mg = d->acmod->mgau;
+    int i, j, k, m;
+
+    mg->frame_idx = 0;
+    if (d->kind == KIND_PTM) {
+        ptm_mgau_t *s = (ptm_mgau_t *)mg;
+        for (i = 0; i < s->n_fast_hist; ++i) {
+            for (j = 0; j < s->g->n_mgau; ++j)
+                for (k = 0; k < s->g->n_feat; ++k)
+                    for (m = 0; m < s->max_topn; ++m) {
+                        s->hist[i].topn[j][k][m].cw = m;
+                        s->hist[i].topn[j][k][m].score = WORST_DIST;
+                    }
+            bitvec_set_all(s->hist[i].mgau_active, s->g->n_mgau);
+        }
+    }
+    else if (d->kind == KIND_SEMI) {
+        s2_semi_mgau_t *s = (s2_semi_mgau_t *)mg;
+        for (i = 0; i < s->n_topn_hist; ++i)
+            for (j = 0; j < s->g->n_feat; ++j) {
+                for (k = 0; k < s->max_topn; ++k) {
+                    s->topn_hist[i][j][k].score = WORST_DIST;
+                    s->topn_hist[i][j][k].codeword = k;
+                }
+                s->topn_hist_n[i][j] = 0;
+            }
+    }
+}
+
+static void
+feat_ptrs(refdrv_t *d, const float *row, mfcc_t **ptrs)
+{
+    gauden_t *g = drv_gauden(d);
+    int f, off = 0;
+    for (f = 0; f < g->n_feat; ++f) {
+        ptrs[f] = (mfcc_t *)row + off;
+        off += g->featlen[f];
+    }
+}
+
+/* Score T frames of features with the reference back-end's own frame_eval, all senones
+ * (compallsen), frame_idx advanced like acmod_advance (acmod.c:868-877).
+ * topn_out (optional): PTM [T][n_mgau][n_feat][topn][2] / SEMI [T][n_feat][topn][2] int32
+ * {cw, normalised score} after each frame. */
+int
+refdrv_score(refdrv_t *d, const float *feats, int T, int16 *senscr, int reset, int32 *topn_out)
+{
+    ps_mgau_t *mg = d->acmod->mgau;
+    int n_sen = bin_mdef_n_sen(d->acmod->mdef);
+    mfcc_t *ptrs[16];
+    int t, base;
+
+    if (reset) refdrv_reset(d);
+    base = mg->frame_idx;
+    for (t = 0; t < T; ++t) {
+        feat_ptrs(d, feats + (size_t)t * d->sumlen, ptrs);
+        ps_mgau_frame_eval(mg, senscr + (size_t)t * n_sen, NULL, 0, ptrs, base + t, TRUE);
+        mg->frame_idx = base + t + 1;
+        if (topn_out && d->kind == KIND_PTM) {
+            ptm_mgau_t *s = (ptm_mgau_t *)mg;
+            size_t n = (size_t)s->g->n_mgau * s->g->n_feat * s->max_topn;
+            memcpy(topn_out + t * n * 2, s->f->topn[0][0], n * sizeof(ptm_topn_t));
+        }
+        else if (topn_out && d->kind == KIND_SEMI) {
+            s2_semi_mgau_t *s = (s2_semi_mgau_t *)mg;
+            size_t n = (size_t)s->g->n_feat * s->max_topn;
+            int f, k;
+            for (f = 0; f < s->g->n_feat; ++f)
+                for (k = 0; k < s->max_topn; ++k) {
+                    topn_out[(t * n + f * s->max_topn + k) * 2] = s->f[f][k].codeword;
+                    topn_out[(t * n + f * s->max_topn + k) * 2 + 1] = s->f[f][k].score;
+                }
+        }
+    }
+    return 0;
+}
+
+/* Same, but with per-frame active-senone flags (compallsen = no): the flags go through the
+ * reference's own bitvec -> delta-list coder (acmod_flags2list, acmod.c:1224-1275).
+ * flags: [T][n_sen] bytes.  n_active_out/list_out (optional): the delta list per frame. */
+int
+refdrv_score_active(refdrv_t *d, const float *feats, int T, const uint8 *flags,
+                    int16 *senscr, int reset, int32 *n_active_out, uint8 *list_out)
+{
+    acmod_t *a = d->acmod;
+    ps_mgau_t *mg = a->mgau;
+    int n_sen = bin_mdef_n_sen(a->mdef);
+    mfcc_t *ptrs[16];
+    int t, s, base, n;
+    uint8 save = a->compallsen;
+
+    if (reset) refdrv_reset(d);
+    base = mg->frame_idx;
+    a->compallsen = FALSE;
+    for (t = 0; t < T; ++t) {
+        acmod_clear_active(a);
+        for (s = 0; s < n_sen; ++s)
+            if (flags[(size_t)t * n_sen + s])
+                bitvec_set(a->senone_active_vec, s);
+        n = acmod_flags2list(a);
+        if (n_active_out) n_active_out[t] = n;
+        if (list_out) memcpy(list_out + (size_t)t * n_sen, a->senone_active, n);
+        feat_ptrs(d, feats + (size_t)t * d->sumlen, ptrs);
+        ps_mgau_frame_eval(mg, senscr + (size_t)t * n_sen, a->senone_active, n, ptrs, base + t, FALSE);
+        mg->frame_idx = base + t + 1;
+    }
+    a->compallsen = save;
+    return 0;
+}
+
+/* CPU baseline: wall-clock seconds for reps passes of refdrv_score over the same features. */
+double
+refdrv_time_score(refdrv_t *d, const float *feats, int T, int reps)
+{
+    int n_sen = bin_mdef_n_sen(d->acmod->mdef);
+    int16 *scr = malloc((size_t)T * n_sen * sizeof(*scr));
+    double t0, t1;
+    int r;
+
+    refdrv_score(d, feats, T < 16 ? T : 16, scr, 1, NULL); /* warm caches */
+    t0 = now_s();
+    for (r = 0; r < reps; ++r)
+        refdrv_score(d, feats, T, scr, 1, NULL);
+    t1 = now_s();
+    free(scr);
+    return t1 - t0;
+}
+
+/* ------------------------------------------------------------------------------------- */
+/* HMM evaluation through the reference's hmm.c                                           */
+
+typedef struct refhmmctx_s {
+    hmm_context_t *ctx;
+    uint8 ***tp;
+    uint16 **sseq;
+    int n_tmat, n_sseq, n_emit;
+} refhmmctx_t;
+
+/* tp_flat: uint8 [n_tmat][n_emit][n_emit+1]; sseq_flat: uint16 [n_sseq][n_emit]. */
+refhmmctx_t *
+refdrv_hmmctx_new(int n_emit, const uint8 *tp_flat, int n_tmat, const uint16 *sseq_flat, int n_sseq)
+{
+    refhmmctx_t *c = calloc(1, sizeof(*c));
+    c->n_emit = n_emit;
+    c->n_tmat = n_tmat;
+    c->n_sseq = n_sseq;
+    c->tp = (uint8 ***)ckd_calloc_3d(n_tmat, n_emit, n_emit + 1, 1);
+    memcpy(c->tp[0][0], tp_flat, (size_t)n_tmat * n_emit * (n_emit + 1));
+    c->sseq = (uint16 **)ckd_calloc_2d(n_sseq, n_emit, sizeof(uint16));
+    memcpy(c->sseq[0], sseq_flat, (size_t)n_sseq * n_emit * sizeof(uint16));
+    c->ctx = hmm_context_init(n_emit, c->tp, NULL, c->sseq);
+    return c;
+}
+
+void
+refdrv_hmmctx_free(refhmmctx_t *c)
+{
+    if (!c) return;
+    hmm_context_free(c->ctx);
+    ckd_free_3d(c->tp);
+    ckd_free_2d(c->sseq);
+    free(c);
+}
+
+int refdrv_sizeof_hmm(void) { return (int)sizeof(hmm_t); }
+
+/* hmms: array of n real hmm_t records (88 bytes each; the ctx field is overwritten here).
+ * Calls hmm_vit_eval (hmm.c:787) on each and returns max bestscore (WORST_SCORE if n==0),
+ * like evaluate_hmms (phone_loop_search.c:202-221). */
+int32
+refdrv_hmm_vit_eval(refhmmctx_t *c, void *hmms, int n, const int16 *senscr)
+{
+    hmm_t *h = hmms;
+    int32 best = WORST_SCORE;
+    int i;
+    hmm_context_set_senscore(c->ctx, senscr);
+    for (i = 0; i < n; ++i) {
+        int32 s;
+        h[i].ctx = c->ctx;
+        s = hmm_vit_eval(&h[i]);
+        if (s BETTER_THAN best) best = s;
+    }
+    return best;
+}
+
+/* hmm_init (hmm.c:85-105) on caller-provided storage. */
+void
+refdrv_hmm_init(refhmmctx_t *c, void *hmms, int n, const int32 *mpx, const int32 *ssid, const int32 *tmatid)
+{
+    hmm_t *h = hmms;
+    int i;
+    for (i = 0; i < n; ++i)
+        hmm_init(c->ctx, &h[i], mpx[i], ssid[i], tmatid[i]);
+}
+
+void refdrv_hmm_enter(void *hmms, int i, int32 score, int32 histid, int frame) { hmm_enter((hmm_t *)hmms + i, score, histid, frame); }
+void refdrv_hmm_clear(void *hmms, int i) { hmm_clear((hmm_t *)hmms + i); }
+void refdrv_hmm_clear_scores(void *hmms, int i) { hmm_clear_scores((hmm_t *)hmms + i); }
+void refdrv_hmm_normalize(void *hmms, int i, int32 best) { hmm_normalize((hmm_t *)hmms + i, best); }
+
+double
+refdrv_time_hmm_vit_eval(refhmmctx_t *c, void *hmms, int n, const int16 *senscr, int reps)
+{
+    void *copy = malloc((size_t)n * sizeof(hmm_t));
+    double t0, t = 0;
+    int r;
+    for (r = 0; r < reps; ++r) {
+        memcpy(copy, hmms, (size_t)n * sizeof(hmm_t));
+        t0 = now_s();
+        refdrv_hmm_vit_eval(c, copy, n, senscr);
+        t += now_s() - t0;
+    }
+    free(copy);
+    return t;
+}
+
+/* ------------------------------------------------------------------------------------- */
+/* The reference's own phone loop (phone_loop_search.c) run over PCM; per frame dumps
+ * every phone HMM (as 88-byte hmm_t), best_score and penalties.                          */
+
+int
+refdrv_phoneloop_run(refdrv_t *d, const int16 *pcm, long n_samples, const char *kv,
+                     int max_frames, void *hmm_out, int32 *best_out, int32 *pen_out,
+                     int16 *senscr_out, float *feat_out)
+{
+    acmod_t *a = d->acmod;
+    phone_loop_search_t *pls;
+    const int16 *p = pcm;
+    size_t n = n_samples;
+    int T, t, np, n_sen = bin_mdef_n_sen(a->mdef);
+
+    if (kv) {
+        char *buf = strdup(kv), *save = NULL, *tok;
+        for (tok = strtok_r(buf, "\n", &save); tok; tok = strtok_r(NULL, "\n", &save)) {
+            char *eq = strchr(tok, '=');
+            if (!eq) continue;
+            *eq = 0;
+            ps_config_set_str(d->config, tok, eq + 1);
+        }
+        free(buf);
+    }
+    if (d->pls) ps_search_free(d->pls);
+    d->pls = phone_loop_search_init(d->config, a, NULL);
+    pls = (phone_loop_search_t *)d->pls;
+    np = pls->n_phones;
+
+    refdrv_reset(d);
+    cmn_snapshot(d, 1);
+    acmod_start_utt(a);
+    acmod_process_raw(a, &p, &n, TRUE);
+    acmod_end_utt(a);
+    T = a->n_feat_frame;
+    ps_search_start(d->pls);
+    for (t = 0; t < T && t < max_frames; ++t) {
+        int fi = t;
+        if (feat_out)
+            memcpy(feat_out + (size_t)t * d->sumlen, a->feat_buf[t][0], d->sumlen * sizeof(float));
+        ps_search_step(d->pls, t);
+        if (senscr_out)
+            memcpy(senscr_out + (size_t)t * n_sen, acmod_score(a, &fi), n_sen * sizeof(int16));
+        if (hmm_out)
+            memcpy((char *)hmm_out + (size_t)t * np * sizeof(hmm_t), pls->hmms, np * sizeof(hmm_t));
+        if (best_out) best_out[t] = pls->best_score;
+        if (pen_out) memcpy(pen_out + (size_t)t * np, pls->penalties, np * sizeof(int32));
+        acmod_advance(a);
+    }
+    ps_search_finish(d->pls);
+    return T;
+}
+
+int
+refdrv_phoneloop_params(refdrv_t *d, int32 *out)
+{
+    phone_loop_search_t *pls = (phone_loop_search_t *)d->pls;
+    if (!pls) return -1;
+    out[0] = pls->n_phones;
+    out[1] = pls->beam;
+    out[2] = pls->pbeam;
+    out[3] = pls->pip;
+    out[4] = pls->window;
+    memcpy(out + 6, &pls->penalty_weight, sizeof(double)); /* out[6..7] = float64 */
+    return 0;
+}

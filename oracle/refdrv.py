@@ -1,0 +1,212 @@
+"""ctypes binding for oracle/_ref/libpsref.so -- TEST INFRASTRUCTURE ONLY.
+
+libpsref.so is the unmodified reference (cmusphinx/pocketsphinx 5.1.1) compiled by
+oracle/Makefile plus oracle/ref_driver.c.  Only tests/, __graft_entry__.smoke() and
+bench.py's CPU-baseline / --impl reference legs may import this module.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_ref", "libpsref.so")
+
+KIND_NAMES = {0: "ptm", 1: "s2_semi", 2: "ms"}
+
+# Byte-for-byte mirror of hmm_t (src/hmm.h:169-182): 88 bytes on LP64.
+HMM_DTYPE = np.dtype({
+    "names": ["ctx", "score", "history", "out_score", "out_history", "ssid", "senid",
+              "bestscore", "tmatid", "frame", "mpx", "n_emit_state"],
+    "formats": ["<u8", ("<i4", 5), ("<i4", 5), "<i4", "<i4", "<u2", ("<u2", 5),
+                "<i4", "<i2", "<i4", "u1", "u1"],
+    "offsets": [0, 8, 28, 48, 52, 56, 58, 68, 72, 76, 80, 81],
+    "itemsize": 88,
+})
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(LIB_PATH)
+        L.refdrv_open.restype = C.c_void_p
+        L.refdrv_open.argtypes = [C.c_char_p, C.c_char_p]
+        L.refdrv_close.argtypes = [C.c_void_p]
+        L.refdrv_dims.argtypes = [C.c_void_p, C.c_void_p]
+        L.refdrv_export.restype = C.c_long
+        L.refdrv_export.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long]
+        L.refdrv_featurize.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_int]
+        L.refdrv_reset.argtypes = [C.c_void_p]
+        L.refdrv_score.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.refdrv_score_active.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.c_int, C.c_void_p, C.c_void_p]
+        L.refdrv_time_score.restype = C.c_double
+        L.refdrv_time_score.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.refdrv_hmmctx_new.restype = C.c_void_p
+        L.refdrv_hmmctx_new.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.refdrv_hmmctx_free.argtypes = [C.c_void_p]
+        L.refdrv_hmm_vit_eval.restype = C.c_int32
+        L.refdrv_hmm_vit_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.refdrv_hmm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.refdrv_hmm_enter.argtypes = [C.c_void_p, C.c_int, C.c_int32, C.c_int32, C.c_int]
+        L.refdrv_hmm_clear.argtypes = [C.c_void_p, C.c_int]
+        L.refdrv_hmm_clear_scores.argtypes = [C.c_void_p, C.c_int]
+        L.refdrv_hmm_normalize.argtypes = [C.c_void_p, C.c_int, C.c_int32]
+        L.refdrv_time_hmm_vit_eval.restype = C.c_double
+        L.refdrv_time_hmm_vit_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.refdrv_phoneloop_run.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_char_p, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.refdrv_phoneloop_params.argtypes = [C.c_void_p, C.c_void_p]
+        assert L.refdrv_sizeof_hmm() == HMM_DTYPE.itemsize
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class RefModel:
+    """One reference acmod_t (fe + feat + mdef + tmat + mgau back-end), all senones computed."""
+
+    def __init__(self, hmmdir, **kv):
+        s = "\n".join("%s=%s" % (k, v) for k, v in kv.items()).encode() or None
+        self.h = lib().refdrv_open(hmmdir.encode(), s)
+        if not self.h:
+            raise RuntimeError("reference acmod_init failed for " + hmmdir)
+        d = np.zeros(32, np.int32)
+        lib().refdrv_dims(self.h, _p(d))
+        self.kind = KIND_NAMES[int(d[0])]
+        (self.n_sen, self.n_mgau, self.n_feat, self.n_density, self.topn, self.sumlen,
+         self.n_emit_state, self.n_tmat, self.n_sseq, self.n_ciphone, self.n_ci_sen) = map(int, d[1:12])
+        self.mixw_4bit = bool(d[12])
+        self.logadd8_size = int(d[13])
+        self.ds_ratio = int(d[14])
+        self.aw = int(d[15])
+        self.ms_logadd_size, self.ms_logadd_width, self.ms_logadd_zero = int(d[16]), int(d[17]), int(d[18])
+        self.featlen = [int(x) for x in d[20:20 + self.n_feat]]
+
+    def close(self):
+        if self.h:
+            lib().refdrv_close(self.h)
+            self.h = None
+
+    def export(self, what, dtype):
+        n = lib().refdrv_export(self.h, what.encode(), None, 0)
+        if n < 0:
+            raise KeyError(what)
+        buf = np.zeros(n // np.dtype(dtype).itemsize, dtype)
+        if n:
+            lib().refdrv_export(self.h, what.encode(), _p(buf), n)
+        return buf
+
+    def packed(self):
+        """Model arrays in the layout pocketsphinx_b200.model.PackedModel expects."""
+        m = dict(kind=self.kind, n_sen=self.n_sen, n_mgau=self.n_mgau, n_feat=self.n_feat,
+                 n_density=self.n_density, topn=self.topn, featlen=np.array(self.featlen, np.int32),
+                 n_emit_state=self.n_emit_state, aw=self.aw, ds_ratio=self.ds_ratio,
+                 n_ciphone=self.n_ciphone, n_ci_sen=self.n_ci_sen,
+                 mean=self.export("mean", np.float32), var=self.export("var", np.float32),
+                 det=self.export("det", np.float32), mixw=self.export("mixw", np.uint8),
+                 mixw_cb=self.export("mixw_cb", np.uint8), sen2cb=self.export("sen2cb", np.int32),
+                 logadd8=self.export("logadd8", np.uint8),
+                 tp=self.export("tp", np.uint8).reshape(self.n_tmat, self.n_emit_state, self.n_emit_state + 1),
+                 sseq=self.export("sseq", np.uint16).reshape(self.n_sseq, self.n_emit_state),
+                 phone_ssid=self.export("phone_ssid", np.int32),
+                 phone_tmat=self.export("phone_tmat", np.int32))
+        if self.kind == "ms":
+            wdt = {1: np.uint8, 2: np.uint16, 4: np.uint32}[self.ms_logadd_width]
+            m["logadd_ms"] = self.export("logadd_ms", wdt).astype(np.uint32)
+            m["logadd_ms_zero"] = self.ms_logadd_zero
+        if self.kind == "s2_semi":
+            m["topn_beam"] = self.export("topn_beam", np.uint8)
+        return m
+
+    def featurize(self, pcm, max_frames=None):
+        pcm = np.ascontiguousarray(pcm, np.int16)
+        cap = max_frames or (len(pcm) // 160 + 16)
+        out = np.zeros((cap, self.sumlen), np.float32)
+        T = lib().refdrv_featurize(self.h, _p(pcm), len(pcm), _p(out), cap)
+        return out[:min(T, cap)].copy()
+
+    def score(self, feats, reset=True, want_topn=False):
+        feats = np.ascontiguousarray(feats, np.float32)
+        T = feats.shape[0]
+        scr = np.zeros((T, self.n_sen), np.int16)
+        topn = None
+        if want_topn and self.kind == "ptm":
+            topn = np.zeros((T, self.n_mgau, self.n_feat, self.topn, 2), np.int32)
+        elif want_topn and self.kind == "s2_semi":
+            topn = np.zeros((T, self.n_feat, self.topn, 2), np.int32)
+        lib().refdrv_score(self.h, _p(feats), T, _p(scr), int(reset), _p(topn))
+        return (scr, topn) if want_topn else scr
+
+    def score_active(self, feats, flags, reset=True):
+        feats = np.ascontiguousarray(feats, np.float32)
+        flags = np.ascontiguousarray(flags, np.uint8)
+        T = feats.shape[0]
+        scr = np.zeros((T, self.n_sen), np.int16)
+        nact = np.zeros(T, np.int32)
+        lists = np.zeros((T, self.n_sen), np.uint8)
+        lib().refdrv_score_active(self.h, _p(feats), T, _p(flags), _p(scr), int(reset), _p(nact), _p(lists))
+        return scr, nact, lists
+
+    def time_score(self, feats, reps=1):
+        feats = np.ascontiguousarray(feats, np.float32)
+        return lib().refdrv_time_score(self.h, _p(feats), feats.shape[0], reps)
+
+    def phoneloop(self, pcm, **kv):
+        pcm = np.ascontiguousarray(pcm, np.int16)
+        kv.setdefault("pl_window", 5)
+        s = "\n".join("%s=%s" % (k, v) for k, v in kv.items()).encode()
+        cap = len(pcm) // 160 + 16
+        np_ = self.n_ciphone
+        hm = np.zeros((cap, np_), HMM_DTYPE)
+        best = np.zeros(cap, np.int32)
+        pen = np.zeros((cap, np_), np.int32)
+        scr = np.zeros((cap, self.n_sen), np.int16)
+        feat = np.zeros((cap, self.sumlen), np.float32)
+        T = lib().refdrv_phoneloop_run(self.h, _p(pcm), len(pcm), s, cap, _p(hm), _p(best), _p(pen), _p(scr), _p(feat))
+        par = np.zeros(8, np.int32)
+        lib().refdrv_phoneloop_params(self.h, _p(par))
+        params = dict(n_phones=int(par[0]), beam=int(par[1]), pbeam=int(par[2]), pip=int(par[3]),
+                      window=int(par[4]), penalty_weight=float(par[6:8].view(np.float64)[0]))
+        return dict(T=T, hmm=hm[:T], best=best[:T], pen=pen[:T], senscr=scr[:T], feat=feat[:T], params=params)
+
+
+class RefHmmCtx:
+    """hmm_context_t over caller-supplied tp / sseq tables; evaluates real 88-byte hmm_t arrays."""
+
+    def __init__(self, tp, sseq):
+        tp = np.ascontiguousarray(tp, np.uint8)
+        sseq = np.ascontiguousarray(sseq, np.uint16)
+        self.n_emit = tp.shape[1]
+        assert tp.shape[2] == self.n_emit + 1 and sseq.shape[1] == self.n_emit
+        self.h = lib().refdrv_hmmctx_new(self.n_emit, _p(tp), tp.shape[0], _p(sseq), sseq.shape[0])
+
+    def close(self):
+        if self.h:
+            lib().refdrv_hmmctx_free(self.h)
+            self.h = None
+
+    def init(self, n, mpx, ssid, tmatid):
+        hm = np.zeros(n, HMM_DTYPE)
+        lib().refdrv_hmm_init(self.h, _p(hm), n, _p(np.ascontiguousarray(mpx, np.int32)),
+                              _p(np.ascontiguousarray(ssid, np.int32)), _p(np.ascontiguousarray(tmatid, np.int32)))
+        return hm
+
+    def vit_eval(self, hmms, senscr):
+        senscr = np.ascontiguousarray(senscr, np.int16)
+        assert hmms.dtype == HMM_DTYPE and hmms.flags.c_contiguous
+        return int(lib().refdrv_hmm_vit_eval(self.h, _p(hmms), len(hmms), _p(senscr)))
+
+    def time_vit_eval(self, hmms, senscr, reps=1):
+        senscr = np.ascontiguousarray(senscr, np.int16)
+        return lib().refdrv_time_hmm_vit_eval(self.h, _p(hmms), len(hmms), _p(senscr), reps)
