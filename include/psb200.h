@@ -1,0 +1,212 @@
+/* psb200.h -- C ABI of the B200-native PocketSphinx hot path (libpsb200.so).
+ *
+ * Plain C, no CUDA or torch types in any signature: a host program (the reference's own C,
+ * or anything with an FFI) binds these exactly like the symbols they stand in for.  Every
+ * entry point names the reference interface it replaces (paths relative to the
+ * cmusphinx/pocketsphinx 5.1.1 tree).  All functions return 0 on success and a negative
+ * psb_status_t on failure (the reference's "<0 + E_ERROR, never exit()" convention,
+ * include/pocketsphinx/err.h:80-88); psb_last_error() gives the message for the calling
+ * thread.  Handles are opaque; one handle may be used from one thread at a time, different
+ * handles from different threads (each owns its CUDA stream).
+ *
+ * Numerics contract: int16 senone scores, int32 path scores, histories and best scores are
+ * bit-identical to the reference's default (float) build for the same inputs.
+ */
+#ifndef PSB200_H
+#define PSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSB_ABI_VERSION 1
+
+typedef enum psb_status_e {
+    PSB_OK = 0,
+    PSB_ERR_ARG = -1,        /* bad argument / unsupported shape */
+    PSB_ERR_CUDA = -2,       /* CUDA runtime error (message in psb_last_error) */
+    PSB_ERR_NOMEM = -3,
+    PSB_ERR_STATE = -4       /* call not valid in the handle's current state */
+} psb_status_t;
+
+enum { PSB_KIND_PTM = 0, PSB_KIND_SEMI = 1, PSB_KIND_MS = 2 };
+
+#define PSB_MAX_FEAT 8
+#define PSB_MAX_TOPN 8
+#define PSB_HMM_MAX_NSTATE 5          /* hmm.h:159 */
+#define PSB_WORST_SCORE ((int32_t)0xE0000000)   /* hmm.h:83 */
+
+const char *psb_last_error(void);
+int psb_abi_version(void);
+int psb_device_count(void);
+
+/* ------------------------------------------------------------------------------------ */
+/* Acoustic model (replaces what ptm_mgau_init ptm_mgau.c:805, s2_semi_mgau_init
+ * s2_semi_mgau.c:1236 and ms_mgau_init ms_mgau.c:80 build in host memory: gauden_t +
+ * mixture weights + sen2cb + the 8-bit log-add table).  Arrays are in the reference's
+ * in-memory order *after* its loaders ran (gauden_dist_precompute, ms_gauden.c:264-308):
+ *   mean, var  float [n_mgau][n_feat][n_density][featlen[f]]
+ *   det        float [n_mgau][n_feat][n_density]
+ *   mixw       ptm/semi: uint8 [n_feat][n_density][row], row = n_sen or (n_sen+1)/2 (4-bit)
+ *              ms:       uint8 pdf[n_sen][n_feat][n_density] (n_mgau > 1)
+ *                         or   pdf[n_feat][n_density][n_sen] (n_mgau == 1)  (ms_senone.h:73-80)
+ *   mixw_cb    16 bytes or NULL;  sen2cb int32 [n_sen];  logadd8 uint8 [256]
+ *   logadd_ms  uint32 [logadd_ms_size] (the shifted logmath table, ms back-end only)
+ * Pointers are host pointers unless on_device != 0 (then they are device pointers on
+ * `device`, e.g. after an NCCL broadcast of the packed model).                            */
+typedef struct psb_model_desc_s {
+    int32_t kind, n_sen, n_mgau, n_feat, n_density, topn;
+    int32_t featlen[PSB_MAX_FEAT];
+    int32_t ds_ratio;           /* -ds   (ptm_mgau.c:242) */
+    int32_t aw;                 /* -aw   (ms_senone.c:396) */
+    int32_t logadd_ms_size, logadd_ms_zero;
+    int32_t on_device;
+    const float *mean, *var, *det;
+    const uint8_t *mixw, *mixw_cb;
+    const int32_t *sen2cb;
+    const uint8_t *logadd8;
+    const uint32_t *logadd_ms;
+    const uint8_t *topn_beam;   /* semi: [n_feat] or NULL (s2_semi_mgau.c:1302-1309) */
+} psb_model_desc_t;
+
+typedef struct psb_model_s psb_model_t;
+
+int psb_model_create(const psb_model_desc_t *desc, int device, psb_model_t **out);
+void psb_model_free(psb_model_t *m);
+/* ps_mgaufuncs_t.transform (acmod.h:108-109; gauden_mllr_transform ms_gauden.c:512):
+ * the host applies MLLR and re-precomputes; this re-uploads the Gaussians. */
+int psb_model_update_gaussians(psb_model_t *m, const float *mean, const float *var, const float *det);
+int psb_model_n_sen(const psb_model_t *m);
+int psb_model_device(const psb_model_t *m);
+
+/* ------------------------------------------------------------------------------------ */
+/* Per-stream scorer: the drop-in behind ps_mgau_t's vtable (acmod.h:98-125).
+ * psb_scorer_frame_eval has the argument meaning of ps_mgaufuncs_t.frame_eval
+ * (acmod.h:101-107) as called from acmod_score (acmod.c:1108-1114): host buffers, senscr is
+ * int16[n_sen] owned by the caller and fully defined on return, senone_active is the uint8
+ * delta list from acmod_flags2list (acmod.c:1224-1275), feat[f] points at stream f of the
+ * frame, frame is absolute, past frames (frame < frame_idx, within n_hist) are re-scored from
+ * the top-N history ring (ptm_mgau.c:419-451).  frame_idx is ps_mgau_t.frame_idx: the host
+ * mirrors acmod_start_utt / acmod_advance / acmod_rewind (acmod.c:419,862,874) through
+ * psb_scorer_set_frame_idx.  n_hist = pl_window + 2 (ptm_mgau.c:884).                      */
+typedef struct psb_scorer_s psb_scorer_t;
+
+int psb_scorer_create(psb_model_t *m, int32_t n_hist, psb_scorer_t **out);
+void psb_scorer_free(psb_scorer_t *s);
+int psb_scorer_reset(psb_scorer_t *s);       /* ptm_mgau_reset_fast_hist (ptm_mgau.c:777) */
+int psb_scorer_set_frame_idx(psb_scorer_t *s, int32_t frame_idx);
+int32_t psb_scorer_get_frame_idx(const psb_scorer_t *s);
+int psb_scorer_frame_eval(psb_scorer_t *s, int16_t *senscr, const uint8_t *senone_active,
+                          int32_t n_senone_active, const float *const *feat, int32_t frame,
+                          int32_t compallsen);
+
+/* ------------------------------------------------------------------------------------ */
+/* Batched utterance scoring (the acmod_score loop of SURVEY 8d config 2: all senones,
+ * every utterance starting from the post-init top-N state).
+ *   feats    float [total_frames][sumlen]   utterance u owns rows utt_off[u]..utt_off[u+1]-1
+ *   utt_off  int32 [n_utt + 1]
+ *   senscr   int16 [total_frames][n_sen]
+ * _host: host buffers; the H2D copy of feats and the D2H copy of senscr are part of the call.
+ * _device: device buffers on the model's device (utt_off stays a host array); asynchronous
+ * on the batch's stream until psb_batch_sync.                                              */
+typedef struct psb_batch_s psb_batch_t;
+
+int psb_batch_create(psb_model_t *m, int32_t max_utts, int64_t max_frames, psb_batch_t **out);
+void psb_batch_free(psb_batch_t *b);
+int psb_batch_score_host(psb_batch_t *b, const float *feats, const int32_t *utt_off,
+                         int32_t n_utt, int16_t *senscr);
+int psb_batch_score_device(psb_batch_t *b, const float *d_feats, const int32_t *utt_off,
+                           int32_t n_utt, int16_t *d_senscr);
+int psb_batch_sync(psb_batch_t *b);
+/* device address of the batch's own score matrix after psb_batch_score_device(..., NULL) */
+int16_t *psb_batch_senscr_device(psb_batch_t *b);
+/* timing of the last score call's kernels on the batch stream (CUDA events), ms:
+ * out[0] transpose, out[1] gaussian top-N, out[2] senone eval */
+int psb_batch_last_kernel_ms(psb_batch_t *b, float *out3);
+/* debugging/parity: copy the per-frame top-N records of the last call to the host:
+ * rec int32 [total_frames][n_mgau*n_feat][4] = {top>>10, cw[4] bytes, e[4] bytes, 0} */
+int psb_batch_get_topn(psb_batch_t *b, int32_t *rec, int64_t n_frames);
+
+/* ------------------------------------------------------------------------------------ */
+/* HMM evaluation.  psb_hmm_t is the reference's hmm_t byte for byte (hmm.h:169-182, 88 bytes
+ * on LP64): the search modules touch its fields directly (hmm.h:185-213), so the layout is
+ * ABI.  The ctx pointer is ignored by this library.                                        */
+typedef struct psb_hmm_s {
+    void *ctx;
+    int32_t score[PSB_HMM_MAX_NSTATE];
+    int32_t history[PSB_HMM_MAX_NSTATE];
+    int32_t out_score;
+    int32_t out_history;
+    uint16_t ssid;
+    uint16_t senid[PSB_HMM_MAX_NSTATE];
+    int32_t bestscore;
+    int16_t tmatid;
+    int32_t frame;
+    uint8_t mpx;
+    uint8_t n_emit_state;
+} psb_hmm_t;
+
+/* hmm_context_init (hmm.h:218-224): tp uint8 [n_tmat][n_emit][n_emit+1] (tmat.h:57-63),
+ * sseq uint16 [n_sseq][n_emit] (bin_mdef.h:137). */
+typedef struct psb_hmmctx_s psb_hmmctx_t;
+
+int psb_hmmctx_create(int32_t n_emit_state, const uint8_t *tp, int32_t n_tmat,
+                      const uint16_t *sseq, int32_t n_sseq, int32_t n_sen, int device,
+                      psb_hmmctx_t **out);
+void psb_hmmctx_free(psb_hmmctx_t *c);
+
+/* The batched twin of "for each active hmm: hmm_vit_eval(hmm); best = max" as in
+ * evaluate_hmms (phone_loop_search.c:202-221), eval_*_chan (ngram_search_fwdtree.c:606-699),
+ * fsg_search_hmm_eval (fsg_search.c:336-408): hmms is a host array of n records updated in
+ * place; senscr is the frame's host int16[n_sen] (hmm_context_set_senscore); *best gets the
+ * max bestscore (PSB_WORST_SCORE when n == 0). */
+int psb_hmm_vit_eval_batch(psb_hmmctx_t *c, psb_hmm_t *hmms, int32_t n, const int16_t *senscr,
+                           int32_t *best);
+/* Same through an array of pointers (the active lists are arrays of chan_t*,
+ * ngram_search.h:278; hmm_t is the first member of chan_t / root_chan_t / fsg_pnode_t). */
+int psb_hmm_vit_eval_ptrs(psb_hmmctx_t *c, psb_hmm_t *const *hmms, int32_t n,
+                          const int16_t *senscr, int32_t *best);
+
+/* ------------------------------------------------------------------------------------ */
+/* Device-resident phone-loop Viterbi over whole utterances: the frame-synchronous caller
+ * of hmm_vit_eval in phone_loop_search.c (start :155, renormalize :177, evaluate_hmms :193,
+ * store_scores :216, prune_hmms :241, phone_transition :263, step :301) run for every
+ * utterance of a batch, consuming senone scores already on the device.
+ * ssid/tmatid: the n_phones HMMs (CI phones for the reference's phone loop).
+ * beam/pbeam/pip: already >> SENSCR_SHIFT (phone_loop_search.c:106-108).                  */
+typedef struct psb_phoneloop_s psb_phoneloop_t;
+
+int psb_phoneloop_create(psb_hmmctx_t *c, int32_t n_phones, const int32_t *ssid,
+                         const int32_t *tmatid, int32_t window, int32_t beam, int32_t pbeam,
+                         int32_t pip, double penalty_weight, psb_phoneloop_t **out);
+void psb_phoneloop_free(psb_phoneloop_t *p);
+/* d_senscr int16 [total_frames][n_sen] on the device; outputs (device, may be NULL):
+ *   d_best int32 [total_frames]              best_score after each frame
+ *   d_pen  int32 [total_frames][n_phones]    penalties after each frame
+ * final HMM states (host, may be NULL): psb_hmm_t [n_utt][n_phones] */
+int psb_phoneloop_run_device(psb_phoneloop_t *p, const int16_t *d_senscr, const int32_t *utt_off,
+                             int32_t n_utt, int32_t *d_best, int32_t *d_pen, psb_hmm_t *final_hmms,
+                             void *stream_of_batch /* psb_batch_t* or NULL */);
+/* host-buffer twin (copies in/out inside the call); per-frame HMM dump optional:
+ * hmm_trace psb_hmm_t [total_frames][n_phones] */
+int psb_phoneloop_run_host(psb_phoneloop_t *p, const int16_t *senscr, const int32_t *utt_off,
+                           int32_t n_utt, int32_t *best, int32_t *pen, psb_hmm_t *hmm_trace);
+
+/* ------------------------------------------------------------------------------------ */
+/* End-to-end: host features in -> senone scores -> phone-loop Viterbi -> host results out
+ * (best[total_frames], pen[total_frames][n_phones]); senscr (host, may be NULL) also
+ * returned when wanted.  This is the call bench.py times as "e2e". */
+int psb_decode_batch_host(psb_batch_t *b, psb_phoneloop_t *p, const float *feats,
+                          const int32_t *utt_off, int32_t n_utt, int32_t *best, int32_t *pen,
+                          int16_t *senscr);
+
+/* number of kernels launched by this library in the calling process so far */
+int64_t psb_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSB200_H */

@@ -1,0 +1,138 @@
+"""Generate tests/golden/*.npz from the compiled reference (oracle/_ref/libpsref.so).
+
+Run in the build container only (needs /root/reference):  python -m oracle.make_golden
+Everything written here is OUTPUT of the unmodified reference run on its own shipped models
+and test audio: packed model arrays as its loaders leave them in memory, features from its
+fe/feat front end, int16 senone scores from its ps_mgau back-ends, hmm_t states from its
+hmm.c / phone_loop_search.c.  The GPU box has no /root/reference; tests there use these files.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import refdrv  # noqa: E402
+from pocketsphinx_b200.model import PackedModel  # noqa: E402
+
+REF = os.environ.get("PS_REFERENCE", "/root/reference")
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def save_model(name, pm_dict, keep_phones=None):
+    pm = PackedModel.from_dict(pm_dict)
+    if keep_phones is not None:          # en-us has 137k triphones; the CI phones are enough
+        pm.phone_ssid = pm.phone_ssid[:keep_phones]
+        pm.phone_tmat = pm.phone_tmat[:keep_phones]
+    path = os.path.join(OUT, name)
+    pm.save(path)
+    print(name, os.path.getsize(path) // 1024, "KiB")
+    return pm
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    pcm = np.fromfile(os.path.join(REF, "test/data/goforward.raw"), np.int16)
+
+    # ---- en-us PTM (BASELINE config 1): goforward.raw, 278 frames, all senones ----
+    m = refdrv.RefModel(os.path.join(REF, "model/en-us/en-us"))
+    save_model("en_us_ptm_model.npz", m.packed(), keep_phones=4096)
+    pl = m.phoneloop(pcm)                       # first utterance of a fresh decoder
+    feats = pl["feat"]
+    scr, topn = m.score(feats, want_topn=True)
+    assert (scr == pl["senscr"]).all()
+    par = pl["params"]
+    np.savez_compressed(
+        os.path.join(OUT, "en_us_goforward.npz"), feats=feats, senscr=scr,
+        topn_last=topn[-1], topn_first=topn[0],
+        pl_hmm=pl["hmm"].view(np.uint8).reshape(pl["hmm"].shape + (88,)), pl_best=pl["best"], pl_pen=pl["pen"],
+        pl_params=np.array([par["n_phones"], par["beam"], par["pbeam"], par["pip"], par["window"]], np.int32),
+        pl_weight=np.float64(par["penalty_weight"]))
+    # active-list mode (compallsen = no): random flags with a few wide gaps
+    rng = np.random.default_rng(7)
+    T = 40
+    flags = (rng.random((T, m.n_sen)) < 0.3).astype(np.uint8)
+    flags[:, 1000:1700] = 0
+    flags[5] = 0
+    flags[6, :] = 0
+    flags[6, 4000] = 1
+    ascr, nact, lists = m.score_active(feats[:T], flags)
+    np.savez_compressed(os.path.join(OUT, "en_us_active.npz"), flags=np.packbits(flags, axis=1),
+                        n_sen=m.n_sen, senscr=ascr, nact=nact)
+    m.close()
+
+    # ---- tidigits semi-continuous (4 streams, 256 Gaussians, 4-bit clustered sendump) ----
+    m = refdrv.RefModel(os.path.join(REF, "test/data/tidigits/hmm"))
+    print("tidigits:", m.kind, m.n_sen, m.n_mgau, m.n_feat, m.n_density, m.featlen, "4bit" if m.mixw_4bit else "8bit")
+    save_model("tidigits_sc_model.npz", m.packed())
+    f = m.featurize(pcm)
+    s, tn = m.score(f, want_topn=True)
+    np.savez_compressed(os.path.join(OUT, "tidigits_goforward.npz"), feats=f, senscr=s, topn=tn)
+    m.close()
+
+    # ---- an4 continuous (ms back-end, 1 Gaussian per senone) ----
+    m = refdrv.RefModel(os.path.join(REF, "test/data/an4_ci_cont"))
+    print("an4:", m.kind, m.n_sen, m.n_mgau, m.n_feat, m.n_density, m.featlen, "topn", m.topn)
+    save_model("an4_cont_model.npz", m.packed())
+    f = m.featurize(pcm)
+    s = m.score(f)
+    np.savez_compressed(os.path.join(OUT, "an4_goforward.npz"), feats=f, senscr=s)
+    m.close()
+
+    # ---- en-us through the ms back-end too (-senmgau .ptm. forces ms_mgau_init first) ----
+    # not shipped: en-us has no mixture_weights file, only a sendump; skipped.
+
+    # ---- hmm_vit_eval: random states through the reference's five specialisations ----
+    rng = np.random.default_rng(11)
+    cases = {}
+    for n_emit in (3, 5, 4, 1):
+        n_tmat, n_sseq, n_sen, n = 7, 50, 200, 4096
+        tp = np.full((n_tmat, n_emit, n_emit + 1), 255, np.uint8)
+        for t in range(n_tmat):
+            for i in range(n_emit):
+                tp[t, i, i] = rng.integers(0, 60)
+                tp[t, i, i + 1] = rng.integers(0, 60)
+                if i + 2 <= n_emit and rng.random() < 0.5:
+                    tp[t, i, i + 2] = rng.integers(0, 90)
+        sseq = rng.integers(0, n_sen, (n_sseq, n_emit)).astype(np.uint16)
+        ctx = refdrv.RefHmmCtx(tp, sseq)
+        senscr = rng.integers(0, 700, n_sen).astype(np.int16)
+        mpx = (rng.random(n) < 0.5).astype(np.int32)
+        hm = ctx.init(n, mpx, rng.integers(0, n_sseq, n), rng.integers(0, n_tmat, n))
+        # random but plausible path scores, some states dead, some mpx slots empty
+        sc = rng.integers(-200000, 0, (n, 5)).astype(np.int32)
+        dead = rng.random((n, 5)) < 0.25
+        sc[dead] = -0x20000000
+        near = rng.random((n, 5)) < 0.03
+        sc[near] = -0x20000000 + rng.integers(-300, 300, near.sum())
+        hm["score"] = sc
+        hm["history"] = rng.integers(-1, 1000, (n, 5))
+        hm["out_score"] = rng.integers(-200000, 0, n)
+        hm["out_history"] = rng.integers(-1, 1000, n)
+        for st in range(1, n_emit):
+            sel = (mpx == 1) & (rng.random(n) < 0.7)
+            hm["senid"][sel, st] = rng.integers(0, n_sseq, sel.sum())
+        # dead states of mpx HMMs keep BAD_SSID like the search leaves them
+        badsel = (mpx[:, None] == 1) & dead & (np.arange(5)[None, :] > 0)
+        hm["senid"][badsel] = 0xffff
+        before = hm.copy()
+        best = ctx.vit_eval(hm, senscr)
+        before["ctx"] = 0
+        hm["ctx"] = 0
+        cases["n%d_tp" % n_emit] = tp
+        cases["n%d_sseq" % n_emit] = sseq
+        cases["n%d_senscr" % n_emit] = senscr
+        cases["n%d_before" % n_emit] = before.view(np.uint8).reshape(n, 88)
+        cases["n%d_after" % n_emit] = hm.view(np.uint8).reshape(n, 88)
+        cases["n%d_best" % n_emit] = np.int32(best)
+        ctx.close()
+    np.savez_compressed(os.path.join(OUT, "hmm_vit_eval.npz"), **cases)
+    for fn in sorted(os.listdir(OUT)):
+        print("%8d KiB  %s" % (os.path.getsize(os.path.join(OUT, fn)) // 1024, fn))
+
+
+if __name__ == "__main__":
+    main()

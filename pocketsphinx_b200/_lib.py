@@ -1,0 +1,86 @@
+"""ctypes loader for libpsb200.so (the C-ABI declared in include/psb200.h).
+
+There is no CPU fallback: if the library is missing, or a call fails, this raises.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpsb200.so")
+
+MAX_FEAT = 8
+
+
+class PsbError(RuntimeError):
+    pass
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_sen", C.c_int32), ("n_mgau", C.c_int32), ("n_feat", C.c_int32),
+                ("n_density", C.c_int32), ("topn", C.c_int32), ("featlen", C.c_int32 * MAX_FEAT),
+                ("ds_ratio", C.c_int32), ("aw", C.c_int32), ("logadd_ms_size", C.c_int32),
+                ("logadd_ms_zero", C.c_int32), ("on_device", C.c_int32),
+                ("mean", C.c_void_p), ("var", C.c_void_p), ("det", C.c_void_p), ("mixw", C.c_void_p),
+                ("mixw_cb", C.c_void_p), ("sen2cb", C.c_void_p), ("logadd8", C.c_void_p),
+                ("logadd_ms", C.c_void_p), ("topn_beam", C.c_void_p)]
+
+
+# every symbol include/psb200.h declares: (name, restype, argtypes)
+_VP, _I32, _I64 = C.c_void_p, C.c_int32, C.c_int64
+SYMBOLS = [
+    ("psb_last_error", C.c_char_p, []),
+    ("psb_abi_version", C.c_int, []),
+    ("psb_device_count", C.c_int, []),
+    ("psb_model_create", C.c_int, [C.POINTER(ModelDesc), C.c_int, C.POINTER(_VP)]),
+    ("psb_model_free", None, [_VP]),
+    ("psb_model_update_gaussians", C.c_int, [_VP, _VP, _VP, _VP]),
+    ("psb_model_n_sen", C.c_int, [_VP]),
+    ("psb_model_device", C.c_int, [_VP]),
+    ("psb_scorer_create", C.c_int, [_VP, _I32, C.POINTER(_VP)]),
+    ("psb_scorer_free", None, [_VP]),
+    ("psb_scorer_reset", C.c_int, [_VP]),
+    ("psb_scorer_set_frame_idx", C.c_int, [_VP, _I32]),
+    ("psb_scorer_get_frame_idx", _I32, [_VP]),
+    ("psb_scorer_frame_eval", C.c_int, [_VP, _VP, _VP, _I32, _VP, _I32, _I32]),
+    ("psb_batch_create", C.c_int, [_VP, _I32, _I64, C.POINTER(_VP)]),
+    ("psb_batch_free", None, [_VP]),
+    ("psb_batch_score_host", C.c_int, [_VP, _VP, _VP, _I32, _VP]),
+    ("psb_batch_score_device", C.c_int, [_VP, _VP, _VP, _I32, _VP]),
+    ("psb_batch_sync", C.c_int, [_VP]),
+    ("psb_batch_senscr_device", _VP, [_VP]),
+    ("psb_batch_last_kernel_ms", C.c_int, [_VP, _VP]),
+    ("psb_batch_get_topn", C.c_int, [_VP, _VP, _I64]),
+    ("psb_hmmctx_create", C.c_int, [_I32, _VP, _I32, _VP, _I32, _I32, C.c_int, C.POINTER(_VP)]),
+    ("psb_hmmctx_free", None, [_VP]),
+    ("psb_hmm_vit_eval_batch", C.c_int, [_VP, _VP, _I32, _VP, _VP]),
+    ("psb_hmm_vit_eval_ptrs", C.c_int, [_VP, _VP, _I32, _VP, _VP]),
+    ("psb_phoneloop_create", C.c_int, [_VP, _I32, _VP, _VP, _I32, _I32, _I32, _I32, C.c_double, C.POINTER(_VP)]),
+    ("psb_phoneloop_free", None, [_VP]),
+    ("psb_phoneloop_run_device", C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP]),
+    ("psb_phoneloop_run_host", C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP]),
+    ("psb_decode_batch_host", C.c_int, [_VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP]),
+    ("psb_kernel_launch_count", _I64, []),
+]
+
+_lib = None
+
+
+def lib():
+    """Load libpsb200.so and bind every ABI symbol; raises if the library or a symbol is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PsbError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(L, name)           # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise PsbError("%s failed (%d): %s" % (what or "psb call", rc, lib().psb_last_error().decode()))

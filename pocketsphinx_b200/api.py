@@ -1,0 +1,261 @@
+"""Host-side mirror of the reference's operator interface for the hot path, over the C-ABI.
+
+Names follow the reference: a `Mgau` is a ps_mgau_t-like scorer (frame_eval / transform /
+free, acmod.h:98-125), `HmmContext.vit_eval` is the batched hmm_vit_eval (hmm.h:282),
+`PhoneLoop` runs phone_loop_search.c's frame loop on the device.  Everything goes through
+libpsb200.so; nothing here computes scores on the CPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ModelDesc, PsbError, check, lib
+from .model import PackedModel
+
+KIND_ID = {"ptm": 0, "s2_semi": 1, "ms": 2}
+
+# the reference's hmm_t, byte for byte (hmm.h:169-182)
+HMM_DTYPE = np.dtype({
+    "names": ["ctx", "score", "history", "out_score", "out_history", "ssid", "senid",
+              "bestscore", "tmatid", "frame", "mpx", "n_emit_state"],
+    "formats": ["<u8", ("<i4", 5), ("<i4", 5), "<i4", "<i4", "<u2", ("<u2", 5),
+                "<i4", "<i2", "<i4", "u1", "u1"],
+    "offsets": [0, 8, 28, 48, 52, 56, 58, 68, 72, 76, 80, 81],
+    "itemsize": 88,
+})
+
+
+def _p(a):
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):          # torch tensor (host-pinned or device)
+        return a.data_ptr()
+    return a.ctypes.data if a.size else None
+
+
+def device_count():
+    return lib().psb_device_count()
+
+
+class Model:
+    """Device-resident acoustic model (psb_model_t)."""
+
+    def __init__(self, pm: PackedModel, device=0, device_ptrs=None):
+        self.pm = pm
+        d = ModelDesc()
+        d.kind = KIND_ID[pm.kind]
+        d.n_sen, d.n_mgau, d.n_feat, d.n_density, d.topn = pm.n_sen, pm.n_mgau, pm.n_feat, pm.n_density, pm.topn
+        for i, v in enumerate(pm.featlen):
+            d.featlen[i] = int(v)
+        d.ds_ratio = int(pm.ds_ratio)
+        d.aw = int(pm.aw)
+        d.logadd_ms_size = int(pm.logadd_ms.size)
+        d.logadd_ms_zero = int(pm.logadd_ms_zero)
+        if device_ptrs is None:
+            d.on_device = 0
+            d.mean, d.var, d.det, d.mixw = _p(pm.mean), _p(pm.var), _p(pm.det), _p(pm.mixw)
+            d.mixw_cb = _p(pm.mixw_cb) if pm.mixw_4bit else None
+            d.sen2cb, d.logadd8 = _p(pm.sen2cb), _p(pm.logadd8)
+            d.logadd_ms = _p(pm.logadd_ms)
+            d.topn_beam = _p(pm.topn_beam) if pm.topn_beam.size else None
+        else:                           # e.g. torch tensors filled by an NCCL broadcast
+            d.on_device = 1
+            for k in ("mean", "var", "det", "mixw", "mixw_cb", "sen2cb", "logadd8", "logadd_ms", "topn_beam"):
+                setattr(d, k, _p(device_ptrs.get(k)))
+        self._keep = device_ptrs
+        h = C.c_void_p()
+        check(lib().psb_model_create(C.byref(d), device, C.byref(h)), "psb_model_create")
+        self.h = h
+        self.device = device
+
+    def update_gaussians(self, mean, var, det):
+        """ps_mgaufuncs_t.transform: re-upload MLLR-adapted Gaussians."""
+        mean = np.ascontiguousarray(mean, np.float32)
+        var = np.ascontiguousarray(var, np.float32)
+        det = np.ascontiguousarray(det, np.float32)
+        check(lib().psb_model_update_gaussians(self.h, _p(mean), _p(var), _p(det)), "psb_model_update_gaussians")
+
+    def close(self):
+        if self.h:
+            lib().psb_model_free(self.h)
+            self.h = None
+
+
+class Mgau:
+    """ps_mgau_t twin: one decoder's scorer with its history ring and frame_idx."""
+
+    def __init__(self, model: Model, pl_window=0):
+        self.model = model
+        h = C.c_void_p()
+        check(lib().psb_scorer_create(model.h, pl_window + 2, C.byref(h)), "psb_scorer_create")
+        self.h = h
+
+    @property
+    def frame_idx(self):
+        return lib().psb_scorer_get_frame_idx(self.h)
+
+    @frame_idx.setter
+    def frame_idx(self, v):
+        check(lib().psb_scorer_set_frame_idx(self.h, int(v)), "psb_scorer_set_frame_idx")
+
+    def reset(self):
+        check(lib().psb_scorer_reset(self.h), "psb_scorer_reset")
+
+    def frame_eval(self, feat_row, frame, senone_active=None, compallsen=True):
+        pm = self.model.pm
+        feat_row = np.ascontiguousarray(feat_row, np.float32)
+        ptrs = (C.c_void_p * pm.n_feat)()
+        off = 0
+        for f in range(pm.n_feat):
+            ptrs[f] = feat_row.ctypes.data + 4 * off
+            off += int(pm.featlen[f])
+        scr = np.zeros(pm.n_sen, np.int16)
+        n = 0
+        if senone_active is not None:
+            senone_active = np.ascontiguousarray(senone_active, np.uint8)
+            n = len(senone_active)
+        check(lib().psb_scorer_frame_eval(self.h, _p(scr), _p(senone_active), n, ptrs, int(frame), int(compallsen)),
+              "psb_scorer_frame_eval")
+        return scr
+
+    def close(self):
+        if self.h:
+            lib().psb_scorer_free(self.h)
+            self.h = None
+
+
+class Batch:
+    """Batched utterance scoring workspace (psb_batch_t)."""
+
+    def __init__(self, model: Model, max_utts, max_frames):
+        self.model = model
+        h = C.c_void_p()
+        check(lib().psb_batch_create(model.h, int(max_utts), int(max_frames), C.byref(h)), "psb_batch_create")
+        self.h = h
+
+    @staticmethod
+    def offsets(lengths):
+        off = np.zeros(len(lengths) + 1, np.int32)
+        np.cumsum(lengths, out=off[1:])
+        return off
+
+    def score_host(self, feats, utt_off, out=None):
+        """feats: [total][sumlen] float32 host array (numpy or pinned torch); returns int16 [total][n_sen]."""
+        pm = self.model.pm
+        total = int(utt_off[-1])
+        if out is None:
+            out = np.zeros((total, pm.n_sen), np.int16)
+        utt_off = np.ascontiguousarray(utt_off, np.int32)
+        check(lib().psb_batch_score_host(self.h, _p(feats), _p(utt_off), len(utt_off) - 1, _p(out)),
+              "psb_batch_score_host")
+        return out
+
+    def score_device(self, d_feats_ptr, utt_off, d_senscr_ptr=None):
+        utt_off = np.ascontiguousarray(utt_off, np.int32)
+        check(lib().psb_batch_score_device(self.h, d_feats_ptr, _p(utt_off), len(utt_off) - 1, d_senscr_ptr),
+              "psb_batch_score_device")
+
+    def sync(self):
+        check(lib().psb_batch_sync(self.h), "psb_batch_sync")
+
+    def senscr_device_ptr(self):
+        return lib().psb_batch_senscr_device(self.h)
+
+    def last_kernel_ms(self):
+        out = np.zeros(3, np.float32)
+        check(lib().psb_batch_last_kernel_ms(self.h, _p(out)), "psb_batch_last_kernel_ms")
+        return dict(transpose=float(out[0]), topn=float(out[1]), senone=float(out[2]))
+
+    def get_topn(self, n_frames):
+        rec = np.zeros((n_frames, self.model.pm.n_mgau * self.model.pm.n_feat, 4), np.int32)
+        check(lib().psb_batch_get_topn(self.h, _p(rec), n_frames), "psb_batch_get_topn")
+        return rec
+
+    def decode_host(self, phoneloop, feats, utt_off, want_senscr=False, best=None, pen=None, senscr=None):
+        """End to end: host features -> senone scores -> phone-loop Viterbi -> host results."""
+        pm = self.model.pm
+        utt_off = np.ascontiguousarray(utt_off, np.int32)
+        total = int(utt_off[-1])
+        if best is None:
+            best = np.zeros(total, np.int32)
+        if pen is None:
+            pen = np.zeros((total, phoneloop.n_phones), np.int32)
+        if want_senscr and senscr is None:
+            senscr = np.zeros((total, pm.n_sen), np.int16)
+        check(lib().psb_decode_batch_host(self.h, phoneloop.h, _p(feats), _p(utt_off), len(utt_off) - 1,
+                                          _p(best), _p(pen), _p(senscr) if want_senscr else None),
+              "psb_decode_batch_host")
+        return (best, pen, senscr) if want_senscr else (best, pen)
+
+    def close(self):
+        if self.h:
+            lib().psb_batch_free(self.h)
+            self.h = None
+
+
+class HmmContext:
+    """hmm_context_t twin (hmm.h:145-154) on the device."""
+
+    def __init__(self, tp, sseq, n_sen, device=0):
+        self.tp = np.ascontiguousarray(tp, np.uint8)
+        self.sseq = np.ascontiguousarray(sseq, np.uint16)
+        self.n_emit = self.tp.shape[1]
+        self.n_sen = n_sen
+        h = C.c_void_p()
+        check(lib().psb_hmmctx_create(self.n_emit, _p(self.tp), self.tp.shape[0], _p(self.sseq),
+                                      self.sseq.shape[0], n_sen, device, C.byref(h)), "psb_hmmctx_create")
+        self.h = h
+
+    def vit_eval(self, hmms, senscr):
+        """In-place batched hmm_vit_eval over an array of 88-byte hmm_t records; returns best score."""
+        assert hmms.dtype == HMM_DTYPE and hmms.flags.c_contiguous
+        senscr = np.ascontiguousarray(senscr, np.int16)
+        best = C.c_int32()
+        check(lib().psb_hmm_vit_eval_batch(self.h, _p(hmms) if len(hmms) else None, len(hmms), _p(senscr),
+                                           C.byref(best)), "psb_hmm_vit_eval_batch")
+        return best.value
+
+    def vit_eval_ptrs(self, hmms, index, senscr):
+        """Same through an active list of pointers into `hmms` (chan_t* style)."""
+        senscr = np.ascontiguousarray(senscr, np.int16)
+        ptrs = (C.c_void_p * len(index))(*[hmms.ctypes.data + 88 * int(i) for i in index])
+        best = C.c_int32()
+        check(lib().psb_hmm_vit_eval_ptrs(self.h, ptrs, len(index), _p(senscr), C.byref(best)),
+              "psb_hmm_vit_eval_ptrs")
+        return best.value
+
+    def close(self):
+        if self.h:
+            lib().psb_hmmctx_free(self.h)
+            self.h = None
+
+
+class PhoneLoop:
+    """phone_loop_search.c on the device over batches of utterances."""
+
+    def __init__(self, ctx: HmmContext, ssid, tmatid, window, beam, pbeam, pip, penalty_weight):
+        self.ctx = ctx
+        ssid = np.ascontiguousarray(ssid, np.int32)
+        tmatid = np.ascontiguousarray(tmatid, np.int32)
+        self.n_phones = len(ssid)
+        h = C.c_void_p()
+        check(lib().psb_phoneloop_create(ctx.h, self.n_phones, _p(ssid), _p(tmatid), window, beam, pbeam, pip,
+                                         float(penalty_weight), C.byref(h)), "psb_phoneloop_create")
+        self.h = h
+
+    def run_host(self, senscr, utt_off, trace=False):
+        senscr = np.ascontiguousarray(senscr, np.int16)
+        utt_off = np.ascontiguousarray(utt_off, np.int32)
+        total = int(utt_off[-1])
+        best = np.zeros(total, np.int32)
+        pen = np.zeros((total, self.n_phones), np.int32)
+        tr = np.zeros((total, self.n_phones), HMM_DTYPE) if trace else None
+        check(lib().psb_phoneloop_run_host(self.h, _p(senscr), _p(utt_off), len(utt_off) - 1, _p(best), _p(pen),
+                                           _p(tr)), "psb_phoneloop_run_host")
+        return dict(best=best, pen=pen, hmm=tr)
+
+    def close(self):
+        if self.h:
+            lib().psb_phoneloop_free(self.h)
+            self.h = None

@@ -1,0 +1,371 @@
+// psb_api.cu -- extern "C" entry points of libpsb200.so: model upload and batched scoring.
+#include "psb_internal.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+std::atomic<long long> g_psb_launches{0};
+
+static thread_local char g_err[512] = "";
+
+void psb_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *psb_last_error(void) { return g_err; }
+extern "C" int psb_abi_version(void) { return PSB_ABI_VERSION; }
+extern "C" int64_t psb_kernel_launch_count(void) { return g_psb_launches.load(); }
+
+extern "C" int psb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------
+// model
+
+static int upload(void **dst, const void *src, size_t bytes, bool src_on_device)
+{
+    PSB_CUDA(cudaMalloc(dst, bytes ? bytes : 1));
+    if (bytes)
+        PSB_CUDA(cudaMemcpy(*dst, src, bytes, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    return PSB_OK;
+}
+
+// Gaussians -> per-(codebook, stream) record blocks {det, mean0, var0, mean1, var1, ...}.
+static int build_records(psb_model_t *m, const float *mean, const float *var, const float *det,
+                         bool on_device)
+{
+    const size_t n_gau = (size_t)m->n_mgau * m->n_density * m->sumlen;
+    const size_t n_det = (size_t)m->n_mgau * m->n_feat * m->n_density;
+    std::vector<float> hm(n_gau), hv(n_gau), hd(n_det);
+    cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost;
+    PSB_CUDA(cudaMemcpy(hm.data(), mean, n_gau * sizeof(float), kind));
+    PSB_CUDA(cudaMemcpy(hv.data(), var, n_gau * sizeof(float), kind));
+    PSB_CUDA(cudaMemcpy(hd.data(), det, n_det * sizeof(float), kind));
+    size_t total = 0;
+    m->rec_off.assign(m->K, 0);
+    for (int cb = 0; cb < m->n_mgau; ++cb)
+        for (int f = 0; f < m->n_feat; ++f) {
+            m->rec_off[cb * m->n_feat + f] = total;
+            total += (size_t)m->n_density * rec_floats(m->featlen[f]);
+        }
+    std::vector<float> rec(total, 0.f);
+    for (int cb = 0; cb < m->n_mgau; ++cb)
+        for (int f = 0; f < m->n_feat; ++f) {
+            const int fl = m->featlen[f], rf = rec_floats(fl);
+            const size_t src = ((size_t)cb * m->sumlen + m->featoff[f]) * m->n_density;
+            float *r = rec.data() + m->rec_off[cb * m->n_feat + f];
+            for (int c = 0; c < m->n_density; ++c) {
+                r[(size_t)c * rf] = hd[((size_t)cb * m->n_feat + f) * m->n_density + c];
+                for (int j = 0; j < fl; ++j) {
+                    r[(size_t)c * rf + 1 + 2 * j] = hm[src + (size_t)c * fl + j];
+                    r[(size_t)c * rf + 2 + 2 * j] = hv[src + (size_t)c * fl + j];
+                }
+            }
+        }
+    if (!m->d_rec) {
+        PSB_CUDA(cudaMalloc(&m->d_rec, total * sizeof(float)));
+        PSB_CUDA(cudaMalloc(&m->d_rec_off, m->K * sizeof(size_t)));
+        PSB_CUDA(cudaMemcpy(m->d_rec_off, m->rec_off.data(), m->K * sizeof(size_t), cudaMemcpyHostToDevice));
+    }
+    PSB_CUDA(cudaMemcpy(m->d_rec, rec.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+    return PSB_OK;
+}
+
+extern "C" int psb_model_create(const psb_model_desc_t *d, int device, psb_model_t **out)
+{
+    PSB_REQUIRE(d && out, "psb_model_create: null argument");
+    PSB_REQUIRE(d->kind >= PSB_KIND_PTM && d->kind <= PSB_KIND_MS, "unknown model kind %d", d->kind);
+    PSB_REQUIRE(d->n_feat >= 1 && d->n_feat <= PSB_MAX_FEAT, "n_feat %d out of range", d->n_feat);
+    PSB_REQUIRE(d->n_sen > 0 && d->n_mgau > 0 && d->n_density > 0, "empty model");
+    PSB_REQUIRE(d->topn >= 1 && d->topn <= PSB_MAX_TOPN, "topn %d out of range", d->topn);
+    PSB_REQUIRE(d->mean && d->var && d->det && d->mixw && d->sen2cb, "missing model array");
+    PSB_CUDA(cudaSetDevice(device));
+    psb_model_t *m = new psb_model_t();
+    m->device = device;
+    m->kind = d->kind; m->n_sen = d->n_sen; m->n_mgau = d->n_mgau; m->n_feat = d->n_feat;
+    m->n_density = d->n_density; m->topn = d->topn;
+    m->ds_ratio = d->ds_ratio > 0 ? d->ds_ratio : 1;
+    m->aw = d->aw != 0 ? d->aw : 1;
+    m->sumlen = 0;
+    for (int f = 0; f < d->n_feat; ++f) {
+        m->featlen[f] = d->featlen[f];
+        m->featoff[f] = m->sumlen;
+        m->sumlen += d->featlen[f];
+    }
+    m->K = m->n_mgau * m->n_feat;
+    m->mixw_4bit = d->mixw_cb != nullptr;
+    m->logadd_ms_size = d->logadd_ms_size;
+    m->logadd_ms_zero = d->logadd_ms_zero;
+    m->d_rec = nullptr; m->d_rec_off = nullptr; m->d_mixw = nullptr; m->d_mixw_cb = nullptr;
+    m->d_sen2cb = nullptr; m->d_sen2cb32 = nullptr; m->d_logadd8 = nullptr; m->d_logadd_ms = nullptr;
+    m->has_topn_beam = false;
+    const bool dev = d->on_device != 0;
+    int rc = build_records(m, d->mean, d->var, d->det, dev);
+    if (rc) { psb_model_free(m); return rc; }
+
+    // senone -> codebook map
+    std::vector<int32_t> s2c(m->n_sen);
+    if (cudaMemcpy(s2c.data(), d->sen2cb, m->n_sen * sizeof(int32_t),
+                   dev ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost) != cudaSuccess) {
+        psb_set_error("copying sen2cb failed");
+        psb_model_free(m);
+        return PSB_ERR_CUDA;
+    }
+    std::vector<uint16_t> s2c16(m->n_sen);
+    for (int i = 0; i < m->n_sen; ++i) {
+        if (s2c[i] < 0 || s2c[i] >= m->n_mgau) {
+            psb_set_error("sen2cb[%d] = %d out of range", i, s2c[i]);
+            psb_model_free(m);
+            return PSB_ERR_ARG;
+        }
+        s2c16[i] = (uint16_t)s2c[i];
+    }
+    if ((rc = upload((void **)&m->d_sen2cb, s2c16.data(), m->n_sen * sizeof(uint16_t), false)) ||
+        (rc = upload((void **)&m->d_sen2cb32, s2c.data(), m->n_sen * sizeof(int32_t), false))) {
+        psb_model_free(m);
+        return rc;
+    }
+
+    // mixture weights
+    if (m->kind == PSB_KIND_MS) {
+        m->mixw_row = m->n_sen;
+        m->mixw_stride = m->n_sen;
+        rc = upload((void **)&m->d_mixw, d->mixw, (size_t)m->n_sen * m->n_feat * m->n_density, dev);
+    }
+    else {
+        m->mixw_row = m->mixw_4bit ? (m->n_sen + 1) / 2 : m->n_sen;
+        m->mixw_stride = roundup(m->mixw_row, 128);
+        const size_t rows = (size_t)m->n_feat * m->n_density;
+        rc = upload((void **)&m->d_mixw, nullptr, 0, false);
+        if (!rc) {
+            cudaFree(m->d_mixw);
+            m->d_mixw = nullptr;
+            if (cudaMalloc(&m->d_mixw, rows * m->mixw_stride) != cudaSuccess ||
+                cudaMemset(m->d_mixw, 0, rows * m->mixw_stride) != cudaSuccess ||
+                cudaMemcpy2D(m->d_mixw, m->mixw_stride, d->mixw, m->mixw_row, m->mixw_row, rows,
+                             dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice) != cudaSuccess) {
+                psb_set_error("uploading mixture weights failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = PSB_ERR_CUDA;
+            }
+        }
+    }
+    if (!rc && m->mixw_4bit) rc = upload((void **)&m->d_mixw_cb, d->mixw_cb, 16, dev);
+    if (!rc && d->logadd8) rc = upload((void **)&m->d_logadd8, d->logadd8, 256, dev);
+    if (!rc && m->kind != PSB_KIND_MS && !d->logadd8) {
+        psb_set_error("logadd8 table required for ptm/semi models");
+        rc = PSB_ERR_ARG;
+    }
+    if (!rc && m->kind == PSB_KIND_MS) {
+        if (!d->logadd_ms || d->logadd_ms_size <= 0) {
+            psb_set_error("logadd_ms table required for ms models");
+            rc = PSB_ERR_ARG;
+        }
+        else
+            rc = upload((void **)&m->d_logadd_ms, d->logadd_ms, (size_t)d->logadd_ms_size * sizeof(uint32_t), dev);
+    }
+    if (!rc && d->topn_beam) {
+        uint8_t tb[PSB_MAX_FEAT] = {0};
+        if (cudaMemcpy(tb, d->topn_beam, m->n_feat, dev ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost) != cudaSuccess)
+            rc = PSB_ERR_CUDA;
+        for (int f = 0; f < m->n_feat; ++f) {
+            m->topn_beam[f] = tb[f];
+            if (tb[f]) m->has_topn_beam = true;
+        }
+    }
+    if (rc) { psb_model_free(m); return rc; }
+    *out = m;
+    return PSB_OK;
+}
+
+extern "C" void psb_model_free(psb_model_t *m)
+{
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaFree(m->d_rec); cudaFree(m->d_rec_off); cudaFree(m->d_mixw); cudaFree(m->d_mixw_cb);
+    cudaFree(m->d_sen2cb); cudaFree(m->d_sen2cb32); cudaFree(m->d_logadd8); cudaFree(m->d_logadd_ms);
+    delete m;
+}
+
+extern "C" int psb_model_update_gaussians(psb_model_t *m, const float *mean, const float *var, const float *det)
+{
+    PSB_REQUIRE(m && mean && var && det, "psb_model_update_gaussians: null argument");
+    PSB_CUDA(cudaSetDevice(m->device));
+    PSB_CUDA(cudaDeviceSynchronize());
+    return build_records(m, mean, var, det, false);
+}
+
+extern "C" int psb_model_n_sen(const psb_model_t *m) { return m ? m->n_sen : 0; }
+extern "C" int psb_model_device(const psb_model_t *m) { return m ? m->device : -1; }
+
+// ---------------------------------------------------------------------------------------
+// batch
+
+extern "C" int psb_batch_create(psb_model_t *m, int32_t max_utts, int64_t max_frames, psb_batch_t **out)
+{
+    PSB_REQUIRE(m && out && max_utts > 0 && max_frames > 0, "psb_batch_create: bad argument");
+    PSB_CUDA(cudaSetDevice(m->device));
+    psb_batch_t *b = new psb_batch_t();
+    memset(b, 0, sizeof(*b));
+    b->m = m;
+    b->max_utts = max_utts;
+    b->max_frames = max_frames;
+    cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_feats, (size_t)max_frames * m->sumlen * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_senscr, (size_t)max_frames * m->n_sen * sizeof(int16_t));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_topn, (size_t)max_frames * m->K * sizeof(int4));
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&b->ev[i]);
+    if (e != cudaSuccess) {
+        psb_set_error("psb_batch_create: %s", cudaGetErrorString(e));
+        psb_batch_free(b);
+        return e == cudaErrorMemoryAllocation ? PSB_ERR_NOMEM : PSB_ERR_CUDA;
+    }
+    b->have_ev = true;
+    *out = b;
+    return PSB_OK;
+}
+
+extern "C" void psb_batch_free(psb_batch_t *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->m->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    cudaFree(b->d_feats); cudaFree(b->d_senscr); cudaFree(b->d_featT); cudaFree(b->d_topn); cudaFree(b->d_tab);
+    cudaFree(b->d_best); cudaFree(b->d_pen); cudaFree(b->d_off);
+    if (b->h_tab) cudaFreeHost(b->h_tab);
+    if (b->h_feats) cudaFreeHost(b->h_feats);
+    if (b->h_senscr) cudaFreeHost(b->h_senscr);
+    if (b->h_best) cudaFreeHost(b->h_best);
+    if (b->h_pen) cudaFreeHost(b->h_pen);
+    if (b->have_ev) for (int i = 0; i < 4; ++i) cudaEventDestroy(b->ev[i]);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+static int score_dispatch(psb_batch_t *b, const float *d_feats, const int32_t *utt_off, int32_t n_utt,
+                          int16_t *d_senscr)
+{
+    switch (b->m->kind) {
+    case PSB_KIND_PTM:
+        return psb_launch_ptm_batch(b, d_feats, utt_off, n_utt, d_senscr);
+    default:
+        psb_set_error("batched scoring for model kind %d is not built yet", b->m->kind);
+        return PSB_ERR_ARG;
+    }
+}
+
+static int check_offsets(const psb_batch_t *b, const int32_t *utt_off, int32_t n_utt)
+{
+    PSB_REQUIRE(utt_off && n_utt >= 0, "bad utt_off / n_utt");
+    PSB_REQUIRE(utt_off[0] == 0, "utt_off[0] must be 0");
+    for (int u = 0; u < n_utt; ++u)
+        PSB_REQUIRE(utt_off[u + 1] >= utt_off[u], "utt_off must be non-decreasing");
+    PSB_REQUIRE(n_utt <= b->max_utts && utt_off[n_utt] <= b->max_frames, "batch exceeds psb_batch_create limits");
+    return PSB_OK;
+}
+
+extern "C" int psb_batch_score_device(psb_batch_t *b, const float *d_feats, const int32_t *utt_off,
+                                      int32_t n_utt, int16_t *d_senscr)
+{
+    PSB_REQUIRE(b && d_feats, "psb_batch_score_device: null argument");
+    int rc = check_offsets(b, utt_off, n_utt);
+    if (rc) return rc;
+    PSB_CUDA(cudaSetDevice(b->m->device));
+    return score_dispatch(b, d_feats, utt_off, n_utt, d_senscr ? d_senscr : b->d_senscr);
+}
+
+extern "C" int psb_batch_score_host(psb_batch_t *b, const float *feats, const int32_t *utt_off,
+                                    int32_t n_utt, int16_t *senscr)
+{
+    PSB_REQUIRE(b && feats && senscr, "psb_batch_score_host: null argument");
+    int rc = check_offsets(b, utt_off, n_utt);
+    if (rc) return rc;
+    PSB_CUDA(cudaSetDevice(b->m->device));
+    const size_t total = utt_off[n_utt];
+    if (total == 0) return PSB_OK;
+    PSB_CUDA(cudaMemcpyAsync(b->d_feats, feats, total * b->m->sumlen * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+    rc = score_dispatch(b, b->d_feats, utt_off, n_utt, b->d_senscr);
+    if (rc) return rc;
+    PSB_CUDA(cudaMemcpyAsync(senscr, b->d_senscr, total * b->m->n_sen * sizeof(int16_t), cudaMemcpyDeviceToHost, b->stream));
+    PSB_CUDA(cudaStreamSynchronize(b->stream));
+    return PSB_OK;
+}
+
+extern "C" int psb_batch_sync(psb_batch_t *b)
+{
+    PSB_REQUIRE(b, "psb_batch_sync: null");
+    PSB_CUDA(cudaSetDevice(b->m->device));
+    PSB_CUDA(cudaStreamSynchronize(b->stream));
+    return PSB_OK;
+}
+
+extern "C" int16_t *psb_batch_senscr_device(psb_batch_t *b) { return b ? b->d_senscr : nullptr; }
+
+extern "C" int psb_batch_last_kernel_ms(psb_batch_t *b, float *out3)
+{
+    PSB_REQUIRE(b && out3, "psb_batch_last_kernel_ms: null");
+    PSB_CUDA(cudaSetDevice(b->m->device));
+    PSB_CUDA(cudaStreamSynchronize(b->stream));
+    for (int i = 0; i < 3; ++i) PSB_CUDA(cudaEventElapsedTime(&out3[i], b->ev[i], b->ev[i + 1]));
+    return PSB_OK;
+}
+
+extern "C" int psb_batch_get_topn(psb_batch_t *b, int32_t *rec, int64_t n_frames)
+{
+    PSB_REQUIRE(b && rec && n_frames <= b->max_frames, "psb_batch_get_topn: bad argument");
+    PSB_CUDA(cudaSetDevice(b->m->device));
+    PSB_CUDA(cudaStreamSynchronize(b->stream));
+    PSB_CUDA(cudaMemcpy(rec, b->d_topn, (size_t)n_frames * b->m->K * sizeof(int4), cudaMemcpyDeviceToHost));
+    return PSB_OK;
+}
+
+cudaStream_t psb_batch_stream(psb_batch_t *b) { return b->stream; }
+
+// End-to-end: host features -> senone scores -> phone-loop Viterbi -> host results.
+extern "C" int psb_decode_batch_host(psb_batch_t *b, psb_phoneloop_t *p, const float *feats, const int32_t *utt_off,
+                                     int32_t n_utt, int32_t *best, int32_t *pen, int16_t *senscr)
+{
+    PSB_REQUIRE(b && p && feats, "psb_decode_batch_host: null argument");
+    int rc = check_offsets(b, utt_off, n_utt);
+    if (rc) return rc;
+    PSB_CUDA(cudaSetDevice(b->m->device));
+    const size_t total = utt_off[n_utt], H = psb_phoneloop_n_phones(p);
+    if (total == 0) return PSB_OK;
+    if ((size_t)n_utt + 1 > b->off_cap) {
+        cudaFree(b->d_off);
+        b->off_cap = (size_t)n_utt + 1 + 1024;
+        PSB_CUDA(cudaMalloc(&b->d_off, b->off_cap * 4));
+    }
+    if (total * H > b->pen_cap) {
+        cudaFree(b->d_best); cudaFree(b->d_pen);
+        b->d_best = b->d_pen = nullptr;
+        b->pen_cap = (size_t)b->max_frames * H;
+        PSB_CUDA(cudaMalloc(&b->d_best, (size_t)b->max_frames * 4));
+        PSB_CUDA(cudaMalloc(&b->d_pen, b->pen_cap * 4));
+    }
+    PSB_CUDA(cudaMemcpyAsync(b->d_feats, feats, total * b->m->sumlen * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+    PSB_CUDA(cudaMemcpyAsync(b->d_off, utt_off, (size_t)(n_utt + 1) * 4, cudaMemcpyHostToDevice, b->stream));
+    rc = score_dispatch(b, b->d_feats, utt_off, n_utt, b->d_senscr);
+    if (rc) return rc;
+    rc = psb_phoneloop_launch(p, b->d_senscr, b->d_off, n_utt, best ? b->d_best : nullptr, pen ? b->d_pen : nullptr,
+                              nullptr, nullptr, b->stream);
+    if (rc) return rc;
+    if (best) PSB_CUDA(cudaMemcpyAsync(best, b->d_best, total * 4, cudaMemcpyDeviceToHost, b->stream));
+    if (pen) PSB_CUDA(cudaMemcpyAsync(pen, b->d_pen, total * H * 4, cudaMemcpyDeviceToHost, b->stream));
+    if (senscr)
+        PSB_CUDA(cudaMemcpyAsync(senscr, b->d_senscr, total * b->m->n_sen * sizeof(int16_t), cudaMemcpyDeviceToHost, b->stream));
+    PSB_CUDA(cudaStreamSynchronize(b->stream));
+    return PSB_OK;
+}

@@ -1,0 +1,115 @@
+// psb_internal.cuh -- shared declarations of libpsb200.so (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/psb200.h"
+
+#define PSB_SENSCR_SHIFT 10      // hmm.h:72
+#define PSB_MAX_NEG_ASCR 96      // tied_mgau_common.h:91
+#define PSB_TMAT_WORST (-255)    // hmm.h:89
+#define PSB_BAD_SSID 0xffff
+
+void psb_set_error(const char *fmt, ...);
+extern std::atomic<long long> g_psb_launches;
+
+#define PSB_CUDA(call)                                                                   \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            psb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,                  \
+                          cudaGetErrorString(e__));                                      \
+            return PSB_ERR_CUDA;                                                         \
+        }                                                                                \
+    } while (0)
+
+#define PSB_LAUNCH_CHECK()                                                               \
+    do {                                                                                 \
+        g_psb_launches.fetch_add(1, std::memory_order_relaxed);                          \
+        cudaError_t e__ = cudaGetLastError();                                            \
+        if (e__ != cudaSuccess) {                                                        \
+            psb_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__,              \
+                          cudaGetErrorString(e__));                                      \
+            return PSB_ERR_CUDA;                                                         \
+        }                                                                                \
+    } while (0)
+
+#define PSB_REQUIRE(cond, ...)                                                           \
+    do {                                                                                 \
+        if (!(cond)) {                                                                   \
+            psb_set_error(__VA_ARGS__);                                                  \
+            return PSB_ERR_ARG;                                                          \
+        }                                                                                \
+    } while (0)
+
+static inline int roundup(int x, int m) { return (x + m - 1) / m * m; }
+
+// Gaussian record of one codeword in HBM/SMEM: {det, mean0, var0, mean1, var1, ...} padded
+// with zeros to a multiple of 4 floats so that a warp-uniform LDS.128 stream feeds the
+// distance loop.
+static inline int rec_floats(int featlen) { return roundup(1 + 2 * featlen, 4); }
+
+struct psb_model_s {
+    int device;
+    int kind, n_sen, n_mgau, n_feat, n_density, topn, ds_ratio, aw;
+    int featlen[PSB_MAX_FEAT], featoff[PSB_MAX_FEAT], sumlen;
+    int K;                        // n_mgau * n_feat (codebook, stream) pairs
+    bool mixw_4bit;
+    int mixw_row;                 // bytes per (feat, codeword) row as given by the host
+    int mixw_stride;              // padded row pitch on the device (multiple of 128)
+    int logadd_ms_size, logadd_ms_zero;
+    // device buffers
+    float *d_rec;                 // records; (cb, f) block at rec_off[cb * n_feat + f]
+    std::vector<size_t> rec_off;  // float offsets, host copy
+    size_t *d_rec_off;
+    uint8_t *d_mixw;              // [n_feat][n_density][mixw_stride] (ptm/semi) or raw pdf (ms)
+    uint8_t *d_mixw_cb;           // 16 bytes or null
+    uint16_t *d_sen2cb;           // [n_sen] (ptm)
+    int32_t *d_sen2cb32;          // [n_sen] (ms)
+    uint8_t *d_logadd8;           // [256]
+    uint32_t *d_logadd_ms;
+    uint8_t topn_beam[PSB_MAX_FEAT];
+    bool has_topn_beam;
+};
+
+struct psb_batch_s {
+    psb_model_t *m;
+    cudaStream_t stream;
+    int max_utts;
+    long long max_frames;
+    // device
+    float *d_feats;               // [max_frames][sumlen] staging for the _host path
+    int16_t *d_senscr;            // [max_frames][n_sen]
+    float *d_featT;               // transposed groups
+    size_t featT_cap;             // floats
+    int4 *d_topn;                 // [max_frames][K]
+    int32_t *d_tab;               // per-call lane/group tables
+    size_t tab_cap;
+    int32_t *h_tab;               // pinned
+    // pinned host staging for the _host path
+    float *h_feats;
+    int16_t *h_senscr;
+    cudaEvent_t ev[4];
+    bool have_ev;
+    long long last_frames;
+    // phone-loop outputs for psb_decode_batch_host
+    int32_t *d_best, *d_pen;
+    int32_t *h_best, *h_pen;
+    size_t pen_cap;
+    int32_t *d_off;               // utt_off on the device for the phone loop
+    size_t off_cap;
+};
+
+// ---- launchers implemented in the .cu files ----
+cudaStream_t psb_batch_stream(psb_batch_t *b);
+int psb_phoneloop_launch(psb_phoneloop_t *p, const int16_t *d_senscr, const int32_t *d_utt_off, int32_t n_utt,
+                         int32_t *d_best, int32_t *d_pen, psb_hmm_t *d_final, psb_hmm_t *d_trace, cudaStream_t st);
+int psb_phoneloop_n_phones(const psb_phoneloop_t *p);
+int psb_launch_ptm_batch(psb_batch_t *b, const float *d_feats, const int32_t *utt_off,
+                         int32_t n_utt, int16_t *d_senscr);

@@ -1,0 +1,187 @@
+"""GPU (-m gpu): the CUDA path through the C-ABI against the reference's golden vectors and
+against the CPU oracle on seeded inputs.  Integer outputs must be bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import assert_hmm_equal, golden, hmm_view
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from pocketsphinx_b200 import api
+    assert api.device_count() > 0, "no CUDA device visible"
+    return api
+
+
+@pytest.fixture(scope="module")
+def en_us_dev(api, en_us):
+    m = api.Model(en_us)
+    yield m
+    m.close()
+
+
+def test_ptm_batch_goforward_matches_reference(api, en_us_dev):
+    g = golden("en_us_goforward.npz")
+    b = api.Batch(en_us_dev, 4, 1024)
+    scr = b.score_host(g["feats"], np.array([0, 278], np.int32))
+    assert np.array_equal(scr, g["senscr"])
+    b.close()
+
+
+def test_ptm_batch_ragged_matches_oracle(api, en_us, en_us_dev):
+    from oracle import oracle
+    g = golden("en_us_goforward.npz")
+    f = g["feats"]
+    # 70 utterances of uneven length (0, 1, ... frames), cut from different places
+    rng = np.random.default_rng(3)
+    lens = [0, 1, 2, 33, 278] + [int(x) for x in rng.integers(1, 120, 65)]
+    chunks = [f[s:s + n] for n, s in zip(lens, rng.integers(0, 278 - 120, len(lens)))]
+    chunks[4] = f
+    lens = [len(c) for c in chunks]
+    feats = np.concatenate(chunks)
+    off = api.Batch.offsets(lens)
+    b = api.Batch(en_us_dev, 128, 8192)
+    scr = b.score_host(feats, off)
+    om = oracle.OracleModel(en_us)
+    for u, c in enumerate(chunks):
+        if len(c) == 0:
+            continue
+        want = om.score_utt(c)
+        got = scr[off[u]:off[u + 1]]
+        assert np.array_equal(got, want), "utterance %d (len %d)" % (u, len(c))
+    # idempotent, and an empty batch is fine
+    scr2 = b.score_host(feats, off)
+    assert np.array_equal(scr, scr2)
+    b.score_host(np.zeros((0, 39), np.float32), np.zeros(1, np.int32))
+    b.close()
+
+
+@pytest.mark.parametrize("n_density,n_sen", [(256, 5138), (128, 1000), (64, 300)])
+def test_ptm_batch_synthetic_matches_oracle(api, n_density, n_sen):
+    from oracle import oracle
+    from pocketsphinx_b200.model import synth_feats, synth_ptm
+    pm = synth_ptm(seed=5, n_density=n_density, n_sen=n_sen)
+    feats = synth_feats(pm, 40, 24, seed=9)
+    m = api.Model(pm)
+    b = api.Batch(m, 64, 4096)
+    off = api.Batch.offsets([24] * 40)
+    scr = b.score_host(feats.reshape(-1, pm.sumlen), off)
+    om = oracle.OracleModel(pm)
+    for u in range(40):
+        assert np.array_equal(scr[off[u]:off[u + 1]], om.score_utt(feats[u])), "utterance %d" % u
+    b.close()
+    m.close()
+
+
+def test_scorer_frame_eval_compallsen(api, en_us_dev):
+    g = golden("en_us_goforward.npz")
+    s = api.Mgau(en_us_dev, pl_window=0)
+    for t in range(60):
+        scr = s.frame_eval(g["feats"][t], t)
+        s.frame_idx = t + 1                      # acmod_advance
+        assert np.array_equal(scr, g["senscr"][t]), "frame %d" % t
+    # re-scoring the previous frame from the history ring gives the same scores
+    again = s.frame_eval(g["feats"][59], 59)
+    assert np.array_equal(again, g["senscr"][59])
+    s.close()
+
+
+def test_scorer_frame_eval_active_lists(api, en_us_dev):
+    from oracle import oracle
+    g = golden("en_us_active.npz")
+    gf = golden("en_us_goforward.npz")
+    n_sen = int(g["n_sen"])
+    flags = np.unpackbits(g["flags"], axis=1)[:, :n_sen]
+    s = api.Mgau(en_us_dev, pl_window=0)
+    for t in range(flags.shape[0]):
+        lst = oracle.flags2list(flags[t])
+        scr = s.frame_eval(gf["feats"][t], t, lst, compallsen=False)
+        s.frame_idx = t + 1
+        assert np.array_equal(scr, g["senscr"][t]), "frame %d" % t
+    s.close()
+
+
+def test_scorer_lookahead_ring_matches_oracle(api, en_us, en_us_dev):
+    """pl_window = 5: frame F scored for the phone loop with CI senones, then frame F-5 re-scored
+    from the ring with a different active list (ps_search_forward, pocketsphinx.c:1173-1197)."""
+    from oracle import oracle
+    gf = golden("en_us_goforward.npz")
+    rng = np.random.default_rng(1)
+    om = oracle.OracleModel(en_us)
+    dec = om.decoder(n_hist=7)
+    s = api.Mgau(en_us_dev, pl_window=5)
+    ci = np.zeros(en_us.n_sen, np.uint8)
+    ci[:en_us.n_ci_sen] = 1
+    ci_list = oracle.flags2list(ci)
+    for F in range(40):
+        a = s.frame_eval(gf["feats"][F], F, ci_list, compallsen=False)
+        o = dec.frame_eval(gf["feats"][F], F, ci_list, compallsen=False)
+        assert np.array_equal(a, o), "lookahead frame %d" % F
+        if F >= 5:
+            fl = (rng.random(en_us.n_sen) < 0.2).astype(np.uint8)
+            lst = oracle.flags2list(fl)
+            a = s.frame_eval(gf["feats"][F - 5], F - 5, lst, compallsen=False)
+            o = dec.frame_eval(gf["feats"][F - 5], F - 5, lst, compallsen=False)
+            assert np.array_equal(a, o), "search frame %d" % (F - 5)
+        s.frame_idx = F + 1
+        dec.set_frame_idx(F + 1)
+    s.close()
+    dec.close()
+
+
+@pytest.mark.parametrize("n_emit", [3, 5, 4, 1])
+def test_hmm_vit_eval_batch(api, n_emit):
+    g = golden("hmm_vit_eval.npz")
+    senscr = g["n%d_senscr" % n_emit]
+    ctx = api.HmmContext(g["n%d_tp" % n_emit], g["n%d_sseq" % n_emit], len(senscr))
+    hm = hmm_view(g["n%d_before" % n_emit]).copy()
+    want = hmm_view(g["n%d_after" % n_emit])
+    hm["ctx"] = 0x1234                      # caller's pointer must survive
+    best = ctx.vit_eval(hm, senscr)
+    assert best == int(g["n%d_best" % n_emit])
+    assert (hm["ctx"] == 0x1234).all()
+    assert_hmm_equal(hm, want, n_emit, "n_emit=%d" % n_emit)
+    # active-list-of-pointers entry on a subset
+    hm2 = hmm_view(g["n%d_before" % n_emit]).copy()
+    idx = np.arange(0, len(hm2), 3)
+    ctx.vit_eval_ptrs(hm2, idx, senscr)
+    assert_hmm_equal(hm2[idx], want[idx], n_emit, "ptrs")
+    untouched = np.setdiff1d(np.arange(len(hm2)), idx)
+    assert_hmm_equal(hm2[untouched], hmm_view(g["n%d_before" % n_emit])[untouched], n_emit, "untouched")
+    assert ctx.vit_eval(hm[:0], senscr) == -0x20000000
+    ctx.close()
+
+
+def test_phoneloop_matches_reference(api, en_us):
+    g = golden("en_us_goforward.npz")
+    n, beam, pbeam, pip, window = [int(x) for x in g["pl_params"]]
+    ctx = api.HmmContext(en_us.tp, en_us.sseq, en_us.n_sen)
+    pl = api.PhoneLoop(ctx, en_us.phone_ssid[:n], en_us.phone_tmat[:n], window, beam, pbeam, pip, float(g["pl_weight"]))
+    # the same utterance three times in one batch, plus a truncated copy
+    scr = np.concatenate([g["senscr"], g["senscr"][:100], g["senscr"]])
+    off = api.Batch.offsets([278, 100, 278])
+    r = pl.run_host(scr, off, trace=True)
+    want = hmm_view(g["pl_hmm"])
+    for u, (a, n_fr) in enumerate(zip(off[:-1], [278, 100, 278])):
+        assert np.array_equal(r["best"][a:a + n_fr], g["pl_best"][:n_fr]), "utt %d best" % u
+        assert np.array_equal(r["pen"][a:a + n_fr], g["pl_pen"][:n_fr]), "utt %d penalties" % u
+        assert_hmm_equal(r["hmm"][a:a + n_fr], want[:n_fr], 3, "utt %d" % u)
+    pl.close()
+    ctx.close()
+
+
+def test_decode_host_end_to_end(api, en_us, en_us_dev):
+    g = golden("en_us_goforward.npz")
+    n, beam, pbeam, pip, window = [int(x) for x in g["pl_params"]]
+    ctx = api.HmmContext(en_us.tp, en_us.sseq, en_us.n_sen)
+    pl = api.PhoneLoop(ctx, en_us.phone_ssid[:n], en_us.phone_tmat[:n], window, beam, pbeam, pip, float(g["pl_weight"]))
+    b = api.Batch(en_us_dev, 8, 2048)
+    feats = np.concatenate([g["feats"], g["feats"][:50], g["feats"]])
+    off = api.Batch.offsets([278, 50, 278])
+    best, pen, scr = b.decode_host(pl, feats, off, want_senscr=True)
+    assert np.array_equal(scr[:278], g["senscr"]) and np.array_equal(scr[328:], g["senscr"])
+    assert np.array_equal(best[:278], g["pl_best"]) and np.array_equal(best[328:], g["pl_best"])
+    assert np.array_equal(pen[278:328], g["pl_pen"][:50])
+    b.close(); pl.close(); ctx.close()
