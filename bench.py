@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the PocketSphinx hot path (senone evaluation + Viterbi) on B200.
+
+One "step" = one pass of the hot path over one batch of synthetic utterances: GMM senone
+evaluation of every frame (all senones, like `-compallsen yes`) followed by the phone-loop
+Viterbi (phone_loop_search.c: every CI-phone HMM through hmm_vit_eval each frame, beam
+pruning, phone transitions, look-ahead penalties) over the freshly computed scores.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--model baseline|en-us] [--utts U] [--secs S]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each key means.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from pocketsphinx_b200.model import PackedModel, synth_feats, synth_ptm  # noqa: E402
+
+FRAMES_PER_SEC_AUDIO = 100          # 10 ms frames
+PL = dict(window=5, beam=-225, pbeam=-225, pip=0, weight=3.0)   # pl_beam 1e-10 etc. >> 10
+
+
+def frames_for(secs):
+    # fe/ with 25.6 ms windows and 10 ms shift: 10 s of 16 kHz audio -> 998 frames
+    return max(1, int(secs * FRAMES_PER_SEC_AUDIO) - 2)
+
+
+def load_model(name):
+    if name == "baseline":
+        return synth_ptm(seed=0, n_density=256, n_sen=5138), "synthetic PTM 42x3x256x13, 5138 senones (BASELINE.json shape)"
+    if name == "en-us":
+        pm = PackedModel.load(os.path.join(ROOT, "tests", "golden", "en_us_ptm_model.npz"))
+        return pm, "shipped en-us PTM 42x3x128x13, 5126 senones (packed fixture)"
+    raise SystemExit("unknown --model " + name)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_baseline(pm, feats, n_frames_per_utt, budget_s=15.0, threads=1):
+    """The CPU restatement (oracle/, bit-exact vs the compiled reference on its own models)
+    timed on host cores over a bounded sample of the same workload."""
+    from oracle import oracle
+    om = oracle.OracleModel(pm)
+    # calibrate on one short slice, then size the sample to the budget
+    t0 = time.perf_counter()
+    scr = om.score_utt(feats[0][:64])
+    dt = max(1e-4, time.perf_counter() - t0)
+    per_frame = dt / 64
+    n_utt = int(max(1, min(len(feats), budget_s * threads / (per_frame * n_frames_per_utt))))
+    n_utt = max(threads, n_utt - n_utt % threads) if n_utt >= threads else n_utt
+
+    def work(u):
+        s = om.score_utt(feats[u])
+        oracle.phoneloop_run(pm.tp, pm.sseq, pm.phone_ssid[:pm.n_ciphone], pm.phone_tmat[:pm.n_ciphone], s,
+                             PL["window"], PL["beam"], PL["pbeam"], PL["pip"], PL["weight"])
+        return len(s)
+
+    t0 = time.perf_counter()
+    if threads == 1:
+        done = sum(work(u) for u in range(n_utt))
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(threads) as ex:        # ctypes releases the GIL inside the oracle
+            done = sum(ex.map(work, range(n_utt)))
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": "%d utterances x %d frames of the same batch, senone eval + phone loop, %.1f s" % (
+                n_utt, n_frames_per_utt, dt)}
+
+
+def run_reference(args, pm, desc, feats, T):
+    """--impl reference: the reference algorithm's CPU implementation on all host cores."""
+    cores = os.cpu_count() or 1
+    steps = []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base = cpu_baseline(pm, feats, T, budget_s=max(3.0, 60.0 / (args.warmup + args.steps)), threads=cores)
+        if i >= args.warmup:
+            steps.append(base["value"])
+    v = float(np.mean(steps))
+    base["value"] = v
+    out = {"impl": "reference", "metric": "frames/sec senone-eval+Viterbi", "value": v, "unit": "frames/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32->i16/i32",
+           "data": "synthetic", "config": {"workload": workload_name(args, pm), "model": desc},
+           "cpu_baseline": base,
+           "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def workload_name(args, pm):
+    return "ptm_%dx%dx%d_%dsen_%dutt_x_%ds" % (pm.n_mgau, pm.n_feat, pm.n_density, pm.n_sen, args.utts, args.secs)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="baseline", choices=["baseline", "en-us"])
+    ap.add_argument("--utts", type=int, default=1000, help="utterances per GPU per step")
+    ap.add_argument("--secs", type=int, default=10, help="seconds of 16 kHz audio per utterance")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    pm, desc = load_model(args.model)
+    T = frames_for(args.secs)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        feats = synth_feats(pm, min(args.utts, 64), T, seed=1234)
+        run_reference(args, pm, desc, feats, T)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pocketsphinx_b200 import api
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # ---- acoustic model: rank 0 holds it, one NCCL broadcast per packed buffer at init ----
+    names = ["mean", "var", "det", "mixw", "sen2cb", "logadd8"]
+    dev = {}
+    for k in names:
+        t = torch.from_numpy(getattr(pm, k)).cuda() if (rank == 0 or world == 1) else \
+            torch.empty(getattr(pm, k).shape, dtype=torch.from_numpy(getattr(pm, k)).dtype, device="cuda")
+        if world > 1:
+            dist.broadcast(t, 0)
+        dev[k] = t
+    torch.cuda.synchronize()
+    model = api.Model(pm, device=local, device_ptrs=dev)
+
+    # ---- this rank's shard of utterances (weak scaling: utts per GPU fixed) ----
+    U = args.utts
+    feats_np = synth_feats(pm, U, T, seed=1234 + rank)
+    total = U * T
+    off = api.Batch.offsets([T] * U)
+    feats_pinned = torch.from_numpy(feats_np.reshape(total, pm.sumlen)).pin_memory()
+    d_feats = feats_pinned.cuda()
+    batch = api.Batch(model, U, total)
+    ctx = api.HmmContext(pm.tp, pm.sseq, pm.n_sen, device=local)
+    H = pm.n_ciphone
+    pl = api.PhoneLoop(ctx, pm.phone_ssid[:H], pm.phone_tmat[:H], PL["window"], PL["beam"], PL["pbeam"], PL["pip"],
+                       PL["weight"])
+    best_pinned = torch.empty(total, dtype=torch.int32).pin_memory()
+    pen_pinned = torch.empty((total, H), dtype=torch.int32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        batch.sync()
+
+    # ---- device-resident throughput: features already in HBM ----
+    launches0 = api.lib().psb_kernel_launch_count()
+    for _ in range(args.warmup):
+        batch.decode_device(pl, d_feats.data_ptr(), off)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches1 = api.lib().psb_kernel_launch_count()
+    batch.event_record(0)
+    kern = {"transpose": 0.0, "topn": 0.0, "senone": 0.0}
+    for _ in range(args.steps):
+        batch.decode_device(pl, d_feats.data_ptr(), off)
+    batch.event_record(1)
+    ms_total = batch.event_elapsed_ms()
+    barrier()
+    launches = api.lib().psb_kernel_launch_count() - launches1
+    km = batch.last_kernel_ms()          # kernel split of the last step (events on the same stream)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+
+    # ---- end to end through the public host-buffer call: H2D + kernels + D2H every step ----
+    for _ in range(2):
+        batch.decode_host(pl, feats_pinned, off, best=best_pinned, pen=pen_pinned)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        batch.decode_host(pl, feats_pinned, off, best=best_pinned, pen=pen_pinned)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+
+    t = torch.tensor([ms_step, e2e_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        hbm_peak, peak_src, sm_max = peaks()
+        frames_all = total * world
+        value = frames_all / (ms_step * 1e-3)
+        # roofline of the dominant kernel (ptm_topn_kernel), algorithmic bytes per launch:
+        # per frame 4*sumlen feature bytes read + 16*K top-N record bytes written, plus the
+        # Gaussians once per launch (DESIGN.md "Kernels").
+        K = pm.n_mgau * pm.n_feat
+        gau_bytes = (pm.mean.nbytes + pm.var.nbytes + pm.det.nbytes)
+        topn_bytes = total * (4 * pm.sumlen + 16 * K) + gau_bytes
+        topn_gbs = topn_bytes / (km["topn"] * 1e-3) / 1e9
+        stage_bytes = total * (4 * pm.sumlen + 2 * pm.n_sen + 2 * 16 * K) + gau_bytes + pm.mixw.nbytes
+        gmm_ms = km["transpose"] + km["topn"] + km["senone"]
+        flop = 4.0 * pm.n_mgau * pm.n_density * pm.sumlen * total      # sub, mul, mul, sub per (codeword, dim)
+        sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
+        fp32_peak = 148 * 128 * sm_mhz * 1e6 / 1e12                     # non-FMA FP32 lane-ops/s (TFLOP/s)
+        out = {
+            "metric": "frames/sec senone-eval+Viterbi", "value": value, "unit": "frames/s",
+            "xRT": FRAMES_PER_SEC_AUDIO / value,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32->i16/i32", "data": "synthetic",
+            "config": {"workload": workload_name(args, pm), "model": desc,
+                       "utts_per_gpu": U, "frames_per_utt": T, "frames_per_step_per_gpu": total,
+                       "viterbi": "phone loop, %d CI-phone HMMs x %d states, window %d" % (H, pm.n_emit_state, PL["window"]),
+                       "features": "synthetic dynamic features (AR(1) walk between model means), not PCM",
+                       "parallelism": "utterances sharded, %d per GPU, no per-frame collective" % U,
+                       "l2": "per-step working set (%.1f GB of scores) exceeds L2; no explicit flush" % (total * pm.n_sen * 2 / 1e9)},
+            "gpu_launches": int(launches),
+            "kernel_ms_last_step": {**km, "phoneloop_and_rest": max(0.0, ms_step - gmm_ms)},
+            "roofline": {"bound": "hbm", "kernel": "ptm_topn_kernel", "achieved": topn_gbs, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": topn_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": topn_bytes,
+                         "note": "compute-bound by construction (SURVEY 8d): model is SMEM/L2 resident"},
+            "roofline_fp32": {"bound": "fp32 non-FMA issue", "kernel": "ptm_topn_kernel",
+                              "achieved": flop / (km["topn"] * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                              "frac": flop / (km["topn"] * 1e-3) / 1e12 / fp32_peak,
+                              "peak_source": "148 SMs x 128 lanes x sampled SM clock"},
+            "gmm_stage": {"ms": gmm_ms, "algorithmic_bytes": stage_bytes,
+                          "achieved_gbs": stage_bytes / (gmm_ms * 1e-3) / 1e9},
+            "e2e": {"value": frames_all / (e2e_ms * 1e-3), "unit": "frames/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(total * pm.sumlen * 4 + (U + 1) * 4),
+                    "d2h_bytes_per_step": int(total * 4 + total * H * 4),
+                    "call": "psb_decode_batch_host (pinned host features in, best scores + penalties out)"},
+            "clocks": clocks,
+        }
+        if world == 1:
+            out["cpu_baseline"] = cpu_baseline(pm, feats_np, T, budget_s=args.cpu_budget, threads=1)
+        print(json.dumps(out))
+    batch.close(); pl.close(); ctx.close(); model.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -126,6 +126,10 @@ int16_t *psb_batch_senscr_device(psb_batch_t *b);
 /* timing of the last score call's kernels on the batch stream (CUDA events), ms:
  * out[0] transpose, out[1] gaussian top-N, out[2] senone eval */
 int psb_batch_last_kernel_ms(psb_batch_t *b, float *out3);
+/* CUDA-event stopwatch on the batch's stream (the stream every kernel of this batch is
+ * launched on): record slot 0/1, then elapsed ms between them (synchronises). */
+int psb_batch_event_record(psb_batch_t *b, int slot);
+int psb_batch_event_elapsed_ms(psb_batch_t *b, float *ms);
 /* debugging/parity: copy the per-frame top-N records of the last call to the host:
  * rec int32 [total_frames][n_mgau*n_feat][4] = {top>>10, cw[4] bytes, e[4] bytes, 0} */
 int psb_batch_get_topn(psb_batch_t *b, int32_t *rec, int64_t n_frames);
@@ -202,6 +206,12 @@ int psb_phoneloop_run_host(psb_phoneloop_t *p, const int16_t *senscr, const int3
 int psb_decode_batch_host(psb_batch_t *b, psb_phoneloop_t *p, const float *feats,
                           const int32_t *utt_off, int32_t n_utt, int32_t *best, int32_t *pen,
                           int16_t *senscr);
+
+/* Device-resident twin: d_feats on the device, results left in the batch's own device buffers
+ * (d_best int32 [total], d_pen int32 [total][n_phones]; addresses returned through the
+ * out-pointers, which may be NULL); asynchronous on the batch's stream. */
+int psb_decode_batch_device(psb_batch_t *b, psb_phoneloop_t *p, const float *d_feats,
+                            const int32_t *utt_off, int32_t n_utt, int32_t **d_best, int32_t **d_pen);
 
 /* number of kernels launched by this library in the calling process so far */
 int64_t psb_kernel_launch_count(void);

@@ -50,6 +50,8 @@ SYMBOLS = [
     ("psb_batch_senscr_device", _VP, [_VP]),
     ("psb_batch_last_kernel_ms", C.c_int, [_VP, _VP]),
     ("psb_batch_get_topn", C.c_int, [_VP, _VP, _I64]),
+    ("psb_batch_event_record", C.c_int, [_VP, C.c_int]),
+    ("psb_batch_event_elapsed_ms", C.c_int, [_VP, _VP]),
     ("psb_hmmctx_create", C.c_int, [_I32, _VP, _I32, _VP, _I32, _I32, C.c_int, C.POINTER(_VP)]),
     ("psb_hmmctx_free", None, [_VP]),
     ("psb_hmm_vit_eval_batch", C.c_int, [_VP, _VP, _I32, _VP, _VP]),
@@ -59,6 +61,7 @@ SYMBOLS = [
     ("psb_phoneloop_run_device", C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP]),
     ("psb_phoneloop_run_host", C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP]),
     ("psb_decode_batch_host", C.c_int, [_VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP]),
+    ("psb_decode_batch_device", C.c_int, [_VP, _VP, _VP, _VP, _I32, _VP, _VP]),
     ("psb_kernel_launch_count", _I64, []),
 ]
 

@@ -167,6 +167,28 @@ class Batch:
         check(lib().psb_batch_last_kernel_ms(self.h, _p(out)), "psb_batch_last_kernel_ms")
         return dict(transpose=float(out[0]), topn=float(out[1]), senone=float(out[2]))
 
+    def event_record(self, slot):
+        check(lib().psb_batch_event_record(self.h, slot), "psb_batch_event_record")
+
+    def event_elapsed_ms(self):
+        ms = C.c_float()
+        check(lib().psb_batch_event_elapsed_ms(self.h, C.byref(ms)), "psb_batch_event_elapsed_ms")
+        return ms.value
+
+    def run_phoneloop_device(self, phoneloop, utt_off, d_best_ptr=None, d_pen_ptr=None):
+        """Phone loop over this batch's device-resident scores, on this batch's stream."""
+        utt_off = np.ascontiguousarray(utt_off, np.int32)
+        check(lib().psb_phoneloop_run_device(phoneloop.h, self.senscr_device_ptr(), _p(utt_off), len(utt_off) - 1,
+                                             d_best_ptr, d_pen_ptr, None, self.h), "psb_phoneloop_run_device")
+
+    def decode_device(self, phoneloop, d_feats_ptr, utt_off):
+        """Asynchronous device-resident decode; returns device addresses of best / penalties."""
+        utt_off = np.ascontiguousarray(utt_off, np.int32)
+        pb, pp = C.c_void_p(), C.c_void_p()
+        check(lib().psb_decode_batch_device(self.h, phoneloop.h, d_feats_ptr, _p(utt_off), len(utt_off) - 1,
+                                            C.byref(pb), C.byref(pp)), "psb_decode_batch_device")
+        return pb.value, pp.value
+
     def get_topn(self, n_frames):
         rec = np.zeros((n_frames, self.model.pm.n_mgau * self.model.pm.n_feat, 4), np.int32)
         check(lib().psb_batch_get_topn(self.h, _p(rec), n_frames), "psb_batch_get_topn")

@@ -227,6 +227,7 @@ extern "C" int psb_batch_create(psb_model_t *m, int32_t max_utts, int64_t max_fr
     if (e == cudaSuccess) e = cudaMalloc(&b->d_senscr, (size_t)max_frames * m->n_sen * sizeof(int16_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_topn, (size_t)max_frames * m->K * sizeof(int4));
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&b->ev[i]);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&b->tev[i]);
     if (e != cudaSuccess) {
         psb_set_error("psb_batch_create: %s", cudaGetErrorString(e));
         psb_batch_free(b);
@@ -250,6 +251,7 @@ extern "C" void psb_batch_free(psb_batch_t *b)
     if (b->h_best) cudaFreeHost(b->h_best);
     if (b->h_pen) cudaFreeHost(b->h_pen);
     if (b->have_ev) for (int i = 0; i < 4; ++i) cudaEventDestroy(b->ev[i]);
+    if (b->have_ev) for (int i = 0; i < 2; ++i) cudaEventDestroy(b->tev[i]);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }
@@ -279,9 +281,10 @@ static int check_offsets(const psb_batch_t *b, const int32_t *utt_off, int32_t n
 extern "C" int psb_batch_score_device(psb_batch_t *b, const float *d_feats, const int32_t *utt_off,
                                       int32_t n_utt, int16_t *d_senscr)
 {
-    PSB_REQUIRE(b && d_feats, "psb_batch_score_device: null argument");
+    PSB_REQUIRE(b, "psb_batch_score_device: null batch");
     int rc = check_offsets(b, utt_off, n_utt);
     if (rc) return rc;
+    PSB_REQUIRE(utt_off[n_utt] == 0 || d_feats, "psb_batch_score_device: null buffer");
     PSB_CUDA(cudaSetDevice(b->m->device));
     return score_dispatch(b, d_feats, utt_off, n_utt, d_senscr ? d_senscr : b->d_senscr);
 }
@@ -289,9 +292,10 @@ extern "C" int psb_batch_score_device(psb_batch_t *b, const float *d_feats, cons
 extern "C" int psb_batch_score_host(psb_batch_t *b, const float *feats, const int32_t *utt_off,
                                     int32_t n_utt, int16_t *senscr)
 {
-    PSB_REQUIRE(b && feats && senscr, "psb_batch_score_host: null argument");
+    PSB_REQUIRE(b, "psb_batch_score_host: null batch");
     int rc = check_offsets(b, utt_off, n_utt);
     if (rc) return rc;
+    PSB_REQUIRE(utt_off[n_utt] == 0 || (feats && senscr), "psb_batch_score_host: null buffer");
     PSB_CUDA(cudaSetDevice(b->m->device));
     const size_t total = utt_off[n_utt];
     if (total == 0) return PSB_OK;
@@ -333,39 +337,80 @@ extern "C" int psb_batch_get_topn(psb_batch_t *b, int32_t *rec, int64_t n_frames
 
 cudaStream_t psb_batch_stream(psb_batch_t *b) { return b->stream; }
 
-// End-to-end: host features -> senone scores -> phone-loop Viterbi -> host results.
-extern "C" int psb_decode_batch_host(psb_batch_t *b, psb_phoneloop_t *p, const float *feats, const int32_t *utt_off,
-                                     int32_t n_utt, int32_t *best, int32_t *pen, int16_t *senscr)
+// Shared by the host and device decode entry points: scores + phone loop on the batch stream.
+static int decode_common(psb_batch_t *b, psb_phoneloop_t *p, const float *d_feats, const int32_t *utt_off,
+                         int32_t n_utt, bool want_best, bool want_pen)
 {
-    PSB_REQUIRE(b && p && feats, "psb_decode_batch_host: null argument");
-    int rc = check_offsets(b, utt_off, n_utt);
-    if (rc) return rc;
-    PSB_CUDA(cudaSetDevice(b->m->device));
-    const size_t total = utt_off[n_utt], H = psb_phoneloop_n_phones(p);
-    if (total == 0) return PSB_OK;
+    const size_t H = psb_phoneloop_n_phones(p);
     if ((size_t)n_utt + 1 > b->off_cap) {
         cudaFree(b->d_off);
         b->off_cap = (size_t)n_utt + 1 + 1024;
         PSB_CUDA(cudaMalloc(&b->d_off, b->off_cap * 4));
     }
-    if (total * H > b->pen_cap) {
+    if ((size_t)b->max_frames * H > b->pen_cap) {
         cudaFree(b->d_best); cudaFree(b->d_pen);
         b->d_best = b->d_pen = nullptr;
         b->pen_cap = (size_t)b->max_frames * H;
         PSB_CUDA(cudaMalloc(&b->d_best, (size_t)b->max_frames * 4));
         PSB_CUDA(cudaMalloc(&b->d_pen, b->pen_cap * 4));
     }
-    PSB_CUDA(cudaMemcpyAsync(b->d_feats, feats, total * b->m->sumlen * sizeof(float), cudaMemcpyHostToDevice, b->stream));
     PSB_CUDA(cudaMemcpyAsync(b->d_off, utt_off, (size_t)(n_utt + 1) * 4, cudaMemcpyHostToDevice, b->stream));
-    rc = score_dispatch(b, b->d_feats, utt_off, n_utt, b->d_senscr);
+    int rc = score_dispatch(b, d_feats, utt_off, n_utt, b->d_senscr);
     if (rc) return rc;
-    rc = psb_phoneloop_launch(p, b->d_senscr, b->d_off, n_utt, best ? b->d_best : nullptr, pen ? b->d_pen : nullptr,
-                              nullptr, nullptr, b->stream);
+    return psb_phoneloop_launch(p, b->d_senscr, b->d_off, n_utt, want_best ? b->d_best : nullptr,
+                                want_pen ? b->d_pen : nullptr, nullptr, nullptr, b->stream);
+}
+
+// End-to-end: host features -> senone scores -> phone-loop Viterbi -> host results.
+extern "C" int psb_decode_batch_host(psb_batch_t *b, psb_phoneloop_t *p, const float *feats, const int32_t *utt_off,
+                                     int32_t n_utt, int32_t *best, int32_t *pen, int16_t *senscr)
+{
+    PSB_REQUIRE(b && p, "psb_decode_batch_host: null handle");
+    int rc = check_offsets(b, utt_off, n_utt);
+    if (rc) return rc;
+    PSB_REQUIRE(utt_off[n_utt] == 0 || feats, "psb_decode_batch_host: null buffer");
+    PSB_CUDA(cudaSetDevice(b->m->device));
+    const size_t total = utt_off[n_utt], H = psb_phoneloop_n_phones(p);
+    if (total == 0) return PSB_OK;
+    PSB_CUDA(cudaMemcpyAsync(b->d_feats, feats, total * b->m->sumlen * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+    rc = decode_common(b, p, b->d_feats, utt_off, n_utt, best != nullptr, pen != nullptr);
     if (rc) return rc;
     if (best) PSB_CUDA(cudaMemcpyAsync(best, b->d_best, total * 4, cudaMemcpyDeviceToHost, b->stream));
     if (pen) PSB_CUDA(cudaMemcpyAsync(pen, b->d_pen, total * H * 4, cudaMemcpyDeviceToHost, b->stream));
     if (senscr)
         PSB_CUDA(cudaMemcpyAsync(senscr, b->d_senscr, total * b->m->n_sen * sizeof(int16_t), cudaMemcpyDeviceToHost, b->stream));
     PSB_CUDA(cudaStreamSynchronize(b->stream));
+    return PSB_OK;
+}
+
+extern "C" int psb_decode_batch_device(psb_batch_t *b, psb_phoneloop_t *p, const float *d_feats, const int32_t *utt_off,
+                                       int32_t n_utt, int32_t **d_best, int32_t **d_pen)
+{
+    PSB_REQUIRE(b && p, "psb_decode_batch_device: null handle");
+    int rc = check_offsets(b, utt_off, n_utt);
+    if (rc) return rc;
+    PSB_REQUIRE(utt_off[n_utt] == 0 || d_feats, "psb_decode_batch_device: null buffer");
+    PSB_CUDA(cudaSetDevice(b->m->device));
+    if (utt_off[n_utt] == 0) return PSB_OK;
+    rc = decode_common(b, p, d_feats, utt_off, n_utt, true, true);
+    if (d_best) *d_best = b->d_best;
+    if (d_pen) *d_pen = b->d_pen;
+    return rc;
+}
+
+extern "C" int psb_batch_event_record(psb_batch_t *b, int slot)
+{
+    PSB_REQUIRE(b && (slot == 0 || slot == 1), "psb_batch_event_record: bad argument");
+    PSB_CUDA(cudaSetDevice(b->m->device));
+    PSB_CUDA(cudaEventRecord(b->tev[slot], b->stream));
+    return PSB_OK;
+}
+
+extern "C" int psb_batch_event_elapsed_ms(psb_batch_t *b, float *ms)
+{
+    PSB_REQUIRE(b && ms, "psb_batch_event_elapsed_ms: bad argument");
+    PSB_CUDA(cudaSetDevice(b->m->device));
+    PSB_CUDA(cudaEventSynchronize(b->tev[1]));
+    PSB_CUDA(cudaEventElapsedTime(ms, b->tev[0], b->tev[1]));
     return PSB_OK;
 }

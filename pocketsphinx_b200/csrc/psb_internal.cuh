@@ -96,6 +96,7 @@ struct psb_batch_s {
     float *h_feats;
     int16_t *h_senscr;
     cudaEvent_t ev[4];
+    cudaEvent_t tev[2];           // user stopwatch (psb_batch_event_record)
     bool have_ev;
     long long last_frames;
     // phone-loop outputs for psb_decode_batch_host
