@@ -110,7 +110,7 @@ transpose_feats_kernel(const float *__restrict__ feats, float *__restrict__ feat
 // min(96, (norm - .x) + .z byte j) exactly (norm >= .x, so saturating byte j at 255 is safe).
 
 template <int FL>
-__global__ void __launch_bounds__(TOPN_WARPS * 32, 6)
+__global__ void __launch_bounds__(TOPN_WARPS * 32, 7)
 ptm_topn_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec_off,
                 const int32_t *__restrict__ klist, const float *__restrict__ featT, GroupTabs tabs,
                 int4 *__restrict__ out, int n_groups, int nd, int n_feat, int D,
@@ -118,7 +118,7 @@ ptm_topn_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec_of
 {
     constexpr int RECF = (1 + 2 * FL + 3) / 4 * 4;
     constexpr int RECQ = RECF / 4;
-    extern __shared__ float4 srec[];          // [nd][RECQ]
+    extern __shared__ float4 srec[];          // [nd][RECQ] records
     const int k = klist[blockIdx.x];
     const int f = k % n_feat;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -136,7 +136,6 @@ ptm_topn_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec_of
     const long long off = tabs.lane_off[g * 32 + lane];
     const int maxT = tabs.grp_maxT[g];
     const float *xT = featT + tabs.grp_base[g] + (long long)featoff[f] * 32 + lane;
-    const int ndw = nd >> 5;
 
     int cw[TOPN], sc[TOPN];
 #pragma unroll
@@ -158,18 +157,19 @@ ptm_topn_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec_of
         if (t >= len) continue;
 
         // ---- eval_topn (ptm_mgau.c:88-136): re-score last frame's codewords, stable sort ----
-        unsigned mask[MAX_NDW];
-#pragma unroll
-        for (int w = 0; w < MAX_NDW; ++w) mask[w] = 0u;
+        // The scan must skip the codewords already listed (ptm_mgau.c:212-218).  Only *seeds* can
+        // be met by the scan (inserted codewords lie behind it), so two registers suffice:
+        // seedpack = the four seed codewords (one byte each), seedbit = byte i is 1 << (cw_i & 7)
+        // while seed i is still listed, 0 once it has been evicted.
+        unsigned seedpack = 0u, seedbit = 0u;
         {
             int ncw[TOPN], nsc[TOPN];
 #pragma unroll
             for (int i = 0; i < TOPN; ++i) {
                 const int c = cw[i];
                 const int s = f2i_clamped(gau_dist<FL>(srec + c * RECQ, x));
-#pragma unroll
-                for (int w = 0; w < MAX_NDW; ++w)
-                    mask[w] |= ((c >> 5) == w) ? (1u << (c & 31)) : 0u;
+                seedpack |= (unsigned)c << (8 * i);
+                seedbit |= (1u << (c & 7)) << (8 * i);
                 // insert (c, s) into the sorted prefix nsc[0..i-1]: entries with score < s move down
                 int p = 0;
 #pragma unroll
@@ -186,18 +186,25 @@ ptm_topn_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec_of
         }
 
         // ---- eval_cb (ptm_mgau.c:152-226) unless this frame is skipped by -ds (:242) ----
-        // mask[] is rotated one word per 32 codewords so that mask[0] is always the current
-        // word (static register index, one copy of the loop body): logical word L sits at
-        // physical position (L - w) & 7 while word w is being scanned.
         if (t % ds_ratio == 0) {
             float thresh = (float)sc[TOPN - 1];
-            for (int w = 0; w < ndw; ++w) {
-                const float4 *rw = srec + (size_t)w * 32 * RECQ;
-#pragma unroll 2
-                for (int cc = 0; cc < 32; ++cc) {
-                    const float d = gau_dist<FL>(rw + cc * RECQ, x);
-                    if (d >= thresh && !((mask[0] >> cc) & 1u)) {
-                        const int c = w * 32 + cc;
+            const unsigned seedchunk = (seedpack >> 3) & 0x1f1f1f1fu;   // chunk (8 codewords) of each seed
+            for (int ch = 0; ch < nd / 8; ++ch) {
+                const float4 *rq = srec + (size_t)ch * 8 * RECQ;
+                // m8 = bits of this chunk's codewords that are listed seeds
+                unsigned m8;
+                {
+                    const unsigned t = seedchunk ^ ((unsigned)ch * 0x01010101u);      // zero byte = match
+                    const unsigned nz = (((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t) & 0x80808080u;
+                    const unsigned hit = ((nz ^ 0x80808080u) >> 7) * 0xffu;           // 0xff per matching byte
+                    const unsigned b = seedbit & hit;
+                    m8 = (b | (b >> 8) | (b >> 16) | (b >> 24)) & 0xffu;
+                }
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    const float d = gau_dist<FL>(rq + cc * RECQ, x);
+                    if (d >= thresh && !(m8 & (1u << cc))) {
+                        const int c = ch * 8 + cc;
                         const int s = f2i_clamped(d);
                         const int ev = cw[TOPN - 1];
                         // insertion_sort_cb (:140-149): entries with score <= s shift down
@@ -210,19 +217,17 @@ ptm_topn_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec_of
 #pragma unroll
                         for (int j = 0; j < TOPN; ++j)
                             if (j == p) { sc[j] = s; cw[j] = c; }
-                        // the evicted codeword is scannable again (it may lie ahead)
-                        const int pw = ((ev >> 5) - w) & (MAX_NDW - 1);
-                        const unsigned bit = 1u << (ev & 31);
-#pragma unroll
-                        for (int w2 = 0; w2 < MAX_NDW; ++w2)
-                            mask[w2] &= ~((pw == w2) ? bit : 0u);
+                        // An evicted seed becomes scannable again (it may lie ahead of the scan).
+                        {
+                            const unsigned t2 = seedpack ^ ((unsigned)ev * 0x01010101u);
+                            const unsigned nz2 = (((t2 & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t2) & 0x80808080u;
+                            const unsigned keep = (nz2 >> 7) * 0xffu;                   // 0 for the byte == ev
+                            seedbit &= keep;
+                            if ((ev >> 3) == ch) m8 &= ~(1u << (ev & 7));
+                        }
                         thresh = (float)sc[TOPN - 1];
                     }
                 }
-                const unsigned m0 = mask[0];
-#pragma unroll
-                for (int w2 = 0; w2 < MAX_NDW - 1; ++w2) mask[w2] = mask[w2 + 1];
-                mask[MAX_NDW - 1] = m0;
             }
         }
 
@@ -256,59 +261,64 @@ ptm_senone_kernel(const int4 *__restrict__ topn, const uint8_t *__restrict__ mix
                   int n_sen, int n_feat, int nd, int K, int mixw_stride)
 {
     extern __shared__ int smem_i[];
-    int4 *recs = reinterpret_cast<int4 *>(smem_i);                 // [K]
-    int *norm = smem_i + 4 * K;                                    // [n_feat] (+ pad to 8)
-    int *red = norm + 8;                                           // [32]
-    uint8_t *ns = reinterpret_cast<uint8_t *>(red + 32);           // [K*4]
-    uint8_t *tab = ns + 4 * K;                                     // [256]
-    uint8_t *cb16 = tab + 256;                                     // [16]
-    int16_t *asc = reinterpret_cast<int16_t *>(cb16 + 16);         // [n_sen]
+    // per (codebook, stream) pair i: rowoff[i] = byte offsets of the four listed codewords'
+    // mixture-weight rows, nsc[i] = their normalised scores (0..96)
+    uint4 *rowoff = reinterpret_cast<uint4 *>(smem_i);             // [K]
+    uint4 *nsc = rowoff + K;                                        // [K]
+    int *norm = reinterpret_cast<int *>(nsc + K);                   // [8]
+    int *red = norm + 8;                                            // [32]
+    uint8_t *tab = reinterpret_cast<uint8_t *>(red + 32);           // [256]
+    uint8_t *cb16 = tab + 256;                                      // [16]
+    int16_t *asc = reinterpret_cast<int16_t *>(cb16 + 16);          // [n_sen]
     const long long frame = blockIdx.x;
     const int tid = threadIdx.x;
 
-    for (int i = tid; i < K; i += blockDim.x) recs[i] = topn[frame * K + i];
     if (tid < 256) tab[tid] = logadd_tab[tid];
     if (FOURBIT && tid < 16) cb16[tid] = mixw_cb[tid];
     if (tid < n_feat) norm[tid] = PSB_WORST_SCORE;                 // ptm_mgau.c:273
     __syncthreads();
     // ptm_mgau_codebook_norm (ptm_mgau.c:266-295), all codebooks active
-    for (int i = tid; i < K; i += blockDim.x) atomicMax(&norm[i % n_feat], recs[i].x);
+    int4 r = make_int4(0, 0, 0, 0);
+    if (tid < K) {
+        r = topn[frame * K + tid];
+        atomicMax(&norm[tid % n_feat], r.x);
+    }
     __syncthreads();
-    for (int i = tid; i < K; i += blockDim.x) {
-        const int base = norm[i % n_feat] - recs[i].x;
-        const unsigned eb = (unsigned)recs[i].z;
+    if (tid < K) {
+        const int f = tid % n_feat;
+        const int base = norm[f] - r.x;
+        const unsigned eb = (unsigned)r.z, cwb = (unsigned)r.y;
+        unsigned ro[TOPN], nv[TOPN];
 #pragma unroll
         for (int j = 0; j < TOPN; ++j) {
             int v = base + (int)((eb >> (8 * j)) & 0xff);
-            ns[4 * i + j] = (uint8_t)(v > PSB_MAX_NEG_ASCR ? PSB_MAX_NEG_ASCR : v);
+            nv[j] = (unsigned)(v > PSB_MAX_NEG_ASCR ? PSB_MAX_NEG_ASCR : v);
+            ro[j] = ((unsigned)f * nd + ((cwb >> (8 * j)) & 0xff)) * (unsigned)mixw_stride;
         }
+        rowoff[tid] = make_uint4(ro[0], ro[1], ro[2], ro[3]);
+        nsc[tid] = make_uint4(nv[0], nv[1], nv[2], nv[3]);
     }
     __syncthreads();
 
     // ptm_mgau_senone_eval (ptm_mgau.c:327-403), compallsen
     int best = 0x7fffffff;
     for (int s = tid; s < n_sen; s += blockDim.x) {
-        const int cb = sen2cb[s];
+        const int i0 = (int)sen2cb[s] * n_feat;
+        const unsigned so = FOURBIT ? (unsigned)(s >> 1) : (unsigned)s;
         int ascore = 0;
         for (int f = 0; f < n_feat; ++f) {
-            const int i = cb * n_feat + f;
-            const unsigned cwb = (unsigned)recs[i].y;
-            const uint8_t *row = mixw + (size_t)f * nd * mixw_stride;
-            int fden = 0;
-#pragma unroll
-            for (int j = 0; j < TOPN; ++j) {
-                const int c = (cwb >> (8 * j)) & 0xff;
-                int w;
-                if (FOURBIT) {
-                    int b = row[(size_t)c * mixw_stride + (s >> 1)];
-                    b = (b & 1) ? b >> 4 : b & 0x0f;           // sic: ptm_mgau.c:376-377
-                    w = cb16[b];
-                }
-                else
-                    w = row[(size_t)c * mixw_stride + s];
-                const int v = w + ns[4 * i + j];
-                fden = j == 0 ? v : logadd8(tab, fden, v);
+            const uint4 ro = rowoff[i0 + f], nv = nsc[i0 + f];
+            int w0 = mixw[ro.x + so], w1 = mixw[ro.y + so], w2 = mixw[ro.z + so], w3 = mixw[ro.w + so];
+            if (FOURBIT) {                                     // sic: low bit of the byte (ptm_mgau.c:376-377)
+                w0 = cb16[(w0 & 1) ? w0 >> 4 : w0 & 0x0f];
+                w1 = cb16[(w1 & 1) ? w1 >> 4 : w1 & 0x0f];
+                w2 = cb16[(w2 & 1) ? w2 >> 4 : w2 & 0x0f];
+                w3 = cb16[(w3 & 1) ? w3 >> 4 : w3 & 0x0f];
             }
+            int fden = w0 + (int)nv.x;
+            fden = logadd8(tab, fden, w1 + (int)nv.y);
+            fden = logadd8(tab, fden, w2 + (int)nv.z);
+            fden = logadd8(tab, fden, w3 + (int)nv.w);
             ascore += fden;
         }
         best = min(best, ascore);
@@ -459,7 +469,9 @@ int psb_launch_ptm_batch(psb_batch_t *b, const float *d_feats, const int32_t *ut
     }
     if (b->have_ev) PSB_CUDA(cudaEventRecord(b->ev[2], b->stream));
     {
-        size_t smem = (size_t)K * 16 + 8 * 4 + 32 * 4 + (size_t)K * 4 + 256 + 16 + (size_t)m->n_sen * 2;
+        size_t smem = (size_t)K * 32 + 8 * 4 + 32 * 4 + 256 + 16 + (size_t)m->n_sen * 2;
+        PSB_REQUIRE(K <= 512, "ptm_senone_kernel handles at most 512 (codebook, stream) pairs (got %d)", K);
+        PSB_REQUIRE((size_t)m->n_feat * m->n_density * m->mixw_stride < (1ull << 32), "mixture-weight table too large for 32-bit offsets");
         if (m->mixw_4bit) {
             PSB_CUDA(cudaFuncSetAttribute(ptm_senone_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ptm_senone_kernel<true><<<(unsigned)total, 512, smem, b->stream>>>(
