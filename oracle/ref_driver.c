@@ -605,3 +605,83 @@ refdrv_phoneloop_params(refdrv_t *d, int32 *out)
     memcpy(out + 6, &pls->penalty_weight, sizeof(double)); /* out[6..7] = float64 */
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------- */
+/* Full decoder (ps_init / ps_process_raw / ps_get_hyp) with the GMM back-end optionally
+ * replaced by the CUDA one through integration/ps_mgau_cuda.c: the drop-in test.          */
+
+ps_mgau_t *cuda_mgau_wrap(acmod_t *acmod, ps_mgau_t *host, const char *libpath, int device);
+long cuda_mgau_n_calls(ps_mgau_t *mg);
+
+/* Returns the number of frames (<0 on error).  hyp/seg are NUL-terminated text; seg has one
+ * "word start end ascr lscr" line per segment.  stats[0] = hypothesis score, [1] = number of
+ * frame_eval calls served by the CUDA back-end (0 on the host path), [2] = n_sen. */
+int
+refdrv_decode(const char *hmmdir, const char *lm, const char *dict, const char *kv,
+              const int16 *pcm, long n_samples, int use_cuda, const char *libpath,
+              char *hyp, int hyp_cap, char *seg, int seg_cap, int32 *stats)
+{
+    ps_config_t *config;
+    ps_decoder_t *ps;
+    const char *h;
+    int32 score = 0;
+    ps_seg_t *it;
+    int n, nfr;
+    long calls = 0;
+
+    err_set_loglevel(ERR_ERROR);
+    config = ps_config_init(NULL);
+    ps_config_set_str(config, "hmm", hmmdir);
+    ps_config_set_str(config, "lm", lm);
+    ps_config_set_str(config, "dict", dict);
+    ps_config_set_str(config, "dither", "no");
+    if (kv) {
+        char *buf = strdup(kv), *save = NULL, *tok;
+        for (tok = strtok_r(buf, "\n", &save); tok; tok = strtok_r(NULL, "\n", &save)) {
+            char *eq = strchr(tok, '=');
+            if (!eq) continue;
+            *eq = 0;
+            ps_config_set_str(config, tok, eq + 1);
+        }
+        free(buf);
+    }
+    ps = ps_init(config);
+    if (ps == NULL) {
+        ps_config_free(config);
+        return -1;
+    }
+    if (use_cuda) {
+        ps_mgau_t *g = cuda_mgau_wrap(ps->acmod, ps->acmod->mgau, libpath, 0);
+        if (g == NULL) {
+            ps_free(ps);
+            ps_config_free(config);
+            return -2;
+        }
+        ps->acmod->mgau = g;
+    }
+    ps_start_utt(ps);
+    ps_process_raw(ps, pcm, n_samples, FALSE, TRUE);
+    ps_end_utt(ps);
+    nfr = ps_get_n_frames(ps);
+    h = ps_get_hyp(ps, &score);
+    snprintf(hyp, hyp_cap, "%s", h ? h : "");
+    n = 0;
+    seg[0] = 0;
+    for (it = ps_seg_iter(ps); it; it = ps_seg_next(it)) {
+        int sf, ef;
+        int32 ascr, lscr, lback;
+        ps_seg_frames(it, &sf, &ef);
+        ps_seg_prob(it, &ascr, &lscr, &lback);
+        n += snprintf(seg + n, n < seg_cap ? seg_cap - n : 0, "%s %d %d %d %d\n", ps_seg_word(it), sf, ef, ascr, lscr);
+        if (n >= seg_cap) break;
+    }
+    if (use_cuda) calls = cuda_mgau_n_calls(ps->acmod->mgau);
+    if (stats) {
+        stats[0] = score;
+        stats[1] = (int32)calls;
+        stats[2] = bin_mdef_n_sen(ps->acmod->mdef);
+    }
+    ps_free(ps);
+    ps_config_free(config);
+    return nfr;
+}

@@ -64,6 +64,8 @@ def lib():
         L.refdrv_phoneloop_run.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_char_p, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.refdrv_phoneloop_params.argtypes = [C.c_void_p, C.c_void_p]
+        L.refdrv_decode.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_long, C.c_int,
+                                    C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_void_p]
         assert L.refdrv_sizeof_hmm() == HMM_DTYPE.itemsize
         _lib = L
     return _lib
@@ -210,3 +212,19 @@ class RefHmmCtx:
     def time_vit_eval(self, hmms, senscr, reps=1):
         senscr = np.ascontiguousarray(senscr, np.int16)
         return lib().refdrv_time_hmm_vit_eval(self.h, _p(hmms), len(hmms), _p(senscr), reps)
+
+
+def decode(hmmdir, lm, dic, pcm, use_cuda=False, libpath=None, **kv):
+    """Full reference decode (fwdtree + fwdflat + bestpath by default) of one utterance; with
+    use_cuda the GMM back-end is the CUDA one bound through integration/ps_mgau_cuda.c."""
+    pcm = np.ascontiguousarray(pcm, np.int16)
+    s = "\n".join("%s=%s" % (k, v) for k, v in kv.items()).encode() or None
+    hyp = C.create_string_buffer(4096)
+    seg = C.create_string_buffer(65536)
+    stats = np.zeros(4, np.int32)
+    n = lib().refdrv_decode(hmmdir.encode(), lm.encode(), dic.encode(), s, _p(pcm), len(pcm), int(use_cuda),
+                            libpath.encode() if libpath else None, hyp, 4096, seg, 65536, _p(stats))
+    if n < 0:
+        raise RuntimeError("refdrv_decode failed (%d)" % n)
+    return dict(n_frames=n, hyp=hyp.value.decode(), seg=seg.value.decode(), score=int(stats[0]),
+                cuda_calls=int(stats[1]), n_sen=int(stats[2]))
