@@ -81,6 +81,30 @@ static int build_records(psb_model_t *m, const float *mean, const float *var, co
         PSB_CUDA(cudaMemcpy(m->d_rec_off, m->rec_off.data(), m->K * sizeof(size_t), cudaMemcpyHostToDevice));
     }
     PSB_CUDA(cudaMemcpy(m->d_rec, rec.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+    if (m->kind == PSB_KIND_MS) {
+        // codebook-minor copy for ms_dist_kernel: per stream f (at float offset featoff[f]*nd*2*n_mgau)
+        // [(d*fl + j)*2 + {mean,var}][cb]; determinants [f][d][cb]
+        std::vector<float> gT(n_gau * 2), dT(n_det);
+        for (int cb = 0; cb < m->n_mgau; ++cb)
+            for (int f = 0; f < m->n_feat; ++f) {
+                const int fl = m->featlen[f];
+                const size_t src = ((size_t)cb * m->sumlen + m->featoff[f]) * m->n_density;
+                const size_t dst = (size_t)m->featoff[f] * m->n_density * 2 * m->n_mgau;
+                for (int c = 0; c < m->n_density; ++c) {
+                    dT[((size_t)f * m->n_density + c) * m->n_mgau + cb] = hd[((size_t)cb * m->n_feat + f) * m->n_density + c];
+                    for (int j = 0; j < fl; ++j) {
+                        gT[dst + ((size_t)(c * fl + j) * 2) * m->n_mgau + cb] = hm[src + (size_t)c * fl + j];
+                        gT[dst + ((size_t)(c * fl + j) * 2 + 1) * m->n_mgau + cb] = hv[src + (size_t)c * fl + j];
+                    }
+                }
+            }
+        if (!m->d_msT) {
+            PSB_CUDA(cudaMalloc(&m->d_msT, gT.size() * sizeof(float)));
+            PSB_CUDA(cudaMalloc(&m->d_msdetT, dT.size() * sizeof(float)));
+        }
+        PSB_CUDA(cudaMemcpy(m->d_msT, gT.data(), gT.size() * sizeof(float), cudaMemcpyHostToDevice));
+        PSB_CUDA(cudaMemcpy(m->d_msdetT, dT.data(), dT.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     return PSB_OK;
 }
 
@@ -112,8 +136,13 @@ extern "C" int psb_model_create(const psb_model_desc_t *d, int device, psb_model
     m->d_rec = nullptr; m->d_rec_off = nullptr; m->d_mixw = nullptr; m->d_mixw_cb = nullptr;
     m->d_sen2cb = nullptr; m->d_sen2cb32 = nullptr; m->d_logadd8 = nullptr; m->d_logadd_ms = nullptr;
     m->has_topn_beam = false;
+    m->d_topn_beam = nullptr;
+    m->d_msT = m->d_msdetT = nullptr; m->d_featlen = m->d_featoff = nullptr;
+    for (int f = 0; f < PSB_MAX_FEAT; ++f) m->topn_beam[f] = 0;
     const bool dev = d->on_device != 0;
     int rc = build_records(m, d->mean, d->var, d->det, dev);
+    if (!rc) rc = upload((void **)&m->d_featlen, m->featlen, sizeof(m->featlen), false);
+    if (!rc) rc = upload((void **)&m->d_featoff, m->featoff, sizeof(m->featoff), false);
     if (rc) { psb_model_free(m); return rc; }
 
     // senone -> codebook map
@@ -185,6 +214,11 @@ extern "C" int psb_model_create(const psb_model_desc_t *d, int device, psb_model
             if (tb[f]) m->has_topn_beam = true;
         }
     }
+    if (!rc) {
+        int32_t tb[PSB_MAX_FEAT] = {0};
+        for (int f = 0; f < m->n_feat; ++f) tb[f] = m->has_topn_beam ? m->topn_beam[f] : 0;
+        rc = upload((void **)&m->d_topn_beam, tb, sizeof(tb), false);
+    }
     if (rc) { psb_model_free(m); return rc; }
     *out = m;
     return PSB_OK;
@@ -196,6 +230,7 @@ extern "C" void psb_model_free(psb_model_t *m)
     cudaSetDevice(m->device);
     cudaFree(m->d_rec); cudaFree(m->d_rec_off); cudaFree(m->d_mixw); cudaFree(m->d_mixw_cb);
     cudaFree(m->d_sen2cb); cudaFree(m->d_sen2cb32); cudaFree(m->d_logadd8); cudaFree(m->d_logadd_ms);
+    cudaFree(m->d_topn_beam); cudaFree(m->d_msT); cudaFree(m->d_msdetT); cudaFree(m->d_featlen); cudaFree(m->d_featoff);
     delete m;
 }
 
@@ -225,7 +260,7 @@ extern "C" int psb_batch_create(psb_model_t *m, int32_t max_utts, int64_t max_fr
     cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_feats, (size_t)max_frames * m->sumlen * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_senscr, (size_t)max_frames * m->n_sen * sizeof(int16_t));
-    if (e == cudaSuccess) e = cudaMalloc(&b->d_topn, (size_t)max_frames * m->K * sizeof(int4));
+    if (e == cudaSuccess && m->kind != PSB_KIND_MS) e = cudaMalloc(&b->d_topn, (size_t)max_frames * m->K * sizeof(int4));
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&b->ev[i]);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&b->tev[i]);
     if (e != cudaSuccess) {
@@ -244,7 +279,7 @@ extern "C" void psb_batch_free(psb_batch_t *b)
     cudaSetDevice(b->m->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
     cudaFree(b->d_feats); cudaFree(b->d_senscr); cudaFree(b->d_featT); cudaFree(b->d_topn); cudaFree(b->d_tab);
-    cudaFree(b->d_best); cudaFree(b->d_pen); cudaFree(b->d_off);
+    cudaFree(b->d_best); cudaFree(b->d_pen); cudaFree(b->d_off); cudaFree(b->d_msdist); cudaFree(b->d_msbest);
     if (b->h_tab) cudaFreeHost(b->h_tab);
     if (b->h_feats) cudaFreeHost(b->h_feats);
     if (b->h_senscr) cudaFreeHost(b->h_senscr);
@@ -261,7 +296,10 @@ static int score_dispatch(psb_batch_t *b, const float *d_feats, const int32_t *u
 {
     switch (b->m->kind) {
     case PSB_KIND_PTM:
+    case PSB_KIND_SEMI:
         return psb_launch_ptm_batch(b, d_feats, utt_off, n_utt, d_senscr);
+    case PSB_KIND_MS:
+        return psb_launch_ms_batch(b, d_feats, utt_off, n_utt, d_senscr);
     default:
         psb_set_error("batched scoring for model kind %d is not built yet", b->m->kind);
         return PSB_ERR_ARG;

@@ -74,7 +74,10 @@ struct psb_model_s {
     int32_t *d_sen2cb32;          // [n_sen] (ms)
     uint8_t *d_logadd8;           // [256]
     uint32_t *d_logadd_ms;
+    float *d_msT, *d_msdetT;      // ms back-end: codebook-minor Gaussians (see psb_ms.cu)
+    int32_t *d_featlen, *d_featoff;
     uint8_t topn_beam[PSB_MAX_FEAT];
+    int32_t *d_topn_beam;         // [PSB_MAX_FEAT]
     bool has_topn_beam;
 };
 
@@ -104,6 +107,9 @@ struct psb_batch_s {
     int32_t *h_best, *h_pen;
     size_t pen_cap;
     int32_t *d_off;               // utt_off on the device for the phone loop
+    void *d_msdist;               // ms back-end: per-chunk top-N distance lists
+    int32_t *d_msbest;
+    size_t ms_cap;
     size_t off_cap;
 };
 
@@ -114,3 +120,4 @@ int psb_phoneloop_launch(psb_phoneloop_t *p, const int16_t *d_senscr, const int3
 int psb_phoneloop_n_phones(const psb_phoneloop_t *p);
 int psb_launch_ptm_batch(psb_batch_t *b, const float *d_feats, const int32_t *utt_off,
                          int32_t n_utt, int16_t *d_senscr);
+int psb_launch_ms_batch(psb_batch_t *b, const float *d_feats, const int32_t *utt_off, int32_t n_utt, int16_t *d_senscr);

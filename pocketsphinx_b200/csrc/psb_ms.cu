@@ -1,0 +1,217 @@
+// psb_ms.cu -- batched senone evaluation for the generic multi-stream / continuous back-end
+// (ms_cont_mgau_frame_eval, ms_mgau.c:192-282): per-codebook ordered top-N distances without
+// seeding (gauden_dist / compute_dist, ms_gauden.c:378-509), per-senone mixture with the wide
+// log-add table (senone_eval, ms_senone.c:358-407), best-score normalisation with int16 clamps.
+//
+// Frames are independent on this path (no top-N recurrence), so the grid is (codebook tile x
+// frame tile).  Gaussians are stored codebook-minor ("transposed") so that a warp whose lanes are
+// consecutive codebooks reads each (density, dimension) parameter pair with one coalesced
+// transaction, and each thread carries FT frames through the parameter stream to divide the
+// L2 traffic by FT.
+#include "psb_internal.cuh"
+
+#include <algorithm>
+
+namespace {
+
+constexpr int FT = 4;          // frames per thread in ms_dist_kernel
+constexpr int MAXNT = 8;
+
+struct MsDist { int id; float dist; };
+
+// One thread = one codebook, all streams, FT frames.  out: [frame][cb][f][NT] {id, dist}
+template <int NT>
+__global__ void __launch_bounds__(128)
+ms_dist_kernel(const float *__restrict__ gT, const float *__restrict__ detT, const float *__restrict__ feats,
+               int2 *__restrict__ out, long long frame0, long long n_frames, int n_mgau, int n_feat, int nd,
+               int sumlen, const int32_t *__restrict__ featlen, const int32_t *__restrict__ featoff)
+{
+    extern __shared__ float sx[];                     // [FT][sumlen]
+    const long long fbase = (long long)blockIdx.y * FT;
+    for (int i = threadIdx.x; i < FT * sumlen; i += blockDim.x) {
+        const long long fr = fbase + i / sumlen;
+        sx[i] = fr < n_frames ? feats[(frame0 + fr) * sumlen + i % sumlen] : 0.f;
+    }
+    __syncthreads();
+    const int cb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cb >= n_mgau) return;
+    const bool all = NT >= nd;                        // compute_dist_all (ms_gauden.c:378-419)
+    for (int f = 0; f < n_feat; ++f) {
+        const int fl = featlen[f], fo = featoff[f];
+        int id[FT][NT];
+        float ds[FT][NT];
+#pragma unroll
+        for (int q = 0; q < FT; ++q)
+#pragma unroll
+            for (int i = 0; i < NT; ++i) { id[q][i] = 0; ds[q][i] = (float)INT_MIN; }     // WORST_DIST (:447-448)
+        const float *gp = gT + ((size_t)fo * nd * 2) * n_mgau + cb;
+        for (int d = 0; d < nd; ++d) {
+            float dv[FT];
+            const float det = detT[((size_t)f * nd + d) * n_mgau + cb];
+#pragma unroll
+            for (int q = 0; q < FT; ++q) dv[q] = det;
+            for (int j = 0; j < fl; ++j) {
+                const float m = gp[((size_t)(d * fl + j) * 2) * n_mgau];
+                const float v = gp[((size_t)(d * fl + j) * 2 + 1) * n_mgau];
+#pragma unroll
+                for (int q = 0; q < FT; ++q) {
+                    const float diff = __fsub_rn(sx[q * sumlen + fo + j], m);
+                    dv[q] = __fsub_rn(dv[q], __fmul_rn(__fmul_rn(diff, diff), v));       // :467-470
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < FT; ++q) {
+                if (all) {
+#pragma unroll
+                    for (int i = 0; i < NT; ++i)
+                        if (i == d) { id[q][i] = d; ds[q][i] = dv[q]; }
+                }
+                else if (dv[q] >= ds[q][NT - 1]) {     // early exit is result-neutral (:457,:474)
+                    // insert before the first entry that is not better (strict '<' scan, :478-483)
+                    int p = 0;
+#pragma unroll
+                    for (int i = 0; i < NT; ++i) p += (dv[q] < ds[q][i]) ? 1 : 0;
+#pragma unroll
+                    for (int i = NT - 1; i > 0; --i)
+                        if (i > p) { ds[q][i] = ds[q][i - 1]; id[q][i] = id[q][i - 1]; }
+#pragma unroll
+                    for (int i = 0; i < NT; ++i)
+                        if (i == p) { ds[q][i] = dv[q]; id[q][i] = d; }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < FT; ++q) {
+            const long long fr = fbase + q;
+            if (fr >= n_frames) break;
+            int2 *o = out + ((fr * n_mgau + cb) * n_feat + f) * NT;
+#pragma unroll
+            for (int i = 0; i < NT; ++i) o[i] = make_int2(id[q][i], __float_as_int(ds[q][i]));
+        }
+    }
+}
+
+// logmath_add with the shifted table (logmath.c:402-446)
+__device__ __forceinline__ int logadd_wide(const uint32_t *__restrict__ tab, int size, int zero, int x, int y)
+{
+    if (x <= zero) return y;
+    if (y <= zero) return x;
+    int d, r;
+    if (x > y) { d = x - y; r = x; }
+    else { d = y - x; r = y; }
+    if (d < 0 || d >= size) return r;
+    return r + (int)tab[d];
+}
+
+// senone_eval (ms_senone.c:358-407) + the first clamp; raw scores and the per-frame minimum.
+__global__ void __launch_bounds__(256)
+ms_senone_kernel(const int2 *__restrict__ dist, const uint8_t *__restrict__ pdf, const int32_t *__restrict__ sen2cb,
+                 const uint32_t *__restrict__ tab, int tab_size, int tab_zero, int16_t *__restrict__ senscr,
+                 int32_t *__restrict__ best, long long frame0, int n_sen, int n_mgau, int n_feat, int nd, int nt,
+                 int n_used, int aw, int transposed)
+{
+    const long long fr = blockIdx.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    int scr = 0x7fffffff;
+    if (s < n_sen) {
+        const int cb = sen2cb[s];
+        scr = 0;
+        for (int f = 0; f < n_feat; ++f) {
+            const int2 *l = dist + ((fr * n_mgau + cb) * n_feat + f) * nt;
+            int fscr = 0;
+            for (int t = 0; t < n_used; ++t) {
+                const int2 e = l[t];
+                const float dv = __int_as_float(e.y);
+                int fden;
+                if (dv < (float)INT_MIN) fden = INT_MIN >> PSB_SENSCR_SHIFT;
+                else fden = (__float2int_rz(dv) + ((1 << PSB_SENSCR_SHIFT) - 1)) >> PSB_SENSCR_SHIFT;
+                const int w = transposed ? pdf[((size_t)f * nd + e.x) * n_sen + s]
+                                         : pdf[((size_t)s * n_feat + f) * nd + e.x];
+                const int fw = fden - w;
+                fscr = t == 0 ? fw : logadd_wide(tab, tab_size, tab_zero, fscr, fw);
+            }
+            scr -= fscr;
+        }
+        scr /= aw;                                     // C division, truncation toward zero (:396)
+        scr = min(32767, max(-32768, scr));            // :399-404
+        senscr[(frame0 + fr) * n_sen + s] = (int16_t)scr;
+    }
+    // per-frame minimum (ms_mgau.c:218-224)
+    scr = __reduce_min_sync(0xffffffffu, scr);
+    if ((threadIdx.x & 31) == 0 && scr != 0x7fffffff) atomicMin(&best[fr], scr);
+}
+
+// normalise: senscr - best with the second clamp (ms_mgau.c:227-235)
+__global__ void __launch_bounds__(256)
+ms_norm_kernel(int16_t *__restrict__ senscr, const int32_t *__restrict__ best, long long frame0, int n_sen)
+{
+    const long long fr = blockIdx.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sen) return;
+    int16_t *p = senscr + (frame0 + fr) * n_sen + s;
+    int bs = (int)*p - best[fr];
+    *p = (int16_t)min(32767, max(-32768, bs));
+}
+
+__global__ void fill_i32(int32_t *p, long long n, int32_t v)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace
+
+int psb_launch_ms_batch(psb_batch_t *b, const float *d_feats, const int32_t *utt_off, int32_t n_utt, int16_t *d_senscr)
+{
+    psb_model_t *m = b->m;
+    PSB_REQUIRE(m->kind == PSB_KIND_MS, "psb_launch_ms_batch: model is not ms");
+    const long long total = utt_off[n_utt];
+    b->last_frames = total;
+    if (total == 0) return PSB_OK;
+    int nt = 1;
+    while (nt < m->topn) nt <<= 1;
+    PSB_REQUIRE(nt <= MAXNT, "ms batch kernels support -topn up to %d (got %d)", MAXNT, m->topn);
+    const int n_used = std::min(m->topn, m->n_density);     // ms_mgau_init clamps topn (ms_mgau.c:137-143)
+    PSB_REQUIRE(m->topn >= m->n_density || nt == m->topn, "ms batch kernels need a power-of-two -topn (got %d)", m->topn);
+    const size_t per_frame = (size_t)m->n_mgau * m->n_feat * nt * sizeof(int2);
+    const size_t budget = (size_t)2 << 30;
+    long long chunk = std::max<long long>(FT, std::min<long long>(total, (long long)(budget / per_frame) / FT * FT));
+    chunk = std::min<long long>(chunk, 65535);              // gridDim.y
+    if (b->ms_cap < (size_t)chunk * per_frame) {
+        cudaFree(b->d_msdist); cudaFree(b->d_msbest);
+        b->d_msdist = nullptr; b->d_msbest = nullptr;
+        b->ms_cap = (size_t)chunk * per_frame;
+        PSB_CUDA(cudaMalloc(&b->d_msdist, b->ms_cap));
+        PSB_CUDA(cudaMalloc(&b->d_msbest, 65536 * sizeof(int32_t)));
+    }
+    if (b->have_ev) PSB_CUDA(cudaEventRecord(b->ev[0], b->stream));
+    if (b->have_ev) PSB_CUDA(cudaEventRecord(b->ev[1], b->stream));
+    for (long long f0 = 0; f0 < total; f0 += chunk) {
+        const long long n = std::min(chunk, total - f0);
+        dim3 g1((m->n_mgau + 127) / 128, (unsigned)((n + FT - 1) / FT));
+        size_t smem = (size_t)FT * m->sumlen * sizeof(float);
+        int2 *dist = reinterpret_cast<int2 *>(b->d_msdist);
+#define LAUNCH(NT) ms_dist_kernel<NT><<<g1, 128, smem, b->stream>>>(m->d_msT, m->d_msdetT, d_feats, dist, f0, n, \
+        m->n_mgau, m->n_feat, m->n_density, m->sumlen, m->d_featlen, m->d_featoff)
+        switch (nt) {
+        case 1: LAUNCH(1); break;
+        case 2: LAUNCH(2); break;
+        case 4: LAUNCH(4); break;
+        default: LAUNCH(8); break;
+        }
+#undef LAUNCH
+        PSB_LAUNCH_CHECK();
+        fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->d_msbest, n, 0x7fffffff);
+        PSB_LAUNCH_CHECK();
+        dim3 g2((m->n_sen + 255) / 256, (unsigned)n);
+        ms_senone_kernel<<<g2, 256, 0, b->stream>>>(dist, m->d_mixw, m->d_sen2cb32, m->d_logadd_ms, m->logadd_ms_size,
+                                                    m->logadd_ms_zero, d_senscr, b->d_msbest, f0, m->n_sen, m->n_mgau,
+                                                    m->n_feat, m->n_density, nt, n_used, m->aw, m->n_mgau == 1);
+        PSB_LAUNCH_CHECK();
+        ms_norm_kernel<<<g2, 256, 0, b->stream>>>(d_senscr, b->d_msbest, f0, m->n_sen);
+        PSB_LAUNCH_CHECK();
+    }
+    if (b->have_ev) PSB_CUDA(cudaEventRecord(b->ev[2], b->stream));
+    if (b->have_ev) PSB_CUDA(cudaEventRecord(b->ev[3], b->stream));
+    return PSB_OK;
+}

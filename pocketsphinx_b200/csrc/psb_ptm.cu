@@ -39,8 +39,10 @@ __device__ __forceinline__ int f2i_clamped(float d)
     return __float2int_rz(d);
 }
 
-template <int FL>
-__device__ __forceinline__ float gau_dist(const float4 *__restrict__ r, const float (&x)[FL])
+// dpen (optional) = the partial sum before the last dimension's term: the semi-continuous
+// back-end's early-exit test sees that value (s2_semi_mgau.c:137-143).
+template <int FL, bool PEN = false>
+__device__ __forceinline__ float gau_dist(const float4 *__restrict__ r, const float (&x)[FL], float *dpen = nullptr)
 {
     constexpr int RECF = (1 + 2 * FL + 3) / 4 * 4;
     float rr[RECF];
@@ -55,6 +57,7 @@ __device__ __forceinline__ float gau_dist(const float4 *__restrict__ r, const fl
         float diff = __fsub_rn(x[j], rr[1 + 2 * j]);
         float sq = __fmul_rn(diff, diff);
         float c = __fmul_rn(sq, rr[2 + 2 * j]);
+        if (PEN && j == FL - 1) *dpen = d;
         d = __fsub_rn(d, c);
     }
     return d;
@@ -109,12 +112,17 @@ transpose_feats_kernel(const float *__restrict__ feats, float *__restrict__ feat
 // From these, ptm_mgau_codebook_norm's value min(96, norm - (score_j >> 10)) is
 // min(96, (norm - .x) + .z byte j) exactly (norm >= .x, so saturating byte j at 255 is safe).
 
-template <int FL>
+// SEMI = false: PTM (ptm_mgau.c); SEMI = true: semi-continuous (s2_semi_mgau.c:70-203), whose
+// scan accepts a codeword iff the partial sum before the last dimension is >= (float)worst AND
+// the truncated final score is >= worst (int), and whose record is already normalised per stream
+// (mgau_norm :186-203): .x = number of entries inside topn_beam, .y = codeword bytes,
+// .z = bytes min(96, -((score_j >> 10) - (score_0 >> 10))).
+template <int FL, bool SEMI>
 __global__ void __launch_bounds__(TOPN_WARPS * 32, 7)
 ptm_topn_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec_off,
                 const int32_t *__restrict__ klist, const float *__restrict__ featT, GroupTabs tabs,
                 int4 *__restrict__ out, int n_groups, int nd, int n_feat, int D,
-                const int32_t *__restrict__ featoff, int K, int ds_ratio)
+                const int32_t *__restrict__ featoff, int K, int ds_ratio, const int32_t *__restrict__ topn_beam)
 {
     constexpr int RECF = (1 + 2 * FL + 3) / 4 * 4;
     constexpr int RECQ = RECF / 4;
@@ -202,8 +210,12 @@ ptm_topn_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec_of
                 }
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc) {
-                    const float d = gau_dist<FL>(rq + cc * RECQ, x);
-                    if (d >= thresh && !(m8 & (1u << cc))) {
+                    float dpen;
+                    const float d = gau_dist<FL, SEMI>(rq + cc * RECQ, x, &dpen);
+                    bool hit;
+                    if (SEMI) hit = dpen >= thresh && f2i_clamped(d) >= sc[TOPN - 1];
+                    else hit = d >= thresh;
+                    if (hit && !(m8 & (1u << cc))) {
                         const int c = ch * 8 + cc;
                         const int s = f2i_clamped(d);
                         const int ev = cw[TOPN - 1];
@@ -234,14 +246,21 @@ ptm_topn_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec_of
         // ---- emit the record ----
         const int top = sc[0] >> PSB_SENSCR_SHIFT;
         unsigned cwb = 0, eb = 0;
+        int n_in_beam = TOPN;
 #pragma unroll
         for (int j = 0; j < TOPN; ++j) {
             int e = top - (sc[j] >> PSB_SENSCR_SHIFT);
-            e = e > 255 ? 255 : e;
+            if (SEMI) {
+                e = e > PSB_MAX_NEG_ASCR ? PSB_MAX_NEG_ASCR : e;          // mgau_norm :196-198
+                const int beam = topn_beam[f];
+                if (beam && e > beam && n_in_beam == TOPN) n_in_beam = j;   // :199-200
+            }
+            else
+                e = e > 255 ? 255 : e;
             cwb |= (unsigned)cw[j] << (8 * j);
             eb |= (unsigned)e << (8 * j);
         }
-        out[(off + t) * K + k] = make_int4(top, (int)cwb, (int)eb, 0);
+        out[(off + t) * K + k] = make_int4(SEMI ? n_in_beam : top, (int)cwb, (int)eb, 0);
     }
 }
 
@@ -340,17 +359,80 @@ ptm_senone_kernel(const int4 *__restrict__ topn, const uint8_t *__restrict__ mix
         dst[s] = (int16_t)(asc[s] - best);                       // ptm_mgau.c:398-400
 }
 
-template <int FL>
+// s2_semi_mgau_frame_eval's senone part, compallsen (get_scores_{8b,4b}_feat_all,
+// s2_semi_mgau.c:425-444, 797-831): per stream, log-add mixw + score over the entries inside
+// the beam, accumulate into the int16 score.  The 4-bit variant walks senone pairs and stops at
+// n_sen & ~1 (:809); nibbles: even senone = low, odd = high (:813-814).
+template <bool FOURBIT>
+__global__ void __launch_bounds__(256)
+semi_senone_kernel(const int4 *__restrict__ topn, const uint8_t *__restrict__ mixw,
+                   const uint8_t *__restrict__ mixw_cb, const uint8_t *__restrict__ logadd_tab,
+                   int16_t *__restrict__ senscr, int n_sen, int n_feat, int nd, int mixw_stride)
+{
+    extern __shared__ int smem_i[];
+    uint4 *rowoff = reinterpret_cast<uint4 *>(smem_i);             // [n_feat]
+    uint4 *nsc = rowoff + n_feat;                                   // [n_feat]
+    uint8_t *tab = reinterpret_cast<uint8_t *>(nsc + n_feat);       // [256]
+    uint8_t *cb16 = tab + 256;                                      // [16]
+    __shared__ int cnt[PSB_MAX_FEAT];
+    const long long frame = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (tid < 256) tab[tid] = logadd_tab[tid];
+    if (FOURBIT && tid < 16) cb16[tid] = mixw_cb[tid];
+    if (tid < n_feat) {
+        const int4 r = topn[frame * n_feat + tid];
+        const unsigned cwb = (unsigned)r.y, eb = (unsigned)r.z;
+        unsigned ro[TOPN], nv[TOPN];
+#pragma unroll
+        for (int j = 0; j < TOPN; ++j) {
+            ro[j] = ((unsigned)tid * nd + ((cwb >> (8 * j)) & 0xff)) * (unsigned)mixw_stride;
+            nv[j] = (eb >> (8 * j)) & 0xff;
+        }
+        rowoff[tid] = make_uint4(ro[0], ro[1], ro[2], ro[3]);
+        nsc[tid] = make_uint4(nv[0], nv[1], nv[2], nv[3]);
+        cnt[tid] = r.x;
+    }
+    __syncthreads();
+    const int s = blockIdx.y * blockDim.x + tid;
+    if (s >= n_sen) return;
+    int16_t acc = 0;
+    if (!FOURBIT || s < (n_sen & ~1)) {
+        for (int f = 0; f < n_feat; ++f) {
+            const uint4 ro = rowoff[f], nv = nsc[f];
+            const unsigned rr[TOPN] = {ro.x, ro.y, ro.z, ro.w}, vv[TOPN] = {nv.x, nv.y, nv.z, nv.w};
+            const int n = cnt[f];
+            int tmp = 0;
+#pragma unroll
+            for (int k = 0; k < TOPN; ++k) {
+                if (k == 0 || k < n) {
+                    int w;
+                    if (FOURBIT) {
+                        const int b = mixw[rr[k] + (unsigned)(s >> 1)];
+                        w = cb16[(s & 1) ? b >> 4 : b & 0x0f];
+                    }
+                    else
+                        w = mixw[rr[k] + (unsigned)s];
+                    const int v = w + (int)vv[k];
+                    tmp = k == 0 ? v : logadd8(tab, tmp, v);
+                }
+            }
+            acc = (int16_t)(acc + tmp);                      // int16 += (s2_semi_mgau.c:441)
+        }
+    }
+    senscr[frame * n_sen + s] = acc;
+}
+
+template <int FL, bool SEMI>
 int launch_topn(psb_batch_t *b, const int32_t *d_klist, int n_k, const GroupTabs &tabs, int n_groups,
                 const int32_t *d_featoff)
 {
     psb_model_t *m = b->m;
     size_t smem = (size_t)m->n_density * rec_floats(FL) * sizeof(float);
-    PSB_CUDA(cudaFuncSetAttribute(ptm_topn_kernel<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PSB_CUDA(cudaFuncSetAttribute(ptm_topn_kernel<FL, SEMI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(n_k, (n_groups + TOPN_WARPS - 1) / TOPN_WARPS);
-    ptm_topn_kernel<FL><<<grid, TOPN_WARPS * 32, smem, b->stream>>>(
+    ptm_topn_kernel<FL, SEMI><<<grid, TOPN_WARPS * 32, smem, b->stream>>>(
         m->d_rec, m->d_rec_off, d_klist, b->d_featT, tabs, b->d_topn, n_groups, m->n_density,
-        m->n_feat, m->sumlen, d_featoff, m->K, m->ds_ratio);
+        m->n_feat, m->sumlen, d_featoff, m->K, m->ds_ratio, m->d_topn_beam);
     PSB_LAUNCH_CHECK();
     return PSB_OK;
 }
@@ -362,8 +444,9 @@ int psb_launch_ptm_batch(psb_batch_t *b, const float *d_feats, const int32_t *ut
                          int16_t *d_senscr)
 {
     psb_model_t *m = b->m;
-    PSB_REQUIRE(m->kind == PSB_KIND_PTM, "psb_launch_ptm_batch: model is not PTM");
-    PSB_REQUIRE(m->topn == TOPN, "PTM batch kernels are built for -topn 4 (got %d)", m->topn);
+    PSB_REQUIRE(m->kind == PSB_KIND_PTM || m->kind == PSB_KIND_SEMI, "psb_launch_ptm_batch: model is neither PTM nor semi-continuous");
+    const bool semi = m->kind == PSB_KIND_SEMI;
+    PSB_REQUIRE(m->topn == TOPN, "tied-mixture batch kernels are built for -topn 4 (got %d)", m->topn);
     PSB_REQUIRE(m->n_density % 32 == 0 && m->n_density <= 32 * MAX_NDW,
                 "PTM batch kernels need n_density in {32..256, multiple of 32} (got %d)", m->n_density);
     const long long total = utt_off[n_utt];
@@ -456,7 +539,8 @@ int psb_launch_ptm_batch(psb_batch_t *b, const float *d_feats, const int32_t *ut
         for (size_t i = 0; i < fls.size(); ++i) {
             int n_k = (int)byfl[i].size(), rc;
             switch (fls[i]) {
-#define CASE(FL) case FL: rc = launch_topn<FL>(b, d_klist + pos, n_k, tabs, n_groups, d_featoff); break;
+#define CASE(FL) case FL: rc = semi ? launch_topn<FL, true>(b, d_klist + pos, n_k, tabs, n_groups, d_featoff) \
+                                   : launch_topn<FL, false>(b, d_klist + pos, n_k, tabs, n_groups, d_featoff); break;
                 CASE(13) CASE(12) CASE(24) CASE(3) CASE(39) CASE(1) CASE(2) CASE(4) CASE(8) CASE(16) CASE(26) CASE(32)
 #undef CASE
             default:
@@ -468,7 +552,22 @@ int psb_launch_ptm_batch(psb_batch_t *b, const float *d_feats, const int32_t *ut
         }
     }
     if (b->have_ev) PSB_CUDA(cudaEventRecord(b->ev[2], b->stream));
-    {
+    if (semi) {
+        size_t smem = (size_t)K * 32 + 256 + 16;
+        PSB_REQUIRE(K <= 512, "semi_senone_kernel handles at most 512 streams (got %d)", K);
+        const int threads = 256;
+        dim3 grid((m->n_sen + threads - 1) / threads, (unsigned)total);
+        PSB_REQUIRE(total <= 65535LL * 32768, "too many frames for one launch");
+        if (m->mixw_4bit)
+            semi_senone_kernel<true><<<dim3((unsigned)total, (m->n_sen + threads - 1) / threads), threads, smem, b->stream>>>(
+                b->d_topn, m->d_mixw, m->d_mixw_cb, m->d_logadd8, d_senscr, m->n_sen, m->n_feat, m->n_density, m->mixw_stride);
+        else
+            semi_senone_kernel<false><<<dim3((unsigned)total, (m->n_sen + threads - 1) / threads), threads, smem, b->stream>>>(
+                b->d_topn, m->d_mixw, m->d_mixw_cb, m->d_logadd8, d_senscr, m->n_sen, m->n_feat, m->n_density, m->mixw_stride);
+        (void)grid;
+        PSB_LAUNCH_CHECK();
+    }
+    else {
         size_t smem = (size_t)K * 32 + 8 * 4 + 32 * 4 + 256 + 16 + (size_t)m->n_sen * 2;
         PSB_REQUIRE(K <= 512, "ptm_senone_kernel handles at most 512 (codebook, stream) pairs (got %d)", K);
         PSB_REQUIRE((size_t)m->n_feat * m->n_density * m->mixw_stride < (1ull << 32), "mixture-weight table too large for 32-bit offsets");

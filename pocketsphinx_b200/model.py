@@ -218,3 +218,75 @@ def synth_feats(model, n_utt, n_frames, seed=0, rho=0.9, noise=0.15):
         out[:, t] = x
     out += rng.normal(0, noise, out.shape).astype(np.float32)
     return out
+
+
+def _synth_gaussians(rng, n_mgau, featlens, n_density, scale=None):
+    """Random Gaussians in the reference's precomputed form (var = trunc(1/(2s^2)/ln b) >= 1,
+    det = sum_j trunc(ln(1/sqrt(2 pi s^2))/ln b)), flattened [n_mgau][n_feat][n_density][len]."""
+    lb = np.log(1.0001)
+    means, varis, dets = [[] for _ in range(n_mgau)], [[] for _ in range(n_mgau)], []
+    det = np.empty((n_mgau, len(featlens), n_density), np.float32)
+    for f, fl in enumerate(featlens):
+        sc = 1.0 if scale is None else scale[f]
+        mu = (rng.normal(0, 1, (n_mgau, n_density, fl)) * sc).astype(np.float32)
+        s2 = rng.uniform(0.05, 2.0, (n_mgau, n_density, fl)) * sc * sc
+        v = np.maximum(np.trunc((1.0 / (2.0 * s2)) / lb), 1.0).astype(np.float32)
+        det[:, f] = np.trunc(np.log(1.0 / np.sqrt(2.0 * np.pi * s2)) / lb).sum(-1)
+        for cb in range(n_mgau):
+            means[cb].append(mu[cb].ravel())
+            varis[cb].append(v[cb].ravel())
+    mean = np.concatenate([np.concatenate(m) for m in means])
+    var = np.concatenate([np.concatenate(v) for v in varis])
+    return mean, var, det
+
+
+def synth_semi(seed=0, featlens=(12, 24, 3, 12), n_density=256, n_sen=670, topn=4, four_bit=False,
+               topn_beam=None):
+    """Synthetic semi-continuous model (one shared codebook, s2_semi_mgau.c), 8-bit or 4-bit
+    clustered mixture weights."""
+    rng = np.random.default_rng(seed)
+    n_feat = len(featlens)
+    mean, var, det = _synth_gaussians(rng, 1, featlens, n_density)
+    lb = np.log(1.0001)
+    w = rng.gamma(0.3, 1.0, (n_sen, n_feat, n_density)) + 1e-7
+    w /= w.sum(-1, keepdims=True)
+    q = np.minimum((np.trunc(-np.log(w) / lb).astype(np.int64)) >> 10, 159).astype(np.uint8)
+    q = q.transpose(1, 2, 0).copy()                        # [f][cw][sen]
+    mixw_cb = np.zeros(0, np.uint8)
+    if four_bit:
+        mixw_cb = np.sort(rng.choice(np.arange(0, 160), 16, replace=False)).astype(np.uint8)
+        idx = np.abs(q[..., None].astype(np.int32) - mixw_cb[None, None, None, :].astype(np.int32)).argmin(-1).astype(np.uint8)
+        row = (n_sen + 1) // 2
+        packed = np.zeros((n_feat, n_density, row), np.uint8)
+        packed[..., :n_sen // 2] |= idx[..., 0:n_sen - (n_sen & 1):2]
+        packed[..., :n_sen // 2] |= idx[..., 1:n_sen:2] << 4
+        if n_sen & 1:
+            packed[..., row - 1] |= idx[..., n_sen - 1]
+        q = packed
+    return PackedModel(kind="s2_semi", n_sen=n_sen, n_mgau=1, n_feat=n_feat, n_density=n_density, topn=topn,
+                       featlen=np.array(featlens, np.int32), mean=mean, var=var, det=det, mixw=q, mixw_cb=mixw_cb,
+                       sen2cb=np.zeros(n_sen, np.int32), logadd8=make_logadd8(),
+                       topn_beam=np.array(topn_beam if topn_beam is not None else [0] * n_feat, np.uint8))
+
+
+def synth_ms(seed=0, n_sen=5138, n_density=8, featlens=(39,), topn=4, n_mgau=None, aw=1):
+    """Synthetic model for the generic ms back-end.  n_mgau=None: continuous (.cont.: one codebook
+    per senone, pdf[sen][feat][cw]); n_mgau=1: pdf[feat][cw][sen]; other: PTM-like tying."""
+    rng = np.random.default_rng(seed)
+    n_feat = len(featlens)
+    cont = n_mgau is None
+    n_mgau = n_sen if cont else n_mgau
+    mean, var, det = _synth_gaussians(rng, n_mgau, featlens, n_density)
+    lb = np.log(1.0001)
+    w = rng.gamma(0.5, 1.0, (n_sen, n_feat, n_density)) + 1e-7
+    w /= w.sum(-1, keepdims=True)
+    p = np.trunc(-np.log(w) / lb).astype(np.int64) + 511       # ms_senone.c:237-245
+    pdf = np.where(p < (255 << 10), p >> 10, 255).astype(np.uint8)
+    if n_mgau == 1:
+        pdf = pdf.transpose(1, 2, 0).copy()
+    sen2cb = np.arange(n_sen, dtype=np.int32) if cont else rng.integers(0, n_mgau, n_sen).astype(np.int32)
+    tab = make_logadd8().astype(np.uint32)                      # same table, used on non-negated logs
+    return PackedModel(kind="ms", n_sen=n_sen, n_mgau=n_mgau, n_feat=n_feat, n_density=n_density, topn=topn,
+                       featlen=np.array(featlens, np.int32), mean=mean, var=var, det=det, mixw=pdf,
+                       sen2cb=sen2cb, logadd8=make_logadd8(), aw=aw, logadd_ms=tab,
+                       logadd_ms_zero=-(1 << 31) >> 12)

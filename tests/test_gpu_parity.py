@@ -185,3 +185,55 @@ def test_decode_host_end_to_end(api, en_us, en_us_dev):
     assert np.array_equal(best[:278], g["pl_best"]) and np.array_equal(best[328:], g["pl_best"])
     assert np.array_equal(pen[278:328], g["pl_pen"][:50])
     b.close(); pl.close(); ctx.close()
+
+
+# ---------------------------------------------------------------------------------------
+# semi-continuous (s2_semi_mgau) and generic multi-stream (ms_mgau) back-ends, batched
+
+def _batch_vs_oracle(api, pm, feats_by_utt):
+    from oracle import oracle
+    m = api.Model(pm)
+    lens = [len(f) for f in feats_by_utt]
+    b = api.Batch(m, len(lens) + 1, sum(lens) + 8)
+    off = api.Batch.offsets(lens)
+    scr = b.score_host(np.concatenate(feats_by_utt), off)
+    om = oracle.OracleModel(pm)
+    for u, f in enumerate(feats_by_utt):
+        want = om.score_utt(f)
+        got = scr[off[u]:off[u + 1]]
+        bad = np.argwhere(got != want)
+        assert bad.size == 0, "utt %d: first mismatch (frame, senone) %s: got %s want %s" % (
+            u, bad[0].tolist(), got[tuple(bad[0])], want[tuple(bad[0])])
+    b.close()
+    m.close()
+    return scr, off
+
+
+def test_semi_tidigits_matches_reference(api, tidigits):
+    g = golden("tidigits_goforward.npz")
+    scr, off = _batch_vs_oracle(api, tidigits, [g["feats"], g["feats"][:37]])
+    assert np.array_equal(scr[:len(g["feats"])], g["senscr"])
+
+
+@pytest.mark.parametrize("four_bit,beam,n_sen", [(False, None, 670), (True, None, 671), (False, [40, 0, 25, 96], 300)])
+def test_semi_synthetic_matches_oracle(api, four_bit, beam, n_sen):
+    from pocketsphinx_b200.model import synth_feats, synth_semi
+    pm = synth_semi(seed=3, n_sen=n_sen, four_bit=four_bit, topn_beam=beam)
+    feats = synth_feats(pm, 35, 30, seed=4)
+    _batch_vs_oracle(api, pm, list(feats))
+
+
+def test_ms_an4_matches_reference(api, an4):
+    g = golden("an4_goforward.npz")
+    scr, off = _batch_vs_oracle(api, an4, [g["feats"], g["feats"][:10]])
+    assert np.array_equal(scr[:len(g["feats"])], g["senscr"])
+
+
+@pytest.mark.parametrize("kw", [dict(n_sen=700, n_density=8, topn=4), dict(n_sen=300, n_density=4, topn=4),
+                                dict(n_sen=500, n_density=16, topn=2, featlens=(13, 13, 13), n_mgau=42),
+                                dict(n_sen=400, n_density=32, topn=8, featlens=(12, 24, 3, 12), n_mgau=1, aw=3)])
+def test_ms_synthetic_matches_oracle(api, kw):
+    from pocketsphinx_b200.model import synth_feats, synth_ms
+    pm = synth_ms(seed=8, **kw)
+    feats = synth_feats(pm, 9, 21, seed=5)
+    _batch_vs_oracle(api, pm, list(feats))
