@@ -526,8 +526,10 @@ int psb_launch_ptm_batch(psb_batch_t *b, const float *d_feats, const int32_t *ut
 
     if (b->have_ev) PSB_CUDA(cudaEventRecord(b->ev[0], b->stream));
     {
-        const int warps = 8;
+        int warps = 8;
+        while (warps > 1 && (size_t)warps * 32 * (D + 1) * sizeof(float) > 48 * 1024) warps >>= 1;
         size_t smem = (size_t)warps * 32 * (D + 1) * sizeof(float);
+        PSB_REQUIRE(smem <= 48 * 1024, "feature vectors of %d floats are too long for transpose_feats_kernel", D);
         long long blocks = (items + warps - 1) / warps;
         transpose_feats_kernel<<<(unsigned)blocks, warps * 32, smem, b->stream>>>(
             d_feats, b->d_featT, tabs, d_warp_base, n_groups, D);
