@@ -36,12 +36,38 @@ def frames_for(secs):
 
 
 def load_model(name):
+    """Returns (PackedModel, description, raw parameters or None)."""
     if name == "baseline":
-        return synth_ptm(seed=0, n_density=256, n_sen=5138), "synthetic PTM 42x3x256x13, 5138 senones (BASELINE.json shape)"
+        pm, raw = synth_ptm(seed=0, n_density=256, n_sen=5138, return_raw=True)
+        return pm, "synthetic PTM 42x3x256x13, 5138 senones (BASELINE.json shape)", raw
     if name == "en-us":
         pm = PackedModel.load(os.path.join(ROOT, "tests", "golden", "en_us_ptm_model.npz"))
-        return pm, "shipped en-us PTM 42x3x128x13, 5126 senones (packed fixture)"
+        return pm, "shipped en-us PTM 42x3x128x13, 5126 senones (packed fixture)", None
     raise SystemExit("unknown --model " + name)
+
+
+_REF_DIR = None
+
+
+def reference_model_dir(name, pm, raw):
+    """A model directory the compiled reference (oracle/_ref/libpsref.so) can load, or None."""
+    global _REF_DIR
+    from oracle import refdrv
+    if not refdrv.available():
+        return None
+    if name == "en-us":
+        d = os.path.join(ROOT, "oracle", "_ref", "model", "en-us")
+        return d if os.path.isdir(d) else None
+    if _REF_DIR is None:
+        import tempfile
+        from pocketsphinx_b200 import s3io
+        _REF_DIR = tempfile.mkdtemp(prefix="psb200_model_")
+        s3io.write_model_dir(_REF_DIR, kind=pm.kind, n_mgau=pm.n_mgau, n_feat=pm.n_feat, n_density=pm.n_density,
+                             featlen=pm.featlen, mean=raw["mean"], var_raw=raw["var_raw"], tp_float=raw["tp_float"],
+                             sen2ci=pm.sen2cb, n_ci=pm.n_mgau, n_emit=pm.n_emit_state, n_ci_sen=pm.n_ci_sen,
+                             mixw_q=raw["mixw_q"],
+                             feat_params="-feat 1s_c_d_dd\n-svspec 0-12/13-25/26-38\n-cmn batch\n-agc none\n")
+    return _REF_DIR
 
 
 def peaks():
@@ -94,45 +120,63 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_baseline(pm, feats, n_frames_per_utt, budget_s=15.0, threads=1):
-    """The CPU restatement (oracle/, bit-exact vs the compiled reference on its own models)
-    timed on host cores over a bounded sample of the same workload."""
-    from oracle import oracle
+def cpu_baseline(args, pm, raw, feats, n_frames_per_utt, budget_s=15.0, threads=1):
+    """The reference's CPU implementation of the path on host cores over a bounded sample of the
+    same workload: senone evaluation through the COMPILED REFERENCE (oracle/_ref/libpsref.so:
+    ptm_mgau_frame_eval itself, kind "reference") when it is present, else through the C port
+    (oracle/ps_oracle.c, bit-exact vs the reference, kind "port"); the phone loop (<1 % of the
+    time) always through the port."""
+    import threading as th
+    from oracle import oracle, refdrv
+    ref_dir = reference_model_dir(args.model, pm, raw)
+    kind = "reference" if ref_dir else "port"
     om = oracle.OracleModel(pm)
+    local = th.local()
+
+    def scorer():
+        if kind == "port":
+            return om.score_utt
+        if not hasattr(local, "ref"):
+            local.ref = refdrv.RefModel(ref_dir)
+        return local.ref.score
+
     # calibrate on one short slice, then size the sample to the budget
+    sc = scorer()
     t0 = time.perf_counter()
-    scr = om.score_utt(feats[0][:64])
-    dt = max(1e-4, time.perf_counter() - t0)
-    per_frame = dt / 64
+    sc(feats[0][:64])
+    per_frame = max(1e-6, (time.perf_counter() - t0) / 64)
     n_utt = int(max(1, min(len(feats), budget_s * threads / (per_frame * n_frames_per_utt))))
-    n_utt = max(threads, n_utt - n_utt % threads) if n_utt >= threads else n_utt
+    if n_utt >= threads:
+        n_utt -= n_utt % threads
 
     def work(u):
-        s = om.score_utt(feats[u])
+        s = scorer()(feats[u])
         oracle.phoneloop_run(pm.tp, pm.sseq, pm.phone_ssid[:pm.n_ciphone], pm.phone_tmat[:pm.n_ciphone], s,
                              PL["window"], PL["beam"], PL["pbeam"], PL["pip"], PL["weight"])
         return len(s)
 
+    if threads > 1:                       # load one reference model per worker before timing
+        from concurrent.futures import ThreadPoolExecutor
+        ex = ThreadPoolExecutor(threads)
+        list(ex.map(lambda _: scorer()(feats[0][:4]), range(threads * 2)))
     t0 = time.perf_counter()
     if threads == 1:
         done = sum(work(u) for u in range(n_utt))
     else:
-        from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(threads) as ex:        # ctypes releases the GIL inside the oracle
-            done = sum(ex.map(work, range(n_utt)))
+        done = sum(ex.map(work, range(n_utt)))       # ctypes releases the GIL inside the C code
     dt = time.perf_counter() - t0
-    return {"value": done / dt, "unit": "frames/s", "cores": threads, "kind": "port",
-            "sample": "%d utterances x %d frames of the same batch, senone eval + phone loop, %.1f s" % (
-                n_utt, n_frames_per_utt, dt)}
+    return {"value": done / dt, "unit": "frames/s", "cores": threads, "kind": kind,
+            "sample": "%d utterances x %d frames of the same batch, senone eval (%s) + phone loop, %.1f s" % (
+                n_utt, n_frames_per_utt, "compiled reference" if kind == "reference" else "C port", dt)}
 
 
-def run_reference(args, pm, desc, feats, T):
+def run_reference(args, pm, raw, desc, feats, T):
     """--impl reference: the reference algorithm's CPU implementation on all host cores."""
     cores = os.cpu_count() or 1
     steps = []
     base = None
     for i in range(args.warmup + args.steps):
-        base = cpu_baseline(pm, feats, T, budget_s=max(3.0, 60.0 / (args.warmup + args.steps)), threads=cores)
+        base = cpu_baseline(args, pm, raw, feats, T, budget_s=max(3.0, 60.0 / (args.warmup + args.steps)), threads=cores)
         if i >= args.warmup:
             steps.append(base["value"])
     v = float(np.mean(steps))
@@ -165,14 +209,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    pm, desc = load_model(args.model)
+    pm, desc, raw = load_model(args.model)
     T = frames_for(args.secs)
 
     if args.impl == "reference":
         if rank != 0:
             return
-        feats = synth_feats(pm, min(args.utts, 64), T, seed=1234)
-        run_reference(args, pm, desc, feats, T)
+        feats = synth_feats(pm, min(args.utts, max(64, 2 * (os.cpu_count() or 1))), T, seed=1234)
+        run_reference(args, pm, raw, desc, feats, T)
         return
 
     import torch
@@ -184,14 +228,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     # ---- acoustic model: rank 0 holds it, one NCCL broadcast per packed buffer at init ----
-    names = ["mean", "var", "det", "mixw", "sen2cb", "logadd8"]
-    dev = {}
-    for k in names:
-        t = torch.from_numpy(getattr(pm, k)).cuda() if (rank == 0 or world == 1) else \
-            torch.empty(getattr(pm, k).shape, dtype=torch.from_numpy(getattr(pm, k)).dtype, device="cuda")
-        if world > 1:
-            dist.broadcast(t, 0)
-        dev[k] = t
+    from pocketsphinx_b200 import dist as pdist
+    dev = pdist.broadcast_model(pm, src=0, device=torch.device("cuda", local))
     torch.cuda.synchronize()
     model = api.Model(pm, device=local, device_ptrs=dev)
 
@@ -247,10 +285,7 @@ def main():
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
 
-    t = torch.tensor([ms_step, e2e_ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step, e2e_ms = float(t[0]), float(t[1])
+    ms_step, e2e_ms = pdist.reduce_max_ms([ms_step, e2e_ms], device="cuda")
 
     if rank == 0:
         hbm_peak, peak_src, sm_max = peaks()
@@ -299,7 +334,7 @@ def main():
             "clocks": clocks,
         }
         if world == 1:
-            out["cpu_baseline"] = cpu_baseline(pm, feats_np, T, budget_s=args.cpu_budget, threads=1)
+            out["cpu_baseline"] = cpu_baseline(args, pm, raw, feats_np, T, budget_s=args.cpu_budget, threads=1)
         print(json.dumps(out))
     batch.close(); pl.close(); ctx.close(); model.close()
     if world > 1:

@@ -135,23 +135,21 @@ def make_logadd8(base=1.0001, shift=10):
 
 
 def synth_ptm(seed=0, n_mgau=42, n_feat=3, n_density=256, featlen=13, n_sen=5138, topn=4,
-              n_tmat=None, n_emit_state=3, skip_arcs=False):
+              n_tmat=None, n_emit_state=3, skip_arcs=False, return_raw=False):
     """Synthetic PTM model of the BASELINE.json shape (42 cb x 3 streams x 256 Gaussians x 13
-    dims, 5138 senones).  Value ranges follow the shipped en-us model:
-    precomputed var >= 1, det in roughly [-5.5e5, 4.8e5], 8-bit mixw in 0..159.
+    dims, 5138 senones).  Generated as RAW parameters (means, variances, transition
+    probabilities, quantised mixture weights) and passed through mirrors of the reference's
+    loaders (s3io.precompute_gaussians / quantize_tmat), so that the same model can also be
+    written as Sphinx-3 files (s3io.write_model_dir) and loaded by the unmodified reference.
     CI senones first (n_emit_state per codebook), the rest in contiguous per-codebook runs."""
+    from . import s3io
     rng = np.random.default_rng(seed)
     fl = np.full(n_feat, featlen, np.int32)
-    mean = rng.normal(0.0, 1.0, (n_mgau, n_feat, n_density, featlen)).astype(np.float32)
-    # stream scales roughly like cepstra / deltas / delta-deltas
     scale = np.array([3.0, 1.0, 0.5] + [1.0] * max(0, n_feat - 3), np.float32)[:n_feat]
-    mean *= scale[None, :, None, None]
-    sigma2 = (rng.uniform(0.05, 2.0, (n_mgau, n_feat, n_density, featlen)).astype(np.float64)
-              * (scale[None, :, None, None].astype(np.float64) ** 2))
-    lb = np.log(1.0001)
-    var = np.trunc((1.0 / (2.0 * sigma2)) / lb).astype(np.float32)        # logmath_ln_to_log
-    var = np.maximum(var, 1.0)
-    det = np.trunc(np.log(1.0 / np.sqrt(2.0 * np.pi * sigma2)) / lb).sum(-1).astype(np.float32)
+    mean = (rng.normal(0.0, 1.0, (n_mgau, n_feat, n_density, featlen)) * scale[None, :, None, None]).astype(np.float32)
+    var_raw = (rng.uniform(0.05, 2.0, (n_mgau, n_feat, n_density, featlen))
+               * (scale[None, :, None, None].astype(np.float64) ** 2)).astype(np.float32)
+    var, det = s3io.precompute_gaussians(var_raw, n_mgau, n_feat, n_density, fl)
     n_ci = n_mgau * n_emit_state
     assert n_sen > n_ci
     sen2cb = np.empty(n_sen, np.int32)
@@ -159,23 +157,41 @@ def synth_ptm(seed=0, n_mgau=42, n_feat=3, n_density=256, featlen=13, n_sen=5138
     cuts = np.sort(rng.choice(np.arange(1, n_sen - n_ci), n_mgau - 1, replace=False))
     sizes = np.diff(np.concatenate([[0], cuts, [n_sen - n_ci]]))
     sen2cb[n_ci:] = np.repeat(np.arange(n_mgau), sizes)
-    # mixture weights: -log >> 10 of a floored distribution; most mass on few codewords
+    # mixture weights as the sendump stores them: 0..159, most mass on few codewords
+    lb = np.log(1.0001)
     w = rng.gamma(0.3, 1.0, (n_sen, n_feat, n_density)) + 1e-7
     w /= w.sum(-1, keepdims=True)
     q = (np.trunc(-np.log(w) / lb).astype(np.int64)) >> 10
     mixw = np.minimum(q, 159).astype(np.uint8).transpose(1, 2, 0).copy()    # [f][cw][sen]
     n_tmat = n_tmat or n_mgau
-    tp = synth_tmat(rng, n_tmat, n_emit_state, skip_arcs)
+    tp_float = synth_tmat_float(rng, n_tmat, n_emit_state, skip_arcs)
+    tp = s3io.quantize_tmat(tp_float)
     n_sseq = 4096
     sseq = np.empty((n_sseq, n_emit_state), np.uint16)
     sseq[:n_mgau] = np.arange(n_ci).reshape(n_mgau, n_emit_state)
     sseq[n_mgau:] = rng.integers(0, n_sen, (n_sseq - n_mgau, n_emit_state))
-    return PackedModel(kind="ptm", n_sen=n_sen, n_mgau=n_mgau, n_feat=n_feat, n_density=n_density,
-                       topn=topn, featlen=fl, mean=mean, var=var, det=det, mixw=mixw, sen2cb=sen2cb,
-                       logadd8=make_logadd8(), n_emit_state=n_emit_state, tp=tp, sseq=sseq,
-                       phone_ssid=np.arange(n_mgau, dtype=np.int32),
-                       phone_tmat=np.arange(n_mgau, dtype=np.int32) % n_tmat,
-                       n_ciphone=n_mgau, n_ci_sen=n_ci)
+    pm = PackedModel(kind="ptm", n_sen=n_sen, n_mgau=n_mgau, n_feat=n_feat, n_density=n_density,
+                     topn=topn, featlen=fl, mean=mean, var=var, det=det, mixw=mixw, sen2cb=sen2cb,
+                     logadd8=make_logadd8(), n_emit_state=n_emit_state, tp=tp, sseq=sseq,
+                     phone_ssid=np.arange(n_mgau, dtype=np.int32),
+                     phone_tmat=np.arange(n_mgau, dtype=np.int32) % n_tmat,
+                     n_ciphone=n_mgau, n_ci_sen=n_ci)
+    if return_raw:
+        return pm, dict(mean=mean, var_raw=var_raw, tp_float=tp_float, mixw_q=mixw)
+    return pm
+
+
+def synth_tmat_float(rng, n_tmat, n_emit_state, skip_arcs=False):
+    """float32 tp[n_tmat][n][n+1] for a Bakis topology (upper triangular, at most one skip)."""
+    n = n_emit_state
+    tp = np.zeros((n_tmat, n, n + 1), np.float32)
+    for t in range(n_tmat):
+        for i in range(n):
+            nxt = [i, i + 1] + ([i + 2] if skip_arcs and i + 2 <= n else [])
+            p = rng.dirichlet(np.ones(len(nxt)) * 2.0)
+            for j, pj in zip(nxt, p):
+                tp[t, i, j] = pj
+    return tp
 
 
 def synth_tmat(rng, n_tmat, n_emit_state, skip_arcs=False):
@@ -221,32 +237,29 @@ def synth_feats(model, n_utt, n_frames, seed=0, rho=0.9, noise=0.15):
 
 
 def _synth_gaussians(rng, n_mgau, featlens, n_density, scale=None):
-    """Random Gaussians in the reference's precomputed form (var = trunc(1/(2s^2)/ln b) >= 1,
-    det = sum_j trunc(ln(1/sqrt(2 pi s^2))/ln b)), flattened [n_mgau][n_feat][n_density][len]."""
-    lb = np.log(1.0001)
-    means, varis, dets = [[] for _ in range(n_mgau)], [[] for _ in range(n_mgau)], []
-    det = np.empty((n_mgau, len(featlens), n_density), np.float32)
+    """Random raw Gaussians, flattened [n_mgau][n_feat][n_density][len]: (mean, raw variance)."""
+    means, varis = [[] for _ in range(n_mgau)], [[] for _ in range(n_mgau)]
     for f, fl in enumerate(featlens):
         sc = 1.0 if scale is None else scale[f]
         mu = (rng.normal(0, 1, (n_mgau, n_density, fl)) * sc).astype(np.float32)
-        s2 = rng.uniform(0.05, 2.0, (n_mgau, n_density, fl)) * sc * sc
-        v = np.maximum(np.trunc((1.0 / (2.0 * s2)) / lb), 1.0).astype(np.float32)
-        det[:, f] = np.trunc(np.log(1.0 / np.sqrt(2.0 * np.pi * s2)) / lb).sum(-1)
+        s2 = (rng.uniform(0.05, 2.0, (n_mgau, n_density, fl)) * sc * sc).astype(np.float32)
         for cb in range(n_mgau):
             means[cb].append(mu[cb].ravel())
-            varis[cb].append(v[cb].ravel())
+            varis[cb].append(s2[cb].ravel())
     mean = np.concatenate([np.concatenate(m) for m in means])
-    var = np.concatenate([np.concatenate(v) for v in varis])
-    return mean, var, det
+    var_raw = np.concatenate([np.concatenate(v) for v in varis])
+    return mean, var_raw
 
 
 def synth_semi(seed=0, featlens=(12, 24, 3, 12), n_density=256, n_sen=670, topn=4, four_bit=False,
-               topn_beam=None):
+               topn_beam=None, return_raw=False):
     """Synthetic semi-continuous model (one shared codebook, s2_semi_mgau.c), 8-bit or 4-bit
     clustered mixture weights."""
+    from . import s3io
     rng = np.random.default_rng(seed)
     n_feat = len(featlens)
-    mean, var, det = _synth_gaussians(rng, 1, featlens, n_density)
+    mean, var_raw = _synth_gaussians(rng, 1, featlens, n_density)
+    var, det = s3io.precompute_gaussians(var_raw, 1, n_feat, n_density, featlens)
     lb = np.log(1.0001)
     w = rng.gamma(0.3, 1.0, (n_sen, n_feat, n_density)) + 1e-7
     w /= w.sum(-1, keepdims=True)
@@ -263,30 +276,54 @@ def synth_semi(seed=0, featlens=(12, 24, 3, 12), n_density=256, n_sen=670, topn=
         if n_sen & 1:
             packed[..., row - 1] |= idx[..., n_sen - 1]
         q = packed
-    return PackedModel(kind="s2_semi", n_sen=n_sen, n_mgau=1, n_feat=n_feat, n_density=n_density, topn=topn,
-                       featlen=np.array(featlens, np.int32), mean=mean, var=var, det=det, mixw=q, mixw_cb=mixw_cb,
-                       sen2cb=np.zeros(n_sen, np.int32), logadd8=make_logadd8(),
-                       topn_beam=np.array(topn_beam if topn_beam is not None else [0] * n_feat, np.uint8))
+    tp_float = synth_tmat_float(rng, 10, 3)
+    pm = PackedModel(kind="s2_semi", n_sen=n_sen, n_mgau=1, n_feat=n_feat, n_density=n_density, topn=topn,
+                     featlen=np.array(featlens, np.int32), mean=mean, var=var, det=det, mixw=q, mixw_cb=mixw_cb,
+                     sen2cb=np.zeros(n_sen, np.int32), logadd8=make_logadd8(), tp=s3io.quantize_tmat(tp_float),
+                     topn_beam=np.array(topn_beam if topn_beam is not None else [0] * n_feat, np.uint8))
+    if return_raw:
+        return pm, dict(mean=mean, var_raw=var_raw, tp_float=tp_float, mixw_q=q, mixw_cb=mixw_cb if four_bit else None)
+    return pm
 
 
-def synth_ms(seed=0, n_sen=5138, n_density=8, featlens=(39,), topn=4, n_mgau=None, aw=1):
+def synth_ms(seed=0, n_sen=5138, n_density=8, featlens=(39,), topn=4, n_mgau=None, aw=1, return_raw=False):
     """Synthetic model for the generic ms back-end.  n_mgau=None: continuous (.cont.: one codebook
     per senone, pdf[sen][feat][cw]); n_mgau=1: pdf[feat][cw][sen]; other: PTM-like tying."""
+    from . import s3io
     rng = np.random.default_rng(seed)
     n_feat = len(featlens)
     cont = n_mgau is None
     n_mgau = n_sen if cont else n_mgau
-    mean, var, det = _synth_gaussians(rng, n_mgau, featlens, n_density)
-    lb = np.log(1.0001)
-    w = rng.gamma(0.5, 1.0, (n_sen, n_feat, n_density)) + 1e-7
-    w /= w.sum(-1, keepdims=True)
-    p = np.trunc(-np.log(w) / lb).astype(np.int64) + 511       # ms_senone.c:237-245
-    pdf = np.where(p < (255 << 10), p >> 10, 255).astype(np.uint8)
+    mean, var_raw = _synth_gaussians(rng, n_mgau, featlens, n_density)
+    var, det = s3io.precompute_gaussians(var_raw, n_mgau, n_feat, n_density, featlens)
+    w = (rng.gamma(0.5, 1.0, (n_sen, n_feat, n_density)) + 1e-7).astype(np.float32)
+    pdf = s3io.quantize_mixw_ms(w)                          # [sen][feat][cw]
     if n_mgau == 1:
         pdf = pdf.transpose(1, 2, 0).copy()
     sen2cb = np.arange(n_sen, dtype=np.int32) if cont else rng.integers(0, n_mgau, n_sen).astype(np.int32)
-    tab = make_logadd8().astype(np.uint32)                      # same table, used on non-negated logs
-    return PackedModel(kind="ms", n_sen=n_sen, n_mgau=n_mgau, n_feat=n_feat, n_density=n_density, topn=topn,
-                       featlen=np.array(featlens, np.int32), mean=mean, var=var, det=det, mixw=pdf,
-                       sen2cb=sen2cb, logadd8=make_logadd8(), aw=aw, logadd_ms=tab,
-                       logadd_ms_zero=-(1 << 31) >> 12)
+    tab = make_logadd8().astype(np.uint32)                  # same table, used on non-negated logs
+    tp_float = synth_tmat_float(rng, 10, 3)
+    pm = PackedModel(kind="ms", n_sen=n_sen, n_mgau=n_mgau, n_feat=n_feat, n_density=n_density, topn=topn,
+                     featlen=np.array(featlens, np.int32), mean=mean, var=var, det=det, mixw=pdf,
+                     sen2cb=sen2cb, logadd8=make_logadd8(), aw=aw, logadd_ms=tab, tp=s3io.quantize_tmat(tp_float),
+                     logadd_ms_zero=-(1 << 31) >> 12)
+    if return_raw:
+        return pm, dict(mean=mean, var_raw=var_raw, tp_float=tp_float, mixw_float=w)
+    return pm
+
+
+def quantize_for_ties(pm, seed=0):
+    """Return (model, feature generator) whose Gaussian exponents are small integers so that many
+    codewords tie exactly at the float and int level: exercises the order-dependent tie rules of
+    eval_topn / eval_cb."""
+    import copy
+    q = copy.deepcopy(pm)
+    rng = np.random.default_rng(seed)
+    q.mean = np.round(q.mean).astype(np.float32)
+    q.var = (rng.integers(1, 4, q.var.shape) * 256).astype(np.float32)
+    q.det = (rng.integers(-6, 1, q.det.shape) * 512).astype(np.float32)
+
+    def feats(n_utt, n_frames, s=1):
+        r = np.random.default_rng(s)
+        return r.integers(-3, 4, (n_utt, n_frames, q.sumlen)).astype(np.float32)
+    return q, feats
