@@ -102,7 +102,9 @@ class Mgau:
     def reset(self):
         check(lib().psb_scorer_reset(self.h), "psb_scorer_reset")
 
-    def frame_eval(self, feat_row, frame, senone_active=None, compallsen=True):
+    def frame_eval(self, feat_row, frame, senone_active=None, compallsen=True, out=None):
+        """out: the caller-owned int16[n_sen] buffer (acmod->senone_scores); the ms back-end leaves
+        the entries of unlisted senones untouched, so pass the same buffer across calls."""
         pm = self.model.pm
         feat_row = np.ascontiguousarray(feat_row, np.float32)
         ptrs = (C.c_void_p * pm.n_feat)()
@@ -110,7 +112,7 @@ class Mgau:
         for f in range(pm.n_feat):
             ptrs[f] = feat_row.ctypes.data + 4 * off
             off += int(pm.featlen[f])
-        scr = np.zeros(pm.n_sen, np.int16)
+        scr = np.zeros(pm.n_sen, np.int16) if out is None else out
         n = 0
         if senone_active is not None:
             senone_active = np.ascontiguousarray(senone_active, np.uint8)

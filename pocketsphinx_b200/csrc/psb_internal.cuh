@@ -120,4 +120,7 @@ int psb_phoneloop_launch(psb_phoneloop_t *p, const int16_t *d_senscr, const int3
 int psb_phoneloop_n_phones(const psb_phoneloop_t *p);
 int psb_launch_ptm_batch(psb_batch_t *b, const float *d_feats, const int32_t *utt_off,
                          int32_t n_utt, int16_t *d_senscr);
+int psb_ms_score_one(psb_model_t *m, cudaStream_t st, const float *d_feat, void *d_dist, int32_t *d_best,
+                     int16_t *d_senscr, const int32_t *d_list, int n_items);
+size_t psb_ms_dist_bytes(const psb_model_t *m);
 int psb_launch_ms_batch(psb_batch_t *b, const float *d_feats, const int32_t *utt_off, int32_t n_utt, int16_t *d_senscr);

@@ -108,10 +108,12 @@ __global__ void __launch_bounds__(256)
 ms_senone_kernel(const int2 *__restrict__ dist, const uint8_t *__restrict__ pdf, const int32_t *__restrict__ sen2cb,
                  const uint32_t *__restrict__ tab, int tab_size, int tab_zero, int16_t *__restrict__ senscr,
                  int32_t *__restrict__ best, long long frame0, int n_sen, int n_mgau, int n_feat, int nd, int nt,
-                 int n_used, int aw, int transposed)
+                 int n_used, int aw, int transposed, const int32_t *__restrict__ list, int n_items)
 {
+    // list == nullptr: all senones (n_items == n_sen); else the absolute ids of the active list
     const long long fr = blockIdx.y;
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = it < n_items ? (list ? list[it] : it) : n_sen;
     int scr = 0x7fffffff;
     if (s < n_sen) {
         const int cb = sen2cb[s];
@@ -143,11 +145,13 @@ ms_senone_kernel(const int2 *__restrict__ dist, const uint8_t *__restrict__ pdf,
 
 // normalise: senscr - best with the second clamp (ms_mgau.c:227-235)
 __global__ void __launch_bounds__(256)
-ms_norm_kernel(int16_t *__restrict__ senscr, const int32_t *__restrict__ best, long long frame0, int n_sen)
+ms_norm_kernel(int16_t *__restrict__ senscr, const int32_t *__restrict__ best, long long frame0, int n_sen,
+               const int32_t *__restrict__ list, int n_items)
 {
     const long long fr = blockIdx.y;
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_sen) return;
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    const int s = list ? list[it] : it;
     int16_t *p = senscr + (frame0 + fr) * n_sen + s;
     int bs = (int)*p - best[fr];
     *p = (int16_t)min(32767, max(-32768, bs));
@@ -206,12 +210,57 @@ int psb_launch_ms_batch(psb_batch_t *b, const float *d_feats, const int32_t *utt
         dim3 g2((m->n_sen + 255) / 256, (unsigned)n);
         ms_senone_kernel<<<g2, 256, 0, b->stream>>>(dist, m->d_mixw, m->d_sen2cb32, m->d_logadd_ms, m->logadd_ms_size,
                                                     m->logadd_ms_zero, d_senscr, b->d_msbest, f0, m->n_sen, m->n_mgau,
-                                                    m->n_feat, m->n_density, nt, n_used, m->aw, m->n_mgau == 1);
+                                                    m->n_feat, m->n_density, nt, n_used, m->aw, m->n_mgau == 1, nullptr, m->n_sen);
         PSB_LAUNCH_CHECK();
-        ms_norm_kernel<<<g2, 256, 0, b->stream>>>(d_senscr, b->d_msbest, f0, m->n_sen);
+        ms_norm_kernel<<<g2, 256, 0, b->stream>>>(d_senscr, b->d_msbest, f0, m->n_sen, nullptr, m->n_sen);
         PSB_LAUNCH_CHECK();
     }
     if (b->have_ev) PSB_CUDA(cudaEventRecord(b->ev[2], b->stream));
     if (b->have_ev) PSB_CUDA(cudaEventRecord(b->ev[3], b->stream));
     return PSB_OK;
+}
+
+// One frame for the per-frame scorer (psb_scorer.cu): distances for every codebook (results for
+// codebooks no listed senone uses are simply not read, which equals the reference skipping them,
+// ms_mgau.c:238-252), then only the listed senones are evaluated, normalised among themselves and
+// written; d_senscr entries of unlisted senones are left untouched (:254-276).
+int psb_ms_score_one(psb_model_t *m, cudaStream_t st, const float *d_feat, void *d_dist, int32_t *d_best,
+                     int16_t *d_senscr, const int32_t *d_list, int n_items)
+{
+    int nt = 1;
+    while (nt < m->topn) nt <<= 1;
+    PSB_REQUIRE(nt <= MAXNT, "ms kernels support -topn up to %d (got %d)", MAXNT, m->topn);
+    PSB_REQUIRE(m->topn >= m->n_density || nt == m->topn, "ms kernels need a power-of-two -topn (got %d)", m->topn);
+    const int n_used = std::min(m->topn, m->n_density);
+    dim3 g1((m->n_mgau + 127) / 128, 1);
+    size_t smem = (size_t)FT * m->sumlen * sizeof(float);
+    int2 *dist = reinterpret_cast<int2 *>(d_dist);
+#define LAUNCH(NT) ms_dist_kernel<NT><<<g1, 128, smem, st>>>(m->d_msT, m->d_msdetT, d_feat, dist, 0, 1, \
+        m->n_mgau, m->n_feat, m->n_density, m->sumlen, m->d_featlen, m->d_featoff)
+    switch (nt) {
+    case 1: LAUNCH(1); break;
+    case 2: LAUNCH(2); break;
+    case 4: LAUNCH(4); break;
+    default: LAUNCH(8); break;
+    }
+#undef LAUNCH
+    PSB_LAUNCH_CHECK();
+    fill_i32<<<1, 32, 0, st>>>(d_best, 1, 0x7fffffff);
+    PSB_LAUNCH_CHECK();
+    if (n_items == 0) return PSB_OK;
+    dim3 g2((n_items + 255) / 256, 1);
+    ms_senone_kernel<<<g2, 256, 0, st>>>(dist, m->d_mixw, m->d_sen2cb32, m->d_logadd_ms, m->logadd_ms_size,
+                                         m->logadd_ms_zero, d_senscr, d_best, 0, m->n_sen, m->n_mgau, m->n_feat,
+                                         m->n_density, nt, n_used, m->aw, m->n_mgau == 1, d_list, n_items);
+    PSB_LAUNCH_CHECK();
+    ms_norm_kernel<<<g2, 256, 0, st>>>(d_senscr, d_best, 0, m->n_sen, d_list, n_items);
+    PSB_LAUNCH_CHECK();
+    return PSB_OK;
+}
+
+size_t psb_ms_dist_bytes(const psb_model_t *m)
+{
+    int nt = 1;
+    while (nt < m->topn) nt <<= 1;
+    return (size_t)m->n_mgau * m->n_feat * nt * sizeof(int2);
 }

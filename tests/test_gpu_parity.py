@@ -253,3 +253,71 @@ def test_ptm_and_semi_tie_stress(api):
         sc = topn[..., 1]
         assert (sc[..., :-1] == sc[..., 1:]).mean() > 0.05
         _batch_vs_oracle(api, pm, list(feats))
+
+
+# ---------------------------------------------------------------------------------------
+# per-frame scorers (the ps_mgau_t drop-in) for the semi-continuous and ms back-ends
+
+def _scorer_vs_oracle(api, pm, feats, n_hist_window, rng, p_active=0.3, lookback=0):
+    """Drive Mgau.frame_eval and the oracle's frame_eval with identical call sequences."""
+    from oracle import oracle
+    m = api.Model(pm)
+    s = api.Mgau(m, pl_window=n_hist_window)
+    dec = oracle.OracleModel(pm).decoder(n_hist=n_hist_window + 2)
+    host = np.zeros(pm.n_sen, np.int16)      # the caller-owned buffer (persists across calls)
+    want = np.zeros(pm.n_sen, np.int16)
+    for t in range(len(feats)):
+        mode = t % 3
+        if mode == 0:
+            lst, compall = None, True
+        else:
+            fl = (rng.random(pm.n_sen) < p_active).astype(np.uint8)
+            if mode == 2:
+                fl[pm.n_sen // 3: pm.n_sen // 3 + 300] = 0          # a gap that needs bridging
+            lst, compall = oracle.flags2list(fl), False
+        got = s.frame_eval(feats[t], t, lst, compallsen=compall, out=host)
+        dec.frame_eval_into(want, feats[t], t, lst, compallsen=compall)
+        assert np.array_equal(got, want), "frame %d (mode %d)" % (t, mode)
+        if lookback and t >= lookback:
+            fl = (rng.random(pm.n_sen) < p_active).astype(np.uint8)
+            lst = oracle.flags2list(fl)
+            got = s.frame_eval(feats[t - lookback], t - lookback, lst, compallsen=False, out=host)
+            dec.frame_eval_into(want, feats[t - lookback], t - lookback, lst, compallsen=False)
+            assert np.array_equal(got, want), "re-scored frame %d" % (t - lookback)
+        s.frame_idx = t + 1
+        dec.set_frame_idx(t + 1)
+    s.close(); dec.close(); m.close()
+
+
+def test_scorer_semi_tidigits(api, tidigits):
+    g = golden("tidigits_goforward.npz")
+    m = api.Model(tidigits)
+    s = api.Mgau(m, pl_window=0)
+    for t in range(40):
+        assert np.array_equal(s.frame_eval(g["feats"][t], t), g["senscr"][t]), "frame %d" % t
+        s.frame_idx = t + 1
+    s.close(); m.close()
+    _scorer_vs_oracle(api, tidigits, g["feats"][:45], 3, np.random.default_rng(2), lookback=3)
+
+
+@pytest.mark.parametrize("four_bit,beam", [(False, None), (True, [30, 0, 20, 96])])
+def test_scorer_semi_synthetic(api, four_bit, beam):
+    from pocketsphinx_b200.model import synth_feats, synth_semi
+    pm = synth_semi(seed=11, n_sen=901, four_bit=four_bit, topn_beam=beam)
+    feats = synth_feats(pm, 1, 36, seed=12)[0]
+    _scorer_vs_oracle(api, pm, feats, 2, np.random.default_rng(3), lookback=2)
+
+
+def test_scorer_ms(api, an4):
+    from pocketsphinx_b200.model import synth_feats, synth_ms
+    g = golden("an4_goforward.npz")
+    m = api.Model(an4)
+    s = api.Mgau(m, pl_window=0)
+    for t in range(30):
+        assert np.array_equal(s.frame_eval(g["feats"][t], t), g["senscr"][t]), "frame %d" % t
+        s.frame_idx = t + 1
+    s.close(); m.close()
+    pm = synth_ms(seed=13, n_sen=800, n_density=8, topn=4)
+    _scorer_vs_oracle(api, pm, synth_feats(pm, 1, 30, seed=14)[0], 0, np.random.default_rng(4))
+    pm = synth_ms(seed=15, n_sen=500, n_density=16, topn=2, featlens=(13, 13, 13), n_mgau=42)
+    _scorer_vs_oracle(api, pm, synth_feats(pm, 1, 24, seed=16)[0], 0, np.random.default_rng(5))
