@@ -23,6 +23,8 @@
 
 #include "acmod.h"
 #include "ptm_mgau.h"
+#include "s2_semi_mgau.h"
+#include "ms_mgau.h"
 #include "tied_mgau_common.h"
 #include "util/ckd_alloc.h"
 
@@ -33,6 +35,8 @@ typedef struct cuda_mgau_s {
     ps_mgau_t *host;           /* the reference back-end that loaded the files (kept for transform) */
     psb_model_t *model;
     psb_scorer_t *scorer;
+    gauden_t *g;               /* the wrapped back-end's Gaussians (all three keep a gauden_t) */
+    int32 n_sen;
     void *dl;
     /* bound entry points */
     int (*model_create)(const psb_model_desc_t *, int, psb_model_t **);
@@ -80,38 +84,86 @@ flatten_gauden(gauden_t *g, float **mean, float **var)
     return sumlen;
 }
 
-/* Wrap an initialised PTM back-end.  Returns NULL (after E_ERROR) if the GPU path is not
- * available; the caller then simply keeps using `host`. */
+/* Wrap an initialised host back-end ("ptm", "s2_semi" or "ms").  Returns NULL (after E_ERROR)
+ * if the GPU path is not available; the caller then simply keeps using `host`. */
 ps_mgau_t *
 cuda_mgau_wrap(acmod_t *acmod, ps_mgau_t *host, const char *libpath, int device)
 {
-    ptm_mgau_t *p = (ptm_mgau_t *)host;
-    gauden_t *g = p->g;
+    const char *name = host->vt->name;
     cuda_mgau_t *c;
     psb_model_desc_t d;
+    gauden_t *g;
     float *mean = NULL, *var = NULL;
-    int32 *s2c;
-    uint8 *mixw;
-    size_t row;
+    int32 *s2c = NULL;
+    uint32 *wide = NULL;
+    uint8 *mixw = NULL;
+    int32 n_sen, n_hist = 2;
     int f, cw, i, rc;
 
 #ifdef FIXED_POINT
     E_ERROR("cuda_mgau: FIXED_POINT builds are not supported\n");
     return NULL;
 #endif
-    if (strcmp(host->vt->name, "ptm") != 0) {
-        E_ERROR("cuda_mgau: only the ptm back-end can be wrapped so far (got %s)\n", host->vt->name);
+    memset(&d, 0, sizeof(d));
+    if (strcmp(name, "ptm") == 0) {
+        ptm_mgau_t *p = (ptm_mgau_t *)host;
+        size_t row;
+        g = p->g; n_sen = p->n_sen; n_hist = p->n_fast_hist;
+        d.kind = PSB_KIND_PTM; d.topn = p->max_topn; d.ds_ratio = p->ds_ratio;
+        row = p->mixw_cb ? (size_t)(n_sen + 1) / 2 : (size_t)n_sen;
+        mixw = ckd_calloc((size_t)g->n_feat * g->n_density, row);
+        for (f = 0; f < g->n_feat; ++f)
+            for (cw = 0; cw < g->n_density; ++cw)
+                memcpy(mixw + ((size_t)f * g->n_density + cw) * row, p->mixw[f][cw], row);
+        d.mixw_cb = p->mixw_cb;
+        s2c = ckd_calloc(n_sen, sizeof(*s2c));
+        for (i = 0; i < n_sen; ++i) s2c[i] = p->sen2cb[i];
+        d.logadd8 = (const uint8_t *)LOGMATH_TABLE(p->lmath_8b)->table;
+    }
+    else if (strcmp(name, "s2_semi") == 0) {
+        s2_semi_mgau_t *p = (s2_semi_mgau_t *)host;
+        size_t row;
+        g = p->g; n_sen = p->n_sen; n_hist = p->n_topn_hist;
+        d.kind = PSB_KIND_SEMI; d.topn = p->max_topn; d.ds_ratio = p->ds_ratio;
+        row = p->mixw_cb ? (size_t)(n_sen + 1) / 2 : (size_t)n_sen;
+        mixw = ckd_calloc((size_t)g->n_feat * g->n_density, row);
+        for (f = 0; f < g->n_feat; ++f)
+            for (cw = 0; cw < g->n_density; ++cw)
+                memcpy(mixw + ((size_t)f * g->n_density + cw) * row, p->mixw[f][cw], row);
+        d.mixw_cb = p->mixw_cb;
+        s2c = ckd_calloc(n_sen, sizeof(*s2c));
+        d.logadd8 = (const uint8_t *)LOGMATH_TABLE(p->lmath_8b)->table;
+        d.topn_beam = p->topn_beam;
+    }
+    else if (strcmp(name, "ms") == 0) {
+        ms_mgau_model_t *p = (ms_mgau_model_t *)host;
+        senone_t *sen = p->s;
+        logadd_t *t = LOGMATH_TABLE(sen->lmath);
+        g = p->g; n_sen = sen->n_sen;
+        d.kind = PSB_KIND_MS; d.topn = p->topn; d.aw = sen->aw;
+        mixw = ckd_calloc((size_t)sen->n_sen * sen->n_feat, sen->n_cw);
+        memcpy(mixw, sen->pdf[0][0], (size_t)sen->n_sen * sen->n_feat * sen->n_cw);
+        s2c = ckd_calloc(n_sen, sizeof(*s2c));
+        for (i = 0; i < n_sen; ++i) s2c[i] = sen->mgau[i];
+        wide = ckd_calloc(t->table_size, sizeof(*wide));
+        for (i = 0; i < (int)t->table_size; ++i)
+            wide[i] = t->width == 1 ? ((uint8 *)t->table)[i] : t->width == 2 ? ((uint16 *)t->table)[i] : ((uint32 *)t->table)[i];
+        d.logadd_ms = wide;
+        d.logadd_ms_size = t->table_size;
+        d.logadd_ms_zero = logmath_get_zero(sen->lmath);
+    }
+    else {
+        E_ERROR("cuda_mgau: unknown back-end %s\n", name);
         return NULL;
     }
     c = ckd_calloc(1, sizeof(*c));
     c->dl = dlopen(libpath ? libpath : "libpsb200.so", RTLD_NOW | RTLD_LOCAL);
     if (c->dl == NULL) {
         E_ERROR("cuda_mgau: %s\n", dlerror());
-        ckd_free(c);
-        return NULL;
+        goto fail;
     }
 #define BIND(field, sym) do { *(void **)&c->field = dlsym(c->dl, sym); \
-        if (!c->field) { E_ERROR("cuda_mgau: missing symbol %s\n", sym); dlclose(c->dl); ckd_free(c); return NULL; } } while (0)
+        if (!c->field) { E_ERROR("cuda_mgau: missing symbol %s\n", sym); goto fail; } } while (0)
     BIND(model_create, "psb_model_create");
     BIND(model_free, "psb_model_free");
     BIND(model_update, "psb_model_update_gaussians");
@@ -121,50 +173,40 @@ cuda_mgau_wrap(acmod_t *acmod, ps_mgau_t *host, const char *libpath, int device)
     BIND(scorer_frame_eval, "psb_scorer_frame_eval");
     BIND(last_error, "psb_last_error");
 #undef BIND
-
-    memset(&d, 0, sizeof(d));
-    d.kind = PSB_KIND_PTM;
-    d.n_sen = p->n_sen;
+    d.n_sen = n_sen;
     d.n_mgau = g->n_mgau;
     d.n_feat = g->n_feat;
     d.n_density = g->n_density;
-    d.topn = p->max_topn;
     for (f = 0; f < g->n_feat; ++f) d.featlen[f] = g->featlen[f];
-    d.ds_ratio = p->ds_ratio;
     flatten_gauden(g, &mean, &var);
     d.mean = mean;
     d.var = var;
     d.det = g->det[0][0];
-    row = p->mixw_cb ? (size_t)(p->n_sen + 1) / 2 : (size_t)p->n_sen;
-    mixw = ckd_calloc((size_t)g->n_feat * g->n_density, row);
-    for (f = 0; f < g->n_feat; ++f)
-        for (cw = 0; cw < g->n_density; ++cw)
-            memcpy(mixw + ((size_t)f * g->n_density + cw) * row, p->mixw[f][cw], row);
     d.mixw = mixw;
-    d.mixw_cb = p->mixw_cb;
-    s2c = ckd_calloc(p->n_sen, sizeof(*s2c));
-    for (i = 0; i < p->n_sen; ++i) s2c[i] = p->sen2cb[i];
     d.sen2cb = s2c;
-    d.logadd8 = (const uint8_t *)LOGMATH_TABLE(p->lmath_8b)->table;
-
     rc = c->model_create(&d, device, &c->model);
-    ckd_free(mean); ckd_free(var); ckd_free(mixw); ckd_free(s2c);
     if (rc == 0)
-        rc = c->scorer_create(c->model, p->n_fast_hist, &c->scorer);
+        rc = c->scorer_create(c->model, n_hist, &c->scorer);
     if (rc != 0) {
         E_ERROR("cuda_mgau: %s\n", c->last_error());
-        if (c->model) c->model_free(c->model);
-        dlclose(c->dl);
-        ckd_free(c);
-        return NULL;
+        goto fail;
     }
+    ckd_free(mean); ckd_free(var); ckd_free(mixw); ckd_free(s2c); ckd_free(wide);
     (void)acmod;
     c->host = host;
+    c->g = g;
+    c->n_sen = n_sen;
     c->base.vt = &cuda_mgau_funcs;
     c->base.frame_idx = host->frame_idx;
-    E_INFO("cuda_mgau: PTM model on device %d (%d codebooks x %d streams x %d densities, %d senones)\n",
-           device, g->n_mgau, g->n_feat, g->n_density, p->n_sen);
+    E_INFO("cuda_mgau: %s model on device %d (%d codebooks x %d streams x %d densities, %d senones)\n",
+           name, device, g->n_mgau, g->n_feat, g->n_density, n_sen);
     return &c->base;
+fail:
+    ckd_free(mean); ckd_free(var); ckd_free(mixw); ckd_free(s2c); ckd_free(wide);
+    if (c->model) c->model_free(c->model);
+    if (c->dl) dlclose(c->dl);
+    ckd_free(c);
+    return NULL;
 }
 
 static int
@@ -182,7 +224,7 @@ cuda_mgau_frame_eval(ps_mgau_t *mg, int16 *senscr, uint8 *senone_active, int32 n
     if (rc != 0) {
         /* acmod_score ignores the return value (acmod.c:1108): log and leave senscr defined */
         E_ERROR("cuda_mgau: frame %d: %s\n", frame, c->last_error());
-        memset(senscr, 0, ((ptm_mgau_t *)c->host)->n_sen * sizeof(*senscr));
+        memset(senscr, 0, c->n_sen * sizeof(*senscr));
         return -1;
     }
     return 0;
@@ -192,7 +234,7 @@ static int
 cuda_mgau_transform(ps_mgau_t *mg, ps_mllr_t *mllr)
 {
     cuda_mgau_t *c = (cuda_mgau_t *)mg;
-    gauden_t *g = ((ptm_mgau_t *)c->host)->g;
+    gauden_t *g = c->g;
     float *mean, *var;
     int rc;
     /* the host re-reads and adapts the Gaussians (gauden_mllr_transform, ms_gauden.c:512) ... */
