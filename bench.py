@@ -24,7 +24,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from pocketsphinx_b200.model import PackedModel, synth_feats, synth_ptm  # noqa: E402
+from pocketsphinx_b200.model import PackedModel, synth_feats, synth_ms, synth_ptm, synth_semi  # noqa: E402
 
 FRAMES_PER_SEC_AUDIO = 100          # 10 ms frames
 PL = dict(window=5, beam=-225, pbeam=-225, pip=0, weight=3.0)   # pl_beam 1e-10 etc. >> 10
@@ -43,6 +43,18 @@ def load_model(name):
     if name == "en-us":
         pm = PackedModel.load(os.path.join(ROOT, "tests", "golden", "en_us_ptm_model.npz"))
         return pm, "shipped en-us PTM 42x3x128x13, 5126 senones (packed fixture)", None
+    if name == "semi":       # BASELINE.json config 3: semi-continuous, 1 codebook x 4 streams x 256, 5138 senones
+        pm, raw = synth_semi(seed=0, n_density=256, n_sen=5138, return_raw=True)
+        pm.n_ciphone, pm.n_ci_sen = 42, 126
+        pm.sseq = np.arange(126, dtype=np.uint16).reshape(42, 3)
+        pm.phone_ssid, pm.phone_tmat = np.arange(42, dtype=np.int32), np.arange(42, dtype=np.int32) % 10
+        return pm, "synthetic semi-continuous 1x4x256x{12,24,3,12}, 5138 senones (BASELINE.json config 3 shape)", raw
+    if name == "cont":       # BASELINE.json config 4: continuous, 8 Gaussians/senone x 39 dims, 5138 senones
+        pm, raw = synth_ms(seed=0, n_sen=5138, n_density=8, featlens=(39,), topn=4, return_raw=True)
+        pm.n_ciphone, pm.n_ci_sen = 42, 126
+        pm.sseq = np.arange(126, dtype=np.uint16).reshape(42, 3)
+        pm.phone_ssid, pm.phone_tmat = np.arange(42, dtype=np.int32), np.arange(42, dtype=np.int32) % 10
+        return pm, "synthetic continuous ms 5138 senones x 8 Gaussians x 39 dims, topn 4 (BASELINE.json config 4 shape)", raw
     raise SystemExit("unknown --model " + name)
 
 
@@ -58,6 +70,8 @@ def reference_model_dir(name, pm, raw):
     if name == "en-us":
         d = os.path.join(ROOT, "oracle", "_ref", "model", "en-us")
         return d if os.path.isdir(d) else None
+    if pm.kind != "ptm":
+        return None                      # CPU baseline through the C port for the secondary shapes
     if _REF_DIR is None:
         import tempfile
         from pocketsphinx_b200 import s3io
@@ -170,9 +184,21 @@ def cpu_baseline(args, pm, raw, feats, n_frames_per_utt, budget_s=15.0, threads=
                 n_utt, n_frames_per_utt, "compiled reference" if kind == "reference" else "C port", dt)}
 
 
+def host_cores():
+    """Usable host threads: nproc, capped by the cgroup CPU quota when there is one."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(p) + 0.5)))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def run_reference(args, pm, raw, desc, feats, T):
     """--impl reference: the reference algorithm's CPU implementation on all host cores."""
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     steps = []
     base = None
     for i in range(args.warmup + args.steps):
@@ -191,7 +217,7 @@ def run_reference(args, pm, raw, desc, feats, T):
 
 
 def workload_name(args, pm):
-    return "ptm_%dx%dx%d_%dsen_%dutt_x_%ds" % (pm.n_mgau, pm.n_feat, pm.n_density, pm.n_sen, args.utts, args.secs)
+    return "%s_%dx%dx%d_%dsen_%dutt_x_%ds" % (pm.kind, pm.n_mgau, pm.n_feat, pm.n_density, pm.n_sen, args.utts, args.secs)
 
 
 def main():
@@ -200,7 +226,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--model", default="baseline", choices=["baseline", "en-us"])
+    ap.add_argument("--model", default="baseline", choices=["baseline", "en-us", "semi", "cont"])
     ap.add_argument("--utts", type=int, default=1000, help="utterances per GPU per step")
     ap.add_argument("--secs", type=int, default=10, help="seconds of 16 kHz audio per utterance")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
@@ -215,7 +241,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        feats = synth_feats(pm, min(args.utts, max(64, 2 * (os.cpu_count() or 1))), T, seed=1234)
+        feats = synth_feats(pm, min(args.utts, max(64, 2 * host_cores())), T, seed=1234)
         run_reference(args, pm, raw, desc, feats, T)
         return
 
@@ -295,6 +321,7 @@ def main():
         # per frame 4*sumlen feature bytes read + 16*K top-N record bytes written, plus the
         # Gaussians once per launch (DESIGN.md "Kernels").
         K = pm.n_mgau * pm.n_feat
+        # (ms models: the whole GMM stage is bracketed as "topn" by psb_launch_ms_batch)
         gau_bytes = (pm.mean.nbytes + pm.var.nbytes + pm.det.nbytes)
         topn_bytes = total * (4 * pm.sumlen + 16 * K) + gau_bytes
         topn_gbs = topn_bytes / (km["topn"] * 1e-3) / 1e9
@@ -317,7 +344,7 @@ def main():
                        "l2": "per-step working set (%.1f GB of scores) exceeds L2; no explicit flush" % (total * pm.n_sen * 2 / 1e9)},
             "gpu_launches": int(launches),
             "kernel_ms_last_step": {**km, "phoneloop_and_rest": max(0.0, ms_step - gmm_ms)},
-            "roofline": {"bound": "hbm", "kernel": "ptm_topn_kernel", "achieved": topn_gbs, "peak": hbm_peak,
+            "roofline": {"bound": "hbm", "kernel": "ptm_topn_kernel" if pm.kind != "ms" else "ms_dist_kernel+ms_senone_kernel", "achieved": topn_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": topn_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": topn_bytes,
                          "note": "compute-bound by construction (SURVEY 8d): model is SMEM/L2 resident"},
