@@ -345,7 +345,11 @@ def main():
             "gpu_launches": int(launches),
             "kernel_ms_last_step": {**km, "phoneloop_and_rest": max(0.0, ms_step - gmm_ms)},
             "roofline": {"bound": "hbm", "kernel": "ptm_topn_kernel" if pm.kind != "ms" else "ms_dist_kernel+ms_senone_kernel", "achieved": topn_gbs, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": topn_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": topn_gbs / hbm_peak,
+                         # dram__bytes_read+write of ptm_topn_kernel from the committed ncu capture
+                         # (profiles/r01_topn_senone_v1_summary.txt: 351.0 MB for 98 000 frames), scaled to this launch
+                         "traffic": (351.0e6 / 98000.0) * total if pm.kind == "ptm" and pm.n_density == 256 else None,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": topn_bytes,
                          "note": "compute-bound by construction (SURVEY 8d): model is SMEM/L2 resident"},
             "roofline_fp32": {"bound": "fp32 non-FMA issue", "kernel": "ptm_topn_kernel",

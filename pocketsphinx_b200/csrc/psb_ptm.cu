@@ -138,7 +138,7 @@ ptm_topn_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec_of
     }
     __syncthreads();
 
-    const int g = blockIdx.y * TOPN_WARPS + warp;
+    const int g = blockIdx.y * (blockDim.x >> 5) + warp;
     if (g >= n_groups) return;
     const int len = tabs.lane_len[g * 32 + lane];
     const long long off = tabs.lane_off[g * 32 + lane];
@@ -429,8 +429,11 @@ int launch_topn(psb_batch_t *b, const int32_t *d_klist, int n_k, const GroupTabs
     psb_model_t *m = b->m;
     size_t smem = (size_t)m->n_density * rec_floats(FL) * sizeof(float);
     PSB_CUDA(cudaFuncSetAttribute(ptm_topn_kernel<FL, SEMI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(n_k, (n_groups + TOPN_WARPS - 1) / TOPN_WARPS);
-    ptm_topn_kernel<FL, SEMI><<<grid, TOPN_WARPS * 32, smem, b->stream>>>(
+    // few (pair, group) items (semi-continuous models, small batches): one warp per CTA spreads
+    // them over more SMs; otherwise 4 warps share one staged codebook
+    const int warps = (long long)n_k * ((n_groups + TOPN_WARPS - 1) / TOPN_WARPS) >= 4 * 148 ? TOPN_WARPS : 1;
+    dim3 grid(n_k, (n_groups + warps - 1) / warps);
+    ptm_topn_kernel<FL, SEMI><<<grid, warps * 32, smem, b->stream>>>(
         m->d_rec, m->d_rec_off, d_klist, b->d_featT, tabs, b->d_topn, n_groups, m->n_density,
         m->n_feat, m->sumlen, d_featoff, m->K, m->ds_ratio, m->d_topn_beam);
     PSB_LAUNCH_CHECK();
