@@ -2,6 +2,7 @@
 #include "psb_internal.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -81,6 +82,38 @@ static int build_records(psb_model_t *m, const float *mean, const float *var, co
         PSB_CUDA(cudaMemcpy(m->d_rec_off, m->rec_off.data(), m->K * sizeof(size_t), cudaMemcpyHostToDevice));
     }
     PSB_CUDA(cudaMemcpy(m->d_rec, rec.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+    if (m->kind != PSB_KIND_MS && m->n_density % 2 == 0) {
+        // pair-interleaved, negated copy for ptm_topn2_kernel: per (cb, f) nd/2 pair records
+        // {detA, detB, -muA_0, -muB_0, -vA_0, -vB_0, ...} padded to a multiple of 4 floats
+        size_t total2 = 0;
+        std::vector<size_t> off2(m->K);
+        for (int cb = 0; cb < m->n_mgau; ++cb)
+            for (int f = 0; f < m->n_feat; ++f) {
+                off2[cb * m->n_feat + f] = total2;
+                total2 += (size_t)(m->n_density / 2) * roundup(2 + 4 * m->featlen[f], 4);
+            }
+        std::vector<float> rec2(total2, 0.f);
+        for (int cb = 0; cb < m->n_mgau; ++cb)
+            for (int f = 0; f < m->n_feat; ++f) {
+                const int fl = m->featlen[f], rf2 = roundup(2 + 4 * fl, 4);
+                const size_t src = ((size_t)cb * m->sumlen + m->featoff[f]) * m->n_density;
+                float *r = rec2.data() + off2[cb * m->n_feat + f];
+                for (int c = 0; c < m->n_density; ++c) {
+                    float *rp = r + (size_t)(c >> 1) * rf2 + (c & 1);
+                    rp[0] = hd[((size_t)cb * m->n_feat + f) * m->n_density + c];
+                    for (int j = 0; j < fl; ++j) {
+                        rp[2 + 4 * j] = -hm[src + (size_t)c * fl + j];
+                        rp[4 + 4 * j] = -hv[src + (size_t)c * fl + j];
+                    }
+                }
+            }
+        if (!m->d_rec2) {
+            PSB_CUDA(cudaMalloc(&m->d_rec2, total2 * sizeof(float)));
+            PSB_CUDA(cudaMalloc(&m->d_rec2_off, m->K * sizeof(size_t)));
+            PSB_CUDA(cudaMemcpy(m->d_rec2_off, off2.data(), m->K * sizeof(size_t), cudaMemcpyHostToDevice));
+        }
+        PSB_CUDA(cudaMemcpy(m->d_rec2, rec2.data(), total2 * sizeof(float), cudaMemcpyHostToDevice));
+    }
     if (m->kind == PSB_KIND_MS) {
         // codebook-minor copy for ms_dist_kernel: per stream f (at float offset featoff[f]*nd*2*n_mgau)
         // [(d*fl + j)*2 + {mean,var}][cb]; determinants [f][d][cb]
@@ -133,7 +166,7 @@ extern "C" int psb_model_create(const psb_model_desc_t *d, int device, psb_model
     m->mixw_4bit = d->mixw_cb != nullptr;
     m->logadd_ms_size = d->logadd_ms_size;
     m->logadd_ms_zero = d->logadd_ms_zero;
-    m->d_rec = nullptr; m->d_rec_off = nullptr; m->d_mixw = nullptr; m->d_mixw_cb = nullptr;
+    m->d_rec = nullptr; m->d_rec_off = nullptr; m->d_rec2 = nullptr; m->d_rec2_off = nullptr; m->d_mixw = nullptr; m->d_mixw_cb = nullptr;
     m->d_sen2cb = nullptr; m->d_sen2cb32 = nullptr; m->d_logadd8 = nullptr; m->d_logadd_ms = nullptr;
     m->has_topn_beam = false;
     m->d_topn_beam = nullptr;
@@ -228,7 +261,7 @@ extern "C" void psb_model_free(psb_model_t *m)
 {
     if (!m) return;
     cudaSetDevice(m->device);
-    cudaFree(m->d_rec); cudaFree(m->d_rec_off); cudaFree(m->d_mixw); cudaFree(m->d_mixw_cb);
+    cudaFree(m->d_rec); cudaFree(m->d_rec_off); cudaFree(m->d_rec2); cudaFree(m->d_rec2_off); cudaFree(m->d_mixw); cudaFree(m->d_mixw_cb);
     cudaFree(m->d_sen2cb); cudaFree(m->d_sen2cb32); cudaFree(m->d_logadd8); cudaFree(m->d_logadd_ms);
     cudaFree(m->d_topn_beam); cudaFree(m->d_msT); cudaFree(m->d_msdetT); cudaFree(m->d_featlen); cudaFree(m->d_featoff);
     delete m;
@@ -257,6 +290,10 @@ extern "C" int psb_batch_create(psb_model_t *m, int32_t max_utts, int64_t max_fr
     b->m = m;
     b->max_utts = max_utts;
     b->max_frames = max_frames;
+    {
+        const char *v = getenv("PSB_TOPN_VARIANT");     // tuning knob; default = packed FP32, 2 warps/CTA
+        b->topn_variant = v ? atoi(v) : 1;
+    }
     cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_feats, (size_t)max_frames * m->sumlen * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_senscr, (size_t)max_frames * m->n_sen * sizeof(int16_t));

@@ -68,6 +68,8 @@ struct psb_model_s {
     float *d_rec;                 // records; (cb, f) block at rec_off[cb * n_feat + f]
     std::vector<size_t> rec_off;  // float offsets, host copy
     size_t *d_rec_off;
+    float *d_rec2;                // pair-interleaved, negated records for the packed-FP32 kernels
+    size_t *d_rec2_off;
     uint8_t *d_mixw;              // [n_feat][n_density][mixw_stride] (ptm/semi) or raw pdf (ms)
     uint8_t *d_mixw_cb;           // 16 bytes or null
     uint16_t *d_sen2cb;           // [n_sen] (ptm)
@@ -102,6 +104,7 @@ struct psb_batch_s {
     cudaEvent_t tev[2];           // user stopwatch (psb_batch_event_record)
     bool have_ev;
     long long last_frames;
+    int topn_variant;             // 0 scalar kernel, 1/2 packed-FP32 kernels (PSB_TOPN_VARIANT)
     // phone-loop outputs for psb_decode_batch_host
     int32_t *d_best, *d_pen;
     int32_t *h_best, *h_pen;

@@ -264,6 +264,178 @@ ptm_topn_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec_of
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Packed-FP32 variant (Blackwell FADD2/FMUL2, PTX add/mul.rn.f32x2): two *codewords* per
+// instruction.  Records are stored pair-interleaved with NEGATED means and variance terms,
+//   {detA, detB, -muA_0, -muB_0, -vA_0, -vB_0, -muA_1, ...}            (psb_api.cu build_records)
+// so that the reference's sub / mul / mul / sub chain becomes add / mul / mul / add on float2:
+//   x - mu == x + (-mu),  (sq * v) negated == sq * (-v),  d - c == d + (-c)   -- all exact in IEEE,
+// and __fadd2_rn/__fmul2_rn round each half exactly like __fadd_rn/__fmul_rn (sm_100_rt.h).
+// Halves the FP instruction count of the issue-bound scan (52 -> 26 per codeword).
+template <int FL, bool PEN = false>
+__device__ __forceinline__ float2 gau_dist2(const float4 *__restrict__ r, const float2 (&xx)[FL], float2 *dpen = nullptr)
+{
+    constexpr int RECF2 = (2 + 4 * FL + 3) / 4 * 4;
+    float2 rr[RECF2 / 2];
+#pragma unroll
+    for (int q = 0; q < RECF2 / 4; ++q) {
+        const float4 v = r[q];
+        rr[2 * q] = make_float2(v.x, v.y);
+        rr[2 * q + 1] = make_float2(v.z, v.w);
+    }
+    float2 d = rr[0];
+#pragma unroll
+    for (int j = 0; j < FL; ++j) {
+        float2 t = __fadd2_rn(xx[j], rr[1 + 2 * j]);
+        t = __fmul2_rn(t, t);
+        t = __fmul2_rn(t, rr[2 + 2 * j]);
+        if (PEN && j == FL - 1) *dpen = d;
+        d = __fadd2_rn(d, t);
+    }
+    return d;
+}
+
+template <int FL, bool SEMI, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+ptm_topn2_kernel(const float *__restrict__ rec2, const size_t *__restrict__ rec2_off,
+                 const int32_t *__restrict__ klist, const float *__restrict__ featT, GroupTabs tabs,
+                 int4 *__restrict__ out, int n_groups, int nd, int n_feat, int D,
+                 const int32_t *__restrict__ featoff, int K, int ds_ratio, const int32_t *__restrict__ topn_beam)
+{
+    constexpr int RECF2 = (2 + 4 * FL + 3) / 4 * 4;
+    constexpr int RECQ2 = RECF2 / 4;
+    extern __shared__ float4 srec[];          // [nd/2][RECQ2] pair records
+    const int k = klist[blockIdx.x];
+    const int f = k % n_feat;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(rec2 + rec2_off[k]);
+        for (int i = threadIdx.x; i < (nd >> 1) * RECQ2; i += blockDim.x)
+            srec[i] = src[i];
+    }
+    __syncthreads();
+    const int g = blockIdx.y * WARPS + warp;
+    if (g >= n_groups) return;
+    const int len = tabs.lane_len[g * 32 + lane];
+    const long long off = tabs.lane_off[g * 32 + lane];
+    const int maxT = tabs.grp_maxT[g];
+    const float *xT = featT + tabs.grp_base[g] + (long long)featoff[f] * 32 + lane;
+
+    int cw[TOPN], sc[TOPN];
+#pragma unroll
+    for (int i = 0; i < TOPN; ++i) { cw[i] = i; sc[i] = INT_MIN; }
+    float xn[FL];
+#pragma unroll
+    for (int j = 0; j < FL; ++j) xn[j] = maxT > 0 ? xT[j * 32] : 0.f;
+
+    for (int t = 0; t < maxT; ++t) {
+        float2 xx[FL];
+#pragma unroll
+        for (int j = 0; j < FL; ++j) xx[j] = make_float2(xn[j], xn[j]);
+        if (t + 1 < maxT) {
+            const float *nx = xT + (long long)(t + 1) * D * 32;
+#pragma unroll
+            for (int j = 0; j < FL; ++j) xn[j] = nx[j * 32];
+        }
+        if (t >= len) continue;
+
+        // ---- eval_topn: re-score the listed codewords (each through its pair record) ----
+        unsigned seedpack = 0u, seedbit = 0u;
+        {
+            int ncw[TOPN], nsc[TOPN];
+#pragma unroll
+            for (int i = 0; i < TOPN; ++i) {
+                const int c = cw[i];
+                const float2 d2 = gau_dist2<FL>(srec + (c >> 1) * RECQ2, xx);
+                const int s = f2i_clamped((c & 1) ? d2.y : d2.x);
+                seedpack |= (unsigned)c << (8 * i);
+                seedbit |= (1u << (c & 7)) << (8 * i);
+                int p = 0;
+#pragma unroll
+                for (int j = 0; j < i; ++j) p += (s > nsc[j]) ? 0 : 1;
+#pragma unroll
+                for (int j = TOPN - 2; j >= 0; --j)
+                    if (j < i && j >= p) { nsc[j + 1] = nsc[j]; ncw[j + 1] = ncw[j]; }
+#pragma unroll
+                for (int j = 0; j < TOPN; ++j)
+                    if (j == p) { nsc[j] = s; ncw[j] = c; }
+            }
+#pragma unroll
+            for (int i = 0; i < TOPN; ++i) { cw[i] = ncw[i]; sc[i] = nsc[i]; }
+        }
+
+        // ---- eval_cb: scan in codeword order, two codewords per packed distance ----
+        if (t % ds_ratio == 0) {
+            float thresh = (float)sc[TOPN - 1];
+            const unsigned seedchunk = (seedpack >> 3) & 0x1f1f1f1fu;
+            for (int ch = 0; ch < nd / 8; ++ch) {
+                const float4 *rq = srec + (size_t)ch * 4 * RECQ2;
+                unsigned m8;
+                {
+                    const unsigned tt = seedchunk ^ ((unsigned)ch * 0x01010101u);
+                    const unsigned nz = (((tt & 0x7f7f7f7fu) + 0x7f7f7f7fu) | tt) & 0x80808080u;
+                    const unsigned hitb = ((nz ^ 0x80808080u) >> 7) * 0xffu;
+                    const unsigned b = seedbit & hitb;
+                    m8 = (b | (b >> 8) | (b >> 16) | (b >> 24)) & 0xffu;
+                }
+#pragma unroll
+                for (int pp = 0; pp < 4; ++pp) {
+                    float2 dpen2;
+                    const float2 d2 = gau_dist2<FL, SEMI>(rq + pp * RECQ2, xx, &dpen2);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int cc = 2 * pp + h;
+                        const float d = h ? d2.y : d2.x;
+                        bool hit;
+                        if (SEMI) hit = (h ? dpen2.y : dpen2.x) >= thresh && f2i_clamped(d) >= sc[TOPN - 1];
+                        else hit = d >= thresh;
+                        if (hit && !(m8 & (1u << cc))) {
+                            const int c = ch * 8 + cc;
+                            const int s = f2i_clamped(d);
+                            const int ev = cw[TOPN - 1];
+                            int p = 0;
+#pragma unroll
+                            for (int j = 0; j < TOPN - 1; ++j) p += (s >= sc[j]) ? 0 : 1;
+#pragma unroll
+                            for (int j = TOPN - 2; j >= 0; --j)
+                                if (j >= p) { sc[j + 1] = sc[j]; cw[j + 1] = cw[j]; }
+#pragma unroll
+                            for (int j = 0; j < TOPN; ++j)
+                                if (j == p) { sc[j] = s; cw[j] = c; }
+                            {
+                                const unsigned t2 = seedpack ^ ((unsigned)ev * 0x01010101u);
+                                const unsigned nz2 = (((t2 & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t2) & 0x80808080u;
+                                seedbit &= (nz2 >> 7) * 0xffu;
+                                if ((ev >> 3) == ch) m8 &= ~(1u << (ev & 7));
+                            }
+                            thresh = (float)sc[TOPN - 1];
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- emit the record (same format as ptm_topn_kernel) ----
+        const int top = sc[0] >> PSB_SENSCR_SHIFT;
+        unsigned cwb = 0, eb = 0;
+        int n_in_beam = TOPN;
+#pragma unroll
+        for (int j = 0; j < TOPN; ++j) {
+            int e = top - (sc[j] >> PSB_SENSCR_SHIFT);
+            if (SEMI) {
+                e = e > PSB_MAX_NEG_ASCR ? PSB_MAX_NEG_ASCR : e;
+                const int beam = topn_beam[f];
+                if (beam && e > beam && n_in_beam == TOPN) n_in_beam = j;
+            }
+            else
+                e = e > 255 ? 255 : e;
+            cwb |= (unsigned)cw[j] << (8 * j);
+            eb |= (unsigned)e << (8 * j);
+        }
+        out[(off + t) * K + k] = make_int4(SEMI ? n_in_beam : top, (int)cwb, (int)eb, 0);
+    }
+}
+
 // fast_logmath_add (tied_mgau_common.h:111-127) on negated logs
 __device__ __forceinline__ int logadd8(const uint8_t *tab, int x, int y)
 {
@@ -422,11 +594,34 @@ semi_senone_kernel(const int4 *__restrict__ topn, const uint8_t *__restrict__ mi
     senscr[frame * n_sen + s] = acc;
 }
 
+template <int FL, bool SEMI, int WARPS, int MINB>
+int launch_topn2(psb_batch_t *b, const int32_t *d_klist, int n_k, const GroupTabs &tabs, int n_groups,
+                 const int32_t *d_featoff)
+{
+    psb_model_t *m = b->m;
+    constexpr int RECF2 = (2 + 4 * FL + 3) / 4 * 4;
+    size_t smem = (size_t)(m->n_density / 2) * RECF2 * sizeof(float);
+    auto kern = ptm_topn2_kernel<FL, SEMI, WARPS, MINB>;
+    PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(n_k, (n_groups + WARPS - 1) / WARPS);
+    kern<<<grid, WARPS * 32, smem, b->stream>>>(m->d_rec2, m->d_rec2_off, d_klist, b->d_featT, tabs, b->d_topn, n_groups,
+                                               m->n_density, m->n_feat, m->sumlen, d_featoff, m->K, m->ds_ratio,
+                                               m->d_topn_beam);
+    PSB_LAUNCH_CHECK();
+    return PSB_OK;
+}
+
 template <int FL, bool SEMI>
 int launch_topn(psb_batch_t *b, const int32_t *d_klist, int n_k, const GroupTabs &tabs, int n_groups,
                 const int32_t *d_featoff)
 {
     psb_model_t *m = b->m;
+    if (FL <= 16 && m->d_rec2 && b->topn_variant != 0) {
+        // packed-FP32 kernels (FL <= 16 keeps the register budget): variant 1 = 2 warps/CTA with a
+        // large register budget (two balanced waves), variant 2 = 4 warps/CTA at 72 registers
+        if (b->topn_variant == 2) return launch_topn2<FL <= 16 ? FL : 1, SEMI, 4, 7>(b, d_klist, n_k, tabs, n_groups, d_featoff);
+        return launch_topn2<FL <= 16 ? FL : 1, SEMI, 2, 7>(b, d_klist, n_k, tabs, n_groups, d_featoff);
+    }
     size_t smem = (size_t)m->n_density * rec_floats(FL) * sizeof(float);
     PSB_CUDA(cudaFuncSetAttribute(ptm_topn_kernel<FL, SEMI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // few (pair, group) items (semi-continuous models, small batches): one warp per CTA spreads
