@@ -271,7 +271,10 @@ ptm_topn_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec_of
 // so that the reference's sub / mul / mul / sub chain becomes add / mul / mul / add on float2:
 //   x - mu == x + (-mu),  (sq * v) negated == sq * (-v),  d - c == d + (-c)   -- all exact in IEEE,
 // and __fadd2_rn/__fmul2_rn round each half exactly like __fadd_rn/__fmul_rn (sm_100_rt.h).
-// Halves the FP instruction count of the issue-bound scan (52 -> 26 per codeword).
+// The final accumulation stays SCALAR on purpose: ptxas (12.9) contracts mul.rn.f32x2 followed by
+// add.rn.f32x2 into FFMA2 even with explicit .rn and -fmad=false, which would skip the separate
+// rounding of the product; scalar add.rn.f32 is never contracted.  FP issue slots per codeword:
+// 52 scalar -> 32.5 (FADD2 + 2 FMUL2 per pair of codewords and dimension, plus one FADD each).
 template <int FL, bool PEN = false>
 __device__ __forceinline__ float2 gau_dist2(const float4 *__restrict__ r, const float2 (&xx)[FL], float2 *dpen = nullptr)
 {
@@ -290,7 +293,8 @@ __device__ __forceinline__ float2 gau_dist2(const float4 *__restrict__ r, const 
         t = __fmul2_rn(t, t);
         t = __fmul2_rn(t, rr[2 + 2 * j]);
         if (PEN && j == FL - 1) *dpen = d;
-        d = __fadd2_rn(d, t);
+        d.x = __fadd_rn(d.x, t.x);
+        d.y = __fadd_rn(d.y, t.y);
     }
     return d;
 }

@@ -35,3 +35,26 @@ def test_no_cpu_fallback_without_gpu():
         pytest.skip("a GPU is present")
     with pytest.raises(api.PsbError):
         api.Model(synth_ptm(n_density=32, n_sen=200))
+
+
+def test_no_fused_multiply_add_in_distance_kernels():
+    """The Gaussian exponent must round the product and the subtraction separately
+    (ptm_mgau.c:64-69).  ptxas contracts mul+add pairs -- including packed mul.rn.f32x2 /
+    add.rn.f32x2 even with explicit .rn -- so the build is checked: no FFMA / FFMA2 / HFMA-free
+    distance kernels only (a contracted FMA would silently break bit-exactness)."""
+    import shutil
+    import subprocess
+    import pytest
+    from pocketsphinx_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    fn, bad = None, []
+    for line in sass.splitlines():
+        if "Function :" in line:
+            fn = line.split("Function :")[1].strip()
+        elif fn and any(k in fn for k in ("topn", "ms_dist")) and "FFMA" in line:
+            bad.append((fn[:60], line.strip()[:80]))
+    assert not bad, bad[:5]
+    assert "FMUL2" in sass and "FADD2" in sass, "packed FP32 path missing from the build"
