@@ -213,6 +213,16 @@ int psb_decode_batch_host(psb_batch_t *b, psb_phoneloop_t *p, const float *feats
 int psb_decode_batch_device(psb_batch_t *b, psb_phoneloop_t *p, const float *d_feats,
                             const int32_t *utt_off, int32_t n_utt, int32_t **d_best, int32_t **d_pen);
 
+/* ------------------------------------------------------------------------------------ */
+/* Senone-dump wire format (acmod_write_senfh_header / acmod_write_scores / acmod_read_scores,
+ * acmod.c:335-346, 880-1017): lets GPU-computed scores drive the unmodified reference search
+ * through ps_decode_senscr (pocketsphinx.c:1200) or `pocketsphinx_batch -senin yes`.  Host only.
+ * write: all-senone frames.  read: returns frames read (<= max_frames) or <0; frames with partial
+ * lists are expanded with SENSCR_DUMMY (0x7fff) like acmod_read_scores_internal. */
+int psb_sendump_write(const char *path, const char *mdef_file, int32_t n_sen, double logbase,
+                      const int16_t *senscr, int64_t n_frames);
+int64_t psb_sendump_read(const char *path, int32_t *n_sen_out, int16_t *senscr, int64_t max_frames);
+
 /* number of kernels launched by this library in the calling process so far */
 int64_t psb_kernel_launch_count(void);
 

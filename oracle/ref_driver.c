@@ -685,3 +685,73 @@ refdrv_decode(const char *hmmdir, const char *lm, const char *dict, const char *
     ps_config_free(config);
     return nfr;
 }
+
+
+/* ------------------------------------------------------------------------------------- */
+/* Senone-dump interoperability: decode from a .sen file (ps_decode_senscr), and have the
+ * reference itself write one (acmod_set_senfh) while decoding PCM with -compallsen yes.    */
+int
+refdrv_decode_senscr(const char *hmmdir, const char *lm, const char *dict, const char *kv, const char *senfile,
+                     const int16 *pcm, long n_samples, const char *senout,
+                     char *hyp, int hyp_cap, char *seg, int seg_cap, int32 *stats)
+{
+    ps_config_t *config;
+    ps_decoder_t *ps;
+    const char *h;
+    int32 score = 0;
+    ps_seg_t *it;
+    FILE *fh = NULL;
+    int n = 0, nfr;
+
+    err_set_loglevel(ERR_ERROR);
+    config = ps_config_init(NULL);
+    ps_config_set_str(config, "hmm", hmmdir);
+    ps_config_set_str(config, "lm", lm);
+    ps_config_set_str(config, "dict", dict);
+    ps_config_set_str(config, "dither", "no");
+    ps_config_set_bool(config, "compallsen", TRUE);
+    if (kv) {
+        char *buf = strdup(kv), *save = NULL, *tok;
+        for (tok = strtok_r(buf, "\n", &save); tok; tok = strtok_r(NULL, "\n", &save)) {
+            char *eq = strchr(tok, '=');
+            if (!eq) continue;
+            *eq = 0;
+            ps_config_set_str(config, tok, eq + 1);
+        }
+        free(buf);
+    }
+    ps = ps_init(config);
+    if (ps == NULL) { ps_config_free(config); return -1; }
+    if (senfile) {
+        fh = fopen(senfile, "rb");
+        if (fh == NULL) { ps_free(ps); ps_config_free(config); return -3; }
+        nfr = ps_decode_senscr(ps, fh);
+        fclose(fh);
+    }
+    else {
+        if (senout) {
+            fh = fopen(senout, "wb");
+            acmod_set_senfh(ps->acmod, fh);
+        }
+        ps_start_utt(ps);
+        ps_process_raw(ps, pcm, n_samples, FALSE, TRUE);
+        ps_end_utt(ps);
+        nfr = ps_get_n_frames(ps);
+        /* acmod_end_utt closed the dump file (acmod.c:460-463) */
+    }
+    h = ps_get_hyp(ps, &score);
+    snprintf(hyp, hyp_cap, "%s", h ? h : "");
+    seg[0] = 0;
+    for (it = ps_seg_iter(ps); it; it = ps_seg_next(it)) {
+        int sf, ef;
+        int32 ascr, lscr, lback;
+        ps_seg_frames(it, &sf, &ef);
+        ps_seg_prob(it, &ascr, &lscr, &lback);
+        n += snprintf(seg + n, n < seg_cap ? seg_cap - n : 0, "%s %d %d %d %d\n", ps_seg_word(it), sf, ef, ascr, lscr);
+        if (n >= seg_cap) break;
+    }
+    if (stats) { stats[0] = score; stats[1] = 0; stats[2] = bin_mdef_n_sen(ps->acmod->mdef); }
+    ps_free(ps);
+    ps_config_free(config);
+    return nfr;
+}

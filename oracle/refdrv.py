@@ -66,6 +66,8 @@ def lib():
         L.refdrv_phoneloop_params.argtypes = [C.c_void_p, C.c_void_p]
         L.refdrv_decode.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_long, C.c_int,
                                     C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_void_p]
+        L.refdrv_decode_senscr.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p,
+                                           C.c_long, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_void_p]
         assert L.refdrv_sizeof_hmm() == HMM_DTYPE.itemsize
         _lib = L
     return _lib
@@ -228,3 +230,20 @@ def decode(hmmdir, lm, dic, pcm, use_cuda=False, libpath=None, **kv):
         raise RuntimeError("refdrv_decode failed (%d)" % n)
     return dict(n_frames=n, hyp=hyp.value.decode(), seg=seg.value.decode(), score=int(stats[0]),
                 cuda_calls=int(stats[1]), n_sen=int(stats[2]))
+
+
+def decode_senscr(hmmdir, lm, dic, senfile=None, pcm=None, senout=None, **kv):
+    """-compallsen yes decode: from a senone dump (ps_decode_senscr) when senfile is given, else
+    from PCM (optionally writing the reference's own dump to senout)."""
+    s = "\n".join("%s=%s" % (k, v) for k, v in kv.items()).encode() or None
+    hyp = C.create_string_buffer(4096)
+    seg = C.create_string_buffer(65536)
+    stats = np.zeros(4, np.int32)
+    if pcm is not None:
+        pcm = np.ascontiguousarray(pcm, np.int16)
+    n = lib().refdrv_decode_senscr(hmmdir.encode(), lm.encode(), dic.encode(), s,
+                                   senfile.encode() if senfile else None, _p(pcm), 0 if pcm is None else len(pcm),
+                                   senout.encode() if senout else None, hyp, 4096, seg, 65536, _p(stats))
+    if n < 0:
+        raise RuntimeError("refdrv_decode_senscr failed (%d)" % n)
+    return dict(n_frames=n, hyp=hyp.value.decode(), seg=seg.value.decode(), score=int(stats[0]))

@@ -62,6 +62,8 @@ SYMBOLS = [
     ("psb_phoneloop_run_host", C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP]),
     ("psb_decode_batch_host", C.c_int, [_VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP]),
     ("psb_decode_batch_device", C.c_int, [_VP, _VP, _VP, _VP, _I32, _VP, _VP]),
+    ("psb_sendump_write", C.c_int, [C.c_char_p, C.c_char_p, _I32, C.c_double, _VP, _I64]),
+    ("psb_sendump_read", _I64, [C.c_char_p, _VP, _VP, _I64]),
     ("psb_kernel_launch_count", _I64, []),
 ]
 

@@ -283,3 +283,23 @@ class PhoneLoop:
         if self.h:
             lib().psb_phoneloop_free(self.h)
             self.h = None
+
+
+def sendump_write(path, senscr, mdef_file="(none)", logbase=1.0001):
+    """Write [T][n_sen] int16 scores as a reference senone dump (.sen)."""
+    senscr = np.ascontiguousarray(senscr, np.int16)
+    check(lib().psb_sendump_write(path.encode(), mdef_file.encode(), senscr.shape[1], float(logbase), _p(senscr),
+                                  senscr.shape[0]), "psb_sendump_write")
+
+
+def sendump_read(path, max_frames=1 << 20):
+    n_sen = C.c_int32()
+    n = lib().psb_sendump_read(path.encode(), C.byref(n_sen), None, 0)
+    if n < 0:
+        raise PsbError("psb_sendump_read failed: " + lib().psb_last_error().decode())
+    size = (__import__("os").path.getsize(path) // (2 * n_sen.value)) + 1
+    out = np.zeros((min(size, max_frames), n_sen.value), np.int16)
+    n = lib().psb_sendump_read(path.encode(), C.byref(n_sen), _p(out), out.shape[0])
+    if n < 0:
+        raise PsbError("psb_sendump_read failed: " + lib().psb_last_error().decode())
+    return out[:n]

@@ -291,8 +291,8 @@ extern "C" int psb_batch_create(psb_model_t *m, int32_t max_utts, int64_t max_fr
     b->max_utts = max_utts;
     b->max_frames = max_frames;
     {
-        const char *v = getenv("PSB_TOPN_VARIANT");     // tuning knob; default = packed FP32, 2 warps/CTA
-        b->topn_variant = v ? atoi(v) : 1;
+        const char *v = getenv("PSB_TOPN_VARIANT");     // tuning knob; default = packed FP32, 4 warps/CTA
+        b->topn_variant = v ? atoi(v) : 2;
     }
     cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_feats, (size_t)max_frames * m->sumlen * sizeof(float));

@@ -443,9 +443,7 @@ ptm_topn2_kernel(const float *__restrict__ rec2, const size_t *__restrict__ rec2
 // fast_logmath_add (tied_mgau_common.h:111-127) on negated logs
 __device__ __forceinline__ int logadd8(const uint8_t *tab, int x, int y)
 {
-    const int d = x - y;
-    const int r = d > 0 ? y : x;
-    return r - tab[d > 0 ? d : -d];
+    return min(x, y) - tab[abs(x - y)];
 }
 
 template <bool FOURBIT>
@@ -499,11 +497,11 @@ ptm_senone_kernel(const int4 *__restrict__ topn, const uint8_t *__restrict__ mix
     int best = 0x7fffffff;
     for (int s = tid; s < n_sen; s += blockDim.x) {
         const int i0 = (int)sen2cb[s] * n_feat;
-        const unsigned so = FOURBIT ? (unsigned)(s >> 1) : (unsigned)s;
+        const uint8_t *__restrict__ mw = mixw + (FOURBIT ? (s >> 1) : s);     // column of this senone
         int ascore = 0;
         for (int f = 0; f < n_feat; ++f) {
             const uint4 ro = rowoff[i0 + f], nv = nsc[i0 + f];
-            int w0 = mixw[ro.x + so], w1 = mixw[ro.y + so], w2 = mixw[ro.z + so], w3 = mixw[ro.w + so];
+            int w0 = mw[ro.x], w1 = mw[ro.y], w2 = mw[ro.z], w3 = mw[ro.w];
             if (FOURBIT) {                                     // sic: low bit of the byte (ptm_mgau.c:376-377)
                 w0 = cb16[(w0 & 1) ? w0 >> 4 : w0 & 0x0f];
                 w1 = cb16[(w1 & 1) ? w1 >> 4 : w1 & 0x0f];
