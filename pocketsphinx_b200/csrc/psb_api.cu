@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 std::atomic<long long> g_psb_launches{0};
@@ -285,14 +286,17 @@ extern "C" int psb_batch_create(psb_model_t *m, int32_t max_utts, int64_t max_fr
 {
     PSB_REQUIRE(m && out && max_utts > 0 && max_frames > 0, "psb_batch_create: bad argument");
     PSB_CUDA(cudaSetDevice(m->device));
-    psb_batch_t *b = new psb_batch_t();
-    memset(b, 0, sizeof(*b));
+    psb_batch_t *b = new psb_batch_t();      // value-initialised: all pointers null, counters zero
     b->m = m;
     b->max_utts = max_utts;
     b->max_frames = max_frames;
     {
         const char *v = getenv("PSB_TOPN_VARIANT");     // tuning knob; default = packed FP32, 4 warps/CTA
         b->topn_variant = v ? atoi(v) : 2;
+        const char *p = getenv("PSB_PIPELINE");         // sub-batches in flight for psb_decode_batch_*
+        b->n_pipe = p ? atoi(p) : 3;
+        if (b->n_pipe < 1) b->n_pipe = 1;
+        if (b->n_pipe > 8) b->n_pipe = 8;
     }
     cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_feats, (size_t)max_frames * m->sumlen * sizeof(float));
@@ -300,6 +304,8 @@ extern "C" int psb_batch_create(psb_model_t *m, int32_t max_utts, int64_t max_fr
     if (e == cudaSuccess && m->kind != PSB_KIND_MS) e = cudaMalloc(&b->d_topn, (size_t)max_frames * m->K * sizeof(int4));
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&b->ev[i]);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&b->tev[i]);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->fork_ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->join_ev, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         psb_set_error("psb_batch_create: %s", cudaGetErrorString(e));
         psb_batch_free(b);
@@ -315,6 +321,18 @@ extern "C" void psb_batch_free(psb_batch_t *b)
     if (!b) return;
     cudaSetDevice(b->m->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
+    for (psb_batch_t *k : b->kids) {            // sub-batches own only their stream, tables, featT, events
+        cudaStreamSynchronize(k->stream);
+        if (k->h_off) cudaFreeHost(k->h_off);
+        cudaFree(k->d_featT); cudaFree(k->d_tab); cudaFree(k->d_off); cudaFree(k->d_msdist); cudaFree(k->d_msbest);
+        if (k->h_tab) cudaFreeHost(k->h_tab);
+        for (int i = 0; i < 4; ++i) cudaEventDestroy(k->ev[i]);
+        cudaEventDestroy(k->join_ev);
+        cudaStreamDestroy(k->stream);
+        delete k;
+    }
+    if (b->fork_ev) cudaEventDestroy(b->fork_ev);
+    if (b->join_ev) cudaEventDestroy(b->join_ev);
     cudaFree(b->d_feats); cudaFree(b->d_senscr); cudaFree(b->d_featT); cudaFree(b->d_topn); cudaFree(b->d_tab);
     cudaFree(b->d_best); cudaFree(b->d_pen); cudaFree(b->d_off); cudaFree(b->d_msdist); cudaFree(b->d_msbest);
     if (b->h_tab) cudaFreeHost(b->h_tab);
@@ -361,6 +379,7 @@ extern "C" int psb_batch_score_device(psb_batch_t *b, const float *d_feats, cons
     if (rc) return rc;
     PSB_REQUIRE(utt_off[n_utt] == 0 || d_feats, "psb_batch_score_device: null buffer");
     PSB_CUDA(cudaSetDevice(b->m->device));
+    b->last_pipelined = false;
     return score_dispatch(b, d_feats, utt_off, n_utt, d_senscr ? d_senscr : b->d_senscr);
 }
 
@@ -374,6 +393,7 @@ extern "C" int psb_batch_score_host(psb_batch_t *b, const float *feats, const in
     PSB_CUDA(cudaSetDevice(b->m->device));
     const size_t total = utt_off[n_utt];
     if (total == 0) return PSB_OK;
+    b->last_pipelined = false;
     PSB_CUDA(cudaMemcpyAsync(b->d_feats, feats, total * b->m->sumlen * sizeof(float), cudaMemcpyHostToDevice, b->stream));
     rc = score_dispatch(b, b->d_feats, utt_off, n_utt, b->d_senscr);
     if (rc) return rc;
@@ -397,6 +417,17 @@ extern "C" int psb_batch_last_kernel_ms(psb_batch_t *b, float *out3)
     PSB_REQUIRE(b && out3, "psb_batch_last_kernel_ms: null");
     PSB_CUDA(cudaSetDevice(b->m->device));
     PSB_CUDA(cudaStreamSynchronize(b->stream));
+    out3[0] = out3[1] = out3[2] = 0.f;
+    if (b->last_pipelined) {
+        // pipelined decode: sum of the sub-batches' own kernel intervals (they overlap in time)
+        for (psb_batch_t *k : b->kids)
+            for (int i = 0; i < 3; ++i) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, k->ev[i], k->ev[i + 1]) == cudaSuccess) out3[i] += ms;
+                else cudaGetLastError();
+            }
+        return PSB_OK;
+    }
     for (int i = 0; i < 3; ++i) PSB_CUDA(cudaEventElapsedTime(&out3[i], b->ev[i], b->ev[i + 1]));
     return PSB_OK;
 }
@@ -412,16 +443,42 @@ extern "C" int psb_batch_get_topn(psb_batch_t *b, int32_t *rec, int64_t n_frames
 
 cudaStream_t psb_batch_stream(psb_batch_t *b) { return b->stream; }
 
-// Shared by the host and device decode entry points: scores + phone loop on the batch stream.
-static int decode_common(psb_batch_t *b, psb_phoneloop_t *p, const float *d_feats, const int32_t *utt_off,
-                         int32_t n_utt, bool want_best, bool want_pen)
+// One sub-batch of the pipelined decode: a light psb_batch_t with its own stream, tables and
+// lane-major feature copy, pointing into the parent's big buffers.
+static int get_kid(psb_batch_t *b, int i, psb_batch_t **out)
 {
-    const size_t H = psb_phoneloop_n_phones(p);
-    if ((size_t)n_utt + 1 > b->off_cap) {
-        cudaFree(b->d_off);
-        b->off_cap = (size_t)n_utt + 1 + 1024;
-        PSB_CUDA(cudaMalloc(&b->d_off, b->off_cap * 4));
+    while ((int)b->kids.size() <= i) {
+        psb_batch_t *k = new psb_batch_t();
+        k->m = b->m; k->max_utts = b->max_utts; k->max_frames = b->max_frames; k->topn_variant = b->topn_variant;
+        k->is_kid = true; k->n_pipe = 1;
+        cudaError_t e = cudaStreamCreateWithFlags(&k->stream, cudaStreamNonBlocking);
+        for (int j = 0; j < 4 && e == cudaSuccess; ++j) e = cudaEventCreate(&k->ev[j]);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&k->join_ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            psb_set_error("pipelined decode: %s", cudaGetErrorString(e));
+            delete k;
+            return PSB_ERR_CUDA;
+        }
+        k->have_ev = true;
+        b->kids.push_back(k);
     }
+    *out = b->kids[i];
+    return PSB_OK;
+}
+
+// Shared by the host and device decode entry points.  The batch is cut into n_pipe contiguous
+// utterance ranges of about equal frame counts; each range runs copy-in -> transpose -> top-N ->
+// senone -> phone loop -> copy-out on its own stream, so the FP32-bound top-N kernel of one
+// range overlaps the integer/LSU-bound senone kernel and the PCIe copies of the others.  The
+// parent's stream forks into and joins the sub-streams with events, so psb_batch_event_record /
+// psb_batch_sync on the parent still bracket all the work.
+static int decode_common(psb_batch_t *b, psb_phoneloop_t *p, const float *feats, bool feats_on_host,
+                         const int32_t *utt_off, int32_t n_utt, int32_t *h_best, int32_t *h_pen, int16_t *h_senscr,
+                         bool want_best, bool want_pen)
+{
+    psb_model_t *m = b->m;
+    const size_t H = psb_phoneloop_n_phones(p);
+    const long long total = utt_off[n_utt];
     if ((size_t)b->max_frames * H > b->pen_cap) {
         cudaFree(b->d_best); cudaFree(b->d_pen);
         b->d_best = b->d_pen = nullptr;
@@ -429,11 +486,58 @@ static int decode_common(psb_batch_t *b, psb_phoneloop_t *p, const float *d_feat
         PSB_CUDA(cudaMalloc(&b->d_best, (size_t)b->max_frames * 4));
         PSB_CUDA(cudaMalloc(&b->d_pen, b->pen_cap * 4));
     }
-    PSB_CUDA(cudaMemcpyAsync(b->d_off, utt_off, (size_t)(n_utt + 1) * 4, cudaMemcpyHostToDevice, b->stream));
-    int rc = score_dispatch(b, d_feats, utt_off, n_utt, b->d_senscr);
-    if (rc) return rc;
-    return psb_phoneloop_launch(p, b->d_senscr, b->d_off, n_utt, want_best ? b->d_best : nullptr,
-                                want_pen ? b->d_pen : nullptr, nullptr, nullptr, b->stream);
+    const int S = std::max(1, std::min<int>(b->n_pipe, n_utt));
+    PSB_CUDA(cudaEventRecord(b->fork_ev, b->stream));
+    int u0 = 0;
+    for (int s = 0; s < S; ++s) {
+        // utterances [u0, u1) with about total/S frames
+        int u1 = u0;
+        const long long target = total * (s + 1) / S;
+        while (u1 < n_utt && (utt_off[u1 + 1] <= target || u1 == u0)) ++u1;
+        if (s == S - 1) u1 = n_utt;
+        if (u1 == u0) continue;
+        psb_batch_t *k;
+        int rc = get_kid(b, s, &k);
+        if (rc) return rc;
+        const long long f0 = utt_off[u0], nf = utt_off[u1] - f0;
+        const int nu = u1 - u0;
+        if ((size_t)nu + 1 > k->off_cap) {
+            cudaFree(k->d_off);
+            if (k->h_off) cudaFreeHost(k->h_off);
+            k->d_off = nullptr; k->h_off = nullptr;
+            k->off_cap = (size_t)nu + 1 + 256;
+            PSB_CUDA(cudaMalloc(&k->d_off, k->off_cap * 4));
+            PSB_CUDA(cudaMallocHost(&k->h_off, k->off_cap * 4));
+        }
+        PSB_CUDA(cudaStreamSynchronize(k->stream));          // the previous call's copy from h_off is done
+        int32_t *off = k->h_off;
+        for (int i = 0; i <= nu; ++i) off[i] = utt_off[u0 + i] - (int32_t)f0;
+        PSB_CUDA(cudaStreamWaitEvent(k->stream, b->fork_ev, 0));
+        const float *d_f = feats + f0 * m->sumlen;
+        if (feats_on_host) {
+            PSB_CUDA(cudaMemcpyAsync(b->d_feats + f0 * m->sumlen, feats + f0 * m->sumlen, (size_t)nf * m->sumlen * sizeof(float),
+                                     cudaMemcpyHostToDevice, k->stream));
+            d_f = b->d_feats + f0 * m->sumlen;
+        }
+        PSB_CUDA(cudaMemcpyAsync(k->d_off, off, (size_t)(nu + 1) * 4, cudaMemcpyHostToDevice, k->stream));
+        k->d_topn = b->d_topn ? b->d_topn + f0 * m->K : nullptr;
+        rc = score_dispatch(k, d_f, off, nu, b->d_senscr + f0 * m->n_sen);
+        if (rc) return rc;
+        rc = psb_phoneloop_launch(p, b->d_senscr + f0 * m->n_sen, k->d_off, nu, want_best ? b->d_best + f0 : nullptr,
+                                  want_pen ? b->d_pen + f0 * H : nullptr, nullptr, nullptr, k->stream);
+        if (rc) return rc;
+        if (h_best) PSB_CUDA(cudaMemcpyAsync(h_best + f0, b->d_best + f0, (size_t)nf * 4, cudaMemcpyDeviceToHost, k->stream));
+        if (h_pen) PSB_CUDA(cudaMemcpyAsync(h_pen + f0 * H, b->d_pen + f0 * H, (size_t)nf * H * 4, cudaMemcpyDeviceToHost, k->stream));
+        if (h_senscr)
+            PSB_CUDA(cudaMemcpyAsync(h_senscr + f0 * m->n_sen, b->d_senscr + f0 * m->n_sen, (size_t)nf * m->n_sen * 2,
+                                     cudaMemcpyDeviceToHost, k->stream));
+        PSB_CUDA(cudaEventRecord(k->join_ev, k->stream));
+        PSB_CUDA(cudaStreamWaitEvent(b->stream, k->join_ev, 0));
+        u0 = u1;
+    }
+    b->last_frames = total;
+    b->last_pipelined = true;
+    return PSB_OK;
 }
 
 // End-to-end: host features -> senone scores -> phone-loop Viterbi -> host results.
@@ -445,15 +549,9 @@ extern "C" int psb_decode_batch_host(psb_batch_t *b, psb_phoneloop_t *p, const f
     if (rc) return rc;
     PSB_REQUIRE(utt_off[n_utt] == 0 || feats, "psb_decode_batch_host: null buffer");
     PSB_CUDA(cudaSetDevice(b->m->device));
-    const size_t total = utt_off[n_utt], H = psb_phoneloop_n_phones(p);
-    if (total == 0) return PSB_OK;
-    PSB_CUDA(cudaMemcpyAsync(b->d_feats, feats, total * b->m->sumlen * sizeof(float), cudaMemcpyHostToDevice, b->stream));
-    rc = decode_common(b, p, b->d_feats, utt_off, n_utt, best != nullptr, pen != nullptr);
+    if (utt_off[n_utt] == 0) return PSB_OK;
+    rc = decode_common(b, p, feats, true, utt_off, n_utt, best, pen, senscr, best != nullptr, pen != nullptr);
     if (rc) return rc;
-    if (best) PSB_CUDA(cudaMemcpyAsync(best, b->d_best, total * 4, cudaMemcpyDeviceToHost, b->stream));
-    if (pen) PSB_CUDA(cudaMemcpyAsync(pen, b->d_pen, total * H * 4, cudaMemcpyDeviceToHost, b->stream));
-    if (senscr)
-        PSB_CUDA(cudaMemcpyAsync(senscr, b->d_senscr, total * b->m->n_sen * sizeof(int16_t), cudaMemcpyDeviceToHost, b->stream));
     PSB_CUDA(cudaStreamSynchronize(b->stream));
     return PSB_OK;
 }
@@ -467,7 +565,7 @@ extern "C" int psb_decode_batch_device(psb_batch_t *b, psb_phoneloop_t *p, const
     PSB_REQUIRE(utt_off[n_utt] == 0 || d_feats, "psb_decode_batch_device: null buffer");
     PSB_CUDA(cudaSetDevice(b->m->device));
     if (utt_off[n_utt] == 0) return PSB_OK;
-    rc = decode_common(b, p, d_feats, utt_off, n_utt, true, true);
+    rc = decode_common(b, p, d_feats, false, utt_off, n_utt, nullptr, nullptr, nullptr, true, true);
     if (d_best) *d_best = b->d_best;
     if (d_pen) *d_pen = b->d_pen;
     return rc;
