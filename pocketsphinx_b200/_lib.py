@@ -64,6 +64,7 @@ SYMBOLS = [
     ("psb_decode_batch_device", C.c_int, [_VP, _VP, _VP, _VP, _I32, _VP, _VP]),
     ("psb_sendump_write", C.c_int, [C.c_char_p, C.c_char_p, _I32, C.c_double, _VP, _I64]),
     ("psb_sendump_read", _I64, [C.c_char_p, _VP, _VP, _I64]),
+    ("psb_batch_set_pipeline", C.c_int, [_VP, C.c_int]),
     ("psb_kernel_launch_count", _I64, []),
 ]
 

@@ -169,6 +169,9 @@ class Batch:
         check(lib().psb_batch_last_kernel_ms(self.h, _p(out)), "psb_batch_last_kernel_ms")
         return dict(transpose=float(out[0]), topn=float(out[1]), senone=float(out[2]))
 
+    def set_pipeline(self, n):
+        check(lib().psb_batch_set_pipeline(self.h, int(n)), "psb_batch_set_pipeline")
+
     def event_record(self, slot):
         check(lib().psb_batch_event_record(self.h, slot), "psb_batch_event_record")
 

@@ -294,7 +294,7 @@ extern "C" int psb_batch_create(psb_model_t *m, int32_t max_utts, int64_t max_fr
         const char *v = getenv("PSB_TOPN_VARIANT");     // tuning knob; default = packed FP32, 4 warps/CTA
         b->topn_variant = v ? atoi(v) : 2;
         const char *p = getenv("PSB_PIPELINE");         // sub-batches in flight for psb_decode_batch_*
-        b->n_pipe = p ? atoi(p) : 3;
+        b->n_pipe = p ? atoi(p) : 2;
         if (b->n_pipe < 1) b->n_pipe = 1;
         if (b->n_pipe > 8) b->n_pipe = 8;
     }
@@ -585,5 +585,12 @@ extern "C" int psb_batch_event_elapsed_ms(psb_batch_t *b, float *ms)
     PSB_CUDA(cudaSetDevice(b->m->device));
     PSB_CUDA(cudaEventSynchronize(b->tev[1]));
     PSB_CUDA(cudaEventElapsedTime(ms, b->tev[0], b->tev[1]));
+    return PSB_OK;
+}
+
+extern "C" int psb_batch_set_pipeline(psb_batch_t *b, int n)
+{
+    PSB_REQUIRE(b && n >= 1 && n <= 8, "psb_batch_set_pipeline: n must be 1..8");
+    b->n_pipe = n;
     return PSB_OK;
 }

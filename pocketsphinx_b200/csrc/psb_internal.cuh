@@ -117,7 +117,7 @@ struct psb_batch_s {
     // pipelined decode: sub-batches on their own streams sharing this batch's big buffers
     std::vector<psb_batch_t *> kids;
     cudaEvent_t fork_ev, join_ev;
-    int n_pipe;                   // PSB_PIPELINE (default 3); 1 = everything on `stream`
+    int n_pipe;                   // PSB_PIPELINE (default 2); 1 = everything on `stream`
     bool is_kid;
     bool last_pipelined;
     int32_t *h_off;               // pinned copy of a sub-batch's utterance offsets
