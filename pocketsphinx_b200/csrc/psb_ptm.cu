@@ -440,6 +440,201 @@ ptm_topn2_kernel(const float *__restrict__ rec2, const size_t *__restrict__ rec2
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Two utterances per lane ("U2").  ncu on the kernels above shows the warp-uniform LDS.128
+// stream of Gaussian records at ~65 % of the shared-memory pipe with `short scoreboard` the top
+// stall: a broadcast load delivers 8 bytes per wavefront however many lanes listen.  Here every
+// record load feeds TWO utterances per lane: the pair (x_u0, x_u1) goes through one
+// FADD2 / FMUL2 / FMUL2 with the model value as a broadcast scalar operand (so the scalar records
+// are used as they are: t = x + (-mu), t*t, (t*t)*v, then d_u -= t_u with scalar FADDs, which
+// ptxas never contracts).  Shared-memory traffic per (utterance, codeword) halves and each warp
+// carries two independent dependency chains.
+struct U2State {
+    unsigned cwp;           // four listed codewords, byte j = cw_j
+    int sc[TOPN];
+    unsigned seedpack, seedbit;
+    float thresh;
+};
+
+__device__ __forceinline__ void u2_insert(U2State &st, int c, int s, int ch, unsigned &m8)
+{
+    const int ev = (int)(st.cwp >> 24);
+    int p = 0;
+#pragma unroll
+    for (int j = 0; j < TOPN - 1; ++j) p += (s >= st.sc[j]) ? 0 : 1;       // insertion_sort_cb (ptm_mgau.c:140-149)
+#pragma unroll
+    for (int j = TOPN - 2; j >= 0; --j)
+        if (j >= p) st.sc[j + 1] = st.sc[j];
+#pragma unroll
+    for (int j = 0; j < TOPN; ++j)
+        if (j == p) st.sc[j] = s;
+    const unsigned lowmask = (1u << (8 * p)) - 1u;                          // p <= 3
+    st.cwp = (st.cwp & lowmask) | ((unsigned)c << (8 * p)) | ((st.cwp << 8) & ~((lowmask << 8) | 0xffu));
+    // an evicted seed becomes scannable again (it may lie ahead of the scan)
+    const unsigned t2 = st.seedpack ^ ((unsigned)ev * 0x01010101u);
+    const unsigned nz2 = (((t2 & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t2) & 0x80808080u;
+    st.seedbit &= (nz2 >> 7) * 0xffu;
+    if ((ev >> 3) == ch) m8 &= ~(1u << (ev & 7));
+    st.thresh = (float)st.sc[TOPN - 1];
+}
+
+template <int FL, bool SEMI>
+__global__ void __launch_bounds__(128, 5)
+ptm_topn_u2_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec_off,
+                   const int32_t *__restrict__ klist, const float *__restrict__ featT, GroupTabs tabs,
+                   int4 *__restrict__ out, int n_groups, int nd, int n_feat, int D,
+                   const int32_t *__restrict__ featoff, int K, int ds_ratio, const int32_t *__restrict__ topn_beam)
+{
+    constexpr int RECF = (1 + 2 * FL + 3) / 4 * 4;
+    constexpr int RECQ = RECF / 4;
+    extern __shared__ float4 srec[];          // [nd][RECQ] scalar records {det, mu0, v0, ...}
+    const int k = klist[blockIdx.x];
+    const int f = k % n_feat;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(rec + rec_off[k]);
+        for (int i = threadIdx.x; i < nd * RECQ; i += blockDim.x)
+            srec[i] = src[i];
+    }
+    __syncthreads();
+    // this warp owns utterance groups g0 = 2w and g1 = 2w + 1 (the second may not exist)
+    const int w = blockIdx.y * (blockDim.x >> 5) + warp;
+    const int g0 = 2 * w, g1 = 2 * w + 1;
+    if (g0 >= n_groups) return;
+    const bool has1 = g1 < n_groups;
+    const int len0 = tabs.lane_len[g0 * 32 + lane], len1 = has1 ? tabs.lane_len[g1 * 32 + lane] : 0;
+    const long long off0 = tabs.lane_off[g0 * 32 + lane], off1 = has1 ? tabs.lane_off[g1 * 32 + lane] : 0;
+    const int maxT = max(tabs.grp_maxT[g0], has1 ? tabs.grp_maxT[g1] : 0);
+    const int maxT1 = has1 ? tabs.grp_maxT[g1] : 0, maxT0 = tabs.grp_maxT[g0];
+    const float *xT0 = featT + tabs.grp_base[g0] + (long long)featoff[f] * 32 + lane;
+    const float *xT1 = has1 ? featT + tabs.grp_base[g1] + (long long)featoff[f] * 32 + lane : xT0;
+
+    U2State st[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        st[u].cwp = 0x03020100u;                                   // codewords 0..3 (ptm_mgau.c:791-792)
+#pragma unroll
+        for (int i = 0; i < TOPN; ++i) st[u].sc[i] = INT_MIN;
+        st[u].seedpack = st[u].seedbit = 0u;
+        st[u].thresh = 0.f;
+    }
+
+    for (int t = 0; t < maxT; ++t) {
+        float2 xx[FL];
+        {
+            const float *p0 = xT0 + (long long)t * D * 32, *p1 = xT1 + (long long)t * D * 32;
+            const bool in0 = t < maxT0, in1 = t < maxT1;
+#pragma unroll
+            for (int j = 0; j < FL; ++j) xx[j] = make_float2(in0 ? p0[j * 32] : 0.f, in1 ? p1[j * 32] : 0.f);
+        }
+        const bool act0 = t < len0, act1 = t < len1;
+        if (!act0 && !act1) continue;
+
+        // ---- eval_topn per utterance (scalar distances through per-lane record addresses) ----
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            float x[FL];
+#pragma unroll
+            for (int j = 0; j < FL; ++j) x[j] = u ? xx[j].y : xx[j].x;
+            int ncw[TOPN], nsc[TOPN];
+            unsigned sp = 0u, sb = 0u;
+#pragma unroll
+            for (int i = 0; i < TOPN; ++i) {
+                const int c = (st[u].cwp >> (8 * i)) & 0xff;
+                const int s = f2i_clamped(gau_dist<FL>(srec + c * RECQ, x));
+                sp |= (unsigned)c << (8 * i);
+                sb |= (1u << (c & 7)) << (8 * i);
+                int p = 0;
+#pragma unroll
+                for (int j = 0; j < i; ++j) p += (s > nsc[j]) ? 0 : 1;
+#pragma unroll
+                for (int j = TOPN - 2; j >= 0; --j)
+                    if (j < i && j >= p) { nsc[j + 1] = nsc[j]; ncw[j + 1] = ncw[j]; }
+#pragma unroll
+                for (int j = 0; j < TOPN; ++j)
+                    if (j == p) { nsc[j] = s; ncw[j] = c; }
+            }
+            unsigned cp = 0u;
+#pragma unroll
+            for (int i = 0; i < TOPN; ++i) { st[u].sc[i] = nsc[i]; cp |= (unsigned)ncw[i] << (8 * i); }
+            st[u].cwp = cp;
+            st[u].seedpack = sp;
+            st[u].seedbit = sb;
+            st[u].thresh = (float)nsc[TOPN - 1];
+        }
+
+        // ---- eval_cb: one record stream, two utterances ----
+        if (t % ds_ratio == 0) {
+            const unsigned sch0 = (st[0].seedpack >> 3) & 0x1f1f1f1fu, sch1 = (st[1].seedpack >> 3) & 0x1f1f1f1fu;
+            for (int ch = 0; ch < nd / 8; ++ch) {
+                const float4 *rq = srec + (size_t)ch * 8 * RECQ;
+                unsigned m8[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const unsigned tt = (u ? sch1 : sch0) ^ ((unsigned)ch * 0x01010101u);
+                    const unsigned nz = (((tt & 0x7f7f7f7fu) + 0x7f7f7f7fu) | tt) & 0x80808080u;
+                    const unsigned b = st[u].seedbit & (((nz ^ 0x80808080u) >> 7) * 0xffu);
+                    m8[u] = (b | (b >> 8) | (b >> 16) | (b >> 24)) & 0xffu;
+                }
+                if (!act0) m8[0] = 0xffu;          // a finished utterance never inserts
+                if (!act1) m8[1] = 0xffu;
+#pragma unroll 2
+                for (int cc = 0; cc < 8; ++cc) {
+                    const float4 *r = rq + cc * RECQ;
+                    float rr[RECF];
+#pragma unroll
+                    for (int q = 0; q < RECQ; ++q) {
+                        const float4 v = r[q];
+                        rr[4 * q] = v.x; rr[4 * q + 1] = v.y; rr[4 * q + 2] = v.z; rr[4 * q + 3] = v.w;
+                    }
+                    float d0 = rr[0], d1 = rr[0], p0 = rr[0], p1 = rr[0];
+#pragma unroll
+                    for (int j = 0; j < FL; ++j) {
+                        float2 tt = __fadd2_rn(xx[j], make_float2(-rr[1 + 2 * j], -rr[1 + 2 * j]));
+                        tt = __fmul2_rn(tt, tt);
+                        tt = __fmul2_rn(tt, make_float2(rr[2 + 2 * j], rr[2 + 2 * j]));
+                        if (SEMI && j == FL - 1) { p0 = d0; p1 = d1; }
+                        d0 = __fsub_rn(d0, tt.x);
+                        d1 = __fsub_rn(d1, tt.y);
+                    }
+                    const int c = ch * 8 + cc;
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const float d = u ? d1 : d0;
+                        bool hit;
+                        if (SEMI) hit = (u ? p1 : p0) >= st[u].thresh && f2i_clamped(d) >= st[u].sc[TOPN - 1];
+                        else hit = d >= st[u].thresh;
+                        if (hit && !((m8[u] >> cc) & 1u))
+                            u2_insert(st[u], c, f2i_clamped(d), ch, m8[u]);
+                    }
+                }
+            }
+        }
+
+        // ---- emit the records ----
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u ? !act1 : !act0) continue;
+            const int top = st[u].sc[0] >> PSB_SENSCR_SHIFT;
+            unsigned eb = 0;
+            int n_in_beam = TOPN;
+#pragma unroll
+            for (int j = 0; j < TOPN; ++j) {
+                int e = top - (st[u].sc[j] >> PSB_SENSCR_SHIFT);
+                if (SEMI) {
+                    e = e > PSB_MAX_NEG_ASCR ? PSB_MAX_NEG_ASCR : e;
+                    const int beam = topn_beam[f];
+                    if (beam && e > beam && n_in_beam == TOPN) n_in_beam = j;
+                }
+                else
+                    e = e > 255 ? 255 : e;
+                eb |= (unsigned)e << (8 * j);
+            }
+            out[((u ? off1 : off0) + t) * K + k] = make_int4(SEMI ? n_in_beam : top, (int)st[u].cwp, (int)eb, 0);
+        }
+    }
+}
+
 // fast_logmath_add (tied_mgau_common.h:111-127) on negated logs
 __device__ __forceinline__ int logadd8(const uint8_t *tab, int x, int y)
 {
@@ -618,6 +813,21 @@ int launch_topn(psb_batch_t *b, const int32_t *d_klist, int n_k, const GroupTabs
                 const int32_t *d_featoff)
 {
     psb_model_t *m = b->m;
+    if (FL <= 16 && b->topn_variant == 3) {
+        // two utterances per lane: 64 utterances per warp, 4 warps per CTA
+        constexpr int FLU = FL <= 16 ? FL : 1;
+        size_t smem = (size_t)m->n_density * rec_floats(FLU) * sizeof(float);
+        auto kern = ptm_topn_u2_kernel<FLU, SEMI>;
+        PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int n_w = (n_groups + 1) / 2;
+        const int warps = (long long)n_k * ((n_w + 3) / 4) >= 2 * 148 ? 4 : 1;
+        dim3 grid(n_k, (n_w + warps - 1) / warps);
+        kern<<<grid, warps * 32, smem, b->stream>>>(m->d_rec, m->d_rec_off, d_klist, b->d_featT, tabs, b->d_topn, n_groups,
+                                                   m->n_density, m->n_feat, m->sumlen, d_featoff, m->K, m->ds_ratio,
+                                                   m->d_topn_beam);
+        PSB_LAUNCH_CHECK();
+        return PSB_OK;
+    }
     if (FL <= 16 && m->d_rec2 && b->topn_variant != 0) {
         // packed-FP32 kernels (FL <= 16 keeps the register budget): variant 1 = 2 warps/CTA with a
         // large register budget (two balanced waves), variant 2 = 4 warps/CTA at 72 registers
