@@ -420,8 +420,9 @@ extern "C" int psb_batch_last_kernel_ms(psb_batch_t *b, float *out3)
     out3[0] = out3[1] = out3[2] = 0.f;
     if (b->last_pipelined) {
         // pipelined decode: sum of the sub-batches' own kernel intervals (they overlap in time)
-        for (psb_batch_t *k : b->kids)
+        for (int q = 0; q < b->last_kids && q < (int)b->kids.size(); ++q)
             for (int i = 0; i < 3; ++i) {
+                psb_batch_t *k = b->kids[q];
                 float ms = 0.f;
                 if (cudaEventElapsedTime(&ms, k->ev[i], k->ev[i + 1]) == cudaSuccess) out3[i] += ms;
                 else cudaGetLastError();
@@ -537,6 +538,7 @@ static int decode_common(psb_batch_t *b, psb_phoneloop_t *p, const float *feats,
     }
     b->last_frames = total;
     b->last_pipelined = true;
+    b->last_kids = S;
     return PSB_OK;
 }
 

@@ -120,6 +120,7 @@ struct psb_batch_s {
     int n_pipe;                   // PSB_PIPELINE (default 2); 1 = everything on `stream`
     bool is_kid;
     bool last_pipelined;
+    int last_kids;                // sub-batches used by the last decode call
     int32_t *h_off;               // pinned copy of a sub-batch's utterance offsets
 };
 
