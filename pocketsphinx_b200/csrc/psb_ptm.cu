@@ -791,6 +791,115 @@ semi_senone_kernel(const int4 *__restrict__ topn, const uint8_t *__restrict__ mi
     senscr[frame * n_sen + s] = acc;
 }
 
+// Four consecutive senones per thread (8-bit mixture weights).  ncu on ptm_senone_kernel shows
+// the L1/LSU data pipe at ~90 %: one byte gather per (senone, codeword) and one broadcast LDS of
+// row offsets per (senone, stream).  Senones of one codebook are contiguous, so a thread that
+// owns senones 4q..4q+3 fetches each weight row with ONE aligned 32-bit load (four senones'
+// bytes) and reads the codebook's offsets/scores once; quads that straddle a codebook boundary
+// (a few per cent) take the per-senone path.
+__global__ void __launch_bounds__(512)
+ptm_senone4_kernel(const int4 *__restrict__ topn, const uint8_t *__restrict__ mixw,
+                   const uint16_t *__restrict__ sen2cb, const uint8_t *__restrict__ logadd_tab,
+                   int16_t *__restrict__ senscr, int n_sen, int n_feat, int nd, int K, int mixw_stride)
+{
+    extern __shared__ int smem_i[];
+    uint4 *rowoff = reinterpret_cast<uint4 *>(smem_i);             // [K]
+    uint4 *nsc = rowoff + K;                                        // [K]
+    int *norm = reinterpret_cast<int *>(nsc + K);                   // [8]
+    int *red = norm + 8;                                            // [32]
+    uint8_t *tab = reinterpret_cast<uint8_t *>(red + 32);           // [256]
+    int16_t *asc = reinterpret_cast<int16_t *>(tab + 256 + 16);     // [n_sen rounded up to 4]
+    const long long frame = blockIdx.x;
+    const int tid = threadIdx.x;
+
+    if (tid < 256) tab[tid] = logadd_tab[tid];
+    if (tid < n_feat) norm[tid] = PSB_WORST_SCORE;
+    __syncthreads();
+    int4 r = make_int4(0, 0, 0, 0);
+    if (tid < K) {
+        r = topn[frame * K + tid];
+        atomicMax(&norm[tid % n_feat], r.x);
+    }
+    __syncthreads();
+    if (tid < K) {
+        const int f = tid % n_feat;
+        const int base = norm[f] - r.x;
+        const unsigned eb = (unsigned)r.z, cwb = (unsigned)r.y;
+        unsigned ro[TOPN], nv[TOPN];
+#pragma unroll
+        for (int j = 0; j < TOPN; ++j) {
+            int v = base + (int)((eb >> (8 * j)) & 0xff);
+            nv[j] = (unsigned)(v > PSB_MAX_NEG_ASCR ? PSB_MAX_NEG_ASCR : v);
+            ro[j] = ((unsigned)f * nd + ((cwb >> (8 * j)) & 0xff)) * (unsigned)mixw_stride;
+        }
+        rowoff[tid] = make_uint4(ro[0], ro[1], ro[2], ro[3]);
+        nsc[tid] = make_uint4(nv[0], nv[1], nv[2], nv[3]);
+    }
+    __syncthreads();
+
+    int best = 0x7fffffff;
+    const int n_quads = (n_sen + 3) >> 2;
+    for (int q = tid; q < n_quads; q += blockDim.x) {
+        const int s0 = q << 2;
+        int cb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cb[i] = s0 + i < n_sen ? (int)sen2cb[s0 + i] : -1;
+        int a[4] = {0, 0, 0, 0};
+        if (cb[0] == cb[1] && cb[0] == cb[2] && cb[0] == cb[3]) {
+            const int i0 = cb[0] * n_feat;
+            const uint8_t *mw = mixw + s0;
+            for (int f = 0; f < n_feat; ++f) {
+                const uint4 ro = rowoff[i0 + f], nv = nsc[i0 + f];
+                const unsigned w0 = *reinterpret_cast<const unsigned *>(mw + ro.x);
+                const unsigned w1 = *reinterpret_cast<const unsigned *>(mw + ro.y);
+                const unsigned w2 = *reinterpret_cast<const unsigned *>(mw + ro.z);
+                const unsigned w3 = *reinterpret_cast<const unsigned *>(mw + ro.w);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    int fden = (int)((w0 >> (8 * i)) & 0xff) + (int)nv.x;
+                    fden = logadd8(tab, fden, (int)((w1 >> (8 * i)) & 0xff) + (int)nv.y);
+                    fden = logadd8(tab, fden, (int)((w2 >> (8 * i)) & 0xff) + (int)nv.z);
+                    fden = logadd8(tab, fden, (int)((w3 >> (8 * i)) & 0xff) + (int)nv.w);
+                    a[i] += fden;
+                }
+            }
+        }
+        else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (cb[i] < 0) continue;
+                const int i0 = cb[i] * n_feat;
+                const uint8_t *mw = mixw + s0 + i;
+                for (int f = 0; f < n_feat; ++f) {
+                    const uint4 ro = rowoff[i0 + f], nv = nsc[i0 + f];
+                    int fden = mw[ro.x] + (int)nv.x;
+                    fden = logadd8(tab, fden, mw[ro.y] + (int)nv.y);
+                    fden = logadd8(tab, fden, mw[ro.z] + (int)nv.z);
+                    fden = logadd8(tab, fden, mw[ro.w] + (int)nv.w);
+                    a[i] += fden;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (cb[i] >= 0) best = min(best, a[i]);
+        *reinterpret_cast<short4 *>(asc + s0) = make_short4((short)a[0], (short)a[1], (short)a[2], (short)a[3]);
+    }
+    best = __reduce_min_sync(0xffffffffu, best);
+    if ((tid & 31) == 0) red[tid >> 5] = best;
+    __syncthreads();
+    if (tid < 32) {
+        int v = tid < (int)(blockDim.x >> 5) ? red[tid] : 0x7fffffff;
+        v = __reduce_min_sync(0xffffffffu, v);
+        if (tid == 0) red[0] = v;
+    }
+    __syncthreads();
+    best = red[0];
+    int16_t *dst = senscr + frame * n_sen;
+    for (int s = tid; s < n_sen; s += blockDim.x)
+        dst[s] = (int16_t)(asc[s] - best);                       // ptm_mgau.c:398-400
+}
+
 template <int FL, bool SEMI, int WARPS, int MINB>
 int launch_topn2(psb_batch_t *b, const int32_t *d_klist, int n_k, const GroupTabs &tabs, int n_groups,
                  const int32_t *d_featoff)
@@ -989,11 +1098,22 @@ int psb_launch_ptm_batch(psb_batch_t *b, const float *d_feats, const int32_t *ut
                 b->d_topn, m->d_mixw, m->d_mixw_cb, m->d_sen2cb, m->d_logadd8, d_senscr, m->n_sen, m->n_feat,
                 m->n_density, K, m->mixw_stride);
         }
-        else {
+        else if (b->topn_variant == 0) {
             PSB_CUDA(cudaFuncSetAttribute(ptm_senone_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ptm_senone_kernel<false><<<(unsigned)total, 512, smem, b->stream>>>(
                 b->d_topn, m->d_mixw, m->d_mixw_cb, m->d_sen2cb, m->d_logadd8, d_senscr, m->n_sen, m->n_feat,
                 m->n_density, K, m->mixw_stride);
+        }
+        else {
+            // four senones per thread; threads sized so that the quads divide evenly over the block
+            const int n_quads = (m->n_sen + 3) / 4;
+            const int iters = (n_quads + 511) / 512;
+            const int threads = std::max(128, roundup((n_quads + iters - 1) / iters, 32));
+            const size_t smem4 = smem + 8;
+            PSB_CUDA(cudaFuncSetAttribute(ptm_senone4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+            ptm_senone4_kernel<<<(unsigned)total, threads, smem4, b->stream>>>(
+                b->d_topn, m->d_mixw, m->d_sen2cb, m->d_logadd8, d_senscr, m->n_sen, m->n_feat, m->n_density, K,
+                m->mixw_stride);
         }
         PSB_LAUNCH_CHECK();
     }
