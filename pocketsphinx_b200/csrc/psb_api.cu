@@ -168,7 +168,7 @@ extern "C" int psb_model_create(const psb_model_desc_t *d, int device, psb_model
     m->logadd_ms_size = d->logadd_ms_size;
     m->logadd_ms_zero = d->logadd_ms_zero;
     m->d_rec = nullptr; m->d_rec_off = nullptr; m->d_rec2 = nullptr; m->d_rec2_off = nullptr; m->d_mixw = nullptr; m->d_mixw_cb = nullptr;
-    m->d_sen2cb = nullptr; m->d_sen2cb32 = nullptr; m->d_logadd8 = nullptr; m->d_logadd_ms = nullptr;
+    m->d_sen2cb = nullptr; m->d_sen2cb32 = nullptr; m->d_quadcb = nullptr; m->d_bsen = nullptr; m->n_bsen = 0; m->d_logadd8 = nullptr; m->d_logadd_ms = nullptr;
     m->has_topn_beam = false;
     m->d_topn_beam = nullptr;
     m->d_msT = m->d_msdetT = nullptr; m->d_featlen = m->d_featoff = nullptr;
@@ -195,6 +195,24 @@ extern "C" int psb_model_create(const psb_model_desc_t *d, int device, psb_model
             return PSB_ERR_ARG;
         }
         s2c16[i] = (uint16_t)s2c[i];
+    }
+    {
+        const int nq = (m->n_sen + 3) / 4;
+        std::vector<int16_t> quadcb(nq, -1);
+        std::vector<int32_t> bsen;
+        for (int q = 0; q < nq; ++q) {
+            const int s0 = 4 * q;
+            bool uni = s0 + 3 < m->n_sen && m->n_mgau <= 32767;
+            for (int i = 1; uni && i < 4; ++i) uni = s2c[s0 + i] == s2c[s0];
+            if (uni) quadcb[q] = (int16_t)s2c[s0];
+            else for (int i = 0; i < 4 && s0 + i < m->n_sen; ++i) bsen.push_back(s0 + i);
+        }
+        m->n_bsen = (int)bsen.size();
+        if ((rc = upload((void **)&m->d_quadcb, quadcb.data(), nq * sizeof(int16_t), false)) ||
+            (rc = upload((void **)&m->d_bsen, bsen.data(), bsen.size() * sizeof(int32_t), false))) {
+            psb_model_free(m);
+            return rc;
+        }
     }
     if ((rc = upload((void **)&m->d_sen2cb, s2c16.data(), m->n_sen * sizeof(uint16_t), false)) ||
         (rc = upload((void **)&m->d_sen2cb32, s2c.data(), m->n_sen * sizeof(int32_t), false))) {
@@ -263,7 +281,7 @@ extern "C" void psb_model_free(psb_model_t *m)
     if (!m) return;
     cudaSetDevice(m->device);
     cudaFree(m->d_rec); cudaFree(m->d_rec_off); cudaFree(m->d_rec2); cudaFree(m->d_rec2_off); cudaFree(m->d_mixw); cudaFree(m->d_mixw_cb);
-    cudaFree(m->d_sen2cb); cudaFree(m->d_sen2cb32); cudaFree(m->d_logadd8); cudaFree(m->d_logadd_ms);
+    cudaFree(m->d_sen2cb); cudaFree(m->d_sen2cb32); cudaFree(m->d_quadcb); cudaFree(m->d_bsen); cudaFree(m->d_logadd8); cudaFree(m->d_logadd_ms);
     cudaFree(m->d_topn_beam); cudaFree(m->d_msT); cudaFree(m->d_msdetT); cudaFree(m->d_featlen); cudaFree(m->d_featoff);
     delete m;
 }

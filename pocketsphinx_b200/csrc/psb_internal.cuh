@@ -74,6 +74,9 @@ struct psb_model_s {
     uint8_t *d_mixw_cb;           // 16 bytes or null
     uint16_t *d_sen2cb;           // [n_sen] (ptm)
     int32_t *d_sen2cb32;          // [n_sen] (ms)
+    int16_t *d_quadcb;            // [ceil(n_sen/4)] codebook of a uniform senone quad, else -1
+    int32_t *d_bsen;              // senones of the non-uniform quads
+    int n_bsen;
     uint8_t *d_logadd8;           // [256]
     uint32_t *d_logadd_ms;
     float *d_msT, *d_msdetT;      // ms back-end: codebook-minor Gaussians (see psb_ms.cu)

@@ -799,9 +799,12 @@ semi_senone_kernel(const int4 *__restrict__ topn, const uint8_t *__restrict__ mi
 // (a few per cent) take the per-senone path.
 __global__ void __launch_bounds__(512)
 ptm_senone4_kernel(const int4 *__restrict__ topn, const uint8_t *__restrict__ mixw,
-                   const uint16_t *__restrict__ sen2cb, const uint8_t *__restrict__ logadd_tab,
+                   const uint16_t *__restrict__ sen2cb, const int16_t *__restrict__ quadcb,
+                   const int32_t *__restrict__ bsen, int n_bsen, const uint8_t *__restrict__ logadd_tab,
                    int16_t *__restrict__ senscr, int n_sen, int n_feat, int nd, int K, int mixw_stride)
 {
+    // quadcb[q] = codebook of senones 4q..4q+3 when all four exist and share it, else -1;
+    // bsen[] = the senones of the other quads (codebook boundaries, tail), handled one by one.
     extern __shared__ int smem_i[];
     uint4 *rowoff = reinterpret_cast<uint4 *>(smem_i);             // [K]
     uint4 *nsc = rowoff + K;                                        // [K]
@@ -840,50 +843,46 @@ ptm_senone4_kernel(const int4 *__restrict__ topn, const uint8_t *__restrict__ mi
     int best = 0x7fffffff;
     const int n_quads = (n_sen + 3) >> 2;
     for (int q = tid; q < n_quads; q += blockDim.x) {
-        const int s0 = q << 2;
-        int cb[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) cb[i] = s0 + i < n_sen ? (int)sen2cb[s0 + i] : -1;
-        int a[4] = {0, 0, 0, 0};
-        if (cb[0] == cb[1] && cb[0] == cb[2] && cb[0] == cb[3]) {
-            const int i0 = cb[0] * n_feat;
-            const uint8_t *mw = mixw + s0;
-            for (int f = 0; f < n_feat; ++f) {
-                const uint4 ro = rowoff[i0 + f], nv = nsc[i0 + f];
-                const unsigned w0 = *reinterpret_cast<const unsigned *>(mw + ro.x);
-                const unsigned w1 = *reinterpret_cast<const unsigned *>(mw + ro.y);
-                const unsigned w2 = *reinterpret_cast<const unsigned *>(mw + ro.z);
-                const unsigned w3 = *reinterpret_cast<const unsigned *>(mw + ro.w);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    int fden = (int)((w0 >> (8 * i)) & 0xff) + (int)nv.x;
-                    fden = logadd8(tab, fden, (int)((w1 >> (8 * i)) & 0xff) + (int)nv.y);
-                    fden = logadd8(tab, fden, (int)((w2 >> (8 * i)) & 0xff) + (int)nv.z);
-                    fden = logadd8(tab, fden, (int)((w3 >> (8 * i)) & 0xff) + (int)nv.w);
-                    a[i] += fden;
-                }
+        const int c = quadcb[q];
+        if (c < 0) continue;
+        const int s0 = q << 2, i0 = c * n_feat;
+        const uint8_t *mw = mixw + s0;
+        int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        for (int f = 0; f < n_feat; ++f) {
+            const uint4 ro = rowoff[i0 + f], nv = nsc[i0 + f];
+            const unsigned w0 = *reinterpret_cast<const unsigned *>(mw + ro.x);
+            const unsigned w1 = *reinterpret_cast<const unsigned *>(mw + ro.y);
+            const unsigned w2 = *reinterpret_cast<const unsigned *>(mw + ro.z);
+            const unsigned w3 = *reinterpret_cast<const unsigned *>(mw + ro.w);
+#define PSB_SEN(i, acc)                                                                         \
+            {                                                                                   \
+                int fden = (int)((w0 >> (8 * i)) & 0xff) + (int)nv.x;                           \
+                fden = logadd8(tab, fden, (int)((w1 >> (8 * i)) & 0xff) + (int)nv.y);           \
+                fden = logadd8(tab, fden, (int)((w2 >> (8 * i)) & 0xff) + (int)nv.z);           \
+                fden = logadd8(tab, fden, (int)((w3 >> (8 * i)) & 0xff) + (int)nv.w);           \
+                acc += fden;                                                                    \
             }
+            PSB_SEN(0, a0) PSB_SEN(1, a1) PSB_SEN(2, a2) PSB_SEN(3, a3)
+#undef PSB_SEN
         }
-        else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (cb[i] < 0) continue;
-                const int i0 = cb[i] * n_feat;
-                const uint8_t *mw = mixw + s0 + i;
-                for (int f = 0; f < n_feat; ++f) {
-                    const uint4 ro = rowoff[i0 + f], nv = nsc[i0 + f];
-                    int fden = mw[ro.x] + (int)nv.x;
-                    fden = logadd8(tab, fden, mw[ro.y] + (int)nv.y);
-                    fden = logadd8(tab, fden, mw[ro.z] + (int)nv.z);
-                    fden = logadd8(tab, fden, mw[ro.w] + (int)nv.w);
-                    a[i] += fden;
-                }
-            }
+        best = min(min(best, a0), min(min(a1, a2), a3));
+        *reinterpret_cast<short4 *>(asc + s0) = make_short4((short)a0, (short)a1, (short)a2, (short)a3);
+    }
+    for (int i = tid; i < n_bsen; i += blockDim.x) {
+        const int s = bsen[i];
+        const int i0 = (int)sen2cb[s] * n_feat;
+        const uint8_t *mw = mixw + s;
+        int ascore = 0;
+        for (int f = 0; f < n_feat; ++f) {
+            const uint4 ro = rowoff[i0 + f], nv = nsc[i0 + f];
+            int fden = mw[ro.x] + (int)nv.x;
+            fden = logadd8(tab, fden, mw[ro.y] + (int)nv.y);
+            fden = logadd8(tab, fden, mw[ro.z] + (int)nv.z);
+            fden = logadd8(tab, fden, mw[ro.w] + (int)nv.w);
+            ascore += fden;
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (cb[i] >= 0) best = min(best, a[i]);
-        *reinterpret_cast<short4 *>(asc + s0) = make_short4((short)a[0], (short)a[1], (short)a[2], (short)a[3]);
+        best = min(best, ascore);
+        asc[s] = (int16_t)ascore;
     }
     best = __reduce_min_sync(0xffffffffu, best);
     if ((tid & 31) == 0) red[tid >> 5] = best;
@@ -1112,8 +1111,8 @@ int psb_launch_ptm_batch(psb_batch_t *b, const float *d_feats, const int32_t *ut
             const size_t smem4 = smem + 8;
             PSB_CUDA(cudaFuncSetAttribute(ptm_senone4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
             ptm_senone4_kernel<<<(unsigned)total, threads, smem4, b->stream>>>(
-                b->d_topn, m->d_mixw, m->d_sen2cb, m->d_logadd8, d_senscr, m->n_sen, m->n_feat, m->n_density, K,
-                m->mixw_stride);
+                b->d_topn, m->d_mixw, m->d_sen2cb, m->d_quadcb, m->d_bsen, m->n_bsen, m->d_logadd8, d_senscr, m->n_sen,
+                m->n_feat, m->n_density, K, m->mixw_stride);
         }
         PSB_LAUNCH_CHECK();
     }
