@@ -815,7 +815,7 @@ ptm_senone4_kernel(const int4 *__restrict__ topn, const uint8_t *__restrict__ mi
     const long long frame = blockIdx.x;
     const int tid = threadIdx.x;
 
-    if (tid < 256) tab[tid] = logadd_tab[tid];
+    for (int i = tid; i < 256; i += blockDim.x) tab[i] = logadd_tab[i];
     if (tid < n_feat) norm[tid] = PSB_WORST_SCORE;
     __syncthreads();
     int4 r = make_int4(0, 0, 0, 0);
@@ -1107,7 +1107,8 @@ int psb_launch_ptm_batch(psb_batch_t *b, const float *d_feats, const int32_t *ut
             // four senones per thread; threads sized so that the quads divide evenly over the block
             const int n_quads = (m->n_sen + 3) / 4;
             const int iters = (n_quads + 511) / 512;
-            const int threads = std::max(128, roundup((n_quads + iters - 1) / iters, 32));
+            // at least 256 threads (log-add table staging) and one thread per (codebook, stream) pair
+            const int threads = std::min(512, std::max(std::max(256, roundup(K, 32)), roundup((n_quads + iters - 1) / iters, 32)));
             const size_t smem4 = smem + 8;
             PSB_CUDA(cudaFuncSetAttribute(ptm_senone4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
             ptm_senone4_kernel<<<(unsigned)total, threads, smem4, b->stream>>>(

@@ -321,3 +321,38 @@ def test_scorer_ms(api, an4):
     _scorer_vs_oracle(api, pm, synth_feats(pm, 1, 30, seed=14)[0], 0, np.random.default_rng(4))
     pm = synth_ms(seed=15, n_sen=500, n_density=16, topn=2, featlens=(13, 13, 13), n_mgau=42)
     _scorer_vs_oracle(api, pm, synth_feats(pm, 1, 24, seed=16)[0], 0, np.random.default_rng(5))
+
+
+@pytest.mark.parametrize("n_emit,H,window,skip", [(3, 1500, 0, False), (5, 200, 3, True), (3, 64, 5, True)])
+def test_phoneloop_large_and_5state_vs_oracle(api, n_emit, H, window, skip):
+    """The device phone loop as a generic HMM-set Viterbi: thousands of HMMs per utterance in
+    shared-memory SoA, 5-state topologies with skip arcs, ragged utterances -- against the oracle's
+    restatement of phone_loop_search.c (itself pinned on the reference's trace)."""
+    from oracle import oracle
+    from pocketsphinx_b200.model import synth_tmat_float
+    from pocketsphinx_b200 import s3io
+    rng = np.random.default_rng(21)
+    n_sen, n_tmat = 900, 12
+    tp = s3io.quantize_tmat(synth_tmat_float(rng, n_tmat, n_emit, skip))
+    sseq = rng.integers(0, n_sen, (H, n_emit)).astype(np.uint16)
+    ssid = np.arange(H, dtype=np.int32)
+    tmat = rng.integers(0, n_tmat, H).astype(np.int32)
+    lens = [40, 1, 23]
+    senscr = rng.integers(0, 400, (sum(lens), n_sen)).astype(np.int16)
+    senscr[:, rng.integers(0, n_sen, 50)] = 0            # some very good senones every frame
+    off = api.Batch.offsets(lens)
+    ctx = api.HmmContext(tp, sseq, n_sen)
+    pl = api.PhoneLoop(ctx, ssid, tmat, window, -300, -250, -7, 2.5)
+    got = pl.run_host(senscr, off, trace=True)
+    for u in range(len(lens)):
+        a, b = off[u], off[u + 1]
+        want = oracle.phoneloop_run(tp, sseq, ssid, tmat, senscr[a:b], max(window, 1) if window else 1,
+                                    -300, -250, -7, 2.5) if window else None
+        if window == 0:
+            # the oracle's penalty ring needs window >= 1; penalties are not produced when window == 0
+            want = oracle.phoneloop_run(tp, sseq, ssid, tmat, senscr[a:b], 1, -300, -250, -7, 2.5)
+        assert np.array_equal(got["best"][a:b], want["best"]), "utt %d best" % u
+        if window:
+            assert np.array_equal(got["pen"][a:b], want["pen"]), "utt %d penalties" % u
+        assert_hmm_equal(got["hmm"][a:b], want["hmm"], n_emit, "utt %d" % u)
+    pl.close(); ctx.close()
