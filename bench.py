@@ -324,7 +324,7 @@ def main():
         hbm_peak, peak_src, sm_max = peaks()
         frames_all = total * world
         value = frames_all / (ms_step * 1e-3)
-        # roofline of the dominant kernel (ptm_topn_kernel), algorithmic bytes per launch:
+        # roofline of the dominant kernel (the top-N kernel), algorithmic bytes per launch:
         # per frame 4*sumlen feature bytes read + 16*K top-N record bytes written, plus the
         # Gaussians once per launch (DESIGN.md "Kernels").
         K = pm.n_mgau * pm.n_feat
@@ -337,6 +337,10 @@ def main():
         flop = 4.0 * pm.n_mgau * pm.n_density * pm.sumlen * total      # sub, mul, mul, sub per (codeword, dim)
         sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
         fp32_peak = 148 * 128 * sm_mhz * 1e6 / 1e12                     # non-FMA FP32 lane-ops/s (TFLOP/s)
+        variant = int(os.environ.get("PSB_TOPN_VARIANT", "5"))
+        topn_name = {"ms": "ms_dist_kernel+ms_senone_kernel", "s2_semi": "ptm_topn2_kernel<SEMI>"}.get(
+            pm.kind, {0: "ptm_topn_kernel", 1: "ptm_topn2_kernel", 2: "ptm_topn2_kernel", 3: "ptm_topn_u2_kernel",
+                      4: "ptm_topnq_kernel<NU=2>", 5: "ptm_topnq_kernel<NU=1>"}.get(variant, "ptm_topnq_kernel<NU=1>"))
         out = {
             "metric": "frames/sec senone-eval+Viterbi", "value": value, "unit": "frames/s",
             "xRT": FRAMES_PER_SEC_AUDIO / value,
@@ -351,15 +355,15 @@ def main():
                        "l2": "per-step working set (%.1f GB of scores) exceeds L2; no explicit flush" % (total * pm.n_sen * 2 / 1e9)},
             "gpu_launches": int(launches),
             "kernel_ms_unpipelined": {**km, "note": "separate single-stream pass; the timed region pipelines 2 sub-batches"},
-            "roofline": {"bound": "hbm", "kernel": "ptm_topn_kernel" if pm.kind != "ms" else "ms_dist_kernel+ms_senone_kernel", "achieved": topn_gbs, "peak": hbm_peak,
+            "roofline": {"bound": "hbm", "kernel": topn_name, "achieved": topn_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": topn_gbs / hbm_peak,
-                         # dram__bytes_read+write of ptm_topn_kernel from the committed ncu capture
-                         # (profiles/r01_topn_senone_v1_summary.txt: 351.0 MB for 98 000 frames), scaled to this launch
-                         "traffic": (351.0e6 / 98000.0) * total if pm.kind == "ptm" and pm.n_density == 256 else None,
+                         # dram__bytes_read+write of ptm_topnq_kernel from the committed ncu capture
+                         # (profiles/r01_topnq_v5_summary.txt: 88.4 + 212.7 MB for 98 000 frames), scaled to this launch
+                         "traffic": (301.0e6 / 98000.0) * total if topn_name.startswith("ptm_topnq") and pm.n_density == 256 else None,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": topn_bytes,
                          "note": "compute-bound by construction (SURVEY 8d): model is SMEM/L2 resident"},
-            "roofline_fp32": {"bound": "fp32 non-FMA issue", "kernel": "ptm_topn_kernel",
+            "roofline_fp32": {"bound": "fp32 non-FMA issue", "kernel": topn_name,
                               "achieved": flop / (km["topn"] * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
                               "frac": flop / (km["topn"] * 1e-3) / 1e12 / fp32_peak,
                               "peak_source": "148 SMs x 128 lanes x sampled SM clock"},

@@ -32,7 +32,10 @@ logadd8(const uint8_t *tab, int mlx, int mly)
     int d, r;
     if (mlx > mly) { d = mlx - mly; r = mly; }
     else { d = mly - mlx; r = mlx; }
-    return r - tab[d];
+    /* mixw + ascr can reach 255 + 96, so d can exceed the reference's 256-entry table
+     * (logmath.c:116-120), where the reference reads past its allocation.  The table is
+     * identically 0 from entry ~30 on; continue it with zeros. */
+    return r - (d < 256 ? tab[d] : 0);
 }
 
 static size_t

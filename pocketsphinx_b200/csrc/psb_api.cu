@@ -244,7 +244,15 @@ extern "C" int psb_model_create(const psb_model_desc_t *d, int device, psb_model
         }
     }
     if (!rc && m->mixw_4bit) rc = upload((void **)&m->d_mixw_cb, d->mixw_cb, 16, dev);
-    if (!rc && d->logadd8) rc = upload((void **)&m->d_logadd8, d->logadd8, 256, dev);
+    if (!rc && d->logadd8) {
+        // 256 entries from the caller (logmath.c:116-120), continued with zeros: see logadd8()
+        if (cudaMalloc((void **)&m->d_logadd8, PSB_LOGADD8_N) != cudaSuccess ||
+            cudaMemset(m->d_logadd8, 0, PSB_LOGADD8_N) != cudaSuccess ||
+            cudaMemcpy(m->d_logadd8, d->logadd8, 256, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice) != cudaSuccess) {
+            psb_set_error("uploading the log-add table failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = PSB_ERR_CUDA;
+        }
+    }
     if (!rc && m->kind != PSB_KIND_MS && !d->logadd8) {
         psb_set_error("logadd8 table required for ptm/semi models");
         rc = PSB_ERR_ARG;
@@ -309,8 +317,9 @@ extern "C" int psb_batch_create(psb_model_t *m, int32_t max_utts, int64_t max_fr
     b->max_utts = max_utts;
     b->max_frames = max_frames;
     {
-        const char *v = getenv("PSB_TOPN_VARIANT");     // tuning knob; default = packed FP32, 4 warps/CTA
-        b->topn_variant = v ? atoi(v) : 2;
+        // tuning knob; default = packed FP32 with deferred insertion (ptm_topnq_kernel), 4 warps/CTA
+        const char *v = getenv("PSB_TOPN_VARIANT");
+        b->topn_variant = v ? atoi(v) : 5;
         const char *p = getenv("PSB_PIPELINE");         // sub-batches in flight for psb_decode_batch_*
         b->n_pipe = p ? atoi(p) : 2;
         if (b->n_pipe < 1) b->n_pipe = 1;

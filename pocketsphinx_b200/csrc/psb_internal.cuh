@@ -15,6 +15,7 @@
 #define PSB_MAX_NEG_ASCR 96      // tied_mgau_common.h:91
 #define PSB_TMAT_WORST (-255)    // hmm.h:89
 #define PSB_BAD_SSID 0xffff
+#define PSB_LOGADD8_N 512        // 8-bit add table: 256 entries (logmath.c:116-120) continued with zeros
 
 void psb_set_error(const char *fmt, ...);
 extern std::atomic<long long> g_psb_launches;
@@ -77,7 +78,7 @@ struct psb_model_s {
     int16_t *d_quadcb;            // [ceil(n_sen/4)] codebook of a uniform senone quad, else -1
     int32_t *d_bsen;              // senones of the non-uniform quads
     int n_bsen;
-    uint8_t *d_logadd8;           // [256]
+    uint8_t *d_logadd8;           // [PSB_LOGADD8_N]: the 256-entry table continued with zeros
     uint32_t *d_logadd_ms;
     float *d_msT, *d_msdetT;      // ms back-end: codebook-minor Gaussians (see psb_ms.cu)
     int32_t *d_featlen, *d_featoff;
@@ -107,7 +108,8 @@ struct psb_batch_s {
     cudaEvent_t tev[2];           // user stopwatch (psb_batch_event_record)
     bool have_ev;
     long long last_frames;
-    int topn_variant;             // 0 scalar kernel, 1/2 packed-FP32 kernels (PSB_TOPN_VARIANT)
+    int topn_variant;             // PSB_TOPN_VARIANT: 0 scalar, 1/2 packed FP32, 3 two utterances per lane,
+                                  // 4/5 packed + deferred insertion (2 / 1 utterances per lane); default 5
     // phone-loop outputs for psb_decode_batch_host
     int32_t *d_best, *d_pen;
     int32_t *h_best, *h_pen;

@@ -635,7 +635,254 @@ ptm_topn_u2_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec
     }
 }
 
-// fast_logmath_add (tied_mgau_common.h:111-127) on negated logs
+// ---------------------------------------------------------------------------------------
+// Deferred-insertion kernel ("Q").  ncu on ptm_topn2_kernel: 39 % of the executed instructions
+// are NOT distance arithmetic -- the insertion path runs for a warp whenever ANY of its 32
+// utterances accepts the current codeword (~80 of 256 codewords per frame), each time with one
+// or two lanes live -- and the warp-uniform LDS.128 record stream sits at 64 % of the
+// shared-memory data pipe (a broadcast delivers 8 bytes per wavefront).  Two changes:
+//  * NU utterances per lane share every record load: the pair record {A,B} is used as is, each
+//    utterance keeps its own duplicated feature registers (x,x), so there is no repacking and
+//    LDS traffic per (utterance, codeword) drops by NU.
+//  * The scan only FILTERS: a codeword whose distance passes `d >= thresh` against a stale
+//    (= lower or equal, the worst score only rises during a scan) threshold is pushed on a small
+//    per-utterance queue in shared memory (distance) and a register (codeword byte).  All lanes
+//    drain their queues together -- when any queue is nearly full and at the end of the frame --
+//    replaying eval_cb's tests literally and in codeword order against the then-current list:
+//    `d < thresh -> continue`, `already listed -> continue`, insertion_sort_cb
+//    (ptm_mgau.c:207-222).  The queued set is a superset of the codewords the reference inserts
+//    and every skipped codeword fails the reference's own test at its own scan position, so the
+//    list after the drain equals the reference's.
+constexpr int QCAP = 4;               // queue slots per utterance (codeword bytes fit one register)
+
+struct QState {
+    unsigned cwp;           // listed codewords, byte j = cw_j
+    int sc[TOPN];
+    float thresh;           // (float)sc[TOPN-1] as of the last drain; +inf for a finished utterance
+    unsigned qc;            // queued codewords, newest in byte 0
+    unsigned qw;            // shared-window byte address of the next free queue slot (this lane's
+                            // column; slots are NT floats apart)
+};
+
+__device__ __forceinline__ void sts_f32(unsigned addr, float v)
+{
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(unsigned addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void q_insert(QState &st, int c, int s)
+{
+    int p = 0;
+#pragma unroll
+    for (int j = 0; j < TOPN - 1; ++j) p += (s >= st.sc[j]) ? 0 : 1;       // insertion_sort_cb (ptm_mgau.c:140-149)
+#pragma unroll
+    for (int j = TOPN - 2; j >= 0; --j)
+        if (j >= p) st.sc[j + 1] = st.sc[j];
+#pragma unroll
+    for (int j = 0; j < TOPN; ++j)
+        if (j == p) st.sc[j] = s;
+    const unsigned lowmask = (1u << (8 * p)) - 1u;                          // p <= 3
+    st.cwp = (st.cwp & lowmask) | ((unsigned)c << (8 * p)) | ((st.cwp << 8) & ~((lowmask << 8) | 0xffu));
+}
+
+// q: this lane's slot 0 of the utterance's queue, slots are `stride` floats apart
+template <int stride>
+__device__ __forceinline__ void q_drain(QState &st, unsigned q, bool active)
+{
+    const int qn = (int)(st.qw - q) / (stride * 4);
+#pragma unroll
+    for (int i = 0; i < QCAP; ++i) {
+        if (i < qn) {
+            const float d = lds_f32(q + i * stride * 4);
+            if (d >= (float)st.sc[TOPN - 1]) {                              // ptm_mgau.c:207
+                const unsigned c = (st.qc >> (8 * (qn - 1 - i))) & 0xffu;
+                const unsigned x = st.cwp ^ (c * 0x01010101u);              // zero byte <=> already listed (:209-215)
+                if (!((x - 0x01010101u) & ~x & 0x80808080u))
+                    q_insert(st, (int)c, f2i_clamped(d));
+            }
+        }
+    }
+    st.qw = q;
+    if (active) st.thresh = (float)st.sc[TOPN - 1];
+}
+
+template <int FL, int NU, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+ptm_topnq_kernel(const float *__restrict__ rec2, const size_t *__restrict__ rec2_off,
+                 const int32_t *__restrict__ klist, const float *__restrict__ featT, GroupTabs tabs,
+                 int4 *__restrict__ out, int n_groups, int nd, int n_feat, int D,
+                 const int32_t *__restrict__ featoff, int K, int ds_ratio)
+{
+    constexpr int RECF2 = (2 + 4 * FL + 3) / 4 * 4;
+    constexpr int RECQ2 = RECF2 / 4;
+    constexpr int NT = WARPS * 32;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ float4 srec[];          // [nd/2][RECQ2] pair records, then float q[NU][QCAP][NT]
+    const unsigned qbase = (unsigned)__cvta_generic_to_shared(
+        reinterpret_cast<float *>(srec + (size_t)(nd >> 1) * RECQ2) + threadIdx.x);
+    constexpr unsigned QU = QCAP * NT * 4;      // bytes between the queues of two utterances of a lane
+    const int k = klist[blockIdx.x];
+    const int f = k % n_feat;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(rec2 + rec2_off[k]);
+        for (int i = threadIdx.x; i < (nd >> 1) * RECQ2; i += blockDim.x)
+            srec[i] = src[i];
+    }
+    __syncthreads();
+    // this warp owns utterance groups NU*w .. NU*w + NU-1 (the trailing ones may not exist)
+    const int w = blockIdx.y * WARPS + warp;
+    if (NU * w >= n_groups) return;
+    int len[NU], gmaxT[NU];
+    long long off[NU];
+    const float *xT[NU];
+    int maxT = 0;
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+        const int g = NU * w + u;
+        const bool has = g < n_groups;
+        len[u] = has ? tabs.lane_len[g * 32 + lane] : 0;
+        off[u] = has ? tabs.lane_off[g * 32 + lane] : 0;
+        gmaxT[u] = has ? tabs.grp_maxT[g] : 0;
+        xT[u] = featT + (has ? tabs.grp_base[g] : 0) + (long long)featoff[f] * 32 + lane;
+        maxT = max(maxT, gmaxT[u]);
+    }
+
+    QState st[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+        st[u].cwp = 0x03020100u;                                   // codewords 0..3 (ptm_mgau.c:791-792)
+#pragma unroll
+        for (int i = 0; i < TOPN; ++i) st[u].sc[i] = INT_MIN;
+        st[u].thresh = 0.f;
+        st[u].qc = 0u;
+        st[u].qw = qbase + u * QU;
+    }
+
+    for (int t = 0; t < maxT; ++t) {
+        float2 xx[NU][FL];
+        bool act[NU], any = false;
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            const float *p = xT[u] + (long long)t * D * 32;
+            const bool in = t < gmaxT[u];
+#pragma unroll
+            for (int j = 0; j < FL; ++j) {
+                const float v = in ? p[j * 32] : 0.f;
+                xx[u][j] = make_float2(v, v);
+            }
+            act[u] = t < len[u];
+            any |= act[u];
+        }
+        if (!__any_sync(FULL, any)) continue;                       // warp-uniform: the votes below need all lanes
+
+        // ---- eval_topn per utterance: re-score the listed codewords (ptm_mgau.c:88-135) ----
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            int ncw[TOPN], nsc[TOPN];
+#pragma unroll
+            for (int i = 0; i < TOPN; ++i) {
+                const int c = (st[u].cwp >> (8 * i)) & 0xff;
+                const float2 d2 = gau_dist2<FL>(srec + (c >> 1) * RECQ2, xx[u]);
+                const int s = f2i_clamped((c & 1) ? d2.y : d2.x);
+                int p = 0;
+#pragma unroll
+                for (int j = 0; j < i; ++j) p += (s > nsc[j]) ? 0 : 1;
+#pragma unroll
+                for (int j = TOPN - 2; j >= 0; --j)
+                    if (j < i && j >= p) { nsc[j + 1] = nsc[j]; ncw[j + 1] = ncw[j]; }
+#pragma unroll
+                for (int j = 0; j < TOPN; ++j)
+                    if (j == p) { nsc[j] = s; ncw[j] = c; }
+            }
+            unsigned cp = 0u;
+#pragma unroll
+            for (int i = 0; i < TOPN; ++i) { st[u].sc[i] = nsc[i]; cp |= (unsigned)ncw[i] << (8 * i); }
+            st[u].cwp = cp;
+            st[u].thresh = act[u] ? (float)nsc[TOPN - 1] : __int_as_float(0x7f800000);
+        }
+
+        // ---- eval_cb: filter in codeword order, one record stream for NU utterances ----
+        if (t % ds_ratio == 0) {
+#pragma unroll 2
+            for (int pp = 0; pp < (nd >> 1); ++pp) {
+                const float4 *r = srec + (size_t)pp * RECQ2;
+                float2 rr[RECF2 / 2];
+#pragma unroll
+                for (int q = 0; q < RECQ2; ++q) {
+                    const float4 v = r[q];
+                    rr[2 * q] = make_float2(v.x, v.y);
+                    rr[2 * q + 1] = make_float2(v.z, v.w);
+                }
+                float2 d[NU];
+#pragma unroll
+                for (int u = 0; u < NU; ++u) d[u] = rr[0];
+#pragma unroll
+                for (int j = 0; j < FL; ++j) {
+#pragma unroll
+                    for (int u = 0; u < NU; ++u) {
+                        float2 tt = __fadd2_rn(xx[u][j], rr[1 + 2 * j]);
+                        tt = __fmul2_rn(tt, tt);
+                        tt = __fmul2_rn(tt, rr[2 + 2 * j]);
+                        d[u].x = __fadd_rn(d[u].x, tt.x);             // scalar on purpose: see gau_dist2
+                        d[u].y = __fadd_rn(d[u].y, tt.y);
+                    }
+                }
+                bool full = false;
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    if (d[u].x >= st[u].thresh) {
+                        sts_f32(st[u].qw, d[u].x);
+                        st[u].qc = __byte_perm(st[u].qc, (unsigned)(2 * pp), 0x2104);
+                        st[u].qw += NT * 4;
+                    }
+                    if (d[u].y >= st[u].thresh) {
+                        sts_f32(st[u].qw, d[u].y);
+                        st[u].qc = __byte_perm(st[u].qc, (unsigned)(2 * pp + 1), 0x2104);
+                        st[u].qw += NT * 4;
+                    }
+                    full |= st[u].qw > qbase + u * QU + (QCAP - 2) * NT * 4;
+                }
+                if (__any_sync(FULL, full)) {
+#pragma unroll
+                    for (int u = 0; u < NU; ++u) q_drain<NT>(st[u], qbase + u * QU, act[u]);
+                }
+            }
+            bool pend = false;
+#pragma unroll
+            for (int u = 0; u < NU; ++u) pend |= st[u].qw != qbase + u * QU;
+            if (__any_sync(FULL, pend)) {
+#pragma unroll
+                for (int u = 0; u < NU; ++u) q_drain<NT>(st[u], qbase + u * QU, act[u]);
+            }
+        }
+
+        // ---- emit the records (same format as ptm_topn_kernel) ----
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            if (!act[u]) continue;
+            const int top = st[u].sc[0] >> PSB_SENSCR_SHIFT;
+            unsigned eb = 0;
+#pragma unroll
+            for (int j = 0; j < TOPN; ++j) {
+                int e = top - (st[u].sc[j] >> PSB_SENSCR_SHIFT);
+                e = e > 255 ? 255 : e;
+                eb |= (unsigned)e << (8 * j);
+            }
+            out[(off[u] + t) * K + k] = make_int4(top, (int)st[u].cwp, (int)eb, 0);
+        }
+    }
+}
+
+// fast_logmath_add (tied_mgau_common.h:111-127) on negated logs.  mixw + normalised score can
+// reach 255 + 96, so |x - y| can exceed the reference's 256-entry table (logmath.c:116-120):
+// the reference then reads past its allocation (undefined); the add table is identically 0 from
+// entry ~30 on, so the kernels continue it with zeros up to PSB_LOGADD8_N entries.
 __device__ __forceinline__ int logadd8(const uint8_t *tab, int x, int y)
 {
     return min(x, y) - tab[abs(x - y)];
@@ -655,13 +902,13 @@ ptm_senone_kernel(const int4 *__restrict__ topn, const uint8_t *__restrict__ mix
     uint4 *nsc = rowoff + K;                                        // [K]
     int *norm = reinterpret_cast<int *>(nsc + K);                   // [8]
     int *red = norm + 8;                                            // [32]
-    uint8_t *tab = reinterpret_cast<uint8_t *>(red + 32);           // [256]
-    uint8_t *cb16 = tab + 256;                                      // [16]
+    uint8_t *tab = reinterpret_cast<uint8_t *>(red + 32);           // [PSB_LOGADD8_N]
+    uint8_t *cb16 = tab + PSB_LOGADD8_N;                            // [16]
     int16_t *asc = reinterpret_cast<int16_t *>(cb16 + 16);          // [n_sen]
     const long long frame = blockIdx.x;
     const int tid = threadIdx.x;
 
-    if (tid < 256) tab[tid] = logadd_tab[tid];
+    for (int i = tid; i < PSB_LOGADD8_N; i += blockDim.x) tab[i] = logadd_tab[i];
     if (FOURBIT && tid < 16) cb16[tid] = mixw_cb[tid];
     if (tid < n_feat) norm[tid] = PSB_WORST_SCORE;                 // ptm_mgau.c:273
     __syncthreads();
@@ -741,12 +988,12 @@ semi_senone_kernel(const int4 *__restrict__ topn, const uint8_t *__restrict__ mi
     extern __shared__ int smem_i[];
     uint4 *rowoff = reinterpret_cast<uint4 *>(smem_i);             // [n_feat]
     uint4 *nsc = rowoff + n_feat;                                   // [n_feat]
-    uint8_t *tab = reinterpret_cast<uint8_t *>(nsc + n_feat);       // [256]
-    uint8_t *cb16 = tab + 256;                                      // [16]
+    uint8_t *tab = reinterpret_cast<uint8_t *>(nsc + n_feat);       // [PSB_LOGADD8_N]
+    uint8_t *cb16 = tab + PSB_LOGADD8_N;                            // [16]
     __shared__ int cnt[PSB_MAX_FEAT];
     const long long frame = blockIdx.x;
     const int tid = threadIdx.x;
-    if (tid < 256) tab[tid] = logadd_tab[tid];
+    for (int i = tid; i < PSB_LOGADD8_N; i += blockDim.x) tab[i] = logadd_tab[i];
     if (FOURBIT && tid < 16) cb16[tid] = mixw_cb[tid];
     if (tid < n_feat) {
         const int4 r = topn[frame * n_feat + tid];
@@ -810,12 +1057,12 @@ ptm_senone4_kernel(const int4 *__restrict__ topn, const uint8_t *__restrict__ mi
     uint4 *nsc = rowoff + K;                                        // [K]
     int *norm = reinterpret_cast<int *>(nsc + K);                   // [8]
     int *red = norm + 8;                                            // [32]
-    uint8_t *tab = reinterpret_cast<uint8_t *>(red + 32);           // [256]
-    int16_t *asc = reinterpret_cast<int16_t *>(tab + 256 + 16);     // [n_sen rounded up to 4]
+    uint8_t *tab = reinterpret_cast<uint8_t *>(red + 32);           // [PSB_LOGADD8_N]
+    int16_t *asc = reinterpret_cast<int16_t *>(tab + PSB_LOGADD8_N + 16);     // [n_sen rounded up to 4]
     const long long frame = blockIdx.x;
     const int tid = threadIdx.x;
 
-    for (int i = tid; i < 256; i += blockDim.x) tab[i] = logadd_tab[i];
+    for (int i = tid; i < PSB_LOGADD8_N; i += blockDim.x) tab[i] = logadd_tab[i];
     if (tid < n_feat) norm[tid] = PSB_WORST_SCORE;
     __syncthreads();
     int4 r = make_int4(0, 0, 0, 0);
@@ -916,11 +1163,35 @@ int launch_topn2(psb_batch_t *b, const int32_t *d_klist, int n_k, const GroupTab
     return PSB_OK;
 }
 
+template <int FL, int NU, int WARPS, int MINB>
+int launch_topnq(psb_batch_t *b, const int32_t *d_klist, int n_k, const GroupTabs &tabs, int n_groups,
+                 const int32_t *d_featoff)
+{
+    psb_model_t *m = b->m;
+    constexpr int RECF2 = (2 + 4 * FL + 3) / 4 * 4;
+    const size_t smem = (size_t)(m->n_density / 2) * RECF2 * sizeof(float)
+                        + (size_t)NU * QCAP * WARPS * 32 * sizeof(float);
+    auto kern = ptm_topnq_kernel<FL, NU, WARPS, MINB>;
+    PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int n_w = (n_groups + NU - 1) / NU;
+    dim3 grid(n_k, (n_w + WARPS - 1) / WARPS);
+    kern<<<grid, WARPS * 32, smem, b->stream>>>(m->d_rec2, m->d_rec2_off, d_klist, b->d_featT, tabs, b->d_topn, n_groups,
+                                               m->n_density, m->n_feat, m->sumlen, d_featoff, m->K, m->ds_ratio);
+    PSB_LAUNCH_CHECK();
+    return PSB_OK;
+}
+
 template <int FL, bool SEMI>
 int launch_topn(psb_batch_t *b, const int32_t *d_klist, int n_k, const GroupTabs &tabs, int n_groups,
                 const int32_t *d_featoff)
 {
     psb_model_t *m = b->m;
+    if (!SEMI && FL <= 16 && m->d_rec2 && b->topn_variant >= 4) {
+        // deferred-insertion kernels: 4 = two utterances per lane, 5 = one
+        constexpr int FLQ = FL <= 16 ? FL : 1;
+        if (b->topn_variant == 4) return launch_topnq<FLQ, 2, 2, 7>(b, d_klist, n_k, tabs, n_groups, d_featoff);
+        return launch_topnq<FLQ, 1, 4, 7>(b, d_klist, n_k, tabs, n_groups, d_featoff);
+    }
     if (FL <= 16 && b->topn_variant == 3) {
         // two utterances per lane: 64 utterances per warp, 4 warps per CTA
         constexpr int FLU = FL <= 16 ? FL : 1;
@@ -939,7 +1210,7 @@ int launch_topn(psb_batch_t *b, const int32_t *d_klist, int n_k, const GroupTabs
     if (FL <= 16 && m->d_rec2 && b->topn_variant != 0) {
         // packed-FP32 kernels (FL <= 16 keeps the register budget): variant 1 = 2 warps/CTA with a
         // large register budget (two balanced waves), variant 2 = 4 warps/CTA at 72 registers
-        if (b->topn_variant == 2) return launch_topn2<FL <= 16 ? FL : 1, SEMI, 4, 7>(b, d_klist, n_k, tabs, n_groups, d_featoff);
+        if (b->topn_variant != 1) return launch_topn2<FL <= 16 ? FL : 1, SEMI, 4, 7>(b, d_klist, n_k, tabs, n_groups, d_featoff);
         return launch_topn2<FL <= 16 ? FL : 1, SEMI, 2, 7>(b, d_klist, n_k, tabs, n_groups, d_featoff);
     }
     size_t smem = (size_t)m->n_density * rec_floats(FL) * sizeof(float);
@@ -1073,7 +1344,7 @@ int psb_launch_ptm_batch(psb_batch_t *b, const float *d_feats, const int32_t *ut
     }
     if (b->have_ev) PSB_CUDA(cudaEventRecord(b->ev[2], b->stream));
     if (semi) {
-        size_t smem = (size_t)K * 32 + 256 + 16;
+        size_t smem = (size_t)K * 32 + PSB_LOGADD8_N + 16;
         PSB_REQUIRE(K <= 512, "semi_senone_kernel handles at most 512 streams (got %d)", K);
         const int threads = 256;
         dim3 grid((m->n_sen + threads - 1) / threads, (unsigned)total);
@@ -1088,7 +1359,7 @@ int psb_launch_ptm_batch(psb_batch_t *b, const float *d_feats, const int32_t *ut
         PSB_LAUNCH_CHECK();
     }
     else {
-        size_t smem = (size_t)K * 32 + 8 * 4 + 32 * 4 + 256 + 16 + (size_t)m->n_sen * 2;
+        size_t smem = (size_t)K * 32 + 8 * 4 + 32 * 4 + PSB_LOGADD8_N + 16 + (size_t)m->n_sen * 2;
         PSB_REQUIRE(K <= 512, "ptm_senone_kernel handles at most 512 (codebook, stream) pairs (got %d)", K);
         PSB_REQUIRE((size_t)m->n_feat * m->n_density * m->mixw_stride < (1ull << 32), "mixture-weight table too large for 32-bit offsets");
         if (m->mixw_4bit) {

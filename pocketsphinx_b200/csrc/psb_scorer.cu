@@ -122,14 +122,14 @@ scorer_senone_kernel(int32_t *__restrict__ slot_cw, int32_t *__restrict__ slot_s
     int *cw = sc + K * topn;                            // [K*topn]
     int *norm = cw + K * topn;                          // [8]
     int *red = norm + 8;                                // [32]
-    uint8_t *tab = reinterpret_cast<uint8_t *>(red + 32);   // [256]
-    uint8_t *cb16 = tab + 256;                          // [16]
+    uint8_t *tab = reinterpret_cast<uint8_t *>(red + 32);   // [PSB_LOGADD8_N]
+    uint8_t *cb16 = tab + PSB_LOGADD8_N;                // [16]
     uint8_t *act = cb16 + 16;                           // [n_mgau]
     int16_t *asc = reinterpret_cast<int16_t *>(act + ((n_mgau + 15) & ~15));   // [n_sen]
 
     for (int i = tid; i < K * topn; i += blockDim.x) { sc[i] = slot_sc[i]; cw[i] = slot_cw[i]; }
     for (int i = tid; i < n_mgau; i += blockDim.x) act[i] = active[i];
-    if (tid < 256) tab[tid] = logadd_tab[tid];
+    for (int i = tid; i < PSB_LOGADD8_N; i += blockDim.x) tab[i] = logadd_tab[i];
     if (FOURBIT && tid < 16) cb16[tid] = mixw_cb[tid];
     if (tid < n_feat) norm[tid] = PSB_WORST_SCORE;
     for (int i = tid; i < n_sen; i += blockDim.x) asc[i] = 0;            // memset (:333)
@@ -207,9 +207,9 @@ scorer_semi_senone_kernel(int32_t *__restrict__ slot_cw, int32_t *__restrict__ s
                           int16_t *__restrict__ senscr, int n_sen, int n_feat, int nd, int topn, int mixw_stride)
 {
     __shared__ int sc[PSB_MAX_FEAT * PSB_MAX_TOPN], cw[PSB_MAX_FEAT * PSB_MAX_TOPN], cnt[PSB_MAX_FEAT];
-    __shared__ uint8_t tab[256], cb16[16];
+    __shared__ uint8_t tab[PSB_LOGADD8_N], cb16[16];
     const int tid = threadIdx.x;
-    if (tid < 256) tab[tid] = logadd_tab[tid];
+    for (int i = tid; i < PSB_LOGADD8_N; i += blockDim.x) tab[i] = logadd_tab[i];
     if (FOURBIT && tid < 16) cb16[tid] = mixw_cb[tid];
     if (tid < n_feat * topn) { sc[tid] = slot_sc[tid]; cw[tid] = slot_cw[tid]; }
     __syncthreads();
@@ -410,7 +410,7 @@ extern "C" int psb_scorer_frame_eval(psb_scorer_t *s, int16_t *senscr, const uin
         }
         else {
             const int K = m->K;
-            size_t smem = ((size_t)2 * K * m->topn + 8 + 32) * 4 + 256 + 16 + ((m->n_mgau + 15) & ~15) + (size_t)m->n_sen * 2;
+            size_t smem = ((size_t)2 * K * m->topn + 8 + 32) * 4 + PSB_LOGADD8_N + 16 + ((m->n_mgau + 15) & ~15) + (size_t)m->n_sen * 2;
             PSB_REQUIRE(smem <= 227 * 1024, "model too large for scorer_senone_kernel (%zu bytes of shared memory)", smem);
             if (m->mixw_4bit) {
                 PSB_CUDA(cudaFuncSetAttribute(scorer_senone_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -356,3 +356,47 @@ def test_phoneloop_large_and_5state_vs_oracle(api, n_emit, H, window, skip):
             assert np.array_equal(got["pen"][a:b], want["pen"]), "utt %d penalties" % u
         assert_hmm_equal(got["hmm"][a:b], want["hmm"], n_emit, "utt %d" % u)
     pl.close(); ctx.close()
+
+
+# ---------------------------------------------------------------------------------------
+# every top-N kernel variant (PSB_TOPN_VARIANT, read at psb_batch_create) must give the same bits
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+def test_topn_kernel_variants(api, en_us_dev, variant, monkeypatch):
+    from oracle import oracle
+    from pocketsphinx_b200.model import quantize_for_ties, synth_feats, synth_ptm
+    monkeypatch.setenv("PSB_TOPN_VARIANT", str(variant))
+    # (1) shipped model, real features
+    g = golden("en_us_goforward.npz")
+    b = api.Batch(en_us_dev, 4, 1024)
+    assert np.array_equal(b.score_host(g["feats"], np.array([0, 278], np.int32)), g["senscr"])
+    b.close()
+    # (2) BASELINE shape, ragged batch of 70 utterances (3 lane groups: an odd group count, padding
+    #     lanes, zero-length utterances)
+    pm = synth_ptm(seed=11, n_density=256, n_sen=600)
+    rng = np.random.default_rng(4)
+    lens = [0, 1, 40, 0, 17] + [int(x) for x in rng.integers(1, 40, 65)]
+    feats = synth_feats(pm, len(lens), 40, seed=3)
+    _batch_vs_oracle(api, pm, [feats[u][:n].reshape(n, pm.sumlen) for u, n in enumerate(lens)])
+    # (3) exact ties everywhere
+    pmq, gen = quantize_for_ties(synth_ptm(seed=2, n_density=64, n_sen=400), seed=6)
+    _batch_vs_oracle(api, pmq, list(gen(40, 25, s=9)))
+    # (4) frame down-sampling (-ds 2): odd frames only re-score the listed codewords
+    pm2 = synth_ptm(seed=12, n_density=128, n_sen=300)
+    pm2.ds_ratio = 2
+    f2 = synth_feats(pm2, 33, 20, seed=5)
+    _batch_vs_oracle(api, pm2, [f2[u].reshape(-1, pm2.sumlen) for u in range(33)])
+
+
+def test_ptm_and_semi_mixw_extremes(api):
+    """Mixture weights of 0 and 255 next to each other: |x - y| in fast_logmath_add exceeds the
+    reference's 256-entry table (undefined there); both sides continue the table with zeros."""
+    from pocketsphinx_b200.model import synth_feats, synth_ptm, synth_semi
+    for pm in (synth_ptm(seed=21, n_density=64, n_sen=500), synth_semi(seed=21, n_density=64, n_sen=300)):
+        rng = np.random.default_rng(8)
+        mw = pm.mixw.copy()
+        mask = rng.random(mw.shape) < 0.5
+        mw[mask] = np.where(rng.random(mask.sum()) < 0.5, 0, 255).astype(mw.dtype)
+        pm.mixw = np.ascontiguousarray(mw)
+        feats = synth_feats(pm, 20, 12, seed=2)
+        _batch_vs_oracle(api, pm, [feats[u].reshape(-1, pm.sumlen) for u in range(20)])
