@@ -297,14 +297,14 @@ def main():
     ms_total = batch.event_elapsed_ms()
     barrier()
     launches = api.lib().psb_kernel_launch_count() - launches1
-    # per-kernel durations for the roofline: two extra steps on ONE stream (the timed region above
-    # keeps two sub-batches in flight, whose kernels overlap and cannot be timed individually)
+    # per-kernel durations for the roofline: two extra steps forced onto ONE stream (with
+    # PSB_PIPELINE > 1 the timed region's kernels overlap and cannot be timed individually)
     batch.set_pipeline(1)
     for _ in range(2):
         batch.decode_device(pl, d_feats.data_ptr(), off)
     batch.sync()
     km = batch.last_kernel_ms()          # CUDA events around each kernel on the stream it runs on
-    batch.set_pipeline(int(os.environ.get("PSB_PIPELINE", "2")))
+    batch.set_pipeline(int(os.environ.get("PSB_PIPELINE", "0")))
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
 
@@ -354,7 +354,7 @@ def main():
                        "parallelism": "utterances sharded, %d per GPU, no per-frame collective" % U,
                        "l2": "per-step working set (%.1f GB of scores) exceeds L2; no explicit flush" % (total * pm.n_sen * 2 / 1e9)},
             "gpu_launches": int(launches),
-            "kernel_ms_unpipelined": {**km, "note": "separate single-stream pass; the timed region pipelines 2 sub-batches"},
+            "kernel_ms_unpipelined": {**km, "note": "separate single-stream pass after the timed region"},
             "roofline": {"bound": "hbm", "kernel": topn_name, "achieved": topn_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": topn_gbs / hbm_peak,
                          # dram__bytes_read+write of ptm_topnq_kernel from the committed ncu capture

@@ -223,8 +223,9 @@ int psb_sendump_write(const char *path, const char *mdef_file, int32_t n_sen, do
                       const int16_t *senscr, int64_t n_frames);
 int64_t psb_sendump_read(const char *path, int32_t *n_sen_out, int16_t *senscr, int64_t max_frames);
 
-/* Number of sub-batches psb_decode_batch_* keeps in flight on separate streams (default 2, env
- * PSB_PIPELINE; 1 = one stream, which is what per-kernel timing wants). */
+/* Number of sub-batches psb_decode_batch_* keeps in flight on separate streams.  0 = auto (the
+ * default, also env PSB_PIPELINE): 2 for host buffers (copies overlap kernels), 1 for resident
+ * features; 1 = one stream, which is what per-kernel timing wants; up to 8. */
 int psb_batch_set_pipeline(psb_batch_t *b, int n);
 
 /* number of kernels launched by this library in the calling process so far */

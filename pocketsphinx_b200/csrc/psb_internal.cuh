@@ -122,7 +122,7 @@ struct psb_batch_s {
     // pipelined decode: sub-batches on their own streams sharing this batch's big buffers
     std::vector<psb_batch_t *> kids;
     cudaEvent_t fork_ev, join_ev;
-    int n_pipe;                   // PSB_PIPELINE (default 2); 1 = everything on `stream`
+    int n_pipe;                   // PSB_PIPELINE: 0 = auto (default), 1 = everything on `stream`, n = n ranges
     bool is_kid;
     bool last_pipelined;
     int last_kids;                // sub-batches used by the last decode call
