@@ -134,6 +134,51 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def viterbi_stage(api, torch, ctx, batch, pm, off, U, T, hbm_peak, n_active=6081, n_frames=48):
+    """Stage-wise Viterbi number: every utterance keeps n_active hmm_t instances alive
+    (the survey measured 6 081 active HMMs per frame for en-us fwdtree at default beams), all of
+    them take one hmm_vit_eval step per frame against that frame's senone scores (the ones the
+    GMM stage just left in HBM) with a per-utterance best-score reduction: evaluate_channels
+    (ngram_search_fwdtree.c:702-715) for a whole batch, state resident in HBM as SoA.  Which HMMs
+    are active is the search's business (row f-1, not built): instances are drawn at random from
+    the model's senone sequences, all entered at frame 0."""
+    if pm.n_emit_state not in (3, 5) or len(pm.sseq) == 0:
+        return None
+    ns = pm.n_emit_state
+    rng = np.random.default_rng(99)
+    n = U * n_active
+    hm = np.zeros(n, api.HMM_DTYPE)
+    ssid = rng.integers(0, len(pm.sseq), n)
+    hm["score"][:, :] = -0x20000000
+    hm["score"][:, 0] = 0                                      # hmm_enter(score 0, history -1, frame 0)
+    hm["history"][:, :] = -1
+    hm["out_score"] = -0x20000000
+    hm["out_history"] = -1
+    hm["bestscore"] = -0x20000000
+    hm["ssid"] = ssid
+    hm["senid"][:, :ns] = pm.sseq[ssid]
+    hm["tmatid"] = rng.integers(0, pm.tp.shape[0], n)
+    hm["n_emit_state"] = ns
+    hs = api.HmmSet(ctx, n, U)
+    hs.upload(hm, np.arange(U + 1, dtype=np.int64) * n_active)
+    F = min(n_frames, T)
+    d_row0 = torch.from_numpy(np.asarray(off[:U], np.int64)).cuda()
+    d_best = torch.empty((F, U), dtype=torch.int32, device="cuda")
+    hs.eval_frames_device(batch.senscr_device_ptr(), 3, d_best.data_ptr(), d_row0=d_row0.data_ptr())   # warm-up
+    ms = hs.eval_frames_device(batch.senscr_device_ptr(), F, d_best.data_ptr(), d_row0=d_row0.data_ptr())
+    hs.close()
+    # algorithmic bytes per instance and frame: state read + written (score, history per state,
+    # exit score + history, best) + senone ids, transition id and the int16 score gathers
+    alg = (2 * ns * 4) * 2 + 2 * 4 * 2 + 4 + 2 * ns + 2 + 2 * ns
+    gbs = n * alg * F / (ms * 1e-3) / 1e9
+    return {"kernel": "hmmset_eval_kernel", "active_hmms_per_utt": n_active, "utts": U, "frames_timed": F,
+            "ms_per_frame_of_batch": ms / F, "hmm_updates_per_s": n * F / (ms * 1e-3),
+            "frames_per_s": U * F / (ms * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                         "algorithmic_bytes_per_hmm": alg},
+            "note": "not part of `value`: the headline Viterbi is the reference's phone loop (42 HMMs per utterance)"}
+
+
 def cpu_baseline(args, pm, raw, feats, n_frames_per_utt, budget_s=15.0, threads=1):
     """The reference's CPU implementation of the path on host cores over a bounded sample of the
     same workload: senone evaluation through the COMPILED REFERENCE (oracle/_ref/libpsref.so:
@@ -376,6 +421,10 @@ def main():
             "clocks": clocks,
         }
         if world == 1:
+            batch.set_pipeline(1)                           # leave the whole batch's scores in one buffer
+            batch.decode_device(pl, d_feats.data_ptr(), off)
+            batch.sync()
+            out["viterbi_stage"] = viterbi_stage(api, torch, ctx, batch, pm, off, U, T, hbm_peak)
             out["cpu_baseline"] = cpu_baseline(args, pm, raw, feats_np, T, budget_s=args.cpu_budget, threads=1)
         print(json.dumps(out))
     batch.close(); pl.close(); ctx.close(); model.close()

@@ -174,6 +174,31 @@ int psb_hmm_vit_eval_batch(psb_hmmctx_t *c, psb_hmm_t *hmms, int32_t n, const in
 int psb_hmm_vit_eval_ptrs(psb_hmmctx_t *c, psb_hmm_t *const *hmms, int32_t n,
                           const int16_t *senscr, int32_t *best);
 
+/* Device-resident HMM sets: the instances that evaluate_channels
+ * (ngram_search_fwdtree.c:702-715), fsg_search_hmm_eval (fsg_search.c:336-408),
+ * kws_search_hmm_eval (kws_search.c:194) and phmm_eval_all (allphone_search.c:349) walk every
+ * frame, kept in HBM between frames as a structure of arrays instead of crossing the bus as
+ * 88-byte records.  Instances are grouped in n_seg segments (one per utterance / decoder);
+ * segment s owns instances [seg_off[s], seg_off[s+1]) and has its own senone-score row and best
+ * score per frame. */
+typedef struct psb_hmmset_s psb_hmmset_t;
+int psb_hmmset_create(psb_hmmctx_t *c, int64_t n_max, int32_t n_seg_max, psb_hmmset_t **out);
+void psb_hmmset_free(psb_hmmset_t *s);
+/* host hmm_t records -> device SoA (hmm_init / hmm_enter happen on the host), and back */
+int psb_hmmset_upload(psb_hmmset_t *s, const psb_hmm_t *hmms, int64_t n, const int64_t *seg_off,
+                      int32_t n_seg);
+int psb_hmmset_download(psb_hmmset_t *s, psb_hmm_t *hmms);
+/* n_frames consecutive frames: in frame t every instance of segment s takes one hmm_vit_eval
+ * step (hmm.c:787-805) against the device int16 row  d_senscr[(d_row0[s] + t) * n_sen]  (with
+ * d_row0 == NULL: row t * n_seg + s) and d_best[t * n_seg + s] = max bestscore of the segment
+ * (PSB_WORST_SCORE if it is empty or finished: d_n_rows[s] <= t, d_n_rows may be NULL).
+ * *ms (may be NULL) = device time of the n_frames launches (CUDA events on the set's stream). */
+int psb_hmmset_eval_frames_device(psb_hmmset_t *s, const int16_t *d_senscr, const int64_t *d_row0,
+                                  const int32_t *d_n_rows, int32_t n_frames, int32_t *d_best,
+                                  float *ms);
+/* one frame from host buffers: senscr int16 [n_seg][n_sen], best int32 [n_seg] */
+int psb_hmmset_eval_host(psb_hmmset_t *s, const int16_t *senscr, int32_t *best);
+
 /* ------------------------------------------------------------------------------------ */
 /* Device-resident phone-loop Viterbi over whole utterances: the frame-synchronous caller
  * of hmm_vit_eval in phone_loop_search.c (start :155, renormalize :177, evaluate_hmms :193,

@@ -56,6 +56,12 @@ SYMBOLS = [
     ("psb_hmmctx_free", None, [_VP]),
     ("psb_hmm_vit_eval_batch", C.c_int, [_VP, _VP, _I32, _VP, _VP]),
     ("psb_hmm_vit_eval_ptrs", C.c_int, [_VP, _VP, _I32, _VP, _VP]),
+    ("psb_hmmset_create", C.c_int, [_VP, C.c_int64, _I32, C.POINTER(_VP)]),
+    ("psb_hmmset_free", None, [_VP]),
+    ("psb_hmmset_upload", C.c_int, [_VP, _VP, C.c_int64, _VP, _I32]),
+    ("psb_hmmset_download", C.c_int, [_VP, _VP]),
+    ("psb_hmmset_eval_frames_device", C.c_int, [_VP, _VP, _VP, _VP, _I32, _VP, C.POINTER(C.c_float)]),
+    ("psb_hmmset_eval_host", C.c_int, [_VP, _VP, _VP]),
     ("psb_phoneloop_create", C.c_int, [_VP, _I32, _VP, _VP, _I32, _I32, _I32, _I32, C.c_double, C.POINTER(_VP)]),
     ("psb_phoneloop_free", None, [_VP]),
     ("psb_phoneloop_run_device", C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP]),

@@ -258,6 +258,54 @@ class HmmContext:
             self.h = None
 
 
+class HmmSet:
+    """Device-resident HMM instances in segments (one per utterance): the batched
+    evaluate_channels / fsg_search_hmm_eval / phmm_eval_all loop with state kept in HBM."""
+
+    def __init__(self, ctx: HmmContext, n_max, n_seg_max):
+        self.ctx = ctx
+        h = C.c_void_p()
+        check(lib().psb_hmmset_create(ctx.h, int(n_max), int(n_seg_max), C.byref(h)), "psb_hmmset_create")
+        self.h = h
+        self.n = 0
+        self.n_seg = 0
+
+    def upload(self, hmms, seg_off):
+        assert hmms.dtype == HMM_DTYPE and hmms.flags.c_contiguous
+        seg_off = np.ascontiguousarray(seg_off, np.int64)
+        check(lib().psb_hmmset_upload(self.h, _p(hmms) if len(hmms) else None, len(hmms), _p(seg_off),
+                                      len(seg_off) - 1), "psb_hmmset_upload")
+        self.n, self.n_seg = len(hmms), len(seg_off) - 1
+
+    def download(self, hmms=None):
+        if hmms is None:
+            hmms = np.zeros(self.n, HMM_DTYPE)
+        assert hmms.dtype == HMM_DTYPE and hmms.flags.c_contiguous and len(hmms) == self.n
+        check(lib().psb_hmmset_download(self.h, _p(hmms) if self.n else None), "psb_hmmset_download")
+        return hmms
+
+    def eval_host(self, senscr):
+        """One frame; senscr int16 [n_seg][n_sen]; returns best int32 [n_seg]."""
+        senscr = np.ascontiguousarray(senscr, np.int16)
+        assert senscr.shape == (self.n_seg, self.ctx.n_sen)
+        best = np.zeros(self.n_seg, np.int32)
+        check(lib().psb_hmmset_eval_host(self.h, _p(senscr), _p(best)), "psb_hmmset_eval_host")
+        return best
+
+    def eval_frames_device(self, d_senscr, n_frames, d_best, d_row0=None, d_n_rows=None):
+        """Device pointers (ints); returns the device time of the n_frames launches in ms."""
+        ms = C.c_float()
+        check(lib().psb_hmmset_eval_frames_device(self.h, C.c_void_p(d_senscr), C.c_void_p(d_row0) if d_row0 else None,
+                                                  C.c_void_p(d_n_rows) if d_n_rows else None, int(n_frames),
+                                                  C.c_void_p(d_best), C.byref(ms)), "psb_hmmset_eval_frames_device")
+        return ms.value
+
+    def close(self):
+        if self.h:
+            lib().psb_hmmset_free(self.h)
+            self.h = None
+
+
 class PhoneLoop:
     """phone_loop_search.c on the device over batches of utterances."""
 

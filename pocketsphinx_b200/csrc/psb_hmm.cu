@@ -3,6 +3,8 @@
 
 #include <string.h>
 
+#include <algorithm>
+
 #include <vector>
 
 struct psb_hmmctx_s {
@@ -520,5 +522,377 @@ extern "C" int psb_phoneloop_run_host(psb_phoneloop_t *p, const int16_t *senscr,
     }
     if (e != cudaSuccess) { psb_set_error("psb_phoneloop_run_host: %s", cudaGetErrorString(e)); rc = PSB_ERR_CUDA; }
     cudaFree(d_scr); cudaFree(d_off); cudaFree(d_best); cudaFree(d_pen); cudaFree(d_tr);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------
+// Device-resident HMM sets (SURVEY 8 b5 at the reference's real activity level, first brick of
+// row f-1): what evaluate_channels (ngram_search_fwdtree.c:702-715), fsg_search_hmm_eval
+// (fsg_search.c:336-408), phmm_eval_all (allphone_search.c:349) iterate over every frame --
+// ~6 000 hmm_t per utterance on en-us -- kept in HBM between frames as a structure of arrays so
+// that one frame is one coalesced streaming pass: 41 B read + 36 B written per 3-state instance
+// (SURVEY 8d counts 74 B), against 176 B for the 88-byte hmm_t records themselves.  Instances are
+// grouped in segments (one per utterance); every segment has its own senone-score row per frame
+// and its own best score, like one decoder each.  Inside the set every segment is padded to a
+// multiple of four instances so that a thread owns four neighbours and moves them with 128-bit
+// (state) and 64-bit (ids) accesses; padding instances are inert (WORST_SCORE, senone 0) and
+// never reach the best score.
+constexpr int HS_V = 4;                     // instances per thread
+constexpr int HS_THREADS = 256;
+constexpr int HS_TILE = HS_V * HS_THREADS;  // instances per CTA
+
+struct psb_hmmset_s {
+    psb_hmmctx_t *c;
+    int64_t n_max, n, pitch;
+    int32_t n_seg_max, n_seg;
+    int64_t max_seg_len;
+    int32_t *d_i32;               // [(2*NS + 4)][pitch]: score[NS] hist[NS] out_score out_hist best frame
+    uint16_t *d_u16;              // [(NS + 2)][pitch]: senid[NS] ssid tmatid(int16)
+    uint8_t *d_mpx;               // [pitch]
+    int64_t *d_seg_off;           // [n_seg_max + 1] caller's offsets (AoS order)
+    int64_t *d_seg_base;          // [n_seg_max + 1] padded offsets inside the set
+    psb_hmm_t *d_aos;             // staging for upload / download
+    cudaStream_t stream;
+    cudaEvent_t ev[2];
+};
+
+namespace {
+
+struct HmmSetDev {
+    int32_t *i32;
+    uint16_t *u16;
+    uint8_t *mpx;
+    const int64_t *seg_off, *seg_base;
+    int64_t pitch;
+    int n_seg;
+};
+
+static HmmSetDev dev_set(const psb_hmmset_t *s)
+{
+    HmmSetDev d;
+    d.i32 = s->d_i32; d.u16 = s->d_u16; d.mpx = s->d_mpx; d.seg_off = s->d_seg_off; d.seg_base = s->d_seg_base;
+    d.pitch = s->pitch; d.n_seg = s->n_seg;
+    return d;
+}
+
+template <bool TO_SOA>
+__global__ void __launch_bounds__(256)
+hmmset_convert_kernel(psb_hmm_t *aos, HmmSetDev s, int64_t n, int ns)
+{
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // index in the caller's array
+    if (a >= n) return;
+    int lo = 0, hi = s.n_seg;                                           // segment of a: seg_off[lo] <= a < seg_off[lo+1]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s.seg_off[mid] <= a) lo = mid; else hi = mid;
+    }
+    const int64_t i = s.seg_base[lo] + (a - s.seg_off[lo]);
+    psb_hmm_t *p = aos + a;
+    int32_t *score = s.i32 + i, *hist = s.i32 + (int64_t)ns * s.pitch + i;
+    int32_t *tail = s.i32 + (int64_t)2 * ns * s.pitch + i;
+    uint16_t *senid = s.u16 + i, *ids = s.u16 + (int64_t)ns * s.pitch + i;
+    if (TO_SOA) {
+        for (int k = 0; k < ns; ++k) {
+            score[k * s.pitch] = p->score[k];
+            hist[k * s.pitch] = p->history[k];
+            senid[k * s.pitch] = p->senid[k];
+        }
+        tail[0] = p->out_score; tail[s.pitch] = p->out_history; tail[2 * s.pitch] = p->bestscore; tail[3 * s.pitch] = p->frame;
+        ids[0] = p->ssid; ids[s.pitch] = (uint16_t)p->tmatid;
+        s.mpx[i] = p->mpx;
+    }
+    else {
+        for (int k = 0; k < PSB_HMM_MAX_NSTATE; ++k) {
+            p->score[k] = k < ns ? score[k * s.pitch] : 0;
+            p->history[k] = k < ns ? hist[k * s.pitch] : 0;
+            p->senid[k] = k < ns ? senid[k * s.pitch] : 0;
+        }
+        p->out_score = tail[0]; p->out_history = tail[s.pitch]; p->bestscore = tail[2 * s.pitch]; p->frame = tail[3 * s.pitch];
+        p->ssid = ids[0]; p->tmatid = (int16_t)ids[s.pitch];
+        p->mpx = s.mpx[i]; p->n_emit_state = (uint8_t)ns;
+        p->ctx = nullptr;
+    }
+}
+
+__global__ void fill_i32_kernel(int32_t *p, int64_t n, int32_t v)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__device__ __forceinline__ int comp(const int4 &v, int q) { return q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w; }
+__device__ __forceinline__ void setc(int4 &v, int q, int x)
+{
+    if (q == 0) v.x = x; else if (q == 1) v.y = x; else if (q == 2) v.z = x; else v.w = x;
+}
+
+// One hmm_vit_eval per instance, four instances per thread, one CTA row (blockIdx.y) per
+// segment.  row0[seg] + t is the segment's senone-score row of this frame (staged in shared
+// memory: the gathers of a tile hit ~3 x HS_TILE random int16 of it); segments with
+// n_rows[seg] <= t are finished.  NS = 3 or 5 (0: any topology, runtime count).
+template <int NS>
+__global__ void __launch_bounds__(HS_THREADS)
+hmmset_eval_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr, const int64_t *__restrict__ row0,
+                   const int32_t *__restrict__ n_rows, int t, int32_t *__restrict__ best_out)
+{
+    extern __shared__ int16_t srow[];         // [n_sen]
+    __shared__ int red[HS_THREADS / 32];
+    const int seg = blockIdx.y;
+    if (n_rows && t >= n_rows[seg]) return;
+    const int64_t n = s.seg_off[seg + 1] - s.seg_off[seg];
+    const int64_t j0 = ((int64_t)blockIdx.x * HS_THREADS + threadIdx.x) * HS_V;   // first of this thread's four
+    if ((int64_t)blockIdx.x * HS_TILE >= n) return;
+    {
+        const int16_t *row = senscr + (row0 ? row0[seg] + t : (int64_t)t * gridDim.y + seg) * c.n_sen;
+        if ((((uintptr_t)row) & 3) == 0) {
+            const int *r32 = reinterpret_cast<const int *>(row);
+            int *s32 = reinterpret_cast<int *>(srow);
+            for (int i = threadIdx.x; i < (c.n_sen >> 1); i += HS_THREADS) s32[i] = r32[i];
+            if ((c.n_sen & 1) && threadIdx.x == 0) srow[c.n_sen - 1] = row[c.n_sen - 1];
+        }
+        else
+            for (int i = threadIdx.x; i < c.n_sen; i += HS_THREADS) srow[i] = row[i];
+    }
+    __syncthreads();
+    constexpr int NL = NS > 0 ? NS : PSB_HMM_MAX_NSTATE;
+    const int ns = NS > 0 ? NS : c.n_emit;
+    int best = PSB_WORST_SCORE;
+    if (j0 < n) {
+        const int64_t i = s.seg_base[seg] + j0;                       // multiple of four
+        int32_t *score = s.i32 + i, *hist = s.i32 + (int64_t)ns * s.pitch + i;
+        int32_t *tail = s.i32 + (int64_t)2 * ns * s.pitch + i;
+        uint16_t *senid = s.u16 + i;
+        const uint16_t *ids = s.u16 + (int64_t)ns * s.pitch + i;
+        int4 sc[NL], hi[NL], osc, ohi, bst;
+        uint2 sid[NL];
+#pragma unroll
+        for (int k = 0; k < NL; ++k)
+            if (k < ns) {
+                sc[k] = *reinterpret_cast<const int4 *>(score + k * s.pitch);
+                hi[k] = *reinterpret_cast<const int4 *>(hist + k * s.pitch);
+                sid[k] = *reinterpret_cast<const uint2 *>(senid + k * s.pitch);
+            }
+        osc = *reinterpret_cast<const int4 *>(tail);
+        ohi = *reinterpret_cast<const int4 *>(tail + s.pitch);
+        const uint2 tm = *reinterpret_cast<const uint2 *>(ids + s.pitch);
+        const uchar4 mp = *reinterpret_cast<const uchar4 *>(s.mpx + i);
+        bool any_mpx = false;
+#pragma unroll
+        for (int q = 0; q < HS_V; ++q) {
+            HmmReg h;
+#pragma unroll
+            for (int k = 0; k < PSB_HMM_MAX_NSTATE; ++k) {
+                const bool in = k < NL && k < ns;
+                h.score[k] = in ? comp(sc[k < NL ? k : 0], q) : PSB_WORST_SCORE;
+                h.hist[k] = in ? comp(hi[k < NL ? k : 0], q) : -1;
+                const unsigned w = (q < 2) ? sid[k < NL ? k : 0].x : sid[k < NL ? k : 0].y;
+                h.senid[k] = in ? (int)((q & 1) ? (w >> 16) : (w & 0xffffu)) : PSB_BAD_SSID;
+            }
+            h.out_score = comp(osc, q);
+            h.out_hist = comp(ohi, q);
+            h.best = PSB_WORST_SCORE;                 // every hmm_step variant overwrites it
+            const unsigned tw = (q < 2) ? tm.x : tm.y;
+            const int tmatid = (int16_t)((q & 1) ? (tw >> 16) : (tw & 0xffffu));
+            const bool mpx = (q == 0 ? mp.x : q == 1 ? mp.y : q == 2 ? mp.z : mp.w) != 0;
+            const int b = hmm_step(h, c, tmatid, mpx, srow);
+            if (j0 + q < n) best = max(best, b);
+#pragma unroll
+            for (int k = 0; k < NL; ++k)
+                if (k < ns) {
+                    setc(sc[k], q, h.score[k]);
+                    setc(hi[k], q, h.hist[k]);
+                    if (mpx) {
+                        unsigned &w = (q < 2) ? sid[k].x : sid[k].y;
+                        w = (q & 1) ? ((w & 0xffffu) | ((unsigned)h.senid[k] << 16)) : ((w & 0xffff0000u) | ((unsigned)h.senid[k] & 0xffffu));
+                        any_mpx = true;
+                    }
+                }
+            setc(osc, q, h.out_score);
+            setc(ohi, q, h.out_hist);
+            setc(bst, q, h.best);
+        }
+#pragma unroll
+        for (int k = 0; k < NL; ++k)
+            if (k < ns) {
+                *reinterpret_cast<int4 *>(score + k * s.pitch) = sc[k];
+                *reinterpret_cast<int4 *>(hist + k * s.pitch) = hi[k];
+                if (any_mpx) *reinterpret_cast<uint2 *>(senid + k * s.pitch) = sid[k];
+            }
+        *reinterpret_cast<int4 *>(tail) = osc;
+        *reinterpret_cast<int4 *>(tail + s.pitch) = ohi;
+        *reinterpret_cast<int4 *>(tail + 2 * s.pitch) = bst;
+    }
+    best = __reduce_max_sync(0xffffffffu, best);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int v = threadIdx.x < (HS_THREADS >> 5) ? red[threadIdx.x] : PSB_WORST_SCORE;
+        v = __reduce_max_sync(0xffffffffu, v);
+        if (threadIdx.x == 0) atomicMax(best_out + seg, v);
+    }
+}
+
+}  // namespace
+
+extern "C" void psb_hmmset_free(psb_hmmset_t *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->c->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->d_i32); cudaFree(s->d_u16); cudaFree(s->d_mpx); cudaFree(s->d_seg_off); cudaFree(s->d_seg_base); cudaFree(s->d_aos);
+    if (s->ev[0]) cudaEventDestroy(s->ev[0]);
+    if (s->ev[1]) cudaEventDestroy(s->ev[1]);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+extern "C" int psb_hmmset_create(psb_hmmctx_t *c, int64_t n_max, int32_t n_seg_max, psb_hmmset_t **out)
+{
+    PSB_REQUIRE(c && out && n_max > 0 && n_seg_max > 0 && n_seg_max <= 65535, "psb_hmmset_create: bad argument");
+    PSB_CUDA(cudaSetDevice(c->device));
+    psb_hmmset_t *s = new psb_hmmset_t();
+    s->c = c; s->n_max = n_max; s->n_seg_max = n_seg_max;
+    s->pitch = ((n_max + (int64_t)(HS_V - 1) * n_seg_max + HS_V - 1) / HS_V) * HS_V;   // every segment may pad up to 3
+    const int ns = c->n_emit;
+    cudaError_t e = cudaMalloc(&s->d_i32, (size_t)(2 * ns + 4) * s->pitch * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_u16, (size_t)(ns + 2) * s->pitch * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_mpx, (size_t)s->pitch);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_seg_off, (size_t)(n_seg_max + 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_seg_base, (size_t)(n_seg_max + 1) * 8);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev[0]);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev[1]);
+    if (e != cudaSuccess) {
+        psb_set_error("psb_hmmset_create: %s", cudaGetErrorString(e));
+        psb_hmmset_free(s);
+        return PSB_ERR_CUDA;
+    }
+    *out = s;
+    return PSB_OK;
+}
+
+static int hmmset_staging(psb_hmmset_t *s)
+{
+    if (!s->d_aos) PSB_CUDA(cudaMalloc(&s->d_aos, (size_t)s->n_max * sizeof(psb_hmm_t)));
+    return PSB_OK;
+}
+
+extern "C" int psb_hmmset_upload(psb_hmmset_t *s, const psb_hmm_t *hmms, int64_t n, const int64_t *seg_off, int32_t n_seg)
+{
+    PSB_REQUIRE(s && n >= 0 && n <= s->n_max && n_seg > 0 && n_seg <= s->n_seg_max && seg_off && (n == 0 || hmms),
+                "psb_hmmset_upload: bad argument");
+    PSB_REQUIRE(seg_off[0] == 0 && seg_off[n_seg] == n, "psb_hmmset_upload: seg_off must run from 0 to n");
+    PSB_CUDA(cudaSetDevice(s->c->device));
+    int64_t mx = 0;
+    std::vector<int64_t> base((size_t)n_seg + 1);
+    base[0] = 0;
+    for (int i = 0; i < n_seg; ++i) {
+        PSB_REQUIRE(seg_off[i + 1] >= seg_off[i], "psb_hmmset_upload: seg_off not monotone at %d", i);
+        const int64_t len = seg_off[i + 1] - seg_off[i];
+        mx = std::max<int64_t>(mx, len);
+        base[(size_t)i + 1] = base[(size_t)i] + (len + HS_V - 1) / HS_V * HS_V;
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        int rc = validate_hmm(s->c, &hmms[i], (int)i);
+        if (rc) return rc;
+    }
+    int rc = hmmset_staging(s);
+    if (rc) return rc;
+    s->n = n; s->n_seg = n_seg; s->max_seg_len = mx;
+    PSB_CUDA(cudaMemcpyAsync(s->d_seg_off, seg_off, (size_t)(n_seg + 1) * 8, cudaMemcpyHostToDevice, s->stream));
+    PSB_CUDA(cudaMemcpyAsync(s->d_seg_base, base.data(), (size_t)(n_seg + 1) * 8, cudaMemcpyHostToDevice, s->stream));
+    // inert padding: WORST_SCORE everywhere, senone / transition matrix 0, not multiplexed
+    const int ns = s->c->n_emit;
+    const int64_t ni = (int64_t)(2 * ns + 4) * s->pitch;
+    fill_i32_kernel<<<(unsigned)((ni + 255) / 256), 256, 0, s->stream>>>(s->d_i32, ni, PSB_WORST_SCORE);
+    PSB_LAUNCH_CHECK();
+    PSB_CUDA(cudaMemsetAsync(s->d_u16, 0, (size_t)(ns + 2) * s->pitch * 2, s->stream));
+    PSB_CUDA(cudaMemsetAsync(s->d_mpx, 0, (size_t)s->pitch, s->stream));
+    if (n) {
+        PSB_CUDA(cudaMemcpyAsync(s->d_aos, hmms, (size_t)n * sizeof(psb_hmm_t), cudaMemcpyHostToDevice, s->stream));
+        hmmset_convert_kernel<true><<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(s->d_aos, dev_set(s), n, ns);
+        PSB_LAUNCH_CHECK();
+    }
+    PSB_CUDA(cudaStreamSynchronize(s->stream));
+    return PSB_OK;
+}
+
+extern "C" int psb_hmmset_download(psb_hmmset_t *s, psb_hmm_t *hmms)
+{
+    PSB_REQUIRE(s && (s->n == 0 || hmms), "psb_hmmset_download: bad argument");
+    if (s->n == 0) return PSB_OK;
+    PSB_CUDA(cudaSetDevice(s->c->device));
+    int rc = hmmset_staging(s);
+    if (rc) return rc;
+    hmmset_convert_kernel<false><<<(unsigned)((s->n + 255) / 256), 256, 0, s->stream>>>(s->d_aos, dev_set(s), s->n, s->c->n_emit);
+    PSB_LAUNCH_CHECK();
+    std::vector<psb_hmm_t> tmp((size_t)s->n);
+    PSB_CUDA(cudaMemcpyAsync(tmp.data(), s->d_aos, (size_t)s->n * sizeof(psb_hmm_t), cudaMemcpyDeviceToHost, s->stream));
+    PSB_CUDA(cudaStreamSynchronize(s->stream));
+    for (int64_t i = 0; i < s->n; ++i) {        // keep the caller's ctx pointers
+        void *ctx = hmms[i].ctx;
+        hmms[i] = tmp[(size_t)i];
+        hmms[i].ctx = ctx;
+    }
+    return PSB_OK;
+}
+
+extern "C" int psb_hmmset_eval_frames_device(psb_hmmset_t *s, const int16_t *d_senscr, const int64_t *d_row0,
+                                             const int32_t *d_n_rows, int32_t n_frames, int32_t *d_best, float *ms)
+{
+    PSB_REQUIRE(s && d_senscr && d_best && n_frames >= 0, "psb_hmmset_eval_frames_device: bad argument");
+    if (ms) *ms = 0.f;
+    if (n_frames == 0 || s->n_seg == 0) return PSB_OK;
+    PSB_CUDA(cudaSetDevice(s->c->device));
+    const int64_t nb = (int64_t)n_frames * s->n_seg;
+    fill_i32_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, s->stream>>>(d_best, nb, PSB_WORST_SCORE);
+    PSB_LAUNCH_CHECK();
+    if (s->n == 0) {
+        PSB_CUDA(cudaStreamSynchronize(s->stream));
+        return PSB_OK;
+    }
+    const dim3 grid((unsigned)((s->max_seg_len + HS_TILE - 1) / HS_TILE), (unsigned)s->n_seg);
+    const HmmSetDev sd = dev_set(s);
+    const HmmCtxDev cd = dev_ctx(s->c);
+    const size_t smem = ((size_t)cd.n_sen * 2 + 15) & ~(size_t)15;
+    PSB_REQUIRE(smem <= 200 * 1024, "psb_hmmset: %d senones do not fit the shared-memory score row", cd.n_sen);
+    PSB_CUDA(cudaFuncSetAttribute(hmmset_eval_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PSB_CUDA(cudaFuncSetAttribute(hmmset_eval_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PSB_CUDA(cudaFuncSetAttribute(hmmset_eval_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PSB_CUDA(cudaEventRecord(s->ev[0], s->stream));
+    for (int t = 0; t < n_frames; ++t) {
+        int32_t *best = d_best + (size_t)t * s->n_seg;
+        if (cd.n_emit == 3) hmmset_eval_kernel<3><<<grid, HS_THREADS, smem, s->stream>>>(sd, cd, d_senscr, d_row0, d_n_rows, t, best);
+        else if (cd.n_emit == 5) hmmset_eval_kernel<5><<<grid, HS_THREADS, smem, s->stream>>>(sd, cd, d_senscr, d_row0, d_n_rows, t, best);
+        else hmmset_eval_kernel<0><<<grid, HS_THREADS, smem, s->stream>>>(sd, cd, d_senscr, d_row0, d_n_rows, t, best);
+        PSB_LAUNCH_CHECK();
+    }
+    PSB_CUDA(cudaEventRecord(s->ev[1], s->stream));
+    PSB_CUDA(cudaStreamSynchronize(s->stream));
+    if (ms) PSB_CUDA(cudaEventElapsedTime(ms, s->ev[0], s->ev[1]));
+    return PSB_OK;
+}
+
+extern "C" int psb_hmmset_eval_host(psb_hmmset_t *s, const int16_t *senscr, int32_t *best)
+{
+    // one frame, host rows [n_seg][n_sen] in, host best[n_seg] out (tests and small callers)
+    PSB_REQUIRE(s && senscr && best, "psb_hmmset_eval_host: bad argument");
+    PSB_CUDA(cudaSetDevice(s->c->device));
+    int16_t *d_scr = nullptr;
+    int32_t *d_best = nullptr;
+    const size_t nb = (size_t)s->n_seg * s->c->n_sen * 2;
+    PSB_CUDA(cudaMalloc(&d_scr, nb));
+    cudaError_t e = cudaMalloc(&d_best, (size_t)s->n_seg * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(d_scr, senscr, nb, cudaMemcpyHostToDevice);
+    int rc = PSB_OK;
+    if (e == cudaSuccess) {
+        rc = psb_hmmset_eval_frames_device(s, d_scr, nullptr, nullptr, 1, d_best, nullptr);
+        if (!rc) e = cudaMemcpy(best, d_best, (size_t)s->n_seg * 4, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_scr); cudaFree(d_best);
+    if (e != cudaSuccess) {
+        psb_set_error("psb_hmmset_eval_host: %s", cudaGetErrorString(e));
+        return PSB_ERR_CUDA;
+    }
     return rc;
 }

@@ -400,3 +400,53 @@ def test_ptm_and_semi_mixw_extremes(api):
         pm.mixw = np.ascontiguousarray(mw)
         feats = synth_feats(pm, 20, 12, seed=2)
         _batch_vs_oracle(api, pm, [feats[u].reshape(-1, pm.sumlen) for u in range(20)])
+
+
+# ---------------------------------------------------------------------------------------
+# device-resident HMM sets (segments = utterances), several frames, against hmm_vit_eval
+
+@pytest.mark.parametrize("n_emit", [3, 5, 4])
+def test_hmmset_frames_match_oracle(api, n_emit):
+    import torch
+    from oracle import oracle
+    g = golden("hmm_vit_eval.npz")
+    tp, sseq = g["n%d_tp" % n_emit], g["n%d_sseq" % n_emit]
+    n_sen = len(g["n%d_senscr" % n_emit])
+    hm0 = hmm_view(g["n%d_before" % n_emit]).copy()            # 4096 random records, mixed mpx
+    # the golden's single step through the set (segment 0 of 1)
+    ctx = api.HmmContext(tp, sseq, n_sen)
+    hs = api.HmmSet(ctx, len(hm0) + 7, 16)
+    hs.upload(hm0, [0, len(hm0)])
+    best = hs.eval_host(g["n%d_senscr" % n_emit][None, :])
+    assert best[0] == int(g["n%d_best" % n_emit])
+    got = hs.download()
+    assert_hmm_equal(got, hmm_view(g["n%d_after" % n_emit]), n_emit, "golden step")
+    # ragged segments (one empty), own score rows, 6 frames, one segment finishing early
+    rng = np.random.default_rng(12)
+    seg_off = np.array([0, 1000, 1000, 1257, 4096], np.int64)
+    n_seg, T = len(seg_off) - 1, 6
+    n_rows = np.array([6, 6, 4, 6], np.int32)
+    senscr = rng.integers(0, 900, (T, n_seg, n_sen)).astype(np.int16)
+    hs.upload(hm0, seg_off)
+    d_scr = torch.from_numpy(senscr).cuda()
+    d_best = torch.zeros((T, n_seg), dtype=torch.int32, device="cuda")
+    d_nrows = torch.from_numpy(n_rows).cuda()
+    ms = hs.eval_frames_device(d_scr.data_ptr(), T, d_best.data_ptr(), d_n_rows=d_nrows.data_ptr())
+    assert ms >= 0.0
+    got = hs.download()
+    gbest = d_best.cpu().numpy()
+    octx = oracle.OracleHmmCtx(tp, sseq)
+    want = hm0.copy()
+    for s in range(n_seg):
+        a, b = seg_off[s], seg_off[s + 1]
+        for t in range(T):
+            if t >= n_rows[s] or a == b:
+                assert gbest[t, s] == -0x20000000
+                continue
+            seg = np.ascontiguousarray(want[a:b])
+            wb = octx.vit_eval(seg, senscr[t, s])
+            want[a:b] = seg
+            assert gbest[t, s] == wb, "segment %d frame %d" % (s, t)
+    assert_hmm_equal(got, want, n_emit, "after %d frames" % T)
+    hs.close()
+    ctx.close()
