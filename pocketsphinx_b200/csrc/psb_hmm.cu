@@ -1,6 +1,7 @@
 // psb_hmm.cu -- batched hmm_vit_eval and the device-resident phone-loop Viterbi.
 #include "psb_hmm.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -538,8 +539,7 @@ extern "C" int psb_phoneloop_run_host(psb_phoneloop_t *p, const int16_t *senscr,
 // (state) and 64-bit (ids) accesses; padding instances are inert (WORST_SCORE, senone 0) and
 // never reach the best score.
 constexpr int HS_V = 4;                     // instances per thread
-constexpr int HS_THREADS = 256;
-constexpr int HS_TILE = HS_V * HS_THREADS;  // instances per CTA
+// threads per CTA: 128 (default; measured 112.7 us vs 118.2 us per 6.08 M-instance frame) or 256 (PSB_HMMSET_THREADS)
 
 struct psb_hmmset_s {
     psb_hmmctx_t *c;
@@ -630,8 +630,8 @@ __device__ __forceinline__ void setc(int4 &v, int q, int x)
 // segment.  row0[seg] + t is the segment's senone-score row of this frame (staged in shared
 // memory: the gathers of a tile hit ~3 x HS_TILE random int16 of it); segments with
 // n_rows[seg] <= t are finished.  NS = 3 or 5 (0: any topology, runtime count).
-template <int NS>
-__global__ void __launch_bounds__(HS_THREADS)
+template <int NS, int HS_THREADS>
+__global__ void __launch_bounds__(HS_THREADS, (NS == 3 ? 3 : 2) * (256 / HS_THREADS))
 hmmset_eval_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr, const int64_t *__restrict__ row0,
                    const int32_t *__restrict__ n_rows, int t, int32_t *__restrict__ best_out)
 {
@@ -641,41 +641,46 @@ hmmset_eval_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr,
     if (n_rows && t >= n_rows[seg]) return;
     const int64_t n = s.seg_off[seg + 1] - s.seg_off[seg];
     const int64_t j0 = ((int64_t)blockIdx.x * HS_THREADS + threadIdx.x) * HS_V;   // first of this thread's four
-    if ((int64_t)blockIdx.x * HS_TILE >= n) return;
+    if ((int64_t)blockIdx.x * HS_THREADS * HS_V >= n) return;
+    // issue this thread's state loads first: they are in flight while the CTA stages the score row
+    constexpr int NL = NS > 0 ? NS : PSB_HMM_MAX_NSTATE;
+    const int ns = NS > 0 ? NS : c.n_emit;
+    const bool live = j0 < n;
+    const int64_t i = s.seg_base[seg] + (live ? j0 : 0);              // multiple of four
+    int32_t *score = s.i32 + i, *hist = s.i32 + (int64_t)ns * s.pitch + i;
+    int32_t *tail = s.i32 + (int64_t)2 * ns * s.pitch + i;
+    uint16_t *senid = s.u16 + i;
+    const uint16_t *ids = s.u16 + (int64_t)ns * s.pitch + i;
+    int4 sc[NL], hi[NL], osc, ohi, bst;
+    uint2 sid[NL], tm = make_uint2(0u, 0u);
+    uchar4 mp = make_uchar4(0, 0, 0, 0);
+    if (live) {
+#pragma unroll
+        for (int k = 0; k < NL; ++k)
+            if (k < ns) {
+                sc[k] = __ldcs(reinterpret_cast<const int4 *>(score + k * s.pitch));
+                hi[k] = __ldcs(reinterpret_cast<const int4 *>(hist + k * s.pitch));
+                sid[k] = __ldcs(reinterpret_cast<const uint2 *>(senid + k * s.pitch));
+            }
+        osc = __ldcs(reinterpret_cast<const int4 *>(tail));
+        ohi = __ldcs(reinterpret_cast<const int4 *>(tail + s.pitch));
+        tm = __ldcs(reinterpret_cast<const uint2 *>(ids + s.pitch));
+        mp = __ldcs(reinterpret_cast<const uchar4 *>(s.mpx + i));
+    }
     {
         const int16_t *row = senscr + (row0 ? row0[seg] + t : (int64_t)t * gridDim.y + seg) * c.n_sen;
         if ((((uintptr_t)row) & 3) == 0) {
             const int *r32 = reinterpret_cast<const int *>(row);
             int *s32 = reinterpret_cast<int *>(srow);
-            for (int i = threadIdx.x; i < (c.n_sen >> 1); i += HS_THREADS) s32[i] = r32[i];
+            for (int q = threadIdx.x; q < (c.n_sen >> 1); q += HS_THREADS) s32[q] = r32[q];
             if ((c.n_sen & 1) && threadIdx.x == 0) srow[c.n_sen - 1] = row[c.n_sen - 1];
         }
         else
-            for (int i = threadIdx.x; i < c.n_sen; i += HS_THREADS) srow[i] = row[i];
+            for (int q = threadIdx.x; q < c.n_sen; q += HS_THREADS) srow[q] = row[q];
     }
     __syncthreads();
-    constexpr int NL = NS > 0 ? NS : PSB_HMM_MAX_NSTATE;
-    const int ns = NS > 0 ? NS : c.n_emit;
     int best = PSB_WORST_SCORE;
-    if (j0 < n) {
-        const int64_t i = s.seg_base[seg] + j0;                       // multiple of four
-        int32_t *score = s.i32 + i, *hist = s.i32 + (int64_t)ns * s.pitch + i;
-        int32_t *tail = s.i32 + (int64_t)2 * ns * s.pitch + i;
-        uint16_t *senid = s.u16 + i;
-        const uint16_t *ids = s.u16 + (int64_t)ns * s.pitch + i;
-        int4 sc[NL], hi[NL], osc, ohi, bst;
-        uint2 sid[NL];
-#pragma unroll
-        for (int k = 0; k < NL; ++k)
-            if (k < ns) {
-                sc[k] = *reinterpret_cast<const int4 *>(score + k * s.pitch);
-                hi[k] = *reinterpret_cast<const int4 *>(hist + k * s.pitch);
-                sid[k] = *reinterpret_cast<const uint2 *>(senid + k * s.pitch);
-            }
-        osc = *reinterpret_cast<const int4 *>(tail);
-        ohi = *reinterpret_cast<const int4 *>(tail + s.pitch);
-        const uint2 tm = *reinterpret_cast<const uint2 *>(ids + s.pitch);
-        const uchar4 mp = *reinterpret_cast<const uchar4 *>(s.mpx + i);
+    if (live) {
         bool any_mpx = false;
 #pragma unroll
         for (int q = 0; q < HS_V; ++q) {
@@ -714,13 +719,13 @@ hmmset_eval_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr,
 #pragma unroll
         for (int k = 0; k < NL; ++k)
             if (k < ns) {
-                *reinterpret_cast<int4 *>(score + k * s.pitch) = sc[k];
-                *reinterpret_cast<int4 *>(hist + k * s.pitch) = hi[k];
-                if (any_mpx) *reinterpret_cast<uint2 *>(senid + k * s.pitch) = sid[k];
+                __stcs(reinterpret_cast<int4 *>(score + k * s.pitch), sc[k]);
+                __stcs(reinterpret_cast<int4 *>(hist + k * s.pitch), hi[k]);
+                if (any_mpx) __stcs(reinterpret_cast<uint2 *>(senid + k * s.pitch), sid[k]);
             }
-        *reinterpret_cast<int4 *>(tail) = osc;
-        *reinterpret_cast<int4 *>(tail + s.pitch) = ohi;
-        *reinterpret_cast<int4 *>(tail + 2 * s.pitch) = bst;
+        __stcs(reinterpret_cast<int4 *>(tail), osc);
+        __stcs(reinterpret_cast<int4 *>(tail + s.pitch), ohi);
+        __stcs(reinterpret_cast<int4 *>(tail + 2 * s.pitch), bst);
     }
     best = __reduce_max_sync(0xffffffffu, best);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
@@ -851,20 +856,37 @@ extern "C" int psb_hmmset_eval_frames_device(psb_hmmset_t *s, const int16_t *d_s
         PSB_CUDA(cudaStreamSynchronize(s->stream));
         return PSB_OK;
     }
-    const dim3 grid((unsigned)((s->max_seg_len + HS_TILE - 1) / HS_TILE), (unsigned)s->n_seg);
+    static const int threads = [] {
+        const char *v = getenv("PSB_HMMSET_THREADS");
+        return v && atoi(v) == 256 ? 256 : 128;
+    }();
+    const int tile = threads * HS_V;
+    const dim3 grid((unsigned)((s->max_seg_len + tile - 1) / tile), (unsigned)s->n_seg);
     const HmmSetDev sd = dev_set(s);
     const HmmCtxDev cd = dev_ctx(s->c);
     const size_t smem = ((size_t)cd.n_sen * 2 + 15) & ~(size_t)15;
     PSB_REQUIRE(smem <= 200 * 1024, "psb_hmmset: %d senones do not fit the shared-memory score row", cd.n_sen);
-    PSB_CUDA(cudaFuncSetAttribute(hmmset_eval_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PSB_CUDA(cudaFuncSetAttribute(hmmset_eval_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PSB_CUDA(cudaFuncSetAttribute(hmmset_eval_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto launch = [&](auto kern, int t, int32_t *best) {
+        kern<<<grid, threads, smem, s->stream>>>(sd, cd, d_senscr, d_row0, d_n_rows, t, best);
+    };
+#define PSB_HS_ATTR(NS, NT) PSB_CUDA(cudaFuncSetAttribute(hmmset_eval_kernel<NS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+    if (smem > 48 * 1024) {
+        PSB_HS_ATTR(3, 256); PSB_HS_ATTR(5, 256); PSB_HS_ATTR(0, 256); PSB_HS_ATTR(3, 128); PSB_HS_ATTR(5, 128); PSB_HS_ATTR(0, 128);
+    }
+#undef PSB_HS_ATTR
     PSB_CUDA(cudaEventRecord(s->ev[0], s->stream));
     for (int t = 0; t < n_frames; ++t) {
         int32_t *best = d_best + (size_t)t * s->n_seg;
-        if (cd.n_emit == 3) hmmset_eval_kernel<3><<<grid, HS_THREADS, smem, s->stream>>>(sd, cd, d_senscr, d_row0, d_n_rows, t, best);
-        else if (cd.n_emit == 5) hmmset_eval_kernel<5><<<grid, HS_THREADS, smem, s->stream>>>(sd, cd, d_senscr, d_row0, d_n_rows, t, best);
-        else hmmset_eval_kernel<0><<<grid, HS_THREADS, smem, s->stream>>>(sd, cd, d_senscr, d_row0, d_n_rows, t, best);
+        if (threads == 256) {
+            if (cd.n_emit == 3) launch(hmmset_eval_kernel<3, 256>, t, best);
+            else if (cd.n_emit == 5) launch(hmmset_eval_kernel<5, 256>, t, best);
+            else launch(hmmset_eval_kernel<0, 256>, t, best);
+        }
+        else {
+            if (cd.n_emit == 3) launch(hmmset_eval_kernel<3, 128>, t, best);
+            else if (cd.n_emit == 5) launch(hmmset_eval_kernel<5, 128>, t, best);
+            else launch(hmmset_eval_kernel<0, 128>, t, best);
+        }
         PSB_LAUNCH_CHECK();
     }
     PSB_CUDA(cudaEventRecord(s->ev[1], s->stream));
