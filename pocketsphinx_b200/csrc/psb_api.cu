@@ -252,6 +252,11 @@ extern "C" int psb_model_create(const psb_model_desc_t *d, int device, psb_model
             psb_set_error("uploading the log-add table failed: %s", cudaGetErrorString(cudaGetLastError()));
             rc = PSB_ERR_CUDA;
         }
+        else {
+            uint8_t t[256];
+            if (cudaMemcpy(t, m->d_logadd8, 256, cudaMemcpyDeviceToHost) == cudaSuccess)
+                for (int i = 0; i < 256; ++i) m->logadd8_max = std::max<int>(m->logadd8_max, t[i]);
+        }
     }
     if (!rc && m->kind != PSB_KIND_MS && !d->logadd8) {
         psb_set_error("logadd8 table required for ptm/semi models");

@@ -78,6 +78,7 @@ struct psb_model_s {
     int16_t *d_quadcb;            // [ceil(n_sen/4)] codebook of a uniform senone quad, else -1
     int32_t *d_bsen;              // senones of the non-uniform quads
     int n_bsen;
+    int logadd8_max;              // largest entry of the 8-bit add table (bias bound of the 16x2 senone kernel)
     uint8_t *d_logadd8;           // [PSB_LOGADD8_N]: the 256-entry table continued with zeros
     uint32_t *d_logadd_ms;
     float *d_msT, *d_msdetT;      // ms back-end: codebook-minor Gaussians (see psb_ms.cu)

@@ -879,6 +879,8 @@ ptm_topnq_kernel(const float *__restrict__ rec2, const size_t *__restrict__ rec2
     }
 }
 
+constexpr int SEN_BIAS = 64;          // > 3 * tab[0] for any 8-bit add table the 16x2 senone kernel accepts
+
 // fast_logmath_add (tied_mgau_common.h:111-127) on negated logs.  mixw + normalised score can
 // reach 255 + 96, so |x - y| can exceed the reference's 256-entry table (logmath.c:116-120):
 // the reference then reads past its allocation (undefined); the add table is identically 0 from
@@ -1055,7 +1057,8 @@ ptm_senone4_kernel(const int4 *__restrict__ topn, const uint8_t *__restrict__ mi
     extern __shared__ int smem_i[];
     uint4 *rowoff = reinterpret_cast<uint4 *>(smem_i);             // [K]
     uint4 *nsc = rowoff + K;                                        // [K]
-    int *norm = reinterpret_cast<int *>(nsc + K);                   // [8]
+    uint4 *nvp = nsc + K;                                           // [K] (score + SEN_BIAS) in both halfwords
+    int *norm = reinterpret_cast<int *>(nvp + K);                   // [8]
     int *red = norm + 8;                                            // [32]
     uint8_t *tab = reinterpret_cast<uint8_t *>(red + 32);           // [PSB_LOGADD8_N]
     int16_t *asc = reinterpret_cast<int16_t *>(tab + PSB_LOGADD8_N + 16);     // [n_sen rounded up to 4]
@@ -1084,6 +1087,8 @@ ptm_senone4_kernel(const int4 *__restrict__ topn, const uint8_t *__restrict__ mi
         }
         rowoff[tid] = make_uint4(ro[0], ro[1], ro[2], ro[3]);
         nsc[tid] = make_uint4(nv[0], nv[1], nv[2], nv[3]);
+        nvp[tid] = make_uint4((nv[0] + SEN_BIAS) * 0x10001u, (nv[1] + SEN_BIAS) * 0x10001u,
+                              (nv[2] + SEN_BIAS) * 0x10001u, (nv[3] + SEN_BIAS) * 0x10001u);
     }
     __syncthreads();
 
@@ -1094,24 +1099,37 @@ ptm_senone4_kernel(const int4 *__restrict__ topn, const uint8_t *__restrict__ mi
         if (c < 0) continue;
         const int s0 = q << 2, i0 = c * n_feat;
         const uint8_t *mw = mixw + s0;
-        int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        // Two senones per 32-bit word (unsigned 16x2), all values biased by SEN_BIAS so that the
+        // slightly negative intermediate results of fast_logmath_add (>= -3 * tab[0]) stay
+        // non-negative halfwords: min, max and |x - y| are bias-free, r - tab[d] carries it.
+        unsigned acc01 = 0u, acc23 = 0u;
         for (int f = 0; f < n_feat; ++f) {
-            const uint4 ro = rowoff[i0 + f], nv = nsc[i0 + f];
+            const uint4 ro = rowoff[i0 + f], nv = nvp[i0 + f];
             const unsigned w0 = *reinterpret_cast<const unsigned *>(mw + ro.x);
             const unsigned w1 = *reinterpret_cast<const unsigned *>(mw + ro.y);
             const unsigned w2 = *reinterpret_cast<const unsigned *>(mw + ro.z);
             const unsigned w3 = *reinterpret_cast<const unsigned *>(mw + ro.w);
-#define PSB_SEN(i, acc)                                                                         \
+            unsigned x01 = __byte_perm(w0, 0u, 0x4140) + nv.x;       // (mixw + score + bias) of senones 0,1
+            unsigned x23 = __byte_perm(w0, 0u, 0x4342) + nv.x;       // ... of senones 2,3
+#define PSB_LADD2(x, w, sel, nvj)                                                               \
             {                                                                                   \
-                int fden = (int)((w0 >> (8 * i)) & 0xff) + (int)nv.x;                           \
-                fden = logadd8(tab, fden, (int)((w1 >> (8 * i)) & 0xff) + (int)nv.y);           \
-                fden = logadd8(tab, fden, (int)((w2 >> (8 * i)) & 0xff) + (int)nv.z);           \
-                fden = logadd8(tab, fden, (int)((w3 >> (8 * i)) & 0xff) + (int)nv.w);           \
-                acc += fden;                                                                    \
+                const unsigned y = __byte_perm(w, 0u, sel);                                     \
+                const unsigned mn = __viaddmin_u16x2(y, nvj, x);                                \
+                const unsigned mx = __viaddmax_u16x2(y, nvj, x);                                \
+                const unsigned d = mx - mn;                                                     \
+                const unsigned t = (unsigned)tab[d & 0xffffu] | ((unsigned)tab[d >> 16] << 16); \
+                x = mn - t;                                                                     \
             }
-            PSB_SEN(0, a0) PSB_SEN(1, a1) PSB_SEN(2, a2) PSB_SEN(3, a3)
-#undef PSB_SEN
+            PSB_LADD2(x01, w1, 0x4140, nv.y) PSB_LADD2(x23, w1, 0x4342, nv.y)
+            PSB_LADD2(x01, w2, 0x4140, nv.z) PSB_LADD2(x23, w2, 0x4342, nv.z)
+            PSB_LADD2(x01, w3, 0x4140, nv.w) PSB_LADD2(x23, w3, 0x4342, nv.w)
+#undef PSB_LADD2
+            acc01 += x01;
+            acc23 += x23;
         }
+        const int unbias = n_feat * SEN_BIAS;
+        const int a0 = (int)(acc01 & 0xffffu) - unbias, a1 = (int)(acc01 >> 16) - unbias;
+        const int a2 = (int)(acc23 & 0xffffu) - unbias, a3 = (int)(acc23 >> 16) - unbias;
         best = min(min(best, a0), min(min(a1, a2), a3));
         *reinterpret_cast<short4 *>(asc + s0) = make_short4((short)a0, (short)a1, (short)a2, (short)a3);
     }
@@ -1368,7 +1386,7 @@ int psb_launch_ptm_batch(psb_batch_t *b, const float *d_feats, const int32_t *ut
                 b->d_topn, m->d_mixw, m->d_mixw_cb, m->d_sen2cb, m->d_logadd8, d_senscr, m->n_sen, m->n_feat,
                 m->n_density, K, m->mixw_stride);
         }
-        else if (b->topn_variant == 0) {
+        else if (b->topn_variant == 0 || (TOPN - 1) * m->logadd8_max >= SEN_BIAS) {
             PSB_CUDA(cudaFuncSetAttribute(ptm_senone_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ptm_senone_kernel<false><<<(unsigned)total, 512, smem, b->stream>>>(
                 b->d_topn, m->d_mixw, m->d_mixw_cb, m->d_sen2cb, m->d_logadd8, d_senscr, m->n_sen, m->n_feat,
@@ -1380,7 +1398,7 @@ int psb_launch_ptm_batch(psb_batch_t *b, const float *d_feats, const int32_t *ut
             const int iters = (n_quads + 511) / 512;
             // at least 256 threads (log-add table staging) and one thread per (codebook, stream) pair
             const int threads = std::min(512, std::max(std::max(256, roundup(K, 32)), roundup((n_quads + iters - 1) / iters, 32)));
-            const size_t smem4 = smem + 8;
+            const size_t smem4 = smem + 8 + (size_t)K * 16;
             PSB_CUDA(cudaFuncSetAttribute(ptm_senone4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
             ptm_senone4_kernel<<<(unsigned)total, threads, smem4, b->stream>>>(
                 b->d_topn, m->d_mixw, m->d_sen2cb, m->d_quadcb, m->d_bsen, m->n_bsen, m->d_logadd8, d_senscr, m->n_sen,
