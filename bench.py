@@ -179,6 +179,43 @@ def viterbi_stage(api, torch, ctx, batch, pm, off, U, T, hbm_peak, n_active=6081
             "note": "not part of `value`: the headline Viterbi is the reference's phone loop (42 HMMs per utterance)"}
 
 
+def frontend_stage(api, torch, U, secs, budget_s=4.0):
+    """Row f-2, reported beside the headline (not part of `value`): int16 PCM -> cepstra -> batch CMN
+    -> 1s_c_d_dd features for the whole batch on the device (en-us feat.params: 25 mel filters,
+    DCT-II, lifter 22, noise removal on), against the compiled reference's fe/ + feat/ on one core."""
+    from pocketsphinx_b200.fe_tables import make_fe_desc
+    desc = make_fe_desc()
+    n = int(secs * 16000)
+    rng = np.random.default_rng(7)
+    base = np.clip(rng.normal(0, 2500, (16, n)), -32768, 32767).astype(np.int16)      # 16 distinct utterances, tiled
+    pcm = np.ascontiguousarray(np.tile(base, ((U + 15) // 16, 1))[:U]).reshape(-1)
+    off = np.arange(U + 1, dtype=np.int64) * n
+    fe = api.FrontEnd(desc)
+    T = fe.n_frames(n)
+    d_pcm = torch.from_numpy(pcm).cuda()
+    d_feats = torch.empty((U * T, 3 * desc["n_cep"]), dtype=torch.float32, device="cuda")
+    fe.process_device(d_pcm.data_ptr(), off, d_feats.data_ptr())
+    ms = min(fe.process_device(d_pcm.data_ptr(), off, d_feats.data_ptr())[1] for _ in range(3))
+    fe.close()
+    out = {"kernels": "fe_frame_kernel + fe_utt_kernel", "utts": U, "frames_per_utt": T, "ms": ms,
+           "frames_per_s": U * T / (ms * 1e-3),
+           "algorithmic_bytes": int(pcm.nbytes + U * T * 3 * desc["n_cep"] * 4),
+           "note": "not part of `value`; parity with the reference at 1e-4 relative (tests/test_gpu_fe.py)"}
+    try:
+        from oracle import refdrv
+        if refdrv.available():
+            ref = refdrv.RefModel(os.path.join(os.path.dirname(refdrv.LIB_PATH), "model", "en-us"))
+            t0, k = time.perf_counter(), 0
+            while time.perf_counter() - t0 < budget_s:
+                ref.featurize_fresh(base[k % 16])
+                k += 1
+            out["cpu_reference_frames_per_s_1core"] = k * T / (time.perf_counter() - t0)
+            ref.close()
+    except Exception as e:                                  # the CPU side is informational only
+        out["cpu_reference_error"] = str(e)[:100]
+    return out
+
+
 def cpu_baseline(args, pm, raw, feats, n_frames_per_utt, budget_s=15.0, threads=1):
     """The reference's CPU implementation of the path on host cores over a bounded sample of the
     same workload: senone evaluation through the COMPILED REFERENCE (oracle/_ref/libpsref.so:
@@ -425,6 +462,7 @@ def main():
             batch.decode_device(pl, d_feats.data_ptr(), off)
             batch.sync()
             out["viterbi_stage"] = viterbi_stage(api, torch, ctx, batch, pm, off, U, T, hbm_peak)
+            out["frontend_stage"] = frontend_stage(api, torch, U, args.secs)
             out["cpu_baseline"] = cpu_baseline(args, pm, raw, feats_np, T, budget_s=args.cpu_budget, threads=1)
         print(json.dumps(out))
     batch.close(); pl.close(); ctx.close(); model.close()

@@ -253,6 +253,41 @@ int64_t psb_sendump_read(const char *path, int32_t *n_sen_out, int16_t *senscr, 
  * features; 1 = one stream, which is what per-kernel timing wants; up to 8. */
 int psb_batch_set_pipeline(psb_batch_t *b, int n);
 
+/* ------------------------------------------------------------------------------------ */
+/* Batched front end: int16 PCM -> cepstra -> batch CMN -> 1s_c_d_dd features
+ * for whole batches, every utterance a fresh stream (ps_start_stream + ps_process_raw(full_utt),
+ * pocketsphinx.c:1073, acmod.c:528-560).  The tables are the arrays the reference's own fe_t /
+ * melfb_t hold after fe_init (fe_internal.h:100-180): a C host passes those pointers. */
+typedef struct psb_fe_desc_s {
+    int32_t frame_size, frame_shift, fft_size, fft_order;   /* fe_t */
+    int32_t n_filt, n_cep;                                  /* melfb_t.num_filters, fe_t.num_cepstra */
+    int32_t remove_dc, remove_noise;                        /* -remove_dc, -remove_noise (fe_noise.c) */
+    int32_t transform;                                      /* 0 legacy, 1 dct, 2 htk (fe_internal.h) */
+    int32_t lifter_val;                                     /* -lifter, 0 = none */
+    int32_t window;                                         /* feat_window_size: 3 (1s_c_d_dd) */
+    int32_t cmn;                                            /* 0 none, 1 batch (cmn.h) */
+    int32_t n_coeffs;                                       /* sum of filt_width */
+    float pre_emphasis_alpha, sqrt_inv_n, sqrt_inv_2n;
+    const double *hamming;                                  /* [frame_size / 2] fe_t.hamming_window */
+    const double *ccc, *sss;                                /* [fft_size / 4] FFT twiddles */
+    const int16_t *spec_start, *filt_start, *filt_width;    /* [n_filt] */
+    const float *filt_coeffs;                               /* [n_coeffs] */
+    const float *mel_cosine;                                /* [n_cep][n_filt] */
+    const float *lifter;                                    /* [n_cep] or NULL */
+} psb_fe_desc_t;
+typedef struct psb_fe_s psb_fe_t;
+int psb_fe_create(const psb_fe_desc_t *d, int device, psb_fe_t **out);
+void psb_fe_free(psb_fe_t *fe);
+/* frames fe_process_frames + fe_end_utt produce for n_samples (fe_interface.c:352-545) */
+int32_t psb_fe_n_frames(const psb_fe_t *fe, int64_t n_samples);
+/* pcm: the utterances' samples back to back, samp_off int64[n_utt + 1] (host).  Outputs:
+ * frame_off int32[n_utt + 1] (host), feats float [frames][3 * n_cep], mfcc (may be NULL) float
+ * [frames][n_cep] = the cepstra after CMN.  *ms (may be NULL) = device time of the two kernels. */
+int psb_fe_process_host(psb_fe_t *fe, const int16_t *pcm, const int64_t *samp_off, int32_t n_utt,
+                        float *feats, float *mfcc, int32_t *frame_off);
+int psb_fe_process_device(psb_fe_t *fe, const int16_t *d_pcm, const int64_t *samp_off, int32_t n_utt,
+                          float *d_feats, float *d_mfcc, int32_t *frame_off, float *ms);
+
 /* number of kernels launched by this library in the calling process so far */
 int64_t psb_kernel_launch_count(void);
 

@@ -27,6 +27,9 @@
 #include "phone_loop_search.h"
 #include "util/ckd_alloc.h"
 #include "tied_mgau_common.h"
+#include "fe/fe_internal.h"
+#include "fe/fe_noise.h"
+#include "feat/feat.h"
 
 /* s2_semi_mgau.c:64-67 keeps this struct private; layout restated for history reset/dump. */
 struct vqFeature_s {
@@ -294,6 +297,89 @@ refdrv_export(refdrv_t *d, const char *what, void *out, long cap)
     }
 #undef EMIT
     return need;
+}
+
+/* Front-end parameters and tables exactly as fe_init / fe_build_melfilters / fe_compute_melcosine
+ * left them (fe_internal.h:100-180).  out: int32[16] then float[4]:
+ *  [0] frame_size [1] frame_shift [2] fft_size [3] fft_order [4] num_filters [5] num_cepstra
+ *  [6] remove_dc [7] remove_noise [8] transform [9] lifter_val [10] log_spec [11] dither
+ *  [12] n_filt_coeffs [13] feat window_size [14] cmn type [15] feat cepsize;
+ *  f[0] pre_emphasis_alpha f[1] sqrt_inv_n f[2] sqrt_inv_2n f[3] sampling_rate */
+int
+refdrv_fe_info(refdrv_t *d, int32 *out, float *fout)
+{
+    fe_t *fe = d->acmod->fe;
+    melfb_t *mf = fe->mel_fb;
+    int i, n = 0;
+    for (i = 0; i < mf->num_filters; ++i) n += mf->filt_width[i];
+    out[0] = fe->frame_size; out[1] = fe->frame_shift; out[2] = fe->fft_size; out[3] = fe->fft_order;
+    out[4] = mf->num_filters; out[5] = fe->num_cepstra; out[6] = fe->remove_dc; out[7] = fe->noise_stats != NULL;
+    out[8] = fe->transform; out[9] = mf->lifter_val; out[10] = fe->log_spec; out[11] = fe->dither;
+    out[12] = n; out[13] = feat_window_size(d->acmod->fcb); out[14] = d->acmod->fcb->cmn; out[15] = feat_cepsize(d->acmod->fcb);
+    fout[0] = fe->pre_emphasis_alpha; fout[1] = mf->sqrt_inv_n; fout[2] = mf->sqrt_inv_2n; fout[3] = fe->sampling_rate;
+    return 0;
+}
+
+long
+refdrv_fe_export(refdrv_t *d, const char *what, void *out, long cap)
+{
+    fe_t *fe = d->acmod->fe;
+    melfb_t *mf = fe->mel_fb;
+    long need = -1;
+    int i, n = 0;
+#define EMIT(ptr, nbytes) do { need = (long)(nbytes); \
+        if (out && cap >= need) memcpy(out, (ptr), need); } while (0)
+    for (i = 0; i < mf->num_filters; ++i) n += mf->filt_width[i];
+    if (!strcmp(what, "hamming")) EMIT(fe->hamming_window, (long)(fe->frame_size / 2) * sizeof(window_t));
+    else if (!strcmp(what, "ccc")) EMIT(fe->ccc, (long)(fe->fft_size / 4) * sizeof(frame_t));
+    else if (!strcmp(what, "sss")) EMIT(fe->sss, (long)(fe->fft_size / 4) * sizeof(frame_t));
+    else if (!strcmp(what, "spec_start")) EMIT(mf->spec_start, (long)mf->num_filters * sizeof(int16));
+    else if (!strcmp(what, "filt_start")) EMIT(mf->filt_start, (long)mf->num_filters * sizeof(int16));
+    else if (!strcmp(what, "filt_width")) EMIT(mf->filt_width, (long)mf->num_filters * sizeof(int16));
+    else if (!strcmp(what, "filt_coeffs")) EMIT(mf->filt_coeffs, (long)n * sizeof(mfcc_t));
+    else if (!strcmp(what, "mel_cosine")) EMIT(mf->mel_cosine[0], (long)mf->num_cepstra * mf->num_filters * sizeof(mfcc_t));
+    else if (!strcmp(what, "lifter")) { if (mf->lifter_val) EMIT(mf->lifter, (long)mf->num_cepstra * sizeof(mfcc_t)); else need = 0; }
+#undef EMIT
+    return need;
+}
+
+/* PCM -> cepstra (before CMN) through fe_process_frames + fe_end_utt, noise tracker reset first
+ * (ps_start_stream, pocketsphinx.c:1073-1083): what a fresh stream produces.  out [T][num_cepstra]. */
+int
+refdrv_mfcc(refdrv_t *d, const int16 *pcm, long n_samples, float *out, int max_frames)
+{
+    fe_t *fe = d->acmod->fe;
+    const int16 *p = pcm;
+    size_t n = n_samples;
+    int32 nfr = 0, T, t, last = 0;
+    mfcc_t **buf;
+
+    fe_reset_noisestats(fe->noise_stats);
+    fe_start_utt(fe);
+    fe_process_frames(fe, NULL, &n, NULL, &nfr);
+    T = nfr + 1;
+    buf = (mfcc_t **)ckd_calloc_2d(T, fe->num_cepstra, sizeof(mfcc_t));
+    nfr = T;
+    p = pcm; n = n_samples;
+    if (n_samples > 0 && T > 1) fe_process_frames(fe, &p, &n, buf, &nfr);
+    else {
+        /* fewer samples than one frame: fe_process_frames only buffers them */
+        int32 z = 1;
+        fe_process_frames(fe, &p, &n, buf, &z);
+        nfr = 0;
+    }
+    fe_end_utt(fe, buf[nfr], &last);
+    nfr += last;
+    for (t = 0; t < nfr && t < max_frames; ++t)
+        memcpy(out + (size_t)t * fe->num_cepstra, buf[t], fe->num_cepstra * sizeof(mfcc_t));
+    ckd_free_2d(buf);
+    return nfr;
+}
+
+void
+refdrv_fe_reset(refdrv_t *d)
+{
+    fe_reset_noisestats(d->acmod->fe->noise_stats);
 }
 
 /* PCM -> dynamic features through the reference fe/ + feat/ (full-utterance mode, as

@@ -44,6 +44,11 @@ def lib():
         L.refdrv_export.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long]
         L.refdrv_featurize.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_int]
         L.refdrv_reset.argtypes = [C.c_void_p]
+        L.refdrv_fe_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.refdrv_fe_export.restype = C.c_long
+        L.refdrv_fe_export.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long]
+        L.refdrv_mfcc.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_int]
+        L.refdrv_fe_reset.argtypes = [C.c_void_p]
         L.refdrv_score.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.refdrv_score_active.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_int, C.c_void_p, C.c_void_p]
@@ -132,6 +137,51 @@ class RefModel:
         if self.kind == "s2_semi":
             m["topn_beam"] = self.export("topn_beam", np.uint8)
         return m
+
+    def fe_export(self, what, dtype):
+        n = lib().refdrv_fe_export(self.h, what.encode(), None, 0)
+        if n < 0:
+            raise KeyError(what)
+        buf = np.zeros(n // np.dtype(dtype).itemsize, dtype)
+        if n:
+            lib().refdrv_fe_export(self.h, what.encode(), _p(buf), n)
+        return buf
+
+    def fe_desc(self):
+        """Front-end parameters and tables as the reference's fe_init left them (dict)."""
+        i = np.zeros(16, np.int32)
+        f = np.zeros(4, np.float32)
+        lib().refdrv_fe_info(self.h, _p(i), _p(f))
+        d = dict(frame_size=int(i[0]), frame_shift=int(i[1]), fft_size=int(i[2]), fft_order=int(i[3]),
+                 n_filt=int(i[4]), n_cep=int(i[5]), remove_dc=int(i[6]), remove_noise=int(i[7]),
+                 transform=int(i[8]), lifter_val=int(i[9]), log_spec=int(i[10]), dither=int(i[11]),
+                 window=int(i[13]), cmn=int(i[14]), cepsize=int(i[15]),
+                 alpha=np.float32(f[0]), sqrt_inv_n=np.float32(f[1]), sqrt_inv_2n=np.float32(f[2]),
+                 sampling_rate=float(f[3]))
+        d["hamming"] = self.fe_export("hamming", np.float64)
+        d["ccc"] = self.fe_export("ccc", np.float64)
+        d["sss"] = self.fe_export("sss", np.float64)
+        for k in ("spec_start", "filt_start", "filt_width"):
+            d[k] = self.fe_export(k, np.int16)
+        d["filt_coeffs"] = self.fe_export("filt_coeffs", np.float32)
+        d["mel_cosine"] = self.fe_export("mel_cosine", np.float32).reshape(d["n_cep"], d["n_filt"])
+        d["lifter"] = self.fe_export("lifter", np.float32)
+        return d
+
+    def mfcc(self, pcm):
+        """Cepstra before CMN from a fresh stream (noise tracker reset)."""
+        pcm = np.ascontiguousarray(pcm, np.int16)
+        cap = len(pcm) // 160 + 16
+        i = np.zeros(16, np.int32); f = np.zeros(4, np.float32)
+        lib().refdrv_fe_info(self.h, _p(i), _p(f))
+        out = np.zeros((cap, int(i[5])), np.float32)
+        T = lib().refdrv_mfcc(self.h, _p(pcm), len(pcm), _p(out), cap)
+        return out[:T].copy()
+
+    def featurize_fresh(self, pcm):
+        """featurize() as the first utterance of a fresh stream (noise tracker reset first)."""
+        lib().refdrv_fe_reset(self.h)
+        return self.featurize(pcm)
 
     def featurize(self, pcm, max_frames=None):
         pcm = np.ascontiguousarray(pcm, np.int16)

@@ -27,6 +27,16 @@ class ModelDesc(C.Structure):
 
 # every symbol include/psb200.h declares: (name, restype, argtypes)
 _VP, _I32, _I64 = C.c_void_p, C.c_int32, C.c_int64
+class FeDesc(C.Structure):
+    _fields_ = [("frame_size", C.c_int32), ("frame_shift", C.c_int32), ("fft_size", C.c_int32), ("fft_order", C.c_int32),
+                ("n_filt", C.c_int32), ("n_cep", C.c_int32), ("remove_dc", C.c_int32), ("remove_noise", C.c_int32),
+                ("transform", C.c_int32), ("lifter_val", C.c_int32), ("window", C.c_int32), ("cmn", C.c_int32),
+                ("n_coeffs", C.c_int32), ("pre_emphasis_alpha", C.c_float), ("sqrt_inv_n", C.c_float),
+                ("sqrt_inv_2n", C.c_float), ("hamming", C.c_void_p), ("ccc", C.c_void_p), ("sss", C.c_void_p),
+                ("spec_start", C.c_void_p), ("filt_start", C.c_void_p), ("filt_width", C.c_void_p),
+                ("filt_coeffs", C.c_void_p), ("mel_cosine", C.c_void_p), ("lifter", C.c_void_p)]
+
+
 SYMBOLS = [
     ("psb_last_error", C.c_char_p, []),
     ("psb_abi_version", C.c_int, []),
@@ -62,6 +72,11 @@ SYMBOLS = [
     ("psb_hmmset_download", C.c_int, [_VP, _VP]),
     ("psb_hmmset_eval_frames_device", C.c_int, [_VP, _VP, _VP, _VP, _I32, _VP, C.POINTER(C.c_float)]),
     ("psb_hmmset_eval_host", C.c_int, [_VP, _VP, _VP]),
+    ("psb_fe_create", C.c_int, [C.POINTER(FeDesc), C.c_int, C.POINTER(_VP)]),
+    ("psb_fe_free", None, [_VP]),
+    ("psb_fe_n_frames", C.c_int32, [_VP, C.c_int64]),
+    ("psb_fe_process_host", C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP]),
+    ("psb_fe_process_device", C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP, C.POINTER(C.c_float)]),
     ("psb_phoneloop_create", C.c_int, [_VP, _I32, _VP, _VP, _I32, _I32, _I32, _I32, C.c_double, C.POINTER(_VP)]),
     ("psb_phoneloop_free", None, [_VP]),
     ("psb_phoneloop_run_device", C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP]),

@@ -354,3 +354,69 @@ def sendump_read(path, max_frames=1 << 20):
     if n < 0:
         raise PsbError("psb_sendump_read failed: " + lib().psb_last_error().decode())
     return out[:n]
+
+
+class FrontEnd:
+    """fe/ + feat/ for whole batches on the device (every utterance a fresh stream).  `desc` is the
+    dict of fe_tables.make_fe_desc() -- or the same arrays taken out of the reference's fe_t."""
+
+    def __init__(self, desc, device=0):
+        from ._lib import FeDesc
+        self.desc = desc
+        self._keep = {}
+        d = FeDesc()
+        for k in ("frame_size", "frame_shift", "fft_size", "fft_order", "n_filt", "n_cep", "remove_dc", "remove_noise",
+                  "transform", "lifter_val", "window", "cmn"):
+            setattr(d, k, int(desc[k]))
+        d.pre_emphasis_alpha = float(desc["alpha"])
+        d.sqrt_inv_n = float(desc["sqrt_inv_n"])
+        d.sqrt_inv_2n = float(desc["sqrt_inv_2n"])
+        for k, dt in (("hamming", np.float64), ("ccc", np.float64), ("sss", np.float64), ("spec_start", np.int16),
+                      ("filt_start", np.int16), ("filt_width", np.int16), ("filt_coeffs", np.float32),
+                      ("mel_cosine", np.float32), ("lifter", np.float32)):
+            a = np.ascontiguousarray(desc[k], dt)
+            self._keep[k] = a
+            setattr(d, k, a.ctypes.data if a.size else None)
+        d.n_coeffs = int(self._keep["filt_coeffs"].size)
+        self.n_cep = int(desc["n_cep"])
+        h = C.c_void_p()
+        check(lib().psb_fe_create(C.byref(d), device, C.byref(h)), "psb_fe_create")
+        self.h = h
+
+    def n_frames(self, n_samples):
+        return lib().psb_fe_n_frames(self.h, int(n_samples))
+
+    @staticmethod
+    def sample_offsets(lens):
+        off = np.zeros(len(lens) + 1, np.int64)
+        np.cumsum(lens, out=off[1:])
+        return off
+
+    def process_host(self, pcm, samp_off, want_mfcc=False):
+        """pcm int16 (utterances back to back), samp_off int64 [n_utt+1] -> (feats [T][3*n_cep],
+        frame_off int32 [n_utt+1][, mfcc after CMN [T][n_cep]])."""
+        pcm = np.ascontiguousarray(pcm, np.int16)
+        samp_off = np.ascontiguousarray(samp_off, np.int64)
+        n_utt = len(samp_off) - 1
+        total = sum(self.n_frames(int(samp_off[u + 1] - samp_off[u])) for u in range(n_utt))
+        feats = np.zeros((total, 3 * self.n_cep), np.float32)
+        mfcc = np.zeros((total, self.n_cep), np.float32) if want_mfcc else None
+        frame_off = np.zeros(n_utt + 1, np.int32)
+        check(lib().psb_fe_process_host(self.h, _p(pcm) if pcm.size else None, _p(samp_off), n_utt, _p(feats) if total else None,
+                                        _p(mfcc) if (want_mfcc and total) else None, _p(frame_off)), "psb_fe_process_host")
+        return (feats, frame_off, mfcc) if want_mfcc else (feats, frame_off)
+
+    def process_device(self, d_pcm_ptr, samp_off, d_feats_ptr):
+        """Device buffers; returns (frame_off int32 [n_utt+1], device ms of the two kernels)."""
+        samp_off = np.ascontiguousarray(samp_off, np.int64)
+        n_utt = len(samp_off) - 1
+        frame_off = np.zeros(n_utt + 1, np.int32)
+        ms = C.c_float()
+        check(lib().psb_fe_process_device(self.h, C.c_void_p(d_pcm_ptr), _p(samp_off), n_utt, C.c_void_p(d_feats_ptr),
+                                          None, _p(frame_off), C.byref(ms)), "psb_fe_process_device")
+        return frame_off, ms.value
+
+    def close(self):
+        if self.h:
+            lib().psb_fe_free(self.h)
+            self.h = None

@@ -450,3 +450,63 @@ def test_hmmset_frames_match_oracle(api, n_emit):
     assert_hmm_equal(got, want, n_emit, "after %d frames" % T)
     hs.close()
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------
+# BASELINE.json config 2 at FULL size (1000 utterances x 998 frames, 5138 senones): properties
+# that do not need the oracle on every frame, plus the oracle on a sample of utterances.
+
+def test_full_size_properties(api, monkeypatch):
+    import torch
+    import zlib
+    from oracle import oracle
+    from pocketsphinx_b200.model import synth_feats, synth_ptm
+    pm = synth_ptm(seed=0)
+    U, T = 1000, 998
+    feats = synth_feats(pm, U, T, seed=77)
+    flat = np.ascontiguousarray(feats.reshape(U * T, pm.sumlen))
+    off = api.Batch.offsets([T] * U)
+    m = api.Model(pm)
+    ctx = api.HmmContext(pm.tp, pm.sseq, pm.n_sen)
+    H = pm.n_ciphone
+    pl = api.PhoneLoop(ctx, pm.phone_ssid[:H], pm.phone_tmat[:H], 5, -1080, -1080, 0, 3.0)
+    d_feats = torch.from_numpy(flat).cuda()
+
+    def run(variant, pipe):
+        monkeypatch.setenv("PSB_TOPN_VARIANT", str(variant))
+        b = api.Batch(m, U, U * T)
+        b.set_pipeline(pipe)
+        best, pen = b.decode_host(pl, flat, off)
+        scr = torch.empty((U * T, pm.n_sen), dtype=torch.int16, device="cuda")
+        b.score_device(d_feats.data_ptr(), off, scr.data_ptr())
+        b.sync()
+        # a checksum of per-row checksums of the 10 GB score matrix, computed on the device
+        w = torch.arange(1, pm.n_sen + 1, device="cuda", dtype=torch.int64)
+        rows = torch.zeros(U * T, dtype=torch.int64, device="cuda")
+        for a in range(0, U * T, 65536):
+            rows[a:a + 65536] = (scr[a:a + 65536].to(torch.int64) * w).sum(1)
+        sample = {u: scr[off[u]:off[u + 1]].cpu().numpy() for u in (0, 499, 999)}
+        mins = scr.view(U * T, pm.n_sen).min(1).values.cpu().numpy()
+        b.close()
+        return best, pen, rows.cpu().numpy(), sample, mins
+
+    best5, pen5, rows5, sample5, mins5 = run(5, 1)
+    # every frame's best senone scores 0 (ptm_mgau.c:398-400) and the phone loop saw every frame
+    assert (mins5 == 0).all()
+    assert best5.shape == (U * T,) and pen5.shape == (U * T, H)
+    # oracle on three whole utterances
+    om = oracle.OracleModel(pm)
+    for u, got in sample5.items():
+        assert np.array_equal(got, om.score_utt(feats[u])), "utterance %d" % u
+    # same bits from the packed kernel without deferred insertion, and from two ranges in flight
+    best2, pen2, rows2, _, _ = run(2, 2)
+    assert np.array_equal(rows5, rows2)
+    assert np.array_equal(best5, best2) and np.array_equal(pen5, pen2)
+    # utterance order does not matter: reversed batch gives the reversed result
+    monkeypatch.setenv("PSB_TOPN_VARIANT", "5")
+    b = api.Batch(m, U, U * T)
+    rbest, rpen = b.decode_host(pl, np.ascontiguousarray(feats[::-1].reshape(U * T, pm.sumlen)), off)
+    assert np.array_equal(rbest.reshape(U, T)[::-1], best5.reshape(U, T))
+    assert np.array_equal(rpen.reshape(U, T, H)[::-1], pen5.reshape(U, T, H))
+    b.close(); pl.close(); ctx.close(); m.close()
+    assert zlib.crc32(rows5.tobytes()) == zlib.crc32(rows2.tobytes())
