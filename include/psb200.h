@@ -254,6 +254,25 @@ int64_t psb_sendump_read(const char *path, int32_t *n_sen_out, int16_t *senscr, 
 int psb_batch_set_pipeline(psb_batch_t *b, int n);
 
 /* ------------------------------------------------------------------------------------ */
+/* Forced alignment for whole batches: state_align_search.c (start :43, step :184-219 =
+ * renormalise, evaluate_hmms :64, prune_hmms :88, phone_transition :109, record_transitions :153;
+ * finish :221-279 = backtrace).  Utterance u owns frames [utt_off[u], utt_off[u+1]) of the int16
+ * score matrix [frames][n_sen] (all senones: -compallsen yes) and phones [ph_off[u], ph_off[u+1])
+ * given as (ssid, tmatid) like hmm_init(hmmctx, hmm, FALSE, ssid, tmatid) (:455); sf / ef are the
+ * per-phone alignment constraints of state_align_search_init (:462-469), NULL = always active.
+ * Outputs per emitting state (index = phone * n_emit_state + j, ps_alignment_entry_t): start,
+ * duration, score; -1 where the backtrace never visits the state.  status[u]: 0, -1 ("Failed to
+ * reach final state"), -2 - frame ("Alignment failed in frame").  All arrays but d_senscr: host. */
+int psb_align_batch_device(psb_hmmctx_t *c, const int16_t *d_senscr, const int32_t *utt_off,
+                           int32_t n_utt, const int32_t *ph_off, const int32_t *ssid,
+                           const int32_t *tmatid, const int32_t *sf, const int32_t *ef,
+                           int32_t *st_start, int32_t *st_dur, int32_t *st_score, int32_t *status);
+int psb_align_batch_host(psb_hmmctx_t *c, const int16_t *senscr, const int32_t *utt_off,
+                         int32_t n_utt, const int32_t *ph_off, const int32_t *ssid,
+                         const int32_t *tmatid, const int32_t *sf, const int32_t *ef,
+                         int32_t *st_start, int32_t *st_dur, int32_t *st_score, int32_t *status);
+
+/* ------------------------------------------------------------------------------------ */
 /* Batched front end: int16 PCM -> cepstra -> batch CMN -> 1s_c_d_dd features
  * for whole batches, every utterance a fresh stream (ps_start_stream + ps_process_raw(full_utt),
  * pocketsphinx.c:1073, acmod.c:528-560).  The tables are the arrays the reference's own fe_t /

@@ -33,8 +33,25 @@ def save_model(name, pm_dict, keep_phones=None):
     return pm
 
 
+def make_align():
+    """en_us_align.npz: the reference's own state_align_search (ps_set_alignment) on goforward.raw
+    with its transcript, all senones, no look-ahead: phone chain and state-level alignment."""
+    pcm = np.fromfile(os.path.join(REF, "test/data/goforward.raw"), np.int16)
+    out = {}
+    for tag, words in (("a", "<s> go forward ten meters </s>"), ("b", "go forward ten meters"),
+                       ("c", "<s> go forward ten meters </s> <s> go forward </s>")):
+        a = refdrv.align(os.path.join(REF, "model/en-us/en-us"), os.path.join(REF, "model/en-us/cmudict-en-us.dict"),
+                         words, pcm)
+        for k in ("ssid", "tmatid", "start", "dur", "score"):
+            out[tag + "_" + k] = a[k]
+        print("align", tag, len(a["ssid"]), "phones", a["dur"].sum(), "frames covered")
+    np.savez_compressed(os.path.join(OUT, "en_us_align.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "align":
+        return make_align()
     pcm = np.fromfile(os.path.join(REF, "test/data/goforward.raw"), np.int16)
 
     # ---- en-us PTM (BASELINE config 1): goforward.raw, 278 frames, all senones ----
@@ -130,6 +147,7 @@ def main():
         cases["n%d_best" % n_emit] = np.int32(best)
         ctx.close()
     np.savez_compressed(os.path.join(OUT, "hmm_vit_eval.npz"), **cases)
+    make_align()
     for fn in sorted(os.listdir(OUT)):
         print("%8d KiB  %s" % (os.path.getsize(os.path.join(OUT, fn)) // 1024, fn))
 

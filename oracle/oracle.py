@@ -217,3 +217,26 @@ def phoneloop_run(tp, sseq, ssid, tmatid, senscr, window, beam, pbeam, pip, pena
     lib().pso_phoneloop_run(p, _p(senscr), n_sen, T, _p(hm), _p(best), _p(pen))
     lib().pso_phoneloop_free(p)
     return dict(hmm=hm, best=best, pen=pen)
+
+
+def align_run(tp, sseq, ssid, tmatid, senscr, sf=None, ef=None):
+    """state_align_search.c semantics for one utterance over a [T][n_sen] score matrix.
+    Returns (status, start, dur, score) per emitting state."""
+    tp = np.ascontiguousarray(tp, np.uint8)
+    sseq = np.ascontiguousarray(sseq, np.uint16)
+    ssid = np.ascontiguousarray(ssid, np.int32)
+    tmatid = np.ascontiguousarray(tmatid, np.int32)
+    senscr = np.ascontiguousarray(senscr, np.int16)
+    T, n_sen = senscr.shape
+    n_emit = tp.shape[1]
+    n_st = len(ssid) * n_emit
+    out = np.zeros((3, n_st), np.int32)
+    sf = None if sf is None else np.ascontiguousarray(sf, np.int32)
+    ef = None if ef is None else np.ascontiguousarray(ef, np.int32)
+    f = lib().pso_align_run
+    f.restype = C.c_int32
+    f.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                  C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = f(n_emit, _p(tp), _p(sseq), len(ssid), _p(ssid), _p(tmatid), _p(sf), _p(ef), _p(senscr), n_sen, T,
+           _p(out[0]), _p(out[1]), _p(out[2]))
+    return int(rc), out[0].copy(), out[1].copy(), out[2].copy()

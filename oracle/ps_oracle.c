@@ -1153,3 +1153,102 @@ pso_phoneloop_run(pso_phoneloop_t *p, const int16_t *senscr, int32_t n_sen, int3
         if (pen_out) memcpy(pen_out + (size_t)t * p->n_phones, p->penalties, p->n_phones * sizeof(int32_t));
     }
 }
+
+/* ---------------------------------------------------------------------------------------
+ * Forced alignment: state_align_search.c restated (start :43-53, renormalize :55-62,
+ * evaluate_hmms :64-86, prune_hmms :88-107, phone_transition :109-136, record_transitions
+ * :153-182, step :184-219, finish :221-279).  One utterance; phones given as (ssid, tmatid),
+ * constraints sf/ef per phone (NULL = always active: 0 / INT_MAX).  Outputs per emitting state
+ * of every phone (state index = phone * n_emit + j): start, duration, score, all -1 where the
+ * reference's backtrace never visits the state.  Returns 0, -1 ("Failed to reach final state"),
+ * or -2 - frame ("Alignment failed in frame"). */
+int32_t
+pso_align_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, int32_t n_phones,
+              const int32_t *ssid, const int32_t *tmatid, const int32_t *sf, const int32_t *ef,
+              const int16_t *senscr, int32_t n_sen, int32_t T,
+              int32_t *st_start, int32_t *st_dur, int32_t *st_score)
+{
+    pso_hmmctx_t ctx;
+    pso_hmm_t *hmms = calloc(n_phones, sizeof(*hmms));
+    const int32_t n_st = n_phones * n_emit_state;
+    int32_t *tok_id = malloc((size_t)(T > 0 ? T : 1) * n_st * sizeof(int32_t));
+    int32_t *tok_sc = malloc((size_t)(T > 0 ? T : 1) * n_st * sizeof(int32_t));
+    int32_t best_score = 0, frame = 0, rc = 0;
+    int i, j, f;
+
+    memset(&ctx, 0, sizeof(ctx));
+    ctx.n_emit_state = n_emit_state; ctx.tp = tp; ctx.sseq = sseq;
+    for (i = 0; i < n_phones; ++i)
+        pso_hmm_init(&ctx, &hmms[i], 0, ssid[i], tmatid[i]);
+    for (i = 0; i < n_st; ++i) st_start[i] = st_dur[i] = st_score[i] = -1;
+    pso_hmm_enter(&hmms[0], 0, 0, 0);                                    /* start */
+    for (f = 0; f < T; ++f) {
+        const int nf = f + 1;
+        int32_t bs = PSO_WORST_SCORE;
+        ctx.senscore = senscr + (size_t)f * n_sen;
+        if (best_score - 0x300000 < PSO_WORST_SCORE)                      /* step :199-203 */
+            for (i = 0; i < n_phones; ++i) pso_hmm_normalize(&hmms[i], best_score);
+        for (i = 0; i < n_phones; ++i) {                                  /* evaluate_hmms */
+            int32_t score;
+            if (hmms[i].frame < f) continue;
+            score = pso_hmm_vit_eval(&ctx, &hmms[i]);
+            if (score > bs) bs = score;
+        }
+        best_score = bs;
+        for (i = 0; i < n_phones; ++i) {                                  /* prune_hmms */
+            if (hmms[i].frame < f) continue;
+            if (nf > (ef ? ef[i] : INT32_MAX)) continue;
+            hmms[i].frame = nf;
+        }
+        for (i = 0; i < n_phones - 1; ++i) {                              /* phone_transition */
+            pso_hmm_t *h = &hmms[i], *nh = &hmms[i + 1];
+            int32_t newphone_score;
+            if (h->frame != nf) continue;
+            if (nf < (sf ? sf[i + 1] : 0)) continue;
+            newphone_score = h->out_score;
+            if (nh->frame < f || newphone_score > nh->score[0])
+                pso_hmm_enter(nh, newphone_score, h->out_history, nf);
+        }
+        for (i = 0; i < n_st; ++i) {                                      /* record_transitions */
+            tok_id[(size_t)f * n_st + i] = -1;
+            tok_sc[(size_t)f * n_st + i] = -1;
+        }
+        for (i = 0; i < n_phones; ++i) {
+            if (hmms[i].frame < f) continue;
+            for (j = 0; j < n_emit_state; ++j) {
+                const int s = i * n_emit_state + j;
+                tok_id[(size_t)f * n_st + s] = hmms[i].history[j];
+                tok_sc[(size_t)f * n_st + s] = hmms[i].score[j];
+                hmms[i].history[j] = s;
+            }
+        }
+        frame = f;
+    }
+    /* finish: backtrace */
+    {
+        int32_t last_id, last_sc, cur_id, cur_sc, last_frame, cur_frame;
+        last_id = cur_id = hmms[n_phones - 1].out_history;
+        last_sc = hmms[n_phones - 1].out_score;
+        if (last_id == -1 || T == 0) { rc = -1; goto done; }
+        last_frame = frame + 1;
+        for (cur_frame = frame - 1; cur_frame >= 0; --cur_frame) {
+            const int32_t prev = cur_id;
+            cur_id = tok_id[(size_t)cur_frame * n_st + prev];
+            cur_sc = tok_sc[(size_t)cur_frame * n_st + prev];
+            if (cur_id == -1) { rc = -2 - cur_frame; goto done; }
+            if (cur_id != last_id) {
+                st_start[last_id] = cur_frame + 1;
+                st_dur[last_id] = last_frame - st_start[last_id];
+                st_score[last_id] = last_sc - cur_sc;
+                last_id = cur_id; last_sc = cur_sc;
+                last_frame = cur_frame + 1;
+            }
+        }
+        st_start[0] = 0;                              /* "Update alignment entry for initial state" */
+        st_dur[0] = last_frame;
+        st_score[0] = 0;                              /* the reference leaves the entry's initial 0 */
+    }
+done:
+    free(hmms); free(tok_id); free(tok_sc);
+    return rc;
+}

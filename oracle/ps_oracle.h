@@ -143,7 +143,14 @@ void pso_phoneloop_run(pso_phoneloop_t *p, const int16_t *senscr, int32_t n_sen,
 
 double pso_time_score_utt(const pso_model_t *m, const float *feats, int32_t T, int32_t reps);
 
+/* ---- forced alignment (state_align_search.c) ---- */
+int32_t pso_align_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, int32_t n_phones,
+                      const int32_t *ssid, const int32_t *tmatid, const int32_t *sf, const int32_t *ef,
+                      const int16_t *senscr, int32_t n_sen, int32_t T,
+                      int32_t *st_start, int32_t *st_dur, int32_t *st_score);
+
 #ifdef __cplusplus
 }
 #endif
 #endif
+

@@ -841,3 +841,75 @@ refdrv_decode_senscr(const char *hmmdir, const char *lm, const char *dict, const
     ps_config_free(config);
     return nfr;
 }
+
+/* Forced alignment through the reference's own state_align_search (state_align_search.c) on one
+ * utterance: `words` (dictionary words separated by blanks, e.g. "<s> go forward ten meters </s>")
+ * -> ps_alignment_t (ps_alignment_add_word with no timing, ps_alignment_populate) ->
+ * ps_set_alignment -> ps_start_utt / ps_process_raw(full) / ps_end_utt.  Outputs the phone
+ * sequence (ssid, tmatid) and, per emitting state, start / duration / score of the resulting
+ * alignment.  info: [0] frames, [1] n_phones, [2] n_states, [3] n_emit_state.  Returns 0, or <0. */
+#include "ps_alignment_internal.h"
+int
+refdrv_align(const char *hmmdir, const char *dict, const char *kv, const char *words,
+             const int16 *pcm, long n_samples, int32 *ph_ssid, int32 *ph_tmat, int cap_ph,
+             int32 *st_start, int32 *st_dur, int32 *st_score, int cap_st, int32 *info)
+{
+    ps_config_t *config;
+    ps_decoder_t *ps;
+    ps_alignment_t *al;
+    ps_alignment_iter_t *it;
+    char *buf, *save = NULL, *tok;
+    int i, rc = 0;
+
+    err_set_loglevel(ERR_ERROR);
+    config = ps_config_init(NULL);
+    ps_config_set_str(config, "hmm", hmmdir);
+    ps_config_set_str(config, "dict", dict);
+    ps_config_set_str(config, "dither", "no");
+    ps_config_set_str(config, "compallsen", "yes");
+    ps_config_set_str(config, "pl_window", "0");
+    ps_config_set_str(config, "lm", NULL);
+    if (kv) {
+        char *b2 = strdup(kv), *s2 = NULL, *t2;
+        for (t2 = strtok_r(b2, "\n", &s2); t2; t2 = strtok_r(NULL, "\n", &s2)) {
+            char *eq = strchr(t2, '=');
+            if (!eq) continue;
+            *eq = 0;
+            ps_config_set_str(config, t2, eq + 1);
+        }
+        free(b2);
+    }
+    ps = ps_init(config);
+    if (ps == NULL) { ps_config_free(config); return -1; }
+    al = ps_alignment_init(ps->d2p);
+    buf = strdup(words);
+    for (tok = strtok_r(buf, " \t\n", &save); tok; tok = strtok_r(NULL, " \t\n", &save)) {
+        int32 wid = dict_wordid(ps->dict, tok);
+        if (wid == BAD_S3WID) { rc = -2; break; }
+        ps_alignment_add_word(al, wid, 0, 0);
+    }
+    free(buf);
+    if (rc == 0 && ps_alignment_populate(al) < 0) rc = -3;
+    if (rc == 0 && ps_set_alignment(ps, al) < 0) rc = -4;
+    if (rc == 0) {
+        ps_start_utt(ps);
+        ps_process_raw(ps, pcm, n_samples, FALSE, TRUE);
+        if (ps_end_utt(ps) < 0) rc = -5;
+        info[0] = ps_get_n_frames(ps);
+        info[1] = ps_alignment_n_phones(al);
+        info[2] = ps_alignment_n_states(al);
+        info[3] = bin_mdef_n_emit_state(ps->acmod->mdef);
+        for (i = 0, it = ps_alignment_phones(al); it; it = ps_alignment_iter_next(it), ++i) {
+            ps_alignment_entry_t *e = ps_alignment_iter_get(it);
+            if (i < cap_ph) { ph_ssid[i] = e->id.pid.ssid; ph_tmat[i] = e->id.pid.tmatid; }
+        }
+        for (i = 0, it = ps_alignment_states(al); it; it = ps_alignment_iter_next(it), ++i) {
+            ps_alignment_entry_t *e = ps_alignment_iter_get(it);
+            if (i < cap_st) { st_start[i] = e->start; st_dur[i] = e->duration; st_score[i] = e->score; }
+        }
+    }
+    ps_alignment_free(al);
+    ps_free(ps);
+    ps_config_free(config);
+    return rc;
+}

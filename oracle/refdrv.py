@@ -49,6 +49,9 @@ def lib():
         L.refdrv_fe_export.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long]
         L.refdrv_mfcc.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_int]
         L.refdrv_fe_reset.argtypes = [C.c_void_p]
+        L.refdrv_align.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_long,
+                                   C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                   C.c_void_p]
         L.refdrv_score.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.refdrv_score_active.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_int, C.c_void_p, C.c_void_p]
@@ -297,3 +300,21 @@ def decode_senscr(hmmdir, lm, dic, senfile=None, pcm=None, senout=None, **kv):
     if n < 0:
         raise RuntimeError("refdrv_decode_senscr failed (%d)" % n)
     return dict(n_frames=n, hyp=hyp.value.decode(), seg=seg.value.decode(), score=int(stats[0]))
+
+
+def align(hmmdir, dictfile, words, pcm, **kv):
+    """The reference's state_align_search on one utterance (compallsen, no look-ahead).
+    Returns dict(n_frames, ssid, tmatid, start, dur, score, n_emit)."""
+    pcm = np.ascontiguousarray(pcm, np.int16)
+    s = "\n".join("%s=%s" % (k, v) for k, v in kv.items()).encode() or None
+    cap = 4096
+    ssid = np.zeros(cap, np.int32); tmat = np.zeros(cap, np.int32)
+    st = np.zeros((3, cap * 5), np.int32)
+    info = np.zeros(8, np.int32)
+    rc = lib().refdrv_align(hmmdir.encode(), dictfile.encode(), s, words.encode(), _p(pcm), len(pcm),
+                            _p(ssid), _p(tmat), cap, _p(st[0]), _p(st[1]), _p(st[2]), cap * 5, _p(info))
+    if rc < 0:
+        raise RuntimeError("refdrv_align failed: %d" % rc)
+    nph, nst = int(info[1]), int(info[2])
+    return dict(n_frames=int(info[0]), n_emit=int(info[3]), ssid=ssid[:nph].copy(), tmatid=tmat[:nph].copy(),
+                start=st[0, :nst].copy(), dur=st[1, :nst].copy(), score=st[2, :nst].copy())

@@ -252,6 +252,31 @@ class HmmContext:
               "psb_hmm_vit_eval_ptrs")
         return best.value
 
+    def align(self, senscr, utt_off, ph_off, ssid, tmatid, sf=None, ef=None, device_ptr=None):
+        """state_align_search over a batch.  senscr: host int16 [frames][n_sen] (or device_ptr);
+        returns (status [n_utt], start, dur, score per emitting state)."""
+        utt_off = np.ascontiguousarray(utt_off, np.int32)
+        ph_off = np.ascontiguousarray(ph_off, np.int32)
+        ssid = np.ascontiguousarray(ssid, np.int32)
+        tmatid = np.ascontiguousarray(tmatid, np.int32)
+        sf = None if sf is None else np.ascontiguousarray(sf, np.int32)
+        ef = None if ef is None else np.ascontiguousarray(ef, np.int32)
+        n_utt = len(utt_off) - 1
+        n_st = max(1, int(ph_off[-1]) * self.n_emit)
+        out = np.zeros((3, n_st), np.int32)
+        status = np.zeros(max(1, n_utt), np.int32)
+        if device_ptr is not None:
+            check(lib().psb_align_batch_device(self.h, C.c_void_p(device_ptr), _p(utt_off), n_utt, _p(ph_off), _p(ssid),
+                                               _p(tmatid), _p(sf), _p(ef), _p(out[0]), _p(out[1]), _p(out[2]), _p(status)),
+                  "psb_align_batch_device")
+        else:
+            senscr = np.ascontiguousarray(senscr, np.int16)
+            check(lib().psb_align_batch_host(self.h, _p(senscr), _p(utt_off), n_utt, _p(ph_off), _p(ssid), _p(tmatid),
+                                             _p(sf), _p(ef), _p(out[0]), _p(out[1]), _p(out[2]), _p(status)),
+                  "psb_align_batch_host")
+        k = int(ph_off[-1]) * self.n_emit
+        return status[:n_utt], out[0, :k], out[1, :k], out[2, :k]
+
     def close(self):
         if self.h:
             lib().psb_hmmctx_free(self.h)

@@ -918,3 +918,240 @@ extern "C" int psb_hmmset_eval_host(psb_hmmset_t *s, const int16_t *senscr, int3
     }
     return rc;
 }
+
+// ---------------------------------------------------------------------------------------
+// Forced alignment: state_align_search.c on the device for whole batches (SURVEY 8 row b5 lists
+// its evaluate_hmms, state_align_search.c:65).  One CTA per utterance, the utterance's phone
+// chain in shared memory (SoA), time is the loop inside the kernel: renormalise (:199-203),
+// evaluate_hmms (:64-86), prune_hmms (:88-107), phone_transition (:109-136, a left-to-right
+// scan whose hmm_enter can cascade through not-yet-active successors, so one thread walks it in
+// the reference's order), record_transitions (:153-182) into a token table in HBM, and at the end
+// the backtrace of state_align_search_finish (:221-279).
+namespace {
+
+__global__ void __launch_bounds__(128)
+align_kernel(const int16_t *__restrict__ senscr, const int32_t *__restrict__ utt_off, HmmCtxDev c,
+             const int32_t *__restrict__ ph_off, const uint16_t *__restrict__ senid_g,
+             const int32_t *__restrict__ tmatid_g, const int32_t *__restrict__ sf_g, const int32_t *__restrict__ ef_g,
+             int32_t *__restrict__ tok_id, int32_t *__restrict__ tok_sc, const int64_t *__restrict__ tok_off,
+             int32_t *__restrict__ st_start, int32_t *__restrict__ st_dur, int32_t *__restrict__ st_score,
+             int32_t *__restrict__ status)
+{
+    extern __shared__ int sm[];
+    const int u = blockIdx.x, tid = threadIdx.x, N = c.n_emit;
+    const int p0 = ph_off[u], H = ph_off[u + 1] - p0;
+    const long long f0 = utt_off[u];
+    const int T = utt_off[u + 1] - utt_off[u];
+    const int n_st = H * N;
+    int *score = sm;                       // [N][H]
+    int *hist = score + N * H;             // [N][H]
+    int *out_score = hist + N * H;         // [H]
+    int *out_hist = out_score + H;         // [H]
+    int *frame = out_hist + H;             // [H]
+    int *sval = frame + H;                 // [32]
+    int *sidx = sval + 32;                 // [32]
+    int32_t *tid_u = tok_id + tok_off[u], *tsc_u = tok_sc + tok_off[u];
+    int32_t *ss = st_start + (size_t)p0 * N, *sd = st_dur + (size_t)p0 * N, *sc = st_score + (size_t)p0 * N;
+
+    for (int i = tid; i < n_st; i += blockDim.x) { ss[i] = -1; sd[i] = -1; sc[i] = -1; }
+    if (H == 0) { if (tid == 0) status[u] = -1; return; }
+    // hmm_init -> hmm_clear (hmm.c:85-105, 180-196), then state_align_search_start: hmm_enter(hmms, 0, 0, 0)
+    for (int i = tid; i < H; i += blockDim.x) {
+        for (int s = 0; s < N; ++s) { score[s * H + i] = PSB_WORST_SCORE; hist[s * H + i] = -1; }
+        out_score[i] = PSB_WORST_SCORE; out_hist[i] = -1; frame[i] = -1;
+    }
+    __syncthreads();
+    if (tid == 0) { score[0] = 0; hist[0] = 0; frame[0] = 0; }
+    int best_score = 0;
+    __syncthreads();
+
+    for (int t = 0; t < T; ++t) {
+        const int16_t *row = senscr + (f0 + t) * c.n_sen;
+        const int nf = t + 1;
+        const bool renorm = best_score - 0x300000 < PSB_WORST_SCORE;
+        int bs = PSB_WORST_SCORE;
+        for (int i = tid; i < H; i += blockDim.x) {
+            HmmReg h;
+#pragma unroll
+            for (int s = 0; s < PSB_HMM_MAX_NSTATE; ++s) {
+                h.score[s] = s < N ? score[s * H + i] : PSB_WORST_SCORE;
+                h.hist[s] = s < N ? hist[s * H + i] : -1;
+                h.senid[s] = s < N ? senid_g[(size_t)(p0 + i) * N + s] : PSB_BAD_SSID;
+            }
+            h.out_score = out_score[i]; h.out_hist = out_hist[i]; h.best = PSB_WORST_SCORE;
+            if (renorm) {                                    // hmm_normalize, every phone
+#pragma unroll
+                for (int s = 0; s < PSB_HMM_MAX_NSTATE; ++s)
+                    if (s < N && h.score[s] > PSB_WORST_SCORE) h.score[s] -= best_score;
+                if (h.out_score > PSB_WORST_SCORE) h.out_score -= best_score;
+            }
+            if (frame[i] >= t) {
+                const int b = hmm_step(h, c, tmatid_g[p0 + i], false, row);
+                if (b > bs) bs = b;
+            }
+#pragma unroll
+            for (int s = 0; s < PSB_HMM_MAX_NSTATE; ++s)
+                if (s < N) { score[s * H + i] = h.score[s]; hist[s * H + i] = h.hist[s]; }
+            out_score[i] = h.out_score; out_hist[i] = h.out_hist;
+            // prune_hmms: stays active unless the alignment constraint ends it
+            if (frame[i] >= t && !(nf > (ef_g ? ef_g[p0 + i] : INT_MAX))) frame[i] = nf;
+        }
+        int dummy;
+        bs = block_reduce_max_pair<int>(bs, 0, sidx, sval, dummy);      // (contains the barriers)
+        best_score = bs;
+        __syncthreads();
+        if (tid == 0) {                                                  // phone_transition, in order
+            for (int i = 0; i < H - 1; ++i) {
+                if (frame[i] != nf) continue;
+                if (nf < (sf_g ? sf_g[p0 + i + 1] : 0)) continue;
+                const int nps = out_score[i];
+                if (frame[i + 1] < t || nps > score[i + 1]) {            // hmm_enter(nhmm, score, history, nf)
+                    score[i + 1] = nps; hist[i + 1] = out_hist[i]; frame[i + 1] = nf;
+                }
+            }
+        }
+        __syncthreads();
+        // record_transitions
+        int32_t *ti = tid_u + (size_t)t * n_st, *ts = tsc_u + (size_t)t * n_st;
+        for (int i = tid; i < H; i += blockDim.x) {
+            const bool on = frame[i] >= t;
+            for (int s = 0; s < N; ++s) {
+                const int idx = i * N + s;
+                ti[idx] = on ? hist[s * H + i] : -1;
+                ts[idx] = on ? score[s * H + i] : -1;
+                if (on) hist[s * H + i] = idx;
+            }
+        }
+        __syncthreads();
+    }
+    // state_align_search_finish
+    if (tid == 0) {
+        int rc = 0;
+        int last_id = out_hist[H - 1], last_sc = out_score[H - 1], cur_id = last_id, cur_sc;
+        if (last_id == -1 || T == 0) rc = -1;
+        else {
+            int last_frame = T;
+            for (int cf = T - 2; cf >= 0; --cf) {
+                const int prev = cur_id;
+                cur_id = tid_u[(size_t)cf * n_st + prev];
+                cur_sc = tsc_u[(size_t)cf * n_st + prev];
+                if (cur_id == -1) { rc = -2 - cf; break; }
+                if (cur_id != last_id) {
+                    ss[last_id] = cf + 1;
+                    sd[last_id] = last_frame - (cf + 1);
+                    sc[last_id] = last_sc - cur_sc;
+                    last_id = cur_id; last_sc = cur_sc;
+                    last_frame = cf + 1;
+                }
+            }
+            if (rc == 0) { ss[0] = 0; sd[0] = last_frame; sc[0] = 0; }
+        }
+        status[u] = rc;
+    }
+}
+
+}  // namespace
+
+extern "C" int psb_align_batch_device(psb_hmmctx_t *c, const int16_t *d_senscr, const int32_t *utt_off, int32_t n_utt,
+                                      const int32_t *ph_off, const int32_t *ssid, const int32_t *tmatid,
+                                      const int32_t *sf, const int32_t *ef,
+                                      int32_t *st_start, int32_t *st_dur, int32_t *st_score, int32_t *status)
+{
+    PSB_REQUIRE(c && utt_off && ph_off && n_utt >= 0 && st_start && st_dur && st_score && status,
+                "psb_align_batch_device: bad argument");
+    if (n_utt == 0) return PSB_OK;
+    PSB_REQUIRE(utt_off[0] == 0 && ph_off[0] == 0, "psb_align_batch_device: offsets must start at 0");
+    const int N = c->n_emit;
+    const int total_ph = ph_off[n_utt];
+    PSB_REQUIRE(total_ph == 0 || (ssid && tmatid), "psb_align_batch_device: phones missing");
+    PSB_REQUIRE(d_senscr || utt_off[n_utt] == 0, "psb_align_batch_device: scores missing");
+    PSB_CUDA(cudaSetDevice(c->device));
+    std::vector<uint16_t> sseq((size_t)c->n_sseq * N);
+    PSB_CUDA(cudaMemcpy(sseq.data(), c->d_sseq, sseq.size() * 2, cudaMemcpyDeviceToHost));
+    std::vector<uint16_t> senid((size_t)std::max(total_ph, 1) * N);
+    std::vector<int64_t> tok_off((size_t)n_utt + 1);
+    int max_h = 0;
+    tok_off[0] = 0;
+    for (int u = 0; u < n_utt; ++u) {
+        const int H = ph_off[u + 1] - ph_off[u], T = utt_off[u + 1] - utt_off[u];
+        PSB_REQUIRE(H >= 0 && T >= 0, "psb_align_batch_device: offsets not monotone at %d", u);
+        max_h = std::max(max_h, H);
+        tok_off[(size_t)u + 1] = tok_off[(size_t)u] + (int64_t)T * H * N;
+    }
+    for (int i = 0; i < total_ph; ++i) {
+        PSB_REQUIRE(ssid[i] >= 0 && ssid[i] < c->n_sseq, "ssid[%d] out of range", i);
+        PSB_REQUIRE(tmatid[i] >= 0 && tmatid[i] < c->n_tmat, "tmatid[%d] out of range", i);
+        for (int s = 0; s < N; ++s) {
+            const uint16_t v = sseq[(size_t)ssid[i] * N + s];           // hmm_init, non-mpx (hmm.c:99-102)
+            PSB_REQUIRE(v < c->n_sen, "senone id %d out of range", v);
+            senid[(size_t)i * N + s] = v;
+        }
+    }
+    const size_t smem = ((size_t)(2 * N + 3) * max_h + 64) * sizeof(int);
+    PSB_REQUIRE(smem <= 200 * 1024, "psb_align_batch_device: %d phones in one utterance do not fit shared memory", max_h);
+    // device buffers (freed on every path below)
+    int32_t *d_i32 = nullptr, *d_tok = nullptr;
+    uint16_t *d_senid = nullptr;
+    int64_t *d_tok_off = nullptr;
+    const size_t n_state = (size_t)total_ph * N;
+    // one int32 block: utt_off | ph_off | tmatid | sf | ef | start | dur | score | status
+    const size_t o_utt = 0, o_ph = o_utt + n_utt + 1, o_tm = o_ph + n_utt + 1, o_sf = o_tm + total_ph, o_ef = o_sf + total_ph,
+                 o_ss = o_ef + total_ph, o_sd = o_ss + n_state, o_sc = o_sd + n_state, o_st = o_sc + n_state,
+                 n_i32 = o_st + n_utt;
+    cudaError_t e = cudaMalloc((void **)&d_i32, std::max<size_t>(n_i32, 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_tok, std::max<size_t>((size_t)tok_off[(size_t)n_utt] * 2, 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_senid, senid.size() * 2);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_tok_off, tok_off.size() * 8);
+    cudaStream_t st = c->stream;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_i32 + o_utt, utt_off, ((size_t)n_utt + 1) * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_i32 + o_ph, ph_off, ((size_t)n_utt + 1) * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && total_ph) e = cudaMemcpyAsync(d_i32 + o_tm, tmatid, (size_t)total_ph * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && total_ph && sf) e = cudaMemcpyAsync(d_i32 + o_sf, sf, (size_t)total_ph * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && total_ph && ef) e = cudaMemcpyAsync(d_i32 + o_ef, ef, (size_t)total_ph * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_senid, senid.data(), senid.size() * 2, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_tok_off, tok_off.data(), tok_off.size() * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        align_kernel<<<(unsigned)n_utt, 128, smem, st>>>(d_senscr, d_i32 + o_utt, dev_ctx(c), d_i32 + o_ph, d_senid, d_i32 + o_tm,
+                                                        sf ? d_i32 + o_sf : nullptr, ef ? d_i32 + o_ef : nullptr, d_tok,
+                                                        d_tok + tok_off[(size_t)n_utt], d_tok_off, d_i32 + o_ss, d_i32 + o_sd,
+                                                        d_i32 + o_sc, d_i32 + o_st);
+        g_psb_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && n_state) e = cudaMemcpyAsync(st_start, d_i32 + o_ss, n_state * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && n_state) e = cudaMemcpyAsync(st_dur, d_i32 + o_sd, n_state * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && n_state) e = cudaMemcpyAsync(st_score, d_i32 + o_sc, n_state * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_i32 + o_st, (size_t)n_utt * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_i32); cudaFree(d_tok); cudaFree(d_senid); cudaFree(d_tok_off);
+    if (e != cudaSuccess) {
+        psb_set_error("psb_align_batch_device: %s", cudaGetErrorString(e));
+        return PSB_ERR_CUDA;
+    }
+    return PSB_OK;
+}
+
+extern "C" int psb_align_batch_host(psb_hmmctx_t *c, const int16_t *senscr, const int32_t *utt_off, int32_t n_utt,
+                                    const int32_t *ph_off, const int32_t *ssid, const int32_t *tmatid,
+                                    const int32_t *sf, const int32_t *ef,
+                                    int32_t *st_start, int32_t *st_dur, int32_t *st_score, int32_t *status)
+{
+    PSB_REQUIRE(c && utt_off && n_utt >= 0, "psb_align_batch_host: bad argument");
+    if (n_utt == 0) return PSB_OK;
+    PSB_CUDA(cudaSetDevice(c->device));
+    const size_t nb = (size_t)utt_off[n_utt] * c->n_sen * 2;
+    PSB_REQUIRE(nb == 0 || senscr, "psb_align_batch_host: scores missing");
+    int16_t *d = nullptr;
+    PSB_CUDA(cudaMalloc((void **)&d, std::max<size_t>(nb, 2)));
+    cudaError_t e = nb ? cudaMemcpy(d, senscr, nb, cudaMemcpyHostToDevice) : cudaSuccess;
+    int rc = PSB_OK;
+    if (e == cudaSuccess)
+        rc = psb_align_batch_device(c, d, utt_off, n_utt, ph_off, ssid, tmatid, sf, ef, st_start, st_dur, st_score, status);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        psb_set_error("psb_align_batch_host: %s", cudaGetErrorString(e));
+        return PSB_ERR_CUDA;
+    }
+    return rc;
+}

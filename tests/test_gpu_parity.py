@@ -510,3 +510,67 @@ def test_full_size_properties(api, monkeypatch):
     assert np.array_equal(rpen.reshape(U, T, H)[::-1], pen5.reshape(U, T, H))
     b.close(); pl.close(); ctx.close(); m.close()
     assert zlib.crc32(rows5.tobytes()) == zlib.crc32(rows2.tobytes())
+
+
+# ---------------------------------------------------------------------------------------
+# forced alignment (state_align_search.c) for batches
+
+def test_align_goforward_matches_reference(api, en_us, en_us_dev):
+    g, ga = golden("en_us_goforward.npz"), golden("en_us_align.npz")
+    b = api.Batch(en_us_dev, 4, 1024)
+    scr = b.score_host(g["feats"], np.array([0, 278], np.int32))          # our scores (bit-exact, tested above)
+    b.close()
+    ctx = api.HmmContext(en_us.tp, en_us.sseq, en_us.n_sen)
+    tags = ["a", "b", "c"]
+    utt_off = np.arange(len(tags) + 1, dtype=np.int32) * 278
+    ph_off = np.concatenate([[0], np.cumsum([len(ga[t + "_ssid"]) for t in tags])]).astype(np.int32)
+    status, st, du, sc = ctx.align(np.concatenate([scr] * len(tags)), utt_off, ph_off,
+                                   np.concatenate([ga[t + "_ssid"] for t in tags]),
+                                   np.concatenate([ga[t + "_tmatid"] for t in tags]))
+    assert (status == 0).all()
+    for k, t in enumerate(tags):
+        sl = slice(ph_off[k] * 3, ph_off[k + 1] * 3)
+        assert np.array_equal(st[sl], ga[t + "_start"]), t
+        assert np.array_equal(du[sl], ga[t + "_dur"]), t
+        assert np.array_equal(sc[sl], ga[t + "_score"]), t
+    ctx.close()
+
+
+@pytest.mark.parametrize("n_emit", [3, 5])
+def test_align_batch_matches_oracle(api, n_emit):
+    import torch
+    from oracle import oracle
+    from pocketsphinx_b200.model import synth_ptm
+    pm = synth_ptm(seed=31, n_density=32, n_sen=300, n_emit_state=n_emit, skip_arcs=(n_emit == 5))
+    rng = np.random.default_rng(17)
+    n_phones = [1, 2, 5, 40, 150, 3, 12, 60, 7, 0]
+    frames = [30, 3, 4, 200, 700, 300, 36, 190, 500, 10]      # some too short to reach the end
+    ssid = [rng.integers(0, len(pm.sseq), n).astype(np.int32) for n in n_phones]
+    tmat = [rng.integers(0, pm.tp.shape[0], n).astype(np.int32) for n in n_phones]
+    scr = [rng.integers(0, 400, (t, pm.n_sen)).astype(np.int16) for t in frames]
+    # renormalisation: one utterance with huge negative scores so that best_score sinks below the bound
+    scr[8] = rng.integers(20000, 32000, (frames[8], pm.n_sen)).astype(np.int16)
+    sf = [np.zeros(n, np.int32) for n in n_phones]
+    ef = [np.full(n, 2**31 - 1, np.int32) for n in n_phones]
+    # alignment constraints on utterance 7: phones pinned to windows of ~3 frames per phone
+    for i in range(n_phones[7]):
+        sf[7][i] = max(0, 3 * i - 4)
+        ef[7][i] = 3 * i + 12
+    utt_off = np.concatenate([[0], np.cumsum(frames)]).astype(np.int32)
+    ph_off = np.concatenate([[0], np.cumsum(n_phones)]).astype(np.int32)
+    ctx = api.HmmContext(pm.tp, pm.sseq, pm.n_sen)
+    d_scr = torch.from_numpy(np.concatenate(scr)).cuda()
+    status, st, du, sc = ctx.align(None, utt_off, ph_off, np.concatenate(ssid), np.concatenate(tmat),
+                                   sf=np.concatenate(sf), ef=np.concatenate(ef), device_ptr=d_scr.data_ptr())
+    n_ok = 0
+    for u in range(len(frames)):
+        sl = slice(ph_off[u] * n_emit, ph_off[u + 1] * n_emit)
+        if n_phones[u] == 0:
+            assert status[u] == -1
+            continue
+        rc, wst, wdu, wsc = oracle.align_run(pm.tp, pm.sseq, ssid[u], tmat[u], scr[u], sf=sf[u], ef=ef[u])
+        assert status[u] == rc, "utterance %d: status %d, oracle %d" % (u, status[u], rc)
+        assert np.array_equal(st[sl], wst) and np.array_equal(du[sl], wdu) and np.array_equal(sc[sl], wsc), "utterance %d" % u
+        n_ok += rc == 0
+    assert n_ok >= 5                                           # the test exercises successes and failures
+    ctx.close()
