@@ -179,6 +179,24 @@ def viterbi_stage(api, torch, ctx, batch, pm, off, U, T, hbm_peak, n_active=6081
             "note": "not part of `value`: the headline Viterbi is the reference's phone loop (42 HMMs per utterance)"}
 
 
+def align_stage(api, ctx, batch, pm, off, U, T, n_phones=100):
+    """Batched forced alignment (state_align_search.c) over the scores the GMM stage left in HBM:
+    every utterance is aligned to its own chain of n_phones phones (random senone sequences; a 10 s
+    utterance has about that many).  Wall clock of the whole call: phone upload, the kernel (one CTA
+    per utterance, token table in HBM), backtrace, state-level result download."""
+    rng = np.random.default_rng(5)
+    ph_off = np.arange(U + 1, dtype=np.int32) * n_phones
+    ssid = rng.integers(0, len(pm.sseq), U * n_phones).astype(np.int32)
+    tmat = rng.integers(0, pm.tp.shape[0], U * n_phones).astype(np.int32)
+    ctx.align(None, off, ph_off, ssid, tmat, device_ptr=batch.senscr_device_ptr())       # warm-up
+    t0 = time.perf_counter()
+    status, st, du, sc = ctx.align(None, off, ph_off, ssid, tmat, device_ptr=batch.senscr_device_ptr())
+    dt = time.perf_counter() - t0
+    return {"kernel": "align_kernel", "utts": U, "phones_per_utt": n_phones, "ms": dt * 1e3,
+            "frames_per_s": U * T / dt, "aligned_ok": int((status == 0).sum()),
+            "note": "not part of `value`; bit-exact vs the reference's state_align_search (tests)"}
+
+
 def frontend_stage(api, torch, U, secs, budget_s=4.0):
     """Row f-2, reported beside the headline (not part of `value`): int16 PCM -> cepstra -> batch CMN
     -> 1s_c_d_dd features for the whole batch on the device (en-us feat.params: 25 mel filters,
@@ -462,6 +480,8 @@ def main():
             batch.decode_device(pl, d_feats.data_ptr(), off)
             batch.sync()
             out["viterbi_stage"] = viterbi_stage(api, torch, ctx, batch, pm, off, U, T, hbm_peak)
+            if pm.n_emit_state in (3, 5) and len(pm.sseq):
+                out["align_stage"] = align_stage(api, ctx, batch, pm, off, U, T)
             out["frontend_stage"] = frontend_stage(api, torch, U, args.secs)
             out["cpu_baseline"] = cpu_baseline(args, pm, raw, feats_np, T, budget_s=args.cpu_budget, threads=1)
         print(json.dumps(out))
