@@ -193,6 +193,7 @@ def align_stage(api, ctx, batch, pm, off, U, T, n_phones=100):
     status, st, du, sc = ctx.align(None, off, ph_off, ssid, tmat, device_ptr=batch.senscr_device_ptr())
     dt = time.perf_counter() - t0
     return {"kernel": "align_kernel", "utts": U, "phones_per_utt": n_phones, "ms": dt * 1e3,
+            "kernel_ms": api.lib().psb_align_last_kernel_ms(ctx.h),
             "frames_per_s": U * T / dt, "aligned_ok": int((status == 0).sum()),
             "note": "not part of `value`; bit-exact vs the reference's state_align_search (tests)"}
 

@@ -267,6 +267,8 @@ int psb_align_batch_device(psb_hmmctx_t *c, const int16_t *d_senscr, const int32
                            int32_t n_utt, const int32_t *ph_off, const int32_t *ssid,
                            const int32_t *tmatid, const int32_t *sf, const int32_t *ef,
                            int32_t *st_start, int32_t *st_dur, int32_t *st_score, int32_t *status);
+/* device time (CUDA events on the context's stream) of the last psb_align_batch_* kernel */
+float psb_align_last_kernel_ms(const psb_hmmctx_t *c);
 int psb_align_batch_host(psb_hmmctx_t *c, const int16_t *senscr, const int32_t *utt_off,
                          int32_t n_utt, const int32_t *ph_off, const int32_t *ssid,
                          const int32_t *tmatid, const int32_t *sf, const int32_t *ef,

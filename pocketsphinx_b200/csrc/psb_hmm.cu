@@ -19,6 +19,13 @@ struct psb_hmmctx_s {
     size_t hmm_cap;
     int16_t *d_senscr, *h_senscr;
     int32_t *d_best, *h_best;
+    // grow-only workspace of psb_align_batch_* (token table, phone tables, results)
+    int32_t *d_al_i32, *d_al_tok;
+    uint16_t *d_al_senid;
+    int64_t *d_al_tokoff;
+    size_t al_i32_cap, al_tok_cap, al_senid_cap, al_tokoff_cap;
+    cudaEvent_t al_ev[2];
+    float last_align_ms;
 };
 
 struct psb_phoneloop_s {
@@ -297,6 +304,9 @@ extern "C" void psb_hmmctx_free(psb_hmmctx_t *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_tp); cudaFree(c->d_sseq); cudaFree(c->d_hmms); cudaFree(c->d_senscr); cudaFree(c->d_best);
+    cudaFree(c->d_al_i32); cudaFree(c->d_al_tok); cudaFree(c->d_al_senid); cudaFree(c->d_al_tokoff);
+    if (c->al_ev[0]) cudaEventDestroy(c->al_ev[0]);
+    if (c->al_ev[1]) cudaEventDestroy(c->al_ev[1]);
     if (c->h_hmms) cudaFreeHost(c->h_hmms);
     if (c->h_senscr) cudaFreeHost(c->h_senscr);
     if (c->h_best) cudaFreeHost(c->h_best);
@@ -935,7 +945,7 @@ align_kernel(const int16_t *__restrict__ senscr, const int32_t *__restrict__ utt
              const int32_t *__restrict__ tmatid_g, const int32_t *__restrict__ sf_g, const int32_t *__restrict__ ef_g,
              int32_t *__restrict__ tok_id, int32_t *__restrict__ tok_sc, const int64_t *__restrict__ tok_off,
              int32_t *__restrict__ st_start, int32_t *__restrict__ st_dur, int32_t *__restrict__ st_score,
-             int32_t *__restrict__ status)
+             int32_t *__restrict__ status, bool seq_scan)
 {
     extern __shared__ int sm[];
     const int u = blockIdx.x, tid = threadIdx.x, N = c.n_emit;
@@ -1000,14 +1010,41 @@ align_kernel(const int16_t *__restrict__ senscr, const int32_t *__restrict__ utt
         bs = block_reduce_max_pair<int>(bs, 0, sidx, sval, dummy);      // (contains the barriers)
         best_score = bs;
         __syncthreads();
-        if (tid == 0) {                                                  // phone_transition, in order
-            for (int i = 0; i < H - 1; ++i) {
-                if (frame[i] != nf) continue;
-                if (nf < (sf_g ? sf_g[p0 + i + 1] : 0)) continue;
-                const int nps = out_score[i];
-                if (frame[i + 1] < t || nps > score[i + 1]) {            // hmm_enter(nhmm, score, history, nf)
-                    score[i + 1] = nps; hist[i + 1] = out_hist[i]; frame[i + 1] = nf;
+        // phone_transition.  Reference order: for i = 0..H-2, if phone i is active in nf (by pruning
+        // OR because iteration i-1 just entered it) and the window of phone i+1 is open and
+        // (phone i+1 is idle or out_score[i] beats its state-0 score): hmm_enter(i+1).  With
+        //   P[i] = frame[i] == nf after pruning,  G[j] = window(j) && (idle(j) || out[j-1] > score0[j])
+        // (G reads nothing an earlier iteration writes), "active" is A[i] = P[i] | (G[i] & A[i-1]):
+        // a carry chain.  One warp resolves 32 phones per step with a 64-bit add
+        // (generate = P, propagate = G & ~P), the carry links the steps; E[j] = A[j-1] & G[j].
+        if (seq_scan) {
+            if (tid == 0)
+                for (int i = 0; i < H - 1; ++i) {
+                    if (frame[i] != nf) continue;
+                    if (nf < (sf_g ? sf_g[p0 + i + 1] : 0)) continue;
+                    const int nps = out_score[i];
+                    if (frame[i + 1] < t || nps > score[i + 1]) {        // hmm_enter(nhmm, score, history, nf)
+                        score[i + 1] = nps; hist[i + 1] = out_hist[i]; frame[i + 1] = nf;
+                    }
                 }
+        }
+        else if (tid < 32) {
+            unsigned carry = 0u;
+            for (int base = 0; base < H; base += 32) {
+                const int j = base + tid;
+                const bool in = j < H;
+                const bool P = in && frame[j] == nf;
+                const bool G = in && j >= 1 && nf >= (sf_g ? sf_g[p0 + j] : 0) &&
+                               (frame[j] < t || out_score[j - 1] > score[j]);
+                const unsigned g = __ballot_sync(0xffffffffu, P);
+                const unsigned pp = __ballot_sync(0xffffffffu, G) & ~g;
+                const unsigned long long x = (unsigned long long)(g | pp), y = (unsigned long long)g;
+                const unsigned long long cin = (x + y + carry) ^ x ^ y;  // bit k = A[base + k - 1]
+                if (G && ((cin >> tid) & 1ull)) {                        // hmm_enter(phone j, out_score[j-1], out_hist[j-1], nf)
+                    score[j] = out_score[j - 1]; hist[j] = out_hist[j - 1]; frame[j] = nf;
+                }
+                carry = (unsigned)(cin >> 32) & 1u;
+                __syncwarp();
             }
         }
         __syncthreads();
@@ -1089,47 +1126,65 @@ extern "C" int psb_align_batch_device(psb_hmmctx_t *c, const int16_t *d_senscr, 
     }
     const size_t smem = ((size_t)(2 * N + 3) * max_h + 64) * sizeof(int);
     PSB_REQUIRE(smem <= 200 * 1024, "psb_align_batch_device: %d phones in one utterance do not fit shared memory", max_h);
-    // device buffers (freed on every path below)
-    int32_t *d_i32 = nullptr, *d_tok = nullptr;
-    uint16_t *d_senid = nullptr;
-    int64_t *d_tok_off = nullptr;
+    // grow-only workspace in the context: one int32 block
+    //   utt_off | ph_off | tmatid | sf | ef | start | dur | score | status
+    // plus the token table (2 x frames x states), the senone ids and the token offsets
     const size_t n_state = (size_t)total_ph * N;
-    // one int32 block: utt_off | ph_off | tmatid | sf | ef | start | dur | score | status
     const size_t o_utt = 0, o_ph = o_utt + n_utt + 1, o_tm = o_ph + n_utt + 1, o_sf = o_tm + total_ph, o_ef = o_sf + total_ph,
                  o_ss = o_ef + total_ph, o_sd = o_ss + n_state, o_sc = o_sd + n_state, o_st = o_sc + n_state,
                  n_i32 = o_st + n_utt;
-    cudaError_t e = cudaMalloc((void **)&d_i32, std::max<size_t>(n_i32, 1) * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_tok, std::max<size_t>((size_t)tok_off[(size_t)n_utt] * 2, 1) * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_senid, senid.size() * 2);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_tok_off, tok_off.size() * 8);
+    const size_t n_tok = (size_t)tok_off[(size_t)n_utt] * 2;
+    auto grow = [](void **p, size_t *cap, size_t need, size_t elem) -> cudaError_t {
+        if (need <= *cap) return cudaSuccess;
+        if (*p) cudaFree(*p);
+        *p = nullptr; *cap = 0;
+        const size_t want = need + need / 8 + 256;
+        cudaError_t e = cudaMalloc(p, want * elem);
+        if (e == cudaSuccess) *cap = want;
+        return e;
+    };
+    cudaError_t e = grow((void **)&c->d_al_i32, &c->al_i32_cap, n_i32, 4);
+    if (e == cudaSuccess) e = grow((void **)&c->d_al_tok, &c->al_tok_cap, std::max<size_t>(n_tok, 1), 4);
+    if (e == cudaSuccess) e = grow((void **)&c->d_al_senid, &c->al_senid_cap, senid.size(), 2);
+    if (e == cudaSuccess) e = grow((void **)&c->d_al_tokoff, &c->al_tokoff_cap, tok_off.size(), 8);
+    if (e == cudaSuccess && !c->al_ev[0]) e = cudaEventCreate(&c->al_ev[0]);
+    if (e == cudaSuccess && !c->al_ev[1]) e = cudaEventCreate(&c->al_ev[1]);
+    int32_t *d_i32 = c->d_al_i32, *d_tok = c->d_al_tok;
     cudaStream_t st = c->stream;
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_i32 + o_utt, utt_off, ((size_t)n_utt + 1) * 4, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_i32 + o_ph, ph_off, ((size_t)n_utt + 1) * 4, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && total_ph) e = cudaMemcpyAsync(d_i32 + o_tm, tmatid, (size_t)total_ph * 4, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && total_ph && sf) e = cudaMemcpyAsync(d_i32 + o_sf, sf, (size_t)total_ph * 4, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && total_ph && ef) e = cudaMemcpyAsync(d_i32 + o_ef, ef, (size_t)total_ph * 4, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_senid, senid.data(), senid.size() * 2, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_tok_off, tok_off.data(), tok_off.size() * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_al_senid, senid.data(), senid.size() * 2, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_al_tokoff, tok_off.data(), tok_off.size() * 8, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaEventRecord(c->al_ev[0], st);
     if (e == cudaSuccess) {
-        align_kernel<<<(unsigned)n_utt, 128, smem, st>>>(d_senscr, d_i32 + o_utt, dev_ctx(c), d_i32 + o_ph, d_senid, d_i32 + o_tm,
+        align_kernel<<<(unsigned)n_utt, 128, smem, st>>>(d_senscr, d_i32 + o_utt, dev_ctx(c), d_i32 + o_ph, c->d_al_senid, d_i32 + o_tm,
                                                         sf ? d_i32 + o_sf : nullptr, ef ? d_i32 + o_ef : nullptr, d_tok,
-                                                        d_tok + tok_off[(size_t)n_utt], d_tok_off, d_i32 + o_ss, d_i32 + o_sd,
-                                                        d_i32 + o_sc, d_i32 + o_st);
+                                                        d_tok + tok_off[(size_t)n_utt], c->d_al_tokoff, d_i32 + o_ss, d_i32 + o_sd,
+                                                        d_i32 + o_sc, d_i32 + o_st, getenv("PSB_ALIGN_SEQ_SCAN") != nullptr);
         g_psb_launches.fetch_add(1, std::memory_order_relaxed);
         e = cudaGetLastError();
     }
+    if (e == cudaSuccess) e = cudaEventRecord(c->al_ev[1], st);
     if (e == cudaSuccess && n_state) e = cudaMemcpyAsync(st_start, d_i32 + o_ss, n_state * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && n_state) e = cudaMemcpyAsync(st_dur, d_i32 + o_sd, n_state * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && n_state) e = cudaMemcpyAsync(st_score, d_i32 + o_sc, n_state * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_i32 + o_st, (size_t)n_utt * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_i32); cudaFree(d_tok); cudaFree(d_senid); cudaFree(d_tok_off);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&c->last_align_ms, c->al_ev[0], c->al_ev[1]);
     if (e != cudaSuccess) {
         psb_set_error("psb_align_batch_device: %s", cudaGetErrorString(e));
         return PSB_ERR_CUDA;
     }
     return PSB_OK;
+}
+
+extern "C" float psb_align_last_kernel_ms(const psb_hmmctx_t *c)
+{
+    return c ? c->last_align_ms : 0.f;
 }
 
 extern "C" int psb_align_batch_host(psb_hmmctx_t *c, const int16_t *senscr, const int32_t *utt_off, int32_t n_utt,
