@@ -365,7 +365,7 @@ extern "C" void psb_batch_free(psb_batch_t *b)
     }
     if (b->fork_ev) cudaEventDestroy(b->fork_ev);
     if (b->join_ev) cudaEventDestroy(b->join_ev);
-    cudaFree(b->d_feats); cudaFree(b->d_senscr); cudaFree(b->d_featT); cudaFree(b->d_topn); cudaFree(b->d_tab);
+    cudaFree(b->d_feats); cudaFree(b->d_senscr); cudaFree(b->d_featT); cudaFree(b->d_topn); cudaFree(b->d_tab); cudaFree(b->d_semi_dist); cudaFree(b->d_uttoff);
     cudaFree(b->d_best); cudaFree(b->d_pen); cudaFree(b->d_off); cudaFree(b->d_msdist); cudaFree(b->d_msbest);
     if (b->h_tab) cudaFreeHost(b->h_tab);
     if (b->h_feats) cudaFreeHost(b->h_feats);

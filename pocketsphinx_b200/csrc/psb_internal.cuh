@@ -109,6 +109,8 @@ struct psb_batch_s {
     cudaEvent_t tev[2];           // user stopwatch (psb_batch_event_record)
     bool have_ev;
     long long last_frames;
+    float2 *d_semi_dist; size_t semi_cap;      // semi-continuous split path: {d, partial} per (stream, frame, codeword)
+    int32_t *d_uttoff; size_t uttoff_cap;
     int topn_variant;             // PSB_TOPN_VARIANT: 0 scalar, 1/2 packed FP32, 3 two utterances per lane,
                                   // 4/5 packed + deferred insertion (2 / 1 utterances per lane); default 5
     // phone-loop outputs for psb_decode_batch_host

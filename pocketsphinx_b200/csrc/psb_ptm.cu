@@ -879,6 +879,143 @@ ptm_topnq_kernel(const float *__restrict__ rec2, const size_t *__restrict__ rec2
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Semi-continuous models have ONE codebook per stream (K = n_feat pairs, 4 for s2_4x), so the
+// lane-per-utterance kernels above leave most of the machine idle (512 utterances = 16 CTAs).
+// Their distance work is small (4 x 256 Gaussians per frame), so it is taken out of the
+// time recurrence: semi_dist_kernel computes every (frame, codeword) distance in parallel and
+// parks {d, partial-before-last-dim} in HBM (8 B x n_density x K per frame), and
+// semi_scan_kernel -- one WARP per (utterance, stream), lanes = codewords -- replays
+// eval_topn / the scan of mgau_dist (s2_semi_mgau.c:70-183) per frame with the list held
+// redundantly (uniformly) in every lane: ballots pick the codewords that pass the current
+// threshold, they are handled in ascending order with the exact accept / skip-if-listed /
+// insert rules, re-tested against the list as it stands.  No staleness, no queues, no
+// divergence; 4 x n_utt warps instead of 4 x n_utt / 32.
+template <int FL>
+__global__ void __launch_bounds__(256)
+semi_dist_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec_off, const int32_t *__restrict__ klist,
+                 const float *__restrict__ feats, float2 *__restrict__ dist, long long total, int nd, int n_feat, int D,
+                 const int32_t *__restrict__ featoff)
+{
+    constexpr int RECF = (1 + 2 * FL + 3) / 4 * 4;
+    const int k = klist[blockIdx.y];
+    const long long fr = blockIdx.x;
+    const int c = threadIdx.x;
+    if (c >= nd) return;
+    float x[FL];
+    const float *xp = feats + fr * D + featoff[k % n_feat];
+#pragma unroll
+    for (int j = 0; j < FL; ++j) x[j] = xp[j];
+    float dpen;
+    const float d = gau_dist<FL, true>(reinterpret_cast<const float4 *>(rec + rec_off[k] + (size_t)c * RECF), x, &dpen);
+    dist[((size_t)k * total + fr) * nd + c] = make_float2(d, dpen);
+}
+
+struct ScanList {
+    unsigned cwp;
+    int sc[TOPN];
+};
+
+__device__ __forceinline__ void scan_insert(ScanList &L, int c, int s)
+{
+    int p = 0;
+#pragma unroll
+    for (int j = 0; j < TOPN - 1; ++j) p += (s >= L.sc[j]) ? 0 : 1;        // insertion sort, s2_semi_mgau.c:157-167
+#pragma unroll
+    for (int j = TOPN - 2; j >= 0; --j)
+        if (j >= p) L.sc[j + 1] = L.sc[j];
+#pragma unroll
+    for (int j = 0; j < TOPN; ++j)
+        if (j == p) L.sc[j] = s;
+    const unsigned lowmask = (1u << (8 * p)) - 1u;
+    L.cwp = (L.cwp & lowmask) | ((unsigned)c << (8 * p)) | ((L.cwp << 8) & ~((lowmask << 8) | 0xffu));
+}
+
+// NDW = n_density / 32 codewords per lane
+template <int NDW>
+__global__ void __launch_bounds__(128)
+semi_scan_kernel(const float2 *__restrict__ dist, const int32_t *__restrict__ utt_off, int n_utt, int K, long long total,
+                 int nd, int ds_ratio, const int32_t *__restrict__ topn_beam, int4 *__restrict__ out)
+{
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (w >= n_utt * K) return;
+    const int u = w / K, k = w % K;
+    const long long f0 = utt_off[u];
+    const int T = utt_off[u + 1] - utt_off[u];
+    const float2 *row = dist + ((size_t)k * total + f0) * nd;
+    ScanList L;
+    L.cwp = 0x03020100u;                                           // s2_semi_mgau.c:1319-1327
+#pragma unroll
+    for (int i = 0; i < TOPN; ++i) L.sc[i] = INT_MIN;
+    for (int t = 0; t < T; ++t, row += nd) {
+        float2 v[NDW];
+#pragma unroll
+        for (int i = 0; i < NDW; ++i) v[i] = row[i * 32 + lane];
+        // eval_topn (:70-109): re-score the listed codewords, stable descending sort (strict >)
+        {
+            int ncw[TOPN], nsc[TOPN];
+#pragma unroll
+            for (int i = 0; i < TOPN; ++i) {
+                const int c = (L.cwp >> (8 * i)) & 0xff;
+                float dv = 0.f;
+#pragma unroll
+                for (int q = 0; q < NDW; ++q) {
+                    const float cand = __shfl_sync(0xffffffffu, v[q].x, c & 31);
+                    if ((c >> 5) == q) dv = cand;
+                }
+                const int s = f2i_clamped(dv);
+                int p = 0;
+#pragma unroll
+                for (int j = 0; j < i; ++j) p += (s > nsc[j]) ? 0 : 1;
+#pragma unroll
+                for (int j = TOPN - 2; j >= 0; --j)
+                    if (j < i && j >= p) { nsc[j + 1] = nsc[j]; ncw[j + 1] = ncw[j]; }
+#pragma unroll
+                for (int j = 0; j < TOPN; ++j)
+                    if (j == p) { nsc[j] = s; ncw[j] = c; }
+            }
+            unsigned cp = 0u;
+#pragma unroll
+            for (int i = 0; i < TOPN; ++i) { L.sc[i] = nsc[i]; cp |= (unsigned)ncw[i] << (8 * i); }
+            L.cwp = cp;
+        }
+        if (t % ds_ratio == 0) {
+#pragma unroll
+            for (int q = 0; q < NDW; ++q) {
+                // accept iff the partial sum before the last dimension is >= (float)worst AND the
+                // truncated final score is >= worst (:137-155)
+                unsigned m = __ballot_sync(0xffffffffu, v[q].y >= (float)L.sc[TOPN - 1] && f2i_clamped(v[q].x) >= L.sc[TOPN - 1]);
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float dv = __shfl_sync(0xffffffffu, v[q].x, b), pv = __shfl_sync(0xffffffffu, v[q].y, b);
+                    const int c = q * 32 + b, s = f2i_clamped(dv);
+                    if (!(pv >= (float)L.sc[TOPN - 1] && s >= L.sc[TOPN - 1])) continue;   // the list moved on
+                    const unsigned xx = L.cwp ^ ((unsigned)c * 0x01010101u);
+                    if ((xx - 0x01010101u) & ~xx & 0x80808080u) continue;                  // already listed (:145-150)
+                    scan_insert(L, c, s);
+                }
+            }
+        }
+        if (lane == 0) {
+            // mgau_norm (:186-203): record as ptm_topn_kernel<SEMI> writes it
+            const int f = k;                                       // one codebook: pair index = stream
+            const int top = L.sc[0] >> PSB_SENSCR_SHIFT;
+            unsigned eb = 0;
+            int n_in_beam = TOPN;
+#pragma unroll
+            for (int j = 0; j < TOPN; ++j) {
+                int e = top - (L.sc[j] >> PSB_SENSCR_SHIFT);
+                e = e > PSB_MAX_NEG_ASCR ? PSB_MAX_NEG_ASCR : e;
+                const int beam = topn_beam[f];
+                if (beam && e > beam && n_in_beam == TOPN) n_in_beam = j;
+                eb |= (unsigned)e << (8 * j);
+            }
+            out[(f0 + t) * K + k] = make_int4(n_in_beam, (int)L.cwp, (int)eb, 0);
+        }
+    }
+}
+
 constexpr int SEN_BIAS = 64;          // > 3 * tab[0] for any 8-bit add table the 16x2 senone kernel accepts
 
 // fast_logmath_add (tied_mgau_common.h:111-127) on negated logs.  mixw + normalised score can
@@ -1343,7 +1480,52 @@ int psb_launch_ptm_batch(psb_batch_t *b, const float *d_feats, const int32_t *ut
         PSB_LAUNCH_CHECK();
     }
     if (b->have_ev) PSB_CUDA(cudaEventRecord(b->ev[1], b->stream));
-    {
+    // semi-continuous: distances out of the time loop, one warp per (utterance, stream)
+    const bool semi_split = semi && m->n_mgau == 1 && b->topn_variant != 0 && m->n_density <= 256 &&
+                            (m->n_density == 64 || m->n_density == 128 || m->n_density == 256);
+    if (semi_split) {
+        const size_t need_d = (size_t)K * total * m->n_density;
+        if (need_d > b->semi_cap) {
+            if (b->d_semi_dist) cudaFree(b->d_semi_dist);
+            b->d_semi_dist = nullptr;
+            b->semi_cap = need_d + need_d / 8;
+            PSB_CUDA(cudaMalloc(&b->d_semi_dist, b->semi_cap * sizeof(float2)));
+        }
+        if ((size_t)n_utt + 1 > b->uttoff_cap) {
+            if (b->d_uttoff) cudaFree(b->d_uttoff);
+            b->d_uttoff = nullptr;
+            b->uttoff_cap = (size_t)n_utt + 1 + 64;
+            PSB_CUDA(cudaMalloc(&b->d_uttoff, b->uttoff_cap * sizeof(int32_t)));
+        }
+        PSB_CUDA(cudaMemcpyAsync(b->d_uttoff, utt_off, ((size_t)n_utt + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
+        PSB_REQUIRE(total <= 0x7fffffffLL, "too many frames for one launch");
+        int pos = 0;
+        for (size_t i = 0; i < fls.size(); ++i) {
+            const int n_k = (int)byfl[i].size();
+            const dim3 grid((unsigned)total, (unsigned)n_k);
+            switch (fls[i]) {
+#define CASE(FL) case FL: semi_dist_kernel<FL><<<grid, roundup(m->n_density, 32), 0, b->stream>>>(                     \
+                    m->d_rec, m->d_rec_off, d_klist + pos, d_feats, b->d_semi_dist, total, m->n_density, m->n_feat, D, d_featoff); break;
+                CASE(13) CASE(12) CASE(24) CASE(3) CASE(39) CASE(1) CASE(2) CASE(4) CASE(8) CASE(16) CASE(26) CASE(32)
+#undef CASE
+            default:
+                psb_set_error("no semi_dist_kernel instantiation for stream length %d", fls[i]);
+                return PSB_ERR_ARG;
+            }
+            PSB_LAUNCH_CHECK();
+            pos += n_k;
+        }
+        const int warps = 4;
+        const unsigned blocks = (unsigned)(((long long)n_utt * K + warps - 1) / warps);
+        if (m->n_density == 256)
+            semi_scan_kernel<8><<<blocks, warps * 32, 0, b->stream>>>(b->d_semi_dist, b->d_uttoff, n_utt, K, total, 256, m->ds_ratio, m->d_topn_beam, b->d_topn);
+        else if (m->n_density == 128)
+            semi_scan_kernel<4><<<blocks, warps * 32, 0, b->stream>>>(b->d_semi_dist, b->d_uttoff, n_utt, K, total, 128, m->ds_ratio, m->d_topn_beam, b->d_topn);
+        else
+            semi_scan_kernel<2><<<blocks, warps * 32, 0, b->stream>>>(b->d_semi_dist, b->d_uttoff, n_utt, K, total, 64, m->ds_ratio, m->d_topn_beam, b->d_topn);
+        PSB_LAUNCH_CHECK();
+    }
+    else {
         int pos = 0;
         for (size_t i = 0; i < fls.size(); ++i) {
             int n_k = (int)byfl[i].size(), rc;
