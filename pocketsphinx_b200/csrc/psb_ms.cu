@@ -10,6 +10,8 @@
 // L2 traffic by FT.
 #include "psb_internal.cuh"
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 namespace {
@@ -163,6 +165,106 @@ __global__ void fill_i32(int32_t *p, long long n, int32_t v)
     if (i < n) p[i] = v;
 }
 
+
+// EXPERIMENT (PSB_MS_REGTILE=1; bit-identical, but measured SLOWER on B200: 247 ms vs 174 ms for
+// 255 k frames of the 5138 x 8 x 39 model, so it is off by default).
+// Register-tiled variant for small codebooks (n_density <= ND_MAX, the continuous-model case):
+// ms_dist_kernel issues one shared-memory load per 4 flops (the feature value of each frame for
+// every (density, dimension)); here a chunk of CH dimensions of the FT frames sits in registers
+// while ALL densities stream past it, so per 4 * FT flops there are two coalesced parameter loads
+// and no feature load.  Every (frame, density) sum still adds its dimensions in ascending order
+// and the top-N insertion runs over the densities in order afterwards: same bits.
+constexpr int ND_MAX = 8;
+constexpr int CH = 13;
+template <int NT>
+__global__ void __launch_bounds__(128)
+ms_dist_reg_kernel(const float *__restrict__ gT, const float *__restrict__ detT, const float *__restrict__ feats,
+                   int2 *__restrict__ out, long long frame0, long long n_frames, int n_mgau, int n_feat, int nd,
+                   int sumlen, const int32_t *__restrict__ featlen, const int32_t *__restrict__ featoff)
+{
+    extern __shared__ float sx[];                     // [FT][sumlen]
+    const long long fbase = (long long)blockIdx.y * FT;
+    for (int i = threadIdx.x; i < FT * sumlen; i += blockDim.x) {
+        const long long fr = fbase + i / sumlen;
+        sx[i] = fr < n_frames ? feats[(frame0 + fr) * sumlen + i % sumlen] : 0.f;
+    }
+    __syncthreads();
+    const int cb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cb >= n_mgau) return;
+    const bool all = NT >= nd;
+    for (int f = 0; f < n_feat; ++f) {
+        const int fl = featlen[f], fo = featoff[f];
+        const float *gp = gT + ((size_t)fo * nd * 2) * n_mgau + cb;
+        float dv[FT][ND_MAX];
+#pragma unroll
+        for (int d = 0; d < ND_MAX; ++d) {
+            const float det = d < nd ? detT[((size_t)f * nd + d) * n_mgau + cb] : 0.f;
+#pragma unroll
+            for (int q = 0; q < FT; ++q) dv[q][d] = det;
+        }
+        for (int j0 = 0; j0 < fl; j0 += CH) {
+            float x[FT][CH];
+#pragma unroll
+            for (int q = 0; q < FT; ++q)
+#pragma unroll
+                for (int jj = 0; jj < CH; ++jj) x[q][jj] = j0 + jj < fl ? sx[q * sumlen + fo + j0 + jj] : 0.f;
+#pragma unroll
+            for (int d = 0; d < ND_MAX; ++d) {
+                if (d >= nd) break;
+#pragma unroll
+                for (int jj = 0; jj < CH; ++jj) {
+                    if (j0 + jj >= fl) break;
+                    const float m = gp[((size_t)(d * fl + j0 + jj) * 2) * n_mgau];
+                    const float v = gp[((size_t)(d * fl + j0 + jj) * 2 + 1) * n_mgau];
+#pragma unroll
+                    for (int q = 0; q < FT; ++q) {
+                        const float diff = __fsub_rn(x[q][jj], m);
+                        dv[q][d] = __fsub_rn(dv[q][d], __fmul_rn(__fmul_rn(diff, diff), v));
+                    }
+                }
+            }
+        }
+        int id[FT][NT];
+        float ds[FT][NT];
+#pragma unroll
+        for (int q = 0; q < FT; ++q)
+#pragma unroll
+            for (int i = 0; i < NT; ++i) { id[q][i] = 0; ds[q][i] = (float)INT_MIN; }
+#pragma unroll
+        for (int d = 0; d < ND_MAX; ++d) {
+            if (d >= nd) break;
+#pragma unroll
+            for (int q = 0; q < FT; ++q) {
+                const float val = dv[q][d];
+                if (all) {
+#pragma unroll
+                    for (int i = 0; i < NT; ++i)
+                        if (i == d) { id[q][i] = d; ds[q][i] = val; }
+                }
+                else if (val >= ds[q][NT - 1]) {
+                    int p = 0;
+#pragma unroll
+                    for (int i = 0; i < NT; ++i) p += (val < ds[q][i]) ? 1 : 0;
+#pragma unroll
+                    for (int i = NT - 1; i > 0; --i)
+                        if (i > p) { ds[q][i] = ds[q][i - 1]; id[q][i] = id[q][i - 1]; }
+#pragma unroll
+                    for (int i = 0; i < NT; ++i)
+                        if (i == p) { ds[q][i] = val; id[q][i] = d; }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < FT; ++q) {
+            const long long fr = fbase + q;
+            if (fr >= n_frames) break;
+            int2 *o = out + ((fr * n_mgau + cb) * n_feat + f) * NT;
+#pragma unroll
+            for (int i = 0; i < NT; ++i) o[i] = make_int2(id[q][i], __float_as_int(ds[q][i]));
+        }
+    }
+}
+
 }  // namespace
 
 int psb_launch_ms_batch(psb_batch_t *b, const float *d_feats, const int32_t *utt_off, int32_t n_utt, int16_t *d_senscr)
@@ -195,8 +297,12 @@ int psb_launch_ms_batch(psb_batch_t *b, const float *d_feats, const int32_t *utt
         dim3 g1((m->n_mgau + 127) / 128, (unsigned)((n + FT - 1) / FT));
         size_t smem = (size_t)FT * m->sumlen * sizeof(float);
         int2 *dist = reinterpret_cast<int2 *>(b->d_msdist);
-#define LAUNCH(NT) ms_dist_kernel<NT><<<g1, 128, smem, b->stream>>>(m->d_msT, m->d_msdetT, d_feats, dist, f0, n, \
-        m->n_mgau, m->n_feat, m->n_density, m->sumlen, m->d_featlen, m->d_featoff)
+        static const bool reg_tile = getenv("PSB_MS_REGTILE") != nullptr;   // experiment, off: measured slower (247 vs 174 ms)
+#define LAUNCH(NT) do { if (reg_tile && m->n_density <= ND_MAX)                                                          \
+            ms_dist_reg_kernel<NT><<<g1, 128, smem, b->stream>>>(m->d_msT, m->d_msdetT, d_feats, dist, f0, n,             \
+                m->n_mgau, m->n_feat, m->n_density, m->sumlen, m->d_featlen, m->d_featoff);                             \
+        else ms_dist_kernel<NT><<<g1, 128, smem, b->stream>>>(m->d_msT, m->d_msdetT, d_feats, dist, f0, n,                \
+                m->n_mgau, m->n_feat, m->n_density, m->sumlen, m->d_featlen, m->d_featoff); } while (0)
         switch (nt) {
         case 1: LAUNCH(1); break;
         case 2: LAUNCH(2); break;
