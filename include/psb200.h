@@ -308,6 +308,15 @@ int psb_fe_process_host(psb_fe_t *fe, const int16_t *pcm, const int64_t *samp_of
                         float *feats, float *mfcc, int32_t *frame_off);
 int psb_fe_process_device(psb_fe_t *fe, const int16_t *d_pcm, const int64_t *samp_off, int32_t n_utt,
                           float *d_feats, float *d_mfcc, int32_t *frame_off, float *ms);
+/* device copy of the features of the last psb_fe_process_host call, and their dimension */
+const float *psb_fe_device_feats(const psb_fe_t *fe);
+int32_t psb_fe_feat_dim(const psb_fe_t *fe);
+/* From audio to phone-loop results in one call: front end, senone scores and Viterbi on the
+ * device, features never leave it.  frame_off int32[n_utt + 1] (out) indexes best / pen / senscr
+ * like utt_off of psb_decode_batch_host. */
+int psb_decode_batch_pcm_host(psb_batch_t *b, psb_fe_t *fe, psb_phoneloop_t *p, const int16_t *pcm,
+                              const int64_t *samp_off, int32_t n_utt, int32_t *frame_off,
+                              int32_t *best, int32_t *pen, int16_t *senscr);
 
 /* number of kernels launched by this library in the calling process so far */
 int64_t psb_kernel_launch_count(void);

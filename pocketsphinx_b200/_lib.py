@@ -79,6 +79,9 @@ SYMBOLS = [
     ("psb_fe_free", None, [_VP]),
     ("psb_fe_n_frames", C.c_int32, [_VP, C.c_int64]),
     ("psb_fe_process_host", C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP]),
+    ("psb_fe_device_feats", _VP, [_VP]),
+    ("psb_fe_feat_dim", C.c_int32, [_VP]),
+    ("psb_decode_batch_pcm_host", C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP]),
     ("psb_fe_process_device", C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP, C.POINTER(C.c_float)]),
     ("psb_phoneloop_create", C.c_int, [_VP, _I32, _VP, _VP, _I32, _I32, _I32, _I32, C.c_double, C.POINTER(_VP)]),
     ("psb_phoneloop_free", None, [_VP]),

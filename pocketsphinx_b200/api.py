@@ -215,6 +215,22 @@ class Batch:
               "psb_decode_batch_host")
         return (best, pen, senscr) if want_senscr else (best, pen)
 
+    def decode_pcm_host(self, fe, phoneloop, pcm, samp_off, want_senscr=False):
+        """Audio in, phone-loop results out: (frame_off, best, pen[, senscr])."""
+        pm = self.model.pm
+        pcm = np.ascontiguousarray(pcm, np.int16)
+        samp_off = np.ascontiguousarray(samp_off, np.int64)
+        n_utt = len(samp_off) - 1
+        total = sum(fe.n_frames(int(samp_off[u + 1] - samp_off[u])) for u in range(n_utt))
+        frame_off = np.zeros(n_utt + 1, np.int32)
+        best = np.zeros(total, np.int32)
+        pen = np.zeros((total, phoneloop.n_phones), np.int32)
+        senscr = np.zeros((total, pm.n_sen), np.int16) if want_senscr else None
+        check(lib().psb_decode_batch_pcm_host(self.h, fe.h, phoneloop.h, _p(pcm) if pcm.size else None, _p(samp_off), n_utt,
+                                              _p(frame_off), _p(best), _p(pen), _p(senscr) if want_senscr else None),
+              "psb_decode_batch_pcm_host")
+        return (frame_off, best, pen, senscr) if want_senscr else (frame_off, best, pen)
+
     def close(self):
         if self.h:
             lib().psb_batch_free(self.h)

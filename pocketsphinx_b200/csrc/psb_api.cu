@@ -609,6 +609,27 @@ extern "C" int psb_decode_batch_device(psb_batch_t *b, psb_phoneloop_t *p, const
     return rc;
 }
 
+// From audio: int16 PCM -> device front end (psb_fe.cu) -> senone scores -> phone loop, host results.
+// The features never leave the device.
+extern "C" int psb_decode_batch_pcm_host(psb_batch_t *b, psb_fe_t *fe, psb_phoneloop_t *p, const int16_t *pcm,
+                                         const int64_t *samp_off, int32_t n_utt, int32_t *frame_off, int32_t *best,
+                                         int32_t *pen, int16_t *senscr)
+{
+    PSB_REQUIRE(b && fe && p && samp_off && frame_off && n_utt >= 0, "psb_decode_batch_pcm_host: bad argument");
+    PSB_REQUIRE(psb_fe_feat_dim(fe) == b->m->sumlen, "psb_decode_batch_pcm_host: the front end makes %d-dimensional features, the model wants %d",
+                psb_fe_feat_dim(fe), b->m->sumlen);
+    int rc = psb_fe_process_host(fe, pcm, samp_off, n_utt, nullptr, nullptr, frame_off);
+    if (rc) return rc;
+    rc = check_offsets(b, frame_off, n_utt);
+    if (rc) return rc;
+    PSB_CUDA(cudaSetDevice(b->m->device));
+    if (frame_off[n_utt] == 0) return PSB_OK;
+    rc = decode_common(b, p, psb_fe_device_feats(fe), false, frame_off, n_utt, best, pen, senscr, best != nullptr, pen != nullptr);
+    if (rc) return rc;
+    PSB_CUDA(cudaStreamSynchronize(b->stream));
+    return PSB_OK;
+}
+
 extern "C" int psb_batch_event_record(psb_batch_t *b, int slot)
 {
     PSB_REQUIRE(b && (slot == 0 || slot == 1), "psb_batch_event_record: bad argument");

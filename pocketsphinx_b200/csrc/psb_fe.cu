@@ -510,3 +510,13 @@ extern "C" int psb_fe_process_host(psb_fe_t *fe, const int16_t *pcm, const int64
     if (total && mfcc) PSB_CUDA(cudaMemcpy(mfcc, fe->d_mfcc, (size_t)total * fe->n_cep * 4, cudaMemcpyDeviceToHost));
     return PSB_OK;
 }
+
+extern "C" const float *psb_fe_device_feats(const psb_fe_t *fe)
+{
+    return fe ? fe->d_feats : nullptr;
+}
+
+extern "C" int32_t psb_fe_feat_dim(const psb_fe_t *fe)
+{
+    return fe ? 3 * fe->n_cep : 0;
+}

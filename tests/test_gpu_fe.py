@@ -129,3 +129,23 @@ def test_fe_feeds_the_scorer(api, en_us):
     same = (got_feats.view(np.uint32) == want_feats.view(np.uint32)).mean()
     assert same > 0.99
     b.close(); m.close(); fe.close(); ref.close()
+
+
+def test_decode_from_pcm(api, en_us):
+    """psb_decode_batch_pcm_host == front end, then psb_decode_batch_host on its features."""
+    from pocketsphinx_b200.fe_tables import make_fe_desc
+    go = np.fromfile(os.path.join(REF, "data", "goforward.raw"), np.int16)
+    utts = [go, go[5000:30000], go[:300]]
+    off = api.FrontEnd.sample_offsets([len(u) for u in utts])
+    fe = api.FrontEnd(make_fe_desc())
+    m = api.Model(en_us)
+    b = api.Batch(m, 8, 1024)
+    ctx = api.HmmContext(en_us.tp, en_us.sseq, en_us.n_sen)
+    H = en_us.n_ciphone
+    pl = api.PhoneLoop(ctx, en_us.phone_ssid[:H], en_us.phone_tmat[:H], 5, -1080, -1080, 0, 3.0)
+    foff, best, pen, scr = b.decode_pcm_host(fe, pl, np.concatenate(utts), off, want_senscr=True)
+    feats, foff2 = fe.process_host(np.concatenate(utts), off)
+    assert np.array_equal(foff, foff2)
+    best2, pen2, scr2 = b.decode_host(pl, feats, foff2, want_senscr=True)
+    assert np.array_equal(best, best2) and np.array_equal(pen, pen2) and np.array_equal(scr, scr2)
+    b.close(); pl.close(); ctx.close(); m.close(); fe.close()
