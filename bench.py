@@ -159,7 +159,7 @@ def viterbi_stage(api, torch, ctx, batch, pm, off, U, T, hbm_peak, n_active=6081
     hm["senid"][:, :ns] = pm.sseq[ssid]
     hm["tmatid"] = rng.integers(0, pm.tp.shape[0], n)
     hm["n_emit_state"] = ns
-    hs = api.HmmSet(ctx, n, U)
+    hs = api.HmmSet(ctx, n + U * 512, U)                       # slack: segments start on storage-tile boundaries
     hs.upload(hm, np.arange(U + 1, dtype=np.int64) * n_active)
     F = min(n_frames, T)
     d_row0 = torch.from_numpy(np.asarray(off[:U], np.int64)).cuda()

@@ -549,6 +549,7 @@ extern "C" int psb_phoneloop_run_host(psb_phoneloop_t *p, const int16_t *senscr,
 // (state) and 64-bit (ids) accesses; padding instances are inert (WORST_SCORE, senone 0) and
 // never reach the best score.
 constexpr int HS_V = 4;                     // instances per thread
+constexpr int HS_TS = 512;                  // storage tile: [tile][field][HS_TS], so a CTA's fields are one contiguous block
 // threads per CTA: 128 (default; measured 112.7 us vs 118.2 us per 6.08 M-instance frame) or 256 (PSB_HMMSET_THREADS)
 
 struct psb_hmmset_s {
@@ -556,8 +557,8 @@ struct psb_hmmset_s {
     int64_t n_max, n, pitch;
     int32_t n_seg_max, n_seg;
     int64_t max_seg_len;
-    int32_t *d_i32;               // [(2*NS + 4)][pitch]: score[NS] hist[NS] out_score out_hist best frame
-    uint16_t *d_u16;              // [(NS + 2)][pitch]: senid[NS] ssid tmatid(int16)
+    int32_t *d_i32;               // [pitch / HS_TS][2*NS + 4][HS_TS]: score[NS] hist[NS] out_score out_hist best frame
+    uint16_t *d_u16;              // [pitch / HS_TS][NS + 2][HS_TS]: senid[NS] ssid tmatid(int16)
     uint8_t *d_mpx;               // [pitch]
     int64_t *d_seg_off;           // [n_seg_max + 1] caller's offsets (AoS order)
     int64_t *d_seg_base;          // [n_seg_max + 1] padded offsets inside the set
@@ -598,27 +599,28 @@ hmmset_convert_kernel(psb_hmm_t *aos, HmmSetDev s, int64_t n, int ns)
     }
     const int64_t i = s.seg_base[lo] + (a - s.seg_off[lo]);
     psb_hmm_t *p = aos + a;
-    int32_t *score = s.i32 + i, *hist = s.i32 + (int64_t)ns * s.pitch + i;
-    int32_t *tail = s.i32 + (int64_t)2 * ns * s.pitch + i;
-    uint16_t *senid = s.u16 + i, *ids = s.u16 + (int64_t)ns * s.pitch + i;
+    const int64_t b32 = (i / HS_TS) * (int64_t)(2 * ns + 4) * HS_TS + (i % HS_TS);
+    const int64_t b16 = (i / HS_TS) * (int64_t)(ns + 2) * HS_TS + (i % HS_TS);
+    int32_t *score = s.i32 + b32, *hist = score + ns * HS_TS, *tail = score + 2 * ns * HS_TS;
+    uint16_t *senid = s.u16 + b16, *ids = senid + ns * HS_TS;
     if (TO_SOA) {
         for (int k = 0; k < ns; ++k) {
-            score[k * s.pitch] = p->score[k];
-            hist[k * s.pitch] = p->history[k];
-            senid[k * s.pitch] = p->senid[k];
+            score[k * HS_TS] = p->score[k];
+            hist[k * HS_TS] = p->history[k];
+            senid[k * HS_TS] = p->senid[k];
         }
-        tail[0] = p->out_score; tail[s.pitch] = p->out_history; tail[2 * s.pitch] = p->bestscore; tail[3 * s.pitch] = p->frame;
-        ids[0] = p->ssid; ids[s.pitch] = (uint16_t)p->tmatid;
+        tail[0] = p->out_score; tail[HS_TS] = p->out_history; tail[2 * HS_TS] = p->bestscore; tail[3 * HS_TS] = p->frame;
+        ids[0] = p->ssid; ids[HS_TS] = (uint16_t)p->tmatid;
         s.mpx[i] = p->mpx;
     }
     else {
         for (int k = 0; k < PSB_HMM_MAX_NSTATE; ++k) {
-            p->score[k] = k < ns ? score[k * s.pitch] : 0;
-            p->history[k] = k < ns ? hist[k * s.pitch] : 0;
-            p->senid[k] = k < ns ? senid[k * s.pitch] : 0;
+            p->score[k] = k < ns ? score[k * HS_TS] : 0;
+            p->history[k] = k < ns ? hist[k * HS_TS] : 0;
+            p->senid[k] = k < ns ? senid[k * HS_TS] : 0;
         }
-        p->out_score = tail[0]; p->out_history = tail[s.pitch]; p->bestscore = tail[2 * s.pitch]; p->frame = tail[3 * s.pitch];
-        p->ssid = ids[0]; p->tmatid = (int16_t)ids[s.pitch];
+        p->out_score = tail[0]; p->out_history = tail[HS_TS]; p->bestscore = tail[2 * HS_TS]; p->frame = tail[3 * HS_TS];
+        p->ssid = ids[0]; p->tmatid = (int16_t)ids[HS_TS];
         p->mpx = s.mpx[i]; p->n_emit_state = (uint8_t)ns;
         p->ctx = nullptr;
     }
@@ -657,10 +659,11 @@ hmmset_eval_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr,
     const int ns = NS > 0 ? NS : c.n_emit;
     const bool live = j0 < n;
     const int64_t i = s.seg_base[seg] + (live ? j0 : 0);              // multiple of four
-    int32_t *score = s.i32 + i, *hist = s.i32 + (int64_t)ns * s.pitch + i;
-    int32_t *tail = s.i32 + (int64_t)2 * ns * s.pitch + i;
-    uint16_t *senid = s.u16 + i;
-    const uint16_t *ids = s.u16 + (int64_t)ns * s.pitch + i;
+    const int64_t b32 = (i / HS_TS) * (int64_t)(2 * ns + 4) * HS_TS + (i % HS_TS);
+    const int64_t b16 = (i / HS_TS) * (int64_t)(ns + 2) * HS_TS + (i % HS_TS);
+    int32_t *score = s.i32 + b32, *hist = score + ns * HS_TS, *tail = score + 2 * ns * HS_TS;
+    uint16_t *senid = s.u16 + b16;
+    const uint16_t *ids = senid + ns * HS_TS;
     int4 sc[NL], hi[NL], osc, ohi, bst;
     uint2 sid[NL], tm = make_uint2(0u, 0u);
     uchar4 mp = make_uchar4(0, 0, 0, 0);
@@ -668,13 +671,13 @@ hmmset_eval_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr,
 #pragma unroll
         for (int k = 0; k < NL; ++k)
             if (k < ns) {
-                sc[k] = __ldcs(reinterpret_cast<const int4 *>(score + k * s.pitch));
-                hi[k] = __ldcs(reinterpret_cast<const int4 *>(hist + k * s.pitch));
-                sid[k] = __ldcs(reinterpret_cast<const uint2 *>(senid + k * s.pitch));
+                sc[k] = __ldcs(reinterpret_cast<const int4 *>(score + k * HS_TS));
+                hi[k] = __ldcs(reinterpret_cast<const int4 *>(hist + k * HS_TS));
+                sid[k] = __ldcs(reinterpret_cast<const uint2 *>(senid + k * HS_TS));
             }
         osc = __ldcs(reinterpret_cast<const int4 *>(tail));
-        ohi = __ldcs(reinterpret_cast<const int4 *>(tail + s.pitch));
-        tm = __ldcs(reinterpret_cast<const uint2 *>(ids + s.pitch));
+        ohi = __ldcs(reinterpret_cast<const int4 *>(tail + HS_TS));
+        tm = __ldcs(reinterpret_cast<const uint2 *>(ids + HS_TS));
         mp = __ldcs(reinterpret_cast<const uchar4 *>(s.mpx + i));
     }
     {
@@ -729,13 +732,13 @@ hmmset_eval_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr,
 #pragma unroll
         for (int k = 0; k < NL; ++k)
             if (k < ns) {
-                __stcs(reinterpret_cast<int4 *>(score + k * s.pitch), sc[k]);
-                __stcs(reinterpret_cast<int4 *>(hist + k * s.pitch), hi[k]);
-                if (any_mpx) __stcs(reinterpret_cast<uint2 *>(senid + k * s.pitch), sid[k]);
+                __stcs(reinterpret_cast<int4 *>(score + k * HS_TS), sc[k]);
+                __stcs(reinterpret_cast<int4 *>(hist + k * HS_TS), hi[k]);
+                if (any_mpx) __stcs(reinterpret_cast<uint2 *>(senid + k * HS_TS), sid[k]);
             }
         __stcs(reinterpret_cast<int4 *>(tail), osc);
-        __stcs(reinterpret_cast<int4 *>(tail + s.pitch), ohi);
-        __stcs(reinterpret_cast<int4 *>(tail + 2 * s.pitch), bst);
+        __stcs(reinterpret_cast<int4 *>(tail + HS_TS), ohi);
+        __stcs(reinterpret_cast<int4 *>(tail + 2 * HS_TS), bst);
     }
     best = __reduce_max_sync(0xffffffffu, best);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
@@ -767,7 +770,7 @@ extern "C" int psb_hmmset_create(psb_hmmctx_t *c, int64_t n_max, int32_t n_seg_m
     PSB_CUDA(cudaSetDevice(c->device));
     psb_hmmset_t *s = new psb_hmmset_t();
     s->c = c; s->n_max = n_max; s->n_seg_max = n_seg_max;
-    s->pitch = ((n_max + (int64_t)(HS_V - 1) * n_seg_max + HS_V - 1) / HS_V) * HS_V;   // every segment may pad up to 3
+    s->pitch = ((n_max + (int64_t)(HS_V - 1) * n_seg_max + HS_TS - 1) / HS_TS) * HS_TS;   // every segment may pad up to 3
     const int ns = c->n_emit;
     cudaError_t e = cudaMalloc(&s->d_i32, (size_t)(2 * ns + 4) * s->pitch * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_u16, (size_t)(ns + 2) * s->pitch * 2);
@@ -801,12 +804,20 @@ extern "C" int psb_hmmset_upload(psb_hmmset_t *s, const psb_hmm_t *hmms, int64_t
     int64_t mx = 0;
     std::vector<int64_t> base((size_t)n_seg + 1);
     base[0] = 0;
-    for (int i = 0; i < n_seg; ++i) {
-        PSB_REQUIRE(seg_off[i + 1] >= seg_off[i], "psb_hmmset_upload: seg_off not monotone at %d", i);
-        const int64_t len = seg_off[i + 1] - seg_off[i];
-        mx = std::max<int64_t>(mx, len);
-        base[(size_t)i + 1] = base[(size_t)i] + (len + HS_V - 1) / HS_V * HS_V;
+    // large segments start on a storage-tile boundary when the capacity allows it (then every CTA
+    // reads and writes whole contiguous tiles); otherwise segments are only padded to HS_V
+    for (int pass = 0; pass < 2; ++pass) {
+        const int big = pass == 0 ? HS_TS : HS_V;
+        for (int i = 0; i < n_seg; ++i) {
+            PSB_REQUIRE(seg_off[i + 1] >= seg_off[i], "psb_hmmset_upload: seg_off not monotone at %d", i);
+            const int64_t len = seg_off[i + 1] - seg_off[i];
+            const int pad = len >= HS_TS ? big : HS_V;
+            mx = std::max<int64_t>(mx, len);
+            base[(size_t)i + 1] = base[(size_t)i] + (len + pad - 1) / pad * pad;
+        }
+        if (base[(size_t)n_seg] <= s->pitch) break;
     }
+    PSB_REQUIRE(base[(size_t)n_seg] <= s->pitch, "psb_hmmset_upload: internal capacity exceeded");
     for (int64_t i = 0; i < n; ++i) {
         int rc = validate_hmm(s->c, &hmms[i], (int)i);
         if (rc) return rc;

@@ -16,7 +16,7 @@ ssid = rng.integers(0, len(pm.sseq), n)
 hm["score"][:, :] = -0x20000000; hm["score"][:, 0] = 0
 hm["history"][:, :] = -1; hm["out_score"] = -0x20000000; hm["out_history"] = -1; hm["bestscore"] = -0x20000000
 hm["ssid"] = ssid; hm["senid"][:, :ns] = pm.sseq[ssid]; hm["tmatid"] = rng.integers(0, pm.tp.shape[0], n); hm["n_emit_state"] = ns
-hs = api.HmmSet(ctx, n, U)
+hs = api.HmmSet(ctx, n + (U * 512 if os.environ.get('ALIGN_TILES', '1') == '1' else 0), U)
 hs.upload(hm, np.arange(U + 1, dtype=np.int64) * A)
 scr = torch.randint(0, 600, (F * U, pm.n_sen), dtype=torch.int16, device="cuda")
 row0 = torch.arange(U, dtype=torch.int64, device="cuda") * F
