@@ -275,6 +275,22 @@ int psb_align_batch_host(psb_hmmctx_t *c, const int16_t *senscr, const int32_t *
                          int32_t *st_start, int32_t *st_dur, int32_t *st_score, int32_t *status);
 
 /* ------------------------------------------------------------------------------------ */
+/* Keyword spotting for whole batches: kws_search.c (start :577, step :599-628 = hmm_eval :194,
+ * hmm_prune :234, trans :256-348) with one keyphrase set for all utterances.  The phone loop is
+ * n_pl phones (ssid, tmatid) as kws_search_reinit builds it (:464-476, all CI phones); keyphrase k
+ * owns the HMM chain [kp_off[k], kp_off[k+1]) of (kp_ssid, kp_tmat) (:510-538) and the threshold
+ * kp_thresh[k]; beam and plp as kws_search_init computes them (:425-432).  d_senscr: device int16
+ * [frames][n_sen], all senones.  Every detection the reference would pass to kws_detections_add
+ * (:286-294) is returned as a row {frame, keyphrase, start frame, prob, ascr} in hits
+ * [n_utt][cap_per_utt][5] (host), in the reference's order; n_hits[u] (host) counts them (rows past
+ * cap_per_utt are dropped).  The host applies kws_detections_add unchanged. */
+int psb_kws_batch_device(psb_hmmctx_t *c, const int16_t *d_senscr, const int32_t *utt_off, int32_t n_utt,
+                         int32_t n_pl, const int32_t *pl_ssid, const int32_t *pl_tmat, int32_t n_kp,
+                         const int32_t *kp_off, const int32_t *kp_thresh, const int32_t *kp_ssid,
+                         const int32_t *kp_tmat, int32_t beam, int32_t plp, int32_t *hits,
+                         int32_t cap_per_utt, int32_t *n_hits);
+
+/* ------------------------------------------------------------------------------------ */
 /* Batched front end: int16 PCM -> cepstra -> batch CMN -> 1s_c_d_dd features
  * for whole batches, every utterance a fresh stream (ps_start_stream + ps_process_raw(full_utt),
  * pocketsphinx.c:1073, acmod.c:528-560).  The tables are the arrays the reference's own fe_t /

@@ -48,10 +48,32 @@ def make_align():
     np.savez_compressed(os.path.join(OUT, "en_us_align.npz"), **out)
 
 
+def make_kws():
+    """en_us_kws.npz: the reference's own kws_search on goforward.raw (all senones, no look-ahead)
+    for a single keyphrase and for a four-entry list: configuration as kws_search_reinit built it
+    and the final detection list."""
+    import tempfile
+    pcm = np.fromfile(os.path.join(REF, "test/data/goforward.raw"), np.int16)
+    hmm, dic = os.path.join(REF, "model/en-us/en-us"), os.path.join(REF, "model/en-us/cmudict-en-us.dict")
+    out = {}
+    with tempfile.NamedTemporaryFile("w", suffix=".list", delete=False) as f:
+        f.write("forward /1e-20/\nten meters /1e-30/\ngo /1e-10/\nbackward /1e-40/\n")
+    for tag, kw in (("a", dict(keyphrase="forward", kws_threshold="1e-20")), ("b", dict(keyfile=f.name))):
+        a = refdrv.kws(hmm, dic, pcm, **kw)
+        for k in ("pl_ssid", "pl_tmat", "kp_off", "kp_thresh", "kp_ssid", "kp_tmat", "det"):
+            out[tag + "_" + k] = a[k]
+        out[tag + "_beam"], out[tag + "_plp"] = np.int32(a["beam"]), np.int32(a["plp"])
+        print("kws", tag, len(a["kp_off"]) - 1, "keyphrases", len(a["det"]), "detections")
+    os.unlink(f.name)
+    np.savez_compressed(os.path.join(OUT, "en_us_kws.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "align":
         return make_align()
+    if len(sys.argv) > 1 and sys.argv[1] == "kws":
+        return make_kws()
     pcm = np.fromfile(os.path.join(REF, "test/data/goforward.raw"), np.int16)
 
     # ---- en-us PTM (BASELINE config 1): goforward.raw, 278 frames, all senones ----
@@ -148,6 +170,7 @@ def main():
         ctx.close()
     np.savez_compressed(os.path.join(OUT, "hmm_vit_eval.npz"), **cases)
     make_align()
+    make_kws()
     for fn in sorted(os.listdir(OUT)):
         print("%8d KiB  %s" % (os.path.getsize(os.path.join(OUT, fn)) // 1024, fn))
 

@@ -240,3 +240,39 @@ def align_run(tp, sseq, ssid, tmatid, senscr, sf=None, ef=None):
     rc = f(n_emit, _p(tp), _p(sseq), len(ssid), _p(ssid), _p(tmatid), _p(sf), _p(ef), _p(senscr), n_sen, T,
            _p(out[0]), _p(out[1]), _p(out[2]))
     return int(rc), out[0].copy(), out[1].copy(), out[2].copy()
+
+
+def kws_run(tp, sseq, pl_ssid, pl_tmat, kp_off, kp_thresh, kp_ssid, kp_tmat, beam, plp, senscr):
+    """kws_search.c semantics for one utterance; returns the raw hits [n][5] =
+    (frame, keyphrase, sf, prob, ascr) in the order the reference hands them to kws_detections_add."""
+    tp = np.ascontiguousarray(tp, np.uint8); sseq = np.ascontiguousarray(sseq, np.uint16)
+    a = [np.ascontiguousarray(x, np.int32) for x in (pl_ssid, pl_tmat, kp_off, kp_thresh, kp_ssid, kp_tmat)]
+    senscr = np.ascontiguousarray(senscr, np.int16)
+    T, n_sen = senscr.shape
+    cap = max(1, T * (len(a[2]) - 1))
+    hits = np.zeros((cap, 5), np.int32)
+    f = lib().pso_kws_run
+    f.restype = C.c_int32
+    f.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                  C.c_void_p, C.c_int32]
+    n = f(tp.shape[1], _p(tp), _p(sseq), len(a[0]), _p(a[0]), _p(a[1]), len(a[2]) - 1, _p(a[2]), _p(a[3]), _p(a[4]),
+          _p(a[5]), int(beam), int(plp), _p(senscr), n_sen, T, _p(hits), cap)
+    return hits[:n].copy()
+
+
+def kws_detections(hits):
+    """kws_detections_add (kws_detections.c:55-80) applied to raw hits in order: overlapping
+    detections of one keyphrase keep the better one.  Returns rows (keyphrase, sf, ef, prob, ascr) in
+    the reference's list order (newest first: glist_add_ptr prepends)."""
+    lst = []
+    for frame, k, sf, prob, ascr in hits.tolist():
+        ef = frame
+        for d in lst:
+            if d[0] == k and d[1] < ef and d[2] > sf:
+                if d[3] < prob:
+                    d[1], d[2], d[3], d[4] = sf, ef, prob, ascr
+                break
+        else:
+            lst.insert(0, [k, sf, ef, prob, ascr])
+    return np.array(lst, np.int32).reshape(-1, 5)

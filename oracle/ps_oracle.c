@@ -1252,3 +1252,80 @@ done:
     free(hmms); free(tok_id); free(tok_sc);
     return rc;
 }
+
+/* ---------------------------------------------------------------------------------------
+ * Keyword spotting: kws_search.c restated (start :577-597, step :599-628 = hmm_eval :194-229,
+ * hmm_prune :234-251, trans :256-348).  One utterance.  Phone loop of n_pl phones, n_kp keyphrases
+ * whose HMM chains are concatenated (kp_off).  Every detection the reference would hand to
+ * kws_detections_add is appended to hits as (frame, keyphrase, sf, prob, ascr), in its order
+ * (frame-major, keyphrases in list order); returns their number (at most cap are stored). */
+#define PSO_KWS_MAX 1500
+int32_t
+pso_kws_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq,
+            int32_t n_pl, const int32_t *pl_ssid, const int32_t *pl_tmat,
+            int32_t n_kp, const int32_t *kp_off, const int32_t *kp_thresh,
+            const int32_t *kp_ssid, const int32_t *kp_tmat, int32_t beam, int32_t plp,
+            const int16_t *senscr, int32_t n_sen, int32_t T, int32_t *hits, int32_t cap)
+{
+    pso_hmmctx_t ctx;
+    const int32_t n_k = kp_off[n_kp];
+    pso_hmm_t *pl = calloc(n_pl > 0 ? n_pl : 1, sizeof(*pl)), *kh = calloc(n_k > 0 ? n_k : 1, sizeof(*kh));
+    int32_t n_hits = 0, frame, i, k;
+
+    memset(&ctx, 0, sizeof(ctx));
+    ctx.n_emit_state = n_emit_state; ctx.tp = tp; ctx.sseq = sseq;
+    for (i = 0; i < n_pl; ++i) pso_hmm_init(&ctx, &pl[i], 0, pl_ssid[i], pl_tmat[i]);
+    for (i = 0; i < n_k; ++i) pso_hmm_init(&ctx, &kh[i], 0, kp_ssid[i], kp_tmat[i]);
+    for (i = 0; i < n_pl; ++i) { pso_hmm_clear(&pl[i]); pso_hmm_enter(&pl[i], 0, -1, 0); }   /* start */
+    for (frame = 0; frame < T; ++frame) {
+        int32_t bestscore = PSO_WORST_SCORE, thresh, best_out = PSO_WORST_SCORE;
+        pso_hmm_t *plb = NULL;
+        ctx.senscore = senscr + (size_t)frame * n_sen;
+        for (i = 0; i < n_pl; ++i) {                                      /* hmm_eval */
+            int32_t sc = pso_hmm_vit_eval(&ctx, &pl[i]);
+            if (sc > bestscore) bestscore = sc;
+        }
+        for (i = 0; i < n_k; ++i)
+            if (kh[i].frame > 0) {
+                int32_t sc = pso_hmm_vit_eval(&ctx, &kh[i]);
+                if (sc > bestscore) bestscore = sc;
+            }
+        thresh = bestscore + beam;                                        /* hmm_prune */
+        for (i = 0; i < n_k; ++i)
+            if (kh[i].frame > 0 && kh[i].bestscore < thresh) pso_hmm_clear(&kh[i]);
+        for (i = 0; i < n_pl; ++i)                                        /* trans */
+            if (pl[i].out_score > best_out) { best_out = pl[i].out_score; plb = &pl[i]; }
+        if (!plb) continue;
+        for (k = 0; k < n_kp; ++k) {
+            pso_hmm_t *last;
+            if (kp_off[k + 1] - kp_off[k] < 1) continue;
+            last = &kh[kp_off[k + 1] - 1];
+            if (last->frame > 0 && plb->out_score > PSO_WORST_SCORE
+                && last->out_score - plb->out_score >= kp_thresh[k]) {
+                if (n_hits < cap) {
+                    int32_t *h = hits + (size_t)n_hits * 5;
+                    h[0] = frame; h[1] = k; h[2] = last->out_history;
+                    h[3] = last->out_score - plb->out_score - PSO_KWS_MAX; h[4] = last->out_score;
+                }
+                ++n_hits;
+            }
+        }
+        for (i = 0; i < n_pl; ++i)
+            if (plb->out_score + plp > pl[i].score[0])
+                pso_hmm_enter(&pl[i], plb->out_score + plp, plb->out_history, frame + 1);
+        for (k = 0; k < n_kp; ++k) {
+            const int32_t o = kp_off[k], n = kp_off[k + 1] - kp_off[k];
+            if (n < 1) continue;
+            for (i = n - 1; i > 0; --i) {
+                pso_hmm_t *pred = &kh[o + i - 1], *h = &kh[o + i];
+                if (pred->frame > 0)
+                    if (!(h->frame > 0) || pred->out_score > h->score[0])
+                        pso_hmm_enter(h, pred->out_score, pred->out_history, frame + 1);
+            }
+            if (plb->out_score > kh[o].score[0])
+                pso_hmm_enter(&kh[o], plb->out_score, frame, frame + 1);
+        }
+    }
+    free(pl); free(kh);
+    return n_hits;
+}

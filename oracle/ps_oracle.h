@@ -149,6 +149,13 @@ int32_t pso_align_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *s
                       const int16_t *senscr, int32_t n_sen, int32_t T,
                       int32_t *st_start, int32_t *st_dur, int32_t *st_score);
 
+/* ---- keyword spotting (kws_search.c) ---- */
+int32_t pso_kws_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq,
+                    int32_t n_pl, const int32_t *pl_ssid, const int32_t *pl_tmat,
+                    int32_t n_kp, const int32_t *kp_off, const int32_t *kp_thresh,
+                    const int32_t *kp_ssid, const int32_t *kp_tmat, int32_t beam, int32_t plp,
+                    const int16_t *senscr, int32_t n_sen, int32_t T, int32_t *hits, int32_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -913,3 +913,89 @@ refdrv_align(const char *hmmdir, const char *dict, const char *kv, const char *w
     ps_config_free(config);
     return rc;
 }
+
+/* Keyword spotting through the reference's own kws_search (kws_search.c) on one utterance:
+ * `keyfile` is a kws list ("phrase /threshold/" per line) or NULL with a single `keyphrase`.
+ * Exports the search's configuration in list order -- phone loop (ssid, tmatid) [n_pl], the
+ * keyphrases' HMM chains kp_off[n_kp+1] / (ssid, tmatid) / threshold, beam and plp -- and the final
+ * detection list (kp index, sf, ef, prob, ascr) in list order.  info: [0] frames [1] n_pl [2] n_kp
+ * [3] total kp hmms [4] beam [5] plp [6] n_detections.  Returns 0 or <0. */
+#include "kws_search.h"
+int
+refdrv_kws(const char *hmmdir, const char *dict, const char *kv, const char *keyphrase, const char *keyfile,
+           const int16 *pcm, long n_samples, int32 *pl_ssid, int32 *pl_tmat, int32 *kp_off, int32 *kp_thresh,
+           int32 *kp_ssid, int32 *kp_tmat, int cap, int32 *det, int cap_det, int32 *info)
+{
+    ps_config_t *config;
+    ps_decoder_t *ps;
+    kws_search_t *kwss;
+    gnode_t *gn;
+    int i, k, n;
+
+    err_set_loglevel(ERR_ERROR);
+    config = ps_config_init(NULL);
+    ps_config_set_str(config, "hmm", hmmdir);
+    ps_config_set_str(config, "dict", dict);
+    ps_config_set_str(config, "dither", "no");
+    ps_config_set_str(config, "compallsen", "yes");
+    ps_config_set_str(config, "pl_window", "0");
+    ps_config_set_str(config, "lm", NULL);
+    if (keyfile) ps_config_set_str(config, "kws", keyfile);
+    else ps_config_set_str(config, "keyphrase", keyphrase);
+    if (kv) {
+        char *b2 = strdup(kv), *s2 = NULL, *t2;
+        for (t2 = strtok_r(b2, "\n", &s2); t2; t2 = strtok_r(NULL, "\n", &s2)) {
+            char *eq = strchr(t2, '=');
+            if (!eq) continue;
+            *eq = 0;
+            ps_config_set_str(config, t2, eq + 1);
+        }
+        free(b2);
+    }
+    ps = ps_init(config);
+    if (ps == NULL) { ps_config_free(config); return -1; }
+    if (ps->search == NULL || strcmp(ps_search_type(ps->search), PS_SEARCH_TYPE_KWS) != 0) {
+        ps_free(ps); ps_config_free(config);
+        return -2;
+    }
+    kwss = (kws_search_t *)ps->search;
+    ps_start_utt(ps);
+    ps_process_raw(ps, pcm, n_samples, FALSE, TRUE);
+    ps_end_utt(ps);
+    info[0] = ps_get_n_frames(ps);
+    info[1] = kwss->n_pl;
+    info[4] = kwss->beam;
+    info[5] = kwss->plp;
+    for (i = 0; i < kwss->n_pl && i < cap; ++i) {
+        pl_ssid[i] = hmm_nonmpx_ssid(&kwss->pl_hmms[i]);
+        pl_tmat[i] = kwss->pl_hmms[i].tmatid;
+    }
+    k = 0; n = 0;
+    kp_off[0] = 0;
+    for (gn = kwss->keyphrases; gn; gn = gnode_next(gn)) {
+        kws_keyphrase_t *kp = gnode_ptr(gn);
+        for (i = 0; i < kp->n_hmms; ++i, ++n)
+            if (n < cap) { kp_ssid[n] = hmm_nonmpx_ssid(&kp->hmms[i]); kp_tmat[n] = kp->hmms[i].tmatid; }
+        kp_thresh[k] = kp->threshold;
+        kp_off[++k] = n;
+    }
+    info[2] = k;
+    info[3] = n;
+    n = 0;
+    for (gn = kwss->detections->detect_list; gn; gn = gnode_next(gn)) {
+        kws_detection_t *d = gnode_ptr(gn);
+        gnode_t *g2;
+        int idx = 0, which = -1;
+        for (g2 = kwss->keyphrases; g2; g2 = gnode_next(g2), ++idx)
+            if (strcmp(((kws_keyphrase_t *)gnode_ptr(g2))->word, d->keyphrase) == 0) which = idx;
+        if (n < cap_det) {
+            det[n * 5 + 0] = which; det[n * 5 + 1] = d->sf; det[n * 5 + 2] = d->ef;
+            det[n * 5 + 3] = d->prob; det[n * 5 + 4] = d->ascr;
+        }
+        ++n;
+    }
+    info[6] = n;
+    ps_free(ps);
+    ps_config_free(config);
+    return 0;
+}

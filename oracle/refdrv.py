@@ -49,6 +49,8 @@ def lib():
         L.refdrv_fe_export.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long]
         L.refdrv_mfcc.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_int]
         L.refdrv_fe_reset.argtypes = [C.c_void_p]
+        L.refdrv_kws.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_long] + \
+            [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.refdrv_align.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_long,
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                    C.c_void_p]
@@ -318,3 +320,26 @@ def align(hmmdir, dictfile, words, pcm, **kv):
     nph, nst = int(info[1]), int(info[2])
     return dict(n_frames=int(info[0]), n_emit=int(info[3]), ssid=ssid[:nph].copy(), tmatid=tmat[:nph].copy(),
                 start=st[0, :nst].copy(), dur=st[1, :nst].copy(), score=st[2, :nst].copy())
+
+
+def kws(hmmdir, dictfile, pcm, keyphrase=None, keyfile=None, **kv):
+    """The reference's kws_search on one utterance (compallsen, no look-ahead).  Returns the search
+    configuration (phone loop, keyphrase HMM chains, thresholds, beam, plp) and its detections
+    [n][5] = (keyphrase index, sf, ef, prob, ascr) in list order."""
+    pcm = np.ascontiguousarray(pcm, np.int16)
+    s = "\n".join("%s=%s" % (k, v) for k, v in kv.items()).encode() or None
+    cap = 4096
+    pl_ssid = np.zeros(cap, np.int32); pl_tmat = np.zeros(cap, np.int32)
+    kp_off = np.zeros(cap, np.int32); kp_thr = np.zeros(cap, np.int32)
+    kp_ssid = np.zeros(cap, np.int32); kp_tmat = np.zeros(cap, np.int32)
+    det = np.zeros((cap, 5), np.int32)
+    info = np.zeros(8, np.int32)
+    rc = lib().refdrv_kws(hmmdir.encode(), dictfile.encode(), s, keyphrase.encode() if keyphrase else None,
+                          keyfile.encode() if keyfile else None, _p(pcm), len(pcm), _p(pl_ssid), _p(pl_tmat), _p(kp_off),
+                          _p(kp_thr), _p(kp_ssid), _p(kp_tmat), cap, _p(det), cap, _p(info))
+    if rc < 0:
+        raise RuntimeError("refdrv_kws failed: %d" % rc)
+    n_pl, n_kp, n_k, n_det = int(info[1]), int(info[2]), int(info[3]), int(info[6])
+    return dict(n_frames=int(info[0]), beam=int(info[4]), plp=int(info[5]), pl_ssid=pl_ssid[:n_pl].copy(),
+                pl_tmat=pl_tmat[:n_pl].copy(), kp_off=kp_off[:n_kp + 1].copy(), kp_thresh=kp_thr[:n_kp].copy(),
+                kp_ssid=kp_ssid[:n_k].copy(), kp_tmat=kp_tmat[:n_k].copy(), det=det[:n_det].copy())

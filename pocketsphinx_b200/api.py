@@ -268,6 +268,21 @@ class HmmContext:
               "psb_hmm_vit_eval_ptrs")
         return best.value
 
+    def kws(self, d_senscr_ptr, utt_off, pl_ssid, pl_tmat, kp_off, kp_thresh, kp_ssid, kp_tmat, beam, plp, cap=None):
+        """kws_search over a batch (scores on the device).  Returns a list of raw hit arrays
+        [n][5] = (frame, keyphrase, start frame, prob, ascr), one per utterance."""
+        utt_off = np.ascontiguousarray(utt_off, np.int32)
+        a = [np.ascontiguousarray(x, np.int32) for x in (pl_ssid, pl_tmat, kp_off, kp_thresh, kp_ssid, kp_tmat)]
+        n_utt, n_kp = len(utt_off) - 1, len(a[2]) - 1
+        if cap is None:
+            cap = max(1, int(np.diff(utt_off).max(initial=1)) * max(1, n_kp))
+        hits = np.zeros((max(1, n_utt), cap, 5), np.int32)
+        n_hits = np.zeros(max(1, n_utt), np.int32)
+        check(lib().psb_kws_batch_device(self.h, C.c_void_p(d_senscr_ptr), _p(utt_off), n_utt, len(a[0]), _p(a[0]), _p(a[1]),
+                                         n_kp, _p(a[2]), _p(a[3]), _p(a[4]), _p(a[5]), int(beam), int(plp), _p(hits), cap,
+                                         _p(n_hits)), "psb_kws_batch_device")
+        return [hits[u, :min(int(n_hits[u]), cap)].copy() for u in range(n_utt)], n_hits[:n_utt].copy()
+
     def align(self, senscr, utt_off, ph_off, ssid, tmatid, sf=None, ef=None, device_ptr=None):
         """state_align_search over a batch.  senscr: host int16 [frames][n_sen] (or device_ptr);
         returns (status [n_utt], start, dur, score per emitting state)."""

@@ -1221,3 +1221,204 @@ extern "C" int psb_align_batch_host(psb_hmmctx_t *c, const int16_t *senscr, cons
     }
     return rc;
 }
+
+// ---------------------------------------------------------------------------------------
+// Keyword spotting: kws_search.c on the device for whole batches (SURVEY 8 row b5 lists its
+// kws_search_hmm_eval, kws_search.c:194).  One CTA per utterance; the phone loop (all CI phones)
+// and the keyphrases' HMM chains sit side by side in shared memory (SoA); per frame
+// kws_search_hmm_eval (:194-229), kws_search_hmm_prune (:234-251) and kws_search_trans (:256-348):
+// first-best exit score of the phone loop, detections, phone-loop re-entry, chain transitions
+// (decided from the state BEFORE any entry of this frame, which is what the reference's reverse
+// loop order achieves) and the chains' start from the phone loop.  Every detection the reference
+// would pass to kws_detections_add comes back as a row (frame, keyphrase, start frame, prob, ascr)
+// in the reference's order; the host applies the unchanged list logic (kws_detections.c:55-80).
+namespace {
+
+constexpr int KWS_MAX_SCORE = 1500;         // KWS_MAX, kws_search.c:59
+
+__global__ void __launch_bounds__(128)
+kws_kernel(const int16_t *__restrict__ senscr, const int32_t *__restrict__ utt_off, HmmCtxDev c,
+           int n_pl, int n_kp, const int32_t *__restrict__ kp_off, const int32_t *__restrict__ kp_thresh,
+           const uint16_t *__restrict__ senid_g, const int32_t *__restrict__ tmatid_g, const int32_t *__restrict__ kp_of,
+           int beam, int plp, int32_t *__restrict__ hits, int cap, int32_t *__restrict__ n_hits)
+{
+    extern __shared__ int sm[];
+    const int u = blockIdx.x, tid = threadIdx.x, N = c.n_emit;
+    const int H = n_pl + kp_off[n_kp];
+    const long long f0 = utt_off[u];
+    const int T = utt_off[u + 1] - utt_off[u];
+    int *score = sm;                       // [N][H]
+    int *hist = score + N * H;             // [N][H]
+    int *out_score = hist + N * H;         // [H]
+    int *out_hist = out_score + H;         // [H]
+    int *bestsc = out_hist + H;            // [H]
+    int *frame = bestsc + H;               // [H]
+    int *sval = frame + H;                 // [32]
+    int *sidx = sval + 32;                 // [32]
+    int32_t *my_hits = hits + (size_t)u * cap * 5;
+    int nh = 0;
+
+    // kws_search_reinit: hmm_init (= hmm_clear); kws_search_start: phone loop hmm_clear + hmm_enter(0, -1, 0)
+    for (int i = tid; i < H; i += blockDim.x) {
+        for (int s = 0; s < N; ++s) { score[s * H + i] = PSB_WORST_SCORE; hist[s * H + i] = -1; }
+        out_score[i] = PSB_WORST_SCORE; out_hist[i] = -1; bestsc[i] = PSB_WORST_SCORE; frame[i] = -1;
+        if (i < n_pl) { score[i] = 0; hist[i] = -1; frame[i] = 0; }
+    }
+    __syncthreads();
+
+    for (int t = 0; t < T; ++t) {
+        const int16_t *row = senscr + (f0 + t) * c.n_sen;
+        int bs = PSB_WORST_SCORE;
+        // kws_search_hmm_eval: the phone loop always, keyphrase HMMs when active (frame > 0)
+        for (int i = tid; i < H; i += blockDim.x) {
+            if (i >= n_pl && !(frame[i] > 0)) continue;
+            HmmReg h;
+#pragma unroll
+            for (int s = 0; s < PSB_HMM_MAX_NSTATE; ++s) {
+                h.score[s] = s < N ? score[s * H + i] : PSB_WORST_SCORE;
+                h.hist[s] = s < N ? hist[s * H + i] : -1;
+                h.senid[s] = s < N ? senid_g[(size_t)i * N + s] : PSB_BAD_SSID;
+            }
+            h.out_score = out_score[i]; h.out_hist = out_hist[i]; h.best = bestsc[i];
+            const int b = hmm_step(h, c, tmatid_g[i], false, row);
+            if (b > bs) bs = b;
+#pragma unroll
+            for (int s = 0; s < PSB_HMM_MAX_NSTATE; ++s)
+                if (s < N) { score[s * H + i] = h.score[s]; hist[s * H + i] = h.hist[s]; }
+            out_score[i] = h.out_score; out_hist[i] = h.out_hist; bestsc[i] = h.best;
+        }
+        int dummy;
+        bs = block_reduce_max_pair<int>(bs, 0, sidx, sval, dummy);
+        // kws_search_hmm_prune: hmm_clear on active keyphrase HMMs below the beam
+        const int thresh = bs + beam;
+        int cand = PSB_WORST_SCORE, cidx = 0x7fffffff;
+        for (int i = tid; i < H; i += blockDim.x) {
+            if (i >= n_pl) {
+                if (frame[i] > 0 && bestsc[i] < thresh) {
+                    for (int s = 0; s < N; ++s) { score[s * H + i] = PSB_WORST_SCORE; hist[s * H + i] = -1; }
+                    out_score[i] = PSB_WORST_SCORE; out_hist[i] = -1; bestsc[i] = PSB_WORST_SCORE; frame[i] = -1;
+                }
+            }
+            else if (out_score[i] > cand) { cand = out_score[i]; cidx = i; }   // first best exit of the phone loop
+        }
+        int plb;
+        cand = block_reduce_max_pair<int>(cand, cidx, sidx, sval, plb);   // ties -> smallest index = first in scan order
+        __syncthreads();
+        if (cand > PSB_WORST_SCORE) {                                     // else "out probs are not ready yet"
+            const int plb_out = cand, plb_hist = out_hist[plb];
+            // detections, in keyphrase order
+            if (tid == 0)
+                for (int k = 0; k < n_kp; ++k) {
+                    if (kp_off[k + 1] - kp_off[k] < 1) continue;
+                    const int last = n_pl + kp_off[k + 1] - 1;
+                    if (frame[last] > 0 && out_score[last] - plb_out >= kp_thresh[k]) {
+                        if (nh < cap) {
+                            int32_t *hrow = my_hits + (size_t)nh * 5;
+                            hrow[0] = t; hrow[1] = k; hrow[2] = out_hist[last];
+                            hrow[3] = out_score[last] - plb_out - KWS_MAX_SCORE; hrow[4] = out_score[last];
+                        }
+                        ++nh;
+                    }
+                }
+            // transitions: decide from the pre-entry state, then apply
+            int e_sc[4], e_hi[4];
+            bool e_on[4];
+            int q = 0;
+            for (int i = tid; i < H; i += blockDim.x, ++q) {
+                bool on = false; int sc = 0, hi = 0;
+                if (i < n_pl) {                                            // phone-loop re-entry (:303-311)
+                    if (plb_out + plp > score[i]) { on = true; sc = plb_out + plp; hi = plb_hist; }
+                }
+                else {
+                    const int j = i - n_pl, k = kp_of[j];
+                    if (j > kp_off[k]) {                                   // inside a chain (:320-332)
+                        if (frame[i - 1] > 0 && (!(frame[i] > 0) || out_score[i - 1] > score[i])) {
+                            on = true; sc = out_score[i - 1]; hi = out_hist[i - 1];
+                        }
+                    }
+                    else if (plb_out > score[i]) { on = true; sc = plb_out; hi = t; }   // chain start (:335-340)
+                }
+                if (q < 4) { e_on[q] = on; e_sc[q] = sc; e_hi[q] = hi; }
+            }
+            __syncthreads();
+            q = 0;
+            for (int i = tid; i < H; i += blockDim.x, ++q)
+                if (q < 4 && e_on[q]) { score[i] = e_sc[q]; hist[i] = e_hi[q]; frame[i] = t + 1; }   // hmm_enter
+        }
+        __syncthreads();
+    }
+    if (tid == 0) n_hits[u] = nh;
+}
+
+}  // namespace
+
+extern "C" int psb_kws_batch_device(psb_hmmctx_t *c, const int16_t *d_senscr, const int32_t *utt_off, int32_t n_utt,
+                                    int32_t n_pl, const int32_t *pl_ssid, const int32_t *pl_tmat, int32_t n_kp,
+                                    const int32_t *kp_off, const int32_t *kp_thresh, const int32_t *kp_ssid,
+                                    const int32_t *kp_tmat, int32_t beam, int32_t plp, int32_t *hits,
+                                    int32_t cap_per_utt, int32_t *n_hits)
+{
+    PSB_REQUIRE(c && utt_off && n_utt >= 0 && n_pl > 0 && pl_ssid && pl_tmat && n_kp >= 0 && kp_off && hits && n_hits &&
+                cap_per_utt > 0, "psb_kws_batch_device: bad argument");
+    if (n_utt == 0) return PSB_OK;
+    PSB_REQUIRE(utt_off[0] == 0 && kp_off[0] == 0, "psb_kws_batch_device: offsets must start at 0");
+    PSB_REQUIRE(d_senscr || utt_off[n_utt] == 0, "psb_kws_batch_device: scores missing");
+    const int N = c->n_emit, n_k = kp_off[n_kp], H = n_pl + n_k;
+    PSB_REQUIRE(n_k == 0 || (kp_ssid && kp_tmat && kp_thresh), "psb_kws_batch_device: keyphrase tables missing");
+    PSB_REQUIRE(H <= 4 * 128, "psb_kws_batch_device: %d HMMs exceed the 512 this kernel keeps per utterance", H);
+    PSB_CUDA(cudaSetDevice(c->device));
+    std::vector<uint16_t> sseq((size_t)c->n_sseq * N);
+    PSB_CUDA(cudaMemcpy(sseq.data(), c->d_sseq, sseq.size() * 2, cudaMemcpyDeviceToHost));
+    std::vector<uint16_t> senid((size_t)H * N);
+    std::vector<int32_t> ibuf;                       // utt_off | kp_off | kp_thresh | tmatid[H] | kp_of[n_k]
+    ibuf.insert(ibuf.end(), utt_off, utt_off + n_utt + 1);
+    const size_t o_kpoff = ibuf.size();
+    ibuf.insert(ibuf.end(), kp_off, kp_off + n_kp + 1);
+    const size_t o_thr = ibuf.size();
+    for (int k = 0; k < n_kp; ++k) ibuf.push_back(kp_thresh[k]);
+    const size_t o_tm = ibuf.size();
+    for (int i = 0; i < H; ++i) {
+        const int ss = i < n_pl ? pl_ssid[i] : kp_ssid[i - n_pl], tm = i < n_pl ? pl_tmat[i] : kp_tmat[i - n_pl];
+        PSB_REQUIRE(ss >= 0 && ss < c->n_sseq, "kws: ssid %d out of range", ss);
+        PSB_REQUIRE(tm >= 0 && tm < c->n_tmat, "kws: tmatid %d out of range", tm);
+        for (int s = 0; s < N; ++s) {
+            const uint16_t v = sseq[(size_t)ss * N + s];
+            PSB_REQUIRE(v < c->n_sen, "senone id %d out of range", v);
+            senid[(size_t)i * N + s] = v;
+        }
+        ibuf.push_back(tm);
+    }
+    const size_t o_of = ibuf.size();
+    for (int k = 0; k < n_kp; ++k) {
+        PSB_REQUIRE(kp_off[k + 1] >= kp_off[k], "psb_kws_batch_device: kp_off not monotone at %d", k);
+        for (int j = kp_off[k]; j < kp_off[k + 1]; ++j) ibuf.push_back(k);
+    }
+    const size_t o_nh = ibuf.size();
+    ibuf.resize(o_nh + (size_t)n_utt, 0);
+    const size_t smem = ((size_t)(2 * N + 4) * H + 64) * sizeof(int);
+    int32_t *d_i = nullptr, *d_hits = nullptr;
+    uint16_t *d_senid = nullptr;
+    const size_t hits_n = (size_t)n_utt * cap_per_utt * 5;
+    cudaError_t e = cudaMalloc((void **)&d_i, ibuf.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_hits, hits_n * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_senid, senid.size() * 2);
+    cudaStream_t st = c->stream;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_i, ibuf.data(), ibuf.size() * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_senid, senid.data(), senid.size() * 2, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        kws_kernel<<<(unsigned)n_utt, 128, smem, st>>>(d_senscr, d_i, dev_ctx(c), n_pl, n_kp, d_i + o_kpoff, d_i + o_thr, d_senid,
+                                                      d_i + o_tm, d_i + o_of, beam, plp, d_hits, cap_per_utt, d_i + o_nh);
+        g_psb_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hits, d_hits, hits_n * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(n_hits, d_i + o_nh, (size_t)n_utt * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_i); cudaFree(d_hits); cudaFree(d_senid);
+    if (e != cudaSuccess) {
+        psb_set_error("psb_kws_batch_device: %s", cudaGetErrorString(e));
+        return PSB_ERR_CUDA;
+    }
+    return PSB_OK;
+}

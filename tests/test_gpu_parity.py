@@ -574,3 +574,60 @@ def test_align_batch_matches_oracle(api, n_emit):
         n_ok += rc == 0
     assert n_ok >= 5                                           # the test exercises successes and failures
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------
+# keyword spotting (kws_search.c) for batches
+
+def test_kws_goforward_matches_reference(api, en_us, en_us_dev):
+    import torch
+    from oracle import oracle
+    g, gk = golden("en_us_goforward.npz"), golden("en_us_kws.npz")
+    b = api.Batch(en_us_dev, 4, 1024)
+    scr = b.score_host(g["feats"], np.array([0, 278], np.int32))
+    b.close()
+    ctx = api.HmmContext(en_us.tp, en_us.sseq, en_us.n_sen)
+    d_scr = torch.from_numpy(np.concatenate([scr, scr[:150]])).cuda()
+    utt_off = np.array([0, 278, 428], np.int32)
+    for tag in ("a", "b"):
+        cfg = [gk[tag + "_" + k] for k in ("pl_ssid", "pl_tmat", "kp_off", "kp_thresh", "kp_ssid", "kp_tmat")]
+        hits, n = ctx.kws(d_scr.data_ptr(), utt_off, *cfg, int(gk[tag + "_beam"]), int(gk[tag + "_plp"]))
+        assert np.array_equal(oracle.kws_detections(hits[0]), gk[tag + "_det"]), tag     # the reference's own detections
+        for u, (a, e) in enumerate(((0, 278), (0, 150))):
+            want = oracle.kws_run(en_us.tp, en_us.sseq, *cfg, int(gk[tag + "_beam"]), int(gk[tag + "_plp"]), scr[a:e])
+            assert n[u] == len(want) and np.array_equal(hits[u], want), (tag, u)
+    ctx.close()
+
+
+@pytest.mark.parametrize("n_emit", [3, 5])
+def test_kws_batch_matches_oracle(api, n_emit):
+    import torch
+    from oracle import oracle
+    from pocketsphinx_b200.model import synth_ptm
+    pm = synth_ptm(seed=41, n_density=32, n_sen=300, n_emit_state=n_emit, skip_arcs=(n_emit == 5))
+    rng = np.random.default_rng(23)
+    n_pl = 30
+    pl_ssid = rng.integers(0, len(pm.sseq), n_pl).astype(np.int32)
+    pl_tmat = rng.integers(0, pm.tp.shape[0], n_pl).astype(np.int32)
+    chains = [4, 1, 9, 0, 17]                                   # one empty keyphrase (word missing from the dictionary)
+    kp_off = np.concatenate([[0], np.cumsum(chains)]).astype(np.int32)
+    kp_ssid = rng.integers(0, len(pm.sseq), kp_off[-1]).astype(np.int32)
+    kp_tmat = rng.integers(0, pm.tp.shape[0], kp_off[-1]).astype(np.int32)
+    kp_thresh = np.array([-200, -3000, -100, 0, -50000], np.int32)
+    frames = [120, 1, 60, 300]
+    scr = [rng.integers(0, 300, (t, pm.n_sen)).astype(np.int16) for t in frames]
+    utt_off = np.concatenate([[0], np.cumsum(frames)]).astype(np.int32)
+    ctx = api.HmmContext(pm.tp, pm.sseq, pm.n_sen)
+    d_scr = torch.from_numpy(np.concatenate(scr)).cuda()
+    total_hits = 0
+    for beam, plp in ((-1080, -23), (-150, -400)):
+        hits, n = ctx.kws(d_scr.data_ptr(), utt_off, pl_ssid, pl_tmat, kp_off, kp_thresh, kp_ssid, kp_tmat, beam, plp)
+        for u in range(len(frames)):
+            want = oracle.kws_run(pm.tp, pm.sseq, pl_ssid, pl_tmat, kp_off, kp_thresh, kp_ssid, kp_tmat, beam, plp, scr[u])
+            assert n[u] == len(want) and np.array_equal(hits[u], want), "utterance %d beam %d" % (u, beam)
+            total_hits += len(want)
+        # truncation: the count is still the full number
+        h2, n2 = ctx.kws(d_scr.data_ptr(), utt_off, pl_ssid, pl_tmat, kp_off, kp_thresh, kp_ssid, kp_tmat, beam, plp, cap=3)
+        assert np.array_equal(n2, n) and all(np.array_equal(a, b[:3]) for a, b in zip(h2, hits))
+    assert total_hits > 50
+    ctx.close()
