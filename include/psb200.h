@@ -291,6 +291,22 @@ int psb_kws_batch_device(psb_hmmctx_t *c, const int16_t *d_senscr, const int32_t
                          int32_t cap_per_utt, int32_t *n_hits);
 
 /* ------------------------------------------------------------------------------------ */
+/* Phone decoding for whole batches: allphone_search.c without a phone LM (start :640-677, step
+ * :700-722 = phmm_eval_all :349, phmm_exit :380, phmm_trans :458).  The PHMM graph is given in the
+ * order the reference walks ci_phmm[] (ci-major, list order): node i = (ssid[i], tmatid[i]),
+ * successors succ[succ_off[i] .. succ_off[i+1]) (plink_t lists, :186-262), `start` = the silence
+ * PHMM entered by allphone_search_start; beam / pbeam / inspen as allphone_search_init computes
+ * them (:581-602).  Every history_t the reference appends (:402-444) comes back as a row
+ * {ef, node, predecessor entry, score} in hist [n_utt][cap_per_utt][4] (host), n_hist[u] counts
+ * them; the host's allphone_backtrace (:765-840) works on that table unchanged.  Graphs up to a
+ * few thousand nodes (shared memory): the context-independent graph has one node per phone. */
+int psb_allphone_batch_device(psb_hmmctx_t *c, const int16_t *d_senscr, const int32_t *utt_off,
+                              int32_t n_utt, int32_t n_nodes, const int32_t *ssid, const int32_t *tmatid,
+                              const int32_t *succ_off, const int32_t *succ, int32_t start, int32_t beam,
+                              int32_t pbeam, int32_t inspen, int32_t *hist, int32_t cap_per_utt,
+                              int32_t *n_hist);
+
+/* ------------------------------------------------------------------------------------ */
 /* Batched front end: int16 PCM -> cepstra -> batch CMN -> 1s_c_d_dd features
  * for whole batches, every utterance a fresh stream (ps_start_stream + ps_process_raw(full_utt),
  * pocketsphinx.c:1073, acmod.c:528-560).  The tables are the arrays the reference's own fe_t /

@@ -68,8 +68,23 @@ def make_kws():
     np.savez_compressed(os.path.join(OUT, "en_us_kws.npz"), **out)
 
 
+def make_allphone():
+    """en_us_allphone.npz: the reference's own allphone_search (no phone LM, context-independent
+    graph = the default -allphone_ci yes) on goforward.raw: graph, parameters, history count and
+    the phone segmentation."""
+    pcm = np.fromfile(os.path.join(REF, "test/data/goforward.raw"), np.int16)
+    a = refdrv.allphone(os.path.join(REF, "model/en-us/en-us"), pcm)
+    out = {k: a[k] for k in ("ci", "ssid", "tmatid", "succ_off", "succ", "segs")}
+    for k in ("start", "beam", "pbeam", "inspen", "n_history"):
+        out[k] = np.int32(a[k])
+    print("allphone", len(a["ci"]), "nodes", len(a["succ"]), "links", a["n_history"], "history entries", len(a["segs"]), "segments")
+    np.savez_compressed(os.path.join(OUT, "en_us_allphone.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "allphone":
+        return make_allphone()
     if len(sys.argv) > 1 and sys.argv[1] == "align":
         return make_align()
     if len(sys.argv) > 1 and sys.argv[1] == "kws":
@@ -171,6 +186,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "hmm_vit_eval.npz"), **cases)
     make_align()
     make_kws()
+    make_allphone()
     for fn in sorted(os.listdir(OUT)):
         print("%8d KiB  %s" % (os.path.getsize(os.path.join(OUT, fn)) // 1024, fn))
 

@@ -1329,3 +1329,67 @@ pso_kws_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq,
     free(pl); free(kh);
     return n_hits;
 }
+
+/* ---------------------------------------------------------------------------------------
+ * Phone decoding: allphone_search.c without a phone LM restated (start :640-677, step :700-722 =
+ * phmm_eval_all :349-378, phmm_exit :380-456, phmm_trans :458-524).  One utterance.  The graph is
+ * n_nodes PHMMs (ssid, tmatid) in the reference's walk order with successor lists in CSR form.
+ * Every history entry is returned as a row (ef, node, hist, score); returns their number (at most
+ * cap are stored). */
+int32_t
+pso_allphone_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, int32_t n_nodes,
+                 const int32_t *ssid, const int32_t *tmatid, const int32_t *succ_off, const int32_t *succ,
+                 int32_t start, int32_t beam, int32_t pbeam, int32_t inspen,
+                 const int16_t *senscr, int32_t n_sen, int32_t T, int32_t *hist, int32_t cap)
+{
+    pso_hmmctx_t ctx;
+    pso_hmm_t *h = calloc(n_nodes > 0 ? n_nodes : 1, sizeof(*h));
+    int32_t n_hist = 0, frame, i, l;
+    /* history scores are needed by phmm_trans even past cap: keep a private copy */
+    int32_t hcap = 1024, *hscore = malloc(hcap * sizeof(int32_t)), *hnode = malloc(hcap * sizeof(int32_t));
+
+    memset(&ctx, 0, sizeof(ctx));
+    ctx.n_emit_state = n_emit_state; ctx.tp = tp; ctx.sseq = sseq;
+    for (i = 0; i < n_nodes; ++i) { pso_hmm_init(&ctx, &h[i], 0, ssid[i], tmatid[i]); pso_hmm_clear(&h[i]); }
+    pso_hmm_enter(&h[start], 0, 0, 0);
+    for (frame = 0; frame < T; ++frame) {
+        const int32_t nf = frame + 1, first = n_hist;
+        int32_t best = PSO_WORST_SCORE, th, k;
+        ctx.senscore = senscr + (size_t)frame * n_sen;
+        for (i = 0; i < n_nodes; ++i)                                    /* phmm_eval_all */
+            if (h[i].frame == frame) {
+                int32_t sc = pso_hmm_vit_eval(&ctx, &h[i]);
+                if (sc > best) best = sc;
+            }
+        th = best + pbeam;                                               /* phmm_exit */
+        for (i = 0; i < n_nodes; ++i)
+            if (h[i].frame == frame) {
+                if (h[i].bestscore >= th) {
+                    if (n_hist == hcap) {
+                        hcap *= 2;
+                        hscore = realloc(hscore, hcap * sizeof(int32_t));
+                        hnode = realloc(hnode, hcap * sizeof(int32_t));
+                    }
+                    hscore[n_hist] = h[i].out_score; hnode[n_hist] = i;
+                    if (n_hist < cap) {
+                        int32_t *r = hist + (size_t)n_hist * 4;
+                        r[0] = frame; r[1] = i; r[2] = h[i].out_history; r[3] = h[i].out_score;
+                    }
+                    ++n_hist;
+                    h[i].frame = nf;
+                }
+                else pso_hmm_clear(&h[i]);
+            }
+        for (k = first; k < n_hist; ++k) {                               /* phmm_trans */
+            const int32_t from = hnode[k];
+            for (l = succ_off[from]; l < succ_off[from + 1]; ++l) {
+                pso_hmm_t *to = &h[succ[l]];
+                const int32_t newscore = hscore[k] + inspen;
+                if (newscore > best + beam && newscore > to->score[0])
+                    pso_hmm_enter(to, newscore, k, nf);
+            }
+        }
+    }
+    free(h); free(hscore); free(hnode);
+    return n_hist;
+}

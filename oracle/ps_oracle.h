@@ -156,6 +156,12 @@ int32_t pso_kws_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sse
                     const int32_t *kp_ssid, const int32_t *kp_tmat, int32_t beam, int32_t plp,
                     const int16_t *senscr, int32_t n_sen, int32_t T, int32_t *hits, int32_t cap);
 
+/* ---- phone decoding (allphone_search.c, no phone LM) ---- */
+int32_t pso_allphone_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, int32_t n_nodes,
+                         const int32_t *ssid, const int32_t *tmatid, const int32_t *succ_off, const int32_t *succ,
+                         int32_t start, int32_t beam, int32_t pbeam, int32_t inspen,
+                         const int16_t *senscr, int32_t n_sen, int32_t T, int32_t *hist, int32_t cap);
+
 #ifdef __cplusplus
 }
 #endif

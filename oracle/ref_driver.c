@@ -999,3 +999,92 @@ refdrv_kws(const char *hmmdir, const char *dict, const char *kv, const char *key
     ps_config_free(config);
     return 0;
 }
+
+/* Phone decoding through the reference's own allphone_search (allphone_search.c) without a phone
+ * LM (unconstrained loop, insertion penalty only) on one utterance.  Exports the search graph in
+ * the order phmm_eval_all / phmm_exit walk it (ci-major, list order): per node (ci, ssid, tmatid),
+ * successor lists in CSR form, the start node, beam / pbeam / inspen, and the resulting phone
+ * segmentation (ci, sf, ef, score, tscore).  info: [0] frames [1] n_nodes [2] n_links [3] start
+ * [4] beam [5] pbeam [6] inspen [7] n_segments [8] n_history.  Returns 0 or <0. */
+#include "allphone_search.h"
+int
+refdrv_allphone(const char *hmmdir, const char *kv, const int16 *pcm, long n_samples,
+                int32 *node_ci, int32 *node_ssid, int32 *node_tmat, int32 *succ_off, int cap_nodes,
+                int32 *succ, int cap_links, int32 *segs, int cap_segs, int32 *info)
+{
+    ps_config_t *config;
+    ps_decoder_t *ps;
+    allphone_search_t *ap;
+    bin_mdef_t *mdef;
+    phmm_t **nodes, *p;
+    gnode_t *gn;
+    int n_nodes = 0, n_links = 0, ci, i, n;
+
+    err_set_loglevel(ERR_ERROR);
+    config = ps_config_init(NULL);
+    ps_config_set_str(config, "hmm", hmmdir);
+    ps_config_set_str(config, "dither", "no");
+    ps_config_set_str(config, "compallsen", "yes");
+    ps_config_set_str(config, "pl_window", "0");
+    ps_config_set_str(config, "lm", NULL);
+    ps_config_set_str(config, "dict", NULL);
+    if (kv) {
+        char *b2 = strdup(kv), *s2 = NULL, *t2;
+        for (t2 = strtok_r(b2, "\n", &s2); t2; t2 = strtok_r(NULL, "\n", &s2)) {
+            char *eq = strchr(t2, '=');
+            if (!eq) continue;
+            *eq = 0;
+            ps_config_set_str(config, t2, eq + 1);
+        }
+        free(b2);
+    }
+    ps = ps_init(config);
+    if (ps == NULL) { ps_config_free(config); return -1; }
+    if (ps_add_allphone(ps, "_ap", NULL) < 0 || ps_activate_search(ps, "_ap") < 0) {
+        ps_free(ps); ps_config_free(config);
+        return -2;
+    }
+    ap = (allphone_search_t *)ps->search;
+    mdef = ps->acmod->mdef;
+    ps_start_utt(ps);
+    ps_process_raw(ps, pcm, n_samples, FALSE, TRUE);
+    ps_end_utt(ps);
+    for (ci = 0; ci < bin_mdef_n_ciphone(mdef); ++ci)
+        for (p = ap->ci_phmm[ci]; p; p = p->next) ++n_nodes;
+    nodes = calloc(n_nodes > 0 ? n_nodes : 1, sizeof(*nodes));
+    for (ci = 0, i = 0; ci < bin_mdef_n_ciphone(mdef); ++ci)
+        for (p = ap->ci_phmm[ci]; p; p = p->next) nodes[i++] = p;
+    info[3] = -1;
+    succ_off[0] = 0;
+    for (i = 0; i < n_nodes; ++i) {
+        plink_t *l;
+        if (i < cap_nodes) {
+            node_ci[i] = nodes[i]->ci; node_ssid[i] = hmm_nonmpx_ssid(&nodes[i]->hmm); node_tmat[i] = nodes[i]->hmm.tmatid;
+        }
+        if (nodes[i]->ci == bin_mdef_silphone(mdef) && nodes[i]->pid == bin_mdef_silphone(mdef) && info[3] < 0) info[3] = i;
+        for (l = nodes[i]->succlist; l; l = l->next) {
+            int j;
+            for (j = 0; j < n_nodes && nodes[j] != l->phmm; ++j) ;
+            if (n_links < cap_links) succ[n_links] = j;
+            ++n_links;
+        }
+        if (i + 1 <= cap_nodes) succ_off[i + 1] = n_links;
+    }
+    info[0] = ps_get_n_frames(ps); info[1] = n_nodes; info[2] = n_links;
+    info[4] = ap->beam; info[5] = ap->pbeam; info[6] = ap->inspen;
+    n = 0;
+    for (gn = ap->segments; gn; gn = gnode_next(gn)) {
+        phseg_t *s = gnode_ptr(gn);
+        if (n < cap_segs) {
+            segs[n * 5 + 0] = s->ci; segs[n * 5 + 1] = s->sf; segs[n * 5 + 2] = s->ef;
+            segs[n * 5 + 3] = s->score; segs[n * 5 + 4] = s->tscore;
+        }
+        ++n;
+    }
+    info[7] = n;
+    info[8] = (int32)blkarray_list_n_valid(ap->history);
+    free(nodes);
+    ps_free(ps);
+    ps_config_free(config);
+    return 0;
+}

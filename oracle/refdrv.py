@@ -51,6 +51,8 @@ def lib():
         L.refdrv_fe_reset.argtypes = [C.c_void_p]
         L.refdrv_kws.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_long] + \
             [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.refdrv_allphone.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.refdrv_align.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_long,
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                    C.c_void_p]
@@ -343,3 +345,24 @@ def kws(hmmdir, dictfile, pcm, keyphrase=None, keyfile=None, **kv):
     return dict(n_frames=int(info[0]), beam=int(info[4]), plp=int(info[5]), pl_ssid=pl_ssid[:n_pl].copy(),
                 pl_tmat=pl_tmat[:n_pl].copy(), kp_off=kp_off[:n_kp + 1].copy(), kp_thresh=kp_thr[:n_kp].copy(),
                 kp_ssid=kp_ssid[:n_k].copy(), kp_tmat=kp_tmat[:n_k].copy(), det=det[:n_det].copy())
+
+
+def allphone(hmmdir, pcm, **kv):
+    """The reference's allphone_search without a phone LM on one utterance: graph, parameters and
+    the phone segmentation [n][5] = (ci, sf, ef, score, tscore)."""
+    pcm = np.ascontiguousarray(pcm, np.int16)
+    s = "\n".join("%s=%s" % (k, v) for k, v in kv.items()).encode() or None
+    cap_n, cap_l, cap_s = 1 << 16, 1 << 22, 4096
+    ci = np.zeros(cap_n, np.int32); ssid = np.zeros(cap_n, np.int32); tmat = np.zeros(cap_n, np.int32)
+    soff = np.zeros(cap_n + 1, np.int32); succ = np.zeros(cap_l, np.int32)
+    segs = np.zeros((cap_s, 5), np.int32)
+    info = np.zeros(16, np.int32)
+    rc = lib().refdrv_allphone(hmmdir.encode(), s, _p(pcm), len(pcm), _p(ci), _p(ssid), _p(tmat), _p(soff), cap_n,
+                               _p(succ), cap_l, _p(segs), cap_s, _p(info))
+    if rc < 0:
+        raise RuntimeError("refdrv_allphone failed: %d" % rc)
+    n, nl = int(info[1]), int(info[2])
+    assert n <= cap_n and nl <= cap_l
+    return dict(n_frames=int(info[0]), ci=ci[:n].copy(), ssid=ssid[:n].copy(), tmatid=tmat[:n].copy(),
+                succ_off=soff[:n + 1].copy(), succ=succ[:nl].copy(), start=int(info[3]), beam=int(info[4]),
+                pbeam=int(info[5]), inspen=int(info[6]), segs=segs[:int(info[7])].copy(), n_history=int(info[8]))

@@ -1422,3 +1422,210 @@ extern "C" int psb_kws_batch_device(psb_hmmctx_t *c, const int16_t *d_senscr, co
     }
     return PSB_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// Phone decoding: allphone_search.c without a phone LM, for whole batches (SURVEY 8 row b5 lists
+// its phmm_eval_all, allphone_search.c:349).  One CTA per utterance, the PHMM graph's state in
+// shared memory (SoA): per frame phmm_eval_all (:349-378), phmm_exit (:380-456: every active node
+// whose best score is inside pbeam appends a history entry -- numbered in node order by a block
+// prefix sum -- the others are cleared) and phmm_trans (:458-524).  The reference pushes the new
+// history entries to their successors one by one, each entering its target if it beats the
+// beam and the target's state-0 score so far; per target that is "the first maximum over its
+// exited predecessors", so the kernel pulls: every node scans its predecessor list (CSR, node
+// order = history order).  The history table (ef, node, predecessor entry, score) goes back to
+// the host, whose unchanged allphone_backtrace (:765-840) turns it into the phone segmentation.
+namespace {
+
+__global__ void __launch_bounds__(128)
+allphone_kernel(const int16_t *__restrict__ senscr, const int32_t *__restrict__ utt_off, HmmCtxDev c, int H,
+                const uint16_t *__restrict__ senid_g, const int32_t *__restrict__ tmatid_g,
+                const int32_t *__restrict__ pred_off, const int32_t *__restrict__ pred, int start,
+                int beam, int pbeam, int inspen, int32_t *__restrict__ hist_out, int cap, int32_t *__restrict__ n_hist)
+{
+    extern __shared__ int sm[];
+    const int u = blockIdx.x, tid = threadIdx.x, N = c.n_emit, nt = blockDim.x;
+    const long long f0 = utt_off[u];
+    const int T = utt_off[u + 1] - utt_off[u];
+    int *score = sm;                       // [N][H]
+    int *hist = score + N * H;             // [N][H]
+    int *out_score = hist + N * H;         // [H]
+    int *out_hist = out_score + H;         // [H]
+    int *bestsc = out_hist + H;            // [H]
+    int *frame = bestsc + H;               // [H]
+    int *ex_idx = frame + H;               // [H] history index of the entry this node appended this frame, or -1
+    int *sval = ex_idx + H;                // [32]
+    int *sidx = sval + 32;                 // [32]
+    int *wsum = sidx + 32;                 // [32]
+    int32_t *my_hist = hist_out + (size_t)u * cap * 4;
+    int nh = 0;                                                   // uniform across the block
+    const int chunk = (H + nt - 1) / nt, c0 = min(H, tid * chunk), c1 = min(H, c0 + chunk);
+
+    // allphone_search_start: hmm_clear everything, hmm_enter(silence, 0, 0, 0)
+    for (int i = tid; i < H; i += nt) {
+        for (int s = 0; s < N; ++s) { score[s * H + i] = PSB_WORST_SCORE; hist[s * H + i] = -1; }
+        out_score[i] = PSB_WORST_SCORE; out_hist[i] = -1; bestsc[i] = PSB_WORST_SCORE; frame[i] = -1; ex_idx[i] = -1;
+    }
+    __syncthreads();
+    if (tid == 0) { score[start] = 0; hist[start] = 0; frame[start] = 0; }
+    __syncthreads();
+
+    for (int t = 0; t < T; ++t) {
+        const int16_t *row = senscr + (f0 + t) * c.n_sen;
+        const int nf = t + 1;
+        int bs = PSB_WORST_SCORE;
+        for (int i = tid; i < H; i += nt) {                       // phmm_eval_all
+            if (frame[i] != t) continue;
+            HmmReg h;
+#pragma unroll
+            for (int s = 0; s < PSB_HMM_MAX_NSTATE; ++s) {
+                h.score[s] = s < N ? score[s * H + i] : PSB_WORST_SCORE;
+                h.hist[s] = s < N ? hist[s * H + i] : -1;
+                h.senid[s] = s < N ? senid_g[(size_t)i * N + s] : PSB_BAD_SSID;
+            }
+            h.out_score = out_score[i]; h.out_hist = out_hist[i]; h.best = bestsc[i];
+            const int b = hmm_step(h, c, tmatid_g[i], false, row);
+            if (b > bs) bs = b;
+#pragma unroll
+            for (int s = 0; s < PSB_HMM_MAX_NSTATE; ++s)
+                if (s < N) { score[s * H + i] = h.score[s]; hist[s * H + i] = h.hist[s]; }
+            out_score[i] = h.out_score; out_hist[i] = h.out_hist; bestsc[i] = h.best;
+        }
+        int dummy;
+        const int best = block_reduce_max_pair<int>(bs, 0, sidx, sval, dummy);
+        __syncthreads();
+        // phmm_exit: history entries numbered in node order (contiguous chunk per thread + block scan)
+        const int th = best + pbeam;
+        int cnt = 0;
+        for (int i = c0; i < c1; ++i) cnt += (frame[i] == t && bestsc[i] >= th) ? 1 : 0;
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((tid & 31) >= o) incl += v;
+        }
+        if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+        __syncthreads();
+        int base = nh, total = 0;
+        for (int w = 0; w < (nt >> 5); ++w) {
+            if (w < (tid >> 5)) base += wsum[w];
+            total += wsum[w];
+        }
+        int k = base + incl - cnt;
+        for (int i = c0; i < c1; ++i) {
+            if (frame[i] != t) { ex_idx[i] = -1; continue; }
+            if (bestsc[i] >= th) {
+                if (k < cap) {
+                    int32_t *r = my_hist + (size_t)k * 4;
+                    r[0] = t; r[1] = i; r[2] = out_hist[i]; r[3] = out_score[i];
+                }
+                ex_idx[i] = k++;
+                frame[i] = nf;
+            }
+            else {                                                // hmm_clear
+                for (int s = 0; s < N; ++s) { score[s * H + i] = PSB_WORST_SCORE; hist[s * H + i] = -1; }
+                out_score[i] = PSB_WORST_SCORE; out_hist[i] = -1; bestsc[i] = PSB_WORST_SCORE; frame[i] = -1;
+                ex_idx[i] = -1;
+            }
+        }
+        nh += total;
+        __syncthreads();
+        // phmm_trans, pulled per target: first maximum over the exited predecessors
+        const int floor_ = best + beam;
+        for (int i = tid; i < H; i += nt) {
+            int cand = INT_MIN, ck = -1;
+            for (int l = pred_off[i]; l < pred_off[i + 1]; ++l) {
+                const int p = pred[l];
+                if (ex_idx[p] >= 0 && out_score[p] > cand) { cand = out_score[p]; ck = ex_idx[p]; }
+            }
+            if (ck >= 0) {
+                const int newscore = cand + inspen;
+                if (newscore > floor_ && newscore > score[i]) { score[i] = newscore; hist[i] = ck; frame[i] = nf; }   // hmm_enter
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) n_hist[u] = nh;
+}
+
+}  // namespace
+
+extern "C" int psb_allphone_batch_device(psb_hmmctx_t *c, const int16_t *d_senscr, const int32_t *utt_off, int32_t n_utt,
+                                         int32_t n_nodes, const int32_t *ssid, const int32_t *tmatid,
+                                         const int32_t *succ_off, const int32_t *succ, int32_t start, int32_t beam,
+                                         int32_t pbeam, int32_t inspen, int32_t *hist, int32_t cap_per_utt, int32_t *n_hist)
+{
+    PSB_REQUIRE(c && utt_off && n_utt >= 0 && n_nodes > 0 && ssid && tmatid && succ_off && hist && n_hist && cap_per_utt > 0 &&
+                start >= 0 && start < n_nodes, "psb_allphone_batch_device: bad argument");
+    if (n_utt == 0) return PSB_OK;
+    PSB_REQUIRE(utt_off[0] == 0 && succ_off[0] == 0, "psb_allphone_batch_device: offsets must start at 0");
+    PSB_REQUIRE(d_senscr || utt_off[n_utt] == 0, "psb_allphone_batch_device: scores missing");
+    const int N = c->n_emit, H = n_nodes, n_links = succ_off[n_nodes];
+    PSB_REQUIRE(n_links == 0 || succ, "psb_allphone_batch_device: successor lists missing");
+    const size_t smem = ((size_t)(2 * N + 5) * H + 96) * sizeof(int);
+    PSB_REQUIRE(smem <= 200 * 1024, "psb_allphone_batch_device: a graph of %d PHMMs does not fit shared memory "
+                "(context-independent graphs, -allphone_ci yes, have one node per phone)", H);
+    PSB_CUDA(cudaSetDevice(c->device));
+    std::vector<uint16_t> sseq((size_t)c->n_sseq * N);
+    PSB_CUDA(cudaMemcpy(sseq.data(), c->d_sseq, sseq.size() * 2, cudaMemcpyDeviceToHost));
+    std::vector<uint16_t> senid((size_t)H * N);
+    // predecessor lists in node order (= the order the reference appends and walks history entries)
+    std::vector<int32_t> ibuf;                       // utt_off | tmatid[H] | pred_off[H+1] | pred[n_links] | n_hist[n_utt]
+    ibuf.insert(ibuf.end(), utt_off, utt_off + n_utt + 1);
+    const size_t o_tm = ibuf.size();
+    for (int i = 0; i < H; ++i) {
+        PSB_REQUIRE(ssid[i] >= 0 && ssid[i] < c->n_sseq, "allphone: ssid[%d] out of range", i);
+        PSB_REQUIRE(tmatid[i] >= 0 && tmatid[i] < c->n_tmat, "allphone: tmatid[%d] out of range", i);
+        for (int s = 0; s < N; ++s) {
+            const uint16_t v = sseq[(size_t)ssid[i] * N + s];
+            PSB_REQUIRE(v < c->n_sen, "senone id %d out of range", v);
+            senid[(size_t)i * N + s] = v;
+        }
+        ibuf.push_back(tmatid[i]);
+    }
+    std::vector<int32_t> pcount((size_t)H + 1, 0);
+    for (int i = 0; i < H; ++i) {
+        PSB_REQUIRE(succ_off[i + 1] >= succ_off[i], "psb_allphone_batch_device: succ_off not monotone at %d", i);
+        for (int l = succ_off[i]; l < succ_off[i + 1]; ++l) {
+            PSB_REQUIRE(succ[l] >= 0 && succ[l] < H, "allphone: successor %d out of range", succ[l]);
+            ++pcount[(size_t)succ[l] + 1];
+        }
+    }
+    for (int i = 0; i < H; ++i) pcount[(size_t)i + 1] += pcount[(size_t)i];
+    const size_t o_poff = ibuf.size();
+    ibuf.insert(ibuf.end(), pcount.begin(), pcount.end());
+    const size_t o_pred = ibuf.size();
+    ibuf.resize(o_pred + (size_t)n_links);
+    {
+        std::vector<int32_t> fill(pcount.begin(), pcount.end() - 1);
+        for (int i = 0; i < H; ++i)                               // ascending `from` => ascending inside every list
+            for (int l = succ_off[i]; l < succ_off[i + 1]; ++l) ibuf[o_pred + (size_t)fill[(size_t)succ[l]]++] = i;
+    }
+    const size_t o_nh = ibuf.size();
+    ibuf.resize(o_nh + (size_t)n_utt, 0);
+    int32_t *d_i = nullptr, *d_hist = nullptr;
+    uint16_t *d_senid = nullptr;
+    const size_t hist_n = (size_t)n_utt * cap_per_utt * 4;
+    cudaError_t e = cudaMalloc((void **)&d_i, ibuf.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_hist, hist_n * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_senid, senid.size() * 2);
+    cudaStream_t st = c->stream;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_i, ibuf.data(), ibuf.size() * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_senid, senid.data(), senid.size() * 2, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(allphone_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        allphone_kernel<<<(unsigned)n_utt, 128, smem, st>>>(d_senscr, d_i, dev_ctx(c), H, d_senid, d_i + o_tm, d_i + o_poff,
+                                                           d_i + o_pred, start, beam, pbeam, inspen, d_hist, cap_per_utt,
+                                                           d_i + o_nh);
+        g_psb_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hist, d_hist, hist_n * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(n_hist, d_i + o_nh, (size_t)n_utt * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_i); cudaFree(d_hist); cudaFree(d_senid);
+    if (e != cudaSuccess) {
+        psb_set_error("psb_allphone_batch_device: %s", cudaGetErrorString(e));
+        return PSB_ERR_CUDA;
+    }
+    return PSB_OK;
+}

@@ -631,3 +631,57 @@ def test_kws_batch_matches_oracle(api, n_emit):
         assert np.array_equal(n2, n) and all(np.array_equal(a, b[:3]) for a, b in zip(h2, hits))
     assert total_hits > 50
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------
+# phone decoding (allphone_search.c, no phone LM) for batches
+
+def test_allphone_goforward_matches_reference(api, en_us, en_us_dev):
+    import torch
+    from oracle import oracle
+    g, ga = golden("en_us_goforward.npz"), golden("en_us_allphone.npz")
+    b = api.Batch(en_us_dev, 4, 1024)
+    scr = b.score_host(g["feats"], np.array([0, 278], np.int32))
+    b.close()
+    ctx = api.HmmContext(en_us.tp, en_us.sseq, en_us.n_sen)
+    d_scr = torch.from_numpy(np.concatenate([scr, scr[:100]])).cuda()
+    args = (ga["ssid"], ga["tmatid"], ga["succ_off"], ga["succ"], int(ga["start"]), int(ga["beam"]), int(ga["pbeam"]),
+            int(ga["inspen"]))
+    hist, n = ctx.allphone(d_scr.data_ptr(), np.array([0, 278, 378], np.int32), *args)
+    assert n[0] == int(ga["n_history"])
+    segs = oracle.allphone_backtrace(hist[0], ga["ci"], 277, int(ga["inspen"]))
+    assert np.array_equal(segs, ga["segs"])                                     # the reference's own segmentation
+    want, wn = oracle.allphone_run(en_us.tp, en_us.sseq, *args, scr[:100])
+    assert n[1] == wn and np.array_equal(hist[1], want)
+    ctx.close()
+
+
+@pytest.mark.parametrize("n_emit", [3, 5])
+def test_allphone_batch_matches_oracle(api, n_emit):
+    import torch
+    from oracle import oracle
+    from pocketsphinx_b200.model import synth_ptm
+    pm = synth_ptm(seed=51, n_density=32, n_sen=300, n_emit_state=n_emit, skip_arcs=(n_emit == 5))
+    rng = np.random.default_rng(29)
+    H = 300                                                     # sparse random graph, some nodes without successors
+    ssid = rng.integers(0, len(pm.sseq), H).astype(np.int32)
+    tmat = rng.integers(0, pm.tp.shape[0], H).astype(np.int32)
+    deg = rng.integers(0, 12, H)
+    succ_off = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+    succ = np.concatenate([rng.choice(H, d, replace=False) for d in deg]).astype(np.int32)
+    frames = [90, 1, 40, 200]
+    scr = [rng.integers(0, 300, (t, pm.n_sen)).astype(np.int16) for t in frames]
+    utt_off = np.concatenate([[0], np.cumsum(frames)]).astype(np.int32)
+    ctx = api.HmmContext(pm.tp, pm.sseq, pm.n_sen)
+    d_scr = torch.from_numpy(np.concatenate(scr)).cuda()
+    total = 0
+    for beam, pbeam, inspen in ((-1080, -1080, 0), (-300, -120, -35)):
+        hist, n = ctx.allphone(d_scr.data_ptr(), utt_off, ssid, tmat, succ_off, succ, 7, beam, pbeam, inspen)
+        for u in range(len(frames)):
+            want, wn = oracle.allphone_run(pm.tp, pm.sseq, ssid, tmat, succ_off, succ, 7, beam, pbeam, inspen, scr[u])
+            assert n[u] == wn and np.array_equal(hist[u], want), "utterance %d beam %d" % (u, beam)
+            total += wn
+        h2, n2 = ctx.allphone(d_scr.data_ptr(), utt_off, ssid, tmat, succ_off, succ, 7, beam, pbeam, inspen, cap=5)
+        assert np.array_equal(n2, n) and all(np.array_equal(a, b[:5]) for a, b in zip(h2, hist))
+    assert total > 1000
+    ctx.close()
