@@ -1381,6 +1381,98 @@ int launch_topn(psb_batch_t *b, const int32_t *d_klist, int n_k, const GroupTabs
     return PSB_OK;
 }
 
+// Semi-continuous senone evaluation, 8-bit weights: one CTA per frame, four senones per thread,
+// two senones per 32-bit word (the 16x2 arithmetic of ptm_senone4_kernel).  get_scores_8b_feat_*
+// (s2_semi_mgau.c:206-330): per stream the first n = mgau_norm count (at least one) listed codewords
+// are log-added, streams are summed in int16 (:441), no best-score normalisation.
+__global__ void __launch_bounds__(512)
+semi_senone4_kernel(const int4 *__restrict__ topn, const uint8_t *__restrict__ mixw,
+                    const uint8_t *__restrict__ logadd_tab, int16_t *__restrict__ senscr, int n_sen, int n_feat, int nd,
+                    int mixw_stride)
+{
+    __shared__ uint4 rowoff[PSB_MAX_FEAT], nvp[PSB_MAX_FEAT], nsc[PSB_MAX_FEAT];
+    __shared__ int cnt[PSB_MAX_FEAT];
+    __shared__ uint8_t tab[PSB_LOGADD8_N];
+    const long long frame = blockIdx.x;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < PSB_LOGADD8_N; i += blockDim.x) tab[i] = logadd_tab[i];
+    if (tid < n_feat) {
+        const int4 r = topn[frame * n_feat + tid];
+        const unsigned cwb = (unsigned)r.y, eb = (unsigned)r.z;
+        unsigned ro[TOPN], nv[TOPN];
+#pragma unroll
+        for (int j = 0; j < TOPN; ++j) {
+            ro[j] = ((unsigned)tid * nd + ((cwb >> (8 * j)) & 0xff)) * (unsigned)mixw_stride;
+            nv[j] = (eb >> (8 * j)) & 0xff;
+        }
+        rowoff[tid] = make_uint4(ro[0], ro[1], ro[2], ro[3]);
+        nsc[tid] = make_uint4(nv[0], nv[1], nv[2], nv[3]);
+        nvp[tid] = make_uint4((nv[0] + SEN_BIAS) * 0x10001u, (nv[1] + SEN_BIAS) * 0x10001u,
+                              (nv[2] + SEN_BIAS) * 0x10001u, (nv[3] + SEN_BIAS) * 0x10001u);
+        cnt[tid] = r.x;
+    }
+    __syncthreads();
+    int16_t *dst = senscr + frame * n_sen;
+    const int n_quads = n_sen >> 2;
+    for (int q = tid; q < n_quads; q += blockDim.x) {
+        const int s0 = q << 2;
+        const uint8_t *mw = mixw + s0;
+        short a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        for (int f = 0; f < n_feat; ++f) {
+            const uint4 ro = rowoff[f], nv = nvp[f];
+            const int n = cnt[f];
+            const unsigned w0 = *reinterpret_cast<const unsigned *>(mw + ro.x);
+            unsigned x01 = __byte_perm(w0, 0u, 0x4140) + nv.x, x23 = __byte_perm(w0, 0u, 0x4342) + nv.x;
+#define PSB_LADD2(x, w, sel, nvj)                                                               \
+            {                                                                                   \
+                const unsigned y = __byte_perm(w, 0u, sel);                                     \
+                const unsigned mn = __viaddmin_u16x2(y, nvj, x);                                \
+                const unsigned mx = __viaddmax_u16x2(y, nvj, x);                                \
+                const unsigned d = mx - mn;                                                     \
+                const unsigned t = (unsigned)tab[d & 0xffffu] | ((unsigned)tab[d >> 16] << 16); \
+                x = mn - t;                                                                     \
+            }
+            if (n > 1) {
+                const unsigned w1 = *reinterpret_cast<const unsigned *>(mw + ro.y);
+                PSB_LADD2(x01, w1, 0x4140, nv.y) PSB_LADD2(x23, w1, 0x4342, nv.y)
+            }
+            if (n > 2) {
+                const unsigned w2 = *reinterpret_cast<const unsigned *>(mw + ro.z);
+                PSB_LADD2(x01, w2, 0x4140, nv.z) PSB_LADD2(x23, w2, 0x4342, nv.z)
+            }
+            if (n > 3) {
+                const unsigned w3 = *reinterpret_cast<const unsigned *>(mw + ro.w);
+                PSB_LADD2(x01, w3, 0x4140, nv.w) PSB_LADD2(x23, w3, 0x4342, nv.w)
+            }
+#undef PSB_LADD2
+            a0 = (short)(a0 + (int)(x01 & 0xffffu) - SEN_BIAS);          // int16 += (s2_semi_mgau.c:441)
+            a1 = (short)(a1 + (int)(x01 >> 16) - SEN_BIAS);
+            a2 = (short)(a2 + (int)(x23 & 0xffffu) - SEN_BIAS);
+            a3 = (short)(a3 + (int)(x23 >> 16) - SEN_BIAS);
+        }
+        if ((((uintptr_t)(dst + s0)) & 7) == 0)
+            *reinterpret_cast<short4 *>(dst + s0) = make_short4(a0, a1, a2, a3);
+        else { dst[s0] = a0; dst[s0 + 1] = a1; dst[s0 + 2] = a2; dst[s0 + 3] = a3; }
+    }
+    for (int s = (n_quads << 2) + tid; s < n_sen; s += blockDim.x) {       // tail senones one by one
+        int16_t acc = 0;
+        for (int f = 0; f < n_feat; ++f) {
+            const uint4 ro = rowoff[f], nv = nsc[f];
+            const unsigned rr[TOPN] = {ro.x, ro.y, ro.z, ro.w}, vv[TOPN] = {nv.x, nv.y, nv.z, nv.w};
+            const int n = cnt[f];
+            int tmp = 0;
+#pragma unroll
+            for (int k = 0; k < TOPN; ++k)
+                if (k == 0 || k < n) {
+                    const int v = mixw[rr[k] + (unsigned)s] + (int)vv[k];
+                    tmp = k == 0 ? v : logadd8(tab, tmp, v);
+                }
+            acc = (int16_t)(acc + tmp);
+        }
+        dst[s] = acc;
+    }
+}
+
 }  // namespace
 
 // Host side of one batched scoring pass.  d_feats: [total][D] on the device.
@@ -1549,7 +1641,11 @@ int psb_launch_ptm_batch(psb_batch_t *b, const float *d_feats, const int32_t *ut
         const int threads = 256;
         dim3 grid((m->n_sen + threads - 1) / threads, (unsigned)total);
         PSB_REQUIRE(total <= 65535LL * 32768, "too many frames for one launch");
-        if (m->mixw_4bit)
+        if (!m->mixw_4bit && b->topn_variant != 0 && (TOPN - 1) * m->logadd8_max < SEN_BIAS && m->mixw_stride % 4 == 0 &&
+            m->n_feat <= PSB_MAX_FEAT)
+            semi_senone4_kernel<<<(unsigned)total, 512, 0, b->stream>>>(b->d_topn, m->d_mixw, m->d_logadd8, d_senscr, m->n_sen,
+                                                                      m->n_feat, m->n_density, m->mixw_stride);
+        else if (m->mixw_4bit)
             semi_senone_kernel<true><<<dim3((unsigned)total, (m->n_sen + threads - 1) / threads), threads, smem, b->stream>>>(
                 b->d_topn, m->d_mixw, m->d_mixw_cb, m->d_logadd8, d_senscr, m->n_sen, m->n_feat, m->n_density, m->mixw_stride);
         else
