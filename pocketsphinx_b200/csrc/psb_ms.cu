@@ -93,6 +93,91 @@ ms_dist_kernel(const float *__restrict__ gT, const float *__restrict__ detT, con
     }
 }
 
+// EXPERIMENT (PSB_MS_PACKED=1; bit-identical -- the whole GPU suite passes with it -- but measured
+// slightly SLOWER on B200: 181 ms vs 174 ms, the kernel is not issue-bound).
+// Packed-FP32 variant of ms_dist_kernel: the FT = 4 frames of a thread go through FADD2 / FMUL2 two
+// at a time (features staged as float2 pairs, the mean and variance term are scalar-broadcast
+// operands); x - m == x + (-m) exactly, every product and difference is rounded separately and the
+// running sums stay scalar (ptxas would contract a packed multiply-add).  Same bits, fewer issue
+// slots: 2 LDG + 2 LDS.64 + 1 negate + 6 packed + 4 scalar per (density, dimension) instead of
+// 2 LDG + 4 LDS + 16 scalar.
+template <int NT>
+__global__ void __launch_bounds__(128)
+ms_dist2_kernel(const float *__restrict__ gT, const float *__restrict__ detT, const float *__restrict__ feats,
+               int2 *__restrict__ out, long long frame0, long long n_frames, int n_mgau, int n_feat, int nd,
+               int sumlen, const int32_t *__restrict__ featlen, const int32_t *__restrict__ featoff)
+{
+    extern __shared__ float sx[];                     // [FT / 2][sumlen][2]: frame pairs interleaved
+    const long long fbase = (long long)blockIdx.y * FT;
+    for (int i = threadIdx.x; i < FT * sumlen; i += blockDim.x) {
+        const int q = i / sumlen, j = i % sumlen;
+        const long long fr = fbase + q;
+        sx[((q >> 1) * sumlen + j) * 2 + (q & 1)] = fr < n_frames ? feats[(frame0 + fr) * sumlen + j] : 0.f;
+    }
+    __syncthreads();
+    const float2 *sx2 = reinterpret_cast<const float2 *>(sx);
+    const int cb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cb >= n_mgau) return;
+    const bool all = NT >= nd;                        // compute_dist_all (ms_gauden.c:378-419)
+    for (int f = 0; f < n_feat; ++f) {
+        const int fl = featlen[f], fo = featoff[f];
+        int id[FT][NT];
+        float ds[FT][NT];
+#pragma unroll
+        for (int q = 0; q < FT; ++q)
+#pragma unroll
+            for (int i = 0; i < NT; ++i) { id[q][i] = 0; ds[q][i] = (float)INT_MIN; }     // WORST_DIST (:447-448)
+        const float *gp = gT + ((size_t)fo * nd * 2) * n_mgau + cb;
+        for (int d = 0; d < nd; ++d) {
+            float dv[FT];
+            const float det = detT[((size_t)f * nd + d) * n_mgau + cb];
+#pragma unroll
+            for (int q = 0; q < FT; ++q) dv[q] = det;
+            for (int j = 0; j < fl; ++j) {
+                const float m = gp[((size_t)(d * fl + j) * 2) * n_mgau];
+                const float v = gp[((size_t)(d * fl + j) * 2 + 1) * n_mgau];
+                const float2 nm = make_float2(-m, -m), vv = make_float2(v, v);
+#pragma unroll
+                for (int q = 0; q < FT; q += 2) {
+                    float2 t = __fadd2_rn(sx2[(q >> 1) * sumlen + fo + j], nm);
+                    t = __fmul2_rn(t, t);
+                    t = __fmul2_rn(t, vv);
+                    dv[q] = __fsub_rn(dv[q], t.x);                                        // :467-470
+                    dv[q + 1] = __fsub_rn(dv[q + 1], t.y);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < FT; ++q) {
+                if (all) {
+#pragma unroll
+                    for (int i = 0; i < NT; ++i)
+                        if (i == d) { id[q][i] = d; ds[q][i] = dv[q]; }
+                }
+                else if (dv[q] >= ds[q][NT - 1]) {     // early exit is result-neutral (:457,:474)
+                    // insert before the first entry that is not better (strict '<' scan, :478-483)
+                    int p = 0;
+#pragma unroll
+                    for (int i = 0; i < NT; ++i) p += (dv[q] < ds[q][i]) ? 1 : 0;
+#pragma unroll
+                    for (int i = NT - 1; i > 0; --i)
+                        if (i > p) { ds[q][i] = ds[q][i - 1]; id[q][i] = id[q][i - 1]; }
+#pragma unroll
+                    for (int i = 0; i < NT; ++i)
+                        if (i == p) { ds[q][i] = dv[q]; id[q][i] = d; }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < FT; ++q) {
+            const long long fr = fbase + q;
+            if (fr >= n_frames) break;
+            int2 *o = out + ((fr * n_mgau + cb) * n_feat + f) * NT;
+#pragma unroll
+            for (int i = 0; i < NT; ++i) o[i] = make_int2(id[q][i], __float_as_int(ds[q][i]));
+        }
+    }
+}
+
 // logmath_add with the shifted table (logmath.c:402-446)
 __device__ __forceinline__ int logadd_wide(const uint32_t *__restrict__ tab, int size, int zero, int x, int y)
 {
@@ -297,9 +382,12 @@ int psb_launch_ms_batch(psb_batch_t *b, const float *d_feats, const int32_t *utt
         dim3 g1((m->n_mgau + 127) / 128, (unsigned)((n + FT - 1) / FT));
         size_t smem = (size_t)FT * m->sumlen * sizeof(float);
         int2 *dist = reinterpret_cast<int2 *>(b->d_msdist);
+        static const bool packed = getenv("PSB_MS_PACKED") != nullptr;       // experiment, off: bit-identical, 181 vs 174 ms
         static const bool reg_tile = getenv("PSB_MS_REGTILE") != nullptr;   // experiment, off: measured slower (247 vs 174 ms)
 #define LAUNCH(NT) do { if (reg_tile && m->n_density <= ND_MAX)                                                          \
             ms_dist_reg_kernel<NT><<<g1, 128, smem, b->stream>>>(m->d_msT, m->d_msdetT, d_feats, dist, f0, n,             \
+                m->n_mgau, m->n_feat, m->n_density, m->sumlen, m->d_featlen, m->d_featoff);                             \
+        else if (packed) ms_dist2_kernel<NT><<<g1, 128, smem, b->stream>>>(m->d_msT, m->d_msdetT, d_feats, dist, f0, n,   \
                 m->n_mgau, m->n_feat, m->n_density, m->sumlen, m->d_featlen, m->d_featoff);                             \
         else ms_dist_kernel<NT><<<g1, 128, smem, b->stream>>>(m->d_msT, m->d_msdetT, d_feats, dist, f0, n,                \
                 m->n_mgau, m->n_feat, m->n_density, m->sumlen, m->d_featlen, m->d_featoff); } while (0)
