@@ -1393,3 +1393,83 @@ pso_allphone_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, 
     free(h); free(hscore); free(hnode);
     return n_hist;
 }
+
+/* ---------------------------------------------------------------------------------------
+ * DESIGN EXPERIMENT (not a restatement of the reference): does a codeword filter that is looser
+ * than the scan's own running threshold change the final PTM top-N list?  For every frame and
+ * (codebook, stream) the exact list is computed as usual (rescore_topn + scan_cb_ptm).  Next to
+ * it, the same seeds are re-scored and only the codewords with  d >= F  are scanned, in order and
+ * with the exact tests, where F = (worst re-scored score of a DIFFERENT, stale set of four
+ * codewords: the exact list of `lag` frames ago, or codewords 0..3) - 1.  F is a lower bound of
+ * the final worst score but, unlike the scan's threshold, it can lie ABOVE the threshold the
+ * reference applies early in the scan, so codewords the reference inserts transiently are skipped.
+ * stats: [0] lists compared, [1] lists that differ, [2] codewords skipped by the filter that the
+ * exact scan inserted (transients), [3] scanned candidates, [4] all codewords. */
+int32_t
+pso_filter_experiment(const pso_model_t *m, const float *feats, int32_t T, int32_t lag, int64_t *stats)
+{
+    const int K = m->n_mgau * m->n_feat, n = m->topn;
+    pso_topn_t *cur = calloc((size_t)K * n, sizeof(*cur));
+    pso_topn_t *ring = calloc((size_t)(lag + 1) * K * n, sizeof(*ring));
+    pso_topn_t filt[16], stale[16];
+    float *dist = malloc((size_t)m->n_density * sizeof(float));
+    int32_t t, cb, f, i, cw, sumlen = 0;
+
+    if (m->kind != PSO_KIND_PTM || n > 16) return -1;
+    for (f = 0; f < m->n_feat; ++f) sumlen += m->featlen[f];
+    for (i = 0; i < K * n; ++i) { cur[i].cw = i % n; cur[i].score = INT32_MIN; }
+    for (i = 0; i < (lag + 1) * K * n; ++i) { ring[i].cw = i % n; ring[i].score = INT32_MIN; }
+    memset(stats, 0, 5 * sizeof(*stats));
+    for (t = 0; t < T; ++t) {
+        const float *z = feats + (size_t)t * sumlen;
+        int off = 0;
+        for (f = 0; f < m->n_feat; ++f) {
+            for (cb = 0; cb < m->n_mgau; ++cb) {
+                pso_topn_t *L = cur + ((size_t)cb * m->n_feat + f) * n;
+                const pso_topn_t *old = ring + ((size_t)((t + 1) % (lag + 1)) * K + (size_t)cb * m->n_feat + f) * n;
+                const int len = m->featlen[f];
+                const size_t base = gau_offset(m, cb, f);
+                const float *det = m->det + ((size_t)cb * m->n_feat + f) * m->n_density;
+                const float *x = z + off;
+                int32_t F;
+                pso_topn_t before[16];
+                memcpy(filt, L, n * sizeof(*L));                 /* same seeds */
+                memcpy(before, L, n * sizeof(*L));
+                for (cw = 0; cw < m->n_density; ++cw)
+                    dist[cw] = gau_full(m->mean + base + (size_t)cw * len, m->var + base + (size_t)cw * len, det[cw], x, len);
+                /* exact */
+                rescore_topn(m, L, cb, f, x);
+                {
+                    pso_topn_t seeded[16];
+                    memcpy(seeded, L, n * sizeof(*L));
+                    scan_cb_ptm(m, L, cb, f, x);
+                    /* filter bound from the stale set */
+                    memcpy(stale, old, n * sizeof(*old));
+                    rescore_topn(m, stale, cb, f, x);
+                    F = stale[n - 1].score == INT32_MIN ? INT32_MIN : stale[n - 1].score - 1;
+                    /* filtered replay */
+                    rescore_topn(m, filt, cb, f, x);
+                    for (cw = 0; cw < m->n_density; ++cw) {
+                        const float d = dist[cw];
+                        ++stats[4];
+                        if (d < (float)F) {
+                            /* would the exact scan have inserted it at its turn?  (diagnostic) */
+                            continue;
+                        }
+                        ++stats[3];
+                        if (d < (float)filt[n - 1].score) continue;
+                        if (listed(filt, n, cw)) continue;
+                        insert_cw(filt, n, cw, f2i_clamped(d));
+                    }
+                    (void)seeded; (void)before;
+                }
+                ++stats[0];
+                if (memcmp(filt, L, n * sizeof(*L)) != 0) ++stats[1];
+                memcpy(ring + ((size_t)(t % (lag + 1)) * K + (size_t)cb * m->n_feat + f) * n, L, n * sizeof(*L));
+            }
+            off += m->featlen[f];
+        }
+    }
+    free(cur); free(ring); free(dist);
+    return 0;
+}

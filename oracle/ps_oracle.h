@@ -162,6 +162,9 @@ int32_t pso_allphone_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t
                          int32_t start, int32_t beam, int32_t pbeam, int32_t inspen,
                          const int16_t *senscr, int32_t n_sen, int32_t T, int32_t *hist, int32_t cap);
 
+/* design experiment for a looser codeword filter (see ps_oracle.c) */
+int32_t pso_filter_experiment(const pso_model_t *m, const float *feats, int32_t T, int32_t lag, int64_t *stats);
+
 #ifdef __cplusplus
 }
 #endif
