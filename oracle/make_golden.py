@@ -78,6 +78,16 @@ def make_allphone():
     for k in ("start", "beam", "pbeam", "inspen", "n_history"):
         out[k] = np.int32(a[k])
     print("allphone", len(a["ci"]), "nodes", len(a["succ"]), "links", a["n_history"], "history entries", len(a["segs"]), "segments")
+    # the same search with the shipped phone LM: dense bigram / trigram score tables tabulated
+    # through the search's own LM object, and the resulting segmentation
+    b = refdrv.allphone(os.path.join(REF, "model/en-us/en-us"), pcm,
+                        allphone=os.path.join(REF, "model/en-us/en-us-phone.lm.bin"))
+    assert np.array_equal(b["ssid"], a["ssid"]) and np.array_equal(b["succ"], a["succ"])
+    out["lm_bg"], out["lm_tg"], out["lm_segs"] = b["bg"], b["tg"], b["segs"]
+    out["lm_n_history"] = np.int32(b["n_history"])
+    for k in ("beam", "pbeam"):
+        assert int(b[k]) == int(a[k])
+    print("allphone + phone LM", len(b["segs"]), "segments")
     np.savez_compressed(os.path.join(OUT, "en_us_allphone.npz"), **out)
 
 

@@ -324,3 +324,49 @@ def allphone_backtrace(hist, node_ci, last_frame, inspen):
         segs.insert(0, [int(node_ci[node]), sf, ef, asc, inspen])
         best_idx = hh
     return np.array(segs, np.int32).reshape(-1, 5)
+
+
+def allphone_lm_run(tp, sseq, ssid, tmatid, succ_off, succ, start, beam, pbeam, node_ci, bg, tg, senscr, cap=None):
+    """allphone_search.c with a phone LM (dense bigram / trigram tables); history rows
+    [n][5] = (ef, node, hist, score, tscore)."""
+    tp = np.ascontiguousarray(tp, np.uint8); sseq = np.ascontiguousarray(sseq, np.uint16)
+    a = [np.ascontiguousarray(x, np.int32) for x in (ssid, tmatid, succ_off, succ, node_ci, bg, tg)]
+    senscr = np.ascontiguousarray(senscr, np.int16)
+    T, n_sen = senscr.shape
+    n_ci = int(round(len(a[5].ravel()) ** 0.5))
+    cap = cap or max(1, T * len(a[0]))
+    hist = np.zeros((cap, 5), np.int32)
+    f = lib().pso_allphone_lm_run
+    f.restype = C.c_int32
+    f.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                  C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                  C.c_int32, C.c_void_p, C.c_int32]
+    n = f(tp.shape[1], _p(tp), _p(sseq), len(a[0]), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), int(start), int(beam),
+          int(pbeam), n_ci, _p(a[4]), _p(a[5]), _p(a[6]), _p(senscr), n_sen, T, _p(hist), cap)
+    return hist[:min(n, cap)].copy(), n
+
+
+def allphone_backtrace_lm(hist, node_ci, last_frame):
+    """allphone_backtrace for history rows that carry their own tscore (5 columns)."""
+    n = len(hist)
+    hi = n - 1
+    frm = last = last_frame
+    while hi > 0:
+        if hist[hi][0] <= last_frame:
+            frm = last = int(hist[hi][0])
+            break
+        hi -= 1
+    best, best_idx = -2**31, -1
+    while frm == last and hi > 0:
+        frm = int(hist[hi][0])
+        if hist[hi][3] > best and frm == last:
+            best, best_idx = int(hist[hi][3]), hi
+        hi -= 1
+    segs = []
+    while best_idx > 0:
+        ef, node, hh, score, tscore = [int(x) for x in hist[best_idx]]
+        sf = int(hist[hh][0]) + 1 if hh > 0 else 0
+        asc = score - (int(hist[hh][3]) if hh > 0 else 0) - tscore
+        segs.insert(0, [int(node_ci[node]), sf, ef, asc, tscore])
+        best_idx = hh
+    return np.array(segs, np.int32).reshape(-1, 5)

@@ -1473,3 +1473,80 @@ pso_filter_experiment(const pso_model_t *m, const float *feats, int32_t T, int32
     free(cur); free(ring); free(dist);
     return 0;
 }
+
+/* allphone_search.c WITH a phone LM (phmm_exit :416-441, phmm_trans :497-513): same search as
+ * pso_allphone_run, but every transition carries its own LM score.  bg [n_ci][n_ci] and
+ * tg [n_ci][n_ci][n_ci] are the LM scores >> SENSCR_SHIFT tabulated with the reference's argument
+ * positions; node_ci maps nodes to CI phones.  History rows get a fifth column, tscore, computed
+ * the way phmm_exit does -- including its reading the SAME history entry for "pred" and
+ * "pred_pred" (:417-423), so the trigram it scores is (pred, pred, p). */
+int32_t
+pso_allphone_lm_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, int32_t n_nodes,
+                    const int32_t *ssid, const int32_t *tmatid, const int32_t *succ_off, const int32_t *succ,
+                    int32_t start, int32_t beam, int32_t pbeam, int32_t n_ci, const int32_t *node_ci,
+                    const int32_t *bg, const int32_t *tg,
+                    const int16_t *senscr, int32_t n_sen, int32_t T, int32_t *hist, int32_t cap)
+{
+    pso_hmmctx_t ctx;
+    pso_hmm_t *h = calloc(n_nodes > 0 ? n_nodes : 1, sizeof(*h));
+    int32_t n_hist = 0, frame, i, l;
+    int32_t hcap = 1024;
+    int32_t *hscore = malloc(hcap * sizeof(int32_t)), *hnode = malloc(hcap * sizeof(int32_t)), *hhist = malloc(hcap * sizeof(int32_t));
+
+    memset(&ctx, 0, sizeof(ctx));
+    ctx.n_emit_state = n_emit_state; ctx.tp = tp; ctx.sseq = sseq;
+    for (i = 0; i < n_nodes; ++i) { pso_hmm_init(&ctx, &h[i], 0, ssid[i], tmatid[i]); pso_hmm_clear(&h[i]); }
+    pso_hmm_enter(&h[start], 0, 0, 0);
+    for (frame = 0; frame < T; ++frame) {
+        const int32_t nf = frame + 1, first = n_hist;
+        int32_t best = PSO_WORST_SCORE, th, k;
+        ctx.senscore = senscr + (size_t)frame * n_sen;
+        for (i = 0; i < n_nodes; ++i)
+            if (h[i].frame == frame) {
+                int32_t sc = pso_hmm_vit_eval(&ctx, &h[i]);
+                if (sc > best) best = sc;
+            }
+        th = best + pbeam;
+        for (i = 0; i < n_nodes; ++i)
+            if (h[i].frame == frame) {
+                if (h[i].bestscore >= th) {
+                    int32_t tscore = 0;
+                    const int32_t hh = h[i].out_history;
+                    if (n_hist == hcap) {
+                        hcap *= 2;
+                        hscore = realloc(hscore, hcap * sizeof(int32_t));
+                        hnode = realloc(hnode, hcap * sizeof(int32_t));
+                        hhist = realloc(hhist, hcap * sizeof(int32_t));
+                    }
+                    if (hh > 0) {
+                        const int32_t pc = node_ci[hnode[hh]];
+                        if (hhist[hh] > 0) tscore = tg[((size_t)pc * n_ci + pc) * n_ci + node_ci[i]];   /* pred_pred == pred */
+                        else tscore = bg[(size_t)pc * n_ci + node_ci[i]];
+                    }
+                    hscore[n_hist] = h[i].out_score; hnode[n_hist] = i; hhist[n_hist] = hh;
+                    if (n_hist < cap) {
+                        int32_t *r = hist + (size_t)n_hist * 5;
+                        r[0] = frame; r[1] = i; r[2] = hh; r[3] = h[i].out_score; r[4] = tscore;
+                    }
+                    ++n_hist;
+                    h[i].frame = nf;
+                }
+                else pso_hmm_clear(&h[i]);
+            }
+        for (k = first; k < n_hist; ++k) {
+            const int32_t from = hnode[k], fc = node_ci[from];
+            for (l = succ_off[from]; l < succ_off[from + 1]; ++l) {
+                pso_hmm_t *to = &h[succ[l]];
+                const int32_t tc = node_ci[succ[l]];
+                int32_t tscore, newscore;
+                if (hhist[k] > 0) tscore = tg[((size_t)node_ci[hnode[hhist[k]]] * n_ci + fc) * n_ci + tc];
+                else tscore = bg[(size_t)fc * n_ci + tc];
+                newscore = hscore[k] + tscore;
+                if (newscore > best + beam && newscore > to->score[0])
+                    pso_hmm_enter(to, newscore, k, nf);
+            }
+        }
+    }
+    free(h); free(hscore); free(hnode); free(hhist);
+    return n_hist;
+}

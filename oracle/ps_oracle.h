@@ -162,6 +162,11 @@ int32_t pso_allphone_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t
                          int32_t start, int32_t beam, int32_t pbeam, int32_t inspen,
                          const int16_t *senscr, int32_t n_sen, int32_t T, int32_t *hist, int32_t cap);
 
+int32_t pso_allphone_lm_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, int32_t n_nodes,
+                            const int32_t *ssid, const int32_t *tmatid, const int32_t *succ_off, const int32_t *succ,
+                            int32_t start, int32_t beam, int32_t pbeam, int32_t n_ci, const int32_t *node_ci,
+                            const int32_t *bg, const int32_t *tg,
+                            const int16_t *senscr, int32_t n_sen, int32_t T, int32_t *hist, int32_t cap);
 /* design experiment for a looser codeword filter (see ps_oracle.c) */
 int32_t pso_filter_experiment(const pso_model_t *m, const float *feats, int32_t T, int32_t lag, int64_t *stats);
 

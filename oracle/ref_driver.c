@@ -1007,10 +1007,29 @@ refdrv_kws(const char *hmmdir, const char *dict, const char *kv, const char *key
  * segmentation (ci, sf, ef, score, tscore).  info: [0] frames [1] n_nodes [2] n_links [3] start
  * [4] beam [5] pbeam [6] inspen [7] n_segments [8] n_history.  Returns 0 or <0. */
 #include "allphone_search.h"
+/* lm_tables (may be NULL; used when kv sets "allphone" to a phone LM): int32 [n_ci*n_ci] bigram
+ * then [n_ci*n_ci*n_ci] trigram scores >> SENSCR_SHIFT, tabulated through the search's own LM
+ * object with the argument positions of phmm_exit / phmm_trans (allphone_search.c:420-441,
+ * 497-513): bg[a][b] = ngram_bg_score(lm, wid[a], wid[b]), tg[a][b][c] = ngram_tg_score(lm,
+ * wid[a], wid[b], wid[c]).  info[9] = 1 if an LM is in use, info[10] = n_ci. */
+int
+refdrv_allphone_lm(const char *hmmdir, const char *kv, const int16 *pcm, long n_samples,
+                   int32 *node_ci, int32 *node_ssid, int32 *node_tmat, int32 *succ_off, int cap_nodes,
+                   int32 *succ, int cap_links, int32 *segs, int cap_segs, int32 *info, int32 *lm_tables);
+
 int
 refdrv_allphone(const char *hmmdir, const char *kv, const int16 *pcm, long n_samples,
                 int32 *node_ci, int32 *node_ssid, int32 *node_tmat, int32 *succ_off, int cap_nodes,
                 int32 *succ, int cap_links, int32 *segs, int cap_segs, int32 *info)
+{
+    return refdrv_allphone_lm(hmmdir, kv, pcm, n_samples, node_ci, node_ssid, node_tmat, succ_off, cap_nodes, succ,
+                              cap_links, segs, cap_segs, info, NULL);
+}
+
+int
+refdrv_allphone_lm(const char *hmmdir, const char *kv, const int16 *pcm, long n_samples,
+                   int32 *node_ci, int32 *node_ssid, int32 *node_tmat, int32 *succ_off, int cap_nodes,
+                   int32 *succ, int cap_links, int32 *segs, int cap_segs, int32 *info, int32 *lm_tables)
 {
     ps_config_t *config;
     ps_decoder_t *ps;
@@ -1040,9 +1059,12 @@ refdrv_allphone(const char *hmmdir, const char *kv, const int16 *pcm, long n_sam
     }
     ps = ps_init(config);
     if (ps == NULL) { ps_config_free(config); return -1; }
-    if (ps_add_allphone(ps, "_ap", NULL) < 0 || ps_activate_search(ps, "_ap") < 0) {
-        ps_free(ps); ps_config_free(config);
-        return -2;
+    if (ps->search == NULL || strcmp(ps_search_type(ps->search), PS_SEARCH_TYPE_ALLPHONE) != 0) {
+        /* no "allphone" LM in the configuration: unconstrained loop */
+        if (ps_add_allphone(ps, "_ap", NULL) < 0 || ps_activate_search(ps, "_ap") < 0) {
+            ps_free(ps); ps_config_free(config);
+            return -2;
+        }
     }
     ap = (allphone_search_t *)ps->search;
     mdef = ps->acmod->mdef;
@@ -1083,6 +1105,20 @@ refdrv_allphone(const char *hmmdir, const char *kv, const int16 *pcm, long n_sam
     }
     info[7] = n;
     info[8] = (int32)blkarray_list_n_valid(ap->history);
+    info[9] = ap->lm != NULL;
+    info[10] = bin_mdef_n_ciphone(mdef);
+    if (ap->lm && lm_tables) {
+        const int nc = bin_mdef_n_ciphone(mdef);
+        int a, b, c3;
+        int32 n_used;
+        for (a = 0; a < nc; ++a)
+            for (b = 0; b < nc; ++b) {
+                lm_tables[a * nc + b] = ngram_bg_score(ap->lm, ap->ci2lmwid[a], ap->ci2lmwid[b], &n_used) >> SENSCR_SHIFT;
+                for (c3 = 0; c3 < nc; ++c3)
+                    lm_tables[nc * nc + (a * nc + b) * nc + c3] =
+                        ngram_tg_score(ap->lm, ap->ci2lmwid[a], ap->ci2lmwid[b], ap->ci2lmwid[c3], &n_used) >> SENSCR_SHIFT;
+            }
+    }
     free(nodes);
     ps_free(ps);
     ps_config_free(config);

@@ -53,6 +53,7 @@ def lib():
             [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.refdrv_allphone.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.refdrv_allphone_lm.argtypes = L.refdrv_allphone.argtypes + [C.c_void_p]
         L.refdrv_align.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_long,
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                    C.c_void_p]
@@ -357,12 +358,18 @@ def allphone(hmmdir, pcm, **kv):
     soff = np.zeros(cap_n + 1, np.int32); succ = np.zeros(cap_l, np.int32)
     segs = np.zeros((cap_s, 5), np.int32)
     info = np.zeros(16, np.int32)
-    rc = lib().refdrv_allphone(hmmdir.encode(), s, _p(pcm), len(pcm), _p(ci), _p(ssid), _p(tmat), _p(soff), cap_n,
-                               _p(succ), cap_l, _p(segs), cap_s, _p(info))
+    lmt = np.zeros(64 * 64 + 64 * 64 * 64, np.int32)
+    rc = lib().refdrv_allphone_lm(hmmdir.encode(), s, _p(pcm), len(pcm), _p(ci), _p(ssid), _p(tmat), _p(soff), cap_n,
+                                  _p(succ), cap_l, _p(segs), cap_s, _p(info), _p(lmt))
     if rc < 0:
         raise RuntimeError("refdrv_allphone failed: %d" % rc)
     n, nl = int(info[1]), int(info[2])
     assert n <= cap_n and nl <= cap_l
-    return dict(n_frames=int(info[0]), ci=ci[:n].copy(), ssid=ssid[:n].copy(), tmatid=tmat[:n].copy(),
+    nc = int(info[10])
+    extra = {}
+    if info[9]:
+        assert nc <= 64
+        extra = dict(bg=lmt[:nc * nc].reshape(nc, nc).copy(), tg=lmt[nc * nc:nc * nc + nc ** 3].reshape(nc, nc, nc).copy())
+    return dict(**extra, n_frames=int(info[0]), ci=ci[:n].copy(), ssid=ssid[:n].copy(), tmatid=tmat[:n].copy(),
                 succ_off=soff[:n + 1].copy(), succ=succ[:nl].copy(), start=int(info[3]), beam=int(info[4]),
                 pbeam=int(info[5]), inspen=int(info[6]), segs=segs[:int(info[7])].copy(), n_history=int(info[8]))
