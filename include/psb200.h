@@ -305,6 +305,18 @@ int psb_allphone_batch_device(psb_hmmctx_t *c, const int16_t *d_senscr, const in
                               const int32_t *succ_off, const int32_t *succ, int32_t start, int32_t beam,
                               int32_t pbeam, int32_t inspen, int32_t *hist, int32_t cap_per_utt,
                               int32_t *n_hist);
+/* The same with a phone LM (-allphone <lm>): node_ci[n_nodes] maps nodes to CI phones, bg
+ * [n_ci][n_ci] and tg [n_ci][n_ci][n_ci] are the LM scores >> SENSCR_SHIFT tabulated by the host
+ * through its own LM object with the argument positions of phmm_exit / phmm_trans
+ * (allphone_search.c:420-441, 497-513): bg[a][b] = ngram_bg_score(lm, wid[a], wid[b]),
+ * tg[a][b][c] = ngram_tg_score(lm, wid[a], wid[b], wid[c]).  History rows have five columns:
+ * {ef, node, predecessor entry, score, tscore}; cap_per_utt must hold every entry (n_hist[u] <=
+ * cap_per_utt), because later frames look their predecessors up in the table. */
+int psb_allphone_lm_batch_device(psb_hmmctx_t *c, const int16_t *d_senscr, const int32_t *utt_off,
+                                 int32_t n_utt, int32_t n_nodes, const int32_t *ssid, const int32_t *tmatid,
+                                 const int32_t *succ_off, const int32_t *succ, int32_t start, int32_t beam,
+                                 int32_t pbeam, int32_t n_ci, const int32_t *node_ci, const int32_t *bg,
+                                 const int32_t *tg, int32_t *hist, int32_t cap_per_utt, int32_t *n_hist);
 
 /* ------------------------------------------------------------------------------------ */
 /* Batched front end: int16 PCM -> cepstra -> batch CMN -> 1s_c_d_dd features

@@ -73,6 +73,7 @@ SYMBOLS = [
     ("psb_hmmset_eval_frames_device", C.c_int, [_VP, _VP, _VP, _VP, _I32, _VP, C.POINTER(C.c_float)]),
     ("psb_hmmset_eval_host", C.c_int, [_VP, _VP, _VP]),
     ("psb_allphone_batch_device", C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP, _I32, _VP]),
+    ("psb_allphone_lm_batch_device", C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _I32, _VP]),
     ("psb_kws_batch_device", C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP, _VP, _I32, _VP, _VP, _VP, _VP, _I32, _I32, _VP, _I32, _VP]),
     ("psb_align_batch_device", C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     ("psb_align_last_kernel_ms", C.c_float, [_VP]),

@@ -283,6 +283,23 @@ class HmmContext:
                                               _p(hist), cap, _p(n_hist)), "psb_allphone_batch_device")
         return [hist[u, :min(int(n_hist[u]), cap)].copy() for u in range(n_utt)], n_hist[:n_utt].copy()
 
+    def allphone_lm(self, d_senscr_ptr, utt_off, ssid, tmatid, succ_off, succ, start, beam, pbeam, node_ci, bg, tg):
+        """allphone_search with a phone LM (dense bigram / trigram tables).  History rows
+        [n][5] = (ef, node, predecessor entry, score, tscore)."""
+        utt_off = np.ascontiguousarray(utt_off, np.int32)
+        a = [np.ascontiguousarray(x, np.int32) for x in (ssid, tmatid, succ_off, succ, node_ci, bg, tg)]
+        n_utt = len(utt_off) - 1
+        n_ci = a[5].shape[0]
+        assert a[5].shape == (n_ci, n_ci) and a[6].shape == (n_ci, n_ci, n_ci)
+        cap = max(1, int(np.diff(utt_off).max(initial=1)) * len(a[0]))
+        hist = np.zeros((max(1, n_utt), cap, 5), np.int32)
+        n_hist = np.zeros(max(1, n_utt), np.int32)
+        check(lib().psb_allphone_lm_batch_device(self.h, C.c_void_p(d_senscr_ptr), _p(utt_off), n_utt, len(a[0]), _p(a[0]),
+                                                 _p(a[1]), _p(a[2]), _p(a[3]), int(start), int(beam), int(pbeam), n_ci,
+                                                 _p(a[4]), _p(a[5]), _p(a[6]), _p(hist), cap, _p(n_hist)),
+              "psb_allphone_lm_batch_device")
+        return [hist[u, :min(int(n_hist[u]), cap)].copy() for u in range(n_utt)], n_hist[:n_utt].copy()
+
     def kws(self, d_senscr_ptr, utt_off, pl_ssid, pl_tmat, kp_off, kp_thresh, kp_ssid, kp_tmat, beam, plp, cap=None):
         """kws_search over a batch (scores on the device).  Returns a list of raw hit arrays
         [n][5] = (frame, keyphrase, start frame, prob, ascr), one per utterance."""

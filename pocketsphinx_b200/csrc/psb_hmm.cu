@@ -1436,12 +1436,18 @@ extern "C" int psb_kws_batch_device(psb_hmmctx_t *c, const int16_t *d_senscr, co
 // the host, whose unchanged allphone_backtrace (:765-840) turns it into the phone segmentation.
 namespace {
 
+// LM = true: every transition carries its own phone-LM score from dense tables (bg [n_ci][n_ci],
+// tg [n_ci][n_ci][n_ci], scores >> SENSCR_SHIFT tabulated by the host with the argument positions of
+// phmm_exit / phmm_trans, allphone_search.c:416-441, 497-513); history rows get a fifth column.
+template <bool LM>
 __global__ void __launch_bounds__(128)
 allphone_kernel(const int16_t *__restrict__ senscr, const int32_t *__restrict__ utt_off, HmmCtxDev c, int H,
                 const uint16_t *__restrict__ senid_g, const int32_t *__restrict__ tmatid_g,
                 const int32_t *__restrict__ pred_off, const int32_t *__restrict__ pred, int start,
-                int beam, int pbeam, int inspen, int32_t *__restrict__ hist_out, int cap, int32_t *__restrict__ n_hist)
+                int beam, int pbeam, int inspen, int32_t *__restrict__ hist_out, int cap, int32_t *__restrict__ n_hist,
+                int n_ci, const int32_t *__restrict__ node_ci, const int32_t *__restrict__ bg, const int32_t *__restrict__ tg)
 {
+    constexpr int ROW = LM ? 5 : 4;
     extern __shared__ int sm[];
     const int u = blockIdx.x, tid = threadIdx.x, N = c.n_emit, nt = blockDim.x;
     const long long f0 = utt_off[u];
@@ -1456,7 +1462,8 @@ allphone_kernel(const int16_t *__restrict__ senscr, const int32_t *__restrict__ 
     int *sval = ex_idx + H;                // [32]
     int *sidx = sval + 32;                 // [32]
     int *wsum = sidx + 32;                 // [32]
-    int32_t *my_hist = hist_out + (size_t)u * cap * 4;
+    int *pci = wsum + 32;                  // [H] (LM) CI phone of the predecessor entry of this node's new entry, or -1
+    int32_t *my_hist = hist_out + (size_t)u * cap * ROW;
     int nh = 0;                                                   // uniform across the block
     const int chunk = (H + nt - 1) / nt, c0 = min(H, tid * chunk), c1 = min(H, c0 + chunk);
 
@@ -1514,8 +1521,20 @@ allphone_kernel(const int16_t *__restrict__ senscr, const int32_t *__restrict__ 
         for (int i = c0; i < c1; ++i) {
             if (frame[i] != t) { ex_idx[i] = -1; continue; }
             if (bestsc[i] >= th) {
+                if (LM) {
+                    // phmm_exit's tscore (:416-441); it reads the SAME entry as pred and pred_pred
+                    const int hh = out_hist[i];
+                    int tscore = 0, pc = -1;
+                    if (hh > 0 && hh < cap) {
+                        pc = node_ci[my_hist[(size_t)hh * ROW + 1]];
+                        tscore = my_hist[(size_t)hh * ROW + 2] > 0 ? tg[((size_t)pc * n_ci + pc) * n_ci + node_ci[i]]
+                                                                  : bg[(size_t)pc * n_ci + node_ci[i]];
+                    }
+                    pci[i] = pc;
+                    if (k < cap) my_hist[(size_t)k * ROW + 4] = tscore;
+                }
                 if (k < cap) {
-                    int32_t *r = my_hist + (size_t)k * 4;
+                    int32_t *r = my_hist + (size_t)k * ROW;
                     r[0] = t; r[1] = i; r[2] = out_hist[i]; r[3] = out_score[i];
                 }
                 ex_idx[i] = k++;
@@ -1535,12 +1554,17 @@ allphone_kernel(const int16_t *__restrict__ senscr, const int32_t *__restrict__ 
             int cand = INT_MIN, ck = -1;
             for (int l = pred_off[i]; l < pred_off[i + 1]; ++l) {
                 const int p = pred[l];
-                if (ex_idx[p] >= 0 && out_score[p] > cand) { cand = out_score[p]; ck = ex_idx[p]; }
+                if (ex_idx[p] < 0) continue;
+                int ns;
+                if (LM) {
+                    const int fc = node_ci[p], tc = node_ci[i];
+                    ns = out_score[p] + (pci[p] >= 0 ? tg[((size_t)pci[p] * n_ci + fc) * n_ci + tc] : bg[(size_t)fc * n_ci + tc]);
+                }
+                else
+                    ns = out_score[p] + inspen;
+                if (ns > cand) { cand = ns; ck = ex_idx[p]; }
             }
-            if (ck >= 0) {
-                const int newscore = cand + inspen;
-                if (newscore > floor_ && newscore > score[i]) { score[i] = newscore; hist[i] = ck; frame[i] = nf; }   // hmm_enter
-            }
+            if (ck >= 0 && cand > floor_ && cand > score[i]) { score[i] = cand; hist[i] = ck; frame[i] = nf; }   // hmm_enter
         }
         __syncthreads();
     }
@@ -1549,11 +1573,14 @@ allphone_kernel(const int16_t *__restrict__ senscr, const int32_t *__restrict__ 
 
 }  // namespace
 
-extern "C" int psb_allphone_batch_device(psb_hmmctx_t *c, const int16_t *d_senscr, const int32_t *utt_off, int32_t n_utt,
-                                         int32_t n_nodes, const int32_t *ssid, const int32_t *tmatid,
-                                         const int32_t *succ_off, const int32_t *succ, int32_t start, int32_t beam,
-                                         int32_t pbeam, int32_t inspen, int32_t *hist, int32_t cap_per_utt, int32_t *n_hist)
+static int allphone_common(psb_hmmctx_t *c, const int16_t *d_senscr, const int32_t *utt_off, int32_t n_utt,
+                           int32_t n_nodes, const int32_t *ssid, const int32_t *tmatid,
+                           const int32_t *succ_off, const int32_t *succ, int32_t start, int32_t beam,
+                           int32_t pbeam, int32_t inspen, int32_t *hist, int32_t cap_per_utt, int32_t *n_hist,
+                           int32_t n_ci, const int32_t *node_ci, const int32_t *bg, const int32_t *tg)
 {
+    const bool lm = bg != nullptr;
+    const int ROW = lm ? 5 : 4;
     PSB_REQUIRE(c && utt_off && n_utt >= 0 && n_nodes > 0 && ssid && tmatid && succ_off && hist && n_hist && cap_per_utt > 0 &&
                 start >= 0 && start < n_nodes, "psb_allphone_batch_device: bad argument");
     if (n_utt == 0) return PSB_OK;
@@ -1561,7 +1588,7 @@ extern "C" int psb_allphone_batch_device(psb_hmmctx_t *c, const int16_t *d_sensc
     PSB_REQUIRE(d_senscr || utt_off[n_utt] == 0, "psb_allphone_batch_device: scores missing");
     const int N = c->n_emit, H = n_nodes, n_links = succ_off[n_nodes];
     PSB_REQUIRE(n_links == 0 || succ, "psb_allphone_batch_device: successor lists missing");
-    const size_t smem = ((size_t)(2 * N + 5) * H + 96) * sizeof(int);
+    const size_t smem = ((size_t)(2 * N + 6) * H + 96) * sizeof(int);
     PSB_REQUIRE(smem <= 200 * 1024, "psb_allphone_batch_device: a graph of %d PHMMs does not fit shared memory "
                 "(context-independent graphs, -allphone_ci yes, have one node per phone)", H);
     PSB_CUDA(cudaSetDevice(c->device));
@@ -1602,20 +1629,39 @@ extern "C" int psb_allphone_batch_device(psb_hmmctx_t *c, const int16_t *d_sensc
     }
     const size_t o_nh = ibuf.size();
     ibuf.resize(o_nh + (size_t)n_utt, 0);
+    size_t o_ci = 0, o_bg = 0, o_tg = 0;
+    if (lm) {
+        PSB_REQUIRE(n_ci > 0 && node_ci && tg, "psb_allphone_lm_batch_device: LM tables missing");
+        o_ci = ibuf.size();
+        for (int i = 0; i < H; ++i) {
+            PSB_REQUIRE(node_ci[i] >= 0 && node_ci[i] < n_ci, "allphone: node_ci[%d] out of range", i);
+            ibuf.push_back(node_ci[i]);
+        }
+        o_bg = ibuf.size();
+        ibuf.insert(ibuf.end(), bg, bg + (size_t)n_ci * n_ci);
+        o_tg = ibuf.size();
+        ibuf.insert(ibuf.end(), tg, tg + (size_t)n_ci * n_ci * n_ci);
+    }
     int32_t *d_i = nullptr, *d_hist = nullptr;
     uint16_t *d_senid = nullptr;
-    const size_t hist_n = (size_t)n_utt * cap_per_utt * 4;
+    const size_t hist_n = (size_t)n_utt * cap_per_utt * ROW;
     cudaError_t e = cudaMalloc((void **)&d_i, ibuf.size() * 4);
     if (e == cudaSuccess) e = cudaMalloc((void **)&d_hist, hist_n * 4);
     if (e == cudaSuccess) e = cudaMalloc((void **)&d_senid, senid.size() * 2);
     cudaStream_t st = c->stream;
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_i, ibuf.data(), ibuf.size() * 4, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_senid, senid.data(), senid.size() * 2, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(allphone_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(allphone_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(allphone_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
-        allphone_kernel<<<(unsigned)n_utt, 128, smem, st>>>(d_senscr, d_i, dev_ctx(c), H, d_senid, d_i + o_tm, d_i + o_poff,
-                                                           d_i + o_pred, start, beam, pbeam, inspen, d_hist, cap_per_utt,
-                                                           d_i + o_nh);
+        if (lm)
+            allphone_kernel<true><<<(unsigned)n_utt, 128, smem, st>>>(d_senscr, d_i, dev_ctx(c), H, d_senid, d_i + o_tm, d_i + o_poff,
+                                                                     d_i + o_pred, start, beam, pbeam, inspen, d_hist, cap_per_utt,
+                                                                     d_i + o_nh, n_ci, d_i + o_ci, d_i + o_bg, d_i + o_tg);
+        else
+            allphone_kernel<false><<<(unsigned)n_utt, 128, smem, st>>>(d_senscr, d_i, dev_ctx(c), H, d_senid, d_i + o_tm, d_i + o_poff,
+                                                                      d_i + o_pred, start, beam, pbeam, inspen, d_hist, cap_per_utt,
+                                                                      d_i + o_nh, 0, nullptr, nullptr, nullptr);
         g_psb_launches.fetch_add(1, std::memory_order_relaxed);
         e = cudaGetLastError();
     }
@@ -1628,4 +1674,24 @@ extern "C" int psb_allphone_batch_device(psb_hmmctx_t *c, const int16_t *d_sensc
         return PSB_ERR_CUDA;
     }
     return PSB_OK;
+}
+
+extern "C" int psb_allphone_batch_device(psb_hmmctx_t *c, const int16_t *d_senscr, const int32_t *utt_off, int32_t n_utt,
+                                         int32_t n_nodes, const int32_t *ssid, const int32_t *tmatid,
+                                         const int32_t *succ_off, const int32_t *succ, int32_t start, int32_t beam,
+                                         int32_t pbeam, int32_t inspen, int32_t *hist, int32_t cap_per_utt, int32_t *n_hist)
+{
+    return allphone_common(c, d_senscr, utt_off, n_utt, n_nodes, ssid, tmatid, succ_off, succ, start, beam, pbeam, inspen, hist,
+                           cap_per_utt, n_hist, 0, nullptr, nullptr, nullptr);
+}
+
+extern "C" int psb_allphone_lm_batch_device(psb_hmmctx_t *c, const int16_t *d_senscr, const int32_t *utt_off, int32_t n_utt,
+                                            int32_t n_nodes, const int32_t *ssid, const int32_t *tmatid,
+                                            const int32_t *succ_off, const int32_t *succ, int32_t start, int32_t beam,
+                                            int32_t pbeam, int32_t n_ci, const int32_t *node_ci, const int32_t *bg,
+                                            const int32_t *tg, int32_t *hist, int32_t cap_per_utt, int32_t *n_hist)
+{
+    PSB_REQUIRE(bg && tg && node_ci && n_ci > 0, "psb_allphone_lm_batch_device: LM tables missing");
+    return allphone_common(c, d_senscr, utt_off, n_utt, n_nodes, ssid, tmatid, succ_off, succ, start, beam, pbeam, 0, hist,
+                           cap_per_utt, n_hist, n_ci, node_ci, bg, tg);
 }

@@ -685,3 +685,23 @@ def test_allphone_batch_matches_oracle(api, n_emit):
         assert np.array_equal(n2, n) and all(np.array_equal(a, b[:5]) for a, b in zip(h2, hist))
     assert total > 1000
     ctx.close()
+
+
+def test_allphone_lm_goforward_matches_reference(api, en_us, en_us_dev):
+    """With the shipped phone LM (dense score tables out of the reference's LM object)."""
+    import torch
+    from oracle import oracle
+    g, ga = golden("en_us_goforward.npz"), golden("en_us_allphone.npz")
+    b = api.Batch(en_us_dev, 4, 1024)
+    scr = b.score_host(g["feats"], np.array([0, 278], np.int32))
+    b.close()
+    ctx = api.HmmContext(en_us.tp, en_us.sseq, en_us.n_sen)
+    d_scr = torch.from_numpy(np.concatenate([scr, scr[40:160]])).cuda()
+    args = (ga["ssid"], ga["tmatid"], ga["succ_off"], ga["succ"], int(ga["start"]), int(ga["beam"]), int(ga["pbeam"]),
+            ga["ci"], ga["lm_bg"], ga["lm_tg"])
+    hist, n = ctx.allphone_lm(d_scr.data_ptr(), np.array([0, 278, 398], np.int32), *args)
+    assert n[0] == int(ga["lm_n_history"])
+    assert np.array_equal(oracle.allphone_backtrace_lm(hist[0], ga["ci"], 277), ga["lm_segs"])   # the reference's segmentation
+    want, wn = oracle.allphone_lm_run(en_us.tp, en_us.sseq, *args, scr[40:160])
+    assert n[1] == wn and np.array_equal(hist[1], want)
+    ctx.close()
