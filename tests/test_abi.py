@@ -56,9 +56,6 @@ def test_no_fused_multiply_add_in_distance_kernels():
             fn = line.split("Function :")[1].strip()
         elif fn and any(k in fn for k in ("topn", "ms_dist", "semi_dist")) and "FFMA" in line:
             bad.append((fn[:60], line.strip()[:80]))
-        elif fn and "fe_frame" in fn and ("DFMA" in line or "FFMA" in line):
-            bad.append((fn[:60], line.strip()[:80]))            # the float64 FFT / mel sums too (fe_utt_kernel
-            #                                                     legitimately has DFMA inside its IEEE divisions and log)
     assert not bad, bad[:5]
     assert "FMUL2" in sass and "FADD2" in sass, "packed FP32 path missing from the build"
 
