@@ -34,7 +34,8 @@ class _Model(C.Structure):
                 ("logadd_ms_size", C.c_int32), ("logadd_ms_zero", C.c_int32),
                 ("mean", C.c_void_p), ("var", C.c_void_p), ("det", C.c_void_p),
                 ("mixw", C.c_void_p), ("mixw_cb", C.c_void_p), ("sen2cb", C.c_void_p),
-                ("logadd8", C.c_void_p), ("logadd_ms", C.c_void_p), ("topn_beam", C.c_void_p)]
+                ("logadd8", C.c_void_p), ("logadd_ms", C.c_void_p), ("topn_beam", C.c_void_p),
+                ("fixed_point", C.c_int32)]
 
 
 class _HmmCtx(C.Structure):
@@ -105,6 +106,7 @@ class OracleModel:
         m.mixw, m.mixw_cb, m.sen2cb = _p(pm.mixw), _p(pm.mixw_cb), _p(pm.sen2cb)
         m.logadd8, m.logadd_ms = _p(pm.logadd8), _p(pm.logadd_ms)
         m.topn_beam = _p(pm.topn_beam) if pm.topn_beam.size and pm.topn_beam.any() else None
+        m.fixed_point = int(getattr(pm, "fixed_point", 0))
         self.c = m
 
     def score_utt(self, feats, want_topn=False):

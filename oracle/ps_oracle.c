@@ -67,6 +67,24 @@ gau_full(const float *mean, const float *var, float det, const float *x, int len
     return d;
 }
 
+/* ---- fixed point (-DFIXED_POINT build) --------------------------------- */
+/* MFCCMUL = FIXMUL (fe/fixpoint.h:98-100): the 64-bit product shifted right by the radix (12),
+ * truncated to 32 bits. */
+static int32_t
+fx_mul(int32_t a, int32_t b)
+{
+    return (int32_t)(uint32_t)(((int64_t)a * (int64_t)b) >> 12);
+}
+
+/* GMMSUB (tied_mgau_common.h:62-66) is written ((a)-(b) > a) ? INT_MIN : (a)-(b) on signed ints;
+ * gcc folds the overflow test to (b < 0) at every optimisation level, which is what the
+ * reference's own build computes: (b < 0) ? INT_MIN : wrap32(a - b). */
+static int32_t
+fx_gmmsub(int32_t a, int32_t b)
+{
+    return b < 0 ? INT32_MIN : (int32_t)((uint32_t)a - (uint32_t)b);
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* state                                                                                 */
 
@@ -152,6 +170,32 @@ rescore_topn(const pso_model_t *m, pso_topn_t *topn, int cb, int f, const float 
     }
 }
 
+/* eval_topn in the fixed-point build (ptm_mgau.c:88-136): no early exit, every step through
+ * GMMSUB. */
+static void
+rescore_topn_fx(const pso_model_t *m, pso_topn_t *topn, int cb, int f, const int32_t *x)
+{
+    int len = m->featlen[f], i, j;
+    size_t base = gau_offset(m, cb, f);
+    const int32_t *det = (const int32_t *)m->det + ((size_t)cb * m->n_feat + f) * m->n_density;
+    const int32_t *mean0 = (const int32_t *)m->mean + base, *var0 = (const int32_t *)m->var + base;
+
+    for (i = 0; i < m->topn; ++i) {
+        int32_t cw = topn[i].cw, d = det[cw];
+        const int32_t *mean = mean0 + (size_t)cw * len, *var = var0 + (size_t)cw * len;
+        pso_topn_t v;
+        for (j = 0; j < len; ++j) {
+            int32_t diff = (int32_t)((uint32_t)x[j] - (uint32_t)mean[j]);
+            d = fx_gmmsub(d, fx_mul(fx_mul(diff, diff), var[j]));
+        }
+        v.cw = cw;
+        v.score = d;                     /* already an int; the INT_MIN clamp (:129-132) is a no-op */
+        for (j = i - 1; j >= 0 && v.score > topn[j].score; --j)
+            topn[j + 1] = topn[j];
+        topn[j + 1] = v;
+    }
+}
+
 /* insertion_sort_cb (ptm_mgau.c:140-149) / the tail of eval_cb (s2_semi_mgau.c:156-161):
  * drop the worst entry, shift down every entry whose score is <= intd. */
 static void
@@ -213,6 +257,45 @@ scan_cb_ptm(const pso_model_t *m, pso_topn_t *topn, int cb, int f, const float *
         if (d < thresh) continue;
         if (listed(topn, n, cw)) continue;
         insert_cw(topn, n, cw, f2i_clamped(d));
+    }
+}
+
+/* eval_cb in the fixed-point build: the same loop structure with int arithmetic.  The early exits
+ * are NOT result-neutral here (a wrapped subtraction can climb back above the threshold), so the
+ * loop is restated literally: tests before the leading ceplen%4 dimensions one at a time, then
+ * before every group of four. */
+static void
+scan_cb_ptm_fx(const pso_model_t *m, pso_topn_t *topn, int cb, int f, const int32_t *x)
+{
+    int len = m->featlen[f], n = m->topn, cw;
+    size_t base = gau_offset(m, cb, f);
+    const int32_t *det = (const int32_t *)m->det + ((size_t)cb * m->n_feat + f) * m->n_density;
+    const int32_t *mean0 = (const int32_t *)m->mean + base, *var0 = (const int32_t *)m->var + base;
+
+    for (cw = 0; cw < m->n_density; ++cw) {
+        const int32_t *mean = mean0 + (size_t)cw * len, *var = var0 + (size_t)cw * len;
+        int32_t d = det[cw], thresh = topn[n - 1].score;
+        int j = 0, k;
+
+        while (j < len % 4 && d >= thresh) {
+            int32_t diff = (int32_t)((uint32_t)x[j] - (uint32_t)mean[j]);
+            d = fx_gmmsub(d, fx_mul(fx_mul(diff, diff), var[j]));
+            ++j;
+        }
+        while (j < len && d >= thresh) {
+            int32_t c[4];
+            for (k = 0; k < 4; ++k) {
+                int32_t diff = (int32_t)((uint32_t)x[j + k] - (uint32_t)mean[j + k]);
+                c[k] = fx_mul(fx_mul(diff, diff), var[j + k]);
+            }
+            for (k = 0; k < 4; ++k)
+                d = fx_gmmsub(d, c[k]);
+            j += 4;
+        }
+        if (j < len) continue;
+        if (d < thresh) continue;
+        if (listed(topn, n, cw)) continue;
+        insert_cw(topn, n, cw, d);
     }
 }
 
@@ -353,12 +436,18 @@ ptm_frame_eval(pso_gmm_t *g, int16_t *senscr, const uint8_t *list, int32_t n_lis
         /* ptm_mgau_codebook_eval (:232-254) */
         for (cb = 0; cb < m->n_mgau; ++cb)
             for (f = 0, off = 0; f < m->n_feat; off += m->featlen[f], ++f)
-                rescore_topn(m, slot + ((size_t)cb * m->n_feat + f) * m->topn, cb, f, feat + off);
+                if (m->fixed_point)
+                    rescore_topn_fx(m, slot + ((size_t)cb * m->n_feat + f) * m->topn, cb, f, (const int32_t *)feat + off);
+                else
+                    rescore_topn(m, slot + ((size_t)cb * m->n_feat + f) * m->topn, cb, f, feat + off);
         if (frame % m->ds_ratio == 0)
             for (cb = 0; cb < m->n_mgau; ++cb) {
                 if (!active[cb]) continue;
                 for (f = 0, off = 0; f < m->n_feat; off += m->featlen[f], ++f)
-                    scan_cb_ptm(m, slot + ((size_t)cb * m->n_feat + f) * m->topn, cb, f, feat + off);
+                    if (m->fixed_point)
+                        scan_cb_ptm_fx(m, slot + ((size_t)cb * m->n_feat + f) * m->topn, cb, f, (const int32_t *)feat + off);
+                    else
+                        scan_cb_ptm(m, slot + ((size_t)cb * m->n_feat + f) * m->topn, cb, f, feat + off);
             }
         ptm_norm(m, slot, active);
     }

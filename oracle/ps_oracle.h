@@ -49,6 +49,9 @@ typedef struct pso_model_s {
     const uint8_t *logadd8;        /* 256-entry table of logmath_init(base, 10, 1) */
     const uint32_t *logadd_ms;     /* ms: wide table widened to uint32 */
     const uint8_t *topn_beam;      /* semi: [n_feat] or NULL */
+    int32_t fixed_point;           /* 1: the -DFIXED_POINT build's arithmetic (PTM only): mean / var /
+                                    * det / features are int32 (Q12 means and features), bit-cast into the
+                                    * float pointers; see the "fixed point" block of ps_oracle.c */
 } pso_model_t;
 
 typedef struct pso_topn_s { int32_t cw, score; } pso_topn_t;

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_ref", "libpsref.so")
+LIB_PATH = os.environ.get("PSREF_LIB") or os.path.join(HERE, "_ref", "libpsref.so")   # PSREF_LIB: e.g. _ref/libpsref_fx.so
 
 KIND_NAMES = {0: "ptm", 1: "s2_semi", 2: "ms"}
 
