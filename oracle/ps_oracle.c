@@ -329,6 +329,31 @@ scan_cb_semi(const pso_model_t *m, pso_topn_t *topn, int f, const float *x)
     }
 }
 
+/* eval_cb, semi-continuous flavour in the fixed-point build (s2_semi_mgau.c:112-170): the test
+ * before every dimension and the final test compare ints. */
+static void
+scan_cb_semi_fx(const pso_model_t *m, pso_topn_t *topn, int f, const int32_t *x)
+{
+    int len = m->featlen[f], n = m->topn, cw;
+    size_t base = gau_offset(m, 0, f);
+    const int32_t *det = (const int32_t *)m->det + (size_t)f * m->n_density;
+    const int32_t *mean0 = (const int32_t *)m->mean + base, *var0 = (const int32_t *)m->var + base;
+
+    for (cw = 0; cw < m->n_density; ++cw) {
+        const int32_t *mean = mean0 + (size_t)cw * len, *var = var0 + (size_t)cw * len;
+        int32_t d = det[cw];
+        int j;
+        for (j = 0; j < len && d >= topn[n - 1].score; ++j) {
+            int32_t diff = (int32_t)((uint32_t)x[j] - (uint32_t)mean[j]);
+            d = fx_gmmsub(d, fx_mul(fx_mul(diff, diff), var[j]));
+        }
+        if (j < len) continue;
+        if (d < topn[n - 1].score) continue;
+        if (listed(topn, n, cw)) continue;
+        insert_cw(topn, n, cw, d);
+    }
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* PTM                                                                                   */
 
@@ -527,9 +552,16 @@ semi_frame_eval(pso_gmm_t *g, int16_t *senscr, const uint8_t *list, int32_t n_li
             if (prev != idx)
                 memcpy(t, g->hist + per * prev + (size_t)f * m->topn, m->topn * sizeof(*t));
             /* mgau_dist (:172-183) */
-            rescore_topn(m, t, 0, f, feat + off);
-            if (frame % m->ds_ratio == 0)
-                scan_cb_semi(m, t, f, feat + off);
+            if (m->fixed_point) {
+                rescore_topn_fx(m, t, 0, f, (const int32_t *)feat + off);
+                if (frame % m->ds_ratio == 0)
+                    scan_cb_semi_fx(m, t, f, (const int32_t *)feat + off);
+            }
+            else {
+                rescore_topn(m, t, 0, f, feat + off);
+                if (frame % m->ds_ratio == 0)
+                    scan_cb_semi(m, t, f, feat + off);
+            }
             g->hist_n[(size_t)idx * m->n_feat + f] = (uint8_t)semi_norm(m, t, f);
         }
         semi_senones(m, t, f, g->hist_n[(size_t)idx * m->n_feat + f], senscr, list, n_list, compall);

@@ -31,6 +31,23 @@ np.savez(%r, feats=feats.view(np.int32), senscr=scr, topn=topn,
 """
 
 
+def test_fixed_point_semi_oracle_matches_fixed_point_reference(tmp_path):
+    """The semi-continuous back-end (tidigits, 4-bit clustered weights) in the fixed-point build."""
+    from oracle import oracle
+    from pocketsphinx_b200.model import PackedModel
+    ref_dir = os.path.dirname(refdrv.LIB_PATH)
+    out = str(tmp_path / "fxs.npz")
+    code = DUMP % (ROOT, os.path.join(ref_dir, "model", "tidigits_hmm"), os.path.join(ref_dir, "data", "goforward.raw"), out)
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PSREF_LIB=FX), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    fx = np.load(out)
+    pm = PackedModel.load(os.path.join(HERE, "golden", "tidigits_sc_model.npz"))
+    pm.mean, pm.var, pm.det = fx["mean"].view(np.float32), fx["var"].view(np.float32), fx["det"].view(np.float32)
+    pm.fixed_point = 1
+    got, topn = oracle.OracleModel(pm).score_utt(fx["feats"].view(np.float32), want_topn=True)
+    assert np.array_equal(topn, fx["topn"]) and np.array_equal(got, fx["senscr"])
+
+
 def test_fixed_point_ptm_oracle_matches_fixed_point_reference(tmp_path):
     from oracle import oracle
     from pocketsphinx_b200.model import PackedModel
