@@ -91,8 +91,31 @@ def make_allphone():
     np.savez_compressed(os.path.join(OUT, "en_us_allphone.npz"), **out)
 
 
+def make_fsg():
+    """en_us_fsg.npz: the reference's own fsg_search on goforward.raw for two grammars -- its shipped
+    test/data/goforward.fsg and tests/golden/commands.fsg (ours: loops, null transitions out of the
+    start state and between states, a single-phone word) -- with the default beams and with -maxhmmpf
+    low enough to trigger the beam narrowing: flattened lextree, links, null arcs, parameters, the
+    complete history table, hypothesis and score."""
+    pcm = np.fromfile(os.path.join(REF, "test/data/goforward.raw"), np.int16)
+    hd, dic = os.path.join(REF, "model/en-us/en-us"), os.path.join(REF, "model/en-us/cmudict-en-us.dict")
+    out = {}
+    for tag, path, kv in (("go", os.path.join(REF, "test/data/goforward.fsg"), {}),
+                          ("go_hmmpf", os.path.join(REF, "test/data/goforward.fsg"), dict(maxhmmpf="20")),
+                          ("cmd", os.path.join(OUT, "commands.fsg"), {}),
+                          ("cmd_wide", os.path.join(OUT, "commands.fsg"), dict(beam="1e-80", pbeam="1e-80", wbeam="1e-60")),
+                          ("cmd_hmmpf", os.path.join(OUT, "commands.fsg"), dict(maxhmmpf="100", wip="0.2", pip="0.5"))):
+        r = refdrv.fsg(hd, dic, path, pcm, **kv)
+        for k, v in r.items():
+            out[tag + "." + k] = np.array("\n".join(v)) if k == "vocab" else np.array(v)
+        print("fsg", tag, len(r["pnodes"]), "pnodes", len(r["links"]), "links", len(r["hist"]), "history entries:", r["hyp"], r["score"])
+    np.savez_compressed(os.path.join(OUT, "en_us_fsg.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "fsg":
+        return make_fsg()
     if len(sys.argv) > 1 and sys.argv[1] == "allphone":
         return make_allphone()
     if len(sys.argv) > 1 and sys.argv[1] == "align":

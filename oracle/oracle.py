@@ -372,3 +372,67 @@ def allphone_backtrace_lm(hist, node_ci, last_frame):
         segs.insert(0, [int(node_ci[node]), sf, ef, asc, tscore])
         best_idx = hh
     return np.array(segs, np.int32).reshape(-1, 5)
+
+
+def fsg_run(tp, sseq, g, senscr, cap=None):
+    """fsg_search.c for one utterance on a flattened lextree `g` (what refdrv.fsg / the golden file
+    hold: pnodes, roots, links, nulloff, nullarc, beams, ...); returns the history table
+    [n][13] = (link, frame, score, pred, lc, rc.bv[8])."""
+    tp = np.ascontiguousarray(tp, np.uint8); sseq = np.ascontiguousarray(sseq, np.uint16)
+    pn, roots, links, nulloff, nullarc = (np.ascontiguousarray(g[k], np.int32)
+                                          for k in ("pnodes", "roots", "links", "nulloff", "nullarc"))
+    senscr = np.ascontiguousarray(senscr, np.int16)
+    T, n_sen = senscr.shape
+    cap = cap or max(1024, 8 * T * max(1, len(links)))
+    hist = np.zeros((cap, 13), np.int32)
+    f = lib().pso_fsg_run
+    f.restype = C.c_int32
+    f.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                  C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p, C.c_int32, C.c_int32,
+                                                                            C.c_void_p, C.c_int32]
+    n = f(tp.shape[1], _p(tp), _p(sseq), len(pn), _p(pn), len(roots), _p(roots), len(links), _p(links), _p(nulloff),
+          _p(nullarc), int(g["n_ciphone"]), int(g["silcipid"]), int(g["start_state"]), int(g["beam"]), int(g["pbeam"]),
+          int(g["wbeam"]), int(g["maxhmmpf"]), _p(senscr), n_sen, T, _p(hist), cap)
+    assert n <= cap
+    return hist[:n].copy()
+
+
+def fsg_find_exit(hist, links, frame_idx, final_state, final=True):
+    """fsg_search_find_exit (fsg_search.c:886-958): best word exit in the last frame <= frame_idx that
+    has one (preferring, and when final requiring, the grammar's final state).  Returns (index, score)."""
+    bp = len(hist) - 1
+    frm = last = frame_idx
+    while bp > 0:
+        if hist[bp][1] <= frame_idx:
+            frm = last = int(hist[bp][1])
+            break
+        bp -= 1
+    if bp <= 0:
+        return bp, None
+    best, besthist = -(1 << 31), -1
+    while frm == last:
+        l, score = int(hist[bp][0]), int(hist[bp][2])
+        if l < 0:
+            break
+        to = int(links[l][1])
+        if score == best and to == final_state:
+            besthist = bp
+        elif score > best and (not final or to == final_state):
+            best, besthist = score, bp
+        bp -= 1
+        if bp < 0:
+            break
+        frm = int(hist[bp][1])
+    return besthist, (best if besthist >= 0 else None)
+
+
+def fsg_hyp_wids(hist, links, bp):
+    """The word ids along the predecessor chain of entry bp (fsg_search_hyp, fsg_search.c:1012-1060),
+    in time order; null transitions (wid < 0) are kept out like in the reference."""
+    out = []
+    while bp > 0:
+        l = int(hist[bp][0])
+        if l >= 0 and links[l][2] >= 0:
+            out.append(int(links[l][2]))
+        bp = int(hist[bp][3])
+    return out[::-1]

@@ -1671,3 +1671,208 @@ pso_allphone_lm_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sse
     free(h); free(hscore); free(hnode); free(hhist);
     return n_hist;
 }
+
+/* ---------------------------------------------------------------------------------------
+ * Grammar decoding: fsg_search.c + fsg_history.c restated for one utterance, all senones computed.
+ * Inputs are the reference's own lextree flattened by oracle/ref_driver.c:refdrv_fsg
+ * (pnodes [n][16] = ssid, tmatid, next, sibling, logs2prob, ci_ext, ppos, leaf, ctxt.bv[8];
+ * links [n][5] = from, to, wid, logs2prob, all-right-contexts flag; null arcs per state in
+ * fsg_model_arcs order).  Output: the history table rows (link, frame, score, pred, lc, rc.bv[8])
+ * in table order; returns their number (at most cap rows are stored).
+ *   start       fsg_search.c:770-817      step          :683-761
+ *   hmm_eval    :335-407 (incl. the maxhmmpf beam narrowing)
+ *   prune_prop  :516-560  pnode_trans :410-441  pnode_exit :444-507
+ *   null_prop   :566-614  word_trans  :621-680
+ *   history     fsg_history.c:132-213 (entry_add, right-context subtraction), :220-240 (end_frame)
+ * The active lists are glists built by PREPENDING (glist_add_ptr); an array filled in order of
+ * insertion and walked backwards visits the same sequence. */
+typedef struct { int32_t link, frame, score, pred, lc; uint32_t rc[8]; } fsg_hent_t;
+typedef struct fsg_fent_s { fsg_hent_t e; struct fsg_fent_s *next; } fsg_fent_t;
+typedef struct {
+    fsg_hent_t *ent; int32_t n, cap;
+    fsg_fent_t **frame_entries;         /* [n_state * n_ci] */
+    int32_t n_state, n_ci;
+    const int32_t *links;
+} fsg_hist_t;
+
+static void
+fsg_hist_append(fsg_hist_t *h, const fsg_hent_t *e)
+{
+    if (h->n == h->cap) { h->cap = h->cap ? h->cap * 2 : 1024; h->ent = realloc(h->ent, h->cap * sizeof(*h->ent)); }
+    h->ent[h->n++] = *e;
+}
+
+static uint32_t
+fsg_ctxt_sub(uint32_t *src, const uint32_t *sub)        /* fsg_lextree.c:333-341 */
+{
+    uint32_t res = 0; int i;
+    for (i = 0; i < 8; ++i) res |= (src[i] = ~sub[i] & src[i]);
+    return res;
+}
+
+static void
+fsg_hist_add(fsg_hist_t *h, int32_t link, int32_t frame, int32_t score, int32_t pred, int32_t lc, const uint32_t *rc_in)
+{
+    fsg_hent_t ne;
+    fsg_fent_t **slot, *gn, *prev = NULL, *nn;
+    ne.link = link; ne.frame = frame; ne.score = score; ne.pred = pred; ne.lc = lc;
+    memcpy(ne.rc, rc_in, sizeof(ne.rc));
+    if (frame < 0) { fsg_hist_append(h, &ne); return; }
+    slot = &h->frame_entries[(size_t)h->links[link * 5 + 1] * h->n_ci + lc];
+    for (gn = *slot; gn; gn = gn->next) {
+        if (score > gn->e.score) break;
+        if (fsg_ctxt_sub(ne.rc, gn->e.rc) == 0) return;
+        prev = gn;
+    }
+    nn = malloc(sizeof(*nn));
+    nn->e = ne;
+    if (!prev) { nn->next = *slot; *slot = nn; }
+    else { nn->next = prev->next; prev->next = nn; }
+    prev = nn;
+    while (gn) {
+        if (fsg_ctxt_sub(gn->e.rc, ne.rc) == 0) { prev->next = gn->next; free(gn); gn = prev->next; }
+        else { prev = gn; gn = gn->next; }
+    }
+}
+
+static void
+fsg_hist_end_frame(fsg_hist_t *h)
+{
+    int32_t i;
+    for (i = 0; i < h->n_state * h->n_ci; ++i) {
+        fsg_fent_t *gn = h->frame_entries[i], *nx;
+        for (; gn; gn = nx) { nx = gn->next; fsg_hist_append(h, &gn->e); free(gn); }
+        h->frame_entries[i] = NULL;
+    }
+}
+
+int32_t
+pso_fsg_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq,
+            int32_t n_pnode, const int32_t *pn, int32_t n_state, const int32_t *roots,
+            int32_t n_link, const int32_t *links, const int32_t *nulloff, const int32_t *nullarc,
+            int32_t n_ci, int32_t silcipid, int32_t start_state,
+            int32_t beam_orig, int32_t pbeam_orig, int32_t wbeam_orig, int32_t maxhmmpf,
+            const int16_t *senscr, int32_t n_sen, int32_t T, int32_t *hist_out, int32_t cap)
+{
+    pso_hmmctx_t ctx;
+    pso_hmm_t *hmm = calloc(n_pnode > 0 ? n_pnode : 1, sizeof(*hmm));
+    int32_t *act = malloc((size_t)(n_pnode + 1) * sizeof(int32_t)), *nxt = malloc((size_t)(n_pnode + 1) * sizeof(int32_t));
+    int32_t n_act = 0, n_nxt = 0, frame, i, k, bestscore, bpidx_start, beam, pbeam, wbeam, pass;
+    float beam_factor = 1.0f;
+    fsg_hist_t H;
+    uint32_t all[8];
+    (void)n_link;
+
+    memset(&ctx, 0, sizeof(ctx));
+    ctx.n_emit_state = n_emit_state; ctx.tp = tp; ctx.sseq = sseq;
+    for (i = 0; i < n_pnode; ++i) { pso_hmm_init(&ctx, &hmm[i], 0, pn[i * 16], pn[i * 16 + 1]); pso_hmm_clear(&hmm[i]); }
+    memset(&H, 0, sizeof(H));
+    H.n_state = n_state; H.n_ci = n_ci; H.links = links;
+    H.frame_entries = calloc((size_t)n_state * n_ci, sizeof(*H.frame_entries));
+    memset(all, 0xff, sizeof(all));
+    beam = beam_orig; pbeam = pbeam_orig; wbeam = wbeam_orig;
+
+    /* fsg_search_start: dummy entry, then the null/word transitions of the step with frame = -1 */
+    frame = -1; bestscore = 0; bpidx_start = 0;
+    fsg_hist_add(&H, -1, -1, 0, -1, silcipid, all);
+    for (pass = 0;; ++pass) {
+        int32_t n_entries, bp, th;
+        if (frame >= 0) {
+            ctx.senscore = senscr + (size_t)frame * n_sen;
+            bpidx_start = H.n;
+            /* hmm_eval */
+            bestscore = PSO_WORST_SCORE;
+            for (k = n_act - 1; k >= 0; --k) {
+                int32_t sc = pso_hmm_vit_eval(&ctx, &hmm[act[k]]);
+                if (sc > bestscore) bestscore = sc;
+            }
+            if (maxhmmpf != -1 && n_act > maxhmmpf) {
+                if (beam_factor > 0.1) {
+                    beam_factor *= 0.9f;
+                    beam = (int32_t)(beam_orig * beam_factor);
+                    pbeam = (int32_t)(pbeam_orig * beam_factor);
+                    wbeam = (int32_t)(wbeam_orig * beam_factor);
+                }
+            }
+            else { beam_factor = 1.0f; beam = beam_orig; pbeam = pbeam_orig; wbeam = wbeam_orig; }
+            /* prune_prop */
+            {
+                const int32_t thresh = bestscore + beam, pth = bestscore + pbeam, wth = bestscore + wbeam, nf = frame + 1;
+                for (k = n_act - 1; k >= 0; --k) {
+                    const int32_t p = act[k];
+                    const int32_t *r = pn + (size_t)p * 16;
+                    pso_hmm_t *h = &hmm[p];
+                    if (h->bestscore < thresh) continue;
+                    if (h->frame == frame) { h->frame = nf; nxt[n_nxt++] = p; }
+                    if (!r[7]) {
+                        if (h->out_score >= pth) {                              /* pnode_trans */
+                            int32_t c;
+                            for (c = r[2]; c >= 0; c = pn[(size_t)c * 16 + 3]) {
+                                const int32_t ns = h->out_score + pn[(size_t)c * 16 + 4];
+                                if (ns > thresh && ns > hmm[c].score[0]) {
+                                    if (hmm[c].frame < nf) nxt[n_nxt++] = c;
+                                    pso_hmm_enter(&hmm[c], ns, h->out_history, nf);
+                                }
+                            }
+                        }
+                    }
+                    else if (h->out_score >= wth) {                             /* pnode_exit */
+                        const int32_t l = r[2];
+                        fsg_hist_add(&H, l, frame, h->out_score, h->out_history, r[5],
+                                     links[l * 5 + 4] ? all : (const uint32_t *)(r + 8));
+                    }
+                }
+            }
+            fsg_hist_end_frame(&H);
+        }
+        /* null_prop */
+        th = bestscore + wbeam;
+        n_entries = H.n;
+        for (bp = bpidx_start; bp < n_entries; ++bp) {
+            const int32_t s = H.ent[bp].link >= 0 ? links[H.ent[bp].link * 5 + 1] : start_state;
+            for (k = nulloff[s]; k < nulloff[s + 1]; ++k) {
+                const int32_t l = nullarc[k];
+                const int32_t ns = H.ent[bp].score + (links[l * 5 + 3] >> 10);
+                if (ns >= th) {
+                    fsg_hent_t src = H.ent[bp];          /* by value: the table may be reallocated */
+                    fsg_hist_add(&H, l, src.frame, ns, bp, src.lc, src.rc);
+                }
+            }
+        }
+        if (frame >= 0) fsg_hist_end_frame(&H);
+        /* word_trans */
+        n_entries = H.n;
+        th = bestscore + beam;
+        for (bp = bpidx_start; bp < n_entries; ++bp) {
+            const fsg_hent_t *e = &H.ent[bp];
+            const int32_t d = e->link >= 0 ? links[e->link * 5 + 1] : start_state, lc = e->lc, nf = frame + 1;
+            int32_t root;
+            for (root = roots[d]; root >= 0; root = pn[(size_t)root * 16 + 3]) {
+                const int32_t *r = pn + (size_t)root * 16;
+                const int32_t rc = r[5];
+                if ((((const uint32_t *)(r + 8))[lc >> 5] & (1u << (lc & 31))) && (e->rc[rc >> 5] & (1u << (rc & 31)))) {
+                    const int32_t ns = e->score + r[4];
+                    if (ns > th && ns > hmm[root].score[0]) {
+                        if (hmm[root].frame < nf) nxt[n_nxt++] = root;
+                        pso_hmm_enter(&hmm[root], ns, bp, nf);
+                    }
+                }
+            }
+        }
+        /* deactivate what did not survive, swap lists */
+        if (frame >= 0)
+            for (k = n_act - 1; k >= 0; --k)
+                if (hmm[act[k]].frame == frame) pso_hmm_clear(&hmm[act[k]]);
+        { int32_t *t = act; act = nxt; nxt = t; n_act = n_nxt; n_nxt = 0; }
+        ++frame;
+        if (frame >= T) break;
+    }
+    for (i = 0; i < H.n && i < cap; ++i) {
+        int32_t *r = hist_out + (size_t)i * 13;
+        r[0] = H.ent[i].link; r[1] = H.ent[i].frame; r[2] = H.ent[i].score; r[3] = H.ent[i].pred; r[4] = H.ent[i].lc;
+        memcpy(r + 5, H.ent[i].rc, 32);
+    }
+    i = H.n;
+    free(H.ent); free(H.frame_entries); free(hmm); free(act); free(nxt);
+    return i;
+}

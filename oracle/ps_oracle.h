@@ -173,6 +173,14 @@ int32_t pso_allphone_lm_run(int32_t n_emit_state, const uint8_t *tp, const uint1
 /* design experiment for a looser codeword filter (see ps_oracle.c) */
 int32_t pso_filter_experiment(const pso_model_t *m, const float *feats, int32_t T, int32_t lag, int64_t *stats);
 
+/* fsg_search.c + fsg_history.c for one utterance (see ps_oracle.c); hist_out [cap][13]. */
+int32_t pso_fsg_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq,
+                    int32_t n_pnode, const int32_t *pn, int32_t n_state, const int32_t *roots,
+                    int32_t n_link, const int32_t *links, const int32_t *nulloff, const int32_t *nullarc,
+                    int32_t n_ci, int32_t silcipid, int32_t start_state,
+                    int32_t beam_orig, int32_t pbeam_orig, int32_t wbeam_orig, int32_t maxhmmpf,
+                    const int16_t *senscr, int32_t n_sen, int32_t T, int32_t *hist_out, int32_t cap);
+
 #ifdef __cplusplus
 }
 #endif

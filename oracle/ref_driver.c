@@ -1124,3 +1124,175 @@ refdrv_allphone_lm(const char *hmmdir, const char *kv, const int16 *pcm, long n_
     ps_config_free(config);
     return 0;
 }
+
+/* Grammar decoding through the reference's own fsg_search (fsg_search.c) on one utterance, with
+ * everything the search works on flattened for the oracle:
+ *   i32 block layout (all int32, returned through `blob`, sizes in info):
+ *     pnodes  [n_pnode][16]: ssid, tmatid, next (succ pnode id, or link id for leaves, -1), sibling id,
+ *                            logs2prob, ci_ext, ppos, leaf, ctxt.bv[8]
+ *     roots   [n_state]    : first root pnode of the state (-1 none)
+ *     links   [n_link][5]  : from_state, to_state, wid, logs2prob, all_ctxt (filler or single-phone word)
+ *     nulloff [n_state+1], nullarc [n_null]: null arcs leaving each state, as link ids, in the
+ *                            order fsg_model_arcs iterates them
+ *     hist    [n_hist][13] : link id (-1 = the dummy start entry), frame, score, pred, lc, rc.bv[8]
+ *   info: [0] frames [1] n_pnode [2] n_state [3] n_link [4] n_null [5] n_hist [6] beam [7] pbeam
+ *         [8] wbeam [9] maxhmmpf [10] silcipid [11] n_ciphone [12] start_state [13] final_state
+ *         [14] hyp score
+ * vocab: the grammar's word strings by wid, newline separated.
+ * Pnode ids follow alloc_head[s] / alloc_next, state by state. */
+#include "fsg_search_internal.h"
+#include "fsg_lextree.h"
+#include "fsg_history.h"
+static int
+fsg_link_id(fsg_link_t **tab, int *n, fsg_link_t *l)
+{
+    int i;
+    for (i = 0; i < *n; ++i) if (tab[i] == l) return i;
+    tab[(*n)++] = l;
+    return *n - 1;
+}
+
+long
+refdrv_fsg(const char *hmmdir, const char *dict, const char *fsgfile, const char *kv,
+           const int16 *pcm, long n_samples, int32 *blob, long cap, int32 *info, char *hyp, int hyp_cap,
+           char *vocab, int vocab_cap)
+{
+    ps_config_t *config;
+    ps_decoder_t *ps;
+    fsg_search_t *fs;
+    fsg_lextree_t *lt;
+    fsg_model_t *fsg;
+    fsg_pnode_t **pn, *p;
+    fsg_link_t **links;
+    int n_pn = 0, n_link = 0, n_state, s, i, k, n_null = 0, n_hist;
+    long need, o;
+    const char *h;
+    int32 score = 0;
+
+    err_set_loglevel(ERR_ERROR);
+    config = ps_config_init(NULL);
+    ps_config_set_str(config, "hmm", hmmdir);
+    ps_config_set_str(config, "dict", dict);
+    ps_config_set_str(config, "fsg", fsgfile);
+    ps_config_set_str(config, "lm", NULL);
+    ps_config_set_str(config, "dither", "no");
+    ps_config_set_str(config, "compallsen", "yes");
+    ps_config_set_str(config, "pl_window", "0");
+    ps_config_set_str(config, "bestpath", "no");
+    if (kv) {
+        char *b2 = strdup(kv), *s2 = NULL, *t2;
+        for (t2 = strtok_r(b2, "\n", &s2); t2; t2 = strtok_r(NULL, "\n", &s2)) {
+            char *eq = strchr(t2, '=');
+            if (!eq) continue;
+            *eq = 0;
+            ps_config_set_str(config, t2, eq + 1);
+        }
+        free(b2);
+    }
+    ps = ps_init(config);
+    if (ps == NULL) { ps_config_free(config); return -1; }
+    if (ps->search == NULL || strcmp(ps_search_type(ps->search), PS_SEARCH_TYPE_FSG) != 0) {
+        ps_free(ps); ps_config_free(config);
+        return -2;
+    }
+    fs = (fsg_search_t *)ps->search;
+    ps_start_utt(ps);
+    ps_process_raw(ps, pcm, n_samples, FALSE, TRUE);
+    ps_end_utt(ps);
+    h = ps_get_hyp(ps, &score);
+    snprintf(hyp, hyp_cap, "%s", h ? h : "");
+    lt = fs->lextree;
+    fsg = fs->fsg;
+    n_state = fsg_model_n_state(fsg);
+    if (vocab && vocab_cap > 0) {                     /* word strings by wid, newline separated */
+        int w, len = 0;
+        vocab[0] = 0;
+        for (w = 0; w < fsg_model_n_word(fsg); ++w)
+            len += snprintf(vocab + len, len < vocab_cap ? vocab_cap - len : 0, "%s\n", fsg_model_word_str(fsg, w));
+    }
+    for (s = 0; s < n_state; ++s)
+        for (p = lt->alloc_head[s]; p; p = p->alloc_next) ++n_pn;
+    pn = calloc(n_pn > 0 ? n_pn : 1, sizeof(*pn));
+    for (s = 0, i = 0; s < n_state; ++s)
+        for (p = lt->alloc_head[s]; p; p = p->alloc_next) pn[i++] = p;
+    links = calloc((size_t)n_pn + 4096, sizeof(*links));
+    /* null arcs first pass: count, and register links */
+    for (s = 0; s < n_state; ++s) {
+        fsg_arciter_t *it;
+        for (it = fsg_model_arcs(fsg, s); it; it = fsg_arciter_next(it))
+            if (fsg_link_wid(fsg_arciter_get(it)) == -1) { fsg_link_id(links, &n_link, fsg_arciter_get(it)); ++n_null; }
+    }
+    for (i = 0; i < n_pn; ++i)
+        if (pn[i]->leaf) fsg_link_id(links, &n_link, pn[i]->next.fsglink);
+    n_hist = fsg_history_n_entries(fs->history);
+    for (i = 0; i < n_hist; ++i) {
+        fsg_hist_entry_t *e = fsg_history_entry_get(fs->history, i);
+        if (e->fsglink) fsg_link_id(links, &n_link, e->fsglink);
+    }
+    need = (long)n_pn * 16 + n_state + (long)n_link * 5 + (n_state + 1) + n_null + (long)n_hist * 13;
+    info[0] = ps_get_n_frames(ps); info[1] = n_pn; info[2] = n_state; info[3] = n_link; info[4] = n_null;
+    info[5] = n_hist; info[6] = fs->beam_orig; info[7] = fs->pbeam_orig; info[8] = fs->wbeam_orig;
+    info[9] = ps_config_int(config, "maxhmmpf");
+    info[10] = bin_mdef_ciphone_id(ps->acmod->mdef, "SIL"); info[11] = bin_mdef_n_ciphone(ps->acmod->mdef);
+    info[12] = fsg_model_start_state(fsg); info[13] = fsg_model_final_state(fsg); info[14] = score;
+    info[15] = -1;
+    if (blob && cap >= need) {
+        o = 0;
+        for (i = 0; i < n_pn; ++i) {
+            int32 *r = blob + o + (long)i * 16;
+            int j;
+            p = pn[i];
+            r[0] = hmm_nonmpx_ssid(&p->hmm); r[1] = p->hmm.tmatid;
+            if (p->leaf) r[2] = fsg_link_id(links, &n_link, p->next.fsglink);
+            else {
+                r[2] = -1;
+                for (j = 0; j < n_pn; ++j) if (pn[j] == p->next.succ) { r[2] = j; break; }
+            }
+            r[3] = -1;
+            for (j = 0; j < n_pn; ++j) if (pn[j] == p->sibling) { r[3] = j; break; }
+            r[4] = p->logs2prob; r[5] = p->ci_ext; r[6] = p->ppos; r[7] = p->leaf;
+            for (j = 0; j < 8; ++j) r[8 + j] = (int32)p->ctxt.bv[j];
+        }
+        o += (long)n_pn * 16;
+        for (s = 0; s < n_state; ++s) {
+            blob[o + s] = -1;
+            for (i = 0; i < n_pn; ++i) if (pn[i] == lt->root[s]) { blob[o + s] = i; break; }
+        }
+        o += n_state;
+        for (i = 0; i < n_link; ++i) {
+            fsg_link_t *l = links[i];
+            int32 *r = blob + o + (long)i * 5;
+            r[0] = l->from_state; r[1] = l->to_state; r[2] = l->wid; r[3] = l->logs2prob;
+            r[4] = 0;
+            if (l->wid >= 0)
+                r[4] = fsg_model_is_filler(fsg, l->wid)
+                    || dict_is_single_phone(ps->dict, dict_wordid(ps->dict, fsg_model_word_str(fsg, l->wid)));
+        }
+        o += (long)n_link * 5;
+        {
+            long oo = o + n_state + 1;
+            k = 0;
+            for (s = 0; s < n_state; ++s) {
+                fsg_arciter_t *it;
+                blob[o + s] = k;
+                for (it = fsg_model_arcs(fsg, s); it; it = fsg_arciter_next(it))
+                    if (fsg_link_wid(fsg_arciter_get(it)) == -1)
+                        blob[oo + k++] = fsg_link_id(links, &n_link, fsg_arciter_get(it));
+            }
+            blob[o + n_state] = k;
+            o = oo + n_null;
+        }
+        for (i = 0; i < n_hist; ++i) {
+            fsg_hist_entry_t *e = fsg_history_entry_get(fs->history, i);
+            int32 *r = blob + o + (long)i * 13;
+            int j;
+            r[0] = e->fsglink ? fsg_link_id(links, &n_link, e->fsglink) : -1;
+            r[1] = e->frame; r[2] = e->score; r[3] = e->pred; r[4] = e->lc;
+            for (j = 0; j < 8; ++j) r[5 + j] = (int32)e->rc.bv[j];
+        }
+    }
+    free(pn); free(links);
+    ps_free(ps);
+    ps_config_free(config);
+    return need;
+}

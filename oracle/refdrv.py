@@ -373,3 +373,36 @@ def allphone(hmmdir, pcm, **kv):
     return dict(**extra, n_frames=int(info[0]), ci=ci[:n].copy(), ssid=ssid[:n].copy(), tmatid=tmat[:n].copy(),
                 succ_off=soff[:n + 1].copy(), succ=succ[:nl].copy(), start=int(info[3]), beam=int(info[4]),
                 pbeam=int(info[5]), inspen=int(info[6]), segs=segs[:int(info[7])].copy(), n_history=int(info[8]))
+
+
+def fsg(hmmdir, dictfile, fsgfile, pcm, **kv):
+    """The reference's fsg_search on one utterance (compallsen, no look-ahead, no bestpath): the
+    flattened lextree, links, null arcs, beams, and the history table + hypothesis it produced."""
+    pcm = np.ascontiguousarray(pcm, np.int16)
+    s = "\n".join("%s=%s" % (k, v) for k, v in kv.items()).encode() or None
+    L = lib()
+    L.refdrv_fsg.restype = C.c_long
+    L.refdrv_fsg.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_long, C.c_void_p,
+                             C.c_long, C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    cap = 1 << 22
+    blob = np.zeros(cap, np.int32)
+    info = np.zeros(16, np.int32)
+    hyp = C.create_string_buffer(4096)
+    vocab = C.create_string_buffer(1 << 16)
+    need = L.refdrv_fsg(hmmdir.encode(), dictfile.encode(), fsgfile.encode(), s, _p(pcm), len(pcm), _p(blob), cap,
+                        _p(info), hyp, 4096, vocab, 1 << 16)
+    if need < 0 or need > cap:
+        raise RuntimeError("refdrv_fsg failed: %d" % need)
+    n_pn, n_state, n_link, n_null, n_hist = (int(x) for x in info[1:6])
+    o = 0
+    pnodes = blob[o:o + n_pn * 16].reshape(n_pn, 16).copy(); o += n_pn * 16
+    roots = blob[o:o + n_state].copy(); o += n_state
+    links = blob[o:o + n_link * 5].reshape(n_link, 5).copy(); o += n_link * 5
+    nulloff = blob[o:o + n_state + 1].copy(); o += n_state + 1
+    nullarc = blob[o:o + n_null].copy(); o += n_null
+    hist = blob[o:o + n_hist * 13].reshape(n_hist, 13).copy()
+    return dict(n_frames=int(info[0]), pnodes=pnodes, roots=roots, links=links, nulloff=nulloff, nullarc=nullarc,
+                hist=hist, beam=int(info[6]), pbeam=int(info[7]), wbeam=int(info[8]), maxhmmpf=int(info[9]),
+                silcipid=int(info[10]), n_ciphone=int(info[11]), start_state=int(info[12]),
+                final_state=int(info[13]), score=int(info[14]), hyp=hyp.value.decode(),
+                vocab=vocab.value.decode().split("\n")[:-1])
