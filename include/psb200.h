@@ -319,6 +319,36 @@ int psb_allphone_lm_batch_device(psb_hmmctx_t *c, const int16_t *d_senscr, const
                                  const int32_t *tg, int32_t *hist, int32_t cap_per_utt, int32_t *n_hist);
 
 /* ------------------------------------------------------------------------------------ */
+/* Grammar decoding for whole batches: fsg_search.c (-fsg / -jsgf; start :770-817, step :683-761 =
+ * hmm_eval :335, hmm_prune_prop :516, null_prop :566, word_trans :621) with fsg_history.c's
+ * right-context bookkeeping (:132-240), every utterance against the same grammar.  The host keeps
+ * fsg_search_init / fsg_lextree_init and flattens what they built (fsg_lextree.h:137-190;
+ * oracle/ref_driver.c:refdrv_fsg shows the loop):
+ *   pnodes [n_pnode][16] = ssid, tmatid, next (first successor, or the link id of a leaf, or -1),
+ *                          sibling, logs2prob, ci_ext, ppos, leaf, ctxt.bv[8]; ids in alloc order
+ *   roots  [n_state]      first root pnode of each state's lextree (-1: none)
+ *   links  [n_link][5]    from_state, to_state, wid (-1: null), logs2prob, 1 if exits of this word
+ *                          apply to every right context (filler or single-phone word, :468-474)
+ *   nulloff [n_state+1], nullarc: the null arcs leaving each state as link ids, in fsg_model_arcs order
+ *   beam / pbeam / wbeam as fsg_search_init computes them (beam_orig...), maxhmmpf (-1: off).
+ * Every fsg_hist_entry_t the reference makes permanent comes back, in table order, as a row
+ *   {link (-1: the start entry), frame, score, pred, lc, rc.bv[8]}
+ * in hist [n_utt][cap_per_utt][13] (host); n_hist[u] counts them (rows past cap_per_utt are
+ * dropped).  The host's fsg_search_find_exit / fsg_search_hyp / fsg_search_lattice work on that
+ * table unchanged.  The lextree must be a tree under each state (it is, fsg_lextree.c:354-600). */
+typedef struct psb_fsg_desc_s {
+    int32_t n_pnode;  const int32_t *pnodes;
+    int32_t n_state;  const int32_t *roots;
+    int32_t n_link;   const int32_t *links;
+    const int32_t *nulloff, *nullarc;
+    int32_t n_ciphone, silcipid, start_state;
+    int32_t beam, pbeam, wbeam, maxhmmpf;
+} psb_fsg_desc_t;
+int psb_fsg_batch_device(psb_hmmctx_t *c, const psb_fsg_desc_t *g, const int16_t *d_senscr,
+                         const int32_t *utt_off, int32_t n_utt, int32_t *hist, int32_t cap_per_utt,
+                         int32_t *n_hist);
+
+/* ------------------------------------------------------------------------------------ */
 /* Batched front end: int16 PCM -> cepstra -> batch CMN -> 1s_c_d_dd features
  * for whole batches, every utterance a fresh stream (ps_start_stream + ps_process_raw(full_utt),
  * pocketsphinx.c:1073, acmod.c:528-560).  The tables are the arrays the reference's own fe_t /

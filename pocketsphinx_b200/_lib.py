@@ -37,6 +37,13 @@ class FeDesc(C.Structure):
                 ("filt_coeffs", C.c_void_p), ("mel_cosine", C.c_void_p), ("lifter", C.c_void_p)]
 
 
+class FsgDesc(C.Structure):
+    _fields_ = [("n_pnode", C.c_int32), ("pnodes", C.c_void_p), ("n_state", C.c_int32), ("roots", C.c_void_p),
+                ("n_link", C.c_int32), ("links", C.c_void_p), ("nulloff", C.c_void_p), ("nullarc", C.c_void_p),
+                ("n_ciphone", C.c_int32), ("silcipid", C.c_int32), ("start_state", C.c_int32), ("beam", C.c_int32),
+                ("pbeam", C.c_int32), ("wbeam", C.c_int32), ("maxhmmpf", C.c_int32)]
+
+
 SYMBOLS = [
     ("psb_last_error", C.c_char_p, []),
     ("psb_abi_version", C.c_int, []),
@@ -75,6 +82,7 @@ SYMBOLS = [
     ("psb_allphone_batch_device", C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP, _I32, _VP]),
     ("psb_allphone_lm_batch_device", C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _I32, _VP]),
     ("psb_kws_batch_device", C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP, _VP, _I32, _VP, _VP, _VP, _VP, _I32, _I32, _VP, _I32, _VP]),
+    ("psb_fsg_batch_device", C.c_int, [_VP, C.POINTER(FsgDesc), _VP, _VP, _I32, _VP, _I32, _VP]),
     ("psb_align_batch_device", C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     ("psb_align_last_kernel_ms", C.c_float, [_VP]),
     ("psb_align_batch_host", C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),

@@ -283,6 +283,25 @@ class HmmContext:
                                               _p(hist), cap, _p(n_hist)), "psb_allphone_batch_device")
         return [hist[u, :min(int(n_hist[u]), cap)].copy() for u in range(n_utt)], n_hist[:n_utt].copy()
 
+    def fsg(self, d_senscr_ptr, utt_off, g, cap):
+        """fsg_search over a batch, every utterance against the flattened grammar lextree `g` (a mapping
+        with pnodes, roots, links, nulloff, nullarc, n_ciphone, silcipid, start_state, beam, pbeam,
+        wbeam, maxhmmpf).  Returns the list of history tables [n][13] = (link, frame, score, pred,
+        lc, rc.bv[8]) and the entry counts."""
+        from ._lib import FsgDesc
+        utt_off = np.ascontiguousarray(utt_off, np.int32)
+        n_utt = len(utt_off) - 1
+        a = {k: np.ascontiguousarray(g[k], np.int32) for k in ("pnodes", "roots", "links", "nulloff", "nullarc")}
+        d = FsgDesc(len(a["pnodes"]), a["pnodes"].ctypes.data, len(a["roots"]), a["roots"].ctypes.data,
+                    len(a["links"]), a["links"].ctypes.data, a["nulloff"].ctypes.data,
+                    a["nullarc"].ctypes.data if len(a["nullarc"]) else None, int(g["n_ciphone"]), int(g["silcipid"]),
+                    int(g["start_state"]), int(g["beam"]), int(g["pbeam"]), int(g["wbeam"]), int(g["maxhmmpf"]))
+        hist = np.zeros((max(n_utt, 1), int(cap), 13), np.int32)
+        n_hist = np.zeros(max(n_utt, 1), np.int32)
+        check(lib().psb_fsg_batch_device(self.h, C.byref(d), C.c_void_p(d_senscr_ptr), _p(utt_off), n_utt, _p(hist),
+                                         int(cap), _p(n_hist)), "psb_fsg_batch_device")
+        return [hist[u, :min(int(n_hist[u]), int(cap))] for u in range(n_utt)], n_hist[:n_utt]
+
     def allphone_lm(self, d_senscr_ptr, utt_off, ssid, tmatid, succ_off, succ, start, beam, pbeam, node_ci, bg, tg):
         """allphone_search with a phone LM (dense bigram / trigram tables).  History rows
         [n][5] = (ef, node, predecessor entry, score, tscore)."""

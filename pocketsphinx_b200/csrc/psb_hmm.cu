@@ -1695,3 +1695,146 @@ extern "C" int psb_allphone_lm_batch_device(psb_hmmctx_t *c, const int16_t *d_se
     return allphone_common(c, d_senscr, utt_off, n_utt, n_nodes, ssid, tmatid, succ_off, succ, start, beam, pbeam, 0, hist,
                            cap_per_utt, n_hist, n_ci, node_ci, bg, tg);
 }
+
+// ---------------------------------------------------------------------------------------
+// Grammar decoding: fsg_search.c for whole batches (the lextree search that is
+// small enough to live entirely on the device).  One CTA per utterance; the phases and the
+// reasoning that makes them equal to the reference's list walks are in psb_fsg_core.h, which a host
+// harness (tests/emul/) runs against the reference's golden history tables.  HMM state and the
+// per-frame scratch live in global memory (L2-resident: ~80 KB per utterance for a 250-node
+// lextree); only the frame scalars are in shared memory.
+#include "psb_fsg_host.h"
+
+namespace {
+
+struct FsgDevEval {
+    HmmCtxDev c;
+    const uint16_t *senid_g;
+    const int32_t *tmatid_g;
+    const int16_t *row;
+    int P;
+    __device__ __forceinline__ int operator()(const FsgWork &W, int p) const
+    {
+        HmmReg h;
+        const int N = c.n_emit;
+#pragma unroll
+        for (int s = 0; s < PSB_HMM_MAX_NSTATE; ++s) {
+            h.score[s] = s < N ? W.score[s * P + p] : PSB_WORST_SCORE;
+            h.hist[s] = s < N ? W.hist[s * P + p] : -1;
+            h.senid[s] = s < N ? senid_g[(size_t)p * N + s] : PSB_BAD_SSID;
+        }
+        h.out_score = W.out_score[p]; h.out_hist = W.out_hist[p]; h.best = W.best[p];
+        const int b = hmm_step(h, c, tmatid_g[p], false, row);
+#pragma unroll
+        for (int s = 0; s < PSB_HMM_MAX_NSTATE; ++s)
+            if (s < N) { W.score[s * P + p] = h.score[s]; W.hist[s * P + p] = h.hist[s]; }
+        W.out_score[p] = h.out_score; W.out_hist[p] = h.out_hist; W.best[p] = h.best;
+        return b;
+    }
+};
+
+constexpr int FSG_THREADS = 128;
+
+__global__ void __launch_bounds__(FSG_THREADS)
+fsg_search_kernel(const int16_t *__restrict__ senscr, const int32_t *__restrict__ utt_off, HmmCtxDev c, FsgGraph G,
+                  const uint16_t *__restrict__ senid_g, const int32_t *__restrict__ tmatid_g,
+                  int32_t *work, size_t work_words, int32_t *hist_out, int cap, int32_t *n_hist)
+{
+    __shared__ FsgScalars S;
+    const int u = blockIdx.x;
+    const long long f0 = utt_off[u];
+    const int T = utt_off[u + 1] - utt_off[u];
+    FsgWork W;
+    fsg_work_carve(work + (size_t)u * work_words, G, W);
+    W.hist_out = hist_out + (size_t)u * cap * FSG_ROW;
+    W.cap = cap;
+    FsgDevEval ev{c, senid_g, tmatid_g, nullptr, G.P};
+    fsg_start(G, W, &S);
+    for (int f = 0; f < T; ++f) {
+        if (S.overflow) break;                               // uniform: written before the last barrier of the step
+        ev.row = senscr + (f0 + f) * c.n_sen;
+        fsg_step(G, W, &S, f, ev);
+    }
+    if (threadIdx.x == 0) n_hist[u] = S.overflow ? -1 : S.n_hist;
+}
+
+}  // namespace
+
+static_assert(FSG_WORST_SCORE == PSB_WORST_SCORE, "score floor");
+static_assert(FSG_MAX_NSTATE == PSB_HMM_MAX_NSTATE, "state count");
+
+extern "C" int psb_fsg_batch_device(psb_hmmctx_t *c, const psb_fsg_desc_t *g, const int16_t *d_senscr,
+                                    const int32_t *utt_off, int32_t n_utt, int32_t *hist, int32_t cap_per_utt,
+                                    int32_t *n_hist)
+{
+    PSB_REQUIRE(c && g && utt_off && n_utt >= 0 && hist && n_hist && cap_per_utt > 0, "psb_fsg_batch_device: bad argument");
+    if (n_utt == 0) return PSB_OK;
+    PSB_REQUIRE(utt_off[0] == 0, "psb_fsg_batch_device: offsets must start at 0");
+    PSB_REQUIRE(d_senscr || utt_off[n_utt] == 0, "psb_fsg_batch_device: scores missing");
+    for (int u = 0; u < n_utt; ++u)
+        PSB_REQUIRE(utt_off[u + 1] >= utt_off[u], "psb_fsg_batch_device: utt_off not monotone at %d", u);
+    PSB_REQUIRE(g->start_state >= 0 && g->start_state < g->n_state, "psb_fsg_batch_device: start state out of range");
+    PSB_REQUIRE(g->silcipid >= 0 && g->silcipid < g->n_ciphone, "psb_fsg_batch_device: silence phone out of range");
+    FsgFlat flat;
+    std::string err;
+    if (fsg_flatten(g->n_pnode, g->pnodes, g->n_state, g->roots, g->n_link, g->links, g->nulloff, g->nullarc,
+                    g->n_ciphone, flat, err) != 0) {
+        psb_set_error("psb_fsg_batch_device: %s", err.c_str());
+        return PSB_ERR_ARG;
+    }
+    const int N = c->n_emit, P = flat.P;
+    PSB_CUDA(cudaSetDevice(c->device));
+    std::vector<uint16_t> sseq((size_t)c->n_sseq * N);
+    PSB_CUDA(cudaMemcpy(sseq.data(), c->d_sseq, sseq.size() * 2, cudaMemcpyDeviceToHost));
+    std::vector<uint16_t> senid((size_t)P * N);
+    for (int i = 0; i < P; ++i) {
+        PSB_REQUIRE(flat.ssid[i] >= 0 && flat.ssid[i] < c->n_sseq, "fsg: pnode %d: ssid out of range", i);
+        PSB_REQUIRE(flat.tmatid[i] >= 0 && flat.tmatid[i] < c->n_tmat, "fsg: pnode %d: tmatid out of range", i);
+        for (int s = 0; s < N; ++s) {
+            const uint16_t v = sseq[(size_t)flat.ssid[i] * N + s];
+            PSB_REQUIRE(v < c->n_sen, "senone id %d out of range", v);
+            senid[(size_t)i * N + s] = v;
+        }
+    }
+    // one int32 block: graph | tmatid[P] | utt_off[n_utt+1] | n_hist[n_utt]
+    std::vector<int32_t> ibuf(flat.buf);
+    const size_t o_tm = ibuf.size();
+    ibuf.insert(ibuf.end(), flat.tmatid.begin(), flat.tmatid.end());
+    const size_t o_uo = ibuf.size();
+    ibuf.insert(ibuf.end(), utt_off, utt_off + n_utt + 1);
+    const size_t o_nh = ibuf.size();
+    ibuf.resize(o_nh + (size_t)n_utt, 0);
+    const size_t work_words = fsg_work_words(flat, N);
+    const size_t hist_n = (size_t)n_utt * cap_per_utt * FSG_ROW;
+    int32_t *d_i = nullptr, *d_hist = nullptr, *d_work = nullptr;
+    uint16_t *d_senid = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_i, ibuf.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_hist, hist_n * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_work, work_words * (size_t)n_utt * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_senid, senid.size() * 2);
+    cudaStream_t st = c->stream;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_i, ibuf.data(), ibuf.size() * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_senid, senid.data(), senid.size() * 2, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        FsgGraph G;
+        memset(&G, 0, sizeof(G));
+        fsg_graph_bind(flat, d_i, G);
+        G.n_ci = g->n_ciphone; G.n_emit = N; G.silcipid = g->silcipid; G.start_state = g->start_state;
+        G.beam = g->beam; G.pbeam = g->pbeam; G.wbeam = g->wbeam; G.maxhmmpf = g->maxhmmpf;
+        fsg_search_kernel<<<(unsigned)n_utt, FSG_THREADS, 0, st>>>(d_senscr, d_i + o_uo, dev_ctx(c), G, d_senid, d_i + o_tm,
+                                                                  d_work, work_words, d_hist, cap_per_utt, d_i + o_nh);
+        g_psb_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hist, d_hist, hist_n * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(n_hist, d_i + o_nh, (size_t)n_utt * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_i); cudaFree(d_hist); cudaFree(d_work); cudaFree(d_senid);
+    if (e != cudaSuccess) {
+        psb_set_error("psb_fsg_batch_device: %s", cudaGetErrorString(e));
+        return PSB_ERR_CUDA;
+    }
+    for (int u = 0; u < n_utt; ++u)
+        PSB_REQUIRE(n_hist[u] >= 0, "psb_fsg_batch_device: scratch overflow in utterance %d (internal)", u);
+    return PSB_OK;
+}
