@@ -112,8 +112,36 @@ def make_fsg():
     np.savez_compressed(os.path.join(OUT, "en_us_fsg.npz"), **out)
 
 
+def make_fwdtree():
+    """en_us_fwdtree.npz: the reference's own first pass (ngram_search_fwdtree, turtle LM + dictionary,
+    no fwdflat / bestpath / look-ahead) on goforward.raw: the flattened search (lextree, dictionary and
+    dict2pid tables, dense trigram table, parameters) and what it produced -- every backpointer-table
+    entry, the right-context score stack, bp_table_idx, hypothesis and score -- for the default
+    settings, wide and narrow beams, absolute pruning (-maxwpf, -maxhmmpf) and non-default penalties."""
+    pcm = np.fromfile(os.path.join(REF, "test/data/goforward.raw"), np.int16)
+    hd = os.path.join(REF, "model/en-us/en-us")
+    out = {}
+    for tag, kv in (("default", {}),
+                    ("wide", dict(beam="1e-80", pbeam="1e-80", wbeam="1e-60", lpbeam="1e-60", lponlybeam="1e-50")),
+                    ("narrow", dict(beam="1e-30", pbeam="1e-25", wbeam="1e-15", lpbeam="1e-20", lponlybeam="1e-15")),
+                    ("maxwpf", dict(maxwpf="5")),
+                    ("abs", dict(maxhmmpf="50", maxwpf="10")),
+                    ("pen", dict(nwpen="0.5", pip="0.7", wip="0.3", lw="9.5", silprob="0.01", fillprob="1e-4"))):
+        r = refdrv.fwdtree(hd, os.path.join(REF, "test/data/turtle.lm.bin"), os.path.join(REF, "test/data/turtle.dic"), pcm, **kv)
+        for k in ("info", "model", "bp", "bss", "bp_idx", "words"):
+            out[tag + "." + k] = r[k]
+        out[tag + ".vocab"] = np.array("\n".join(r["vocab"]))
+        out[tag + ".hyp"] = np.array(r["hyp"])
+        out[tag + ".score"] = np.int32(r["score"])
+        print("fwdtree", tag, r["n_root"], "root", r["n_nonroot"], "non-root channels,", r["bpidx"], "bp entries,",
+              r["bss_head"], "rc scores:", r["hyp"], r["score"])
+    np.savez_compressed(os.path.join(OUT, "en_us_fwdtree.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "fwdtree":
+        return make_fwdtree()
     if len(sys.argv) > 1 and sys.argv[1] == "fsg":
         return make_fsg()
     if len(sys.argv) > 1 and sys.argv[1] == "allphone":

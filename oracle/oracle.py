@@ -436,3 +436,56 @@ def fsg_hyp_wids(hist, links, bp):
             out.append(int(links[l][2]))
         bp = int(hist[bp][3])
     return out[::-1]
+
+
+def fwdtree_run(tp, sseq, ci_tmat, info, model, senscr):
+    """ngram_search_fwdtree.c for one utterance on the flattened search `info` / `model`
+    (refdrv.fwdtree / the golden file); returns (bp table [n][10], bscore_stack, bp_table_idx)."""
+    tp = np.ascontiguousarray(tp, np.uint8); sseq = np.ascontiguousarray(sseq, np.uint16)
+    ci_tmat = np.ascontiguousarray(ci_tmat, np.int32)
+    info = np.ascontiguousarray(info, np.int32); model = np.ascontiguousarray(model, np.int32)
+    senscr = np.ascontiguousarray(senscr, np.int16)
+    T, n_sen = senscr.shape
+    bp_cap, bss_cap = 64 * (T + 16), 64 * (T + 16) * 64
+    bp = np.zeros((bp_cap, 10), np.int32); bss = np.zeros(bss_cap, np.int32); bp_idx = np.zeros(T + 2, np.int32)
+    bss_n = C.c_int32()
+    f = lib().pso_fwdtree_run
+    f.restype = C.c_int32
+    f.argtypes = [C.c_int32] + [C.c_void_p] * 6 + [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                                    C.c_void_p, C.c_void_p]
+    n = f(tp.shape[1], _p(tp), _p(sseq), _p(ci_tmat), _p(info), _p(model), _p(senscr), n_sen, T, _p(bp), bp_cap, _p(bss),
+          bss_cap, C.byref(bss_n), _p(bp_idx))
+    assert n <= bp_cap and bss_n.value <= bss_cap
+    return bp[:n].copy(), bss[:bss_n.value].copy(), bp_idx[:T + 1].copy()
+
+
+def fwdtree_find_exit(bp, bp_idx, n_frame, finish_wid):
+    """ngram_search_find_exit (ngram_search.c:501-541) with frame_idx = -1: </s> in the last frame
+    that has exits, else its best-scoring entry.  Returns (index or -1, score)."""
+    if n_frame == 0:
+        return -1, None
+    f = n_frame - 1
+    end = int(bp_idx[f])
+    while f >= 0 and bp_idx[f] == end:
+        f -= 1
+    if f < 0:
+        return -1, None
+    best, best_exit = -0x20000000, -1
+    for b in range(int(bp_idx[f]), end):
+        if bp[b][2] == finish_wid or bp[b][4] > best:
+            best, best_exit = int(bp[b][4]), b
+        if bp[b][2] == finish_wid:
+            break
+    return best_exit, best
+
+
+def fwdtree_hyp(bp, b, words, vocab, start_wid, finish_wid):
+    """ngram_search_bp_hyp (:545-590): base strings of the real words (dict_real_word: neither
+    filler nor <s> / </s>) along the backpointer chain."""
+    out = []
+    while b != -1:
+        w = int(bp[b][2])
+        b = int(bp[b][3])
+        if not words[w][4] and int(words[w][5]) not in (start_wid, finish_wid):
+            out.append(vocab[int(words[w][5])])
+    return " ".join(reversed(out))

@@ -1876,3 +1876,460 @@ pso_fsg_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq,
     free(H.ent); free(H.frame_entries); free(hmm); free(act); free(nxt);
     return i;
 }
+
+/* ---------------------------------------------------------------------------------------
+ * N-gram lextree decoding, first pass: ngram_search_fwdtree.c (search step :1454-1496 =
+ * evaluate_channels :702, prune_channels :1130 [prune_root_chan :723, prune_nonroot_chan :800,
+ * last_phone_transition :885, prune_word_chan :1042], bptable_maxwpf :1188, word_transition :1241,
+ * deactivate_channels :1432; start :470) with the backpointer-table side of ngram_search.c
+ * (mark_bptable :324, set_real_wid :343, save_bp :378, alloc_all_rc :593, exit_score :655) restated
+ * for one utterance, all senones computed, no phone-loop look-ahead (pls == NULL).  `info` and
+ * `model` are what oracle/ref_driver.c:refdrv_fwdtree exports (the reference's own lextree,
+ * dictionary / dict2pid tables, dense trigram table, parameters).  Output: the backpointer table
+ * rows (frame, valid, wid, bp, score, s_idx, real_wid, prev_real_wid, last_phone, last2_phone), the
+ * right-context score stack and bp_table_idx; returns the number of entries, *bss_out the stack size. */
+typedef struct { int32_t frame, valid, wid, bp, score, s_idx, real_wid, prev_real_wid, last_phone, last2_phone; } ft_bp_t;
+typedef struct { int32_t wid, score, bp, next; } ft_cand_t;
+typedef struct {
+    /* model */
+    int32_t n_words, n_root, n_nonroot, n_1ph, n_1ph_lm, n_ci, sil, n_lm;
+    int32_t beam, pbeam, wbeam, lpbeam, lponlybeam, maxhmmpf, maxwpf, nwpen, pip, silpen, fillpen;
+    int32_t start_wid, finish_wid, silence_wid, filler_start, filler_end;
+    const int32_t *roots, *nonroot, *words, *w1ph, *r1ph, *rs_n, *rs_ssid, *rs_cimap, *ldiph, *lm, *ci_tmat;
+    pso_hmmctx_t ctx;
+    /* channels */
+    pso_hmm_t *rh, *nh, *h1;          /* root, non-root, single-phone words */
+    pso_hmm_t **wc;                   /* [n_words] right-context fan-out of multi-phone words, by rc id */
+    uint8_t **wc_alloc;
+    int32_t *w2h1;                    /* word -> index of its permanent channel, or -1 */
+    /* search state */
+    int32_t *acl[2], n_acl[2], *awl[2], n_awl[2];
+    uint8_t *word_active;
+    int32_t *word_lat_idx, *lt_sf, *lt_dscr, *lt_bp;
+    ft_cand_t *cand; int32_t n_cand;
+    int32_t *csf_ef, *csf_cand;
+    int32_t *brc_score, *brc_path, *brc_lc;
+    ft_bp_t *bp; int32_t bpidx, bp_cap;
+    int32_t *bss; int32_t bss_head, bss_cap;
+    int32_t *bp_idx;
+    int32_t best_score, last_phone_best_score, dynamic_beam;
+    int64_t n_root_eval, n_nonroot_eval;
+} ft_t;
+
+#define FT_W(s, w, k) ((s)->words[(size_t)(w) * 8 + (k)])        /* 0 first 1 last 2 last2 3 single 4 filler 5 base 6 homophone 7 lmidx */
+
+static int32_t
+ft_nrc(const ft_t *s, int32_t w) { return s->rs_n[(size_t)FT_W(s, w, 1) * s->n_ci + FT_W(s, w, 2)]; }
+
+static int32_t
+ft_tg(const ft_t *s, int32_t w, int32_t h1, int32_t h2)
+{
+    const int32_t n = s->n_lm + 1;
+    const int32_t a = FT_W(s, w, 7), b = h1 < 0 ? 0 : FT_W(s, h1, 7) + 1, c = h2 < 0 ? 0 : FT_W(s, h2, 7) + 1;
+    return s->lm[((size_t)a * n + b) * n + c];
+}
+
+static int32_t
+ft_exit_score(const ft_t *s, const ft_bp_t *e, int32_t rcphone)           /* ngram_search.c:655-676 */
+{
+    if (e->last2_phone == -1) return e->score;
+    return s->bss[e->s_idx + s->rs_cimap[((size_t)e->last_phone * s->n_ci + e->last2_phone) * s->n_ci + rcphone]];
+}
+
+static void
+ft_set_real_wid(ft_t *s, int32_t bp)                                      /* :343-373 */
+{
+    ft_bp_t *e = &s->bp[bp], *prev = e->bp == -1 ? NULL : &s->bp[e->bp];
+    if (FT_W(s, e->wid, 4)) {
+        if (prev) { e->real_wid = prev->real_wid; e->prev_real_wid = prev->prev_real_wid; }
+        else { e->real_wid = FT_W(s, e->wid, 5); e->prev_real_wid = -1; }
+    }
+    else {
+        e->real_wid = FT_W(s, e->wid, 5);
+        e->prev_real_wid = prev ? prev->real_wid : -1;
+    }
+}
+
+static void
+ft_save_bp(ft_t *s, int32_t frame, int32_t w, int32_t score, int32_t path, int32_t rc)   /* :378-497 */
+{
+    int32_t bp = s->word_lat_idx[w];
+    if (bp != -1) {
+        ft_bp_t *e = &s->bp[bp];
+        if (e->score < score) {
+            if (e->bp != path) {
+                int32_t a0 = e->bp == -1 ? -1 : s->bp[e->bp].prev_real_wid, a1 = e->bp == -1 ? -1 : s->bp[e->bp].real_wid;
+                int32_t b0 = path == -1 ? -1 : s->bp[path].prev_real_wid, b1 = path == -1 ? -1 : s->bp[path].real_wid;
+                if (a0 != b0 || a1 != b1) ft_set_real_wid(s, bp);          /* (still on the old path: :436-438) */
+                e->bp = path;
+            }
+            e->score = score;
+        }
+        if (e->s_idx != -1) s->bss[e->s_idx + rc] = score;
+    }
+    else {
+        ft_bp_t *e;
+        int32_t i, rcsize;
+        if (s->bpidx >= s->bp_cap) { s->bp_cap *= 2; s->bp = realloc(s->bp, (size_t)s->bp_cap * sizeof(*s->bp)); }
+        if (s->bss_head >= s->bss_cap - s->n_ci) { s->bss_cap *= 2; s->bss = realloc(s->bss, (size_t)s->bss_cap * sizeof(*s->bss)); }
+        s->word_lat_idx[w] = s->bpidx;
+        e = &s->bp[s->bpidx];
+        e->wid = w; e->frame = frame; e->bp = path; e->score = score; e->s_idx = s->bss_head; e->valid = 1;
+        e->last_phone = FT_W(s, w, 1);
+        if (FT_W(s, w, 3)) { e->last2_phone = -1; e->s_idx = -1; rcsize = 0; }
+        else { e->last2_phone = FT_W(s, w, 2); rcsize = ft_nrc(s, w); }
+        for (i = 0; i < rcsize; ++i) s->bss[s->bss_head + i] = PSO_WORST_SCORE;
+        if (rcsize) s->bss[s->bss_head + rc] = score;
+        ft_set_real_wid(s, s->bpidx);
+        s->bpidx++;
+        s->bss_head += rcsize;
+    }
+}
+
+static void
+ft_alloc_all_rc(ft_t *s, int32_t w)                                        /* :593-639 */
+{
+    const int32_t n = ft_nrc(s, w), last = FT_W(s, w, 1), last2 = FT_W(s, w, 2);
+    int32_t i;
+    if (!s->wc[w]) { s->wc[w] = calloc(n > 0 ? n : 1, sizeof(pso_hmm_t)); s->wc_alloc[w] = calloc(n > 0 ? n : 1, 1); }
+    for (i = 0; i < n; ++i)
+        if (!s->wc_alloc[w][i]) {
+            pso_hmm_init(&s->ctx, &s->wc[w][i], 0, s->rs_ssid[((size_t)last * s->n_ci + last2) * s->n_ci + i], s->ci_tmat[last]);
+            s->wc_alloc[w][i] = 1;
+        }
+}
+
+int32_t
+pso_fwdtree_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, const int32_t *ci_tmat,
+                const int32_t *info, const int32_t *model, const int16_t *senscr, int32_t n_sen, int32_t T,
+                int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap, int32_t *bss_n, int32_t *bp_idx_out)
+{
+    ft_t S, *s = &S;
+    int32_t i, w, frame, n_done = 0;
+    const int32_t *m = model;
+    memset(s, 0, sizeof(*s));
+    s->n_words = info[1]; s->n_root = info[2]; s->n_nonroot = info[3]; s->n_1ph = info[4]; s->n_1ph_lm = info[5];
+    s->n_ci = info[6]; s->sil = info[7]; s->beam = info[8]; s->pbeam = info[9]; s->wbeam = info[10]; s->lpbeam = info[11];
+    s->lponlybeam = info[12]; s->maxhmmpf = info[13]; s->maxwpf = info[14]; s->nwpen = info[15]; s->pip = info[16];
+    s->silpen = info[17]; s->fillpen = info[18]; s->start_wid = info[19]; s->finish_wid = info[20]; s->silence_wid = info[21];
+    s->filler_start = info[22]; s->filler_end = info[23]; s->n_lm = info[26];
+    {
+        const size_t nc = (size_t)s->n_ci;
+        s->roots = m; m += (size_t)s->n_root * 5;  s->nonroot = m; m += (size_t)s->n_nonroot * 6;
+        s->words = m; m += (size_t)s->n_words * 8;  s->w1ph = m; m += s->n_1ph;  s->r1ph = m; m += (size_t)s->n_1ph * 4;
+        s->rs_n = m; m += nc * nc;  s->rs_ssid = m; m += nc * nc * nc;  s->rs_cimap = m; m += nc * nc * nc;
+        s->ldiph = m; m += nc * nc * nc;  s->lm = m;
+    }
+    s->ctx.n_emit_state = n_emit_state; s->ctx.tp = tp; s->ctx.sseq = sseq; s->ci_tmat = ci_tmat;
+    s->rh = calloc(s->n_root + 1, sizeof(pso_hmm_t)); s->nh = calloc(s->n_nonroot + 1, sizeof(pso_hmm_t));
+    s->h1 = calloc(s->n_1ph + 1, sizeof(pso_hmm_t));
+    s->wc = calloc(s->n_words, sizeof(*s->wc)); s->wc_alloc = calloc(s->n_words, sizeof(*s->wc_alloc));
+    s->w2h1 = malloc(s->n_words * sizeof(int32_t));
+    for (w = 0; w < s->n_words; ++w) s->w2h1[w] = -1;
+    for (i = 0; i < s->n_root; ++i) pso_hmm_init(&s->ctx, &s->rh[i], 1, 0, s->roots[i * 5 + 4]);
+    for (i = 0; i < s->n_nonroot; ++i) pso_hmm_init(&s->ctx, &s->nh[i], 0, s->nonroot[i * 6], s->nonroot[i * 6 + 1]);
+    for (i = 0; i < s->n_1ph; ++i) {
+        pso_hmm_init(&s->ctx, &s->h1[i], 1, s->r1ph[i * 4 + 2], s->r1ph[i * 4 + 3]);
+        s->w2h1[s->w1ph[i]] = i;
+    }
+    for (i = 0; i < 2; ++i) { s->acl[i] = malloc((s->n_nonroot + 1) * sizeof(int32_t)); s->awl[i] = malloc((s->n_words + 1) * sizeof(int32_t)); }
+    s->word_active = calloc(s->n_words, 1);
+    s->word_lat_idx = malloc(s->n_words * sizeof(int32_t)); s->lt_sf = malloc(s->n_words * sizeof(int32_t));
+    s->lt_dscr = calloc(s->n_words, sizeof(int32_t)); s->lt_bp = calloc(s->n_words, sizeof(int32_t));
+    s->cand = malloc((s->n_words + 1) * sizeof(ft_cand_t));
+    s->csf_ef = malloc((s->n_words + 1) * sizeof(int32_t)); s->csf_cand = malloc((s->n_words + 1) * sizeof(int32_t));
+    s->brc_score = malloc(s->n_ci * sizeof(int32_t)); s->brc_path = calloc(s->n_ci, sizeof(int32_t)); s->brc_lc = calloc(s->n_ci, sizeof(int32_t));
+    s->bp_cap = 2048; s->bp = malloc((size_t)s->bp_cap * sizeof(*s->bp));
+    s->bss_cap = 16384 + 2 * s->n_ci; s->bss = malloc((size_t)s->bss_cap * sizeof(*s->bss));
+    s->bp_idx = malloc(((size_t)T + 2) * sizeof(int32_t));
+    /* ngram_fwdtree_start :470-520 */
+    for (w = 0; w < s->n_words; ++w) { s->word_lat_idx[w] = -1; s->lt_sf[w] = -1; }
+    s->best_score = 0;
+    pso_hmm_enter(&s->h1[s->w2h1[s->start_wid]], 0, -1, 0);
+
+    for (frame = 0; frame < T; ++frame) {
+        const int32_t nf = frame + 1, cur = frame & 1, nxt = nf & 1;
+        int32_t bs, k, j, thresh, newphone_thresh, lastphn_thresh;
+        s->ctx.senscore = senscr + (size_t)frame * n_sen;
+        s->bp_idx[frame] = s->bpidx;                                       /* mark_bptable */
+        if (s->best_score <= PSO_WORST_SCORE) break;
+        if (s->best_score + 2 * s->beam < PSO_WORST_SCORE) {               /* renormalize_scores :566-603 */
+            const int32_t norm = s->best_score;
+            for (i = 0; i < s->n_root; ++i) if (s->rh[i].frame == frame) pso_hmm_normalize(&s->rh[i], norm);
+            for (i = 0; i < s->n_acl[cur]; ++i) pso_hmm_normalize(&s->nh[s->acl[cur][i]], norm);
+            for (i = 0; i < s->n_awl[cur]; ++i) {
+                w = s->awl[cur][i];
+                for (j = 0; j < ft_nrc(s, w); ++j) if (s->wc_alloc[w][j]) pso_hmm_normalize(&s->wc[w][j], norm);
+            }
+            for (i = 0; i < s->n_1ph; ++i) if (s->h1[i].frame == frame) pso_hmm_normalize(&s->h1[i], norm);
+        }
+        /* evaluate_channels :702-716 */
+        bs = PSO_WORST_SCORE;
+        for (i = 0; i < s->n_root; ++i)
+            if (s->rh[i].frame == frame) { const int32_t sc = pso_hmm_vit_eval(&s->ctx, &s->rh[i]); if (sc > bs) bs = sc; ++s->n_root_eval; }
+        s->best_score = bs;
+        bs = PSO_WORST_SCORE;
+        s->n_nonroot_eval += s->n_acl[cur];
+        for (i = 0; i < s->n_acl[cur]; ++i) { const int32_t sc = pso_hmm_vit_eval(&s->ctx, &s->nh[s->acl[cur][i]]); if (sc > bs) bs = sc; }
+        if (bs > s->best_score) s->best_score = bs;
+        bs = PSO_WORST_SCORE; k = 0; j = 0;
+        for (i = 0; i < s->n_awl[cur]; ++i) {
+            int32_t r;
+            w = s->awl[cur][i];
+            s->word_active[w] = 0;
+            for (r = 0; r < ft_nrc(s, w); ++r)
+                if (s->wc_alloc[w][r]) { const int32_t sc = pso_hmm_vit_eval(&s->ctx, &s->wc[w][r]); if (sc > bs) bs = sc; ++k; }
+        }
+        for (i = 0; i < s->n_1ph; ++i) {
+            int32_t sc;
+            if (s->h1[i].frame < frame) continue;
+            sc = pso_hmm_vit_eval(&s->ctx, &s->h1[i]);
+            if (sc > bs && s->w1ph[i] != s->finish_wid) bs = sc;
+            ++j;
+        }
+        s->n_nonroot_eval += k + j;
+        if (bs > s->best_score) s->best_score = bs;
+        s->last_phone_best_score = bs;
+        /* prune_channels :1130-1180 */
+        s->n_cand = 0;
+        s->dynamic_beam = s->beam;
+        if (s->maxhmmpf != -1 && s->n_root_eval + s->n_nonroot_eval > s->maxhmmpf) {
+            int32_t bins[256], bw = -s->beam / 256, nh = 0;
+            memset(bins, 0, sizeof(bins));
+            for (i = 0; i < s->n_root; ++i) { int32_t b = (s->best_score - s->rh[i].bestscore) / bw; if (b >= 256) b = 255; ++bins[b]; }
+            for (i = 0; i < s->n_acl[cur]; ++i) { int32_t b = (s->best_score - s->nh[s->acl[cur][i]].bestscore) / bw; if (b >= 256) b = 255; ++bins[b]; }
+            for (i = 0; i < 256; ++i) { nh += bins[i]; if (nh > s->maxhmmpf) break; }
+            s->dynamic_beam = -(i * bw);
+        }
+        thresh = s->best_score + s->dynamic_beam; newphone_thresh = s->best_score + s->pbeam; lastphn_thresh = s->best_score + s->lpbeam;
+        /* prune_root_chan :723-794 */
+        s->n_acl[nxt] = 0;
+        for (i = 0; i < s->n_root; ++i) {
+            pso_hmm_t *rh = &s->rh[i];
+            int32_t nps, c;
+            if (rh->frame < frame) continue;
+            if (!(rh->bestscore > thresh)) continue;
+            rh->frame = nf;
+            nps = rh->out_score + s->pip;
+            if (nps > newphone_thresh)
+                for (c = s->roots[i * 5 + 3]; c >= 0; c = s->nonroot[c * 6 + 5])
+                    if (s->nh[c].frame < frame || nps > s->nh[c].score[0]) {
+                        pso_hmm_enter(&s->nh[c], nps, rh->out_history, nf);
+                        s->acl[nxt][s->n_acl[nxt]++] = c;
+                    }
+            if (nps > lastphn_thresh)
+                for (w = s->roots[i * 5 + 2]; w >= 0; w = FT_W(s, w, 6)) {
+                    ft_cand_t *cp = &s->cand[s->n_cand++];
+                    cp->wid = w; cp->score = nps - s->nwpen; cp->bp = rh->out_history;
+                }
+        }
+        /* prune_nonroot_chan :800-878 */
+        for (i = 0; i < s->n_acl[cur]; ++i) {
+            const int32_t id = s->acl[cur][i];
+            pso_hmm_t *h = &s->nh[id];
+            if (h->bestscore > thresh) {
+                int32_t nps, c;
+                if (h->frame != nf) { h->frame = nf; s->acl[nxt][s->n_acl[nxt]++] = id; }
+                nps = h->out_score + s->pip;
+                if (nps > newphone_thresh)
+                    for (c = s->nonroot[id * 6 + 4]; c >= 0; c = s->nonroot[c * 6 + 5])
+                        if (s->nh[c].frame < frame || nps > s->nh[c].score[0]) {
+                            if (s->nh[c].frame != nf) s->acl[nxt][s->n_acl[nxt]++] = c;
+                            pso_hmm_enter(&s->nh[c], nps, h->out_history, nf);
+                        }
+                if (nps > lastphn_thresh)
+                    for (w = s->nonroot[id * 6 + 3]; w >= 0; w = FT_W(s, w, 6)) {
+                        ft_cand_t *cp = &s->cand[s->n_cand++];
+                        cp->wid = w; cp->score = nps - s->nwpen; cp->bp = h->out_history;
+                    }
+            }
+            else if (h->frame != nf) pso_hmm_clear(h);
+        }
+        /* last_phone_transition :885-1035 */
+        {
+            int32_t n_csf = 0, bestscore, th;
+            s->n_awl[nxt] = 0;
+            for (i = 0; i < s->n_cand; ++i) {
+                ft_cand_t *cp = &s->cand[i];
+                const ft_bp_t *e;
+                if (cp->bp == -1) continue;
+                e = &s->bp[cp->bp];
+                cp->score -= ft_exit_score(s, e, FT_W(s, cp->wid, 0));
+                if (s->lt_sf[cp->wid] != e->frame + 1) {
+                    for (j = 0; j < n_csf; ++j) if (s->csf_ef[j] == e->frame) break;
+                    if (j < n_csf) cp->next = s->csf_cand[j];
+                    else { j = n_csf++; cp->next = -1; s->csf_ef[j] = e->frame; }
+                    s->csf_cand[j] = i;
+                    s->lt_dscr[cp->wid] = PSO_WORST_SCORE;
+                    s->lt_sf[cp->wid] = e->frame + 1;
+                }
+            }
+            for (i = 0; i < n_csf; ++i) {
+                int32_t bp;
+                for (bp = s->bp_idx[s->csf_ef[i]]; bp < s->bp_idx[s->csf_ef[i] + 1]; ++bp) {
+                    const ft_bp_t *e = &s->bp[bp];
+                    if (!e->valid) continue;
+                    for (j = s->csf_cand[i]; j >= 0; j = s->cand[j].next) {
+                        const ft_cand_t *cp = &s->cand[j];
+                        int32_t dscr = ft_exit_score(s, e, FT_W(s, cp->wid, 0));
+                        if (dscr > PSO_WORST_SCORE) dscr += ft_tg(s, FT_W(s, cp->wid, 5), e->real_wid, e->prev_real_wid);
+                        if (dscr > s->lt_dscr[cp->wid]) { s->lt_dscr[cp->wid] = dscr; s->lt_bp[cp->wid] = bp; }
+                    }
+                }
+            }
+            bestscore = s->last_phone_best_score;
+            for (i = 0; i < s->n_cand; ++i) {
+                ft_cand_t *cp = &s->cand[i];
+                cp->score += s->lt_dscr[cp->wid];
+                cp->bp = s->lt_bp[cp->wid];
+                if (cp->score > bestscore) bestscore = cp->score;
+            }
+            s->last_phone_best_score = bestscore;
+            th = bestscore + s->lponlybeam;
+            for (i = 0; i < s->n_cand; ++i) {
+                const ft_cand_t *cp = &s->cand[i];
+                int32_t r;
+                if (!(cp->score > th)) continue;
+                w = cp->wid;
+                ft_alloc_all_rc(s, w);
+                k = 0;
+                for (r = 0; r < ft_nrc(s, w); ++r) {
+                    pso_hmm_t *h = &s->wc[w][r];
+                    if (h->frame < frame || cp->score > h->score[0]) { pso_hmm_enter(h, cp->score, cp->bp, nf); ++k; }
+                }
+                if (k > 0) { s->awl[nxt][s->n_awl[nxt]++] = w; s->word_active[w] = 1; }
+            }
+        }
+        /* prune_word_chan :1042-1126 */
+        {
+            const int32_t newword_thresh = s->last_phone_best_score + s->wbeam, lp_thresh = s->last_phone_best_score + s->lponlybeam;
+            for (i = 0; i < s->n_awl[cur]; ++i) {
+                int32_t r;
+                w = s->awl[cur][i];
+                k = 0;
+                for (r = 0; r < ft_nrc(s, w); ++r) {
+                    pso_hmm_t *h;
+                    if (!s->wc_alloc[w][r]) continue;
+                    h = &s->wc[w][r];
+                    if (h->bestscore > lp_thresh) {
+                        h->frame = nf; ++k;
+                        if (h->out_score > newword_thresh) ft_save_bp(s, frame, w, h->out_score, h->out_history, r);
+                    }
+                    else if (h->frame != nf) s->wc_alloc[w][r] = 0;         /* hmm_deinit + listelem_free */
+                }
+                if (k > 0 && !s->word_active[w]) { s->awl[nxt][s->n_awl[nxt]++] = w; s->word_active[w] = 1; }
+            }
+            for (i = 0; i < s->n_1ph; ++i) {
+                pso_hmm_t *h = &s->h1[i];
+                if (h->frame < frame) continue;
+                if (h->bestscore > lp_thresh) {
+                    h->frame = nf;
+                    if (h->out_score > newword_thresh) ft_save_bp(s, frame, s->w1ph[i], h->out_score, h->out_history, 0);
+                }
+            }
+        }
+        /* bptable_maxwpf :1188-1238 */
+        if (s->maxwpf != -1 && s->maxwpf != s->n_words) {
+            int32_t bp, n = 0, bestscr = INT32_MIN, bestbp = -1;
+            for (bp = s->bp_idx[frame]; bp < s->bpidx; ++bp)
+                if (FT_W(s, s->bp[bp].wid, 4)) {
+                    if (s->bp[bp].score > bestscr) { bestscr = s->bp[bp].score; bestbp = bp; }
+                    s->bp[bp].valid = 0; ++n;
+                }
+            if (bestbp >= 0) { s->bp[bestbp].valid = 1; --n; }
+            n = (s->bpidx - s->bp_idx[frame]) - n;
+            for (; n > s->maxwpf; --n) {
+                int32_t worstscr = INT32_MAX, worstbp = -1;
+                for (bp = s->bp_idx[frame]; bp < s->bpidx; ++bp)
+                    if (s->bp[bp].valid && s->bp[bp].score < worstscr) { worstscr = s->bp[bp].score; worstbp = bp; }
+                if (worstbp < 0) break;
+                s->bp[worstbp].valid = 0;
+            }
+        }
+        /* word_transition :1241-1430 */
+        {
+            int32_t bp, rc;
+            const int32_t nc = s->n_ci;
+            for (i = nc - 1; i >= 0; --i) s->brc_score[i] = PSO_WORST_SCORE;
+            k = 0;
+            for (bp = s->bp_idx[frame]; bp < s->bpidx; ++bp) {
+                const ft_bp_t *e = &s->bp[bp];
+                s->word_lat_idx[e->wid] = -1;
+                if (e->wid == s->finish_wid) continue;
+                ++k;
+                if (e->last2_phone == -1) {
+                    for (rc = 0; rc < nc; ++rc)
+                        if (e->score > s->brc_score[rc]) { s->brc_score[rc] = e->score; s->brc_path[rc] = bp; s->brc_lc[rc] = e->last_phone; }
+                }
+                else {
+                    const int32_t *cimap = s->rs_cimap + ((size_t)e->last_phone * nc + e->last2_phone) * nc;
+                    const int32_t *rcss = s->bss + e->s_idx;
+                    for (rc = 0; rc < nc; ++rc)
+                        if (rcss[cimap[rc]] > s->brc_score[rc]) { s->brc_score[rc] = rcss[cimap[rc]]; s->brc_path[rc] = bp; s->brc_lc[rc] = e->last_phone; }
+                }
+            }
+            if (k > 0) {
+                const int32_t th = s->best_score + s->dynamic_beam;
+                int32_t newscore;
+                for (i = 0; i < s->n_root; ++i) {
+                    const int32_t ci = s->roots[i * 5], ci2 = s->roots[i * 5 + 1];
+                    newscore = s->brc_score[ci] + s->nwpen + s->pip;
+                    if (newscore > th && (s->rh[i].frame < frame || newscore > s->rh[i].score[0])) {
+                        pso_hmm_enter(&s->rh[i], newscore, s->brc_path[ci], nf);
+                        s->rh[i].senid[0] = (uint16_t)s->ldiph[((size_t)ci * nc + ci2) * nc + s->brc_lc[ci]];
+                    }
+                }
+                for (i = 0; i < s->n_1ph_lm; ++i) s->lt_dscr[s->w1ph[i]] = INT32_MIN;
+                for (bp = s->bp_idx[frame]; bp < s->bpidx; ++bp) {
+                    const ft_bp_t *e = &s->bp[bp];
+                    if (!e->valid) continue;
+                    for (i = 0; i < s->n_1ph_lm; ++i) {
+                        w = s->w1ph[i];
+                        newscore = ft_exit_score(s, e, FT_W(s, w, 0));
+                        if (newscore != PSO_WORST_SCORE) newscore += ft_tg(s, FT_W(s, w, 5), e->real_wid, e->prev_real_wid);
+                        if (newscore > s->lt_dscr[w]) { s->lt_dscr[w] = newscore; s->lt_bp[w] = bp; }
+                    }
+                }
+                for (i = 0; i < s->n_1ph_lm; ++i) {
+                    pso_hmm_t *h = &s->h1[i];
+                    w = s->w1ph[i];
+                    if (w == s->start_wid) continue;
+                    newscore = (int32_t)((uint32_t)s->lt_dscr[w] + (uint32_t)s->pip);
+                    if (newscore > th && (h->frame < frame || newscore > h->score[0])) {
+                        pso_hmm_enter(h, newscore, s->lt_bp[w], nf);
+                        h->senid[0] = (uint16_t)s->ldiph[((size_t)s->r1ph[i * 4] * nc + s->r1ph[i * 4 + 1]) * nc
+                                                        + FT_W(s, s->bp[s->lt_bp[w]].wid, 1)];
+                    }
+                }
+                {
+                    pso_hmm_t *h = &s->h1[s->w2h1[s->silence_wid]];
+                    newscore = s->brc_score[s->sil] + s->silpen + s->pip;
+                    if (newscore > th && (h->frame < frame || newscore > h->score[0])) pso_hmm_enter(h, newscore, s->brc_path[s->sil], nf);
+                }
+                for (w = s->filler_start; w <= s->filler_end; ++w) {
+                    pso_hmm_t *h;
+                    if (w == s->silence_wid || w == s->start_wid || s->w2h1[w] < 0) continue;
+                    h = &s->h1[s->w2h1[w]];
+                    newscore = s->brc_score[s->sil] + s->fillpen + s->pip;
+                    if (newscore > th && (h->frame < frame || newscore > h->score[0])) pso_hmm_enter(h, newscore, s->brc_path[s->sil], nf);
+                }
+            }
+        }
+        /* deactivate_channels :1432-1451 */
+        for (i = 0; i < s->n_root; ++i) if (s->rh[i].frame == frame) pso_hmm_clear(&s->rh[i]);
+        for (i = 0; i < s->n_1ph; ++i) if (s->h1[i].frame == frame) pso_hmm_clear(&s->h1[i]);
+        ++n_done;
+    }
+    s->bp_idx[n_done] = s->bpidx;                                          /* ngram_fwdtree_finish :1507 */
+    for (i = 0; i < s->bpidx && i < bp_cap; ++i) memcpy(bp_out + (size_t)i * 10, &s->bp[i], 10 * sizeof(int32_t));
+    for (i = 0; i < s->bss_head && i < bss_cap; ++i) bss_out[i] = s->bss[i];
+    for (i = 0; i <= n_done; ++i) bp_idx_out[i] = s->bp_idx[i];
+    *bss_n = s->bss_head;
+    i = s->bpidx;
+    for (w = 0; w < s->n_words; ++w) { free(s->wc[w]); free(s->wc_alloc[w]); }
+    free(s->rh); free(s->nh); free(s->h1); free(s->wc); free(s->wc_alloc); free(s->w2h1);
+    free(s->acl[0]); free(s->acl[1]); free(s->awl[0]); free(s->awl[1]); free(s->word_active); free(s->word_lat_idx);
+    free(s->lt_sf); free(s->lt_dscr); free(s->lt_bp); free(s->cand); free(s->csf_ef); free(s->csf_cand);
+    free(s->brc_score); free(s->brc_path); free(s->brc_lc); free(s->bp); free(s->bss); free(s->bp_idx);
+    return i;
+}

@@ -1296,3 +1296,185 @@ refdrv_fsg(const char *hmmdir, const char *dict, const char *fsgfile, const char
     ps_config_free(config);
     return need;
 }
+
+/* N-gram lextree decoding, first pass only: the reference's own ngram_search_fwdtree (fwdflat and
+ * bestpath off, no phone-loop look-ahead, all senones) on one utterance, with everything that pass
+ * works on flattened for the oracle.  int32 sections, in this order (sizes from info):
+ *   roots    [n_root][5]      ciphone, ci2phone, penult_phn_wid, next (non-root id or -1), tmatid
+ *   nonroot  [n_nonroot][6]   ssid, tmatid, ciphone, penult_phn_wid, next, alt   (ids: depth-first from the roots)
+ *   words    [n_words][8]     first phone, last phone, second-last phone (-1: single phone), single-phone,
+ *                             filler, basewid, homophone_set[w], index into the LM table (-1: not a base word)
+ *   w1ph     [n_1ph_words]    single_phone_wid[]
+ *   r1ph     [n_1ph_words][4] their permanent root channels: ciphone, ci2phone, ssid, tmatid
+ *   rs_n     [n_ci][n_ci]     dict2pid rssid(last, second-last): n_ssid
+ *   rs_ssid  [n_ci][n_ci][n_ci]   ssid[] padded with -1;   rs_cimap [n_ci][n_ci][n_ci]
+ *   ldiph    [n_ci][n_ci][n_ci]   ldiph_lc[b][r][l]
+ *   lm       [n_lm][n_lm+1][n_lm+1]  ngram_tg_score(w, h1, h2) >> SENSCR_SHIFT, history index 0 = none (-1)
+ *   bp       [bpidx][10]      frame, valid, wid, bp, score, s_idx, real_wid, prev_real_wid, last_phone, last2_phone
+ *   bss      [bss_head]       bscore_stack
+ *   bpidx_f  [n_frame+1]      bp_table_idx
+ * info: 0 n_frame 1 n_words 2 n_root 3 n_nonroot 4 n_1ph_words 5 n_1ph_LMwords 6 n_ci 7 silence phone
+ *   8 beam 9 pbeam 10 wbeam 11 lpbeam 12 lponlybeam 13 maxhmmpf 14 maxwpf 15 nwpen 16 pip 17 silpen
+ *   18 fillpen 19 start wid 20 finish wid 21 silence wid 22 filler_start 23 filler_end 24 bpidx
+ *   25 bss_head 26 n_lm 27 hyp score */
+#include "ngram_search.h"
+#include "ngram_search_fwdtree.h"
+static int
+fwd_count(chan_t *h)
+{
+    int n = 0;
+    for (; h; h = h->alt) n += 1 + fwd_count(h->next);
+    return n;
+}
+static void
+fwd_collect(chan_t *h, chan_t **tab, int *n)
+{
+    for (; h; h = h->alt) { tab[(*n)++] = h; fwd_collect(h->next, tab, n); }
+}
+static int
+fwd_id(chan_t **tab, int n, chan_t *h)
+{
+    int i;
+    if (h == NULL) return -1;
+    for (i = 0; i < n; ++i) if (tab[i] == h) return i;
+    return -2;
+}
+
+long
+refdrv_fwdtree(const char *hmmdir, const char *lm, const char *dictfile, const char *kv,
+               const int16 *pcm, long n_samples, int32 *blob, long cap, int32 *info, char *hyp, int hyp_cap,
+               char *vocab, int vocab_cap)
+{
+    ps_config_t *config;
+    ps_decoder_t *ps;
+    ngram_search_t *ngs;
+    dict_t *dict;
+    dict2pid_t *d2p;
+    bin_mdef_t *mdef;
+    chan_t **tab;
+    int32 *lmidx;
+    int n_nonroot = 0, n_ci, n_words, n_lm = 0, i, j, k, w;
+    long need, o;
+    const char *h;
+    int32 score = 0;
+
+    err_set_loglevel(ERR_ERROR);
+    config = ps_config_init(NULL);
+    ps_config_set_str(config, "hmm", hmmdir);
+    ps_config_set_str(config, "lm", lm);
+    ps_config_set_str(config, "dict", dictfile);
+    ps_config_set_str(config, "dither", "no");
+    ps_config_set_str(config, "compallsen", "yes");
+    ps_config_set_str(config, "pl_window", "0");
+    ps_config_set_str(config, "fwdflat", "no");
+    ps_config_set_str(config, "bestpath", "no");
+    if (kv) {
+        char *b2 = strdup(kv), *s2 = NULL, *t2;
+        for (t2 = strtok_r(b2, "\n", &s2); t2; t2 = strtok_r(NULL, "\n", &s2)) {
+            char *eq = strchr(t2, '=');
+            if (!eq) continue;
+            *eq = 0;
+            ps_config_set_str(config, t2, eq + 1);
+        }
+        free(b2);
+    }
+    ps = ps_init(config);
+    if (ps == NULL) { ps_config_free(config); return -1; }
+    if (ps->search == NULL || strcmp(ps_search_type(ps->search), PS_SEARCH_TYPE_NGRAM) != 0) {
+        ps_free(ps); ps_config_free(config);
+        return -2;
+    }
+    ngs = (ngram_search_t *)ps->search;
+    ps_start_utt(ps);
+    ps_process_raw(ps, pcm, n_samples, FALSE, TRUE);
+    ps_end_utt(ps);
+    h = ps_get_hyp(ps, &score);
+    snprintf(hyp, hyp_cap, "%s", h ? h : "");
+    dict = ps_search_dict(ngs);
+    d2p = ps_search_dict2pid(ngs);
+    mdef = ps->acmod->mdef;
+    n_ci = bin_mdef_n_ciphone(mdef);
+    n_words = ps_search_n_words(ngs);
+    if (vocab && vocab_cap > 0) {                     /* word strings by wid, newline separated */
+        int len = 0;
+        vocab[0] = 0;
+        for (w = 0; w < n_words; ++w)
+            len += snprintf(vocab + len, len < vocab_cap ? vocab_cap - len : 0, "%s\n", dict_wordstr(dict, w));
+    }
+    for (i = 0; i < ngs->n_root_chan; ++i) n_nonroot += fwd_count(ngs->root_chan[i].next);
+    tab = calloc(n_nonroot + 1, sizeof(*tab));
+    k = 0;
+    for (i = 0; i < ngs->n_root_chan; ++i) fwd_collect(ngs->root_chan[i].next, tab, &k);
+    lmidx = calloc(n_words, sizeof(*lmidx));
+    for (w = 0; w < n_words; ++w) lmidx[w] = dict_basewid(dict, w) == w ? n_lm++ : -1;
+    need = (long)ngs->n_root_chan * 5 + (long)n_nonroot * 6 + (long)n_words * 8 + ngs->n_1ph_words * 5L
+        + (long)n_ci * n_ci + 3L * n_ci * n_ci * n_ci + (long)n_lm * (n_lm + 1) * (n_lm + 1)
+        + (long)ngs->bpidx * 10 + ngs->bss_head + ngs->n_frame + 1;
+    memset(info, 0, 32 * sizeof(int32));
+    info[0] = ngs->n_frame; info[1] = n_words; info[2] = ngs->n_root_chan; info[3] = n_nonroot;
+    info[4] = ngs->n_1ph_words; info[5] = ngs->n_1ph_LMwords; info[6] = n_ci; info[7] = mdef->sil;
+    info[8] = ngs->beam; info[9] = ngs->pbeam; info[10] = ngs->wbeam; info[11] = ngs->lpbeam; info[12] = ngs->lponlybeam;
+    info[13] = ngs->maxhmmpf; info[14] = ngs->maxwpf; info[15] = ngs->nwpen; info[16] = ngs->pip;
+    info[17] = ngs->silpen; info[18] = ngs->fillpen; info[19] = dict_startwid(dict); info[20] = ps_search_finish_wid(ngs);
+    info[21] = ps_search_silence_wid(ngs); info[22] = dict_filler_start(dict); info[23] = dict_filler_end(dict);
+    info[24] = ngs->bpidx; info[25] = ngs->bss_head; info[26] = n_lm; info[27] = score;
+    if (blob && cap >= need) {
+        o = 0;
+        for (i = 0; i < ngs->n_root_chan; ++i) {
+            root_chan_t *r = &ngs->root_chan[i];
+            blob[o++] = r->ciphone; blob[o++] = r->ci2phone; blob[o++] = r->penult_phn_wid;
+            blob[o++] = fwd_id(tab, n_nonroot, r->next); blob[o++] = r->hmm.tmatid;
+        }
+        for (i = 0; i < n_nonroot; ++i) {
+            chan_t *c = tab[i];
+            blob[o++] = hmm_nonmpx_ssid(&c->hmm); blob[o++] = c->hmm.tmatid; blob[o++] = c->ciphone;
+            blob[o++] = c->info.penult_phn_wid; blob[o++] = fwd_id(tab, n_nonroot, c->next); blob[o++] = fwd_id(tab, n_nonroot, c->alt);
+        }
+        for (w = 0; w < n_words; ++w) {
+            blob[o++] = dict_first_phone(dict, w); blob[o++] = dict_last_phone(dict, w);
+            blob[o++] = dict_is_single_phone(dict, w) ? -1 : dict_second_last_phone(dict, w);
+            blob[o++] = dict_is_single_phone(dict, w); blob[o++] = dict_filler_word(dict, w);
+            blob[o++] = dict_basewid(dict, w); blob[o++] = ngs->homophone_set[w]; blob[o++] = lmidx[w];
+        }
+        for (i = 0; i < ngs->n_1ph_words; ++i) blob[o++] = ngs->single_phone_wid[i];
+        for (i = 0; i < ngs->n_1ph_words; ++i) {
+            root_chan_t *r = (root_chan_t *)ngs->word_chan[ngs->single_phone_wid[i]];
+            blob[o++] = r->ciphone; blob[o++] = r->ci2phone;
+            blob[o++] = bin_mdef_pid2ssid(mdef, r->ciphone); blob[o++] = r->hmm.tmatid;
+        }
+        for (i = 0; i < n_ci; ++i) for (j = 0; j < n_ci; ++j) blob[o++] = dict2pid_rssid(d2p, i, j)->n_ssid;
+        for (i = 0; i < n_ci; ++i) for (j = 0; j < n_ci; ++j) {
+            xwdssid_t *x = dict2pid_rssid(d2p, i, j);
+            for (k = 0; k < n_ci; ++k) blob[o++] = (x->ssid && k < x->n_ssid) ? x->ssid[k] : -1;
+        }
+        for (i = 0; i < n_ci; ++i) for (j = 0; j < n_ci; ++j) {
+            xwdssid_t *x = dict2pid_rssid(d2p, i, j);
+            for (k = 0; k < n_ci; ++k) blob[o++] = x->cimap ? x->cimap[k] : -1;
+        }
+        for (i = 0; i < n_ci; ++i) for (j = 0; j < n_ci; ++j) for (k = 0; k < n_ci; ++k)
+            blob[o++] = (d2p->ldiph_lc[i] && d2p->ldiph_lc[i][j]) ? dict2pid_ldiph_lc(d2p, i, j, k) : -1;
+        {
+            int32 *rev = calloc(n_lm + 1, sizeof(*rev));
+            rev[0] = -1;
+            for (w = 0; w < n_words; ++w) if (lmidx[w] >= 0) rev[lmidx[w] + 1] = w;
+            for (i = 0; i < n_lm; ++i) for (j = 0; j <= n_lm; ++j) for (k = 0; k <= n_lm; ++k) {
+                int32 n_used;
+                blob[o++] = ngram_tg_score(ngs->lmset, rev[i + 1], rev[j], rev[k], &n_used) >> SENSCR_SHIFT;
+            }
+            free(rev);
+        }
+        for (i = 0; i < ngs->bpidx; ++i) {
+            bptbl_t *b = &ngs->bp_table[i];
+            blob[o++] = b->frame; blob[o++] = b->valid; blob[o++] = b->wid; blob[o++] = b->bp; blob[o++] = b->score;
+            blob[o++] = b->s_idx; blob[o++] = b->real_wid; blob[o++] = b->prev_real_wid; blob[o++] = b->last_phone;
+            blob[o++] = b->last2_phone;
+        }
+        for (i = 0; i < ngs->bss_head; ++i) blob[o++] = ngs->bscore_stack[i];
+        for (i = 0; i <= ngs->n_frame; ++i) blob[o++] = ngs->bp_table_idx[i];
+        if (o != need) need = -3;
+    }
+    free(tab); free(lmidx);
+    ps_free(ps);
+    ps_config_free(config);
+    return need;
+}

@@ -406,3 +406,48 @@ def fsg(hmmdir, dictfile, fsgfile, pcm, **kv):
                 silcipid=int(info[10]), n_ciphone=int(info[11]), start_state=int(info[12]),
                 final_state=int(info[13]), score=int(info[14]), hyp=hyp.value.decode(),
                 vocab=vocab.value.decode().split("\n")[:-1])
+
+
+def fwdtree(hmmdir, lm, dictfile, pcm, **kv):
+    """The reference's first pass (ngram_search_fwdtree; no fwdflat / bestpath / look-ahead) on one
+    utterance: the flattened lextree, dictionary and dict2pid tables, the LM as a dense trigram score
+    table, the search parameters, and the complete backpointer table + right-context score stack."""
+    pcm = np.ascontiguousarray(pcm, np.int16)
+    s = "\n".join("%s=%s" % (k, v) for k, v in kv.items()).encode() or None
+    L = lib()
+    L.refdrv_fwdtree.restype = C.c_long
+    L.refdrv_fwdtree.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_long, C.c_void_p,
+                                 C.c_long, C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    info = np.zeros(32, np.int32)
+    hyp = C.create_string_buffer(4096)
+    vocab = C.create_string_buffer(1 << 20)
+    args = (hmmdir.encode(), lm.encode(), dictfile.encode(), s, _p(pcm), len(pcm))
+    need = L.refdrv_fwdtree(*args, None, 0, _p(info), hyp, 4096, None, 0)
+    if need < 0:
+        raise RuntimeError("refdrv_fwdtree failed: %d" % need)
+    blob = np.zeros(need, np.int32)
+    if L.refdrv_fwdtree(*args, _p(blob), need, _p(info), hyp, 4096, vocab, 1 << 20) != need:
+        raise RuntimeError("refdrv_fwdtree: inconsistent size")
+    keys = ("n_frame n_words n_root n_nonroot n_1ph_words n_1ph_LMwords n_ci sil beam pbeam wbeam lpbeam lponlybeam "
+            "maxhmmpf maxwpf nwpen pip silpen fillpen start_wid finish_wid silence_wid filler_start filler_end bpidx "
+            "bss_head n_lm score").split()
+    r = {k: int(info[i]) for i, k in enumerate(keys)}
+    o = [0]
+
+    def take(*shape):
+        n = int(np.prod(shape))
+        a = blob[o[0]:o[0] + n].reshape(shape).copy()
+        o[0] += n
+        return a
+    nc, nl = r["n_ci"], r["n_lm"]
+    r["roots"] = take(r["n_root"], 5); r["nonroot"] = take(r["n_nonroot"], 6); r["words"] = take(r["n_words"], 8)
+    r["w1ph"] = take(r["n_1ph_words"]); r["r1ph"] = take(r["n_1ph_words"], 4)
+    r["rs_n"] = take(nc, nc); r["rs_ssid"] = take(nc, nc, nc); r["rs_cimap"] = take(nc, nc, nc); r["ldiph"] = take(nc, nc, nc)
+    r["lm"] = take(nl, nl + 1, nl + 1)
+    r["bp"] = take(r["bpidx"], 10); r["bss"] = take(r["bss_head"]); r["bp_idx"] = take(r["n_frame"] + 1)
+    assert o[0] == need
+    r["hyp"] = hyp.value.decode()
+    r["vocab"] = vocab.value.decode().split("\n")[:-1]
+    r["info"] = info.copy()
+    r["model"] = blob[:need - (r["bpidx"] * 10 + r["bss_head"] + r["n_frame"] + 1)].copy()
+    return r
