@@ -126,7 +126,9 @@ def make_fwdtree():
                     ("narrow", dict(beam="1e-30", pbeam="1e-25", wbeam="1e-15", lpbeam="1e-20", lponlybeam="1e-15")),
                     ("maxwpf", dict(maxwpf="5")),
                     ("abs", dict(maxhmmpf="50", maxwpf="10")),
-                    ("pen", dict(nwpen="0.5", pip="0.7", wip="0.3", lw="9.5", silprob="0.01", fillprob="1e-4"))):
+                    ("pen", dict(nwpen="0.5", pip="0.7", wip="0.3", lw="9.5", silprob="0.01", fillprob="1e-4")),
+                    # the shipped default: phone-loop look-ahead on (its penalties are en_us_goforward.npz:pl_pen)
+                    ("lookahead", dict(pl_window="5"))):
         r = refdrv.fwdtree(hd, os.path.join(REF, "test/data/turtle.lm.bin"), os.path.join(REF, "test/data/turtle.dic"), pcm, **kv)
         for k in ("info", "model", "bp", "bss", "bp_idx", "words"):
             out[tag + "." + k] = r[k]

@@ -438,9 +438,12 @@ def fsg_hyp_wids(hist, links, bp):
     return out[::-1]
 
 
-def fwdtree_run(tp, sseq, ci_tmat, info, model, senscr):
+def fwdtree_run(tp, sseq, ci_tmat, info, model, senscr, pl_pen=None, pl_window=0):
     """ngram_search_fwdtree.c for one utterance on the flattened search `info` / `model`
-    (refdrv.fwdtree / the golden file); returns (bp table [n][10], bscore_stack, bp_table_idx)."""
+    (refdrv.fwdtree / the golden file); returns (bp table [n][10], bscore_stack, bp_table_idx).
+    pl_pen [T][n_ci] + pl_window: the phone loop's penalties after each of ITS steps and its window;
+    frame t of the search runs after the phone loop has seen frame min(t + window, T - 1)
+    (ps_search_forward / ps_end_utt, pocketsphinx.c:1172-1195, 1329-1333)."""
     tp = np.ascontiguousarray(tp, np.uint8); sseq = np.ascontiguousarray(sseq, np.uint16)
     ci_tmat = np.ascontiguousarray(ci_tmat, np.int32)
     info = np.ascontiguousarray(info, np.int32); model = np.ascontiguousarray(model, np.int32)
@@ -449,11 +452,15 @@ def fwdtree_run(tp, sseq, ci_tmat, info, model, senscr):
     bp_cap, bss_cap = 64 * (T + 16), 64 * (T + 16) * 64
     bp = np.zeros((bp_cap, 10), np.int32); bss = np.zeros(bss_cap, np.int32); bp_idx = np.zeros(T + 2, np.int32)
     bss_n = C.c_int32()
+    pen = None
+    if pl_pen is not None and pl_window > 0 and T > 0:
+        pen = np.ascontiguousarray(np.asarray(pl_pen, np.int32)[np.minimum(np.arange(T) + pl_window, T - 1)])
     f = lib().pso_fwdtree_run
     f.restype = C.c_int32
-    f.argtypes = [C.c_int32] + [C.c_void_p] * 6 + [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
-                                                    C.c_void_p, C.c_void_p]
-    n = f(tp.shape[1], _p(tp), _p(sseq), _p(ci_tmat), _p(info), _p(model), _p(senscr), n_sen, T, _p(bp), bp_cap, _p(bss),
+    f.argtypes = [C.c_int32] + [C.c_void_p] * 6 + [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                                    C.c_int32, C.c_void_p, C.c_void_p]
+    n = f(tp.shape[1], _p(tp), _p(sseq), _p(ci_tmat), _p(info), _p(model), _p(senscr), n_sen, T,
+          _p(pen) if pen is not None else None, _p(bp), bp_cap, _p(bss),
           bss_cap, C.byref(bss_n), _p(bp_idx))
     assert n <= bp_cap and bss_n.value <= bss_cap
     return bp[:n].copy(), bss[:bss_n.value].copy(), bp_idx[:T + 1].copy()

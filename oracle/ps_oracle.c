@@ -1883,7 +1883,8 @@ pso_fsg_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq,
  * last_phone_transition :885, prune_word_chan :1042], bptable_maxwpf :1188, word_transition :1241,
  * deactivate_channels :1432; start :470) with the backpointer-table side of ngram_search.c
  * (mark_bptable :324, set_real_wid :343, save_bp :378, alloc_all_rc :593, exit_score :655) restated
- * for one utterance, all senones computed, no phone-loop look-ahead (pls == NULL).  `info` and
+ * for one utterance, all senones computed; pen [T][n_ci] = the phone-loop look-ahead penalties in
+ * force while frame t is searched (pls->penalties, NULL without look-ahead).  `info` and
  * `model` are what oracle/ref_driver.c:refdrv_fwdtree exports (the reference's own lextree,
  * dictionary / dict2pid tables, dense trigram table, parameters).  Output: the backpointer table
  * rows (frame, valid, wid, bp, score, s_idx, real_wid, prev_real_wid, last_phone, last2_phone), the
@@ -2002,11 +2003,12 @@ ft_alloc_all_rc(ft_t *s, int32_t w)                                        /* :5
 int32_t
 pso_fwdtree_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, const int32_t *ci_tmat,
                 const int32_t *info, const int32_t *model, const int16_t *senscr, int32_t n_sen, int32_t T,
-                int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap, int32_t *bss_n, int32_t *bp_idx_out)
+                const int32_t *pen, int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap, int32_t *bss_n, int32_t *bp_idx_out)
 {
     ft_t S, *s = &S;
     int32_t i, w, frame, n_done = 0;
-    const int32_t *m = model;
+    const int32_t *m = model, *pl = NULL;
+#define FT_PL(ci) (pl ? pl[ci] : 0)      /* phone_loop_search_score, phone_loop_search.h:103 */
     memset(s, 0, sizeof(*s));
     s->n_words = info[1]; s->n_root = info[2]; s->n_nonroot = info[3]; s->n_1ph = info[4]; s->n_1ph_lm = info[5];
     s->n_ci = info[6]; s->sil = info[7]; s->beam = info[8]; s->pbeam = info[9]; s->wbeam = info[10]; s->lpbeam = info[11];
@@ -2051,6 +2053,7 @@ pso_fwdtree_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, c
         const int32_t nf = frame + 1, cur = frame & 1, nxt = nf & 1;
         int32_t bs, k, j, thresh, newphone_thresh, lastphn_thresh;
         s->ctx.senscore = senscr + (size_t)frame * n_sen;
+        pl = pen ? pen + (size_t)frame * s->n_ci : NULL;
         s->bp_idx[frame] = s->bpidx;                                       /* mark_bptable */
         if (s->best_score <= PSO_WORST_SCORE) break;
         if (s->best_score + 2 * s->beam < PSO_WORST_SCORE) {               /* renormalize_scores :566-603 */
@@ -2111,15 +2114,17 @@ pso_fwdtree_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, c
             if (!(rh->bestscore > thresh)) continue;
             rh->frame = nf;
             nps = rh->out_score + s->pip;
-            if (nps > newphone_thresh)
+            if (pl || nps > newphone_thresh)
                 for (c = s->roots[i * 5 + 3]; c >= 0; c = s->nonroot[c * 6 + 5])
-                    if (s->nh[c].frame < frame || nps > s->nh[c].score[0]) {
+                    if (nps + FT_PL(s->nonroot[c * 6 + 2]) > newphone_thresh && (s->nh[c].frame < frame || nps > s->nh[c].score[0])) {
                         pso_hmm_enter(&s->nh[c], nps, rh->out_history, nf);
                         s->acl[nxt][s->n_acl[nxt]++] = c;
                     }
-            if (nps > lastphn_thresh)
+            if (pl || nps > lastphn_thresh)
                 for (w = s->roots[i * 5 + 2]; w >= 0; w = FT_W(s, w, 6)) {
-                    ft_cand_t *cp = &s->cand[s->n_cand++];
+                    ft_cand_t *cp;
+                    if (!(nps + FT_PL(FT_W(s, w, 1)) > lastphn_thresh)) continue;
+                    cp = &s->cand[s->n_cand++];
                     cp->wid = w; cp->score = nps - s->nwpen; cp->bp = rh->out_history;
                 }
         }
@@ -2131,15 +2136,17 @@ pso_fwdtree_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, c
                 int32_t nps, c;
                 if (h->frame != nf) { h->frame = nf; s->acl[nxt][s->n_acl[nxt]++] = id; }
                 nps = h->out_score + s->pip;
-                if (nps > newphone_thresh)
+                if (pl || nps > newphone_thresh)
                     for (c = s->nonroot[id * 6 + 4]; c >= 0; c = s->nonroot[c * 6 + 5])
-                        if (s->nh[c].frame < frame || nps > s->nh[c].score[0]) {
+                        if (nps + FT_PL(s->nonroot[c * 6 + 2]) > newphone_thresh && (s->nh[c].frame < frame || nps > s->nh[c].score[0])) {
                             if (s->nh[c].frame != nf) s->acl[nxt][s->n_acl[nxt]++] = c;
                             pso_hmm_enter(&s->nh[c], nps, h->out_history, nf);
                         }
-                if (nps > lastphn_thresh)
+                if (pl || nps > lastphn_thresh)
                     for (w = s->nonroot[id * 6 + 3]; w >= 0; w = FT_W(s, w, 6)) {
-                        ft_cand_t *cp = &s->cand[s->n_cand++];
+                        ft_cand_t *cp;
+                        if (!(nps + FT_PL(FT_W(s, w, 1)) > lastphn_thresh)) continue;
+                        cp = &s->cand[s->n_cand++];
                         cp->wid = w; cp->score = nps - s->nwpen; cp->bp = h->out_history;
                     }
             }
@@ -2274,7 +2281,7 @@ pso_fwdtree_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, c
                 for (i = 0; i < s->n_root; ++i) {
                     const int32_t ci = s->roots[i * 5], ci2 = s->roots[i * 5 + 1];
                     newscore = s->brc_score[ci] + s->nwpen + s->pip;
-                    if (newscore > th && (s->rh[i].frame < frame || newscore > s->rh[i].score[0])) {
+                    if (newscore + FT_PL(ci) > th && (s->rh[i].frame < frame || newscore > s->rh[i].score[0])) {
                         pso_hmm_enter(&s->rh[i], newscore, s->brc_path[ci], nf);
                         s->rh[i].senid[0] = (uint16_t)s->ldiph[((size_t)ci * nc + ci2) * nc + s->brc_lc[ci]];
                     }
@@ -2295,7 +2302,7 @@ pso_fwdtree_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, c
                     w = s->w1ph[i];
                     if (w == s->start_wid) continue;
                     newscore = (int32_t)((uint32_t)s->lt_dscr[w] + (uint32_t)s->pip);
-                    if (newscore > th && (h->frame < frame || newscore > h->score[0])) {
+                    if ((int64_t)newscore + FT_PL(s->r1ph[i * 4]) > th && (h->frame < frame || newscore > h->score[0])) {
                         pso_hmm_enter(h, newscore, s->lt_bp[w], nf);
                         h->senid[0] = (uint16_t)s->ldiph[((size_t)s->r1ph[i * 4] * nc + s->r1ph[i * 4 + 1]) * nc
                                                         + FT_W(s, s->bp[s->lt_bp[w]].wid, 1)];
@@ -2304,14 +2311,14 @@ pso_fwdtree_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, c
                 {
                     pso_hmm_t *h = &s->h1[s->w2h1[s->silence_wid]];
                     newscore = s->brc_score[s->sil] + s->silpen + s->pip;
-                    if (newscore > th && (h->frame < frame || newscore > h->score[0])) pso_hmm_enter(h, newscore, s->brc_path[s->sil], nf);
+                    if (newscore + FT_PL(s->r1ph[s->w2h1[s->silence_wid] * 4]) > th && (h->frame < frame || newscore > h->score[0])) pso_hmm_enter(h, newscore, s->brc_path[s->sil], nf);
                 }
                 for (w = s->filler_start; w <= s->filler_end; ++w) {
                     pso_hmm_t *h;
                     if (w == s->silence_wid || w == s->start_wid || s->w2h1[w] < 0) continue;
                     h = &s->h1[s->w2h1[w]];
                     newscore = s->brc_score[s->sil] + s->fillpen + s->pip;
-                    if (newscore > th && (h->frame < frame || newscore > h->score[0])) pso_hmm_enter(h, newscore, s->brc_path[s->sil], nf);
+                    if (newscore + FT_PL(s->r1ph[s->w2h1[w] * 4]) > th && (h->frame < frame || newscore > h->score[0])) pso_hmm_enter(h, newscore, s->brc_path[s->sil], nf);
                 }
             }
         }
@@ -2331,5 +2338,6 @@ pso_fwdtree_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, c
     free(s->acl[0]); free(s->acl[1]); free(s->awl[0]); free(s->awl[1]); free(s->word_active); free(s->word_lat_idx);
     free(s->lt_sf); free(s->lt_dscr); free(s->lt_bp); free(s->cand); free(s->csf_ef); free(s->csf_cand);
     free(s->brc_score); free(s->brc_path); free(s->brc_lc); free(s->bp); free(s->bss); free(s->bp_idx);
+#undef FT_PL
     return i;
 }

@@ -185,7 +185,7 @@ int32_t pso_fsg_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sse
  * oracle/ref_driver.c:refdrv_fwdtree, ci_tmat[n_ci] = transition matrix of every CI phone. */
 int32_t pso_fwdtree_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, const int32_t *ci_tmat,
                         const int32_t *info, const int32_t *model, const int16_t *senscr, int32_t n_sen, int32_t T,
-                        int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap, int32_t *bss_n,
+                        const int32_t *pen, int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap, int32_t *bss_n,
                         int32_t *bp_idx_out);
 
 #ifdef __cplusplus

@@ -9,7 +9,7 @@ import pytest
 
 from conftest import golden
 
-TAGS = ("default", "wide", "narrow", "maxwpf", "abs", "pen")
+TAGS = ("default", "wide", "narrow", "maxwpf", "abs", "pen", "lookahead")
 
 
 def _case(g, tag):
@@ -23,7 +23,9 @@ def test_fwdtree_oracle_matches_reference_golden(tag):
     scr = golden("en_us_goforward.npz")["senscr"]
     c = _case(golden("en_us_fwdtree.npz"), tag)
     n_ci = int(c["info"][6])
-    bp, bss, bp_idx = oracle.fwdtree_run(m["tp"], m["sseq"], m["phone_tmat"][:n_ci], c["info"], c["model"], scr)
+    gf = golden("en_us_goforward.npz")
+    la = dict(pl_pen=gf["pl_pen"], pl_window=int(gf["pl_params"][4])) if tag == "lookahead" else {}
+    bp, bss, bp_idx = oracle.fwdtree_run(m["tp"], m["sseq"], m["phone_tmat"][:n_ci], c["info"], c["model"], scr, **la)
     assert bp.shape == c["bp"].shape and np.array_equal(bp, c["bp"])
     assert np.array_equal(bss, c["bss"]) and np.array_equal(bp_idx, c["bp_idx"])
     b, score = oracle.fwdtree_find_exit(bp, bp_idx, len(scr), int(c["info"][20]))
