@@ -137,6 +137,20 @@ def make_fwdtree():
         out[tag + ".score"] = np.int32(r["score"])
         print("fwdtree", tag, r["n_root"], "root", r["n_nonroot"], "non-root channels,", r["bpidx"], "bp entries,",
               r["bss_head"], "rc scores:", r["hyp"], r["score"])
+    # second pass (ngram_search_fwdflat) on top of the first: the shipped default pipeline (look-ahead on in
+    # the first pass), wide and narrow second-pass beams with other end-frame / start-window limits
+    for tag, kv in (("flat_default", dict(pl_window="5")),
+                    ("flat_wide", dict(fwdflatbeam="1e-80", fwdflatwbeam="1e-40", fwdflatefwid="1", fwdflatsfwin="60")),
+                    ("flat_narrow", dict(fwdflatbeam="1e-30", fwdflatwbeam="1e-10", fwdflatefwid="8", fwdflatsfwin="5",
+                                         fwdflatlw="12"))):
+        r = refdrv.fwdtree(hd, os.path.join(REF, "test/data/turtle.lm.bin"), os.path.join(REF, "test/data/turtle.dic"), pcm,
+                           fwdflat="yes", **kv)
+        for k in ("info", "model", "bp", "bss", "bp_idx", "words"):
+            out[tag + "." + k] = r[k]
+        out[tag + ".vocab"] = np.array("\n".join(r["vocab"]))
+        out[tag + ".hyp"] = np.array(r["hyp"])
+        out[tag + ".score"] = np.int32(r["score"])
+        print("fwdflat", tag, r["bpidx"], "bp entries,", r["bss_head"], "rc scores:", r["hyp"], r["score"])
     np.savez_compressed(os.path.join(OUT, "en_us_fwdtree.npz"), **out)
 
 

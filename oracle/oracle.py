@@ -496,3 +496,25 @@ def fwdtree_hyp(bp, b, words, vocab, start_wid, finish_wid):
         if not words[w][4] and int(words[w][5]) not in (start_wid, finish_wid):
             out.append(vocab[int(words[w][5])])
     return " ".join(reversed(out))
+
+
+def fwdflat_run(tp, sseq, ci_tmat, ci_ssid, info, model, bp_first, senscr):
+    """ngram_search_fwdflat.c for one utterance: bp_first = the first pass's backpointer table,
+    info / model from an export made with fwdflat=yes.  Returns (bp table, bscore_stack, bp_table_idx)."""
+    tp = np.ascontiguousarray(tp, np.uint8); sseq = np.ascontiguousarray(sseq, np.uint16)
+    ci_tmat = np.ascontiguousarray(ci_tmat, np.int32); ci_ssid = np.ascontiguousarray(ci_ssid, np.int32)
+    info = np.ascontiguousarray(info, np.int32); model = np.ascontiguousarray(model, np.int32)
+    bp_first = np.ascontiguousarray(bp_first, np.int32)
+    senscr = np.ascontiguousarray(senscr, np.int16)
+    T, n_sen = senscr.shape
+    bp_cap, bss_cap = 64 * (T + 16), 64 * (T + 16) * 64
+    bp = np.zeros((bp_cap, 10), np.int32); bss = np.zeros(bss_cap, np.int32); bp_idx = np.zeros(T + 2, np.int32)
+    bss_n = C.c_int32()
+    f = lib().pso_fwdflat_run
+    f.restype = C.c_int32
+    f.argtypes = [C.c_int32] + [C.c_void_p] * 7 + [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    n = f(tp.shape[1], _p(tp), _p(sseq), _p(ci_tmat), _p(ci_ssid), _p(info), _p(model), _p(bp_first), len(bp_first),
+          _p(senscr), n_sen, T, _p(bp), bp_cap, _p(bss), bss_cap, C.byref(bss_n), _p(bp_idx))
+    assert n <= bp_cap and bss_n.value <= bss_cap
+    return bp[:n].copy(), bss[:bss_n.value].copy(), bp_idx[:T + 1].copy()

@@ -1897,6 +1897,9 @@ typedef struct {
     int32_t beam, pbeam, wbeam, lpbeam, lponlybeam, maxhmmpf, maxwpf, nwpen, pip, silpen, fillpen;
     int32_t start_wid, finish_wid, silence_wid, filler_start, filler_end;
     const int32_t *roots, *nonroot, *words, *w1ph, *r1ph, *rs_n, *rs_ssid, *rs_cimap, *ldiph, *lm, *ci_tmat;
+    const int32_t *inlm, *pron_off, *pron_ci, *pron_ssid;
+    int32_t fwdflatbeam, fwdflatwbeam, min_ef_width, max_sf_win;
+    float lwf;
     pso_hmmctx_t ctx;
     /* channels */
     pso_hmm_t *rh, *nh, *h1;          /* root, non-root, single-phone words */
@@ -2000,15 +2003,12 @@ ft_alloc_all_rc(ft_t *s, int32_t w)                                        /* :5
         }
 }
 
-int32_t
-pso_fwdtree_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, const int32_t *ci_tmat,
-                const int32_t *info, const int32_t *model, const int16_t *senscr, int32_t n_sen, int32_t T,
-                const int32_t *pen, int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap, int32_t *bss_n, int32_t *bp_idx_out)
+static void
+ft_setup(ft_t *s, int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, const int32_t *ci_tmat,
+         const int32_t *info, const int32_t *model, int32_t T)
 {
-    ft_t S, *s = &S;
-    int32_t i, w, frame, n_done = 0;
-    const int32_t *m = model, *pl = NULL;
-#define FT_PL(ci) (pl ? pl[ci] : 0)      /* phone_loop_search_score, phone_loop_search.h:103 */
+    const int32_t *m = model;
+    int32_t i, w;
     memset(s, 0, sizeof(*s));
     s->n_words = info[1]; s->n_root = info[2]; s->n_nonroot = info[3]; s->n_1ph = info[4]; s->n_1ph_lm = info[5];
     s->n_ci = info[6]; s->sil = info[7]; s->beam = info[8]; s->pbeam = info[9]; s->wbeam = info[10]; s->lpbeam = info[11];
@@ -2044,6 +2044,35 @@ pso_fwdtree_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, c
     s->bp_cap = 2048; s->bp = malloc((size_t)s->bp_cap * sizeof(*s->bp));
     s->bss_cap = 16384 + 2 * s->n_ci; s->bss = malloc((size_t)s->bss_cap * sizeof(*s->bss));
     s->bp_idx = malloc(((size_t)T + 2) * sizeof(int32_t));
+    s->inlm = m + (size_t)s->n_lm * (s->n_lm + 1) * (s->n_lm + 1);
+    s->pron_off = s->inlm + s->n_words;
+    s->pron_ci = s->pron_off + s->n_words + 1;
+    s->pron_ssid = s->pron_ci + info[33];
+    s->fwdflatbeam = info[28]; s->fwdflatwbeam = info[29]; s->min_ef_width = info[30]; s->max_sf_win = info[31];
+    memcpy(&s->lwf, &info[32], 4);
+}
+
+static void
+ft_free(ft_t *s)
+{
+    int32_t w;
+    for (w = 0; w < s->n_words; ++w) { free(s->wc[w]); free(s->wc_alloc[w]); }
+    free(s->rh); free(s->nh); free(s->h1); free(s->wc); free(s->wc_alloc); free(s->w2h1);
+    free(s->acl[0]); free(s->acl[1]); free(s->awl[0]); free(s->awl[1]); free(s->word_active); free(s->word_lat_idx);
+    free(s->lt_sf); free(s->lt_dscr); free(s->lt_bp); free(s->cand); free(s->csf_ef); free(s->csf_cand);
+    free(s->brc_score); free(s->brc_path); free(s->brc_lc); free(s->bp); free(s->bss); free(s->bp_idx);
+}
+
+int32_t
+pso_fwdtree_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, const int32_t *ci_tmat,
+                const int32_t *info, const int32_t *model, const int16_t *senscr, int32_t n_sen, int32_t T,
+                const int32_t *pen, int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap, int32_t *bss_n, int32_t *bp_idx_out)
+{
+    ft_t S, *s = &S;
+    int32_t i, w, frame, n_done = 0;
+    const int32_t *pl = NULL;
+#define FT_PL(ci) (pl ? pl[ci] : 0)      /* phone_loop_search_score, phone_loop_search.h:103 */
+    ft_setup(s, n_emit_state, tp, sseq, ci_tmat, info, model, T);
     /* ngram_fwdtree_start :470-520 */
     for (w = 0; w < s->n_words; ++w) { s->word_lat_idx[w] = -1; s->lt_sf[w] = -1; }
     s->best_score = 0;
@@ -2333,11 +2362,239 @@ pso_fwdtree_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, c
     for (i = 0; i <= n_done; ++i) bp_idx_out[i] = s->bp_idx[i];
     *bss_n = s->bss_head;
     i = s->bpidx;
-    for (w = 0; w < s->n_words; ++w) { free(s->wc[w]); free(s->wc_alloc[w]); }
-    free(s->rh); free(s->nh); free(s->h1); free(s->wc); free(s->wc_alloc); free(s->w2h1);
-    free(s->acl[0]); free(s->acl[1]); free(s->awl[0]); free(s->awl[1]); free(s->word_active); free(s->word_lat_idx);
-    free(s->lt_sf); free(s->lt_dscr); free(s->lt_bp); free(s->cand); free(s->csf_ef); free(s->csf_cand);
-    free(s->brc_score); free(s->brc_path); free(s->brc_lc); free(s->bp); free(s->bss); free(s->bp_idx);
+    ft_free(s);
 #undef FT_PL
+    return i;
+}
+
+/* ---------------------------------------------------------------------------------------
+ * N-gram decoding, second pass: ngram_search_fwdflat.c (start :371-414 with
+ * build_fwdflat_wordlist :224-300 and build_fwdflat_chan :306-368, search step :813-875 =
+ * fwdflat_eval_chan :445, fwdflat_prune_chan :483-607, fwdflat_word_transition :643-782 with
+ * get_expand_wordlist :610-640) restated for one utterance.  Input: the FIRST pass's backpointer
+ * table (bp_in [n_bp_in][10], the utterance vocabulary and the start-frame windows come from it) and
+ * the same flattened search as pso_fwdtree_run (exported with fwdflat=yes so that info holds
+ * fwdflatbeam / fwdflatwbeam / fwdflatefwid / fwdflatsfwin / the language-weight ratio).
+ * ci_ssid[n_ci]: senone sequence of every CI phone (roots start from it).  Output as pso_fwdtree_run. */
+typedef struct { int32_t wid, fef, lef, next; } ff_node_t;
+
+int32_t
+pso_fwdflat_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, const int32_t *ci_tmat, const int32_t *ci_ssid,
+                const int32_t *info, const int32_t *model, const int32_t *bp_in, int32_t n_bp_in,
+                const int16_t *senscr, int32_t n_sen, int32_t T,
+                int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap, int32_t *bss_n, int32_t *bp_idx_out)
+{
+    ft_t S, *s = &S;
+    int32_t i, w, f, frame, n_done = 0, n_node = 0, nwd = 0;
+    ff_node_t *node = malloc(((size_t)n_bp_in + 1) * sizeof(*node));
+    int32_t *head = malloc(((size_t)T + 1) * sizeof(int32_t));
+    int32_t *wordlist, *expand, *n_int;
+    uint8_t *expand_flag;
+    pso_hmm_t *fr, **fi;
+
+    ft_setup(s, n_emit_state, tp, sseq, ci_tmat, info, model, T);
+    wordlist = malloc((s->n_words + 1) * sizeof(int32_t)); expand = malloc((s->n_words + 1) * sizeof(int32_t));
+    expand_flag = calloc(s->n_words, 1);
+    fr = calloc(s->n_words, sizeof(*fr)); fi = calloc(s->n_words, sizeof(*fi)); n_int = calloc(s->n_words, sizeof(int32_t));
+    /* build_fwdflat_wordlist */
+    for (f = 0; f <= T; ++f) head[f] = -1;
+    for (i = 0; i < n_bp_in; ++i) {
+        const int32_t *b = bp_in + (size_t)i * 10;
+        const int32_t sf = b[3] < 0 ? 0 : bp_in[(size_t)b[3] * 10] + 1, ef = b[0], wid = b[2];
+        int32_t n;
+        if (!s->inlm[wid]) continue;
+        for (n = head[sf]; n >= 0 && node[n].wid != wid; n = node[n].next);
+        if (n >= 0) node[n].lef = ef;
+        else { n = n_node++; node[n].wid = wid; node[n].fef = node[n].lef = ef; node[n].next = head[sf]; head[sf] = n; }
+    }
+    for (f = 0; f < T; ++f) {
+        int32_t prev = -1, n, nx;
+        for (n = head[f]; n >= 0; n = nx) {
+            nx = node[n].next;
+            if (node[n].lef - node[n].fef < s->min_ef_width || (node[n].wid == s->finish_wid && node[n].lef < T - 1)) {
+                if (prev < 0) head[f] = nx; else node[prev].next = nx;
+            }
+            else prev = n;
+        }
+    }
+    memset(s->word_active, 0, s->n_words);
+    for (f = 0; f < T; ++f) {
+        int32_t n;
+        for (n = head[f]; n >= 0; n = node[n].next)
+            if (!s->word_active[node[n].wid]) { s->word_active[node[n].wid] = 1; wordlist[nwd++] = node[n].wid; }
+    }
+    wordlist[nwd] = -1;
+    /* build_fwdflat_chan */
+    for (i = 0; i < nwd; ++i) {
+        int32_t p, len;
+        w = wordlist[i];
+        if (FT_W(s, w, 3)) continue;
+        len = s->pron_off[w + 1] - s->pron_off[w];
+        pso_hmm_init(&s->ctx, &fr[w], 1, ci_ssid[FT_W(s, w, 0)], ci_tmat[FT_W(s, w, 0)]);
+        n_int[w] = len - 2;
+        fi[w] = calloc(len > 2 ? len - 2 : 1, sizeof(pso_hmm_t));
+        for (p = 1; p < len - 1; ++p)
+            pso_hmm_init(&s->ctx, &fi[w][p - 1], 0, s->pron_ssid[s->pron_off[w] + p], ci_tmat[s->pron_ci[s->pron_off[w] + p]]);
+        ft_alloc_all_rc(s, w);
+    }
+    /* ngram_fwdflat_start */
+    for (w = 0; w < s->n_words; ++w) { s->word_lat_idx[w] = -1; s->lt_sf[w] = -1; }
+    for (i = 0; i < s->n_1ph; ++i) pso_hmm_clear(&s->h1[i]);
+    pso_hmm_enter(&s->h1[s->w2h1[s->start_wid]], 0, -1, 0);
+    s->awl[0][0] = s->start_wid; s->n_awl[0] = 1;
+    s->best_score = 0;
+
+#define FF_ROOT(w) (FT_W(s, (w), 3) ? &s->h1[s->w2h1[(w)]] : &fr[(w)])
+    for (frame = 0; frame < T; ++frame) {
+        const int32_t cf = frame, nf = frame + 1, cur = cf & 1, nxt = nf & 1, nw = s->n_awl[cur], pip = s->pip;
+        int32_t thresh, wordthresh, bestscore, k, r;
+        s->ctx.senscore = senscr + (size_t)frame * n_sen;
+        s->bp_idx[frame] = s->bpidx;
+        if (s->best_score <= PSO_WORST_SCORE) break;
+        if (s->best_score + 2 * s->beam < PSO_WORST_SCORE) {                /* fwdflat_renormalize_scores :785-810 */
+            const int32_t norm = s->best_score;
+            for (i = 0; i < nw; ++i) {
+                pso_hmm_t *rh;
+                w = s->awl[cur][i]; rh = FF_ROOT(w);
+                if (rh->frame == cf) pso_hmm_normalize(rh, norm);
+                if (FT_W(s, w, 3)) continue;
+                for (k = 0; k < n_int[w]; ++k) if (fi[w][k].frame == cf) pso_hmm_normalize(&fi[w][k], norm);
+                for (r = 0; r < ft_nrc(s, w); ++r) if (s->wc[w][r].frame == cf) pso_hmm_normalize(&s->wc[w][r], norm);
+            }
+        }
+        /* fwdflat_eval_chan */
+        bestscore = PSO_WORST_SCORE;
+        for (i = 0; i < nw; ++i) {
+            pso_hmm_t *rh;
+            w = s->awl[cur][i]; rh = FF_ROOT(w);
+            if (rh->frame == cf) { const int32_t sc = pso_hmm_vit_eval(&s->ctx, rh); if (sc > bestscore && w != s->finish_wid) bestscore = sc; }
+            if (FT_W(s, w, 3)) continue;
+            for (k = 0; k < n_int[w]; ++k)
+                if (fi[w][k].frame == cf) { const int32_t sc = pso_hmm_vit_eval(&s->ctx, &fi[w][k]); if (sc > bestscore) bestscore = sc; }
+            for (r = 0; r < ft_nrc(s, w); ++r)
+                if (s->wc[w][r].frame == cf) { const int32_t sc = pso_hmm_vit_eval(&s->ctx, &s->wc[w][r]); if (sc > bestscore) bestscore = sc; }
+        }
+        s->best_score = bestscore;
+        /* fwdflat_prune_chan */
+        memset(s->word_active, 0, s->n_words);
+        thresh = s->best_score + s->fwdflatbeam; wordthresh = s->best_score + s->fwdflatwbeam;
+        for (i = 0; i < nw; ++i) {
+            pso_hmm_t *rh;
+            int32_t newscore, nrc, ni;
+            w = s->awl[cur][i]; rh = FF_ROOT(w);
+            nrc = FT_W(s, w, 3) ? 0 : ft_nrc(s, w); ni = FT_W(s, w, 3) ? 0 : n_int[w];
+            if (rh->frame == cf && rh->bestscore > thresh) {
+                rh->frame = nf; s->word_active[w] = 1;
+                newscore = rh->out_score;
+                if (!FT_W(s, w, 3)) {
+                    newscore += pip;
+                    if (newscore > thresh) {
+                        if (ni == 0) {
+                            for (r = 0; r < nrc; ++r)
+                                if (s->wc[w][r].frame < cf || newscore > s->wc[w][r].score[0]) pso_hmm_enter(&s->wc[w][r], newscore, rh->out_history, nf);
+                        }
+                        else if (fi[w][0].frame < cf || newscore > fi[w][0].score[0]) pso_hmm_enter(&fi[w][0], newscore, rh->out_history, nf);
+                    }
+                }
+                else if (newscore > wordthresh) ft_save_bp(s, cf, w, newscore, rh->out_history, 0);
+            }
+            for (k = 0; k < ni; ++k) {
+                pso_hmm_t *h = &fi[w][k];
+                if (h->frame < cf) continue;
+                if (h->bestscore > thresh) {
+                    h->frame = nf; s->word_active[w] = 1;
+                    newscore = h->out_score + pip;
+                    if (newscore > thresh) {
+                        if (k == ni - 1) {
+                            for (r = 0; r < nrc; ++r)
+                                if (s->wc[w][r].frame < cf || newscore > s->wc[w][r].score[0]) pso_hmm_enter(&s->wc[w][r], newscore, h->out_history, nf);
+                        }
+                        else if (fi[w][k + 1].frame < cf || newscore > fi[w][k + 1].score[0]) pso_hmm_enter(&fi[w][k + 1], newscore, h->out_history, nf);
+                    }
+                }
+                else if (h->frame != nf) pso_hmm_clear_scores(h);
+            }
+            for (r = 0; r < nrc; ++r) {
+                pso_hmm_t *h = &s->wc[w][r];
+                if (h->frame < cf) continue;
+                if (h->bestscore > thresh) {
+                    h->frame = nf; s->word_active[w] = 1;
+                    if (h->out_score > wordthresh) ft_save_bp(s, cf, w, h->out_score, h->out_history, r);
+                }
+                else if (h->frame != nf) pso_hmm_clear_scores(h);
+            }
+        }
+        /* fwdflat_word_transition */
+        {
+            int32_t best_silrc_score = PSO_WORST_SCORE, best_silrc_bp = 0, b, sf = cf - s->max_sf_win, ef = cf + s->max_sf_win, nexp = 0, newscore;
+            if (sf < 0) sf = 0;
+            if (ef > T) ef = T;
+            memset(expand_flag, 0, s->n_words);
+            for (f = sf; f < ef; ++f) {
+                int32_t n;
+                for (n = head[f]; n >= 0; n = node[n].next)
+                    if (!expand_flag[node[n].wid]) { expand[nexp++] = node[n].wid; expand_flag[node[n].wid] = 1; }
+            }
+            for (b = s->bp_idx[cf]; b < s->bpidx; ++b) {
+                const ft_bp_t *e = &s->bp[b];
+                const int32_t *cimap = NULL, *rcss = s->bss + e->s_idx;
+                int32_t silscore;
+                s->word_lat_idx[e->wid] = -1;
+                if (e->wid == s->finish_wid) continue;
+                if (e->last2_phone != -1) cimap = s->rs_cimap + ((size_t)e->last_phone * s->n_ci + e->last2_phone) * s->n_ci;
+                for (i = 0; i < nexp; ++i) {
+                    pso_hmm_t *rh;
+                    w = expand[i];
+                    newscore = cimap ? rcss[cimap[FT_W(s, w, 0)]] : e->score;
+                    if (newscore == PSO_WORST_SCORE) continue;
+                    newscore = (int32_t)((float)newscore + s->lwf * (float)ft_tg(s, FT_W(s, w, 5), e->real_wid, e->prev_real_wid));
+                    newscore += pip;
+                    if (!(newscore > thresh)) continue;
+                    rh = FF_ROOT(w);
+                    if (rh->frame < cf || newscore > rh->score[0]) {
+                        const int32_t ci = FT_W(s, w, 0), ci2 = FT_W(s, w, 3) ? s->sil : s->pron_ci[s->pron_off[w] + 1];
+                        pso_hmm_enter(rh, newscore, b, nf);
+                        rh->senid[0] = (uint16_t)s->ldiph[((size_t)ci * s->n_ci + ci2) * s->n_ci + FT_W(s, e->wid, 1)];
+                        s->word_active[w] = 1;
+                    }
+                }
+                silscore = cimap ? rcss[cimap[s->sil]] : e->score;
+                if (silscore > best_silrc_score) { best_silrc_score = silscore; best_silrc_bp = b; }
+            }
+            newscore = best_silrc_score + s->silpen + pip;
+            if (newscore > thresh && newscore > PSO_WORST_SCORE) {
+                pso_hmm_t *rh = &s->h1[s->w2h1[s->silence_wid]];
+                if (rh->frame < cf || newscore > rh->score[0]) { pso_hmm_enter(rh, newscore, best_silrc_bp, nf); s->word_active[s->silence_wid] = 1; }
+            }
+            newscore = best_silrc_score + s->fillpen + pip;
+            if (newscore > thresh && newscore > PSO_WORST_SCORE)
+                for (w = s->filler_start; w <= s->filler_end; ++w) {
+                    pso_hmm_t *rh;
+                    if (w == s->silence_wid || s->w2h1[w] < 0) continue;
+                    rh = &s->h1[s->w2h1[w]];
+                    if (rh->frame < cf || newscore > rh->score[0]) { pso_hmm_enter(rh, newscore, best_silrc_bp, nf); s->word_active[w] = 1; }
+                }
+            for (i = 0; i < nw; ++i) {
+                pso_hmm_t *rh = FF_ROOT(s->awl[cur][i]);
+                if (rh->frame == cf) pso_hmm_clear_scores(rh);
+            }
+        }
+        /* next active word list :852-866 */
+        k = 0;
+        for (i = 0; i < nwd; ++i) if (s->word_active[wordlist[i]] && wordlist[i] < s->start_wid) s->awl[nxt][k++] = wordlist[i];
+        for (w = s->start_wid; w < s->n_words; ++w) if (s->word_active[w]) s->awl[nxt][k++] = w;
+        s->n_awl[nxt] = k;
+        ++n_done;
+    }
+#undef FF_ROOT
+    s->bp_idx[n_done] = s->bpidx;
+    for (i = 0; i < s->bpidx && i < bp_cap; ++i) memcpy(bp_out + (size_t)i * 10, &s->bp[i], 10 * sizeof(int32_t));
+    for (i = 0; i < s->bss_head && i < bss_cap; ++i) bss_out[i] = s->bss[i];
+    for (i = 0; i <= n_done; ++i) bp_idx_out[i] = s->bp_idx[i];
+    *bss_n = s->bss_head;
+    i = s->bpidx;
+    for (w = 0; w < s->n_words; ++w) free(fi[w]);
+    free(fr); free(fi); free(n_int); free(wordlist); free(expand); free(expand_flag); free(node); free(head);
+    ft_free(s);
     return i;
 }

@@ -188,6 +188,13 @@ int32_t pso_fwdtree_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t 
                         const int32_t *pen, int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap, int32_t *bss_n,
                         int32_t *bp_idx_out);
 
+/* ngram_search_fwdflat.c for one utterance, from the first pass's backpointer table (see ps_oracle.c). */
+int32_t pso_fwdflat_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, const int32_t *ci_tmat,
+                        const int32_t *ci_ssid, const int32_t *info, const int32_t *model, const int32_t *bp_in,
+                        int32_t n_bp_in, const int16_t *senscr, int32_t n_sen, int32_t T,
+                        int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap, int32_t *bss_n,
+                        int32_t *bp_idx_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1310,13 +1310,18 @@ refdrv_fsg(const char *hmmdir, const char *dict, const char *fsgfile, const char
  *   rs_ssid  [n_ci][n_ci][n_ci]   ssid[] padded with -1;   rs_cimap [n_ci][n_ci][n_ci]
  *   ldiph    [n_ci][n_ci][n_ci]   ldiph_lc[b][r][l]
  *   lm       [n_lm][n_lm+1][n_lm+1]  ngram_tg_score(w, h1, h2) >> SENSCR_SHIFT, history index 0 = none (-1)
+ *   inlm     [n_words]        ngram_model_set_known_wid(basewid)
+ *   pron_off [n_words+1], pron_ci [n_pron], pron_ssid [n_pron]: pronunciations; dict2pid_internal ssid for
+ *                             word-internal positions 1..len-2, -1 elsewhere
  *   bp       [bpidx][10]      frame, valid, wid, bp, score, s_idx, real_wid, prev_real_wid, last_phone, last2_phone
  *   bss      [bss_head]       bscore_stack
  *   bpidx_f  [n_frame+1]      bp_table_idx
  * info: 0 n_frame 1 n_words 2 n_root 3 n_nonroot 4 n_1ph_words 5 n_1ph_LMwords 6 n_ci 7 silence phone
  *   8 beam 9 pbeam 10 wbeam 11 lpbeam 12 lponlybeam 13 maxhmmpf 14 maxwpf 15 nwpen 16 pip 17 silpen
  *   18 fillpen 19 start wid 20 finish wid 21 silence wid 22 filler_start 23 filler_end 24 bpidx
- *   25 bss_head 26 n_lm 27 hyp score */
+ *   25 bss_head 26 n_lm 27 hyp score 28 fwdflatbeam 29 fwdflatwbeam 30 fwdflatefwid 31 fwdflatsfwin
+ *   32 fwdflat_fwdtree_lw_ratio (float32 bits) 33 n_pron   (info holds 40 ints)
+ * With fwdflat=yes in kv the tables returned are those of the second pass (ngram_search_fwdflat.c). */
 #include "ngram_search.h"
 #include "ngram_search_fwdtree.h"
 static int
@@ -1353,7 +1358,7 @@ refdrv_fwdtree(const char *hmmdir, const char *lm, const char *dictfile, const c
     bin_mdef_t *mdef;
     chan_t **tab;
     int32 *lmidx;
-    int n_nonroot = 0, n_ci, n_words, n_lm = 0, i, j, k, w;
+    int n_nonroot = 0, n_ci, n_words, n_lm = 0, n_pron = 0, i, j, k, w;
     long need, o;
     const char *h;
     int32 score = 0;
@@ -1407,10 +1412,12 @@ refdrv_fwdtree(const char *hmmdir, const char *lm, const char *dictfile, const c
     for (i = 0; i < ngs->n_root_chan; ++i) fwd_collect(ngs->root_chan[i].next, tab, &k);
     lmidx = calloc(n_words, sizeof(*lmidx));
     for (w = 0; w < n_words; ++w) lmidx[w] = dict_basewid(dict, w) == w ? n_lm++ : -1;
+    for (w = 0; w < n_words; ++w) n_pron += dict_pronlen(dict, w);
     need = (long)ngs->n_root_chan * 5 + (long)n_nonroot * 6 + (long)n_words * 8 + ngs->n_1ph_words * 5L
         + (long)n_ci * n_ci + 3L * n_ci * n_ci * n_ci + (long)n_lm * (n_lm + 1) * (n_lm + 1)
+        + n_words + (n_words + 1) + 2L * n_pron
         + (long)ngs->bpidx * 10 + ngs->bss_head + ngs->n_frame + 1;
-    memset(info, 0, 32 * sizeof(int32));
+    memset(info, 0, 40 * sizeof(int32));
     info[0] = ngs->n_frame; info[1] = n_words; info[2] = ngs->n_root_chan; info[3] = n_nonroot;
     info[4] = ngs->n_1ph_words; info[5] = ngs->n_1ph_LMwords; info[6] = n_ci; info[7] = mdef->sil;
     info[8] = ngs->beam; info[9] = ngs->pbeam; info[10] = ngs->wbeam; info[11] = ngs->lpbeam; info[12] = ngs->lponlybeam;
@@ -1418,6 +1425,8 @@ refdrv_fwdtree(const char *hmmdir, const char *lm, const char *dictfile, const c
     info[17] = ngs->silpen; info[18] = ngs->fillpen; info[19] = dict_startwid(dict); info[20] = ps_search_finish_wid(ngs);
     info[21] = ps_search_silence_wid(ngs); info[22] = dict_filler_start(dict); info[23] = dict_filler_end(dict);
     info[24] = ngs->bpidx; info[25] = ngs->bss_head; info[26] = n_lm; info[27] = score;
+    info[28] = ngs->fwdflatbeam; info[29] = ngs->fwdflatwbeam; info[30] = ngs->min_ef_width; info[31] = ngs->max_sf_win;
+    memcpy(&info[32], &ngs->fwdflat_fwdtree_lw_ratio, 4); info[33] = n_pron;
     if (blob && cap >= need) {
         o = 0;
         for (i = 0; i < ngs->n_root_chan; ++i) {
@@ -1463,6 +1472,12 @@ refdrv_fwdtree(const char *hmmdir, const char *lm, const char *dictfile, const c
             }
             free(rev);
         }
+        for (w = 0; w < n_words; ++w) blob[o++] = ngram_model_set_known_wid(ngs->lmset, dict_basewid(dict, w)) ? 1 : 0;
+        for (w = 0, k = 0; w < n_words; ++w) { blob[o++] = k; k += dict_pronlen(dict, w); }
+        blob[o++] = k;
+        for (w = 0; w < n_words; ++w) for (j = 0; j < dict_pronlen(dict, w); ++j) blob[o++] = dict_pron(dict, w, j);
+        for (w = 0; w < n_words; ++w) for (j = 0; j < dict_pronlen(dict, w); ++j)
+            blob[o++] = (j >= 1 && j < dict_pronlen(dict, w) - 1) ? dict2pid_internal(d2p, w, j) : -1;
         for (i = 0; i < ngs->bpidx; ++i) {
             bptbl_t *b = &ngs->bp_table[i];
             blob[o++] = b->frame; blob[o++] = b->valid; blob[o++] = b->wid; blob[o++] = b->bp; blob[o++] = b->score;

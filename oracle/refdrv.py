@@ -418,7 +418,7 @@ def fwdtree(hmmdir, lm, dictfile, pcm, **kv):
     L.refdrv_fwdtree.restype = C.c_long
     L.refdrv_fwdtree.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_long, C.c_void_p,
                                  C.c_long, C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
-    info = np.zeros(32, np.int32)
+    info = np.zeros(40, np.int32)
     hyp = C.create_string_buffer(4096)
     vocab = C.create_string_buffer(1 << 20)
     args = (hmmdir.encode(), lm.encode(), dictfile.encode(), s, _p(pcm), len(pcm))
@@ -430,7 +430,7 @@ def fwdtree(hmmdir, lm, dictfile, pcm, **kv):
         raise RuntimeError("refdrv_fwdtree: inconsistent size")
     keys = ("n_frame n_words n_root n_nonroot n_1ph_words n_1ph_LMwords n_ci sil beam pbeam wbeam lpbeam lponlybeam "
             "maxhmmpf maxwpf nwpen pip silpen fillpen start_wid finish_wid silence_wid filler_start filler_end bpidx "
-            "bss_head n_lm score").split()
+            "bss_head n_lm score fwdflatbeam fwdflatwbeam min_ef_width max_sf_win lwf_bits n_pron").split()
     r = {k: int(info[i]) for i, k in enumerate(keys)}
     o = [0]
 
@@ -444,6 +444,8 @@ def fwdtree(hmmdir, lm, dictfile, pcm, **kv):
     r["w1ph"] = take(r["n_1ph_words"]); r["r1ph"] = take(r["n_1ph_words"], 4)
     r["rs_n"] = take(nc, nc); r["rs_ssid"] = take(nc, nc, nc); r["rs_cimap"] = take(nc, nc, nc); r["ldiph"] = take(nc, nc, nc)
     r["lm"] = take(nl, nl + 1, nl + 1)
+    r["inlm"] = take(r["n_words"]); r["pron_off"] = take(r["n_words"] + 1)
+    r["pron_ci"] = take(r["n_pron"]); r["pron_ssid"] = take(r["n_pron"])
     r["bp"] = take(r["bpidx"], 10); r["bss"] = take(r["bss_head"]); r["bp_idx"] = take(r["n_frame"] + 1)
     assert o[0] == need
     r["hyp"] = hyp.value.decode()

@@ -51,3 +51,31 @@ def test_fwdtree_settings_match_reference(scored, kv):
     b, score = oracle.fwdtree_find_exit(bp, bp_idx, r["n_frame"], r["finish_wid"])
     assert score == r["score"]
     assert oracle.fwdtree_hyp(bp, b, r["words"], r["vocab"], r["start_wid"], r["finish_wid"]) == r["hyp"]
+
+
+@needs_lm
+@pytest.mark.parametrize("kv", [
+    dict(fwdflatefwid="1", fwdflatsfwin="60", fwdflatlw="12"),
+    dict(fwdflatlw="3.3", lw="7.1", pip="0.6", beam="1e-30"),
+    dict(maxwpf="4", maxhmmpf="100", pl_window="3"),
+])
+def test_both_passes_match_reference(scored, kv):
+    """First pass (with look-ahead where asked) chained into the second (ngram_search_fwdflat.c)."""
+    pk, pcm, scr = scored
+    hd = os.path.join(REF, "model", "en-us")
+    r = refdrv.fwdtree(hd, LM, DIC, pcm, fwdflat="yes", **kv)
+    nc = r["n_ci"]
+    la = {}
+    if "pl_window" in kv:
+        ref = refdrv.RefModel(hd)
+        pl = ref.phoneloop(pcm, **{k: v for k, v in kv.items() if k.startswith("pl_")})
+        ref.close()
+        la = dict(pl_pen=pl["pen"], pl_window=int(kv["pl_window"]))
+    bp1, _, _ = oracle.fwdtree_run(pk["tp"], pk["sseq"], pk["phone_tmat"][:nc], r["info"], r["model"], scr, **la)
+    bp, bss, bp_idx = oracle.fwdflat_run(pk["tp"], pk["sseq"], pk["phone_tmat"][:nc], pk["phone_ssid"][:nc], r["info"],
+                                         r["model"], bp1, scr)
+    assert bp.shape == r["bp"].shape and np.array_equal(bp, r["bp"])
+    assert np.array_equal(bss, r["bss"]) and np.array_equal(bp_idx, r["bp_idx"])
+    b, score = oracle.fwdtree_find_exit(bp, bp_idx, r["n_frame"], r["finish_wid"])
+    assert score == r["score"]
+    assert oracle.fwdtree_hyp(bp, b, r["words"], r["vocab"], r["start_wid"], r["finish_wid"]) == r["hyp"]

@@ -43,3 +43,27 @@ def test_fwdtree_golden_covers_the_interesting_paths():
     multi = d["bp"][:, 5] >= 0
     assert multi.sum() > 300 and (d["bss"] > -0x20000000).sum() > 10 * multi.sum()        # several right contexts per exit
     assert (d["bp"][:, 6] != d["bp"][:, 2]).any()                                     # fillers inherit the LM state
+
+
+@pytest.mark.parametrize("tag", ("flat_default", "flat_wide", "flat_narrow"))
+def test_fwdflat_oracle_matches_reference_golden(tag):
+    """Both passes chained: pso_fwdtree_run's table feeds pso_fwdflat_run (ngram_search_fwdflat.c), whose
+    table must equal the one the reference's second pass left behind."""
+    from oracle import oracle
+    m = golden("en_us_ptm_model.npz")
+    gf = golden("en_us_goforward.npz")
+    scr = gf["senscr"]
+    c = _case(golden("en_us_fwdtree.npz"), tag)
+    n_ci = int(c["info"][6])
+    la = dict(pl_pen=gf["pl_pen"], pl_window=int(gf["pl_params"][4])) if tag == "flat_default" else {}
+    bp1, _, _ = oracle.fwdtree_run(m["tp"], m["sseq"], m["phone_tmat"][:n_ci], c["info"], c["model"], scr, **la)
+    bp, bss, bp_idx = oracle.fwdflat_run(m["tp"], m["sseq"], m["phone_tmat"][:n_ci], m["phone_ssid"][:n_ci], c["info"],
+                                         c["model"], bp1, scr)
+    assert bp.shape == c["bp"].shape and np.array_equal(bp, c["bp"])
+    assert np.array_equal(bss, c["bss"]) and np.array_equal(bp_idx, c["bp_idx"])
+    b, score = oracle.fwdtree_find_exit(bp, bp_idx, len(scr), int(c["info"][20]))
+    assert b >= 0 and score == int(c["score"])
+    vocab = str(c["vocab"]).split("\n")
+    assert oracle.fwdtree_hyp(bp, b, c["words"], vocab, int(c["info"][19]), int(c["info"][20])) == str(c["hyp"])
+    if tag == "flat_default":                                  # the first pass's table with look-ahead is the fixture's, too
+        assert np.array_equal(bp1, _case(golden("en_us_fwdtree.npz"), "lookahead")["bp"])
