@@ -349,6 +349,38 @@ int psb_fsg_batch_device(psb_hmmctx_t *c, const psb_fsg_desc_t *g, const int16_t
                          int32_t *n_hist);
 
 /* ------------------------------------------------------------------------------------ */
+/* N-gram decoding, first pass, for whole batches: ngram_search_fwdtree.c (search step :1454-1496,
+ * start :470) with the backpointer-table half of ngram_search.c (save_bp :378, alloc_all_rc :593,
+ * exit_score :655), every utterance against the same lextree, dictionary and language model.  The
+ * host keeps ngram_search_init / ngram_fwdtree_init (create_search_channels :174) and flattens what
+ * they built into int32 sections; oracle/ref_driver.c:refdrv_fwdtree is that loop and documents
+ * the layout:
+ *   info  [40]  sizes (n_words, n_root_chan, n_nonroot_chan, n_1ph_words, n_1ph_LMwords, n_ciphone),
+ *               beams (beam, pbeam, wbeam, lpbeam, lponlybeam), maxhmmpf, maxwpf, nwpen, pip, silpen,
+ *               fillpen, <s> / </s> / <sil> ids, filler range, number of LM base words
+ *   model       roots | non-root channels | words | single-phone words and their channels |
+ *               dict2pid rssid (n_ssid, ssid[], cimap[]) | ldiph_lc | dense trigram scores
+ *               tg[w][h1][h2] = ngram_tg_score(...) >> SENSCR_SHIFT over the LM's base words
+ *   ci_tmat [n_ciphone]  bin_mdef_pid2tmatid of every CI phone
+ * (the dense table limits this entry point to vocabularies of a few hundred words).  d_pen: optional
+ * phone-loop penalties in force while each frame is searched ([total frames][n_ciphone], device;
+ * pls->penalties, phone_loop_search.h:103).  Per utterance u the reference's own tables come back:
+ *   bp      [n_utt][bp_cap_per_utt][10]  bptbl_t rows: frame, valid, wid, bp, score, s_idx, real_wid,
+ *                                        prev_real_wid, last_phone, last2_phone
+ *   bss     [n_utt][bss_cap_per_utt]     bscore_stack
+ *   bp_idx  [total frames + n_utt]       bp_table_idx, utt_off[u] + u is utterance u's first slot
+ *   result  [n_utt][3]                   entries, stack size, frames searched
+ * on which ngram_search_find_exit / ngram_search_bp_hyp / the second pass work unchanged.  A full
+ * table is an error (PSB_ERR_ARG): later frames read earlier entries. */
+typedef struct psb_ngram_desc_s {
+    const int32_t *info, *model, *ci_tmat;
+} psb_ngram_desc_t;
+int psb_ngram_fwdtree_batch_device(psb_hmmctx_t *c, const psb_ngram_desc_t *g, const int16_t *d_senscr,
+                                   const int32_t *d_pen, const int32_t *utt_off, int32_t n_utt, int32_t *bp,
+                                   int32_t bp_cap_per_utt, int32_t *bss, int32_t bss_cap_per_utt,
+                                   int32_t *bp_idx, int32_t *result);
+
+/* ------------------------------------------------------------------------------------ */
 /* Batched front end: int16 PCM -> cepstra -> batch CMN -> 1s_c_d_dd features
  * for whole batches, every utterance a fresh stream (ps_start_stream + ps_process_raw(full_utt),
  * pocketsphinx.c:1073, acmod.c:528-560).  The tables are the arrays the reference's own fe_t /

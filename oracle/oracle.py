@@ -438,12 +438,13 @@ def fsg_hyp_wids(hist, links, bp):
     return out[::-1]
 
 
-def fwdtree_run(tp, sseq, ci_tmat, info, model, senscr, pl_pen=None, pl_window=0):
+def fwdtree_run(tp, sseq, ci_tmat, info, model, senscr, pl_pen=None, pl_window=0, pen_in_force=None):
     """ngram_search_fwdtree.c for one utterance on the flattened search `info` / `model`
     (refdrv.fwdtree / the golden file); returns (bp table [n][10], bscore_stack, bp_table_idx).
     pl_pen [T][n_ci] + pl_window: the phone loop's penalties after each of ITS steps and its window;
     frame t of the search runs after the phone loop has seen frame min(t + window, T - 1)
-    (ps_search_forward / ps_end_utt, pocketsphinx.c:1172-1195, 1329-1333)."""
+    (ps_search_forward / ps_end_utt, pocketsphinx.c:1172-1195, 1329-1333).  pen_in_force [T][n_ci]
+    gives the penalties per SEARCH frame directly instead."""
     tp = np.ascontiguousarray(tp, np.uint8); sseq = np.ascontiguousarray(sseq, np.uint16)
     ci_tmat = np.ascontiguousarray(ci_tmat, np.int32)
     info = np.ascontiguousarray(info, np.int32); model = np.ascontiguousarray(model, np.int32)
@@ -453,7 +454,10 @@ def fwdtree_run(tp, sseq, ci_tmat, info, model, senscr, pl_pen=None, pl_window=0
     bp = np.zeros((bp_cap, 10), np.int32); bss = np.zeros(bss_cap, np.int32); bp_idx = np.zeros(T + 2, np.int32)
     bss_n = C.c_int32()
     pen = None
-    if pl_pen is not None and pl_window > 0 and T > 0:
+    if pen_in_force is not None and T > 0:
+        pen = np.ascontiguousarray(pen_in_force, np.int32)
+        assert pen.shape[0] == T
+    elif pl_pen is not None and pl_window > 0 and T > 0:
         pen = np.ascontiguousarray(np.asarray(pl_pen, np.int32)[np.minimum(np.arange(T) + pl_window, T - 1)])
     f = lib().pso_fwdtree_run
     f.restype = C.c_int32

@@ -44,6 +44,10 @@ class FsgDesc(C.Structure):
                 ("pbeam", C.c_int32), ("wbeam", C.c_int32), ("maxhmmpf", C.c_int32)]
 
 
+class NgramDesc(C.Structure):
+    _fields_ = [("info", C.c_void_p), ("model", C.c_void_p), ("ci_tmat", C.c_void_p)]
+
+
 SYMBOLS = [
     ("psb_last_error", C.c_char_p, []),
     ("psb_abi_version", C.c_int, []),
@@ -83,6 +87,7 @@ SYMBOLS = [
     ("psb_allphone_lm_batch_device", C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _I32, _VP]),
     ("psb_kws_batch_device", C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP, _VP, _I32, _VP, _VP, _VP, _VP, _I32, _I32, _VP, _I32, _VP]),
     ("psb_fsg_batch_device", C.c_int, [_VP, C.POINTER(FsgDesc), _VP, _VP, _I32, _VP, _I32, _VP]),
+    ("psb_ngram_fwdtree_batch_device", C.c_int, [_VP, C.POINTER(NgramDesc), _VP, _VP, _VP, _I32, _VP, _I32, _VP, _I32, _VP, _VP]),
     ("psb_align_batch_device", C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     ("psb_align_last_kernel_ms", C.c_float, [_VP]),
     ("psb_align_batch_host", C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),

@@ -37,6 +37,7 @@
 
 #if defined(__CUDACC__) && !defined(PSB_FSG_HOST_EMUL)
 #define FSG_HD __device__ __forceinline__
+#define FSG_HDH __host__ __device__ __forceinline__
 #define FSG_FOR(i, n) for (int i = (int)threadIdx.x; i < (n); i += (int)blockDim.x)
 #define FSG_SYNC() __syncthreads()
 #define FSG_LEADER() (threadIdx.x == 0)
@@ -44,6 +45,7 @@
 #define FSG_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #else
 #define FSG_HD static inline
+#define FSG_HDH static inline
 #ifdef PSB_FSG_EMUL_REVERSE
 #define FSG_FOR(i, n) for (int i = (n) - 1; i >= 0; --i)
 #else
@@ -51,7 +53,8 @@
 #endif
 #define FSG_SYNC() ((void)0)
 #define FSG_LEADER() (1)
-#define FSG_ATOMIC_MAX(p, v) do { if ((v) > *(p)) *(p) = (v); } while (0)
+static inline void fsg_host_max(int *p, int v) { if (v > *p) *p = v; }
+#define FSG_ATOMIC_MAX(p, v) fsg_host_max((p), (v))
 #define FSG_ATOMIC_ADD(p, v) (*(p) += (v))
 #endif
 
@@ -106,10 +109,10 @@ struct FsgScalars {
 
 #if defined(__CUDACC__) && !defined(PSB_FSG_HOST_EMUL)
 // In-place exclusive scan of a[0..n) by the whole block; returns the total to every thread.
-__device__ inline int fsg_exscan(int32_t *a, int n, FsgScalars *S)
+__device__ inline int fsg_exscan(int32_t *a, int n, int *scan /* [34], shared */)
 {
     const int tid = (int)threadIdx.x, nt = (int)blockDim.x, lane = tid & 31, w = tid >> 5;
-    if (tid == 0) S->scan[33] = 0;
+    if (tid == 0) scan[33] = 0;
     __syncthreads();
     for (int base = 0; base < n; base += nt) {
         const int i = base + tid;
@@ -120,25 +123,25 @@ __device__ inline int fsg_exscan(int32_t *a, int n, FsgScalars *S)
             const int t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
-        if (lane == 31) S->scan[w] = incl;
+        if (lane == 31) scan[w] = incl;
         __syncthreads();
-        const int carry = S->scan[33];
+        const int carry = scan[33];
         int wbase = 0;
-        for (int j = 0; j < w; ++j) wbase += S->scan[j];
+        for (int j = 0; j < w; ++j) wbase += scan[j];
         if (i < n) a[i] = carry + wbase + incl - v;
         __syncthreads();
-        if (tid == nt - 1) S->scan[33] = carry + wbase + incl;
+        if (tid == nt - 1) scan[33] = carry + wbase + incl;
         __syncthreads();
     }
-    const int total = S->scan[33];
+    const int total = scan[33];
     __syncthreads();                                  // the next scan resets scan[33]
     return total;
 }
 #else
-static inline int fsg_exscan(int32_t *a, int n, FsgScalars *S)
+static inline int fsg_exscan(int32_t *a, int n, int *scan)
 {
     int run = 0;
-    (void)S;
+    (void)scan;
     for (int i = 0; i < n; ++i) { const int v = a[i]; a[i] = run; run += v; }
     return run;
 }
@@ -243,7 +246,7 @@ FSG_HD void fsg_cross_word(const FsgGraph &G, const FsgWork &W, FsgScalars *S, i
         W.cnt[b] = c;
     }
     FSG_SYNC();
-    const int n2c = fsg_exscan(W.cnt, n1, S);
+    const int n2c = fsg_exscan(W.cnt, n1, S->scan);
     if (n2c > G.CC || n1 + n2c > G.CC) {                                  // cannot happen: CC = P * (1 + widest null fan-out)
         if (FSG_LEADER()) S->overflow = 1;
         FSG_SYNC();
@@ -381,8 +384,8 @@ FSG_HD void fsg_step(const FsgGraph &G, const FsgWork &W, FsgScalars *S, int f, 
         W.cnt[w] = c; W.ecnt[w] = e; W.kflag[w] = flag;
     }
     FSG_SYNC();
-    const int n_ins = fsg_exscan(W.cnt, n_act, S);
-    const int n_exit = fsg_exscan(W.ecnt, n_act, S);
+    const int n_ins = fsg_exscan(W.cnt, n_act, S->scan);
+    const int n_exit = fsg_exscan(W.ecnt, n_act, S->scan);
     if (FSG_LEADER()) { S->n_ins = n_ins; S->n_exit = n_exit; }
     FSG_FOR(w, n_act) {                                                      // ... applied
         const int p = act[n_act - 1 - w], flag = W.kflag[w];

@@ -1,0 +1,70 @@
+// tests/emul/ngs_emul.cpp -- TEST INFRASTRUCTURE.  Host build of the device first pass's phase code
+// (pocketsphinx_b200/csrc/psb_ngs_core.h), run one "thread" at a time in ascending or
+// (-DPSB_FSG_EMUL_REVERSE) descending order; the HMM update comes from the oracle.  See fsg_emul.cpp.
+#define PSB_FSG_HOST_EMUL 1
+#include <stdlib.h>
+#include <string.h>
+#include "../../pocketsphinx_b200/csrc/psb_ngs_host.h"
+extern "C" {
+#include "../../oracle/ps_oracle.h"
+}
+
+namespace {
+struct OracleEval {
+    pso_hmmctx_t ctx;
+    const NgsGraph *G;
+    int operator()(const NgsWork &W, int c, bool mpx)
+    {
+        pso_hmm_t h;
+        const int N = G->n_emit, M = G->M;
+        memset(&h, 0, sizeof(h));
+        h.mpx = mpx; h.n_emit_state = (uint8_t)N; h.tmatid = (int16_t)G->tmatid[c];
+        h.ssid = mpx ? PSO_BAD_SSID : 0;
+        for (int s = 0; s < N; ++s) {
+            h.score[s] = W.score[s * M + c]; h.history[s] = W.hist[s * M + c];
+            h.senid[s] = (uint16_t)(mpx ? W.mss[s * M + c] : G->senid[(size_t)c * N + s]);
+        }
+        h.out_score = W.out_score[c]; h.out_history = W.out_hist[c]; h.bestscore = W.best[c]; h.frame = W.frame[c];
+        const int b = pso_hmm_vit_eval(&ctx, &h);
+        for (int s = 0; s < N; ++s) {
+            W.score[s * M + c] = h.score[s]; W.hist[s * M + c] = h.history[s];
+            if (mpx) W.mss[s * M + c] = h.senid[s];
+        }
+        W.out_score[c] = h.out_score; W.out_hist[c] = h.out_history; W.best[c] = h.bestscore;
+        return b;
+    }
+};
+}
+
+extern "C" int32_t
+ngs_emul_run(int32_t n_emit_state, const uint8_t *tp, int32_t n_tmat, const uint16_t *sseq, int32_t n_sseq, const int32_t *ci_tmat,
+             const int32_t *info, const int32_t *model, const int16_t *senscr, int32_t n_sen, int32_t T,
+             const int32_t *pen, int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap, int32_t *bss_n, int32_t *bp_idx_out)
+{
+    NgsFlat flat;
+    std::string err;
+    if (ngs_flatten(info, model, ci_tmat, sseq, n_sseq, n_emit_state, n_tmat, n_sen, flat, err) != 0) {
+        fprintf(stderr, "%s\n", err.c_str());
+        return -1;
+    }
+    ngs_bind(flat, flat.buf.data());
+    const NgsGraph &G = flat.G;
+    std::vector<int32_t> work(ngs_work_words(G), 0x5a5a5a5a);
+    NgsWork W;
+    ngs_work_carve(work.data(), G, W);
+    W.bp = bp_out; W.bss = bss_out; W.bp_idx = bp_idx_out; W.pen = pen; W.bp_cap = bp_cap; W.bss_cap = bss_cap;
+    NgsScalars S;
+    memset(&S, 0x5a, sizeof(S));
+    OracleEval ev;
+    memset(&ev.ctx, 0, sizeof(ev.ctx));
+    ev.ctx.n_emit_state = n_emit_state; ev.ctx.tp = tp; ev.ctx.sseq = sseq; ev.G = &G;
+    ngs_start(G, W, &S);
+    for (int f = 0; f < T && !S.stop && !S.error; ++f) {
+        ev.ctx.senscore = senscr + (size_t)f * n_sen;
+        ngs_step(G, W, &S, f, ev);
+    }
+    if (S.error) { fprintf(stderr, "ngs_emul: error %d at frame %d: bpidx %d bss_head %d n_acl %d n_awl %d\n", S.error, S.n_done, S.bpidx, S.bss_head, S.n_acl, S.n_awl); return -1 - S.error; }
+    bp_idx_out[S.n_done] = S.bpidx;
+    *bss_n = S.bss_head;
+    return S.bpidx;
+}
