@@ -374,9 +374,23 @@ int psb_fsg_batch_device(psb_hmmctx_t *c, const psb_fsg_desc_t *g, const int16_t
  * table is an error (PSB_ERR_ARG): later frames read earlier entries. */
 typedef struct psb_ngram_desc_s {
     const int32_t *info, *model, *ci_tmat;
+    const int32_t *ci_ssid;     /* [n_ciphone] bin_mdef_pid2ssid of every CI phone; second pass only (may be NULL for the first) */
 } psb_ngram_desc_t;
 int psb_ngram_fwdtree_batch_device(psb_hmmctx_t *c, const psb_ngram_desc_t *g, const int16_t *d_senscr,
                                    const int32_t *d_pen, const int32_t *utt_off, int32_t n_utt, int32_t *bp,
+                                   int32_t bp_cap_per_utt, int32_t *bss, int32_t bss_cap_per_utt,
+                                   int32_t *bp_idx, int32_t *result);
+/* Second pass: ngram_search_fwdflat.c (start :371 with build_fwdflat_wordlist :224 and
+ * build_fwdflat_chan :306, search step :813 = fwdflat_eval_chan :445, fwdflat_prune_chan :483,
+ * fwdflat_word_transition :643) over whole utterances.  info / model as above, exported with the
+ * second pass configured (info[28..33]: fwdflatbeam, fwdflatwbeam, fwdflatefwid, fwdflatsfwin, the
+ * float32 bits of fwdflatlw / lw, pronunciation count; model continues with the LM-membership flags
+ * and the pronunciations with their dict2pid_internal ssids).  bp_first [n_utt][first_cap_per_utt][10]
+ * + n_first[n_utt]: every utterance's FIRST-pass table (the utterance vocabulary and the start-frame
+ * windows come from it).  Outputs as for the first pass. */
+int psb_ngram_fwdflat_batch_device(psb_hmmctx_t *c, const psb_ngram_desc_t *g, const int16_t *d_senscr,
+                                   const int32_t *utt_off, int32_t n_utt, const int32_t *bp_first,
+                                   int32_t first_cap_per_utt, const int32_t *n_first, int32_t *bp,
                                    int32_t bp_cap_per_utt, int32_t *bss, int32_t bss_cap_per_utt,
                                    int32_t *bp_idx, int32_t *result);
 

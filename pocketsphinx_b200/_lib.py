@@ -45,7 +45,7 @@ class FsgDesc(C.Structure):
 
 
 class NgramDesc(C.Structure):
-    _fields_ = [("info", C.c_void_p), ("model", C.c_void_p), ("ci_tmat", C.c_void_p)]
+    _fields_ = [("info", C.c_void_p), ("model", C.c_void_p), ("ci_tmat", C.c_void_p), ("ci_ssid", C.c_void_p)]
 
 
 SYMBOLS = [
@@ -88,6 +88,7 @@ SYMBOLS = [
     ("psb_kws_batch_device", C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP, _VP, _I32, _VP, _VP, _VP, _VP, _I32, _I32, _VP, _I32, _VP]),
     ("psb_fsg_batch_device", C.c_int, [_VP, C.POINTER(FsgDesc), _VP, _VP, _I32, _VP, _I32, _VP]),
     ("psb_ngram_fwdtree_batch_device", C.c_int, [_VP, C.POINTER(NgramDesc), _VP, _VP, _VP, _I32, _VP, _I32, _VP, _I32, _VP, _VP]),
+    ("psb_ngram_fwdflat_batch_device", C.c_int, [_VP, C.POINTER(NgramDesc), _VP, _VP, _I32, _VP, _I32, _VP, _VP, _I32, _VP, _I32, _VP, _VP]),
     ("psb_align_batch_device", C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     ("psb_align_last_kernel_ms", C.c_float, [_VP]),
     ("psb_align_batch_host", C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),

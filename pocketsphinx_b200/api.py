@@ -310,7 +310,7 @@ class HmmContext:
         n_utt = len(utt_off) - 1
         info = np.ascontiguousarray(info, np.int32); model = np.ascontiguousarray(model, np.int32)
         ci_tmat = np.ascontiguousarray(ci_tmat, np.int32)
-        d = NgramDesc(info.ctypes.data, model.ctypes.data, ci_tmat.ctypes.data)
+        d = NgramDesc(info.ctypes.data, model.ctypes.data, ci_tmat.ctypes.data, None)
         bp = np.zeros((max(n_utt, 1), int(bp_cap), 10), np.int32)
         bss = np.zeros((max(n_utt, 1), int(bss_cap)), np.int32)
         bp_idx = np.zeros(int(utt_off[-1]) + max(n_utt, 1), np.int32)
@@ -319,6 +319,35 @@ class HmmContext:
                                                    C.c_void_p(d_pen_ptr) if d_pen_ptr else None, _p(utt_off), n_utt, _p(bp),
                                                    int(bp_cap), _p(bss), int(bss_cap), _p(bp_idx), _p(res)),
               "psb_ngram_fwdtree_batch_device")
+        out = []
+        for u in range(n_utt):
+            T = int(utt_off[u + 1] - utt_off[u])
+            o = int(utt_off[u]) + u
+            out.append((bp[u, :res[u, 0]].copy(), bss[u, :res[u, 1]].copy(), bp_idx[o:o + T + 1].copy()))
+        return out
+
+    def ngram_fwdflat(self, d_senscr_ptr, utt_off, info, model, ci_tmat, ci_ssid, first_tables, bp_cap, bss_cap):
+        """ngram_search_fwdflat over a batch; first_tables = the first pass's bp table of every utterance.
+        Returns per utterance (bp table [n][10], bscore_stack, bp_table_idx [T+1])."""
+        from ._lib import NgramDesc
+        utt_off = np.ascontiguousarray(utt_off, np.int32)
+        n_utt = len(utt_off) - 1
+        info = np.ascontiguousarray(info, np.int32); model = np.ascontiguousarray(model, np.int32)
+        ci_tmat = np.ascontiguousarray(ci_tmat, np.int32); ci_ssid = np.ascontiguousarray(ci_ssid, np.int32)
+        d = NgramDesc(info.ctypes.data, model.ctypes.data, ci_tmat.ctypes.data, ci_ssid.ctypes.data)
+        cap_in = max([len(t) for t in first_tables] + [1])
+        first = np.zeros((max(n_utt, 1), cap_in, 10), np.int32)
+        n_first = np.zeros(max(n_utt, 1), np.int32)
+        for u, t in enumerate(first_tables):
+            first[u, :len(t)] = t
+            n_first[u] = len(t)
+        bp = np.zeros((max(n_utt, 1), int(bp_cap), 10), np.int32)
+        bss = np.zeros((max(n_utt, 1), int(bss_cap)), np.int32)
+        bp_idx = np.zeros(int(utt_off[-1]) + max(n_utt, 1), np.int32)
+        res = np.zeros((max(n_utt, 1), 3), np.int32)
+        check(lib().psb_ngram_fwdflat_batch_device(self.h, C.byref(d), C.c_void_p(d_senscr_ptr), _p(utt_off), n_utt, _p(first),
+                                                   cap_in, _p(n_first), _p(bp), int(bp_cap), _p(bss), int(bss_cap), _p(bp_idx),
+                                                   _p(res)), "psb_ngram_fwdflat_batch_device")
         out = []
         for u in range(n_utt):
             T = int(utt_off[u + 1] - utt_off[u])

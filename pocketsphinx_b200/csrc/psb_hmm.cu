@@ -1976,3 +1976,156 @@ extern "C" int psb_ngram_fwdtree_batch_device(psb_hmmctx_t *c, const psb_ngram_d
     }
     return PSB_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// N-gram decoding, second pass (ngram_search_fwdflat.c) for whole batches: SURVEY 8 row f-4.  One
+// CTA per utterance, one thread per active word (psb_ngf_core.h, host-emulated against the
+// reference's second-pass backpointer tables by tests/emul/ngf_emul.cpp).  Input: every
+// utterance's first-pass backpointer table (from psb_ngram_fwdtree_batch_device or the host).
+#include "psb_ngf_host.h"
+
+namespace {
+
+struct NgfDevEval {
+    HmmCtxDev c;
+    const NgfGraph *G;
+    const int16_t *row;
+    __device__ __forceinline__ int operator()(const NgfWork &W, int ch, bool mpx) const
+    {
+        HmmReg h;
+        const int N = c.n_emit, M = G->M;
+#pragma unroll
+        for (int s = 0; s < PSB_HMM_MAX_NSTATE; ++s) {
+            h.score[s] = s < N ? W.score[s * M + ch] : PSB_WORST_SCORE;
+            h.hist[s] = s < N ? W.hist[s * M + ch] : -1;
+            h.senid[s] = s < N ? (mpx ? W.mss[s * M + ch] : G->senid[(size_t)ch * N + s]) : PSB_BAD_SSID;
+        }
+        h.out_score = W.out_score[ch]; h.out_hist = W.out_hist[ch]; h.best = W.best[ch];
+        const int b = hmm_step(h, c, G->tmatid[ch], mpx, row);
+#pragma unroll
+        for (int s = 0; s < PSB_HMM_MAX_NSTATE; ++s)
+            if (s < N) {
+                W.score[s * M + ch] = h.score[s]; W.hist[s * M + ch] = h.hist[s];
+                if (mpx) W.mss[s * M + ch] = h.senid[s];
+            }
+        W.out_score[ch] = h.out_score; W.out_hist[ch] = h.out_hist; W.best[ch] = h.best;
+        return b;
+    }
+};
+
+__global__ void __launch_bounds__(NGS_THREADS)
+ngs_fwdflat_kernel(const int16_t *__restrict__ senscr, const int32_t *__restrict__ utt_off, HmmCtxDev c, NgfGraph G,
+                   int32_t *work, size_t work_words, const int32_t *bp_in, int in_cap, const int32_t *n_in,
+                   int32_t *bp_out, int bp_cap, int32_t *bss_out, int bss_cap, int32_t *bp_idx_out, int32_t *result)
+{
+    __shared__ NgfScalars S;
+    const int u = blockIdx.x;
+    const long long f0 = utt_off[u];
+    const int T = utt_off[u + 1] - utt_off[u];
+    NgfWork W;
+    ngf_work_carve(work + (size_t)u * work_words, G, T, W);
+    W.bp = bp_out + (size_t)u * bp_cap * NGS_BP_ROW;
+    W.bss = bss_out + (size_t)u * bss_cap;
+    W.bp_idx = bp_idx_out + f0 + u;
+    W.bp_in = bp_in + (size_t)u * in_cap * NGS_BP_ROW;
+    W.n_bp_in = n_in[u];
+    W.bp_cap = bp_cap; W.bss_cap = bss_cap;
+    NgfDevEval ev{c, &G, nullptr};
+    ngf_start(G, W, &S);
+    for (int f = 0; f < T; ++f) {
+        if (S.stop || S.error) break;
+        ev.row = senscr + (f0 + f) * c.n_sen;
+        ngf_step(G, W, &S, f, ev);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        W.bp_idx[S.n_done] = S.bpidx;                        // ngram_fwdflat_finish :937
+        result[u * 3] = S.bpidx; result[u * 3 + 1] = S.bss_head; result[u * 3 + 2] = S.error ? -S.error : S.n_done;
+    }
+}
+
+}  // namespace
+
+extern "C" int psb_ngram_fwdflat_batch_device(psb_hmmctx_t *c, const psb_ngram_desc_t *g, const int16_t *d_senscr,
+                                              const int32_t *utt_off, int32_t n_utt, const int32_t *bp_first,
+                                              int32_t first_cap_per_utt, const int32_t *n_first, int32_t *bp,
+                                              int32_t bp_cap_per_utt, int32_t *bss, int32_t bss_cap_per_utt,
+                                              int32_t *bp_idx, int32_t *result)
+{
+    PSB_REQUIRE(c && g && g->info && g->model && g->ci_tmat && g->ci_ssid && utt_off && n_utt >= 0 && bp_first && n_first && bp &&
+                bss && bp_idx && result && first_cap_per_utt > 0 && bp_cap_per_utt > 0 && bss_cap_per_utt > 0,
+                "psb_ngram_fwdflat_batch_device: bad argument (the descriptor needs ci_ssid for this pass)");
+    if (n_utt == 0) return PSB_OK;
+    PSB_REQUIRE(utt_off[0] == 0, "psb_ngram_fwdflat_batch_device: offsets must start at 0");
+    PSB_REQUIRE(d_senscr || utt_off[n_utt] == 0, "psb_ngram_fwdflat_batch_device: scores missing");
+    int t_max = 0;
+    for (int u = 0; u < n_utt; ++u) {
+        PSB_REQUIRE(utt_off[u + 1] >= utt_off[u], "psb_ngram_fwdflat_batch_device: utt_off not monotone at %d", u);
+        PSB_REQUIRE(n_first[u] >= 0 && n_first[u] <= first_cap_per_utt, "psb_ngram_fwdflat_batch_device: n_first[%d] out of range", u);
+        const int32_t *b = bp_first + (size_t)u * first_cap_per_utt * NGS_BP_ROW;
+        const int T = utt_off[u + 1] - utt_off[u];
+        for (int i = 0; i < n_first[u]; ++i) {
+            const int32_t *r = b + (size_t)i * NGS_BP_ROW;
+            PSB_REQUIRE(r[3] >= -1 && r[3] < i && r[2] >= 0 && r[2] < g->info[1] && r[0] >= 0 && r[0] < (T > 0 ? T : 1),
+                        "psb_ngram_fwdflat_batch_device: utterance %d: first-pass entry %d is inconsistent", u, i);
+        }
+        if (T > t_max) t_max = T;
+    }
+    PSB_CUDA(cudaSetDevice(c->device));
+    const int N = c->n_emit;
+    std::vector<uint16_t> sseq((size_t)c->n_sseq * N);
+    PSB_CUDA(cudaMemcpy(sseq.data(), c->d_sseq, sseq.size() * 2, cudaMemcpyDeviceToHost));
+    NgfFlat flat;
+    std::string err;
+    if (ngf_flatten(g->info, g->model, g->ci_tmat, g->ci_ssid, sseq.data(), c->n_sseq, N, c->n_tmat, c->n_sen, flat, err) != 0) {
+        psb_set_error("psb_ngram_fwdflat_batch_device: %s", err.c_str());
+        return PSB_ERR_ARG;
+    }
+    std::vector<int32_t> ibuf(flat.buf);
+    const size_t o_uo = ibuf.size();
+    ibuf.insert(ibuf.end(), utt_off, utt_off + n_utt + 1);
+    const size_t o_nin = ibuf.size();
+    ibuf.insert(ibuf.end(), n_first, n_first + n_utt);
+    const size_t o_res = ibuf.size();
+    ibuf.resize(o_res + (size_t)n_utt * 3, 0);
+    const size_t work_words = ngf_work_words(flat.G, t_max);
+    const size_t total_frames = (size_t)utt_off[n_utt];
+    const size_t n_in = (size_t)n_utt * first_cap_per_utt * NGS_BP_ROW, n_bp = (size_t)n_utt * bp_cap_per_utt * NGS_BP_ROW,
+                 n_bss = (size_t)n_utt * bss_cap_per_utt, n_idx = total_frames + (size_t)n_utt;
+    int32_t *d_i = nullptr, *d_work = nullptr, *d_in = nullptr, *d_bp = nullptr, *d_bss = nullptr, *d_idx = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_i, ibuf.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_work, work_words * (size_t)n_utt * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_in, n_in * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_bp, n_bp * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_bss, n_bss * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_idx, n_idx * 4);
+    cudaStream_t st = c->stream;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_i, ibuf.data(), ibuf.size() * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, bp_first, n_in * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_idx, 0, n_idx * 4, st);
+    if (e == cudaSuccess) {
+        ngf_bind(flat, d_i);
+        ngs_fwdflat_kernel<<<(unsigned)n_utt, NGS_THREADS, 0, st>>>(d_senscr, d_i + o_uo, dev_ctx(c), flat.G, d_work, work_words, d_in,
+                                                                   first_cap_per_utt, d_i + o_nin, d_bp, bp_cap_per_utt, d_bss,
+                                                                   bss_cap_per_utt, d_idx, d_i + o_res);
+        g_psb_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bp, d_bp, n_bp * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bss, d_bss, n_bss * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bp_idx, d_idx, n_idx * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(result, d_i + o_res, (size_t)n_utt * 12, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_i); cudaFree(d_work); cudaFree(d_in); cudaFree(d_bp); cudaFree(d_bss); cudaFree(d_idx);
+    if (e != cudaSuccess) {
+        psb_set_error("psb_ngram_fwdflat_batch_device: %s", cudaGetErrorString(e));
+        return PSB_ERR_CUDA;
+    }
+    for (int u = 0; u < n_utt; ++u) {
+        PSB_REQUIRE(result[u * 3 + 2] != -1, "psb_ngram_fwdflat_batch_device: utterance %d overflowed the backpointer table "
+                    "or the score stack (%d entries / %d scores allowed)", u, bp_cap_per_utt, bss_cap_per_utt);
+        PSB_REQUIRE(result[u * 3 + 2] >= 0, "psb_ngram_fwdflat_batch_device: utterance %d needs score renormalisation "
+                    "(not done on the device)", u);
+    }
+    return PSB_OK;
+}

@@ -1,0 +1,70 @@
+// tests/emul/ngf_emul.cpp -- TEST INFRASTRUCTURE.  Host build of the device second pass's phase code
+// (pocketsphinx_b200/csrc/psb_ngf_core.h); see fsg_emul.cpp / ngs_emul.cpp.
+#define PSB_FSG_HOST_EMUL 1
+#include <stdlib.h>
+#include <string.h>
+#include "../../pocketsphinx_b200/csrc/psb_ngf_host.h"
+extern "C" {
+#include "../../oracle/ps_oracle.h"
+}
+
+namespace {
+struct OracleEval {
+    pso_hmmctx_t ctx;
+    const NgfGraph *G;
+    int operator()(const NgfWork &W, int c, bool mpx)
+    {
+        pso_hmm_t h;
+        const int N = G->n_emit, M = G->M;
+        memset(&h, 0, sizeof(h));
+        h.mpx = mpx; h.n_emit_state = (uint8_t)N; h.tmatid = (int16_t)G->tmatid[c];
+        h.ssid = mpx ? PSO_BAD_SSID : 0;
+        for (int s = 0; s < N; ++s) {
+            h.score[s] = W.score[s * M + c]; h.history[s] = W.hist[s * M + c];
+            h.senid[s] = (uint16_t)(mpx ? W.mss[s * M + c] : G->senid[(size_t)c * N + s]);
+        }
+        h.out_score = W.out_score[c]; h.out_history = W.out_hist[c]; h.bestscore = W.best[c]; h.frame = W.frame[c];
+        const int b = pso_hmm_vit_eval(&ctx, &h);
+        for (int s = 0; s < N; ++s) {
+            W.score[s * M + c] = h.score[s]; W.hist[s * M + c] = h.history[s];
+            if (mpx) W.mss[s * M + c] = h.senid[s];
+        }
+        W.out_score[c] = h.out_score; W.out_hist[c] = h.out_history; W.best[c] = h.bestscore;
+        return b;
+    }
+};
+}
+
+extern "C" int32_t
+ngf_emul_run(int32_t n_emit_state, const uint8_t *tp, int32_t n_tmat, const uint16_t *sseq, int32_t n_sseq, const int32_t *ci_tmat,
+             const int32_t *ci_ssid, const int32_t *info, const int32_t *model, const int32_t *bp_in, int32_t n_bp_in,
+             const int16_t *senscr, int32_t n_sen, int32_t T,
+             int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap, int32_t *bss_n, int32_t *bp_idx_out)
+{
+    NgfFlat flat;
+    std::string err;
+    if (ngf_flatten(info, model, ci_tmat, ci_ssid, sseq, n_sseq, n_emit_state, n_tmat, n_sen, flat, err) != 0) {
+        fprintf(stderr, "%s\n", err.c_str());
+        return -1;
+    }
+    ngf_bind(flat, flat.buf.data());
+    const NgfGraph &G = flat.G;
+    std::vector<int32_t> work(ngf_work_words(G, T), 0x5a5a5a5a);
+    NgfWork W;
+    ngf_work_carve(work.data(), G, T, W);
+    W.bp = bp_out; W.bss = bss_out; W.bp_idx = bp_idx_out; W.bp_in = bp_in; W.n_bp_in = n_bp_in; W.bp_cap = bp_cap; W.bss_cap = bss_cap;
+    NgfScalars S;
+    memset(&S, 0x5a, sizeof(S));
+    OracleEval ev;
+    memset(&ev.ctx, 0, sizeof(ev.ctx));
+    ev.ctx.n_emit_state = n_emit_state; ev.ctx.tp = tp; ev.ctx.sseq = sseq; ev.G = &G;
+    ngf_start(G, W, &S);
+    for (int f = 0; f < T && !S.stop && !S.error; ++f) {
+        ev.ctx.senscore = senscr + (size_t)f * n_sen;
+        ngf_step(G, W, &S, f, ev);
+    }
+    if (S.error) { fprintf(stderr, "ngf_emul: error %d at frame %d\n", S.error, S.n_done); return -1 - S.error; }
+    bp_idx_out[S.n_done] = S.bpidx;
+    *bss_n = S.bss_head;
+    return S.bpidx;
+}

@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle, refdrv
+from test_ngf_emul import emuls, run_second  # noqa: F401  (fixture)
 from test_ngs_emul import emul, run_emul  # noqa: F401  (fixture)
 
 pytestmark = pytest.mark.skipif(not refdrv.available(), reason="oracle/_ref/libpsref.so not built")
@@ -84,3 +85,30 @@ def test_other_settings(emul, seed):  # noqa: F811
         la = dict(pl_pen=pl["pen"], pl_window=int(kv["pl_window"]))
     pk, scr = _score(pcm)
     _check(emul, pk, scr, refdrv.fwdtree(HD, LM, DIC, pcm, **kv), **la)
+
+
+@needs_lm
+@pytest.mark.parametrize("seed", _seeds())
+def test_both_passes_other_audio_and_settings(emuls, seed):  # noqa: F811
+    """Second pass (ngram_search_fwdflat.c) chained behind the first, both through the phase code."""
+    f1, f2 = emuls
+    go = np.fromfile(os.path.join(REF, "data", "goforward.raw"), np.int16)
+    rng = np.random.default_rng(1000 + seed)
+    pieces = np.split(go, np.sort(rng.integers(0, len(go), 4)))
+    pcm = np.concatenate([pieces[i] for i in rng.permutation(len(pieces))]).astype(np.float64)
+    pcm = np.clip(pcm * rng.uniform(0.5, 1.2) + rng.normal(0, rng.uniform(0, 800), len(pcm)), -32768, 32767).astype(np.int16)
+    kv = [dict(), dict(fwdflatbeam="1e-70", fwdflatwbeam="1e-30", fwdflatefwid="2", fwdflatsfwin="40"),
+          dict(fwdflatbeam="1e-40", fwdflatwbeam="1e-12", fwdflatlw="11", maxwpf="10"),
+          dict(fwdflatefwid="6", fwdflatsfwin="8", lw="4", fwdflatlw="9.5", pip="0.8")][seed % 4]
+    pk, scr = _score(pcm)
+    r = refdrv.fwdtree(HD, LM, DIC, pcm, fwdflat="yes", **kv)
+    nc = r["n_ci"]
+    n1, bp1, _, _ = run_emul(f1, pk, r["info"], r["model"], scr, 16384, 1 << 19)
+    assert n1 >= 0
+    want1 = oracle.fwdtree_run(pk["tp"], pk["sseq"], pk["phone_tmat"][:nc], r["info"], r["model"], scr)[0]
+    assert np.array_equal(bp1, want1)
+    got = oracle.fwdflat_run(pk["tp"], pk["sseq"], pk["phone_tmat"][:nc], pk["phone_ssid"][:nc], r["info"], r["model"], bp1, scr)
+    assert np.array_equal(got[0], r["bp"]) and np.array_equal(got[1], r["bss"]) and np.array_equal(got[2], r["bp_idx"])
+    n, bp, bss, idx = run_second(f2, pk, r["info"], r["model"], bp1, scr, len(r["bp"]) + 8, len(r["bss"]) + 64)
+    assert n == len(r["bp"]) and np.array_equal(bp, r["bp"])
+    assert np.array_equal(bss, r["bss"]) and np.array_equal(idx, r["bp_idx"])
