@@ -40,28 +40,51 @@
 #define FSG_HDH __host__ __device__ __forceinline__
 #define FSG_FOR(i, n) for (int i = (int)threadIdx.x; i < (n); i += (int)blockDim.x)
 #define FSG_SYNC() __syncthreads()
-#define FSG_LEADER() (threadIdx.x == 0)
+#define FSG_IF_LEADER if (threadIdx.x == 0)
 #define FSG_ATOMIC_MAX(p, v) atomicMax((p), (v))
 #define FSG_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #define FSG_ATOMIC_MIN(p, v) atomicMin((p), (v))
+#define FSG_ATOMIC_MAX_AT(a, i, v) atomicMax(&(a)[i], (v))
+#define FSG_ATOMIC_MIN_AT(a, i, v) atomicMin(&(a)[i], (v))
+#define FSG_ATOMIC_ADD_AT(a, i, v) atomicAdd(&(a)[i], (v))
 #define FSG_FADD(a, b) __fadd_rn((a), (b))
 #define FSG_FMUL(a, b) __fmul_rn((a), (b))
+typedef int32_t *fsg_wp;
+typedef uint32_t *fsg_wup;
+typedef int fsg_int;
+typedef float fsg_float;
+typedef long long fsg_ll;
 #else
 #define FSG_HD static inline
 #define FSG_HDH static inline
+#ifdef PSB_FSG_RACECHECK                /* tests only: tests/emul/psb_fsg_racecheck.h, see tests/test_emul_racecheck.py */
+#include "psb_fsg_racecheck.h"
+#else
 #ifdef PSB_FSG_EMUL_REVERSE
 #define FSG_FOR(i, n) for (int i = (n) - 1; i >= 0; --i)
 #else
 #define FSG_FOR(i, n) for (int i = 0; i < (n); ++i)
 #endif
 #define FSG_SYNC() ((void)0)
-#define FSG_LEADER() (1)
+#define FSG_IF_LEADER
 static inline void fsg_host_max(int *p, int v) { if (v > *p) *p = v; }
+static inline void fsg_host_min(int *p, int v) { if (v < *p) *p = v; }
 #define FSG_ATOMIC_MAX(p, v) fsg_host_max((p), (v))
 #define FSG_ATOMIC_ADD(p, v) (*(p) += (v))
-static inline void fsg_host_min(int *p, int v) { if (v < *p) *p = v; }
 #define FSG_ATOMIC_MIN(p, v) fsg_host_min((p), (v))
-#define FSG_FADD(a, b) ((a) + (b))      /* harness is built with -ffp-contract=off */
+#define FSG_ATOMIC_MAX_AT(a, i, v) fsg_host_max(&(a)[i], (v))
+#define FSG_ATOMIC_MIN_AT(a, i, v) fsg_host_min(&(a)[i], (v))
+#define FSG_ATOMIC_ADD_AT(a, i, v) ((a)[i] += (v))
+#define FSG_COLLECTIVE_BEGIN() ((void)0)
+#define FSG_COLLECTIVE_END() ((void)0)
+#define FSG_RAW(a) (a)
+typedef int32_t *fsg_wp;            /* pointer into an utterance's mutable state */
+typedef uint32_t *fsg_wup;
+typedef int fsg_int;                /* block-shared scalar */
+typedef float fsg_float;
+typedef long long fsg_ll;
+#endif
+#define FSG_FADD(a, b) ((a) + (b))      /* harnesses are built with -ffp-contract=off */
 #define FSG_FMUL(a, b) ((a) * (b))
 #endif
 
@@ -92,31 +115,31 @@ struct FsgGraph {
 
 // Per-utterance state in global memory.
 struct FsgWork {
-    int32_t *score, *hist;                          // [n_emit][P]
-    int32_t *out_score, *out_hist, *best, *frame;   // [P]
-    int32_t *pos, *posf;                            // [P] walk position in the frame posf
-    int32_t *act[2];                                // [P] active lists, insertion order
-    int32_t *cnt, *ecnt, *kflag;                    // [CC+1]
-    int32_t *c_link, *c_score, *c_pred, *c_lc, *c_grp, *c_alive;   // [CC] candidates
-    uint32_t *c_rc, *c_rcf;                         // [CC][8]
-    int32_t *ne_dest, *ne_score, *ne_lc;            // [CC] this frame's history entries
-    uint32_t *ne_rc;                                // [CC][8]
-    int32_t *rfirst;                                // [R]
-    int32_t *hist_out;                              // [cap][FSG_ROW]
+    fsg_wp score, hist;                          // [n_emit][P]
+    fsg_wp out_score, out_hist, best, frame;   // [P]
+    fsg_wp pos, posf;                            // [P] walk position in the frame posf
+    fsg_wp act[2];                                // [P] active lists, insertion order
+    fsg_wp cnt, ecnt, kflag;                    // [CC+1]
+    fsg_wp c_link, c_score, c_pred, c_lc, c_grp, c_alive;   // [CC] candidates
+    fsg_wup c_rc, c_rcf;                         // [CC][8]
+    fsg_wp ne_dest, ne_score, ne_lc;            // [CC] this frame's history entries
+    fsg_wup ne_rc;                                // [CC][8]
+    fsg_wp rfirst;                                // [R]
+    fsg_wp hist_out;                              // [cap][FSG_ROW]
     int cap;
 };
 
 struct FsgScalars {
-    int cur, n_act, n_ins, n_exit, n_newroot;
-    int best, beam, pbeam, wbeam, thresh, pth, wth;
-    int n_hist, bp_start, n_new, n_res, overflow;
-    float beam_factor;
+    fsg_int cur, n_act, n_ins, n_exit, n_newroot;
+    fsg_int best, beam, pbeam, wbeam, thresh, pth, wth;
+    fsg_int n_hist, bp_start, n_new, n_res, overflow;
+    fsg_float beam_factor;
     int scan[34];
 };
 
 #if defined(__CUDACC__) && !defined(PSB_FSG_HOST_EMUL)
 // In-place exclusive scan of a[0..n) by the whole block; returns the total to every thread.
-__device__ inline int fsg_exscan(int32_t *a, int n, int *scan /* [34], shared */)
+__device__ inline int fsg_exscan(fsg_wp a, int n, int *scan /* [34], shared */)
 {
     const int tid = (int)threadIdx.x, nt = (int)blockDim.x, lane = tid & 31, w = tid >> 5;
     if (tid == 0) scan[33] = 0;
@@ -145,11 +168,13 @@ __device__ inline int fsg_exscan(int32_t *a, int n, int *scan /* [34], shared */
     return total;
 }
 #else
-static inline int fsg_exscan(int32_t *a, int n, int *scan)
+static inline int fsg_exscan(fsg_wp a, int n, int *scan)
 {
     int run = 0;
     (void)scan;
-    for (int i = 0; i < n; ++i) { const int v = a[i]; a[i] = run; run += v; }
+    FSG_COLLECTIVE_BEGIN();                            /* the device scan starts and ends with a barrier */
+    for (int i = 0; i < n; ++i) { const int v = FSG_RAW(a)[i]; FSG_RAW(a)[i] = run; run += v; }
+    FSG_COLLECTIVE_END();
     return run;
 }
 #endif
@@ -164,9 +189,9 @@ FSG_HD void fsg_work_carve(int32_t *b, const FsgGraph &G, FsgWork &W)
     W.cnt = b; b += CC + 1;  W.ecnt = b; b += CC + 1;  W.kflag = b; b += CC + 1;
     W.c_link = b; b += CC;  W.c_score = b; b += CC;  W.c_pred = b; b += CC;  W.c_lc = b; b += CC;
     W.c_grp = b; b += CC;  W.c_alive = b; b += CC;
-    W.c_rc = (uint32_t *)b; b += 8 * CC;  W.c_rcf = (uint32_t *)b; b += 8 * CC;
+    W.c_rc = fsg_wup((uint32_t *)b); b += 8 * CC;  W.c_rcf = fsg_wup((uint32_t *)b); b += 8 * CC;
     W.ne_dest = b; b += CC;  W.ne_score = b; b += CC;  W.ne_lc = b; b += CC;
-    W.ne_rc = (uint32_t *)b; b += 8 * CC;
+    W.ne_rc = fsg_wup((uint32_t *)b); b += 8 * CC;
     W.rfirst = b;
 }
 
@@ -192,7 +217,7 @@ FSG_HD bool fsg_parent_enters(const FsgGraph &G, const FsgWork &W, const FsgScal
 // direct: the frame < 0 shortcut (fsg_history.c:143-156), entries are appended as they come.
 FSG_HD void fsg_resolve(const FsgGraph &G, const FsgWork &W, FsgScalars *S, int n, int ne_base, int frame, bool direct)
 {
-    if (FSG_LEADER()) S->n_res = 0;
+    FSG_IF_LEADER S->n_res = 0;
     FSG_SYNC();
     FSG_FOR(i, n) {
         uint32_t rc[8], any = 0;
@@ -231,7 +256,7 @@ FSG_HD void fsg_resolve(const FsgGraph &G, const FsgWork &W, FsgScalars *S, int 
         }
         const int bp = S->bp_start + e;
         if (bp < W.cap) {
-            int32_t *r = W.hist_out + (size_t)bp * FSG_ROW;
+            fsg_wp r = W.hist_out + (size_t)bp * FSG_ROW;
             r[0] = l; r[1] = frame; r[2] = W.c_score[i]; r[3] = W.c_pred[i]; r[4] = W.c_lc[i];
             for (int q = 0; q < 8; ++q) r[5 + q] = (int32_t)W.c_rcf[i * 8 + q];
         }
@@ -255,7 +280,7 @@ FSG_HD void fsg_cross_word(const FsgGraph &G, const FsgWork &W, FsgScalars *S, i
     FSG_SYNC();
     const int n2c = fsg_exscan(W.cnt, n1, S->scan);
     if (n2c > G.CC || n1 + n2c > G.CC) {                                  // cannot happen: CC = P * (1 + widest null fan-out)
-        if (FSG_LEADER()) S->overflow = 1;
+        FSG_IF_LEADER S->overflow = 1;
         FSG_SYNC();
         return;
     }
@@ -275,7 +300,7 @@ FSG_HD void fsg_cross_word(const FsgGraph &G, const FsgWork &W, FsgScalars *S, i
     fsg_resolve(G, W, S, n2c, n1, frame, frame < 0);
     const int n_new = n1 + S->n_res;
     const int thresh = S->best + S->beam;
-    int32_t *nxt = W.act[S->cur ^ 1];
+    fsg_wp nxt = W.act[S->cur ^ 1];
     FSG_FOR(ri, G.R) {
         const int p = G.root_list[ri], d = G.root_state[ri], rc = G.ci_ext[p];
         int cur = W.score[p], first = -1, h = -1;
@@ -296,7 +321,7 @@ FSG_HD void fsg_cross_word(const FsgGraph &G, const FsgWork &W, FsgScalars *S, i
         }
         W.rfirst[ri] = key;
     }
-    if (FSG_LEADER()) S->n_newroot = 0;
+    FSG_IF_LEADER S->n_newroot = 0;
     FSG_SYNC();
     FSG_FOR(ri, G.R) {
         const int key = W.rfirst[ri];
@@ -310,7 +335,7 @@ FSG_HD void fsg_cross_word(const FsgGraph &G, const FsgWork &W, FsgScalars *S, i
         FSG_ATOMIC_ADD(&S->n_newroot, 1);
     }
     FSG_SYNC();
-    if (FSG_LEADER()) {
+    FSG_IF_LEADER {
         S->n_hist += n_new;
         S->n_act = S->n_ins + S->n_newroot;
         S->cur ^= 1;
@@ -323,7 +348,7 @@ FSG_HD void fsg_cross_word(const FsgGraph &G, const FsgWork &W, FsgScalars *S, i
 FSG_HD void fsg_start(const FsgGraph &G, const FsgWork &W, FsgScalars *S)
 {
     FSG_FOR(p, G.P) { fsg_clear_node(G, W, p); W.pos[p] = -1; W.posf[p] = -2; }
-    if (FSG_LEADER()) {
+    FSG_IF_LEADER {
         S->cur = 0; S->n_act = 0; S->n_ins = 0; S->n_exit = 0; S->n_newroot = 0;
         S->best = 0; S->beam = G.beam; S->pbeam = G.pbeam; S->wbeam = G.wbeam; S->beam_factor = 1.0f;
         S->n_hist = 0; S->bp_start = 0; S->overflow = 0;
@@ -341,9 +366,9 @@ template <class Eval>
 FSG_HD void fsg_step(const FsgGraph &G, const FsgWork &W, FsgScalars *S, int f, Eval &eval)
 {
     const int n_act = S->n_act, nf = f + 1;
-    const int32_t *act = W.act[S->cur];
-    int32_t *nxt = W.act[S->cur ^ 1];
-    if (FSG_LEADER()) { S->best = FSG_WORST_SCORE; S->bp_start = S->n_hist; }
+    const fsg_wp act = W.act[S->cur];
+    fsg_wp nxt = W.act[S->cur ^ 1];
+    FSG_IF_LEADER { S->best = FSG_WORST_SCORE; S->bp_start = S->n_hist; }
     FSG_SYNC();
     FSG_FOR(w, n_act) {                                                      // hmm_eval :335-373
         const int p = act[n_act - 1 - w];
@@ -352,7 +377,7 @@ FSG_HD void fsg_step(const FsgGraph &G, const FsgWork &W, FsgScalars *S, int f, 
         FSG_ATOMIC_MAX(&S->best, b);
     }
     FSG_SYNC();
-    if (FSG_LEADER()) {                                                      // :378-400
+    FSG_IF_LEADER {                                                      // :378-400
         if (G.maxhmmpf != -1 && n_act > G.maxhmmpf) {
             if (S->beam_factor > 0.1) {
                 S->beam_factor *= 0.9f;
@@ -393,7 +418,7 @@ FSG_HD void fsg_step(const FsgGraph &G, const FsgWork &W, FsgScalars *S, int f, 
     FSG_SYNC();
     const int n_ins = fsg_exscan(W.cnt, n_act, S->scan);
     const int n_exit = fsg_exscan(W.ecnt, n_act, S->scan);
-    if (FSG_LEADER()) { S->n_ins = n_ins; S->n_exit = n_exit; }
+    FSG_IF_LEADER { S->n_ins = n_ins; S->n_exit = n_exit; }
     FSG_FOR(w, n_act) {                                                      // ... applied
         const int p = act[n_act - 1 - w], flag = W.kflag[w];
         int o = W.cnt[w];

@@ -34,21 +34,21 @@ struct NgfGraph {
 };
 
 struct NgfWork {
-    int32_t *score, *hist, *mss;                     // [n_emit][M]
-    int32_t *out_score, *out_hist, *best, *frame;    // [M]
-    int32_t *awl[2];                                 // [n_words]
-    int32_t *word_active, *wordlist, *first_sf, *wl_key;   // [n_words]
-    int32_t *node_first, *node_last;                 // [T][n_words] entry index of the first / last exit per (sf, word), or -1
-    int32_t *node_cnt;                               // [T+1][n_words] surviving nodes with start frame < f (prefix count)
-    int32_t *cnt, *cnt2, *cnt3;                      // [LW]
-    int32_t *bp, *bss, *bp_idx;                      // outputs
+    fsg_wp score, hist, mss;                     // [n_emit][M]
+    fsg_wp out_score, out_hist, best, frame;    // [M]
+    fsg_wp awl[2];                                 // [n_words]
+    fsg_wp word_active, wordlist, first_sf, wl_key;   // [n_words]
+    fsg_wp node_first, node_last;                 // [T][n_words] entry index of the first / last exit per (sf, word), or -1
+    fsg_wp node_cnt;                               // [T+1][n_words] surviving nodes with start frame < f (prefix count)
+    fsg_wp cnt, cnt2, cnt3;                      // [LW]
+    fsg_wp bp, bss, bp_idx;                      // outputs
     const int32_t *bp_in;                            // first pass: [n_bp_in][10]
     int n_bp_in, bp_cap, bss_cap, T;
 };
 
 struct NgfScalars {
-    int cur, n_awl, n_awl_nxt, nwd, best, best_score, bpidx, bss_head, stop, error, n_done;
-    int silrc_score, silrc_bp;
+    fsg_int cur, n_awl, n_awl_nxt, nwd, best, best_score, bpidx, bss_head, stop, error, n_done;
+    fsg_int silrc_score, silrc_bp;
     int scan[34];
 };
 
@@ -93,8 +93,8 @@ FSG_HD int ngf_tg(const NgfGraph &G, int w, int h1, int h2)
 
 FSG_HD void ngf_set_real_wid(const NgfGraph &G, const NgfWork &W, int bp)
 {
-    int32_t *e = W.bp + (size_t)bp * NGS_BP_ROW;
-    const int32_t *prev = e[3] == -1 ? nullptr : W.bp + (size_t)e[3] * NGS_BP_ROW;
+    fsg_wp e = W.bp + (size_t)bp * NGS_BP_ROW;
+    const fsg_wp prev = e[3] == -1 ? fsg_wp(nullptr) : W.bp + (size_t)e[3] * NGS_BP_ROW;
     if (NGS_W(G, e[2], 4)) {
         if (prev) { e[6] = prev[6]; e[7] = prev[7]; }
         else { e[6] = NGS_W(G, e[2], 5); e[7] = -1; }
@@ -109,11 +109,11 @@ FSG_HD void ngf_save_bp(const NgfGraph &G, const NgfWork &W, int *entry, int new
                         int score, int path, int rc)                         /* ngram_search.c:378-497, see ngs_save_bp */
 {
     if (*entry != -1) {
-        int32_t *e = W.bp + (size_t)*entry * NGS_BP_ROW;
+        fsg_wp e = W.bp + (size_t)*entry * NGS_BP_ROW;
         if (e[4] < score) {
             if (e[3] != path) {
-                const int32_t *po = e[3] == -1 ? nullptr : W.bp + (size_t)e[3] * NGS_BP_ROW;
-                const int32_t *pn = path == -1 ? nullptr : W.bp + (size_t)path * NGS_BP_ROW;
+                const fsg_wp po = e[3] == -1 ? fsg_wp(nullptr) : W.bp + (size_t)e[3] * NGS_BP_ROW;
+                const fsg_wp pn = path == -1 ? fsg_wp(nullptr) : W.bp + (size_t)path * NGS_BP_ROW;
                 const int a0 = po ? po[7] : -1, a1 = po ? po[6] : -1, b0 = pn ? pn[7] : -1, b1 = pn ? pn[6] : -1;
                 if (a0 != b0 || a1 != b1) ngf_set_real_wid(G, W, *entry);
                 e[3] = path;
@@ -123,7 +123,7 @@ FSG_HD void ngf_save_bp(const NgfGraph &G, const NgfWork &W, int *entry, int new
         if (e[5] != -1) W.bss[e[5] + rc] = score;
     }
     else {
-        int32_t *e = W.bp + (size_t)new_bp * NGS_BP_ROW;
+        fsg_wp e = W.bp + (size_t)new_bp * NGS_BP_ROW;
         int rcsize;
         *entry = new_bp;
         e[2] = w; e[0] = frame; e[3] = path; e[4] = score; e[5] = new_s; e[1] = 1;
@@ -154,7 +154,7 @@ FSG_HD void ngf_start(const NgfGraph &G, const NgfWork &W, NgfScalars *S)
     FSG_FOR(c, G.M) { ngf_clear(G, W, c); for (int s = 0; s < G.n_emit; ++s) W.mss[s * G.M + c] = NGS_BAD_SSID; }
     FSG_FOR(x, T * nw) { W.node_first[x] = INT_MAX; W.node_last[x] = -1; }
     FSG_FOR(w, nw) { W.word_active[w] = 0; W.first_sf[w] = -1; }
-    if (FSG_LEADER()) {
+    FSG_IF_LEADER {
         S->cur = 0; S->n_awl = 0; S->n_awl_nxt = 0; S->nwd = 0; S->best_score = 0; S->bpidx = 0; S->bss_head = 0;
         S->stop = 0; S->error = 0; S->n_done = 0;
     }
@@ -165,8 +165,8 @@ FSG_HD void ngf_start(const NgfGraph &G, const NgfWork &W, NgfScalars *S)
         const int32_t *b = W.bp_in + (size_t)i * NGS_BP_ROW;
         const int sf = b[3] < 0 ? 0 : W.bp_in[(size_t)b[3] * NGS_BP_ROW] + 1, wid = b[2];
         if (!G.inlm[wid] || sf >= T) continue;
-        FSG_ATOMIC_MIN(&W.node_first[(size_t)sf * nw + wid], i);
-        FSG_ATOMIC_MAX(&W.node_last[(size_t)sf * nw + wid], i);
+        FSG_ATOMIC_MIN_AT(W.node_first, (size_t)sf * nw + wid, i);
+        FSG_ATOMIC_MAX_AT(W.node_last, (size_t)sf * nw + wid, i);
     }
     FSG_SYNC();
     FSG_FOR(x, T * nw) if (W.node_first[x] == INT_MAX) W.node_first[x] = -1;
@@ -197,7 +197,7 @@ FSG_HD void ngf_start(const NgfGraph &G, const NgfWork &W, NgfScalars *S)
         FSG_ATOMIC_ADD(&S->nwd, 1);
     }
     FSG_SYNC();
-    if (FSG_LEADER()) {
+    FSG_IF_LEADER {
         ngf_enter(W, G.ch_off[G.start_wid], 0, -1, 0);
         W.awl[0][0] = G.start_wid; S->n_awl = 1;
     }
@@ -208,9 +208,9 @@ template <class Eval>
 FSG_HD void ngf_step(const NgfGraph &G, const NgfWork &W, NgfScalars *S, int cf, Eval &eval)
 {
     const int nf = cf + 1, cur = S->cur, nxt = cur ^ 1, nw = S->n_awl, pip = G.pip, nwords = G.n_words, T = W.T;
-    const int32_t *awl = W.awl[cur];
-    int32_t *nawl = W.awl[nxt];
-    if (FSG_LEADER()) {
+    const fsg_wp awl = W.awl[cur];
+    fsg_wp nawl = W.awl[nxt];
+    FSG_IF_LEADER {
         W.bp_idx[cf] = S->bpidx;
         if (S->best_score <= FSG_WORST_SCORE) S->stop = 1;
         else if (S->best_score + 2 * G.beam < FSG_WORST_SCORE) S->error = 2;
@@ -229,7 +229,7 @@ FSG_HD void ngf_step(const NgfGraph &G, const NgfWork &W, NgfScalars *S, int cf,
     }
     FSG_FOR(w, nwords) W.word_active[w] = 0;
     FSG_SYNC();
-    if (FSG_LEADER()) S->best_score = S->best;
+    FSG_IF_LEADER S->best_score = S->best;
     FSG_SYNC();
     const int thresh = S->best_score + G.fwdflatbeam, wordthresh = S->best_score + G.fwdflatwbeam;
     // fwdflat_prune_chan :483-607, pass 1: which words exit (decided by what evaluation left)
@@ -247,7 +247,7 @@ FSG_HD void ngf_step(const NgfGraph &G, const NgfWork &W, NgfScalars *S, int cf,
     const int n_new_bp = fsg_exscan(W.cnt, nw, S->scan);
     const int n_new_bss = fsg_exscan(W.cnt2, nw, S->scan);
     if (S->bpidx + n_new_bp > W.bp_cap || S->bss_head + n_new_bss > W.bss_cap) {
-        if (FSG_LEADER()) S->error = 1;
+        FSG_IF_LEADER S->error = 1;
         FSG_SYNC();
         return;
     }
@@ -298,12 +298,12 @@ FSG_HD void ngf_step(const NgfGraph &G, const NgfWork &W, NgfScalars *S, int cf,
     FSG_SYNC();
     const int bp0 = S->bpidx, bp1 = bp0 + n_new_bp;
     FSG_SYNC();
-    if (FSG_LEADER()) {
+    FSG_IF_LEADER {
         S->bpidx = bp1; S->bss_head += n_new_bss;
         // best exit into silence (:745-752): first maximum over the frame's exits
         int best = FSG_WORST_SCORE, bb = 0;
         for (int b = bp0; b < bp1; ++b) {
-            const int32_t *e = W.bp + (size_t)b * NGS_BP_ROW;
+            const fsg_wp e = W.bp + (size_t)b * NGS_BP_ROW;
             if (e[2] == G.finish_wid) continue;
             const int sc = e[9] == -1 ? e[4] : W.bss[e[5] + G.rs_cimap[((size_t)e[8] * G.n_ci + e[9]) * G.n_ci + G.sil]];
             if (sc > best) { best = sc; bb = b; }
@@ -322,7 +322,7 @@ FSG_HD void ngf_step(const NgfGraph &G, const NgfWork &W, NgfScalars *S, int cf,
             const int c0 = G.ch_off[w], first = NGS_W(G, w, 0);
             const int ci2 = NGS_W(G, w, 3) ? G.sil : G.pron_ci[G.pron_off[w] + 1];
             for (int b = bp0; b < bp1; ++b) {
-                const int32_t *e = W.bp + (size_t)b * NGS_BP_ROW;
+                const fsg_wp e = W.bp + (size_t)b * NGS_BP_ROW;
                 if (e[2] == G.finish_wid) continue;
                 int ns = e[9] == -1 ? e[4] : W.bss[e[5] + G.rs_cimap[((size_t)e[8] * G.n_ci + e[9]) * G.n_ci + first]];
                 if (ns == FSG_WORST_SCORE) continue;
@@ -359,6 +359,6 @@ FSG_HD void ngf_step(const NgfGraph &G, const NgfWork &W, NgfScalars *S, int cf,
     FSG_FOR(k, nwd) { const int w = W.wordlist[k]; if (W.word_active[w] && w < G.start_wid) nawl[W.cnt[k]] = w; }
     FSG_FOR(w, nwords) if (w >= G.start_wid && W.word_active[w]) nawl[n1 + W.cnt3[w]] = w;
     FSG_SYNC();
-    if (FSG_LEADER()) { S->cur = nxt; S->n_awl = n1 + n2; S->n_done = cf + 1; }
+    FSG_IF_LEADER { S->cur = nxt; S->n_awl = n1 + n2; S->n_done = cf + 1; }
     FSG_SYNC();
 }

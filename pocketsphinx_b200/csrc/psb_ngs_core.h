@@ -54,26 +54,26 @@ struct NgsGraph {
 };
 
 struct NgsWork {
-    int32_t *score, *hist, *mss;                     // [n_emit][M]  (mss: per-state ssid of multiplexed channels)
-    int32_t *out_score, *out_hist, *best, *frame;    // [M]
-    int32_t *alloc;                                  // [n_rcchan]
-    int32_t *pos, *posf, *eflag;                     // [n_nonroot]
-    int32_t *acl[2], *awl[2];                        // [n_nonroot], [n_words]
-    int32_t *word_active, *lt_sf, *lt_dscr, *lt_bp;  // [n_words]
-    int32_t *cand_wid, *cand_score, *cand_bp;        // [n_words]
-    int32_t *cnt, *cnt2, *cnt3, *flag;               // [LW]
-    int32_t *brc_score, *brc_path, *brc_lc;          // [n_ci]
-    int32_t *bins;                                   // [256]
-    int32_t *bp, *bss, *bp_idx;                      // outputs: [bp_cap][10], [bss_cap], [T+1]
+    fsg_wp score, hist, mss;                     // [n_emit][M]  (mss: per-state ssid of multiplexed channels)
+    fsg_wp out_score, out_hist, best, frame;    // [M]
+    fsg_wp alloc;                                  // [n_rcchan]
+    fsg_wp pos, posf, eflag;                     // [n_nonroot]
+    fsg_wp acl[2], awl[2];                        // [n_nonroot], [n_words]
+    fsg_wp word_active, lt_sf, lt_dscr, lt_bp;  // [n_words]
+    fsg_wp cand_wid, cand_score, cand_bp;        // [n_words]
+    fsg_wp cnt, cnt2, cnt3, flag;               // [LW]
+    fsg_wp brc_score, brc_path, brc_lc;          // [n_ci]
+    fsg_wp bins;                                   // [256]
+    fsg_wp bp, bss, bp_idx;                      // outputs: [bp_cap][10], [bss_cap], [T+1]
     const int32_t *pen;                              // [T][n_ci] look-ahead penalties in force per search frame, or null
     int bp_cap, bss_cap;
 };
 
 struct NgsScalars {
-    int cur, n_acl, n_acl_nxt, n_awl, n_awl_nxt, n_cand;
-    int best_all, best_last, best_score, last_phone_best, dynamic_beam, thresh, npth, lpth;
-    int bpidx, bss_head, stop, error, n_done, k_nonfinish, ev_root, ev_last;
-    long long n_root_eval, n_nonroot_eval;
+    fsg_int cur, n_acl, n_acl_nxt, n_awl, n_awl_nxt, n_cand;
+    fsg_int best_all, best_last, best_score, last_phone_best, dynamic_beam, thresh, npth, lpth;
+    fsg_int bpidx, bss_head, stop, error, n_done, k_nonfinish, ev_root, ev_last;
+    fsg_ll n_root_eval, n_nonroot_eval;
     int scan[34];
 };
 
@@ -121,7 +121,7 @@ FSG_HD int ngs_tg(const NgsGraph &G, int w, int h1, int h2)
     return G.lm[((size_t)a * n + b) * n + c];
 }
 
-FSG_HD int ngs_exit_score(const NgsGraph &G, const NgsWork &W, const int32_t *e, int rcphone)   /* ngram_search.c:655-676 */
+FSG_HD int ngs_exit_score(const NgsGraph &G, const NgsWork &W, const fsg_wp e, int rcphone)   /* ngram_search.c:655-676 */
 {
     if (e[9] == -1) return e[4];
     return W.bss[e[5] + G.rs_cimap[((size_t)e[8] * G.n_ci + e[9]) * G.n_ci + rcphone]];
@@ -129,8 +129,8 @@ FSG_HD int ngs_exit_score(const NgsGraph &G, const NgsWork &W, const int32_t *e,
 
 FSG_HD void ngs_set_real_wid(const NgsGraph &G, const NgsWork &W, int bp)                       /* :343-373 */
 {
-    int32_t *e = W.bp + (size_t)bp * NGS_BP_ROW;
-    const int32_t *prev = e[3] == -1 ? nullptr : W.bp + (size_t)e[3] * NGS_BP_ROW;
+    fsg_wp e = W.bp + (size_t)bp * NGS_BP_ROW;
+    const fsg_wp prev = e[3] == -1 ? fsg_wp(nullptr) : W.bp + (size_t)e[3] * NGS_BP_ROW;
     if (NGS_W(G, e[2], 4)) {
         if (prev) { e[6] = prev[6]; e[7] = prev[7]; }
         else { e[6] = NGS_W(G, e[2], 5); e[7] = -1; }
@@ -147,13 +147,13 @@ FSG_HD void ngs_save_bp(const NgsGraph &G, const NgsWork &W, int *entry, int new
                         int score, int path, int rc)
 {
     if (*entry != -1) {
-        int32_t *e = W.bp + (size_t)*entry * NGS_BP_ROW;
+        fsg_wp e = W.bp + (size_t)*entry * NGS_BP_ROW;
         if (e[4] < score) {
             if (e[3] != path) {
                 // The reference re-derives the entry's LM state here BEFORE it moves to the new path
                 // (:420-440): it lags one update behind, which is visible after a second change.
-                const int32_t *po = e[3] == -1 ? nullptr : W.bp + (size_t)e[3] * NGS_BP_ROW;
-                const int32_t *pn = path == -1 ? nullptr : W.bp + (size_t)path * NGS_BP_ROW;
+                const fsg_wp po = e[3] == -1 ? fsg_wp(nullptr) : W.bp + (size_t)e[3] * NGS_BP_ROW;
+                const fsg_wp pn = path == -1 ? fsg_wp(nullptr) : W.bp + (size_t)path * NGS_BP_ROW;
                 const int a0 = po ? po[7] : -1, a1 = po ? po[6] : -1, b0 = pn ? pn[7] : -1, b1 = pn ? pn[6] : -1;
                 if (a0 != b0 || a1 != b1) ngs_set_real_wid(G, W, *entry);
                 e[3] = path;
@@ -163,7 +163,7 @@ FSG_HD void ngs_save_bp(const NgsGraph &G, const NgsWork &W, int *entry, int new
         if (e[5] != -1) W.bss[e[5] + rc] = score;
     }
     else {
-        int32_t *e = W.bp + (size_t)new_bp * NGS_BP_ROW;
+        fsg_wp e = W.bp + (size_t)new_bp * NGS_BP_ROW;
         int rcsize;
         *entry = new_bp;
         e[2] = w; e[0] = frame; e[3] = path; e[4] = score; e[5] = new_s; e[1] = 1;
@@ -186,14 +186,14 @@ FSG_HD void ngs_start(const NgsGraph &G, const NgsWork &W, NgsScalars *S)       
     FSG_FOR(i, G.n_rcchan) W.alloc[i] = 0;
     FSG_FOR(w, G.n_words) { W.lt_sf[w] = -1; W.lt_dscr[w] = 0; W.lt_bp[w] = 0; W.word_active[w] = 0; }
     FSG_FOR(i, G.n_nonroot) { W.pos[i] = -1; W.posf[i] = -2; W.eflag[i] = 0; }
-    if (FSG_LEADER()) {
+    FSG_IF_LEADER {
         S->cur = 0; S->n_acl = S->n_acl_nxt = S->n_awl = S->n_awl_nxt = S->n_cand = 0;
         S->best_score = 0; S->last_phone_best = 0; S->dynamic_beam = G.beam;
         S->bpidx = 0; S->bss_head = 0; S->stop = 0; S->error = 0; S->n_done = 0;
         S->n_root_eval = 0; S->n_nonroot_eval = 0;
     }
     FSG_SYNC();
-    if (FSG_LEADER()) ngs_enter(W, G.o_1ph + G.w2h1[G.start_wid], 0, -1, 0);
+    FSG_IF_LEADER ngs_enter(W, G.o_1ph + G.w2h1[G.start_wid], 0, -1, 0);
     FSG_SYNC();
 }
 
@@ -216,9 +216,9 @@ template <class Eval>
 FSG_HD void ngs_step(const NgsGraph &G, const NgsWork &W, NgsScalars *S, int f, Eval &eval)
 {
     const int nf = f + 1, cur = S->cur, nxt = cur ^ 1, n_acl = S->n_acl, n_awl = S->n_awl, M = G.M;
-    int32_t *acl = W.acl[cur], *nacl = W.acl[nxt], *awl = W.awl[cur], *nawl = W.awl[nxt];
+    fsg_wp acl = W.acl[cur], nacl = W.acl[nxt], awl = W.awl[cur], nawl = W.awl[nxt];
     // ---- ngram_fwdtree_search :1454-1482
-    if (FSG_LEADER()) {
+    FSG_IF_LEADER {
         W.bp_idx[f] = S->bpidx;
         if (S->best_score <= FSG_WORST_SCORE) S->stop = 1;
         else if (S->best_score + 2 * G.beam < FSG_WORST_SCORE) S->error = 2;        // renormalisation: not on the device
@@ -250,7 +250,7 @@ FSG_HD void ngs_step(const NgsGraph &G, const NgsWork &W, NgsScalars *S, int f, 
     }
     FSG_SYNC();
     // ---- prune_channels :1130-1180: beams
-    if (FSG_LEADER()) {
+    FSG_IF_LEADER {
         S->best_score = S->best_all > S->best_last ? S->best_all : S->best_last;
         S->last_phone_best = S->best_last;
         S->n_root_eval += S->ev_root; S->n_nonroot_eval += n_acl + S->ev_last;
@@ -262,17 +262,17 @@ FSG_HD void ngs_step(const NgsGraph &G, const NgsWork &W, NgsScalars *S, int f, 
         const int bw = -G.beam / 256;
         FSG_FOR(b, 256) W.bins[b] = 0;
         FSG_SYNC();
-        FSG_FOR(i, G.n_root) { int b = (S->best_score - W.best[i]) / bw; if (b >= 256) b = 255; FSG_ATOMIC_ADD(&W.bins[b], 1); }
-        FSG_FOR(k, n_acl) { int b = (S->best_score - W.best[G.o_nonroot + acl[k]]) / bw; if (b >= 256) b = 255; FSG_ATOMIC_ADD(&W.bins[b], 1); }
+        FSG_FOR(i, G.n_root) { int b = (S->best_score - W.best[i]) / bw; if (b >= 256) b = 255; FSG_ATOMIC_ADD_AT(W.bins, b, 1); }
+        FSG_FOR(k, n_acl) { int b = (S->best_score - W.best[G.o_nonroot + acl[k]]) / bw; if (b >= 256) b = 255; FSG_ATOMIC_ADD_AT(W.bins, b, 1); }
         FSG_SYNC();
-        if (FSG_LEADER()) {
+        FSG_IF_LEADER {
             int i, nh = 0;
             for (i = 0; i < 256; ++i) { nh += W.bins[i]; if (nh > G.maxhmmpf) break; }
             S->dynamic_beam = -(i * bw);
         }
         FSG_SYNC();
     }
-    if (FSG_LEADER()) { S->thresh = S->best_score + S->dynamic_beam; S->npth = S->best_score + G.pbeam; S->lpth = S->best_score + G.lpbeam; }
+    FSG_IF_LEADER { S->thresh = S->best_score + S->dynamic_beam; S->npth = S->best_score + G.pbeam; S->lpth = S->best_score + G.lpbeam; }
     FSG_SYNC();
     const int thresh = S->thresh, npth = S->npth, lpth = S->lpth;
     // ---- prune_root_chan :723-794.  cnt = children entered, cnt2 = last-phone candidates
@@ -385,17 +385,17 @@ FSG_HD void ngs_step(const NgsGraph &G, const NgsWork &W, NgsScalars *S, int f, 
     FSG_SYNC();
     const int n_cand = n_cand_roots + n_cand_nonroot;
     // ---- last_phone_transition :885-1035
-    if (FSG_LEADER()) { S->n_acl_nxt = n_from_roots + n_from_nonroot; S->n_cand = n_cand; S->best_all = S->last_phone_best; }
+    FSG_IF_LEADER { S->n_acl_nxt = n_from_roots + n_from_nonroot; S->n_cand = n_cand; S->best_all = S->last_phone_best; }
     FSG_FOR(i, n_cand) {
         const int w = W.cand_wid[i], bp0 = W.cand_bp[i];
         if (bp0 == -1) continue;
-        const int32_t *e0 = W.bp + (size_t)bp0 * NGS_BP_ROW;
+        const fsg_wp e0 = W.bp + (size_t)bp0 * NGS_BP_ROW;
         const int ef = e0[0], first = NGS_W(G, w, 0);
         W.cand_score[i] -= ngs_exit_score(G, W, e0, first);
         if (W.lt_sf[w] != ef + 1) {
             int dbest = FSG_WORST_SCORE, bbest = W.lt_bp[w];
             for (int bp = W.bp_idx[ef]; bp < W.bp_idx[ef + 1]; ++bp) {
-                const int32_t *e = W.bp + (size_t)bp * NGS_BP_ROW;
+                const fsg_wp e = W.bp + (size_t)bp * NGS_BP_ROW;
                 if (!e[1]) continue;
                 int dscr = ngs_exit_score(G, W, e, first);
                 if (dscr > FSG_WORST_SCORE) dscr += ngs_tg(G, NGS_W(G, w, 5), e[6], e[7]);
@@ -412,7 +412,7 @@ FSG_HD void ngs_step(const NgsGraph &G, const NgsWork &W, NgsScalars *S, int f, 
         FSG_ATOMIC_MAX(&S->best_all, W.cand_score[i]);
     }
     FSG_SYNC();
-    if (FSG_LEADER()) S->last_phone_best = S->best_all;
+    FSG_IF_LEADER S->last_phone_best = S->best_all;
     FSG_SYNC();
     {
         const int th = S->last_phone_best + G.lponlybeam;
@@ -465,7 +465,7 @@ FSG_HD void ngs_step(const NgsGraph &G, const NgsWork &W, NgsScalars *S, int f, 
     const int n_new_bss = fsg_exscan(W.cnt2, n_items, S->scan);
     const int n_awl_wc = fsg_exscan(W.cnt3, n_items, S->scan);
     if (S->bpidx + n_new_bp > W.bp_cap || S->bss_head + n_new_bss > W.bss_cap) {
-        if (FSG_LEADER()) S->error = 1;
+        FSG_IF_LEADER S->error = 1;
         FSG_SYNC();
         return;
     }
@@ -496,15 +496,17 @@ FSG_HD void ngs_step(const NgsGraph &G, const NgsWork &W, NgsScalars *S, int f, 
     }
     FSG_SYNC();
     const int bp0 = S->bpidx, bp1 = bp0 + n_new_bp;
+#ifndef NGS_TEST_INJECT_RACE                                                  /* tests/test_emul_racecheck.py removes this barrier to prove the detector sees it */
     FSG_SYNC();                                                               // everyone has read bpidx before it moves
-    if (FSG_LEADER()) { S->bpidx = bp1; S->bss_head += n_new_bss; S->n_awl_nxt = n_awl_lp + n_awl_wc; S->k_nonfinish = 0; }
+#endif
+    FSG_IF_LEADER { S->bpidx = bp1; S->bss_head += n_new_bss; S->n_awl_nxt = n_awl_lp + n_awl_wc; S->k_nonfinish = 0; }
     FSG_SYNC();
     // ---- bptable_maxwpf :1188-1238
     if (G.maxwpf != -1 && G.maxwpf != G.n_words) {
-        if (FSG_LEADER()) {                                                     // fillers: only the best stays valid
+        FSG_IF_LEADER {                                                     // fillers: only the best stays valid
             int n = 0, bestscr = INT_MIN, bestbp = -1;
             for (int bp = bp0; bp < bp1; ++bp) {
-                int32_t *e = W.bp + (size_t)bp * NGS_BP_ROW;
+                fsg_wp e = W.bp + (size_t)bp * NGS_BP_ROW;
                 if (NGS_W(G, e[2], 4)) { if (e[4] > bestscr) { bestscr = e[4]; bestbp = bp; } e[1] = 0; ++n; }
             }
             if (bestbp >= 0) { W.bp[(size_t)bestbp * NGS_BP_ROW + 1] = 1; --n; }
@@ -514,12 +516,12 @@ FSG_HD void ngs_step(const NgsGraph &G, const NgsWork &W, NgsScalars *S, int f, 
         const int n_drop = S->scan[32];
         if (n_drop > 0) {
             FSG_FOR(x, bp1 - bp0) {
-                const int32_t *e = W.bp + (size_t)(bp0 + x) * NGS_BP_ROW;
+                const fsg_wp e = W.bp + (size_t)(bp0 + x) * NGS_BP_ROW;
                 int rank = -1;
                 if (e[1]) {
                     rank = 0;
                     for (int y = 0; y < bp1 - bp0; ++y) {
-                        const int32_t *o = W.bp + (size_t)(bp0 + y) * NGS_BP_ROW;
+                        const fsg_wp o = W.bp + (size_t)(bp0 + y) * NGS_BP_ROW;
                         if (y != x && o[1] && (o[4] < e[4] || (o[4] == e[4] && y < x))) ++rank;
                     }
                 }
@@ -534,7 +536,7 @@ FSG_HD void ngs_step(const NgsGraph &G, const NgsWork &W, NgsScalars *S, int f, 
     FSG_FOR(rc, G.n_ci) {
         int best = FSG_WORST_SCORE, path = W.brc_path[rc], lc = W.brc_lc[rc], k = 0;
         for (int bp = bp0; bp < bp1; ++bp) {
-            const int32_t *e = W.bp + (size_t)bp * NGS_BP_ROW;
+            const fsg_wp e = W.bp + (size_t)bp * NGS_BP_ROW;
             if (e[2] == G.finish_wid) continue;
             ++k;
             const int sc = e[9] == -1 ? e[4] : W.bss[e[5] + G.rs_cimap[((size_t)e[8] * G.n_ci + e[9]) * G.n_ci + rc]];
@@ -559,7 +561,7 @@ FSG_HD void ngs_step(const NgsGraph &G, const NgsWork &W, NgsScalars *S, int f, 
             if (i < G.n_1ph_lm && w != G.start_wid) {
                 int dbest = INT_MIN, bbest = W.lt_bp[w];
                 for (int bp = bp0; bp < bp1; ++bp) {
-                    const int32_t *e = W.bp + (size_t)bp * NGS_BP_ROW;
+                    const fsg_wp e = W.bp + (size_t)bp * NGS_BP_ROW;
                     if (!e[1]) continue;
                     int ns = ngs_exit_score(G, W, e, NGS_W(G, w, 0));
                     if (ns != FSG_WORST_SCORE) ns += ngs_tg(G, NGS_W(G, w, 5), e[6], e[7]);
@@ -575,7 +577,7 @@ FSG_HD void ngs_step(const NgsGraph &G, const NgsWork &W, NgsScalars *S, int f, 
             else if (i < G.n_1ph_lm) {                                           // <s>: only the cache is refreshed (:1339-1362)
                 int dbest = INT_MIN, bbest = W.lt_bp[w];
                 for (int bp = bp0; bp < bp1; ++bp) {
-                    const int32_t *e = W.bp + (size_t)bp * NGS_BP_ROW;
+                    const fsg_wp e = W.bp + (size_t)bp * NGS_BP_ROW;
                     if (!e[1]) continue;
                     int ns = ngs_exit_score(G, W, e, NGS_W(G, w, 0));
                     if (ns != FSG_WORST_SCORE) ns += ngs_tg(G, NGS_W(G, w, 5), e[6], e[7]);
@@ -598,7 +600,7 @@ FSG_HD void ngs_step(const NgsGraph &G, const NgsWork &W, NgsScalars *S, int f, 
     // ---- deactivate_channels :1432-1451
     FSG_FOR(i, G.n_root) if (W.frame[i] == f) ngs_clear(G, W, i);
     FSG_FOR(i, G.n_1ph) if (W.frame[G.o_1ph + i] == f) ngs_clear(G, W, G.o_1ph + i);
-    if (FSG_LEADER()) { S->cur = nxt; S->n_acl = S->n_acl_nxt; S->n_awl = S->n_awl_nxt; S->n_done = f + 1; }
+    FSG_IF_LEADER { S->cur = nxt; S->n_acl = S->n_acl_nxt; S->n_awl = S->n_awl_nxt; S->n_done = f + 1; }
     FSG_SYNC();
     (void)M;
 }

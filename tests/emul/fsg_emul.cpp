@@ -57,15 +57,25 @@ fsg_emul_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq,
     fsg_work_carve(work.data(), G, W);
     W.hist_out = hist_out; W.cap = cap;
     FsgScalars S;
-    memset(&S, 0x5a, sizeof(S));
+    memset((void *)&S, 0x5a, sizeof(S));
     OracleEval ev;
     memset(&ev.ctx, 0, sizeof(ev.ctx));
     ev.ctx.n_emit_state = n_emit_state; ev.ctx.tp = tp; ev.ctx.sseq = sseq;
     ev.G = &G; ev.ssid = flat.ssid.data(); ev.tmatid = flat.tmatid.data();
+    FSG_SYNC();                                              // (race-check builds: a fresh phase per run)
     fsg_start(G, W, &S);
     for (int f = 0; f < T && !S.overflow; ++f) {
         ev.ctx.senscore = senscr + (size_t)f * n_sen;
         fsg_step(G, W, &S, f, ev);
     }
     return S.overflow ? -2 : S.n_hist;
+}
+
+extern "C" long emul_race_count(void)
+{
+#ifdef PSB_FSG_RACECHECK
+    return fsgrace::st().n_races;
+#else
+    return -1;
+#endif
 }

@@ -54,17 +54,27 @@ ngs_emul_run(int32_t n_emit_state, const uint8_t *tp, int32_t n_tmat, const uint
     ngs_work_carve(work.data(), G, W);
     W.bp = bp_out; W.bss = bss_out; W.bp_idx = bp_idx_out; W.pen = pen; W.bp_cap = bp_cap; W.bss_cap = bss_cap;
     NgsScalars S;
-    memset(&S, 0x5a, sizeof(S));
+    memset((void *)&S, 0x5a, sizeof(S));
     OracleEval ev;
     memset(&ev.ctx, 0, sizeof(ev.ctx));
     ev.ctx.n_emit_state = n_emit_state; ev.ctx.tp = tp; ev.ctx.sseq = sseq; ev.G = &G;
+    FSG_SYNC();                                              // (race-check builds: a fresh phase per run)
     ngs_start(G, W, &S);
     for (int f = 0; f < T && !S.stop && !S.error; ++f) {
         ev.ctx.senscore = senscr + (size_t)f * n_sen;
         ngs_step(G, W, &S, f, ev);
     }
-    if (S.error) { fprintf(stderr, "ngs_emul: error %d at frame %d: bpidx %d bss_head %d n_acl %d n_awl %d\n", S.error, S.n_done, S.bpidx, S.bss_head, S.n_acl, S.n_awl); return -1 - S.error; }
+    if (S.error) { fprintf(stderr, "ngs_emul: error %d at frame %d: bpidx %d bss_head %d n_acl %d n_awl %d\n", (int)S.error, (int)S.n_done, (int)S.bpidx, (int)S.bss_head, (int)S.n_acl, (int)S.n_awl); return -1 - (int)S.error; }
     bp_idx_out[S.n_done] = S.bpidx;
     *bss_n = S.bss_head;
     return S.bpidx;
+}
+
+extern "C" long emul_race_count(void)
+{
+#ifdef PSB_FSG_RACECHECK
+    return fsgrace::st().n_races;
+#else
+    return -1;
+#endif
 }
