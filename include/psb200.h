@@ -394,6 +394,11 @@ int psb_ngram_fwdflat_batch_device(psb_hmmctx_t *c, const psb_ngram_desc_t *g, c
                                    int32_t bp_cap_per_utt, int32_t *bss, int32_t bss_cap_per_utt,
                                    int32_t *bp_idx, int32_t *result);
 
+/* Self-test of the search kernels' block-wide exclusive scan (the one building block the host
+ * emulation of their phase code cannot execute): scans a[0..n) in place on `device` with one CTA,
+ * total[0] = the sum, total[1] = the result of an empty scan issued right behind it (must be 0). */
+int psb_selftest_block_scan(int device, int32_t *a, int32_t n, int32_t *total);
+
 /* ------------------------------------------------------------------------------------ */
 /* Batched front end: int16 PCM -> cepstra -> batch CMN -> 1s_c_d_dd features
  * for whole batches, every utterance a fresh stream (ps_start_stream + ps_process_raw(full_utt),

@@ -2129,3 +2129,39 @@ extern "C" int psb_ngram_fwdflat_batch_device(psb_hmmctx_t *c, const psb_ngram_d
     }
     return PSB_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// Self-test hook for the one building block of the search kernels that host emulation cannot run:
+// the block-wide exclusive scan (fsg_exscan, psb_fsg_core.h).  One CTA scans a[0..n) in place.
+namespace {
+__global__ void __launch_bounds__(NGS_THREADS)
+exscan_selftest_kernel(int32_t *a, int n, int32_t *total)
+{
+    __shared__ int scan[34];
+    const int t = fsg_exscan(a, n, scan);
+    const int t2 = fsg_exscan(a + n, 0, scan);               // an empty scan right behind it (scan[33] reuse)
+    if (threadIdx.x == blockDim.x - 1) { total[0] = t; total[1] = t2; }
+}
+}  // namespace
+
+extern "C" int psb_selftest_block_scan(int device, int32_t *a, int32_t n, int32_t *total)
+{
+    PSB_REQUIRE(a && total && n >= 0, "psb_selftest_block_scan: bad argument");
+    PSB_CUDA(cudaSetDevice(device));
+    int32_t *d = nullptr;
+    PSB_CUDA(cudaMalloc((void **)&d, ((size_t)n + 2) * 4));
+    cudaError_t e = cudaMemcpy(d, a, (size_t)n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        exscan_selftest_kernel<<<1, NGS_THREADS>>>(d, n, d + n);
+        g_psb_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(a, d, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(total, d + n, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        psb_set_error("psb_selftest_block_scan: %s", cudaGetErrorString(e));
+        return PSB_ERR_CUDA;
+    }
+    return PSB_OK;
+}

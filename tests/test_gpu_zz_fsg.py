@@ -71,3 +71,18 @@ def test_fsg_rejects_bad_graphs(api, en_us):
     with pytest.raises(PsbError):
         ctx.fsg(d_scr.data_ptr(), np.array([0, 10], np.int32), c, 64)
     ctx.close()
+
+
+def test_block_scan_selftest(api):
+    """fsg_exscan on the device against numpy, lengths around the chunk (128) and warp (32) boundaries."""
+    import ctypes as C
+    from pocketsphinx_b200._lib import check, lib
+    rng = np.random.default_rng(2)
+    for n in (0, 1, 31, 32, 33, 127, 128, 129, 255, 256, 257, 1000, 4097):
+        a = rng.integers(0, 5, n).astype(np.int32)
+        want = np.concatenate([[0], np.cumsum(a)[:-1]]).astype(np.int32) if n else a.copy()
+        got = a.copy()
+        total = np.zeros(2, np.int32)
+        check(lib().psb_selftest_block_scan(0, got.ctypes.data_as(C.c_void_p), n, total.ctypes.data_as(C.c_void_p)),
+              "psb_selftest_block_scan")
+        assert np.array_equal(got, want) and total[0] == a.sum() and total[1] == 0, n
