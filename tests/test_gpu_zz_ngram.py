@@ -112,3 +112,45 @@ def test_fwdflat_batch_matches_reference_and_oracle(api, en_us, tag):
         bp, bss, idx = out[u]
         assert np.array_equal(bp, want[0]) and np.array_equal(bss, want[1]) and np.array_equal(idx, want[2]), u
     ctx.close()
+
+
+@pytest.mark.timeout(600)
+def test_all_searches_on_tidigits_against_the_live_reference(api, tidigits):
+    """5-state HMMs, another phone set, dictionary, grammar and LM: the reference runs live on the GPU
+    box (oracle/_ref travels with its copy of the tidigits model)."""
+    import torch
+    from oracle import refdrv
+    if not refdrv.available():
+        pytest.skip("oracle/_ref/libpsref.so not built")
+    ref_dir = os.path.dirname(refdrv.LIB_PATH)
+    hd = os.path.join(ref_dir, "model", "tidigits_hmm")
+    dic = os.path.join(ref_dir, "model", "tidigits_lm", "tidigits.dic")
+    pcm = np.fromfile(os.path.join(ref_dir, "data", "goforward.raw"), np.int16)
+    ref = refdrv.RefModel(hd)
+    scr = np.ascontiguousarray(ref.score(ref.featurize_fresh(pcm)))
+    ref.close()
+    d_scr = torch.from_numpy(np.concatenate([scr, scr[:90]])).cuda()
+    utt_off = np.array([0, len(scr), len(scr) + 90], np.int32)
+    ctx = api.HmmContext(tidigits.tp, tidigits.sseq, tidigits.n_sen)
+    # grammar search
+    from oracle import oracle
+    g = refdrv.fsg(hd, dic, os.path.join(ref_dir, "model", "tidigits_lm", "tidigits.fsg"), pcm)
+    hist, n = ctx.fsg(d_scr.data_ptr(), utt_off, g, len(g["hist"]) + 64)
+    assert n[0] == len(g["hist"]) and np.array_equal(hist[0], g["hist"])
+    assert np.array_equal(hist[1], oracle.fsg_run(tidigits.tp, tidigits.sseq, g, scr[:90]))
+    # both n-gram passes
+    lm = os.path.join(ref_dir, "model", "tidigits_lm", "tidigits.lm.bin")
+    first = refdrv.fwdtree(hd, lm, dic, pcm)
+    both = refdrv.fwdtree(hd, lm, dic, pcm, fwdflat="yes")
+    nc = both["n_ci"]
+    cit, cis = tidigits.phone_tmat[:nc], tidigits.phone_ssid[:nc]
+    out1 = ctx.ngram_fwdtree(d_scr.data_ptr(), utt_off, both["info"], both["model"], cit, len(first["bp"]) + 64, len(first["bss"]) + 4096)
+    assert np.array_equal(out1[0][0], first["bp"]) and np.array_equal(out1[0][1], first["bss"]) and np.array_equal(out1[0][2], first["bp_idx"])
+    want1 = oracle.fwdtree_run(tidigits.tp, tidigits.sseq, cit, both["info"], both["model"], scr[:90])
+    assert np.array_equal(out1[1][0], want1[0]) and np.array_equal(out1[1][1], want1[1])
+    out2 = ctx.ngram_fwdflat(d_scr.data_ptr(), utt_off, both["info"], both["model"], cit, cis, [o[0] for o in out1],
+                             len(both["bp"]) + 64, len(both["bss"]) + 4096)
+    assert np.array_equal(out2[0][0], both["bp"]) and np.array_equal(out2[0][1], both["bss"]) and np.array_equal(out2[0][2], both["bp_idx"])
+    want2 = oracle.fwdflat_run(tidigits.tp, tidigits.sseq, cit, cis, both["info"], both["model"], want1[0], scr[:90])
+    assert np.array_equal(out2[1][0], want2[0]) and np.array_equal(out2[1][1], want2[1])
+    ctx.close()
