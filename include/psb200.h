@@ -373,7 +373,10 @@ int psb_fsg_batch_device(psb_hmmctx_t *c, const psb_fsg_desc_t *g, const int16_t
  * on which ngram_search_find_exit / ngram_search_bp_hyp / the second pass work unchanged.  A full
  * table is an error (PSB_ERR_ARG): later frames read earlier entries. */
 typedef struct psb_ngram_desc_s {
-    const int32_t *info, *model, *ci_tmat;
+    const int32_t *info;        /* [40] */
+    const int32_t *model;       /* the sections, back to back */
+    int64_t model_len;          /* int32 words in `model` (checked against the sizes info implies) */
+    const int32_t *ci_tmat;     /* [n_ciphone] */
     const int32_t *ci_ssid;     /* [n_ciphone] bin_mdef_pid2ssid of every CI phone; second pass only (may be NULL for the first) */
 } psb_ngram_desc_t;
 int psb_ngram_fwdtree_batch_device(psb_hmmctx_t *c, const psb_ngram_desc_t *g, const int16_t *d_senscr,

@@ -310,7 +310,7 @@ class HmmContext:
         n_utt = len(utt_off) - 1
         info = np.ascontiguousarray(info, np.int32); model = np.ascontiguousarray(model, np.int32)
         ci_tmat = np.ascontiguousarray(ci_tmat, np.int32)
-        d = NgramDesc(info.ctypes.data, model.ctypes.data, ci_tmat.ctypes.data, None)
+        d = NgramDesc(info.ctypes.data, model.ctypes.data, len(model), ci_tmat.ctypes.data, None)
         bp = np.zeros((max(n_utt, 1), int(bp_cap), 10), np.int32)
         bss = np.zeros((max(n_utt, 1), int(bss_cap)), np.int32)
         bp_idx = np.zeros(int(utt_off[-1]) + max(n_utt, 1), np.int32)
@@ -334,7 +334,7 @@ class HmmContext:
         n_utt = len(utt_off) - 1
         info = np.ascontiguousarray(info, np.int32); model = np.ascontiguousarray(model, np.int32)
         ci_tmat = np.ascontiguousarray(ci_tmat, np.int32); ci_ssid = np.ascontiguousarray(ci_ssid, np.int32)
-        d = NgramDesc(info.ctypes.data, model.ctypes.data, ci_tmat.ctypes.data, ci_ssid.ctypes.data)
+        d = NgramDesc(info.ctypes.data, model.ctypes.data, len(model), ci_tmat.ctypes.data, ci_ssid.ctypes.data)
         cap_in = max([len(t) for t in first_tables] + [1])
         first = np.zeros((max(n_utt, 1), cap_in, 10), np.int32)
         n_first = np.zeros(max(n_utt, 1), np.int32)

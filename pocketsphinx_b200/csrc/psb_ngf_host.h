@@ -12,7 +12,7 @@ struct NgfFlat {
 };
 
 static inline int
-ngf_flatten(const int32_t *info, const int32_t *model, const int32_t *ci_tmat, const int32_t *ci_ssid, const uint16_t *sseq,
+ngf_flatten(const int32_t *info, const int32_t *model, long long model_len, const int32_t *ci_tmat, const int32_t *ci_ssid, const uint16_t *sseq,
             int n_sseq, int n_emit, int n_tmat, int n_sen, NgfFlat &o, std::string &err)
 {
     NgfGraph &G = o.G;
@@ -25,6 +25,13 @@ ngf_flatten(const int32_t *info, const int32_t *model, const int32_t *ci_tmat, c
     G.pip = info[16]; G.silpen = info[17]; G.fillpen = info[18]; G.start_wid = info[19]; G.finish_wid = info[20];
     G.silence_wid = info[21]; G.filler_start = info[22]; G.filler_end = info[23];
     const size_t nc = (size_t)n_ci;
+    if (n_root < 0 || n_nonroot < 0 || n_1ph < 0 || n_ci > 256 || n_lm > 2048) NGS_FAIL("ngram search: sizes out of range");
+    {
+        const unsigned long long need = (unsigned long long)n_root * 5 + (unsigned long long)n_nonroot * 6 + (unsigned long long)n_words * 8 +
+            (unsigned long long)n_1ph * 5 + nc * nc + 3ull * nc * nc * nc + (unsigned long long)n_lm * (n_lm + 1) * (n_lm + 1) +
+            (unsigned long long)n_words * 2 + 1 + 2ull * n_pron;
+        if (model_len < 0 || (unsigned long long)model_len < need) NGS_FAIL("ngram search: model block holds %lld words, the second pass needs %llu", model_len, need);
+    }
     const int32_t *m = model;
     m += (size_t)n_root * 5 + (size_t)n_nonroot * 6;
     const int32_t *words = m; m += (size_t)n_words * 8;

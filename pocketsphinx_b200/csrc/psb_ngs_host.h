@@ -21,7 +21,7 @@ struct NgsFlat {
 
 // info[40] + model sections as exported; ci_tmat[n_ci]; sseq [n_sseq][n_emit].
 static inline int
-ngs_flatten(const int32_t *info, const int32_t *model, const int32_t *ci_tmat, const uint16_t *sseq, int n_sseq, int n_emit,
+ngs_flatten(const int32_t *info, const int32_t *model, long long model_len, const int32_t *ci_tmat, const uint16_t *sseq, int n_sseq, int n_emit,
             int n_tmat, int n_sen, NgsFlat &o, std::string &err)
 {
     NgsGraph &G = o.G;
@@ -34,6 +34,12 @@ ngs_flatten(const int32_t *info, const int32_t *model, const int32_t *ci_tmat, c
     if (G.n_words <= 0 || G.n_root < 0 || G.n_nonroot < 0 || G.n_1ph <= 0 || G.n_ci <= 0 || G.n_lm <= 0) NGS_FAIL("ngram search: empty tables");
     if (G.n_1ph_lm > G.n_1ph) NGS_FAIL("ngram search: n_1ph_LMwords > n_1ph_words");
     const size_t nc = (size_t)G.n_ci;
+    if (G.n_ci > 256 || G.n_lm > 2048) NGS_FAIL("ngram search: %d phones / %d LM words exceed what the dense tables are meant for", G.n_ci, G.n_lm);
+    {
+        const unsigned long long need = (unsigned long long)G.n_root * 5 + (unsigned long long)G.n_nonroot * 6 + (unsigned long long)G.n_words * 8 +
+            (unsigned long long)G.n_1ph * 5 + nc * nc + 3ull * nc * nc * nc + (unsigned long long)G.n_lm * (G.n_lm + 1) * (G.n_lm + 1);
+        if (model_len < 0 || (unsigned long long)model_len < need) NGS_FAIL("ngram search: model block holds %lld words, the sizes in info need %llu", model_len, need);
+    }
     const int32_t *m = model;
     const int32_t *roots = m; m += (size_t)G.n_root * 5;
     const int32_t *nonroot = m; m += (size_t)G.n_nonroot * 6;

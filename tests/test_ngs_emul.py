@@ -13,7 +13,7 @@ import pytest
 from conftest import ROOT, golden
 
 TAGS = ("default", "wide", "narrow", "maxwpf", "abs", "pen", "lookahead")
-ARGT = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+ARGT = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
         C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
 
 
@@ -53,7 +53,7 @@ def run_emul(f, m, info, model, scr, bp_cap, bss_cap, pl_pen=None, pl_window=0):
     bss = np.zeros(bss_cap, np.int32)
     idx = np.zeros(T + 2, np.int32)
     bn = C.c_int32()
-    n = f(tp.shape[1], _p(tp), tp.shape[0], _p(sseq), len(sseq), _p(cit), _p(info), _p(model), _p(scr), scr.shape[1], T,
+    n = f(tp.shape[1], _p(tp), tp.shape[0], _p(sseq), len(sseq), _p(cit), _p(info), _p(model), len(model), _p(scr), scr.shape[1], T,
           _p(pen), _p(bp), bp_cap, _p(bss), bss_cap, C.byref(bn), _p(idx))
     return n, bp[:max(n, 0)], bss[:bn.value if n >= 0 else 0], idx[:T + 1]
 
@@ -93,3 +93,4 @@ def test_graph_validation(emul):
     model[n_root * 5 + 5] = 0                                   # non-root channel 0: alt -> itself/another: two parents
     model[n_root * 5 + 4] = 0
     assert run_emul(emul, m, c["info"], model, gf["senscr"][:5], 64, 4096)[0] == -1
+    assert run_emul(emul, m, c["info"], c["model"][:1000], gf["senscr"][:5], 64, 4096)[0] == -1      # block shorter than info says
