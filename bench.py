@@ -235,6 +235,65 @@ def frontend_stage(api, torch, U, secs, budget_s=4.0):
     return out
 
 
+def search_stage(api, torch, U=256):
+    """Rows f-1 / f-4, reported beside the headline (not part of `value`), ONLY with PSB_RUN_UNVERIFIED=1:
+    the three search kernels (fsg_search_kernel, ngs_fwdtree_kernel, ngs_fwdflat_kernel) over U copies
+    of the reference's own utterance (goforward.raw: its golden senone scores, its flattened grammar /
+    lextree / turtle LM from tests/golden/), wall clock of each call including table download, with the
+    first utterance's tables compared against the reference's golden ones."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    gd = os.path.join(here, "tests", "golden")
+    m = np.load(os.path.join(gd, "en_us_ptm_model.npz"))
+    gf = np.load(os.path.join(gd, "en_us_goforward.npz"))
+    scr = gf["senscr"]
+    T = len(scr)
+    d_scr = torch.from_numpy(np.ascontiguousarray(np.tile(scr, (U, 1)))).cuda()
+    off = (np.arange(U + 1, dtype=np.int64) * T).astype(np.int32)
+    ctx = api.HmmContext(m["tp"], m["sseq"], int(m["n_sen"]))
+    out = {"utts": U, "frames_per_utt": T, "note": "not part of `value`; kernels first run on hardware in round 2"}
+
+    def case(g, tag):
+        return {k[len(tag) + 1:]: g[k] for k in g.files if k.startswith(tag + ".")}
+
+    def timed(fn):
+        fn()
+        t0 = time.perf_counter()
+        r = fn()
+        return r, time.perf_counter() - t0
+    c = case(np.load(os.path.join(gd, "en_us_fsg.npz")), "cmd")
+    (hist, n), dt = timed(lambda: ctx.fsg(d_scr.data_ptr(), off, c, len(c["hist"]) + 64))
+    out["fsg"] = {"kernel": "fsg_search_kernel", "pnodes": int(len(c["pnodes"])), "ms": dt * 1e3, "utts_per_s": U / dt,
+                  "frames_per_s": U * T / dt, "matches_reference": bool(np.array_equal(hist[0], c["hist"]) and (n == n[0]).all())}
+    c = case(np.load(os.path.join(gd, "en_us_fwdtree.npz")), "flat_default")
+    first_ref = case(np.load(os.path.join(gd, "en_us_fwdtree.npz")), "lookahead")
+    nci = int(c["info"][6])
+    cit, cis = m["phone_tmat"][:nci], m["phone_ssid"][:nci]
+    win = int(gf["pl_params"][4])
+    pen = np.ascontiguousarray(gf["pl_pen"][np.minimum(np.arange(T) + win, T - 1)], np.int32)
+    d_pen = torch.from_numpy(np.ascontiguousarray(np.tile(pen, (U, 1)))).cuda()
+    first, dt1 = timed(lambda: ctx.ngram_fwdtree(d_scr.data_ptr(), off, c["info"], c["model"], cit, 2048, 1 << 15, d_pen.data_ptr()))
+    out["fwdtree"] = {"kernel": "ngs_fwdtree_kernel", "channels": int(c["info"][2] + c["info"][3]), "ms": dt1 * 1e3,
+                      "utts_per_s": U / dt1, "frames_per_s": U * T / dt1,
+                      "matches_reference": bool(np.array_equal(first[0][0], first_ref["bp"]))}
+    tabs = [f[0] for f in first]
+    second, dt2 = timed(lambda: ctx.ngram_fwdflat(d_scr.data_ptr(), off, c["info"], c["model"], cit, cis, tabs, 2048, 1 << 15))
+    out["fwdflat"] = {"kernel": "ngs_fwdflat_kernel", "ms": dt2 * 1e3, "utts_per_s": U / dt2, "frames_per_s": U * T / dt2,
+                      "matches_reference": bool(np.array_equal(second[0][0], c["bp"]))}
+    ctx.close()
+    try:
+        from oracle import refdrv
+        lm = os.path.join(os.path.dirname(refdrv.LIB_PATH), "data", "turtle.lm.bin")
+        if refdrv.available() and os.path.exists(lm):
+            rd = os.path.dirname(refdrv.LIB_PATH)
+            pcm = np.fromfile(os.path.join(rd, "data", "goforward.raw"), np.int16)
+            t0 = time.perf_counter()
+            refdrv.decode(os.path.join(rd, "model", "en-us"), lm, os.path.join(rd, "data", "turtle.dic"), pcm, bestpath="no")
+            out["cpu_reference_full_decode_ms_1core"] = (time.perf_counter() - t0) * 1e3      # init + GMM + both passes
+    except Exception as e:
+        out["cpu_reference_error"] = str(e)[:100]
+    return out
+
+
 def cpu_baseline(args, pm, raw, feats, n_frames_per_utt, budget_s=15.0, threads=1):
     """The reference's CPU implementation of the path on host cores over a bounded sample of the
     same workload: senone evaluation through the COMPILED REFERENCE (oracle/_ref/libpsref.so:
@@ -484,6 +543,11 @@ def main():
             if pm.n_emit_state in (3, 5) and len(pm.sseq):
                 out["align_stage"] = align_stage(api, ctx, batch, pm, off, U, T)
             out["frontend_stage"] = frontend_stage(api, torch, U, args.secs)
+            if os.environ.get("PSB_RUN_UNVERIFIED") == "1":
+                try:
+                    out["search_stage"] = search_stage(api, torch)
+                except Exception as e:                      # never let the unverified kernels break the headline line
+                    out["search_stage"] = {"error": str(e)[:200]}
             out["cpu_baseline"] = cpu_baseline(args, pm, raw, feats_np, T, budget_s=args.cpu_budget, threads=1)
         print(json.dumps(out))
     batch.close(); pl.close(); ctx.close(); model.close()
