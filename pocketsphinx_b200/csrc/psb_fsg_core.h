@@ -25,7 +25,7 @@
 //  * null_prop (:566-614) = the same resolve step over (new entry x null arc) candidates;
 //    word_trans (:621-680) is pulled per root: the first maximum over this frame's entries.
 //
-// The same source is compiled twice: by nvcc into fsg_search_kernel (psb_fsg.cu), and by g++ with
+// The same source is compiled twice: by nvcc into fsg_search_kernel (psb_search.cu), and by g++ with
 // PSB_FSG_HOST_EMUL into a TEST harness (tests/emul/fsg_emul.cpp) that runs every FSG_FOR loop to
 // completion, forwards or (PSB_FSG_EMUL_REVERSE) backwards, to check the phase logic -- including
 // its freedom from intra-phase ordering assumptions -- against the reference's golden history
