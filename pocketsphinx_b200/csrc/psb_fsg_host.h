@@ -1,6 +1,6 @@
 // psb_fsg_host.h -- host-side preparation of the grammar search: checks the flattened lextree a
 // caller hands to psb_fsg_batch_device and lays it out as one int32 block for the device
-// (FsgGraph, psb_fsg_core.h).  Shared by psb_fsg.cu and the emulation harness under tests/emul/.
+// (FsgGraph, psb_fsg_core.h).  Shared by psb_search.cu and the emulation harness under tests/emul/.
 #pragma once
 #include <stdint.h>
 #include <stdio.h>
