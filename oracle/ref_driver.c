@@ -1143,14 +1143,7 @@ refdrv_allphone_lm(const char *hmmdir, const char *kv, const int16 *pcm, long n_
 #include "fsg_search_internal.h"
 #include "fsg_lextree.h"
 #include "fsg_history.h"
-static int
-fsg_link_id(fsg_link_t **tab, int *n, fsg_link_t *l)
-{
-    int i;
-    for (i = 0; i < *n; ++i) if (tab[i] == l) return i;
-    tab[(*n)++] = l;
-    return *n - 1;
-}
+#include "ps_search_cuda.h"
 
 long
 refdrv_fsg(const char *hmmdir, const char *dict, const char *fsgfile, const char *kv,
@@ -1160,11 +1153,9 @@ refdrv_fsg(const char *hmmdir, const char *dict, const char *fsgfile, const char
     ps_config_t *config;
     ps_decoder_t *ps;
     fsg_search_t *fs;
-    fsg_lextree_t *lt;
     fsg_model_t *fsg;
-    fsg_pnode_t **pn, *p;
-    fsg_link_t **links;
-    int n_pn = 0, n_link = 0, n_state, s, i, k, n_null = 0, n_hist;
+    cuda_fsg_graph_t g;
+    int n_pn, n_link, n_state, i, n_null, n_hist;
     long need, o;
     const char *h;
     int32 score = 0;
@@ -1201,97 +1192,42 @@ refdrv_fsg(const char *hmmdir, const char *dict, const char *fsgfile, const char
     ps_end_utt(ps);
     h = ps_get_hyp(ps, &score);
     snprintf(hyp, hyp_cap, "%s", h ? h : "");
-    lt = fs->lextree;
     fsg = fs->fsg;
-    n_state = fsg_model_n_state(fsg);
     if (vocab && vocab_cap > 0) {                     /* word strings by wid, newline separated */
         int w, len = 0;
         vocab[0] = 0;
         for (w = 0; w < fsg_model_n_word(fsg); ++w)
             len += snprintf(vocab + len, len < vocab_cap ? vocab_cap - len : 0, "%s\n", fsg_model_word_str(fsg, w));
     }
-    for (s = 0; s < n_state; ++s)
-        for (p = lt->alloc_head[s]; p; p = p->alloc_next) ++n_pn;
-    pn = calloc(n_pn > 0 ? n_pn : 1, sizeof(*pn));
-    for (s = 0, i = 0; s < n_state; ++s)
-        for (p = lt->alloc_head[s]; p; p = p->alloc_next) pn[i++] = p;
-    links = calloc((size_t)n_pn + 4096, sizeof(*links));
-    /* null arcs first pass: count, and register links */
-    for (s = 0; s < n_state; ++s) {
-        fsg_arciter_t *it;
-        for (it = fsg_model_arcs(fsg, s); it; it = fsg_arciter_next(it))
-            if (fsg_link_wid(fsg_arciter_get(it)) == -1) { fsg_link_id(links, &n_link, fsg_arciter_get(it)); ++n_null; }
-    }
-    for (i = 0; i < n_pn; ++i)
-        if (pn[i]->leaf) fsg_link_id(links, &n_link, pn[i]->next.fsglink);
+    /* the flattening itself is the maintainer-side binding: integration/ps_search_cuda.c */
+    if (cuda_fsg_export(fs, &g) != 0) { ps_free(ps); ps_config_free(config); return -3; }
+    n_pn = g.desc.n_pnode; n_state = g.desc.n_state; n_link = g.desc.n_link; n_null = g.nulloff[n_state];
     n_hist = fsg_history_n_entries(fs->history);
-    for (i = 0; i < n_hist; ++i) {
-        fsg_hist_entry_t *e = fsg_history_entry_get(fs->history, i);
-        if (e->fsglink) fsg_link_id(links, &n_link, e->fsglink);
-    }
     need = (long)n_pn * 16 + n_state + (long)n_link * 5 + (n_state + 1) + n_null + (long)n_hist * 13;
     info[0] = ps_get_n_frames(ps); info[1] = n_pn; info[2] = n_state; info[3] = n_link; info[4] = n_null;
-    info[5] = n_hist; info[6] = fs->beam_orig; info[7] = fs->pbeam_orig; info[8] = fs->wbeam_orig;
-    info[9] = ps_config_int(config, "maxhmmpf");
-    info[10] = bin_mdef_ciphone_id(ps->acmod->mdef, "SIL"); info[11] = bin_mdef_n_ciphone(ps->acmod->mdef);
-    info[12] = fsg_model_start_state(fsg); info[13] = fsg_model_final_state(fsg); info[14] = score;
+    info[5] = n_hist; info[6] = g.desc.beam; info[7] = g.desc.pbeam; info[8] = g.desc.wbeam;
+    info[9] = g.desc.maxhmmpf; info[10] = g.desc.silcipid; info[11] = g.desc.n_ciphone;
+    info[12] = g.desc.start_state; info[13] = fsg_model_final_state(fsg); info[14] = score;
     info[15] = -1;
     if (blob && cap >= need) {
         o = 0;
-        for (i = 0; i < n_pn; ++i) {
-            int32 *r = blob + o + (long)i * 16;
-            int j;
-            p = pn[i];
-            r[0] = hmm_nonmpx_ssid(&p->hmm); r[1] = p->hmm.tmatid;
-            if (p->leaf) r[2] = fsg_link_id(links, &n_link, p->next.fsglink);
-            else {
-                r[2] = -1;
-                for (j = 0; j < n_pn; ++j) if (pn[j] == p->next.succ) { r[2] = j; break; }
-            }
-            r[3] = -1;
-            for (j = 0; j < n_pn; ++j) if (pn[j] == p->sibling) { r[3] = j; break; }
-            r[4] = p->logs2prob; r[5] = p->ci_ext; r[6] = p->ppos; r[7] = p->leaf;
-            for (j = 0; j < 8; ++j) r[8 + j] = (int32)p->ctxt.bv[j];
-        }
-        o += (long)n_pn * 16;
-        for (s = 0; s < n_state; ++s) {
-            blob[o + s] = -1;
-            for (i = 0; i < n_pn; ++i) if (pn[i] == lt->root[s]) { blob[o + s] = i; break; }
-        }
-        o += n_state;
-        for (i = 0; i < n_link; ++i) {
-            fsg_link_t *l = links[i];
-            int32 *r = blob + o + (long)i * 5;
-            r[0] = l->from_state; r[1] = l->to_state; r[2] = l->wid; r[3] = l->logs2prob;
-            r[4] = 0;
-            if (l->wid >= 0)
-                r[4] = fsg_model_is_filler(fsg, l->wid)
-                    || dict_is_single_phone(ps->dict, dict_wordid(ps->dict, fsg_model_word_str(fsg, l->wid)));
-        }
-        o += (long)n_link * 5;
-        {
-            long oo = o + n_state + 1;
-            k = 0;
-            for (s = 0; s < n_state; ++s) {
-                fsg_arciter_t *it;
-                blob[o + s] = k;
-                for (it = fsg_model_arcs(fsg, s); it; it = fsg_arciter_next(it))
-                    if (fsg_link_wid(fsg_arciter_get(it)) == -1)
-                        blob[oo + k++] = fsg_link_id(links, &n_link, fsg_arciter_get(it));
-            }
-            blob[o + n_state] = k;
-            o = oo + n_null;
-        }
+        memcpy(blob + o, g.pnodes, (size_t)n_pn * 16 * sizeof(int32)); o += (long)n_pn * 16;
+        memcpy(blob + o, g.roots, (size_t)n_state * sizeof(int32)); o += n_state;
+        memcpy(blob + o, g.links, (size_t)n_link * 5 * sizeof(int32)); o += (long)n_link * 5;
+        memcpy(blob + o, g.nulloff, ((size_t)n_state + 1) * sizeof(int32)); o += n_state + 1;
+        memcpy(blob + o, g.nullarc, (size_t)n_null * sizeof(int32)); o += n_null;
         for (i = 0; i < n_hist; ++i) {
             fsg_hist_entry_t *e = fsg_history_entry_get(fs->history, i);
             int32 *r = blob + o + (long)i * 13;
-            int j;
-            r[0] = e->fsglink ? fsg_link_id(links, &n_link, e->fsglink) : -1;
+            int j, id = -1;
+            if (e->fsglink) for (j = 0; j < g.n_link; ++j) if (g.link_ptr[j] == e->fsglink) { id = j; break; }
+            if (e->fsglink && id < 0) need = -4;              /* a history link the lextree does not know */
+            r[0] = id;
             r[1] = e->frame; r[2] = e->score; r[3] = e->pred; r[4] = e->lc;
             for (j = 0; j < 8; ++j) r[5 + j] = (int32)e->rc.bv[j];
         }
     }
-    free(pn); free(links);
+    cuda_fsg_free(&g);
     ps_free(ps);
     ps_config_free(config);
     return need;
@@ -1324,45 +1260,11 @@ refdrv_fsg(const char *hmmdir, const char *dict, const char *fsgfile, const char
  * With fwdflat=yes in kv the tables returned are those of the second pass (ngram_search_fwdflat.c). */
 #include "ngram_search.h"
 #include "ngram_search_fwdtree.h"
-static int
-fwd_count(chan_t *h)
-{
-    int n = 0;
-    for (; h; h = h->alt) n += 1 + fwd_count(h->next);
-    return n;
-}
-static void
-fwd_collect(chan_t *h, chan_t **tab, int *n)
-{
-    for (; h; h = h->alt) { tab[(*n)++] = h; fwd_collect(h->next, tab, n); }
-}
-static int
-fwd_id(chan_t **tab, int n, chan_t *h)
-{
-    int i;
-    if (h == NULL) return -1;
-    for (i = 0; i < n; ++i) if (tab[i] == h) return i;
-    return -2;
-}
-
-long
-refdrv_fwdtree(const char *hmmdir, const char *lm, const char *dictfile, const char *kv,
-               const int16 *pcm, long n_samples, int32 *blob, long cap, int32 *info, char *hyp, int hyp_cap,
-               char *vocab, int vocab_cap)
+static ps_decoder_t *
+ngram_decoder(const char *hmmdir, const char *lm, const char *dictfile, const char *kv, ps_config_t **cfg)
 {
     ps_config_t *config;
     ps_decoder_t *ps;
-    ngram_search_t *ngs;
-    dict_t *dict;
-    dict2pid_t *d2p;
-    bin_mdef_t *mdef;
-    chan_t **tab;
-    int32 *lmidx;
-    int n_nonroot = 0, n_ci, n_words, n_lm = 0, n_pron = 0, i, j, k, w;
-    long need, o;
-    const char *h;
-    int32 score = 0;
-
     err_set_loglevel(ERR_ERROR);
     config = ps_config_init(NULL);
     ps_config_set_str(config, "hmm", hmmdir);
@@ -1384,11 +1286,31 @@ refdrv_fwdtree(const char *hmmdir, const char *lm, const char *dictfile, const c
         free(b2);
     }
     ps = ps_init(config);
-    if (ps == NULL) { ps_config_free(config); return -1; }
+    if (ps == NULL) { ps_config_free(config); return NULL; }
     if (ps->search == NULL || strcmp(ps_search_type(ps->search), PS_SEARCH_TYPE_NGRAM) != 0) {
         ps_free(ps); ps_config_free(config);
-        return -2;
+        return NULL;
     }
+    *cfg = config;
+    return ps;
+}
+
+long
+refdrv_fwdtree(const char *hmmdir, const char *lm, const char *dictfile, const char *kv,
+               const int16 *pcm, long n_samples, int32 *blob, long cap, int32 *info, char *hyp, int hyp_cap,
+               char *vocab, int vocab_cap)
+{
+    ps_config_t *config;
+    ps_decoder_t *ps;
+    ngram_search_t *ngs;
+    dict_t *dict;
+    cuda_ngram_graph_t g;
+    int i, w, n_words;
+    long need, o;
+    const char *h;
+    int32 score = 0;
+
+    if ((ps = ngram_decoder(hmmdir, lm, dictfile, kv, &config)) == NULL) return -1;
     ngs = (ngram_search_t *)ps->search;
     ps_start_utt(ps);
     ps_process_raw(ps, pcm, n_samples, FALSE, TRUE);
@@ -1396,9 +1318,6 @@ refdrv_fwdtree(const char *hmmdir, const char *lm, const char *dictfile, const c
     h = ps_get_hyp(ps, &score);
     snprintf(hyp, hyp_cap, "%s", h ? h : "");
     dict = ps_search_dict(ngs);
-    d2p = ps_search_dict2pid(ngs);
-    mdef = ps->acmod->mdef;
-    n_ci = bin_mdef_n_ciphone(mdef);
     n_words = ps_search_n_words(ngs);
     if (vocab && vocab_cap > 0) {                     /* word strings by wid, newline separated */
         int len = 0;
@@ -1406,78 +1325,14 @@ refdrv_fwdtree(const char *hmmdir, const char *lm, const char *dictfile, const c
         for (w = 0; w < n_words; ++w)
             len += snprintf(vocab + len, len < vocab_cap ? vocab_cap - len : 0, "%s\n", dict_wordstr(dict, w));
     }
-    for (i = 0; i < ngs->n_root_chan; ++i) n_nonroot += fwd_count(ngs->root_chan[i].next);
-    tab = calloc(n_nonroot + 1, sizeof(*tab));
-    k = 0;
-    for (i = 0; i < ngs->n_root_chan; ++i) fwd_collect(ngs->root_chan[i].next, tab, &k);
-    lmidx = calloc(n_words, sizeof(*lmidx));
-    for (w = 0; w < n_words; ++w) lmidx[w] = dict_basewid(dict, w) == w ? n_lm++ : -1;
-    for (w = 0; w < n_words; ++w) n_pron += dict_pronlen(dict, w);
-    need = (long)ngs->n_root_chan * 5 + (long)n_nonroot * 6 + (long)n_words * 8 + ngs->n_1ph_words * 5L
-        + (long)n_ci * n_ci + 3L * n_ci * n_ci * n_ci + (long)n_lm * (n_lm + 1) * (n_lm + 1)
-        + n_words + (n_words + 1) + 2L * n_pron
-        + (long)ngs->bpidx * 10 + ngs->bss_head + ngs->n_frame + 1;
-    memset(info, 0, 40 * sizeof(int32));
-    info[0] = ngs->n_frame; info[1] = n_words; info[2] = ngs->n_root_chan; info[3] = n_nonroot;
-    info[4] = ngs->n_1ph_words; info[5] = ngs->n_1ph_LMwords; info[6] = n_ci; info[7] = mdef->sil;
-    info[8] = ngs->beam; info[9] = ngs->pbeam; info[10] = ngs->wbeam; info[11] = ngs->lpbeam; info[12] = ngs->lponlybeam;
-    info[13] = ngs->maxhmmpf; info[14] = ngs->maxwpf; info[15] = ngs->nwpen; info[16] = ngs->pip;
-    info[17] = ngs->silpen; info[18] = ngs->fillpen; info[19] = dict_startwid(dict); info[20] = ps_search_finish_wid(ngs);
-    info[21] = ps_search_silence_wid(ngs); info[22] = dict_filler_start(dict); info[23] = dict_filler_end(dict);
-    info[24] = ngs->bpidx; info[25] = ngs->bss_head; info[26] = n_lm; info[27] = score;
-    info[28] = ngs->fwdflatbeam; info[29] = ngs->fwdflatwbeam; info[30] = ngs->min_ef_width; info[31] = ngs->max_sf_win;
-    memcpy(&info[32], &ngs->fwdflat_fwdtree_lw_ratio, 4); info[33] = n_pron;
+    /* the flattening itself is the maintainer-side binding: integration/ps_search_cuda.c */
+    if (cuda_ngram_export(ngs, &g) != 0) { ps_free(ps); ps_config_free(config); return -3; }
+    need = (long)g.model_len + (long)ngs->bpidx * 10 + ngs->bss_head + ngs->n_frame + 1;
+    memcpy(info, g.info, 40 * sizeof(int32));
+    info[0] = ngs->n_frame; info[24] = ngs->bpidx; info[25] = ngs->bss_head; info[27] = score;
     if (blob && cap >= need) {
-        o = 0;
-        for (i = 0; i < ngs->n_root_chan; ++i) {
-            root_chan_t *r = &ngs->root_chan[i];
-            blob[o++] = r->ciphone; blob[o++] = r->ci2phone; blob[o++] = r->penult_phn_wid;
-            blob[o++] = fwd_id(tab, n_nonroot, r->next); blob[o++] = r->hmm.tmatid;
-        }
-        for (i = 0; i < n_nonroot; ++i) {
-            chan_t *c = tab[i];
-            blob[o++] = hmm_nonmpx_ssid(&c->hmm); blob[o++] = c->hmm.tmatid; blob[o++] = c->ciphone;
-            blob[o++] = c->info.penult_phn_wid; blob[o++] = fwd_id(tab, n_nonroot, c->next); blob[o++] = fwd_id(tab, n_nonroot, c->alt);
-        }
-        for (w = 0; w < n_words; ++w) {
-            blob[o++] = dict_first_phone(dict, w); blob[o++] = dict_last_phone(dict, w);
-            blob[o++] = dict_is_single_phone(dict, w) ? -1 : dict_second_last_phone(dict, w);
-            blob[o++] = dict_is_single_phone(dict, w); blob[o++] = dict_filler_word(dict, w);
-            blob[o++] = dict_basewid(dict, w); blob[o++] = ngs->homophone_set[w]; blob[o++] = lmidx[w];
-        }
-        for (i = 0; i < ngs->n_1ph_words; ++i) blob[o++] = ngs->single_phone_wid[i];
-        for (i = 0; i < ngs->n_1ph_words; ++i) {
-            root_chan_t *r = (root_chan_t *)ngs->word_chan[ngs->single_phone_wid[i]];
-            blob[o++] = r->ciphone; blob[o++] = r->ci2phone;
-            blob[o++] = bin_mdef_pid2ssid(mdef, r->ciphone); blob[o++] = r->hmm.tmatid;
-        }
-        for (i = 0; i < n_ci; ++i) for (j = 0; j < n_ci; ++j) blob[o++] = dict2pid_rssid(d2p, i, j)->n_ssid;
-        for (i = 0; i < n_ci; ++i) for (j = 0; j < n_ci; ++j) {
-            xwdssid_t *x = dict2pid_rssid(d2p, i, j);
-            for (k = 0; k < n_ci; ++k) blob[o++] = (x->ssid && k < x->n_ssid) ? x->ssid[k] : -1;
-        }
-        for (i = 0; i < n_ci; ++i) for (j = 0; j < n_ci; ++j) {
-            xwdssid_t *x = dict2pid_rssid(d2p, i, j);
-            for (k = 0; k < n_ci; ++k) blob[o++] = x->cimap ? x->cimap[k] : -1;
-        }
-        for (i = 0; i < n_ci; ++i) for (j = 0; j < n_ci; ++j) for (k = 0; k < n_ci; ++k)
-            blob[o++] = (d2p->ldiph_lc[i] && d2p->ldiph_lc[i][j]) ? dict2pid_ldiph_lc(d2p, i, j, k) : -1;
-        {
-            int32 *rev = calloc(n_lm + 1, sizeof(*rev));
-            rev[0] = -1;
-            for (w = 0; w < n_words; ++w) if (lmidx[w] >= 0) rev[lmidx[w] + 1] = w;
-            for (i = 0; i < n_lm; ++i) for (j = 0; j <= n_lm; ++j) for (k = 0; k <= n_lm; ++k) {
-                int32 n_used;
-                blob[o++] = ngram_tg_score(ngs->lmset, rev[i + 1], rev[j], rev[k], &n_used) >> SENSCR_SHIFT;
-            }
-            free(rev);
-        }
-        for (w = 0; w < n_words; ++w) blob[o++] = ngram_model_set_known_wid(ngs->lmset, dict_basewid(dict, w)) ? 1 : 0;
-        for (w = 0, k = 0; w < n_words; ++w) { blob[o++] = k; k += dict_pronlen(dict, w); }
-        blob[o++] = k;
-        for (w = 0; w < n_words; ++w) for (j = 0; j < dict_pronlen(dict, w); ++j) blob[o++] = dict_pron(dict, w, j);
-        for (w = 0; w < n_words; ++w) for (j = 0; j < dict_pronlen(dict, w); ++j)
-            blob[o++] = (j >= 1 && j < dict_pronlen(dict, w) - 1) ? dict2pid_internal(d2p, w, j) : -1;
+        memcpy(blob, g.model, (size_t)g.model_len * sizeof(int32));
+        o = (long)g.model_len;
         for (i = 0; i < ngs->bpidx; ++i) {
             bptbl_t *b = &ngs->bp_table[i];
             blob[o++] = b->frame; blob[o++] = b->valid; blob[o++] = b->wid; blob[o++] = b->bp; blob[o++] = b->score;
@@ -1488,8 +1343,109 @@ refdrv_fwdtree(const char *hmmdir, const char *lm, const char *dictfile, const c
         for (i = 0; i <= ngs->n_frame; ++i) blob[o++] = ngs->bp_table_idx[i];
         if (o != need) need = -3;
     }
-    free(tab); free(lmidx);
+    cuda_ngram_free(&g);
     ps_free(ps);
     ps_config_free(config);
     return need;
+}
+
+/* Round trips through the binding: decode normally, WIPE the search's own result tables, import tables
+ * computed elsewhere (the oracle, the host-emulated phase code, the device) with cuda_*_import, and let
+ * the reference's unchanged code (fsg_search_hyp; ngram_search_hyp with lattice + bestpath when
+ * configured) produce hypothesis and score from them. */
+long
+refdrv_fsg_roundtrip(const char *hmmdir, const char *dict, const char *fsgfile, const char *kv,
+                     const int16 *pcm, long n_samples, const int32 *rows, int32 n_rows, int32 n_frames,
+                     char *hyp, int hyp_cap, int32 *score_out)
+{
+    ps_config_t *config;
+    ps_decoder_t *ps;
+    fsg_search_t *fs;
+    cuda_fsg_graph_t g;
+    const char *h;
+    int32 score = 0;
+    long rv = 0;
+
+    err_set_loglevel(ERR_ERROR);
+    config = ps_config_init(NULL);
+    ps_config_set_str(config, "hmm", hmmdir);
+    ps_config_set_str(config, "dict", dict);
+    ps_config_set_str(config, "fsg", fsgfile);
+    ps_config_set_str(config, "lm", NULL);
+    ps_config_set_str(config, "dither", "no");
+    ps_config_set_str(config, "compallsen", "yes");
+    ps_config_set_str(config, "pl_window", "0");
+    ps_config_set_str(config, "bestpath", "no");
+    if (kv) {
+        char *b2 = strdup(kv), *s2 = NULL, *t2;
+        for (t2 = strtok_r(b2, "\n", &s2); t2; t2 = strtok_r(NULL, "\n", &s2)) {
+            char *eq = strchr(t2, '=');
+            if (!eq) continue;
+            *eq = 0;
+            ps_config_set_str(config, t2, eq + 1);
+        }
+        free(b2);
+    }
+    ps = ps_init(config);
+    if (ps == NULL) { ps_config_free(config); return -1; }
+    if (ps->search == NULL || strcmp(ps_search_type(ps->search), PS_SEARCH_TYPE_FSG) != 0) { ps_free(ps); ps_config_free(config); return -2; }
+    fs = (fsg_search_t *)ps->search;
+    ps_start_utt(ps);
+    ps_process_raw(ps, pcm, n_samples, FALSE, TRUE);
+    ps_end_utt(ps);
+    if (cuda_fsg_export(fs, &g) != 0) { ps_free(ps); ps_config_free(config); return -3; }
+    if (cuda_fsg_import(fs, &g, rows, n_rows, n_frames) != 0) rv = -4;
+    else {
+        h = ps_get_hyp(ps, &score);
+        snprintf(hyp, hyp_cap, "%s", h ? h : "");
+        *score_out = score;
+        rv = fsg_history_n_entries(fs->history);
+    }
+    cuda_fsg_free(&g);
+    ps_free(ps);
+    ps_config_free(config);
+    return rv;
+}
+
+long
+refdrv_ngram_roundtrip(const char *hmmdir, const char *lm, const char *dictfile, const char *kv,
+                       const int16 *pcm, long n_samples, const int32 *bp, int32 n_bp, const int32 *bss, int32 n_bss,
+                       const int32 *bp_idx, int32 n_frames, char *hyp, int hyp_cap, int32 *score_out,
+                       char *seg, int seg_cap)
+{
+    ps_config_t *config;
+    ps_decoder_t *ps;
+    ngram_search_t *ngs;
+    const char *h;
+    int32 score = 0;
+    long rv;
+
+    if ((ps = ngram_decoder(hmmdir, lm, dictfile, kv, &config)) == NULL) return -1;
+    ngs = (ngram_search_t *)ps->search;
+    ps_start_utt(ps);
+    ps_process_raw(ps, pcm, n_samples, FALSE, TRUE);
+    ps_end_utt(ps);
+    /* wipe, so that nothing of the reference's own pass can leak into the result */
+    memset(ngs->bp_table, 0xff, (size_t)ngs->bp_table_size * sizeof(*ngs->bp_table));
+    memset(ngs->bscore_stack, 0xff, (size_t)ngs->bscore_stack_size * sizeof(*ngs->bscore_stack));
+    if (cuda_ngram_import(ngs, bp, n_bp, bss, n_bss, bp_idx, n_frames) != 0) rv = -4;
+    else {
+        ps_seg_t *it;
+        int len = 0;
+        h = ps_get_hyp(ps, &score);
+        snprintf(hyp, hyp_cap, "%s", h ? h : "");
+        *score_out = score;
+        if (seg && seg_cap > 0) {
+            seg[0] = 0;
+            for (it = ps_seg_iter(ps); it; it = ps_seg_next(it)) {
+                int sf, ef;
+                ps_seg_frames(it, &sf, &ef);
+                len += snprintf(seg + len, len < seg_cap ? seg_cap - len : 0, "%s %d %d\n", ps_seg_word(it), sf, ef);
+            }
+        }
+        rv = ngs->bpidx;
+    }
+    ps_free(ps);
+    ps_config_free(config);
+    return rv;
 }

@@ -453,3 +453,45 @@ def fwdtree(hmmdir, lm, dictfile, pcm, **kv):
     r["info"] = info.copy()
     r["model"] = blob[:need - (r["bpidx"] * 10 + r["bss_head"] + r["n_frame"] + 1)].copy()
     return r
+
+
+def fsg_roundtrip(hmmdir, dictfile, fsgfile, pcm, rows, n_frames, **kv):
+    """Decode with the reference, replace its history table by `rows` through the maintainer-side binding
+    (integration/ps_search_cuda.c: cuda_fsg_import) and let its own fsg_search_hyp answer."""
+    pcm = np.ascontiguousarray(pcm, np.int16)
+    rows = np.ascontiguousarray(rows, np.int32)
+    s = "\n".join("%s=%s" % (k, v) for k, v in kv.items()).encode() or None
+    L = lib()
+    L.refdrv_fsg_roundtrip.restype = C.c_long
+    L.refdrv_fsg_roundtrip.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_long, C.c_void_p,
+                                       C.c_int32, C.c_int32, C.c_char_p, C.c_int, C.c_void_p]
+    hyp = C.create_string_buffer(4096)
+    score = np.zeros(1, np.int32)
+    n = L.refdrv_fsg_roundtrip(hmmdir.encode(), dictfile.encode(), fsgfile.encode(), s, _p(pcm), len(pcm), _p(rows), len(rows),
+                               int(n_frames), hyp, 4096, _p(score))
+    if n < 0:
+        raise RuntimeError("refdrv_fsg_roundtrip failed: %d" % n)
+    return dict(hyp=hyp.value.decode(), score=int(score[0]), n_entries=int(n))
+
+
+def ngram_roundtrip(hmmdir, lm, dictfile, pcm, bp, bss, bp_idx, **kv):
+    """Decode with the reference, wipe its backpointer table / score stack, import (bp, bss, bp_idx)
+    through cuda_ngram_import and let its own ngram_search_hyp (lattice + bestpath when configured) and
+    segment iterator answer."""
+    pcm = np.ascontiguousarray(pcm, np.int16)
+    bp = np.ascontiguousarray(bp, np.int32); bss = np.ascontiguousarray(bss, np.int32)
+    bp_idx = np.ascontiguousarray(bp_idx, np.int32)
+    s = "\n".join("%s=%s" % (k, v) for k, v in kv.items()).encode() or None
+    L = lib()
+    L.refdrv_ngram_roundtrip.restype = C.c_long
+    L.refdrv_ngram_roundtrip.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_long, C.c_void_p,
+                                         C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_char_p, C.c_int,
+                                         C.c_void_p, C.c_char_p, C.c_int]
+    hyp = C.create_string_buffer(4096)
+    seg = C.create_string_buffer(65536)
+    score = np.zeros(1, np.int32)
+    n = L.refdrv_ngram_roundtrip(hmmdir.encode(), lm.encode(), dictfile.encode(), s, _p(pcm), len(pcm), _p(bp), len(bp), _p(bss),
+                                 len(bss), _p(bp_idx), len(bp_idx) - 1, hyp, 4096, _p(score), seg, 65536)
+    if n < 0:
+        raise RuntimeError("refdrv_ngram_roundtrip failed: %d" % n)
+    return dict(hyp=hyp.value.decode(), score=int(score[0]), seg=seg.value.decode(), n_entries=int(n))
