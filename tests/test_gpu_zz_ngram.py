@@ -154,3 +154,34 @@ def test_all_searches_on_tidigits_against_the_live_reference(api, tidigits):
     want2 = oracle.fwdflat_run(tidigits.tp, tidigits.sseq, cit, cis, both["info"], both["model"], want1[0], scr[:90])
     assert np.array_equal(out2[1][0], want2[0]) and np.array_equal(out2[1][1], want2[1])
     ctx.close()
+
+
+@pytest.mark.timeout(600)
+def test_default_pipeline_drop_in_through_the_binding(api, en_us):
+    """The shipped default configuration (look-ahead, both passes, lattice + bestpath): device tables are
+    imported into the reference through integration/ps_search_cuda.c and its own ngram_search_hyp must
+    give the hypothesis and score of an undisturbed reference decode."""
+    import torch
+    from oracle import refdrv
+    if not refdrv.available():
+        pytest.skip("oracle/_ref/libpsref.so not built")
+    rd = os.path.dirname(refdrv.LIB_PATH)
+    hd, lm, dic = os.path.join(rd, "model", "en-us"), os.path.join(rd, "data", "turtle.lm.bin"), os.path.join(rd, "data", "turtle.dic")
+    pcm = np.fromfile(os.path.join(rd, "data", "goforward.raw"), np.int16)
+    kv = dict(fwdflat="yes", bestpath="yes", pl_window="5")
+    want = refdrv.fwdtree(hd, lm, dic, pcm, **kv)
+    ref = refdrv.RefModel(hd)
+    scr = np.ascontiguousarray(ref.score(ref.featurize_fresh(pcm)))
+    pl = ref.phoneloop(pcm)
+    ref.close()
+    T, nc = len(scr), want["n_ci"]
+    pen = np.ascontiguousarray(pl["pen"][np.minimum(np.arange(T) + 5, T - 1)], np.int32)
+    d_scr, d_pen = torch.from_numpy(scr).cuda(), torch.from_numpy(pen).cuda()
+    utt_off = np.array([0, T], np.int32)
+    ctx = api.HmmContext(en_us.tp, en_us.sseq, en_us.n_sen)
+    cit, cis = en_us.phone_tmat[:nc], en_us.phone_ssid[:nc]
+    first = ctx.ngram_fwdtree(d_scr.data_ptr(), utt_off, want["info"], want["model"], cit, 8192, 1 << 18, d_pen.data_ptr())
+    bp, bss, idx = ctx.ngram_fwdflat(d_scr.data_ptr(), utt_off, want["info"], want["model"], cit, cis, [first[0][0]], 8192, 1 << 18)[0]
+    ctx.close()
+    rt = refdrv.ngram_roundtrip(hd, lm, dic, pcm, bp, bss, idx, **kv)
+    assert rt["hyp"] == want["hyp"] == "go forward ten meters" and rt["score"] == want["score"]
