@@ -91,51 +91,6 @@ FSG_HD int ngf_tg(const NgfGraph &G, int w, int h1, int h2)
     return G.lm[((size_t)a * n + b) * n + c];
 }
 
-FSG_HD void ngf_set_real_wid(const NgfGraph &G, const NgfWork &W, int bp)
-{
-    fsg_wp e = W.bp + (size_t)bp * NGS_BP_ROW;
-    const fsg_wp prev = e[3] == -1 ? fsg_wp(nullptr) : W.bp + (size_t)e[3] * NGS_BP_ROW;
-    if (NGS_W(G, e[2], 4)) {
-        if (prev) { e[6] = prev[6]; e[7] = prev[7]; }
-        else { e[6] = NGS_W(G, e[2], 5); e[7] = -1; }
-    }
-    else {
-        e[6] = NGS_W(G, e[2], 5);
-        e[7] = prev ? prev[6] : -1;
-    }
-}
-
-FSG_HD void ngf_save_bp(const NgfGraph &G, const NgfWork &W, int *entry, int new_bp, int new_s, int frame, int w,
-                        int score, int path, int rc)                         /* ngram_search.c:378-497, see ngs_save_bp */
-{
-    if (*entry != -1) {
-        fsg_wp e = W.bp + (size_t)*entry * NGS_BP_ROW;
-        if (e[4] < score) {
-            if (e[3] != path) {
-                const fsg_wp po = e[3] == -1 ? fsg_wp(nullptr) : W.bp + (size_t)e[3] * NGS_BP_ROW;
-                const fsg_wp pn = path == -1 ? fsg_wp(nullptr) : W.bp + (size_t)path * NGS_BP_ROW;
-                const int a0 = po ? po[7] : -1, a1 = po ? po[6] : -1, b0 = pn ? pn[7] : -1, b1 = pn ? pn[6] : -1;
-                if (a0 != b0 || a1 != b1) ngf_set_real_wid(G, W, *entry);
-                e[3] = path;
-            }
-            e[4] = score;
-        }
-        if (e[5] != -1) W.bss[e[5] + rc] = score;
-    }
-    else {
-        fsg_wp e = W.bp + (size_t)new_bp * NGS_BP_ROW;
-        int rcsize;
-        *entry = new_bp;
-        e[2] = w; e[0] = frame; e[3] = path; e[4] = score; e[5] = new_s; e[1] = 1;
-        e[8] = NGS_W(G, w, 1);
-        if (NGS_W(G, w, 3)) { e[9] = -1; e[5] = -1; rcsize = 0; }
-        else { e[9] = NGS_W(G, w, 2); rcsize = G.rs_n[(size_t)e[8] * G.n_ci + e[9]]; }
-        for (int i = 0; i < rcsize; ++i) W.bss[new_s + i] = FSG_WORST_SCORE;
-        if (rcsize) W.bss[new_s + rc] = score;
-        ngf_set_real_wid(G, W, new_bp);
-    }
-}
-
 // does (sf, w) keep its node?  (build_fwdflat_wordlist: too few end points, or </s> not ending the utterance)
 FSG_HD bool ngf_node_ok(const NgfGraph &G, const NgfWork &W, int sf, int w)
 {
@@ -269,7 +224,7 @@ FSG_HD void ngf_step(const NgfGraph &G, const NgfWork &W, NgfScalars *S, int cf,
                     else if (W.frame[c0 + 1] < cf || ns > W.score[c0 + 1]) ngf_enter(W, c0 + 1, ns, W.out_hist[c0], nf);
                 }
             }
-            else if (ns > wordthresh) ngf_save_bp(G, W, &entry, new_bp, new_s, cf, w, ns, W.out_hist[c0], 0);
+            else if (ns > wordthresh) ngs_save_bp(G, W, &entry, new_bp, new_s, cf, w, ns, W.out_hist[c0], 0);
         }
         for (int k = 0; k < ni; ++k) {
             const int c = c0 + 1 + k;
@@ -290,7 +245,7 @@ FSG_HD void ngf_step(const NgfGraph &G, const NgfWork &W, NgfScalars *S, int cf,
             if (W.frame[c] < cf) continue;
             if (W.best[c] > thresh) {
                 W.frame[c] = nf; W.word_active[w] = 1;
-                if (W.out_score[c] > wordthresh) ngf_save_bp(G, W, &entry, new_bp, new_s, cf, w, W.out_score[c], W.out_hist[c], c - rc0);
+                if (W.out_score[c] > wordthresh) ngs_save_bp(G, W, &entry, new_bp, new_s, cf, w, W.out_score[c], W.out_hist[c], c - rc0);
             }
             else if (W.frame[c] != nf) ngf_clear_scores(G, W, c);
         }

@@ -127,7 +127,8 @@ FSG_HD int ngs_exit_score(const NgsGraph &G, const NgsWork &W, const fsg_wp e, i
     return W.bss[e[5] + G.rs_cimap[((size_t)e[8] * G.n_ci + e[9]) * G.n_ci + rcphone]];
 }
 
-FSG_HD void ngs_set_real_wid(const NgsGraph &G, const NgsWork &W, int bp)                       /* :343-373 */
+template <class GraphT, class WorkT>
+FSG_HD void ngs_set_real_wid(const GraphT &G, const WorkT &W, int bp)                       /* :343-373 */
 {
     fsg_wp e = W.bp + (size_t)bp * NGS_BP_ROW;
     const fsg_wp prev = e[3] == -1 ? fsg_wp(nullptr) : W.bp + (size_t)e[3] * NGS_BP_ROW;
@@ -141,9 +142,11 @@ FSG_HD void ngs_set_real_wid(const NgsGraph &G, const NgsWork &W, int bp)       
     }
 }
 
-// One word's exits of one frame, made in order by one thread (save_bp).  *entry = -1 before the
+// One word's exits of one frame, made in order by one thread (save_bp).  Shared with the second pass
+// (psb_ngf_core.h): any graph / work pair with words, rs_n, n_ci and bp, bss.  *entry = -1 before the
 // first; new entries take index new_bp / stack offset new_s (from the scans).
-FSG_HD void ngs_save_bp(const NgsGraph &G, const NgsWork &W, int *entry, int new_bp, int new_s, int frame, int w,
+template <class GraphT, class WorkT>
+FSG_HD void ngs_save_bp(const GraphT &G, const WorkT &W, int *entry, int new_bp, int new_s, int frame, int w,
                         int score, int path, int rc)
 {
     if (*entry != -1) {

@@ -202,11 +202,14 @@ extern "C" int psb_fsg_batch_device(psb_hmmctx_t *c, const psb_fsg_desc_t *g, co
 
 namespace {
 
-struct NgsDevEval {
+// hmm_vit_eval on channel `ch` of a channel-indexed SoA work area (first and second pass share it):
+// multiplexed channels carry their per-state senone sequences in W.mss, the others use G.senid.
+template <class GraphT, class WorkT>
+struct ChanDevEval {
     HmmCtxDev c;
-    const NgsGraph *G;
+    const GraphT *G;
     const int16_t *row;
-    __device__ __forceinline__ int operator()(const NgsWork &W, int ch, bool mpx) const
+    __device__ __forceinline__ int operator()(const WorkT &W, int ch, bool mpx) const
     {
         HmmReg h;
         const int N = c.n_emit, M = G->M;
@@ -228,6 +231,7 @@ struct NgsDevEval {
         return b;
     }
 };
+typedef ChanDevEval<NgsGraph, NgsWork> NgsDevEval;
 
 constexpr int NGS_THREADS = SRCH_THREADS;
 
@@ -348,32 +352,7 @@ extern "C" int psb_ngram_fwdtree_batch_device(psb_hmmctx_t *c, const psb_ngram_d
 
 namespace {
 
-struct NgfDevEval {
-    HmmCtxDev c;
-    const NgfGraph *G;
-    const int16_t *row;
-    __device__ __forceinline__ int operator()(const NgfWork &W, int ch, bool mpx) const
-    {
-        HmmReg h;
-        const int N = c.n_emit, M = G->M;
-#pragma unroll
-        for (int s = 0; s < PSB_HMM_MAX_NSTATE; ++s) {
-            h.score[s] = s < N ? W.score[s * M + ch] : PSB_WORST_SCORE;
-            h.hist[s] = s < N ? W.hist[s * M + ch] : -1;
-            h.senid[s] = s < N ? (mpx ? W.mss[s * M + ch] : G->senid[(size_t)ch * N + s]) : PSB_BAD_SSID;
-        }
-        h.out_score = W.out_score[ch]; h.out_hist = W.out_hist[ch]; h.best = W.best[ch];
-        const int b = hmm_step(h, c, G->tmatid[ch], mpx, row);
-#pragma unroll
-        for (int s = 0; s < PSB_HMM_MAX_NSTATE; ++s)
-            if (s < N) {
-                W.score[s * M + ch] = h.score[s]; W.hist[s * M + ch] = h.hist[s];
-                if (mpx) W.mss[s * M + ch] = h.senid[s];
-            }
-        W.out_score[ch] = h.out_score; W.out_hist[ch] = h.out_hist; W.best[ch] = h.best;
-        return b;
-    }
-};
+typedef ChanDevEval<NgfGraph, NgfWork> NgfDevEval;
 
 __global__ void __launch_bounds__(NGS_THREADS)
 ngs_fwdflat_kernel(const int16_t *__restrict__ senscr, const int32_t *__restrict__ utt_off, HmmCtxDev c, NgfGraph G,

@@ -4,36 +4,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include "../../pocketsphinx_b200/csrc/psb_ngf_host.h"
-extern "C" {
-#include "../../oracle/ps_oracle.h"
-}
+#include "chan_eval.h"
 
-namespace {
-struct OracleEval {
-    pso_hmmctx_t ctx;
-    const NgfGraph *G;
-    int operator()(const NgfWork &W, int c, bool mpx)
-    {
-        pso_hmm_t h;
-        const int N = G->n_emit, M = G->M;
-        memset(&h, 0, sizeof(h));
-        h.mpx = mpx; h.n_emit_state = (uint8_t)N; h.tmatid = (int16_t)G->tmatid[c];
-        h.ssid = mpx ? PSO_BAD_SSID : 0;
-        for (int s = 0; s < N; ++s) {
-            h.score[s] = W.score[s * M + c]; h.history[s] = W.hist[s * M + c];
-            h.senid[s] = (uint16_t)(mpx ? W.mss[s * M + c] : G->senid[(size_t)c * N + s]);
-        }
-        h.out_score = W.out_score[c]; h.out_history = W.out_hist[c]; h.bestscore = W.best[c]; h.frame = W.frame[c];
-        const int b = pso_hmm_vit_eval(&ctx, &h);
-        for (int s = 0; s < N; ++s) {
-            W.score[s * M + c] = h.score[s]; W.hist[s * M + c] = h.history[s];
-            if (mpx) W.mss[s * M + c] = h.senid[s];
-        }
-        W.out_score[c] = h.out_score; W.out_hist[c] = h.out_history; W.best[c] = h.bestscore;
-        return b;
-    }
-};
-}
+typedef OracleChanEval<NgfGraph, NgfWork> OracleEval;
 
 extern "C" int32_t
 ngf_emul_run(int32_t n_emit_state, const uint8_t *tp, int32_t n_tmat, const uint16_t *sseq, int32_t n_sseq, const int32_t *ci_tmat,
