@@ -269,9 +269,8 @@ def search_stage(api, torch, U=256):
     nci = int(c["info"][6])
     cit, cis = m["phone_tmat"][:nci], m["phone_ssid"][:nci]
     win = int(gf["pl_params"][4])
-    pen = np.ascontiguousarray(gf["pl_pen"][np.minimum(np.arange(T) + win, T - 1)], np.int32)
-    d_pen = torch.from_numpy(np.ascontiguousarray(np.tile(pen, (U, 1)))).cuda()
-    first, dt1 = timed(lambda: ctx.ngram_fwdtree(d_scr.data_ptr(), off, c["info"], c["model"], cit, 2048, 1 << 15, d_pen.data_ptr()))
+    d_pen = torch.from_numpy(np.ascontiguousarray(np.tile(gf["pl_pen"].astype(np.int32), (U, 1)))).cuda()
+    first, dt1 = timed(lambda: ctx.ngram_fwdtree(d_scr.data_ptr(), off, c["info"], c["model"], cit, 2048, 1 << 15, d_pen.data_ptr(), win))
     out["fwdtree"] = {"kernel": "ngs_fwdtree_kernel", "channels": int(c["info"][2] + c["info"][3]), "ms": dt1 * 1e3,
                       "utts_per_s": U / dt1, "frames_per_s": U * T / dt1,
                       "matches_reference": bool(np.array_equal(first[0][0], first_ref["bp"]))}

@@ -363,8 +363,11 @@ int psb_fsg_batch_device(psb_hmmctx_t *c, const psb_fsg_desc_t *g, const int16_t
  *               tg[w][h1][h2] = ngram_tg_score(...) >> SENSCR_SHIFT over the LM's base words
  *   ci_tmat [n_ciphone]  bin_mdef_pid2tmatid of every CI phone
  * (the dense table limits this entry point to vocabularies of a few hundred words).  d_pen: optional
- * phone-loop penalties in force while each frame is searched ([total frames][n_ciphone], device;
- * pls->penalties, phone_loop_search.h:103).  Per utterance u the reference's own tables come back:
+ * look-ahead: the phone loop's penalties after each of ITS frames ([total frames][n_ciphone], device:
+ * what psb_decode_batch_device / psb_phoneloop_run_device leave behind = pls->penalties,
+ * phone_loop_search.h:103) and its window pl_window; search frame t of an utterance of T frames runs
+ * when the phone loop has seen frame min(t + pl_window, T - 1), as ps_search_forward / ps_end_utt
+ * schedule it (pocketsphinx.c:1172-1195, 1329-1333).  Per utterance u the reference's own tables come back:
  *   bp      [n_utt][bp_cap_per_utt][10]  bptbl_t rows: frame, valid, wid, bp, score, s_idx, real_wid,
  *                                        prev_real_wid, last_phone, last2_phone
  *   bss     [n_utt][bss_cap_per_utt]     bscore_stack
@@ -380,7 +383,7 @@ typedef struct psb_ngram_desc_s {
     const int32_t *ci_ssid;     /* [n_ciphone] bin_mdef_pid2ssid of every CI phone; second pass only (may be NULL for the first) */
 } psb_ngram_desc_t;
 int psb_ngram_fwdtree_batch_device(psb_hmmctx_t *c, const psb_ngram_desc_t *g, const int16_t *d_senscr,
-                                   const int32_t *d_pen, const int32_t *utt_off, int32_t n_utt, int32_t *bp,
+                                   const int32_t *d_pen, int32_t pl_window, const int32_t *utt_off, int32_t n_utt, int32_t *bp,
                                    int32_t bp_cap_per_utt, int32_t *bss, int32_t bss_cap_per_utt,
                                    int32_t *bp_idx, int32_t *result);
 /* Second pass: ngram_search_fwdflat.c (start :371 with build_fwdflat_wordlist :224 and

@@ -302,8 +302,9 @@ class HmmContext:
                                          int(cap), _p(n_hist)), "psb_fsg_batch_device")
         return [hist[u, :min(int(n_hist[u]), int(cap))] for u in range(n_utt)], n_hist[:n_utt]
 
-    def ngram_fwdtree(self, d_senscr_ptr, utt_off, info, model, ci_tmat, bp_cap, bss_cap, d_pen_ptr=None):
+    def ngram_fwdtree(self, d_senscr_ptr, utt_off, info, model, ci_tmat, bp_cap, bss_cap, d_pen_ptr=None, pl_window=0):
         """ngram_search_fwdtree over a batch (flattened search `info` / `model`, see include/psb200.h).
+        d_pen_ptr / pl_window: the phone loop's device penalty table and its window (look-ahead).
         Returns per utterance (bp table [n][10], bscore_stack, bp_table_idx [T+1])."""
         from ._lib import NgramDesc
         utt_off = np.ascontiguousarray(utt_off, np.int32)
@@ -316,7 +317,7 @@ class HmmContext:
         bp_idx = np.zeros(int(utt_off[-1]) + max(n_utt, 1), np.int32)
         res = np.zeros((max(n_utt, 1), 3), np.int32)
         check(lib().psb_ngram_fwdtree_batch_device(self.h, C.byref(d), C.c_void_p(d_senscr_ptr),
-                                                   C.c_void_p(d_pen_ptr) if d_pen_ptr else None, _p(utt_off), n_utt, _p(bp),
+                                                   C.c_void_p(d_pen_ptr) if d_pen_ptr else None, int(pl_window), _p(utt_off), n_utt, _p(bp),
                                                    int(bp_cap), _p(bss), int(bss_cap), _p(bp_idx), _p(res)),
               "psb_ngram_fwdtree_batch_device")
         out = []

@@ -65,7 +65,8 @@ struct NgsWork {
     fsg_wp brc_score, brc_path, brc_lc;          // [n_ci]
     fsg_wp bins;                                   // [256]
     fsg_wp bp, bss, bp_idx;                      // outputs: [bp_cap][10], [bss_cap], [T+1]
-    const int32_t *pen;                              // [T][n_ci] look-ahead penalties in force per search frame, or null
+    const int32_t *pen;                              // [T][n_ci] the phone loop's penalties after each of ITS frames, or null
+    int pl_window, T;                                // frame f of the search runs when the phone loop has seen frame min(f + window, T - 1)
     int bp_cap, bss_cap;
 };
 
@@ -101,7 +102,13 @@ FSG_HDH size_t ngs_work_words(const NgsGraph &G)
 }
 
 FSG_HD int ngs_nrc(const NgsGraph &G, int w) { return G.wc_off[w + 1] - G.wc_off[w]; }
-FSG_HD int ngs_pl(const NgsWork &W, const NgsGraph &G, int f, int ci) { return W.pen ? W.pen[(size_t)f * G.n_ci + ci] : 0; }
+FSG_HD int ngs_pl(const NgsWork &W, const NgsGraph &G, int f, int ci)          /* phone_loop_search_score at search frame f */
+{
+    if (!W.pen) return 0;
+    int t = f + W.pl_window;                                                  /* ps_search_forward / ps_end_utt, pocketsphinx.c:1172-1195, 1329-1333 */
+    if (t > W.T - 1) t = W.T - 1;
+    return W.pen[(size_t)t * G.n_ci + ci];
+}
 
 FSG_HD void ngs_clear(const NgsGraph &G, const NgsWork &W, int c)               /* hmm_clear */
 {

@@ -237,7 +237,7 @@ constexpr int NGS_THREADS = SRCH_THREADS;
 
 __global__ void __launch_bounds__(NGS_THREADS)
 ngs_fwdtree_kernel(const int16_t *__restrict__ senscr, const int32_t *__restrict__ utt_off, HmmCtxDev c, NgsGraph G,
-                   int32_t *work, size_t work_words, const int32_t *pen, int32_t *bp_out, int bp_cap, int32_t *bss_out,
+                   int32_t *work, size_t work_words, const int32_t *pen, int pl_window, int32_t *bp_out, int bp_cap, int32_t *bss_out,
                    int bss_cap, int32_t *bp_idx_out, int32_t *result /* [n_utt][3]: bpidx, bss_head, frames done (or -error) */, int n_utt)
 {
     PSB_SRCH_UTT(NgsScalars);
@@ -249,6 +249,7 @@ ngs_fwdtree_kernel(const int16_t *__restrict__ senscr, const int32_t *__restrict
     W.bss = bss_out + (size_t)u * bss_cap;
     W.bp_idx = bp_idx_out + f0 + u;                          // T + 1 slots per utterance
     W.pen = pen ? pen + (size_t)f0 * G.n_ci : nullptr;
+    W.pl_window = pl_window; W.T = T;
     W.bp_cap = bp_cap; W.bss_cap = bss_cap;
     NgsDevEval ev{c, &G, nullptr};
     ngs_start(G, W, &S);
@@ -267,16 +268,16 @@ ngs_fwdtree_kernel(const int16_t *__restrict__ senscr, const int32_t *__restrict
 }  // namespace
 
 void PSB_SRCH(psb_ngs_launch)(cudaStream_t st, int n_utt, const int16_t *senscr, const int32_t *utt_off, HmmCtxDev c, NgsGraph G,
-                              int32_t *work, size_t work_words, const int32_t *pen, int32_t *bp, int bp_cap, int32_t *bss, int bss_cap,
-                              int32_t *bp_idx, int32_t *result)
+                              int32_t *work, size_t work_words, const int32_t *pen, int pl_window, int32_t *bp, int bp_cap, int32_t *bss,
+                              int bss_cap, int32_t *bp_idx, int32_t *result)
 {
-    ngs_fwdtree_kernel<<<PSB_SRCH_GRID(n_utt), NGS_THREADS, 0, st>>>(senscr, utt_off, c, G, work, work_words, pen, bp, bp_cap, bss, bss_cap,
+    ngs_fwdtree_kernel<<<PSB_SRCH_GRID(n_utt), NGS_THREADS, 0, st>>>(senscr, utt_off, c, G, work, work_words, pen, pl_window, bp, bp_cap, bss, bss_cap,
                                                                      bp_idx, result, n_utt);
 }
 
 #ifndef PSB_SEARCH_WARP
 extern "C" int psb_ngram_fwdtree_batch_device(psb_hmmctx_t *c, const psb_ngram_desc_t *g, const int16_t *d_senscr,
-                                              const int32_t *d_pen, const int32_t *utt_off, int32_t n_utt, int32_t *bp,
+                                              const int32_t *d_pen, int32_t pl_window, const int32_t *utt_off, int32_t n_utt, int32_t *bp,
                                               int32_t bp_cap_per_utt, int32_t *bss, int32_t bss_cap_per_utt,
                                               int32_t *bp_idx, int32_t *result)
 {
@@ -284,6 +285,7 @@ extern "C" int psb_ngram_fwdtree_batch_device(psb_hmmctx_t *c, const psb_ngram_d
                 bp_cap_per_utt > 0 && bss_cap_per_utt > 0, "psb_ngram_fwdtree_batch_device: bad argument");
     if (n_utt == 0) return PSB_OK;
     PSB_REQUIRE(utt_off[0] == 0, "psb_ngram_fwdtree_batch_device: offsets must start at 0");
+    PSB_REQUIRE(pl_window >= 0, "psb_ngram_fwdtree_batch_device: negative look-ahead window");
     PSB_REQUIRE(d_senscr || utt_off[n_utt] == 0, "psb_ngram_fwdtree_batch_device: scores missing");
     for (int u = 0; u < n_utt; ++u)
         PSB_REQUIRE(utt_off[u + 1] >= utt_off[u], "psb_ngram_fwdtree_batch_device: utt_off not monotone at %d", u);
@@ -318,7 +320,8 @@ extern "C" int psb_ngram_fwdtree_batch_device(psb_hmmctx_t *c, const psb_ngram_d
     if (e == cudaSuccess) {
         ngs_bind(flat, d_i);
         (search_warp_mode() ? psb_ngs_launch_warp : psb_ngs_launch_cta)(st, n_utt, d_senscr, d_i + o_uo, dev_ctx(c), flat.G, d_work, work_words,
-                                                                        d_pen, d_bp, bp_cap_per_utt, d_bss, bss_cap_per_utt, d_idx, d_i + o_res);
+                                                                        d_pen, pl_window, d_bp, bp_cap_per_utt, d_bss, bss_cap_per_utt, d_idx,
+                                                                        d_i + o_res);
         g_psb_launches.fetch_add(1, std::memory_order_relaxed);
         e = cudaGetLastError();
     }

@@ -13,8 +13,8 @@
                               FsgGraph G, const uint16_t *senid, const int32_t *tmatid, int32_t *work, size_t work_words,  \
                               int32_t *hist, int cap, int32_t *n_hist);                                                    \
     void psb_ngs_launch_##sfx(cudaStream_t st, int n_utt, const int16_t *senscr, const int32_t *utt_off, HmmCtxDev c,      \
-                              NgsGraph G, int32_t *work, size_t work_words, const int32_t *pen, int32_t *bp, int bp_cap,   \
-                              int32_t *bss, int bss_cap, int32_t *bp_idx, int32_t *result);                                \
+                              NgsGraph G, int32_t *work, size_t work_words, const int32_t *pen, int pl_window, int32_t *bp, \
+                              int bp_cap, int32_t *bss, int bss_cap, int32_t *bp_idx, int32_t *result);                    \
     void psb_ngf_launch_##sfx(cudaStream_t st, int n_utt, const int16_t *senscr, const int32_t *utt_off, HmmCtxDev c,      \
                               NgfGraph G, int32_t *work, size_t work_words, const int32_t *bp_in, int in_cap,              \
                               const int32_t *n_in, int32_t *bp, int bp_cap, int32_t *bss, int bss_cap, int32_t *bp_idx,    \

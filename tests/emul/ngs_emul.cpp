@@ -12,7 +12,7 @@ typedef OracleChanEval<NgsGraph, NgsWork> OracleEval;
 extern "C" int32_t
 ngs_emul_run(int32_t n_emit_state, const uint8_t *tp, int32_t n_tmat, const uint16_t *sseq, int32_t n_sseq, const int32_t *ci_tmat,
              const int32_t *info, const int32_t *model, int64_t model_len, const int16_t *senscr, int32_t n_sen, int32_t T,
-             const int32_t *pen, int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap, int32_t *bss_n, int32_t *bp_idx_out)
+             const int32_t *pen, int32_t pl_window, int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap, int32_t *bss_n, int32_t *bp_idx_out)
 {
     NgsFlat flat;
     std::string err;
@@ -25,7 +25,7 @@ ngs_emul_run(int32_t n_emit_state, const uint8_t *tp, int32_t n_tmat, const uint
     std::vector<int32_t> work(ngs_work_words(G), 0x5a5a5a5a);
     NgsWork W;
     ngs_work_carve(work.data(), G, W);
-    W.bp = bp_out; W.bss = bss_out; W.bp_idx = bp_idx_out; W.pen = pen; W.bp_cap = bp_cap; W.bss_cap = bss_cap;
+    W.bp = bp_out; W.bss = bss_out; W.bp_idx = bp_idx_out; W.pen = pen; W.pl_window = pl_window; W.T = T; W.bp_cap = bp_cap; W.bss_cap = bss_cap;
     NgsScalars S;
     memset((void *)&S, 0x5a, sizeof(S));
     OracleEval ev;

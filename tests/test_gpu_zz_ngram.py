@@ -43,21 +43,20 @@ def test_fwdtree_batch_matches_reference_and_oracle(api, en_us, tag):
     parts = [scr, scr[:0], scr[:1], scr[:100], scr]
     utt_off = np.concatenate([[0], np.cumsum([len(p) for p in parts])]).astype(np.int32)
     d_scr = torch.from_numpy(np.ascontiguousarray(np.concatenate(parts))).cuda()
-    d_pen, pens = None, [None] * len(parts)
+    d_pen, win, la = None, 0, [{} for _ in parts]
     if tag == "lookahead":
         win = int(gf["pl_params"][4])
-        # penalties in force per search frame; prefixes of the utterance see the same phone-loop history
-        pens = [np.ascontiguousarray(gf["pl_pen"][np.minimum(np.arange(len(p)) + win, max(len(p) - 1, 0))], np.int32)
-                if len(p) else np.zeros((0, n_ci), np.int32) for p in parts]
-        d_pen = torch.from_numpy(np.concatenate(pens)).cuda()
+        # the phone loop's own table per utterance (prefixes of the utterance see the same phone-loop history)
+        d_pen = torch.from_numpy(np.ascontiguousarray(np.concatenate([gf["pl_pen"][:len(p)] for p in parts]), np.int32)).cuda()
+        la = [dict(pl_pen=gf["pl_pen"][:len(p)], pl_window=win) for p in parts]
     ctx = api.HmmContext(en_us.tp, en_us.sseq, en_us.n_sen)
     out = ctx.ngram_fwdtree(d_scr.data_ptr(), utt_off, c["info"], c["model"], cit, len(c["bp"]) + 64, len(c["bss"]) + 4096,
-                            d_pen.data_ptr() if d_pen is not None else None)
+                            d_pen.data_ptr() if d_pen is not None else None, win)
     for u in (0, 4):                                            # the reference's own tables
         bp, bss, idx = out[u]
         assert np.array_equal(bp, c["bp"]) and np.array_equal(bss, c["bss"]) and np.array_equal(idx, c["bp_idx"]), u
     for u in (1, 2, 3):
-        want = oracle.fwdtree_run(en_us.tp, en_us.sseq, cit, c["info"], c["model"], parts[u], pen_in_force=pens[u])
+        want = oracle.fwdtree_run(en_us.tp, en_us.sseq, cit, c["info"], c["model"], parts[u], **la[u])
         bp, bss, idx = out[u]
         assert np.array_equal(bp, want[0]) and np.array_equal(bss, want[1]) and np.array_equal(idx, want[2]), u
     ctx.close()
@@ -91,22 +90,21 @@ def test_fwdflat_batch_matches_reference_and_oracle(api, en_us, tag):
     parts = [scr, scr[:0], scr[:1], scr[:120], scr]
     utt_off = np.concatenate([[0], np.cumsum([len(p) for p in parts])]).astype(np.int32)
     d_scr = torch.from_numpy(np.ascontiguousarray(np.concatenate(parts))).cuda()
-    d_pen, pens = None, [None] * len(parts)
+    d_pen, win, la = None, 0, [{} for _ in parts]
     if tag == "flat_default":
         win = int(gf["pl_params"][4])
-        pens = [np.ascontiguousarray(gf["pl_pen"][np.minimum(np.arange(len(p)) + win, max(len(p) - 1, 0))], np.int32)
-                if len(p) else np.zeros((0, n_ci), np.int32) for p in parts]
-        d_pen = torch.from_numpy(np.concatenate(pens)).cuda()
+        d_pen = torch.from_numpy(np.ascontiguousarray(np.concatenate([gf["pl_pen"][:len(p)] for p in parts]), np.int32)).cuda()
+        la = [dict(pl_pen=gf["pl_pen"][:len(p)], pl_window=win) for p in parts]
     ctx = api.HmmContext(en_us.tp, en_us.sseq, en_us.n_sen)
     first = ctx.ngram_fwdtree(d_scr.data_ptr(), utt_off, c["info"], c["model"], cit, 8192, 1 << 18,
-                              d_pen.data_ptr() if d_pen is not None else None)
+                              d_pen.data_ptr() if d_pen is not None else None, win)
     out = ctx.ngram_fwdflat(d_scr.data_ptr(), utt_off, c["info"], c["model"], cit, cis, [t[0] for t in first],
                             len(c["bp"]) + 64, len(c["bss"]) + 4096)
     for u in (0, 4):
         bp, bss, idx = out[u]
         assert np.array_equal(bp, c["bp"]) and np.array_equal(bss, c["bss"]) and np.array_equal(idx, c["bp_idx"]), u
     for u in (1, 2, 3):
-        bp1 = oracle.fwdtree_run(en_us.tp, en_us.sseq, cit, c["info"], c["model"], parts[u], pen_in_force=pens[u])[0]
+        bp1 = oracle.fwdtree_run(en_us.tp, en_us.sseq, cit, c["info"], c["model"], parts[u], **la[u])[0]
         assert np.array_equal(first[u][0], bp1), u
         want = oracle.fwdflat_run(en_us.tp, en_us.sseq, cit, cis, c["info"], c["model"], bp1, parts[u])
         bp, bss, idx = out[u]
@@ -175,12 +173,11 @@ def test_default_pipeline_drop_in_through_the_binding(api, en_us):
     pl = ref.phoneloop(pcm)
     ref.close()
     T, nc = len(scr), want["n_ci"]
-    pen = np.ascontiguousarray(pl["pen"][np.minimum(np.arange(T) + 5, T - 1)], np.int32)
-    d_scr, d_pen = torch.from_numpy(scr).cuda(), torch.from_numpy(pen).cuda()
+    d_scr, d_pen = torch.from_numpy(scr).cuda(), torch.from_numpy(np.ascontiguousarray(pl["pen"], np.int32)).cuda()
     utt_off = np.array([0, T], np.int32)
     ctx = api.HmmContext(en_us.tp, en_us.sseq, en_us.n_sen)
     cit, cis = en_us.phone_tmat[:nc], en_us.phone_ssid[:nc]
-    first = ctx.ngram_fwdtree(d_scr.data_ptr(), utt_off, want["info"], want["model"], cit, 8192, 1 << 18, d_pen.data_ptr())
+    first = ctx.ngram_fwdtree(d_scr.data_ptr(), utt_off, want["info"], want["model"], cit, 8192, 1 << 18, d_pen.data_ptr(), 5)
     bp, bss, idx = ctx.ngram_fwdflat(d_scr.data_ptr(), utt_off, want["info"], want["model"], cit, cis, [first[0][0]], 8192, 1 << 18)[0]
     ctx.close()
     rt = refdrv.ngram_roundtrip(hd, lm, dic, pcm, bp, bss, idx, **kv)

@@ -14,7 +14,7 @@ from conftest import ROOT, golden
 
 TAGS = ("default", "wide", "narrow", "maxwpf", "abs", "pen", "lookahead")
 ARGT = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
-        C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
 
 
 def _p(a):
@@ -48,13 +48,13 @@ def run_emul(f, m, info, model, scr, bp_cap, bss_cap, pl_pen=None, pl_window=0):
     T = len(scr)
     pen = None
     if pl_pen is not None and pl_window > 0 and T > 0:
-        pen = np.ascontiguousarray(np.asarray(pl_pen, np.int32)[np.minimum(np.arange(T) + pl_window, T - 1)])
+        pen = np.ascontiguousarray(np.asarray(pl_pen, np.int32)[:T])       # the phone loop's own table; the window is applied inside
     bp = np.zeros((bp_cap, 10), np.int32)
     bss = np.zeros(bss_cap, np.int32)
     idx = np.zeros(T + 2, np.int32)
     bn = C.c_int32()
     n = f(tp.shape[1], _p(tp), tp.shape[0], _p(sseq), len(sseq), _p(cit), _p(info), _p(model), len(model), _p(scr), scr.shape[1], T,
-          _p(pen), _p(bp), bp_cap, _p(bss), bss_cap, C.byref(bn), _p(idx))
+          _p(pen), int(pl_window), _p(bp), bp_cap, _p(bss), bss_cap, C.byref(bn), _p(idx))
     return n, bp[:max(n, 0)], bss[:bn.value if n >= 0 else 0], idx[:T + 1]
 
 
