@@ -278,6 +278,10 @@ def search_stage(api, torch, U=256):
     second, dt2 = timed(lambda: ctx.ngram_fwdflat(d_scr.data_ptr(), off, c["info"], c["model"], cit, cis, tabs, 2048, 1 << 15))
     out["fwdflat"] = {"kernel": "ngs_fwdflat_kernel", "ms": dt2 * 1e3, "utts_per_s": U / dt2, "frames_per_s": U * T / dt2,
                       "matches_reference": bool(np.array_equal(second[0][0], c["bp"]))}
+    (both, n_first), dt3 = timed(lambda: ctx.ngram_two_pass(d_scr.data_ptr(), off, c["info"], c["model"], cit, cis, 2048, 1 << 15,
+                                                             d_pen.data_ptr(), win, first_cap=2048, first_bss_cap=1 << 15))
+    out["two_pass"] = {"call": "psb_ngram_two_pass_batch_device", "ms": dt3 * 1e3, "utts_per_s": U / dt3, "frames_per_s": U * T / dt3,
+                       "matches_reference": bool(np.array_equal(both[0][0], c["bp"]) and np.array_equal(both[U - 1][0], c["bp"]))}
     ctx.close()
     try:
         from oracle import refdrv

@@ -400,6 +400,17 @@ int psb_ngram_fwdflat_batch_device(psb_hmmctx_t *c, const psb_ngram_desc_t *g, c
                                    int32_t bp_cap_per_utt, int32_t *bss, int32_t bss_cap_per_utt,
                                    int32_t *bp_idx, int32_t *result);
 
+/* Both passes back to back with the first pass's tables staying on the device (what
+ * ngram_search_finish does: fwdtree over the utterance, acmod_rewind, fwdflat over the same frames,
+ * ngram_search.c:781-820).  Arguments as for the two entry points above; only the second pass's tables
+ * come back (bp / bss / bp_idx / result), first_result [n_utt][3] (may be NULL) gets the first pass's
+ * entry count, stack size and frames. */
+int psb_ngram_two_pass_batch_device(psb_hmmctx_t *c, const psb_ngram_desc_t *g, const int16_t *d_senscr,
+                                    const int32_t *d_pen, int32_t pl_window, const int32_t *utt_off, int32_t n_utt,
+                                    int32_t first_cap_per_utt, int32_t first_bss_cap_per_utt, int32_t *bp,
+                                    int32_t bp_cap_per_utt, int32_t *bss, int32_t bss_cap_per_utt, int32_t *bp_idx,
+                                    int32_t *result, int32_t *first_result);
+
 /* Self-test of the search kernels' block-wide exclusive scan (the one building block the host
  * emulation of their phase code cannot execute): scans a[0..n) in place on `device` with one CTA,
  * total[0] = the sum, total[1] = the result of an empty scan issued right behind it (must be 0). */

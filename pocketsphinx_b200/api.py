@@ -356,6 +356,32 @@ class HmmContext:
             out.append((bp[u, :res[u, 0]].copy(), bss[u, :res[u, 1]].copy(), bp_idx[o:o + T + 1].copy()))
         return out
 
+    def ngram_two_pass(self, d_senscr_ptr, utt_off, info, model, ci_tmat, ci_ssid, bp_cap, bss_cap, d_pen_ptr=None, pl_window=0,
+                       first_cap=None, first_bss_cap=None):
+        """Both n-gram passes back to back on the device (first-pass tables never leave it).  Returns per
+        utterance (bp table, bscore_stack, bp_table_idx) of the second pass, and the first pass's entry counts."""
+        from ._lib import NgramDesc
+        utt_off = np.ascontiguousarray(utt_off, np.int32)
+        n_utt = len(utt_off) - 1
+        info = np.ascontiguousarray(info, np.int32); model = np.ascontiguousarray(model, np.int32)
+        ci_tmat = np.ascontiguousarray(ci_tmat, np.int32); ci_ssid = np.ascontiguousarray(ci_ssid, np.int32)
+        d = NgramDesc(info.ctypes.data, model.ctypes.data, len(model), ci_tmat.ctypes.data, ci_ssid.ctypes.data)
+        bp = np.zeros((max(n_utt, 1), int(bp_cap), 10), np.int32)
+        bss = np.zeros((max(n_utt, 1), int(bss_cap)), np.int32)
+        bp_idx = np.zeros(int(utt_off[-1]) + max(n_utt, 1), np.int32)
+        res = np.zeros((max(n_utt, 1), 3), np.int32)
+        res1 = np.zeros((max(n_utt, 1), 3), np.int32)
+        check(lib().psb_ngram_two_pass_batch_device(self.h, C.byref(d), C.c_void_p(d_senscr_ptr),
+                                                    C.c_void_p(d_pen_ptr) if d_pen_ptr else None, int(pl_window), _p(utt_off), n_utt,
+                                                    int(first_cap or bp_cap), int(first_bss_cap or bss_cap), _p(bp), int(bp_cap), _p(bss),
+                                                    int(bss_cap), _p(bp_idx), _p(res), _p(res1)), "psb_ngram_two_pass_batch_device")
+        out = []
+        for u in range(n_utt):
+            T = int(utt_off[u + 1] - utt_off[u])
+            o = int(utt_off[u]) + u
+            out.append((bp[u, :res[u, 0]].copy(), bss[u, :res[u, 1]].copy(), bp_idx[o:o + T + 1].copy()))
+        return out, res1[:n_utt, 0].copy()
+
     def allphone_lm(self, d_senscr_ptr, utt_off, ssid, tmatid, succ_off, succ, start, beam, pbeam, node_ci, bg, tg):
         """allphone_search with a phone LM (dense bigram / trigram tables).  History rows
         [n][5] = (ef, node, predecessor entry, score, tscore)."""

@@ -359,7 +359,7 @@ typedef ChanDevEval<NgfGraph, NgfWork> NgfDevEval;
 
 __global__ void __launch_bounds__(NGS_THREADS)
 ngs_fwdflat_kernel(const int16_t *__restrict__ senscr, const int32_t *__restrict__ utt_off, HmmCtxDev c, NgfGraph G,
-                   int32_t *work, size_t work_words, const int32_t *bp_in, int in_cap, const int32_t *n_in,
+                   int32_t *work, size_t work_words, const int32_t *bp_in, int in_cap, const int32_t *n_in, int n_in_stride,
                    int32_t *bp_out, int bp_cap, int32_t *bss_out, int bss_cap, int32_t *bp_idx_out, int32_t *result, int n_utt)
 {
     PSB_SRCH_UTT(NgfScalars);
@@ -371,7 +371,8 @@ ngs_fwdflat_kernel(const int16_t *__restrict__ senscr, const int32_t *__restrict
     W.bss = bss_out + (size_t)u * bss_cap;
     W.bp_idx = bp_idx_out + f0 + u;
     W.bp_in = bp_in + (size_t)u * in_cap * NGS_BP_ROW;
-    W.n_bp_in = n_in[u];
+    W.n_bp_in = n_in[(size_t)u * n_in_stride];
+    if (W.n_bp_in < 0 || W.n_bp_in > in_cap) W.n_bp_in = 0;     // a first pass that failed leaves no vocabulary
     W.bp_cap = bp_cap; W.bss_cap = bss_cap;
     NgfDevEval ev{c, &G, nullptr};
     ngf_start(G, W, &S);
@@ -390,10 +391,10 @@ ngs_fwdflat_kernel(const int16_t *__restrict__ senscr, const int32_t *__restrict
 }  // namespace
 
 void PSB_SRCH(psb_ngf_launch)(cudaStream_t st, int n_utt, const int16_t *senscr, const int32_t *utt_off, HmmCtxDev c, NgfGraph G,
-                              int32_t *work, size_t work_words, const int32_t *bp_in, int in_cap, const int32_t *n_in, int32_t *bp,
-                              int bp_cap, int32_t *bss, int bss_cap, int32_t *bp_idx, int32_t *result)
+                              int32_t *work, size_t work_words, const int32_t *bp_in, int in_cap, const int32_t *n_in, int n_in_stride,
+                              int32_t *bp, int bp_cap, int32_t *bss, int bss_cap, int32_t *bp_idx, int32_t *result)
 {
-    ngs_fwdflat_kernel<<<PSB_SRCH_GRID(n_utt), NGS_THREADS, 0, st>>>(senscr, utt_off, c, G, work, work_words, bp_in, in_cap, n_in, bp, bp_cap,
+    ngs_fwdflat_kernel<<<PSB_SRCH_GRID(n_utt), NGS_THREADS, 0, st>>>(senscr, utt_off, c, G, work, work_words, bp_in, in_cap, n_in, n_in_stride, bp, bp_cap,
                                                                      bss, bss_cap, bp_idx, result, n_utt);
 }
 
@@ -458,7 +459,7 @@ extern "C" int psb_ngram_fwdflat_batch_device(psb_hmmctx_t *c, const psb_ngram_d
     if (e == cudaSuccess) {
         ngf_bind(flat, d_i);
         (search_warp_mode() ? psb_ngf_launch_warp : psb_ngf_launch_cta)(st, n_utt, d_senscr, d_i + o_uo, dev_ctx(c), flat.G, d_work, work_words, d_in,
-                                                                        first_cap_per_utt, d_i + o_nin, d_bp, bp_cap_per_utt, d_bss, bss_cap_per_utt,
+                                                                        first_cap_per_utt, d_i + o_nin, 1, d_bp, bp_cap_per_utt, d_bss, bss_cap_per_utt,
                                                                         d_idx, d_i + o_res);
         g_psb_launches.fetch_add(1, std::memory_order_relaxed);
         e = cudaGetLastError();
@@ -482,6 +483,98 @@ extern "C" int psb_ngram_fwdflat_batch_device(psb_hmmctx_t *c, const psb_ngram_d
     return PSB_OK;
 }
 
+// Both passes back to back, the first pass's tables staying on the device (ngram_search_finish :781-820:
+// fwdtree, acmod_rewind, fwdflat over the same frames).  Only the second pass's tables come back, plus
+// the first pass's entry counts for diagnostics.
+extern "C" int psb_ngram_two_pass_batch_device(psb_hmmctx_t *c, const psb_ngram_desc_t *g, const int16_t *d_senscr,
+                                               const int32_t *d_pen, int32_t pl_window, const int32_t *utt_off, int32_t n_utt,
+                                               int32_t first_cap_per_utt, int32_t first_bss_cap_per_utt, int32_t *bp,
+                                               int32_t bp_cap_per_utt, int32_t *bss, int32_t bss_cap_per_utt, int32_t *bp_idx,
+                                               int32_t *result, int32_t *first_result)
+{
+    PSB_REQUIRE(c && g && g->info && g->model && g->ci_tmat && g->ci_ssid && utt_off && n_utt >= 0 && bp && bss && bp_idx && result &&
+                first_cap_per_utt > 0 && first_bss_cap_per_utt > 0 && bp_cap_per_utt > 0 && bss_cap_per_utt > 0 && pl_window >= 0,
+                "psb_ngram_two_pass_batch_device: bad argument");
+    if (n_utt == 0) return PSB_OK;
+    PSB_REQUIRE(utt_off[0] == 0, "psb_ngram_two_pass_batch_device: offsets must start at 0");
+    PSB_REQUIRE(d_senscr || utt_off[n_utt] == 0, "psb_ngram_two_pass_batch_device: scores missing");
+    int t_max = 0;
+    for (int u = 0; u < n_utt; ++u) {
+        PSB_REQUIRE(utt_off[u + 1] >= utt_off[u], "psb_ngram_two_pass_batch_device: utt_off not monotone at %d", u);
+        if (utt_off[u + 1] - utt_off[u] > t_max) t_max = utt_off[u + 1] - utt_off[u];
+    }
+    PSB_CUDA(cudaSetDevice(c->device));
+    const int N = c->n_emit;
+    std::vector<uint16_t> sseq((size_t)c->n_sseq * N);
+    PSB_CUDA(cudaMemcpy(sseq.data(), c->d_sseq, sseq.size() * 2, cudaMemcpyDeviceToHost));
+    NgsFlat f1;
+    NgfFlat f2;
+    std::string err;
+    if (ngs_flatten(g->info, g->model, (long long)g->model_len, g->ci_tmat, sseq.data(), c->n_sseq, N, c->n_tmat, c->n_sen, f1, err) != 0 ||
+        ngf_flatten(g->info, g->model, (long long)g->model_len, g->ci_tmat, g->ci_ssid, sseq.data(), c->n_sseq, N, c->n_tmat, c->n_sen, f2, err) != 0) {
+        psb_set_error("psb_ngram_two_pass_batch_device: %s", err.c_str());
+        return PSB_ERR_ARG;
+    }
+    // one int32 block: first-pass graph | second-pass graph | utt_off | result1 [n_utt][3] | result2 [n_utt][3]
+    std::vector<int32_t> ibuf(f1.buf);
+    const size_t o_g2 = ibuf.size();
+    ibuf.insert(ibuf.end(), f2.buf.begin(), f2.buf.end());
+    const size_t o_uo = ibuf.size();
+    ibuf.insert(ibuf.end(), utt_off, utt_off + n_utt + 1);
+    const size_t o_r1 = ibuf.size();
+    ibuf.resize(o_r1 + (size_t)n_utt * 6, 0);
+    const size_t o_r2 = o_r1 + (size_t)n_utt * 3;
+    const size_t ww1 = ngs_work_words(f1.G), ww2 = ngf_work_words(f2.G, t_max), ww = ww1 > ww2 ? ww1 : ww2;
+    const size_t total_frames = (size_t)utt_off[n_utt], n_idx = total_frames + (size_t)n_utt;
+    const size_t n_bp1 = (size_t)n_utt * first_cap_per_utt * NGS_BP_ROW, n_bss1 = (size_t)n_utt * first_bss_cap_per_utt,
+                 n_bp2 = (size_t)n_utt * bp_cap_per_utt * NGS_BP_ROW, n_bss2 = (size_t)n_utt * bss_cap_per_utt;
+    int32_t *d_i = nullptr, *d_work = nullptr, *d_bp1 = nullptr, *d_bss1 = nullptr, *d_idx1 = nullptr, *d_bp2 = nullptr, *d_bss2 = nullptr,
+            *d_idx2 = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_i, ibuf.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_work, ww * (size_t)n_utt * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_bp1, n_bp1 * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_bss1, n_bss1 * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_idx1, n_idx * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_bp2, n_bp2 * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_bss2, n_bss2 * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_idx2, n_idx * 4);
+    cudaStream_t st = c->stream;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_i, ibuf.data(), ibuf.size() * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_idx1, 0, n_idx * 4, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_idx2, 0, n_idx * 4, st);
+    if (e == cudaSuccess) {
+        const bool warp = search_warp_mode();
+        ngs_bind(f1, d_i);
+        ngf_bind(f2, d_i + o_g2);
+        (warp ? psb_ngs_launch_warp : psb_ngs_launch_cta)(st, n_utt, d_senscr, d_i + o_uo, dev_ctx(c), f1.G, d_work, ww, d_pen, pl_window, d_bp1,
+                                                          first_cap_per_utt, d_bss1, first_bss_cap_per_utt, d_idx1, d_i + o_r1);
+        (warp ? psb_ngf_launch_warp : psb_ngf_launch_cta)(st, n_utt, d_senscr, d_i + o_uo, dev_ctx(c), f2.G, d_work, ww, d_bp1, first_cap_per_utt,
+                                                          d_i + o_r1, 3, d_bp2, bp_cap_per_utt, d_bss2, bss_cap_per_utt, d_idx2, d_i + o_r2);
+        g_psb_launches.fetch_add(2, std::memory_order_relaxed);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bp, d_bp2, n_bp2 * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bss, d_bss2, n_bss2 * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bp_idx, d_idx2, n_idx * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(result, d_i + o_r2, (size_t)n_utt * 12, cudaMemcpyDeviceToHost, st);
+    std::vector<int32_t> r1((size_t)n_utt * 3);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(r1.data(), d_i + o_r1, (size_t)n_utt * 12, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_i); cudaFree(d_work); cudaFree(d_bp1); cudaFree(d_bss1); cudaFree(d_idx1); cudaFree(d_bp2); cudaFree(d_bss2); cudaFree(d_idx2);
+    if (e != cudaSuccess) {
+        psb_set_error("psb_ngram_two_pass_batch_device: %s", cudaGetErrorString(e));
+        return PSB_ERR_CUDA;
+    }
+    if (first_result) memcpy(first_result, r1.data(), r1.size() * 4);
+    for (int u = 0; u < n_utt; ++u) {
+        PSB_REQUIRE(r1[(size_t)u * 3 + 2] != -1, "psb_ngram_two_pass_batch_device: utterance %d: first pass overflowed its tables (%d entries / %d scores)",
+                    u, first_cap_per_utt, first_bss_cap_per_utt);
+        PSB_REQUIRE(result[u * 3 + 2] != -1, "psb_ngram_two_pass_batch_device: utterance %d: second pass overflowed its tables (%d entries / %d scores)",
+                    u, bp_cap_per_utt, bss_cap_per_utt);
+        PSB_REQUIRE(r1[(size_t)u * 3 + 2] >= 0 && result[u * 3 + 2] >= 0, "psb_ngram_two_pass_batch_device: utterance %d needs score renormalisation", u);
+    }
+    return PSB_OK;
+}
 #endif  // !PSB_SEARCH_WARP
 
 // ---------------------------------------------------------------------------------------

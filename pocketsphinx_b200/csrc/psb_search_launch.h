@@ -17,7 +17,8 @@
                               int bp_cap, int32_t *bss, int bss_cap, int32_t *bp_idx, int32_t *result);                    \
     void psb_ngf_launch_##sfx(cudaStream_t st, int n_utt, const int16_t *senscr, const int32_t *utt_off, HmmCtxDev c,      \
                               NgfGraph G, int32_t *work, size_t work_words, const int32_t *bp_in, int in_cap,              \
-                              const int32_t *n_in, int32_t *bp, int bp_cap, int32_t *bss, int bss_cap, int32_t *bp_idx,    \
+                              const int32_t *n_in, int n_in_stride, int32_t *bp, int bp_cap, int32_t *bss, int bss_cap,    \
+                              int32_t *bp_idx,                                                                             \
                               int32_t *result);                                                                            \
     void psb_exscan_launch_##sfx(int32_t *a, int n, int32_t *total);
 PSB_SEARCH_LAUNCHERS(cta)

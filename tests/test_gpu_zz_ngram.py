@@ -182,3 +182,30 @@ def test_default_pipeline_drop_in_through_the_binding(api, en_us):
     ctx.close()
     rt = refdrv.ngram_roundtrip(hd, lm, dic, pcm, bp, bss, idx, **kv)
     assert rt["hyp"] == want["hyp"] == "go forward ten meters" and rt["score"] == want["score"]
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("tag", ("flat_default", "flat_wide", "flat_narrow"))
+def test_two_pass_chained_on_the_device(api, en_us, tag):
+    """psb_ngram_two_pass_batch_device: first-pass tables never leave the device."""
+    import torch
+    gf = golden("en_us_goforward.npz")
+    scr = gf["senscr"]
+    c = _case(golden("en_us_fwdtree.npz"), tag)
+    n_ci = int(c["info"][6])
+    U = 5
+    utt_off = (np.arange(U + 1) * len(scr)).astype(np.int32)
+    d_scr = torch.from_numpy(np.ascontiguousarray(np.tile(scr, (U, 1)))).cuda()
+    d_pen, win = None, 0
+    if tag == "flat_default":
+        win = int(gf["pl_params"][4])
+        d_pen = torch.from_numpy(np.ascontiguousarray(np.tile(gf["pl_pen"].astype(np.int32), (U, 1)))).cuda()
+    ctx = api.HmmContext(en_us.tp, en_us.sseq, en_us.n_sen)
+    out, n_first = ctx.ngram_two_pass(d_scr.data_ptr(), utt_off, c["info"], c["model"], en_us.phone_tmat[:n_ci], en_us.phone_ssid[:n_ci],
+                                      len(c["bp"]) + 64, len(c["bss"]) + 4096, d_pen.data_ptr() if d_pen is not None else None, win,
+                                      first_cap=8192, first_bss_cap=1 << 18)
+    assert (n_first == n_first[0]).all() and n_first[0] > 0
+    for u in range(U):
+        bp, bss, idx = out[u]
+        assert np.array_equal(bp, c["bp"]) and np.array_equal(bss, c["bss"]) and np.array_equal(idx, c["bp_idx"]), u
+    ctx.close()
