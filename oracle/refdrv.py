@@ -225,6 +225,9 @@ class RefModel:
         return lib().refdrv_time_score(self.h, _p(feats), feats.shape[0], reps)
 
     def phoneloop(self, pcm, **kv):
+        """The reference's phone_loop_search over one utterance.  Call it on a FRESH RefModel: the object's
+        live-CMN state (after other utterances) and earlier pl_* settings are not undone, and both change
+        the scores the phone loop sees."""
         pcm = np.ascontiguousarray(pcm, np.int16)
         kv.setdefault("pl_window", 5)
         s = "\n".join("%s=%s" % (k, v) for k, v in kv.items()).encode()

@@ -170,6 +170,8 @@ def test_default_pipeline_drop_in_through_the_binding(api, en_us):
     want = refdrv.fwdtree(hd, lm, dic, pcm, **kv)
     ref = refdrv.RefModel(hd)
     scr = np.ascontiguousarray(ref.score(ref.featurize_fresh(pcm)))
+    ref.close()
+    ref = refdrv.RefModel(hd)                                   # fresh: the phone loop must start from a fresh CMN state
     pl = ref.phoneloop(pcm)
     ref.close()
     T, nc = len(scr), want["n_ci"]

@@ -31,6 +31,8 @@ def scored():
     pcm = np.fromfile(os.path.join(REF, "data", "goforward.raw"), np.int16)
     pk = ref.packed()
     scr = np.ascontiguousarray(ref.score(ref.featurize_fresh(pcm)))
+    ref.close()
+    ref = refdrv.RefModel(HD)                                   # a fresh object: the phone loop must see a fresh CMN state
     pl = ref.phoneloop(pcm)                                     # default look-ahead (window 5)
     ref.close()
     return pk, pcm, scr, pl
