@@ -286,6 +286,7 @@ extern "C" void psb_hmmctx_free(psb_hmmctx_t *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_tp); cudaFree(c->d_sseq); cudaFree(c->d_hmms); cudaFree(c->d_senscr); cudaFree(c->d_best);
     cudaFree(c->d_al_i32); cudaFree(c->d_al_tok); cudaFree(c->d_al_senid); cudaFree(c->d_al_tokoff);
+    for (void *p : c->d_srch) cudaFree(p);
     if (c->al_ev[0]) cudaEventDestroy(c->al_ev[0]);
     if (c->al_ev[1]) cudaEventDestroy(c->al_ev[1]);
     if (c->h_hmms) cudaFreeHost(c->h_hmms);

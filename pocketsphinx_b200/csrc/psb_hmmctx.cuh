@@ -21,6 +21,9 @@ struct psb_hmmctx_s {
     size_t al_i32_cap, al_tok_cap, al_senid_cap, al_tokoff_cap;
     cudaEvent_t al_ev[2];
     float last_align_ms;
+    // grow-only device workspace of the search entry points (psb_search.cu)
+    void *d_srch[10];
+    size_t srch_cap[10];
 };
 
 static inline HmmCtxDev dev_ctx(const psb_hmmctx_t *c)

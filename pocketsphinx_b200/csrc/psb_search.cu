@@ -111,6 +111,23 @@ static bool search_warp_mode()
     return e && e[0] == '1';
 }
 
+// Grow-only device workspace kept in the context: repeated calls (one per batch) do not pay
+// cudaMalloc / cudaFree again (the alignment entry point lost 220 ms per call that way).
+template <class T>
+static cudaError_t srch_reserve(psb_hmmctx_t *c, int slot, size_t count, T **out)
+{
+    const size_t bytes = (count > 0 ? count : 1) * sizeof(T);
+    if (bytes > c->srch_cap[slot]) {
+        cudaFree(c->d_srch[slot]);
+        c->d_srch[slot] = nullptr; c->srch_cap[slot] = 0;
+        const cudaError_t e = cudaMalloc(&c->d_srch[slot], bytes + bytes / 4);
+        if (e != cudaSuccess) return e;
+        c->srch_cap[slot] = bytes + bytes / 4;
+    }
+    *out = (T *)c->d_srch[slot];
+    return cudaSuccess;
+}
+
 static_assert(FSG_WORST_SCORE == PSB_WORST_SCORE, "score floor");
 static_assert(FSG_MAX_NSTATE == PSB_HMM_MAX_NSTATE, "state count");
 
@@ -159,10 +176,10 @@ extern "C" int psb_fsg_batch_device(psb_hmmctx_t *c, const psb_fsg_desc_t *g, co
     const size_t hist_n = (size_t)n_utt * cap_per_utt * FSG_ROW;
     int32_t *d_i = nullptr, *d_hist = nullptr, *d_work = nullptr;
     uint16_t *d_senid = nullptr;
-    cudaError_t e = cudaMalloc((void **)&d_i, ibuf.size() * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_hist, hist_n * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_work, work_words * (size_t)n_utt * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_senid, senid.size() * 2);
+    cudaError_t e = srch_reserve(c, 0, ibuf.size(), &d_i);
+    if (e == cudaSuccess) e = srch_reserve(c, 1, hist_n, &d_hist);
+    if (e == cudaSuccess) e = srch_reserve(c, 2, work_words * (size_t)n_utt, &d_work);
+    if (e == cudaSuccess) e = srch_reserve(c, 3, senid.size(), &d_senid);
     cudaStream_t st = c->stream;
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_i, ibuf.data(), ibuf.size() * 4, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_senid, senid.data(), senid.size() * 2, cudaMemcpyHostToDevice, st);
@@ -180,7 +197,6 @@ extern "C" int psb_fsg_batch_device(psb_hmmctx_t *c, const psb_fsg_desc_t *g, co
     if (e == cudaSuccess) e = cudaMemcpyAsync(hist, d_hist, hist_n * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(n_hist, d_i + o_nh, (size_t)n_utt * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_i); cudaFree(d_hist); cudaFree(d_work); cudaFree(d_senid);
     if (e != cudaSuccess) {
         psb_set_error("psb_fsg_batch_device: %s", cudaGetErrorString(e));
         return PSB_ERR_CUDA;
@@ -309,11 +325,11 @@ extern "C" int psb_ngram_fwdtree_batch_device(psb_hmmctx_t *c, const psb_ngram_d
     const size_t n_bp = (size_t)n_utt * bp_cap_per_utt * NGS_BP_ROW, n_bss = (size_t)n_utt * bss_cap_per_utt,
                  n_idx = total_frames + (size_t)n_utt;
     int32_t *d_i = nullptr, *d_work = nullptr, *d_bp = nullptr, *d_bss = nullptr, *d_idx = nullptr;
-    cudaError_t e = cudaMalloc((void **)&d_i, ibuf.size() * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_work, work_words * (size_t)n_utt * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_bp, n_bp * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_bss, n_bss * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_idx, n_idx * 4);
+    cudaError_t e = srch_reserve(c, 0, ibuf.size(), &d_i);
+    if (e == cudaSuccess) e = srch_reserve(c, 1, work_words * (size_t)n_utt, &d_work);
+    if (e == cudaSuccess) e = srch_reserve(c, 2, n_bp, &d_bp);
+    if (e == cudaSuccess) e = srch_reserve(c, 3, n_bss, &d_bss);
+    if (e == cudaSuccess) e = srch_reserve(c, 4, n_idx, &d_idx);
     cudaStream_t st = c->stream;
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_i, ibuf.data(), ibuf.size() * 4, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_idx, 0, n_idx * 4, st);
@@ -330,7 +346,6 @@ extern "C" int psb_ngram_fwdtree_batch_device(psb_hmmctx_t *c, const psb_ngram_d
     if (e == cudaSuccess) e = cudaMemcpyAsync(bp_idx, d_idx, n_idx * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(result, d_i + o_res, (size_t)n_utt * 12, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_i); cudaFree(d_work); cudaFree(d_bp); cudaFree(d_bss); cudaFree(d_idx);
     if (e != cudaSuccess) {
         psb_set_error("psb_ngram_fwdtree_batch_device: %s", cudaGetErrorString(e));
         return PSB_ERR_CUDA;
@@ -446,12 +461,12 @@ extern "C" int psb_ngram_fwdflat_batch_device(psb_hmmctx_t *c, const psb_ngram_d
     const size_t n_in = (size_t)n_utt * first_cap_per_utt * NGS_BP_ROW, n_bp = (size_t)n_utt * bp_cap_per_utt * NGS_BP_ROW,
                  n_bss = (size_t)n_utt * bss_cap_per_utt, n_idx = total_frames + (size_t)n_utt;
     int32_t *d_i = nullptr, *d_work = nullptr, *d_in = nullptr, *d_bp = nullptr, *d_bss = nullptr, *d_idx = nullptr;
-    cudaError_t e = cudaMalloc((void **)&d_i, ibuf.size() * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_work, work_words * (size_t)n_utt * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_in, n_in * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_bp, n_bp * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_bss, n_bss * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_idx, n_idx * 4);
+    cudaError_t e = srch_reserve(c, 0, ibuf.size(), &d_i);
+    if (e == cudaSuccess) e = srch_reserve(c, 1, work_words * (size_t)n_utt, &d_work);
+    if (e == cudaSuccess) e = srch_reserve(c, 2, n_in, &d_in);
+    if (e == cudaSuccess) e = srch_reserve(c, 3, n_bp, &d_bp);
+    if (e == cudaSuccess) e = srch_reserve(c, 4, n_bss, &d_bss);
+    if (e == cudaSuccess) e = srch_reserve(c, 5, n_idx, &d_idx);
     cudaStream_t st = c->stream;
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_i, ibuf.data(), ibuf.size() * 4, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, bp_first, n_in * 4, cudaMemcpyHostToDevice, st);
@@ -469,7 +484,6 @@ extern "C" int psb_ngram_fwdflat_batch_device(psb_hmmctx_t *c, const psb_ngram_d
     if (e == cudaSuccess) e = cudaMemcpyAsync(bp_idx, d_idx, n_idx * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(result, d_i + o_res, (size_t)n_utt * 12, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_i); cudaFree(d_work); cudaFree(d_in); cudaFree(d_bp); cudaFree(d_bss); cudaFree(d_idx);
     if (e != cudaSuccess) {
         psb_set_error("psb_ngram_fwdflat_batch_device: %s", cudaGetErrorString(e));
         return PSB_ERR_CUDA;
@@ -530,14 +544,14 @@ extern "C" int psb_ngram_two_pass_batch_device(psb_hmmctx_t *c, const psb_ngram_
                  n_bp2 = (size_t)n_utt * bp_cap_per_utt * NGS_BP_ROW, n_bss2 = (size_t)n_utt * bss_cap_per_utt;
     int32_t *d_i = nullptr, *d_work = nullptr, *d_bp1 = nullptr, *d_bss1 = nullptr, *d_idx1 = nullptr, *d_bp2 = nullptr, *d_bss2 = nullptr,
             *d_idx2 = nullptr;
-    cudaError_t e = cudaMalloc((void **)&d_i, ibuf.size() * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_work, ww * (size_t)n_utt * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_bp1, n_bp1 * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_bss1, n_bss1 * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_idx1, n_idx * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_bp2, n_bp2 * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_bss2, n_bss2 * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_idx2, n_idx * 4);
+    cudaError_t e = srch_reserve(c, 0, ibuf.size(), &d_i);
+    if (e == cudaSuccess) e = srch_reserve(c, 1, ww * (size_t)n_utt, &d_work);
+    if (e == cudaSuccess) e = srch_reserve(c, 2, n_bp1, &d_bp1);
+    if (e == cudaSuccess) e = srch_reserve(c, 3, n_bss1, &d_bss1);
+    if (e == cudaSuccess) e = srch_reserve(c, 4, n_idx, &d_idx1);
+    if (e == cudaSuccess) e = srch_reserve(c, 5, n_bp2, &d_bp2);
+    if (e == cudaSuccess) e = srch_reserve(c, 6, n_bss2, &d_bss2);
+    if (e == cudaSuccess) e = srch_reserve(c, 7, n_idx, &d_idx2);
     cudaStream_t st = c->stream;
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_i, ibuf.data(), ibuf.size() * 4, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_idx1, 0, n_idx * 4, st);
@@ -560,7 +574,6 @@ extern "C" int psb_ngram_two_pass_batch_device(psb_hmmctx_t *c, const psb_ngram_
     std::vector<int32_t> r1((size_t)n_utt * 3);
     if (e == cudaSuccess) e = cudaMemcpyAsync(r1.data(), d_i + o_r1, (size_t)n_utt * 12, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_i); cudaFree(d_work); cudaFree(d_bp1); cudaFree(d_bss1); cudaFree(d_idx1); cudaFree(d_bp2); cudaFree(d_bss2); cudaFree(d_idx2);
     if (e != cudaSuccess) {
         psb_set_error("psb_ngram_two_pass_batch_device: %s", cudaGetErrorString(e));
         return PSB_ERR_CUDA;
