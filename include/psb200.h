@@ -393,7 +393,8 @@ int psb_ngram_fwdtree_batch_device(psb_hmmctx_t *c, const psb_ngram_desc_t *g, c
  * float32 bits of fwdflatlw / lw, pronunciation count; model continues with the LM-membership flags
  * and the pronunciations with their dict2pid_internal ssids).  bp_first [n_utt][first_cap_per_utt][10]
  * + n_first[n_utt]: every utterance's FIRST-pass table (the utterance vocabulary and the start-frame
- * windows come from it).  Outputs as for the first pass. */
+ * windows come from it); n_first[u] = -1 runs the second pass alone (-fwdtree no: every LM word is in
+ * the vocabulary and may follow every exit).  Outputs as for the first pass. */
 int psb_ngram_fwdflat_batch_device(psb_hmmctx_t *c, const psb_ngram_desc_t *g, const int16_t *d_senscr,
                                    const int32_t *utt_off, int32_t n_utt, const int32_t *bp_first,
                                    int32_t first_cap_per_utt, const int32_t *n_first, int32_t *bp,

@@ -227,7 +227,7 @@ cuda_ngram_export(ngram_search_t *ngs, cuda_ngram_graph_t *g)
         b[o++] = dict_first_phone(dict, w); b[o++] = dict_last_phone(dict, w);
         b[o++] = dict_is_single_phone(dict, w) ? -1 : dict_second_last_phone(dict, w);
         b[o++] = dict_is_single_phone(dict, w); b[o++] = dict_filler_word(dict, w);
-        b[o++] = dict_basewid(dict, w); b[o++] = ngs->homophone_set[w]; b[o++] = lmidx[w];
+        b[o++] = dict_basewid(dict, w); b[o++] = ngs->homophone_set ? ngs->homophone_set[w] : -1; b[o++] = lmidx[w];
     }
     for (i = 0; i < ngs->n_1ph_words; ++i) b[o++] = ngs->single_phone_wid[i];
     for (i = 0; i < ngs->n_1ph_words; ++i) {

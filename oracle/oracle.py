@@ -508,7 +508,8 @@ def fwdflat_run(tp, sseq, ci_tmat, ci_ssid, info, model, bp_first, senscr):
     tp = np.ascontiguousarray(tp, np.uint8); sseq = np.ascontiguousarray(sseq, np.uint16)
     ci_tmat = np.ascontiguousarray(ci_tmat, np.int32); ci_ssid = np.ascontiguousarray(ci_ssid, np.int32)
     info = np.ascontiguousarray(info, np.int32); model = np.ascontiguousarray(model, np.int32)
-    bp_first = np.ascontiguousarray(bp_first, np.int32)
+    n_first = -1 if bp_first is None else len(bp_first)                     # None: -fwdtree no
+    bp_first = np.zeros((1, 10), np.int32) if bp_first is None else np.ascontiguousarray(bp_first, np.int32)
     senscr = np.ascontiguousarray(senscr, np.int16)
     T, n_sen = senscr.shape
     bp_cap, bss_cap = 64 * (T + 16), 64 * (T + 16) * 64
@@ -518,7 +519,7 @@ def fwdflat_run(tp, sseq, ci_tmat, ci_ssid, info, model, bp_first, senscr):
     f.restype = C.c_int32
     f.argtypes = [C.c_int32] + [C.c_void_p] * 7 + [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
-    n = f(tp.shape[1], _p(tp), _p(sseq), _p(ci_tmat), _p(ci_ssid), _p(info), _p(model), _p(bp_first), len(bp_first),
+    n = f(tp.shape[1], _p(tp), _p(sseq), _p(ci_tmat), _p(ci_ssid), _p(info), _p(model), _p(bp_first), n_first,
           _p(senscr), n_sen, T, _p(bp), bp_cap, _p(bss), bss_cap, C.byref(bss_n), _p(bp_idx))
     assert n <= bp_cap and bss_n.value <= bss_cap
     return bp[:n].copy(), bss[:bss_n.value].copy(), bp_idx[:T + 1].copy()

@@ -2371,7 +2371,8 @@ pso_fwdtree_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, c
  * N-gram decoding, second pass: ngram_search_fwdflat.c (start :371-414 with
  * build_fwdflat_wordlist :224-300 and build_fwdflat_chan :306-368, search step :813-875 =
  * fwdflat_eval_chan :445, fwdflat_prune_chan :483-607, fwdflat_word_transition :643-782 with
- * get_expand_wordlist :610-640) restated for one utterance.  Input: the FIRST pass's backpointer
+ * get_expand_wordlist :610-640) restated for one utterance (n_bp_in < 0: -fwdtree no, every LM word is in
+ * the vocabulary and can follow every exit).  Input: the FIRST pass's backpointer
  * table (bp_in [n_bp_in][10], the utterance vocabulary and the start-frame windows come from it) and
  * the same flattened search as pso_fwdtree_run (exported with fwdflat=yes so that info holds
  * fwdflatbeam / fwdflatwbeam / fwdflatefwid / fwdflatsfwin / the language-weight ratio).
@@ -2385,8 +2386,8 @@ pso_fwdflat_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, c
                 int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap, int32_t *bss_n, int32_t *bp_idx_out)
 {
     ft_t S, *s = &S;
-    int32_t i, w, f, frame, n_done = 0, n_node = 0, nwd = 0;
-    ff_node_t *node = malloc(((size_t)n_bp_in + 1) * sizeof(*node));
+    int32_t i, w, f, frame, n_done = 0, n_node = 0, nwd = 0, all_words = 0;
+    ff_node_t *node = malloc(((size_t)(n_bp_in > 0 ? n_bp_in : 0) + 1) * sizeof(*node));
     int32_t *head = malloc(((size_t)T + 1) * sizeof(int32_t));
     int32_t *wordlist, *expand, *n_int;
     uint8_t *expand_flag;
@@ -2396,34 +2397,42 @@ pso_fwdflat_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, c
     wordlist = malloc((s->n_words + 1) * sizeof(int32_t)); expand = malloc((s->n_words + 1) * sizeof(int32_t));
     expand_flag = calloc(s->n_words, 1);
     fr = calloc(s->n_words, sizeof(*fr)); fi = calloc(s->n_words, sizeof(*fi)); n_int = calloc(s->n_words, sizeof(int32_t));
-    /* build_fwdflat_wordlist */
-    for (f = 0; f <= T; ++f) head[f] = -1;
-    for (i = 0; i < n_bp_in; ++i) {
-        const int32_t *b = bp_in + (size_t)i * 10;
-        const int32_t sf = b[3] < 0 ? 0 : bp_in[(size_t)b[3] * 10] + 1, ef = b[0], wid = b[2];
-        int32_t n;
-        if (!s->inlm[wid]) continue;
-        for (n = head[sf]; n >= 0 && node[n].wid != wid; n = node[n].next);
-        if (n >= 0) node[n].lef = ef;
-        else { n = n_node++; node[n].wid = wid; node[n].fef = node[n].lef = ef; node[n].next = head[sf]; head[sf] = n; }
+    if (n_bp_in < 0) {                                                     /* no first pass: ngram_fwdflat_expand_all :61-87 */
+        for (f = 0; f <= T; ++f) head[f] = -1;
+        for (w = 0; w < s->n_words; ++w) if (s->inlm[w]) wordlist[nwd++] = w;
+        wordlist[nwd] = -1;
+        all_words = 1;
     }
-    for (f = 0; f < T; ++f) {
-        int32_t prev = -1, n, nx;
-        for (n = head[f]; n >= 0; n = nx) {
-            nx = node[n].next;
-            if (node[n].lef - node[n].fef < s->min_ef_width || (node[n].wid == s->finish_wid && node[n].lef < T - 1)) {
-                if (prev < 0) head[f] = nx; else node[prev].next = nx;
-            }
-            else prev = n;
+    else {
+        /* build_fwdflat_wordlist */
+        for (f = 0; f <= T; ++f) head[f] = -1;
+        for (i = 0; i < n_bp_in; ++i) {
+            const int32_t *b = bp_in + (size_t)i * 10;
+            const int32_t sf = b[3] < 0 ? 0 : bp_in[(size_t)b[3] * 10] + 1, ef = b[0], wid = b[2];
+            int32_t n;
+            if (!s->inlm[wid]) continue;
+            for (n = head[sf]; n >= 0 && node[n].wid != wid; n = node[n].next);
+            if (n >= 0) node[n].lef = ef;
+            else { n = n_node++; node[n].wid = wid; node[n].fef = node[n].lef = ef; node[n].next = head[sf]; head[sf] = n; }
         }
+        for (f = 0; f < T; ++f) {
+            int32_t prev = -1, n, nx;
+            for (n = head[f]; n >= 0; n = nx) {
+                nx = node[n].next;
+                if (node[n].lef - node[n].fef < s->min_ef_width || (node[n].wid == s->finish_wid && node[n].lef < T - 1)) {
+                    if (prev < 0) head[f] = nx; else node[prev].next = nx;
+                }
+                else prev = n;
+            }
+        }
+        memset(s->word_active, 0, s->n_words);
+        for (f = 0; f < T; ++f) {
+            int32_t n;
+            for (n = head[f]; n >= 0; n = node[n].next)
+                if (!s->word_active[node[n].wid]) { s->word_active[node[n].wid] = 1; wordlist[nwd++] = node[n].wid; }
+        }
+        wordlist[nwd] = -1;
     }
-    memset(s->word_active, 0, s->n_words);
-    for (f = 0; f < T; ++f) {
-        int32_t n;
-        for (n = head[f]; n >= 0; n = node[n].next)
-            if (!s->word_active[node[n].wid]) { s->word_active[node[n].wid] = 1; wordlist[nwd++] = node[n].wid; }
-    }
-    wordlist[nwd] = -1;
     /* build_fwdflat_chan */
     for (i = 0; i < nwd; ++i) {
         int32_t p, len;
@@ -2530,7 +2539,9 @@ pso_fwdflat_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, c
             if (sf < 0) sf = 0;
             if (ef > T) ef = T;
             memset(expand_flag, 0, s->n_words);
-            for (f = sf; f < ef; ++f) {
+            if (all_words)                                                  /* get_expand_wordlist :615-618: the static list */
+                for (i = 0; i < nwd; ++i) expand[nexp++] = wordlist[i];
+            for (f = sf; f < ef && !all_words; ++f) {
                 int32_t n;
                 for (n = head[f]; n >= 0; n = node[n].next)
                     if (!expand_flag[node[n].wid]) { expand[nexp++] = node[n].wid; expand_flag[node[n].wid] = 1; }

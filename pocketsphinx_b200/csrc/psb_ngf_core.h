@@ -115,29 +115,42 @@ FSG_HD void ngf_start(const NgfGraph &G, const NgfWork &W, NgfScalars *S)
     }
     FSG_SYNC();
     FSG_FOR(w, nw) if (G.ch_off[w + 1] > G.ch_off[w]) W.mss[G.ch_off[w]] = G.root_ssid[w];
-    // nodes: first / last exit per (start frame, word) in table order
-    FSG_FOR(i, W.n_bp_in) {
-        const int32_t *b = W.bp_in + (size_t)i * NGS_BP_ROW;
-        const int sf = b[3] < 0 ? 0 : W.bp_in[(size_t)b[3] * NGS_BP_ROW] + 1, wid = b[2];
-        if (!G.inlm[wid] || sf >= T) continue;
-        FSG_ATOMIC_MIN_AT(W.node_first, (size_t)sf * nw + wid, i);
-        FSG_ATOMIC_MAX_AT(W.node_last, (size_t)sf * nw + wid, i);
-    }
-    FSG_SYNC();
-    FSG_FOR(x, T * nw) if (W.node_first[x] == INT_MAX) W.node_first[x] = -1;
-    FSG_SYNC();
-    // per word: prefix count of surviving nodes over start frames, first such frame
-    FSG_FOR(w, nw) {
-        int run = 0, f0 = -1;
-        for (int f = 0; f < T; ++f) {
-            W.node_cnt[(size_t)f * nw + w] = run;
-            if (ngf_node_ok(G, W, f, w)) { if (f0 < 0) f0 = f; ++run; }
+    if (W.n_bp_in < 0) {
+        // no first pass (-fwdtree no): ngram_fwdflat_expand_all :61-87 -- every LM word is in the
+        // vocabulary (in id order) and may follow every exit (get_expand_wordlist :615-618)
+        FSG_FOR(w, nw) {
+            const int in = G.inlm[w] ? 1 : 0;
+            for (int f = 0; f <= T; ++f) W.node_cnt[(size_t)f * nw + w] = f * in;
+            W.first_sf[w] = in ? 0 : -1;
+            W.wl_key[w] = -w;
         }
-        W.node_cnt[(size_t)T * nw + w] = run;
-        W.first_sf[w] = f0;
-        W.wl_key[w] = f0 < 0 ? -1 : W.node_first[(size_t)f0 * nw + w];
+        FSG_SYNC();
     }
-    FSG_SYNC();
+    else {
+        // nodes: first / last exit per (start frame, word) in table order
+        FSG_FOR(i, W.n_bp_in) {
+            const int32_t *b = W.bp_in + (size_t)i * NGS_BP_ROW;
+            const int sf = b[3] < 0 ? 0 : W.bp_in[(size_t)b[3] * NGS_BP_ROW] + 1, wid = b[2];
+            if (!G.inlm[wid] || sf >= T) continue;
+            FSG_ATOMIC_MIN_AT(W.node_first, (size_t)sf * nw + wid, i);
+            FSG_ATOMIC_MAX_AT(W.node_last, (size_t)sf * nw + wid, i);
+        }
+        FSG_SYNC();
+        FSG_FOR(x, T * nw) if (W.node_first[x] == INT_MAX) W.node_first[x] = -1;
+        FSG_SYNC();
+        // per word: prefix count of surviving nodes over start frames, first such frame
+        FSG_FOR(w, nw) {
+            int run = 0, f0 = -1;
+            for (int f = 0; f < T; ++f) {
+                W.node_cnt[(size_t)f * nw + w] = run;
+                if (ngf_node_ok(G, W, f, w)) { if (f0 < 0) f0 = f; ++run; }
+            }
+            W.node_cnt[(size_t)T * nw + w] = run;
+            W.first_sf[w] = f0;
+            W.wl_key[w] = f0 < 0 ? -1 : W.node_first[(size_t)f0 * nw + w];
+        }
+        FSG_SYNC();
+    }
     // utterance vocabulary: by (first start frame ascending, node creation order descending)
     FSG_FOR(w, nw) {
         const int f0 = W.first_sf[w];
@@ -273,7 +286,8 @@ FSG_HD void ngf_step(const NgfGraph &G, const NgfWork &W, NgfScalars *S, int cf,
         if (ef > T) ef = T;
         FSG_FOR(w, nwords) {
             if (G.ch_off[w + 1] == G.ch_off[w]) continue;
-            if (!(ef > sf && W.node_cnt[(size_t)ef * nwords + w] - W.node_cnt[(size_t)sf * nwords + w] > 0)) continue;
+            if (W.n_bp_in >= 0 ? !(ef > sf && W.node_cnt[(size_t)ef * nwords + w] - W.node_cnt[(size_t)sf * nwords + w] > 0)
+                               : !G.inlm[w]) continue;
             const int c0 = G.ch_off[w], first = NGS_W(G, w, 0);
             const int ci2 = NGS_W(G, w, 3) ? G.sil : G.pron_ci[G.pron_off[w] + 1];
             for (int b = bp0; b < bp1; ++b) {

@@ -387,7 +387,7 @@ ngs_fwdflat_kernel(const int16_t *__restrict__ senscr, const int32_t *__restrict
     W.bp_idx = bp_idx_out + f0 + u;
     W.bp_in = bp_in + (size_t)u * in_cap * NGS_BP_ROW;
     W.n_bp_in = n_in[(size_t)u * n_in_stride];
-    if (W.n_bp_in < 0 || W.n_bp_in > in_cap) W.n_bp_in = 0;     // a first pass that failed leaves no vocabulary
+    if (W.n_bp_in > in_cap) W.n_bp_in = 0;                      // (negative: no first pass, -fwdtree no)
     W.bp_cap = bp_cap; W.bss_cap = bss_cap;
     NgfDevEval ev{c, &G, nullptr};
     ngf_start(G, W, &S);
@@ -429,7 +429,7 @@ extern "C" int psb_ngram_fwdflat_batch_device(psb_hmmctx_t *c, const psb_ngram_d
     int t_max = 0;
     for (int u = 0; u < n_utt; ++u) {
         PSB_REQUIRE(utt_off[u + 1] >= utt_off[u], "psb_ngram_fwdflat_batch_device: utt_off not monotone at %d", u);
-        PSB_REQUIRE(n_first[u] >= 0 && n_first[u] <= first_cap_per_utt, "psb_ngram_fwdflat_batch_device: n_first[%d] out of range", u);
+        PSB_REQUIRE(n_first[u] >= -1 && n_first[u] <= first_cap_per_utt, "psb_ngram_fwdflat_batch_device: n_first[%d] out of range", u);
         const int32_t *b = bp_first + (size_t)u * first_cap_per_utt * NGS_BP_ROW;
         const int T = utt_off[u + 1] - utt_off[u];
         for (int i = 0; i < n_first[u]; ++i) {

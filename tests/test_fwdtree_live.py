@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle, refdrv
+from test_ngf_emul import emuls, run_second  # noqa: F401  (fixture)
 
 pytestmark = pytest.mark.skipif(not refdrv.available(), reason="oracle/_ref/libpsref.so not built")
 REF = os.path.dirname(refdrv.LIB_PATH)
@@ -79,3 +80,20 @@ def test_both_passes_match_reference(scored, kv):
     b, score = oracle.fwdtree_find_exit(bp, bp_idx, r["n_frame"], r["finish_wid"])
     assert score == r["score"]
     assert oracle.fwdtree_hyp(bp, b, r["words"], r["vocab"], r["start_wid"], r["finish_wid"]) == r["hyp"]
+
+
+@needs_lm
+@pytest.mark.parametrize("kv", [dict(), dict(fwdflatbeam="1e-40", fwdflatwbeam="1e-15", fwdflatlw="5")])
+def test_second_pass_alone_matches_reference(emuls, scored, kv):  # noqa: F811
+    """-fwdtree no -fwdflat yes: the flat search over the whole LM vocabulary, frame-synchronous
+    (oracle restatement and the device second pass's phase code without a first-pass table)."""
+    pk, pcm, scr = scored
+    hd = os.path.join(REF, "model", "en-us")
+    r = refdrv.fwdtree(hd, LM, DIC, pcm, fwdtree="no", fwdflat="yes", **kv)
+    nc = r["n_ci"]
+    bp, bss, bp_idx = oracle.fwdflat_run(pk["tp"], pk["sseq"], pk["phone_tmat"][:nc], pk["phone_ssid"][:nc], r["info"], r["model"],
+                                         None, scr)
+    assert bp.shape == r["bp"].shape and np.array_equal(bp, r["bp"])
+    assert np.array_equal(bss, r["bss"]) and np.array_equal(bp_idx, r["bp_idx"])
+    n, bp, bss, bp_idx = run_second(emuls[1], pk, r["info"], r["model"], None, scr, len(r["bp"]) + 8, len(r["bss"]) + 64)
+    assert n == len(r["bp"]) and np.array_equal(bp, r["bp"]) and np.array_equal(bss, r["bss"]) and np.array_equal(bp_idx, r["bp_idx"])

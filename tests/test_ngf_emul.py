@@ -56,14 +56,15 @@ def run_second(f, m, info, model, bp1, scr, bp_cap, bss_cap):
     nci = int(info[6])
     cit = np.ascontiguousarray(m["phone_tmat"][:nci], np.int32)
     cis = np.ascontiguousarray(m["phone_ssid"][:nci], np.int32)
-    bp1 = np.ascontiguousarray(bp1, np.int32)
+    n1 = -1 if bp1 is None else len(bp1)                        # None: no first pass (-fwdtree no)
+    bp1 = np.zeros((1, 10), np.int32) if bp1 is None else np.ascontiguousarray(bp1, np.int32)
     scr = np.ascontiguousarray(scr, np.int16)
     T = len(scr)
     bp = np.zeros((bp_cap, 10), np.int32)
     bss = np.zeros(bss_cap, np.int32)
     idx = np.zeros(T + 2, np.int32)
     bn = C.c_int32()
-    n = f(tp.shape[1], _p(tp), tp.shape[0], _p(sseq), len(sseq), _p(cit), _p(cis), _p(info), _p(model), len(model), _p(bp1), len(bp1),
+    n = f(tp.shape[1], _p(tp), tp.shape[0], _p(sseq), len(sseq), _p(cit), _p(cis), _p(info), _p(model), len(model), _p(bp1), n1,
           _p(scr), scr.shape[1], T, _p(bp), bp_cap, _p(bss), bss_cap, C.byref(bn), _p(idx))
     return n, bp[:max(n, 0)], bss[:bn.value if n >= 0 else 0], idx[:T + 1]
 
