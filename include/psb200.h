@@ -319,11 +319,16 @@ int psb_allphone_lm_batch_device(psb_hmmctx_t *c, const int16_t *d_senscr, const
                                  const int32_t *tg, int32_t *hist, int32_t cap_per_utt, int32_t *n_hist);
 
 /* ------------------------------------------------------------------------------------ */
-/* Grammar decoding for whole batches: fsg_search.c (-fsg / -jsgf; start :770-817, step :683-761 =
+/* STATUS of the search entry points below (psb_fsg_batch_device, psb_ngram_*_batch_device): their phase
+ * code reproduces the reference's tables in host emulation and is race-checked (tests/emul/), the kernels
+ * themselves have not yet run on hardware; the reference-side export / import that
+ * goes with them is integration/ps_search_cuda.c.
+ *
+ * Grammar decoding for whole batches: fsg_search.c (-fsg / -jsgf; start :770-817, step :683-761 =
  * hmm_eval :335, hmm_prune_prop :516, null_prop :566, word_trans :621) with fsg_history.c's
  * right-context bookkeeping (:132-240), every utterance against the same grammar.  The host keeps
  * fsg_search_init / fsg_lextree_init and flattens what they built (fsg_lextree.h:137-190;
- * oracle/ref_driver.c:refdrv_fsg shows the loop):
+ * integration/ps_search_cuda.c:cuda_fsg_export is the loop):
  *   pnodes [n_pnode][16] = ssid, tmatid, next (first successor, or the link id of a leaf, or -1),
  *                          sibling, logs2prob, ci_ext, ppos, leaf, ctxt.bv[8]; ids in alloc order
  *   roots  [n_state]      first root pnode of each state's lextree (-1: none)
@@ -353,8 +358,8 @@ int psb_fsg_batch_device(psb_hmmctx_t *c, const psb_fsg_desc_t *g, const int16_t
  * start :470) with the backpointer-table half of ngram_search.c (save_bp :378, alloc_all_rc :593,
  * exit_score :655), every utterance against the same lextree, dictionary and language model.  The
  * host keeps ngram_search_init / ngram_fwdtree_init (create_search_channels :174) and flattens what
- * they built into int32 sections; oracle/ref_driver.c:refdrv_fwdtree is that loop and documents
- * the layout:
+ * they built into int32 sections; integration/ps_search_cuda.c:cuda_ngram_export is that loop
+ * (oracle/ref_driver.c:refdrv_fwdtree documents the layout):
  *   info  [40]  sizes (n_words, n_root_chan, n_nonroot_chan, n_1ph_words, n_1ph_LMwords, n_ciphone),
  *               beams (beam, pbeam, wbeam, lpbeam, lponlybeam), maxhmmpf, maxwpf, nwpen, pip, silpen,
  *               fillpen, <s> / </s> / <sil> ids, filler range, number of LM base words
