@@ -25,7 +25,7 @@ ngf_flatten(const int32_t *info, const int32_t *model, long long model_len, cons
     G.pip = info[16]; G.silpen = info[17]; G.fillpen = info[18]; G.start_wid = info[19]; G.finish_wid = info[20];
     G.silence_wid = info[21]; G.filler_start = info[22]; G.filler_end = info[23];
     const size_t nc = (size_t)n_ci;
-    if (n_root < 0 || n_nonroot < 0 || n_1ph < 0 || n_ci > 256 || n_lm > 2048) NGS_FAIL("ngram search: sizes out of range");
+    if (n_root < 0 || n_nonroot < 0 || n_1ph < 0 || n_ci > 256 || n_lm > 512) NGS_FAIL("ngram search: sizes out of range (at most 256 phones, 512 LM words with the dense tables)");
     {
         const unsigned long long need = (unsigned long long)n_root * 5 + (unsigned long long)n_nonroot * 6 + (unsigned long long)n_words * 8 +
             (unsigned long long)n_1ph * 5 + nc * nc + 3ull * nc * nc * nc + (unsigned long long)n_lm * (n_lm + 1) * (n_lm + 1) +

@@ -34,7 +34,7 @@ ngs_flatten(const int32_t *info, const int32_t *model, long long model_len, cons
     if (G.n_words <= 0 || G.n_root < 0 || G.n_nonroot < 0 || G.n_1ph <= 0 || G.n_ci <= 0 || G.n_lm <= 0) NGS_FAIL("ngram search: empty tables");
     if (G.n_1ph_lm > G.n_1ph) NGS_FAIL("ngram search: n_1ph_LMwords > n_1ph_words");
     const size_t nc = (size_t)G.n_ci;
-    if (G.n_ci > 256 || G.n_lm > 2048) NGS_FAIL("ngram search: %d phones / %d LM words exceed what the dense tables are meant for", G.n_ci, G.n_lm);
+    if (G.n_ci > 256 || G.n_lm > 512) NGS_FAIL("ngram search: %d phones / %d LM words exceed what the dense tables are meant for (256 / 512)", G.n_ci, G.n_lm);
     {
         const unsigned long long need = (unsigned long long)G.n_root * 5 + (unsigned long long)G.n_nonroot * 6 + (unsigned long long)G.n_words * 8 +
             (unsigned long long)G.n_1ph * 5 + nc * nc + 3ull * nc * nc * nc + (unsigned long long)G.n_lm * (G.n_lm + 1) * (G.n_lm + 1);
