@@ -386,6 +386,11 @@ typedef struct psb_ngram_desc_s {
     int64_t model_len;          /* int32 words in `model` (checked against the sizes info implies) */
     const int32_t *ci_tmat;     /* [n_ciphone] */
     const int32_t *ci_ssid;     /* [n_ciphone] bin_mdef_pid2ssid of every CI phone; second pass only (may be NULL for the first) */
+    const int32_t *lm_arrays;   /* optional: the LM as sorted arrays (integration/ps_search_cuda.c:cuda_ngram_export_lm, layout
+                                   there; scoring = pocketsphinx_b200/csrc/psb_lm_core.h); when given, trigram scores come from
+                                   it, the dense table in `model` may be empty (info[26] = 0) and the LM's size no longer
+                                   matters */
+    int64_t lm_arrays_len;      /* int32 words in lm_arrays */
 } psb_ngram_desc_t;
 int psb_ngram_fwdtree_batch_device(psb_hmmctx_t *c, const psb_ngram_desc_t *g, const int16_t *d_senscr,
                                    const int32_t *d_pen, int32_t pl_window, const int32_t *utt_off, int32_t n_utt, int32_t *bp,

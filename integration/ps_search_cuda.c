@@ -180,7 +180,7 @@ chan_id(chan_t **tab, int n, chan_t *h)
 }
 
 int
-cuda_ngram_export(ngram_search_t *ngs, cuda_ngram_graph_t *g)
+cuda_ngram_export(ngram_search_t *ngs, cuda_ngram_graph_t *g, int dense_lm)
 {
     dict_t *dict = ps_search_dict(ngs);
     dict2pid_t *d2p = ps_search_dict2pid(ngs);
@@ -197,7 +197,8 @@ cuda_ngram_export(ngram_search_t *ngs, cuda_ngram_graph_t *g)
     k = 0;
     for (i = 0; i < ngs->n_root_chan; ++i) collect_chan(ngs->root_chan[i].next, tab, &k);
     lmidx = ckd_calloc(n_words, sizeof(*lmidx));
-    for (w = 0; w < n_words; ++w) lmidx[w] = dict_basewid(dict, w) == w ? n_lm++ : -1;
+    /* dense_lm == 0: no trigram table (vocabularies beyond a few hundred words: cuda_ngram_export_lm instead) */
+    for (w = 0; w < n_words; ++w) lmidx[w] = (dense_lm && dict_basewid(dict, w) == w) ? n_lm++ : -1;
     for (w = 0; w < n_words; ++w) n_pron += dict_pronlen(dict, w);
     need = (size_t)ngs->n_root_chan * 5 + (size_t)n_nonroot * 6 + (size_t)n_words * 8 + (size_t)ngs->n_1ph_words * 5
         + (size_t)n_ci * n_ci + 3 * (size_t)n_ci * n_ci * n_ci + (size_t)n_lm * (n_lm + 1) * (n_lm + 1)
@@ -319,4 +320,91 @@ cuda_ngram_import(ngram_search_t *ngs, const int32 *bp, int32 n, const int32 *bs
     ckd_free(base->hyp_str);
     base->hyp_str = NULL;
     return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* The language model as sorted arrays (for vocabularies where the dense trigram table of
+ * cuda_ngram_export is out of reach).  One trie model of order <= 3 behind the search's model set.
+ * The trie is keyed word -> nearest history word -> next history word (lm_trie.c:665-706): unigram w
+ * owns the bigram entries (w | h1), each of which owns the trigram entries (w | h2 h1); inside a
+ * range entries are sorted by word id.  Probabilities and backoffs are the floats the reference's own
+ * readers return (dequantised), lw / log_wip / log_zero the trie model's (weight_score,
+ * ngram_model_trie.c:709-713).  int32 layout:
+ *   [0] order [1] V [2] n2 [3] n3 [4] lw (float bits) [5] log_wip [6] log_zero [7] n_words
+ *   [8] max_vocab of the bigram level, [9] of the trigram level (uniform_find's upper key bound, lm_trie.c:566)
+ *   widmap [n_words] | uni_prob [V] | uni_bo [V] | uni_next [V+1]
+ *   | bg_word [n2] | bg_prob [n2] | bg_bo [n2] | bg_next [n2+1] | tg_word [n3] | tg_prob [n3]          */
+#include "lm/ngram_model_set.h"
+#include "lm/ngram_model_trie.h"
+#include "lm/lm_trie.h"
+
+static int32
+f2i(float f) { int32 i; memcpy(&i, &f, 4); return i; }
+
+long
+cuda_ngram_export_lm(ngram_search_t *ngs, int32 *out, long cap)
+{
+    ngram_model_set_t *set = (ngram_model_set_t *)ngs->lmset;
+    ngram_model_trie_t *tm;
+    lm_trie_t *t;
+    int order, V, n_words = ps_search_n_words(ngs), w;
+    uint32 n2 = 0, n3 = 0, p;
+    long need, o;
+
+    if (set == NULL || set->n_models != 1 || set->cur != 0) return -1;       /* interpolated sets: not handled */
+    tm = (ngram_model_trie_t *)set->lms[0];
+    t = tm->trie;
+    order = tm->base.n;
+    V = tm->base.n_counts[0];
+    if (order < 1 || order > 3 || t == NULL) return -2;
+    if (order >= 2) n2 = tm->base.n_counts[1];
+    if (order >= 3) n3 = tm->base.n_counts[2];
+    need = 10 + n_words + 2L * V + (V + 1) + 3L * n2 + (n2 + 1) + 2L * n3;
+    if (out == NULL || cap < need) return need;
+    o = 0;
+    out[o++] = order; out[o++] = V; out[o++] = (int32)n2; out[o++] = (int32)n3;
+    out[o++] = f2i(tm->base.lw); out[o++] = tm->base.log_wip; out[o++] = tm->base.log_zero; out[o++] = n_words;
+    out[o++] = order == 3 ? (int32)t->middle_begin[0].base.max_vocab : (order == 2 ? (int32)t->longest->base.max_vocab : 0);
+    out[o++] = order == 3 ? (int32)t->longest->base.max_vocab : 0;
+    for (w = 0; w < n_words; ++w) out[o++] = set->widmap[w][0];
+    for (w = 0; w < V; ++w) out[o++] = f2i(t->unigrams[w].prob);
+    for (w = 0; w < V; ++w) out[o++] = f2i(t->unigrams[w].bo);
+    for (w = 0; w <= V; ++w) out[o++] = (int32)t->unigrams[w].next;
+    if (order == 2) {                                      /* bigrams are the longest order: no backoff, no children */
+        longest_t *l = t->longest;
+        bitarr_address_t a;
+        a.base = l->base.base;
+        for (p = 0; p < n2; ++p) { a.offset = p * l->base.total_bits; out[o + p] = (int32)bitarr_read_int25(a, l->base.word_bits, l->base.word_mask); }
+        o += n2;
+        for (p = 0; p < n2; ++p) { a.offset = p * l->base.total_bits + l->base.word_bits; out[o + p] = f2i(lm_trie_quant_lpread(t->quant, a)); }
+        o += n2;
+        for (p = 0; p < n2; ++p) out[o + p] = 0;
+        o += n2;
+        for (p = 0; p <= n2; ++p) out[o + p] = 0;
+        o += n2 + 1;
+    }
+    else if (order == 3) {
+        middle_t *m = &t->middle_begin[0];
+        longest_t *l = t->longest;
+        bitarr_address_t a;
+        a.base = m->base.base;
+        for (p = 0; p < n2; ++p) { a.offset = p * m->base.total_bits; out[o + p] = (int32)bitarr_read_int25(a, m->base.word_bits, m->base.word_mask); }
+        o += n2;
+        for (p = 0; p < n2; ++p) { a.offset = p * m->base.total_bits + m->base.word_bits; out[o + p] = f2i(lm_trie_quant_mpread(t->quant, a, 0)); }
+        o += n2;
+        for (p = 0; p < n2; ++p) { a.offset = p * m->base.total_bits + m->base.word_bits; out[o + p] = f2i(lm_trie_quant_mboread(t->quant, a, 0)); }
+        o += n2;
+        for (p = 0; p <= n2; ++p) {
+            a.offset = p * m->base.total_bits + m->base.word_bits + m->quant_bits;
+            out[o + p] = (int32)bitarr_read_int25(a, m->next_mask.bits, m->next_mask.mask);
+        }
+        o += n2 + 1;
+        a.base = l->base.base;
+        for (p = 0; p < n3; ++p) { a.offset = p * l->base.total_bits; out[o + p] = (int32)bitarr_read_int25(a, l->base.word_bits, l->base.word_mask); }
+        o += n3;
+        for (p = 0; p < n3; ++p) { a.offset = p * l->base.total_bits + l->base.word_bits; out[o + p] = f2i(lm_trie_quant_lpread(t->quant, a)); }
+        o += n3;
+    }
+    else { o += 3L * n2 + (n2 + 1); }
+    return o == need ? need : -3;
 }

@@ -25,9 +25,12 @@ typedef struct cuda_ngram_graph_s {
     int32 *ci_tmat, *ci_ssid;
 } cuda_ngram_graph_t;
 
-int cuda_ngram_export(ngram_search_t *ngs, cuda_ngram_graph_t *g);
+int cuda_ngram_export(ngram_search_t *ngs, cuda_ngram_graph_t *g, int dense_lm);
 void cuda_ngram_free(cuda_ngram_graph_t *g);
 int cuda_ngram_import(ngram_search_t *ngs, const int32 *bp, int32 n, const int32 *bss, int32 n_bss,
                       const int32 *bp_idx, int32 n_frames);
+
+/* the LM as sorted arrays (layout in ps_search_cuda.c); returns the int32 count needed / written */
+long cuda_ngram_export_lm(ngram_search_t *ngs, int32 *out, long cap);
 
 #endif

@@ -151,6 +151,17 @@ def make_fwdtree():
         out[tag + ".hyp"] = np.array(r["hyp"])
         out[tag + ".score"] = np.int32(r["score"])
         print("fwdflat", tag, r["bpidx"], "bp entries,", r["bss_head"], "rc scores:", r["hyp"], r["score"])
+    # the turtle LM as sorted arrays (integration/ps_search_cuda.c:cuda_ngram_export_lm) for the array-LM mode of
+    # the searches, and a sample of the reference's own trigram scores to pin the array scoring without the reference
+    nw = int(out["default.info"][1])
+    rng = np.random.default_rng(3)
+    q = np.stack([rng.integers(0, nw, 20000), rng.integers(-1, nw, 20000), rng.integers(-1, nw, 20000)], 1).astype(np.int32)
+    out["lmarr"], out["lmarr_scores"] = refdrv.lm_arrays(hd, os.path.join(REF, "test/data/turtle.lm.bin"),
+                                                         os.path.join(REF, "test/data/turtle.dic"), q)
+    out["lmarr_queries"] = q
+    r = refdrv.fwdtree(hd, os.path.join(REF, "test/data/turtle.lm.bin"), os.path.join(REF, "test/data/turtle.dic"), pcm,
+                       dense_lm=False, fwdflat="yes")
+    out["nodense.info"], out["nodense.model"] = r["info"], r["model"]          # same search, exported without the dense table
     np.savez_compressed(os.path.join(OUT, "en_us_fwdtree.npz"), **out)
 
 

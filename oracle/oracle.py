@@ -438,7 +438,7 @@ def fsg_hyp_wids(hist, links, bp):
     return out[::-1]
 
 
-def fwdtree_run(tp, sseq, ci_tmat, info, model, senscr, pl_pen=None, pl_window=0, pen_in_force=None):
+def fwdtree_run(tp, sseq, ci_tmat, info, model, senscr, pl_pen=None, pl_window=0, pen_in_force=None, lm_arrays=None):
     """ngram_search_fwdtree.c for one utterance on the flattened search `info` / `model`
     (refdrv.fwdtree / the golden file); returns (bp table [n][10], bscore_stack, bp_table_idx).
     pl_pen [T][n_ci] + pl_window: the phone loop's penalties after each of ITS steps and its window;
@@ -461,10 +461,11 @@ def fwdtree_run(tp, sseq, ci_tmat, info, model, senscr, pl_pen=None, pl_window=0
         pen = np.ascontiguousarray(np.asarray(pl_pen, np.int32)[np.minimum(np.arange(T) + pl_window, T - 1)])
     f = lib().pso_fwdtree_run
     f.restype = C.c_int32
-    f.argtypes = [C.c_int32] + [C.c_void_p] * 6 + [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+    f.argtypes = [C.c_int32] + [C.c_void_p] * 6 + [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                                     C.c_int32, C.c_void_p, C.c_void_p]
+    lma = None if lm_arrays is None else np.ascontiguousarray(lm_arrays, np.int32)
     n = f(tp.shape[1], _p(tp), _p(sseq), _p(ci_tmat), _p(info), _p(model), _p(senscr), n_sen, T,
-          _p(pen) if pen is not None else None, _p(bp), bp_cap, _p(bss),
+          _p(pen) if pen is not None else None, _p(lma) if lma is not None else None, _p(bp), bp_cap, _p(bss),
           bss_cap, C.byref(bss_n), _p(bp_idx))
     assert n <= bp_cap and bss_n.value <= bss_cap
     return bp[:n].copy(), bss[:bss_n.value].copy(), bp_idx[:T + 1].copy()
@@ -502,7 +503,7 @@ def fwdtree_hyp(bp, b, words, vocab, start_wid, finish_wid):
     return " ".join(reversed(out))
 
 
-def fwdflat_run(tp, sseq, ci_tmat, ci_ssid, info, model, bp_first, senscr):
+def fwdflat_run(tp, sseq, ci_tmat, ci_ssid, info, model, bp_first, senscr, lm_arrays=None):
     """ngram_search_fwdflat.c for one utterance: bp_first = the first pass's backpointer table,
     info / model from an export made with fwdflat=yes.  Returns (bp table, bscore_stack, bp_table_idx)."""
     tp = np.ascontiguousarray(tp, np.uint8); sseq = np.ascontiguousarray(sseq, np.uint16)
@@ -517,9 +518,22 @@ def fwdflat_run(tp, sseq, ci_tmat, ci_ssid, info, model, bp_first, senscr):
     bss_n = C.c_int32()
     f = lib().pso_fwdflat_run
     f.restype = C.c_int32
-    f.argtypes = [C.c_int32] + [C.c_void_p] * 7 + [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+    f.argtypes = [C.c_int32] + [C.c_void_p] * 7 + [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lma = None if lm_arrays is None else np.ascontiguousarray(lm_arrays, np.int32)
     n = f(tp.shape[1], _p(tp), _p(sseq), _p(ci_tmat), _p(ci_ssid), _p(info), _p(model), _p(bp_first), n_first,
-          _p(senscr), n_sen, T, _p(bp), bp_cap, _p(bss), bss_cap, C.byref(bss_n), _p(bp_idx))
+          _p(senscr), n_sen, T, _p(lma) if lma is not None else None, _p(bp), bp_cap, _p(bss), bss_cap, C.byref(bss_n), _p(bp_idx))
     assert n <= bp_cap and bss_n.value <= bss_cap
     return bp[:n].copy(), bss[:bss_n.value].copy(), bp_idx[:T + 1].copy()
+
+
+def lm_scores(lmarr, queries):
+    """tg(w | h1, h2) >> SENSCR_SHIFT from the LM as sorted arrays, for queries [n][3] of dictionary ids."""
+    lmarr = np.ascontiguousarray(lmarr, np.int32)
+    q = np.ascontiguousarray(queries, np.int32)
+    out = np.zeros(len(q), np.int32)
+    f = lib().pso_lm_scores
+    f.restype = None
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    f(_p(lmarr), _p(q), len(q), _p(out))
+    return out

@@ -1878,6 +1878,103 @@ pso_fsg_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq,
 }
 
 /* ---------------------------------------------------------------------------------------
+ * Trigram score from the LM as sorted arrays (integration/ps_search_cuda.c:cuda_ngram_export_lm):
+ * ngram_tg_score(lmset, w, h1, h2) >> SENSCR_SHIFT restated -- ngram_model_set_score
+ * (ngram_model_set.c:685-732, one model) -> ngram_ng_score (ngram_model.c:388-417) ->
+ * ngram_model_trie_score (ngram_model_trie.c:716-742: history cut at the first missing word, float
+ * score truncated to int32, then weight_score = (int32)(score * lw + log_wip)) -> lm_trie_score
+ * (lm_trie.c:653-825: full history = cached backoffs + lm_trie_hist_score, shorter =
+ * lm_trie_nobo_score).  w, h1, h2 are DICTIONARY word ids (h = -1: none). */
+typedef struct {
+    int32_t order, V, n2, n3, log_wip, log_zero, n_words, max_vocab2, max_vocab3;
+    float lw;
+    const int32_t *widmap, *uni_next, *bg_word, *bg_next, *tg_word;
+    const float *uni_prob, *uni_bo, *bg_prob, *bg_bo, *tg_prob;
+} lmarr_t;
+
+static void
+lmarr_bind(lmarr_t *L, const int32_t *a)
+{
+    L->order = a[0]; L->V = a[1]; L->n2 = a[2]; L->n3 = a[3]; memcpy(&L->lw, &a[4], 4);
+    L->log_wip = a[5]; L->log_zero = a[6]; L->n_words = a[7]; L->max_vocab2 = a[8]; L->max_vocab3 = a[9];
+    a += 10;
+    L->widmap = a; a += L->n_words;
+    L->uni_prob = (const float *)a; a += L->V;  L->uni_bo = (const float *)a; a += L->V;  L->uni_next = a; a += L->V + 1;
+    L->bg_word = a; a += L->n2;  L->bg_prob = (const float *)a; a += L->n2;  L->bg_bo = (const float *)a; a += L->n2;
+    L->bg_next = a; a += L->n2 + 1;  L->tg_word = a; a += L->n3;  L->tg_prob = (const float *)a;
+}
+
+/* uniform_find (lm_trie.c:556-592) as it stands: interpolation search between (begin - 1, value 0) and
+ * (end, value max_vocab) in uint32 arithmetic.  On a sorted range it finds exactly the entries that
+ * exist; shipped models contain ranges that are not sorted, where what it finds is a property of this
+ * very procedure -- so no other search will do. */
+static int32_t
+lmarr_find(const int32_t *words, int32_t begin, int32_t end, int32_t key_, uint32_t max_vocab)
+{
+    uint32_t before_it = (uint32_t)begin - 1u, before_v = 0, after_it = (uint32_t)end, after_v = max_vocab, key = (uint32_t)key_;
+    if (key > after_v) return -1;
+    while (after_it - before_it > 1) {
+        const uint32_t off = key - before_v, range = after_v - before_v, width = after_it - before_it - 1;
+        const uint32_t pivot = before_it + (1u + (uint32_t)(size_t)((uint32_t)(off * width) / (range + 1)));
+        const uint32_t mid = (uint32_t)words[pivot];
+        if (mid < key) { before_it = pivot; before_v = mid; }
+        else if (mid > key) { after_it = pivot; after_v = mid; }
+        else return (int32_t)pivot;
+    }
+    return -1;
+}
+
+static int32_t
+lmarr_tg(const lmarr_t *L, int32_t w_dict, int32_t h1_dict, int32_t h2_dict)
+{
+    const int32_t w = w_dict < 0 ? -1 : L->widmap[w_dict];
+    int32_t hist[2], n_hist = 2, i, raw;
+    float score;
+    hist[0] = h1_dict < 0 ? -1 : L->widmap[h1_dict];
+    hist[1] = h2_dict < 0 ? -1 : L->widmap[h2_dict];
+    if (w < 0) return L->log_zero;                                          /* ngram_ng_score: OOV */
+    if (n_hist > L->order - 1) n_hist = L->order - 1;
+    for (i = 0; i < n_hist; ++i) if (hist[i] < 0) { n_hist = i; break; }
+    score = L->uni_prob[w];
+    if (n_hist > 0) {
+        /* bigram (w | h1) */
+        const int32_t b = (w < L->V) ? lmarr_find(L->bg_word, L->uni_next[w], L->uni_next[w + 1], hist[0], L->max_vocab2) : -1;
+        if (n_hist == L->order - 1 && L->order == 3) {                      /* lm_trie_hist_score with update_backoff's cache */
+            float bc0 = L->uni_bo[hist[0]], bc1 = 0.0f;
+            const int32_t hb = lmarr_find(L->bg_word, L->uni_next[hist[0]], L->uni_next[hist[0] + 1], hist[1], L->max_vocab2);
+            if (hb >= 0) bc1 = L->bg_bo[hb];
+            if (b < 0) { score += bc0; score += bc1; }
+            else {
+                const int32_t t = lmarr_find(L->tg_word, L->bg_next[b], L->bg_next[b + 1], hist[1], L->max_vocab3);
+                score = L->bg_prob[b];
+                if (t < 0) score = score + bc1;
+                else score = L->tg_prob[t];
+            }
+        }
+        else if (n_hist == L->order - 1 && L->order == 2) {                 /* bigram LM: longest_find directly */
+            if (b < 0) score = score + L->uni_bo[hist[0]];
+            else score = L->bg_prob[b];
+        }
+        else {                                                              /* lm_trie_nobo_score, one history word of a trigram LM */
+            if (b >= 0) score = L->bg_prob[b];
+            else score = score + (0.0f + L->uni_bo[hist[0]]);
+        }
+    }
+    raw = (int32_t)score;
+    return (int32_t)(raw * L->lw + L->log_wip);
+}
+
+/* scores[i] = tg(q[i][0] | q[i][1], q[i][2]) >> SENSCR_SHIFT for n_q queries */
+void
+pso_lm_scores(const int32_t *lmarr, const int32_t *q, int64_t n_q, int32_t *scores)
+{
+    lmarr_t L;
+    int64_t i;
+    lmarr_bind(&L, lmarr);
+    for (i = 0; i < n_q; ++i) scores[i] = lmarr_tg(&L, q[i * 3], q[i * 3 + 1], q[i * 3 + 2]) >> 10;
+}
+
+/* ---------------------------------------------------------------------------------------
  * N-gram lextree decoding, first pass: ngram_search_fwdtree.c (search step :1454-1496 =
  * evaluate_channels :702, prune_channels :1130 [prune_root_chan :723, prune_nonroot_chan :800,
  * last_phone_transition :885, prune_word_chan :1042], bptable_maxwpf :1188, word_transition :1241,
@@ -1898,6 +1995,7 @@ typedef struct {
     int32_t start_wid, finish_wid, silence_wid, filler_start, filler_end;
     const int32_t *roots, *nonroot, *words, *w1ph, *r1ph, *rs_n, *rs_ssid, *rs_cimap, *ldiph, *lm, *ci_tmat;
     const int32_t *inlm, *pron_off, *pron_ci, *pron_ssid;
+    const lmarr_t *lma;               /* NULL: dense table */
     int32_t fwdflatbeam, fwdflatwbeam, min_ef_width, max_sf_win;
     float lwf;
     pso_hmmctx_t ctx;
@@ -1929,6 +2027,7 @@ static int32_t
 ft_tg(const ft_t *s, int32_t w, int32_t h1, int32_t h2)
 {
     const int32_t n = s->n_lm + 1;
+    if (s->lma) return lmarr_tg(s->lma, w, h1, h2) >> 10;
     const int32_t a = FT_W(s, w, 7), b = h1 < 0 ? 0 : FT_W(s, h1, 7) + 1, c = h2 < 0 ? 0 : FT_W(s, h2, 7) + 1;
     return s->lm[((size_t)a * n + b) * n + c];
 }
@@ -2066,13 +2165,16 @@ ft_free(ft_t *s)
 int32_t
 pso_fwdtree_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, const int32_t *ci_tmat,
                 const int32_t *info, const int32_t *model, const int16_t *senscr, int32_t n_sen, int32_t T,
-                const int32_t *pen, int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap, int32_t *bss_n, int32_t *bp_idx_out)
+                const int32_t *pen, const int32_t *lmarr, int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap, int32_t *bss_n,
+                int32_t *bp_idx_out)
 {
     ft_t S, *s = &S;
+    lmarr_t LMA;
     int32_t i, w, frame, n_done = 0;
     const int32_t *pl = NULL;
 #define FT_PL(ci) (pl ? pl[ci] : 0)      /* phone_loop_search_score, phone_loop_search.h:103 */
     ft_setup(s, n_emit_state, tp, sseq, ci_tmat, info, model, T);
+    if (lmarr) { lmarr_bind(&LMA, lmarr); s->lma = &LMA; }
     /* ngram_fwdtree_start :470-520 */
     for (w = 0; w < s->n_words; ++w) { s->word_lat_idx[w] = -1; s->lt_sf[w] = -1; }
     s->best_score = 0;
@@ -2382,7 +2484,7 @@ typedef struct { int32_t wid, fef, lef, next; } ff_node_t;
 int32_t
 pso_fwdflat_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, const int32_t *ci_tmat, const int32_t *ci_ssid,
                 const int32_t *info, const int32_t *model, const int32_t *bp_in, int32_t n_bp_in,
-                const int16_t *senscr, int32_t n_sen, int32_t T,
+                const int16_t *senscr, int32_t n_sen, int32_t T, const int32_t *lmarr,
                 int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap, int32_t *bss_n, int32_t *bp_idx_out)
 {
     ft_t S, *s = &S;
@@ -2392,8 +2494,10 @@ pso_fwdflat_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, c
     int32_t *wordlist, *expand, *n_int;
     uint8_t *expand_flag;
     pso_hmm_t *fr, **fi;
+    lmarr_t LMA2;
 
     ft_setup(s, n_emit_state, tp, sseq, ci_tmat, info, model, T);
+    if (lmarr) { lmarr_bind(&LMA2, lmarr); s->lma = &LMA2; }
     wordlist = malloc((s->n_words + 1) * sizeof(int32_t)); expand = malloc((s->n_words + 1) * sizeof(int32_t));
     expand_flag = calloc(s->n_words, 1);
     fr = calloc(s->n_words, sizeof(*fr)); fi = calloc(s->n_words, sizeof(*fi)); n_int = calloc(s->n_words, sizeof(int32_t));
@@ -2609,3 +2713,4 @@ pso_fwdflat_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, c
     ft_free(s);
     return i;
 }
+

@@ -185,15 +185,18 @@ int32_t pso_fsg_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sse
  * oracle/ref_driver.c:refdrv_fwdtree, ci_tmat[n_ci] = transition matrix of every CI phone. */
 int32_t pso_fwdtree_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, const int32_t *ci_tmat,
                         const int32_t *info, const int32_t *model, const int16_t *senscr, int32_t n_sen, int32_t T,
-                        const int32_t *pen, int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap, int32_t *bss_n,
-                        int32_t *bp_idx_out);
+                        const int32_t *pen, const int32_t *lmarr, int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap,
+                        int32_t *bss_n, int32_t *bp_idx_out);
 
 /* ngram_search_fwdflat.c for one utterance, from the first pass's backpointer table (see ps_oracle.c). */
 int32_t pso_fwdflat_run(int32_t n_emit_state, const uint8_t *tp, const uint16_t *sseq, const int32_t *ci_tmat,
                         const int32_t *ci_ssid, const int32_t *info, const int32_t *model, const int32_t *bp_in,
-                        int32_t n_bp_in, const int16_t *senscr, int32_t n_sen, int32_t T,
+                        int32_t n_bp_in, const int16_t *senscr, int32_t n_sen, int32_t T, const int32_t *lmarr,
                         int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap, int32_t *bss_n,
                         int32_t *bp_idx_out);
+
+/* trigram scores from the LM as sorted arrays (see ps_oracle.c) */
+void pso_lm_scores(const int32_t *lmarr, const int32_t *q, int64_t n_q, int32_t *scores);
 
 #ifdef __cplusplus
 }

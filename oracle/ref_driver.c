@@ -1298,7 +1298,7 @@ ngram_decoder(const char *hmmdir, const char *lm, const char *dictfile, const ch
 long
 refdrv_fwdtree(const char *hmmdir, const char *lm, const char *dictfile, const char *kv,
                const int16 *pcm, long n_samples, int32 *blob, long cap, int32 *info, char *hyp, int hyp_cap,
-               char *vocab, int vocab_cap)
+               char *vocab, int vocab_cap, int dense_lm)
 {
     ps_config_t *config;
     ps_decoder_t *ps;
@@ -1326,7 +1326,7 @@ refdrv_fwdtree(const char *hmmdir, const char *lm, const char *dictfile, const c
             len += snprintf(vocab + len, len < vocab_cap ? vocab_cap - len : 0, "%s\n", dict_wordstr(dict, w));
     }
     /* the flattening itself is the maintainer-side binding: integration/ps_search_cuda.c */
-    if (cuda_ngram_export(ngs, &g) != 0) { ps_free(ps); ps_config_free(config); return -3; }
+    if (cuda_ngram_export(ngs, &g, dense_lm) != 0) { ps_free(ps); ps_config_free(config); return -3; }
     need = (long)g.model_len + (long)ngs->bpidx * 10 + ngs->bss_head + ngs->n_frame + 1;
     memcpy(info, g.info, 40 * sizeof(int32));
     info[0] = ngs->n_frame; info[24] = ngs->bpidx; info[25] = ngs->bss_head; info[27] = score;
@@ -1448,4 +1448,27 @@ refdrv_ngram_roundtrip(const char *hmmdir, const char *lm, const char *dictfile,
     ps_free(ps);
     ps_config_free(config);
     return rv;
+}
+
+/* The language model behind an n-gram search as sorted arrays (cuda_ngram_export_lm), plus a sample of
+ * the reference's own scores for checking: for every (w, h1, h2) in `q` [n_q][3] (dictionary word ids, -1 =
+ * no history) ngram_tg_score(lmset, w, h1, h2) >> SENSCR_SHIFT is written to scores[n_q]. */
+long
+refdrv_lm_arrays(const char *hmmdir, const char *lm, const char *dictfile, const char *kv, int32 *out, long cap,
+                 const int32 *q, long n_q, int32 *scores)
+{
+    ps_config_t *config;
+    ps_decoder_t *ps;
+    ngram_search_t *ngs;
+    long need, i;
+    if ((ps = ngram_decoder(hmmdir, lm, dictfile, kv, &config)) == NULL) return -1;
+    ngs = (ngram_search_t *)ps->search;
+    need = cuda_ngram_export_lm(ngs, out, cap);
+    for (i = 0; i < n_q && scores; ++i) {
+        int32 n_used;
+        scores[i] = ngram_tg_score(ngs->lmset, q[i * 3], q[i * 3 + 1], q[i * 3 + 2], &n_used) >> SENSCR_SHIFT;
+    }
+    ps_free(ps);
+    ps_config_free(config);
+    return need;
 }

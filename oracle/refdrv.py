@@ -411,7 +411,7 @@ def fsg(hmmdir, dictfile, fsgfile, pcm, **kv):
                 vocab=vocab.value.decode().split("\n")[:-1])
 
 
-def fwdtree(hmmdir, lm, dictfile, pcm, **kv):
+def fwdtree(hmmdir, lm, dictfile, pcm, dense_lm=True, **kv):
     """The reference's first pass (ngram_search_fwdtree; no fwdflat / bestpath / look-ahead) on one
     utterance: the flattened lextree, dictionary and dict2pid tables, the LM as a dense trigram score
     table, the search parameters, and the complete backpointer table + right-context score stack."""
@@ -420,16 +420,16 @@ def fwdtree(hmmdir, lm, dictfile, pcm, **kv):
     L = lib()
     L.refdrv_fwdtree.restype = C.c_long
     L.refdrv_fwdtree.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_long, C.c_void_p,
-                                 C.c_long, C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+                                 C.c_long, C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int]
     info = np.zeros(40, np.int32)
     hyp = C.create_string_buffer(4096)
-    vocab = C.create_string_buffer(1 << 20)
+    vocab = C.create_string_buffer(1 << 22)
     args = (hmmdir.encode(), lm.encode(), dictfile.encode(), s, _p(pcm), len(pcm))
-    need = L.refdrv_fwdtree(*args, None, 0, _p(info), hyp, 4096, None, 0)
+    need = L.refdrv_fwdtree(*args, None, 0, _p(info), hyp, 4096, None, 0, int(dense_lm))
     if need < 0:
         raise RuntimeError("refdrv_fwdtree failed: %d" % need)
     blob = np.zeros(need, np.int32)
-    if L.refdrv_fwdtree(*args, _p(blob), need, _p(info), hyp, 4096, vocab, 1 << 20) != need:
+    if L.refdrv_fwdtree(*args, _p(blob), need, _p(info), hyp, 4096, vocab, 1 << 22, int(dense_lm)) != need:
         raise RuntimeError("refdrv_fwdtree: inconsistent size")
     keys = ("n_frame n_words n_root n_nonroot n_1ph_words n_1ph_LMwords n_ci sil beam pbeam wbeam lpbeam lponlybeam "
             "maxhmmpf maxwpf nwpen pip silpen fillpen start_wid finish_wid silence_wid filler_start filler_end bpidx "
@@ -498,3 +498,22 @@ def ngram_roundtrip(hmmdir, lm, dictfile, pcm, bp, bss, bp_idx, **kv):
     if n < 0:
         raise RuntimeError("refdrv_ngram_roundtrip failed: %d" % n)
     return dict(hyp=hyp.value.decode(), score=int(score[0]), seg=seg.value.decode(), n_entries=int(n))
+
+
+def lm_arrays(hmmdir, lm, dictfile, queries=None, **kv):
+    """The LM behind an n-gram search as sorted arrays (integration/ps_search_cuda.c:cuda_ngram_export_lm) and
+    the reference's own ngram_tg_score(...) >> SENSCR_SHIFT for `queries` [n][3] = (w, h1, h2) dictionary ids."""
+    s = "\n".join("%s=%s" % (k, v) for k, v in kv.items()).encode() or None
+    L = lib()
+    L.refdrv_lm_arrays.restype = C.c_long
+    L.refdrv_lm_arrays.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long,
+                                   C.c_void_p]
+    need = L.refdrv_lm_arrays(hmmdir.encode(), lm.encode(), dictfile.encode(), s, None, 0, None, 0, None)
+    if need < 0:
+        raise RuntimeError("refdrv_lm_arrays failed: %d" % need)
+    arr = np.zeros(need, np.int32)
+    q = np.zeros((0, 3), np.int32) if queries is None else np.ascontiguousarray(queries, np.int32)
+    scores = np.zeros(len(q), np.int32)
+    if L.refdrv_lm_arrays(hmmdir.encode(), lm.encode(), dictfile.encode(), s, _p(arr), need, _p(q), len(q), _p(scores)) != need:
+        raise RuntimeError("refdrv_lm_arrays: inconsistent size")
+    return arr, scores

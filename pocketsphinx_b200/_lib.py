@@ -46,7 +46,7 @@ class FsgDesc(C.Structure):
 
 class NgramDesc(C.Structure):
     _fields_ = [("info", C.c_void_p), ("model", C.c_void_p), ("model_len", C.c_int64), ("ci_tmat", C.c_void_p),
-                ("ci_ssid", C.c_void_p)]
+                ("ci_ssid", C.c_void_p), ("lm_arrays", C.c_void_p), ("lm_arrays_len", C.c_int64)]
 
 
 SYMBOLS = [

@@ -302,7 +302,7 @@ class HmmContext:
                                          int(cap), _p(n_hist)), "psb_fsg_batch_device")
         return [hist[u, :min(int(n_hist[u]), int(cap))] for u in range(n_utt)], n_hist[:n_utt]
 
-    def ngram_fwdtree(self, d_senscr_ptr, utt_off, info, model, ci_tmat, bp_cap, bss_cap, d_pen_ptr=None, pl_window=0):
+    def ngram_fwdtree(self, d_senscr_ptr, utt_off, info, model, ci_tmat, bp_cap, bss_cap, d_pen_ptr=None, pl_window=0, lm_arrays=None):
         """ngram_search_fwdtree over a batch (flattened search `info` / `model`, see include/psb200.h).
         d_pen_ptr / pl_window: the phone loop's device penalty table and its window (look-ahead).
         Returns per utterance (bp table [n][10], bscore_stack, bp_table_idx [T+1])."""
@@ -311,7 +311,9 @@ class HmmContext:
         n_utt = len(utt_off) - 1
         info = np.ascontiguousarray(info, np.int32); model = np.ascontiguousarray(model, np.int32)
         ci_tmat = np.ascontiguousarray(ci_tmat, np.int32)
-        d = NgramDesc(info.ctypes.data, model.ctypes.data, len(model), ci_tmat.ctypes.data, None)
+        lma = None if lm_arrays is None else np.ascontiguousarray(lm_arrays, np.int32)
+        d = NgramDesc(info.ctypes.data, model.ctypes.data, len(model), ci_tmat.ctypes.data, None,
+                      None if lma is None else lma.ctypes.data, 0 if lma is None else len(lma))
         bp = np.zeros((max(n_utt, 1), int(bp_cap), 10), np.int32)
         bss = np.zeros((max(n_utt, 1), int(bss_cap)), np.int32)
         bp_idx = np.zeros(int(utt_off[-1]) + max(n_utt, 1), np.int32)
@@ -327,7 +329,7 @@ class HmmContext:
             out.append((bp[u, :res[u, 0]].copy(), bss[u, :res[u, 1]].copy(), bp_idx[o:o + T + 1].copy()))
         return out
 
-    def ngram_fwdflat(self, d_senscr_ptr, utt_off, info, model, ci_tmat, ci_ssid, first_tables, bp_cap, bss_cap):
+    def ngram_fwdflat(self, d_senscr_ptr, utt_off, info, model, ci_tmat, ci_ssid, first_tables, bp_cap, bss_cap, lm_arrays=None):
         """ngram_search_fwdflat over a batch; first_tables = the first pass's bp table of every utterance.
         Returns per utterance (bp table [n][10], bscore_stack, bp_table_idx [T+1])."""
         from ._lib import NgramDesc
@@ -335,7 +337,9 @@ class HmmContext:
         n_utt = len(utt_off) - 1
         info = np.ascontiguousarray(info, np.int32); model = np.ascontiguousarray(model, np.int32)
         ci_tmat = np.ascontiguousarray(ci_tmat, np.int32); ci_ssid = np.ascontiguousarray(ci_ssid, np.int32)
-        d = NgramDesc(info.ctypes.data, model.ctypes.data, len(model), ci_tmat.ctypes.data, ci_ssid.ctypes.data)
+        lma = None if lm_arrays is None else np.ascontiguousarray(lm_arrays, np.int32)
+        d = NgramDesc(info.ctypes.data, model.ctypes.data, len(model), ci_tmat.ctypes.data, ci_ssid.ctypes.data,
+                      None if lma is None else lma.ctypes.data, 0 if lma is None else len(lma))
         cap_in = max([len(t) for t in first_tables] + [1])
         first = np.zeros((max(n_utt, 1), cap_in, 10), np.int32)
         n_first = np.zeros(max(n_utt, 1), np.int32)
@@ -357,7 +361,7 @@ class HmmContext:
         return out
 
     def ngram_two_pass(self, d_senscr_ptr, utt_off, info, model, ci_tmat, ci_ssid, bp_cap, bss_cap, d_pen_ptr=None, pl_window=0,
-                       first_cap=None, first_bss_cap=None):
+                       first_cap=None, first_bss_cap=None, lm_arrays=None):
         """Both n-gram passes back to back on the device (first-pass tables never leave it).  Returns per
         utterance (bp table, bscore_stack, bp_table_idx) of the second pass, and the first pass's entry counts."""
         from ._lib import NgramDesc
@@ -365,7 +369,9 @@ class HmmContext:
         n_utt = len(utt_off) - 1
         info = np.ascontiguousarray(info, np.int32); model = np.ascontiguousarray(model, np.int32)
         ci_tmat = np.ascontiguousarray(ci_tmat, np.int32); ci_ssid = np.ascontiguousarray(ci_ssid, np.int32)
-        d = NgramDesc(info.ctypes.data, model.ctypes.data, len(model), ci_tmat.ctypes.data, ci_ssid.ctypes.data)
+        lma = None if lm_arrays is None else np.ascontiguousarray(lm_arrays, np.int32)
+        d = NgramDesc(info.ctypes.data, model.ctypes.data, len(model), ci_tmat.ctypes.data, ci_ssid.ctypes.data,
+                      None if lma is None else lma.ctypes.data, 0 if lma is None else len(lma))
         bp = np.zeros((max(n_utt, 1), int(bp_cap), 10), np.int32)
         bss = np.zeros((max(n_utt, 1), int(bss_cap)), np.int32)
         bp_idx = np.zeros(int(utt_off[-1]) + max(n_utt, 1), np.int32)

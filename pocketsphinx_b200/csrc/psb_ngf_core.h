@@ -31,6 +31,8 @@ struct NgfGraph {
     const int32_t *tmatid;     // [M]
     const int32_t *senid;      // [M][n_emit]  non-multiplexed channels
     const int32_t *root_ssid;  // [n_words]    senone sequence a root starts from (its CI phone's)
+    int use_lma;               // 1: trigram scores from the sorted-array LM below instead of the dense table `lm`
+    LmArr lma;
 };
 
 struct NgfWork {
@@ -86,6 +88,7 @@ FSG_HD void ngf_enter(const NgfWork &W, int c, int score, int hist, int nf) { W.
 
 FSG_HD int ngf_tg(const NgfGraph &G, int w, int h1, int h2)
 {
+    if (G.use_lma) return lm_tg_score(G.lma, w, h1, h2) >> 10;           /* >> SENSCR_SHIFT */
     const int n = G.n_lm + 1;
     const int a = NGS_W(G, w, 7), b = h1 < 0 ? 0 : NGS_W(G, h1, 7) + 1, c = h2 < 0 ? 0 : NGS_W(G, h2, 7) + 1;
     return G.lm[((size_t)a * n + b) * n + c];

@@ -8,17 +8,21 @@
 struct NgfFlat {
     std::vector<int32_t> buf;
     NgfGraph G;
-    size_t o_words, o_rs_n, o_rs_cimap, o_ldiph, o_lm, o_inlm, o_pron_off, o_pron_ci, o_ch_off, o_n_int, o_tmatid, o_senid, o_root_ssid;
+    size_t o_words, o_rs_n, o_rs_cimap, o_ldiph, o_lm, o_inlm, o_pron_off, o_pron_ci, o_ch_off, o_n_int, o_tmatid, o_senid, o_root_ssid, o_lma;
+    int32_t lma_hdr[10];
 };
 
 static inline int
-ngf_flatten(const int32_t *info, const int32_t *model, long long model_len, const int32_t *ci_tmat, const int32_t *ci_ssid, const uint16_t *sseq,
-            int n_sseq, int n_emit, int n_tmat, int n_sen, NgfFlat &o, std::string &err)
+ngf_flatten(const int32_t *info, const int32_t *model, long long model_len, const int32_t *lm_arrays, long long lm_arrays_len,
+            const int32_t *ci_tmat, const int32_t *ci_ssid, const uint16_t *sseq, int n_sseq, int n_emit, int n_tmat, int n_sen, NgfFlat &o,
+            std::string &err)
 {
     NgfGraph &G = o.G;
     memset(&G, 0, sizeof(G));
     const int n_words = info[1], n_root = info[2], n_nonroot = info[3], n_1ph = info[4], n_ci = info[6], n_lm = info[26], n_pron = info[33];
-    if (n_words <= 0 || n_ci <= 0 || n_lm <= 0 || n_pron <= 0) NGS_FAIL("ngram search: empty tables");
+    G.use_lma = lm_arrays != nullptr;
+    if (n_words <= 0 || n_ci <= 0 || n_lm < 0 || (n_lm == 0 && !G.use_lma) || n_pron <= 0) NGS_FAIL("ngram search: empty tables");
+    if (G.use_lma && lm_arr_check(lm_arrays, lm_arrays_len, n_words, err) != 0) return -1;
     G.n_words = n_words; G.n_1ph = n_1ph; G.n_ci = n_ci; G.sil = info[7]; G.n_lm = n_lm; G.n_emit = n_emit;
     G.beam = info[8]; G.fwdflatbeam = info[28]; G.fwdflatwbeam = info[29]; G.min_ef_width = info[30]; G.max_sf_win = info[31];
     memcpy(&G.lwf, &info[32], 4);
@@ -53,7 +57,7 @@ ngf_flatten(const int32_t *info, const int32_t *model, long long model_len, cons
         const int32_t *r = words + (size_t)w * 8;
         const int len = pron_off[w + 1] - pron_off[w];
         if (len <= 0 || r[0] < 0 || r[0] >= n_ci || r[1] < 0 || r[1] >= n_ci || r[2] < -1 || r[2] >= n_ci) NGS_FAIL("word %d: pronunciation out of range", w);
-        if (r[5] < 0 || r[5] >= n_words || r[7] < -1 || r[7] >= n_lm) NGS_FAIL("word %d: id out of range", w);
+        if (r[5] < 0 || r[5] >= n_words || r[7] < -1 || (!G.use_lma && r[7] >= n_lm)) NGS_FAIL("word %d: id out of range", w);
         if ((len == 1) != (r[3] != 0)) NGS_FAIL("word %d: single-phone flag disagrees with its pronunciation", w);
         int n = 0;
         if (r[3]) n = 1;
@@ -68,7 +72,7 @@ ngf_flatten(const int32_t *info, const int32_t *model, long long model_len, cons
         root_ssid[(size_t)w] = ci_ssid[r[0]];
     }
     for (int w = 0; w < n_words; ++w)
-        if (words[(size_t)w * 8 + 7] < 0 && words[(size_t)words[(size_t)w * 8 + 5] * 8 + 7] < 0) NGS_FAIL("word %d: base word has no LM index", w);
+        if (!G.use_lma && words[(size_t)w * 8 + 7] < 0 && words[(size_t)words[(size_t)w * 8 + 5] * 8 + 7] < 0) NGS_FAIL("word %d: base word has no LM index", w);
     if (!words[(size_t)G.start_wid * 8 + 3] || !words[(size_t)G.silence_wid * 8 + 3]) NGS_FAIL("<s> / <sil> must be single-phone words");
     G.M = ch_off[(size_t)n_words]; G.LW = n_words + 2;
     std::vector<int32_t> tmatid((size_t)G.M, 0), senid((size_t)G.M * n_emit, NGS_BAD_SSID);
@@ -112,6 +116,8 @@ ngf_flatten(const int32_t *info, const int32_t *model, long long model_len, cons
     o.o_ch_off = put(ch_off.data(), ch_off.size()); o.o_n_int = put(n_int.data(), n_int.size());
     o.o_tmatid = put(tmatid.data(), tmatid.size()); o.o_senid = put(senid.data(), senid.size());
     o.o_root_ssid = put(root_ssid.data(), root_ssid.size());
+    o.o_lma = b.size();
+    if (G.use_lma) { put(lm_arrays, (size_t)lm_arrays_len); memcpy(o.lma_hdr, lm_arrays, sizeof(o.lma_hdr)); }
     b.push_back(0);
     return 0;
 }
@@ -120,6 +126,7 @@ static inline void
 ngf_bind(NgfFlat &o, const int32_t *base)
 {
     NgfGraph &G = o.G;
+    if (G.use_lma) lm_arr_bind(G.lma, o.lma_hdr, base + o.o_lma);
     G.words = base + o.o_words; G.rs_n = base + o.o_rs_n; G.rs_cimap = base + o.o_rs_cimap; G.ldiph = base + o.o_ldiph;
     G.lm = base + o.o_lm; G.inlm = base + o.o_inlm; G.pron_off = base + o.o_pron_off; G.pron_ci = base + o.o_pron_ci;
     G.ch_off = base + o.o_ch_off; G.n_int = base + o.o_n_int; G.tmatid = base + o.o_tmatid; G.senid = base + o.o_senid;

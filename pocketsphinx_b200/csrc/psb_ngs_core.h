@@ -31,6 +31,7 @@
 //    entries, then independent root / single-phone-word entries.
 #pragma once
 #include "psb_fsg_core.h"
+#include "psb_lm_core.h"
 
 #define NGS_BAD_SSID 0xffff
 #define NGS_BP_ROW 10        /* frame, valid, wid, bp, score, s_idx, real_wid, prev_real_wid, last_phone, last2_phone */
@@ -51,6 +52,8 @@ struct NgsGraph {
     const int32_t *parent;     // [n_nonroot]   parent non-root id, or -(root id) - 1
     const int32_t *tmatid;     // [M]
     const int32_t *senid;      // [M][n_emit]   senones of the non-multiplexed channels (non-roots, fan-out)
+    int use_lma;               // 1: trigram scores from the sorted-array LM below instead of the dense table `lm`
+    LmArr lma;
 };
 
 struct NgsWork {
@@ -123,6 +126,7 @@ FSG_HD void ngs_enter(const NgsWork &W, int c, int score, int hist, int nf)     
 
 FSG_HD int ngs_tg(const NgsGraph &G, int w, int h1, int h2)
 {
+    if (G.use_lma) return lm_tg_score(G.lma, w, h1, h2) >> 10;           /* >> SENSCR_SHIFT */
     const int n = G.n_lm + 1;
     const int a = NGS_W(G, w, 7), b = h1 < 0 ? 0 : NGS_W(G, h1, 7) + 1, c = h2 < 0 ? 0 : NGS_W(G, h2, 7) + 1;
     return G.lm[((size_t)a * n + b) * n + c];

@@ -14,15 +14,45 @@ struct NgsFlat {
     std::vector<int32_t> buf;
     NgsGraph G;                 // pointers are offsets into buf until ngs_bind()
     size_t o_roots, o_nonroot, o_words, o_w1ph, o_r1ph, o_rs_n, o_rs_ssid, o_rs_cimap, o_ldiph, o_lm, o_wc_off, o_w2h1,
-           o_parent, o_tmatid, o_senid;
+           o_parent, o_tmatid, o_senid, o_lma;
+    int32_t lma_hdr[10];
 };
 
 #define NGS_FAIL(...) do { char b_[256]; snprintf(b_, sizeof b_, __VA_ARGS__); err = b_; return -1; } while (0)
 
+// The optional array LM (psb_lm_core.h): bounds, so that the device's searches cannot leave the block
+// (ranges need not be sorted: shipped models contain unsorted ones and the search is the reference's own).
+static inline int
+lm_arr_check(const int32_t *a, long long len, int n_words, std::string &err)
+{
+    if (len < 10) NGS_FAIL("LM arrays: block too short");
+    const long long order = a[0], V = a[1], n2 = a[2], n3 = a[3];
+    if (order < 1 || order > 3 || V <= 0 || n2 < 0 || n3 < 0 || a[7] != n_words) NGS_FAIL("LM arrays: bad header (order %lld, %lld unigrams, %d words)", order, V, a[7]);
+    if ((long long)lm_arr_words(a) != len) NGS_FAIL("LM arrays: block holds %lld words, its header needs %zu", len, lm_arr_words(a));
+    if ((order < 2 && n2 != 0) || (order < 3 && n3 != 0)) NGS_FAIL("LM arrays: n-gram counts do not fit the order");
+    LmArr L;
+    lm_arr_bind(L, a, a);
+    for (int w = 0; w < n_words; ++w) if (L.widmap[w] < -1 || L.widmap[w] >= V) NGS_FAIL("LM arrays: widmap[%d] out of range", w);
+    if (L.uni_next[0] != 0 || L.uni_next[V] < 0 || L.uni_next[V] > n2) NGS_FAIL("LM arrays: unigram ranges leave the bigram array");
+    const long long n2_used = L.uni_next[V];            /* (the header may count a few more than the trie links) */
+    for (long long w = 0; w < V; ++w) {
+        if (L.uni_next[w + 1] < L.uni_next[w]) NGS_FAIL("LM arrays: unigram ranges not monotone");
+        for (int p = L.uni_next[w]; p < L.uni_next[w + 1]; ++p)
+            if (L.bg_word[p] < 0 || L.bg_word[p] >= V) NGS_FAIL("LM arrays: bigrams of word %lld out of range", w);
+    }
+    if (n2_used > 0 && (L.bg_next[0] != 0 || L.bg_next[n2_used] < 0 || L.bg_next[n2_used] > n3)) NGS_FAIL("LM arrays: bigram ranges leave the trigram array");
+    for (long long b = 0; b < n2_used; ++b) {
+        if (L.bg_next[b + 1] < L.bg_next[b]) NGS_FAIL("LM arrays: bigram ranges not monotone");
+        for (int p = L.bg_next[b]; p < L.bg_next[b + 1]; ++p)
+            if (L.tg_word[p] < 0 || L.tg_word[p] >= V) NGS_FAIL("LM arrays: trigrams of bigram %lld out of range", b);
+    }
+    return 0;
+}
+
 // info[40] + model sections as exported; ci_tmat[n_ci]; sseq [n_sseq][n_emit].
 static inline int
-ngs_flatten(const int32_t *info, const int32_t *model, long long model_len, const int32_t *ci_tmat, const uint16_t *sseq, int n_sseq, int n_emit,
-            int n_tmat, int n_sen, NgsFlat &o, std::string &err)
+ngs_flatten(const int32_t *info, const int32_t *model, long long model_len, const int32_t *lm_arrays, long long lm_arrays_len,
+            const int32_t *ci_tmat, const uint16_t *sseq, int n_sseq, int n_emit, int n_tmat, int n_sen, NgsFlat &o, std::string &err)
 {
     NgsGraph &G = o.G;
     memset(&G, 0, sizeof(G));
@@ -31,7 +61,9 @@ ngs_flatten(const int32_t *info, const int32_t *model, long long model_len, cons
     G.lponlybeam = info[12]; G.maxhmmpf = info[13]; G.maxwpf = info[14]; G.nwpen = info[15]; G.pip = info[16];
     G.silpen = info[17]; G.fillpen = info[18]; G.start_wid = info[19]; G.finish_wid = info[20]; G.silence_wid = info[21];
     G.filler_start = info[22]; G.filler_end = info[23]; G.n_lm = info[26]; G.n_emit = n_emit;
-    if (G.n_words <= 0 || G.n_root < 0 || G.n_nonroot < 0 || G.n_1ph <= 0 || G.n_ci <= 0 || G.n_lm <= 0) NGS_FAIL("ngram search: empty tables");
+    G.use_lma = lm_arrays != nullptr;
+    if (G.n_words <= 0 || G.n_root < 0 || G.n_nonroot < 0 || G.n_1ph <= 0 || G.n_ci <= 0 || G.n_lm < 0 || (G.n_lm == 0 && !G.use_lma)) NGS_FAIL("ngram search: empty tables");
+    if (G.use_lma && lm_arr_check(lm_arrays, lm_arrays_len, G.n_words, err) != 0) return -1;
     if (G.n_1ph_lm > G.n_1ph) NGS_FAIL("ngram search: n_1ph_LMwords > n_1ph_words");
     const size_t nc = (size_t)G.n_ci;
     if (G.n_ci > 256 || G.n_lm > 512) NGS_FAIL("ngram search: %d phones / %d LM words exceed what the dense tables are meant for (256 / 512)", G.n_ci, G.n_lm);
@@ -58,7 +90,7 @@ ngs_flatten(const int32_t *info, const int32_t *model, long long model_len, cons
     for (int w = 0; w < G.n_words; ++w) {
         const int32_t *r = words + (size_t)w * 8;
         if (r[0] < 0 || r[0] >= G.n_ci || r[1] < 0 || r[1] >= G.n_ci || r[2] < -1 || r[2] >= G.n_ci) NGS_FAIL("word %d: phone out of range", w);
-        if (r[6] < -1 || r[6] >= G.n_words || r[5] < 0 || r[5] >= G.n_words || r[7] < -1 || r[7] >= G.n_lm) NGS_FAIL("word %d: id out of range", w);
+        if (r[6] < -1 || r[6] >= G.n_words || r[5] < 0 || r[5] >= G.n_words || r[7] < -1 || (!G.use_lma && r[7] >= G.n_lm)) NGS_FAIL("word %d: id out of range", w);
         int n = 0;
         if (!r[3]) {
             if (r[2] < 0) NGS_FAIL("word %d: multi-phone word without a second-last phone", w);
@@ -68,7 +100,7 @@ ngs_flatten(const int32_t *info, const int32_t *model, long long model_len, cons
         wc_off[(size_t)w + 1] = wc_off[(size_t)w] + n;
     }
     for (int w = 0; w < G.n_words; ++w)
-        if (words[(size_t)w * 8 + 7] < 0 && words[(size_t)words[(size_t)w * 8 + 5] * 8 + 7] < 0) NGS_FAIL("word %d: base word has no LM index", w);
+        if (!G.use_lma && words[(size_t)w * 8 + 7] < 0 && words[(size_t)words[(size_t)w * 8 + 5] * 8 + 7] < 0) NGS_FAIL("word %d: base word has no LM index", w);
     G.n_rcchan = wc_off[(size_t)G.n_words];
     for (int i = 0; i < G.n_1ph; ++i) {
         if (!wid_ok(w1ph[i]) || !words[(size_t)w1ph[i] * 8 + 3]) NGS_FAIL("single-phone word list entry %d is not a single-phone word", i);
@@ -147,6 +179,8 @@ ngs_flatten(const int32_t *info, const int32_t *model, long long model_len, cons
     o.o_wc_off = put(wc_off.data(), wc_off.size()); o.o_w2h1 = put(w2h1.data(), w2h1.size());
     o.o_parent = put(parent.data(), parent.size()); o.o_tmatid = put(tmatid.data(), tmatid.size());
     o.o_senid = put(senid.data(), senid.size());
+    o.o_lma = b.size();
+    if (G.use_lma) { put(lm_arrays, (size_t)lm_arrays_len); memcpy(o.lma_hdr, lm_arrays, sizeof(o.lma_hdr)); }
     b.push_back(0);
     return 0;
 }
@@ -155,6 +189,7 @@ static inline void
 ngs_bind(NgsFlat &o, const int32_t *base)
 {
     NgsGraph &G = o.G;
+    if (G.use_lma) lm_arr_bind(G.lma, o.lma_hdr, base + o.o_lma);
     G.roots = base + o.o_roots; G.nonroot = base + o.o_nonroot; G.words = base + o.o_words; G.w1ph = base + o.o_w1ph;
     G.r1ph = base + o.o_r1ph; G.rs_n = base + o.o_rs_n; G.rs_ssid = base + o.o_rs_ssid; G.rs_cimap = base + o.o_rs_cimap;
     G.ldiph = base + o.o_ldiph; G.lm = base + o.o_lm; G.wc_off = base + o.o_wc_off; G.w2h1 = base + o.o_w2h1;

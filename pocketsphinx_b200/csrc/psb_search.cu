@@ -311,7 +311,7 @@ extern "C" int psb_ngram_fwdtree_batch_device(psb_hmmctx_t *c, const psb_ngram_d
     PSB_CUDA(cudaMemcpy(sseq.data(), c->d_sseq, sseq.size() * 2, cudaMemcpyDeviceToHost));
     NgsFlat flat;
     std::string err;
-    if (ngs_flatten(g->info, g->model, (long long)g->model_len, g->ci_tmat, sseq.data(), c->n_sseq, N, c->n_tmat, c->n_sen, flat, err) != 0) {
+    if (ngs_flatten(g->info, g->model, (long long)g->model_len, g->lm_arrays, (long long)g->lm_arrays_len, g->ci_tmat, sseq.data(), c->n_sseq, N, c->n_tmat, c->n_sen, flat, err) != 0) {
         psb_set_error("psb_ngram_fwdtree_batch_device: %s", err.c_str());
         return PSB_ERR_ARG;
     }
@@ -445,7 +445,7 @@ extern "C" int psb_ngram_fwdflat_batch_device(psb_hmmctx_t *c, const psb_ngram_d
     PSB_CUDA(cudaMemcpy(sseq.data(), c->d_sseq, sseq.size() * 2, cudaMemcpyDeviceToHost));
     NgfFlat flat;
     std::string err;
-    if (ngf_flatten(g->info, g->model, (long long)g->model_len, g->ci_tmat, g->ci_ssid, sseq.data(), c->n_sseq, N, c->n_tmat, c->n_sen, flat, err) != 0) {
+    if (ngf_flatten(g->info, g->model, (long long)g->model_len, g->lm_arrays, (long long)g->lm_arrays_len, g->ci_tmat, g->ci_ssid, sseq.data(), c->n_sseq, N, c->n_tmat, c->n_sen, flat, err) != 0) {
         psb_set_error("psb_ngram_fwdflat_batch_device: %s", err.c_str());
         return PSB_ERR_ARG;
     }
@@ -524,8 +524,8 @@ extern "C" int psb_ngram_two_pass_batch_device(psb_hmmctx_t *c, const psb_ngram_
     NgsFlat f1;
     NgfFlat f2;
     std::string err;
-    if (ngs_flatten(g->info, g->model, (long long)g->model_len, g->ci_tmat, sseq.data(), c->n_sseq, N, c->n_tmat, c->n_sen, f1, err) != 0 ||
-        ngf_flatten(g->info, g->model, (long long)g->model_len, g->ci_tmat, g->ci_ssid, sseq.data(), c->n_sseq, N, c->n_tmat, c->n_sen, f2, err) != 0) {
+    if (ngs_flatten(g->info, g->model, (long long)g->model_len, g->lm_arrays, (long long)g->lm_arrays_len, g->ci_tmat, sseq.data(), c->n_sseq, N, c->n_tmat, c->n_sen, f1, err) != 0 ||
+        ngf_flatten(g->info, g->model, (long long)g->model_len, g->lm_arrays, (long long)g->lm_arrays_len, g->ci_tmat, g->ci_ssid, sseq.data(), c->n_sseq, N, c->n_tmat, c->n_sen, f2, err) != 0) {
         psb_set_error("psb_ngram_two_pass_batch_device: %s", err.c_str());
         return PSB_ERR_ARG;
     }

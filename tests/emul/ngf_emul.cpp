@@ -10,13 +10,14 @@ typedef OracleChanEval<NgfGraph, NgfWork> OracleEval;
 
 extern "C" int32_t
 ngf_emul_run(int32_t n_emit_state, const uint8_t *tp, int32_t n_tmat, const uint16_t *sseq, int32_t n_sseq, const int32_t *ci_tmat,
-             const int32_t *ci_ssid, const int32_t *info, const int32_t *model, int64_t model_len, const int32_t *bp_in, int32_t n_bp_in,
+             const int32_t *ci_ssid, const int32_t *info, const int32_t *model, int64_t model_len, const int32_t *lm_arrays, int64_t lm_arrays_len,
+             const int32_t *bp_in, int32_t n_bp_in,
              const int16_t *senscr, int32_t n_sen, int32_t T,
              int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap, int32_t *bss_n, int32_t *bp_idx_out)
 {
     NgfFlat flat;
     std::string err;
-    if (ngf_flatten(info, model, model_len, ci_tmat, ci_ssid, sseq, n_sseq, n_emit_state, n_tmat, n_sen, flat, err) != 0) {
+    if (ngf_flatten(info, model, model_len, lm_arrays, lm_arrays_len, ci_tmat, ci_ssid, sseq, n_sseq, n_emit_state, n_tmat, n_sen, flat, err) != 0) {
         fprintf(stderr, "%s\n", err.c_str());
         return -1;
     }

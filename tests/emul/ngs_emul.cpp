@@ -11,12 +11,13 @@ typedef OracleChanEval<NgsGraph, NgsWork> OracleEval;
 
 extern "C" int32_t
 ngs_emul_run(int32_t n_emit_state, const uint8_t *tp, int32_t n_tmat, const uint16_t *sseq, int32_t n_sseq, const int32_t *ci_tmat,
-             const int32_t *info, const int32_t *model, int64_t model_len, const int16_t *senscr, int32_t n_sen, int32_t T,
+             const int32_t *info, const int32_t *model, int64_t model_len, const int32_t *lm_arrays, int64_t lm_arrays_len,
+             const int16_t *senscr, int32_t n_sen, int32_t T,
              const int32_t *pen, int32_t pl_window, int32_t *bp_out, int32_t bp_cap, int32_t *bss_out, int32_t bss_cap, int32_t *bss_n, int32_t *bp_idx_out)
 {
     NgsFlat flat;
     std::string err;
-    if (ngs_flatten(info, model, model_len, ci_tmat, sseq, n_sseq, n_emit_state, n_tmat, n_sen, flat, err) != 0) {
+    if (ngs_flatten(info, model, model_len, lm_arrays, lm_arrays_len, ci_tmat, sseq, n_sseq, n_emit_state, n_tmat, n_sen, flat, err) != 0) {
         fprintf(stderr, "%s\n", err.c_str());
         return -1;
     }

@@ -211,3 +211,26 @@ def test_two_pass_chained_on_the_device(api, en_us, tag):
         bp, bss, idx = out[u]
         assert np.array_equal(bp, c["bp"]) and np.array_equal(bss, c["bss"]) and np.array_equal(idx, c["bp_idx"]), u
     ctx.close()
+
+
+@pytest.mark.timeout(300)
+def test_two_pass_with_the_array_lm(api, en_us):
+    """LM as arrays on the device (psb_lm_core.h: the reference's interpolation search + float backoff sums),
+    model block exported without the dense table."""
+    import torch
+    gf = golden("en_us_goforward.npz")
+    g = golden("en_us_fwdtree.npz")
+    scr = gf["senscr"]
+    want = _case(g, "flat_default")
+    n_ci = int(want["info"][6])
+    U = 3
+    utt_off = (np.arange(U + 1) * len(scr)).astype(np.int32)
+    d_scr = torch.from_numpy(np.ascontiguousarray(np.tile(scr, (U, 1)))).cuda()
+    d_pen = torch.from_numpy(np.ascontiguousarray(np.tile(gf["pl_pen"].astype(np.int32), (U, 1)))).cuda()
+    ctx = api.HmmContext(en_us.tp, en_us.sseq, en_us.n_sen)
+    out, _ = ctx.ngram_two_pass(d_scr.data_ptr(), utt_off, g["nodense.info"], g["nodense.model"], en_us.phone_tmat[:n_ci],
+                                en_us.phone_ssid[:n_ci], len(want["bp"]) + 64, len(want["bss"]) + 4096, d_pen.data_ptr(),
+                                int(gf["pl_params"][4]), first_cap=8192, first_bss_cap=1 << 18, lm_arrays=g["lmarr"])
+    for u in range(U):
+        assert np.array_equal(out[u][0], want["bp"]) and np.array_equal(out[u][1], want["bss"]) and np.array_equal(out[u][2], want["bp_idx"])
+    ctx.close()

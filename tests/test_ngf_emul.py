@@ -13,7 +13,7 @@ from conftest import ROOT, golden
 from test_ngs_emul import run_emul as run_first
 
 TAGS = ("flat_default", "flat_wide", "flat_narrow")
-ARGT = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+ARGT = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
         C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
 
 
@@ -48,7 +48,7 @@ def emuls(request, tmp_path_factory):
     return f1, f2
 
 
-def run_second(f, m, info, model, bp1, scr, bp_cap, bss_cap):
+def run_second(f, m, info, model, bp1, scr, bp_cap, bss_cap, lm_arrays=None):
     tp = np.ascontiguousarray(m["tp"], np.uint8)
     sseq = np.ascontiguousarray(m["sseq"], np.uint16)
     info = np.ascontiguousarray(info, np.int32)
@@ -60,11 +60,12 @@ def run_second(f, m, info, model, bp1, scr, bp_cap, bss_cap):
     bp1 = np.zeros((1, 10), np.int32) if bp1 is None else np.ascontiguousarray(bp1, np.int32)
     scr = np.ascontiguousarray(scr, np.int16)
     T = len(scr)
+    lma = None if lm_arrays is None else np.ascontiguousarray(lm_arrays, np.int32)
     bp = np.zeros((bp_cap, 10), np.int32)
     bss = np.zeros(bss_cap, np.int32)
     idx = np.zeros(T + 2, np.int32)
     bn = C.c_int32()
-    n = f(tp.shape[1], _p(tp), tp.shape[0], _p(sseq), len(sseq), _p(cit), _p(cis), _p(info), _p(model), len(model), _p(bp1), n1,
+    n = f(tp.shape[1], _p(tp), tp.shape[0], _p(sseq), len(sseq), _p(cit), _p(cis), _p(info), _p(model), len(model), _p(lma), 0 if lma is None else len(lma), _p(bp1), n1,
           _p(scr), scr.shape[1], T, _p(bp), bp_cap, _p(bss), bss_cap, C.byref(bn), _p(idx))
     return n, bp[:max(n, 0)], bss[:bn.value if n >= 0 else 0], idx[:T + 1]
 
@@ -103,3 +104,24 @@ def test_second_pass_short_utterances_and_full_tables(emuls):
     scr = gf["senscr"]
     bp1 = oracle.fwdtree_run(m["tp"], m["sseq"], m["phone_tmat"][:nci], c["info"], c["model"], scr)[0]
     assert run_second(f2, m, c["info"], c["model"], bp1, scr, 50, 100000)[0] == -2
+
+
+@pytest.mark.parametrize("model_key", ["flat_default", "nodense"])
+def test_both_passes_with_the_array_lm(emuls, model_key):
+    """Trigram scores from the LM as arrays (psb_lm_core.h) instead of the dense table -- with the table
+    still in the model block, and with a block exported without it (info[26] = 0)."""
+    f1, f2 = emuls
+    m, gf = golden("en_us_ptm_model.npz"), golden("en_us_goforward.npz")
+    g = golden("en_us_fwdtree.npz")
+    want = _case(g, "flat_default")
+    info, model = g[model_key + ".info"], g[model_key + ".model"]
+    if model_key == "nodense":
+        assert int(info[26]) == 0 and len(model) < len(want["model"]) // 3
+    la = dict(pl_pen=gf["pl_pen"], pl_window=int(gf["pl_params"][4]))
+    n1, bp1, _, _ = run_first(f1, m, info, model, gf["senscr"], 8192, 1 << 18, lm_arrays=g["lmarr"], **la)
+    assert n1 > 0 and np.array_equal(bp1, _case(g, "lookahead")["bp"])
+    n, bp, bss, idx = run_second(f2, m, info, model, bp1, gf["senscr"], len(want["bp"]) + 8, len(want["bss"]) + 64, lm_arrays=g["lmarr"])
+    assert n == len(want["bp"]) and np.array_equal(bp, want["bp"]) and np.array_equal(bss, want["bss"]) and np.array_equal(idx, want["bp_idx"])
+    lma = g["lmarr"].copy()
+    lma[10 + int(lma[7]) + 2 * int(lma[1]) + 1] = 10 ** 6       # uni_next[1] beyond the bigram array
+    assert run_first(f1, m, info, model, gf["senscr"][:5], 64, 4096, lm_arrays=lma)[0] == -1

@@ -13,7 +13,7 @@ import pytest
 from conftest import ROOT, golden
 
 TAGS = ("default", "wide", "narrow", "maxwpf", "abs", "pen", "lookahead")
-ARGT = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
+ARGT = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
         C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
 
 
@@ -38,7 +38,7 @@ def emul(request, tmp_path_factory):
     return f
 
 
-def run_emul(f, m, info, model, scr, bp_cap, bss_cap, pl_pen=None, pl_window=0):
+def run_emul(f, m, info, model, scr, bp_cap, bss_cap, pl_pen=None, pl_window=0, lm_arrays=None):
     tp = np.ascontiguousarray(m["tp"], np.uint8)
     sseq = np.ascontiguousarray(m["sseq"], np.uint16)
     info = np.ascontiguousarray(info, np.int32)
@@ -49,11 +49,12 @@ def run_emul(f, m, info, model, scr, bp_cap, bss_cap, pl_pen=None, pl_window=0):
     pen = None
     if pl_pen is not None and pl_window > 0 and T > 0:
         pen = np.ascontiguousarray(np.asarray(pl_pen, np.int32)[:T])       # the phone loop's own table; the window is applied inside
+    lma = None if lm_arrays is None else np.ascontiguousarray(lm_arrays, np.int32)
     bp = np.zeros((bp_cap, 10), np.int32)
     bss = np.zeros(bss_cap, np.int32)
     idx = np.zeros(T + 2, np.int32)
     bn = C.c_int32()
-    n = f(tp.shape[1], _p(tp), tp.shape[0], _p(sseq), len(sseq), _p(cit), _p(info), _p(model), len(model), _p(scr), scr.shape[1], T,
+    n = f(tp.shape[1], _p(tp), tp.shape[0], _p(sseq), len(sseq), _p(cit), _p(info), _p(model), len(model), _p(lma), 0 if lma is None else len(lma), _p(scr), scr.shape[1], T,
           _p(pen), int(pl_window), _p(bp), bp_cap, _p(bss), bss_cap, C.byref(bn), _p(idx))
     return n, bp[:max(n, 0)], bss[:bn.value if n >= 0 else 0], idx[:T + 1]
 

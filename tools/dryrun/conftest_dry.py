@@ -31,26 +31,26 @@ class FakeCtx:
             h, n = TF._run(self.f_fsg, self.m, g, self._scr(ptr, utt_off, u), max(cap, 20000))
             hs.append(h[:cap]); ns.append(n)
         return hs, np.array(ns, np.int32)
-    def ngram_fwdtree(self, ptr, utt_off, info, model, cit, bp_cap, bss_cap, d_pen_ptr=None, pl_window=0):
+    def ngram_fwdtree(self, ptr, utt_off, info, model, cit, bp_cap, bss_cap, d_pen_ptr=None, pl_window=0, lm_arrays=None):
         m = dict(self.m, phone_tmat=np.asarray(cit)); out = []
         for u in range(len(utt_off) - 1):
             pen = self._pen(d_pen_ptr, utt_off, u, len(cit))
-            n, bp, bss, idx = TN.run_emul(self.f1, m, info, model, self._scr(ptr, utt_off, u), bp_cap, bss_cap, pl_pen=pen, pl_window=pl_window)
+            n, bp, bss, idx = TN.run_emul(self.f1, m, info, model, self._scr(ptr, utt_off, u), bp_cap, bss_cap, pl_pen=pen, pl_window=pl_window, lm_arrays=lm_arrays)
             if n < 0:
                 from pocketsphinx_b200._lib import PsbError
                 raise PsbError("overflow")
             out.append((bp, bss, idx))
         return out
-    def ngram_fwdflat(self, ptr, utt_off, info, model, cit, cis, firsts, bp_cap, bss_cap):
+    def ngram_fwdflat(self, ptr, utt_off, info, model, cit, cis, firsts, bp_cap, bss_cap, lm_arrays=None):
         m = dict(self.m, phone_tmat=np.asarray(cit), phone_ssid=np.asarray(cis)); out = []
         for u in range(len(utt_off) - 1):
-            n, bp, bss, idx = TG.run_second(self.f2, m, info, model, firsts[u], self._scr(ptr, utt_off, u), bp_cap, bss_cap)
+            n, bp, bss, idx = TG.run_second(self.f2, m, info, model, firsts[u], self._scr(ptr, utt_off, u), bp_cap, bss_cap, lm_arrays=lm_arrays)
             assert n >= 0
             out.append((bp, bss, idx))
         return out
-    def ngram_two_pass(self, ptr, utt_off, info, model, cit, cis, bp_cap, bss_cap, d_pen_ptr=None, pl_window=0, first_cap=None, first_bss_cap=None):
-        first = self.ngram_fwdtree(ptr, utt_off, info, model, cit, first_cap or bp_cap, first_bss_cap or bss_cap, d_pen_ptr, pl_window)
-        return self.ngram_fwdflat(ptr, utt_off, info, model, cit, cis, [f[0] for f in first], bp_cap, bss_cap), np.array([len(f[0]) for f in first], np.int32)
+    def ngram_two_pass(self, ptr, utt_off, info, model, cit, cis, bp_cap, bss_cap, d_pen_ptr=None, pl_window=0, first_cap=None, first_bss_cap=None, lm_arrays=None):
+        first = self.ngram_fwdtree(ptr, utt_off, info, model, cit, first_cap or bp_cap, first_bss_cap or bss_cap, d_pen_ptr, pl_window, lm_arrays)
+        return self.ngram_fwdflat(ptr, utt_off, info, model, cit, cis, [f[0] for f in first], bp_cap, bss_cap, lm_arrays), np.array([len(f[0]) for f in first], np.int32)
     def close(self): pass
 
 class FakeApi:
