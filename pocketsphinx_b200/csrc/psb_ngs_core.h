@@ -6,8 +6,9 @@
 //
 // What the reference does sequentially, and the closed form used here:
 //  * three coupled active sets -- static tree channels (roots by index, non-roots through an active
-//    list), per-word right-context fan-out of word-final phones (allocated on demand: here every
-//    (word, rc) channel has a fixed slot and "allocated" is a flag), permanent single-phone words.
+//    list), per-word right-context fan-out of word-final phones (allocated on demand: here a word
+//    takes a block of channels from a per-utterance pool while any of them is allocated, "allocated"
+//    being a flag per channel), permanent single-phone words.
 //    All live in ONE channel index space: roots | non-roots | single-phone words | fan-out.
 //  * prune_nonroot_chan (:800-878) walks the active list and, unlike the grammar search, its result
 //    depends on the order: a child that failed the beam BEFORE its parent's turn has been cleared
@@ -40,18 +41,20 @@ struct NgsGraph {
     int n_words, n_root, n_nonroot, n_1ph, n_1ph_lm, n_ci, sil, n_lm, n_emit;
     int beam, pbeam, wbeam, lpbeam, lponlybeam, maxhmmpf, maxwpf, nwpen, pip, silpen, fillpen;
     int start_wid, finish_wid, silence_wid, filler_start, filler_end;
-    int M, o_nonroot, o_1ph, o_rc, n_rcchan, LW;     // LW = scratch length (max of the list sizes) + 1
+    int M, o_nonroot, o_1ph, o_rc, n_rcchan, LW;     // M: channels with per-utterance state; LW = scratch length (max of the list sizes) + 1
+    int RB, n_blocks;          // fan-out pool: n_blocks blocks of RB channels (RB = widest fan-out); a word owns a block while any of
+                               // its right-context channels is allocated.  State index o_rc + block * RB + rc, static index o_rc + wc_off[w] + rc
     const int32_t *roots;      // [n_root][5]   ciphone, ci2phone, penult_phn_wid, next, tmatid
     const int32_t *nonroot;    // [n_nonroot][6] ssid, tmatid, ciphone, penult_phn_wid, next, alt
     const int32_t *words;      // [n_words][8]  first, last, last2, single, filler, basewid, homophone, lmidx
     const int32_t *w1ph;       // [n_1ph]
     const int32_t *r1ph;       // [n_1ph][4]    ciphone, ci2phone, ssid, tmatid
     const int32_t *rs_n, *rs_ssid, *rs_cimap, *ldiph, *lm;
-    const int32_t *wc_off;     // [n_words+1]   fan-out slots of every multi-phone word
+    const int32_t *wc_off;     // [n_words+1]   fan-out entries of every multi-phone word in the STATIC tables (tmatid, senid)
     const int32_t *w2h1;       // [n_words]     index of a single-phone word's permanent channel, or -1
     const int32_t *parent;     // [n_nonroot]   parent non-root id, or -(root id) - 1
-    const int32_t *tmatid;     // [M]
-    const int32_t *senid;      // [M][n_emit]   senones of the non-multiplexed channels (non-roots, fan-out)
+    const int32_t *tmatid;     // [o_rc + n_rcchan]  by static index
+    const int32_t *senid;      // [o_rc + n_rcchan][n_emit]   senones of the non-multiplexed channels (non-roots, fan-out)
     int use_lma;               // 1: trigram scores from the sorted-array LM below instead of the dense table `lm`
     LmArr lma;
 };
@@ -59,7 +62,8 @@ struct NgsGraph {
 struct NgsWork {
     fsg_wp score, hist, mss;                     // [n_emit][M]  (mss: per-state ssid of multiplexed channels)
     fsg_wp out_score, out_hist, best, frame;    // [M]
-    fsg_wp alloc;                                  // [n_rcchan]
+    fsg_wp alloc;                                  // [n_blocks * RB]
+    fsg_wp wblock, free_stack;                     // [n_words] block of a word or -1; [n_blocks] free block ids
     fsg_wp pos, posf, eflag;                     // [n_nonroot]
     fsg_wp acl[2], awl[2];                        // [n_nonroot], [n_words]
     fsg_wp word_active, lt_sf, lt_dscr, lt_bp;  // [n_words]
@@ -76,7 +80,7 @@ struct NgsWork {
 struct NgsScalars {
     fsg_int cur, n_acl, n_acl_nxt, n_awl, n_awl_nxt, n_cand;
     fsg_int best_all, best_last, best_score, last_phone_best, dynamic_beam, thresh, npth, lpth;
-    fsg_int bpidx, bss_head, stop, error, n_done, k_nonfinish, ev_root, ev_last;
+    fsg_int bpidx, bss_head, stop, error, n_done, k_nonfinish, ev_root, ev_last, n_free;
     fsg_ll n_root_eval, n_nonroot_eval;
     int scan[34];
 };
@@ -88,7 +92,7 @@ FSG_HD void ngs_work_carve(int32_t *b, const NgsGraph &G, NgsWork &W)
     const size_t M = (size_t)G.M, N = (size_t)G.n_emit, LW = (size_t)G.LW, nw = (size_t)G.n_words, nn = (size_t)G.n_nonroot + 1;
     W.score = b; b += N * M;  W.hist = b; b += N * M;  W.mss = b; b += N * M;
     W.out_score = b; b += M;  W.out_hist = b; b += M;  W.best = b; b += M;  W.frame = b; b += M;
-    W.alloc = b; b += (size_t)G.n_rcchan + 1;
+    W.alloc = b; b += (size_t)G.n_blocks * G.RB + 1;  W.wblock = b; b += nw;  W.free_stack = b; b += (size_t)G.n_blocks + 1;
     W.pos = b; b += nn;  W.posf = b; b += nn;  W.eflag = b; b += nn;
     W.acl[0] = b; b += nn;  W.acl[1] = b; b += nn;  W.awl[0] = b; b += nw + 1;  W.awl[1] = b; b += nw + 1;
     W.word_active = b; b += nw;  W.lt_sf = b; b += nw;  W.lt_dscr = b; b += nw;  W.lt_bp = b; b += nw;
@@ -101,7 +105,7 @@ FSG_HD void ngs_work_carve(int32_t *b, const NgsGraph &G, NgsWork &W)
 FSG_HDH size_t ngs_work_words(const NgsGraph &G)
 {
     const size_t M = (size_t)G.M, N = (size_t)G.n_emit, LW = (size_t)G.LW, nw = (size_t)G.n_words, nn = (size_t)G.n_nonroot + 1;
-    return 3 * N * M + 4 * M + (size_t)G.n_rcchan + 1 + 5 * nn + 2 * (nw + 1) + 4 * nw + 3 * (nw + 1) + 4 * LW + 3 * (size_t)G.n_ci + 256;
+    return 3 * N * M + 4 * M + (size_t)G.n_blocks * G.RB + 1 + nw + (size_t)G.n_blocks + 1 + 5 * nn + 2 * (nw + 1) + 4 * nw + 3 * (nw + 1) + 4 * LW + 3 * (size_t)G.n_ci + 256;
 }
 
 FSG_HD int ngs_nrc(const NgsGraph &G, int w) { return G.wc_off[w + 1] - G.wc_off[w]; }
@@ -197,14 +201,15 @@ FSG_HD void ngs_start(const NgsGraph &G, const NgsWork &W, NgsScalars *S)       
         for (int s = 0; s < G.n_emit; ++s) W.mss[s * G.M + c] = s == 0 ? 0 : NGS_BAD_SSID;
         if (c >= G.o_1ph && c < G.o_rc) W.mss[c] = G.r1ph[(c - G.o_1ph) * 4 + 2];
     }
-    FSG_FOR(i, G.n_rcchan) W.alloc[i] = 0;
-    FSG_FOR(w, G.n_words) { W.lt_sf[w] = -1; W.lt_dscr[w] = 0; W.lt_bp[w] = 0; W.word_active[w] = 0; }
+    FSG_FOR(i, G.n_blocks * G.RB) W.alloc[i] = 0;
+    FSG_FOR(i, G.n_blocks) W.free_stack[i] = i;
+    FSG_FOR(w, G.n_words) { W.lt_sf[w] = -1; W.lt_dscr[w] = 0; W.lt_bp[w] = 0; W.word_active[w] = 0; W.wblock[w] = -1; }
     FSG_FOR(i, G.n_nonroot) { W.pos[i] = -1; W.posf[i] = -2; W.eflag[i] = 0; }
     FSG_IF_LEADER {
         S->cur = 0; S->n_acl = S->n_acl_nxt = S->n_awl = S->n_awl_nxt = S->n_cand = 0;
         S->best_score = 0; S->last_phone_best = 0; S->dynamic_beam = G.beam;
         S->bpidx = 0; S->bss_head = 0; S->stop = 0; S->error = 0; S->n_done = 0;
-        S->n_root_eval = 0; S->n_nonroot_eval = 0;
+        S->n_root_eval = 0; S->n_nonroot_eval = 0; S->n_free = G.n_blocks;
     }
     FSG_SYNC();
     FSG_IF_LEADER ngs_enter(W, G.o_1ph + G.w2h1[G.start_wid], 0, -1, 0);
@@ -241,24 +246,25 @@ FSG_HD void ngs_step(const NgsGraph &G, const NgsWork &W, NgsScalars *S, int f, 
     FSG_SYNC();
     if (S->stop || S->error) return;
     // ---- evaluate_channels :702-716
-    FSG_FOR(i, G.n_root) if (W.frame[i] == f) { FSG_ATOMIC_MAX(&S->best_all, eval(W, i, true)); FSG_ATOMIC_ADD(&S->ev_root, 1); }
+    FSG_FOR(i, G.n_root) if (W.frame[i] == f) { FSG_ATOMIC_MAX(&S->best_all, eval(W, i, true, i)); FSG_ATOMIC_ADD(&S->ev_root, 1); }
     FSG_FOR(k, n_acl) {
         const int id = acl[k];
         W.pos[id] = k; W.posf[id] = f;
-        FSG_ATOMIC_MAX(&S->best_all, eval(W, G.o_nonroot + id, false));
+        FSG_ATOMIC_MAX(&S->best_all, eval(W, G.o_nonroot + id, false, G.o_nonroot + id));
     }
     FSG_FOR(j, n_awl) {
         const int w = awl[j];
         int k = 0;
         W.word_active[w] = 0;
-        for (int r = G.wc_off[w]; r < G.wc_off[w + 1]; ++r)
-            if (W.alloc[r]) { FSG_ATOMIC_MAX(&S->best_last, eval(W, G.o_rc + r, false)); ++k; }
+        const int blk = W.wblock[w] * G.RB, nrc = ngs_nrc(G, w);
+        for (int r = 0; r < nrc; ++r)
+            if (W.alloc[blk + r]) { FSG_ATOMIC_MAX(&S->best_last, eval(W, G.o_rc + blk + r, false, G.o_rc + G.wc_off[w] + r)); ++k; }
         FSG_ATOMIC_ADD(&S->ev_last, k);
     }
     FSG_FOR(i, G.n_1ph) {
         const int c = G.o_1ph + i;
         if (W.frame[c] < f) continue;
-        const int sc = eval(W, c, true);
+        const int sc = eval(W, c, true, c);
         if (G.w1ph[i] != G.finish_wid) FSG_ATOMIC_MAX(&S->best_last, sc);
         FSG_ATOMIC_ADD(&S->ev_last, 1);
     }
@@ -428,22 +434,34 @@ FSG_HD void ngs_step(const NgsGraph &G, const NgsWork &W, NgsScalars *S, int f, 
     FSG_SYNC();
     FSG_IF_LEADER S->last_phone_best = S->best_all;
     FSG_SYNC();
-    {
-        const int th = S->last_phone_best + G.lponlybeam;
-        FSG_FOR(i, n_cand) {
-            int k = 0;
-            if (W.cand_score[i] > th) {
-                const int w = W.cand_wid[i], sc = W.cand_score[i], last = NGS_W(G, w, 1), last2 = NGS_W(G, w, 2);
-                for (int r = G.wc_off[w]; r < G.wc_off[w + 1]; ++r) {
-                    const int c = G.o_rc + r;
-                    if (!W.alloc[r]) { ngs_clear(G, W, c); W.alloc[r] = 1; }                 // ngram_search_alloc_all_rc
-                    (void)last; (void)last2;
-                    if (W.frame[c] < f || sc > W.score[c]) { ngs_enter(W, c, sc, W.cand_bp[i], nf); ++k; }
-                }
-                if (k > 0) W.word_active[w] = 1;
+    const int th_lp = S->last_phone_best + G.lponlybeam;
+    // words entering their last phone without a fan-out block take one from the pool (order is immaterial)
+    FSG_FOR(i, n_cand) W.cnt2[i] = (W.cand_score[i] > th_lp && W.wblock[W.cand_wid[i]] < 0) ? 1 : 0;
+    FSG_SYNC();
+    const int n_need = fsg_exscan(W.cnt2, n_cand, S->scan);
+    if (n_need > S->n_free) {
+        FSG_IF_LEADER S->error = 3;                                           // fan-out pool exhausted
+        FSG_SYNC();
+        return;
+    }
+    FSG_FOR(i, n_cand) {
+        const int w = W.cand_wid[i];
+        if (W.cand_score[i] > th_lp && W.wblock[w] < 0) W.wblock[w] = W.free_stack[S->n_free - 1 - W.cnt2[i]];
+    }
+    FSG_SYNC();
+    FSG_IF_LEADER S->n_free -= n_need;
+    FSG_FOR(i, n_cand) {
+        int k = 0;
+        if (W.cand_score[i] > th_lp) {
+            const int w = W.cand_wid[i], sc = W.cand_score[i], blk = W.wblock[w] * G.RB, nrc = ngs_nrc(G, w);
+            for (int r = 0; r < nrc; ++r) {
+                const int c = G.o_rc + blk + r;
+                if (!W.alloc[blk + r]) { ngs_clear(G, W, c); W.alloc[blk + r] = 1; }             // ngram_search_alloc_all_rc
+                if (W.frame[c] < f || sc > W.score[c]) { ngs_enter(W, c, sc, W.cand_bp[i], nf); ++k; }
             }
-            W.cnt[i] = k > 0 ? 1 : 0;
+            if (k > 0) W.word_active[w] = 1;
         }
+        W.cnt[i] = k > 0 ? 1 : 0;
     }
     FSG_SYNC();
     const int n_awl_lp = fsg_exscan(W.cnt, n_cand, S->scan);
@@ -458,10 +476,10 @@ FSG_HD void ngs_step(const NgsGraph &G, const NgsWork &W, NgsScalars *S, int f, 
     FSG_FOR(j, n_items) {
         int has_exit = 0, rcsize = 0, k = 0;
         if (j < n_awl) {
-            const int w = awl[j];
-            for (int r = G.wc_off[w]; r < G.wc_off[w + 1]; ++r) {
-                const int c = G.o_rc + r;
-                if (!W.alloc[r]) continue;
+            const int w = awl[j], blk = W.wblock[w] * G.RB, nrc = ngs_nrc(G, w);
+            for (int r = 0; r < nrc; ++r) {
+                const int c = G.o_rc + blk + r;
+                if (!W.alloc[blk + r]) continue;
                 if (W.best[c] > lp_thresh) { ++k; if (W.out_score[c] > newword_thresh) has_exit = 1; }
             }
             if (has_exit) rcsize = ngs_nrc(G, w);
@@ -487,18 +505,20 @@ FSG_HD void ngs_step(const NgsGraph &G, const NgsWork &W, NgsScalars *S, int f, 
         int entry = -1;
         const int new_bp = S->bpidx + W.cnt[j], new_s = S->bss_head + W.cnt2[j];
         if (j < n_awl) {
-            const int w = awl[j];
-            int k = 0;
-            for (int r = G.wc_off[w]; r < G.wc_off[w + 1]; ++r) {
-                const int c = G.o_rc + r;
-                if (!W.alloc[r]) continue;
+            const int w = awl[j], blk = W.wblock[w] * G.RB, nrc = ngs_nrc(G, w);
+            int k = 0, left = 0;
+            for (int r = 0; r < nrc; ++r) {
+                const int c = G.o_rc + blk + r;
+                if (!W.alloc[blk + r]) continue;
                 if (W.best[c] > lp_thresh) {
                     W.frame[c] = nf; ++k;
-                    if (W.out_score[c] > newword_thresh) ngs_save_bp(G, W, &entry, new_bp, new_s, f, w, W.out_score[c], W.out_hist[c], r - G.wc_off[w]);
+                    if (W.out_score[c] > newword_thresh) ngs_save_bp(G, W, &entry, new_bp, new_s, f, w, W.out_score[c], W.out_hist[c], r);
                 }
-                else if (W.frame[c] != nf) W.alloc[r] = 0;
+                else if (W.frame[c] != nf) W.alloc[blk + r] = 0;
+                left += W.alloc[blk + r];
             }
             if (k > 0 && !W.word_active[w]) { nawl[n_awl_lp + W.cnt3[j]] = w; W.word_active[w] = 1; }
+            W.flag[j] = left == 0 ? 1 : 0;                                   // every channel freed: the block goes back
         }
         else {
             const int i = j - n_awl, c = G.o_1ph + i;
@@ -509,6 +529,18 @@ FSG_HD void ngs_step(const NgsGraph &G, const NgsWork &W, NgsScalars *S, int f, 
         }
     }
     FSG_SYNC();
+    // words all of whose fan-out channels were freed return their block to the pool
+    FSG_FOR(j, n_awl) W.cnt3[j] = W.flag[j];
+    FSG_SYNC();
+    const int n_rel = fsg_exscan(W.cnt3, n_awl, S->scan);
+    FSG_FOR(j, n_awl) {
+        if (!W.flag[j]) continue;
+        const int w = awl[j];
+        W.free_stack[S->n_free + W.cnt3[j]] = W.wblock[w];
+        W.wblock[w] = -1;
+    }
+    FSG_SYNC();
+    FSG_IF_LEADER S->n_free += n_rel;
     const int bp0 = S->bpidx, bp1 = bp0 + n_new_bp;
 #ifndef NGS_TEST_INJECT_RACE                                                  /* tests/test_emul_racecheck.py removes this barrier to prove the detector sees it */
     FSG_SYNC();                                                               // everyone has read bpidx before it moves

@@ -5,6 +5,7 @@
 #pragma once
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -128,14 +129,30 @@ ngs_flatten(const int32_t *info, const int32_t *model, long long model_len, cons
         if (chain(r[4], i) != 0) NGS_FAIL("lextree is not a tree below channel %d", i);
     }
     for (int i = 0; i < G.n_nonroot; ++i) if (parent[(size_t)i] == INT32_MIN) NGS_FAIL("non-root channel %d is unreachable", i);
-    G.o_nonroot = G.n_root; G.o_1ph = G.o_nonroot + G.n_nonroot; G.o_rc = G.o_1ph + G.n_1ph; G.M = G.o_rc + G.n_rcchan;
+    G.o_nonroot = G.n_root; G.o_1ph = G.o_nonroot + G.n_nonroot; G.o_rc = G.o_1ph + G.n_1ph;
+    {
+        // fan-out pool: a block per word that can need one when that is affordable (then it can never run dry),
+        // else a fixed number (PSB_NGS_BLOCKS, default 8192: large vocabularies; a dry pool is reported as an error)
+        int n_multi = 0;
+        G.RB = 1;
+        for (int w = 0; w < G.n_words; ++w) {
+            const int n = wc_off[(size_t)w + 1] - wc_off[(size_t)w];
+            if (n > 0) ++n_multi;
+            if (n > G.RB) G.RB = n;
+        }
+        int cap = 8192;
+        if (const char *e = getenv("PSB_NGS_BLOCKS")) { const int v = atoi(e); if (v > 0) cap = v; }
+        G.n_blocks = n_multi < cap ? (n_multi > 0 ? n_multi : 1) : cap;
+        G.M = G.o_rc + G.n_blocks * G.RB;
+    }
+    const int M_static = G.o_rc + G.n_rcchan;
     {
         int lw = G.n_root;
         if (G.n_nonroot > lw) lw = G.n_nonroot;
         if (G.n_words + G.n_1ph > lw) lw = G.n_words + G.n_1ph;
         G.LW = lw + 2;
     }
-    std::vector<int32_t> tmatid((size_t)G.M, 0), senid((size_t)G.M * n_emit, NGS_BAD_SSID);
+    std::vector<int32_t> tmatid((size_t)M_static, 0), senid((size_t)M_static * n_emit, NGS_BAD_SSID);
     auto set_sen = [&](int c, int ssid) -> int {
         if (ssid < 0 || ssid >= n_sseq) return -1;
         for (int s = 0; s < n_emit; ++s) {

@@ -225,18 +225,19 @@ struct ChanDevEval {
     HmmCtxDev c;
     const GraphT *G;
     const int16_t *row;
-    __device__ __forceinline__ int operator()(const WorkT &W, int ch, bool mpx) const
+    __device__ __forceinline__ int operator()(const WorkT &W, int ch, bool mpx, int sid = -1) const      // sid: static-table index
     {
         HmmReg h;
         const int N = c.n_emit, M = G->M;
+        if (sid < 0) sid = ch;
 #pragma unroll
         for (int s = 0; s < PSB_HMM_MAX_NSTATE; ++s) {
             h.score[s] = s < N ? W.score[s * M + ch] : PSB_WORST_SCORE;
             h.hist[s] = s < N ? W.hist[s * M + ch] : -1;
-            h.senid[s] = s < N ? (mpx ? W.mss[s * M + ch] : G->senid[(size_t)ch * N + s]) : PSB_BAD_SSID;
+            h.senid[s] = s < N ? (mpx ? W.mss[s * M + ch] : G->senid[(size_t)sid * N + s]) : PSB_BAD_SSID;
         }
         h.out_score = W.out_score[ch]; h.out_hist = W.out_hist[ch]; h.best = W.best[ch];
-        const int b = hmm_step(h, c, G->tmatid[ch], mpx, row);
+        const int b = hmm_step(h, c, G->tmatid[sid], mpx, row);
 #pragma unroll
         for (int s = 0; s < PSB_HMM_MAX_NSTATE; ++s)
             if (s < N) {
@@ -353,6 +354,8 @@ extern "C" int psb_ngram_fwdtree_batch_device(psb_hmmctx_t *c, const psb_ngram_d
     for (int u = 0; u < n_utt; ++u) {
         PSB_REQUIRE(result[u * 3 + 2] != -1, "psb_ngram_fwdtree_batch_device: utterance %d overflowed the backpointer table "
                     "or the score stack (%d entries / %d scores allowed)", u, bp_cap_per_utt, bss_cap_per_utt);
+        PSB_REQUIRE(result[u * 3 + 2] != -3, "psb_ngram_fwdtree_batch_device: utterance %d ran out of fan-out blocks "
+                    "(PSB_NGS_BLOCKS)", u);
         PSB_REQUIRE(result[u * 3 + 2] >= 0, "psb_ngram_fwdtree_batch_device: utterance %d needs score renormalisation "
                     "(not done on the device)", u);
     }

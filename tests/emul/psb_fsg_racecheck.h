@@ -93,6 +93,7 @@ template <class T> struct Scalar {
     Scalar &operator=(T x) { on_write(&v, (uint32_t)x); v = x; return *this; }
     Scalar &operator=(const Scalar &o) { return *this = (T)o; }
     Scalar &operator+=(T x) { return *this = (T)((T) * this + x); }
+    Scalar &operator-=(T x) { return *this = (T)((T) * this - x); }
     Scalar &operator*=(T x) { return *this = (T)((T) * this * x); }
     Scalar &operator^=(T x) { return *this = (T)((T) * this ^ x); }
 };

@@ -95,3 +95,18 @@ def test_graph_validation(emul):
     model[n_root * 5 + 4] = 0
     assert run_emul(emul, m, c["info"], model, gf["senscr"][:5], 64, 4096)[0] == -1
     assert run_emul(emul, m, c["info"], c["model"][:1000], gf["senscr"][:5], 64, 4096)[0] == -1      # block shorter than info says
+
+
+@pytest.mark.parametrize("blocks,ok", [("60", True), ("30", True), ("6", False)])
+def test_fanout_block_pool_reuse_and_exhaustion(emul, monkeypatch, blocks, ok):
+    """The right-context fan-out lives in a per-utterance pool of blocks (a word owns one while any of its
+    channels is allocated).  Fewer blocks than multi-phone words (about 100 here) forces reuse: same tables;
+    a pool that runs dry is an error, not a wrong answer."""
+    monkeypatch.setenv("PSB_NGS_BLOCKS", blocks)
+    m, gf = golden("en_us_ptm_model.npz"), golden("en_us_goforward.npz")
+    c = _case(golden("en_us_fwdtree.npz"), "default")
+    n, bp, bss, idx = run_emul(emul, m, c["info"], c["model"], gf["senscr"], len(c["bp"]) + 8, len(c["bss"]) + 64)
+    if ok:
+        assert n == len(c["bp"]) and np.array_equal(bp, c["bp"]) and np.array_equal(bss, c["bss"]) and np.array_equal(idx, c["bp_idx"])
+    else:
+        assert n == -4
