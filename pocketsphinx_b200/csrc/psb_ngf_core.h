@@ -21,12 +21,15 @@ struct NgfGraph {
     int n_words, n_1ph, n_ci, sil, n_lm, n_emit;
     int beam, fwdflatbeam, fwdflatwbeam, min_ef_width, max_sf_win, pip, silpen, fillpen;
     int start_wid, finish_wid, silence_wid, filler_start, filler_end;
-    int M, LW;
+    int M, LW;                 // M: channels with per-utterance state (single-phone words + the utterance vocabulary's chains)
+    int n_sp;                  // single-phone words (fixed state slots 0 .. n_sp)
     float lwf;
     const int32_t *words;      // [n_words][8]  first, last, last2, single, filler, basewid, homophone, lmidx
     const int32_t *rs_n, *rs_cimap, *ldiph, *lm, *inlm;
     const int32_t *pron_off, *pron_ci;
-    const int32_t *ch_off;     // [n_words+1]  channels of a word: root, internal phones, fan-out (single-phone: root only)
+    const int32_t *ch_off;     // [n_words+1]  STATIC index (tmatid, senid) of a word's channels: root, internal phones, fan-out
+                               //              (single-phone: root only); state lives at W.wbase[w] + position
+    const int32_t *sp_index;   // [n_words]    slot of a single-phone word among the single-phone words, or -1
     const int32_t *n_int;      // [n_words]    word-internal phones (pronlen - 2), 0 for single-phone words
     const int32_t *tmatid;     // [M]
     const int32_t *senid;      // [M][n_emit]  non-multiplexed channels
@@ -40,6 +43,7 @@ struct NgfWork {
     fsg_wp out_score, out_hist, best, frame;    // [M]
     fsg_wp awl[2];                                 // [n_words]
     fsg_wp word_active, wordlist, first_sf, wl_key;   // [n_words]
+    fsg_wp wbase;                                  // [n_words] first state channel of a word in this utterance, or -1
     fsg_wp node_first, node_last;                 // [T][n_words] entry index of the first / last exit per (sf, word), or -1
     fsg_wp node_cnt;                               // [T+1][n_words] surviving nodes with start frame < f (prefix count)
     fsg_wp cnt, cnt2, cnt3;                      // [LW]
@@ -57,7 +61,7 @@ struct NgfScalars {
 FSG_HDH size_t ngf_work_words(const NgfGraph &G, int T)
 {
     const size_t M = (size_t)G.M, N = (size_t)G.n_emit, nw = (size_t)G.n_words;
-    return 3 * N * M + 4 * M + 2 * (nw + 1) + 4 * nw + 2 * (size_t)T * nw + ((size_t)T + 1) * nw + 3 * (size_t)G.LW;
+    return 3 * N * M + 4 * M + 2 * (nw + 1) + 5 * nw + 2 * (size_t)T * nw + ((size_t)T + 1) * nw + 3 * (size_t)G.LW;
 }
 
 FSG_HD void ngf_work_carve(int32_t *b, const NgfGraph &G, int T, NgfWork &W)
@@ -66,7 +70,7 @@ FSG_HD void ngf_work_carve(int32_t *b, const NgfGraph &G, int T, NgfWork &W)
     W.score = b; b += N * M;  W.hist = b; b += N * M;  W.mss = b; b += N * M;
     W.out_score = b; b += M;  W.out_hist = b; b += M;  W.best = b; b += M;  W.frame = b; b += M;
     W.awl[0] = b; b += nw + 1;  W.awl[1] = b; b += nw + 1;
-    W.word_active = b; b += nw;  W.wordlist = b; b += nw;  W.first_sf = b; b += nw;  W.wl_key = b; b += nw;
+    W.word_active = b; b += nw;  W.wordlist = b; b += nw;  W.first_sf = b; b += nw;  W.wl_key = b; b += nw;  W.wbase = b; b += nw;
     W.node_first = b; b += (size_t)T * nw;  W.node_last = b; b += (size_t)T * nw;  W.node_cnt = b; b += ((size_t)T + 1) * nw;
     W.cnt = b; b += G.LW;  W.cnt2 = b; b += G.LW;  W.cnt3 = b;
     W.T = T;
@@ -109,15 +113,13 @@ FSG_HD bool ngf_node_ok(const NgfGraph &G, const NgfWork &W, int sf, int w)
 FSG_HD void ngf_start(const NgfGraph &G, const NgfWork &W, NgfScalars *S)
 {
     const int nw = G.n_words, T = W.T;
-    FSG_FOR(c, G.M) { ngf_clear(G, W, c); for (int s = 0; s < G.n_emit; ++s) W.mss[s * G.M + c] = NGS_BAD_SSID; }
     FSG_FOR(x, T * nw) { W.node_first[x] = INT_MAX; W.node_last[x] = -1; }
-    FSG_FOR(w, nw) { W.word_active[w] = 0; W.first_sf[w] = -1; }
+    FSG_FOR(w, nw) { W.word_active[w] = 0; W.first_sf[w] = -1; W.wbase[w] = G.sp_index[w]; }
     FSG_IF_LEADER {
         S->cur = 0; S->n_awl = 0; S->n_awl_nxt = 0; S->nwd = 0; S->best_score = 0; S->bpidx = 0; S->bss_head = 0;
         S->stop = 0; S->error = 0; S->n_done = 0;
     }
     FSG_SYNC();
-    FSG_FOR(w, nw) if (G.ch_off[w + 1] > G.ch_off[w]) W.mss[G.ch_off[w]] = G.root_ssid[w];
     if (W.n_bp_in < 0) {
         // no first pass (-fwdtree no): ngram_fwdflat_expand_all :61-87 -- every LM word is in the
         // vocabulary (in id order) and may follow every exit (get_expand_wordlist :615-618)
@@ -168,8 +170,24 @@ FSG_HD void ngf_start(const NgfGraph &G, const NgfWork &W, NgfScalars *S)
         FSG_ATOMIC_ADD(&S->nwd, 1);
     }
     FSG_SYNC();
+    // build_fwdflat_chan :306-368: state channels for the utterance vocabulary only (single-phone words keep
+    // their fixed slots), laid out in vocabulary order by a scan over the chain lengths
+    const int nwd = S->nwd;
+    FSG_FOR(k, nwd) { const int w = W.wordlist[k]; W.cnt[k] = NGS_W(G, w, 3) ? 0 : G.ch_off[w + 1] - G.ch_off[w]; }
+    FSG_SYNC();
+    const int n_chain = fsg_exscan(W.cnt, nwd, S->scan);
+    if (G.n_sp + n_chain > G.M) {
+        FSG_IF_LEADER S->error = 3;                                           // vocabulary does not fit the state area
+        FSG_SYNC();
+        return;
+    }
+    FSG_FOR(k, nwd) { const int w = W.wordlist[k]; if (!NGS_W(G, w, 3)) W.wbase[w] = G.n_sp + W.cnt[k]; }
+    FSG_FOR(c, G.n_sp + n_chain) { ngf_clear(G, W, c); for (int s = 0; s < G.n_emit; ++s) W.mss[s * G.M + c] = NGS_BAD_SSID; }
+    FSG_SYNC();
+    FSG_FOR(w, nw) if (W.wbase[w] >= 0) W.mss[W.wbase[w]] = G.root_ssid[w];
+    FSG_SYNC();
     FSG_IF_LEADER {
-        ngf_enter(W, G.ch_off[G.start_wid], 0, -1, 0);
+        ngf_enter(W, W.wbase[G.start_wid], 0, -1, 0);
         W.awl[0][0] = G.start_wid; S->n_awl = 1;
     }
     FSG_SYNC();
@@ -191,11 +209,11 @@ FSG_HD void ngf_step(const NgfGraph &G, const NgfWork &W, NgfScalars *S, int cf,
     if (S->stop || S->error) return;
     // fwdflat_eval_chan :445-480
     FSG_FOR(j, nw) {
-        const int w = awl[j], c0 = G.ch_off[w], c1 = G.ch_off[w + 1];
+        const int w = awl[j], s0 = G.ch_off[w], c0 = W.wbase[w], c1 = c0 + (G.ch_off[w + 1] - s0);
         int b = FSG_WORST_SCORE;
-        if (W.frame[c0] == cf) { const int sc = eval(W, c0, true); if (w != G.finish_wid && sc > b) b = sc; }
+        if (W.frame[c0] == cf) { const int sc = eval(W, c0, true, s0); if (w != G.finish_wid && sc > b) b = sc; }
         for (int c = c0 + 1; c < c1; ++c)
-            if (W.frame[c] == cf) { const int sc = eval(W, c, false); if (sc > b) b = sc; }
+            if (W.frame[c] == cf) { const int sc = eval(W, c, false, s0 + (c - c0)); if (sc > b) b = sc; }
         FSG_ATOMIC_MAX(&S->best, b);
     }
     FSG_FOR(w, nwords) W.word_active[w] = 0;
@@ -205,7 +223,7 @@ FSG_HD void ngf_step(const NgfGraph &G, const NgfWork &W, NgfScalars *S, int cf,
     const int thresh = S->best_score + G.fwdflatbeam, wordthresh = S->best_score + G.fwdflatwbeam;
     // fwdflat_prune_chan :483-607, pass 1: which words exit (decided by what evaluation left)
     FSG_FOR(j, nw) {
-        const int w = awl[j], c0 = G.ch_off[w], c1 = G.ch_off[w + 1], ni = G.n_int[w];
+        const int w = awl[j], c0 = W.wbase[w], c1 = c0 + (G.ch_off[w + 1] - G.ch_off[w]), ni = G.n_int[w];
         int ex = 0;
         if (NGS_W(G, w, 3)) ex = W.frame[c0] == cf && W.best[c0] > thresh && W.out_score[c0] > wordthresh;
         else
@@ -224,7 +242,7 @@ FSG_HD void ngf_step(const NgfGraph &G, const NgfWork &W, NgfScalars *S, int cf,
     }
     // pass 2: the chain logic, one word per thread
     FSG_FOR(j, nw) {
-        const int w = awl[j], c0 = G.ch_off[w], c1 = G.ch_off[w + 1], ni = G.n_int[w], single = NGS_W(G, w, 3);
+        const int w = awl[j], c0 = W.wbase[w], c1 = c0 + (G.ch_off[w + 1] - G.ch_off[w]), ni = G.n_int[w], single = NGS_W(G, w, 3);
         const int rc0 = c0 + 1 + ni;
         const int new_bp = S->bpidx + W.cnt[j], new_s = S->bss_head + W.cnt2[j];
         int entry = -1;
@@ -288,10 +306,10 @@ FSG_HD void ngf_step(const NgfGraph &G, const NgfWork &W, NgfScalars *S, int cf,
         if (sf < 0) sf = 0;
         if (ef > T) ef = T;
         FSG_FOR(w, nwords) {
-            if (G.ch_off[w + 1] == G.ch_off[w]) continue;
+            if (W.wbase[w] < 0) continue;
             if (W.n_bp_in >= 0 ? !(ef > sf && W.node_cnt[(size_t)ef * nwords + w] - W.node_cnt[(size_t)sf * nwords + w] > 0)
                                : !G.inlm[w]) continue;
-            const int c0 = G.ch_off[w], first = NGS_W(G, w, 0);
+            const int c0 = W.wbase[w], first = NGS_W(G, w, 0);
             const int ci2 = NGS_W(G, w, 3) ? G.sil : G.pron_ci[G.pron_off[w] + 1];
             for (int b = bp0; b < bp1; ++b) {
                 const fsg_wp e = W.bp + (size_t)b * NGS_BP_ROW;
@@ -314,13 +332,13 @@ FSG_HD void ngf_step(const NgfGraph &G, const NgfWork &W, NgfScalars *S, int cf,
         const int ns_sil = S->silrc_score + G.silpen + pip, ns_fill = S->silrc_score + G.fillpen + pip;
         FSG_FOR(w, nwords) {
             if (w < G.filler_start || w > G.filler_end || !NGS_W(G, w, 3)) continue;
-            const int ns = w == G.silence_wid ? ns_sil : ns_fill, c0 = G.ch_off[w];
+            const int ns = w == G.silence_wid ? ns_sil : ns_fill, c0 = W.wbase[w];
             if (!(ns > thresh && ns > FSG_WORST_SCORE)) continue;
             if (W.frame[c0] < cf || ns > W.score[c0]) { ngf_enter(W, c0, ns, S->silrc_bp, nf); W.word_active[w] = 1; }
         }
     }
     FSG_SYNC();
-    FSG_FOR(j, nw) { const int c0 = G.ch_off[awl[j]]; if (W.frame[c0] == cf) ngf_clear_scores(G, W, c0); }
+    FSG_FOR(j, nw) { const int c0 = W.wbase[awl[j]]; if (W.frame[c0] == cf) ngf_clear_scores(G, W, c0); }
     // next active word list :852-866
     const int nwd = S->nwd;
     FSG_FOR(k, nwd) { const int w = W.wordlist[k]; W.cnt[k] = (W.word_active[w] && w < G.start_wid) ? 1 : 0; }

@@ -8,7 +8,7 @@
 struct NgfFlat {
     std::vector<int32_t> buf;
     NgfGraph G;
-    size_t o_words, o_rs_n, o_rs_cimap, o_ldiph, o_lm, o_inlm, o_pron_off, o_pron_ci, o_ch_off, o_n_int, o_tmatid, o_senid, o_root_ssid, o_lma;
+    size_t o_words, o_rs_n, o_rs_cimap, o_ldiph, o_lm, o_inlm, o_pron_off, o_pron_ci, o_ch_off, o_n_int, o_tmatid, o_senid, o_root_ssid, o_sp_index, o_lma;
     int32_t lma_hdr[10];
 };
 
@@ -74,8 +74,20 @@ ngf_flatten(const int32_t *info, const int32_t *model, long long model_len, cons
     for (int w = 0; w < n_words; ++w)
         if (!G.use_lma && words[(size_t)w * 8 + 7] < 0 && words[(size_t)words[(size_t)w * 8 + 5] * 8 + 7] < 0) NGS_FAIL("word %d: base word has no LM index", w);
     if (!words[(size_t)G.start_wid * 8 + 3] || !words[(size_t)G.silence_wid * 8 + 3]) NGS_FAIL("<s> / <sil> must be single-phone words");
-    G.M = ch_off[(size_t)n_words]; G.LW = n_words + 2;
-    std::vector<int32_t> tmatid((size_t)G.M, 0), senid((size_t)G.M * n_emit, NGS_BAD_SSID);
+    const int M_static = ch_off[(size_t)n_words];
+    std::vector<int32_t> sp_index((size_t)n_words, -1);
+    {
+        // state area: the single-phone words' fixed slots + room for an utterance's vocabulary (everything when that
+        // is affordable, else PSB_NGF_CHANNELS, default 65536: a vocabulary that does not fit is reported as an error)
+        G.n_sp = 0;
+        for (int w = 0; w < n_words; ++w) if (words[(size_t)w * 8 + 3]) sp_index[(size_t)w] = G.n_sp++;
+        int cap = 65536;
+        if (const char *e = getenv("PSB_NGF_CHANNELS")) { const int v = atoi(e); if (v > 0) cap = v; }
+        G.M = M_static < cap ? M_static : cap;
+        if (G.M < G.n_sp + 1) G.M = G.n_sp + 1;
+    }
+    G.LW = n_words + 2;
+    std::vector<int32_t> tmatid((size_t)M_static, 0), senid((size_t)M_static * n_emit, NGS_BAD_SSID);
     auto set_sen = [&](int c, int ssid) -> int {
         if (ssid < 0 || ssid >= n_sseq) return -1;
         for (int s = 0; s < n_emit; ++s) {
@@ -116,6 +128,7 @@ ngf_flatten(const int32_t *info, const int32_t *model, long long model_len, cons
     o.o_ch_off = put(ch_off.data(), ch_off.size()); o.o_n_int = put(n_int.data(), n_int.size());
     o.o_tmatid = put(tmatid.data(), tmatid.size()); o.o_senid = put(senid.data(), senid.size());
     o.o_root_ssid = put(root_ssid.data(), root_ssid.size());
+    o.o_sp_index = put(sp_index.data(), sp_index.size());
     o.o_lma = b.size();
     if (G.use_lma) { put(lm_arrays, (size_t)lm_arrays_len); memcpy(o.lma_hdr, lm_arrays, sizeof(o.lma_hdr)); }
     b.push_back(0);
@@ -130,5 +143,5 @@ ngf_bind(NgfFlat &o, const int32_t *base)
     G.words = base + o.o_words; G.rs_n = base + o.o_rs_n; G.rs_cimap = base + o.o_rs_cimap; G.ldiph = base + o.o_ldiph;
     G.lm = base + o.o_lm; G.inlm = base + o.o_inlm; G.pron_off = base + o.o_pron_off; G.pron_ci = base + o.o_pron_ci;
     G.ch_off = base + o.o_ch_off; G.n_int = base + o.o_n_int; G.tmatid = base + o.o_tmatid; G.senid = base + o.o_senid;
-    G.root_ssid = base + o.o_root_ssid;
+    G.root_ssid = base + o.o_root_ssid; G.sp_index = base + o.o_sp_index;
 }

@@ -494,6 +494,8 @@ extern "C" int psb_ngram_fwdflat_batch_device(psb_hmmctx_t *c, const psb_ngram_d
     for (int u = 0; u < n_utt; ++u) {
         PSB_REQUIRE(result[u * 3 + 2] != -1, "psb_ngram_fwdflat_batch_device: utterance %d overflowed the backpointer table "
                     "or the score stack (%d entries / %d scores allowed)", u, bp_cap_per_utt, bss_cap_per_utt);
+        PSB_REQUIRE(result[u * 3 + 2] != -3, "psb_ngram_fwdflat_batch_device: utterance %d: its vocabulary does not fit the state "
+                    "area (PSB_NGF_CHANNELS)", u);
         PSB_REQUIRE(result[u * 3 + 2] >= 0, "psb_ngram_fwdflat_batch_device: utterance %d needs score renormalisation "
                     "(not done on the device)", u);
     }
@@ -587,6 +589,8 @@ extern "C" int psb_ngram_two_pass_batch_device(psb_hmmctx_t *c, const psb_ngram_
                     u, first_cap_per_utt, first_bss_cap_per_utt);
         PSB_REQUIRE(result[u * 3 + 2] != -1, "psb_ngram_two_pass_batch_device: utterance %d: second pass overflowed its tables (%d entries / %d scores)",
                     u, bp_cap_per_utt, bss_cap_per_utt);
+        PSB_REQUIRE(r1[(size_t)u * 3 + 2] != -3 && result[u * 3 + 2] != -3, "psb_ngram_two_pass_batch_device: utterance %d ran out of fan-out blocks "
+                    "(PSB_NGS_BLOCKS) or state channels (PSB_NGF_CHANNELS)", u);
         PSB_REQUIRE(r1[(size_t)u * 3 + 2] >= 0 && result[u * 3 + 2] >= 0, "psb_ngram_two_pass_batch_device: utterance %d needs score renormalisation", u);
     }
     return PSB_OK;

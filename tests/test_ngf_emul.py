@@ -125,3 +125,21 @@ def test_both_passes_with_the_array_lm(emuls, model_key):
     lma = g["lmarr"].copy()
     lma[10 + int(lma[7]) + 2 * int(lma[1]) + 1] = 10 ** 6       # uni_next[1] beyond the bigram array
     assert run_first(f1, m, info, model, gf["senscr"][:5], 64, 4096, lm_arrays=lma)[0] == -1
+
+
+@pytest.mark.parametrize("channels,ok", [("1500", True), ("300", False)])
+def test_state_area_holds_the_utterance_vocabulary_only(emuls, monkeypatch, channels, ok):
+    """Second-pass channels are laid out per utterance over its vocabulary (about 60 of the 110 words here),
+    not over every LM word: a state area smaller than the whole LM's chains still gives the same tables; one
+    that cannot hold the vocabulary is an error."""
+    from oracle import oracle
+    f1, f2 = emuls
+    monkeypatch.setenv("PSB_NGF_CHANNELS", channels)
+    m, gf = golden("en_us_ptm_model.npz"), golden("en_us_goforward.npz")
+    c = _case(golden("en_us_fwdtree.npz"), "flat_wide")
+    bp1 = oracle.fwdtree_run(m["tp"], m["sseq"], m["phone_tmat"][:int(c["info"][6])], c["info"], c["model"], gf["senscr"])[0]
+    n, bp, bss, idx = run_second(f2, m, c["info"], c["model"], bp1, gf["senscr"], len(c["bp"]) + 8, len(c["bss"]) + 64)
+    if ok:
+        assert n == len(c["bp"]) and np.array_equal(bp, c["bp"]) and np.array_equal(bss, c["bss"]) and np.array_equal(idx, c["bp_idx"])
+    else:
+        assert n == -4
