@@ -53,6 +53,7 @@
 #define FSG_ATOMIC_MAX_AT(a, i, v) atomicMax(&(a)[i], (v))
 #define FSG_ATOMIC_MIN_AT(a, i, v) atomicMin(&(a)[i], (v))
 #define FSG_ATOMIC_ADD_AT(a, i, v) atomicAdd(&(a)[i], (v))
+#define FSG_ATOMIC_FETCH_ADD_AT(a, i, v) atomicAdd(&(a)[i], (v))
 #define FSG_FADD(a, b) __fadd_rn((a), (b))
 #define FSG_FMUL(a, b) __fmul_rn((a), (b))
 typedef int32_t *fsg_wp;
@@ -81,6 +82,8 @@ static inline void fsg_host_min(int *p, int v) { if (v < *p) *p = v; }
 #define FSG_ATOMIC_MAX_AT(a, i, v) fsg_host_max(&(a)[i], (v))
 #define FSG_ATOMIC_MIN_AT(a, i, v) fsg_host_min(&(a)[i], (v))
 #define FSG_ATOMIC_ADD_AT(a, i, v) ((a)[i] += (v))
+static inline int fsg_host_fetch_add(int *p, int v) { const int o = *p; *p = o + v; return o; }
+#define FSG_ATOMIC_FETCH_ADD_AT(a, i, v) fsg_host_fetch_add(&(a)[i], (v))
 #define FSG_COLLECTIVE_BEGIN() ((void)0)
 #define FSG_COLLECTIVE_END() ((void)0)
 #define FSG_RAW(a) (a)

@@ -7,12 +7,13 @@
 // and ALL exits of a word touch only that word (fwdflat_prune_chan :483-607).  So: one thread per
 // active word runs the reference's chain logic as it stands; what crosses words is
 //  * the utterance vocabulary (build_fwdflat_wordlist :224-300): per (start frame, word) the first
-//    and last end frame in backpointer-table order -- min / max of entry indices; a word's place in
-//    the list is (first start frame with a surviving node, later-created nodes first), a rank;
+//    and last end frame in backpointer-table order -- the table's entries bucketed by word, grouped
+//    by start frame inside the word; a word's place in the list is (first start frame with a
+//    surviving node, later-created nodes first), a rank;
 //  * the order of the backpointer table: one entry per exiting word, in active-list order = scan;
 //  * word transitions (:643-782): per target word the first maximum over the frame's exits of
 //    exit score + float-scaled trigram score; targets are the words with a node whose start frame
-//    lies in [frame - win, frame + win): a per-word prefix count over frames answers that;
+//    lies in [frame - win, frame + win): the word's sorted node list answers that;
 //  * the next active list (:852-866): vocabulary order, then ids >= <s> ascending = two scans.
 #pragma once
 #include "psb_ngs_core.h"
@@ -44,8 +45,9 @@ struct NgfWork {
     fsg_wp awl[2];                                 // [n_words]
     fsg_wp word_active, wordlist, first_sf, wl_key;   // [n_words]
     fsg_wp wbase;                                  // [n_words] first state channel of a word in this utterance, or -1
-    fsg_wp node_first, node_last;                 // [T][n_words] entry index of the first / last exit per (sf, word), or -1
-    fsg_wp node_cnt;                               // [T+1][n_words] surviving nodes with start frame < f (prefix count)
+    fsg_wp wstart, wn;                             // [n_words+1], [n_words]: a word's segment in the node arrays, surviving nodes in it
+    fsg_wp nd_ent, nd_sf, nd_key;                  // [n_bp_in]: per word, its first-pass entries, then its surviving nodes' start frames
+                                                   //            (ascending) and creation keys (index of the node's first entry)
     fsg_wp cnt, cnt2, cnt3;                      // [LW]
     fsg_wp bp, bss, bp_idx;                      // outputs
     const int32_t *bp_in;                            // first pass: [n_bp_in][10]
@@ -58,20 +60,22 @@ struct NgfScalars {
     int scan[34];
 };
 
-FSG_HDH size_t ngf_work_words(const NgfGraph &G, int T)
+FSG_HDH size_t ngf_work_words(const NgfGraph &G, int T, int n_bp_cap)
 {
     const size_t M = (size_t)G.M, N = (size_t)G.n_emit, nw = (size_t)G.n_words;
-    return 3 * N * M + 4 * M + 2 * (nw + 1) + 5 * nw + 2 * (size_t)T * nw + ((size_t)T + 1) * nw + 3 * (size_t)G.LW;
+    (void)T;
+    return 3 * N * M + 4 * M + 2 * (nw + 1) + 5 * nw + (nw + 1) + nw + 3 * ((size_t)n_bp_cap + 1) + 3 * (size_t)G.LW;
 }
 
-FSG_HD void ngf_work_carve(int32_t *b, const NgfGraph &G, int T, NgfWork &W)
+FSG_HD void ngf_work_carve(int32_t *b, const NgfGraph &G, int T, int n_bp_cap, NgfWork &W)
 {
     const size_t M = (size_t)G.M, N = (size_t)G.n_emit, nw = (size_t)G.n_words;
     W.score = b; b += N * M;  W.hist = b; b += N * M;  W.mss = b; b += N * M;
     W.out_score = b; b += M;  W.out_hist = b; b += M;  W.best = b; b += M;  W.frame = b; b += M;
     W.awl[0] = b; b += nw + 1;  W.awl[1] = b; b += nw + 1;
     W.word_active = b; b += nw;  W.wordlist = b; b += nw;  W.first_sf = b; b += nw;  W.wl_key = b; b += nw;  W.wbase = b; b += nw;
-    W.node_first = b; b += (size_t)T * nw;  W.node_last = b; b += (size_t)T * nw;  W.node_cnt = b; b += ((size_t)T + 1) * nw;
+    W.wstart = b; b += nw + 1;  W.wn = b; b += nw;
+    W.nd_ent = b; b += (size_t)n_bp_cap + 1;  W.nd_sf = b; b += (size_t)n_bp_cap + 1;  W.nd_key = b; b += (size_t)n_bp_cap + 1;
     W.cnt = b; b += G.LW;  W.cnt2 = b; b += G.LW;  W.cnt3 = b;
     W.T = T;
 }
@@ -98,22 +102,10 @@ FSG_HD int ngf_tg(const NgfGraph &G, int w, int h1, int h2)
     return G.lm[((size_t)a * n + b) * n + c];
 }
 
-// does (sf, w) keep its node?  (build_fwdflat_wordlist: too few end points, or </s> not ending the utterance)
-FSG_HD bool ngf_node_ok(const NgfGraph &G, const NgfWork &W, int sf, int w)
-{
-    const int i0 = W.node_first[(size_t)sf * G.n_words + w];
-    if (i0 < 0) return false;
-    const int fef = W.bp_in[(size_t)i0 * NGS_BP_ROW], lef = W.bp_in[(size_t)W.node_last[(size_t)sf * G.n_words + w] * NGS_BP_ROW];
-    if (lef - fef < G.min_ef_width) return false;
-    if (w == G.finish_wid && lef < W.T - 1) return false;
-    return true;
-}
-
 // ngram_fwdflat_start :371-414
 FSG_HD void ngf_start(const NgfGraph &G, const NgfWork &W, NgfScalars *S)
 {
     const int nw = G.n_words, T = W.T;
-    FSG_FOR(x, T * nw) { W.node_first[x] = INT_MAX; W.node_last[x] = -1; }
     FSG_FOR(w, nw) { W.word_active[w] = 0; W.first_sf[w] = -1; W.wbase[w] = G.sp_index[w]; }
     FSG_IF_LEADER {
         S->cur = 0; S->n_awl = 0; S->n_awl_nxt = 0; S->nwd = 0; S->best_score = 0; S->bpidx = 0; S->bss_head = 0;
@@ -125,34 +117,71 @@ FSG_HD void ngf_start(const NgfGraph &G, const NgfWork &W, NgfScalars *S)
         // vocabulary (in id order) and may follow every exit (get_expand_wordlist :615-618)
         FSG_FOR(w, nw) {
             const int in = G.inlm[w] ? 1 : 0;
-            for (int f = 0; f <= T; ++f) W.node_cnt[(size_t)f * nw + w] = f * in;
+            W.wn[w] = 0; W.wstart[w] = 0;
             W.first_sf[w] = in ? 0 : -1;
             W.wl_key[w] = -w;
         }
         FSG_SYNC();
     }
     else {
-        // nodes: first / last exit per (start frame, word) in table order
-        FSG_FOR(i, W.n_bp_in) {
+        // build_fwdflat_wordlist :224-300.  The reference keeps, per start frame, a list of (word, first end
+        // frame, last end frame) nodes, created and updated in backpointer-table order.  Here: the table's
+        // entries are bucketed by word (count, scan, fill), and each word's thread -- its entries are few --
+        // sorts them back into table order, groups them by start frame, drops the nodes with too few end
+        // points (or </s> not ending the utterance) and leaves its surviving nodes sorted by start frame.
+        const int n_in = W.n_bp_in;
+        FSG_FOR(w, nw) { W.wn[w] = 0; W.cnt[w] = 0; }
+        FSG_SYNC();
+        FSG_FOR(i, n_in) {
             const int32_t *b = W.bp_in + (size_t)i * NGS_BP_ROW;
             const int sf = b[3] < 0 ? 0 : W.bp_in[(size_t)b[3] * NGS_BP_ROW] + 1, wid = b[2];
-            if (!G.inlm[wid] || sf >= T) continue;
-            FSG_ATOMIC_MIN_AT(W.node_first, (size_t)sf * nw + wid, i);
-            FSG_ATOMIC_MAX_AT(W.node_last, (size_t)sf * nw + wid, i);
+            if (G.inlm[wid] && sf < T) FSG_ATOMIC_ADD_AT(W.cnt, wid, 1);
         }
         FSG_SYNC();
-        FSG_FOR(x, T * nw) if (W.node_first[x] == INT_MAX) W.node_first[x] = -1;
+        FSG_FOR(w, nw) W.wstart[w] = W.cnt[w];
         FSG_SYNC();
-        // per word: prefix count of surviving nodes over start frames, first such frame
+        const int n_used = fsg_exscan(W.wstart, nw, S->scan);
+        FSG_IF_LEADER W.wstart[nw] = n_used;
+        FSG_FOR(w, nw) W.cnt[w] = 0;
+        FSG_SYNC();
+        FSG_FOR(i, n_in) {
+            const int32_t *b = W.bp_in + (size_t)i * NGS_BP_ROW;
+            const int sf = b[3] < 0 ? 0 : W.bp_in[(size_t)b[3] * NGS_BP_ROW] + 1, wid = b[2];
+            if (G.inlm[wid] && sf < T) W.nd_ent[W.wstart[wid] + FSG_ATOMIC_FETCH_ADD_AT(W.cnt, wid, 1)] = i;
+        }
+        FSG_SYNC();
         FSG_FOR(w, nw) {
-            int run = 0, f0 = -1;
-            for (int f = 0; f < T; ++f) {
-                W.node_cnt[(size_t)f * nw + w] = run;
-                if (ngf_node_ok(G, W, f, w)) { if (f0 < 0) f0 = f; ++run; }
+            const int s0 = W.wstart[w], n = W.wstart[w + 1] - s0;
+            int nn = 0, f0 = -1, k0 = -1;
+            for (int a = 1; a < n; ++a) {                                     // back into table order
+                const int v = W.nd_ent[s0 + a];
+                int p = a - 1;
+                while (p >= 0 && W.nd_ent[s0 + p] > v) { W.nd_ent[s0 + p + 1] = W.nd_ent[s0 + p]; --p; }
+                W.nd_ent[s0 + p + 1] = v;
             }
-            W.node_cnt[(size_t)T * nw + w] = run;
-            W.first_sf[w] = f0;
-            W.wl_key[w] = f0 < 0 ? -1 : W.node_first[(size_t)f0 * nw + w];
+            for (int a = 0; a < n; ++a) {                                     // group by start frame, in creation order
+                const int i = W.nd_ent[s0 + a];
+                const int32_t *b = W.bp_in + (size_t)i * NGS_BP_ROW;
+                const int sf = b[3] < 0 ? 0 : W.bp_in[(size_t)b[3] * NGS_BP_ROW] + 1;
+                int q = 0;
+                while (q < nn && W.nd_sf[s0 + q] != sf) ++q;
+                if (q == nn) { W.nd_sf[s0 + nn] = sf; W.nd_key[s0 + nn] = i; W.nd_ent[s0 + nn] = i; ++nn; }   // nd_ent reused: last entry of node q
+                else W.nd_ent[s0 + q] = i;                                    // (q <= a always: slot q is no longer needed as input)
+            }
+            int m = 0;
+            for (int q = 0; q < nn; ++q) {                                    // too few end points / </s> not at the end: drop
+                const int fef = W.bp_in[(size_t)W.nd_key[s0 + q] * NGS_BP_ROW], lef = W.bp_in[(size_t)W.nd_ent[s0 + q] * NGS_BP_ROW];
+                if (lef - fef < G.min_ef_width || (w == G.finish_wid && lef < T - 1)) continue;
+                W.nd_sf[s0 + m] = W.nd_sf[s0 + q]; W.nd_key[s0 + m] = W.nd_key[s0 + q]; ++m;
+            }
+            for (int a = 1; a < m; ++a) {                                     // by start frame
+                const int vs = W.nd_sf[s0 + a], vk = W.nd_key[s0 + a];
+                int p = a - 1;
+                while (p >= 0 && W.nd_sf[s0 + p] > vs) { W.nd_sf[s0 + p + 1] = W.nd_sf[s0 + p]; W.nd_key[s0 + p + 1] = W.nd_key[s0 + p]; --p; }
+                W.nd_sf[s0 + p + 1] = vs; W.nd_key[s0 + p + 1] = vk;
+            }
+            if (m > 0) { f0 = W.nd_sf[s0]; k0 = W.nd_key[s0]; }
+            W.wn[w] = m; W.first_sf[w] = f0; W.wl_key[w] = k0;
         }
         FSG_SYNC();
     }
@@ -307,8 +336,13 @@ FSG_HD void ngf_step(const NgfGraph &G, const NgfWork &W, NgfScalars *S, int cf,
         if (ef > T) ef = T;
         FSG_FOR(w, nwords) {
             if (W.wbase[w] < 0) continue;
-            if (W.n_bp_in >= 0 ? !(ef > sf && W.node_cnt[(size_t)ef * nwords + w] - W.node_cnt[(size_t)sf * nwords + w] > 0)
-                               : !G.inlm[w]) continue;
+            if (W.n_bp_in < 0) { if (!G.inlm[w]) continue; }
+            else {                                                            // a surviving node starting in [sf, ef)?
+                const int s0 = W.wstart[w], m = W.wn[w];
+                int q = 0;
+                while (q < m && W.nd_sf[s0 + q] < sf) ++q;
+                if (!(q < m && W.nd_sf[s0 + q] < ef)) continue;
+            }
             const int c0 = W.wbase[w], first = NGS_W(G, w, 0);
             const int ci2 = NGS_W(G, w, 3) ? G.sil : G.pron_ci[G.pron_off[w] + 1];
             for (int b = bp0; b < bp1; ++b) {

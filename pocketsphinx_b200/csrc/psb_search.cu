@@ -384,7 +384,7 @@ ngs_fwdflat_kernel(const int16_t *__restrict__ senscr, const int32_t *__restrict
     const long long f0 = utt_off[u];
     const int T = utt_off[u + 1] - utt_off[u];
     NgfWork W;
-    ngf_work_carve(work + (size_t)u * work_words, G, T, W);
+    ngf_work_carve(work + (size_t)u * work_words, G, T, in_cap, W);
     W.bp = bp_out + (size_t)u * bp_cap * NGS_BP_ROW;
     W.bss = bss_out + (size_t)u * bss_cap;
     W.bp_idx = bp_idx_out + f0 + u;
@@ -459,7 +459,7 @@ extern "C" int psb_ngram_fwdflat_batch_device(psb_hmmctx_t *c, const psb_ngram_d
     ibuf.insert(ibuf.end(), n_first, n_first + n_utt);
     const size_t o_res = ibuf.size();
     ibuf.resize(o_res + (size_t)n_utt * 3, 0);
-    const size_t work_words = ngf_work_words(flat.G, t_max);
+    const size_t work_words = ngf_work_words(flat.G, t_max, first_cap_per_utt);
     const size_t total_frames = (size_t)utt_off[n_utt];
     const size_t n_in = (size_t)n_utt * first_cap_per_utt * NGS_BP_ROW, n_bp = (size_t)n_utt * bp_cap_per_utt * NGS_BP_ROW,
                  n_bss = (size_t)n_utt * bss_cap_per_utt, n_idx = total_frames + (size_t)n_utt;
@@ -543,7 +543,7 @@ extern "C" int psb_ngram_two_pass_batch_device(psb_hmmctx_t *c, const psb_ngram_
     const size_t o_r1 = ibuf.size();
     ibuf.resize(o_r1 + (size_t)n_utt * 6, 0);
     const size_t o_r2 = o_r1 + (size_t)n_utt * 3;
-    const size_t ww1 = ngs_work_words(f1.G), ww2 = ngf_work_words(f2.G, t_max), ww = ww1 > ww2 ? ww1 : ww2;
+    const size_t ww1 = ngs_work_words(f1.G), ww2 = ngf_work_words(f2.G, t_max, first_cap_per_utt), ww = ww1 > ww2 ? ww1 : ww2;
     const size_t total_frames = (size_t)utt_off[n_utt], n_idx = total_frames + (size_t)n_utt;
     const size_t n_bp1 = (size_t)n_utt * first_cap_per_utt * NGS_BP_ROW, n_bss1 = (size_t)n_utt * first_bss_cap_per_utt,
                  n_bp2 = (size_t)n_utt * bp_cap_per_utt * NGS_BP_ROW, n_bss2 = (size_t)n_utt * bss_cap_per_utt;

@@ -23,9 +23,10 @@ ngf_emul_run(int32_t n_emit_state, const uint8_t *tp, int32_t n_tmat, const uint
     }
     ngf_bind(flat, flat.buf.data());
     const NgfGraph &G = flat.G;
-    std::vector<int32_t> work(ngf_work_words(G, T), 0x5a5a5a5a);
+    const int n_cap = n_bp_in > 0 ? n_bp_in : 0;
+    std::vector<int32_t> work(ngf_work_words(G, T, n_cap), 0x5a5a5a5a);
     NgfWork W;
-    ngf_work_carve(work.data(), G, T, W);
+    ngf_work_carve(work.data(), G, T, n_cap, W);
     W.bp = bp_out; W.bss = bss_out; W.bp_idx = bp_idx_out; W.bp_in = bp_in; W.n_bp_in = n_bp_in; W.bp_cap = bp_cap; W.bss_cap = bss_cap;
     NgfScalars S;
     memset((void *)&S, 0x5a, sizeof(S));

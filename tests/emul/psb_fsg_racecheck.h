@@ -103,6 +103,7 @@ inline void aadd(Scalar<int> *p, int v) { on_atomic(&p->v); p->v += v; }
 inline void amax_at(const Ptr<int32_t> &a, size_t i, int v) { on_atomic(a.p + i); if (v > a.p[i]) a.p[i] = v; }
 inline void amin_at(const Ptr<int32_t> &a, size_t i, int v) { on_atomic(a.p + i); if (v < a.p[i]) a.p[i] = v; }
 inline void aadd_at(const Ptr<int32_t> &a, size_t i, int v) { on_atomic(a.p + i); a.p[i] += v; }
+inline int afadd_at(const Ptr<int32_t> &a, size_t i, int v) { on_atomic(a.p + i); const int o = a.p[i]; a.p[i] = o + v; return o; }
 }  // namespace fsgrace
 
 #ifdef PSB_FSG_EMUL_REVERSE
@@ -118,6 +119,7 @@ inline void aadd_at(const Ptr<int32_t> &a, size_t i, int v) { on_atomic(a.p + i)
 #define FSG_ATOMIC_MAX_AT(a, i, v) fsgrace::amax_at((a), (i), (v))
 #define FSG_ATOMIC_MIN_AT(a, i, v) fsgrace::amin_at((a), (i), (v))
 #define FSG_ATOMIC_ADD_AT(a, i, v) fsgrace::aadd_at((a), (i), (v))
+#define FSG_ATOMIC_FETCH_ADD_AT(a, i, v) fsgrace::afadd_at((a), (i), (v))
 #define FSG_COLLECTIVE_BEGIN() fsgrace::sync()
 #define FSG_COLLECTIVE_END() fsgrace::sync()
 #define FSG_RAW(a) ((a).p)
