@@ -133,7 +133,7 @@ struct FsgWork {
     fsg_wup c_rc, c_rcf;                         // [CC][8]
     fsg_wp ne_dest, ne_score, ne_lc;            // [CC] this frame's history entries
     fsg_wup ne_rc;                                // [CC][8]
-    fsg_wp rfirst;                                // [R]
+    fsg_wp rfirst, rcnt, rnew;                    // [R] (+1)
     fsg_wp hist_out;                              // [cap][FSG_ROW]
     int cap;
 };
@@ -224,7 +224,7 @@ FSG_HD void fsg_work_carve(int32_t *b, const FsgGraph &G, FsgWork &W)
     W.c_rc = fsg_wup((uint32_t *)b); b += 8 * CC;  W.c_rcf = fsg_wup((uint32_t *)b); b += 8 * CC;
     W.ne_dest = b; b += CC;  W.ne_score = b; b += CC;  W.ne_lc = b; b += CC;
     W.ne_rc = fsg_wup((uint32_t *)b); b += 8 * CC;
-    W.rfirst = b;
+    W.rfirst = b; b += (size_t)G.R + 1;  W.rcnt = b; b += (size_t)G.R + 1;  W.rnew = b;
 }
 
 FSG_HD void fsg_clear_node(const FsgGraph &G, const FsgWork &W, int p)        /* hmm_clear, hmm.c:180-196 */
@@ -353,19 +353,24 @@ FSG_HD void fsg_cross_word(const FsgGraph &G, const FsgWork &W, FsgScalars *S, i
         }
         W.rfirst[ri] = key;
     }
-    FSG_IF_LEADER S->n_newroot = 0;
+    // newly activated roots, compacted in root order (scan), then ranked among themselves by (first entering
+    // entry, sibling order): K is small even when the grammar has thousands of roots
     FSG_SYNC();
-    FSG_FOR(ri, G.R) {
-        const int key = W.rfirst[ri];
-        if (key < 0) continue;
+    FSG_FOR(ri, G.R) W.rcnt[ri] = W.rfirst[ri] >= 0 ? 1 : 0;
+    FSG_SYNC();
+    const int K = fsg_exscan(W.rcnt, G.R, S->scan);
+    FSG_FOR(ri, G.R) if (W.rfirst[ri] >= 0) W.rnew[W.rcnt[ri]] = ri;
+    FSG_SYNC();
+    FSG_FOR(k, K) {
+        const int ri = W.rnew[k], key = W.rfirst[ri];
         int rank = 0;
-        for (int rj = 0; rj < G.R; ++rj) {
-            const int kj = W.rfirst[rj];
-            if (kj >= 0 && (kj < key || (kj == key && rj < ri))) ++rank;
+        for (int j = 0; j < K; ++j) {
+            const int rj = W.rnew[j], kj = W.rfirst[rj];
+            if (kj < key || (kj == key && rj < ri)) ++rank;
         }
         nxt[S->n_ins + rank] = G.root_list[ri];
-        FSG_ATOMIC_ADD(&S->n_newroot, 1);
     }
+    FSG_IF_LEADER S->n_newroot = K;
     FSG_SYNC();
     FSG_IF_LEADER {
         S->n_hist += n_new;

@@ -108,5 +108,5 @@ static inline size_t
 fsg_work_words(const FsgFlat &o, int n_emit)
 {
     const size_t P = o.P, CC = o.CC, R = o.R > 0 ? o.R : 1;
-    return (2 * (size_t)n_emit + 4) * P + 2 * P + 2 * P + 3 * (CC + 1) + 6 * CC + 16 * CC + 3 * CC + 8 * CC + R;
+    return (2 * (size_t)n_emit + 4) * P + 2 * P + 2 * P + 3 * (CC + 1) + 6 * CC + 16 * CC + 3 * CC + 8 * CC + 3 * (R + 1);
 }
