@@ -2,7 +2,7 @@
 # First GPU call of the next round: run the search kernels that have only been verified in host
 # emulation, each test file under its own timeout so that a hang cannot take the
 # box with it, in both bindings of the phase code.  Logs go to gpurun_out/.
-#   gpurun --timeout 900 -- 'bash tools/run_unverified.sh'
+#   gpurun --timeout 1500 -- 'bash tools/run_unverified.sh'
 set -u
 mkdir -p gpurun_out
 export PSB_RUN_UNVERIFIED=1
@@ -18,6 +18,21 @@ for mode in 0 1; do
     done
 done
 unset PSB_SEARCH_WARP
+# One small case of each kernel under the sanitizer (memcheck: out-of-bounds in the carved work
+# areas; racecheck: shared-memory hazards in the block scans).  Slow, so only when the plain runs
+# passed, and never fatal for the exit code: the logs are what is wanted.
+if [ $rc -eq 0 ]; then
+    for tool in memcheck racecheck; do
+        log=gpurun_out/unverified_sanitizer_$tool.log
+        timeout 400 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest -x -q -m gpu \
+            "tests/test_gpu_zz_fsg.py::test_block_scan_selftest" \
+            "tests/test_gpu_zz_fsg.py::test_fsg_batch_matches_reference_and_oracle[go]" \
+            "tests/test_gpu_zz_ngram.py::test_fwdtree_batch_matches_reference_and_oracle[default]" \
+            "tests/test_gpu_zz_ngram.py::test_fwdflat_batch_matches_reference_and_oracle[flat_default]" \
+            > $log 2>&1
+        echo "sanitizer $tool -> exit $?: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $log | tail -n 1)"
+    done
+fi
 timeout 300 python bench.py --steps 2 --warmup 1 > gpurun_out/unverified_bench.log 2>&1
 echo "bench exit $?: $(python - <<'P'
 import json
