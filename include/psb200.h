@@ -426,6 +426,28 @@ int psb_ngram_two_pass_batch_device(psb_hmmctx_t *c, const psb_ngram_desc_t *g, 
                                     int32_t bp_cap_per_utt, int32_t *bss, int32_t bss_cap_per_utt, int32_t *bp_idx,
                                     int32_t *result, int32_t *first_result);
 
+/* Reading the hypothesis out of the returned tables (host code, no device work: the reference does this
+ * on the host as well, once per utterance).  Without -bestpath this is all of ps_get_hyp / ps_seg_iter;
+ * with it the reference's lattice code takes the tables through integration/ps_search_cuda.c.
+ *   psb_fsg_find_exit    fsg_search_find_exit (fsg_search.c:883-954): *entry = the best word exit in the
+ *                        last frame <= frame_idx that has one (final != 0: only exits into final_state),
+ *                        0 if there is no word exit yet, -1 if the final state was not reached
+ *   psb_fsg_backtrace    fsg_search_seg_iter + fsg_seg_bp2itor (:1062-1091, :1122-1180): the predecessor
+ *                        chain of `entry` in time order, seg [cap][7] = {entry, link, wid (-1: null
+ *                        transition), sf, ef, ascr, lscr}; returns its length (>= 0) or an error
+ *   psb_ngram_find_exit  ngram_search_find_exit, frame_idx = -1 (ngram_search.c:498-541): </s> in the last
+ *                        frame with exits, else its best entry; *entry = -1 if no frame has exits
+ *   psb_ngram_backtrace  ngram_search_bp_iter (:958-997): seg [cap][5] = {entry, wid, sf, ef, path score}
+ * Filtering fillers / <s> / </s> out of the word string (dict_real_word) is the caller's: the dictionary's
+ * strings never cross this interface. */
+int psb_fsg_find_exit(const int32_t *hist, int32_t n_hist, const int32_t *links, int32_t n_link,
+                      int32_t frame_idx, int32_t final_state, int32_t final, int32_t *entry, int32_t *score);
+int32_t psb_fsg_backtrace(const int32_t *hist, int32_t n_hist, const int32_t *links, int32_t n_link,
+                          int32_t entry, int32_t *seg, int32_t cap);
+int psb_ngram_find_exit(const int32_t *bp, int32_t n_bp, const int32_t *bp_idx, int32_t n_frame,
+                        int32_t finish_wid, int32_t *entry, int32_t *score);
+int32_t psb_ngram_backtrace(const int32_t *bp, int32_t n_bp, int32_t entry, int32_t *seg, int32_t cap);
+
 /* Self-test of the search kernels' block-wide exclusive scan (the one building block the host
  * emulation of their phase code cannot execute): scans a[0..n) in place on `device` with one CTA,
  * total[0] = the sum, total[1] = the result of an empty scan issued right behind it (must be 0). */

@@ -1191,7 +1191,18 @@ refdrv_fsg(const char *hmmdir, const char *dict, const char *fsgfile, const char
     ps_process_raw(ps, pcm, n_samples, FALSE, TRUE);
     ps_end_utt(ps);
     h = ps_get_hyp(ps, &score);
-    snprintf(hyp, hyp_cap, "%s", h ? h : "");
+    {   /* first line: the hypothesis; then one "word sf ef ascr lscr" line per ps_seg_iter segment */
+        int len = snprintf(hyp, hyp_cap, "%s\n", h ? h : "");
+        ps_seg_t *it;
+        for (it = ps_seg_iter(ps); it && len < hyp_cap; it = ps_seg_next(it)) {
+            int sf, ef;
+            int32 ascr, lscr, lback;
+            ps_seg_frames(it, &sf, &ef);
+            ps_seg_prob(it, &ascr, &lscr, &lback);
+            len += snprintf(hyp + len, hyp_cap - len, "%s %d %d %d %d\n", ps_seg_word(it), sf, ef, ascr, lscr);
+        }
+        if (it) ps_seg_free(it);
+    }
     fsg = fs->fsg;
     if (vocab && vocab_cap > 0) {                     /* word strings by wid, newline separated */
         int w, len = 0;

@@ -390,10 +390,10 @@ def fsg(hmmdir, dictfile, fsgfile, pcm, **kv):
     cap = 1 << 22
     blob = np.zeros(cap, np.int32)
     info = np.zeros(16, np.int32)
-    hyp = C.create_string_buffer(4096)
+    hyp = C.create_string_buffer(1 << 16)
     vocab = C.create_string_buffer(1 << 16)
     need = L.refdrv_fsg(hmmdir.encode(), dictfile.encode(), fsgfile.encode(), s, _p(pcm), len(pcm), _p(blob), cap,
-                        _p(info), hyp, 4096, vocab, 1 << 16)
+                        _p(info), hyp, 1 << 16, vocab, 1 << 16)
     if need < 0 or need > cap:
         raise RuntimeError("refdrv_fsg failed: %d" % need)
     n_pn, n_state, n_link, n_null, n_hist = (int(x) for x in info[1:6])
@@ -407,7 +407,8 @@ def fsg(hmmdir, dictfile, fsgfile, pcm, **kv):
     return dict(n_frames=int(info[0]), pnodes=pnodes, roots=roots, links=links, nulloff=nulloff, nullarc=nullarc,
                 hist=hist, beam=int(info[6]), pbeam=int(info[7]), wbeam=int(info[8]), maxhmmpf=int(info[9]),
                 silcipid=int(info[10]), n_ciphone=int(info[11]), start_state=int(info[12]),
-                final_state=int(info[13]), score=int(info[14]), hyp=hyp.value.decode(),
+                final_state=int(info[13]), score=int(info[14]), hyp=hyp.value.decode().split("\n")[0],
+                seg=[l.split() for l in hyp.value.decode().split("\n")[1:] if l],   # word sf ef ascr lscr
                 vocab=vocab.value.decode().split("\n")[:-1])
 
 

@@ -91,6 +91,10 @@ SYMBOLS = [
     ("psb_ngram_fwdtree_batch_device", C.c_int, [_VP, C.POINTER(NgramDesc), _VP, _VP, _I32, _VP, _I32, _VP, _I32, _VP, _I32, _VP, _VP]),
     ("psb_ngram_fwdflat_batch_device", C.c_int, [_VP, C.POINTER(NgramDesc), _VP, _VP, _I32, _VP, _I32, _VP, _VP, _I32, _VP, _I32, _VP, _VP]),
     ("psb_selftest_block_scan", C.c_int, [C.c_int, _VP, _I32, _VP]),
+    ("psb_fsg_find_exit", C.c_int, [_VP, _I32, _VP, _I32, _I32, _I32, _I32, _VP, _VP]),
+    ("psb_fsg_backtrace", _I32, [_VP, _I32, _VP, _I32, _I32, _VP, _I32]),
+    ("psb_ngram_find_exit", C.c_int, [_VP, _I32, _VP, _I32, _I32, _VP, _VP]),
+    ("psb_ngram_backtrace", _I32, [_VP, _I32, _I32, _VP, _I32]),
     ("psb_ngram_two_pass_batch_device", C.c_int, [_VP, C.POINTER(NgramDesc), _VP, _VP, _I32, _VP, _I32, _I32, _I32, _VP, _I32, _VP, _I32,
                                                    _VP, _VP, _VP]),
     ("psb_align_batch_device", C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),

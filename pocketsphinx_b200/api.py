@@ -549,6 +549,41 @@ def sendump_read(path, max_frames=1 << 20):
     return out[:n]
 
 
+
+def fsg_hyp(hist, links, n_frame, final_state, final=True, cap=4096):
+    """ps_get_hyp / ps_seg_iter of a grammar search without -bestpath, on the table `HmmContext.fsg`
+    returned (fsg_search_find_exit + fsg_search_seg_iter, fsg_search.c:883-954, 1122-1180).  Returns
+    (entry, score, seg [n][7] = entry, link, wid, sf, ef, ascr, lscr); entry <= 0: no hypothesis."""
+    hist = np.ascontiguousarray(hist, np.int32).reshape(-1, 13)
+    links = np.ascontiguousarray(links, np.int32).reshape(-1, 5)
+    entry, score = C.c_int32(-1), C.c_int32(0)
+    check(lib().psb_fsg_find_exit(_p(hist), len(hist), _p(links), len(links), int(n_frame), int(final_state), int(bool(final)),
+                                  C.byref(entry), C.byref(score)), "psb_fsg_find_exit")
+    if entry.value <= 0:
+        return entry.value, None, np.zeros((0, 7), np.int32)
+    seg = np.zeros((cap, 7), np.int32)
+    n = lib().psb_fsg_backtrace(_p(hist), len(hist), _p(links), len(links), entry.value, _p(seg), cap)
+    check(min(n, 0), "psb_fsg_backtrace")
+    return entry.value, score.value, seg[:min(n, cap)].copy()
+
+
+def ngram_hyp(bp, bp_idx, n_frame, finish_wid, cap=4096):
+    """ngram_search_find_exit + ngram_search_bp_iter (ngram_search.c:498-541, 958-997) on a backpointer
+    table the n-gram entry points returned.  Returns (entry, score, seg [n][5] = entry, wid, sf, ef,
+    path score); entry -1: no frame had a word exit."""
+    bp = np.ascontiguousarray(bp, np.int32).reshape(-1, 10)
+    bp_idx = np.ascontiguousarray(bp_idx, np.int32)
+    entry, score = C.c_int32(-1), C.c_int32(0)
+    check(lib().psb_ngram_find_exit(_p(bp), len(bp), _p(bp_idx), int(n_frame), int(finish_wid), C.byref(entry), C.byref(score)),
+          "psb_ngram_find_exit")
+    if entry.value < 0:
+        return -1, None, np.zeros((0, 5), np.int32)
+    seg = np.zeros((cap, 5), np.int32)
+    n = lib().psb_ngram_backtrace(_p(bp), len(bp), entry.value, _p(seg), cap)
+    check(min(n, 0), "psb_ngram_backtrace")
+    return entry.value, score.value, seg[:min(n, cap)].copy()
+
+
 class FrontEnd:
     """fe/ + feat/ for whole batches on the device (every utterance a fresh stream).  `desc` is the
     dict of fe_tables.make_fe_desc() -- or the same arrays taken out of the reference's fe_t."""
