@@ -438,6 +438,10 @@ int psb_ngram_two_pass_batch_device(psb_hmmctx_t *c, const psb_ngram_desc_t *g, 
  *   psb_ngram_find_exit  ngram_search_find_exit, frame_idx = -1 (ngram_search.c:498-541): </s> in the last
  *                        frame with exits, else its best entry; *entry = -1 if no frame has exits
  *   psb_ngram_backtrace  ngram_search_bp_iter (:958-997): seg [cap][5] = {entry, wid, sf, ef, path score}
+ *   psb_ngram_segments   the same chain with ngram_search_bp2itor's scores (:886-928), seg [cap][7] =
+ *                        {entry, wid, sf, ef, path score, ascr, lscr}: needs the search description (first
+ *                        phones, dict2pid cimap, LM) and the score stack; lwf = 1.0 after the first pass
+ *                        alone, the float32 fwdflatlw / lw after a second pass (ngram_search_seg_iter :1033)
  * Filtering fillers / <s> / </s> out of the word string (dict_real_word) is the caller's: the dictionary's
  * strings never cross this interface. */
 int psb_fsg_find_exit(const int32_t *hist, int32_t n_hist, const int32_t *links, int32_t n_link,
@@ -447,6 +451,8 @@ int32_t psb_fsg_backtrace(const int32_t *hist, int32_t n_hist, const int32_t *li
 int psb_ngram_find_exit(const int32_t *bp, int32_t n_bp, const int32_t *bp_idx, int32_t n_frame,
                         int32_t finish_wid, int32_t *entry, int32_t *score);
 int32_t psb_ngram_backtrace(const int32_t *bp, int32_t n_bp, int32_t entry, int32_t *seg, int32_t cap);
+int32_t psb_ngram_segments(const psb_ngram_desc_t *g, const int32_t *bp, int32_t n_bp, const int32_t *bss, int32_t n_bss,
+                           int32_t entry, float lwf, int32_t *seg, int32_t cap);
 
 /* Self-test of the search kernels' block-wide exclusive scan (the one building block the host
  * emulation of their phase code cannot execute): scans a[0..n) in place on `device` with one CTA,

@@ -95,6 +95,7 @@ SYMBOLS = [
     ("psb_fsg_backtrace", _I32, [_VP, _I32, _VP, _I32, _I32, _VP, _I32]),
     ("psb_ngram_find_exit", C.c_int, [_VP, _I32, _VP, _I32, _I32, _VP, _VP]),
     ("psb_ngram_backtrace", _I32, [_VP, _I32, _I32, _VP, _I32]),
+    ("psb_ngram_segments", _I32, [C.POINTER(NgramDesc), _VP, _I32, _VP, _I32, _I32, C.c_float, _VP, _I32]),
     ("psb_ngram_two_pass_batch_device", C.c_int, [_VP, C.POINTER(NgramDesc), _VP, _VP, _I32, _VP, _I32, _I32, _I32, _VP, _I32, _VP, _I32,
                                                    _VP, _VP, _VP]),
     ("psb_align_batch_device", C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),

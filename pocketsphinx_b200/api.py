@@ -584,6 +584,26 @@ def ngram_hyp(bp, bp_idx, n_frame, finish_wid, cap=4096):
     return entry.value, score.value, seg[:min(n, cap)].copy()
 
 
+
+def ngram_segments(info, model, bp, bss, entry, lm_arrays=None, second_pass=False, cap=4096):
+    """ps_seg_iter of an n-gram search without -bestpath (ngram_search_bp2itor, ngram_search.c:886-928):
+    seg [n][7] = entry, wid, sf, ef, path score, ascr, lscr.  second_pass: the tables come from fwdflat,
+    LM scores are scaled by the float32 fwdflat_fwdtree_lw_ratio (its bits are info[32])."""
+    from ._lib import NgramDesc
+    info = np.ascontiguousarray(info, np.int32); model = np.ascontiguousarray(model, np.int32)
+    bp = np.ascontiguousarray(bp, np.int32).reshape(-1, 10); bss = np.ascontiguousarray(bss, np.int32)
+    lma = None if lm_arrays is None else np.ascontiguousarray(lm_arrays, np.int32)
+    d = NgramDesc(info.ctypes.data, model.ctypes.data, len(model), None, None,
+                  None if lma is None else lma.ctypes.data, 0 if lma is None else len(lma))
+    lwf = np.float32(1.0)
+    if second_pass:
+        lwf = info[32:33].view(np.float32)[0]
+    seg = np.zeros((cap, 7), np.int32)
+    n = lib().psb_ngram_segments(C.byref(d), _p(bp), len(bp), _p(bss), len(bss), int(entry), C.c_float(float(lwf)), _p(seg), cap)
+    check(min(n, 0), "psb_ngram_segments")
+    return seg[:min(n, cap)].copy()
+
+
 class FrontEnd:
     """fe/ + feat/ for whole batches on the device (every utterance a fresh stream).  `desc` is the
     dict of fe_tables.make_fe_desc() -- or the same arrays taken out of the reference's fe_t."""

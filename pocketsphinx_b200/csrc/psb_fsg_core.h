@@ -29,7 +29,8 @@
 // PSB_FSG_HOST_EMUL into a TEST harness (tests/emul/fsg_emul.cpp) that runs every FSG_FOR loop to
 // completion, forwards or (PSB_FSG_EMUL_REVERSE) backwards, to check the phase logic -- including
 // its freedom from intra-phase ordering assumptions -- against the reference's golden history
-// tables without a GPU.  libpsb200.so contains no host execution path of this code.
+// tables without a GPU.  libpsb200.so contains no host execution path of the phase code (only the LM
+// lookup helpers of psb_lm_core.h / ngs_tg are __host__ __device__: psb_result.cu scores segments with them).
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -54,8 +55,13 @@
 #define FSG_ATOMIC_MIN_AT(a, i, v) atomicMin(&(a)[i], (v))
 #define FSG_ATOMIC_ADD_AT(a, i, v) atomicAdd(&(a)[i], (v))
 #define FSG_ATOMIC_FETCH_ADD_AT(a, i, v) atomicAdd(&(a)[i], (v))
+#ifdef __CUDA_ARCH__
 #define FSG_FADD(a, b) __fadd_rn((a), (b))
 #define FSG_FMUL(a, b) __fmul_rn((a), (b))
+#else                                   /* host half of the few __host__ __device__ helpers (LM lookups of psb_result.cu): */
+#define FSG_FADD(a, b) ((a) + (b))      /* x86-64 scalar SSE, one rounding per operation, no contraction without -mfma */
+#define FSG_FMUL(a, b) ((a) * (b))
+#endif
 typedef int32_t *fsg_wp;
 typedef uint32_t *fsg_wup;
 typedef int fsg_int;

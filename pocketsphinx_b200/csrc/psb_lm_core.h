@@ -43,7 +43,7 @@ FSG_HDH void lm_arr_bind(LmArr &L, const int32_t *hdr, const int32_t *base)
 // (end, value max_vocab), all in uint32 arithmetic.  On a sorted range it finds exactly the entries that
 // exist; shipped models (en-us.lm.bin) contain ranges that are NOT sorted, and what the reference finds
 // there is a property of this very procedure -- a binary search would disagree.
-FSG_HD int lm_find(const int32_t *words, int begin, int end, int key_, uint32_t max_vocab)
+FSG_HDH int lm_find(const int32_t *words, int begin, int end, int key_, uint32_t max_vocab)
 {
     uint32_t before_it = (uint32_t)begin - 1u, before_v = 0, after_it = (uint32_t)end, after_v = max_vocab;
     const uint32_t key = (uint32_t)key_;
@@ -60,7 +60,7 @@ FSG_HD int lm_find(const int32_t *words, int begin, int end, int key_, uint32_t 
 }
 
 // ngram_tg_score(lmset, w, h1, h2) for DICTIONARY word ids (h = -1: no such history word); not yet >> SENSCR_SHIFT
-FSG_HD int lm_tg_score(const LmArr &L, int w_dict, int h1_dict, int h2_dict)
+FSG_HDH int lm_tg_score(const LmArr &L, int w_dict, int h1_dict, int h2_dict)
 {
     const int w = w_dict < 0 ? -1 : L.widmap[w_dict];
     int h[2], n_hist = 2;

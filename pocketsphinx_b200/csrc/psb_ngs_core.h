@@ -128,7 +128,7 @@ FSG_HD void ngs_enter(const NgsWork &W, int c, int score, int hist, int nf)     
     W.score[c] = score; W.hist[c] = hist; W.frame[c] = nf;
 }
 
-FSG_HD int ngs_tg(const NgsGraph &G, int w, int h1, int h2)
+FSG_HDH int ngs_tg(const NgsGraph &G, int w, int h1, int h2)
 {
     if (G.use_lma) return lm_tg_score(G.lma, w, h1, h2) >> 10;           /* >> SENSCR_SHIFT */
     const int n = G.n_lm + 1;

@@ -3,6 +3,7 @@
 // does this on the host too, once per utterance, over a few thousand rows); no device work, so these
 // entry points also run where there is no GPU.
 #include "psb_internal.cuh"
+#include "psb_ngs_host.h"
 
 #include <limits.h>
 
@@ -131,6 +132,80 @@ extern "C" int32_t psb_ngram_backtrace(const int32_t *bp, int32_t n_bp, int32_t 
         if (cur < cap) {
             int32_t *s = seg + (size_t)cur * 5;
             s[0] = b; s[1] = e[2]; s[2] = e[3] >= 0 ? bp[(size_t)e[3] * 10] + 1 : 0; s[3] = e[0]; s[4] = e[4];
+        }
+        b = e[3];
+    }
+    return n;
+}
+
+// ngram_search_bp2itor (ngram_search.c:886-928) for every entry of the chain: what ps_seg_iter reports
+// without -bestpath.  seg [cap][7] = {entry, wid, sf, ef, path score, ascr, lscr}; the right-context
+// exit score of the predecessor comes from the score stack (ngram_search_exit_score :655-676), the LM
+// score from the search description (dense table or LM arrays), scaled by lwf (the float32
+// fwdflat_fwdtree_lw_ratio after a second pass, 1.0 after the first alone: ngram_search_seg_iter :1033-1036).
+extern "C" int32_t psb_ngram_segments(const psb_ngram_desc_t *g, const int32_t *bp, int32_t n_bp, const int32_t *bss,
+                                      int32_t n_bss, int32_t exit_entry, float lwf, int32_t *seg, int32_t cap)
+{
+    PSB_REQUIRE(g && g->info && g->model && bp && bss && n_bp >= 0 && n_bss >= 0 && (seg || cap == 0) && cap >= 0,
+                "psb_ngram_segments: bad arguments");
+    const int32_t *info = g->info;
+    NgsGraph G;
+    memset(&G, 0, sizeof(G));
+    G.n_words = info[1]; G.n_ci = info[6]; G.n_lm = info[26];
+    const long long n_root = info[2], n_nonroot = info[3], n_1ph = info[4], nc = G.n_ci, nl = G.n_lm;
+    G.use_lma = g->lm_arrays != nullptr;
+    PSB_REQUIRE(G.n_words > 0 && nc > 0 && nc <= 256 && n_root >= 0 && n_nonroot >= 0 && n_1ph >= 0 && nl >= 0 && nl <= 512 &&
+                (nl > 0 || G.use_lma), "psb_ngram_segments: sizes in info out of range");
+    const long long o_words = n_root * 5 + n_nonroot * 6, o_cimap = o_words + (long long)G.n_words * 8 + n_1ph * 5 + nc * nc + nc * nc * nc,
+                    o_lm = o_cimap + 2 * nc * nc * nc, need = o_lm + (G.use_lma ? 0 : nl * (nl + 1) * (nl + 1));
+    PSB_REQUIRE(g->model_len >= need, "psb_ngram_segments: model block holds %lld words, the sizes in info need %lld",
+                (long long)g->model_len, need);
+    G.words = g->model + o_words; G.rs_cimap = g->model + o_cimap; G.lm = g->model + o_lm;
+    if (G.use_lma) {
+        std::string err;
+        if (lm_arr_check(g->lm_arrays, g->lm_arrays_len, G.n_words, err) != 0) PSB_REQUIRE(false, "psb_ngram_segments: %s", err.c_str());
+        lm_arr_bind(G.lma, g->lm_arrays, g->lm_arrays);
+    }
+    const int silence_wid = info[21];
+    const int silpen = info[17], fillpen = info[18];
+    if (exit_entry == -1) return 0;
+    PSB_REQUIRE(exit_entry >= 0 && exit_entry < n_bp, "psb_ngram_segments: entry %d of %d", exit_entry, n_bp);
+    auto lm_ok = [&](int w, bool hist) {                // a dictionary id the LM lookup may be given
+        if (hist && w == -1) return true;
+        if (w < 0 || w >= G.n_words) return false;
+        return G.use_lma || (NGS_W(G, w, 7) >= 0 && NGS_W(G, w, 7) < G.n_lm);
+    };
+    int n = 0;
+    for (int b = exit_entry; b != -1; ++n) {
+        const int32_t *e = bp + (size_t)b * 10;
+        PSB_REQUIRE(e[3] >= -1 && e[3] < b && e[2] >= 0 && e[2] < G.n_words, "psb_ngram_segments: entry %d is not a backpointer row", b);
+        b = e[3];
+    }
+    int cur = n - 1;
+    for (int b = exit_entry; b != -1; --cur) {
+        const int32_t *e = bp + (size_t)b * 10;
+        const int32_t *pe = e[3] >= 0 ? bp + (size_t)e[3] * 10 : nullptr;
+        int32_t ascr = e[4], lscr = 0;
+        if (pe) {
+            int32_t start_score = pe[4];
+            if (pe[9] != -1) {                          // multi-phone predecessor: its exit into this word's first phone
+                PSB_REQUIRE(pe[8] >= 0 && pe[8] < nc && pe[9] >= 0 && pe[9] < nc, "psb_ngram_segments: entry %d: phones out of range", e[3]);
+                const int rc = G.rs_cimap[((size_t)pe[8] * nc + pe[9]) * nc + NGS_W(G, e[2], 0)];
+                PSB_REQUIRE(pe[5] >= 0 && rc >= 0 && (long long)pe[5] + rc < n_bss, "psb_ngram_segments: entry %d: score stack index out of range", e[3]);
+                start_score = bss[pe[5] + rc];
+            }
+            if (e[2] == silence_wid) lscr = silpen;
+            else if (NGS_W(G, e[2], 4)) lscr = fillpen;
+            else {
+                PSB_REQUIRE(lm_ok(e[6], false) && lm_ok(pe[6], true) && lm_ok(pe[7], true), "psb_ngram_segments: entry %d: LM word ids out of range", b);
+                lscr = ngs_tg(G, e[6], pe[6], pe[7]);
+                lscr = (int32_t)((float)lscr * lwf);
+            }
+            ascr = (int32_t)((uint32_t)e[4] - (uint32_t)start_score - (uint32_t)lscr);
+        }
+        if (cur < cap) {
+            int32_t *s = seg + (size_t)cur * 7;
+            s[0] = b; s[1] = e[2]; s[2] = pe ? pe[0] + 1 : 0; s[3] = e[0]; s[4] = e[4]; s[5] = ascr; s[6] = lscr;
         }
         b = e[3];
     }

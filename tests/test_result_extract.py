@@ -135,3 +135,60 @@ def test_ngram_segments_match_the_reference_iterator(kv):
     for s, (word, sf, ef, _, _) in zip(seg, lines):
         assert (int(s[2]), int(s[3])) == (int(sf), int(ef))
         assert r["vocab"][int(r["words"][s[1]][5])] == word.split("(")[0]
+
+
+@live
+@pytest.mark.parametrize("kv", [dict(), dict(fwdflat="yes"), dict(fwdflat="yes", fwdflatlw="7.5", lw="5"),
+                                dict(beam="1e-60", wbeam="1e-40", maxwpf="5"), dict(silprob="0.02", fillprob="1e-5")])
+@pytest.mark.parametrize("arrays", [False, True])
+def test_ngram_segment_scores_match_the_reference_iterator(kv, arrays):
+    """ascr / lscr of every segment (ngram_search_bp2itor): right-context exit scores from the score stack,
+    LM scores from the dense table or the LM arrays, scaled by the float32 fwdflatlw / lw after a second pass."""
+    rd = os.path.dirname(refdrv.LIB_PATH)
+    hd, lm, dic = os.path.join(rd, "model", "en-us"), os.path.join(rd, "data", "turtle.lm.bin"), os.path.join(rd, "data", "turtle.dic")
+    pcm = np.fromfile(os.path.join(rd, "data", "goforward.raw"), np.int16)
+    r = refdrv.fwdtree(hd, lm, dic, pcm, dense_lm=not arrays, **kv)
+    lma = refdrv.lm_arrays(hd, lm, dic, **kv)[0] if arrays else None
+    full = refdrv.decode(hd, lm, dic, pcm, bestpath="no", compallsen="yes", pl_window="0", **dict(dict(fwdflat="no"), **kv))
+    entry, score, chain = api.ngram_hyp(r["bp"], r["bp_idx"], r["n_frame"], r["finish_wid"])
+    seg = api.ngram_segments(r["info"], r["model"], r["bp"], r["bss"], entry, lm_arrays=lma, second_pass=kv.get("fwdflat") == "yes")
+    assert np.array_equal(seg[:, :5], chain)
+    lines = [l.split() for l in full["seg"].split("\n") if l]
+    assert len(lines) == len(seg) > 3
+    for s, (word, sf, ef, ascr, lscr) in zip(seg, lines):
+        assert (int(s[2]), int(s[3]), int(s[5]), int(s[6])) == (int(sf), int(ef), int(ascr), int(lscr)), word
+    assert any(int(l[4]) != 0 for l in lines)
+
+
+def test_ngram_segments_reject_tables_that_leave_the_model():
+    g = golden("en_us_fwdtree.npz")
+    d = _case(g, "default")
+    e = api.ngram_hyp(d["bp"], d["bp_idx"], len(d["bp_idx"]) - 1, int(d["info"][20]))[0]
+    seg = api.ngram_segments(d["info"], d["model"], d["bp"], d["bss"], e)
+    assert len(seg) > 3 and int(seg[:, 5].sum() + seg[:, 6].sum()) == int(d["bp"][e, 4]) + sum(
+        int(d["bp"][p, 4]) - _start(d, p, int(d["bp"][b, 2])) for b, p in zip(seg[1:, 0], seg[:-1, 0]))
+    with pytest.raises(PsbError):
+        api.ngram_segments(d["info"], d["model"][:1000], d["bp"], d["bss"], e)
+    with pytest.raises(PsbError):
+        api.ngram_segments(d["info"], d["model"], d["bp"], d["bss"][:4], e)
+    bp = d["bp"].copy()
+    bp[seg[1, 0], 6] = 10 ** 6
+    with pytest.raises(PsbError):
+        api.ngram_segments(d["info"], d["model"], bp, d["bss"], e)
+    bp = d["bp"].copy()
+    bp[seg[1, 0], 8] = 10 ** 6
+    with pytest.raises(PsbError):
+        api.ngram_segments(d["info"], d["model"], bp, d["bss"], e)
+
+
+def _start(d, p, wid):
+    """ngram_search_exit_score of entry p into word wid, from the oracle's view of the tables."""
+    info, model, bp, bss = d["info"], d["model"], d["bp"], d["bss"]
+    nc = int(info[6])
+    o_words = int(info[2]) * 5 + int(info[3]) * 6
+    words = model[o_words:o_words + int(info[1]) * 8].reshape(-1, 8)
+    o_cimap = o_words + int(info[1]) * 8 + int(info[4]) * 5 + nc * nc + nc ** 3
+    cimap = model[o_cimap:o_cimap + nc ** 3].reshape(nc, nc, nc)
+    if bp[p, 9] == -1:
+        return int(bp[p, 4])
+    return int(bss[bp[p, 5] + cimap[bp[p, 8], bp[p, 9], words[wid, 0]]])
