@@ -40,3 +40,12 @@ def test_large_vocabulary_decode(emuls):  # noqa: F811
     assert n1 == len(first["bp"]) and np.array_equal(bp1, first["bp"]) and np.array_equal(bss1, first["bss"]) and np.array_equal(idx1, first["bp_idx"])
     n2, bp2, bss2, idx2 = run_second(f2, pk, both["info"], both["model"], bp1, scr, len(both["bp"]) + 64, len(both["bss"]) + 4096, lm_arrays=lma)
     assert n2 == len(both["bp"]) and np.array_equal(bp2, both["bp"]) and np.array_equal(bss2, both["bss"]) and np.array_equal(idx2, both["bp_idx"])
+    # ps_seg_iter of the same decode from the tables alone (psb_result.cu): every segment's frames and scores
+    from pocketsphinx_b200 import api
+    full = refdrv.decode(hd, BIG_LM, dic, pcm, bestpath="no", compallsen="yes", pl_window="0", fwdflat="yes")
+    entry, score, _ = api.ngram_hyp(bp2, idx2, both["n_frame"], both["finish_wid"])
+    seg = api.ngram_segments(both["info"], both["model"], bp2, bss2, entry, lm_arrays=lma, second_pass=True)
+    lines = [l.split() for l in full["seg"].split("\n") if l]
+    assert score == full["score"] and len(lines) == len(seg) > 3
+    for s, (word, sf, ef, ascr, lscr) in zip(seg, lines):
+        assert (int(s[2]), int(s[3]), int(s[5]), int(s[6])) == (int(sf), int(ef), int(ascr), int(lscr)), word
