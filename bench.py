@@ -282,6 +282,20 @@ def search_stage(api, torch, U=256):
                                                              d_pen.data_ptr(), win, first_cap=2048, first_bss_cap=1 << 15))
     out["two_pass"] = {"call": "psb_ngram_two_pass_batch_device", "ms": dt3 * 1e3, "utts_per_s": U / dt3, "frames_per_s": U * T / dt3,
                        "matches_reference": bool(np.array_equal(both[0][0], c["bp"]) and np.array_equal(both[U - 1][0], c["bp"]))}
+    try:                                               # the words, read from the tables alone (psb_result.cu)
+        dflt = case(np.load(os.path.join(gd, "en_us_fwdtree.npz")), "default")
+        vocab, words = str(dflt["vocab"]).split("\n"), dflt["words"]
+        t0 = time.perf_counter()
+        hyps = []
+        for bp, bss, idx in both:
+            entry, _, seg = api.ngram_hyp(bp, idx, T, int(c["info"][20]))
+            hyps.append(" ".join(vocab[int(words[w][5])] for w in seg[:, 1]
+                                 if not words[w][4] and int(words[w][5]) not in (int(c["info"][19]), int(c["info"][20]))))
+        out["two_pass"]["hyp"] = hyps[0]
+        out["two_pass"]["all_utts_same_hyp"] = bool(all(h == hyps[0] for h in hyps))
+        out["two_pass"]["hyp_extraction_ms"] = (time.perf_counter() - t0) * 1e3
+    except Exception as e:
+        out["two_pass"]["hyp_error"] = str(e)[:100]
     ctx.close()
     try:
         from oracle import refdrv
