@@ -107,6 +107,13 @@ class PackedModel:
         return cls(**kw)
 
     @classmethod
+    def from_dir(cls, path, **config):
+        """An acoustic-model directory as the reference ships them (s3io.read_model_dir: mdef, means,
+        variances, transition_matrices, sendump / mixture_weights, feat.params), loaded without the reference."""
+        from . import s3io
+        return cls.from_dict(s3io.read_model_dir(path, **config))
+
+    @classmethod
     def load(cls, path):
         with np.load(path, allow_pickle=False) as z:
             return cls.from_dict({k: z[k] for k in z.files})
