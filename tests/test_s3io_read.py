@@ -137,3 +137,19 @@ def test_directory_read_equals_the_golden_model_the_gpu_tests_score_with(name, g
             a = a[:len(b)]                                       # the golden file keeps the first few thousand phones
         assert a.shape == b.shape and np.array_equal(a, b), k
     assert (pm.n_sen, pm.n_mgau, pm.n_density, pm.topn, pm.n_emit_state) == (want.n_sen, want.n_mgau, want.n_density, want.topn, want.n_emit_state)
+
+
+def test_other_endian_files_read_the_same(tmp_path):
+    """bio_readhdr's byte-order word (bio.c:232-262): files written on a big-endian machine."""
+    pm, raw = synth_ms(seed=7, n_sen=30, n_density=4, return_raw=True)
+    d = _write(tmp_path, pm, raw, 10)
+    want = s3io.read_model_dir(d)
+    for name in ("means", "variances", "transition_matrices", "mixture_weights"):
+        p = os.path.join(d, name)
+        b = open(p, "rb").read()
+        cut = b.index(b"endhdr\n") + 7
+        body = np.frombuffer(b[cut:], "<u4").astype(">u4").tobytes()      # every 32-bit word, magic and checksum included
+        open(p, "wb").write(b[:cut] + body)
+    got = s3io.read_model_dir(d)
+    for k in ("mean", "var", "det", "mixw", "tp"):
+        assert np.array_equal(np.asarray(got[k]), np.asarray(want[k])), k
