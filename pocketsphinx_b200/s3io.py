@@ -371,7 +371,8 @@ def read_mdef(path):
     triphones (mdef.c:515-700; triphones would need bin_mdef_read_text's phone reordering: convert such a
     file with the reference's pocketsphinx_mdef_convert).  Returns a dict: n_ciphone, n_phone,
     n_emit_state, n_ci_sen, n_sen, n_tmat, ciname, sseq [n_sseq][n_emit], phone_ssid, phone_tmat,
-    phone_filler, sen2cimap."""
+    phone_filler, sen2cimap, cd_tree (the triphone lookup tree: ctx, n_down, down / pid; None for a CI-only
+    text file), sil (the id of SIL or -1)."""
     with open(path, "rb") as f:
         raw = f.read()
     if raw[:4] in (b"BMDF", b"FDMB"):
@@ -390,7 +391,8 @@ def read_mdef(path):
             names.append(raw[p:e].decode("latin-1"))
             p = e + 1
         p = pos + ((p - pos + 3) & ~3)
-        p += 8 * n_cd_tree                                   # cd_tree_t {int16 ctx, n_down; int32 down}: lookups only
+        cd_tree = np.frombuffer(raw, np.dtype([("ctx", o + "i2"), ("n_down", o + "i2"), ("down", o + "i4")]), n_cd_tree, p)
+        p += 8 * n_cd_tree                                   # cd_tree_t {int16 ctx, n_down; int32 down / pid}
         ent = np.frombuffer(raw, np.dtype([("ssid", o + "i4"), ("tmat", o + "i4"), ("info", "u1", 4)]), n_phone, p)
         p += 12 * n_phone
         sseq_size = struct.unpack_from(o + "i", raw, p)[0]
@@ -428,6 +430,7 @@ def read_mdef(path):
         sseq = np.array(list(uniq), np.uint16).reshape(len(uniq), n_emit)
         ssid, tmat, filler = np.array(ssid, np.int32), np.array(tmat, np.int32), np.array(filler, np.uint8)
         n_phone, base = n_ci, np.arange(n_ci)
+        cd_tree = None
     if sseq.size and int(sseq.max()) >= n_sen:
         raise ValueError("%s: senone id out of range" % path)
     if (ssid < 0).any() or (ssid >= len(sseq)).any() or (tmat < 0).any() or (tmat >= n_tmat).any():
@@ -436,7 +439,8 @@ def read_mdef(path):
     for i in range(n_phone - 1, -1, -1):
         sen2ci[sseq[ssid[i]]] = base[i]
     return dict(n_ciphone=n_ci, n_phone=n_phone, n_emit_state=n_emit, n_ci_sen=n_ci_sen, n_sen=n_sen, n_tmat=n_tmat,
-                ciname=names, sseq=sseq, phone_ssid=ssid, phone_tmat=tmat, phone_filler=filler, sen2cimap=sen2ci)
+                ciname=names, sseq=sseq, phone_ssid=ssid, phone_tmat=tmat, phone_filler=filler, sen2cimap=sen2ci,
+                cd_tree=cd_tree, sil=names.index("SIL") if "SIL" in names else -1)
 
 
 def read_feat_params(path):
