@@ -1,0 +1,71 @@
+"""CPU (needs oracle/_ref/libpsref.so): pocketsphinx_b200.lextree.build_ngram_search -- the flattened n-gram
+search (info + every model section: root / interior channels, word table with homophone chains, single-phone
+words, dict2pid tables, LM membership, pronunciations with their word-internal senone sequences) built from the
+FILES ALONE must equal what the maintainer-side binding exports from a reference decoder: demo LM, tidigits,
+and cmudict + the 72 k-word en-us LM (723 roots, 152 500 interior channels); other beams and penalties."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import refdrv
+from pocketsphinx_b200 import lextree
+
+pytestmark = pytest.mark.skipif(not refdrv.available(), reason="oracle/_ref/libpsref.so not built")
+REF = os.path.dirname(refdrv.LIB_PATH)
+EN, TD = os.path.join(REF, "model", "en-us"), os.path.join(REF, "model", "tidigits_hmm")
+CASES = {"turtle": (EN, os.path.join(REF, "data", "turtle.lm.bin"), os.path.join(REF, "data", "turtle.dic")),
+         "tidigits": (TD, os.path.join(REF, "model", "tidigits_lm", "tidigits.lm.bin"), os.path.join(REF, "model", "tidigits_lm", "tidigits.dic")),
+         "cmudict": (EN, os.path.join(REF, "model", "en-us.lm.bin"), os.path.join(REF, "model", "cmudict-en-us.dict"))}
+RESULT_SLOTS = {0, 24, 25, 27}                                   # frames, table sizes and score of the driver's decode
+
+
+def from_files(hd, lm, dic, **kv):
+    g = lextree.ngram_search_from_files(hd, dic, lm, **kv)
+    return g["info"], g["model"], g["lm_arrays"]
+
+
+@pytest.mark.parametrize("name,kv", [("turtle", {}), ("tidigits", {}), ("cmudict", {}),
+                                     ("turtle", dict(beam="1e-60", wbeam="1e-40", pbeam="1e-55", maxwpf="5", maxhmmpf="500", lw="9.5",
+                                                     fwdflatlw="7", silprob="0.02", fillprob="1e-5", pip="0.5", nwpen="0.8",
+                                                     fwdflatbeam="1e-50", fwdflatefwid="3", fwdflatsfwin="20"))],
+                         ids=["turtle", "tidigits", "cmudict-72k", "turtle-settings"])
+def test_search_description_equals_the_exported_one(name, kv):
+    hd, lm, dic = CASES[name]
+    if not os.path.exists(lm):
+        pytest.skip("LM file not present")
+    pcm = np.fromfile(os.path.join(REF, "data", "goforward.raw"), np.int16)
+    r = refdrv.fwdtree(hd, lm, dic, pcm, dense_lm=False, fwdflat="yes", **kv)
+    info, model, arr = from_files(hd, lm, dic, **kv)
+    assert [i for i in range(40) if i not in RESULT_SLOTS and info[i] != r["info"][i]] == []
+    assert model.shape == r["model"].shape and np.array_equal(model, r["model"])
+    assert np.array_equal(arr, refdrv.lm_arrays(hd, lm, dic, **kv)[0])
+    if name == "cmudict":
+        assert info[2] > 700 and info[3] > 150_000
+
+
+def test_files_alone_decode_like_the_reference():
+    """End to end on the CPU side: description + LM block from the files, the oracle's first and second pass on the
+    reference's senone scores -> the reference's own backpointer tables and hypothesis."""
+    from oracle import oracle
+    from pocketsphinx_b200 import api
+    hd, lm, dic = CASES["turtle"]
+    pcm = np.fromfile(os.path.join(REF, "data", "goforward.raw"), np.int16)
+    want = refdrv.fwdtree(hd, lm, dic, pcm, dense_lm=False, fwdflat="yes")
+    first = refdrv.fwdtree(hd, lm, dic, pcm, dense_lm=False)
+    info, model, arr = from_files(hd, lm, dic)
+    ref = refdrv.RefModel(hd)
+    pk = ref.packed()
+    scr = np.ascontiguousarray(ref.score(ref.featurize_fresh(pcm)))
+    ref.close()
+    nc = int(info[6])
+    o1 = oracle.fwdtree_run(pk["tp"], pk["sseq"], pk["phone_tmat"][:nc], info, model, scr, lm_arrays=arr)
+    assert np.array_equal(o1[0], first["bp"]) and np.array_equal(o1[1], first["bss"])
+    o2 = oracle.fwdflat_run(pk["tp"], pk["sseq"], pk["phone_tmat"][:nc], pk["phone_ssid"][:nc], info, model, o1[0], scr, lm_arrays=arr)
+    assert np.array_equal(o2[0], want["bp"]) and np.array_equal(o2[1], want["bss"]) and np.array_equal(o2[2], want["bp_idx"])
+    g = lextree.ngram_search_from_files(hd, dic, lm)
+    words = g["words"]
+    assert np.array_equal(g["ci_tmat"], pk["phone_tmat"][:nc]) and np.array_equal(g["ci_ssid"], pk["phone_ssid"][:nc])
+    entry, score, seg = api.ngram_hyp(o2[0], o2[2], len(scr), int(info[20]))
+    real = [words[w].split("(")[0] for w in seg[:, 1] if not (int(info[22]) <= w <= int(info[23]))]
+    assert " ".join(real) == want["hyp"] == "go forward ten meters"
