@@ -69,3 +69,14 @@ def test_files_alone_decode_like_the_reference():
     entry, score, seg = api.ngram_hyp(o2[0], o2[2], len(scr), int(info[20]))
     real = [words[w].split("(")[0] for w in seg[:, 1] if not (int(info[22]) <= w <= int(info[23]))]
     assert " ".join(real) == want["hyp"] == "go forward ten meters"
+
+
+def test_files_alone_equals_the_golden_description_the_gpu_tests_use():
+    """tests/golden/en_us_fwdtree.npz (nodense.info / nodense.model / lmarr) is what the gated GPU tests hand to the
+    kernels with the array LM; the same blocks come out of the files, so those tests also cover this path."""
+    from conftest import golden
+    g = golden("en_us_fwdtree.npz")
+    hd, lm, dic = CASES["turtle"]
+    d = lextree.ngram_search_from_files(hd, dic, lm)
+    assert [i for i in range(40) if i not in RESULT_SLOTS and d["info"][i] != g["nodense.info"][i]] == []
+    assert np.array_equal(d["model"], g["nodense.model"]) and np.array_equal(d["lm_arrays"], g["lmarr"])
