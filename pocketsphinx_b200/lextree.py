@@ -166,7 +166,7 @@ def build_ngram_search(md, words, prons, base, filler_start, widmap, unknown_wid
 def ngram_search_from_files(hmm_dir, dict_file, lm_file, filler_dict=None, **config):
     """Everything `HmmContext.ngram_fwdtree / ngram_fwdflat / ngram_two_pass` take besides the senone scores,
     from an acoustic-model directory, a dictionary and a binary trie LM (the reference's -hmm / -dict / -lm):
-    dict(info, model, lm_arrays, ci_tmat, ci_ssid, words).  filler_dict defaults to the model's `noisedict`
+    dict(info, model, lm_arrays, ci_tmat, ci_ssid, words, base).  filler_dict defaults to the model's `noisedict`
     (-fdict); config: the reference's search settings by name (beam, wbeam, lw, wip, fwdflatlw, ...)."""
     import os
 
@@ -187,4 +187,4 @@ def ngram_search_from_files(hmm_dir, dict_file, lm_file, filler_dict=None, **con
                                      arr[10:10 + len(words)], unk, **config)
     n_ci = md["n_ciphone"]
     return dict(info=info, model=model, lm_arrays=arr, ci_tmat=md["phone_tmat"][:n_ci].astype(np.int32),
-                ci_ssid=md["phone_ssid"][:n_ci].astype(np.int32), words=words)
+                ci_ssid=md["phone_ssid"][:n_ci].astype(np.int32), words=words, base=base)

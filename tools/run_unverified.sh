@@ -9,7 +9,7 @@ export PSB_RUN_UNVERIFIED=1
 rc=0
 for mode in 0 1; do
     export PSB_SEARCH_WARP=$mode
-    for f in tests/test_gpu_zz_fsg.py tests/test_gpu_zz_ngram.py; do
+    for f in tests/test_gpu_zz_fsg.py tests/test_gpu_zz_ngram.py tests/test_gpu_zz_decoder.py; do
         log=gpurun_out/unverified_$(basename $f .py)_warp$mode.log
         timeout 300 python -m pytest $f -x -q -m gpu > $log 2>&1
         r=$?
