@@ -25,7 +25,7 @@ def _logs(p, logbase=1.0001):
 
 
 class Decoder:
-    def __init__(self, hmm, dict, lm, max_utts=64, max_frames=1 << 16, device=0, **config):
+    def __init__(self, hmm, dict_file, lm_file, max_utts=64, max_frames=1 << 16, device=0, **config):
         cfg = {k: str(v) for k, v in config.items()}
         self.pm = PackedModel.from_dir(hmm, **{k: v for k, v in cfg.items() if k in ("varfloor", "tmatfloor", "mixwfloor", "topn", "ds", "aw")})
         fp = {}
@@ -45,7 +45,7 @@ class Decoder:
             fe_kw["remove_dc"] = fp["remove_dc"] in ("yes", "1", "true")
         self.fe = api.FrontEnd(make_fe_desc(**fe_kw), device)
         search_cfg = {k: v for k, v in cfg.items() if k in lextree.DEFAULTS}
-        self.search = lextree.ngram_search_from_files(hmm, dict, lm, **search_cfg)
+        self.search = lextree.ngram_search_from_files(hmm, dict_file, lm_file, **search_cfg)
         self.model = api.Model(self.pm, device)
         self.batch = api.Batch(self.model, max_utts, max_frames)
         self.ctx = api.HmmContext(self.pm.tp, self.pm.sseq, self.pm.n_sen)
