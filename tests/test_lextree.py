@@ -80,3 +80,28 @@ def test_files_alone_equals_the_golden_description_the_gpu_tests_use():
     d = lextree.ngram_search_from_files(hd, dic, lm)
     assert [i for i in range(40) if i not in RESULT_SLOTS and d["info"][i] != g["nodense.info"][i]] == []
     assert np.array_equal(d["model"], g["nodense.model"]) and np.array_equal(d["lm_arrays"], g["lmarr"])
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_random_sub_dictionaries_against_the_export(tmp_path, seed):
+    """4000 random cmudict lines (odd seeds: shuffled, so alternates can precede or lose their base word and are
+    dropped like dict_add_word drops them), random beam and weights, the 72 k-word LM: description and LM block from
+    the files equal the export."""
+    import random
+    hd, lm, big = CASES["cmudict"]
+    if not os.path.exists(lm):
+        pytest.skip("LM file not present")
+    rng = random.Random(seed)
+    lines = open(big, encoding="latin-1").read().split("\n")
+    sub = [lines[i] for i in sorted(rng.sample(range(len(lines)), 4000)) if lines[i].strip()]
+    if seed % 2:
+        rng.shuffle(sub)
+    p = str(tmp_path / "sub.dic")
+    open(p, "w", encoding="latin-1").write("\n".join(sub) + "\n")
+    kv = dict(beam="1e-%d" % rng.randint(30, 80), lw=str(rng.choice([5, 6.5, 9.5])), wip=str(rng.choice([0.2, 0.65])))
+    pcm = np.fromfile(os.path.join(REF, "data", "goforward.raw"), np.int16)[:8000]
+    r = refdrv.fwdtree(hd, lm, p, pcm, dense_lm=False, fwdflat="yes", **kv)
+    g = lextree.ngram_search_from_files(hd, p, lm, **kv)
+    assert [i for i in range(40) if i not in RESULT_SLOTS and g["info"][i] != r["info"][i]] == []
+    assert np.array_equal(g["model"], r["model"]) and np.array_equal(g["lm_arrays"], refdrv.lm_arrays(hd, lm, p, **kv)[0])
+    assert len(g["words"]) < len(sub) + 10 and int(g["info"][3]) > 5000
