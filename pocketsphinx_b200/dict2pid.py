@@ -98,6 +98,7 @@ def build(md, prons):
     ssid = md["phone_ssid"]
     ldiph = np.full((n, n, n), BAD_SSID, np.int32)
     rdiph = np.full((n, n, n), BAD_SSID, np.int32)
+    lrdiph = np.full((n, n, n), BAD_SSID, np.int32)
     seen_l, seen_r, single = set(), set(), set()
     for p in prons:
         if len(p) >= 2:
@@ -117,6 +118,7 @@ def build(md, prons):
             for l in range(n):                                  # populate_lrdiph (:270-298): also the silence-context
                 for r in range(n):                              # rows of the other two tables, unconditionally
                     s = ssid[tri.nearest(b, l, r, WPOS_SINGLE)]
+                    lrdiph[b, l, r] = s
                     if r == tri.sil:
                         ldiph[b, r, l] = s
                     if l == tri.sil:
@@ -131,4 +133,34 @@ def build(md, prons):
                 rs_n[b, l] = k
                 rs_ssid[b, l, :k] = com[:k]
                 rs_cimap[b, l] = cimap
-    return dict(rs_n=rs_n, rs_ssid=rs_ssid, rs_cimap=rs_cimap, ldiph_lc=ldiph)
+    return dict(rs_n=rs_n, rs_ssid=rs_ssid, rs_cimap=rs_cimap, ldiph_lc=ldiph, lrdiph_rc=lrdiph)
+
+
+def alignment_phones(md, prons, tabs, wids):
+    """ps_alignment_populate (ps_alignment.c:131-218): the phone chain of a word sequence with its cross-word
+    contexts -- silence to the left of the first word and to the right of the last, the neighbours' last / first
+    phones in between -- as (ssid, tmatid, cipid) per phone: what HmmContext.align takes.  prons: the dictionary's
+    pronunciations (CI phone ids by word id), tabs: build(md, prons), wids: the transcript's dictionary ids."""
+    tri = TriphoneIndex(md)
+    ssid_of, tmat_of, sil = md["phone_ssid"], md["phone_tmat"], md["sil"]
+    ssid, cipid = [], []
+    lc = sil
+    for i, w in enumerate(wids):
+        p = prons[w]
+        rc = prons[wids[i + 1]][0] if i + 1 < len(wids) else sil
+        if len(p) == 1:
+            ssid.append(int(tabs["lrdiph_rc"][p[0], lc, rc]))
+        else:
+            ssid.append(int(tabs["ldiph_lc"][p[0], p[1], lc]))
+        cipid.append(p[0])
+        for j in range(1, len(p) - 1):
+            ssid.append(int(ssid_of[tri.nearest(p[j], p[j - 1], p[j + 1], WPOS_INTERNAL)]))
+            cipid.append(p[j])
+        if len(p) > 1:
+            ssid.append(int(tabs["rs_ssid"][p[-1], p[-2], tabs["rs_cimap"][p[-1], p[-2], rc]]))
+            cipid.append(p[-1])
+        lc = p[-1]
+    if BAD_SSID in ssid or -1 in ssid:
+        raise ValueError("a word of the transcript has no senone sequence in this context")
+    cipid = np.array(cipid, np.int32)
+    return np.array(ssid, np.int32), tmat_of[cipid].astype(np.int32), cipid

@@ -56,3 +56,36 @@ def test_triphone_lookup_backs_off_like_the_reference():
                 assert p == ci["AA"]                             # the last resort is the base phone itself
     noise = [i for i in range(n) if md["phone_filler"][i] and i != md["sil"]]
     assert noise and tri.phone_id(ci["AA"], noise[0], ci["B"], 0) == tri.phone_id(ci["AA"], md["sil"], ci["B"], 0)   # fillers count as silence
+
+
+@pytest.fixture(scope="module")
+def cmu():
+    hd, dic = EN, os.path.join(REF, "model", "cmudict-en-us.dict")
+    md = s3io.read_mdef(os.path.join(hd, "mdef"))
+    words, prons, base, fs = lmio.read_dict(dic, os.path.join(hd, "noisedict"), md["ciname"])
+    ci = {n: i for i, n in enumerate(md["ciname"])}
+    pr = [[ci[x] for x in p] for p in prons]
+    return md, {w: i for i, w in enumerate(words)}, pr, dict2pid.build(md, pr)
+
+
+def test_alignment_phone_chains_equal_the_golden_ones(cmu):
+    """ps_alignment_populate from the files alone: the (ssid, tmatid) chains tests/golden/en_us_align.npz holds for
+    three transcripts -- the inputs the GPU-verified forced-alignment kernel is tested with."""
+    from conftest import golden
+    md, idx, pr, tabs = cmu
+    g = golden("en_us_align.npz")
+    for tag, text in (("a", "<s> go forward ten meters </s>"), ("b", "go forward ten meters"),
+                      ("c", "<s> go forward ten meters </s> <s> go forward </s>")):
+        s, t, c = dict2pid.alignment_phones(md, pr, tabs, [idx[w] for w in text.split()])
+        assert np.array_equal(s, g[tag + "_ssid"]) and np.array_equal(t, g[tag + "_tmatid"]), tag
+
+
+@pytest.mark.parametrize("text", ["a", "<s> a i </s>", "<sil> the a an </s>", "go <sil> forward(2) a ten", "++noise++ meters ++breath++ a"])
+def test_alignment_phone_chains_live(cmu, text):
+    """Single-phone words next to each other, fillers as neighbours, alternate pronunciations: against the reference."""
+    md, idx, pr, tabs = cmu
+    text = " ".join(w for w in text.split() if w in idx)
+    pcm = np.fromfile(os.path.join(REF, "data", "goforward.raw"), np.int16)
+    want = refdrv.align(EN, os.path.join(REF, "model", "cmudict-en-us.dict"), text, pcm)
+    s, t, c = dict2pid.alignment_phones(md, pr, tabs, [idx[w] for w in text.split()])
+    assert np.array_equal(s, want["ssid"]) and np.array_equal(t, want["tmatid"])
