@@ -164,3 +164,25 @@ def alignment_phones(md, prons, tabs, wids):
         raise ValueError("a word of the transcript has no senone sequence in this context")
     cipid = np.array(cipid, np.int32)
     return np.array(ssid, np.int32), tmat_of[cipid].astype(np.int32), cipid
+
+
+def keyphrase_phones(md, prons, tabs, wids):
+    """The HMM chain kws_search_reinit builds for one keyphrase (kws_search.c:552-585): every word with silence as
+    its outer context (first phone: ldiph_lc with a silence left context -- also for single-phone words, whose
+    right context is silence too; last phone: the right-context entry for silence; word-internal triphones in
+    between) -> (ssid, tmatid) per phone, what HmmContext.kws takes per keyphrase."""
+    tri = TriphoneIndex(md)
+    ssid_of, tmat_of, sil = md["phone_ssid"], md["phone_tmat"], md["sil"]
+    ssid, cipid = [], []
+    for w in wids:
+        p = prons[w]
+        for j, ci in enumerate(p):
+            if j == 0:
+                ssid.append(int(tabs["ldiph_lc"][ci, p[1] if len(p) > 1 else sil, sil]))
+            elif j == len(p) - 1:
+                ssid.append(int(tabs["rs_ssid"][ci, p[j - 1], tabs["rs_cimap"][ci, p[j - 1], sil]]))
+            else:
+                ssid.append(int(ssid_of[tri.nearest(ci, p[j - 1], p[j + 1], WPOS_INTERNAL)]))
+            cipid.append(ci)
+    cipid = np.array(cipid, np.int32)
+    return np.array(ssid, np.int32), tmat_of[cipid].astype(np.int32)

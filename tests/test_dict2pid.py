@@ -89,3 +89,19 @@ def test_alignment_phone_chains_live(cmu, text):
     want = refdrv.align(EN, os.path.join(REF, "model", "cmudict-en-us.dict"), text, pcm)
     s, t, c = dict2pid.alignment_phones(md, pr, tabs, [idx[w] for w in text.split()])
     assert np.array_equal(s, want["ssid"]) and np.array_equal(t, want["tmatid"])
+
+
+def test_keyphrase_chains_equal_the_golden_ones(cmu):
+    """kws_search_reinit's keyphrase HMM chains from the files alone: the configuration tests/golden/en_us_kws.npz
+    holds (what the GPU-verified keyword-spotting kernel is tested with), the phone-loop part included."""
+    from conftest import golden
+    md, idx, pr, tabs = cmu
+    g = golden("en_us_kws.npz")
+    n = md["n_ciphone"]
+    # the key list "forward / ten meters / go / backward": the reference keeps it in reverse file order (glist prepend)
+    for tag, phrases in (("a", ["forward"]), ("b", ["backward", "go", "ten meters", "forward"])):
+        chains = [dict2pid.keyphrase_phones(md, pr, tabs, [idx[w] for w in ph.split()]) for ph in phrases]
+        assert np.array_equal(np.concatenate([c[0] for c in chains]), g[tag + "_kp_ssid"])
+        assert np.array_equal(np.concatenate([c[1] for c in chains]), g[tag + "_kp_tmat"])
+        assert np.array_equal(np.cumsum([0] + [len(c[0]) for c in chains]), g[tag + "_kp_off"])
+        assert np.array_equal(md["phone_ssid"][:n], g[tag + "_pl_ssid"]) and np.array_equal(md["phone_tmat"][:n], g[tag + "_pl_tmat"])
