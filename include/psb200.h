@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define PSB_ABI_VERSION 1
+#define PSB_ABI_VERSION 2
 
 typedef enum psb_status_e {
     PSB_OK = 0,
@@ -70,6 +70,11 @@ typedef struct psb_model_desc_s {
     const uint8_t *logadd8;
     const uint32_t *logadd_ms;
     const uint8_t *topn_beam;   /* semi: [n_feat] or NULL (s2_semi_mgau.c:1302-1309) */
+    int32_t fixed_point;        /* != 0: the host is a -DFIXED_POINT build (mfcc_t = int32 Q12,
+                                 * fe/fixpoint.h:98-100): mean / var / det and every feature value are
+                                 * int32 bit patterns carried in the float-typed arrays, and the Gaussian
+                                 * arithmetic is FIXMUL / GMMSUB with the early exits of
+                                 * ptm_mgau.c:182-206 / s2_semi_mgau.c:137-143 (ptm and semi only) */
 } psb_model_desc_t;
 
 typedef struct psb_model_s psb_model_t;

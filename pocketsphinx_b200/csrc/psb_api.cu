@@ -83,7 +83,7 @@ static int build_records(psb_model_t *m, const float *mean, const float *var, co
         PSB_CUDA(cudaMemcpy(m->d_rec_off, m->rec_off.data(), m->K * sizeof(size_t), cudaMemcpyHostToDevice));
     }
     PSB_CUDA(cudaMemcpy(m->d_rec, rec.data(), total * sizeof(float), cudaMemcpyHostToDevice));
-    if (m->kind != PSB_KIND_MS && m->n_density % 2 == 0) {
+    if (m->kind != PSB_KIND_MS && m->n_density % 2 == 0 && !m->fixed_point) {
         // pair-interleaved, negated copy for ptm_topn2_kernel: per (cb, f) nd/2 pair records
         // {detA, detB, -muA_0, -muB_0, -vA_0, -vB_0, ...} padded to a multiple of 4 floats
         size_t total2 = 0;
@@ -165,6 +165,12 @@ extern "C" int psb_model_create(const psb_model_desc_t *d, int device, psb_model
     }
     m->K = m->n_mgau * m->n_feat;
     m->mixw_4bit = d->mixw_cb != nullptr;
+    m->fixed_point = d->fixed_point != 0;
+    if (m->fixed_point && d->kind == PSB_KIND_MS) {
+        psb_set_error("fixed-point arithmetic is implemented for ptm and semi-continuous models only");
+        delete m;
+        return PSB_ERR_ARG;
+    }
     m->logadd_ms_size = d->logadd_ms_size;
     m->logadd_ms_zero = d->logadd_ms_zero;
     m->d_rec = nullptr; m->d_rec_off = nullptr; m->d_rec2 = nullptr; m->d_rec2_off = nullptr; m->d_mixw = nullptr; m->d_mixw_cb = nullptr;

@@ -62,6 +62,7 @@ struct psb_model_s {
     int featlen[PSB_MAX_FEAT], featoff[PSB_MAX_FEAT], sumlen;
     int K;                        // n_mgau * n_feat (codebook, stream) pairs
     bool mixw_4bit;
+    bool fixed_point;             // FIXED_POINT build arithmetic: mean/var/det/features are int32 (Q12) bit patterns
     int mixw_row;                 // bytes per (feat, codeword) row as given by the host
     int mixw_stride;              // padded row pitch on the device (multiple of 128)
     int logadd_ms_size, logadd_ms_zero;

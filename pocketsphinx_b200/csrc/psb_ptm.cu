@@ -63,6 +63,45 @@ __device__ __forceinline__ float gau_dist(const float4 *__restrict__ r, const fl
     return d;
 }
 
+// FIXED_POINT build of the reference (mfcc_t = int32 Q12): the same records and the
+// same feature rows carry int32 bit patterns.  FIXMUL (fe/fixpoint.h:98-100) is the 64-bit product
+// shifted right by 12 and truncated to 32 bits; GMMSUB (tied_mgau_common.h:62-66) as gcc compiles it
+// is (b < 0) ? INT_MIN : wrap32(a - b).  The scan's early exits are observable here (a wrapped
+// subtraction can climb back over the threshold), so next to the final value the minimum of d at
+// the reference's test points is returned: PTM tests before each of the leading FL % 4 dimensions,
+// then before every group of four (ptm_mgau.c:182-206); the semi-continuous scan before every
+// dimension (s2_semi_mgau.c:137-143); both once more after the last one.  A codeword survives the
+// scan iff that minimum is >= the worst listed score.
+__device__ __forceinline__ int fx_mul(int a, int b)
+{
+    return (int)(unsigned)(((long long)a * (long long)b) >> 12);
+}
+__device__ __forceinline__ int fx_gmmsub(int a, int b)
+{
+    return b < 0 ? INT_MIN : (int)((unsigned)a - (unsigned)b);
+}
+template <int FL, bool SEMI>
+__device__ __forceinline__ int gau_dist_fx(const float4 *__restrict__ r, const float (&x)[FL], int *dmin)
+{
+    constexpr int RECF = (1 + 2 * FL + 3) / 4 * 4;
+    int rr[RECF];
+#pragma unroll
+    for (int q = 0; q < RECF / 4; ++q) {
+        float4 v = r[q];
+        rr[4 * q + 0] = __float_as_int(v.x); rr[4 * q + 1] = __float_as_int(v.y);
+        rr[4 * q + 2] = __float_as_int(v.z); rr[4 * q + 3] = __float_as_int(v.w);
+    }
+    int d = rr[0], mn = rr[0];
+#pragma unroll
+    for (int j = 0; j < FL; ++j) {
+        if (SEMI || j < FL % 4 || (j - FL % 4) % 4 == 0) mn = min(mn, d);
+        const int diff = (int)((unsigned)__float_as_int(x[j]) - (unsigned)rr[1 + 2 * j]);
+        d = fx_gmmsub(d, fx_mul(fx_mul(diff, diff), rr[2 + 2 * j]));
+    }
+    *dmin = min(mn, d);
+    return d;
+}
+
 // Lane/group tables built on the host per call (see psb_launch_ptm_batch):
 //   lane_len[g*32+l]  frames of the utterance owned by lane l of group g (0 = padding lane)
 //   lane_off[g*32+l]  flat frame offset of that utterance in feats / outputs
@@ -117,7 +156,7 @@ transpose_feats_kernel(const float *__restrict__ feats, float *__restrict__ feat
 // the truncated final score is >= worst (int), and whose record is already normalised per stream
 // (mgau_norm :186-203): .x = number of entries inside topn_beam, .y = codeword bytes,
 // .z = bytes min(96, -((score_j >> 10) - (score_0 >> 10))).
-template <int FL, bool SEMI>
+template <int FL, bool SEMI, bool FX = false>
 __global__ void __launch_bounds__(TOPN_WARPS * 32, 7)
 ptm_topn_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec_off,
                 const int32_t *__restrict__ klist, const float *__restrict__ featT, GroupTabs tabs,
@@ -175,7 +214,9 @@ ptm_topn_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec_of
 #pragma unroll
             for (int i = 0; i < TOPN; ++i) {
                 const int c = cw[i];
-                const int s = f2i_clamped(gau_dist<FL>(srec + c * RECQ, x));
+                int s, smin;
+                if (FX) s = gau_dist_fx<FL, SEMI>(srec + c * RECQ, x, &smin);       // no early exit in eval_topn
+                else s = f2i_clamped(gau_dist<FL>(srec + c * RECQ, x));
                 seedpack |= (unsigned)c << (8 * i);
                 seedbit |= (1u << (c & 7)) << (8 * i);
                 // insert (c, s) into the sorted prefix nsc[0..i-1]: entries with score < s move down
@@ -210,14 +251,22 @@ ptm_topn_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec_of
                 }
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc) {
-                    float dpen;
-                    const float d = gau_dist<FL, SEMI>(rq + cc * RECQ, x, &dpen);
+                    float dpen, d;
+                    int di, dmin;
                     bool hit;
-                    if (SEMI) hit = dpen >= thresh && f2i_clamped(d) >= sc[TOPN - 1];
-                    else hit = d >= thresh;
+                    if (FX) {
+                        di = gau_dist_fx<FL, SEMI>(rq + cc * RECQ, x, &dmin);
+                        hit = dmin >= sc[TOPN - 1];
+                    }
+                    else {
+                        d = gau_dist<FL, SEMI>(rq + cc * RECQ, x, &dpen);
+                        di = f2i_clamped(d);
+                        if (SEMI) hit = dpen >= thresh && di >= sc[TOPN - 1];
+                        else hit = d >= thresh;
+                    }
                     if (hit && !(m8 & (1u << cc))) {
                         const int c = ch * 8 + cc;
-                        const int s = f2i_clamped(d);
+                        const int s = di;
                         const int ev = cw[TOPN - 1];
                         // insertion_sort_cb (:140-149): entries with score <= s shift down
                         int p = 0;
@@ -1341,6 +1390,19 @@ int launch_topn(psb_batch_t *b, const int32_t *d_klist, int n_k, const GroupTabs
                 const int32_t *d_featoff)
 {
     psb_model_t *m = b->m;
+    if (m->fixed_point) {
+        // FIXED_POINT arithmetic: the scalar kernel with integer distances (one variant)
+        size_t smem = (size_t)m->n_density * rec_floats(FL) * sizeof(float);
+        auto kern = ptm_topn_kernel<FL, SEMI, true>;
+        PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int warps = (long long)n_k * ((n_groups + TOPN_WARPS - 1) / TOPN_WARPS) >= 4 * 148 ? TOPN_WARPS : 1;
+        dim3 grid(n_k, (n_groups + warps - 1) / warps);
+        kern<<<grid, warps * 32, smem, b->stream>>>(m->d_rec, m->d_rec_off, d_klist, b->d_featT, tabs, b->d_topn, n_groups,
+                                                   m->n_density, m->n_feat, m->sumlen, d_featoff, m->K, m->ds_ratio,
+                                                   m->d_topn_beam);
+        PSB_LAUNCH_CHECK();
+        return PSB_OK;
+    }
     if (!SEMI && FL <= 16 && m->d_rec2 && b->topn_variant >= 4) {
         // deferred-insertion kernels: 4 = two utterances per lane, 5 = one
         constexpr int FLQ = FL <= 16 ? FL : 1;
@@ -1573,7 +1635,7 @@ int psb_launch_ptm_batch(psb_batch_t *b, const float *d_feats, const int32_t *ut
     }
     if (b->have_ev) PSB_CUDA(cudaEventRecord(b->ev[1], b->stream));
     // semi-continuous: distances out of the time loop, one warp per (utterance, stream)
-    const bool semi_split = semi && m->n_mgau == 1 && b->topn_variant != 0 && m->n_density <= 256 &&
+    const bool semi_split = semi && !m->fixed_point && m->n_mgau == 1 && b->topn_variant != 0 && m->n_density <= 256 &&
                             (m->n_density == 64 || m->n_density == 128 || m->n_density == 256);
     if (semi_split) {
         const size_t need_d = (size_t)K * total * m->n_density;

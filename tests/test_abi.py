@@ -17,7 +17,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == bound, (declared ^ bound)
     for name in declared:
         assert hasattr(L, name)
-    assert L.psb_abi_version() == 1
+    assert L.psb_abi_version() == 2
 
 
 def test_hmm_struct_is_88_bytes():

@@ -1,4 +1,4 @@
-"""GPU, gated like the search kernels it drives (PSB_RUN_UNVERIFIED=1): pocketsphinx_b200.decoder.Decoder --
+"""GPU: pocketsphinx_b200.decoder.Decoder --
 audio in, words out, everything read from the reference's files by the package itself -- against the
 hypothesis, score and segmentation the reference produces for the same configuration (golden: the tables of
 tests/golden/en_us_fwdtree.npz flat_default; live when oracle/_ref/libpsref.so is there)."""
@@ -9,8 +9,7 @@ import pytest
 
 from conftest import ROOT, golden
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("PSB_RUN_UNVERIFIED") != "1",
-                                                  reason="search kernels not yet run on hardware; set PSB_RUN_UNVERIFIED=1")]
+pytestmark = [pytest.mark.gpu]
 REF = os.path.join(ROOT, "oracle", "_ref")
 
 

@@ -1,20 +1,16 @@
 """GPU (-m gpu): psb_fsg_batch_device (the grammar search of fsg_search.c on the device) against the
 reference's golden history tables and against the oracle on ragged batches.
 
-STATUS: fsg_search_kernel was written after this round's GPU minutes were spent.  Its phase code is
-checked on the host against the reference (tests/test_fsg_emul.py), but the kernel itself has not
-run on hardware yet, so this file only runs when PSB_RUN_UNVERIFIED=1 is set (it is the first
-thing to run on the next GPU call).  Nothing in DESIGN.md claims device parity for this path."""
-import os
+First hardware run: round 2, first GPU call (profiles/r02_first_hw_run/): all cases green in both
+bindings of the phase code (CTA / warp per utterance), compute-sanitizer memcheck + racecheck clean.
+The phase code is also checked on the host against the reference (tests/test_fsg_emul.py)."""
 
 import numpy as np
 import pytest
 
 from conftest import golden
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PSB_RUN_UNVERIFIED") != "1",
-                                 reason="fsg_search_kernel not yet run on hardware (set PSB_RUN_UNVERIFIED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 TAGS = ("go", "go_hmmpf", "cmd", "cmd_wide", "cmd_hmmpf")
 

@@ -1,10 +1,10 @@
 """GPU (-m gpu): psb_ngram_fwdtree_batch_device (the first pass of the n-gram search on the device)
 against the reference's golden backpointer tables and against the oracle on ragged batches.
 
-STATUS: ngs_fwdtree_kernel was written after this round's GPU minutes were spent.  Its phase code
-is checked on the host against the reference (tests/test_ngs_emul.py), the kernel itself has not
-run on hardware yet: this file only runs with PSB_RUN_UNVERIFIED=1.  Nothing in DESIGN.md claims
-device parity for this path."""
+First hardware run: round 2, first GPU call (profiles/r02_first_hw_run/): all cases green in both
+bindings of the phase code, compute-sanitizer memcheck + racecheck clean.  The phase code is also
+checked on the host against the reference (tests/test_ngs_emul.py, tests/test_ngf_emul.py)."""
+
 import os
 
 import numpy as np
@@ -12,9 +12,7 @@ import pytest
 
 from conftest import golden
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PSB_RUN_UNVERIFIED") != "1",
-                                 reason="ngs_fwdtree_kernel not yet run on hardware (set PSB_RUN_UNVERIFIED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 TAGS = ("default", "wide", "narrow", "maxwpf", "abs", "pen", "lookahead")
 

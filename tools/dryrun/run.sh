@@ -21,6 +21,6 @@ s = s.replace("d_scr.data_ptr()", "d_scr.numpy().ctypes.data").replace("d_pen.da
 open(sys.argv[2], "w").write(s)
 P
 done
-cd "$D" && PSB_RUN_UNVERIFIED=1 python -m pytest -q -m gpu -p no:cacheprovider --rootdir "$D" . | tail -n 5
+cd "$D" && python -m pytest -q -m gpu -p no:cacheprovider --rootdir "$D" . | tail -n 5
 # the audio-to-words Decoder with the device stages served by the compiled reference and the emulation
 python "$ROOT/tools/dryrun/decoder_dry.py" | tail -n 3

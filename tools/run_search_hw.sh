@@ -1,11 +1,11 @@
 #!/bin/bash
-# First GPU call of the next round: run the search kernels that have only been verified in host
-# emulation, each test file under its own timeout so that a hang cannot take the
-# box with it, in both bindings of the phase code.  Logs go to gpurun_out/.
-#   gpurun --timeout 1500 -- 'bash tools/run_unverified.sh'
+# The search kernels in both bindings of the phase code (CTA / warp per
+# utterance), each test file under its own timeout so that a hang cannot take the box with it, then
+# one small case per kernel under compute-sanitizer.  Logs go to gpurun_out/.  This was the first GPU
+# call of round 2 (all green: profiles/r02_first_hw_run/).
+#   gpurun --timeout 1500 -- 'bash tools/run_search_hw.sh'
 set -u
 mkdir -p gpurun_out
-export PSB_RUN_UNVERIFIED=1
 rc=0
 for mode in 0 1; do
     export PSB_SEARCH_WARP=$mode
