@@ -100,11 +100,16 @@ cuda_mgau_wrap(acmod_t *acmod, ps_mgau_t *host, const char *libpath, int device)
     int32 n_sen, n_hist = 2;
     int f, cw, i, rc;
 
-#ifdef FIXED_POINT
-    E_ERROR("cuda_mgau: FIXED_POINT builds are not supported\n");
-    return NULL;
-#endif
     memset(&d, 0, sizeof(d));
+#ifdef FIXED_POINT
+    /* mfcc_t is int32 (Q12) in this build: the arrays travel as 4-byte words and the library
+     * switches to the FIXMUL / GMMSUB arithmetic (fe/fixpoint.h:98-100, tied_mgau_common.h:62-70). */
+    if (strcmp(name, "ms") == 0) {
+        E_ERROR("cuda_mgau: the ms back-end of a FIXED_POINT build is not supported\n");
+        return NULL;
+    }
+    d.fixed_point = 1;
+#endif
     if (strcmp(name, "ptm") == 0) {
         ptm_mgau_t *p = (ptm_mgau_t *)host;
         size_t row;
@@ -181,7 +186,7 @@ cuda_mgau_wrap(acmod_t *acmod, ps_mgau_t *host, const char *libpath, int device)
     flatten_gauden(g, &mean, &var);
     d.mean = mean;
     d.var = var;
-    d.det = g->det[0][0];
+    d.det = (const float *)g->det[0][0];
     d.mixw = mixw;
     d.sen2cb = s2c;
     rc = c->model_create(&d, device, &c->model);
@@ -242,7 +247,7 @@ cuda_mgau_transform(ps_mgau_t *mg, ps_mllr_t *mllr)
         return -1;
     /* ... and the device copy is refreshed */
     flatten_gauden(g, &mean, &var);
-    rc = c->model_update(c->model, mean, var, g->det[0][0]);
+    rc = c->model_update(c->model, mean, var, (const float *)g->det[0][0]);
     ckd_free(mean);
     ckd_free(var);
     if (rc != 0) E_ERROR("cuda_mgau: %s\n", c->last_error());

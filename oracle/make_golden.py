@@ -165,8 +165,38 @@ def make_fwdtree():
     np.savez_compressed(os.path.join(OUT, "en_us_fwdtree.npz"), **out)
 
 
+def make_fixed_point():
+    """fx_en_us.npz / fx_tidigits.npz: the reference compiled with -DFIXED_POINT (oracle/_ref/libpsref_fx.so,
+    `make -C oracle fx`) on goforward.raw: its Q12 features, every top-N list and its senone scores.  Run as
+    `PSREF_LIB=oracle/_ref/libpsref_fx.so python -m oracle.make_golden fx`.  To keep the files small the model's
+    int32 means / variance terms and the scores are stored as differences from what the float build's goldens
+    give (|d mean| <= 1 after (int32)(mean * 4096), d var in {0, 1}, d senscr within int16): tests/conftest.py
+    `fx_case` puts them back together; the determinants are (int32)det exactly."""
+    assert "fx" in os.path.basename(refdrv.LIB_PATH), "set PSREF_LIB to the FIXED_POINT build"
+    ref_dir = os.path.dirname(refdrv.LIB_PATH)
+    pcm = np.fromfile(os.path.join(ref_dir, "data", "goforward.raw"), np.int16)
+    for name, mdl, gm, gg in (("en_us", "en-us", "en_us_ptm_model.npz", "en_us_goforward.npz"),
+                              ("tidigits", "tidigits_hmm", "tidigits_sc_model.npz", "tidigits_goforward.npz")):
+        ref = refdrv.RefModel(os.path.join(ref_dir, "model", mdl))
+        feats = ref.featurize(pcm).view(np.int32)          # mfcc_t = int32 (Q12), carried as 4-byte words
+        scr, topn = ref.score(feats.view(np.float32), want_topn=True)
+        pm = PackedModel.load(os.path.join(OUT, gm))
+        mean, var, det = ref.export("mean", np.int32).ravel(), ref.export("var", np.int32).ravel(), ref.export("det", np.int32).ravel()
+        dm = mean - (pm.mean.astype(np.float32) * np.float32(4096)).astype(np.int32)
+        dv = var - pm.var.astype(np.int32)
+        assert np.array_equal(det, pm.det.astype(np.int32)) and np.abs(dm).max() <= 1 and dv.min() >= 0 and dv.max() <= 1
+        ds = scr.astype(np.int32) - np.load(os.path.join(OUT, gg))["senscr"]
+        assert np.abs(ds).max() < 32768
+        path = os.path.join(OUT, "fx_%s.npz" % name)
+        np.savez_compressed(path, feats=feats, dmean=dm.astype(np.int8), dvar=dv.astype(np.int8), dsenscr=ds.astype(np.int16),
+                            topn=topn.astype(np.int32))
+        print(path, os.path.getsize(path) // 1024, "KiB;", "%.0f %% of the scores differ from the float build's" % (100 * (ds != 0).mean()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "fx":
+        return make_fixed_point()
     if len(sys.argv) > 1 and sys.argv[1] == "fwdtree":
         return make_fwdtree()
     if len(sys.argv) > 1 and sys.argv[1] == "fsg":

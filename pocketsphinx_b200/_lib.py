@@ -22,7 +22,7 @@ class ModelDesc(C.Structure):
                 ("logadd_ms_zero", C.c_int32), ("on_device", C.c_int32),
                 ("mean", C.c_void_p), ("var", C.c_void_p), ("det", C.c_void_p), ("mixw", C.c_void_p),
                 ("mixw_cb", C.c_void_p), ("sen2cb", C.c_void_p), ("logadd8", C.c_void_p),
-                ("logadd_ms", C.c_void_p), ("topn_beam", C.c_void_p)]
+                ("logadd_ms", C.c_void_p), ("topn_beam", C.c_void_p), ("fixed_point", C.c_int32)]
 
 
 # every symbol include/psb200.h declares: (name, restype, argtypes)

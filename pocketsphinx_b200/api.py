@@ -52,6 +52,7 @@ class Model:
         d.aw = int(pm.aw)
         d.logadd_ms_size = int(pm.logadd_ms.size)
         d.logadd_ms_zero = int(pm.logadd_ms_zero)
+        d.fixed_point = int(getattr(pm, "fixed_point", 0))   # arrays then carry the FIXED_POINT build's int32 bit patterns
         if device_ptrs is None:
             d.on_device = 0
             d.mean, d.var, d.det, d.mixw = _p(pm.mean), _p(pm.var), _p(pm.det), _p(pm.mixw)

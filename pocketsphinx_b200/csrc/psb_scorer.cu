@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256)
 scorer_topn_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec_off, const float *__restrict__ feat,
                    const int32_t *__restrict__ prev_cw, int32_t *__restrict__ cur_cw, int32_t *__restrict__ cur_sc,
                    const uint8_t *__restrict__ active, int nd, int n_feat, int topn,
-                   const int *__restrict__ featlen, const int *__restrict__ featoff, int do_scan)
+                   const int *__restrict__ featlen, const int *__restrict__ featoff, int do_scan, int fx)
 {
     extern __shared__ float sd[];          // [nd] distances (+ [nd] penultimate partial sums when SEMI)
     __shared__ float sx[64];
@@ -52,6 +52,25 @@ scorer_topn_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec
     const int rf = (1 + 2 * fl + 3) / 4 * 4;
     if (threadIdx.x < fl) sx[threadIdx.x] = feat[fo + threadIdx.x];
     __syncthreads();
+    // FIXED_POINT arithmetic (fx): Q12 integers, FIXMUL / GMMSUB, and because the scan's early exits are
+    // observable there, the minimum of d over the reference's test points next to the final value
+    // (see gau_dist_fx in psb_ptm.cu); sd[] then carries int32 bit patterns.
+    if (fx) {
+        for (int c = threadIdx.x; c < nd; c += blockDim.x) {
+            const float *r = rec + rec_off[k] + (size_t)c * rf;
+            int d = __float_as_int(r[0]), mn = d;
+            for (int j = 0; j < fl; ++j) {
+                if (SEMI || j < fl % 4 || (j - fl % 4) % 4 == 0) mn = min(mn, d);
+                const int diff = (int)((unsigned)__float_as_int(sx[j]) - (unsigned)__float_as_int(r[1 + 2 * j]));
+                const int sq = (int)(unsigned)(((long long)diff * diff) >> 12);
+                const int c2 = (int)(unsigned)(((long long)sq * __float_as_int(r[2 + 2 * j])) >> 12);
+                d = c2 < 0 ? INT_MIN : (int)((unsigned)d - (unsigned)c2);
+            }
+            sd[c] = __int_as_float(d);
+            sd[nd + c] = __int_as_float(min(mn, d));
+        }
+    }
+    else
     for (int c = threadIdx.x; c < nd; c += blockDim.x) {
         const float *r = rec + rec_off[k] + (size_t)c * rf;
         float d = r[0], dpen = r[0];
@@ -70,7 +89,7 @@ scorer_topn_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec
     // eval_topn (ptm_mgau.c:88-136 / s2_semi_mgau.c:70-109)
     for (int i = 0; i < topn; ++i) {
         const int c = prev_cw[k * topn + i];
-        const int s = __float2int_rz(sd[c]);
+        const int s = fx ? __float_as_int(sd[c]) : __float2int_rz(sd[c]);
         int j = i - 1;
         while (j >= 0 && s > sc[j]) { sc[j + 1] = sc[j]; cw[j + 1] = cw[j]; --j; }
         sc[j + 1] = s; cw[j + 1] = c;
@@ -80,7 +99,10 @@ scorer_topn_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec
         for (int c = 0; c < nd; ++c) {
             const float d = sd[c];
             const float th = (float)sc[topn - 1];
-            if (SEMI) {
+            if (fx) {
+                if (__float_as_int(sd[nd + c]) < sc[topn - 1]) continue;
+            }
+            else if (SEMI) {
                 if (!(sd[nd + c] >= th)) continue;
                 if (__float2int_rz(d) < sc[topn - 1]) continue;
             }
@@ -88,7 +110,7 @@ scorer_topn_kernel(const float *__restrict__ rec, const size_t *__restrict__ rec
             bool listed = false;
             for (int i = 0; i < topn; ++i) listed |= cw[i] == c;
             if (listed) continue;
-            const int s = __float2int_rz(d);
+            const int s = fx ? __float_as_int(d) : __float2int_rz(d);
             int kk = topn - 1;
             while (kk > 0 && s >= sc[kk - 1]) { sc[kk] = sc[kk - 1]; cw[kk] = cw[kk - 1]; --kk; }
             sc[kk] = s; cw[kk] = c;
@@ -389,11 +411,11 @@ extern "C" int psb_scorer_frame_eval(psb_scorer_t *s, int16_t *senscr, const uin
             if (semi)
                 scorer_topn_kernel<true><<<m->K, threads, 2 * m->n_density * sizeof(float), s->stream>>>(
                     m->d_rec, m->d_rec_off, s->d_feat, s->d_cw + per * prev, cur_cw, cur_sc, cur_act, m->n_density,
-                    m->n_feat, m->topn, m->d_featlen, m->d_featoff, frame % m->ds_ratio == 0);
+                    m->n_feat, m->topn, m->d_featlen, m->d_featoff, frame % m->ds_ratio == 0, m->fixed_point);
             else
-                scorer_topn_kernel<false><<<m->K, threads, m->n_density * sizeof(float), s->stream>>>(
+                scorer_topn_kernel<false><<<m->K, threads, (m->fixed_point ? 2 : 1) * m->n_density * sizeof(float), s->stream>>>(
                     m->d_rec, m->d_rec_off, s->d_feat, s->d_cw + per * prev, cur_cw, cur_sc, cur_act, m->n_density,
-                    m->n_feat, m->topn, m->d_featlen, m->d_featoff, frame % m->ds_ratio == 0);
+                    m->n_feat, m->topn, m->d_featlen, m->d_featoff, frame % m->ds_ratio == 0, m->fixed_point);
             PSB_LAUNCH_CHECK();
         }
         if (semi) {

@@ -37,6 +37,25 @@ def an4():
     return PackedModel.load(os.path.join(GOLDEN, "an4_cont_model.npz"))
 
 
+def fx_case(name):
+    """The FIXED_POINT build's golden case `name` ("en_us" PTM, "tidigits" semi-continuous, 4-bit weights):
+    (PackedModel with fixed_point = 1 and int32 Gaussians carried in float32-typed arrays, Q12 features
+    viewed as float32, expected int16 scores, expected top-N lists).  tests/golden/fx_<name>.npz holds
+    differences from the float build's goldens (oracle/make_golden.py:make_fixed_point)."""
+    from pocketsphinx_b200.model import PackedModel
+    gm, gg = {"en_us": ("en_us_ptm_model.npz", "en_us_goforward.npz"),
+              "tidigits": ("tidigits_sc_model.npz", "tidigits_goforward.npz")}[name]
+    fx = golden("fx_%s.npz" % name)
+    pm = PackedModel.load(os.path.join(GOLDEN, gm))
+    mean = (pm.mean.astype(np.float32) * np.float32(4096)).astype(np.int32) + fx["dmean"]
+    var = pm.var.astype(np.int32) + fx["dvar"]
+    det = pm.det.astype(np.int32)
+    pm.mean, pm.var, pm.det = mean.view(np.float32), var.view(np.float32), det.view(np.float32)
+    pm.fixed_point = 1
+    senscr = (golden(gg)["senscr"].astype(np.int32) + fx["dsenscr"]).astype(np.int16)
+    return pm, np.ascontiguousarray(fx["feats"]).view(np.float32), senscr, fx["topn"]
+
+
 def hmm_view(raw):
     """uint8 [..., 88] golden dump -> structured hmm_t array."""
     from oracle.oracle import HMM_DTYPE

@@ -2,7 +2,7 @@
 restatement of the FIXED_POINT build's PTM arithmetic (Q12 features and means,
 FIXMUL truncated to 32 bits, GMMSUB as gcc compiles it, early exits that are not result-neutral)
 against the reference compiled with -DFIXED_POINT, on its own features of goforward.raw.  This pins
-the oracle for a fixed-point kernel; no such kernel is built yet."""
+the oracle for the fixed-point kernels (tests/test_gpu_fixed_point.py)."""
 import os
 import subprocess
 import sys
@@ -12,10 +12,23 @@ import pytest
 
 from oracle import refdrv
 
+from conftest import fx_case
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 FX = os.path.join(os.path.dirname(refdrv.LIB_PATH), "libpsref_fx.so")
-pytestmark = pytest.mark.skipif(not os.path.exists(FX), reason="oracle/_ref/libpsref_fx.so not built (make -C oracle fx)")
+needs_fx = pytest.mark.skipif(not os.path.exists(FX), reason="oracle/_ref/libpsref_fx.so not built (make -C oracle fx)")
+
+
+@pytest.mark.parametrize("name", ["en_us", "tidigits"])
+def test_fixed_point_oracle_matches_committed_fixture(name):
+    """Runs anywhere: the restatement against tests/golden/fx_*.npz (the FIXED_POINT reference's features,
+    top-N lists and scores on goforward.raw)."""
+    from oracle import oracle
+    pm, feats, want, want_topn = fx_case(name)
+    got, topn = oracle.OracleModel(pm).score_utt(feats, want_topn=True)
+    assert np.array_equal(topn, want_topn) and np.array_equal(got, want)
+
 
 DUMP = r"""
 import sys, numpy as np
@@ -31,6 +44,7 @@ np.savez(%r, feats=feats.view(np.int32), senscr=scr, topn=topn,
 """
 
 
+@needs_fx
 def test_fixed_point_semi_oracle_matches_fixed_point_reference(tmp_path):
     """The semi-continuous back-end (tidigits, 4-bit clustered weights) in the fixed-point build."""
     from oracle import oracle
@@ -48,6 +62,7 @@ def test_fixed_point_semi_oracle_matches_fixed_point_reference(tmp_path):
     assert np.array_equal(topn, fx["topn"]) and np.array_equal(got, fx["senscr"])
 
 
+@needs_fx
 def test_fixed_point_ptm_oracle_matches_fixed_point_reference(tmp_path):
     from oracle import oracle
     from pocketsphinx_b200.model import PackedModel
