@@ -2,9 +2,14 @@
 """bench.py -- frames/sec of the PocketSphinx hot path (senone evaluation + Viterbi) on B200.
 
 One "step" = one pass of the hot path over one batch of synthetic utterances: GMM senone
-evaluation of every frame (all senones, like `-compallsen yes`) followed by the phone-loop
-Viterbi (phone_loop_search.c: every CI-phone HMM through hmm_vit_eval each frame, beam
-pruning, phone transitions, look-ahead penalties) over the freshly computed scores.
+evaluation of every frame (all senones, like `-compallsen yes`), the phone-loop Viterbi
+(phone_loop_search.c: every CI-phone HMM through hmm_vit_eval each frame, beam pruning, phone
+transitions, look-ahead penalties) and the SEARCH-SCALE Viterbi over the freshly computed scores:
+every utterance keeps N_ACTIVE = 6 081 hmm_t instances alive (what SURVEY 8d measured per frame for
+the en-us fwdtree search at default beams) and all of them take one hmm_vit_eval step per frame
+with a per-frame best-score reduction -- evaluate_channels (ngram_search_fwdtree.c:702-715).  Both
+arms run all three stages: ours on the device, the reference arm through the compiled reference's
+ptm_mgau_frame_eval and hmm_vit_eval on the host cores.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                   [--model baseline|en-us] [--utts U] [--secs S]
@@ -28,6 +33,30 @@ from pocketsphinx_b200.model import PackedModel, synth_feats, synth_ms, synth_pt
 
 FRAMES_PER_SEC_AUDIO = 100          # 10 ms frames
 PL = dict(window=5, beam=-225, pbeam=-225, pip=0, weight=3.0)   # pl_beam 1e-10 etc. >> 10
+N_ACTIVE = 6081                     # active HMMs per frame, en-us fwdtree at default beams
+
+
+def channel_template(pm, HMM_DTYPE, n_active=N_ACTIVE):
+    """The search-scale Viterbi's active set, the same on both arms: n_active non-multiplexed hmm_t drawn
+    from the model's senone sequences and transition matrices, all entered at frame 0 with score 0
+    (hmm_enter).  Returns None when the model has no 3-/5-state topology to evaluate."""
+    if pm.n_emit_state not in (3, 5) or len(pm.sseq) == 0:
+        return None
+    ns = pm.n_emit_state
+    rng = np.random.default_rng(99)
+    hm = np.zeros(n_active, HMM_DTYPE)
+    ssid = rng.integers(0, len(pm.sseq), n_active)
+    hm["score"][:, :] = -0x20000000
+    hm["score"][:, 0] = 0
+    hm["history"][:, :] = -1
+    hm["out_score"] = -0x20000000
+    hm["out_history"] = -1
+    hm["bestscore"] = -0x20000000
+    hm["ssid"] = ssid
+    hm["senid"][:, :ns] = pm.sseq[ssid]
+    hm["tmatid"] = rng.integers(0, pm.tp.shape[0], n_active)
+    hm["n_emit_state"] = ns
+    return hm
 
 
 def frames_for(secs):
@@ -82,6 +111,16 @@ def reference_model_dir(name, pm, raw):
                              mixw_q=raw["mixw_q"],
                              feat_params="-feat 1s_c_d_dd\n-svspec 0-12/13-25/26-38\n-cmn batch\n-agc none\n")
     return _REF_DIR
+
+
+def ncu_traffic(kernel, workload):
+    """DRAM bytes per launch of `kernel` at `workload` from a committed ncu capture, or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(kernel + "|" + workload)
+    except (OSError, ValueError):
+        return None
 
 
 def peaks():
@@ -176,7 +215,8 @@ def viterbi_stage(api, torch, ctx, batch, pm, off, U, T, hbm_peak, n_active=6081
             "frames_per_s": U * F / (ms * 1e-3),
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                          "algorithmic_bytes_per_hmm": alg},
-            "note": "not part of `value`: the headline Viterbi is the reference's phone loop (42 HMMs per utterance)"}
+            "note": "the per-frame kernel (state visible in HBM between frames), for comparison with search_viterbi: "
+                    "`value` uses the fused sweep"}
 
 
 def align_stage(api, ctx, batch, pm, off, U, T, n_phones=100):
@@ -322,6 +362,13 @@ def cpu_baseline(args, pm, raw, feats, n_frames_per_utt, budget_s=15.0, threads=
     kind = "reference" if ref_dir else "port"
     om = oracle.OracleModel(pm)
     local = th.local()
+    tmpl = channel_template(pm, oracle.HMM_DTYPE)
+
+    def sweeper():
+        # the compiled reference's hmm_vit_eval (hmm.c:787) when it is there, else the port's
+        if not hasattr(local, "hctx"):
+            local.hctx = refdrv.RefHmmCtx(pm.tp, pm.sseq) if kind == "reference" else oracle.OracleHmmCtx(pm.tp, pm.sseq)
+        return local.hctx
 
     def scorer():
         if kind == "port":
@@ -343,12 +390,14 @@ def cpu_baseline(args, pm, raw, feats, n_frames_per_utt, budget_s=15.0, threads=
         s = scorer()(feats[u])
         oracle.phoneloop_run(pm.tp, pm.sseq, pm.phone_ssid[:pm.n_ciphone], pm.phone_tmat[:pm.n_ciphone], s,
                              PL["window"], PL["beam"], PL["pbeam"], PL["pip"], PL["weight"])
+        if tmpl is not None:
+            sweeper().sweep(tmpl.copy(), s)
         return len(s)
 
     if threads > 1:                       # load one reference model per worker before timing
         from concurrent.futures import ThreadPoolExecutor
         ex = ThreadPoolExecutor(threads)
-        list(ex.map(lambda _: scorer()(feats[0][:4]), range(threads * 2)))
+        list(ex.map(lambda _: (scorer()(feats[0][:4]), sweeper()), range(threads * 2)))
     t0 = time.perf_counter()
     if threads == 1:
         done = sum(work(u) for u in range(n_utt))
@@ -356,8 +405,10 @@ def cpu_baseline(args, pm, raw, feats, n_frames_per_utt, budget_s=15.0, threads=
         done = sum(ex.map(work, range(n_utt)))       # ctypes releases the GIL inside the C code
     dt = time.perf_counter() - t0
     return {"value": done / dt, "unit": "frames/s", "cores": threads, "kind": kind,
-            "sample": "%d utterances x %d frames of the same batch, senone eval (%s) + phone loop, %.1f s" % (
-                n_utt, n_frames_per_utt, "compiled reference" if kind == "reference" else "C port", dt)}
+            "sample": "%d utterances x %d frames of the same batch: senone eval (%s) + phone loop (C port) + %s, %.1f s" % (
+                n_utt, n_frames_per_utt, "compiled reference" if kind == "reference" else "C port",
+                ("hmm_vit_eval over %d active hmm_t per frame (%s)" % (N_ACTIVE, "compiled reference" if kind == "reference" else "C port"))
+                if tmpl is not None else "no search-scale Viterbi for this topology", dt)}
 
 
 def host_cores():
@@ -450,6 +501,27 @@ def main():
     best_pinned = torch.empty(total, dtype=torch.int32).pin_memory()
     pen_pinned = torch.empty((total, H), dtype=torch.int32).pin_memory()
 
+    # ---- search-scale Viterbi: N_ACTIVE entered hmm_t per utterance, resident on the device ----
+    tmpl = channel_template(pm, api.HMM_DTYPE)
+    hs = None
+    if tmpl is not None:
+        hs = api.HmmSet(ctx, U * N_ACTIVE + U * 512, U)       # slack: segments start on storage-tile boundaries
+        hs.upload(np.tile(tmpl, U), np.arange(U + 1, dtype=np.int64) * N_ACTIVE)
+        hs.use_batch_stream(batch)                            # behind the kernels that write the scores
+        hs.snapshot()
+        d_row0 = torch.from_numpy(np.asarray(off[:U], np.int64)).cuda(local)
+        d_nrows = torch.from_numpy(np.diff(np.asarray(off, np.int64)).astype(np.int32)).cuda(local)
+        d_swbest = torch.empty((T, U), dtype=torch.int32, device="cuda:%d" % local)
+        swbest_pinned = torch.empty((T, U), dtype=torch.int32).pin_memory()
+        batch.sync()
+
+    def sweep():
+        # every utterance's active set takes T hmm_vit_eval steps against the scores decode_* just left in HBM
+        if hs is not None:
+            hs.restore()
+            hs.sweep_device(batch.senscr_device_ptr(), total, T, d_swbest.data_ptr(), d_row0=d_row0.data_ptr(),
+                            d_n_rows=d_nrows.data_ptr(), timed=False)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -460,6 +532,7 @@ def main():
     launches0 = api.lib().psb_kernel_launch_count()
     for _ in range(args.warmup):
         batch.decode_device(pl, d_feats.data_ptr(), off)
+        sweep()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -469,6 +542,7 @@ def main():
     kern = {"transpose": 0.0, "topn": 0.0, "senone": 0.0}
     for _ in range(args.steps):
         batch.decode_device(pl, d_feats.data_ptr(), off)
+        sweep()
     batch.event_record(1)
     ms_total = batch.event_elapsed_ms()
     barrier()
@@ -480,21 +554,53 @@ def main():
         batch.decode_device(pl, d_feats.data_ptr(), off)
     batch.sync()
     km = batch.last_kernel_ms()          # CUDA events around each kernel on the stream it runs on
+    sweep_ms = None
+    if hs is not None:                   # the sweep alone (its launch + the state restore), CUDA events on the same stream
+        batch.sync()
+        batch.event_record(0)
+        sweep()
+        batch.event_record(1)
+        sweep_ms = batch.event_elapsed_ms()
     batch.set_pipeline(int(os.environ.get("PSB_PIPELINE", "0")))
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
 
     # ---- end to end through the public host-buffer call: H2D + kernels + D2H every step ----
-    for _ in range(2):
+    def e2e_step():
         batch.decode_host(pl, feats_pinned, off, best=best_pinned, pen=pen_pinned)
+        if hs is not None:
+            sweep()
+            batch.sync()
+            swbest_pinned.copy_(d_swbest)                     # the sweep's result: best path score per frame and utterance
+            torch.cuda.synchronize()
+    for _ in range(2):
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        batch.decode_host(pl, feats_pinned, off, best=best_pinned, pen=pen_pinned)
+        e2e_step()
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    # the same with the senone scores themselves copied back (what the larger-grain boundary hands to a host
+    # search): a bounded sample of the batch so that the pinned buffer stays small
+    Us = min(U, 250)
+    tot_s = int(off[Us])
+    scr_pinned = torch.empty((tot_s, pm.n_sen), dtype=torch.int16).pin_memory()
+    sub = api.Batch(model, Us, tot_s)
+    def e2e_scr_step():
+        sub.decode_host(pl, feats_pinned[:tot_s], off[:Us + 1], want_senscr=True, best=best_pinned[:tot_s], pen=pen_pinned[:tot_s],
+                        senscr=scr_pinned)
+    e2e_scr_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        e2e_scr_step()
+    barrier()
+    e2e_scr_ms = (time.perf_counter() - t0) * 1e3 / 2
+    sub.close()
+    del scr_pinned
 
-    ms_step, e2e_ms = pdist.reduce_max_ms([ms_step, e2e_ms], device="cuda")
+    ms_step, e2e_ms, e2e_scr_ms = pdist.reduce_max_ms([ms_step, e2e_ms, e2e_scr_ms], device="cuda")
 
     if rank == 0:
         hbm_peak, peak_src, sm_max = peaks()
@@ -525,7 +631,10 @@ def main():
             "dtype": "f32->i16/i32", "data": "synthetic",
             "config": {"workload": workload_name(args, pm), "model": desc,
                        "utts_per_gpu": U, "frames_per_utt": T, "frames_per_step_per_gpu": total,
-                       "viterbi": "phone loop, %d CI-phone HMMs x %d states, window %d" % (H, pm.n_emit_state, PL["window"]),
+                       "viterbi": ("phone loop (%d CI-phone HMMs x %d states, window %d) + search-scale hmm_vit_eval over %d active "
+                                   "hmm_t per utterance and frame with a per-frame best-score reduction (evaluate_channels)"
+                                   % (H, pm.n_emit_state, PL["window"], N_ACTIVE)) if hs is not None else
+                                  "phone loop, %d CI-phone HMMs x %d states, window %d" % (H, pm.n_emit_state, PL["window"]),
                        "features": "synthetic dynamic features (AR(1) walk between model means), not PCM",
                        "parallelism": "utterances sharded, %d per GPU, no per-frame collective" % U,
                        "l2": "per-step working set (%.1f GB of scores) exceeds L2; no explicit flush" % (total * pm.n_sen * 2 / 1e9)},
@@ -533,9 +642,9 @@ def main():
             "kernel_ms_unpipelined": {**km, "note": "separate single-stream pass after the timed region"},
             "roofline": {"bound": "hbm", "kernel": topn_name, "achieved": topn_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": topn_gbs / hbm_peak,
-                         # dram__bytes_read+write of ptm_topnq_kernel from the committed ncu capture
-                         # (profiles/r01_topnq_v5_summary.txt: 88.4 + 212.7 MB for 98 000 frames), scaled to this launch
-                         "traffic": (301.0e6 / 98000.0) * total if topn_name.startswith("ptm_topnq") and pm.n_density == 256 else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from an `ncu --set full`
+                         # capture, when one is on file (profiles/ncu_traffic.json, written by profiles/ncu_traffic.py); else null
+                         "traffic": ncu_traffic(topn_name, workload_name(args, pm)),
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": topn_bytes,
                          "note": "compute-bound by construction (SURVEY 8d): model is SMEM/L2 resident"},
@@ -547,10 +656,30 @@ def main():
                           "achieved_gbs": stage_bytes / (gmm_ms * 1e-3) / 1e9},
             "e2e": {"value": frames_all / (e2e_ms * 1e-3), "unit": "frames/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(total * pm.sumlen * 4 + (U + 1) * 4),
-                    "d2h_bytes_per_step": int(total * 4 + total * H * 4),
-                    "call": "psb_decode_batch_host (pinned host features in, best scores + penalties out)"},
+                    "d2h_bytes_per_step": int(total * 4 + total * H * 4 + (total * 4 if hs is not None else 0)),
+                    "call": "psb_decode_batch_host (pinned host features in, phone-loop best scores + penalties out) + "
+                            "psb_hmmset_sweep_device (best path score per frame and utterance out)"},
+            # the same boundary with the int16 senone scores themselves returned to the host (PCIe-bound)
+            "e2e_with_senscr": {"value": tot_s * world / (e2e_scr_ms * 1e-3), "unit": "frames/s", "ms_per_step": e2e_scr_ms,
+                                "sample": "%d utterances of the batch (pinned score buffer kept at %.1f GB)" % (Us, tot_s * pm.n_sen * 2 / 1e9),
+                                "h2d_bytes_per_step": int(tot_s * pm.sumlen * 4), "d2h_bytes_per_step": int(tot_s * (pm.n_sen * 2 + 4 + 4 * H)),
+                                "d2h_gbs": tot_s * (pm.n_sen * 2 + 4 + 4 * H) / (e2e_scr_ms * 1e-3) / 1e9,
+                                "call": "psb_decode_batch_host with senscr != NULL (no search-scale Viterbi: the scores leave the device)"},
             "clocks": clocks,
         }
+        if hs is not None:
+            # registers hold the state, so the kernel's algorithmic traffic is the score rows (read once per CTA of a
+            # segment; L2 serves the repeats) plus the state once: its bound is integer issue, not HBM
+            n_inst = U * N_ACTIVE
+            out["search_viterbi"] = {
+                "kernel": "hmmset_sweep_kernel", "active_hmms_per_utt": N_ACTIVE, "ms": sweep_ms,
+                "share_of_step": sweep_ms / ms_step, "hmm_updates_per_s": n_inst * T / (sweep_ms * 1e-3),
+                "algorithmic_bytes": int(total * pm.n_sen * 2 + 2 * n_inst * (pm.n_emit_state * 10 + 14)),
+                "hbm_streaming_equivalent_gbs": n_inst * T * ((2 * pm.n_emit_state * 4) * 2 + 2 * 4 * 2 + 4 + 2 * pm.n_emit_state + 2 + 2 * pm.n_emit_state)
+                / (sweep_ms * 1e-3) / 1e9,
+                "note": "part of `value`; state in registers for the whole utterance, score rows staged by TMA bulk copies "
+                        "(cp.async.bulk + mbarrier); `hbm_streaming_equivalent_gbs` is what a per-frame kernel that moves the "
+                        "state through HBM (viterbi_stage below) would have to sustain for the same time"}
         if world == 1:
             batch.set_pipeline(1)                           # leave the whole batch's scores in one buffer
             batch.decode_device(pl, d_feats.data_ptr(), off)
@@ -562,6 +691,8 @@ def main():
             out["search_stage"] = search_stage(api, torch)
             out["cpu_baseline"] = cpu_baseline(args, pm, raw, feats_np, T, budget_s=args.cpu_budget, threads=1)
         print(json.dumps(out))
+    if hs is not None:
+        hs.close()
     batch.close(); pl.close(); ctx.close(); model.close()
     if world > 1:
         dist.destroy_process_group()

@@ -201,6 +201,26 @@ int psb_hmmset_download(psb_hmmset_t *s, psb_hmm_t *hmms);
 int psb_hmmset_eval_frames_device(psb_hmmset_t *s, const int16_t *d_senscr, const int64_t *d_row0,
                                   const int32_t *d_n_rows, int32_t n_frames, int32_t *d_best,
                                   float *ms);
+/* The same n_frames steps fused in ONE launch: every CTA keeps its slice of a segment in registers
+ * for the whole run and only the segment's score row of each frame is staged (TMA bulk copy +
+ * mbarrier, two frames ahead) -- the evaluate_channels loop (ngram_search_fwdtree.c:702-715) over a
+ * fixed active set, where nothing else has to see the state between frames.  Same arguments and
+ * bit-identical results (state after the last frame, d_best) as psb_hmmset_eval_frames_device;
+ * rows_total = number of rows of the d_senscr matrix (its last row is never over-read).  Sets with
+ * multiplexed instances, topologies other than 3 / 5 states or an odd senone count are served by
+ * the per-frame launches. */
+int psb_hmmset_sweep_device(psb_hmmset_t *s, const int16_t *d_senscr, int64_t rows_total,
+                            const int64_t *d_row0, const int32_t *d_n_rows, int32_t n_frames,
+                            int32_t *d_best, float *ms);
+/* With ms == NULL psb_hmmset_sweep_device is asynchronous on the set's stream.
+ * psb_hmmset_use_batch_stream: run the set's kernels on batch b's stream, i.e. behind the kernels
+ * that write the scores it reads (b == NULL: back to the set's own stream).
+ * psb_hmmset_snapshot / _restore: keep / bring back a device copy of the mutable state (scores,
+ * histories, exit score / history, best), so that the next batch of utterances starts from the same
+ * entered instances without another upload. */
+int psb_hmmset_use_batch_stream(psb_hmmset_t *s, psb_batch_t *b);
+int psb_hmmset_snapshot(psb_hmmset_t *s);
+int psb_hmmset_restore(psb_hmmset_t *s);
 /* one frame from host buffers: senscr int16 [n_seg][n_sen], best int32 [n_seg] */
 int psb_hmmset_eval_host(psb_hmmset_t *s, const int16_t *senscr, int32_t *best);
 

@@ -201,6 +201,12 @@ class OracleHmmCtx:
         self.c.senscore = _p(senscr)
         return int(lib().pso_hmm_vit_eval_batch(C.byref(self.c), _p(hmms), len(hmms)))
 
+    def sweep(self, hmms, senscr):
+        """T frames of hmm_vit_eval over the same records (updated in place); senscr int16 [T][n_sen];
+        returns best int32 [T] (the evaluate_channels loop over a fixed active set)."""
+        senscr = np.ascontiguousarray(senscr, np.int16)
+        return np.array([self.vit_eval(hmms, senscr[t]) for t in range(len(senscr))], np.int32)
+
 
 def phoneloop_run(tp, sseq, ssid, tmatid, senscr, window, beam, pbeam, pip, penalty_weight):
     """phone_loop_search.c semantics over a [T][n_sen] senone score matrix."""

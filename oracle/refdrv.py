@@ -67,6 +67,8 @@ def lib():
         L.refdrv_hmmctx_free.argtypes = [C.c_void_p]
         L.refdrv_hmm_vit_eval.restype = C.c_int32
         L.refdrv_hmm_vit_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.refdrv_hmm_sweep.restype = None
+        L.refdrv_hmm_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.refdrv_hmm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.refdrv_hmm_enter.argtypes = [C.c_void_p, C.c_int, C.c_int32, C.c_int32, C.c_int]
         L.refdrv_hmm_clear.argtypes = [C.c_void_p, C.c_int]
@@ -272,12 +274,21 @@ class RefHmmCtx:
         assert hmms.dtype == HMM_DTYPE and hmms.flags.c_contiguous
         return int(lib().refdrv_hmm_vit_eval(self.h, _p(hmms), len(hmms), _p(senscr)))
 
+    def sweep(self, hmms, senscr):
+        """T frames of hmm_vit_eval over the same records (updated in place); senscr int16 [T][n_sen];
+        returns best int32 [T]."""
+        senscr = np.ascontiguousarray(senscr, np.int16)
+        assert hmms.dtype == HMM_DTYPE and hmms.flags.c_contiguous and senscr.ndim == 2
+        best = np.zeros(len(senscr), np.int32)
+        lib().refdrv_hmm_sweep(self.h, _p(hmms), len(hmms), _p(senscr), senscr.shape[1], len(senscr), _p(best))
+        return best
+
     def time_vit_eval(self, hmms, senscr, reps=1):
         senscr = np.ascontiguousarray(senscr, np.int16)
         return lib().refdrv_time_hmm_vit_eval(self.h, _p(hmms), len(hmms), _p(senscr), reps)
 
 
-def decode(hmmdir, lm, dic, pcm, use_cuda=False, libpath=None, **kv):
+def decode(hmmdir, lm, dic, pcm, use_cuda=False, libpath=None, twice=False, **kv):
     """Full reference decode (fwdtree + fwdflat + bestpath by default) of one utterance; with
     use_cuda the GMM back-end is the CUDA one bound through integration/ps_mgau_cuda.c."""
     pcm = np.ascontiguousarray(pcm, np.int16)
@@ -285,12 +296,13 @@ def decode(hmmdir, lm, dic, pcm, use_cuda=False, libpath=None, **kv):
     hyp = C.create_string_buffer(4096)
     seg = C.create_string_buffer(65536)
     stats = np.zeros(4, np.int32)
+    stats[3] = 1 if twice else 0          # twice: utt_us times the second of two passes over the utterance
     n = lib().refdrv_decode(hmmdir.encode(), lm.encode(), dic.encode(), s, _p(pcm), len(pcm), int(use_cuda),
                             libpath.encode() if libpath else None, hyp, 4096, seg, 65536, _p(stats))
     if n < 0:
         raise RuntimeError("refdrv_decode failed (%d)" % n)
     return dict(n_frames=n, hyp=hyp.value.decode(), seg=seg.value.decode(), score=int(stats[0]),
-                cuda_calls=int(stats[1]), n_sen=int(stats[2]))
+                cuda_calls=int(stats[1]), n_sen=int(stats[2]), utt_us=int(stats[3]))
 
 
 def decode_senscr(hmmdir, lm, dic, senfile=None, pcm=None, senout=None, **kv):

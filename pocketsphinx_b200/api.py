@@ -494,6 +494,25 @@ class HmmSet:
                                                   C.c_void_p(d_best), C.byref(ms)), "psb_hmmset_eval_frames_device")
         return ms.value
 
+    def sweep_device(self, d_senscr, rows_total, n_frames, d_best, d_row0=None, d_n_rows=None, timed=True):
+        """The same steps fused in one launch (state in registers, score rows by TMA): device pointers
+        (ints), rows_total = rows of the score matrix; returns the device time in ms (timed=False:
+        asynchronous on the set's stream, returns None)."""
+        ms = C.c_float()
+        check(lib().psb_hmmset_sweep_device(self.h, C.c_void_p(d_senscr), int(rows_total), C.c_void_p(d_row0) if d_row0 else None,
+                                            C.c_void_p(d_n_rows) if d_n_rows else None, int(n_frames),
+                                            C.c_void_p(d_best), C.byref(ms) if timed else None), "psb_hmmset_sweep_device")
+        return ms.value if timed else None
+
+    def use_batch_stream(self, batch):
+        check(lib().psb_hmmset_use_batch_stream(self.h, batch.h if batch is not None else None), "psb_hmmset_use_batch_stream")
+
+    def snapshot(self):
+        check(lib().psb_hmmset_snapshot(self.h), "psb_hmmset_snapshot")
+
+    def restore(self):
+        check(lib().psb_hmmset_restore(self.h), "psb_hmmset_restore")
+
     def close(self):
         if self.h:
             lib().psb_hmmset_free(self.h)

@@ -533,13 +533,15 @@ struct psb_hmmset_s {
     int64_t n_max, n, pitch;
     int32_t n_seg_max, n_seg;
     int64_t max_seg_len;
+    bool any_mpx;                 // some instance is multiplexed (hmm_t.mpx): the fused sweep leaves those to the per-frame kernel
     int32_t *d_i32;               // [pitch / HS_TS][2*NS + 4][HS_TS]: score[NS] hist[NS] out_score out_hist best frame
     uint16_t *d_u16;              // [pitch / HS_TS][NS + 2][HS_TS]: senid[NS] ssid tmatid(int16)
     uint8_t *d_mpx;               // [pitch]
     int64_t *d_seg_off;           // [n_seg_max + 1] caller's offsets (AoS order)
     int64_t *d_seg_base;          // [n_seg_max + 1] padded offsets inside the set
     psb_hmm_t *d_aos;             // staging for upload / download
-    cudaStream_t stream;
+    int32_t *d_snap_i32;          // psb_hmmset_snapshot: copy of the mutable state (scores, histories, exits)
+    cudaStream_t stream, own_stream;
     cudaEvent_t ev[2];
 };
 
@@ -726,6 +728,180 @@ hmmset_eval_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr,
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// hmmset_sweep_kernel: the same step fused over frames.  hmmset_eval_kernel streams every
+// instance's state through HBM once per frame (77 B per 3-state instance and frame: the step is
+// HBM-bound and needs one launch per frame).  When nothing else has to see the state between
+// frames -- evaluate_channels over a fixed active set, ngram_search_fwdtree.c:702-715 -- a CTA can
+// keep its slice of a segment (THREADS x V instances) in REGISTERS for the whole utterance and
+// only the segment's int16 score row of each frame has to arrive: 2 * n_sen bytes per frame,
+// staged by the TMA unit (cp.async.bulk global -> shared, completion on an mbarrier) two frames
+// ahead into a double buffer, so that the copy of frame t+2 overlaps the arithmetic of frames t
+// and t+1.  One elected thread arms the barrier and issues the copy; everybody waits on the
+// barrier's phase.  Bulk copies need 16-byte aligned source, destination and size: the copy
+// starts at the row's address rounded down to 16 and ends at its end rounded up, the row is read
+// at its offset inside the buffer; the matrix's LAST row is copied by the threads themselves so
+// that nothing past the allocation is touched.  Per frame one block-wide max (REDUX + one
+// shared-memory hop) and one atomicMax per CTA into best[t][segment].  Results are bit-identical
+// to n_frames calls of hmmset_eval_kernel (tests/test_gpu_parity.py).
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(dst)),
+                 "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+template <int NS, int V, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+hmmset_sweep_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr, long long rows_total,
+                    const int64_t *__restrict__ row0, const int32_t *__restrict__ n_rows, int n_frames,
+                    int32_t *__restrict__ best_out, int n_tmat, int buf_bytes)
+{
+    extern __shared__ __align__(128) unsigned char sw_smem[];       // [2][buf_bytes] score rows, then the transition matrices
+    __shared__ __align__(8) uint64_t full[2];
+    __shared__ int red[2][THREADS / 32];
+    const int seg = blockIdx.y, tid = threadIdx.x;
+    const int64_t n = s.seg_off[seg + 1] - s.seg_off[seg];
+    const int64_t j_base = (int64_t)blockIdx.x * THREADS * V;
+    if (j_base >= n) return;
+    int T = n_frames;
+    if (n_rows) T = min(T, n_rows[seg]);
+    if (T <= 0) return;
+    uint8_t *tps = sw_smem + 2 * (size_t)buf_bytes;
+    for (int q = tid; q < n_tmat * NS * (NS + 1); q += THREADS) tps[q] = c.tp[q];
+
+    // this thread's V instances (THREADS apart: neighbouring threads read neighbouring words)
+    int sc[V][NS], hi[V][NS], sid[V][NS], osc[V], ohi[V], tmo[V];
+    int32_t *p32[V];
+    bool live[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const int64_t j = j_base + (int64_t)v * THREADS + tid;
+        live[v] = j < n;
+        const int64_t i = s.seg_base[seg] + (live[v] ? j : 0);
+        const int64_t b32 = (i / HS_TS) * (int64_t)(2 * NS + 4) * HS_TS + (i % HS_TS);
+        const int64_t b16 = (i / HS_TS) * (int64_t)(NS + 2) * HS_TS + (i % HS_TS);
+        p32[v] = s.i32 + b32;
+        const uint16_t *p16 = s.u16 + b16;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            sc[v][k] = live[v] ? p32[v][k * HS_TS] : PSB_WORST_SCORE;
+            hi[v][k] = live[v] ? p32[v][(NS + k) * HS_TS] : -1;
+            sid[v][k] = live[v] ? p16[k * HS_TS] : 0;
+        }
+        osc[v] = live[v] ? p32[v][2 * NS * HS_TS] : PSB_WORST_SCORE;
+        ohi[v] = live[v] ? p32[v][(2 * NS + 1) * HS_TS] : -1;
+        tmo[v] = live[v] ? (int)(int16_t)p16[(NS + 1) * HS_TS] * NS * (NS + 1) : 0;
+    }
+    const int64_t r0 = row0 ? row0[seg] : seg;
+    const int64_t rstep = row0 ? 1 : gridDim.y;
+    const size_t row_bytes = (size_t)c.n_sen * 2;
+    auto row_addr = [&](int t) { return reinterpret_cast<uintptr_t>(senscr + (size_t)(r0 + (int64_t)t * rstep) * c.n_sen); };
+    auto tma_ok = [&](int t) { return r0 + (int64_t)t * rstep + 1 < rows_total; };
+    auto issue = [&](int t) {                                         // one thread: arm the barrier, start the copy
+        const uintptr_t a = row_addr(t), a16 = a & ~(uintptr_t)15;
+        const unsigned bytes = (unsigned)(((a - a16) + row_bytes + 15) & ~(size_t)15);
+        mbar_expect_tx(&full[t & 1], bytes);
+        tma_bulk_g2s(sw_smem + (size_t)(t & 1) * buf_bytes, reinterpret_cast<const void *>(a16), bytes, &full[t & 1]);
+    };
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (tma_ok(0)) issue(0);
+        if (T > 1 && tma_ok(1)) issue(1);
+    }
+    int best_final[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) best_final[v] = PSB_WORST_SCORE;
+
+    for (int t = 0; t < T; ++t) {
+        const int b = t & 1;
+        unsigned char *buf = sw_smem + (size_t)b * buf_bytes;
+        const uintptr_t a = row_addr(t);
+        const int16_t *srow;
+        if (tma_ok(t)) {
+            mbar_wait(&full[b], (unsigned)(t >> 1) & 1u);
+            srow = reinterpret_cast<const int16_t *>(buf + (a & 15));
+        }
+        else {                                                        // last row of the matrix: plain copy
+            const int16_t *g = reinterpret_cast<const int16_t *>(a);
+            int16_t *d = reinterpret_cast<int16_t *>(buf);
+            for (int q = tid; q < c.n_sen; q += THREADS) d[q] = g[q];
+            __syncthreads();
+            srow = d;
+        }
+        int best = PSB_WORST_SCORE;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            HmmReg h;
+            int obs[PSB_HMM_MAX_NSTATE];
+#pragma unroll
+            for (int k = 0; k < PSB_HMM_MAX_NSTATE; ++k) {
+                h.score[k] = k < NS ? sc[v][k < NS ? k : 0] : PSB_WORST_SCORE;
+                h.hist[k] = k < NS ? hi[v][k < NS ? k : 0] : -1;
+                h.senid[k] = 0;
+                obs[k] = k < NS ? -(int)srow[sid[v][k < NS ? k : 0]] : 0;
+            }
+            h.out_score = osc[v]; h.out_hist = ohi[v]; h.best = PSB_WORST_SCORE;
+            const int bb = NS == 3 ? hmm_step_3st(h, tps + tmo[v], obs) : hmm_step_5st(h, tps + tmo[v], obs);
+            if (live[v]) best = max(best, bb);
+#pragma unroll
+            for (int k = 0; k < NS; ++k) { sc[v][k] = h.score[k]; hi[v][k] = h.hist[k]; }
+            osc[v] = h.out_score; ohi[v] = h.out_hist;
+            best_final[v] = bb;
+        }
+        best = __reduce_max_sync(0xffffffffu, best);
+        if ((tid & 31) == 0) red[b][tid >> 5] = best;
+        __syncthreads();                                              // buf[b] and red[b] are complete / free
+        if (tid == 0 && t + 2 < T && tma_ok(t + 2)) issue(t + 2);
+        if (tid < 32) {
+            int v = tid < THREADS / 32 ? red[b][tid] : PSB_WORST_SCORE;
+            v = __reduce_max_sync(0xffffffffu, v);
+            if (tid == 0) atomicMax(best_out + (size_t)t * gridDim.y + seg, v);
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        if (!live[v]) continue;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            p32[v][k * HS_TS] = sc[v][k];
+            p32[v][(NS + k) * HS_TS] = hi[v][k];
+        }
+        p32[v][2 * NS * HS_TS] = osc[v];
+        p32[v][(2 * NS + 1) * HS_TS] = ohi[v];
+        p32[v][(2 * NS + 2) * HS_TS] = best_final[v];
+    }
+}
+
 }  // namespace
 
 extern "C" void psb_hmmset_free(psb_hmmset_t *s)
@@ -734,9 +910,10 @@ extern "C" void psb_hmmset_free(psb_hmmset_t *s)
     cudaSetDevice(s->c->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->d_i32); cudaFree(s->d_u16); cudaFree(s->d_mpx); cudaFree(s->d_seg_off); cudaFree(s->d_seg_base); cudaFree(s->d_aos);
+    cudaFree(s->d_snap_i32);
     if (s->ev[0]) cudaEventDestroy(s->ev[0]);
     if (s->ev[1]) cudaEventDestroy(s->ev[1]);
-    if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
 }
 
@@ -753,7 +930,8 @@ extern "C" int psb_hmmset_create(psb_hmmctx_t *c, int64_t n_max, int32_t n_seg_m
     if (e == cudaSuccess) e = cudaMalloc(&s->d_mpx, (size_t)s->pitch);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_seg_off, (size_t)(n_seg_max + 1) * 8);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_seg_base, (size_t)(n_seg_max + 1) * 8);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
+    s->stream = s->own_stream;
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev[0]);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev[1]);
     if (e != cudaSuccess) {
@@ -762,6 +940,35 @@ extern "C" int psb_hmmset_create(psb_hmmctx_t *c, int64_t n_max, int32_t n_seg_m
         return PSB_ERR_CUDA;
     }
     *out = s;
+    return PSB_OK;
+}
+
+// Run the set's kernels on a batch's stream (behind the kernels that produce the scores it reads).
+extern "C" int psb_hmmset_use_batch_stream(psb_hmmset_t *s, psb_batch_t *b)
+{
+    PSB_REQUIRE(s, "psb_hmmset_use_batch_stream: null set");
+    PSB_CUDA(cudaStreamSynchronize(s->stream));
+    s->stream = b ? psb_batch_stream(b) : s->own_stream;
+    return PSB_OK;
+}
+
+// Keep / bring back a copy of the mutable state: the same starting instances for the next batch of
+// utterances without another upload (mpx sets also change senone-sequence ids: not snapshotted).
+extern "C" int psb_hmmset_snapshot(psb_hmmset_t *s)
+{
+    PSB_REQUIRE(s && !s->any_mpx, "psb_hmmset_snapshot: null set or multiplexed instances");
+    PSB_CUDA(cudaSetDevice(s->c->device));
+    const size_t nb = (size_t)(2 * s->c->n_emit + 4) * s->pitch * 4;
+    if (!s->d_snap_i32) PSB_CUDA(cudaMalloc(&s->d_snap_i32, nb));
+    PSB_CUDA(cudaMemcpyAsync(s->d_snap_i32, s->d_i32, nb, cudaMemcpyDeviceToDevice, s->stream));
+    return PSB_OK;
+}
+
+extern "C" int psb_hmmset_restore(psb_hmmset_t *s)
+{
+    PSB_REQUIRE(s && s->d_snap_i32, "psb_hmmset_restore: no snapshot");
+    PSB_CUDA(cudaSetDevice(s->c->device));
+    PSB_CUDA(cudaMemcpyAsync(s->d_i32, s->d_snap_i32, (size_t)(2 * s->c->n_emit + 4) * s->pitch * 4, cudaMemcpyDeviceToDevice, s->stream));
     return PSB_OK;
 }
 
@@ -794,9 +1001,11 @@ extern "C" int psb_hmmset_upload(psb_hmmset_t *s, const psb_hmm_t *hmms, int64_t
         if (base[(size_t)n_seg] <= s->pitch) break;
     }
     PSB_REQUIRE(base[(size_t)n_seg] <= s->pitch, "psb_hmmset_upload: internal capacity exceeded");
+    s->any_mpx = false;
     for (int64_t i = 0; i < n; ++i) {
         int rc = validate_hmm(s->c, &hmms[i], (int)i);
         if (rc) return rc;
+        s->any_mpx |= hmms[i].mpx != 0;
     }
     int rc = hmmset_staging(s);
     if (rc) return rc;
@@ -889,6 +1098,52 @@ extern "C" int psb_hmmset_eval_frames_device(psb_hmmset_t *s, const int16_t *d_s
     PSB_CUDA(cudaEventRecord(s->ev[1], s->stream));
     PSB_CUDA(cudaStreamSynchronize(s->stream));
     if (ms) PSB_CUDA(cudaEventElapsedTime(ms, s->ev[0], s->ev[1]));
+    return PSB_OK;
+}
+
+extern "C" int psb_hmmset_sweep_device(psb_hmmset_t *s, const int16_t *d_senscr, int64_t rows_total, const int64_t *d_row0,
+                                       const int32_t *d_n_rows, int32_t n_frames, int32_t *d_best, float *ms)
+{
+    PSB_REQUIRE(s && d_senscr && d_best && n_frames >= 0 && rows_total > 0, "psb_hmmset_sweep_device: bad argument");
+    const HmmCtxDev cd = dev_ctx(s->c);
+    if (s->any_mpx || (cd.n_emit != 3 && cd.n_emit != 5) || (cd.n_sen & 1))
+        return psb_hmmset_eval_frames_device(s, d_senscr, d_row0, d_n_rows, n_frames, d_best, ms);   // per-frame launches
+    if (ms) *ms = 0.f;
+    if (n_frames == 0 || s->n_seg == 0) return PSB_OK;
+    PSB_CUDA(cudaSetDevice(s->c->device));
+    const int64_t nb = (int64_t)n_frames * s->n_seg;
+    fill_i32_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, s->stream>>>(d_best, nb, PSB_WORST_SCORE);
+    PSB_LAUNCH_CHECK();
+    if (s->n == 0) {
+        if (ms) PSB_CUDA(cudaStreamSynchronize(s->stream));
+        return PSB_OK;
+    }
+    constexpr int THREADS = 256, V = 4;
+    const int buf_bytes = (int)(((size_t)cd.n_sen * 2 + 32 + 127) & ~(size_t)127);
+    const int tp_bytes = s->c->n_tmat * cd.n_emit * (cd.n_emit + 1);
+    const size_t smem = 2 * (size_t)buf_bytes + tp_bytes;
+    PSB_REQUIRE(smem <= 200 * 1024, "psb_hmmset_sweep: %d senones / %d transition matrices do not fit shared memory", cd.n_sen, s->c->n_tmat);
+    const dim3 grid((unsigned)((s->max_seg_len + THREADS * V - 1) / (THREADS * V)), (unsigned)s->n_seg);
+    const HmmSetDev sd = dev_set(s);
+    PSB_CUDA(cudaEventRecord(s->ev[0], s->stream));
+    if (cd.n_emit == 3) {
+        auto kern = hmmset_sweep_kernel<3, V, THREADS>;
+        PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, THREADS, smem, s->stream>>>(sd, cd, d_senscr, (long long)rows_total, d_row0, d_n_rows, n_frames, d_best,
+                                                s->c->n_tmat, buf_bytes);
+    }
+    else {
+        auto kern = hmmset_sweep_kernel<5, V, THREADS>;
+        PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, THREADS, smem, s->stream>>>(sd, cd, d_senscr, (long long)rows_total, d_row0, d_n_rows, n_frames, d_best,
+                                                s->c->n_tmat, buf_bytes);
+    }
+    PSB_LAUNCH_CHECK();
+    PSB_CUDA(cudaEventRecord(s->ev[1], s->stream));
+    if (ms) {                                               // ms == NULL: asynchronous on the set's stream
+        PSB_CUDA(cudaStreamSynchronize(s->stream));
+        PSB_CUDA(cudaEventElapsedTime(ms, s->ev[0], s->ev[1]));
+    }
     return PSB_OK;
 }
 

@@ -452,6 +452,64 @@ def test_hmmset_frames_match_oracle(api, n_emit):
     ctx.close()
 
 
+@pytest.mark.parametrize("n_emit,n_sen_odd", [(3, False), (5, False), (3, True)])
+def test_hmmset_sweep_matches_per_frame_and_oracle(api, n_emit, n_sen_odd):
+    """psb_hmmset_sweep_device (all frames in one launch, state in registers, score rows staged by TMA bulk
+    copies) against the per-frame kernel and against hmm_vit_eval of the oracle: ragged segments (one empty,
+    one of a single instance, one spanning several CTAs), segments finishing early, rows addressed through
+    d_row0 up to the very last row of the matrix (the one that is not over-read), every row misaligned
+    differently (n_sen * 2 is not a multiple of 16)."""
+    import torch
+    from oracle import oracle
+    g = golden("hmm_vit_eval.npz")
+    tp, sseq = g["n%d_tp" % n_emit], g["n%d_sseq" % n_emit]
+    n_sen = len(g["n%d_senscr" % n_emit]) - (1 if n_sen_odd else 0)     # odd count: served by the per-frame launches
+    if n_sen % 2 == 1 and not n_sen_odd:
+        n_sen -= 1
+    hm0 = hmm_view(g["n%d_before" % n_emit]).copy()
+    hm0 = hm0[hm0["mpx"] == 0].copy()                                    # the fused kernel takes plain instances
+    hm0 = hm0[(hm0["senid"][:, :n_emit] < n_sen).all(1)].copy()
+    n = len(hm0)
+    assert n > 1500
+    rng = np.random.default_rng(5)
+    seg_off = np.array([0, 1, 1, 260, 1300, n], np.int64)
+    n_seg, T = len(seg_off) - 1, 9
+    n_rows = np.array([9, 9, 5, 9, 7], np.int32)
+    R = 40
+    senscr = rng.integers(0, 900, (R, n_sen)).astype(np.int16)
+    row0 = np.array([3, 0, 11, R - 9, 20], np.int64)                     # segment 3 ends on the matrix's last row
+    ctx = api.HmmContext(tp, sseq, n_sen)
+    d_scr = torch.from_numpy(senscr).cuda()
+    d_row0, d_nrows = torch.from_numpy(row0).cuda(), torch.from_numpy(n_rows).cuda()
+    res = []
+    for fused in (False, True):
+        hs = api.HmmSet(ctx, n + 8 * 512, 16)
+        hs.upload(hm0, seg_off)
+        d_best = torch.zeros((T, n_seg), dtype=torch.int32, device="cuda")
+        if fused:
+            hs.sweep_device(d_scr.data_ptr(), R, T, d_best.data_ptr(), d_row0=d_row0.data_ptr(), d_n_rows=d_nrows.data_ptr())
+        else:
+            hs.eval_frames_device(d_scr.data_ptr(), T, d_best.data_ptr(), d_row0=d_row0.data_ptr(), d_n_rows=d_nrows.data_ptr())
+        res.append((hs.download(), d_best.cpu().numpy()))
+        hs.close()
+    assert np.array_equal(res[0][1], res[1][1])
+    assert_hmm_equal(res[1][0], res[0][0], n_emit, "fused vs per-frame")
+    octx = oracle.OracleHmmCtx(tp, sseq)
+    want = hm0.copy()
+    for s in range(n_seg):
+        a, b = seg_off[s], seg_off[s + 1]
+        for t in range(T):
+            if t >= n_rows[s] or a == b:
+                assert res[1][1][t, s] == -0x20000000
+                continue
+            seg = np.ascontiguousarray(want[a:b])
+            wb = octx.vit_eval(seg, np.concatenate([senscr[row0[s] + t], np.zeros(len(g["n%d_senscr" % n_emit]) - n_sen, np.int16)]))
+            want[a:b] = seg
+            assert res[1][1][t, s] == wb, "segment %d frame %d" % (s, t)
+    assert_hmm_equal(res[1][0], want, n_emit, "after %d frames" % T)
+    ctx.close()
+
+
 # ---------------------------------------------------------------------------------------
 # BASELINE.json config 2 at FULL size (1000 utterances x 998 frames, 5138 senones): properties
 # that do not need the oracle on every frame, plus the oracle on a sample of utterances.
