@@ -200,6 +200,12 @@ class Batch:
         check(lib().psb_batch_get_topn(self.h, _p(rec), n_frames), "psb_batch_get_topn")
         return rec
 
+    def tc_check(self):
+        """(max |filter value - exact distance| / bound, max candidates) of the tensor-core filter (PSB_TC_CHECK=1)."""
+        r, n = C.c_float(), C.c_int32()
+        check(lib().psb_batch_tc_check(self.h, C.byref(r), C.byref(n)), "psb_batch_tc_check")
+        return r.value, n.value
+
     def decode_host(self, phoneloop, feats, utt_off, want_senscr=False, best=None, pen=None, senscr=None):
         """End to end: host features -> senone scores -> phone-loop Viterbi -> host results."""
         pm = self.model.pm

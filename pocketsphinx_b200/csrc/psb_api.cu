@@ -115,6 +115,10 @@ static int build_records(psb_model_t *m, const float *mean, const float *var, co
         }
         PSB_CUDA(cudaMemcpy(m->d_rec2, rec2.data(), total2 * sizeof(float), cudaMemcpyHostToDevice));
     }
+    {
+        int rc = psb_tc_prepare(m, hm.data(), hv.data(), hd.data());
+        if (rc) return rc;
+    }
     if (m->kind == PSB_KIND_MS) {
         // codebook-minor copy for ms_dist_kernel: per stream f (at float offset featoff[f]*nd*2*n_mgau)
         // [(d*fl + j)*2 + {mean,var}][cb]; determinants [f][d][cb]
@@ -177,6 +181,8 @@ extern "C" int psb_model_create(const psb_model_desc_t *d, int device, psb_model
     m->d_sen2cb = nullptr; m->d_sen2cb32 = nullptr; m->d_quadcb = nullptr; m->d_bsen = nullptr; m->n_bsen = 0; m->d_logadd8 = nullptr; m->d_logadd_ms = nullptr;
     m->has_topn_beam = false;
     m->d_topn_beam = nullptr;
+    m->tc_ok = false;
+    m->d_tc_wfrag = m->d_tc_cen = m->d_tc_bnd = nullptr;
     m->d_msT = m->d_msdetT = nullptr; m->d_featlen = m->d_featoff = nullptr;
     for (int f = 0; f < PSB_MAX_FEAT; ++f) m->topn_beam[f] = 0;
     const bool dev = d->on_device != 0;
@@ -302,6 +308,7 @@ extern "C" void psb_model_free(psb_model_t *m)
     cudaFree(m->d_rec); cudaFree(m->d_rec_off); cudaFree(m->d_rec2); cudaFree(m->d_rec2_off); cudaFree(m->d_mixw); cudaFree(m->d_mixw_cb);
     cudaFree(m->d_sen2cb); cudaFree(m->d_sen2cb32); cudaFree(m->d_quadcb); cudaFree(m->d_bsen); cudaFree(m->d_logadd8); cudaFree(m->d_logadd_ms);
     cudaFree(m->d_topn_beam); cudaFree(m->d_msT); cudaFree(m->d_msdetT); cudaFree(m->d_featlen); cudaFree(m->d_featoff);
+    cudaFree(m->d_tc_wfrag); cudaFree(m->d_tc_cen); cudaFree(m->d_tc_bnd);
     delete m;
 }
 
@@ -328,9 +335,10 @@ extern "C" int psb_batch_create(psb_model_t *m, int32_t max_utts, int64_t max_fr
     b->max_utts = max_utts;
     b->max_frames = max_frames;
     {
-        // tuning knob; default = packed FP32 with deferred insertion (ptm_topnq_kernel), 4 warps/CTA
+        // tuning knob; default = tensor-core filter + exact rescoring (psb_ptm_tc.cu) where the model allows it,
+        // else packed FP32 with deferred insertion (ptm_topnq_kernel, variant 5)
         const char *v = getenv("PSB_TOPN_VARIANT");
-        b->topn_variant = v ? atoi(v) : 5;
+        b->topn_variant = v ? atoi(v) : 6;
         const char *p = getenv("PSB_PIPELINE");         // sub-batches in flight for psb_decode_batch_*
         b->n_pipe = p ? atoi(p) : 0;                   // 0 = auto (see decode_common)
         if (b->n_pipe < 0) b->n_pipe = 0;
@@ -363,6 +371,7 @@ extern "C" void psb_batch_free(psb_batch_t *b)
         cudaStreamSynchronize(k->stream);
         if (k->h_off) cudaFreeHost(k->h_off);
         cudaFree(k->d_featT); cudaFree(k->d_tab); cudaFree(k->d_off); cudaFree(k->d_msdist); cudaFree(k->d_msbest);
+        cudaFree(k->d_uttoff); cudaFree(k->d_semi_dist); cudaFree(k->d_tc_flags); cudaFree(k->d_tc_check);
         if (k->h_tab) cudaFreeHost(k->h_tab);
         for (int i = 0; i < 4; ++i) cudaEventDestroy(k->ev[i]);
         cudaEventDestroy(k->join_ev);
@@ -373,6 +382,7 @@ extern "C" void psb_batch_free(psb_batch_t *b)
     if (b->join_ev) cudaEventDestroy(b->join_ev);
     cudaFree(b->d_feats); cudaFree(b->d_senscr); cudaFree(b->d_featT); cudaFree(b->d_topn); cudaFree(b->d_tab); cudaFree(b->d_semi_dist); cudaFree(b->d_uttoff);
     cudaFree(b->d_best); cudaFree(b->d_pen); cudaFree(b->d_off); cudaFree(b->d_msdist); cudaFree(b->d_msbest);
+    cudaFree(b->d_tc_flags); cudaFree(b->d_tc_check);
     if (b->h_tab) cudaFreeHost(b->h_tab);
     if (b->h_feats) cudaFreeHost(b->h_feats);
     if (b->h_senscr) cudaFreeHost(b->h_senscr);
@@ -473,7 +483,8 @@ extern "C" int psb_batch_last_kernel_ms(psb_batch_t *b, float *out3)
 
 extern "C" int psb_batch_get_topn(psb_batch_t *b, int32_t *rec, int64_t n_frames)
 {
-    PSB_REQUIRE(b && rec && n_frames <= b->max_frames, "psb_batch_get_topn: bad argument");
+    PSB_REQUIRE(b && rec && n_frames >= 0 && n_frames <= b->max_frames, "psb_batch_get_topn: bad argument");
+    PSB_REQUIRE(b->d_topn, "psb_batch_get_topn: this model kind keeps no top-N records");
     PSB_CUDA(cudaSetDevice(b->m->device));
     PSB_CUDA(cudaStreamSynchronize(b->stream));
     PSB_CUDA(cudaMemcpy(rec, b->d_topn, (size_t)n_frames * b->m->K * sizeof(int4), cudaMemcpyDeviceToHost));
@@ -511,9 +522,27 @@ static int get_kid(psb_batch_t *b, int i, psb_batch_t **out)
 // range overlaps the integer/LSU-bound senone kernel and the PCIe copies of the others.  The
 // parent's stream forks into and joins the sub-streams with events, so psb_batch_event_record /
 // psb_batch_sync on the parent still bracket all the work.
+static int decode_common_body(psb_batch_t *b, psb_phoneloop_t *p, const float *feats, bool feats_on_host,
+                              const int32_t *utt_off, int32_t n_utt, int32_t *h_best, int32_t *h_pen, int16_t *h_senscr,
+                              bool want_best, bool want_pen);
+
+// An error in the middle of the loop over sub-batches leaves earlier sub-streams with copies into the
+// caller's host buffers in flight: drain every stream before handing the error back.
 static int decode_common(psb_batch_t *b, psb_phoneloop_t *p, const float *feats, bool feats_on_host,
                          const int32_t *utt_off, int32_t n_utt, int32_t *h_best, int32_t *h_pen, int16_t *h_senscr,
                          bool want_best, bool want_pen)
+{
+    const int rc = decode_common_body(b, p, feats, feats_on_host, utt_off, n_utt, h_best, h_pen, h_senscr, want_best, want_pen);
+    if (rc != PSB_OK) {
+        for (psb_batch_t *k : b->kids) cudaStreamSynchronize(k->stream);
+        cudaStreamSynchronize(b->stream);
+    }
+    return rc;
+}
+
+static int decode_common_body(psb_batch_t *b, psb_phoneloop_t *p, const float *feats, bool feats_on_host,
+                              const int32_t *utt_off, int32_t n_utt, int32_t *h_best, int32_t *h_pen, int16_t *h_senscr,
+                              bool want_best, bool want_pen)
 {
     psb_model_t *m = b->m;
     const size_t H = psb_phoneloop_n_phones(p);

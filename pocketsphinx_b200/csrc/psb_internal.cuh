@@ -87,6 +87,9 @@ struct psb_model_s {
     uint8_t topn_beam[PSB_MAX_FEAT];
     int32_t *d_topn_beam;         // [PSB_MAX_FEAT]
     bool has_topn_beam;
+    // tensor-core filter path (psb_ptm_tc.cu): W in mma fragment order, centres, error-bound coefficients
+    bool tc_ok;
+    float *d_tc_wfrag, *d_tc_cen, *d_tc_bnd;
 };
 
 struct psb_batch_s {
@@ -113,7 +116,10 @@ struct psb_batch_s {
     float2 *d_semi_dist; size_t semi_cap;      // semi-continuous split path: {d, partial} per (stream, frame, codeword)
     int32_t *d_uttoff; size_t uttoff_cap;
     int topn_variant;             // PSB_TOPN_VARIANT: 0 scalar, 1/2 packed FP32, 3 two utterances per lane,
-                                  // 4/5 packed + deferred insertion (2 / 1 utterances per lane); default 5
+                                  // 4/5 packed + deferred insertion (2 / 1 utterances per lane),
+                                  // 6 (default) tensor-core filter + exact rescoring where the model allows, else 5
+    unsigned *d_tc_flags; size_t tc_flag_cap, tc_flag_words;   // [K][words]: frames the tie fix-up redoes
+    float *d_tc_check;            // debug (PSB_TC_CHECK=1): max |a - d| / eps, max candidates
     // phone-loop outputs for psb_decode_batch_host
     int32_t *d_best, *d_pen;
     int32_t *h_best, *h_pen;
@@ -140,6 +146,10 @@ int psb_phoneloop_launch(psb_phoneloop_t *p, const int16_t *d_senscr, const int3
 int psb_phoneloop_n_phones(const psb_phoneloop_t *p);
 int psb_launch_ptm_batch(psb_batch_t *b, const float *d_feats, const int32_t *utt_off,
                          int32_t n_utt, int16_t *d_senscr);
+int psb_tc_prepare(psb_model_t *m, const float *hm, const float *hv, const float *hd);
+bool psb_tc_usable(const psb_batch_t *b);
+int psb_launch_ptm_tc(psb_batch_t *b, const float *d_feats, const int32_t *utt_off, int32_t n_utt, const int32_t *d_klist,
+                      const int32_t *d_featoff);
 int psb_ms_score_one(psb_model_t *m, cudaStream_t st, const float *d_feat, void *d_dist, int32_t *d_best,
                      int16_t *d_senscr, const int32_t *d_list, int n_items);
 size_t psb_ms_dist_bytes(const psb_model_t *m);

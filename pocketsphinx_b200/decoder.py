@@ -4,9 +4,8 @@ loop -> first pass -> second pass on the GPU, hypothesis and segments read from 
 (ps_decode_raw + ps_get_hyp / ps_seg_iter with -bestpath no, pocketsphinx.c:1073-1345).  Everything the
 reference loads from files is read here by the package itself (s3io, lmio, dict2pid, lextree).
 
-STATUS: the loaders and the search description are pinned against the reference on the CPU; the three
-stages in front of the search are GPU-verified; the search kernels themselves have not run on hardware yet
-(DESIGN.md 4.10-4.12), so neither has this class -- tests/test_gpu_zz_decoder.py is gated like theirs.
+STATUS: GPU-verified end to end (tests/test_gpu_zz_decoder.py, first hardware run in round 2).  Out of the
+hot-path scope: kept small, not extended.
 """
 import math
 import os
@@ -17,6 +16,11 @@ from . import api, lextree
 from .fe_tables import make_fe_desc
 from .model import PackedModel
 
+# config_macro.h (the reference's defaults for every front-end / feature key this class looks at)
+FE_REFERENCE_DEFAULTS = dict(feat="1s_c_d_dd", cmn="live", agc="none", varnorm="no", lda="", svspec="", dither="no",
+                             round_filters="yes", ncep="13", frate="100", nfft="0", cmninit="40,3,-1", samprate="16000",
+                             wlen="0.025625", nfilt="40", lowerf="133.33334", upperf="6855.4976", alpha="0.97",
+                             transform="legacy", lifter="0", remove_noise="no", remove_dc="no", unit_area="yes", doublebw="no")
 PL_DEFAULTS = dict(pl_window="5", pl_beam="1e-10", pl_pbeam="1e-10", pl_pip="1.0", pl_weight="3.0")
 
 
@@ -28,27 +32,41 @@ class Decoder:
     def __init__(self, hmm, dict_file, lm_file, max_utts=64, max_frames=1 << 16, device=0, **config):
         cfg = {k: str(v) for k, v in config.items()}
         self.pm = PackedModel.from_dir(hmm, **{k: v for k, v in cfg.items() if k in ("varfloor", "tmatfloor", "mixwfloor", "topn", "ds", "aw")})
-        fp = {}
+        # front end: the reference's own defaults (config_macro.h), overlaid by the model's feat.params, then by the
+        # caller -- like ps_init; whatever the device front end does not implement is refused, not ignored
         from .s3io import read_feat_params
+        fp = dict(FE_REFERENCE_DEFAULTS)
         fp.update(read_feat_params(os.path.join(hmm, "feat.params")))
-        if fp.get("feat", "1s_c_d_dd") != "1s_c_d_dd" or fp.get("cmn", "batch") != "batch":
-            raise NotImplementedError("front end: -feat %s / -cmn %s (the device front end covers 1s_c_d_dd with batch CMN)" % (
-                fp.get("feat"), fp.get("cmn")))
-        fe_kw = {}
-        for k, name, conv in (("nfilt", "nfilt", int), ("lowerf", "lowerf", float), ("upperf", "upperf", float), ("lifter", "lifter", int),
-                              ("transform", "transform", str), ("samprate", "samprate", float), ("wlen", "wlen", float)):
-            if k in fp:
-                fe_kw[name] = conv(fp[k])
-        if "remove_noise" in fp:
-            fe_kw["remove_noise"] = fp["remove_noise"] in ("yes", "1", "true")
-        if "remove_dc" in fp:
-            fe_kw["remove_dc"] = fp["remove_dc"] in ("yes", "1", "true")
-        self.fe = api.FrontEnd(make_fe_desc(**fe_kw), device)
+        fp.update({k: v for k, v in cfg.items() if k in FE_REFERENCE_DEFAULTS})
+        yes = ("yes", "1", "true", "True")
+        if fp["cmn"] == "current":                       # the reference's alias for batch (cmn.c: cmn_type_str)
+            fp["cmn"] = "batch"
+        unsupported = []
+        if fp["feat"] != "1s_c_d_dd": unsupported.append("-feat " + fp["feat"])
+        if fp["cmn"] != "batch": unsupported.append("-cmn " + fp["cmn"])
+        if fp["agc"] != "none": unsupported.append("-agc " + fp["agc"])
+        if fp["varnorm"] in yes: unsupported.append("-varnorm yes")
+        if fp["lda"]: unsupported.append("-lda")
+        if fp["svspec"] not in ("", "0-12/13-25/26-38"): unsupported.append("-svspec " + fp["svspec"])
+        if fp["dither"] in yes: unsupported.append("-dither yes")
+        if fp["round_filters"] not in yes: unsupported.append("-round_filters no")
+        if int(fp["ncep"]) != 13: unsupported.append("-ncep " + fp["ncep"])
+        if int(fp["frate"]) != 100: unsupported.append("-frate " + fp["frate"])
+        if int(fp["nfft"]) != 0: unsupported.append("-nfft " + fp["nfft"])
+        if fp["cmninit"] not in ("", FE_REFERENCE_DEFAULTS["cmninit"]) and fp["cmn"] != "batch": unsupported.append("-cmninit")
+        if unsupported:
+            raise NotImplementedError("front end settings the device front end does not implement: " + ", ".join(unsupported))
+        self.fe = api.FrontEnd(make_fe_desc(samprate=float(fp["samprate"]), wlen=float(fp["wlen"]), nfilt=int(fp["nfilt"]),
+                                            lowerf=float(fp["lowerf"]), upperf=float(fp["upperf"]), alpha=float(fp["alpha"]),
+                                            transform=fp["transform"], lifter=int(fp["lifter"]), remove_noise=fp["remove_noise"] in yes,
+                                            remove_dc=fp["remove_dc"] in yes, unit_area=fp["unit_area"] in yes,
+                                            doublebw=fp["doublebw"] in yes), device)
         search_cfg = {k: v for k, v in cfg.items() if k in lextree.DEFAULTS}
         self.search = lextree.ngram_search_from_files(hmm, dict_file, lm_file, **search_cfg)
         self.model = api.Model(self.pm, device)
         self.batch = api.Batch(self.model, max_utts, max_frames)
-        self.ctx = api.HmmContext(self.pm.tp, self.pm.sseq, self.pm.n_sen)
+        self.ctx = api.HmmContext(self.pm.tp, self.pm.sseq, self.pm.n_sen, device=device)
+        self.device = device
         pl = dict(PL_DEFAULTS)
         pl.update({k: v for k, v in cfg.items() if k in PL_DEFAULTS})
         self.pl_window = int(pl["pl_window"])
@@ -69,14 +87,27 @@ class Decoder:
         pcm = np.concatenate([np.ascontiguousarray(u, np.int16) for u in utterances]) if utterances else np.zeros(0, np.int16)
         frame_off, best, pen = self.batch.decode_pcm_host(self.fe, self.phoneloop, pcm, off)
         d_scr = self.batch.senscr_device_ptr()
-        d_pen = torch.from_numpy(np.ascontiguousarray(pen, np.int32)).cuda() if self.pl_window > 0 and len(pen) else None
+        d_pen = (torch.from_numpy(np.ascontiguousarray(pen, np.int32)).to(torch.device("cuda", self.device))
+                 if self.pl_window > 0 and len(pen) else None)
         pen_ptr, win = (d_pen.data_ptr(), self.pl_window) if d_pen is not None else (None, 0)
-        if self.second_pass:
-            tabs, _ = self.ctx.ngram_two_pass(d_scr, frame_off, info, g["model"], g["ci_tmat"], g["ci_ssid"], self.bp_cap, 20 * self.bp_cap,
-                                              pen_ptr, win, first_cap=self.bp_cap, first_bss_cap=20 * self.bp_cap, lm_arrays=g["lm_arrays"])
+        # -latsize is an initial size in the reference (bp_table / bscore_stack double on demand,
+        # ngram_search.c:326-339): a table that fills up is retried with doubled capacities
+        cap = self.bp_cap
+        for _ in range(6):
+            try:
+                if self.second_pass:
+                    tabs, _ = self.ctx.ngram_two_pass(d_scr, frame_off, info, g["model"], g["ci_tmat"], g["ci_ssid"], cap, 20 * cap,
+                                                      pen_ptr, win, first_cap=cap, first_bss_cap=20 * cap, lm_arrays=g["lm_arrays"])
+                else:
+                    tabs = self.ctx.ngram_fwdtree(d_scr, frame_off, info, g["model"], g["ci_tmat"], cap, 20 * cap, pen_ptr, win,
+                                                  lm_arrays=g["lm_arrays"])
+                break
+            except api.PsbError as e:
+                if "overflow" not in str(e):
+                    raise
+                cap *= 2
         else:
-            tabs = self.ctx.ngram_fwdtree(d_scr, frame_off, info, g["model"], g["ci_tmat"], self.bp_cap, 20 * self.bp_cap, pen_ptr, win,
-                                          lm_arrays=g["lm_arrays"])
+            raise RuntimeError("backpointer table still overflows at %d entries per utterance" % cap)
         out = []
         words, base, fs, fe_ = g["words"], g["base"], int(info[22]), int(info[23])
         for u, (bp, bss, idx) in enumerate(tabs):

@@ -361,7 +361,7 @@ def test_phoneloop_large_and_5state_vs_oracle(api, n_emit, H, window, skip):
 # ---------------------------------------------------------------------------------------
 # every top-N kernel variant (PSB_TOPN_VARIANT, read at psb_batch_create) must give the same bits
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
 def test_topn_kernel_variants(api, en_us_dev, variant, monkeypatch):
     from oracle import oracle
     from pocketsphinx_b200.model import quantize_for_ties, synth_feats, synth_ptm
@@ -386,6 +386,57 @@ def test_topn_kernel_variants(api, en_us_dev, variant, monkeypatch):
     pm2.ds_ratio = 2
     f2 = synth_feats(pm2, 33, 20, seed=5)
     _batch_vs_oracle(api, pm2, [f2[u].reshape(-1, pm2.sumlen) for u in range(33)])
+
+
+TC_CHECK = r"""
+import sys, json, numpy as np
+sys.path.insert(0, %r)
+sys.path.insert(0, %r)
+from conftest import golden
+from oracle import oracle
+from pocketsphinx_b200 import api
+from pocketsphinx_b200.model import PackedModel, quantize_for_ties, synth_feats, synth_ptm
+out = {}
+def run(name, pm, chunks):
+    m = api.Model(pm); lens = [len(c) for c in chunks]; off = api.Batch.offsets(lens)
+    b = api.Batch(m, len(chunks) + 1, int(off[-1]) + 1)
+    scr = b.score_host(np.concatenate(chunks), off)
+    om = oracle.OracleModel(pm)
+    ok = all(np.array_equal(scr[off[u]:off[u + 1]], om.score_utt(c)) for u, c in enumerate(chunks) if len(c))
+    r, n = b.tc_check()
+    out[name] = {"identical": bool(ok), "ratio": float(r), "max_candidates": int(n)}
+    b.close(); m.close()
+g = golden("en_us_goforward.npz")
+run("en_us", PackedModel.load(%r), [g["feats"]])
+pm = synth_ptm(seed=0); f = synth_feats(pm, 24, 60, seed=5)
+run("baseline_shape", pm, [f[u] for u in range(24)])
+run("baseline_shape_x100", pm, [f[u] * np.float32(100) for u in range(8)])      # features far outside the model
+pmq, gen = quantize_for_ties(synth_ptm(seed=2, n_density=64, n_sen=400), seed=6)
+run("ties", pmq, list(gen(20, 25, s=9)))
+print(json.dumps(out))
+"""
+
+
+def test_tensor_core_filter_error_bound_holds_on_the_device():
+    """PSB_TC_CHECK=1: the filter kernel compares every TF32 GEMM value it produced with the exact float
+    distance and reports the worst |a - d| / eps (the bound the candidate selection relies on must hold
+    with room to spare: the analysis in psb_ptm_tc.cu allows 0.8 of eps), on the shipped model with real
+    features, the BASELINE shape, features scaled far outside the model's range and tie-stress data."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import GOLDEN, ROOT
+    code = TC_CHECK % (ROOT, os.path.join(ROOT, "tests"), os.path.join(GOLDEN, "en_us_ptm_model.npz"))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PSB_TC_CHECK="1", PSB_TOPN_VARIANT="6"),
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    print(out)
+    for name, v in out.items():
+        assert v["identical"], name
+        assert 0.0 <= v["ratio"] < 0.8, (name, v)
+        assert v["max_candidates"] >= 5, (name, v)
 
 
 def test_ptm_and_semi_mixw_extremes(api):
@@ -560,6 +611,10 @@ def test_full_size_properties(api, monkeypatch):
     best2, pen2, rows2, _, _ = run(2, 2)
     assert np.array_equal(rows5, rows2)
     assert np.array_equal(best5, best2) and np.array_equal(pen5, pen2)
+    # and from the path without the recurrence over time (tensor-core filter + exact rescoring + tie fix-up)
+    best6, pen6, rows6, _, _ = run(6, 1)
+    assert np.array_equal(rows5, rows6)
+    assert np.array_equal(best5, best6) and np.array_equal(pen5, pen6)
     # utterance order does not matter: reversed batch gives the reversed result
     monkeypatch.setenv("PSB_TOPN_VARIANT", "5")
     b = api.Batch(m, U, U * T)
