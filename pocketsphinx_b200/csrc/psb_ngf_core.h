@@ -55,7 +55,7 @@ struct NgfWork {
 };
 
 struct NgfScalars {
-    fsg_int cur, n_awl, n_awl_nxt, nwd, best, best_score, bpidx, bss_head, stop, error, n_done;
+    fsg_int cur, n_awl, n_awl_nxt, nwd, best, best_score, bpidx, bss_head, stop, error, n_done, renorm, norm;
     fsg_int silrc_score, silrc_bp;
     int scan[34];
 };
@@ -84,6 +84,16 @@ FSG_HD void ngf_clear(const NgfGraph &G, const NgfWork &W, int c)
 {
     for (int s = 0; s < G.n_emit; ++s) { W.score[s * G.M + c] = FSG_WORST_SCORE; W.hist[s * G.M + c] = -1; }
     W.out_score[c] = FSG_WORST_SCORE; W.out_hist[c] = -1; W.best[c] = FSG_WORST_SCORE; W.frame[c] = -1;
+}
+
+FSG_HD void ngf_normalize(const NgfGraph &G, const NgfWork &W, int c, int norm)  /* hmm_normalize, hmm.c:206-217 */
+{
+    for (int s = 0; s < G.n_emit; ++s) {
+        const int v = W.score[s * G.M + c];
+        if (v > FSG_WORST_SCORE) W.score[s * G.M + c] = v - norm;
+    }
+    const int o = W.out_score[c];
+    if (o > FSG_WORST_SCORE) W.out_score[c] = o - norm;
 }
 
 FSG_HD void ngf_clear_scores(const NgfGraph &G, const NgfWork &W, int c)      /* hmm_clear_scores, hmm.c:167-178 */
@@ -231,11 +241,22 @@ FSG_HD void ngf_step(const NgfGraph &G, const NgfWork &W, NgfScalars *S, int cf,
     FSG_IF_LEADER {
         W.bp_idx[cf] = S->bpidx;
         if (S->best_score <= FSG_WORST_SCORE) S->stop = 1;
-        else if (S->best_score + 2 * G.beam < FSG_WORST_SCORE) S->error = 2;
+        S->renorm = 0;
+        if (!S->stop && S->best_score + 2 * G.beam < FSG_WORST_SCORE) { S->renorm = 1; S->norm = S->best_score; }
         S->best = FSG_WORST_SCORE;
     }
     FSG_SYNC();
     if (S->stop || S->error) return;
+    if (S->renorm) {
+        // fwdflat_renormalize_scores :785-810: hmm_normalize on the active words' channels of this frame
+        const int norm = S->norm;
+        FSG_FOR(j, nw) {
+            const int w = awl[j], s0 = G.ch_off[w], c0 = W.wbase[w], c1 = c0 + (G.ch_off[w + 1] - s0);
+            for (int c = c0; c < c1; ++c)
+                if (W.frame[c] == cf) ngf_normalize(G, W, c, norm);
+        }
+        FSG_SYNC();
+    }
     // fwdflat_eval_chan :445-480
     FSG_FOR(j, nw) {
         const int w = awl[j], s0 = G.ch_off[w], c0 = W.wbase[w], c1 = c0 + (G.ch_off[w + 1] - s0);

@@ -80,7 +80,7 @@ struct NgsWork {
 struct NgsScalars {
     fsg_int cur, n_acl, n_acl_nxt, n_awl, n_awl_nxt, n_cand;
     fsg_int best_all, best_last, best_score, last_phone_best, dynamic_beam, thresh, npth, lpth;
-    fsg_int bpidx, bss_head, stop, error, n_done, k_nonfinish, ev_root, ev_last, n_free;
+    fsg_int bpidx, bss_head, stop, error, n_done, k_nonfinish, ev_root, ev_last, n_free, renorm, norm;
     fsg_ll n_root_eval, n_nonroot_eval;
     int scan[34];
 };
@@ -115,6 +115,16 @@ FSG_HD int ngs_pl(const NgsWork &W, const NgsGraph &G, int f, int ci)          /
     int t = f + W.pl_window;                                                  /* ps_search_forward / ps_end_utt, pocketsphinx.c:1172-1195, 1329-1333 */
     if (t > W.T - 1) t = W.T - 1;
     return W.pen[(size_t)t * G.n_ci + ci];
+}
+
+FSG_HD void ngs_normalize(const NgsGraph &G, const NgsWork &W, int c, int norm)  /* hmm_normalize, hmm.c:206-217 */
+{
+    for (int s = 0; s < G.n_emit; ++s) {
+        const int v = W.score[s * G.M + c];
+        if (v > FSG_WORST_SCORE) W.score[s * G.M + c] = v - norm;
+    }
+    const int o = W.out_score[c];
+    if (o > FSG_WORST_SCORE) W.out_score[c] = o - norm;
 }
 
 FSG_HD void ngs_clear(const NgsGraph &G, const NgsWork &W, int c)               /* hmm_clear */
@@ -240,11 +250,26 @@ FSG_HD void ngs_step(const NgsGraph &G, const NgsWork &W, NgsScalars *S, int f, 
     FSG_IF_LEADER {
         W.bp_idx[f] = S->bpidx;
         if (S->best_score <= FSG_WORST_SCORE) S->stop = 1;
-        else if (S->best_score + 2 * G.beam < FSG_WORST_SCORE) S->error = 2;        // renormalisation: not on the device
+        S->renorm = 0;
+        if (!S->stop && S->best_score + 2 * G.beam < FSG_WORST_SCORE) { S->renorm = 1; S->norm = S->best_score; }
         S->best_all = FSG_WORST_SCORE; S->best_last = FSG_WORST_SCORE; S->ev_root = 0; S->ev_last = 0;
     }
     FSG_SYNC();
     if (S->stop || S->error) return;
+    if (S->renorm) {
+        // ---- renormalize_scores :566-602: hmm_normalize on every channel that is about to be evaluated
+        // (one writer per channel; nothing else is read in this phase)
+        const int norm = S->norm;
+        FSG_FOR(i, G.n_root) if (W.frame[i] == f) ngs_normalize(G, W, i, norm);
+        FSG_FOR(k, n_acl) ngs_normalize(G, W, G.o_nonroot + acl[k], norm);
+        FSG_FOR(j, n_awl) {
+            const int w = awl[j], blk = W.wblock[w] * G.RB, nrc = ngs_nrc(G, w);
+            for (int r = 0; r < nrc; ++r)
+                if (W.alloc[blk + r]) ngs_normalize(G, W, G.o_rc + blk + r, norm);
+        }
+        FSG_FOR(i, G.n_1ph) if (W.frame[G.o_1ph + i] == f) ngs_normalize(G, W, G.o_1ph + i, norm);
+        FSG_SYNC();
+    }
     // ---- evaluate_channels :702-716
     FSG_FOR(i, G.n_root) if (W.frame[i] == f) { FSG_ATOMIC_MAX(&S->best_all, eval(W, i, true, i)); FSG_ATOMIC_ADD(&S->ev_root, 1); }
     FSG_FOR(k, n_acl) {
