@@ -385,9 +385,13 @@ def cpu_baseline(args, pm, raw, feats, n_frames_per_utt, budget_s=15.0, threads=
     n_utt = int(max(1, min(len(feats), budget_s * threads / (per_frame * n_frames_per_utt))))
     if n_utt >= threads:
         n_utt -= n_utt % threads
+    # a long stream (BASELINE config 5: one 60-minute utterance) does not fit the budget as a whole: a prefix of it
+    t_cap = n_frames_per_utt
+    if n_utt == 1 and per_frame * n_frames_per_utt > 1.5 * budget_s:
+        t_cap = max(256, int(budget_s / per_frame))
 
     def work(u):
-        s = scorer()(feats[u])
+        s = scorer()(feats[u][:t_cap])
         oracle.phoneloop_run(pm.tp, pm.sseq, pm.phone_ssid[:pm.n_ciphone], pm.phone_tmat[:pm.n_ciphone], s,
                              PL["window"], PL["beam"], PL["pbeam"], PL["pip"], PL["weight"])
         if tmpl is not None:
@@ -406,7 +410,7 @@ def cpu_baseline(args, pm, raw, feats, n_frames_per_utt, budget_s=15.0, threads=
     dt = time.perf_counter() - t0
     return {"value": done / dt, "unit": "frames/s", "cores": threads, "kind": kind,
             "sample": "%d utterances x %d frames of the same batch: senone eval (%s) + phone loop (C port) + %s, %.1f s" % (
-                n_utt, n_frames_per_utt, "compiled reference" if kind == "reference" else "C port",
+                n_utt, min(t_cap, n_frames_per_utt), "compiled reference" if kind == "reference" else "C port",
                 ("hmm_vit_eval over %d active hmm_t per frame (%s)" % (N_ACTIVE, "compiled reference" if kind == "reference" else "C port"))
                 if tmpl is not None else "no search-scale Viterbi for this topology", dt)}
 
@@ -444,7 +448,8 @@ def run_reference(args, pm, raw, desc, feats, T):
 
 
 def workload_name(args, pm):
-    return "%s_%dx%dx%d_%dsen_%dutt_x_%ds" % (pm.kind, pm.n_mgau, pm.n_feat, pm.n_density, pm.n_sen, args.utts, args.secs)
+    n = ("%dutt_total" % args.batch_total) if getattr(args, "batch_total", 0) else ("%dutt" % args.utts)
+    return "%s_%dx%dx%d_%dsen_%s_x_%ds" % (pm.kind, pm.n_mgau, pm.n_feat, pm.n_density, pm.n_sen, n, args.secs)
 
 
 def main():
@@ -454,7 +459,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="baseline", choices=["baseline", "en-us", "semi", "cont"])
-    ap.add_argument("--utts", type=int, default=1000, help="utterances per GPU per step")
+    ap.add_argument("--utts", type=int, default=1000, help="utterances per GPU per step (weak scaling)")
+    ap.add_argument("--batch-total", type=int, default=0,
+                    help="fixed batch of this many utterances sharded over the GPUs (strong scaling, BASELINE config 3: 4096); "
+                         "overrides --utts")
     ap.add_argument("--secs", type=int, default=10, help="seconds of 16 kHz audio per utterance")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
@@ -482,12 +490,18 @@ def main():
 
     # ---- acoustic model: rank 0 holds it, one NCCL broadcast per packed buffer at init ----
     from pocketsphinx_b200 import dist as pdist
+    t_b = time.perf_counter()
     dev = pdist.broadcast_model(pm, src=0, device=torch.device("cuda", local))
     torch.cuda.synchronize()
+    bcast_ms = (time.perf_counter() - t_b) * 1e3              # one-off at init: upload on rank 0 + NCCL broadcast
     model = api.Model(pm, device=local, device_ptrs=dev)
 
     # ---- this rank's shard of utterances (weak scaling: utts per GPU fixed) ----
-    U = args.utts
+    # weak scaling: --utts per GPU; strong scaling: --batch-total utterances dealt out over the ranks (equal lengths here, so
+    # equal counts balance the frames; ragged batches would be dealt longest-first, pocketsphinx_b200/dist.py)
+    strong = args.batch_total > 0
+    U = args.utts if not strong else args.batch_total // world + (1 if rank < args.batch_total % world else 0)
+    U_all = args.utts * world if not strong else args.batch_total
     feats_np = synth_feats(pm, U, T, seed=1234 + rank)
     total = U * T
     off = api.Batch.offsets([T] * U)
@@ -604,7 +618,7 @@ def main():
 
     if rank == 0:
         hbm_peak, peak_src, sm_max = peaks()
-        frames_all = total * world
+        frames_all = U_all * T
         value = frames_all / (ms_step * 1e-3)
         # roofline of the dominant kernel (the top-N kernel), algorithmic bytes per launch:
         # per frame 4*sumlen feature bytes read + 16*K top-N record bytes written, plus the
@@ -627,7 +641,7 @@ def main():
             "metric": "frames/sec senone-eval+Viterbi", "value": value, "unit": "frames/s",
             "xRT": FRAMES_PER_SEC_AUDIO / value,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32->i16/i32", "data": "synthetic",
             "config": {"workload": workload_name(args, pm), "model": desc,
                        "utts_per_gpu": U, "frames_per_utt": T, "frames_per_step_per_gpu": total,
@@ -636,7 +650,9 @@ def main():
                                    % (H, pm.n_emit_state, PL["window"], N_ACTIVE)) if hs is not None else
                                   "phone loop, %d CI-phone HMMs x %d states, window %d" % (H, pm.n_emit_state, PL["window"]),
                        "features": "synthetic dynamic features (AR(1) walk between model means), not PCM",
-                       "parallelism": "utterances sharded, %d per GPU, no per-frame collective" % U,
+                       "parallelism": ("fixed batch of %d utterances dealt out over %d GPUs, no per-frame collective" % (U_all, world)) if strong
+                                      else "utterances sharded, %d per GPU, no per-frame collective" % U,
+                       "model_broadcast_ms": bcast_ms,
                        "l2": "per-step working set (%.1f GB of scores) exceeds L2; no explicit flush" % (total * pm.n_sen * 2 / 1e9)},
             "gpu_launches": int(launches),
             "kernel_ms_unpipelined": {**km, "note": "separate single-stream pass after the timed region"},

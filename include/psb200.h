@@ -138,8 +138,9 @@ int psb_batch_event_elapsed_ms(psb_batch_t *b, float *ms);
 /* debugging: with PSB_TC_CHECK=1 in the environment the tensor-core filter kernels (the default top-N path
  * for 13-dimensional PTM streams; PSB_TOPN_VARIANT=5 selects the scan over time instead) measure, over
  * everything this batch has scored, the largest |filter value - exact distance| / error bound (must stay
- * below 1) and the largest candidate count per (frame, codebook-stream pair). */
-int psb_batch_tc_check(psb_batch_t *b, float *ratio, int32_t *max_candidates);
+ * below 1) and the largest candidate count per (frame, codebook-stream pair); stats4 (may be NULL) = rows seen,
+ * rows whose record came from the filter values alone, exact distances computed, rows handed to the tie fix-up. */
+int psb_batch_tc_check(psb_batch_t *b, float *ratio, int32_t *max_candidates, int64_t *stats4);
 /* debugging/parity: copy the per-frame top-N records of the last call to the host:
  * rec int32 [total_frames][n_mgau*n_feat][4] = {top>>10, cw[4] bytes, e[4] bytes, 0} */
 int psb_batch_get_topn(psb_batch_t *b, int32_t *rec, int64_t n_frames);

@@ -203,7 +203,9 @@ class Batch:
     def tc_check(self):
         """(max |filter value - exact distance| / bound, max candidates) of the tensor-core filter (PSB_TC_CHECK=1)."""
         r, n = C.c_float(), C.c_int32()
-        check(lib().psb_batch_tc_check(self.h, C.byref(r), C.byref(n)), "psb_batch_tc_check")
+        st = np.zeros(4, np.int64)
+        check(lib().psb_batch_tc_check(self.h, C.byref(r), C.byref(n), _p(st)), "psb_batch_tc_check")
+        self.tc_stats = dict(rows=int(st[0]), from_filter_alone=int(st[1]), exact_distances=int(st[2]), tie_fixups=int(st[3]))
         return r.value, n.value
 
     def decode_host(self, phoneloop, feats, utt_off, want_senscr=False, best=None, pen=None, senscr=None):

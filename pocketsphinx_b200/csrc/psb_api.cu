@@ -182,7 +182,7 @@ extern "C" int psb_model_create(const psb_model_desc_t *d, int device, psb_model
     m->has_topn_beam = false;
     m->d_topn_beam = nullptr;
     m->tc_ok = false;
-    m->d_tc_wfrag = m->d_tc_cen = m->d_tc_bnd = nullptr;
+    m->d_tc_wfrag = m->d_tc_wumma = m->d_tc_cen = m->d_tc_bnd = nullptr;
     m->d_msT = m->d_msdetT = nullptr; m->d_featlen = m->d_featoff = nullptr;
     for (int f = 0; f < PSB_MAX_FEAT; ++f) m->topn_beam[f] = 0;
     const bool dev = d->on_device != 0;
@@ -308,7 +308,7 @@ extern "C" void psb_model_free(psb_model_t *m)
     cudaFree(m->d_rec); cudaFree(m->d_rec_off); cudaFree(m->d_rec2); cudaFree(m->d_rec2_off); cudaFree(m->d_mixw); cudaFree(m->d_mixw_cb);
     cudaFree(m->d_sen2cb); cudaFree(m->d_sen2cb32); cudaFree(m->d_quadcb); cudaFree(m->d_bsen); cudaFree(m->d_logadd8); cudaFree(m->d_logadd_ms);
     cudaFree(m->d_topn_beam); cudaFree(m->d_msT); cudaFree(m->d_msdetT); cudaFree(m->d_featlen); cudaFree(m->d_featoff);
-    cudaFree(m->d_tc_wfrag); cudaFree(m->d_tc_cen); cudaFree(m->d_tc_bnd);
+    cudaFree(m->d_tc_wfrag); cudaFree(m->d_tc_wumma); cudaFree(m->d_tc_cen); cudaFree(m->d_tc_bnd);
     delete m;
 }
 

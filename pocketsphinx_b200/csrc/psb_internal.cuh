@@ -89,7 +89,7 @@ struct psb_model_s {
     bool has_topn_beam;
     // tensor-core filter path (psb_ptm_tc.cu): W in mma fragment order, centres, error-bound coefficients
     bool tc_ok;
-    float *d_tc_wfrag, *d_tc_cen, *d_tc_bnd;
+    float *d_tc_wfrag, *d_tc_wumma, *d_tc_cen, *d_tc_bnd;
 };
 
 struct psb_batch_s {

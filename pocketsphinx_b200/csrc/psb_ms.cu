@@ -93,6 +93,104 @@ ms_dist_kernel(const float *__restrict__ gT, const float *__restrict__ detT, con
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// ms_dist_tile_kernel: the same distances with the parameter stream taken out of L2.  ms_dist_kernel
+// re-reads every (density, dimension) parameter pair of its 128 codebooks from L2 for every 4 frames
+// (2 loads per 16 floating-point operations: 25 % of the FP32 lane rate, L2-bound).  Here a CTA owns a
+// tile of 32 codebooks (lane = codebook) and keeps ALL their Gaussians in shared memory -- rows of 32
+// floats, one per (stream, density, dimension, {mean, variance term}), conflict-free -- for a whole
+// range of frames; its four warps take eight frames each of a 32-frame block whose feature vectors are
+// staged transposed ([dimension][frame]), so that one warp-uniform LDS.128 pair feeds eight frames.
+// Per (density, dimension): 2 LDS + 2 broadcast LDS.128 for 32 floating-point operations.  Same
+// arithmetic, same order, same insertion rule as ms_dist_kernel: bit-identical lists.
+constexpr int MS_TCB = 32, MS_TFT = 8, MS_TFB = 32;      // codebooks per CTA, frames per thread, frames per block
+
+template <int NT>
+__global__ void __launch_bounds__(128)
+ms_dist_tile_kernel(const float *__restrict__ gT, const float *__restrict__ detT, const float *__restrict__ feats,
+                    int2 *__restrict__ out, long long frame0, long long n_frames, int n_mgau, int n_feat, int nd,
+                    int sumlen, const int32_t *__restrict__ featlen, const int32_t *__restrict__ featoff, int frames_per_cta)
+{
+    extern __shared__ __align__(16) float tsm[];
+    const int n_rows = nd * sumlen * 2, n_det = n_feat * nd;
+    float *par = tsm;                                   // [n_rows][32]
+    float *dets = par + (size_t)n_rows * MS_TCB;        // [n_det][32]
+    float *xs = dets + (size_t)n_det * MS_TCB;          // [sumlen][32]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cb = blockIdx.x * MS_TCB + lane;
+    const int cbr = cb < n_mgau ? cb : n_mgau - 1;      // padding lanes read the last codebook and write nothing
+    for (int r = warp; r < n_rows; r += 4) par[r * MS_TCB + lane] = gT[(size_t)r * n_mgau + cbr];
+    for (int r = warp; r < n_det; r += 4) dets[r * MS_TCB + lane] = detT[(size_t)r * n_mgau + cbr];
+    const bool all = NT >= nd;                          // compute_dist_all (ms_gauden.c:378-419)
+    const long long f_begin = (long long)blockIdx.y * frames_per_cta;
+    const long long f_end = f_begin + frames_per_cta < n_frames ? f_begin + frames_per_cta : n_frames;
+    for (long long fb = f_begin; fb < f_end; fb += MS_TFB) {
+        __syncthreads();                                // the previous block's features are no longer read
+        for (int i = threadIdx.x; i < sumlen * MS_TFB; i += blockDim.x) {
+            const int fr = i & (MS_TFB - 1), j = i / MS_TFB;
+            xs[j * MS_TFB + fr] = fb + fr < n_frames ? feats[(frame0 + fb + fr) * sumlen + j] : 0.f;
+        }
+        __syncthreads();
+        for (int f = 0; f < n_feat; ++f) {
+            const int fl = featlen[f], fo = featoff[f];
+            int id[MS_TFT][NT];
+            float ds[MS_TFT][NT];
+#pragma unroll
+            for (int q = 0; q < MS_TFT; ++q)
+#pragma unroll
+                for (int i = 0; i < NT; ++i) { id[q][i] = 0; ds[q][i] = (float)INT_MIN; }     // WORST_DIST (:447-448)
+            const float *pp = par + (size_t)fo * nd * 2 * MS_TCB + lane;
+            for (int d = 0; d < nd; ++d) {
+                float dv[MS_TFT];
+                const float det = dets[(f * nd + d) * MS_TCB + lane];
+#pragma unroll
+                for (int q = 0; q < MS_TFT; ++q) dv[q] = det;
+                for (int j = 0; j < fl; ++j) {
+                    const float m = pp[((d * fl + j) * 2) * MS_TCB];
+                    const float v = pp[((d * fl + j) * 2 + 1) * MS_TCB];
+                    const float4 xa = *reinterpret_cast<const float4 *>(xs + (fo + j) * MS_TFB + warp * MS_TFT);
+                    const float4 xb = *reinterpret_cast<const float4 *>(xs + (fo + j) * MS_TFB + warp * MS_TFT + 4);
+                    const float xv[MS_TFT] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+                    for (int q = 0; q < MS_TFT; ++q) {
+                        const float diff = __fsub_rn(xv[q], m);
+                        dv[q] = __fsub_rn(dv[q], __fmul_rn(__fmul_rn(diff, diff), v));       // :467-470
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < MS_TFT; ++q) {
+                    if (all) {
+#pragma unroll
+                        for (int i = 0; i < NT; ++i)
+                            if (i == d) { id[q][i] = d; ds[q][i] = dv[q]; }
+                    }
+                    else if (dv[q] >= ds[q][NT - 1]) {     // early exit is result-neutral (:457,:474)
+                        int p = 0;
+#pragma unroll
+                        for (int i = 0; i < NT; ++i) p += (dv[q] < ds[q][i]) ? 1 : 0;
+#pragma unroll
+                        for (int i = NT - 1; i > 0; --i)
+                            if (i > p) { ds[q][i] = ds[q][i - 1]; id[q][i] = id[q][i - 1]; }
+#pragma unroll
+                        for (int i = 0; i < NT; ++i)
+                            if (i == p) { ds[q][i] = dv[q]; id[q][i] = d; }
+                    }
+                }
+            }
+            if (cb < n_mgau) {
+#pragma unroll
+                for (int q = 0; q < MS_TFT; ++q) {
+                    const long long fr = fb + warp * MS_TFT + q;
+                    if (fr >= n_frames) break;
+                    int2 *o = out + ((fr * n_mgau + cb) * n_feat + f) * NT;
+#pragma unroll
+                    for (int i = 0; i < NT; ++i) o[i] = make_int2(id[q][i], __float_as_int(ds[q][i]));
+                }
+            }
+        }
+    }
+}
+
 // EXPERIMENT (PSB_MS_PACKED=1; bit-identical -- the whole GPU suite passes with it -- but measured
 // slightly SLOWER on B200: 181 ms vs 174 ms, the kernel is not issue-bound).
 // Packed-FP32 variant of ms_dist_kernel: the FT = 4 frames of a thread go through FADD2 / FMUL2 two
@@ -352,6 +450,8 @@ ms_dist_reg_kernel(const float *__restrict__ gT, const float *__restrict__ detT,
 
 }  // namespace
 
+static bool reg_tile_env() { static const bool v = getenv("PSB_MS_REGTILE") != nullptr; return v; }
+
 int psb_launch_ms_batch(psb_batch_t *b, const float *d_feats, const int32_t *utt_off, int32_t n_utt, int16_t *d_senscr)
 {
     psb_model_t *m = b->m;
@@ -383,8 +483,20 @@ int psb_launch_ms_batch(psb_batch_t *b, const float *d_feats, const int32_t *utt
         size_t smem = (size_t)FT * m->sumlen * sizeof(float);
         int2 *dist = reinterpret_cast<int2 *>(b->d_msdist);
         static const bool packed = getenv("PSB_MS_PACKED") != nullptr;       // experiment, off: bit-identical, 181 vs 174 ms
+        static const bool no_tile = getenv("PSB_MS_NOTILE") != nullptr;     // PSB_MS_NOTILE=1: the round-1 kernel (parameters streamed from L2)
+        const size_t tile_smem = ((size_t)m->n_density * m->sumlen * 2 + (size_t)m->n_feat * m->n_density + m->sumlen) * MS_TCB * sizeof(float);
+        const bool tile = !no_tile && !packed && !reg_tile_env() && tile_smem <= 100 * 1024;
+        // frames per CTA: enough CTAs for ~4 waves of two resident CTAs per SM, whole 32-frame blocks
+        const int tiles_x = (m->n_mgau + MS_TCB - 1) / MS_TCB;
+        long long fpc = (n * tiles_x + 148LL * 2 * 4 - 1) / (148LL * 2 * 4);
+        fpc = std::max<long long>(MS_TFB, (fpc + MS_TFB - 1) / MS_TFB * MS_TFB);
+        const dim3 gt((unsigned)tiles_x, (unsigned)((n + fpc - 1) / fpc));
         static const bool reg_tile = getenv("PSB_MS_REGTILE") != nullptr;   // experiment, off: measured slower (247 vs 174 ms)
-#define LAUNCH(NT) do { if (reg_tile && m->n_density <= ND_MAX)                                                          \
+#define LAUNCH(NT) do { if (tile) {                                                                                       \
+            PSB_CUDA(cudaFuncSetAttribute(ms_dist_tile_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem)); \
+            ms_dist_tile_kernel<NT><<<gt, 128, tile_smem, b->stream>>>(m->d_msT, m->d_msdetT, d_feats, dist, f0, n,                \
+                m->n_mgau, m->n_feat, m->n_density, m->sumlen, m->d_featlen, m->d_featoff, (int)fpc); }                          \
+        else if (reg_tile && m->n_density <= ND_MAX)                                                          \
             ms_dist_reg_kernel<NT><<<g1, 128, smem, b->stream>>>(m->d_msT, m->d_msdetT, d_feats, dist, f0, n,             \
                 m->n_mgau, m->n_feat, m->n_density, m->sumlen, m->d_featlen, m->d_featoff);                             \
         else if (packed) ms_dist2_kernel<NT><<<g1, 128, smem, b->stream>>>(m->d_msT, m->d_msdetT, d_feats, dist, f0, n,   \

@@ -54,7 +54,9 @@ constexpr int TC_ROWS = 128;          // frames per CTA (4 warps x 2 m-tiles x 1
 constexpr int TC_K = 32;              // GEMM depth: 2 * FL + 1 <= 32
 constexpr int TC_XS = 36;             // row pitch of the X tile in floats (conflict-free fragment loads)
 constexpr int TC_CAP = 18;            // candidate slots per row: the row's X storage, 144 B / 8 B
-constexpr float TC_ERR = 1.25f / 1024.f;   // 2^-10 (two TF32 roundings per product) + 25 % for everything else
+constexpr float TC_ERR = 1.0f / 262144.f;  // 2^-18 of the magnitude sum S: 3 x TF32 leaves 3 * 2^-22 per product, the rest is
+                                           // room for the tensor core's fp32 accumulation (<= 2^-23 per step assumed, 12 steps per
+                                           // chain) and the reference's own 52 roundings; PSB_TC_CHECK=1 measures what is used of it
 
 __device__ __forceinline__ float to_tf32(float x)
 {
@@ -101,32 +103,33 @@ __device__ __forceinline__ void top5_insert(Top5 &t, int s, int c)
     if (t.n < 5) ++t.n;
 }
 
-// Filter + exact rescoring for one (pair, 128-frame tile).
-//   wfrag   [K][NT][4][32] float2   W in mma B-fragment order: b0 = W[8 ks + t][8 n + g], b1 = W[8 ks + t + 4][8 n + g]
-//   cen     [K][16]                 centre m
-//   bnd     [K][32]                 Amax[FL], Bmax[FL], Cmax at [2 FL]
-//   flags   [K][flag_words]         bit (row & 31) of word row >> 5: frame must be redone by the fix-up
+// Filter + resolution for one (pair, 128-frame tile).
+//   wfrag   [K][2][NT][4][32] float2   W (high, then low TF32 halves) in mma B-fragment order:
+//                                      b0 = W[8 ks + t][8 n + g], b1 = W[8 ks + t + 4][8 n + g]
+//   cen     [K][16]                    centre m
+//   bnd     [K][32]                    Amax[FL], Bmax[FL], Cmax at [2 FL]
+//   rec     scalar records {det, mu0, v0, ...} of the model (exact distances of ambiguous rows, read through L1/L2)
+//   flags   [K][flag_words]            bit (row & 31) of word row >> 5: frame must be redone by the fix-up
 //   check   (debug) float[2]: max over everything of |a_c - d_c| / eps, and of the candidate count
+//   stats   (debug) unsigned long long[4]: rows, rows resolved from the filter alone, exact distances, tie flags
 template <int FL, int NT, bool CHECK>
-__global__ void __launch_bounds__(TC_ROWS, 3)
+__global__ void __launch_bounds__(TC_ROWS, 4)
 ptm_tc_kernel(const float *__restrict__ feats, long long total, int D, const int32_t *__restrict__ featoff,
               const int32_t *__restrict__ klist, const float2 *__restrict__ wfrag, const float *__restrict__ cen,
               const float *__restrict__ bnd, const float *__restrict__ rec, const size_t *__restrict__ rec_off,
-              const float *__restrict__ rec2, const size_t *__restrict__ rec2_off, int4 *__restrict__ out,
-              unsigned *__restrict__ flags, long long flag_words, int K, int n_feat, float *__restrict__ check)
+              int4 *__restrict__ out, unsigned *__restrict__ flags, long long flag_words, int K, int n_feat,
+              float *__restrict__ check, unsigned long long *__restrict__ stats)
 {
     constexpr int ND = NT * 8;
-    constexpr int RECF2 = (2 + 4 * FL + 3) / 4 * 4;
-    constexpr int RECQ2 = RECF2 / 4;
+    constexpr int RF = (1 + 2 * FL + 3) / 4 * 4;
     constexpr unsigned FULL = 0xffffffffu;
     static_assert(2 * FL + 1 <= TC_K, "stream too long for one 32-deep GEMM");
-    static_assert((ND / 2) * RECF2 <= NT * 4 * 32 * 2, "pair records must fit the W region");
     extern __shared__ __align__(16) unsigned char tc_smem[];
-    float2 *wf = reinterpret_cast<float2 *>(tc_smem);                               // [NT][4][32]; later the pair records
-    float *xs = reinterpret_cast<float *>(tc_smem + (size_t)NT * 4 * 32 * 8);       // [128][36]; later the candidate lists
-    unsigned *masks = reinterpret_cast<unsigned *>(xs + TC_ROWS * TC_XS);           // [128][8]
-    int *cnt = reinterpret_cast<int *>(masks + TC_ROWS * 8);                        // [128]
-    float *epsr = reinterpret_cast<float *>(cnt + TC_ROWS);                         // [128]
+    float2 *wf = reinterpret_cast<float2 *>(tc_smem);                                   // [NT][4][32]: high halves of W
+    float *xs = reinterpret_cast<float *>(tc_smem + (size_t)NT * 4 * 32 * 8);           // [128][36]; later the candidate lists
+    unsigned *masks = reinterpret_cast<unsigned *>(xs + TC_ROWS * TC_XS);               // [128][8]
+    int *cnt = reinterpret_cast<int *>(masks + TC_ROWS * 8);                            // [128]
+    float *epsr = reinterpret_cast<float *>(cnt + TC_ROWS);                             // [128]
 
     const int k = klist[blockIdx.y];
     const int f = k % n_feat;
@@ -134,9 +137,9 @@ ptm_tc_kernel(const float *__restrict__ feats, long long total, int D, const int
     const long long row = (long long)blockIdx.x * TC_ROWS + tid;
     const bool valid = row < total;
 
-    // ---- stage W, build this thread's X row ----
+    // ---- stage W (both halves), build this thread's X row (fp32: split into TF32 halves at fragment load) ----
     {
-        const float4 *src = reinterpret_cast<const float4 *>(wfrag + (size_t)k * NT * 4 * 32);
+        const float4 *src = reinterpret_cast<const float4 *>(wfrag + (size_t)k * 2 * NT * 4 * 32);
         float4 *dst = reinterpret_cast<float4 *>(wf);
         for (int i = tid; i < NT * 4 * 32 / 2; i += TC_ROWS) dst[i] = src[i];
     }
@@ -151,8 +154,8 @@ ptm_tc_kernel(const float *__restrict__ feats, long long total, int D, const int
             x[j] = valid ? p[j] : 0.f;
             const float y = __fsub_rn(x[j], m[j]);
             const float y2 = __fmul_rn(y, y);
-            xr[j] = to_tf32(y2);
-            xr[FL + j] = to_tf32(y);
+            xr[j] = y2;
+            xr[FL + j] = y;
             S = __fmaf_ru(bb[j], y2, S);
             S = __fmaf_ru(bb[FL + j], fabsf(y), S);
         }
@@ -166,41 +169,61 @@ ptm_tc_kernel(const float *__restrict__ feats, long long total, int D, const int
     }
     __syncthreads();
 
-    // ---- TF32 GEMM of this warp's 32 rows against all codewords, 16 rows at a time ----
+    // ---- 3 x TF32 GEMM (lo*hi + hi*lo + hi*hi) of this warp's 32 rows against all codewords, 16 rows at a time.
+    // The accumulators are never held for all codewords at once: a first sweep over chunks of CH n-tiles keeps only
+    // the row maxima that give the threshold, a second sweep recomputes the same chunks (bit-identical: same
+    // instructions, same order) and extracts the few columns above it.  The tensor pipe has the room (< 10 % busy
+    // with one sweep); 40 accumulator registers instead of 128 double the resident warps. ----
+    constexpr int CH = NT <= 8 ? NT / 2 : 8;             // at least two chunks: the two half maxima per lane come from different chunks
     const int g = lane >> 2, t = lane & 3;
-    unsigned afr[2][4][4];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-        const float *xa = xs + (warp * 32 + mt * 16 + g) * TC_XS, *xb = xa + 8 * TC_XS;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            afr[mt][ks][0] = __float_as_uint(xa[8 * ks + t]);
-            afr[mt][ks][1] = __float_as_uint(xb[8 * ks + t]);
-            afr[mt][ks][2] = __float_as_uint(xa[8 * ks + t + 4]);
-            afr[mt][ks][3] = __float_as_uint(xb[8 * ks + t + 4]);
-        }
-    }
-    __syncwarp();                                            // the rows' X storage now becomes their candidate lists
     uint2 *lists = reinterpret_cast<uint2 *>(xs);            // row r: slots at (r * TC_XS floats) .. + TC_CAP
+    const float2 *wlo = wfrag + ((size_t)k * 2 + 1) * NT * 4 * 32;      // low halves of W: from L1 / L2, same fragment order
 #pragma unroll 1
     for (int mt = 0; mt < 2; ++mt) {
-        float acc[NT][4];
-#pragma unroll
-        for (int n = 0; n < NT; ++n) {
-            acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+        unsigned ah[4][4], al[4][4];
+        {
+            const float *xa = xs + (warp * 32 + mt * 16 + g) * TC_XS, *xb = xa + 8 * TC_XS;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-                const float2 b = wf[(n * 4 + ks) * 32 + lane];
-                mma_tf32(acc[n], afr[mt][ks], b.x, b.y);
+                const float v[4] = {xa[8 * ks + t], xb[8 * ks + t], xa[8 * ks + t + 4], xb[8 * ks + t + 4]};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float h = to_tf32(v[q]);
+                    ah[ks][q] = __float_as_uint(h);
+                    al[ks][q] = __float_as_uint(to_tf32(__fsub_rn(v[q], h)));
+                }
             }
         }
+        __syncwarp();                                        // this m-tile's X rows now become their candidate lists
+        auto chunk = [&](int n0, float (&acc)[CH][4]) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                const int n = n0 + i;
+                acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {             // the small cross terms first
+                    const float2 bh = wf[(n * 4 + ks) * 32 + lane], bl = __ldg(wlo + (n * 4 + ks) * 32 + lane);
+                    mma_tf32(acc[i], al[ks], bh.x, bh.y);
+                    mma_tf32(acc[i], ah[ks], bl.x, bl.y);
+                }
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const float2 bh = wf[(n * 4 + ks) * 32 + lane];
+                    mma_tf32(acc[i], ah[ks], bh.x, bh.y);
+                }
+            }
+        };
         // rows g (acc[.][0..1]) and g + 8 (acc[.][2..3]) of this m-tile: the lane's two half maxima each
         const int r0 = warp * 32 + mt * 16 + g, r1 = r0 + 8;
         float h00 = -INFINITY, h01 = -INFINITY, h10 = -INFINITY, h11 = -INFINITY;
+#pragma unroll 1
+        for (int n0 = 0; n0 < NT; n0 += CH) {
+            float acc[CH][4];
+            chunk(n0, acc);
+            float a = -INFINITY, b = -INFINITY;
 #pragma unroll
-        for (int n = 0; n < NT; ++n) {
-            const float a = fmaxf(acc[n][0], acc[n][1]), b = fmaxf(acc[n][2], acc[n][3]);
-            if (n < NT / 2) { h00 = fmaxf(h00, a); h10 = fmaxf(h10, b); }
+            for (int i = 0; i < CH; ++i) { a = fmaxf(a, fmaxf(acc[i][0], acc[i][1])); b = fmaxf(b, fmaxf(acc[i][2], acc[i][3])); }
+            if (n0 < NT / 2) { h00 = fmaxf(h00, a); h10 = fmaxf(h10, b); }
             else { h01 = fmaxf(h01, a); h11 = fmaxf(h11, b); }
         }
         float hi0 = fmaxf(h00, h01), lo0 = fminf(h00, h01), hi1 = fmaxf(h10, h11), lo1 = fminf(h10, h11);
@@ -213,124 +236,455 @@ ptm_tc_kernel(const float *__restrict__ feats, long long total, int D, const int
         // L' = floor(L0 - eps) - 1, candidates: a_c >= L' - eps; every step rounded towards -inf
         const float thr0 = __fsub_rd(__fsub_rd(floorf(__fsub_rd(fminf(hi0, lo0), e0)), 1.0f), e0);
         const float thr1 = __fsub_rd(__fsub_rd(floorf(__fsub_rd(fminf(hi1, lo1), e1)), 1.0f), e1);
+        const float thr_min = fminf(thr0, thr1);
+        float worst = 0.f;
+#pragma unroll 1
+        for (int n0 = 0; n0 < NT; n0 += CH) {
+            float acc[CH][4];
+            chunk(n0, acc);
 #pragma unroll
-        for (int n = 0; n < NT; ++n) {
+            for (int i = 0; i < CH; ++i) {
+                if (fmaxf(fmaxf(acc[i][0], acc[i][1]), fmaxf(acc[i][2], acc[i][3])) < thr_min) continue;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float a = acc[n][q];
-                if (a >= ((q & 2) ? thr1 : thr0)) {
-                    const int rr = (q & 2) ? r1 : r0, col = 8 * n + 2 * t + (q & 1);
-                    const int slot = atomicAdd(&cnt[rr], 1);
-                    if (slot < TC_CAP) lists[(size_t)rr * (TC_XS / 2) + slot] = make_uint2(__float_as_uint(a), (unsigned)col);
-                    atomicOr(&masks[rr * 8 + (col >> 5)], 1u << (col & 31));
-                }
-            }
-        }
-        if (CHECK) {
-            // exact distances of every column this lane holds (debug only): |a - d| / eps
-            const float *rc = rec + rec_off[k];
-            constexpr int RF = (1 + 2 * FL + 3) / 4 * 4;
-            float worst = 0.f;
-            for (int n = 0; n < NT; ++n)
                 for (int q = 0; q < 4; ++q) {
-                    const int rr = (q & 2) ? r1 : r0, col = 8 * n + 2 * t + (q & 1);
-                    const long long grow = (long long)blockIdx.x * TC_ROWS + rr;
-                    if (grow >= total) continue;
-                    const float *px = feats + grow * D + featoff[f];
-                    const float *r = rc + (size_t)col * RF;
-                    float d = r[0];
-                    for (int j = 0; j < FL; ++j) {
-                        const float df = __fsub_rn(px[j], r[1 + 2 * j]);
-                        d = __fsub_rn(d, __fmul_rn(__fmul_rn(df, df), r[2 + 2 * j]));
+                    const float a = acc[i][q];
+                    if (a >= ((q & 2) ? thr1 : thr0)) {
+                        const int rr = (q & 2) ? r1 : r0, col = 8 * (n0 + i) + 2 * t + (q & 1);
+                        const int slot = atomicAdd(&cnt[rr], 1);
+                        if (slot < TC_CAP) lists[(size_t)rr * (TC_XS / 2) + slot] = make_uint2(__float_as_uint(a), (unsigned)col);
+                        atomicOr(&masks[rr * 8 + (col >> 5)], 1u << (col & 31));
                     }
-                    worst = fmaxf(worst, fabsf(acc[n][q] - d) / epsr[rr]);
-                }
-            atomicMax(reinterpret_cast<int *>(check), __float_as_int(worst));     // non-negative floats order like ints
-        }
-    }
-    __syncthreads();
-
-    // ---- the pair records replace W; every thread narrows its row's candidates to E ----
-    {
-        const float4 *src = reinterpret_cast<const float4 *>(rec2 + rec2_off[k]);
-        float4 *dst = reinterpret_cast<float4 *>(wf);
-        for (int i = tid; i < (ND / 2) * RECQ2; i += TC_ROWS) dst[i] = src[i];
-    }
-    unsigned e[8];
-    {
-        const int n = cnt[tid];
-        if (CHECK) atomicMax(reinterpret_cast<int *>(check) + 1, n);
-        if (!valid) {
-#pragma unroll
-            for (int w = 0; w < 8; ++w) e[w] = 0u;
-        }
-        else if (n > TC_CAP) {
-#pragma unroll
-            for (int w = 0; w < 8; ++w) e[w] = masks[tid * 8 + w];
-        }
-        else {
-            const uint2 *L = lists + (size_t)tid * (TC_XS / 2);
-            float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;      // four largest a_c
-            for (int i = 0; i < n; ++i) {
-                float v = __uint_as_float(L[i].x), u;
-                u = fmaxf(a0, v); v = fminf(a0, v); a0 = u;
-                u = fmaxf(a1, v); v = fminf(a1, v); a1 = u;
-                u = fmaxf(a2, v); v = fminf(a2, v); a2 = u;
-                a3 = fmaxf(a3, v);
-            }
-            const float ee = epsr[tid];
-            const float thr = __fsub_rd(__fsub_rd(__fsub_rd(a3, ee), ee), 1.0f);
-#pragma unroll
-            for (int w = 0; w < 8; ++w) e[w] = 0u;
-            for (int i = 0; i < n; ++i) {
-                const uint2 v = L[i];
-                if (__uint_as_float(v.x) >= thr) {
-#pragma unroll
-                    for (int w = 0; w < 8; ++w)
-                        if ((int)(v.y >> 5) == w) e[w] |= 1u << (v.y & 31);
                 }
             }
+            if (CHECK) {
+                // exact distances of every column this lane holds (debug only): |a - d| / eps
+                const float *rc = rec + rec_off[k];
+                for (int i = 0; i < CH; ++i)
+                    for (int q = 0; q < 4; ++q) {
+                        const int rr = (q & 2) ? r1 : r0, col = 8 * (n0 + i) + 2 * t + (q & 1);
+                        const long long grow = (long long)blockIdx.x * TC_ROWS + rr;
+                        if (grow >= total) continue;
+                        const float *px = feats + grow * D + featoff[f];
+                        const float *r = rc + (size_t)col * RF;
+                        float d = r[0];
+                        for (int j = 0; j < FL; ++j) {
+                            const float df = __fsub_rn(px[j], r[1 + 2 * j]);
+                            d = __fsub_rn(d, __fmul_rn(__fmul_rn(df, df), r[2 + 2 * j]));
+                        }
+                        worst = fmaxf(worst, fabsf(acc[i][q] - d) / epsr[rr]);
+                    }
+            }
         }
+        if (CHECK) atomicMax(reinterpret_cast<int *>(check), __float_as_int(worst));     // non-negative floats order like ints
     }
     __syncthreads();
+    if (!valid) return;
 
-    // ---- exact distances over the union of the warp's E sets, pair by pair; lane = frame ----
-    const float4 *srec = reinterpret_cast<const float4 *>(wf);
-    float2 xx[FL];
-#pragma unroll
-    for (int j = 0; j < FL; ++j) xx[j] = make_float2(x[j], x[j]);
+    // ---- one thread per row: the record straight from the filter values when they leave no doubt ----
+    const int n = cnt[tid];
+    const float ee = epsr[tid];
+    if (CHECK) atomicMax(reinterpret_cast<int *>(check) + 1, n);
     Top5 top;
     top.n = 0; top.c = 0u; top.c4 = 0;
 #pragma unroll
     for (int j = 0; j < 5; ++j) top.s[j] = INT_MIN;
+    bool certain = n <= TC_CAP;
+    if (certain) {
+        // the five largest a_c with their codewords (the list holds every a_c >= thr, at least five)
+        const uint2 *L = lists + (size_t)tid * (TC_XS / 2);
+        float a[5] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        int c[5] = {0, 0, 0, 0, 0};
+        for (int i = 0; i < n; ++i) {
+            float v = __uint_as_float(L[i].x);
+            int cv = (int)L[i].y;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        if (w * 32 >= ND) break;
-        const unsigned u = __reduce_or_sync(FULL, e[w]);
-        unsigned pm = (u | (u >> 1)) & 0x55555555u;
-        while (pm) {
-            const int b = __ffs(pm) - 1;
-            pm &= pm - 1;
-            const int c = w * 32 + b;
-            const float2 d2 = gau_dist2<FL>(srec + (size_t)(c >> 1) * RECQ2, xx);
-            if ((e[w] >> b) & 1u) top5_insert(top, f2i_clamped(d2.x), c);
-            if ((e[w] >> b) & 2u) top5_insert(top, f2i_clamped(d2.y), c + 1);
+            for (int j = 0; j < 5; ++j)
+                if (v > a[j]) { const float tv = a[j]; const int tc = c[j]; a[j] = v; c[j] = cv; v = tv; cv = tc; }
+        }
+        // order and distinctness of the truncated scores: neighbours more than 2 eps + 1 apart, everything
+        // safely negative (truncation is towards zero); s >> 10 of the four best: the same at both ends of
+        // [a - eps, a + eps]
+        const float gap = __fadd_ru(__fadd_ru(ee, ee), 1.0f);
+        int qv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            certain &= __fsub_rd(a[j], a[j + 1]) > gap;
+            const int lo = __float2int_ru(__fsub_rd(a[j], ee)), hi = __float2int_ru(__fadd_ru(a[j], ee));
+            certain &= (lo >> PSB_SENSCR_SHIFT) == (hi >> PSB_SENSCR_SHIFT);
+            qv[j] = lo >> PSB_SENSCR_SHIFT;
+        }
+        certain &= __fadd_ru(a[0], ee) < -2.0f && a[4] > -2.0e9f;
+        if (certain) {
+            unsigned cb = 0, eb = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int ev = qv[0] - qv[j];
+                ev = ev > 255 ? 255 : ev;
+                cb |= (unsigned)c[j] << (8 * j);
+                eb |= (unsigned)ev << (8 * j);
+            }
+            out[row * K + k] = make_int4(qv[0], (int)cb, (int)eb, 0);
+            if (CHECK) { atomicAdd(stats, 1ull); atomicAdd(stats + 1, 1ull); }
+            return;
         }
     }
-    if (!valid) return;
-    // E holds at least the four best; a missing fifth is strictly below the fourth
-    const bool distinct = top.n >= 4 && top.s[0] > top.s[1] && top.s[1] > top.s[2] && top.s[2] > top.s[3] &&
-                          (top.n < 5 || top.s[3] > top.s[4]);
-    const int tp = top.s[0] >> PSB_SENSCR_SHIFT;
-    unsigned eb = 0;
+    // ---- doubt: the reference's exact arithmetic for this row's candidates (few rows, few codewords each) ----
+    {
+        const float *rc = rec + rec_off[k];
+        int n_exact = 0;
+        auto exact = [&](int cw) {
+            const float4 *r4 = reinterpret_cast<const float4 *>(rc + (size_t)cw * RF);
+            const float d = gau_dist<FL>(r4, x);
+            top5_insert(top, f2i_clamped(d), cw);
+            ++n_exact;
+        };
+        if (n <= TC_CAP) {
+            const uint2 *L = lists + (size_t)tid * (TC_XS / 2);
+            // ascending codeword order is not needed: ties are redone by the fix-up
+            for (int i = 0; i < n; ++i) exact((int)L[i].y);
+        }
+        else {
+            for (int w = 0; w < ND / 32; ++w) {
+                unsigned bits = masks[tid * 8 + w];
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    exact(w * 32 + b);
+                }
+            }
+        }
+        const bool distinct = top.n >= 5 && top.s[0] > top.s[1] && top.s[1] > top.s[2] && top.s[2] > top.s[3] && top.s[3] > top.s[4];
+        const int tp = top.s[0] >> PSB_SENSCR_SHIFT;
+        unsigned eb = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        int ev = tp - (top.s[j] >> PSB_SENSCR_SHIFT);
-        ev = ev > 255 ? 255 : ev;
-        eb |= (unsigned)ev << (8 * j);
+        for (int j = 0; j < 4; ++j) {
+            int ev = tp - (top.s[j] >> PSB_SENSCR_SHIFT);
+            ev = ev > 255 ? 255 : ev;
+            eb |= (unsigned)ev << (8 * j);
+        }
+        out[row * K + k] = make_int4(tp, (int)top.c, (int)eb, 0);
+        if (!distinct) atomicOr(&flags[(size_t)k * flag_words + (row >> 5)], 1u << (row & 31));
+        if (CHECK) { atomicAdd(stats, 1ull); atomicAdd(stats + 2, (unsigned long long)n_exact); if (!distinct) atomicAdd(stats + 3, 1ull); }
     }
-    out[row * K + k] = make_int4(tp, (int)top.c, (int)eb, 0);
-    if (!distinct) atomicOr(&flags[(size_t)k * flag_words + (row >> 5)], 1u << (row & 31));
+}
+
+// ---------------------------------------------------------------------------------------
+// The same filter on the 5th-generation tensor cores (tcgen05): the legacy mma.sync path above tops out
+// near 290 TFLOP/s of TF32 (8 cycles per m16n8k8 and sub-core), which makes the 3 x TF32 GEMM -- 6.2 TFLOP
+// per 10^6-frame batch -- the longest stage.  Here one elected thread issues twelve
+// tcgen05.mma.cta_group::1.kind::tf32 (M 128 frames x N n_density x K 8; lo*hi, hi*lo, hi*hi over four
+// K steps) per 128-frame tile, A (the X tile, split into TF32 halves) and B (W, both halves) in shared memory
+// in the canonical K-major no-swizzle layout (8-row x 16-byte core matrices; descriptors built below), the
+// fp32 accumulator in TENSOR MEMORY: 128 lanes x n_density columns.  tcgen05.commit arrives on an mbarrier;
+// after the wait every thread reads ITS OWN frame's row (TMEM lane = frame = thread) with tcgen05.ld.32x32b in
+// slabs of 32 columns, twice: group maxima -> threshold, then the columns above it.  No accumulator registers
+// across the sweep, no shuffles, no shared-memory atomics -- the whole selection is thread-private.  A CTA keeps
+// W resident and walks `tiles_per_cta` consecutive tiles of its pair.
+__device__ __forceinline__ uint64_t umma_smem_desc(const void *p, unsigned lbo_bytes, unsigned sbo_bytes)
+{
+    // cute::UMMA::SmemDescriptor (mma_sm100_desc.hpp): start address, leading / stride byte offsets in 16-byte units,
+    // version 1 (Blackwell) at bit 46, base offset 0, layout type 0 = no swizzle
+    const uint64_t a = (uint64_t)((unsigned)__cvta_generic_to_shared(p) >> 4) & 0x3fffu;
+    return a | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void umma_tf32(unsigned tmem_d, uint64_t adesc, uint64_t bdesc, unsigned idesc, unsigned accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32])
+{
+    unsigned r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void mbar_init1(uint64_t *bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)));
+}
+__device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TCW_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TCD_%=;\n"
+        "bra TCW_%=;\n"
+        "TCD_%=:\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+//   wumma   [K][2][8][ND][4] float   W halves (high, low) in the canonical K-major layout: chunk kc holds k = 4 kc .. 4 kc + 3
+template <int FL, int ND, bool CHECK>
+__global__ void __launch_bounds__(TC_ROWS, 2)
+ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const int32_t *__restrict__ featoff,
+               const int32_t *__restrict__ klist, const float *__restrict__ wumma, const float *__restrict__ cen,
+               const float *__restrict__ bnd, const float *__restrict__ rec, const size_t *__restrict__ rec_off,
+               int4 *__restrict__ out, unsigned *__restrict__ flags, long long flag_words, int K, int n_feat,
+               int tiles_per_cta, float *__restrict__ check, unsigned long long *__restrict__ stats)
+{
+    constexpr int RF = (1 + 2 * FL + 3) / 4 * 4;
+    constexpr int GW = ND / 8;                           // columns per maximum group: 8 groups per row
+    static_assert(2 * FL + 1 <= TC_K && ND % 32 == 0 && ND <= 256, "shape");
+    extern __shared__ __align__(128) unsigned char t5_smem[];
+    float *sW = reinterpret_cast<float *>(t5_smem);                                   // [2][8][ND][4]
+    float *sX = sW + 2 * 8 * ND * 4;                                                  // [2][8][128][4]; later the candidate lists
+    uint2 *lists = reinterpret_cast<uint2 *>(sX);                                     // [128][TC_CAP]
+    __shared__ __align__(8) uint64_t mma_done;
+    __shared__ unsigned tmem_base_s;
+
+    const int k = klist[blockIdx.y];
+    const int f = k % n_feat;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    if (warp == 0) {                                     // 256 (or fewer) TMEM columns for the accumulator
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&tmem_base_s)),
+                     "n"(ND < 32 ? 32 : ND));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        mbar_init1(&mma_done);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(wumma + (size_t)k * 2 * 8 * ND * 4);
+        float4 *dst = reinterpret_cast<float4 *>(sW);
+        for (int i = tid; i < 2 * 8 * ND; i += TC_ROWS) dst[i] = src[i];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_d = tmem_base_s;
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A / B tf32, both K-major, N >> 3, M >> 4
+    constexpr unsigned IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(ND >> 3) << 17) | ((unsigned)(TC_ROWS >> 4) << 24);
+    const float *m = cen + (size_t)k * 16, *bb = bnd + (size_t)k * 32;
+    const float *rc = rec + rec_off[k];
+
+    for (int tile = 0; tile < tiles_per_cta; ++tile) {
+        const long long row = ((long long)blockIdx.x * tiles_per_cta + tile) * TC_ROWS + tid;
+        if (row - tid >= total) break;                   // uniform: the whole tile lies past the end
+        const bool valid = row < total;
+        // ---- this thread's frame: X row (TF32 halves, canonical layout) and its error bound ----
+        float x[FL], ee;
+        {
+            const float *p = feats + (valid ? row : 0) * D + featoff[f];
+            float v[TC_K];
+            float S = bb[2 * FL];
+#pragma unroll
+            for (int j = 0; j < FL; ++j) {
+                x[j] = valid ? p[j] : 0.f;
+                const float y = __fsub_rn(x[j], m[j]);
+                const float y2 = __fmul_rn(y, y);
+                v[j] = y2;
+                v[FL + j] = y;
+                S = __fmaf_ru(bb[j], y2, S);
+                S = __fmaf_ru(bb[FL + j], fabsf(y), S);
+            }
+            v[2 * FL] = 1.0f;
+#pragma unroll
+            for (int j = 2 * FL + 1; j < TC_K; ++j) v[j] = 0.f;
+            ee = __fmaf_ru(S, TC_ERR, 2.0f);
+#pragma unroll
+            for (int kc = 0; kc < 8; ++kc) {
+                float4 h, l;
+                h.x = to_tf32(v[4 * kc]); h.y = to_tf32(v[4 * kc + 1]); h.z = to_tf32(v[4 * kc + 2]); h.w = to_tf32(v[4 * kc + 3]);
+                l.x = to_tf32(__fsub_rn(v[4 * kc], h.x)); l.y = to_tf32(__fsub_rn(v[4 * kc + 1], h.y));
+                l.z = to_tf32(__fsub_rn(v[4 * kc + 2], h.z)); l.w = to_tf32(__fsub_rn(v[4 * kc + 3], h.w));
+                reinterpret_cast<float4 *>(sX)[kc * TC_ROWS + tid] = h;
+                reinterpret_cast<float4 *>(sX)[(8 + kc) * TC_ROWS + tid] = l;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // chunk kc of A at sX + kc * 2048 B (128 rows x 16 B), of B at sW + kc * ND * 16 B; core matrices 128 B apart
+            for (int pass = 0; pass < 3; ++pass) {        // lo*hi, hi*lo, hi*hi
+                const int ha = pass == 0 ? 1 : 0, hb = pass == 1 ? 1 : 0;
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t ad = umma_smem_desc(sX + ((size_t)(ha * 8 + 2 * ks) * TC_ROWS) * 4, TC_ROWS * 16, 128);
+                    const uint64_t bd = umma_smem_desc(sW + ((size_t)(hb * 8 + 2 * ks) * ND) * 4, ND * 16, 128);
+                    umma_tf32(tmem_d, ad, bd, IDESC, (pass | ks) ? 1u : 0u);
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                             (unsigned)__cvta_generic_to_shared(&mma_done))
+                         : "memory");
+        }
+        mbar_wait_parity(&mma_done, (unsigned)tile & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+        // ---- this thread's row of the accumulator: group maxima, threshold, the columns above it ----
+        const unsigned trow = tmem_d + ((unsigned)(warp * 32) << 16);
+        float gm[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gm[i] = -INFINITY;
+#pragma unroll 1
+        for (int c0 = 0; c0 < ND; c0 += 32) {
+            float v[32];
+            tmem_ld32(trow + c0, v);
+            if (GW >= 32) {
+                float mx = v[0];
+#pragma unroll
+                for (int i = 1; i < 32; ++i) mx = fmaxf(mx, v[i]);
+                const int gi = c0 / GW;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (q == gi) gm[q] = fmaxf(gm[q], mx);
+            }
+            else {
+                constexpr int PER = 32 / (GW < 32 ? GW : 32);       // groups inside one 32-column slab
+#pragma unroll
+                for (int s2 = 0; s2 < PER; ++s2) {
+                    float mx = v[s2 * GW];
+#pragma unroll
+                    for (int i = 1; i < GW; ++i) mx = fmaxf(mx, v[s2 * GW + i]);
+                    const int gi = c0 / GW + s2;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (q == gi) gm[q] = fmaxf(gm[q], mx);
+                }
+            }
+        }
+        // five distinct columns >= L0: the fifth largest of the eight group maxima
+        float L0;
+        {
+            float a5[5] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float v = gm[q];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) { const float hi = fmaxf(a5[j], v); v = fminf(a5[j], v); a5[j] = hi; }
+            }
+            L0 = a5[4];
+        }
+        // L' = floor(L0 - eps) - 1, candidates: a_c >= L' - eps; every step rounded towards -inf
+        const float thr = __fsub_rd(__fsub_rd(floorf(__fsub_rd(L0, ee)), 1.0f), ee);
+        __syncthreads();                                  // every warp is past the barrier wait: the X tile is dead, its space takes the lists
+        int n = 0;
+        float worst = 0.f;
+        uint2 *L = lists + (size_t)tid * TC_CAP;
+#pragma unroll 1
+        for (int c0 = 0; c0 < ND; c0 += 32) {
+            float v[32];
+            tmem_ld32(trow + c0, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (v[i] >= thr) {
+                    if (n < TC_CAP) L[n] = make_uint2(__float_as_uint(v[i]), (unsigned)(c0 + i));
+                    ++n;
+                }
+            if (CHECK && valid) {
+                for (int i = 0; i < 32; ++i) {
+                    const float *r = rc + (size_t)(c0 + i) * RF;
+                    float d = r[0];
+                    for (int j = 0; j < FL; ++j) {
+                        const float df = __fsub_rn(x[j], r[1 + 2 * j]);
+                        d = __fsub_rn(d, __fmul_rn(__fmul_rn(df, df), r[2 + 2 * j]));
+                    }
+                    worst = fmaxf(worst, fabsf(v[i] - d) / ee);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (CHECK) {
+            atomicMax(reinterpret_cast<int *>(check), __float_as_int(worst));
+            if (valid) atomicMax(reinterpret_cast<int *>(check) + 1, n);
+        }
+
+        // ---- the record straight from the filter values when they leave no doubt ----
+        if (valid) {
+            bool certain = n <= TC_CAP && n >= 5;
+            if (certain) {
+                float a[5] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                int c[5] = {0, 0, 0, 0, 0};
+                for (int i = 0; i < n; ++i) {
+                    float v = __uint_as_float(L[i].x);
+                    int cv = (int)L[i].y;
+#pragma unroll
+                    for (int j = 0; j < 5; ++j)
+                        if (v > a[j]) { const float tv = a[j]; const int tc = c[j]; a[j] = v; c[j] = cv; v = tv; cv = tc; }
+                }
+                const float gap = __fadd_ru(__fadd_ru(ee, ee), 1.0f);
+                int qv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    certain &= __fsub_rd(a[j], a[j + 1]) > gap;
+                    const int lo = __float2int_ru(__fsub_rd(a[j], ee)), hi = __float2int_ru(__fadd_ru(a[j], ee));
+                    certain &= (lo >> PSB_SENSCR_SHIFT) == (hi >> PSB_SENSCR_SHIFT);
+                    qv[j] = lo >> PSB_SENSCR_SHIFT;
+                }
+                certain &= __fadd_ru(a[0], ee) < -2.0f && a[4] > -2.0e9f;
+                if (certain) {
+                    unsigned cb = 0, eb = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        int ev = qv[0] - qv[j];
+                        ev = ev > 255 ? 255 : ev;
+                        cb |= (unsigned)c[j] << (8 * j);
+                        eb |= (unsigned)ev << (8 * j);
+                    }
+                    out[row * K + k] = make_int4(qv[0], (int)cb, (int)eb, 0);
+                    if (CHECK) { atomicAdd(stats, 1ull); atomicAdd(stats + 1, 1ull); }
+                }
+            }
+            if (!certain) {
+                // doubt: the reference's exact arithmetic for this row's candidates (all codewords if the list overflowed)
+                Top5 top;
+                top.n = 0; top.c = 0u; top.c4 = 0;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) top.s[j] = INT_MIN;
+                int n_exact = 0;
+                const int cnt_l = (n <= TC_CAP && n >= 5) ? n : ND;
+                for (int i = 0; i < cnt_l; ++i) {
+                    const int cw = cnt_l == ND ? i : (int)L[i].y;
+                    const float d = gau_dist<FL>(reinterpret_cast<const float4 *>(rc + (size_t)cw * RF), x);
+                    top5_insert(top, f2i_clamped(d), cw);
+                    ++n_exact;
+                }
+                const bool distinct = top.n >= 5 && top.s[0] > top.s[1] && top.s[1] > top.s[2] && top.s[2] > top.s[3] && top.s[3] > top.s[4];
+                const int tp = top.s[0] >> PSB_SENSCR_SHIFT;
+                unsigned eb = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int ev = tp - (top.s[j] >> PSB_SENSCR_SHIFT);
+                    ev = ev > 255 ? 255 : ev;
+                    eb |= (unsigned)ev << (8 * j);
+                }
+                out[row * K + k] = make_int4(tp, (int)top.c, (int)eb, 0);
+                if (!distinct) atomicOr(&flags[(size_t)k * flag_words + (row >> 5)], 1u << (row & 31));
+                if (CHECK) { atomicAdd(stats, 1ull); atomicAdd(stats + 2, (unsigned long long)n_exact); if (!distinct) atomicAdd(stats + 3, 1ull); }
+            }
+        }
+        __syncthreads();                                  // lists consumed, accumulator read: the next tile may overwrite both
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(ND < 32 ? 32 : ND));
 }
 
 // Frames whose five best scores tie: the reference's loop, literally (eval_topn ptm_mgau.c:88-136,
@@ -425,19 +779,52 @@ int launch_tc(psb_batch_t *b, const float *d_feats, long long total, const int32
     psb_model_t *m = b->m;
     const size_t smem = (size_t)NT * 4 * 32 * 8 + (size_t)TC_ROWS * TC_XS * 4 + (size_t)TC_ROWS * 8 * 4 + TC_ROWS * 4 + TC_ROWS * 4;
     const dim3 grid((unsigned)((total + TC_ROWS - 1) / TC_ROWS), (unsigned)n_k);
+    float *chk = b->d_tc_check;
+    unsigned long long *stats = reinterpret_cast<unsigned long long *>(b->d_tc_check + 4);
     if (check) {
         auto kern = ptm_tc_kernel<FL, NT, true>;
         PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, TC_ROWS, smem, b->stream>>>(d_feats, total, m->sumlen, d_featoff, d_klist, reinterpret_cast<const float2 *>(m->d_tc_wfrag), m->d_tc_cen, m->d_tc_bnd,
-                                                m->d_rec, m->d_rec_off, m->d_rec2, m->d_rec2_off, b->d_topn, b->d_tc_flags,
-                                                (long long)b->tc_flag_words, m->K, m->n_feat, b->d_tc_check);
+        kern<<<grid, TC_ROWS, smem, b->stream>>>(d_feats, total, m->sumlen, d_featoff, d_klist, reinterpret_cast<const float2 *>(m->d_tc_wfrag),
+                                                m->d_tc_cen, m->d_tc_bnd, m->d_rec, m->d_rec_off, b->d_topn, b->d_tc_flags,
+                                                (long long)b->tc_flag_words, m->K, m->n_feat, chk, stats);
     }
     else {
         auto kern = ptm_tc_kernel<FL, NT, false>;
         PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, TC_ROWS, smem, b->stream>>>(d_feats, total, m->sumlen, d_featoff, d_klist, reinterpret_cast<const float2 *>(m->d_tc_wfrag), m->d_tc_cen, m->d_tc_bnd,
-                                                m->d_rec, m->d_rec_off, m->d_rec2, m->d_rec2_off, b->d_topn, b->d_tc_flags,
-                                                (long long)b->tc_flag_words, m->K, m->n_feat, nullptr);
+        kern<<<grid, TC_ROWS, smem, b->stream>>>(d_feats, total, m->sumlen, d_featoff, d_klist, reinterpret_cast<const float2 *>(m->d_tc_wfrag),
+                                                m->d_tc_cen, m->d_tc_bnd, m->d_rec, m->d_rec_off, b->d_topn, b->d_tc_flags,
+                                                (long long)b->tc_flag_words, m->K, m->n_feat, nullptr, nullptr);
+    }
+    PSB_LAUNCH_CHECK();
+    return PSB_OK;
+}
+
+template <int FL, int ND>
+int launch_tc5(psb_batch_t *b, const float *d_feats, long long total, const int32_t *d_klist, int n_k, const int32_t *d_featoff,
+               bool check)
+{
+    psb_model_t *m = b->m;
+    const size_t smem = (size_t)2 * 8 * ND * 16 + (size_t)2 * 8 * TC_ROWS * 16;
+    const long long tiles = (total + TC_ROWS - 1) / TC_ROWS;
+    // W (64 KB at 256 densities) is staged once per CTA: a few tiles per CTA, but still >= 4 waves of 2 CTAs per SM
+    int tpc = 1;
+    while (tpc < 8 && (tiles / (tpc * 2)) * n_k >= 148LL * 2 * 4) tpc *= 2;
+    const dim3 grid((unsigned)((tiles + tpc - 1) / tpc), (unsigned)n_k);
+    float *chk = b->d_tc_check;
+    unsigned long long *stats = reinterpret_cast<unsigned long long *>(b->d_tc_check + 4);
+    if (check) {
+        auto kern = ptm_tc5_kernel<FL, ND, true>;
+        PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, TC_ROWS, smem, b->stream>>>(d_feats, total, m->sumlen, d_featoff, d_klist, m->d_tc_wumma, m->d_tc_cen, m->d_tc_bnd,
+                                                m->d_rec, m->d_rec_off, b->d_topn, b->d_tc_flags, (long long)b->tc_flag_words, m->K,
+                                                m->n_feat, tpc, chk, stats);
+    }
+    else {
+        auto kern = ptm_tc5_kernel<FL, ND, false>;
+        PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, TC_ROWS, smem, b->stream>>>(d_feats, total, m->sumlen, d_featoff, d_klist, m->d_tc_wumma, m->d_tc_cen, m->d_tc_bnd,
+                                                m->d_rec, m->d_rec_off, b->d_topn, b->d_tc_flags, (long long)b->tc_flag_words, m->K,
+                                                m->n_feat, tpc, nullptr, nullptr);
     }
     PSB_LAUNCH_CHECK();
     return PSB_OK;
@@ -455,7 +842,8 @@ int psb_tc_prepare(psb_model_t *m, const float *hm, const float *hv, const float
     for (int f = 0; f < m->n_feat; ++f)
         if (m->featlen[f] != 13) return PSB_OK;              // the kernels are instantiated for 13-dimensional streams
     const int nd = m->n_density, NT = nd / 8, FL = 13, K = m->K;
-    std::vector<float> wf((size_t)K * NT * 4 * 32 * 2, 0.f), cen((size_t)K * 16, 0.f), bnd((size_t)K * 32, 0.f);
+    std::vector<float> wf((size_t)K * 2 * NT * 4 * 32 * 2, 0.f), cen((size_t)K * 16, 0.f), bnd((size_t)K * 32, 0.f);
+    std::vector<float> wu((size_t)K * 2 * 8 * nd * 4, 0.f);     // canonical K-major layout of the tcgen05 path: [half][chunk][n][4]
     std::vector<double> W((size_t)TC_K * nd);
     for (int cb = 0; cb < m->n_mgau; ++cb)
         for (int f = 0; f < m->n_feat; ++f) {
@@ -486,23 +874,36 @@ int psb_tc_prepare(psb_model_t *m, const float *hm, const float *hv, const float
             }
             bb[2 * FL] = (float)(cmax * 1.0001);
             for (int j = 0; j < 2 * FL; ++j) bb[j] = std::nextafter(bb[j] * 1.0001f, INFINITY);
-            float *w = wf.data() + (size_t)k * NT * 4 * 32 * 2;
+            // high and low TF32 halves of the fp32 value of every W entry: w = hi + lo + O(2^-22 w)
+            float *w = wf.data() + (size_t)k * 2 * NT * 4 * 32 * 2;
             for (int n = 0; n < NT; ++n)
                 for (int ks = 0; ks < 4; ++ks)
                     for (int lane = 0; lane < 32; ++lane) {
                         const int g = lane >> 2, t = lane & 3;
-                        float *o = w + ((size_t)(n * 4 + ks) * 32 + lane) * 2;
-                        o[0] = round_tf32_host((float)W[(size_t)(8 * ks + t) * nd + 8 * n + g]);
-                        o[1] = round_tf32_host((float)W[(size_t)(8 * ks + t + 4) * nd + 8 * n + g]);
+                        float *oh = w + ((size_t)(n * 4 + ks) * 32 + lane) * 2, *ol = oh + (size_t)NT * 4 * 32 * 2;
+                        for (int h = 0; h < 2; ++h) {
+                            const float v = (float)W[(size_t)(8 * ks + t + 4 * h) * nd + 8 * n + g];
+                            oh[h] = round_tf32_host(v);
+                            ol[h] = round_tf32_host(v - oh[h]);
+                        }
                     }
+            float *u = wu.data() + (size_t)k * 2 * 8 * nd * 4;
+            for (int kk = 0; kk < TC_K; ++kk)
+                for (int q = 0; q < nd; ++q) {
+                    const float v = (float)W[(size_t)kk * nd + q], h = round_tf32_host(v);
+                    u[((size_t)(kk >> 2) * nd + q) * 4 + (kk & 3)] = h;
+                    u[((size_t)(8 + (kk >> 2)) * nd + q) * 4 + (kk & 3)] = round_tf32_host(v - h);
+                }
             for (int i = 0; i < 32; ++i)
                 if (!std::isfinite(bb[i])) return PSB_OK;    // degenerate model: keep the scan kernels
         }
     if (!m->d_tc_wfrag) {
+        PSB_CUDA(cudaMalloc(&m->d_tc_wumma, wu.size() * sizeof(float)));
         PSB_CUDA(cudaMalloc(&m->d_tc_wfrag, wf.size() * sizeof(float)));
         PSB_CUDA(cudaMalloc(&m->d_tc_cen, cen.size() * sizeof(float)));
         PSB_CUDA(cudaMalloc(&m->d_tc_bnd, bnd.size() * sizeof(float)));
     }
+    PSB_CUDA(cudaMemcpy(m->d_tc_wumma, wu.data(), wu.size() * sizeof(float), cudaMemcpyHostToDevice));
     PSB_CUDA(cudaMemcpy(m->d_tc_wfrag, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice));
     PSB_CUDA(cudaMemcpy(m->d_tc_cen, cen.data(), cen.size() * sizeof(float), cudaMemcpyHostToDevice));
     PSB_CUDA(cudaMemcpy(m->d_tc_bnd, bnd.data(), bnd.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -513,7 +914,7 @@ int psb_tc_prepare(psb_model_t *m, const float *hm, const float *hv, const float
 bool psb_tc_usable(const psb_batch_t *b)
 {
     const psb_model_t *m = b->m;
-    return m->tc_ok && m->ds_ratio == 1 && m->d_rec2 && b->topn_variant >= 6;
+    return m->tc_ok && m->ds_ratio == 1 && b->topn_variant >= 6;
 }
 
 // Top-N records of a whole batch into b->d_topn (same format as the scan kernels write).
@@ -535,20 +936,28 @@ int psb_launch_ptm_tc(psb_batch_t *b, const float *d_feats, const int32_t *utt_o
         b->uttoff_cap = (size_t)n_utt + 1 + 64;
         PSB_CUDA(cudaMalloc(&b->d_uttoff, b->uttoff_cap * sizeof(int32_t)));
     }
-    if (!b->d_tc_check) {
-        PSB_CUDA(cudaMalloc(&b->d_tc_check, 2 * sizeof(float)));
-        PSB_CUDA(cudaMemsetAsync(b->d_tc_check, 0, 2 * sizeof(float), b->stream));
+    if (!b->d_tc_check) {                                     // float[2] check values, then (16-byte offset) four 64-bit counters
+        PSB_CUDA(cudaMalloc(&b->d_tc_check, 64));
+        PSB_CUDA(cudaMemsetAsync(b->d_tc_check, 0, 64, b->stream));
     }
     b->tc_flag_words = fw;
     PSB_CUDA(cudaMemsetAsync(b->d_tc_flags, 0, fw * m->K * 4, b->stream));
     PSB_CUDA(cudaMemcpyAsync(b->d_uttoff, utt_off, ((size_t)n_utt + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
     static const bool check = [] { const char *v = getenv("PSB_TC_CHECK"); return v && atoi(v) != 0; }();
+    static const bool legacy_mma = [] { const char *v = getenv("PSB_TC_IMPL"); return v && !strcmp(v, "mma"); }();   // default: tcgen05
     int rc;
-    switch (m->n_density) {
-    case 256: rc = launch_tc<13, 32>(b, d_feats, total, d_klist, m->K, d_featoff, check); break;
-    case 128: rc = launch_tc<13, 16>(b, d_feats, total, d_klist, m->K, d_featoff, check); break;
-    default: rc = launch_tc<13, 8>(b, d_feats, total, d_klist, m->K, d_featoff, check); break;
-    }
+    if (legacy_mma)
+        switch (m->n_density) {
+        case 256: rc = launch_tc<13, 32>(b, d_feats, total, d_klist, m->K, d_featoff, check); break;
+        case 128: rc = launch_tc<13, 16>(b, d_feats, total, d_klist, m->K, d_featoff, check); break;
+        default: rc = launch_tc<13, 8>(b, d_feats, total, d_klist, m->K, d_featoff, check); break;
+        }
+    else
+        switch (m->n_density) {
+        case 256: rc = launch_tc5<13, 256>(b, d_feats, total, d_klist, m->K, d_featoff, check); break;
+        case 128: rc = launch_tc5<13, 128>(b, d_feats, total, d_klist, m->K, d_featoff, check); break;
+        default: rc = launch_tc5<13, 64>(b, d_feats, total, d_klist, m->K, d_featoff, check); break;
+        }
     if (rc) return rc;
     const long long chains = (long long)n_utt * m->K;
     ptm_fixup_kernel<13><<<(unsigned)((chains + 127) / 128), 128, 0, b->stream>>>(
@@ -558,17 +967,20 @@ int psb_launch_ptm_tc(psb_batch_t *b, const float *d_feats, const int32_t *utt_o
     return PSB_OK;
 }
 
-// debug: {max |a - d| / eps, max candidate count} seen by the filter kernels of this batch (PSB_TC_CHECK=1)
-extern "C" int psb_batch_tc_check(psb_batch_t *b, float *ratio, int32_t *max_candidates)
+// debug (PSB_TC_CHECK=1): max |a - d| / eps and max candidate count seen by the filter kernels of this batch;
+// stats4 = rows, rows resolved from the filter values alone, exact distances computed, rows handed to the tie fix-up
+extern "C" int psb_batch_tc_check(psb_batch_t *b, float *ratio, int32_t *max_candidates, int64_t *stats4)
 {
     PSB_REQUIRE(b && ratio && max_candidates, "psb_batch_tc_check: null argument");
     *ratio = 0.f; *max_candidates = 0;
+    if (stats4) stats4[0] = stats4[1] = stats4[2] = stats4[3] = 0;
     if (!b->d_tc_check) return PSB_OK;
     PSB_CUDA(cudaSetDevice(b->m->device));
     PSB_CUDA(cudaStreamSynchronize(b->stream));
-    float h[2];
+    unsigned char h[64];
     PSB_CUDA(cudaMemcpy(h, b->d_tc_check, sizeof(h), cudaMemcpyDeviceToHost));
-    *ratio = h[0];
-    memcpy(max_candidates, &h[1], 4);
+    memcpy(ratio, h, 4);
+    memcpy(max_candidates, h + 4, 4);
+    if (stats4) memcpy(stats4, h + 16, 32);
     return PSB_OK;
 }

@@ -404,7 +404,7 @@ def run(name, pm, chunks):
     om = oracle.OracleModel(pm)
     ok = all(np.array_equal(scr[off[u]:off[u + 1]], om.score_utt(c)) for u, c in enumerate(chunks) if len(c))
     r, n = b.tc_check()
-    out[name] = {"identical": bool(ok), "ratio": float(r), "max_candidates": int(n)}
+    out[name] = {"identical": bool(ok), "ratio": float(r), "max_candidates": int(n), "stats": b.tc_stats}
     b.close(); m.close()
 g = golden("en_us_goforward.npz")
 run("en_us", PackedModel.load(%r), [g["feats"]])
