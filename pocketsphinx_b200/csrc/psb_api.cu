@@ -371,7 +371,7 @@ extern "C" void psb_batch_free(psb_batch_t *b)
         cudaStreamSynchronize(k->stream);
         if (k->h_off) cudaFreeHost(k->h_off);
         cudaFree(k->d_featT); cudaFree(k->d_tab); cudaFree(k->d_off); cudaFree(k->d_msdist); cudaFree(k->d_msbest);
-        cudaFree(k->d_uttoff); cudaFree(k->d_semi_dist); cudaFree(k->d_tc_flags); cudaFree(k->d_tc_check);
+        cudaFree(k->d_uttoff); cudaFree(k->d_semi_dist); cudaFree(k->d_tc_flags); cudaFree(k->d_tc_check); cudaFree(k->d_tc_items); cudaFree(k->d_tc_nitems);
         if (k->h_tab) cudaFreeHost(k->h_tab);
         for (int i = 0; i < 4; ++i) cudaEventDestroy(k->ev[i]);
         cudaEventDestroy(k->join_ev);
@@ -382,7 +382,7 @@ extern "C" void psb_batch_free(psb_batch_t *b)
     if (b->join_ev) cudaEventDestroy(b->join_ev);
     cudaFree(b->d_feats); cudaFree(b->d_senscr); cudaFree(b->d_featT); cudaFree(b->d_topn); cudaFree(b->d_tab); cudaFree(b->d_semi_dist); cudaFree(b->d_uttoff);
     cudaFree(b->d_best); cudaFree(b->d_pen); cudaFree(b->d_off); cudaFree(b->d_msdist); cudaFree(b->d_msbest);
-    cudaFree(b->d_tc_flags); cudaFree(b->d_tc_check);
+    cudaFree(b->d_tc_flags); cudaFree(b->d_tc_check); cudaFree(b->d_tc_items); cudaFree(b->d_tc_nitems);
     if (b->h_tab) cudaFreeHost(b->h_tab);
     if (b->h_feats) cudaFreeHost(b->h_feats);
     if (b->h_senscr) cudaFreeHost(b->h_senscr);

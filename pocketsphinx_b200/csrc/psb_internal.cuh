@@ -120,6 +120,7 @@ struct psb_batch_s {
                                   // 6 (default) tensor-core filter + exact rescoring where the model allows, else 5
     unsigned *d_tc_flags; size_t tc_flag_cap, tc_flag_words;   // [K][words]: frames the tie fix-up redoes
     float *d_tc_check;            // debug (PSB_TC_CHECK=1): max |a - d| / eps, max candidates
+    uint4 *d_tc_items; unsigned *d_tc_nitems; unsigned tc_item_cap;   // rows the filter left in doubt (ptm_tc_exact_kernel)
     // phone-loop outputs for psb_decode_batch_host
     int32_t *d_best, *d_pen;
     int32_t *h_best, *h_pen;

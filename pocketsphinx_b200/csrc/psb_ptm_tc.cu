@@ -444,7 +444,8 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
                const int32_t *__restrict__ klist, const float *__restrict__ wumma, const float *__restrict__ cen,
                const float *__restrict__ bnd, const float *__restrict__ rec, const size_t *__restrict__ rec_off,
                int4 *__restrict__ out, unsigned *__restrict__ flags, long long flag_words, int K, int n_feat,
-               int tiles_per_cta, float *__restrict__ check, unsigned long long *__restrict__ stats)
+               int tiles_per_cta, uint4 *__restrict__ items, unsigned *__restrict__ n_items, unsigned item_cap,
+               float *__restrict__ check, unsigned long long *__restrict__ stats)
 {
     constexpr int RF = (1 + 2 * FL + 3) / 4 * 4;
     constexpr int GW = ND / 8;                           // columns per maximum group: 8 groups per row
@@ -591,12 +592,18 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
         for (int c0 = 0; c0 < ND; c0 += 32) {
             float v[32];
             tmem_ld32(trow + c0, v);
+            unsigned hit = 0u;                           // branch-free: one compare and one predicated OR per column
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (v[i] >= thr) {
-                    if (n < TC_CAP) L[n] = make_uint2(__float_as_uint(v[i]), (unsigned)(c0 + i));
-                    ++n;
-                }
+            for (int i = 0; i < 32; ++i) hit |= v[i] >= thr ? (1u << i) : 0u;
+            while (hit) {
+                const int i = __ffs(hit) - 1;
+                hit &= hit - 1;
+                float a = v[0];
+#pragma unroll
+                for (int q = 1; q < 32; ++q) a = q == i ? v[q] : a;
+                if (n < TC_CAP) L[n] = make_uint2(__float_as_uint(a), (unsigned)(c0 + i));
+                ++n;
+            }
             if (CHECK && valid) {
                 for (int i = 0; i < 32; ++i) {
                     const float *r = rc + (size_t)(c0 + i) * RF;
@@ -651,8 +658,29 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
                     if (CHECK) { atomicAdd(stats, 1ull); atomicAdd(stats + 1, 1ull); }
                 }
             }
+            // doubt: the row goes to ptm_tc_exact_kernel's work list (one atomic per warp); only when that list is full
+            // is the exact arithmetic done here
+            if (!certain && items) {
+                const unsigned who = __activemask();
+                const unsigned need = __ballot_sync(who, true);
+                const int leader = __ffs(need) - 1;
+                unsigned base = 0;
+                if ((tid & 31) == leader) base = atomicAdd(n_items, (unsigned)__popc(need));
+                base = __shfl_sync(need, base, leader);
+                const unsigned slot = base + (unsigned)__popc(need & ((1u << (tid & 31)) - 1u));
+                if (slot < item_cap) {
+                    const bool listed = n <= TC_CAP && n >= 5;
+                    unsigned wv[5] = {0u, 0u, 0u, 0u, 0u};
+                    if (listed)
+                        for (int i = 0; i < n; ++i) wv[i >> 2] |= (L[i].y & 0xffu) << (8 * (i & 3));
+                    items[2 * (size_t)slot] = make_uint4((unsigned)row, (unsigned)k | ((listed ? (unsigned)n : 255u) << 16), wv[0], wv[1]);
+                    items[2 * (size_t)slot + 1] = make_uint4(wv[2], wv[3], wv[4], (unsigned)(row >> 32));
+                    certain = true;                       // handled
+                    if (CHECK) atomicAdd(stats, 1ull);
+                }
+            }
             if (!certain) {
-                // doubt: the reference's exact arithmetic for this row's candidates (all codewords if the list overflowed)
+                // the reference's exact arithmetic for this row's candidates (all codewords if the list overflowed)
                 Top5 top;
                 top.n = 0; top.c = 0u; top.c4 = 0;
 #pragma unroll
@@ -685,6 +713,53 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(ND < 32 ? 32 : ND));
+}
+
+// Rows the filter values left in doubt (work list of ptm_tc5_kernel): one thread per row, the reference's exact
+// arithmetic for its candidate codewords (all codewords when its list had overflowed), the five best, the record;
+// exact ties go on to the fix-up.  Item: {row low, pair | n << 16, 18 codeword bytes, row high}.
+template <int FL>
+__global__ void __launch_bounds__(128)
+ptm_tc_exact_kernel(const float *__restrict__ feats, int D, const int32_t *__restrict__ featoff, const uint4 *__restrict__ items,
+                    const unsigned *__restrict__ n_items, unsigned item_cap, const float *__restrict__ rec,
+                    const size_t *__restrict__ rec_off, int4 *__restrict__ out, unsigned *__restrict__ flags, long long flag_words,
+                    int K, int n_feat, int nd, unsigned long long *__restrict__ stats)
+{
+    constexpr int RF = (1 + 2 * FL + 3) / 4 * 4;
+    const unsigned count = min(*n_items, item_cap);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const uint4 a = items[2 * (size_t)i], b = items[2 * (size_t)i + 1];
+        const long long row = (long long)a.x | ((long long)b.w << 32);
+        const int k = (int)(a.y & 0xffffu), n = (int)(a.y >> 16);
+        const unsigned wv[5] = {a.z, a.w, b.x, b.y, b.z};
+        const float *px = feats + row * D + featoff[k % n_feat];
+        const float *rc = rec + rec_off[k];
+        float x[FL];
+#pragma unroll
+        for (int j = 0; j < FL; ++j) x[j] = px[j];
+        Top5 top;
+        top.n = 0; top.c = 0u; top.c4 = 0;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) top.s[j] = INT_MIN;
+        const int cnt = n == 255 ? nd : n;
+        for (int q = 0; q < cnt; ++q) {
+            const int cw = n == 255 ? q : (int)((wv[q >> 2] >> (8 * (q & 3))) & 0xffu);
+            const float d = gau_dist<FL>(reinterpret_cast<const float4 *>(rc + (size_t)cw * RF), x);
+            top5_insert(top, f2i_clamped(d), cw);
+        }
+        const bool distinct = top.n >= 5 && top.s[0] > top.s[1] && top.s[1] > top.s[2] && top.s[2] > top.s[3] && top.s[3] > top.s[4];
+        const int tp = top.s[0] >> PSB_SENSCR_SHIFT;
+        unsigned eb = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int ev = tp - (top.s[j] >> PSB_SENSCR_SHIFT);
+            ev = ev > 255 ? 255 : ev;
+            eb |= (unsigned)ev << (8 * j);
+        }
+        out[row * K + k] = make_int4(tp, (int)top.c, (int)eb, 0);
+        if (!distinct) atomicOr(&flags[(size_t)k * flag_words + (row >> 5)], 1u << (row & 31));
+        if (stats) { atomicAdd(stats + 2, (unsigned long long)cnt); if (!distinct) atomicAdd(stats + 3, 1ull); }
+    }
 }
 
 // Frames whose five best scores tie: the reference's loop, literally (eval_topn ptm_mgau.c:88-136,
@@ -760,6 +835,112 @@ ptm_fixup_kernel(const float *__restrict__ feats, int D, const int32_t *__restri
     }
 }
 
+// The same fix-up with a WARP per (utterance, pair) chain: lanes = codewords (ND / 32 each), the flagged frames of the
+// chain in order.  All distances of a frame in parallel, the four seeds fetched by shuffle, then the scan only visits --
+// in ascending codeword order -- the codewords whose distance reaches the seeds' worst score (ballots), each re-tested
+// against the list as it stands: eval_topn + eval_cb literally, like semi_scan_kernel does for semi-continuous models.
+// The thread-per-chain kernel above serialises 260 distances per flagged frame inside one lane (15 ms per 10^6 frames
+// at a 0.04 % tie rate); this one costs a few hundred warp instructions per flagged frame.
+template <int FL, int NDW>
+__global__ void __launch_bounds__(128)
+ptm_fixup_warp_kernel(const float *__restrict__ feats, int D, const int32_t *__restrict__ featoff, const int32_t *__restrict__ utt_off,
+                      int n_utt, const float *__restrict__ rec, const size_t *__restrict__ rec_off, int4 *__restrict__ out,
+                      const unsigned *__restrict__ flags, long long flag_words, int K, int n_feat)
+{
+    constexpr int RF = (1 + 2 * FL + 3) / 4 * 4;
+    constexpr unsigned FULL = 0xffffffffu;
+    const long long id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (id >= (long long)n_utt * K) return;
+    const int u = (int)(id / K), k = (int)(id % K);
+    const int f = k % n_feat;
+    const long long f0 = utt_off[u], f1 = utt_off[u + 1];
+    if (f1 <= f0) return;
+    const unsigned *fl = flags + (size_t)k * flag_words;
+    const float *rc = rec + rec_off[k];
+    for (long long w0 = f0 >> 5; w0 <= (f1 - 1) >> 5; w0 += 32) {
+        const long long wd_l = w0 + lane;
+        unsigned mine = wd_l <= ((f1 - 1) >> 5) ? fl[wd_l] : 0u;
+        unsigned any = __ballot_sync(FULL, mine != 0u);
+        while (any) {
+            const int wl = __ffs(any) - 1;
+            any &= any - 1;
+            unsigned bits = __shfl_sync(FULL, mine, wl);
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const long long row = (w0 + wl) * 32 + b;
+                if (row < f0 || row >= f1) continue;
+                const float *px = feats + row * D + featoff[f];
+                float x[FL];
+#pragma unroll
+                for (int j = 0; j < FL; ++j) x[j] = px[j];
+                float d[NDW];
+#pragma unroll
+                for (int q = 0; q < NDW; ++q) d[q] = gau_dist<FL>(reinterpret_cast<const float4 *>(rc + (size_t)(lane + 32 * q) * RF), x);
+                auto dist_of = [&](int c) {                            // uniform c: the owner lane's value
+                    float v = d[0];
+#pragma unroll
+                    for (int q = 1; q < NDW; ++q) v = (c >> 5) == q ? d[q] : v;
+                    return __shfl_sync(FULL, v, c & 31);
+                };
+                const unsigned seeds = row == f0 ? 0x03020100u : (unsigned)out[(row - 1) * K + k].y;
+                int cw[4], sc[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {                          // eval_topn: stable, strict >
+                    const int c = (seeds >> (8 * i)) & 0xff;
+                    const int s = f2i_clamped(dist_of(c));
+                    int p = 0;
+#pragma unroll
+                    for (int j = 0; j < i; ++j) p += (s > sc[j]) ? 0 : 1;
+#pragma unroll
+                    for (int j = 2; j >= 0; --j)
+                        if (j < i && j >= p) { sc[j + 1] = sc[j]; cw[j + 1] = cw[j]; }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j == p) { sc[j] = s; cw[j] = c; }
+                }
+                const float th0 = (float)sc[3];                        // the scan's threshold only rises from here
+#pragma unroll
+                for (int q = 0; q < NDW; ++q) {
+                    unsigned cand = __ballot_sync(FULL, d[q] >= th0);
+                    while (cand) {
+                        const int l = __ffs(cand) - 1;
+                        cand &= cand - 1;
+                        const int c = l + 32 * q;
+                        const float dv = __shfl_sync(FULL, d[q], l);
+                        if (!(dv >= (float)sc[3])) continue;            // eval_cb :207
+                        if (cw[0] == c || cw[1] == c || cw[2] == c || cw[3] == c) continue;   // :209-215
+                        const int s = f2i_clamped(dv);
+                        int p = 0;
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) p += (s >= sc[j]) ? 0 : 1;     // insertion_sort_cb :140-149
+#pragma unroll
+                        for (int j = 2; j >= 0; --j)
+                            if (j >= p) { sc[j + 1] = sc[j]; cw[j + 1] = cw[j]; }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j == p) { sc[j] = s; cw[j] = c; }
+                    }
+                }
+                if (lane == 0) {
+                    const int tp = sc[0] >> PSB_SENSCR_SHIFT;
+                    unsigned cb = 0, eb = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        int ev = tp - (sc[j] >> PSB_SENSCR_SHIFT);
+                        ev = ev > 255 ? 255 : ev;
+                        cb |= (unsigned)cw[j] << (8 * j);
+                        eb |= (unsigned)ev << (8 * j);
+                    }
+                    out[row * K + k] = make_int4(tp, (int)cb, (int)eb, 0);
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
 float round_tf32_host(float x)
 {
     // cvt.rna.tf32.f32: round to nearest, ties away from zero, 10 explicit mantissa bits
@@ -817,16 +998,25 @@ int launch_tc5(psb_batch_t *b, const float *d_feats, long long total, const int3
         PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, TC_ROWS, smem, b->stream>>>(d_feats, total, m->sumlen, d_featoff, d_klist, m->d_tc_wumma, m->d_tc_cen, m->d_tc_bnd,
                                                 m->d_rec, m->d_rec_off, b->d_topn, b->d_tc_flags, (long long)b->tc_flag_words, m->K,
-                                                m->n_feat, tpc, chk, stats);
+                                                m->n_feat, tpc, b->d_tc_items, b->d_tc_nitems, b->tc_item_cap, chk, stats);
     }
     else {
         auto kern = ptm_tc5_kernel<FL, ND, false>;
         PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, TC_ROWS, smem, b->stream>>>(d_feats, total, m->sumlen, d_featoff, d_klist, m->d_tc_wumma, m->d_tc_cen, m->d_tc_bnd,
                                                 m->d_rec, m->d_rec_off, b->d_topn, b->d_tc_flags, (long long)b->tc_flag_words, m->K,
-                                                m->n_feat, tpc, nullptr, nullptr);
+                                                m->n_feat, tpc, b->d_tc_items, b->d_tc_nitems, b->tc_item_cap, nullptr, nullptr);
     }
     PSB_LAUNCH_CHECK();
+    if (b->d_tc_items) {
+        // the rows in doubt: the count lives on the device, so the grid covers the list's capacity (grid-stride loop, idle
+        // blocks leave at once)
+        const unsigned blocks = (unsigned)std::min<size_t>(((size_t)b->tc_item_cap + 127) / 128, 148 * 64);
+        ptm_tc_exact_kernel<FL><<<blocks, 128, 0, b->stream>>>(d_feats, m->sumlen, d_featoff, b->d_tc_items, b->d_tc_nitems, b->tc_item_cap,
+                                                              m->d_rec, m->d_rec_off, b->d_topn, b->d_tc_flags, (long long)b->tc_flag_words,
+                                                              m->K, m->n_feat, ND, check ? stats : nullptr);
+        PSB_LAUNCH_CHECK();
+    }
     return PSB_OK;
 }
 
@@ -940,6 +1130,18 @@ int psb_launch_ptm_tc(psb_batch_t *b, const float *d_feats, const int32_t *utt_o
         PSB_CUDA(cudaMalloc(&b->d_tc_check, 64));
         PSB_CUDA(cudaMemsetAsync(b->d_tc_check, 0, 64, b->stream));
     }
+    {
+        // work list of the rows the filter leaves in doubt: room for a quarter of all (frame, pair) rows, 32 bytes each
+        const size_t want = std::max<size_t>(4096, (size_t)total * m->K / 4);
+        if (want > b->tc_item_cap || !b->d_tc_items) {
+            cudaFree(b->d_tc_items);
+            b->d_tc_items = nullptr;
+            if (!b->d_tc_nitems) PSB_CUDA(cudaMalloc(&b->d_tc_nitems, 4));
+            b->tc_item_cap = (unsigned)std::min<size_t>(want + want / 8, 0x7fffffffu);
+            PSB_CUDA(cudaMalloc(&b->d_tc_items, (size_t)b->tc_item_cap * 32));
+        }
+        PSB_CUDA(cudaMemsetAsync(b->d_tc_nitems, 0, 4, b->stream));
+    }
     b->tc_flag_words = fw;
     PSB_CUDA(cudaMemsetAsync(b->d_tc_flags, 0, fw * m->K * 4, b->stream));
     PSB_CUDA(cudaMemcpyAsync(b->d_uttoff, utt_off, ((size_t)n_utt + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
@@ -960,9 +1162,20 @@ int psb_launch_ptm_tc(psb_batch_t *b, const float *d_feats, const int32_t *utt_o
         }
     if (rc) return rc;
     const long long chains = (long long)n_utt * m->K;
-    ptm_fixup_kernel<13><<<(unsigned)((chains + 127) / 128), 128, 0, b->stream>>>(
-        d_feats, m->sumlen, d_featoff, b->d_uttoff, n_utt, m->d_rec, m->d_rec_off, b->d_topn, b->d_tc_flags, (long long)fw, m->K,
-        m->n_feat, m->n_density);
+    static const bool thread_fixup = [] { const char *v = getenv("PSB_TC_FIXUP"); return v && !strcmp(v, "thread"); }();
+    if (thread_fixup)
+        ptm_fixup_kernel<13><<<(unsigned)((chains + 127) / 128), 128, 0, b->stream>>>(
+            d_feats, m->sumlen, d_featoff, b->d_uttoff, n_utt, m->d_rec, m->d_rec_off, b->d_topn, b->d_tc_flags, (long long)fw, m->K,
+            m->n_feat, m->n_density);
+    else {
+        const unsigned blocks = (unsigned)((chains * 32 + 127) / 128);
+#define PSB_FIXW(NDW) ptm_fixup_warp_kernel<13, NDW><<<blocks, 128, 0, b->stream>>>(d_feats, m->sumlen, d_featoff, b->d_uttoff, n_utt, \
+            m->d_rec, m->d_rec_off, b->d_topn, b->d_tc_flags, (long long)fw, m->K, m->n_feat)
+        if (m->n_density == 256) PSB_FIXW(8);
+        else if (m->n_density == 128) PSB_FIXW(4);
+        else PSB_FIXW(2);
+#undef PSB_FIXW
+    }
     PSB_LAUNCH_CHECK();
     return PSB_OK;
 }
