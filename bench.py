@@ -123,6 +123,15 @@ def ncu_traffic(kernel, workload):
         return None
 
 
+def tensor_peak_bf16():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["bf16_tflops"])
+    except (OSError, ValueError, KeyError):
+        return 2250.0                                          # nominal dense bf16 (B200_PROFILING.md)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -350,6 +359,45 @@ def search_stage(api, torch, U=256):
     return out
 
 
+def search_coupled_stage(api, torch, batch, pm, off, U, T, kind, gmm_ms_per_frame):
+    """BASELINE configs 3 / 4 as written: the GMM stage of THIS model feeding a search kernel over the scores it just left in
+    HBM -- `fwdtree` (config 3: n-gram first pass) or `fsg` (config 4: grammar search).  The search description is the
+    reference's own flattened lextree / grammar for its test LM and grammar (tests/golden/, 5126 senones: any model with at
+    least as many senone columns can drive it; the synthetic models' scores make it a load test, not a recognition test).
+    Reported beside the headline: frames/s of the search call alone (tables downloaded) and of GMM + search in sequence."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    gd = os.path.join(here, "tests", "golden")
+    m = np.load(os.path.join(gd, "en_us_ptm_model.npz"))
+    if pm.n_sen < int(m["n_sen"]):
+        return {"error": "model has fewer senones than the search description uses"}
+    Us = min(U, 256)
+    offs = np.ascontiguousarray(off[:Us + 1], np.int32)
+    ctx = api.HmmContext(m["tp"], m["sseq"], pm.n_sen)
+
+    def case(g, tag):
+        return {k[len(tag) + 1:]: g[k] for k in g.files if k.startswith(tag + ".")}
+    out = {"search": kind, "utts": Us, "frames_per_utt": T}
+    try:
+        if kind == "fsg":
+            c = case(np.load(os.path.join(gd, "en_us_fsg.npz")), "cmd")
+            fn = lambda: ctx.fsg(batch.senscr_device_ptr(), offs, c, 64 * T)
+        else:
+            c = case(np.load(os.path.join(gd, "en_us_fwdtree.npz")), "default")
+            nci = int(c["info"][6])
+            fn = lambda: ctx.ngram_fwdtree(batch.senscr_device_ptr(), offs, c["info"], c["model"], m["phone_tmat"][:nci], 48 * T, 48 * T * 24)
+        fn()
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        out.update({"search_ms": dt * 1e3, "search_frames_per_s": Us * T / dt,
+                    "gmm_plus_search_frames_per_s": 1.0 / (gmm_ms_per_frame * 1e-3 + dt / (Us * T)),
+                    "note": "not part of `value`; search call = kernel + table download, wall clock"})
+    except Exception as e:
+        out["error"] = str(e)[:200]
+    ctx.close()
+    return out
+
+
 def cpu_baseline(args, pm, raw, feats, n_frames_per_utt, budget_s=15.0, threads=1):
     """The reference's CPU implementation of the path on host cores over a bounded sample of the
     same workload: senone evaluation through the COMPILED REFERENCE (oracle/_ref/libpsref.so:
@@ -465,6 +513,8 @@ def main():
                          "overrides --utts")
     ap.add_argument("--secs", type=int, default=10, help="seconds of 16 kHz audio per utterance")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--search", default="none", choices=["none", "fwdtree", "fsg"],
+                    help="also couple a search kernel to the GMM stage's scores (BASELINE configs 3 / 4), reported as `search_coupled`")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -633,10 +683,15 @@ def main():
         flop = 4.0 * pm.n_mgau * pm.n_density * pm.sumlen * total      # sub, mul, mul, sub per (codeword, dim)
         sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
         fp32_peak = 148 * 128 * sm_mhz * 1e6 / 1e12                     # non-FMA FP32 lane-ops/s (TFLOP/s)
-        variant = int(os.environ.get("PSB_TOPN_VARIANT", "5"))
-        topn_name = {"ms": "ms_dist_kernel+ms_senone_kernel", "s2_semi": "ptm_topn2_kernel<SEMI>"}.get(
+        tf32_peak = tensor_peak_bf16() / 2.0
+        variant = int(os.environ.get("PSB_TOPN_VARIANT", "6"))
+        tc_path = variant >= 6 and pm.kind == "ptm" and all(int(x) == 13 for x in pm.featlen) and pm.n_density in (64, 128, 256) \
+            and int(getattr(pm, "ds_ratio", 1)) == 1
+        topn_name = {"ms": "ms_dist_tile_kernel+ms_senone_kernel", "s2_semi": "semi_dist_kernel+semi_scan_kernel"}.get(
             pm.kind, {0: "ptm_topn_kernel", 1: "ptm_topn2_kernel", 2: "ptm_topn2_kernel", 3: "ptm_topn_u2_kernel",
                       4: "ptm_topnq_kernel<NU=2>", 5: "ptm_topnq_kernel<NU=1>"}.get(variant, "ptm_topnq_kernel<NU=1>"))
+        if tc_path:
+            topn_name = "ptm_tc5_kernel" if os.environ.get("PSB_TC_IMPL") != "mma" else "ptm_tc_kernel"
         out = {
             "metric": "frames/sec senone-eval+Viterbi", "value": value, "unit": "frames/s",
             "xRT": FRAMES_PER_SEC_AUDIO / value,
@@ -668,6 +723,15 @@ def main():
                               "achieved": flop / (km["topn"] * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
                               "frac": flop / (km["topn"] * 1e-3) / 1e12 / fp32_peak,
                               "peak_source": "148 SMs x 128 lanes x sampled SM clock"},
+            # the tensor-core filter of the top-N stage: 3 x TF32 GEMM [frames x 32] x [32 x n_density] per (codebook, stream) pair;
+            # `achieved` counts those GEMM flops over the whole top-N stage (filter + exact rows + tie fix-up).  The stage's
+            # algorithmic FP32 work (roofline_fp32) is what the scan kernels execute and this path mostly skips, so its
+            # fraction there can exceed 1.
+            "roofline_tensor": ({"bound": "tensor", "kernel": topn_name, "achieved": 3 * 2.0 * 32 * pm.n_density * K * total / (km["topn"] * 1e-3) / 1e12,
+                                 "peak": tf32_peak, "unit": "TFLOP/s",
+                                 "frac": 3 * 2.0 * 32 * pm.n_density * K * total / (km["topn"] * 1e-3) / 1e12 / tf32_peak,
+                                 "peak_source": "half the measured dense bf16 rate of MEASURED_PEAKS.json (TF32 runs at half the bf16 rate)"}
+                                if tc_path else None),
             "gmm_stage": {"ms": gmm_ms, "algorithmic_bytes": stage_bytes,
                           "achieved_gbs": stage_bytes / (gmm_ms * 1e-3) / 1e9},
             "e2e": {"value": frames_all / (e2e_ms * 1e-3), "unit": "frames/s", "ms_per_step": e2e_ms,
@@ -705,6 +769,8 @@ def main():
                 out["align_stage"] = align_stage(api, ctx, batch, pm, off, U, T)
             out["frontend_stage"] = frontend_stage(api, torch, U, args.secs)
             out["search_stage"] = search_stage(api, torch)
+            if args.search != "none":
+                out["search_coupled"] = search_coupled_stage(api, torch, batch, pm, off, U, T, args.search, gmm_ms / total)
             out["cpu_baseline"] = cpu_baseline(args, pm, raw, feats_np, T, budget_s=args.cpu_budget, threads=1)
         print(json.dumps(out))
     if hs is not None:
