@@ -370,7 +370,7 @@ def search_coupled_stage(api, torch, batch, pm, off, U, T, kind, gmm_ms_per_fram
     m = np.load(os.path.join(gd, "en_us_ptm_model.npz"))
     if pm.n_sen < int(m["n_sen"]):
         return {"error": "model has fewer senones than the search description uses"}
-    Us = min(U, 256)
+    Us = min(U, 256 if kind == "fsg" else 64)          # the first pass's tables: 128 entries per frame allowed on random scores
     offs = np.ascontiguousarray(off[:Us + 1], np.int32)
     ctx = api.HmmContext(m["tp"], m["sseq"], pm.n_sen)
 
@@ -384,7 +384,7 @@ def search_coupled_stage(api, torch, batch, pm, off, U, T, kind, gmm_ms_per_fram
         else:
             c = case(np.load(os.path.join(gd, "en_us_fwdtree.npz")), "default")
             nci = int(c["info"][6])
-            fn = lambda: ctx.ngram_fwdtree(batch.senscr_device_ptr(), offs, c["info"], c["model"], m["phone_tmat"][:nci], 48 * T, 48 * T * 24)
+            fn = lambda: ctx.ngram_fwdtree(batch.senscr_device_ptr(), offs, c["info"], c["model"], m["phone_tmat"][:nci], 128 * T, 128 * T * 32)
         fn()
         t0 = time.perf_counter()
         fn()

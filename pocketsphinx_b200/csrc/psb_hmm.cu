@@ -796,6 +796,7 @@ hmmset_sweep_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr
 
     // this thread's V instances (THREADS apart: neighbouring threads read neighbouring words)
     int sc[V][NS], hi[V][NS], sid[V][NS], osc[V], ohi[V], tmo[V];
+    unsigned tpk[V][3];                                   // 3-state: the instance's 12 transition bytes in registers
     int32_t *p32[V];
     bool live[V];
 #pragma unroll
@@ -816,6 +817,16 @@ hmmset_sweep_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr
         osc[v] = live[v] ? p32[v][2 * NS * HS_TS] : PSB_WORST_SCORE;
         ohi[v] = live[v] ? p32[v][(2 * NS + 1) * HS_TS] : -1;
         tmo[v] = live[v] ? (int)(int16_t)p16[(NS + 1) * HS_TS] * NS * (NS + 1) : 0;
+    }
+    __syncthreads();                                      // the transition matrices are staged
+    if (NS == 3) {
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const uint8_t *t4 = tps + tmo[v] + 4 * q;
+                tpk[v][q] = (unsigned)t4[0] | ((unsigned)t4[1] << 8) | ((unsigned)t4[2] << 16) | ((unsigned)t4[3] << 24);
+            }
     }
     const int64_t r0 = row0 ? row0[seg] : seg;
     const int64_t rstep = row0 ? 1 : gridDim.y;
@@ -871,7 +882,15 @@ hmmset_sweep_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr
                 obs[k] = k < NS ? -(int)srow[sid[v][k < NS ? k : 0]] : 0;
             }
             h.out_score = osc[v]; h.out_hist = ohi[v]; h.best = PSB_WORST_SCORE;
-            const int bb = NS == 3 ? hmm_step_3st(h, tps + tmo[v], obs) : hmm_step_5st(h, tps + tmo[v], obs);
+            int bb;
+            if (NS == 3) {
+                uint8_t tl[12];                                       // byte extracts from registers, no shared-memory reads
+#pragma unroll
+                for (int q = 0; q < 12; ++q) tl[q] = (uint8_t)(tpk[v][q >> 2] >> (8 * (q & 3)));
+                bb = hmm_step_3st(h, tl, obs);
+            }
+            else
+                bb = hmm_step_5st(h, tps + tmo[v], obs);
             if (live[v]) best = max(best, bb);
 #pragma unroll
             for (int k = 0; k < NS; ++k) { sc[v][k] = h.score[k]; hi[v][k] = h.hist[k]; }

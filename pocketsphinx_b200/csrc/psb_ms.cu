@@ -99,14 +99,14 @@ ms_dist_kernel(const float *__restrict__ gT, const float *__restrict__ detT, con
 // (2 loads per 16 floating-point operations: 25 % of the FP32 lane rate, L2-bound).  Here a CTA owns a
 // tile of 32 codebooks (lane = codebook) and keeps ALL their Gaussians in shared memory -- rows of 32
 // floats, one per (stream, density, dimension, {mean, variance term}), conflict-free -- for a whole
-// range of frames; its four warps take eight frames each of a 32-frame block whose feature vectors are
+// range of frames; its eight warps take eight frames each of a 64-frame block whose feature vectors are
 // staged transposed ([dimension][frame]), so that one warp-uniform LDS.128 pair feeds eight frames.
 // Per (density, dimension): 2 LDS + 2 broadcast LDS.128 for 32 floating-point operations.  Same
 // arithmetic, same order, same insertion rule as ms_dist_kernel: bit-identical lists.
-constexpr int MS_TCB = 32, MS_TFT = 8, MS_TFB = 32;      // codebooks per CTA, frames per thread, frames per block
+constexpr int MS_TCB = 32, MS_TFT = 8, MS_TFB = 64;      // codebooks per CTA, frames per thread, frames per block (8 warps)
 
 template <int NT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256, 2)
 ms_dist_tile_kernel(const float *__restrict__ gT, const float *__restrict__ detT, const float *__restrict__ feats,
                     int2 *__restrict__ out, long long frame0, long long n_frames, int n_mgau, int n_feat, int nd,
                     int sumlen, const int32_t *__restrict__ featlen, const int32_t *__restrict__ featoff, int frames_per_cta)
@@ -115,12 +115,12 @@ ms_dist_tile_kernel(const float *__restrict__ gT, const float *__restrict__ detT
     const int n_rows = nd * sumlen * 2, n_det = n_feat * nd;
     float *par = tsm;                                   // [n_rows][32]
     float *dets = par + (size_t)n_rows * MS_TCB;        // [n_det][32]
-    float *xs = dets + (size_t)n_det * MS_TCB;          // [sumlen][32]
+    float *xs = dets + (size_t)n_det * MS_TCB;          // [sumlen][MS_TFB]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cb = blockIdx.x * MS_TCB + lane;
     const int cbr = cb < n_mgau ? cb : n_mgau - 1;      // padding lanes read the last codebook and write nothing
-    for (int r = warp; r < n_rows; r += 4) par[r * MS_TCB + lane] = gT[(size_t)r * n_mgau + cbr];
-    for (int r = warp; r < n_det; r += 4) dets[r * MS_TCB + lane] = detT[(size_t)r * n_mgau + cbr];
+    for (int r = warp; r < n_rows; r += MS_TFB / MS_TFT) par[r * MS_TCB + lane] = gT[(size_t)r * n_mgau + cbr];
+    for (int r = warp; r < n_det; r += MS_TFB / MS_TFT) dets[r * MS_TCB + lane] = detT[(size_t)r * n_mgau + cbr];
     const bool all = NT >= nd;                          // compute_dist_all (ms_gauden.c:378-419)
     const long long f_begin = (long long)blockIdx.y * frames_per_cta;
     const long long f_end = f_begin + frames_per_cta < n_frames ? f_begin + frames_per_cta : n_frames;
@@ -145,6 +145,7 @@ ms_dist_tile_kernel(const float *__restrict__ gT, const float *__restrict__ detT
                 const float det = dets[(f * nd + d) * MS_TCB + lane];
 #pragma unroll
                 for (int q = 0; q < MS_TFT; ++q) dv[q] = det;
+#pragma unroll 4
                 for (int j = 0; j < fl; ++j) {
                     const float m = pp[((d * fl + j) * 2) * MS_TCB];
                     const float v = pp[((d * fl + j) * 2 + 1) * MS_TCB];
@@ -484,7 +485,8 @@ int psb_launch_ms_batch(psb_batch_t *b, const float *d_feats, const int32_t *utt
         int2 *dist = reinterpret_cast<int2 *>(b->d_msdist);
         static const bool packed = getenv("PSB_MS_PACKED") != nullptr;       // experiment, off: bit-identical, 181 vs 174 ms
         static const bool no_tile = getenv("PSB_MS_NOTILE") != nullptr;     // PSB_MS_NOTILE=1: the round-1 kernel (parameters streamed from L2)
-        const size_t tile_smem = ((size_t)m->n_density * m->sumlen * 2 + (size_t)m->n_feat * m->n_density + m->sumlen) * MS_TCB * sizeof(float);
+        const size_t tile_smem = ((size_t)m->n_density * m->sumlen * 2 + (size_t)m->n_feat * m->n_density) * MS_TCB * sizeof(float)
+                                 + (size_t)m->sumlen * MS_TFB * sizeof(float);
         const bool tile = !no_tile && !packed && !reg_tile_env() && tile_smem <= 100 * 1024;
         // frames per CTA: enough CTAs for ~4 waves of two resident CTAs per SM, whole 32-frame blocks
         const int tiles_x = (m->n_mgau + MS_TCB - 1) / MS_TCB;
@@ -494,7 +496,7 @@ int psb_launch_ms_batch(psb_batch_t *b, const float *d_feats, const int32_t *utt
         static const bool reg_tile = getenv("PSB_MS_REGTILE") != nullptr;   // experiment, off: measured slower (247 vs 174 ms)
 #define LAUNCH(NT) do { if (tile) {                                                                                       \
             PSB_CUDA(cudaFuncSetAttribute(ms_dist_tile_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem)); \
-            ms_dist_tile_kernel<NT><<<gt, 128, tile_smem, b->stream>>>(m->d_msT, m->d_msdetT, d_feats, dist, f0, n,                \
+            ms_dist_tile_kernel<NT><<<gt, 256, tile_smem, b->stream>>>(m->d_msT, m->d_msdetT, d_feats, dist, f0, n,                \
                 m->n_mgau, m->n_feat, m->n_density, m->sumlen, m->d_featlen, m->d_featoff, (int)fpc); }                          \
         else if (reg_tile && m->n_density <= ND_MAX)                                                          \
             ms_dist_reg_kernel<NT><<<g1, 128, smem, b->stream>>>(m->d_msT, m->d_msdetT, d_feats, dist, f0, n,             \

@@ -400,7 +400,7 @@ __device__ __forceinline__ void umma_tf32(unsigned tmem_d, uint64_t adesc, uint6
         : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32])
+__device__ __forceinline__ void tmem_ld32_issue(unsigned taddr, float (&v)[32])
 {
     unsigned r[32];
     asm volatile(
@@ -413,9 +413,14 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32])
           "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);     // not to be read before tmem_wait_ld()
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32])
+{
+    tmem_ld32_issue(taddr, v);
+    tmem_wait_ld();
 }
 
 __device__ __forceinline__ void mbar_init1(uint64_t *bar)
@@ -457,7 +462,10 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
     __shared__ __align__(8) uint64_t mma_done;
     __shared__ unsigned tmem_base_s;
 
-    const int k = klist[blockIdx.y];
+    // grid: x = pair (fastest), y = group of tiles: CTAs that run together read the SAME frames for different pairs, so
+    // the feature rows come out of L2 (with tiles fastest every pair re-read the whole feature matrix from HBM: 23 GB
+    // per 998 k frames in the first ncu capture) while the 126 W blocks (8 MB) stay L2-resident
+    const int k = klist[blockIdx.x];
     const int f = k % n_feat;
     const int tid = threadIdx.x, warp = tid >> 5;
 
@@ -485,7 +493,7 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
     const float *rc = rec + rec_off[k];
 
     for (int tile = 0; tile < tiles_per_cta; ++tile) {
-        const long long row = ((long long)blockIdx.x * tiles_per_cta + tile) * TC_ROWS + tid;
+        const long long row = ((long long)blockIdx.y * tiles_per_cta + tile) * TC_ROWS + tid;
         if (row - tid >= total) break;                   // uniform: the whole tile lies past the end
         const bool valid = row < total;
         // ---- this thread's frame: X row (TF32 halves, canonical layout) and its error bound ----
@@ -990,7 +998,8 @@ int launch_tc5(psb_batch_t *b, const float *d_feats, long long total, const int3
     // W (64 KB at 256 densities) is staged once per CTA: a few tiles per CTA, but still >= 4 waves of 2 CTAs per SM
     int tpc = 1;
     while (tpc < 8 && (tiles / (tpc * 2)) * n_k >= 148LL * 2 * 4) tpc *= 2;
-    const dim3 grid((unsigned)((tiles + tpc - 1) / tpc), (unsigned)n_k);
+    PSB_REQUIRE((tiles + tpc - 1) / tpc <= 65535, "too many frames for one launch of the tensor-core filter");
+    const dim3 grid((unsigned)n_k, (unsigned)((tiles + tpc - 1) / tpc));
     float *chk = b->d_tc_check;
     unsigned long long *stats = reinterpret_cast<unsigned long long *>(b->d_tc_check + 4);
     if (check) {
