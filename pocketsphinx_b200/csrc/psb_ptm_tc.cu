@@ -457,8 +457,12 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
     static_assert(2 * FL + 1 <= TC_K && ND % 32 == 0 && ND <= 256, "shape");
     extern __shared__ __align__(128) unsigned char t5_smem[];
     float *sW = reinterpret_cast<float *>(t5_smem);                                   // [2][8][ND][4]
-    float *sX = sW + 2 * 8 * ND * 4;                                                  // [2][8][128][4]; later the candidate lists
-    uint2 *lists = reinterpret_cast<uint2 *>(sX);                                     // [128][TC_CAP]
+    float *sX = sW + 2 * 8 * ND * 4;                                                  // [2][8][128][4]; after the MMA: lists + staging
+    // thread-private and transposed ([slot][thread]: conflict-free): candidate values, candidate columns, one 32-column slab
+    float *Lv = sX;                                                                   // [TC_CAP][128]
+    unsigned char *Lc = reinterpret_cast<unsigned char *>(Lv + TC_CAP * TC_ROWS);     // [TC_CAP][128]
+    float *stage = reinterpret_cast<float *>(Lc + ((TC_CAP * TC_ROWS + 15) & ~15));   // [32][128]
+    static_assert(TC_CAP * TC_ROWS * 5 + 16 + 32 * TC_ROWS * 4 <= 2 * 8 * TC_ROWS * 16, "lists + staging must fit the X tile");
     __shared__ __align__(8) uint64_t mma_done;
     __shared__ unsigned tmem_base_s;
 
@@ -595,7 +599,6 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
         __syncthreads();                                  // every warp is past the barrier wait: the X tile is dead, its space takes the lists
         int n = 0;
         float worst = 0.f;
-        uint2 *L = lists + (size_t)tid * TC_CAP;
 #pragma unroll 1
         for (int c0 = 0; c0 < ND; c0 += 32) {
             float v[32];
@@ -603,14 +606,15 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
             unsigned hit = 0u;                           // branch-free: one compare and one predicated OR per column
 #pragma unroll
             for (int i = 0; i < 32; ++i) hit |= v[i] >= thr ? (1u << i) : 0u;
-            while (hit) {
-                const int i = __ffs(hit) - 1;
-                hit &= hit - 1;
-                float a = v[0];
+            if (__any_sync(0xffffffffu, hit != 0u)) {    // registers cannot be indexed by a run-time column: through shared memory
 #pragma unroll
-                for (int q = 1; q < 32; ++q) a = q == i ? v[q] : a;
-                if (n < TC_CAP) L[n] = make_uint2(__float_as_uint(a), (unsigned)(c0 + i));
-                ++n;
+                for (int i = 0; i < 32; ++i) stage[i * TC_ROWS + tid] = v[i];
+                while (hit) {
+                    const int i = __ffs(hit) - 1;
+                    hit &= hit - 1;
+                    if (n < TC_CAP) { Lv[n * TC_ROWS + tid] = stage[i * TC_ROWS + tid]; Lc[n * TC_ROWS + tid] = (unsigned char)(c0 + i); }
+                    ++n;
+                }
             }
             if (CHECK && valid) {
                 for (int i = 0; i < 32; ++i) {
@@ -637,8 +641,8 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
                 float a[5] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY};
                 int c[5] = {0, 0, 0, 0, 0};
                 for (int i = 0; i < n; ++i) {
-                    float v = __uint_as_float(L[i].x);
-                    int cv = (int)L[i].y;
+                    float v = Lv[i * TC_ROWS + tid];
+                    int cv = (int)Lc[i * TC_ROWS + tid];
 #pragma unroll
                     for (int j = 0; j < 5; ++j)
                         if (v > a[j]) { const float tv = a[j]; const int tc = c[j]; a[j] = v; c[j] = cv; v = tv; cv = tc; }
@@ -680,7 +684,7 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
                     const bool listed = n <= TC_CAP && n >= 5;
                     unsigned wv[5] = {0u, 0u, 0u, 0u, 0u};
                     if (listed)
-                        for (int i = 0; i < n; ++i) wv[i >> 2] |= (L[i].y & 0xffu) << (8 * (i & 3));
+                        for (int i = 0; i < n; ++i) wv[i >> 2] |= (unsigned)Lc[i * TC_ROWS + tid] << (8 * (i & 3));
                     items[2 * (size_t)slot] = make_uint4((unsigned)row, (unsigned)k | ((listed ? (unsigned)n : 255u) << 16), wv[0], wv[1]);
                     items[2 * (size_t)slot + 1] = make_uint4(wv[2], wv[3], wv[4], (unsigned)(row >> 32));
                     certain = true;                       // handled
@@ -696,7 +700,7 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
                 int n_exact = 0;
                 const int cnt_l = (n <= TC_CAP && n >= 5) ? n : ND;
                 for (int i = 0; i < cnt_l; ++i) {
-                    const int cw = cnt_l == ND ? i : (int)L[i].y;
+                    const int cw = cnt_l == ND ? i : (int)Lc[i * TC_ROWS + tid];
                     const float d = gau_dist<FL>(reinterpret_cast<const float4 *>(rc + (size_t)cw * RF), x);
                     top5_insert(top, f2i_clamped(d), cw);
                     ++n_exact;
