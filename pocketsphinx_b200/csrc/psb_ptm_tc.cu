@@ -402,21 +402,32 @@ __device__ __forceinline__ void umma_tf32(unsigned tmem_d, uint64_t adesc, uint6
 
 __device__ __forceinline__ void tmem_ld32_issue(unsigned taddr, float (&v)[32])
 {
-    unsigned r[32];
+    // destination = the caller's registers themselves (bit-size operands take .f32 registers): no move may sit between the
+    // load and the wait that makes them valid
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+          "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]),
+          "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]),
+          "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
         : "r"(taddr)
         : "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);     // not to be read before tmem_wait_ld()
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the same wait, but the compiler is told that the slab's registers pass through it: nothing that reads them can be
+// scheduled above the wait when the load was issued earlier (software pipelining of the sweeps)
+__device__ __forceinline__ void tmem_wait_ld_dep(float (&v)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]),
+                   "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]), "+f"(v[17]), "+f"(v[18]),
+                   "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]),
+                   "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32])
 {
     tmem_ld32_issue(taddr, v);
@@ -555,10 +566,7 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
         float gm[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) gm[i] = -INFINITY;
-#pragma unroll 1
-        for (int c0 = 0; c0 < ND; c0 += 32) {
-            float v[32];
-            tmem_ld32(trow + c0, v);
+        auto maxima = [&](int c0, const float (&v)[32]) {
             if (GW >= 32) {
                 float mx = v[0];
 #pragma unroll
@@ -581,6 +589,19 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
                         if (q == gi) gm[q] = fmaxf(gm[q], mx);
                 }
             }
+        };
+        {   // two slabs in flight: the load of the next one runs while this one is reduced
+            float va[32], vb[32];
+            tmem_ld32_issue(trow, va);
+#pragma unroll 1
+            for (int c0 = 0; c0 < ND; c0 += 64) {
+                tmem_wait_ld_dep(va);
+                tmem_ld32_issue(trow + c0 + 32, vb);
+                maxima(c0, va);
+                tmem_wait_ld_dep(vb);
+                if (c0 + 64 < ND) tmem_ld32_issue(trow + c0 + 64, va);
+                maxima(c0 + 32, vb);
+            }
         }
         // five distinct columns >= L0: the fifth largest of the eight group maxima
         float L0;
@@ -599,10 +620,7 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
         __syncthreads();                                  // every warp is past the barrier wait: the X tile is dead, its space takes the lists
         int n = 0;
         float worst = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < ND; c0 += 32) {
-            float v[32];
-            tmem_ld32(trow + c0, v);
+        auto collect = [&](int c0, const float (&v)[32]) {
             unsigned hit = 0u;                           // branch-free: one compare and one predicated OR per column
 #pragma unroll
             for (int i = 0; i < 32; ++i) hit |= v[i] >= thr ? (1u << i) : 0u;
@@ -626,6 +644,19 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
                     }
                     worst = fmaxf(worst, fabsf(v[i] - d) / ee);
                 }
+            }
+        };
+        {
+            float va[32], vb[32];
+            tmem_ld32_issue(trow, va);
+#pragma unroll 1
+            for (int c0 = 0; c0 < ND; c0 += 64) {
+                tmem_wait_ld_dep(va);
+                tmem_ld32_issue(trow + c0 + 32, vb);
+                collect(c0, va);
+                tmem_wait_ld_dep(vb);
+                if (c0 + 64 < ND) tmem_ld32_issue(trow + c0 + 64, va);
+                collect(c0 + 32, vb);
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
