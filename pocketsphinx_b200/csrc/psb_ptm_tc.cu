@@ -507,6 +507,14 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
     const float *m = cen + (size_t)k * 16, *bb = bnd + (size_t)k * 32;
     const float *rc = rec + rec_off[k];
 
+    // the next tile's feature row is fetched while this tile's GEMM runs
+    float xn[FL];
+    {
+        const long long r0 = (long long)blockIdx.y * tiles_per_cta * TC_ROWS + tid;
+        const float *p = feats + (r0 < total ? r0 : 0) * D + featoff[f];
+#pragma unroll
+        for (int j = 0; j < FL; ++j) xn[j] = r0 < total ? p[j] : 0.f;
+    }
     for (int tile = 0; tile < tiles_per_cta; ++tile) {
         const long long row = ((long long)blockIdx.y * tiles_per_cta + tile) * TC_ROWS + tid;
         if (row - tid >= total) break;                   // uniform: the whole tile lies past the end
@@ -514,12 +522,11 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
         // ---- this thread's frame: X row (TF32 halves, canonical layout) and its error bound ----
         float x[FL], ee;
         {
-            const float *p = feats + (valid ? row : 0) * D + featoff[f];
             float v[TC_K];
             float S = bb[2 * FL];
 #pragma unroll
             for (int j = 0; j < FL; ++j) {
-                x[j] = valid ? p[j] : 0.f;
+                x[j] = xn[j];
                 const float y = __fsub_rn(x[j], m[j]);
                 const float y2 = __fmul_rn(y, y);
                 v[j] = y2;
@@ -557,6 +564,12 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                              (unsigned)__cvta_generic_to_shared(&mma_done))
                          : "memory");
+        }
+        if (tile + 1 < tiles_per_cta) {
+            const long long rn = row + TC_ROWS;
+            const float *p = feats + (rn < total ? rn : 0) * D + featoff[f];
+#pragma unroll
+            for (int j = 0; j < FL; ++j) xn[j] = rn < total ? p[j] : 0.f;
         }
         mbar_wait_parity(&mma_done, (unsigned)tile & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
