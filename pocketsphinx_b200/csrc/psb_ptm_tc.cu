@@ -156,13 +156,13 @@ ptm_tc_kernel(const float *__restrict__ feats, long long total, int D, const int
             const float y2 = __fmul_rn(y, y);
             xr[j] = y2;
             xr[FL + j] = y;
-            S = __fmaf_ru(bb[j], y2, S);
-            S = __fmaf_ru(bb[FL + j], fabsf(y), S);
+            S = __fadd_ru(S, __fmul_ru(bb[j], y2));
+            S = __fadd_ru(S, __fmul_ru(bb[FL + j], fabsf(y)));
         }
         xr[2 * FL] = 1.0f;
 #pragma unroll
         for (int j = 2 * FL + 1; j < TC_K; ++j) xr[j] = 0.f;
-        epsr[tid] = __fmaf_ru(S, TC_ERR, 2.0f);
+        epsr[tid] = __fadd_ru(__fmul_ru(S, TC_ERR), 2.0f);
         cnt[tid] = 0;
 #pragma unroll
         for (int w = 0; w < 8; ++w) masks[tid * 8 + w] = 0u;
@@ -271,7 +271,7 @@ ptm_tc_kernel(const float *__restrict__ feats, long long total, int D, const int
                             const float df = __fsub_rn(px[j], r[1 + 2 * j]);
                             d = __fsub_rn(d, __fmul_rn(__fmul_rn(df, df), r[2 + 2 * j]));
                         }
-                        worst = fmaxf(worst, fabsf(acc[i][q] - d) / epsr[rr]);
+                        worst = fmaxf(worst, __fdividef(fabsf(acc[i][q] - d), epsr[rr]));
                     }
             }
         }
@@ -531,13 +531,13 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
                 const float y2 = __fmul_rn(y, y);
                 v[j] = y2;
                 v[FL + j] = y;
-                S = __fmaf_ru(bb[j], y2, S);
-                S = __fmaf_ru(bb[FL + j], fabsf(y), S);
+                S = __fadd_ru(S, __fmul_ru(bb[j], y2));               // no FMA anywhere in these kernels: tests/test_abi.py greps for it
+                S = __fadd_ru(S, __fmul_ru(bb[FL + j], fabsf(y)));
             }
             v[2 * FL] = 1.0f;
 #pragma unroll
             for (int j = 2 * FL + 1; j < TC_K; ++j) v[j] = 0.f;
-            ee = __fmaf_ru(S, TC_ERR, 2.0f);
+            ee = __fadd_ru(__fmul_ru(S, TC_ERR), 2.0f);
 #pragma unroll
             for (int kc = 0; kc < 8; ++kc) {
                 float4 h, l;
@@ -655,7 +655,7 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
                         const float df = __fsub_rn(x[j], r[1 + 2 * j]);
                         d = __fsub_rn(d, __fmul_rn(__fmul_rn(df, df), r[2 + 2 * j]));
                     }
-                    worst = fmaxf(worst, fabsf(v[i] - d) / ee);
+                    worst = fmaxf(worst, __fdividef(fabsf(v[i] - d), ee));
                 }
             }
         };
