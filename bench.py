@@ -99,17 +99,22 @@ def reference_model_dir(name, pm, raw):
     if name == "en-us":
         d = os.path.join(ROOT, "oracle", "_ref", "model", "en-us")
         return d if os.path.isdir(d) else None
-    if pm.kind != "ptm":
-        return None                      # CPU baseline through the C port for the secondary shapes
     if _REF_DIR is None:
         import tempfile
         from pocketsphinx_b200 import s3io
         _REF_DIR = tempfile.mkdtemp(prefix="psb200_model_")
+        if pm.kind == "ptm":
+            sen2ci, n_ci = pm.sen2cb, pm.n_mgau
+            fp = "-feat 1s_c_d_dd\n-svspec 0-12/13-25/26-38\n-cmn batch\n-agc none\n"
+        else:                            # semi-continuous / continuous: 42 CI phones x 3 states, the rest tied round-robin
+            sen2ci = np.concatenate([np.repeat(np.arange(42), 3), np.arange(pm.n_sen - 126) % 42]).astype(np.int32)
+            n_ci = 42
+            fp = "-feat s2_4x\n-cmn batch\n-agc none\n" if pm.kind == "s2_semi" else "-feat 1s_c_d_dd\n-cmn batch\n-agc none\n"
         s3io.write_model_dir(_REF_DIR, kind=pm.kind, n_mgau=pm.n_mgau, n_feat=pm.n_feat, n_density=pm.n_density,
                              featlen=pm.featlen, mean=raw["mean"], var_raw=raw["var_raw"], tp_float=raw["tp_float"],
-                             sen2ci=pm.sen2cb, n_ci=pm.n_mgau, n_emit=pm.n_emit_state, n_ci_sen=pm.n_ci_sen,
-                             mixw_q=raw["mixw_q"],
-                             feat_params="-feat 1s_c_d_dd\n-svspec 0-12/13-25/26-38\n-cmn batch\n-agc none\n")
+                             sen2ci=sen2ci, n_ci=n_ci, n_emit=3, n_ci_sen=n_ci * 3,
+                             mixw_q=raw.get("mixw_q"), mixw_cb=raw.get("mixw_cb"), mixw_float=raw.get("mixw_float"),
+                             feat_params=fp)
     return _REF_DIR
 
 
@@ -422,7 +427,8 @@ def cpu_baseline(args, pm, raw, feats, n_frames_per_utt, budget_s=15.0, threads=
         if kind == "port":
             return om.score_utt
         if not hasattr(local, "ref"):
-            local.ref = refdrv.RefModel(ref_dir)
+            kv = {"senmgau": ".cont.", "topn": str(pm.topn)} if pm.kind == "ms" else {}
+            local.ref = refdrv.RefModel(ref_dir, **kv)
         return local.ref.score
 
     # calibrate on one short slice, then size the sample to the budget
