@@ -268,6 +268,8 @@ extern "C" int psb_model_create(const psb_model_desc_t *d, int device, psb_model
             uint8_t t[256];
             if (cudaMemcpy(t, m->d_logadd8, 256, cudaMemcpyDeviceToHost) == cudaSuccess)
                 for (int i = 0; i < 256; ++i) m->logadd8_max = std::max<int>(m->logadd8_max, t[i]);
+                m->logadd8_zero_from = 256;
+                while (m->logadd8_zero_from > 0 && t[m->logadd8_zero_from - 1] == 0) --m->logadd8_zero_from;
         }
     }
     if (!rc && m->kind != PSB_KIND_MS && !d->logadd8) {

@@ -80,6 +80,7 @@ struct psb_model_s {
     int32_t *d_bsen;              // senones of the non-uniform quads
     int n_bsen;
     int logadd8_max;              // largest entry of the 8-bit add table (bias bound of the 16x2 senone kernel)
+    int logadd8_zero_from;        // smallest i with table[j] == 0 for all j >= i (<= 31: the two-index table of the senone kernel applies)
     uint8_t *d_logadd8;           // [PSB_LOGADD8_N]: the 256-entry table continued with zeros
     uint32_t *d_logadd_ms;
     float *d_msT, *d_msdetT;      // ms back-end: codebook-minor Gaussians (see psb_ms.cu)

@@ -1167,6 +1167,10 @@ semi_senone_kernel(const int4 *__restrict__ topn, const uint8_t *__restrict__ mi
 // owns senones 4q..4q+3 fetches each weight row with ONE aligned 32-bit load (four senones'
 // bytes) and reads the codebook's offsets/scores once; quads that straddle a codebook boundary
 // (a few per cent) take the per-senone path.
+// TAB2: the add table is zero from entry 31 on (every logbase-1.0001 >> 10 table is), so the two look-ups of a packed
+// log-add -- tab[d_lo] and tab[d_hi] -- become ONE 32-bit read of a 32 x 32 table of ready-made halfword pairs indexed
+// by the two differences clamped to 31: half the shared-memory instructions of the loop (its limit: LSU data pipe 84 %).
+template <bool TAB2>
 __global__ void __launch_bounds__(512)
 ptm_senone4_kernel(const int4 *__restrict__ topn, const uint8_t *__restrict__ mixw,
                    const uint16_t *__restrict__ sen2cb, const int16_t *__restrict__ quadcb,
@@ -1183,10 +1187,13 @@ ptm_senone4_kernel(const int4 *__restrict__ topn, const uint8_t *__restrict__ mi
     int *red = norm + 8;                                            // [32]
     uint8_t *tab = reinterpret_cast<uint8_t *>(red + 32);           // [PSB_LOGADD8_N]
     int16_t *asc = reinterpret_cast<int16_t *>(tab + PSB_LOGADD8_N + 16);     // [n_sen rounded up to 4]
+    unsigned *tab2 = reinterpret_cast<unsigned *>(asc + ((n_sen + 7) & ~7));  // [32 * 32] (TAB2 only)
     const long long frame = blockIdx.x;
     const int tid = threadIdx.x;
 
     for (int i = tid; i < PSB_LOGADD8_N; i += blockDim.x) tab[i] = logadd_tab[i];
+    if (TAB2)
+        for (int i = tid; i < 1024; i += blockDim.x) tab2[i] = (unsigned)logadd_tab[i & 31] | ((unsigned)logadd_tab[i >> 5] << 16);
     if (tid < n_feat) norm[tid] = PSB_WORST_SCORE;
     __syncthreads();
     int4 r = make_int4(0, 0, 0, 0);
@@ -1238,7 +1245,13 @@ ptm_senone4_kernel(const int4 *__restrict__ topn, const uint8_t *__restrict__ mi
                 const unsigned mn = __viaddmin_u16x2(y, nvj, x);                                \
                 const unsigned mx = __viaddmax_u16x2(y, nvj, x);                                \
                 const unsigned d = mx - mn;                                                     \
-                const unsigned t = (unsigned)tab[d & 0xffffu] | ((unsigned)tab[d >> 16] << 16); \
+                unsigned t;                                                                     \
+                if (TAB2) {                                                                     \
+                    const unsigned dc = __vminu2(d, 0x001f001fu);                               \
+                    t = tab2[(dc & 0x1fu) | (dc >> 11)];                                        \
+                }                                                                               \
+                else                                                                            \
+                    t = (unsigned)tab[d & 0xffffu] | ((unsigned)tab[d >> 16] << 16);            \
                 x = mn - t;                                                                     \
             }
             PSB_LADD2(x01, w1, 0x4140, nv.y) PSB_LADD2(x23, w1, 0x4342, nv.y)
@@ -1680,8 +1693,21 @@ int psb_launch_ptm_batch(psb_batch_t *b, const float *d_feats, const int32_t *ut
             // at least 256 threads (log-add table staging) and one thread per (codebook, stream) pair
             const int threads = std::min(512, std::max(std::max(256, roundup(K, 32)), roundup((n_quads + iters - 1) / iters, 32)));
             const size_t smem4 = smem + 8 + (size_t)K * 16;
-            PSB_CUDA(cudaFuncSetAttribute(ptm_senone4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
-            ptm_senone4_kernel<<<(unsigned)total, threads, smem4, b->stream>>>(
+            // experiment, off by default: measured 30.8 ms vs 18.9 ms per 998 k frames -- the 4 KB two-index table trades two
+            // mostly-broadcast byte reads for one read that bank-conflicts across 1024 words (bit-identical either way)
+            static const bool use_tab2 = getenv("PSB_SENONE_TAB2") && atoi(getenv("PSB_SENONE_TAB2")) == 1;
+            if (m->logadd8_zero_from <= 31 && use_tab2) {
+                const size_t smem5 = smem4 + 16 + 4096;
+                PSB_CUDA(cudaFuncSetAttribute(ptm_senone4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+                ptm_senone4_kernel<true><<<(unsigned)total, threads, smem5, b->stream>>>(
+                    b->d_topn, m->d_mixw, m->d_sen2cb, m->d_quadcb, m->d_bsen, m->n_bsen, m->d_logadd8, d_senscr, m->n_sen,
+                    m->n_feat, m->n_density, K, m->mixw_stride);
+                PSB_LAUNCH_CHECK();
+                if (b->have_ev) PSB_CUDA(cudaEventRecord(b->ev[3], b->stream));
+                return PSB_OK;
+            }
+            PSB_CUDA(cudaFuncSetAttribute(ptm_senone4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+            ptm_senone4_kernel<false><<<(unsigned)total, threads, smem4, b->stream>>>(
                 b->d_topn, m->d_mixw, m->d_sen2cb, m->d_quadcb, m->d_bsen, m->n_bsen, m->d_logadd8, d_senscr, m->n_sen,
                 m->n_feat, m->n_density, K, m->mixw_stride);
         }
