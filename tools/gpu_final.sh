@@ -19,4 +19,6 @@ done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 2 --warmup 1 > gpurun_out/r02_bench_under_ncu.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:hmmset_sweep_kernel -c 1 -o gpurun_out/r02_sweep_kernel python bench.py --steps 1 --warmup 0 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:ptm_tc5_kernel -c 1 -o gpurun_out/r02_tc5_kernel_1000 python tools/prof_tc.py 1000 10 1 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:hmmset_eval_kernel -c 1 -s 20 -o gpurun_out/r02_hmmset_eval_1000 python bench.py --steps 1 --warmup 0 > /dev/null 2>&1
+ncu --set full --clock-control none -k regex:ptm_senone4_kernel -c 1 -o gpurun_out/r02_senone4_1000 python tools/prof_tc.py 1000 10 1 > /dev/null 2>&1
 ls -la gpurun_out/*.ncu-rep | tail -5
