@@ -1137,26 +1137,31 @@ extern "C" int psb_hmmset_sweep_device(psb_hmmset_t *s, const int16_t *d_senscr,
         if (ms) PSB_CUDA(cudaStreamSynchronize(s->stream));
         return PSB_OK;
     }
-    constexpr int THREADS = 256, V = 4;
+    // CTA shape: threads x instances per thread (PSB_SWEEP_SHAPE = 0: 256 x 4 (default), 1: 256 x 2, 2: 128 x 4, 3: 512 x 2)
+    static const int shape = [] { const char *v = getenv("PSB_SWEEP_SHAPE"); return v ? atoi(v) : 0; }();
     const int buf_bytes = (int)(((size_t)cd.n_sen * 2 + 32 + 127) & ~(size_t)127);
     const int tp_bytes = s->c->n_tmat * cd.n_emit * (cd.n_emit + 1);
     const size_t smem = 2 * (size_t)buf_bytes + tp_bytes;
     PSB_REQUIRE(smem <= 200 * 1024, "psb_hmmset_sweep: %d senones / %d transition matrices do not fit shared memory", cd.n_sen, s->c->n_tmat);
-    const dim3 grid((unsigned)((s->max_seg_len + THREADS * V - 1) / (THREADS * V)), (unsigned)s->n_seg);
     const HmmSetDev sd = dev_set(s);
     PSB_CUDA(cudaEventRecord(s->ev[0], s->stream));
+#define PSB_SWEEP(NS, V, THREADS)                                                                                               \
+    do {                                                                                                                       \
+        auto kern = hmmset_sweep_kernel<NS, V, THREADS>;                                                                       \
+        PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                          \
+        const dim3 grid((unsigned)((s->max_seg_len + THREADS * V - 1) / (THREADS * V)), (unsigned)s->n_seg);                   \
+        kern<<<grid, THREADS, smem, s->stream>>>(sd, cd, d_senscr, (long long)rows_total, d_row0, d_n_rows, n_frames, d_best,  \
+                                                s->c->n_tmat, buf_bytes);                                                      \
+    } while (0)
     if (cd.n_emit == 3) {
-        auto kern = hmmset_sweep_kernel<3, V, THREADS>;
-        PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, THREADS, smem, s->stream>>>(sd, cd, d_senscr, (long long)rows_total, d_row0, d_n_rows, n_frames, d_best,
-                                                s->c->n_tmat, buf_bytes);
+        if (shape == 1) PSB_SWEEP(3, 2, 256);
+        else if (shape == 2) PSB_SWEEP(3, 4, 128);
+        else if (shape == 3) PSB_SWEEP(3, 2, 512);
+        else PSB_SWEEP(3, 4, 256);
     }
-    else {
-        auto kern = hmmset_sweep_kernel<5, V, THREADS>;
-        PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, THREADS, smem, s->stream>>>(sd, cd, d_senscr, (long long)rows_total, d_row0, d_n_rows, n_frames, d_best,
-                                                s->c->n_tmat, buf_bytes);
-    }
+    else
+        PSB_SWEEP(5, 4, 256);
+#undef PSB_SWEEP
     PSB_LAUNCH_CHECK();
     PSB_CUDA(cudaEventRecord(s->ev[1], s->stream));
     if (ms) {                                               // ms == NULL: asynchronous on the set's stream
