@@ -616,6 +616,38 @@ __device__ __forceinline__ void setc(int4 &v, int q, int x)
     if (q == 0) v.x = x; else if (q == 1) v.y = x; else if (q == 2) v.z = x; else v.w = x;
 }
 
+// mbarrier + TMA bulk copy (global -> shared, completion counted in bytes on the barrier): used by both set kernels
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(dst)),
+                 "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
 // One hmm_vit_eval per instance, four instances per thread, one CTA row (blockIdx.y) per
 // segment.  row0[seg] + t is the segment's senone-score row of this frame (staged in shared
 // memory: the gathers of a tile hit ~3 x HS_TILE random int16 of it); segments with
@@ -625,7 +657,7 @@ __global__ void __launch_bounds__(HS_THREADS, (NS == 3 ? 3 : 2) * (256 / HS_THRE
 hmmset_eval_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr, const int64_t *__restrict__ row0,
                    const int32_t *__restrict__ n_rows, int t, int32_t *__restrict__ best_out)
 {
-    extern __shared__ int16_t srow[];         // [n_sen]
+    extern __shared__ __align__(16) int16_t srow[];         // [n_sen] + 16 bytes
     __shared__ int red[HS_THREADS / 32];
     const int seg = blockIdx.y;
     if (n_rows && t >= n_rows[seg]) return;
@@ -658,18 +690,35 @@ hmmset_eval_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr,
         tm = __ldcs(reinterpret_cast<const uint2 *>(ids + HS_TS));
         mp = __ldcs(reinterpret_cast<const uchar4 *>(s.mpx + i));
     }
+    // The segment's score row: its 16-byte aligned interior by ONE TMA bulk copy (issued by thread 0, completion on an
+    // mbarrier, in flight together with the state loads above), the few bytes before and after it by plain loads -- nothing
+    // outside the row is touched.  In shared memory the row keeps its alignment within 16 bytes.
+    __shared__ __align__(8) uint64_t row_bar;
+    const int16_t *srow_al;
     {
         const int16_t *row = senscr + (row0 ? row0[seg] + t : (int64_t)t * gridDim.y + seg) * c.n_sen;
-        if ((((uintptr_t)row) & 3) == 0) {
-            const int *r32 = reinterpret_cast<const int *>(row);
-            int *s32 = reinterpret_cast<int *>(srow);
-            for (int q = threadIdx.x; q < (c.n_sen >> 1); q += HS_THREADS) s32[q] = r32[q];
-            if ((c.n_sen & 1) && threadIdx.x == 0) srow[c.n_sen - 1] = row[c.n_sen - 1];
+        const uintptr_t a = reinterpret_cast<uintptr_t>(row);
+        const unsigned mis = (unsigned)(a & 15), nbytes = (unsigned)c.n_sen * 2;
+        unsigned head = (16 - mis) & 15;
+        if (head > nbytes) head = nbytes;
+        const unsigned body = (nbytes - head) & ~15u, tail = nbytes - head - body;
+        unsigned char *dst = reinterpret_cast<unsigned char *>(srow) + mis;           // srow is 16-byte aligned
+        if (threadIdx.x == 0) {
+            mbar_init(&row_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            if (body) {
+                mbar_expect_tx(&row_bar, body);
+                tma_bulk_g2s(dst + head, reinterpret_cast<const unsigned char *>(row) + head, body, &row_bar);
+            }
         }
-        else
-            for (int q = threadIdx.x; q < c.n_sen; q += HS_THREADS) srow[q] = row[q];
+        const unsigned hn = head >> 1, tn = tail >> 1;                                  // int16 elements (rows are 2-byte aligned)
+        if (threadIdx.x < hn) reinterpret_cast<int16_t *>(dst)[threadIdx.x] = row[threadIdx.x];
+        if (threadIdx.x >= 32 && threadIdx.x < 32 + tn)
+            reinterpret_cast<int16_t *>(dst + head + body)[threadIdx.x - 32] = row[((head + body) >> 1) + threadIdx.x - 32];
+        srow_al = reinterpret_cast<const int16_t *>(dst);
+        __syncthreads();                                                                // barrier initialised, head / tail written
+        if (body) mbar_wait(&row_bar, 0u);
     }
-    __syncthreads();
     int best = PSB_WORST_SCORE;
     if (live) {
         bool any_mpx = false;
@@ -690,7 +739,7 @@ hmmset_eval_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr,
             const unsigned tw = (q < 2) ? tm.x : tm.y;
             const int tmatid = (int16_t)((q & 1) ? (tw >> 16) : (tw & 0xffffu));
             const bool mpx = (q == 0 ? mp.x : q == 1 ? mp.y : q == 2 ? mp.z : mp.w) != 0;
-            const int b = hmm_step(h, c, tmatid, mpx, srow);
+            const int b = hmm_step(h, c, tmatid, mpx, srow_al);
             if (j0 + q < n) best = max(best, b);
 #pragma unroll
             for (int k = 0; k < NL; ++k)
@@ -744,37 +793,6 @@ hmmset_eval_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr,
 // that nothing past the allocation is touched.  Per frame one block-wide max (REDUX + one
 // shared-memory hop) and one atomicMax per CTA into best[t][segment].  Results are bit-identical
 // to n_frames calls of hmmset_eval_kernel (tests/test_gpu_parity.py).
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(dst)),
-                 "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
-                 : "memory");
-}
-
 template <int NS, int V, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 hmmset_sweep_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr, long long rows_total,
@@ -1089,7 +1107,7 @@ extern "C" int psb_hmmset_eval_frames_device(psb_hmmset_t *s, const int16_t *d_s
     const dim3 grid((unsigned)((s->max_seg_len + tile - 1) / tile), (unsigned)s->n_seg);
     const HmmSetDev sd = dev_set(s);
     const HmmCtxDev cd = dev_ctx(s->c);
-    const size_t smem = ((size_t)cd.n_sen * 2 + 15) & ~(size_t)15;
+    const size_t smem = (((size_t)cd.n_sen * 2 + 15) & ~(size_t)15) + 16;      // the row keeps its alignment within 16 bytes
     PSB_REQUIRE(smem <= 200 * 1024, "psb_hmmset: %d senones do not fit the shared-memory score row", cd.n_sen);
     auto launch = [&](auto kern, int t, int32_t *best) {
         kern<<<grid, threads, smem, s->stream>>>(sd, cd, d_senscr, d_row0, d_n_rows, t, best);
