@@ -417,18 +417,20 @@ print(json.dumps(out))
 """
 
 
-def test_tensor_core_filter_error_bound_holds_on_the_device():
-    """PSB_TC_CHECK=1: the filter kernel compares every TF32 GEMM value it produced with the exact float
+@pytest.mark.parametrize("impl", ["tcgen05", "mma"])
+def test_tensor_core_filter_error_bound_holds_on_the_device(impl):
+    """PSB_TC_CHECK=1: the filter kernel compares every 3 x TF32 GEMM value it produced with the exact float
     distance and reports the worst |a - d| / eps (the bound the candidate selection relies on must hold
     with room to spare: the analysis in psb_ptm_tc.cu allows 0.8 of eps), on the shipped model with real
-    features, the BASELINE shape, features scaled far outside the model's range and tie-stress data."""
+    features, the BASELINE shape, features scaled far outside the model's range and tie-stress data; for the
+    tcgen05 / tensor-memory kernel (the default) and for the legacy mma.sync variant (PSB_TC_IMPL=mma)."""
     import json
     import os
     import subprocess
     import sys
     from conftest import GOLDEN, ROOT
     code = TC_CHECK % (ROOT, os.path.join(ROOT, "tests"), os.path.join(GOLDEN, "en_us_ptm_model.npz"))
-    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PSB_TC_CHECK="1", PSB_TOPN_VARIANT="6"),
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PSB_TC_CHECK="1", PSB_TOPN_VARIANT="6", PSB_TC_IMPL=impl),
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
