@@ -581,9 +581,11 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
         for (int i = 0; i < 8; ++i) gm[i] = -INFINITY;
         auto maxima = [&](int c0, const float (&v)[32]) {
             if (GW >= 32) {
-                float mx = v[0];
+                // a tree, not a chain: with two warps per scheduler the dependent-issue latency is what counts
+                float m8[8];
 #pragma unroll
-                for (int i = 1; i < 32; ++i) mx = fmaxf(mx, v[i]);
+                for (int i = 0; i < 8; ++i) m8[i] = fmaxf(fmaxf(v[i], v[i + 8]), fmaxf(v[i + 16], v[i + 24]));
+                const float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
                 const int gi = c0 / GW;
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
@@ -634,9 +636,10 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
         int n = 0;
         float worst = 0.f;
         auto collect = [&](int c0, const float (&v)[32]) {
-            unsigned hit = 0u;                           // branch-free: one compare and one predicated OR per column
+            unsigned h4[4] = {0u, 0u, 0u, 0u};            // branch-free: one compare and one predicated OR per column, four chains
 #pragma unroll
-            for (int i = 0; i < 32; ++i) hit |= v[i] >= thr ? (1u << i) : 0u;
+            for (int i = 0; i < 32; ++i) h4[i & 3] |= v[i] >= thr ? (1u << i) : 0u;
+            unsigned hit = (h4[0] | h4[1]) | (h4[2] | h4[3]);
             if (__any_sync(0xffffffffu, hit != 0u)) {    // registers cannot be indexed by a run-time column: through shared memory
 #pragma unroll
                 for (int i = 0; i < 32; ++i) stage[i * TC_ROWS + tid] = v[i];
