@@ -617,6 +617,9 @@ def test_full_size_properties(api, monkeypatch):
     best6, pen6, rows6, _, _ = run(6, 1)
     assert np.array_equal(rows5, rows6)
     assert np.array_equal(best5, best6) and np.array_equal(pen5, pen6)
+    best6p, pen6p, rows6p, _, _ = run(6, 3)                 # ... and with three sub-batches of it in flight on their own streams
+    assert np.array_equal(rows5, rows6p)
+    assert np.array_equal(best5, best6p) and np.array_equal(pen5, pen6p)
     # utterance order does not matter: reversed batch gives the reversed result
     monkeypatch.setenv("PSB_TOPN_VARIANT", "5")
     b = api.Batch(m, U, U * T)
