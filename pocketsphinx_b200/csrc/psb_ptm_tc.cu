@@ -632,7 +632,8 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
         }
         // L' = floor(L0 - eps) - 1, candidates: a_c >= L' - eps; every step rounded towards -inf
         const float thr = __fsub_rd(__fsub_rd(floorf(__fsub_rd(L0, ee)), 1.0f), ee);
-        __syncthreads();                                  // every warp is past the barrier wait: the X tile is dead, its space takes the lists
+        // no block barrier here: any thread that saw the mbarrier flip knows the GEMM is complete, so the X tile is dead for
+        // everybody; lists and staging slab are thread-private
         int n = 0;
         float worst = 0.f;
         auto collect = [&](int c0, const float (&v)[32]) {
