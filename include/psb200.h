@@ -218,6 +218,21 @@ int psb_hmmset_eval_frames_device(psb_hmmset_t *s, const int16_t *d_senscr, cons
 int psb_hmmset_sweep_device(psb_hmmset_t *s, const int16_t *d_senscr, int64_t rows_total,
                             const int64_t *d_row0, const int32_t *d_n_rows, int32_t n_frames,
                             int32_t *d_best, float *ms);
+/* The fused sweep WITH beam pruning between frames -- evaluate_channels (ngram_search_fwdtree.c:702-715) followed by
+ * the beam part of prune_channels (:1130-1181: best score, the -maxhmmpf histogram that narrows the beam) and the
+ * keep-or-clear decision of prune_nonroot_chan (:811, :823-827, :872-874), without the lexicon tree's transitions: an instance is
+ * active in frame frame0 + t iff its frame field equals frame0 + t; active instances take one hmm_vit_eval step; with
+ * best = the segment's maximum and n = the number evaluated, dynamic beam = beam, or, when maxhmmpf >= 0 and
+ * n > maxhmmpf, -(i * bw) with bw = -beam / 256 and i the first of 256 bins of (best - bestscore) / bw (clipped to 255)
+ * at which the running count exceeds maxhmmpf; instances with bestscore > best + dynamic beam move to frame
+ * frame0 + t + 1, the others are hmm_clear'ed (hmm.c:181-196: WORST_SCORE, history -1, frame -1) and stay out.
+ * d_best[t * n_seg + s] as above; d_n_active[t * n_seg + s] (may be NULL) = instances evaluated.  One thread-block
+ * cluster per segment exchanges maxima, counts and histograms through distributed shared memory: a segment may hold
+ * at most 16 x 1024 instances; plain (not multiplexed) 3- or 5-state instances, even senone count. */
+int psb_hmmset_sweep_beam_device(psb_hmmset_t *s, const int16_t *d_senscr, int64_t rows_total,
+                                 const int64_t *d_row0, const int32_t *d_n_rows, int32_t n_frames,
+                                 int32_t frame0, int32_t beam, int32_t maxhmmpf, int32_t *d_best,
+                                 int32_t *d_n_active, float *ms);
 /* With ms == NULL psb_hmmset_sweep_device is asynchronous on the set's stream.
  * psb_hmmset_use_batch_stream: run the set's kernels on batch b's stream, i.e. behind the kernels
  * that write the scores it reads (b == NULL: back to the set's own stream).

@@ -208,6 +208,66 @@ class OracleHmmCtx:
         return np.array([self.vit_eval(hmms, senscr[t]) for t in range(len(senscr))], np.int32)
 
 
+WORST_SCORE = -0x20000000
+
+
+def hmm_clear(hmms, i):
+    """hmm_clear (hmm.c:181-196) on record i of an HMM_DTYPE array."""
+    n = int(hmms["n_emit_state"][i])
+    hmms["score"][i, :n] = WORST_SCORE
+    hmms["history"][i, :n] = -1
+    hmms["out_score"][i] = WORST_SCORE
+    hmms["out_history"][i] = -1
+    hmms["bestscore"][i] = WORST_SCORE
+    hmms["frame"][i] = -1
+
+
+def sweep_beam(ctx, hmms, senscr, frame0, beam, maxhmmpf=-1, clear=hmm_clear):
+    """T frames of "evaluate the active instances, then prune to the beam" over a flat set of hmm_t
+    (updated in place): evaluate_channels (ngram_search_fwdtree.c:702-715) and, of prune_channels
+    (:1130-1181), the best score, the -maxhmmpf histogram (256 bins of width -beam / 256, walked until
+    the running count exceeds maxhmmpf) and prune_nonroot_chan's decision (:811, :823-827, :872-874):
+    bestscore BETTER_THAN best + dynamic beam -> frame = f + 1, else hmm_clear.  No transitions: an
+    instance that leaves never returns.  ctx.vit_eval(records, row) is hmm_vit_eval over an array
+    (OracleHmmCtx or the compiled reference's RefHmmCtx); clear(hmms, i) is hmm_clear.
+    Returns (best int32 [T], n_evaluated int32 [T])."""
+    senscr = np.ascontiguousarray(senscr, np.int16)
+    T = len(senscr)
+    best_out = np.full(T, WORST_SCORE, np.int32)
+    n_out = np.zeros(T, np.int32)
+    for t in range(T):
+        f = frame0 + t
+        idx = np.flatnonzero(hmms["frame"] == f)
+        n_out[t] = len(idx)
+        if len(idx) == 0:
+            continue
+        sub = np.ascontiguousarray(hmms[idx])
+        best = ctx.vit_eval(sub, senscr[t])
+        hmms[idx] = sub
+        best_out[t] = best
+        dyn = beam
+        if maxhmmpf != -1 and len(idx) > maxhmmpf:
+            bw = -beam // 256
+            bins = np.zeros(256, np.int64)
+            for i in idx:
+                b = (best - int(hmms["bestscore"][i])) // bw        # both operands >= 0: C's truncation = floor
+                bins[min(b, 255)] += 1
+            nh, i = 0, 0
+            while i < 256:
+                nh += bins[i]
+                if nh > maxhmmpf:
+                    break
+                i += 1
+            dyn = -(i * bw)
+        thresh = best + dyn
+        for i in idx:
+            if int(hmms["bestscore"][i]) > thresh:
+                hmms["frame"][i] = f + 1
+            else:
+                clear(hmms, i)
+    return best_out, n_out
+
+
 def phoneloop_run(tp, sseq, ssid, tmatid, senscr, window, beam, pbeam, pip, penalty_weight):
     """phone_loop_search.c semantics over a [T][n_sen] senone score matrix."""
     tp = np.ascontiguousarray(tp, np.uint8)

@@ -88,6 +88,7 @@ SYMBOLS = [
     ("psb_hmmset_snapshot", C.c_int, [_VP]),
     ("psb_hmmset_restore", C.c_int, [_VP]),
     ("psb_hmmset_sweep_device", C.c_int, [_VP, _VP, _I64, _VP, _VP, _I32, _VP, C.POINTER(C.c_float)]),
+    ("psb_hmmset_sweep_beam_device", C.c_int, [_VP, _VP, _I64, _VP, _VP, _I32, _I32, _I32, _I32, _VP, _VP, C.POINTER(C.c_float)]),
     ("psb_hmmset_eval_host", C.c_int, [_VP, _VP, _VP]),
     ("psb_allphone_batch_device", C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP, _I32, _VP]),
     ("psb_allphone_lm_batch_device", C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _I32, _VP]),

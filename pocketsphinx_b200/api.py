@@ -512,6 +512,19 @@ class HmmSet:
                                             C.c_void_p(d_best), C.byref(ms) if timed else None), "psb_hmmset_sweep_device")
         return ms.value if timed else None
 
+    def sweep_beam_device(self, d_senscr, rows_total, n_frames, frame0, beam, d_best, maxhmmpf=-1, d_n_active=None,
+                          d_row0=None, d_n_rows=None, timed=True):
+        """The fused sweep with beam pruning between frames (evaluate_channels + the beam part of prune_channels,
+        ngram_search_fwdtree.c:702-715, :1130-1181, without transitions): instances whose frame field equals
+        frame0 + t are evaluated in frame t, survivors of best + dynamic beam move on, the others are hmm_clear'ed.
+        Device pointers (ints); d_n_active [n_frames][n_seg] int32 receives the evaluated counts."""
+        ms = C.c_float()
+        check(lib().psb_hmmset_sweep_beam_device(self.h, C.c_void_p(d_senscr), int(rows_total), C.c_void_p(d_row0) if d_row0 else None,
+                                                 C.c_void_p(d_n_rows) if d_n_rows else None, int(n_frames), int(frame0), int(beam),
+                                                 int(maxhmmpf), C.c_void_p(d_best), C.c_void_p(d_n_active) if d_n_active else None,
+                                                 C.byref(ms) if timed else None), "psb_hmmset_sweep_beam_device")
+        return ms.value if timed else None
+
     def use_batch_stream(self, batch):
         check(lib().psb_hmmset_use_batch_stream(self.h, batch.h if batch is not None else None), "psb_hmmset_use_batch_stream")
 

@@ -793,30 +793,86 @@ hmmset_eval_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr,
 // that nothing past the allocation is touched.  Per frame one block-wide max (REDUX + one
 // shared-memory hop) and one atomicMax per CTA into best[t][segment].  Results are bit-identical
 // to n_frames calls of hmmset_eval_kernel (tests/test_gpu_parity.py).
-template <int NS, int V, int THREADS>
+//
+// BEAM: the same sweep with the beam pruning of prune_channels between frames (ngram_search_fwdtree.c:1130-1181 and the
+// keep-or-hmm_clear decision of prune_nonroot_chan, :811, :823-827, :872-874, without the lexicon-tree transitions): an instance is active
+// in frame f iff its frame field == f (as for the channels evaluate_channels walks); after frame f the segment's best
+// score and number of evaluated instances are known to every CTA of the segment, the -maxhmmpf histogram (256 bins of
+// (best - bestscore) / (-beam / 256), walked until more than maxhmmpf instances are covered) narrows the beam, survivors
+// (bestscore BETTER_THAN best + dynamic beam) move to frame f + 1 and the others are hmm_clear'ed (hmm.c:181-196) and
+// never evaluated again.  The CTAs of one segment form ONE thread-block cluster: every frame each CTA sends its
+// (maximum, count) into every peer's shared memory with st.async, whose completion is counted on the PEER's mbarrier
+// (8 bytes per peer; the peer waits on its own barrier: one distributed-shared-memory store latency per frame -- a
+// barrier.cluster per frame, ~380 cycles plus an L1 flush, measured 2.9x slower); only the rare histogram frames take
+// a barrier.cluster and read the peers' bins (ld.shared::cluster).  No global-memory round trip, no launch per frame.
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned mapa_shared(const void *p, unsigned rank)
+{
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"((unsigned)__cvta_generic_to_shared(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_u32(unsigned addr, unsigned v) { asm volatile("st.shared::cluster.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_cluster_u32(unsigned addr) { unsigned v; asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+// remote store that signals: 8 bytes into a peer's shared memory, completion counted on the PEER's mbarrier (the peer
+// waits on its own barrier -- one DSMEM store latency, no cluster-wide barrier, no L1 flush)
+__device__ __forceinline__ void st_async_v2(unsigned remote_addr, unsigned a, unsigned b, unsigned remote_bar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
+                 :: "r"(remote_addr), "r"(a), "r"(b), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int NS, int V, int THREADS, bool BEAM>
 __global__ void __launch_bounds__(THREADS)
 hmmset_sweep_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr, long long rows_total,
                     const int64_t *__restrict__ row0, const int32_t *__restrict__ n_rows, int n_frames,
-                    int32_t *__restrict__ best_out, int n_tmat, int buf_bytes)
+                    int32_t *__restrict__ best_out, int n_tmat, int buf_bytes, int frame0, int beam, int maxhmmpf,
+                    int32_t *__restrict__ n_active_out)
 {
-    extern __shared__ __align__(128) unsigned char sw_smem[];       // [2][buf_bytes] score rows, then the transition matrices
-    __shared__ __align__(8) uint64_t full[2];
+    static_assert(!BEAM || THREADS == 256, "the histogram walk maps one bin to one thread");
+    // score rows in flight: two for the plain sweep (its frame is longer than half a bulk copy's latency), six under the
+    // beam, where a CTA whose instances have mostly left would otherwise wait for every row (measured: 30 -> see DESIGN 4.19)
+    constexpr int NBUF = BEAM ? 6 : 2;
+    extern __shared__ __align__(128) unsigned char sw_smem[];       // [NBUF][buf_bytes] score rows, then the transition matrices
+    __shared__ __align__(8) uint64_t full[NBUF];
     __shared__ int red[2][THREADS / 32];
+    __shared__ int redc[BEAM ? 2 : 1][THREADS / 32];
+    __shared__ __align__(8) int2 cl_slot[BEAM ? 2 : 1][16];                 // [parity][rank in the cluster] {maximum, count}, written by the peers
+    __shared__ __align__(8) uint64_t xbar[2];                               // ... whose arrival these count
+    __shared__ unsigned hist[BEAM ? 2 : 1][BEAM ? 256 : 1];
+    __shared__ unsigned scan_w[8];
+    __shared__ int found;
     const int seg = blockIdx.y, tid = threadIdx.x;
     const int64_t n = s.seg_off[seg + 1] - s.seg_off[seg];
     const int64_t j_base = (int64_t)blockIdx.x * THREADS * V;
-    if (j_base >= n) return;
+    const bool cta_empty = j_base >= n;                   // BEAM: stays for the cluster's barriers
+    if (!BEAM && cta_empty) return;
     int T = n_frames;
     if (n_rows) T = min(T, n_rows[seg]);
-    if (T <= 0) return;
-    uint8_t *tps = sw_smem + 2 * (size_t)buf_bytes;
+    if (T <= 0) return;                                   // uniform over the segment's CTAs
+    const unsigned my_rank = BEAM ? cluster_ctarank() : 0u, n_rank = BEAM ? cluster_nctarank() : 1u;
+    if (BEAM) {
+        hist[0][tid] = 0u;
+        hist[1][tid] = 0u;
+        if (tid == 0) {
+            mbar_init(&xbar[0], 1);
+            mbar_init(&xbar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    uint8_t *tps = sw_smem + NBUF * (size_t)buf_bytes;
     for (int q = tid; q < n_tmat * NS * (NS + 1); q += THREADS) tps[q] = c.tp[q];
 
     // this thread's V instances (THREADS apart: neighbouring threads read neighbouring words)
     int sc[V][NS], hi[V][NS], sid[V][NS], osc[V], ohi[V], tmo[V];
     unsigned tpk[V][3];                                   // 3-state: the instance's 12 transition bytes in registers
     int32_t *p32[V];
-    bool live[V];
+    bool live[V], act[V], touched[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
         const int64_t j = j_base + (int64_t)v * THREADS + tid;
@@ -835,6 +891,8 @@ hmmset_sweep_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr
         osc[v] = live[v] ? p32[v][2 * NS * HS_TS] : PSB_WORST_SCORE;
         ohi[v] = live[v] ? p32[v][(2 * NS + 1) * HS_TS] : -1;
         tmo[v] = live[v] ? (int)(int16_t)p16[(NS + 1) * HS_TS] * NS * (NS + 1) : 0;
+        act[v] = BEAM ? (live[v] && p32[v][(2 * NS + 3) * HS_TS] == frame0) : live[v];
+        touched[v] = act[v];
     }
     __syncthreads();                                      // the transition matrices are staged
     if (NS == 3) {
@@ -851,33 +909,34 @@ hmmset_sweep_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr
     const size_t row_bytes = (size_t)c.n_sen * 2;
     auto row_addr = [&](int t) { return reinterpret_cast<uintptr_t>(senscr + (size_t)(r0 + (int64_t)t * rstep) * c.n_sen); };
     auto tma_ok = [&](int t) { return r0 + (int64_t)t * rstep + 1 < rows_total; };
+    if (BEAM) cluster_sync_all();                         // every peer runs (its shared memory may be written) and has zeroed its histograms
     auto issue = [&](int t) {                                         // one thread: arm the barrier, start the copy
         const uintptr_t a = row_addr(t), a16 = a & ~(uintptr_t)15;
         const unsigned bytes = (unsigned)(((a - a16) + row_bytes + 15) & ~(size_t)15);
-        mbar_expect_tx(&full[t & 1], bytes);
-        tma_bulk_g2s(sw_smem + (size_t)(t & 1) * buf_bytes, reinterpret_cast<const void *>(a16), bytes, &full[t & 1]);
+        mbar_expect_tx(&full[t % NBUF], bytes);
+        tma_bulk_g2s(sw_smem + (size_t)(t % NBUF) * buf_bytes, reinterpret_cast<const void *>(a16), bytes, &full[t % NBUF]);
     };
     if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+        for (int q = 0; q < NBUF; ++q) mbar_init(&full[q], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0) {
-        if (tma_ok(0)) issue(0);
-        if (T > 1 && tma_ok(1)) issue(1);
-    }
+    if (tid == 0 && !cta_empty)
+        for (int q = 0; q < NBUF && q < T; ++q)
+            if (tma_ok(q)) issue(q);
     int best_final[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) best_final[v] = PSB_WORST_SCORE;
 
     for (int t = 0; t < T; ++t) {
-        const int b = t & 1;
-        unsigned char *buf = sw_smem + (size_t)b * buf_bytes;
+        const int b = t & 1, rb = t % NBUF;
+        unsigned char *buf = sw_smem + (size_t)rb * buf_bytes;
         const uintptr_t a = row_addr(t);
         const int16_t *srow;
-        if (tma_ok(t)) {
-            mbar_wait(&full[b], (unsigned)(t >> 1) & 1u);
+        if (BEAM && cta_empty)
+            srow = reinterpret_cast<const int16_t *>(buf);            // nothing to evaluate
+        else if (tma_ok(t)) {
+            mbar_wait(&full[rb], (unsigned)(t / NBUF) & 1u);
             srow = reinterpret_cast<const int16_t *>(buf + (a & 15));
         }
         else {                                                        // last row of the matrix: plain copy
@@ -887,9 +946,11 @@ hmmset_sweep_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr
             __syncthreads();
             srow = d;
         }
-        int best = PSB_WORST_SCORE;
+        int best = PSB_WORST_SCORE, cnt = 0;
 #pragma unroll
         for (int v = 0; v < V; ++v) {
+            if (BEAM && !act[v]) continue;
+            ++cnt;
             HmmReg h;
             int obs[PSB_HMM_MAX_NSTATE];
 #pragma unroll
@@ -916,18 +977,85 @@ hmmset_sweep_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr
             best_final[v] = bb;
         }
         best = __reduce_max_sync(0xffffffffu, best);
-        if ((tid & 31) == 0) red[b][tid >> 5] = best;
+        if (BEAM) cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if ((tid & 31) == 0) {
+            red[b][tid >> 5] = best;
+            if (BEAM) redc[b][tid >> 5] = cnt;
+        }
         __syncthreads();                                              // buf[b] and red[b] are complete / free
-        if (tid == 0 && t + 2 < T && tma_ok(t + 2)) issue(t + 2);
+        if (tid == 0 && t + NBUF < T && tma_ok(t + NBUF) && !cta_empty) issue(t + NBUF);
         if (tid < 32) {
             int v = tid < THREADS / 32 ? red[b][tid] : PSB_WORST_SCORE;
             v = __reduce_max_sync(0xffffffffu, v);
-            if (tid == 0) atomicMax(best_out + (size_t)t * gridDim.y + seg, v);
+            if (!BEAM) {
+                if (tid == 0) atomicMax(best_out + (size_t)t * gridDim.y + seg, v);
+            }
+            else {
+                int cc = tid < THREADS / 32 ? redc[b][tid] : 0;
+                cc = __reduce_add_sync(0xffffffffu, cc);
+                if (tid == 0) mbar_expect_tx(&xbar[b], n_rank * 8u);  // this frame's n_rank messages (own included)
+                if ((unsigned)tid < n_rank)                           // lane r tells peer r
+                    st_async_v2(mapa_shared(&cl_slot[b][my_rank], (unsigned)tid), (unsigned)v, (unsigned)cc,
+                                mapa_shared(&xbar[b], (unsigned)tid));
+            }
+        }
+        if (BEAM) {
+            // A(t): every CTA's maximum and count have arrived.  A peer can only send frame t + 2 into the same slots
+            // after it has seen this CTA's frame t + 1 message, i.e. after every thread here is done with frame t's.
+            mbar_wait(&xbar[b], (unsigned)(t >> 1) & 1u);
+            int seg_best = PSB_WORST_SCORE, seg_cnt = 0;
+            for (unsigned r = 0; r < n_rank; ++r) {
+                const int2 m = cl_slot[b][r];
+                seg_best = max(seg_best, m.x);
+                seg_cnt += m.y;
+            }
+            if (my_rank == 0 && tid == 0) {
+                best_out[(size_t)t * gridDim.y + seg] = seg_best;
+                if (n_active_out) n_active_out[(size_t)t * gridDim.y + seg] = seg_cnt;
+            }
+            hist[b ^ 1][tid] = 0u;                                    // the peers finished with it before they sent frame t's message
+            int dyn = beam;
+            if (maxhmmpf >= 0 && seg_cnt > maxhmmpf) {                // uniform over the cluster
+                const int bw = -beam / 256;
+#pragma unroll
+                for (int v = 0; v < V; ++v)
+                    if (act[v]) {
+                        int bin = (seg_best - best_final[v]) / bw;
+                        bin = bin > 255 ? 255 : bin;
+                        atomicAdd(&hist[b][bin], 1u);
+                    }
+                if (tid == 0) found = 256;
+                cluster_sync_all();                                   // B(t): every CTA's histogram is complete
+                unsigned tot = 0;
+                for (unsigned r = 0; r < n_rank; ++r) tot += ld_cluster_u32(mapa_shared(&hist[b][tid], r));
+                unsigned incl = tot;                                  // running count over the bins, bin = thread
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+                    if ((tid & 31) >= o) incl += y;
+                }
+                if ((tid & 31) == 31) scan_w[tid >> 5] = incl;
+                __syncthreads();
+                for (int w = 0; w < (tid >> 5); ++w) incl += scan_w[w];
+                if (incl > (unsigned)maxhmmpf) atomicMin(&found, tid);
+                __syncthreads();
+                dyn = -(found * bw);
+            }
+            const int thresh = seg_best + dyn;
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if (act[v] && !(best_final[v] > thresh)) {            // hmm_clear
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) { sc[v][k] = PSB_WORST_SCORE; hi[v][k] = -1; }
+                    osc[v] = PSB_WORST_SCORE; ohi[v] = -1; best_final[v] = PSB_WORST_SCORE;
+                    act[v] = false;
+                }
         }
     }
+    if (BEAM) cluster_sync_all();                         // nobody leaves while a peer may still read its histogram
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-        if (!live[v]) continue;
+        if (!live[v] || !touched[v]) continue;            // BEAM: instances that were never active stay as they are
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
             p32[v][k * HS_TS] = sc[v][k];
@@ -936,6 +1064,7 @@ hmmset_sweep_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr
         p32[v][2 * NS * HS_TS] = osc[v];
         p32[v][(2 * NS + 1) * HS_TS] = ohi[v];
         p32[v][(2 * NS + 2) * HS_TS] = best_final[v];
+        if (BEAM) p32[v][(2 * NS + 3) * HS_TS] = act[v] ? frame0 + T : -1;
     }
 }
 
@@ -1165,11 +1294,11 @@ extern "C" int psb_hmmset_sweep_device(psb_hmmset_t *s, const int16_t *d_senscr,
     PSB_CUDA(cudaEventRecord(s->ev[0], s->stream));
 #define PSB_SWEEP(NS, V, THREADS)                                                                                               \
     do {                                                                                                                       \
-        auto kern = hmmset_sweep_kernel<NS, V, THREADS>;                                                                       \
+        auto kern = hmmset_sweep_kernel<NS, V, THREADS, false>;                                                                \
         PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                          \
         const dim3 grid((unsigned)((s->max_seg_len + THREADS * V - 1) / (THREADS * V)), (unsigned)s->n_seg);                   \
         kern<<<grid, THREADS, smem, s->stream>>>(sd, cd, d_senscr, (long long)rows_total, d_row0, d_n_rows, n_frames, d_best,  \
-                                                s->c->n_tmat, buf_bytes);                                                      \
+                                                s->c->n_tmat, buf_bytes, 0, 0, -1, nullptr);                                   \
     } while (0)
     if (cd.n_emit == 3) {
         if (shape == 1) PSB_SWEEP(3, 2, 256);
@@ -1183,6 +1312,73 @@ extern "C" int psb_hmmset_sweep_device(psb_hmmset_t *s, const int16_t *d_senscr,
     PSB_LAUNCH_CHECK();
     PSB_CUDA(cudaEventRecord(s->ev[1], s->stream));
     if (ms) {                                               // ms == NULL: asynchronous on the set's stream
+        PSB_CUDA(cudaStreamSynchronize(s->stream));
+        PSB_CUDA(cudaEventElapsedTime(ms, s->ev[0], s->ev[1]));
+    }
+    return PSB_OK;
+}
+
+// The fused sweep with beam pruning between frames: one thread-block cluster per segment (hmmset_sweep_kernel<.., BEAM>).
+extern "C" int psb_hmmset_sweep_beam_device(psb_hmmset_t *s, const int16_t *d_senscr, int64_t rows_total, const int64_t *d_row0,
+                                            const int32_t *d_n_rows, int32_t n_frames, int32_t frame0, int32_t beam,
+                                            int32_t maxhmmpf, int32_t *d_best, int32_t *d_n_active, float *ms)
+{
+    PSB_REQUIRE(s && d_senscr && d_best && n_frames >= 0 && rows_total > 0, "psb_hmmset_sweep_beam_device: bad argument");
+    PSB_REQUIRE(beam < 0 && beam > -0x20000000, "psb_hmmset_sweep_beam_device: the beam is a negative log score (got %d)", beam);
+    PSB_REQUIRE(maxhmmpf < 0 || beam <= -256, "psb_hmmset_sweep_beam_device: -maxhmmpf needs a beam of at least 256 score units (bin width -beam/256)");
+    const HmmCtxDev cd = dev_ctx(s->c);
+    PSB_REQUIRE(!s->any_mpx && (cd.n_emit == 3 || cd.n_emit == 5) && !(cd.n_sen & 1),
+                "psb_hmmset_sweep_beam_device: plain 3- or 5-state instances and an even senone count (the fused kernel's shapes)");
+    constexpr int THREADS = 256, V = 4;
+    const int64_t per_seg = (s->max_seg_len + THREADS * V - 1) / (THREADS * V);
+    PSB_REQUIRE(per_seg <= 16, "psb_hmmset_sweep_beam_device: a segment of %lld instances needs %lld CTAs, a cluster holds 16",
+                (long long)s->max_seg_len, (long long)per_seg);
+    if (ms) *ms = 0.f;
+    if (n_frames == 0 || s->n_seg == 0) return PSB_OK;
+    PSB_CUDA(cudaSetDevice(s->c->device));
+    const int64_t nb = (int64_t)n_frames * s->n_seg;
+    fill_i32_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, s->stream>>>(d_best, nb, PSB_WORST_SCORE);
+    PSB_LAUNCH_CHECK();
+    if (d_n_active) PSB_CUDA(cudaMemsetAsync(d_n_active, 0, (size_t)nb * 4, s->stream));
+    if (s->n == 0) {
+        if (ms) PSB_CUDA(cudaStreamSynchronize(s->stream));
+        return PSB_OK;
+    }
+    const int buf_bytes = (int)(((size_t)cd.n_sen * 2 + 32 + 127) & ~(size_t)127);
+    const int tp_bytes = s->c->n_tmat * cd.n_emit * (cd.n_emit + 1);
+    const size_t smem = 6 * (size_t)buf_bytes + tp_bytes;                 // NBUF of the BEAM instantiation
+    PSB_REQUIRE(smem <= 200 * 1024, "psb_hmmset_sweep_beam: %d senones / %d transition matrices do not fit shared memory", cd.n_sen, s->c->n_tmat);
+    const HmmSetDev sd = dev_set(s);
+    const long long rows_ll = rows_total;
+    const int n_tmat = s->c->n_tmat;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)std::max<int64_t>(per_seg, 1), (unsigned)s->n_seg);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cfg.gridDim.x; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    PSB_CUDA(cudaEventRecord(s->ev[0], s->stream));
+#define PSB_SWEEPB(NS)                                                                                                         \
+    do {                                                                                                                       \
+        auto kern = hmmset_sweep_kernel<NS, V, THREADS, true>;                                                                 \
+        PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                          \
+        if (cfg.gridDim.x > 8) PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));       \
+        int n_clusters = 0;                                                                                                    \
+        PSB_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg));                                                     \
+        PSB_REQUIRE(n_clusters > 0, "psb_hmmset_sweep_beam: a cluster of %u CTAs with %zu bytes of shared memory each does not fit the device", \
+                    cfg.gridDim.x, smem);                                                                                      \
+        PSB_CUDA(cudaLaunchKernelEx(&cfg, kern, sd, cd, d_senscr, rows_ll, d_row0, d_n_rows, (int)n_frames, d_best, n_tmat,   \
+                                    buf_bytes, (int)frame0, (int)beam, (int)maxhmmpf, d_n_active));                            \
+        PSB_LAUNCH_CHECK();                                                                                                    \
+    } while (0)
+    if (cd.n_emit == 3) PSB_SWEEPB(3);
+    else PSB_SWEEPB(5);
+#undef PSB_SWEEPB
+    PSB_CUDA(cudaEventRecord(s->ev[1], s->stream));
+    if (ms) {
         PSB_CUDA(cudaStreamSynchronize(s->stream));
         PSB_CUDA(cudaEventElapsedTime(ms, s->ev[0], s->ev[1]));
     }

@@ -454,8 +454,12 @@ __device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, unsigned parity)
 }
 
 //   wumma   [K][2][8][ND][4] float   W halves (high, low) in the canonical K-major layout: chunk kc holds k = 4 kc .. 4 kc + 3
-template <int FL, int ND, bool CHECK>
-__global__ void __launch_bounds__(TC_ROWS, 2)
+// SPLIT = 2: two threads per frame (256 threads per CTA), each sweeping half of the columns of the SAME accumulator row
+// (warps w and w + 4 own the same 32 TMEM lanes): the accumulator sweeps are the longest serial stretch of a tile and the
+// tensor memory (two 256-column accumulators per SM) caps the CTAs at two, so this is the way to put sixteen warps on
+// an SM.  The halves meet twice: eight group maxima per row, and the two candidate sub-lists that thread 0 of the pair resolves.
+template <int FL, int ND, int SPLIT, bool CHECK>
+__global__ void __launch_bounds__(TC_ROWS * SPLIT, 2)
 ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const int32_t *__restrict__ featoff,
                const int32_t *__restrict__ klist, const float *__restrict__ wumma, const float *__restrict__ cen,
                const float *__restrict__ bnd, const float *__restrict__ rec, const size_t *__restrict__ rec_off,
@@ -465,17 +469,23 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
 {
     constexpr int RF = (1 + 2 * FL + 3) / 4 * 4;
     constexpr int GW = ND / 8;                           // columns per maximum group: 8 groups per row
-    static_assert(2 * FL + 1 <= TC_K && ND % 32 == 0 && ND <= 256, "shape");
+    constexpr int NT_ = TC_ROWS * SPLIT;                 // threads
+    constexpr int NDH = ND / SPLIT;                      // columns per thread
+    constexpr int CAPH = SPLIT == 1 ? TC_CAP : 12;       // candidate slots per thread
+    constexpr int SD = 32 / SPLIT;                       // columns staged at a time
+    static_assert(2 * FL + 1 <= TC_K && ND % 32 == 0 && ND <= 256 && NDH % 64 == 0 && (SPLIT == 1 || SPLIT == 2), "shape");
     extern __shared__ __align__(128) unsigned char t5_smem[];
     float *sW = reinterpret_cast<float *>(t5_smem);                                   // [2][8][ND][4]
     float *sX = sW + 2 * 8 * ND * 4;                                                  // [2][8][128][4]; after the MMA: lists + staging
     // thread-private and transposed ([slot][thread]: conflict-free): candidate values, candidate columns, one 32-column slab
-    float *Lv = sX;                                                                   // [TC_CAP][128]
-    unsigned char *Lc = reinterpret_cast<unsigned char *>(Lv + TC_CAP * TC_ROWS);     // [TC_CAP][128]
-    float *stage = reinterpret_cast<float *>(Lc + ((TC_CAP * TC_ROWS + 15) & ~15));   // [32][128]
-    static_assert(TC_CAP * TC_ROWS * 5 + 16 + 32 * TC_ROWS * 4 <= 2 * 8 * TC_ROWS * 16, "lists + staging must fit the X tile");
+    float *Lv = sX;                                                                   // [CAPH][threads]
+    unsigned char *Lc = reinterpret_cast<unsigned char *>(Lv + CAPH * NT_);           // [CAPH][threads]
+    float *stage = reinterpret_cast<float *>(Lc + ((CAPH * NT_ + 15) & ~15));         // [SD][threads]
+    static_assert(CAPH * NT_ * 5 + 16 + SD * NT_ * 4 <= 2 * 8 * TC_ROWS * 16, "lists + staging must fit the X tile");
     __shared__ __align__(8) uint64_t mma_done;
     __shared__ unsigned tmem_base_s;
+    __shared__ float gmx[SPLIT == 1 ? 1 : TC_ROWS * 8];                               // SPLIT = 2: the row's eight group maxima
+    __shared__ int cnt_s[SPLIT == 1 ? 1 : 2 * TC_ROWS];                               // SPLIT = 2: candidates per half
 
     // grid: x = pair (fastest), y = group of tiles: CTAs that run together read the SAME frames for different pairs, so
     // the feature rows come out of L2 (with tiles fastest every pair re-read the whole feature matrix from HBM: 23 GB
@@ -483,6 +493,7 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
     const int k = klist[blockIdx.x];
     const int f = k % n_feat;
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int r = tid & (TC_ROWS - 1), half = tid / TC_ROWS;          // this thread's frame of the tile and its half of the columns
 
     if (warp == 0) {                                     // 256 (or fewer) TMEM columns for the accumulator
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&tmem_base_s)),
@@ -496,7 +507,7 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
     {
         const float4 *src = reinterpret_cast<const float4 *>(wumma + (size_t)k * 2 * 8 * ND * 4);
         float4 *dst = reinterpret_cast<float4 *>(sW);
-        for (int i = tid; i < 2 * 8 * ND; i += TC_ROWS) dst[i] = src[i];
+        for (int i = tid; i < 2 * 8 * ND; i += NT_) dst[i] = src[i];
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -510,14 +521,14 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
     // the next tile's feature row is fetched while this tile's GEMM runs
     float xn[FL];
     {
-        const long long r0 = (long long)blockIdx.y * tiles_per_cta * TC_ROWS + tid;
+        const long long r0 = (long long)blockIdx.y * tiles_per_cta * TC_ROWS + r;
         const float *p = feats + (r0 < total ? r0 : 0) * D + featoff[f];
 #pragma unroll
         for (int j = 0; j < FL; ++j) xn[j] = r0 < total ? p[j] : 0.f;
     }
     for (int tile = 0; tile < tiles_per_cta; ++tile) {
-        const long long row = ((long long)blockIdx.y * tiles_per_cta + tile) * TC_ROWS + tid;
-        if (row - tid >= total) break;                   // uniform: the whole tile lies past the end
+        const long long row = ((long long)blockIdx.y * tiles_per_cta + tile) * TC_ROWS + r;
+        if (row - r >= total) break;                     // uniform: the whole tile lies past the end
         const bool valid = row < total;
         // ---- this thread's frame: X row (TF32 halves, canonical layout) and its error bound ----
         float x[FL], ee;
@@ -540,12 +551,13 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
             ee = __fadd_ru(__fmul_ru(S, TC_ERR), 2.0f);
 #pragma unroll
             for (int kc = 0; kc < 8; ++kc) {
+                if (SPLIT == 2 && (kc & 1) != half) continue;         // the pair shares the conversions and stores
                 float4 h, l;
                 h.x = to_tf32(v[4 * kc]); h.y = to_tf32(v[4 * kc + 1]); h.z = to_tf32(v[4 * kc + 2]); h.w = to_tf32(v[4 * kc + 3]);
                 l.x = to_tf32(__fsub_rn(v[4 * kc], h.x)); l.y = to_tf32(__fsub_rn(v[4 * kc + 1], h.y));
                 l.z = to_tf32(__fsub_rn(v[4 * kc + 2], h.z)); l.w = to_tf32(__fsub_rn(v[4 * kc + 3], h.w));
-                reinterpret_cast<float4 *>(sX)[kc * TC_ROWS + tid] = h;
-                reinterpret_cast<float4 *>(sX)[(8 + kc) * TC_ROWS + tid] = l;
+                reinterpret_cast<float4 *>(sX)[kc * TC_ROWS + r] = h;
+                reinterpret_cast<float4 *>(sX)[(8 + kc) * TC_ROWS + r] = l;
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
@@ -575,7 +587,7 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
         // ---- this thread's row of the accumulator: group maxima, threshold, the columns above it ----
-        const unsigned trow = tmem_d + ((unsigned)(warp * 32) << 16);
+        const unsigned trow = tmem_d + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(half * NDH);
         float gm[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) gm[i] = -INFINITY;
@@ -586,7 +598,7 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
 #pragma unroll
                 for (int i = 0; i < 8; ++i) m8[i] = fmaxf(fmaxf(v[i], v[i + 8]), fmaxf(v[i + 16], v[i + 24]));
                 const float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
-                const int gi = c0 / GW;
+                const int gi = (half * NDH + c0) / GW;
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
                     if (q == gi) gm[q] = fmaxf(gm[q], mx);
@@ -598,7 +610,7 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
                     float mx = v[s2 * GW];
 #pragma unroll
                     for (int i = 1; i < GW; ++i) mx = fmaxf(mx, v[s2 * GW + i]);
-                    const int gi = c0 / GW + s2;
+                    const int gi = (half * NDH + c0) / GW + s2;
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                         if (q == gi) gm[q] = fmaxf(gm[q], mx);
@@ -609,14 +621,21 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
             float va[32], vb[32];
             tmem_ld32_issue(trow, va);
 #pragma unroll 1
-            for (int c0 = 0; c0 < ND; c0 += 64) {
+            for (int c0 = 0; c0 < NDH; c0 += 64) {
                 tmem_wait_ld_dep(va);
                 tmem_ld32_issue(trow + c0 + 32, vb);
                 maxima(c0, va);
                 tmem_wait_ld_dep(vb);
-                if (c0 + 64 < ND) tmem_ld32_issue(trow + c0 + 64, va);
+                if (c0 + 64 < NDH) tmem_ld32_issue(trow + c0 + 64, va);
                 maxima(c0 + 32, vb);
             }
+        }
+        if (SPLIT == 2) {                                 // the other half's group maxima
+#pragma unroll
+            for (int q = 0; q < 4; ++q) gmx[r * 8 + half * 4 + q] = gm[half * 4 + q];
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) gm[q] = gmx[r * 8 + q];
         }
         // five distinct columns >= L0: the fifth largest of the eight group maxima
         float L0;
@@ -640,24 +659,31 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
             unsigned h4[4] = {0u, 0u, 0u, 0u};            // branch-free: one compare and one predicated OR per column, four chains
 #pragma unroll
             for (int i = 0; i < 32; ++i) h4[i & 3] |= v[i] >= thr ? (1u << i) : 0u;
-            unsigned hit = (h4[0] | h4[1]) | (h4[2] | h4[3]);
-            if (__any_sync(0xffffffffu, hit != 0u)) {    // registers cannot be indexed by a run-time column: through shared memory
+            const unsigned hit_all = (h4[0] | h4[1]) | (h4[2] | h4[3]);
+            if (__any_sync(0xffffffffu, hit_all != 0u)) {    // registers cannot be indexed by a run-time column: through shared memory
 #pragma unroll
-                for (int i = 0; i < 32; ++i) stage[i * TC_ROWS + tid] = v[i];
-                while (hit) {
-                    const int i = __ffs(hit) - 1;
-                    hit &= hit - 1;
-                    if (n < TC_CAP) { Lv[n * TC_ROWS + tid] = stage[i * TC_ROWS + tid]; Lc[n * TC_ROWS + tid] = (unsigned char)(c0 + i); }
-                    ++n;
+                for (int part = 0; part < SPLIT; ++part) {
+#pragma unroll
+                    for (int i = 0; i < SD; ++i) stage[i * NT_ + tid] = v[part * SD + i];
+                    unsigned hit = (hit_all >> (part * SD)) & (SD == 32 ? 0xffffffffu : ((1u << SD) - 1u));
+                    while (hit) {
+                        const int i = __ffs(hit) - 1;
+                        hit &= hit - 1;
+                        if (n < CAPH) {
+                            Lv[n * NT_ + tid] = stage[i * NT_ + tid];
+                            Lc[n * NT_ + tid] = (unsigned char)(half * NDH + c0 + part * SD + i);
+                        }
+                        ++n;
+                    }
                 }
             }
             if (CHECK && valid) {
                 for (int i = 0; i < 32; ++i) {
-                    const float *r = rc + (size_t)(c0 + i) * RF;
-                    float d = r[0];
+                    const float *rp = rc + (size_t)(half * NDH + c0 + i) * RF;
+                    float d = rp[0];
                     for (int j = 0; j < FL; ++j) {
-                        const float df = __fsub_rn(x[j], r[1 + 2 * j]);
-                        d = __fsub_rn(d, __fmul_rn(__fmul_rn(df, df), r[2 + 2 * j]));
+                        const float df = __fsub_rn(x[j], rp[1 + 2 * j]);
+                        d = __fsub_rn(d, __fmul_rn(__fmul_rn(df, df), rp[2 + 2 * j]));
                     }
                     worst = fmaxf(worst, __fdividef(fabsf(v[i] - d), ee));
                 }
@@ -667,30 +693,41 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
             float va[32], vb[32];
             tmem_ld32_issue(trow, va);
 #pragma unroll 1
-            for (int c0 = 0; c0 < ND; c0 += 64) {
+            for (int c0 = 0; c0 < NDH; c0 += 64) {
                 tmem_wait_ld_dep(va);
                 tmem_ld32_issue(trow + c0 + 32, vb);
                 collect(c0, va);
                 tmem_wait_ld_dep(vb);
-                if (c0 + 64 < ND) tmem_ld32_issue(trow + c0 + 64, va);
+                if (c0 + 64 < NDH) tmem_ld32_issue(trow + c0 + 64, va);
                 collect(c0 + 32, vb);
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        // SPLIT = 2: thread 0 of the pair takes over with both sub-lists (own slots, then the partner's)
+        int n0 = n, n1 = 0;
+        if (SPLIT == 2) {
+            cnt_s[half * TC_ROWS + r] = n;
+            __syncthreads();
+            n0 = cnt_s[r]; n1 = cnt_s[TC_ROWS + r];
+        }
+        const bool listed = n0 <= CAPH && n1 <= CAPH && n0 + n1 >= 5 && n0 + n1 <= 20;
+        n = n0 + n1;
+        auto cand_v = [&](int i) { return i < n0 ? Lv[i * NT_ + r] : Lv[(i - n0) * NT_ + TC_ROWS + r]; };
+        auto cand_c = [&](int i) { return (int)(i < n0 ? Lc[i * NT_ + r] : Lc[(i - n0) * NT_ + TC_ROWS + r]); };
         if (CHECK) {
             atomicMax(reinterpret_cast<int *>(check), __float_as_int(worst));
-            if (valid) atomicMax(reinterpret_cast<int *>(check) + 1, n);
+            if (valid && half == 0) atomicMax(reinterpret_cast<int *>(check) + 1, n);
         }
 
         // ---- the record straight from the filter values when they leave no doubt ----
-        if (valid) {
-            bool certain = n <= TC_CAP && n >= 5;
+        if (valid && half == 0) {
+            bool certain = listed;
             if (certain) {
                 float a[5] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY};
                 int c[5] = {0, 0, 0, 0, 0};
                 for (int i = 0; i < n; ++i) {
-                    float v = Lv[i * TC_ROWS + tid];
-                    int cv = (int)Lc[i * TC_ROWS + tid];
+                    float v = cand_v(i);
+                    int cv = cand_c(i);
 #pragma unroll
                     for (int j = 0; j < 5; ++j)
                         if (v > a[j]) { const float tv = a[j]; const int tc = c[j]; a[j] = v; c[j] = cv; v = tv; cv = tc; }
@@ -729,10 +766,9 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
                 base = __shfl_sync(need, base, leader);
                 const unsigned slot = base + (unsigned)__popc(need & ((1u << (tid & 31)) - 1u));
                 if (slot < item_cap) {
-                    const bool listed = n <= TC_CAP && n >= 5;
                     unsigned wv[5] = {0u, 0u, 0u, 0u, 0u};
                     if (listed)
-                        for (int i = 0; i < n; ++i) wv[i >> 2] |= (unsigned)Lc[i * TC_ROWS + tid] << (8 * (i & 3));
+                        for (int i = 0; i < n; ++i) wv[i >> 2] |= (unsigned)cand_c(i) << (8 * (i & 3));
                     items[2 * (size_t)slot] = make_uint4((unsigned)row, (unsigned)k | ((listed ? (unsigned)n : 255u) << 16), wv[0], wv[1]);
                     items[2 * (size_t)slot + 1] = make_uint4(wv[2], wv[3], wv[4], (unsigned)(row >> 32));
                     certain = true;                       // handled
@@ -746,9 +782,9 @@ ptm_tc5_kernel(const float *__restrict__ feats, long long total, int D, const in
 #pragma unroll
                 for (int j = 0; j < 5; ++j) top.s[j] = INT_MIN;
                 int n_exact = 0;
-                const int cnt_l = (n <= TC_CAP && n >= 5) ? n : ND;
+                const int cnt_l = listed ? n : ND;
                 for (int i = 0; i < cnt_l; ++i) {
-                    const int cw = cnt_l == ND ? i : (int)Lc[i * TC_ROWS + tid];
+                    const int cw = listed ? cand_c(i) : i;
                     const float d = gau_dist<FL>(reinterpret_cast<const float4 *>(rc + (size_t)cw * RF), x);
                     top5_insert(top, f2i_clamped(d), cw);
                     ++n_exact;
@@ -1040,7 +1076,7 @@ int launch_tc(psb_batch_t *b, const float *d_feats, long long total, const int32
     return PSB_OK;
 }
 
-template <int FL, int ND>
+template <int FL, int ND, int SPLIT>
 int launch_tc5(psb_batch_t *b, const float *d_feats, long long total, const int32_t *d_klist, int n_k, const int32_t *d_featoff,
                bool check)
 {
@@ -1055,16 +1091,16 @@ int launch_tc5(psb_batch_t *b, const float *d_feats, long long total, const int3
     float *chk = b->d_tc_check;
     unsigned long long *stats = reinterpret_cast<unsigned long long *>(b->d_tc_check + 4);
     if (check) {
-        auto kern = ptm_tc5_kernel<FL, ND, true>;
+        auto kern = ptm_tc5_kernel<FL, ND, SPLIT, true>;
         PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, TC_ROWS, smem, b->stream>>>(d_feats, total, m->sumlen, d_featoff, d_klist, m->d_tc_wumma, m->d_tc_cen, m->d_tc_bnd,
+        kern<<<grid, TC_ROWS * SPLIT, smem, b->stream>>>(d_feats, total, m->sumlen, d_featoff, d_klist, m->d_tc_wumma, m->d_tc_cen, m->d_tc_bnd,
                                                 m->d_rec, m->d_rec_off, b->d_topn, b->d_tc_flags, (long long)b->tc_flag_words, m->K,
                                                 m->n_feat, tpc, b->d_tc_items, b->d_tc_nitems, b->tc_item_cap, chk, stats);
     }
     else {
-        auto kern = ptm_tc5_kernel<FL, ND, false>;
+        auto kern = ptm_tc5_kernel<FL, ND, SPLIT, false>;
         PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, TC_ROWS, smem, b->stream>>>(d_feats, total, m->sumlen, d_featoff, d_klist, m->d_tc_wumma, m->d_tc_cen, m->d_tc_bnd,
+        kern<<<grid, TC_ROWS * SPLIT, smem, b->stream>>>(d_feats, total, m->sumlen, d_featoff, d_klist, m->d_tc_wumma, m->d_tc_cen, m->d_tc_bnd,
                                                 m->d_rec, m->d_rec_off, b->d_topn, b->d_tc_flags, (long long)b->tc_flag_words, m->K,
                                                 m->n_feat, tpc, b->d_tc_items, b->d_tc_nitems, b->tc_item_cap, nullptr, nullptr);
     }
@@ -1216,11 +1252,16 @@ int psb_launch_ptm_tc(psb_batch_t *b, const float *d_feats, const int32_t *utt_o
         default: rc = launch_tc<13, 8>(b, d_feats, total, d_klist, m->K, d_featoff, check); break;
         }
     else
+    {
+        static const bool one_thread = [] { const char *v = getenv("PSB_TC_SPLIT"); return !(v && atoi(v) == 2); }();   // two threads per frame measured slower: 37.2 vs 30.7 ms
         switch (m->n_density) {
-        case 256: rc = launch_tc5<13, 256>(b, d_feats, total, d_klist, m->K, d_featoff, check); break;
-        case 128: rc = launch_tc5<13, 128>(b, d_feats, total, d_klist, m->K, d_featoff, check); break;
-        default: rc = launch_tc5<13, 64>(b, d_feats, total, d_klist, m->K, d_featoff, check); break;
+        case 256: rc = one_thread ? launch_tc5<13, 256, 1>(b, d_feats, total, d_klist, m->K, d_featoff, check)
+                                  : launch_tc5<13, 256, 2>(b, d_feats, total, d_klist, m->K, d_featoff, check); break;
+        case 128: rc = one_thread ? launch_tc5<13, 128, 1>(b, d_feats, total, d_klist, m->K, d_featoff, check)
+                                  : launch_tc5<13, 128, 2>(b, d_feats, total, d_klist, m->K, d_featoff, check); break;
+        default: rc = launch_tc5<13, 64, 1>(b, d_feats, total, d_klist, m->K, d_featoff, check); break;
         }
+    }
     if (rc) return rc;
     const long long chains = (long long)n_utt * m->K;
     static const bool thread_fixup = [] { const char *v = getenv("PSB_TC_FIXUP"); return v && !strcmp(v, "thread"); }();

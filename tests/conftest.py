@@ -73,3 +73,20 @@ def assert_hmm_equal(a, b, n_emit, what=""):
             x, y = x[..., :n_emit], y[..., :n_emit]
         assert np.array_equal(x, y), "%s: hmm field %s differs at %s" % (
             what, k, np.argwhere(x != y)[:5].tolist())
+
+
+def beam_case(n_emit, n, seed, frame0=7):
+    """n plain hmm_t drawn from the golden hmm_vit_eval records, all entered with spread-out scores; nine in ten active
+    in frame0 (frame field), the others not (never touched by a beam sweep)."""
+    g = golden("hmm_vit_eval.npz")
+    tp, sseq = g["n%d_tp" % n_emit], g["n%d_sseq" % n_emit]
+    hm = hmm_view(g["n%d_before" % n_emit]).copy()
+    hm = hm[hm["mpx"] == 0]
+    rng = np.random.default_rng(seed)
+    hm = np.ascontiguousarray(hm[rng.integers(0, len(hm), n)])
+    hm["score"][:, 0] = -rng.integers(0, 4000, n).astype(np.int32)          # every instance entered, scores spread out
+    hm["frame"] = frame0
+    hm["frame"][rng.random(n) < 0.1] = frame0 - 1                              # not active: never touched
+    hm["frame"][rng.random(n) < 0.05] = -1
+    n_sen = len(g["n%d_senscr" % n_emit])
+    return tp, sseq, hm, n_sen

@@ -563,6 +563,62 @@ def test_hmmset_sweep_matches_per_frame_and_oracle(api, n_emit, n_sen_odd):
     ctx.close()
 
 
+@pytest.mark.parametrize("n_emit,big,maxhmmpf", [(3, 6081, -1), (3, 6081, 2500), (5, 2300, 900), (3, 9100, 4000)])
+def test_hmmset_sweep_beam_matches_oracle(api, n_emit, big, maxhmmpf):
+    """psb_hmmset_sweep_beam_device -- the fused sweep with beam pruning between frames, one thread-block cluster per
+    segment (maxima / counts / -maxhmmpf histograms exchanged through distributed shared memory) -- against
+    oracle.sweep_beam (pinned on the reference's hmm_vit_eval and hmm_clear in tests/test_hmm_beam_oracle.py): ragged
+    segments (empty, one instance, several CTAs; 9100 instances = a cluster of 9, beyond the portable 8), segments
+    finishing early, instances that are not active and must stay untouched, the histogram walk with and without effect."""
+    import torch
+    from conftest import beam_case
+    from oracle import oracle
+    frame0, beam, T = 7, -3000, 11
+    seg_len = [1, 0, 259, 1040, big]
+    n = sum(seg_len)
+    tp, sseq, hm0, n_sen = beam_case(n_emit, n, 40 + n_emit + big)
+    n_sen -= n_sen & 1
+    hm0 = hm0[(hm0["senid"][:, :n_emit] < n_sen).all(1)]
+    seg_len[-1] -= n - len(hm0)
+    n = len(hm0)
+    seg_off = np.concatenate([[0], np.cumsum(seg_len)]).astype(np.int64)
+    n_seg = len(seg_len)
+    n_rows = np.array([11, 11, 5, 11, 9], np.int32)
+    R = 40
+    rng = np.random.default_rng(6)
+    senscr = rng.integers(0, 900, (R, n_sen)).astype(np.int16)
+    row0 = np.array([3, 0, 12, R - 11, 20], np.int64)                    # segment 3 ends on the matrix's last row
+    ctx = api.HmmContext(tp, sseq, n_sen)
+    d_scr = torch.from_numpy(senscr).cuda()
+    d_row0, d_nrows = torch.from_numpy(row0).cuda(), torch.from_numpy(n_rows).cuda()
+    hs = api.HmmSet(ctx, n + 8 * 512, 16)
+    hs.upload(hm0, seg_off)
+    d_best = torch.zeros((T, n_seg), dtype=torch.int32, device="cuda")
+    d_nact = torch.full((T, n_seg), -1, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()                                             # the set's stream does not wait for torch's
+    hs.sweep_beam_device(d_scr.data_ptr(), R, T, frame0, beam, d_best.data_ptr(), maxhmmpf=maxhmmpf, d_n_active=d_nact.data_ptr(),
+                         d_row0=d_row0.data_ptr(), d_n_rows=d_nrows.data_ptr())
+    got, best, nact = hs.download(), d_best.cpu().numpy(), d_nact.cpu().numpy()
+    hs.close()
+    ctx.close()
+    octx = oracle.OracleHmmCtx(tp, sseq)
+    want = hm0.copy()
+    for s in range(n_seg):
+        a, b = seg_off[s], seg_off[s + 1]
+        Ts = int(min(T, n_rows[s]))
+        seg = np.ascontiguousarray(want[a:b])
+        wb, wn = oracle.sweep_beam(octx, seg, senscr[row0[s]:row0[s] + Ts], frame0, beam, maxhmmpf)
+        want[a:b] = seg
+        assert np.array_equal(best[:Ts, s], wb), "segment %d best" % s
+        assert np.array_equal(nact[:Ts, s], wn), "segment %d counts: %s vs %s" % (s, nact[:Ts, s], wn)
+        assert (best[Ts:, s] == -0x20000000).all() and (nact[Ts:, s] == 0).all()
+    assert_hmm_equal(got, want, n_emit, "beam sweep")
+    big_n = nact[:9, n_seg - 1]
+    assert big_n[0] > big_n[-1] > 0, "the beam must bite: %s" % big_n
+    if maxhmmpf >= 0:
+        assert big_n[0] > maxhmmpf, "the histogram walk must run: %s" % big_n
+
+
 # ---------------------------------------------------------------------------------------
 # BASELINE.json config 2 at FULL size (1000 utterances x 998 frames, 5138 senones): properties
 # that do not need the oracle on every frame, plus the oracle on a sample of utterances.
