@@ -693,7 +693,7 @@ def main():
         variant = int(os.environ.get("PSB_TOPN_VARIANT", "6"))
         tc_path = variant >= 6 and pm.kind == "ptm" and all(int(x) == 13 for x in pm.featlen) and pm.n_density in (64, 128, 256) \
             and int(getattr(pm, "ds_ratio", 1)) == 1
-        topn_name = {"ms": "ms_dist_tile_kernel+ms_senone_kernel", "s2_semi": "semi_dist_kernel+semi_scan_kernel"}.get(
+        topn_name = {"ms": "ms_dist_tile_kernel (distances + mixtures)", "s2_semi": "semi_dist_kernel+semi_scan_kernel"}.get(
             pm.kind, {0: "ptm_topn_kernel", 1: "ptm_topn2_kernel", 2: "ptm_topn2_kernel", 3: "ptm_topn_u2_kernel",
                       4: "ptm_topnq_kernel<NU=2>", 5: "ptm_topnq_kernel<NU=1>"}.get(variant, "ptm_topnq_kernel<NU=1>"))
         if tc_path:

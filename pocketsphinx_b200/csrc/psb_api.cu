@@ -226,6 +226,8 @@ extern "C" int psb_model_create(const psb_model_desc_t *d, int device, psb_model
             return rc;
         }
     }
+    m->sen_is_cb = m->n_mgau == m->n_sen;
+    for (int i = 0; m->sen_is_cb && i < m->n_sen; ++i) m->sen_is_cb = s2c[i] == i;
     if ((rc = upload((void **)&m->d_sen2cb, s2c16.data(), m->n_sen * sizeof(uint16_t), false)) ||
         (rc = upload((void **)&m->d_sen2cb32, s2c.data(), m->n_sen * sizeof(int32_t), false))) {
         psb_model_free(m);

@@ -76,6 +76,7 @@ struct psb_model_s {
     uint8_t *d_mixw_cb;           // 16 bytes or null
     uint16_t *d_sen2cb;           // [n_sen] (ptm)
     int32_t *d_sen2cb32;          // [n_sen] (ms)
+    bool sen_is_cb;               // ms: senone s uses codebook s (continuous models): distances and mixtures in one kernel
     int16_t *d_quadcb;            // [ceil(n_sen/4)] codebook of a uniform senone quad, else -1
     int32_t *d_bsen;              // senones of the non-uniform quads
     int n_bsen;

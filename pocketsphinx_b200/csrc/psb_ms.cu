@@ -94,6 +94,18 @@ ms_dist_kernel(const float *__restrict__ gT, const float *__restrict__ detT, con
 }
 
 // ---------------------------------------------------------------------------------------
+// logmath_add with the shifted table (logmath.c:402-446)
+__device__ __forceinline__ int logadd_wide(const uint32_t *__restrict__ tab, int size, int zero, int x, int y)
+{
+    if (x <= zero) return y;
+    if (y <= zero) return x;
+    int d, r;
+    if (x > y) { d = x - y; r = x; }
+    else { d = y - x; r = y; }
+    if (d < 0 || d >= size) return r;
+    return r + (int)tab[d];
+}
+
 // ms_dist_tile_kernel: the same distances with the parameter stream taken out of L2.  ms_dist_kernel
 // re-reads every (density, dimension) parameter pair of its 128 codebooks from L2 for every 4 frames
 // (2 loads per 16 floating-point operations: 25 % of the FP32 lane rate, L2-bound).  Here a CTA owns a
@@ -103,13 +115,26 @@ ms_dist_kernel(const float *__restrict__ gT, const float *__restrict__ detT, con
 // staged transposed ([dimension][frame]), so that one warp-uniform LDS.128 pair feeds eight frames.
 // Per (density, dimension): 2 LDS + 2 broadcast LDS.128 for 32 floating-point operations.  Same
 // arithmetic, same order, same insertion rule as ms_dist_kernel: bit-identical lists.
-constexpr int MS_TCB = 32, MS_TFT = 8, MS_TFB = 64;      // codebooks per CTA, frames per thread, frames per block (8 warps)
+// TFT = frames per thread: 8 (eight warps per CTA, 127 registers, 16 warps per SM) or 4 (sixteen warps per CTA at 64
+// registers, 32 warps per SM: twice the shared-memory instructions per floating-point operation, twice the warps to hide them).
+constexpr int MS_TCB = 32, MS_TFB = 64;      // codebooks per CTA, frames per block
 
-template <int NT>
-__global__ void __launch_bounds__(256, 2)
+// PK: frame PAIRS through FADD2 / FMUL2 (x - m == x + (-m) exactly, the means are staged negated; every product and
+// difference is rounded separately as before and the running sums stay scalar -- ptxas would contract a packed
+// multiply-add): 3 packed + 2 scalar instructions per pair and (density, dimension) instead of 8 scalar.
+// FUSE (continuous models: senone s owns codebook s): the lane that holds a codebook's list evaluates the senone on the spot --
+// senone_eval (ms_senone.c:358-407) exactly as ms_senone_kernel does, first clamp, raw int16 score, per-frame minimum -- so
+// the lists (16 MB per 64 frames at 5138 x 8) never travel to HBM and back and one launch per chunk goes away.
+struct MsSenArgs {
+    const uint8_t *pdf; const uint32_t *tab; int tab_size, tab_zero; int16_t *senscr; int32_t *best; int n_used, aw;
+};
+
+template <int NT, int MS_TFT, bool PK, bool FUSE>
+__global__ void __launch_bounds__(MS_TFB / MS_TFT * 32, 2)
 ms_dist_tile_kernel(const float *__restrict__ gT, const float *__restrict__ detT, const float *__restrict__ feats,
                     int2 *__restrict__ out, long long frame0, long long n_frames, int n_mgau, int n_feat, int nd,
-                    int sumlen, const int32_t *__restrict__ featlen, const int32_t *__restrict__ featoff, int frames_per_cta)
+                    int sumlen, const int32_t *__restrict__ featlen, const int32_t *__restrict__ featoff, int frames_per_cta,
+                    MsSenArgs sa)
 {
     extern __shared__ __align__(16) float tsm[];
     const int n_rows = nd * sumlen * 2, n_det = n_feat * nd;
@@ -119,18 +144,45 @@ ms_dist_tile_kernel(const float *__restrict__ gT, const float *__restrict__ detT
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cb = blockIdx.x * MS_TCB + lane;
     const int cbr = cb < n_mgau ? cb : n_mgau - 1;      // padding lanes read the last codebook and write nothing
-    for (int r = warp; r < n_rows; r += MS_TFB / MS_TFT) par[r * MS_TCB + lane] = gT[(size_t)r * n_mgau + cbr];
+    for (int r = warp; r < n_rows; r += MS_TFB / MS_TFT) {
+        const float g = gT[(size_t)r * n_mgau + cbr];
+        par[r * MS_TCB + lane] = (PK && !(r & 1)) ? -g : g;      // rows alternate mean, variance term
+    }
     for (int r = warp; r < n_det; r += MS_TFB / MS_TFT) dets[r * MS_TCB + lane] = detT[(size_t)r * n_mgau + cbr];
     const bool all = NT >= nd;                          // compute_dist_all (ms_gauden.c:378-419)
     const long long f_begin = (long long)blockIdx.y * frames_per_cta;
     const long long f_end = f_begin + frames_per_cta < n_frames ? f_begin + frames_per_cta : n_frames;
+    // the next block's features travel while this block is computed: each thread keeps its share in registers
+    constexpr int PRE = MS_TFT == 4 ? 6 : 12, NTHR = MS_TFB / MS_TFT * 32;
+    const bool prefetch = sumlen * MS_TFB <= PRE * NTHR;            // uniform; longer vectors are staged in place
+    float pre[PRE];
+    auto fetch = [&](long long fb) {
+#pragma unroll
+        for (int k = 0; k < PRE; ++k) {
+            const int i = threadIdx.x + k * NTHR, fr = i & (MS_TFB - 1), j = i / MS_TFB;
+            pre[k] = (i < sumlen * MS_TFB && fb + fr < n_frames) ? feats[(frame0 + fb + fr) * sumlen + j] : 0.f;
+        }
+    };
+    if (prefetch && f_begin < f_end) fetch(f_begin);
     for (long long fb = f_begin; fb < f_end; fb += MS_TFB) {
         __syncthreads();                                // the previous block's features are no longer read
-        for (int i = threadIdx.x; i < sumlen * MS_TFB; i += blockDim.x) {
-            const int fr = i & (MS_TFB - 1), j = i / MS_TFB;
-            xs[j * MS_TFB + fr] = fb + fr < n_frames ? feats[(frame0 + fb + fr) * sumlen + j] : 0.f;
+        if (prefetch) {
+#pragma unroll
+            for (int k = 0; k < PRE; ++k) {
+                const int i = threadIdx.x + k * NTHR;
+                if (i < sumlen * MS_TFB) xs[i] = pre[k];             // xs[j * MS_TFB + fr] with i = j * MS_TFB + fr
+            }
         }
+        else
+            for (int i = threadIdx.x; i < sumlen * MS_TFB; i += blockDim.x) {
+                const int fr = i & (MS_TFB - 1), j = i / MS_TFB;
+                xs[j * MS_TFB + fr] = fb + fr < n_frames ? feats[(frame0 + fb + fr) * sumlen + j] : 0.f;
+            }
         __syncthreads();
+        if (prefetch && fb + MS_TFB < f_end) fetch(fb + MS_TFB);
+        int sscr[MS_TFT];
+#pragma unroll
+        for (int q = 0; q < MS_TFT; ++q) sscr[q] = 0;
         for (int f = 0; f < n_feat; ++f) {
             const int fl = featlen[f], fo = featoff[f];
             int id[MS_TFT][NT];
@@ -145,17 +197,35 @@ ms_dist_tile_kernel(const float *__restrict__ gT, const float *__restrict__ detT
                 const float det = dets[(f * nd + d) * MS_TCB + lane];
 #pragma unroll
                 for (int q = 0; q < MS_TFT; ++q) dv[q] = det;
+                const float *pr = pp + (size_t)d * fl * 2 * MS_TCB;          // this density's (mean, variance term) rows
+                const float *xp = xs + fo * MS_TFB + warp * MS_TFT;           // this warp's frames of dimension j
 #pragma unroll 4
-                for (int j = 0; j < fl; ++j) {
-                    const float m = pp[((d * fl + j) * 2) * MS_TCB];
-                    const float v = pp[((d * fl + j) * 2 + 1) * MS_TCB];
-                    const float4 xa = *reinterpret_cast<const float4 *>(xs + (fo + j) * MS_TFB + warp * MS_TFT);
-                    const float4 xb = *reinterpret_cast<const float4 *>(xs + (fo + j) * MS_TFB + warp * MS_TFT + 4);
-                    const float xv[MS_TFT] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+                for (int j = 0; j < fl; ++j, pr += 2 * MS_TCB, xp += MS_TFB) {
+                    const float m = pr[0];
+                    const float v = pr[MS_TCB];
+                    float xv[MS_TFT];
 #pragma unroll
-                    for (int q = 0; q < MS_TFT; ++q) {
-                        const float diff = __fsub_rn(xv[q], m);
-                        dv[q] = __fsub_rn(dv[q], __fmul_rn(__fmul_rn(diff, diff), v));       // :467-470
+                    for (int q = 0; q < MS_TFT; q += 4) {
+                        const float4 xq = *reinterpret_cast<const float4 *>(xp + q);
+                        xv[q] = xq.x; xv[q + 1] = xq.y; xv[q + 2] = xq.z; xv[q + 3] = xq.w;
+                    }
+                    if (PK) {
+                        const float2 nm2 = make_float2(m, m), vv = make_float2(v, v);        // m holds the negated mean
+#pragma unroll
+                        for (int q = 0; q < MS_TFT; q += 2) {
+                            float2 t = __fadd2_rn(make_float2(xv[q], xv[q + 1]), nm2);
+                            t = __fmul2_rn(t, t);
+                            t = __fmul2_rn(t, vv);
+                            dv[q] = __fsub_rn(dv[q], t.x);                                   // :467-470
+                            dv[q + 1] = __fsub_rn(dv[q + 1], t.y);
+                        }
+                    }
+                    else {
+#pragma unroll
+                        for (int q = 0; q < MS_TFT; ++q) {
+                            const float diff = __fsub_rn(xv[q], m);
+                            dv[q] = __fsub_rn(dv[q], __fmul_rn(__fmul_rn(diff, diff), v));   // :467-470
+                        }
                     }
                 }
 #pragma unroll
@@ -166,19 +236,40 @@ ms_dist_tile_kernel(const float *__restrict__ gT, const float *__restrict__ detT
                             if (i == d) { id[q][i] = d; ds[q][i] = dv[q]; }
                     }
                     else if (dv[q] >= ds[q][NT - 1]) {     // early exit is result-neutral (:457,:474)
-                        int p = 0;
+                        // insertion before the first entry that is not better (:478-483) as a swap chain down the sorted
+                        // list: the carried element displaces every entry it is >= to, which is the same final list
+                        float x = dv[q];
+                        int xi = d;
 #pragma unroll
-                        for (int i = 0; i < NT; ++i) p += (dv[q] < ds[q][i]) ? 1 : 0;
-#pragma unroll
-                        for (int i = NT - 1; i > 0; --i)
-                            if (i > p) { ds[q][i] = ds[q][i - 1]; id[q][i] = id[q][i - 1]; }
-#pragma unroll
-                        for (int i = 0; i < NT; ++i)
-                            if (i == p) { ds[q][i] = dv[q]; id[q][i] = d; }
+                        for (int i = 0; i < NT; ++i) {
+                            const bool sw = x >= ds[q][i];
+                            const float tv = ds[q][i];
+                            const int ti = id[q][i];
+                            ds[q][i] = sw ? x : tv; id[q][i] = sw ? xi : ti;
+                            x = sw ? tv : x; xi = sw ? ti : xi;
+                        }
                     }
                 }
             }
-            if (cb < n_mgau) {
+            if (FUSE) {
+                const uint8_t *w8 = sa.pdf + ((size_t)cbr * n_feat + f) * nd;            // this senone's weights of stream f
+#pragma unroll
+                for (int q = 0; q < MS_TFT; ++q) {
+                    int fscr = 0;
+#pragma unroll
+                    for (int i = 0; i < NT; ++i)
+                        if (i < sa.n_used) {
+                            const float dv = ds[q][i];
+                            int fden;
+                            if (dv < (float)INT_MIN) fden = INT_MIN >> PSB_SENSCR_SHIFT;
+                            else fden = (__float2int_rz(dv) + ((1 << PSB_SENSCR_SHIFT) - 1)) >> PSB_SENSCR_SHIFT;
+                            const int fw = fden - (int)w8[id[q][i]];
+                            fscr = i == 0 ? fw : logadd_wide(sa.tab, sa.tab_size, sa.tab_zero, fscr, fw);
+                        }
+                    sscr[q] -= fscr;
+                }
+            }
+            else if (cb < n_mgau) {
 #pragma unroll
                 for (int q = 0; q < MS_TFT; ++q) {
                     const long long fr = fb + warp * MS_TFT + q;
@@ -187,6 +278,18 @@ ms_dist_tile_kernel(const float *__restrict__ gT, const float *__restrict__ detT
 #pragma unroll
                     for (int i = 0; i < NT; ++i) o[i] = make_int2(id[q][i], __float_as_int(ds[q][i]));
                 }
+            }
+        }
+        if (FUSE) {
+#pragma unroll
+            for (int q = 0; q < MS_TFT; ++q) {
+                const long long fr = fb + warp * MS_TFT + q;                              // warp-uniform
+                if (fr >= n_frames) break;
+                int scr = sscr[q] / sa.aw;                                                // C division, truncation toward zero (:396)
+                scr = min(32767, max(-32768, scr));                                       // :399-404
+                if (cb < n_mgau) sa.senscr[(frame0 + fr) * n_mgau + cb] = (int16_t)scr;
+                scr = __reduce_min_sync(0xffffffffu, cb < n_mgau ? scr : 0x7fffffff);     // per-frame minimum (ms_mgau.c:218-224)
+                if (lane == 0 && scr != 0x7fffffff) atomicMin(&sa.best[fr], scr);
             }
         }
     }
@@ -275,18 +378,6 @@ ms_dist2_kernel(const float *__restrict__ gT, const float *__restrict__ detT, co
             for (int i = 0; i < NT; ++i) o[i] = make_int2(id[q][i], __float_as_int(ds[q][i]));
         }
     }
-}
-
-// logmath_add with the shifted table (logmath.c:402-446)
-__device__ __forceinline__ int logadd_wide(const uint32_t *__restrict__ tab, int size, int zero, int x, int y)
-{
-    if (x <= zero) return y;
-    if (y <= zero) return x;
-    int d, r;
-    if (x > y) { d = x - y; r = x; }
-    else { d = y - x; r = y; }
-    if (d < 0 || d >= size) return r;
-    return r + (int)tab[d];
 }
 
 // senone_eval (ms_senone.c:358-407) + the first clamp; raw scores and the per-frame minimum.
@@ -488,16 +579,33 @@ int psb_launch_ms_batch(psb_batch_t *b, const float *d_feats, const int32_t *utt
         const size_t tile_smem = ((size_t)m->n_density * m->sumlen * 2 + (size_t)m->n_feat * m->n_density) * MS_TCB * sizeof(float)
                                  + (size_t)m->sumlen * MS_TFB * sizeof(float);
         const bool tile = !no_tile && !packed && !reg_tile_env() && tile_smem <= 100 * 1024;
+        static const bool tile_tft4 = [] { const char *v = getenv("PSB_MS_TFT"); return !(v && atoi(v) == 8); }();   // frames per thread: 4 (default) or 8
+        static const bool tile_pk = [] { const char *v = getenv("PSB_MS_PK"); return !(v && atoi(v) == 0); }();       // packed FP32 pairs (default) or scalar
         // frames per CTA: enough CTAs for ~4 waves of two resident CTAs per SM, whole 32-frame blocks
         const int tiles_x = (m->n_mgau + MS_TCB - 1) / MS_TCB;
         long long fpc = (n * tiles_x + 148LL * 2 * 4 - 1) / (148LL * 2 * 4);
         fpc = std::max<long long>(MS_TFB, (fpc + MS_TFB - 1) / MS_TFB * MS_TFB);
         const dim3 gt((unsigned)tiles_x, (unsigned)((n + fpc - 1) / fpc));
         static const bool reg_tile = getenv("PSB_MS_REGTILE") != nullptr;   // experiment, off: measured slower (247 vs 174 ms)
+        static const bool no_fuse = [] { const char *v = getenv("PSB_MS_FUSE"); return v && atoi(v) == 0; }();
+        // continuous models: mixtures evaluated by the lane that holds the list (the kernel writes raw scores and minima)
+        const bool fuse = tile && !no_fuse && m->sen_is_cb && tile_tft4 && tile_pk && m->n_mgau > 1;
+        MsSenArgs sa = {m->d_mixw, m->d_logadd_ms, m->logadd_ms_size, m->logadd_ms_zero, d_senscr, b->d_msbest, n_used, m->aw};
+        if (fuse) {
+            fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->d_msbest, n, 0x7fffffff);
+            PSB_LAUNCH_CHECK();
+        }
+#define PSB_MS_TILE(NT, TFT, PKV, FUSEV) do {                                                                              \
+            auto kern = ms_dist_tile_kernel<NT, TFT, PKV, FUSEV>;                                                         \
+            PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));            \
+            kern<<<gt, MS_TFB / TFT * 32, tile_smem, b->stream>>>(m->d_msT, m->d_msdetT, d_feats, dist, f0, n, m->n_mgau, \
+                m->n_feat, m->n_density, m->sumlen, m->d_featlen, m->d_featoff, (int)fpc, sa); } while (0)
 #define LAUNCH(NT) do { if (tile) {                                                                                       \
-            PSB_CUDA(cudaFuncSetAttribute(ms_dist_tile_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem)); \
-            ms_dist_tile_kernel<NT><<<gt, 256, tile_smem, b->stream>>>(m->d_msT, m->d_msdetT, d_feats, dist, f0, n,                \
-                m->n_mgau, m->n_feat, m->n_density, m->sumlen, m->d_featlen, m->d_featoff, (int)fpc); }                          \
+            if (fuse) PSB_MS_TILE(NT, 4, true, true);                                                                      \
+            else if (tile_tft4 && tile_pk) PSB_MS_TILE(NT, 4, true, false);                                                \
+            else if (tile_tft4) PSB_MS_TILE(NT, 4, false, false);                                                          \
+            else if (tile_pk) PSB_MS_TILE(NT, 8, true, false);                                                             \
+            else PSB_MS_TILE(NT, 8, false, false); }                                                                       \
         else if (reg_tile && m->n_density <= ND_MAX)                                                          \
             ms_dist_reg_kernel<NT><<<g1, 128, smem, b->stream>>>(m->d_msT, m->d_msdetT, d_feats, dist, f0, n,             \
                 m->n_mgau, m->n_feat, m->n_density, m->sumlen, m->d_featlen, m->d_featoff);                             \
@@ -512,14 +620,17 @@ int psb_launch_ms_batch(psb_batch_t *b, const float *d_feats, const int32_t *utt
         default: LAUNCH(8); break;
         }
 #undef LAUNCH
-        PSB_LAUNCH_CHECK();
-        fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->d_msbest, n, 0x7fffffff);
+#undef PSB_MS_TILE
         PSB_LAUNCH_CHECK();
         dim3 g2((m->n_sen + 255) / 256, (unsigned)n);
-        ms_senone_kernel<<<g2, 256, 0, b->stream>>>(dist, m->d_mixw, m->d_sen2cb32, m->d_logadd_ms, m->logadd_ms_size,
-                                                    m->logadd_ms_zero, d_senscr, b->d_msbest, f0, m->n_sen, m->n_mgau,
-                                                    m->n_feat, m->n_density, nt, n_used, m->aw, m->n_mgau == 1, nullptr, m->n_sen);
-        PSB_LAUNCH_CHECK();
+        if (!(tile && fuse)) {
+            fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->d_msbest, n, 0x7fffffff);
+            PSB_LAUNCH_CHECK();
+            ms_senone_kernel<<<g2, 256, 0, b->stream>>>(dist, m->d_mixw, m->d_sen2cb32, m->d_logadd_ms, m->logadd_ms_size,
+                                                        m->logadd_ms_zero, d_senscr, b->d_msbest, f0, m->n_sen, m->n_mgau,
+                                                        m->n_feat, m->n_density, nt, n_used, m->aw, m->n_mgau == 1, nullptr, m->n_sen);
+            PSB_LAUNCH_CHECK();
+        }
         ms_norm_kernel<<<g2, 256, 0, b->stream>>>(d_senscr, b->d_msbest, f0, m->n_sen, nullptr, m->n_sen);
         PSB_LAUNCH_CHECK();
     }
