@@ -92,7 +92,10 @@ class Decoder:
         pen_ptr, win = (d_pen.data_ptr(), self.pl_window) if d_pen is not None else (None, 0)
         # -latsize is an initial size in the reference (bp_table / bscore_stack double on demand,
         # ngram_search.c:326-339): a table that fills up is retried with doubled capacities
-        cap = self.bp_cap
+        # ... and long streams start from a size that fits them (about four entries per frame on the reference's test
+        # data): a retry repeats the whole search, the reference's realloc does not
+        longest = int(np.diff(frame_off).max()) if len(frame_off) > 1 else 0
+        cap = max(self.bp_cap, 4 * longest + 1000)
         for _ in range(6):
             try:
                 if self.second_pass:

@@ -43,7 +43,7 @@ class Batch:
     def close(self): pass
 
 decoder.api = types.SimpleNamespace(FrontEnd=FE, Model=Model, Batch=Batch, PhoneLoop=PhoneLoop, HmmContext=D.FakeCtx,
-                                    ngram_hyp=real_api.ngram_hyp, ngram_segments=real_api.ngram_segments)
+                                    ngram_hyp=real_api.ngram_hyp, ngram_segments=real_api.ngram_segments, PsbError=real_api.PsbError)
 go = np.fromfile(os.path.join(REF, "data", "goforward.raw"), np.int16)
 utts = [go, go[:30000]]
 dec = decoder.Decoder(HD, DIC, LM)
