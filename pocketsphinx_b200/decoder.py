@@ -92,17 +92,18 @@ class Decoder:
         pen_ptr, win = (d_pen.data_ptr(), self.pl_window) if d_pen is not None else (None, 0)
         # -latsize is an initial size in the reference (bp_table / bscore_stack double on demand,
         # ngram_search.c:326-339): a table that fills up is retried with doubled capacities
-        # ... and long streams start from a size that fits them (about four entries per frame on the reference's test
-        # data): a retry repeats the whole search, the reference's realloc does not
+        # ... and streams start from a size that fits them (the 72 k-word en-us LM writes about eleven entries per frame
+        # and twenty scores per entry on the reference's test data): a retry repeats the whole search, the reference's
+        # realloc does not
         longest = int(np.diff(frame_off).max()) if len(frame_off) > 1 else 0
-        cap = max(self.bp_cap, 4 * longest + 1000)
+        cap = max(self.bp_cap, 12 * longest + 1000)
         for _ in range(6):
             try:
                 if self.second_pass:
-                    tabs, _ = self.ctx.ngram_two_pass(d_scr, frame_off, info, g["model"], g["ci_tmat"], g["ci_ssid"], cap, 20 * cap,
-                                                      pen_ptr, win, first_cap=cap, first_bss_cap=20 * cap, lm_arrays=g["lm_arrays"])
+                    tabs, _ = self.ctx.ngram_two_pass(d_scr, frame_off, info, g["model"], g["ci_tmat"], g["ci_ssid"], cap, 24 * cap,
+                                                      pen_ptr, win, first_cap=cap, first_bss_cap=24 * cap, lm_arrays=g["lm_arrays"])
                 else:
-                    tabs = self.ctx.ngram_fwdtree(d_scr, frame_off, info, g["model"], g["ci_tmat"], cap, 20 * cap, pen_ptr, win,
+                    tabs = self.ctx.ngram_fwdtree(d_scr, frame_off, info, g["model"], g["ci_tmat"], cap, 24 * cap, pen_ptr, win,
                                                   lm_arrays=g["lm_arrays"])
                 break
             except api.PsbError as e:
