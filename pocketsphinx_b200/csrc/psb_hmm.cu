@@ -836,7 +836,8 @@ hmmset_sweep_kernel(HmmSetDev s, HmmCtxDev c, const int16_t *__restrict__ senscr
 {
     static_assert(!BEAM || THREADS == 256, "the histogram walk maps one bin to one thread");
     // score rows in flight: two for the plain sweep (its frame is longer than half a bulk copy's latency), six under the
-    // beam, where a CTA whose instances have mostly left would otherwise wait for every row (measured: 30 -> see DESIGN 4.19)
+    // beam, where a CTA whose instances have mostly left runs ahead of the copies (measured: no difference, the floor of
+    // the pruned sweep is the per-frame exchange)
     constexpr int NBUF = BEAM ? 6 : 2;
     extern __shared__ __align__(128) unsigned char sw_smem[];       // [NBUF][buf_bytes] score rows, then the transition matrices
     __shared__ __align__(8) uint64_t full[NBUF];
