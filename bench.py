@@ -233,6 +233,26 @@ def viterbi_stage(api, torch, ctx, batch, pm, off, U, T, hbm_peak, n_active=6081
                     "`value` uses the fused sweep"}
 
 
+def beam_stage(torch, hs, batch, total, T, U, d_row0, d_nrows, dev):
+    """The same search-scale sweep with the beam applied between frames on the device (prune_channels' best score and
+    -maxhmmpf histogram, prune_nonroot_chan's keep-or-hmm_clear; one thread-block cluster per utterance):
+    not part of `value` -- the headline's 6 081 instances per frame ARE the reference's post-pruning count -- but timed on
+    the scores the timed step just wrote.  -beam 1e-48 is -1080 in score units (logbase 1.0001, >> 10)."""
+    d_best = torch.empty((T, U), dtype=torch.int32, device="cuda:%d" % dev)
+    d_nact = torch.empty((T, U), dtype=torch.int32, device="cuda:%d" % dev)
+    torch.cuda.synchronize()
+    res = {"kernel": "hmmset_sweep_kernel<BEAM>", "instances_per_utt_at_frame_0": N_ACTIVE, "runs": {}}
+    for name, beam, mh in (("beam_neutral", -0x1fffffff, -1), ("beam_1e-48", -1080, -1), ("beam_1e-48_maxhmmpf_3000", -1080, 3000)):
+        hs.restore()
+        ms = hs.sweep_beam_device(batch.senscr_device_ptr(), total, T, 0, beam, d_best.data_ptr(), maxhmmpf=mh,
+                                  d_n_active=d_nact.data_ptr(), d_row0=d_row0.data_ptr(), d_n_rows=d_nrows.data_ptr(), timed=True)
+        na = d_nact.float().mean(dim=1).cpu().numpy()
+        res["runs"][name] = {"beam": beam, "maxhmmpf": mh, "ms": ms, "active_mean": float(na.mean()), "active_frame_1": float(na[1]) if T > 1 else None,
+                             "active_last": float(na[-1])}
+    hs.restore()
+    return res
+
+
 def align_stage(api, ctx, batch, pm, off, U, T, n_phones=100):
     """Batched forced alignment (state_align_search.c) over the scores the GMM stage left in HBM:
     every utterance is aligned to its own chain of n_phones phones (random senone sequences; a 10 s
@@ -770,6 +790,11 @@ def main():
             batch.set_pipeline(1)                           # leave the whole batch's scores in one buffer
             batch.decode_device(pl, d_feats.data_ptr(), off)
             batch.sync()
+            if hs is not None:
+                try:
+                    out["search_viterbi_beam"] = beam_stage(torch, hs, batch, total, T, U, d_row0, d_nrows, local)
+                except Exception as e:                          # an extra, never the reason for a missing bench line
+                    out["search_viterbi_beam"] = {"error": str(e)[:300]}
             out["viterbi_stage"] = viterbi_stage(api, torch, ctx, batch, pm, off, U, T, hbm_peak)
             if pm.n_emit_state in (3, 5) and len(pm.sseq):
                 out["align_stage"] = align_stage(api, ctx, batch, pm, off, U, T)
